@@ -1,0 +1,1 @@
+from . import ode  # noqa: F401

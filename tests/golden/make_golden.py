@@ -1,0 +1,202 @@
+"""
+Generate golden vectors for the particle-mesh hot path by executing the UNMODIFIED reference source
+(`/root/reference/montecosmo/{nbody,utils}.py`) in float64 under the NumPy stand-in for JAX in `jaxshim/`.
+
+Run in the build container only (needs /root/reference):   python tests/golden/make_golden.py
+Writes tests/golden/*.npz (inputs and outputs together, float64 / complex128).  The GPU box never runs this.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("MCPM_REFERENCE", "/root/reference")
+
+
+def load_reference():
+    sys.path.insert(0, os.path.join(HERE, "jaxshim"))
+    sys.path.insert(0, REF)
+    from montecosmo import nbody, utils  # noqa: E402  (the reference itself)
+    from jax_cosmo import Cosmology  # noqa: E402  (stand-in container)
+    import jax.numpy as jnp  # noqa: E402
+    return nbody, utils, Cosmology, jnp
+
+
+ABACUS = dict(Omega_c=0.26447041, Omega_b=0.04930169, h=0.6736, n_s=0.9649, sigma8=0.8076353990239834,
+              Omega_k=0.0, w0=-1.0, wa=0.0)  # bricks.py:40-50
+OTHER = dict(Omega_c=0.21, Omega_b=0.05, h=0.7, n_s=0.96, sigma8=0.8, Omega_k=0.0, w0=-1.0, wa=0.0)
+
+
+def lattice(mesh_shape, ptcl_shape=None):
+    ptcl_shape = mesh_shape if ptcl_shape is None else ptcl_shape
+    ax = [np.linspace(0, m, p, endpoint=False) for m, p in zip(mesh_shape, ptcl_shape)]
+    return np.stack(np.meshgrid(*ax, indexing="ij"), axis=-1).reshape(-1, 3)
+
+
+def gaussian_field_k(rng, shape, amp=0.05, slope=-1.5):
+    """A smooth random Hermitian spectrum: rfftn of white noise times a power-law amplitude (test input only)."""
+    w = rng.normal(size=shape)
+    kx, ky, kz = np.meshgrid(np.fft.fftfreq(shape[0]), np.fft.fftfreq(shape[1]), np.fft.rfftfreq(shape[2]),
+                             indexing="ij")
+    kk = np.sqrt(kx**2 + ky**2 + kz**2)
+    kk[0, 0, 0] = 1.0
+    t = amp * kk**slope
+    t[0, 0, 0] = 0.0
+    return np.fft.rfftn(w) * t * (np.prod(shape) ** -0.5) * 4.0
+
+
+def main():
+    nbody, utils, Cosmology, jnp = load_reference()
+    A = lambda x: np.asarray(x)
+    out = {}
+
+    # ---- kernels on a non-cubic mesh ---------------------------------------------------------------------------
+    shape = (8, 6, 10)
+    kvec = nbody.rfftk(shape)
+    d = {"shape": np.array(shape), "kx": kvec[0], "ky": kvec[1], "kz": kvec[2]}
+    for fd, tag in [(2, "2"), (4, "4"), (np.inf, "inf")]:
+        d[f"invlaplace_{tag}"] = nbody.invlaplace_hat(kvec, fd) * np.ones(utils.r2chshape(shape))
+        for i in range(3):
+            d[f"gradient{i}_{tag}"] = nbody.gradient_hat(kvec, i, fd) * np.ones(utils.r2chshape(shape))
+    d["gaussian_kcut2"] = nbody.gaussian_hat(kvec, 2.0)
+    for o in (1, 2, 3, 4):
+        d[f"rectangular_hat_{o}"] = nbody.rectangular_hat(kvec, o)
+    d["kaiser_bessel_hat_4"] = A(nbody.kaiser_bessel_hat(kvec, 4, A(nbody.optim_kcut(1.5))))
+    out["kernels"] = d
+
+    # ---- paint / read, all orders, positions outside the box, scalar and per-particle weights ------------------
+    rng = np.random.default_rng(1)
+    shape = (12, 10, 14)
+    pos = rng.uniform(-20.0, 40.0, (700, 3))
+    pos[:40] = np.round(pos[:40])  # exact integers
+    pos[40:80] = np.floor(pos[40:80]) + 0.5  # exact half-integers: half-to-even rounding for odd orders
+    wts = rng.normal(size=700)
+    mesh = rng.normal(size=shape)
+    d = {"shape": np.array(shape), "pos": pos, "weights": wts, "mesh": mesh}
+    for o in (1, 2, 3, 4):
+        d[f"paint_w_{o}"] = A(nbody.paint(jnp.asarray(pos), shape, jnp.asarray(wts), o))
+        d[f"paint_1_{o}"] = A(nbody.paint(jnp.asarray(pos), shape, 1.0, o))
+        d[f"read_{o}"] = A(nbody.read(jnp.asarray(pos), jnp.asarray(mesh), o))
+    d["paint_kb_4"] = A(nbody.paint(jnp.asarray(pos), shape, jnp.asarray(wts), 4, "kaiser_bessel", 1.5))
+    d["read_kb_4"] = A(nbody.read(jnp.asarray(pos), jnp.asarray(mesh), 4, "kaiser_bessel", 1.5))
+    out["paint_read"] = d
+
+    # ---- chreshape: crop and pad, non-cubic ---------------------------------------------------------------------
+    rng = np.random.default_rng(2)
+    d = {}
+    for tag, (src, dst) in {"down": ((12, 10, 8), (8, 6, 6)), "up": ((8, 6, 6), (12, 10, 8)),
+                            "mixed": ((8, 12, 6), (10, 8, 10)), "same": ((8, 8, 8), (8, 8, 8))}.items():
+        m = np.fft.rfftn(rng.normal(size=src))
+        d[f"{tag}_in"] = m
+        d[f"{tag}_src"] = np.array(src)
+        d[f"{tag}_dst"] = np.array(dst)
+        d[f"{tag}_out"] = A(utils.chreshape(jnp.asarray(m), utils.r2chshape(dst)))
+    out["chreshape"] = d
+
+    # ---- interlace / deconv / nufft -----------------------------------------------------------------------------
+    rng = np.random.default_rng(3)
+    final = (8, 8, 8)
+    pos = rng.uniform(-2.0, 10.0, (400, 3))
+    wts = rng.uniform(0.5, 1.5, 400)
+    d = {"final_shape": np.array(final), "pos": pos, "weights": wts}
+    d["interlace_2_2"] = A(nbody.interlace(jnp.asarray(pos), final, jnp.asarray(wts), 2, 2))
+    d["interlace_4_3"] = A(nbody.interlace(jnp.asarray(pos), final, jnp.asarray(wts), 4, 3))
+    d["nufft_same"] = A(nbody.nufft(jnp.asarray(pos), final, None, jnp.asarray(wts), 2, 2))
+    d["nufft_over15"] = A(nbody.nufft(jnp.asarray(pos), final, 1.5, jnp.asarray(wts), 2, 2))
+    d["nufft_over15_nodeconv_o3"] = A(nbody.nufft(jnp.asarray(pos), final, 1.5, 1.0, 3, 2, paint_deconv=False))
+    d["nufft_tuple"] = A(nbody.nufft(jnp.asarray(pos), final, (12, 10, 14), jnp.asarray(wts), 2, 2))
+    rmesh = rng.normal(size=final)
+    d["deconv_real_in"] = rmesh
+    d["deconv_real_2"] = A(nbody.deconv_paint(jnp.asarray(rmesh), 2))
+    cm = np.fft.rfftn(rmesh)
+    d["deconv_cplx_3"] = A(nbody.deconv_paint(jnp.asarray(cm), 3))
+    out["nufft"] = d
+
+    # ---- growth tables ------------------------------------------------------------------------------------------
+    d = {}
+    for tag, par in (("abacus", ABACUS), ("other", OTHER)):
+        c = Cosmology(**par)
+        a = np.array([0.0, 1e-3, 0.0123, 0.1, 0.3333, 0.5, 0.9, 1.0])
+        d[f"{tag}_a"] = a
+        for name in ("a2g", "a2g2", "a2f", "a2f2", "a2dg2dg"):
+            d[f"{tag}_{name}"] = A(getattr(nbody, name)(c, a))
+        g = A(nbody.a2g(c, a))
+        for name in ("g2a", "g2g2", "g2f", "g2f2", "g2dg2dg"):
+            d[f"{tag}_{name}"] = A(getattr(nbody, name)(c, g))
+        d[f"{tag}_params"] = np.array([par[k] for k in ("Omega_c", "Omega_b", "h", "n_s", "sigma8")])
+    out["growth"] = d
+
+    # ---- forces, LPT, N-body at 16^3 (and a 12x10x14 non-cubic force case) -------------------------------------
+    rng = np.random.default_rng(4)
+    shape = (16, 16, 16)
+    dk = gaussian_field_k(rng, shape)
+    q = lattice(shape)
+    pos = q + rng.normal(scale=0.7, size=q.shape)
+    c = Cosmology(**ABACUS)
+    d = {"shape": np.array(shape), "delta_k": dk, "pos": pos}
+    d["pm_forces_paint"] = A(nbody.pm_forces(jnp.asarray(pos), shape, 2))
+    d["pm_forces_paint_deconv_kcut"] = A(nbody.pm_forces(jnp.asarray(pos), shape, 2, paint_deconv=True, kcut=2.5))
+    d["pm_forces_paint_o3_fd"] = A(nbody.pm_forces(jnp.asarray(pos), shape, 3, grad_fd=4, lap_fd=2))
+    d["pm_forces_mesh"] = A(nbody.pm_forces(jnp.asarray(pos), jnp.asarray(dk), 2))
+    d["pm_forces_mesh_ngp_lattice"] = A(nbody.pm_forces(jnp.asarray(q), jnp.asarray(dk), 1))
+    d["pm_forces2"] = A(nbody.pm_forces2(jnp.asarray(pos), jnp.asarray(dk), 2))
+    for order in (1, 2):
+        c._workspace = {}
+        dp, vl = nbody.lpt(c, jnp.asarray(dk), jnp.asarray(q), 0.3, order, 1)
+        d[f"lpt{order}_a0.3_dpos"], d[f"lpt{order}_a0.3_vel"] = A(dp), A(vl)
+    c._workspace = {}
+    dp, vl = nbody.lpt(c, jnp.asarray(dk), jnp.asarray(pos), 0.0, 2, 2)
+    d["lpt2_a0_cic_dpos"], d["lpt2_a0_cic_vel"] = A(dp), A(vl)
+    out["forces_lpt"] = d
+
+    d = {"shape": np.array(shape), "delta_k": dk}
+    c._workspace = {}
+    p, v = nbody.nbody_bf(c, jnp.asarray(dk), jnp.asarray(q), a0=0.0, a1=1.0, n_steps=4)
+    d["bf4_pos"], d["bf4_vel"] = A(p), A(v)
+    c._workspace = {}
+    p, v = nbody.nbody_bf(c, jnp.asarray(dk), jnp.asarray(q), a0=0.1, a1=0.8, n_steps=3, paint_order=3,
+                          lpt_order=1, paint_deconv=True, snapshots=4)
+    d["bf3_snap_pos"], d["bf3_snap_vel"] = A(p), A(v)
+    # BullFrog coefficients per step, as the engine receives them (nbody.py:907-919, 933-938)
+    c._workspace = {}
+    g0, g1 = float(nbody.a2g(c, 0.0)), float(nbody.a2g(c, 1.0))
+    dg = (g1 - g0) / 4
+    vf = nbody.bullfrog_vf(c, dg, shape)
+    alphas = []
+    for n in range(4):
+        gg0 = g0 + n * dg
+        gm, ge = gg0 + dg / 2, gg0 + dg
+        d0, d2 = float(nbody.g2dg2dg(c, gg0)), float(nbody.g2dg2dg(c, ge))
+        lin = (float(nbody.g2g2(c, gg0)) + d0 * dg / 2) / gm - gm
+        alphas.append((d2 - lin) / (d0 - lin))
+    d["bf4_alpha"] = np.array(alphas)
+    d["bf4_g0_dg"] = np.array([g0, dg])
+    out["nbody"] = d
+
+    # non-cubic force + small particle count != cells
+    rng = np.random.default_rng(5)
+    shape = (12, 10, 14)
+    dk = gaussian_field_k(rng, shape)
+    pos = rng.uniform(-5, 20, (333, 3))
+    d = {"shape": np.array(shape), "delta_k": dk, "pos": pos}
+    d["pm_forces_paint"] = A(nbody.pm_forces(jnp.asarray(pos), shape, 2))
+    d["pm_forces_mesh"] = A(nbody.pm_forces(jnp.asarray(pos), jnp.asarray(dk), 2))
+    d["pm_forces2"] = A(nbody.pm_forces2(jnp.asarray(pos), jnp.asarray(dk), 2))
+    out["forces_noncubic"] = d
+
+    # ---- white-noise permutation (next row f-2) -----------------------------------------------------------------
+    rng = np.random.default_rng(6)
+    w = rng.normal(size=(8, 6, 10))
+    d = {"white": w, "rg2cgh": A(utils.rg2cgh(jnp.asarray(w)))}
+    d["cgh2rg_roundtrip"] = A(utils.cgh2rg(jnp.asarray(d["rg2cgh"])))
+    out["rg2cgh"] = d
+
+    for name, dd in out.items():
+        path = os.path.join(HERE, f"{name}.npz")
+        np.savez_compressed(path, **{k: np.asarray(v) for k, v in dd.items()})
+        print(f"{name:18s} {os.path.getsize(path) / 1024:8.1f} KiB  {len(dd)} arrays")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,152 @@
+"""The CPU oracle (oracle/pm_oracle.py) against golden vectors produced by the reference's own source
+(tests/golden/make_golden.py).  float64 both sides: agreement to rounding."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pm_oracle as O
+
+RTOL, ATOL = 1e-11, 1e-12
+
+
+def close(a, b, rtol=RTOL, atol=ATOL):
+    a = a.detach().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol * max(1.0, np.abs(b).max()))
+
+
+def test_kernels(golden):
+    g = golden("kernels")
+    shape = tuple(g["shape"])
+    kvec = O.rfftk(shape)
+    for k, name in zip(kvec, ("kx", "ky", "kz")):
+        close(k, g[name])
+    ones = np.ones(O.r2chshape(shape))
+    for fd, tag in [(2, "2"), (4, "4"), (np.inf, "inf")]:
+        close(O.invlaplace_hat(kvec, fd) * ones, g[f"invlaplace_{tag}"])
+        for i in range(3):
+            close(O.gradient_hat(kvec, i, fd) * ones, g[f"gradient{i}_{tag}"])
+    close(O.gaussian_hat(kvec, 2.0), g["gaussian_kcut2"])
+    for o in (1, 2, 3, 4):
+        close(O.rectangular_hat(kvec, o), g[f"rectangular_hat_{o}"])
+    close(O.kaiser_bessel_hat(kvec, 4, O.optim_kcut(1.5)), g["kaiser_bessel_hat_4"])
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+def test_paint_read(golden, order):
+    g = golden("paint_read")
+    shape = tuple(int(s) for s in g["shape"])
+    close(O.paint(g["pos"], shape, g["weights"], order), g[f"paint_w_{order}"])
+    close(O.paint(g["pos"], shape, 1.0, order), g[f"paint_1_{order}"])
+    close(O.read(g["pos"], g["mesh"], order), g[f"read_{order}"])
+
+
+def test_paint_read_kaiser_bessel(golden):
+    g = golden("paint_read")
+    shape = tuple(int(s) for s in g["shape"])
+    close(O.paint(g["pos"], shape, g["weights"], 4, "kaiser_bessel", 1.5), g["paint_kb_4"])
+    close(O.read(g["pos"], g["mesh"], 4, "kaiser_bessel", 1.5), g["read_kb_4"])
+
+
+@pytest.mark.parametrize("tag", ["down", "up", "mixed", "same"])
+def test_chreshape(golden, tag):
+    g = golden("chreshape")
+    dst = tuple(int(s) for s in g[f"{tag}_dst"])
+    close(O.chreshape(g[f"{tag}_in"], O.r2chshape(dst)), g[f"{tag}_out"])
+
+
+def test_nufft(golden):
+    g = golden("nufft")
+    final = tuple(int(s) for s in g["final_shape"])
+    pos, w = g["pos"], g["weights"]
+    close(O.interlace(O._t(pos), final, w, 2, 2), g["interlace_2_2"])
+    close(O.interlace(O._t(pos), final, w, 4, 3), g["interlace_4_3"])
+    close(O.nufft(pos, final, None, w, 2, 2), g["nufft_same"])
+    close(O.nufft(pos, final, 1.5, w, 2, 2), g["nufft_over15"])
+    close(O.nufft(pos, final, 1.5, 1.0, 3, 2, paint_deconv=False), g["nufft_over15_nodeconv_o3"])
+    close(O.nufft(pos, final, (12, 10, 14), w, 2, 2), g["nufft_tuple"])
+    close(O.deconv_paint(O._t(g["deconv_real_in"]), 2), g["deconv_real_2"])
+    close(O.deconv_paint(O._t(np.fft.rfftn(g["deconv_real_in"]), O.C128), 3), g["deconv_cplx_3"])
+
+
+@pytest.mark.parametrize("tag", ["abacus", "other"])
+def test_growth(golden, tag):
+    g = golden("growth")
+    oc, ob, h, ns, s8 = g[f"{tag}_params"]
+    c = O.Cosmology(Omega_c=oc, Omega_b=ob, h=h, n_s=ns, sigma8=s8)
+    a = g[f"{tag}_a"]
+    for name in ("a2g", "a2g2", "a2f", "a2f2", "a2dg2dg"):
+        close(getattr(O, name)(c, a), g[f"{tag}_{name}"], rtol=1e-10)
+    gg = g[f"{tag}_a2g"]
+    for name in ("g2a", "g2g2", "g2f", "g2f2", "g2dg2dg"):
+        close(getattr(O, name)(c, gg), g[f"{tag}_{name}"], rtol=1e-10)
+
+
+@pytest.mark.parametrize("name", ["forces_lpt", "forces_noncubic"])
+def test_forces(golden, name):
+    g = golden(name)
+    shape = tuple(int(s) for s in g["shape"])
+    pos, dk = g["pos"], O._t(g["delta_k"], O.C128)
+    close(O.pm_forces(pos, shape, 2), g["pm_forces_paint"], rtol=1e-9)
+    close(O.pm_forces(pos, dk, 2), g["pm_forces_mesh"], rtol=1e-9)
+    close(O.pm_forces2(pos, dk, 2), g["pm_forces2"], rtol=1e-9)
+    if name == "forces_lpt":
+        close(O.pm_forces(pos, shape, 2, paint_deconv=True, kcut=2.5), g["pm_forces_paint_deconv_kcut"], rtol=1e-9)
+        close(O.pm_forces(pos, shape, 3, grad_fd=4, lap_fd=2), g["pm_forces_paint_o3_fd"], rtol=1e-9)
+        q = O.regular_pos(shape)
+        close(O.pm_forces(q, dk, 1), g["pm_forces_mesh_ngp_lattice"], rtol=1e-9)
+
+
+def test_lpt(golden):
+    g = golden("forces_lpt")
+    shape = tuple(int(s) for s in g["shape"])
+    dk = O._t(g["delta_k"], O.C128)
+    q = O.regular_pos(shape)
+    c = O.Cosmology()
+    for order in (1, 2):
+        dp, vl = O.lpt(c, dk, q, 0.3, order, 1)
+        close(dp, g[f"lpt{order}_a0.3_dpos"], rtol=1e-9)
+        close(vl, g[f"lpt{order}_a0.3_vel"], rtol=1e-9)
+    dp, vl = O.lpt(c, dk, g["pos"], 0.0, 2, 2)
+    close(dp, g["lpt2_a0_cic_dpos"], rtol=1e-9)
+    close(vl, g["lpt2_a0_cic_vel"], rtol=1e-9)
+
+
+def test_nbody_bf(golden):
+    g = golden("nbody")
+    shape = tuple(int(s) for s in g["shape"])
+    dk = O._t(g["delta_k"], O.C128)
+    q = O.regular_pos(shape)
+    c = O.Cosmology()
+    p, v = O.nbody_bf(c, dk, q, 0.0, 1.0, 4)
+    close(p, g["bf4_pos"], rtol=1e-8, atol=1e-10)
+    close(v, g["bf4_vel"], rtol=1e-8, atol=1e-10)
+    p, v = O.nbody_bf(c, dk, q, 0.1, 0.8, 3, paint_order=3, lpt_order=1, paint_deconv=True, snapshots=4)
+    close(p, g["bf3_snap_pos"], rtol=1e-8, atol=1e-10)
+    close(v, g["bf3_snap_vel"], rtol=1e-8, atol=1e-10)
+    g0, dg = g["bf4_g0_dg"]
+    alphas = [float(O.alpha_bf(c, g0 + n * dg, dg)) for n in range(4)]
+    close(np.array(alphas), g["bf4_alpha"], rtol=1e-10)
+
+
+def test_oracle_properties():
+    """Reference-independent checks listed in SURVEY.md section 4 / 8c."""
+    rng = np.random.default_rng(0)
+    shape = (8, 10, 6)
+    pos = O._t(rng.uniform(-3, 12, (200, 3)))
+    w = O._t(rng.normal(size=200))
+    m = O._t(rng.normal(size=shape))
+    for order in (1, 2, 3, 4):
+        # weight conservation (bricks.py:1101-1102) and read = paint^T
+        assert abs(float(O.paint(pos, shape, w, order).sum() - w.sum())) < 1e-10
+        lhs = float((O.read(pos, m, order) * w).sum())
+        rhs = float((m * O.paint(pos, shape, w, order)).sum())
+        assert abs(lhs - rhs) < 1e-10
+    # NGP / CIC read on lattice returns the mesh values (nbody.py:602)
+    q = O.regular_pos(shape)
+    for order in (1, 2):
+        close(O.read(q, m, order), m.reshape(-1).numpy())
+    # chreshape up-then-down is the identity on a band-limited field, and preserves the mean
+    mk = torch.fft.rfftn(m)
+    up = O.chreshape(mk, O.r2chshape((12, 14, 10)))
+    close(O.chreshape(up, O.r2chshape(shape)), mk.numpy(), rtol=1e-10)
+    assert abs(float(torch.fft.irfftn(up, s=(12, 14, 10)).mean() - m.mean())) < 1e-12

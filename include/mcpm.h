@@ -1,0 +1,202 @@
+/*
+ * mcpm.h  --  C ABI of the B200 particle-mesh engine (libmcpm.so).
+ *
+ * Drop-in boundary for the hot path of hsimonfroy/montecosmo: the Python callables of `montecosmo/nbody.py`
+ * that `model.py:23-25` / `bricks.py:10` import.  The reference has no FFI layer of its own (it is pure JAX), so
+ * each entry point names the reference callable (file:line) whose arithmetic it replaces; an XLA-FFI / ctypes stub
+ * binding these symbols is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - All array pointers are DEVICE pointers owned by the caller; nothing is allocated or freed on the call path
+ *     (engine scratch and cuFFT plans are created once, in mcpm_engine_create).
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it and CUDA-graph capturable.
+ *   - Row-major C order.  pos / vel: float32 [np, 3], cell units, any real value (wrapping is the callee's job).
+ *     Real meshes: float32 [nx, ny, nz].  Half spectra: interleaved complex64 [nx, ny, nz/2+1], forward transform
+ *     unnormalised, inverse divides by nx*ny*nz (numpy "backward" norm, as jnp.fft).  nz must be even.
+ *   - Return value: 0 on success, an MCPM_E* code otherwise; mcpm_last_error() gives the thread-local message.
+ *   - Cotangents of complex arrays use the convention  zbar = dL/dRe(z) + i dL/dIm(z)  (torch).  JAX's convention
+ *     is the complex conjugate of it; the XLA-FFI shim conjugates on the way out.
+ */
+#ifndef MCPM_H_
+#define MCPM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCPM_VERSION 100 /* 0.1.0 */
+
+enum {
+  MCPM_OK = 0,
+  MCPM_EINVAL = 1, /* bad argument (shape, order, null pointer)            */
+  MCPM_ECUDA = 2,  /* CUDA runtime error                                   */
+  MCPM_ECUFFT = 3, /* cuFFT error                                          */
+  MCPM_ENOMEM = 4, /* engine scratch allocation failed                     */
+  MCPM_EUNSUP = 5  /* valid in the reference but not implemented here      */
+};
+
+/* finite-difference order selectors of invlaplace_hat / gradient_hat (nbody.py:109-163): 0 means np.inf */
+enum { MCPM_FD_INF = 0, MCPM_FD_2 = 2, MCPM_FD_4 = 4 };
+
+typedef struct mcpm_engine mcpm_engine; /* opaque: cuFFT plans + scratch for one mesh shape on one device */
+
+int mcpm_version(void);
+const char* mcpm_last_error(void);
+
+/* Engine for real mesh shape (nx, ny, nz) on the current device.  max_batch = largest number of meshes transformed
+ * in one call (6 covers 2LPT).  Scratch = (2*max_batch+2) meshes + cuFFT work area, allocated here, once. */
+int mcpm_engine_create(int nx, int ny, int nz, mcpm_engine** out);
+int mcpm_engine_destroy(mcpm_engine* eng);
+size_t mcpm_engine_scratch_bytes(const mcpm_engine* eng);
+
+/* ---- mass assignment ------------------------------------------------------------------------------------------
+ * Positions are transformed in-kernel as x' = x * scale[d] + shift before assignment (nufft's final->paint units,
+ * nbody.py:569, and interlace's shift, nbody.py:524); pass scale = {1,1,1}, shift = 0 for plain paint / read.
+ * order: 1 NGP, 2 CIC, 3 TSC, 4 PCS (`rectangular`, nbody.py:220-246).  kernel_type 'kaiser_bessel' -> MCPM_EUNSUP. */
+
+/* paint (nbody.py:365-396): mesh[(id0+s) mod n] += w_p * prod_d W(id0_d + s_d - x'_d).
+ * weights may be NULL (then every particle carries `wscalar`), else w_p = weights[p] * wscalar.
+ * accumulate = 0 zeroes `mesh` first. */
+int mcpm_paint(void* stream, const float* pos, const float* weights, float wscalar, int64_t np, int nx, int ny,
+               int nz, int order, const float scale[3], float shift, float* mesh, int accumulate);
+
+/* read (nbody.py:398-427): out[p] = sum_s mesh[(id0+s) mod n] * prod_d W(...);  nmesh meshes at once:
+ * mesh = [nmesh, nx, ny, nz] planes, out = [np, nmesh] interleaved (nmesh = 3 gives a force array [np, 3]). */
+int mcpm_read(void* stream, const float* pos, const float* mesh, int nmesh, int64_t np, int nx, int ny, int nz,
+              int order, const float scale[3], float shift, float* out);
+
+/* d/dx' of read: grad[p, a] = sum_m cot[p, m] * sum_s mesh_m[...] * dW_a * prod_{d != a} W_d, times scale[a].
+ * cot may be NULL (all ones).  This one gather is the position-VJP of both read (cot = out_bar) and paint
+ * (mesh = mesh_bar, cot = weights).  accumulate = 1 adds into grad. */
+int mcpm_read_grad(void* stream, const float* pos, const float* mesh, int nmesh, const float* cot, int64_t np,
+                   int nx, int ny, int nz, int order, const float scale[3], float shift, float* grad,
+                   int accumulate);
+
+/* VJP of paint from the mesh cotangent, one gather: weightsbar[p] = wscalar * read(mesh_bar)[p] and
+ * posbar[p,a] = w_p * scale[a] * sum mesh_bar * dW_a * prod_{d != a} W_d (each output nullable). */
+int mcpm_paint_vjp(void* stream, const float* pos, const float* weights, float wscalar, const float* mesh_bar,
+                   int64_t np, int nx, int ny, int nz, int order, const float scale[3], float shift, float* posbar,
+                   float* weightsbar, int accumulate);
+
+/* three-channel paint (VJP of a 3-mesh read w.r.t. the meshes): mesh3[m] += vscale * vals3[p,m] * W, m = 0..2 */
+int mcpm_paint3(void* stream, const float* pos, const float* vals3, float vscale, int64_t np, int nx, int ny, int nz,
+                int order, float* mesh3, int accumulate);
+
+/* ---- FFT (jnp.fft.rfftn / irfftn call sites nbody.py:589,603,620,627,630) -------------------------------------
+ * batch meshes, contiguous planes.  mcpm_irfftn may overwrite its input (cuFFT C2R). */
+int mcpm_rfftn(mcpm_engine* eng, void* stream, const float* in, void* out_c64, int batch);
+int mcpm_irfftn(mcpm_engine* eng, void* stream, void* in_c64, float* out, int batch);
+
+/* ---- fused Fourier-space passes -------------------------------------------------------------------------------
+ * mcpm_force_spectra: out_j = -gradient_hat_j * invlaplace_hat * [gaussian_hat(kcut)] * [1/rectangular_hat^2]
+ *                             * delta_k, j = 0..2   (nbody.py:591-603).  kcut <= 0 means inf; deconv_order 0 = none.
+ * conj != 0 applies the complex conjugate of the kernel and SUMS the three inputs into one output
+ * (the transpose pass of the backward force: in = [3] spectra, out = [1] spectrum). */
+int mcpm_force_spectra(void* stream, const void* delta_k, void* out3, int nx, int ny, int nz, int lap_fd,
+                       int grad_fd, float kcut, int deconv_order);
+int mcpm_force_spectra_T(void* stream, const void* in3, void* out1, int nx, int ny, int nz, int lap_fd,
+                         int grad_fd, float kcut, int deconv_order, int half_weights, int accumulate);
+
+/* mcpm_hessian_spectra: out_ij = gradient_hat_i * gradient_hat_j * invlaplace_hat * delta_k for
+ * (i,j) in (00, 11, 22, 01, 02, 12)  (nbody.py:611-627).  _T: sum_ij conj(kernel_ij) * in_ij -> one spectrum. */
+int mcpm_hessian_spectra(void* stream, const void* delta_k, void* out6, int nx, int ny, int nz, int lap_fd,
+                         int grad_fd);
+int mcpm_hessian_spectra_T(void* stream, const void* in6, void* out1, int nx, int ny, int nz, int lap_fd,
+                           int grad_fd, int half_weights, int accumulate);
+
+/* 2LPT source from the six real Hessian meshes (nbody.py:615-627): d2 = sum_{i<j} (h_ii h_jj - h_ij^2).
+ * _vjp: hbar6 from d2bar and h6. */
+int mcpm_lpt2_source(void* stream, const float* h6, float* d2, int64_t n);
+int mcpm_lpt2_source_vjp(void* stream, const float* h6, const float* d2bar, float* hbar6, int64_t n);
+
+/* deconv_paint on a half spectrum (nbody.py:315-334): out = in / prod_d sinc(k_d / 2pi)^order. */
+int mcpm_deconv(void* stream, const void* in, void* out, int nx, int ny, int nz, int order);
+
+/* interlace combine (nbody.py:523-526) fused with nufft's Jacobian and deconvolution (nbody.py:571-574):
+ * out = scale / prod sinc^deconv_order * (1/m) sum_{i<m} in_i * exp(+i (i/m) (kx+ky+kz)).
+ * _T (transpose, conj kernel): out_i = conj(...) * in for each i, then ready for N*C2R(./w'). */
+int mcpm_interlace_combine(void* stream, const void* in_m, void* out, int m, int nx, int ny, int nz, float scale,
+                           int deconv_order);
+int mcpm_interlace_combine_T(void* stream, const void* in, void* out_m, int m, int nx, int ny, int nz, float scale,
+                             int deconv_order);
+
+/* chreshape (utils.py:975-1013): Hermitian- and mean-preserving Fourier crop / pad between real shapes. */
+int mcpm_chreshape(void* stream, const void* in, int inx, int iny, int inz, void* out, int onx, int ony, int onz);
+
+/* out = in * t (real transfer, half-spectrum shaped) ; white2lin (bricks.py:152-157) and its transpose */
+int mcpm_scale_spectrum(void* stream, const void* in, const float* t, void* out, int64_t nc);
+
+/* ---- particle updates -----------------------------------------------------------------------------------------
+ * lpt combine (nbody.py:656-665): dpos = d1*F1 - d2*F2 ; vel = F1 - dv2*F2 ; pos_out = pos + dpos (pos_out may be
+ * NULL).  f2 may be NULL (1LPT). */
+int mcpm_lpt_combine(void* stream, const float* pos, const float* f1, const float* f2, float d1, float d2,
+                     float dv2, int64_t np, float* dpos, float* vel, float* pos_out);
+
+/* BullFrog kick fused with the force readout and the following drift (nbody.py:933-951):
+ *   F = read(pos, fmesh[3]) ; vel = alpha*vel + beta*F ; pos += vel * drift.
+ * In place on pos / vel.  force_out may be NULL. */
+int mcpm_kick_drift(void* stream, float* pos, float* vel, const float* fmesh3, int64_t np, int nx, int ny, int nz,
+                    int order, float alpha, float beta, float drift, float* force_out);
+/* pos += vel * drift */
+int mcpm_drift(void* stream, float* pos, const float* vel, float drift, int64_t np);
+
+/* ---- composite operators (same names as montecosmo/nbody.py) --------------------------------------------------
+ * pm_forces with a painted mesh (nbody.py:583-604, mesh given as a shape tuple):
+ * fmesh3 receives the three real force meshes [3, nx, ny, nz]; forces [np, 3] may be NULL. */
+int mcpm_pm_forces(mcpm_engine* eng, void* stream, const float* pos, int64_t np, int order, int paint_deconv,
+                   int lap_fd, int grad_fd, float kcut, float* fmesh3, float* forces);
+/* its VJP w.r.t. pos: fbar [np,3], fmesh3 from the forward (or recomputed by it) -> posbar [np,3] (accumulated
+ * when accumulate != 0). */
+int mcpm_pm_forces_vjp(mcpm_engine* eng, void* stream, const float* pos, const float* fbar, const float* fmesh3,
+                       int64_t np, int order, int paint_deconv, int lap_fd, int grad_fd, float kcut,
+                       float* posbar, int accumulate);
+
+/* pm_forces with a given spectrum (nbody.py:595-604) and pm_forces2 (nbody.py:607-631); read order `order`. */
+int mcpm_pm_forces_mesh(mcpm_engine* eng, void* stream, const float* pos, const void* delta_k, int64_t np,
+                        int order, int lap_fd, int grad_fd, float kcut, float* forces);
+int mcpm_pm_forces2(mcpm_engine* eng, void* stream, const float* pos, const void* delta_k, int64_t np, int order,
+                    int lap_fd, int grad_fd, float* forces, float* h6_out /* nullable: [6,nx,ny,nz] tape */);
+
+/* lpt (nbody.py:634-667), scalar scale factor.  Growth coefficients are host scalars computed by the caller
+ * (d1 = a2g(a), d2 = a2g2(a), dv2 = a2dg2dg(a), nbody.py:750-777) so they stay differentiable on the host.
+ * Outputs dpos, vel [np,3]; tape: f1 [np,3], f2 [np,3], h6 [6,nx,ny,nz] (each nullable when no VJP is wanted). */
+int mcpm_lpt(mcpm_engine* eng, void* stream, const void* delta_k, const float* pos, int64_t np, int lpt_order,
+             int read_order, int lap_fd, int grad_fd, float d1, float d2, float dv2, float* dpos, float* vel,
+             float* f1, float* f2, float* h6);
+/* VJP of lpt w.r.t. delta_k and the three coefficients: dposbar, velbar -> dkbar (complex, convention above),
+ * coefbar[3] (device, float64: d1bar, d2bar, dv2bar). */
+int mcpm_lpt_vjp(mcpm_engine* eng, void* stream, const float* pos, int64_t np, int lpt_order, int read_order,
+                 int lap_fd, int grad_fd, float d1, float d2, float dv2, const float* dposbar, const float* velbar,
+                 const float* f1, const float* f2, const float* h6, void* dkbar, double* coefbar, int accumulate);
+
+/* nbody_bf step loop (nbody.py:933-951, 999): n_steps drift-kick-drift steps in place on (pos, vel).
+ * Per-step host arrays: alpha[s], beta[s] = (1 - alpha) / g1, drift_pre[s], drift_post[s] (= dg/2 each).
+ * Tape (nullable): xk [n_steps, np, 3] positions at kick time, vk [n_steps, np, 3] velocities after the kick,
+ * fm [n_steps, 3, nx, ny, nz] force meshes. */
+int mcpm_nbody_steps(mcpm_engine* eng, void* stream, float* pos, float* vel, int64_t np, int n_steps,
+                     const float* alpha, const float* beta, const float* drift_pre, const float* drift_post,
+                     int order, int paint_deconv, int lap_fd, int grad_fd, float* xk, float* vk, float* fm);
+/* VJP of the loop: (posbar, velbar) at the end -> at the start, in place.  v0 = velocities before the first step.
+ * coefbar (device float64 [n_steps, 4]: alpha, beta, drift_pre, drift_post cotangents) may be NULL. */
+int mcpm_nbody_steps_vjp(mcpm_engine* eng, void* stream, float* posbar, float* velbar, int64_t np, int n_steps,
+                         const float* alpha, const float* beta, const float* drift_pre, const float* drift_post,
+                         int order, int paint_deconv, int lap_fd, int grad_fd, const float* xk, const float* vk,
+                         const float* fm, const float* v0, double* coefbar);
+
+/* nufft (nbody.py:532-577) for paint_shape == engine shape: interlaced, Jacobian-scaled, deconvolved paint returning
+ * the half spectrum at the paint shape (the caller applies mcpm_chreshape to reach final_shape).
+ * pos is in FINAL units; scale[d] = paint_shape[d] / final_shape[d]. */
+int mcpm_nufft(mcpm_engine* eng, void* stream, const float* pos, const float* weights, float wscalar, int64_t np,
+               const float scale[3], int paint_order, int interlace_order, int paint_deconv, void* out_k);
+/* VJP: outbar_k -> posbar [np,3] and weightsbar [np] (each nullable). */
+int mcpm_nufft_vjp(mcpm_engine* eng, void* stream, const float* pos, const float* weights, float wscalar,
+                   int64_t np, const float scale[3], int paint_order, int interlace_order, int paint_deconv,
+                   const void* outbar_k, float* posbar, float* weightsbar);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCPM_H_ */

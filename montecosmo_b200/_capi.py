@@ -1,0 +1,88 @@
+"""ctypes prototypes for include/mcpm.h.  `bind(cdll)` attaches argtypes/restype; `check(lib, code)` raises on error.
+
+Pointer arguments are passed as integers (device addresses from `tensor.data_ptr()`), except the small host arrays
+(`scale[3]`, per-step coefficient arrays) which are ctypes float arrays.
+"""
+import ctypes as C
+
+vp, f32, i32, i64, sz = C.c_void_p, C.c_float, C.c_int, C.c_int64, C.c_size_t
+hp = C.POINTER(C.c_float)  # host float array
+
+MESH = [i32, i32, i32]
+XF = [hp, f32]  # scale[3] (host), shift
+
+SIGNATURES = {
+    "mcpm_version": ([], i32),
+    "mcpm_last_error": ([], C.c_char_p),
+    "mcpm_engine_create": (MESH + [C.POINTER(vp)], i32),
+    "mcpm_engine_destroy": ([vp], i32),
+    "mcpm_engine_scratch_bytes": ([vp], sz),
+    "mcpm_paint": ([vp, vp, vp, f32, i64] + MESH + [i32] + XF + [vp, i32], i32),
+    "mcpm_read": ([vp, vp, vp, i32, i64] + MESH + [i32] + XF + [vp], i32),
+    "mcpm_read_grad": ([vp, vp, vp, i32, vp, i64] + MESH + [i32] + XF + [vp, i32], i32),
+    "mcpm_paint_vjp": ([vp, vp, vp, f32, vp, i64] + MESH + [i32] + XF + [vp, vp, i32], i32),
+    "mcpm_paint3": ([vp, vp, vp, f32, i64] + MESH + [i32, vp, i32], i32),
+    "mcpm_rfftn": ([vp, vp, vp, vp, i32], i32),
+    "mcpm_irfftn": ([vp, vp, vp, vp, i32], i32),
+    "mcpm_force_spectra": ([vp, vp, vp] + MESH + [i32, i32, f32, i32], i32),
+    "mcpm_force_spectra_T": ([vp, vp, vp] + MESH + [i32, i32, f32, i32, i32, i32], i32),
+    "mcpm_hessian_spectra": ([vp, vp, vp] + MESH + [i32, i32], i32),
+    "mcpm_hessian_spectra_T": ([vp, vp, vp] + MESH + [i32, i32, i32, i32], i32),
+    "mcpm_lpt2_source": ([vp, vp, vp, i64], i32),
+    "mcpm_lpt2_source_vjp": ([vp, vp, vp, vp, i64], i32),
+    "mcpm_deconv": ([vp, vp, vp] + MESH + [i32], i32),
+    "mcpm_interlace_combine": ([vp, vp, vp, i32] + MESH + [f32, i32], i32),
+    "mcpm_interlace_combine_T": ([vp, vp, vp, i32] + MESH + [f32, i32], i32),
+    "mcpm_chreshape": ([vp, vp] + MESH + [vp] + MESH, i32),
+    "mcpm_scale_spectrum": ([vp, vp, vp, vp, i64], i32),
+    "mcpm_lpt_combine": ([vp, vp, vp, vp, f32, f32, f32, i64, vp, vp, vp], i32),
+    "mcpm_kick_drift": ([vp, vp, vp, vp, i64] + MESH + [i32, f32, f32, f32, vp], i32),
+    "mcpm_drift": ([vp, vp, vp, f32, i64], i32),
+    "mcpm_pm_forces": ([vp, vp, vp, i64, i32, i32, i32, i32, f32, vp, vp], i32),
+    "mcpm_pm_forces_vjp": ([vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, f32, vp, i32], i32),
+    "mcpm_pm_forces_mesh": ([vp, vp, vp, vp, i64, i32, i32, i32, f32, vp], i32),
+    "mcpm_pm_forces2": ([vp, vp, vp, vp, i64, i32, i32, i32, vp, vp], i32),
+    "mcpm_lpt": ([vp, vp, vp, vp, i64, i32, i32, i32, i32, f32, f32, f32, vp, vp, vp, vp, vp], i32),
+    "mcpm_lpt_vjp": ([vp, vp, vp, i64, i32, i32, i32, i32, f32, f32, f32, vp, vp, vp, vp, vp, vp, vp, i32], i32),
+    "mcpm_nbody_steps": ([vp, vp, vp, vp, i64, i32, hp, hp, hp, hp, i32, i32, i32, i32, vp, vp, vp], i32),
+    "mcpm_nbody_steps_vjp": ([vp, vp, vp, vp, i64, i32, hp, hp, hp, hp, i32, i32, i32, i32, vp, vp, vp, vp, vp], i32),
+    "mcpm_nufft": ([vp, vp, vp, vp, f32, i64, hp, i32, i32, i32, vp], i32),
+    "mcpm_nufft_vjp": ([vp, vp, vp, vp, f32, i64, hp, i32, i32, i32, vp, vp, vp], i32),
+}
+
+ERROR_NAMES = {1: "MCPM_EINVAL", 2: "MCPM_ECUDA", 3: "MCPM_ECUFFT", 4: "MCPM_ENOMEM", 5: "MCPM_EUNSUP"}
+
+
+class McpmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{ERROR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+def bind(lib):
+    """Attach prototypes; raises AttributeError if the library misses a symbol the header declares."""
+    for name, (argtypes, restype) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+    return lib
+
+
+def check(lib, code):
+    if code != 0:
+        raise McpmError(code, lib.mcpm_last_error().decode())
+
+
+def host_floats(values):
+    """Small host float array (scale[3], per-step coefficients)."""
+    values = [float(v) for v in values]
+    return (C.c_float * len(values))(*values)
+
+
+def fd_code(fd):
+    """np.inf / 2 / 4 -> MCPM_FD_* (invlaplace_hat / gradient_hat, nbody.py:109-163)."""
+    if fd in (2, 4):
+        return int(fd)
+    if fd == float("inf"):
+        return 0
+    raise ValueError("Only orders 2, 4, and inf are supported.")

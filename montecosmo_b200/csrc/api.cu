@@ -1,0 +1,316 @@
+// api.cu -- the extern "C" boundary declared in include/mcpm.h.  No exceptions cross it; errors are codes plus a
+// thread-local message.
+#include <exception>
+
+#include "engine.h"
+
+namespace mcpm {
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace mcpm
+
+using namespace mcpm;
+
+struct mcpm_engine {
+  Engine* e;
+};
+
+#define API_BEGIN try {
+#define API_END                                  \
+  }                                              \
+  catch (const std::exception& ex) {             \
+    set_error(std::string("exception: ") + ex.what()); \
+    return MCPM_EINVAL;                          \
+  }                                              \
+  catch (...) {                                  \
+    set_error("unknown exception");              \
+    return MCPM_EINVAL;                          \
+  }
+
+#define NEED(cond, msg)   \
+  do {                    \
+    if (!(cond)) {        \
+      set_error(msg);     \
+      return MCPM_EINVAL; \
+    }                     \
+  } while (0)
+
+static inline const cfloat* C(const void* p) { return reinterpret_cast<const cfloat*>(p); }
+static inline cfloat* C(void* p) { return reinterpret_cast<cfloat*>(p); }
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int mcpm_version(void) { return MCPM_VERSION; }
+const char* mcpm_last_error(void) { return g_last_error.c_str(); }
+
+int mcpm_engine_create(int nx, int ny, int nz, mcpm_engine** out) {
+  API_BEGIN
+  NEED(out, "engine_create: null out");
+  Engine* e = engine_create(nx, ny, nz);
+  if (!e) return MCPM_ENOMEM;
+  *out = new mcpm_engine{e};
+  return MCPM_OK;
+  API_END
+}
+
+int mcpm_engine_destroy(mcpm_engine* eng) {
+  if (!eng) return MCPM_OK;
+  engine_destroy(eng->e);
+  delete eng;
+  return MCPM_OK;
+}
+
+size_t mcpm_engine_scratch_bytes(const mcpm_engine* eng) { return eng ? eng->e->scratch_bytes : 0; }
+
+int mcpm_paint(void* stream, const float* pos, const float* weights, float wscalar, int64_t np, int nx, int ny,
+               int nz, int order, const float scale[3], float shift, float* mesh, int accumulate) {
+  API_BEGIN
+  return paint(as_stream(stream), pos, weights, wscalar, np, nx, ny, nz, order, scale, shift, mesh, accumulate);
+  API_END
+}
+
+int mcpm_read(void* stream, const float* pos, const float* mesh, int nmesh, int64_t np, int nx, int ny, int nz,
+              int order, const float scale[3], float shift, float* out) {
+  API_BEGIN
+  return read(as_stream(stream), pos, mesh, nmesh, np, nx, ny, nz, order, scale, shift, out);
+  API_END
+}
+
+int mcpm_read_grad(void* stream, const float* pos, const float* mesh, int nmesh, const float* cot, int64_t np,
+                   int nx, int ny, int nz, int order, const float scale[3], float shift, float* grad,
+                   int accumulate) {
+  API_BEGIN
+  NEED(nmesh >= 1 && nmesh <= 4, "read_grad: nmesh must be 1..4");
+  const int64_t plane = (int64_t)nx * ny * nz;
+  const float* ms[4] = {mesh, mesh + plane, mesh + 2 * plane, mesh + 3 * plane};
+  return read_grad(as_stream(stream), pos, ms, nmesh, cot, cot ? nmesh : 0, 1.0f, nullptr, np, nx, ny, nz, order,
+                   scale, shift, grad, accumulate);
+  API_END
+}
+
+int mcpm_paint_vjp(void* stream, const float* pos, const float* weights, float wscalar, const float* mesh_bar,
+                   int64_t np, int nx, int ny, int nz, int order, const float scale[3], float shift, float* posbar,
+                   float* weightsbar, int accumulate) {
+  API_BEGIN
+  return paint_vjp(as_stream(stream), pos, weights, wscalar, mesh_bar, np, nx, ny, nz, order, scale, shift, posbar,
+                   weightsbar, accumulate);
+  API_END
+}
+
+int mcpm_paint3(void* stream, const float* pos, const float* vals3, float vscale, int64_t np, int nx, int ny, int nz,
+                int order, float* mesh3, int accumulate) {
+  API_BEGIN
+  return paint3(as_stream(stream), pos, vals3, vscale, nullptr, 0.0f, np, nx, ny, nz, order, mesh3, accumulate);
+  API_END
+}
+
+int mcpm_rfftn(mcpm_engine* eng, void* stream, const float* in, void* out_c64, int batch) {
+  API_BEGIN
+  NEED(eng && in && out_c64 && batch >= 1, "rfftn: bad arguments");
+  return fft_r2c(eng->e->fft, as_stream(stream), in, C(out_c64), batch);
+  API_END
+}
+
+int mcpm_irfftn(mcpm_engine* eng, void* stream, void* in_c64, float* out, int batch) {
+  API_BEGIN
+  NEED(eng && in_c64 && out && batch >= 1, "irfftn: bad arguments");
+  stream_t st = as_stream(stream);
+  if (int e = fft_c2r(eng->e->fft, st, C(in_c64), out, batch)) return e;
+  return scale_real(st, out, eng->e->invN, out, eng->e->N * batch);  // standalone irfftn pays one scaling pass
+  API_END
+}
+
+int mcpm_force_spectra(void* stream, const void* delta_k, void* out3, int nx, int ny, int nz, int lap_fd,
+                       int grad_fd, float kcut, int deconv_order) {
+  API_BEGIN
+  return force_spectra(as_stream(stream), C(delta_k), C(out3), nx, ny, nz, lap_fd, grad_fd, kcut, deconv_order, 1.0f);
+  API_END
+}
+
+int mcpm_force_spectra_T(void* stream, const void* in3, void* out1, int nx, int ny, int nz, int lap_fd,
+                         int grad_fd, float kcut, int deconv_order, int half_weights, int accumulate) {
+  API_BEGIN
+  return force_spectra_T(as_stream(stream), C(in3), C(out1), nx, ny, nz, lap_fd, grad_fd, kcut, deconv_order,
+                         half_weights, accumulate, 1.0f);
+  API_END
+}
+
+int mcpm_hessian_spectra(void* stream, const void* delta_k, void* out6, int nx, int ny, int nz, int lap_fd,
+                         int grad_fd) {
+  API_BEGIN
+  return hessian_spectra(as_stream(stream), C(delta_k), C(out6), nx, ny, nz, lap_fd, grad_fd, 1.0f);
+  API_END
+}
+
+int mcpm_hessian_spectra_T(void* stream, const void* in6, void* out1, int nx, int ny, int nz, int lap_fd,
+                           int grad_fd, int half_weights, int accumulate) {
+  API_BEGIN
+  return hessian_spectra_T(as_stream(stream), C(in6), C(out1), nx, ny, nz, lap_fd, grad_fd, half_weights, accumulate,
+                           1.0f);
+  API_END
+}
+
+int mcpm_lpt2_source(void* stream, const float* h6, float* d2, int64_t n) {
+  API_BEGIN
+  return lpt2_source(as_stream(stream), h6, d2, n);
+  API_END
+}
+
+int mcpm_lpt2_source_vjp(void* stream, const float* h6, const float* d2bar, float* hbar6, int64_t n) {
+  API_BEGIN
+  return lpt2_source_vjp(as_stream(stream), h6, d2bar, hbar6, n);
+  API_END
+}
+
+int mcpm_deconv(void* stream, const void* in, void* out, int nx, int ny, int nz, int order) {
+  API_BEGIN
+  return deconv(as_stream(stream), C(in), C(out), nx, ny, nz, order);
+  API_END
+}
+
+int mcpm_interlace_combine(void* stream, const void* in_m, void* out, int m, int nx, int ny, int nz, float scale,
+                           int deconv_order) {
+  API_BEGIN
+  return interlace_combine(as_stream(stream), C(in_m), C(out), m, nx, ny, nz, scale, deconv_order);
+  API_END
+}
+
+int mcpm_interlace_combine_T(void* stream, const void* in, void* out_m, int m, int nx, int ny, int nz, float scale,
+                             int deconv_order) {
+  API_BEGIN
+  return interlace_combine_T(as_stream(stream), C(in), C(out_m), m, nx, ny, nz, scale, deconv_order,
+                             (float)((double)nx * ny * nz));
+  API_END
+}
+
+int mcpm_chreshape(void* stream, const void* in, int inx, int iny, int inz, void* out, int onx, int ony, int onz) {
+  API_BEGIN
+  NEED(in && out && in != out, "chreshape: in and out must be distinct buffers");
+  return chreshape(as_stream(stream), C(in), inx, iny, inz, C(out), onx, ony, onz);
+  API_END
+}
+
+int mcpm_scale_spectrum(void* stream, const void* in, const float* t, void* out, int64_t nc) {
+  API_BEGIN
+  return scale_spectrum(as_stream(stream), C(in), t, C(out), nc);
+  API_END
+}
+
+int mcpm_lpt_combine(void* stream, const float* pos, const float* f1, const float* f2, float d1, float d2,
+                     float dv2, int64_t np, float* dpos, float* vel, float* pos_out) {
+  API_BEGIN
+  return lpt_combine(as_stream(stream), pos, f1, f2, d1, d2, dv2, np, dpos, vel, pos_out);
+  API_END
+}
+
+int mcpm_kick_drift(void* stream, float* pos, float* vel, const float* fmesh3, int64_t np, int nx, int ny, int nz,
+                    int order, float alpha, float beta, float drift, float* force_out) {
+  API_BEGIN
+  return kick_drift(as_stream(stream), pos, vel, fmesh3, np, nx, ny, nz, order, alpha, beta, drift, pos, vel,
+                    force_out);
+  API_END
+}
+
+int mcpm_drift(void* stream, float* pos, const float* vel, float drift, int64_t np) {
+  API_BEGIN
+  return axpy3(as_stream(stream), pos, vel, drift, 3 * np, pos);
+  API_END
+}
+
+int mcpm_pm_forces(mcpm_engine* eng, void* stream, const float* pos, int64_t np, int order, int paint_deconv,
+                   int lap_fd, int grad_fd, float kcut, float* fmesh3, float* forces) {
+  API_BEGIN
+  NEED(eng, "null engine");
+  return pm_forces(eng->e, as_stream(stream), pos, np, order, paint_deconv, lap_fd, grad_fd, kcut, fmesh3, forces);
+  API_END
+}
+
+int mcpm_pm_forces_vjp(mcpm_engine* eng, void* stream, const float* pos, const float* fbar, const float* fmesh3,
+                       int64_t np, int order, int paint_deconv, int lap_fd, int grad_fd, float kcut,
+                       float* posbar, int accumulate) {
+  API_BEGIN
+  NEED(eng && fmesh3 && fbar && posbar, "pm_forces_vjp: null pointer");
+  return pm_forces_vjp(eng->e, as_stream(stream), pos, fbar, 1.0f, fmesh3, np, order, paint_deconv, lap_fd, grad_fd,
+                       kcut, posbar, accumulate);
+  API_END
+}
+
+int mcpm_pm_forces_mesh(mcpm_engine* eng, void* stream, const float* pos, const void* delta_k, int64_t np,
+                        int order, int lap_fd, int grad_fd, float kcut, float* forces) {
+  API_BEGIN
+  NEED(eng && delta_k && forces, "pm_forces_mesh: null pointer");
+  return pm_forces_mesh(eng->e, as_stream(stream), pos, C(delta_k), np, order, lap_fd, grad_fd, kcut, forces);
+  API_END
+}
+
+int mcpm_pm_forces2(mcpm_engine* eng, void* stream, const float* pos, const void* delta_k, int64_t np, int order,
+                    int lap_fd, int grad_fd, float* forces, float* h6_out) {
+  API_BEGIN
+  NEED(eng && delta_k && forces, "pm_forces2: null pointer");
+  return pm_forces2(eng->e, as_stream(stream), pos, C(delta_k), np, order, lap_fd, grad_fd, forces, h6_out);
+  API_END
+}
+
+int mcpm_lpt(mcpm_engine* eng, void* stream, const void* delta_k, const float* pos, int64_t np, int lpt_order,
+             int read_order, int lap_fd, int grad_fd, float d1, float d2, float dv2, float* dpos, float* vel,
+             float* f1, float* f2, float* h6) {
+  API_BEGIN
+  NEED(eng && delta_k && pos, "lpt: null pointer");
+  return lpt(eng->e, as_stream(stream), C(delta_k), pos, np, lpt_order, read_order, lap_fd, grad_fd, d1, d2, dv2,
+             dpos, vel, f1, f2, h6);
+  API_END
+}
+
+int mcpm_lpt_vjp(mcpm_engine* eng, void* stream, const float* pos, int64_t np, int lpt_order, int read_order,
+                 int lap_fd, int grad_fd, float d1, float d2, float dv2, const float* dposbar, const float* velbar,
+                 const float* f1, const float* f2, const float* h6, void* dkbar, double* coefbar, int accumulate) {
+  API_BEGIN
+  NEED(eng && pos && dposbar && velbar && dkbar, "lpt_vjp: null pointer");
+  return lpt_vjp(eng->e, as_stream(stream), pos, np, lpt_order, read_order, lap_fd, grad_fd, d1, d2, dv2, dposbar,
+                 velbar, f1, f2, h6, C(dkbar), coefbar, accumulate);
+  API_END
+}
+
+int mcpm_nbody_steps(mcpm_engine* eng, void* stream, float* pos, float* vel, int64_t np, int n_steps,
+                     const float* alpha, const float* beta, const float* drift_pre, const float* drift_post,
+                     int order, int paint_deconv, int lap_fd, int grad_fd, float* xk, float* vk, float* fm) {
+  API_BEGIN
+  NEED(eng && pos && vel, "nbody_steps: null pointer");
+  return nbody_steps(eng->e, as_stream(stream), pos, vel, np, n_steps, alpha, beta, drift_pre, drift_post, order,
+                     paint_deconv, lap_fd, grad_fd, xk, vk, fm);
+  API_END
+}
+
+int mcpm_nbody_steps_vjp(mcpm_engine* eng, void* stream, float* posbar, float* velbar, int64_t np, int n_steps,
+                         const float* alpha, const float* beta, const float* drift_pre, const float* drift_post,
+                         int order, int paint_deconv, int lap_fd, int grad_fd, const float* xk, const float* vk,
+                         const float* fm, const float* v0, double* coefbar) {
+  API_BEGIN
+  NEED(eng && posbar && velbar, "nbody_steps_vjp: null pointer");
+  return nbody_steps_vjp(eng->e, as_stream(stream), posbar, velbar, np, n_steps, alpha, beta, drift_pre, drift_post,
+                         order, paint_deconv, lap_fd, grad_fd, xk, vk, fm, v0, coefbar);
+  API_END
+}
+
+int mcpm_nufft(mcpm_engine* eng, void* stream, const float* pos, const float* weights, float wscalar, int64_t np,
+               const float scale[3], int paint_order, int interlace_order, int paint_deconv, void* out_k) {
+  API_BEGIN
+  NEED(eng && pos && out_k, "nufft: null pointer");
+  return nufft(eng->e, as_stream(stream), pos, weights, wscalar, np, scale, paint_order, interlace_order,
+               paint_deconv, C(out_k));
+  API_END
+}
+
+int mcpm_nufft_vjp(mcpm_engine* eng, void* stream, const float* pos, const float* weights, float wscalar,
+                   int64_t np, const float scale[3], int paint_order, int interlace_order, int paint_deconv,
+                   const void* outbar_k, float* posbar, float* weightsbar) {
+  API_BEGIN
+  NEED(eng && pos && outbar_k, "nufft_vjp: null pointer");
+  return nufft_vjp(eng->e, as_stream(stream), pos, weights, wscalar, np, scale, paint_order, interlace_order,
+                   paint_deconv, C(outbar_k), posbar, weightsbar);
+  API_END
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,276 @@
+// engine.cu -- composite operators of montecosmo/nbody.py and their adjoints, orchestrated on one stream with no
+// allocation or synchronisation on the call path: pm_forces (583-604), pm_forces2 (607-631), lpt (634-667), the
+// BullFrog drift-kick-drift loop (933-951, 999), nufft (532-577).
+//
+// FFT normalisation: cuFFT's C2R is unnormalised; the 1/N of irfftn is folded into the Fourier pass that precedes
+// each C2R (`norm` argument), so no separate scaling pass ever touches a mesh.
+#include "engine.h"
+
+namespace mcpm {
+
+Engine* engine_create(int nx, int ny, int nz) {
+  if (nx < 4 || ny < 4 || nz < 4 || (nz & 1)) {
+    set_error("engine: mesh sides must be >= 4 and nz even");
+    return nullptr;
+  }
+  Engine* e = new Engine;
+  e->nx = nx;
+  e->ny = ny;
+  e->nz = nz;
+  e->nzc = nz / 2 + 1;
+  e->N = (int64_t)nx * ny * nz;
+  e->Nc = (int64_t)nx * ny * e->nzc;
+  e->invN = (float)(1.0 / (double)e->N);
+  size_t fftws = 0;
+  e->fft = fft_create(nx, ny, nz, &fftws);
+  if (!e->fft) {
+    delete e;
+    return nullptr;
+  }
+  size_t rb = sizeof(float) * (size_t)e->N * Engine::kR, cb = sizeof(cfloat) * (size_t)e->Nc * Engine::kC;
+  if (rt_malloc((void**)&e->rbuf, rb) || rt_malloc((void**)&e->cbuf, cb)) {
+    set_error("engine: scratch allocation failed");
+    engine_destroy(e);
+    return nullptr;
+  }
+  e->scratch_bytes = rb + cb + fftws;
+  return e;
+}
+
+void engine_destroy(Engine* e) {
+  if (!e) return;
+  if (e->rbuf) rt_free(e->rbuf);
+  if (e->cbuf) rt_free(e->cbuf);
+  if (e->fft) fft_destroy(e->fft);
+  delete e;
+}
+
+#define TRY(x)            \
+  do {                    \
+    if (int _e = (x)) return _e; \
+  } while (0)
+
+// delta_k (any spectrum, preserved) -> three real force meshes fm[3][N]  (nbody.py:595-603 up to the irfftn)
+static int force_meshes_from_spectrum(Engine* E, stream_t st, const cfloat* dk, int lap_fd, int grad_fd, float kcut,
+                                      int deconv_order, float* fm) {
+  TRY(force_spectra(st, dk, E->c(0), E->nx, E->ny, E->nz, lap_fd, grad_fd, kcut, deconv_order, E->invN));
+  TRY(fft_c2r(E->fft, st, E->c(0), fm, 3));
+  return 0;
+}
+
+// pm_forces with a painted density (mesh given as a shape tuple, nbody.py:588-604)
+int pm_forces(Engine* E, stream_t st, const float* pos, int64_t np, int order, int paint_deconv, int lap_fd,
+              int grad_fd, float kcut, float* fmesh3, float* forces) {
+  float* fm = fmesh3 ? fmesh3 : E->r(0);
+  float* rho = E->r(6);
+  TRY(paint(st, pos, nullptr, 1.0f, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, rho, 0));
+  TRY(fft_r2c(E->fft, st, rho, E->c(6), 1));
+  TRY(force_meshes_from_spectrum(E, st, E->c(6), lap_fd, grad_fd, kcut, paint_deconv ? order : 0, fm));
+  if (forces) TRY(read(st, pos, fm, 3, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, forces));
+  return 0;
+}
+
+// VJP of pm_forces w.r.t. pos.  With m_j the force kernel, F_j = read(x, C2R(m_j R2C(paint(x)))):
+//   phibar_j = paint(x, fbar_j);  rhobar = C2R(sum_j conj(m_j) R2C(phibar_j));
+//   xbar = sum_j fbar_j * dread(x, phi_j) + dread(x, rhobar)          (one fused 4-mesh gather)
+// `fbar` enters as cscale * fbar so that the BullFrog backward can pass vbar with cscale = beta.
+int pm_forces_vjp(Engine* E, stream_t st, const float* pos, const float* fbar, float cscale, const float* fmesh3,
+                  int64_t np, int order, int paint_deconv, int lap_fd, int grad_fd, float kcut, float* posbar,
+                  int accumulate) {
+  TRY(paint3(st, pos, fbar, cscale, nullptr, 0.0f, np, E->nx, E->ny, E->nz, order, E->r(0), 0));
+  TRY(fft_r2c(E->fft, st, E->r(0), E->c(0), 3));
+  TRY(force_spectra_T(st, E->c(0), E->c(3), E->nx, E->ny, E->nz, lap_fd, grad_fd, kcut, paint_deconv ? order : 0, 0,
+                      0, E->invN));
+  TRY(fft_c2r(E->fft, st, E->c(3), E->r(3), 1));
+  const float* ms[4] = {fmesh3, fmesh3 + E->N, fmesh3 + 2 * E->N, E->r(3)};
+  TRY(read_grad(st, pos, ms, 4, fbar, 3, cscale, nullptr, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, posbar,
+                accumulate));
+  return 0;
+}
+
+int pm_forces_mesh(Engine* E, stream_t st, const float* pos, const cfloat* dk, int64_t np, int order, int lap_fd,
+                   int grad_fd, float kcut, float* forces) {
+  TRY(force_meshes_from_spectrum(E, st, dk, lap_fd, grad_fd, kcut, 0, E->r(0)));
+  TRY(read(st, pos, E->r(0), 3, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, forces));
+  return 0;
+}
+
+// pm_forces2 (nbody.py:607-631): six Hessian meshes -> 2LPT source -> its spectrum -> forces
+int pm_forces2(Engine* E, stream_t st, const float* pos, const cfloat* dk, int64_t np, int order, int lap_fd,
+               int grad_fd, float* forces, float* h6_out) {
+  float* h6 = h6_out ? h6_out : E->r(0);
+  TRY(hessian_spectra(st, dk, E->c(0), E->nx, E->ny, E->nz, lap_fd, grad_fd, E->invN));
+  TRY(fft_c2r(E->fft, st, E->c(0), h6, 6));
+  TRY(lpt2_source(st, h6, E->r(6), E->N));
+  TRY(fft_r2c(E->fft, st, E->r(6), E->c(6), 1));
+  TRY(force_meshes_from_spectrum(E, st, E->c(6), lap_fd, grad_fd, 0.0f, 0, E->r(0)));
+  TRY(read(st, pos, E->r(0), 3, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, forces));
+  return 0;
+}
+
+int lpt(Engine* E, stream_t st, const cfloat* dk, const float* pos, int64_t np, int lpt_order, int read_order,
+        int lap_fd, int grad_fd, float d1, float d2, float dv2, float* dpos, float* vel, float* f1, float* f2,
+        float* h6) {
+  if (lpt_order != 1 && lpt_order != 2) {
+    set_error("lpt_order must be 1 or 2");
+    return MCPM_EINVAL;
+  }
+  if (!dpos || !vel) {
+    set_error("lpt: dpos and vel are required");
+    return MCPM_EINVAL;
+  }
+  // without a tape the force arrays live in the output buffers and are combined in place
+  float* F1 = f1 ? f1 : vel;
+  float* F2 = f2 ? f2 : dpos;
+  TRY(pm_forces_mesh(E, st, pos, dk, np, read_order, lap_fd, grad_fd, 0.0f, F1));
+  if (lpt_order == 2) TRY(pm_forces2(E, st, pos, dk, np, read_order, lap_fd, grad_fd, F2, h6));
+  TRY(lpt_combine(st, nullptr, F1, lpt_order == 2 ? F2 : nullptr, d1, d2, dv2, np, dpos, vel, nullptr));
+  return 0;
+}
+
+// VJP of lpt w.r.t. delta_k (and the growth coefficients).  F1bar = d1*dposbar + velbar; F2bar = -d2*dposbar - dv2*velbar.
+int lpt_vjp(Engine* E, stream_t st, const float* pos, int64_t np, int lpt_order, int read_order, int lap_fd,
+            int grad_fd, float d1, float d2, float dv2, const float* dposbar, const float* velbar, const float* f1,
+            const float* f2, const float* h6, cfloat* dkbar, double* coefbar, int accumulate) {
+  if (lpt_order == 2) {
+    if (!h6) {
+      set_error("lpt_vjp: the Hessian tape h6 is required for lpt_order 2");
+      return MCPM_EINVAL;
+    }
+    TRY(paint3(st, pos, dposbar, -d2, velbar, -dv2, np, E->nx, E->ny, E->nz, read_order, E->r(0), 0));
+    TRY(fft_r2c(E->fft, st, E->r(0), E->c(0), 3));
+    TRY(force_spectra_T(st, E->c(0), E->c(3), E->nx, E->ny, E->nz, lap_fd, grad_fd, 0.0f, 0, 0, 0, E->invN));
+    TRY(fft_c2r(E->fft, st, E->c(3), E->r(6), 1));  // d2bar (real)
+    TRY(lpt2_source_vjp(st, h6, E->r(6), E->r(0), E->N));
+    TRY(fft_r2c(E->fft, st, E->r(0), E->c(0), 6));
+    TRY(hessian_spectra_T(st, E->c(0), dkbar, E->nx, E->ny, E->nz, lap_fd, grad_fd, 1, accumulate, 1.0f));
+    accumulate = 1;
+  }
+  TRY(paint3(st, pos, dposbar, d1, velbar, 1.0f, np, E->nx, E->ny, E->nz, read_order, E->r(0), 0));
+  TRY(fft_r2c(E->fft, st, E->r(0), E->c(0), 3));
+  TRY(force_spectra_T(st, E->c(0), dkbar, E->nx, E->ny, E->nz, lap_fd, grad_fd, 0.0f, 0, 1, accumulate, 1.0f));
+  if (coefbar) {
+    if (!f1 || (lpt_order == 2 && !f2)) {
+      set_error("lpt_vjp: coefficient cotangents need the f1 / f2 tape");
+      return MCPM_EINVAL;
+    }
+    TRY(dot_accum(st, dposbar, f1, 3 * np, 1.0, coefbar + 0));
+    if (lpt_order == 2) {
+      TRY(dot_accum(st, dposbar, f2, 3 * np, -1.0, coefbar + 1));
+      TRY(dot_accum(st, velbar, f2, 3 * np, -1.0, coefbar + 2));
+    }
+  }
+  return 0;
+}
+
+// BullFrog loop (nbody.py:946-951 per step).  The trailing half drift of step s and the leading half drift of step
+// s+1 use the same velocity, so they run as one drift fused into the kick kernel.
+int nbody_steps(Engine* E, stream_t st, float* pos, float* vel, int64_t np, int n_steps, const float* alpha,
+                const float* beta, const float* drift_pre, const float* drift_post, int order, int paint_deconv,
+                int lap_fd, int grad_fd, float* xk, float* vk, float* fm) {
+  if (n_steps < 0 || (n_steps > 0 && (!alpha || !beta || !drift_pre || !drift_post))) {
+    set_error("nbody_steps: bad step arrays");
+    return MCPM_EINVAL;
+  }
+  if (n_steps == 0) return 0;
+  const int64_t P3 = 3 * np;
+  float* cur = xk ? xk : pos;  // position at kick time of the current step
+  TRY(axpy3(st, pos, vel, drift_pre[0], P3, cur));
+  const float* vin = vel;
+  for (int s = 0; s < n_steps; ++s) {
+    float* fms = fm ? fm + (int64_t)s * 3 * E->N : E->r(0);
+    TRY(pm_forces(E, st, cur, np, order, paint_deconv, lap_fd, grad_fd, 0.0f, fms, nullptr));
+    const bool last = (s == n_steps - 1);
+    float dcomb = drift_post[s] + (last ? 0.0f : drift_pre[s + 1]);
+    float* xout = (xk && !last) ? xk + (int64_t)(s + 1) * P3 : pos;
+    float* vout = vk ? vk + (int64_t)s * P3 : vel;
+    TRY(kick_drift(st, cur, vin, fms, np, E->nx, E->ny, E->nz, order, alpha[s], beta[s], dcomb, xout, vout, nullptr));
+    cur = xout;
+    vin = vout;
+  }
+  if (vk) TRY(rt_copy(vel, vk + (int64_t)(n_steps - 1) * P3, sizeof(float) * P3, st) ? MCPM_ECUDA : 0);
+  return 0;
+}
+
+// Reverse sweep.  Per step (x1 = kick-time position, v1 = alpha v0 + beta F(x1), x_out = x1 + v1 * dcomb):
+//   vbar += xbar * dcomb ; xbar += pm_forces_vjp(x1, beta * vbar) ; [coef cotangents] ; vbar *= alpha
+// and finally vbar += xbar * drift_pre[0].
+int nbody_steps_vjp(Engine* E, stream_t st, float* posbar, float* velbar, int64_t np, int n_steps, const float* alpha,
+                    const float* beta, const float* drift_pre, const float* drift_post, int order, int paint_deconv,
+                    int lap_fd, int grad_fd, const float* xk, const float* vk, const float* fm, const float* v0,
+                    double* coefbar) {
+  if (n_steps <= 0) return 0;
+  if (!xk || !fm) {
+    set_error("nbody_steps_vjp: the tape (xk, fm) from the forward pass is required");
+    return MCPM_EINVAL;
+  }
+  if (coefbar && (!vk || !v0)) {
+    set_error("nbody_steps_vjp: coefficient cotangents need vk and v0");
+    return MCPM_EINVAL;
+  }
+  const int64_t P3 = 3 * np;
+  for (int s = n_steps - 1; s >= 0; --s) {
+    const bool last = (s == n_steps - 1);
+    float dcomb = drift_post[s] + (last ? 0.0f : drift_pre[s + 1]);
+    const float* x1 = xk + (int64_t)s * P3;
+    const float* fms = fm + (int64_t)s * 3 * E->N;
+    if (coefbar) {
+      // d(drift)bar = <xbar, v1>: split evenly is wrong -- both halves see the same xbar, so each gets the full dot
+      const float* v1 = vk + (int64_t)s * P3;
+      TRY(dot_accum(st, posbar, v1, P3, 1.0, coefbar + 4 * s + 3));
+      if (!last) TRY(dot_accum(st, posbar, v1, P3, 1.0, coefbar + 4 * (s + 1) + 2));
+    }
+    TRY(axpy3(st, velbar, posbar, dcomb, P3, velbar));
+    if (coefbar) {
+      const float* vprev = s == 0 ? v0 : vk + (int64_t)(s - 1) * P3;
+      TRY(dot_accum(st, velbar, vprev, P3, 1.0, coefbar + 4 * s + 0));
+      // betabar = <vbar, F>, F = (v1 - alpha v0) / beta
+      const float* v1 = vk + (int64_t)s * P3;
+      if (beta[s] != 0.0f) {
+        TRY(dot_accum(st, velbar, v1, P3, 1.0 / beta[s], coefbar + 4 * s + 1));
+        TRY(dot_accum(st, velbar, vprev, P3, -(double)alpha[s] / beta[s], coefbar + 4 * s + 1));
+      }
+    }
+    TRY(pm_forces_vjp(E, st, x1, velbar, beta[s], fms, np, order, paint_deconv, lap_fd, grad_fd, 0.0f, posbar, 1));
+    TRY(axpy3(st, velbar, velbar, alpha[s] - 1.0f, P3, velbar));  // vbar *= alpha
+  }
+  if (coefbar) TRY(dot_accum(st, posbar, v0, P3, 1.0, coefbar + 2));
+  TRY(axpy3(st, velbar, posbar, drift_pre[0], P3, velbar));
+  return 0;
+}
+
+// nufft at the paint shape (nbody.py:569-574): m interlaced paints -> batched R2C -> one combine pass
+int nufft(Engine* E, stream_t st, const float* pos, const float* weights, float wscalar, int64_t np,
+          const float* scale, int paint_order, int interlace_order, int paint_deconv, cfloat* out_k) {
+  const int m = interlace_order;
+  if (m < 1 || m > Engine::kR - 1) {
+    set_error("nufft: interlace_order must be in 1..6");
+    return MCPM_EINVAL;
+  }
+  float jac = scale ? scale[0] * scale[1] * scale[2] : 1.0f;
+  for (int i = 0; i < m; ++i)
+    TRY(paint(st, pos, weights, wscalar, np, E->nx, E->ny, E->nz, paint_order, scale, (float)i / (float)m, E->r(i), 0));
+  TRY(fft_r2c(E->fft, st, E->r(0), E->c(0), m));
+  TRY(interlace_combine(st, E->c(0), out_k, m, E->nx, E->ny, E->nz, jac, paint_deconv ? paint_order : 0));
+  return 0;
+}
+
+int nufft_vjp(Engine* E, stream_t st, const float* pos, const float* weights, float wscalar, int64_t np,
+              const float* scale, int paint_order, int interlace_order, int paint_deconv, const cfloat* outbar_k,
+              float* posbar, float* weightsbar) {
+  const int m = interlace_order;
+  if (m < 1 || m > Engine::kR - 1) {
+    set_error("nufft: interlace_order must be in 1..6");
+    return MCPM_EINVAL;
+  }
+  float jac = scale ? scale[0] * scale[1] * scale[2] : 1.0f;
+  // out_i = conj(kernel_i) * outbar / w'  (raw C2R supplies the remaining factor N * 1/N)
+  TRY(interlace_combine_T(st, outbar_k, E->c(0), m, E->nx, E->ny, E->nz, jac, paint_deconv ? paint_order : 0, 1.0f));
+  TRY(fft_c2r(E->fft, st, E->c(0), E->r(0), m));
+  for (int i = 0; i < m; ++i)
+    TRY(paint_vjp(st, pos, weights, wscalar, E->r(i), np, E->nx, E->ny, E->nz, paint_order, scale,
+                  (float)i / (float)m, posbar, weightsbar, i > 0));
+  return 0;
+}
+
+}  // namespace mcpm

@@ -1,0 +1,92 @@
+// engine.h -- internal declarations shared by the engine translation units.
+#pragma once
+#include "rt.h"
+
+namespace mcpm {
+
+struct Engine {
+  static constexpr int kR = 7;  // real scratch meshes (6 Hessian / 3 force + 1 density)
+  static constexpr int kC = 7;  // half-spectrum scratch meshes
+  int nx, ny, nz, nzc;
+  int64_t N, Nc;
+  float invN;
+  FftPlans* fft = nullptr;
+  float* rbuf = nullptr;
+  cfloat* cbuf = nullptr;
+  size_t scratch_bytes = 0;
+  float* r(int i) const { return rbuf + (int64_t)i * N; }
+  cfloat* c(int i) const { return cbuf + (int64_t)i * Nc; }
+};
+
+Engine* engine_create(int nx, int ny, int nz);
+void engine_destroy(Engine*);
+
+// paint.cu
+int paint(stream_t, const float* pos, const float* weights, float wscalar, int64_t np, int nx, int ny, int nz,
+          int order, const float* scale, float shift, float* mesh, int accumulate);
+int read(stream_t, const float* pos, const float* mesh, int nmesh, int64_t np, int nx, int ny, int nz, int order,
+         const float* scale, float shift, float* out);
+int read_grad(stream_t, const float* pos, const float* const* meshes, int nmesh, const float* cot, int ncot,
+              float cscale, const float* gw, int64_t np, int nx, int ny, int nz, int order, const float* scale,
+              float shift, float* grad, int accumulate);
+int paint3(stream_t, const float* pos, const float* A, float ca, const float* B, float cb, int64_t np, int nx,
+           int ny, int nz, int order, float* mesh3, int accumulate);
+int paint_vjp(stream_t, const float* pos, const float* weights, float wscalar, const float* mbar, int64_t np, int nx,
+              int ny, int nz, int order, const float* scale, float shift, float* posbar, float* wbar,
+              int accumulate);
+int kick_drift(stream_t, const float* pos, const float* vel, const float* fmesh3, int64_t np, int nx, int ny, int nz,
+               int order, float alpha, float beta, float drift, float* pos_out, float* vel_out, float* force_out);
+int axpy3(stream_t, const float* a, const float* b, float s, int64_t n3, float* out);
+int lpt_combine(stream_t, const float* pos, const float* f1, const float* f2, float d1, float d2, float dv2,
+                int64_t np, float* dpos, float* vel, float* pos_out);
+int dot_accum(stream_t, const float* a, const float* b, int64_t n, double scale, double* out);
+
+// fourier.cu  (`norm` multiplies the output; the engine passes 1/N ahead of a raw C2R)
+int force_spectra(stream_t, const cfloat* dk, cfloat* out3, int nx, int ny, int nz, int lap_fd, int grad_fd,
+                  float kcut, int deconv_order, float norm);
+int force_spectra_T(stream_t, const cfloat* in3, cfloat* out1, int nx, int ny, int nz, int lap_fd, int grad_fd,
+                    float kcut, int deconv_order, int half_weights, int accumulate, float norm);
+int hessian_spectra(stream_t, const cfloat* dk, cfloat* out6, int nx, int ny, int nz, int lap_fd, int grad_fd,
+                    float norm);
+int hessian_spectra_T(stream_t, const cfloat* in6, cfloat* out1, int nx, int ny, int nz, int lap_fd, int grad_fd,
+                      int half_weights, int accumulate, float norm);
+int lpt2_source(stream_t, const float* h6, float* d2, int64_t n);
+int lpt2_source_vjp(stream_t, const float* h6, const float* d2bar, float* hbar6, int64_t n);
+int deconv(stream_t, const cfloat* in, cfloat* out, int nx, int ny, int nz, int order);
+int interlace_combine(stream_t, const cfloat* in_m, cfloat* out, int m, int nx, int ny, int nz, float scale,
+                      int deconv_order);
+int interlace_combine_T(stream_t, const cfloat* in, cfloat* out_m, int m, int nx, int ny, int nz, float scale,
+                        int deconv_order, float norm);
+int scale_spectrum(stream_t, const cfloat* in, const float* t, cfloat* out, int64_t nc);
+int scale_real(stream_t, const float* in, float s, float* out, int64_t n);
+int chreshape(stream_t, const cfloat* in, int inx, int iny, int inz, cfloat* out, int onx, int ony, int onz);
+
+// engine.cu
+int pm_forces(Engine*, stream_t, const float* pos, int64_t np, int order, int paint_deconv, int lap_fd, int grad_fd,
+              float kcut, float* fmesh3, float* forces);
+int pm_forces_vjp(Engine*, stream_t, const float* pos, const float* fbar, float cscale, const float* fmesh3,
+                  int64_t np, int order, int paint_deconv, int lap_fd, int grad_fd, float kcut, float* posbar,
+                  int accumulate);
+int pm_forces_mesh(Engine*, stream_t, const float* pos, const cfloat* dk, int64_t np, int order, int lap_fd,
+                   int grad_fd, float kcut, float* forces);
+int pm_forces2(Engine*, stream_t, const float* pos, const cfloat* dk, int64_t np, int order, int lap_fd, int grad_fd,
+               float* forces, float* h6_out);
+int lpt(Engine*, stream_t, const cfloat* dk, const float* pos, int64_t np, int lpt_order, int read_order, int lap_fd,
+        int grad_fd, float d1, float d2, float dv2, float* dpos, float* vel, float* f1, float* f2, float* h6);
+int lpt_vjp(Engine*, stream_t, const float* pos, int64_t np, int lpt_order, int read_order, int lap_fd, int grad_fd,
+            float d1, float d2, float dv2, const float* dposbar, const float* velbar, const float* f1,
+            const float* f2, const float* h6, cfloat* dkbar, double* coefbar, int accumulate);
+int nbody_steps(Engine*, stream_t, float* pos, float* vel, int64_t np, int n_steps, const float* alpha,
+                const float* beta, const float* drift_pre, const float* drift_post, int order, int paint_deconv,
+                int lap_fd, int grad_fd, float* xk, float* vk, float* fm);
+int nbody_steps_vjp(Engine*, stream_t, float* posbar, float* velbar, int64_t np, int n_steps, const float* alpha,
+                    const float* beta, const float* drift_pre, const float* drift_post, int order, int paint_deconv,
+                    int lap_fd, int grad_fd, const float* xk, const float* vk, const float* fm, const float* v0,
+                    double* coefbar);
+int nufft(Engine*, stream_t, const float* pos, const float* weights, float wscalar, int64_t np, const float* scale,
+          int paint_order, int interlace_order, int paint_deconv, cfloat* out_k);
+int nufft_vjp(Engine*, stream_t, const float* pos, const float* weights, float wscalar, int64_t np,
+              const float* scale, int paint_order, int interlace_order, int paint_deconv, const cfloat* outbar_k,
+              float* posbar, float* weightsbar);
+
+}  // namespace mcpm

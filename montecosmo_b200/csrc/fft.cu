@@ -1,0 +1,174 @@
+// fft.cu -- batched 3-D R2C / C2R on contiguous planes.  Product build: cuFFT plans created once per engine, one
+// shared work area, attached to the caller's stream per call (no allocation, no sync on the call path).
+// Reference call sites: jnp.fft.rfftn / irfftn at nbody.py:589, 603, 620, 627, 630, 525 (unnormalised forward,
+// 1/N inverse).
+#include <map>
+#include <mutex>
+
+#include "rt.h"
+
+#ifndef MCPM_HOSTEMU
+#include <cufft.h>
+#endif
+
+namespace mcpm {
+
+#ifdef MCPM_HOSTEMU
+// Test-only hooks: the host-emulation build has no FFT of its own; tests/hostemu.py registers numpy.fft here.
+typedef void (*fft_hook_t)(const void* in, void* out, int nx, int ny, int nz, int batch);
+static fft_hook_t g_r2c = nullptr, g_c2r = nullptr;
+extern "C" __attribute__((visibility("default"))) void mcpm_hostemu_set_fft(fft_hook_t r2c, fft_hook_t c2r) {
+  g_r2c = r2c;
+  g_c2r = c2r;
+}
+struct FftPlans {
+  int nx, ny, nz;
+};
+FftPlans* fft_create(int nx, int ny, int nz, size_t* work_bytes) {
+  if (work_bytes) *work_bytes = 0;
+  return new FftPlans{nx, ny, nz};
+}
+void fft_destroy(FftPlans* p) { delete p; }
+int fft_r2c(FftPlans* p, stream_t, const float* in, cfloat* out, int batch) {
+  if (!g_r2c) {
+    set_error("hostemu: no FFT hook registered");
+    return MCPM_ECUFFT;
+  }
+  g_r2c(in, out, p->nx, p->ny, p->nz, batch);
+  return 0;
+}
+int fft_c2r(FftPlans* p, stream_t, cfloat* in, float* out, int batch) {
+  if (!g_c2r) {
+    set_error("hostemu: no FFT hook registered");
+    return MCPM_ECUFFT;
+  }
+  g_c2r(in, out, p->nx, p->ny, p->nz, batch);
+  // cuFFT's C2R may overwrite its input: poison it so that orchestration bugs relying on it show up on CPU.
+  size_t nc = (size_t)p->nx * p->ny * (p->nz / 2 + 1) * batch;
+  for (size_t i = 0; i < nc; ++i) in[i] = cfloat{NAN, NAN};
+  return 0;
+}
+
+#else
+struct FftPlans {
+  int nx, ny, nz;
+  void* work = nullptr;
+  size_t work_bytes = 0;
+  std::map<int, cufftHandle> r2c, c2r;  // keyed by batch
+  std::mutex mu;
+};
+
+static int make_plan(FftPlans* p, cufftType type, int batch, cufftHandle* out, size_t* ws) {
+  cufftHandle h;
+  if (cufftCreate(&h) != CUFFT_SUCCESS) return MCPM_ECUFFT;
+  cufftSetAutoAllocation(h, 0);
+  int n[3] = {p->nx, p->ny, p->nz};
+  int nzc = p->nz / 2 + 1;
+  int rembed[3] = {p->nx, p->ny, p->nz};
+  int cembed[3] = {p->nx, p->ny, nzc};
+  int rdist = p->nx * p->ny * p->nz, cdist = p->nx * p->ny * nzc;
+  cufftResult r;
+  if (type == CUFFT_R2C)
+    r = cufftMakePlanMany(h, 3, n, rembed, 1, rdist, cembed, 1, cdist, CUFFT_R2C, batch, ws);
+  else
+    r = cufftMakePlanMany(h, 3, n, cembed, 1, cdist, rembed, 1, rdist, CUFFT_C2R, batch, ws);
+  if (r != CUFFT_SUCCESS) {
+    cufftDestroy(h);
+    set_error("cufftMakePlanMany failed with code " + std::to_string((int)r));
+    return MCPM_ECUFFT;
+  }
+  *out = h;
+  return 0;
+}
+
+// Plans for batch 1, 2, 3 and 6 in both directions, sharing one work area sized for the largest.
+FftPlans* fft_create(int nx, int ny, int nz, size_t* work_bytes) {
+  FftPlans* p = new FftPlans;
+  p->nx = nx;
+  p->ny = ny;
+  p->nz = nz;
+  if ((int64_t)nx * ny * nz >= (int64_t)1 << 31) {
+    set_error("mesh too large for 32-bit cuFFT plan distances");
+    delete p;
+    return nullptr;
+  }
+  size_t maxws = 0;
+  const int batches[4] = {1, 2, 3, 6};
+  for (int b : batches) {
+    size_t ws = 0;
+    cufftHandle h;
+    if (make_plan(p, CUFFT_R2C, b, &h, &ws)) {
+      fft_destroy(p);
+      return nullptr;
+    }
+    p->r2c[b] = h;
+    maxws = ws > maxws ? ws : maxws;
+    if (make_plan(p, CUFFT_C2R, b, &h, &ws)) {
+      fft_destroy(p);
+      return nullptr;
+    }
+    p->c2r[b] = h;
+    maxws = ws > maxws ? ws : maxws;
+  }
+  if (cudaMalloc(&p->work, maxws ? maxws : 1) != cudaSuccess) {
+    set_error("cuFFT work area allocation failed");
+    cudaGetLastError();
+    fft_destroy(p);
+    return nullptr;
+  }
+  p->work_bytes = maxws;
+  for (auto& kv : p->r2c) cufftSetWorkArea(kv.second, p->work);
+  for (auto& kv : p->c2r) cufftSetWorkArea(kv.second, p->work);
+  if (work_bytes) *work_bytes = maxws;
+  return p;
+}
+
+void fft_destroy(FftPlans* p) {
+  if (!p) return;
+  for (auto& kv : p->r2c) cufftDestroy(kv.second);
+  for (auto& kv : p->c2r) cufftDestroy(kv.second);
+  if (p->work) cudaFree(p->work);
+  delete p;
+}
+
+// A batch without its own plan is run as a sequence of the available ones (largest first).
+template <class Exec>
+static int run_batched(std::map<int, cufftHandle>& plans, int batch, Exec exec) {
+  int done = 0;
+  while (done < batch) {
+    int take = 0;
+    for (auto it = plans.rbegin(); it != plans.rend(); ++it)
+      if (it->first <= batch - done) {
+        take = it->first;
+        break;
+      }
+    cufftResult r = exec(plans[take], done);
+    if (r != CUFFT_SUCCESS) {
+      set_error("cufftExec failed with code " + std::to_string((int)r));
+      return MCPM_ECUFFT;
+    }
+    done += take;
+  }
+  return 0;
+}
+
+int fft_r2c(FftPlans* p, stream_t st, const float* in, cfloat* out, int batch) {
+  std::lock_guard<std::mutex> lk(p->mu);
+  const size_t rd = (size_t)p->nx * p->ny * p->nz, cd = (size_t)p->nx * p->ny * (p->nz / 2 + 1);
+  return run_batched(p->r2c, batch, [&](cufftHandle h, int off) {
+    cufftSetStream(h, st);
+    return cufftExecR2C(h, const_cast<float*>(in) + off * rd, reinterpret_cast<cufftComplex*>(out + off * cd));
+  });
+}
+
+int fft_c2r(FftPlans* p, stream_t st, cfloat* in, float* out, int batch) {
+  std::lock_guard<std::mutex> lk(p->mu);
+  const size_t rd = (size_t)p->nx * p->ny * p->nz, cd = (size_t)p->nx * p->ny * (p->nz / 2 + 1);
+  return run_batched(p->c2r, batch, [&](cufftHandle h, int off) {
+    cufftSetStream(h, st);
+    return cufftExecC2R(h, reinterpret_cast<cufftComplex*>(in + off * cd), out + off * rd);
+  });
+}
+#endif
+
+}  // namespace mcpm

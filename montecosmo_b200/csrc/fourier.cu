@@ -1,0 +1,436 @@
+// fourier.cu -- Fourier-space passes around cuFFT, one fused kernel per role.  All kernels recompute the wavevector
+// from the element index (rfftk, nbody.py:50-77) instead of reading baked kernel arrays: every pass is a pure stream
+// over the half spectrum [nx, ny, nz/2+1] of interleaved complex64, one thread per element, coalesced along kz.
+// Reference kernels: invlaplace_hat (nbody.py:109-133), gradient_hat (136-163), gaussian_hat (166-188),
+// rectangular_hat (249-277), deconv_paint (315-334), interlace phase (523-526), chreshape (utils.py:924-1013).
+#include "engine.h"
+
+namespace mcpm {
+
+struct KGrid {
+  int nx, ny, nz, nzc;
+  float tx, ty, tz;  // 2*pi / n
+  int lap_fd, grad_fd;
+};
+
+static KGrid make_kgrid(int nx, int ny, int nz, int lap_fd = 0, int grad_fd = 0) {
+  KGrid g;
+  g.nx = nx;
+  g.ny = ny;
+  g.nz = nz;
+  g.nzc = nz / 2 + 1;
+  g.tx = (float)(6.283185307179586476925 / nx);
+  g.ty = (float)(6.283185307179586476925 / ny);
+  g.tz = (float)(6.283185307179586476925 / nz);
+  g.lap_fd = lap_fd;
+  g.grad_fd = grad_fd;
+  return g;
+}
+
+// numpy.fft.fftfreq index -> signed integer frequency (Nyquist negative); rfftfreq keeps it positive.
+MCPM_HD int signed_freq(int i, int n) { return i < (n + 1) / 2 ? i : i - n; }
+
+struct KVec {
+  float kx, ky, kz;
+};
+
+MCPM_HD KVec kvec_at(const KGrid& g, int64_t e, int& l) {
+  l = (int)(e % g.nzc);
+  int64_t r = e / g.nzc;
+  int j = (int)(r % g.ny);
+  int i = (int)(r / g.ny);
+  KVec k;
+  k.kx = g.tx * (float)signed_freq(i, g.nx);
+  k.ky = g.ty * (float)signed_freq(j, g.ny);
+  k.kz = g.tz * (float)l;
+  return k;
+}
+
+// invlaplace_hat: -1/kk with 0 at kk == 0 (safe_div, utils.py:21-29)
+MCPM_HD float lap_term(float k, int fd) {
+  if (fd == 2) return (cosf(k) - 1.0f) * 2.0f;
+  if (fd == 4) return (cosf(2.0f * k) - 16.0f * cosf(k) + 15.0f) * (1.0f / 6.0f);
+  return k * k;
+}
+MCPM_HD float invlaplace(const KGrid& g, const KVec& k) {
+  float kk = lap_term(k.kx, g.lap_fd) + lap_term(k.ky, g.lap_fd) + lap_term(k.kz, g.lap_fd);
+  return kk == 0.0f ? 0.0f : -1.0f / kk;
+}
+// gradient_hat / i
+MCPM_HD float grad_term(float k, int fd) {
+  if (fd == 2) return sinf(k);
+  if (fd == 4) return (8.0f * sinf(k) - sinf(2.0f * k)) * (1.0f / 6.0f);
+  return k;
+}
+// sinc(k / 2pi) = sin(k/2) / (k/2)
+MCPM_HD float sinc_half(float k) {
+  float x = 0.5f * k;
+  return x == 0.0f ? 1.0f : sinf(x) / x;
+}
+MCPM_HD float powi(float x, int p) {
+  float r = 1.0f;
+  for (int t = 0; t < p; ++t) r *= x;
+  return r;
+}
+MCPM_HD float window_hat(const KVec& k, int order) {
+  return powi(sinc_half(k.kx) * sinc_half(k.ky) * sinc_half(k.kz), order);
+}
+// weight of a half-spectrum element in the real inner product: 1 on the self-conjugate planes kz = 0, Nyquist; else 2
+MCPM_HD float half_weight(int l, int nz) { return (l == 0 || 2 * l == nz) ? 1.0f : 2.0f; }
+
+// common real factor of the force kernel: invlaplace * [gaussian] * [1 / rectangular_hat^2]
+MCPM_HD float force_scalar(const KGrid& g, const KVec& k, float rcut2_half, int deconv_order) {
+  float c = invlaplace(g, k);
+  if (rcut2_half > 0.0f) c *= expf(-(k.kx * k.kx + k.ky * k.ky + k.kz * k.kz) * rcut2_half);
+  if (deconv_order > 0) {
+    float w = window_hat(k, deconv_order);
+    c /= (w * w);
+  }
+  return c;
+}
+
+static float rcut2_half_of(float kcut) {
+  if (!(kcut > 0.0f) || std::isinf(kcut)) return 0.0f;
+  double rcut = 6.283185307179586476925 / kcut;
+  return (float)(0.5 * rcut * rcut);
+}
+
+static int check_dims(int nx, int ny, int nz) {
+  if (nx <= 0 || ny <= 0 || nz <= 0 || (nz & 1)) {
+    set_error("mesh dimensions must be positive and nz even");
+    return MCPM_EINVAL;
+  }
+  return 0;
+}
+static int check_fd(int fd) {
+  if (fd != MCPM_FD_INF && fd != MCPM_FD_2 && fd != MCPM_FD_4) {
+    set_error("Only orders 2, 4, and inf are supported.");
+    return MCPM_EINVAL;
+  }
+  return 0;
+}
+
+// out_j = -(i g_j) * c * delta   (nbody.py:597-603)
+int force_spectra(stream_t st, const cfloat* dk, cfloat* out3, int nx, int ny, int nz, int lap_fd, int grad_fd,
+                  float kcut, int deconv_order, float norm) {
+  if (int e = check_dims(nx, ny, nz)) return e;
+  if (int e = check_fd(lap_fd) ? check_fd(lap_fd) : check_fd(grad_fd)) return e;
+  KGrid g = make_kgrid(nx, ny, nz, lap_fd, grad_fd);
+  const int64_t nc = (int64_t)nx * ny * g.nzc;
+  const float r2 = rcut2_half_of(kcut);
+  launch_1d(st, nc, [=] MCPM_LAMBDA(int64_t e) {
+    int l;
+    KVec k = kvec_at(g, e, l);
+    float c = force_scalar(g, k, r2, deconv_order) * norm;
+    cfloat d = dk[e];
+    // (-i)(a + ib) = b - ia
+    float re = d.im * c, im = -d.re * c;
+    float gx = grad_term(k.kx, g.grad_fd), gy = grad_term(k.ky, g.grad_fd), gz = grad_term(k.kz, g.grad_fd);
+    out3[e] = cfloat{gx * re, gx * im};
+    out3[nc + e] = cfloat{gy * re, gy * im};
+    out3[2 * nc + e] = cfloat{gz * re, gz * im};
+  });
+  return rt_check("force_spectra");
+}
+
+// transpose pass: out (+)= [w'/N] * sum_j conj(-(i g_j) c) in_j = [w'/N] * c * i * sum_j g_j in_j
+int force_spectra_T(stream_t st, const cfloat* in3, cfloat* out1, int nx, int ny, int nz, int lap_fd, int grad_fd,
+                    float kcut, int deconv_order, int half_weights, int accumulate, float norm) {
+  if (int e = check_dims(nx, ny, nz)) return e;
+  if (int e = check_fd(lap_fd) ? check_fd(lap_fd) : check_fd(grad_fd)) return e;
+  KGrid g = make_kgrid(nx, ny, nz, lap_fd, grad_fd);
+  const int64_t nc = (int64_t)nx * ny * g.nzc;
+  const float r2 = rcut2_half_of(kcut);
+  const float invn = (float)(1.0 / ((double)nx * ny * nz));
+  launch_1d(st, nc, [=] MCPM_LAMBDA(int64_t e) {
+    int l;
+    KVec k = kvec_at(g, e, l);
+    float c = force_scalar(g, k, r2, deconv_order) * norm;
+    if (half_weights) c *= half_weight(l, g.nz) * invn;
+    float gx = grad_term(k.kx, g.grad_fd), gy = grad_term(k.ky, g.grad_fd), gz = grad_term(k.kz, g.grad_fd);
+    cfloat a = in3[e], b = in3[nc + e], d = in3[2 * nc + e];
+    float sre = gx * a.re + gy * b.re + gz * d.re;
+    float sim = gx * a.im + gy * b.im + gz * d.im;
+    // i (sre + i sim) = -sim + i sre
+    cfloat o = cfloat{-sim * c, sre * c};
+    if (accumulate) {
+      cfloat p = out1[e];
+      o.re += p.re;
+      o.im += p.im;
+    }
+    out1[e] = o;
+  });
+  return rt_check("force_spectra_T");
+}
+
+// out_ij = (i g_i)(i g_j) * invlaplace * delta = -g_i g_j G delta ; order 00, 11, 22, 01, 02, 12  (nbody.py:611-627)
+int hessian_spectra(stream_t st, const cfloat* dk, cfloat* out6, int nx, int ny, int nz, int lap_fd, int grad_fd,
+                    float norm) {
+  if (int e = check_dims(nx, ny, nz)) return e;
+  if (int e = check_fd(lap_fd) ? check_fd(lap_fd) : check_fd(grad_fd)) return e;
+  KGrid g = make_kgrid(nx, ny, nz, lap_fd, grad_fd);
+  const int64_t nc = (int64_t)nx * ny * g.nzc;
+  launch_1d(st, nc, [=] MCPM_LAMBDA(int64_t e) {
+    int l;
+    KVec k = kvec_at(g, e, l);
+    float c = -invlaplace(g, k) * norm;
+    float gx = grad_term(k.kx, g.grad_fd), gy = grad_term(k.ky, g.grad_fd), gz = grad_term(k.kz, g.grad_fd);
+    cfloat d = dk[e];
+    float re = d.re * c, im = d.im * c;
+    out6[e] = cfloat{gx * gx * re, gx * gx * im};
+    out6[nc + e] = cfloat{gy * gy * re, gy * gy * im};
+    out6[2 * nc + e] = cfloat{gz * gz * re, gz * gz * im};
+    out6[3 * nc + e] = cfloat{gx * gy * re, gx * gy * im};
+    out6[4 * nc + e] = cfloat{gx * gz * re, gx * gz * im};
+    out6[5 * nc + e] = cfloat{gy * gz * re, gy * gz * im};
+  });
+  return rt_check("hessian_spectra");
+}
+
+int hessian_spectra_T(stream_t st, const cfloat* in6, cfloat* out1, int nx, int ny, int nz, int lap_fd, int grad_fd,
+                      int half_weights, int accumulate, float norm) {
+  if (int e = check_dims(nx, ny, nz)) return e;
+  if (int e = check_fd(lap_fd) ? check_fd(lap_fd) : check_fd(grad_fd)) return e;
+  KGrid g = make_kgrid(nx, ny, nz, lap_fd, grad_fd);
+  const int64_t nc = (int64_t)nx * ny * g.nzc;
+  const float invn = (float)(1.0 / ((double)nx * ny * nz));
+  launch_1d(st, nc, [=] MCPM_LAMBDA(int64_t e) {
+    int l;
+    KVec k = kvec_at(g, e, l);
+    float c = -invlaplace(g, k) * norm;
+    if (half_weights) c *= half_weight(l, g.nz) * invn;
+    float gx = grad_term(k.kx, g.grad_fd), gy = grad_term(k.ky, g.grad_fd), gz = grad_term(k.kz, g.grad_fd);
+    float w[6] = {gx * gx, gy * gy, gz * gz, gx * gy, gx * gz, gy * gz};
+    float re = 0.0f, im = 0.0f;
+#pragma unroll
+    for (int t = 0; t < 6; ++t) {
+      cfloat v = in6[t * nc + e];
+      re += w[t] * v.re;
+      im += w[t] * v.im;
+    }
+    cfloat o = cfloat{re * c, im * c};
+    if (accumulate) {
+      cfloat p = out1[e];
+      o.re += p.re;
+      o.im += p.im;
+    }
+    out1[e] = o;
+  });
+  return rt_check("hessian_spectra_T");
+}
+
+// d2 = h00 h11 + h00 h22 + h11 h22 - h01^2 - h02^2 - h12^2   (nbody.py:615-627)
+int lpt2_source(stream_t st, const float* h6, float* d2, int64_t n) {
+  launch_1d(st, n, [=] MCPM_LAMBDA(int64_t e) {
+    float a = h6[e], b = h6[n + e], c = h6[2 * n + e], d = h6[3 * n + e], f = h6[4 * n + e], g = h6[5 * n + e];
+    d2[e] = a * b + c * (a + b) - d * d - f * f - g * g;
+  });
+  return rt_check("lpt2_source");
+}
+
+int lpt2_source_vjp(stream_t st, const float* h6, const float* d2bar, float* hbar6, int64_t n) {
+  launch_1d(st, n, [=] MCPM_LAMBDA(int64_t e) {
+    float a = h6[e], b = h6[n + e], c = h6[2 * n + e], d = h6[3 * n + e], f = h6[4 * n + e], g = h6[5 * n + e];
+    float t = d2bar[e];
+    hbar6[e] = t * (b + c);
+    hbar6[n + e] = t * (a + c);
+    hbar6[2 * n + e] = t * (a + b);
+    hbar6[3 * n + e] = -2.0f * t * d;
+    hbar6[4 * n + e] = -2.0f * t * f;
+    hbar6[5 * n + e] = -2.0f * t * g;
+  });
+  return rt_check("lpt2_source_vjp");
+}
+
+int deconv(stream_t st, const cfloat* in, cfloat* out, int nx, int ny, int nz, int order) {
+  if (int e = check_dims(nx, ny, nz)) return e;
+  KGrid g = make_kgrid(nx, ny, nz);
+  const int64_t nc = (int64_t)nx * ny * g.nzc;
+  launch_1d(st, nc, [=] MCPM_LAMBDA(int64_t e) {
+    int l;
+    KVec k = kvec_at(g, e, l);
+    float c = 1.0f / window_hat(k, order);
+    cfloat v = in[e];
+    out[e] = cfloat{v.re * c, v.im * c};
+  });
+  return rt_check("deconv");
+}
+
+// out = scale / W^p * (1/m) sum_i in_i exp(+i (i/m)(kx+ky+kz))      (nbody.py:523-526, 571-574)
+int interlace_combine(stream_t st, const cfloat* in_m, cfloat* out, int m, int nx, int ny, int nz, float scale,
+                      int deconv_order) {
+  if (int e = check_dims(nx, ny, nz)) return e;
+  if (m < 1 || m > 8) {
+    set_error("interlace order must be in 1..8");
+    return MCPM_EINVAL;
+  }
+  KGrid g = make_kgrid(nx, ny, nz);
+  const int64_t nc = (int64_t)nx * ny * g.nzc;
+  const float invm = 1.0f / (float)m;
+  launch_1d(st, nc, [=] MCPM_LAMBDA(int64_t e) {
+    int l;
+    KVec k = kvec_at(g, e, l);
+    float ks = k.kx + k.ky + k.kz;
+    float c = scale * invm;
+    if (deconv_order > 0) c /= window_hat(k, deconv_order);
+    float re = 0.0f, im = 0.0f;
+    for (int i = 0; i < m; ++i) {
+      cfloat v = in_m[i * nc + e];
+      float sn, cs;
+      sincosf((float)i * invm * ks, &sn, &cs);
+      re += v.re * cs - v.im * sn;
+      im += v.re * sn + v.im * cs;
+    }
+    out[e] = cfloat{re * c, im * c};
+  });
+  return rt_check("interlace_combine");
+}
+
+// transpose: out_i = (norm / w') * conj(kernel_i) * in.  The paint-mesh cotangent is irfftn(out_i) with norm = N,
+// or a raw (unnormalised) C2R of out_i with norm = 1.
+int interlace_combine_T(stream_t st, const cfloat* in, cfloat* out_m, int m, int nx, int ny, int nz, float scale,
+                        int deconv_order, float norm) {
+  if (int e = check_dims(nx, ny, nz)) return e;
+  if (m < 1 || m > 8) {
+    set_error("interlace order must be in 1..8");
+    return MCPM_EINVAL;
+  }
+  KGrid g = make_kgrid(nx, ny, nz);
+  const int64_t nc = (int64_t)nx * ny * g.nzc;
+  const float invm = 1.0f / (float)m;
+  launch_1d(st, nc, [=] MCPM_LAMBDA(int64_t e) {
+    int l;
+    KVec k = kvec_at(g, e, l);
+    float ks = k.kx + k.ky + k.kz;
+    float c = scale * invm * norm / half_weight(l, g.nz);
+    if (deconv_order > 0) c /= window_hat(k, deconv_order);
+    cfloat v = in[e];
+    for (int i = 0; i < m; ++i) {
+      float sn, cs;
+      sincosf((float)i * invm * ks, &sn, &cs);
+      // (cs - i sn)(a + ib)
+      out_m[i * nc + e] = cfloat{(v.re * cs + v.im * sn) * c, (v.im * cs - v.re * sn) * c};
+    }
+  });
+  return rt_check("interlace_combine_T");
+}
+
+int scale_spectrum(stream_t st, const cfloat* in, const float* t, cfloat* out, int64_t nc) {
+  launch_1d(st, nc, [=] MCPM_LAMBDA(int64_t e) {
+    cfloat v = in[e];
+    float s = t[e];
+    out[e] = cfloat{v.re * s, v.im * s};
+  });
+  return rt_check("scale_spectrum");
+}
+
+int scale_real(stream_t st, const float* in, float sc, float* out, int64_t n) {
+  launch_1d(st, n, [=] MCPM_LAMBDA(int64_t e) { out[e] = in[e] * sc; });
+  return rt_check("scale_real");
+}
+
+// ---------------------------------------------------------------------------------------------------- chreshape
+// One thread per OUTPUT element gathers its (at most 4 x 2) sources.  Per axis (utils.py:975-1013):
+//   crop  (s < ms), axes x,y: the new Nyquist row (freq -s/2) = (in[+s/2] + in[-s/2]) / sqrt2
+//   pad   (s > ms), axes x,y: rows of freq -ms/2 and +ms/2 both = in[-ms/2] / sqrt2; |freq| > ms/2 is zero
+//   crop on kz: the new Nyquist plane l = s-1 = (P + conj(P[-kx,-ky])) / sqrt2 evaluated on the INPUT grid
+//   pad  on kz: the old Nyquist plane l = ms-1 is divided by sqrt2; l > ms-1 is zero
+struct AxisSrc {
+  int n;       // number of sources (0, 1 or 2)
+  int idx[2];  // input indices
+  float w;     // common weight
+};
+
+MCPM_HD AxisSrc axis_sources(int i_out, int s, int ms) {
+  AxisSrc a;
+  int f = signed_freq(i_out, s);
+  const float r = 0.70710678118654752440f;
+  if (s < ms) {
+    if (2 * f == -s) {
+      a.n = 2;
+      a.idx[0] = s / 2;
+      a.idx[1] = ms - s / 2;
+      a.w = r;
+    } else {
+      a.n = 1;
+      a.idx[0] = f < 0 ? f + ms : f;
+      a.idx[1] = 0;
+      a.w = 1.0f;
+    }
+  } else if (s > ms) {
+    int h = ms / 2;
+    if (f == -h || f == h) {
+      a.n = 1;
+      a.idx[0] = ms - h;
+      a.idx[1] = 0;
+      a.w = r;
+    } else if (f > -h && f < h) {
+      a.n = 1;
+      a.idx[0] = f < 0 ? f + ms : f;
+      a.idx[1] = 0;
+      a.w = 1.0f;
+    } else {
+      a.n = 0;
+      a.idx[0] = a.idx[1] = 0;
+      a.w = 0.0f;
+    }
+  } else {
+    a.n = 1;
+    a.idx[0] = i_out;
+    a.idx[1] = 0;
+    a.w = 1.0f;
+  }
+  return a;
+}
+
+int chreshape(stream_t st, const cfloat* in, int inx, int iny, int inz, cfloat* out, int onx, int ony, int onz) {
+  if (int e = check_dims(inx, iny, inz)) return e;
+  if (int e = check_dims(onx, ony, onz)) return e;
+  if ((inx & 1) || (iny & 1) || (onx & 1) || (ony & 1)) {
+    set_error("chreshape: mesh sides must be even");
+    return MCPM_EINVAL;
+  }
+  const int inzc = inz / 2 + 1, onzc = onz / 2 + 1;
+  const int64_t nout = (int64_t)onx * ony * onzc;
+  const float scale = (float)(((double)onx * ony * onz) / ((double)inx * iny * inz));
+  launch_1d(st, nout, [=] MCPM_LAMBDA(int64_t e) {
+    int l = (int)(e % onzc);
+    int64_t r = e / onzc;
+    int j = (int)(r % ony);
+    int i = (int)(r / ony);
+    AxisSrc ax = axis_sources(i, onx, inx);
+    AxisSrc ay = axis_sources(j, ony, iny);
+    const float rs = 0.70710678118654752440f;
+    float wl = 1.0f;
+    bool herm = false, zero = false;
+    if (onzc < inzc) {
+      herm = (l == onzc - 1);
+      if (herm) wl = rs;
+    } else if (onzc > inzc) {
+      if (l == inzc - 1) wl = rs;
+      zero = l > inzc - 1;
+    }
+    float re = 0.0f, im = 0.0f;
+    if (!zero) {
+      for (int a = 0; a < ax.n; ++a)
+        for (int b = 0; b < ay.n; ++b) {
+          int ii = ax.idx[a], jj = ay.idx[b];
+          cfloat v = in[((int64_t)ii * iny + jj) * inzc + l];
+          float vr = v.re, vi = v.im;
+          if (herm) {
+            int im_ = ii == 0 ? 0 : inx - ii, jm = jj == 0 ? 0 : iny - jj;
+            cfloat u = in[((int64_t)im_ * iny + jm) * inzc + l];
+            vr += u.re;
+            vi -= u.im;
+          }
+          re += vr;
+          im += vi;
+        }
+    }
+    float w = ax.w * ay.w * wl * scale;
+    out[e] = cfloat{re * w, im * w};
+  });
+  return rt_check("chreshape");
+}
+
+}  // namespace mcpm

@@ -1,0 +1,517 @@
+// paint.cu -- mass assignment: paint (scatter-add), read (gather), read_grad (gather of the window gradient), and
+// the fused readout + BullFrog kick + drift.  Reference: montecosmo/nbody.py:365-427 (paint/read), 933-951 (kick/drift).
+//
+// Layout: pos/vel [np,3] float32 AoS; mesh [nx,ny,nz] float32, z fastest.  One thread per particle.  Particles of a
+// PM run are in Lagrangian-lattice order (z fastest), so the 32 lanes of a warp hold z-neighbours: their loads and
+// their red.global.add.f32 land in a handful of consecutive 128-byte lines, which keeps both the LSU and the L2
+// atomic units at line granularity instead of element granularity.
+#include "engine.h"
+#include "window.h"
+
+namespace mcpm {
+
+struct MeshDims {
+  int nx, ny, nz;
+};
+
+struct PosXform {
+  float sx, sy, sz, shift;
+};
+
+template <int ORDER>
+static void paint_impl(stream_t st, const float* pos, const float* weights, float wscalar, int64_t np, MeshDims n,
+                       PosXform xf, float* mesh) {
+  launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
+    const float* x = pos + 3 * p;
+    int fx, fy, fz;
+    float wx[ORDER], wy[ORDER], wz[ORDER];
+    window_weights<ORDER>(x[0] * xf.sx + xf.shift, fx, wx);
+    window_weights<ORDER>(x[1] * xf.sy + xf.shift, fy, wy);
+    window_weights<ORDER>(x[2] * xf.sz + xf.shift, fz, wz);
+    fx = wrap_index(fx, n.nx);
+    fy = wrap_index(fy, n.ny);
+    fz = wrap_index(fz, n.nz);
+    float wp = weights ? weights[p] * wscalar : wscalar;
+#pragma unroll
+    for (int a = 0; a < ORDER; ++a) {
+      int ia = fx + a;
+      ia = ia >= n.nx ? ia - n.nx : ia;
+#pragma unroll
+      for (int b = 0; b < ORDER; ++b) {
+        int ib = fy + b;
+        ib = ib >= n.ny ? ib - n.ny : ib;
+        float wab = wx[a] * wy[b];
+        float* row = mesh + ((int64_t)ia * n.ny + ib) * n.nz;
+#pragma unroll
+        for (int c = 0; c < ORDER; ++c) {
+          int ic = fz + c;
+          ic = ic >= n.nz ? ic - n.nz : ic;
+          atomic_add(row + ic, wp * (wab * wz[c]));
+        }
+      }
+    }
+  });
+}
+
+template <int ORDER, int NM>
+static void read_impl(stream_t st, const float* pos, const float* mesh, int64_t np, MeshDims n, PosXform xf,
+                      float* out) {
+  const int64_t plane = (int64_t)n.nx * n.ny * n.nz;
+  launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
+    const float* x = pos + 3 * p;
+    int fx, fy, fz;
+    float wx[ORDER], wy[ORDER], wz[ORDER];
+    window_weights<ORDER>(x[0] * xf.sx + xf.shift, fx, wx);
+    window_weights<ORDER>(x[1] * xf.sy + xf.shift, fy, wy);
+    window_weights<ORDER>(x[2] * xf.sz + xf.shift, fz, wz);
+    fx = wrap_index(fx, n.nx);
+    fy = wrap_index(fy, n.ny);
+    fz = wrap_index(fz, n.nz);
+    float acc[NM];
+#pragma unroll
+    for (int m = 0; m < NM; ++m) acc[m] = 0.0f;
+#pragma unroll
+    for (int a = 0; a < ORDER; ++a) {
+      int ia = fx + a;
+      ia = ia >= n.nx ? ia - n.nx : ia;
+#pragma unroll
+      for (int b = 0; b < ORDER; ++b) {
+        int ib = fy + b;
+        ib = ib >= n.ny ? ib - n.ny : ib;
+        float wab = wx[a] * wy[b];
+        int64_t row = ((int64_t)ia * n.ny + ib) * n.nz;
+#pragma unroll
+        for (int c = 0; c < ORDER; ++c) {
+          int ic = fz + c;
+          ic = ic >= n.nz ? ic - n.nz : ic;
+          float w = wab * wz[c];
+#pragma unroll
+          for (int m = 0; m < NM; ++m) acc[m] += mesh[m * plane + row + ic] * w;
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < NM; ++m) out[p * NM + m] = acc[m];
+  });
+}
+
+struct MeshPtrs {
+  const float* p[4];
+};
+
+// grad[p,a] (+)= gscale * scale_a * sum_m c[p,m] * sum_nbr mesh_m * dW_a * prod_{d!=a} W_d,
+// c[p,m] = cscale * cot[p*ncot+m] for m < ncot, 1 otherwise;  gscale_p = gw ? gw[p] : 1.
+// One gather serves the position-VJP of read (cot = out_bar), of paint (mesh = mesh_bar, gw = weights) and the
+// backward force (3 force meshes with cot = beta*vbar, plus the density-cotangent mesh with c = 1).
+template <int ORDER>
+static void read_grad_impl(stream_t st, const float* pos, MeshPtrs ms, int nmesh, const float* cot, int ncot,
+                           float cscale, const float* gw, int64_t np, MeshDims n, PosXform xf, float* grad,
+                           int accumulate) {
+  launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
+    const float* x = pos + 3 * p;
+    int fx, fy, fz;
+    float wx[ORDER], wy[ORDER], wz[ORDER], dx[ORDER], dy[ORDER], dz[ORDER];
+    window_weights_grad<ORDER>(x[0] * xf.sx + xf.shift, fx, wx, dx);
+    window_weights_grad<ORDER>(x[1] * xf.sy + xf.shift, fy, wy, dy);
+    window_weights_grad<ORDER>(x[2] * xf.sz + xf.shift, fz, wz, dz);
+    fx = wrap_index(fx, n.nx);
+    fy = wrap_index(fy, n.ny);
+    fz = wrap_index(fz, n.nz);
+    float c4[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) c4[m] = (m < ncot && cot) ? cscale * cot[p * ncot + m] : 1.0f;
+    float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
+#pragma unroll
+    for (int a = 0; a < ORDER; ++a) {
+      int ia = fx + a;
+      ia = ia >= n.nx ? ia - n.nx : ia;
+#pragma unroll
+      for (int b = 0; b < ORDER; ++b) {
+        int ib = fy + b;
+        ib = ib >= n.ny ? ib - n.ny : ib;
+        int64_t row = ((int64_t)ia * n.ny + ib) * n.nz;
+#pragma unroll
+        for (int c = 0; c < ORDER; ++c) {
+          int ic = fz + c;
+          ic = ic >= n.nz ? ic - n.nz : ic;
+          float v = 0.0f;
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+            if (m < nmesh) v += c4[m] * ms.p[m][row + ic];
+          g0 += v * (dx[a] * wy[b] * wz[c]);
+          g1 += v * (wx[a] * dy[b] * wz[c]);
+          g2 += v * (wx[a] * wy[b] * dz[c]);
+        }
+      }
+    }
+    float gs = gw ? gw[p] : 1.0f;
+    g0 *= xf.sx * gs;
+    g1 *= xf.sy * gs;
+    g2 *= xf.sz * gs;
+    float* g = grad + 3 * p;
+    if (accumulate) {
+      g[0] += g0;
+      g[1] += g1;
+      g[2] += g2;
+    } else {
+      g[0] = g0;
+      g[1] = g1;
+      g[2] = g2;
+    }
+  });
+}
+
+// Three-channel scatter for the adjoints: mesh_m[...] += (ca*A[p,m] + cb*B[p,m]) * W, m = 0..2 (B may be NULL).
+// The index / weight computation is shared by the three channels.
+template <int ORDER>
+static void paint3_impl(stream_t st, const float* pos, const float* A, float ca, const float* B, float cb,
+                        int64_t np, MeshDims n, float* mesh3) {
+  const int64_t plane = (int64_t)n.nx * n.ny * n.nz;
+  launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
+    const float* x = pos + 3 * p;
+    int fx, fy, fz;
+    float wx[ORDER], wy[ORDER], wz[ORDER];
+    window_weights<ORDER>(x[0], fx, wx);
+    window_weights<ORDER>(x[1], fy, wy);
+    window_weights<ORDER>(x[2], fz, wz);
+    fx = wrap_index(fx, n.nx);
+    fy = wrap_index(fy, n.ny);
+    fz = wrap_index(fz, n.nz);
+    float v0 = ca * A[3 * p], v1 = ca * A[3 * p + 1], v2 = ca * A[3 * p + 2];
+    if (B) {
+      v0 += cb * B[3 * p];
+      v1 += cb * B[3 * p + 1];
+      v2 += cb * B[3 * p + 2];
+    }
+#pragma unroll
+    for (int a = 0; a < ORDER; ++a) {
+      int ia = fx + a;
+      ia = ia >= n.nx ? ia - n.nx : ia;
+#pragma unroll
+      for (int b = 0; b < ORDER; ++b) {
+        int ib = fy + b;
+        ib = ib >= n.ny ? ib - n.ny : ib;
+        float wab = wx[a] * wy[b];
+        float* row = mesh3 + ((int64_t)ia * n.ny + ib) * n.nz;
+#pragma unroll
+        for (int c = 0; c < ORDER; ++c) {
+          int ic = fz + c;
+          ic = ic >= n.nz ? ic - n.nz : ic;
+          float w = wab * wz[c];
+          atomic_add(row + ic, v0 * w);
+          atomic_add(row + plane + ic, v1 * w);
+          atomic_add(row + 2 * plane + ic, v2 * w);
+        }
+      }
+    }
+  });
+}
+
+// VJP of paint w.r.t. weights and positions from the mesh cotangent, one gather:
+//   wbar[p] (+)= wscalar * sum mesh_bar * W ;  posbar[p,a] (+)= w_p * scale_a * sum mesh_bar * dW_a ...
+template <int ORDER>
+static void paint_vjp_impl(stream_t st, const float* pos, const float* weights, float wscalar, const float* mbar,
+                           int64_t np, MeshDims n, PosXform xf, float* posbar, float* wbar, int accumulate) {
+  launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
+    const float* x = pos + 3 * p;
+    int fx, fy, fz;
+    float wx[ORDER], wy[ORDER], wz[ORDER], dx[ORDER], dy[ORDER], dz[ORDER];
+    window_weights_grad<ORDER>(x[0] * xf.sx + xf.shift, fx, wx, dx);
+    window_weights_grad<ORDER>(x[1] * xf.sy + xf.shift, fy, wy, dy);
+    window_weights_grad<ORDER>(x[2] * xf.sz + xf.shift, fz, wz, dz);
+    fx = wrap_index(fx, n.nx);
+    fy = wrap_index(fy, n.ny);
+    fz = wrap_index(fz, n.nz);
+    float r = 0.0f, g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
+#pragma unroll
+    for (int a = 0; a < ORDER; ++a) {
+      int ia = fx + a;
+      ia = ia >= n.nx ? ia - n.nx : ia;
+#pragma unroll
+      for (int b = 0; b < ORDER; ++b) {
+        int ib = fy + b;
+        ib = ib >= n.ny ? ib - n.ny : ib;
+        int64_t row = ((int64_t)ia * n.ny + ib) * n.nz;
+#pragma unroll
+        for (int c = 0; c < ORDER; ++c) {
+          int ic = fz + c;
+          ic = ic >= n.nz ? ic - n.nz : ic;
+          float v = mbar[row + ic];
+          r += v * (wx[a] * wy[b] * wz[c]);
+          g0 += v * (dx[a] * wy[b] * wz[c]);
+          g1 += v * (wx[a] * dy[b] * wz[c]);
+          g2 += v * (wx[a] * wy[b] * dz[c]);
+        }
+      }
+    }
+    float wp = weights ? weights[p] * wscalar : wscalar;
+    if (wbar) wbar[p] = (accumulate ? wbar[p] : 0.0f) + r * wscalar;
+    if (posbar) {
+      float* g = posbar + 3 * p;
+      g[0] = (accumulate ? g[0] : 0.0f) + g0 * xf.sx * wp;
+      g[1] = (accumulate ? g[1] : 0.0f) + g1 * xf.sy * wp;
+      g[2] = (accumulate ? g[2] : 0.0f) + g2 * xf.sz * wp;
+    }
+  });
+}
+
+// F = read(pos, fmesh[3]); vel = alpha*vel + beta*F; pos += vel*drift   (nbody.py:933-951)
+template <int ORDER>
+static void kick_drift_impl(stream_t st, const float* pos, const float* vel, const float* fmesh, int64_t np,
+                            MeshDims n, float alpha, float beta, float drift, float* pos_out, float* vel_out,
+                            float* force_out) {
+  const int64_t plane = (int64_t)n.nx * n.ny * n.nz;
+  launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
+    const float* x = pos + 3 * p;
+    const float* v = vel + 3 * p;
+    float x0 = x[0], x1 = x[1], x2 = x[2];
+    int fx, fy, fz;
+    float wx[ORDER], wy[ORDER], wz[ORDER];
+    window_weights<ORDER>(x0, fx, wx);
+    window_weights<ORDER>(x1, fy, wy);
+    window_weights<ORDER>(x2, fz, wz);
+    fx = wrap_index(fx, n.nx);
+    fy = wrap_index(fy, n.ny);
+    fz = wrap_index(fz, n.nz);
+    float f0 = 0.0f, f1 = 0.0f, f2 = 0.0f;
+#pragma unroll
+    for (int a = 0; a < ORDER; ++a) {
+      int ia = fx + a;
+      ia = ia >= n.nx ? ia - n.nx : ia;
+#pragma unroll
+      for (int b = 0; b < ORDER; ++b) {
+        int ib = fy + b;
+        ib = ib >= n.ny ? ib - n.ny : ib;
+        float wab = wx[a] * wy[b];
+        int64_t row = ((int64_t)ia * n.ny + ib) * n.nz;
+#pragma unroll
+        for (int c = 0; c < ORDER; ++c) {
+          int ic = fz + c;
+          ic = ic >= n.nz ? ic - n.nz : ic;
+          float w = wab * wz[c];
+          f0 += fmesh[row + ic] * w;
+          f1 += fmesh[plane + row + ic] * w;
+          f2 += fmesh[2 * plane + row + ic] * w;
+        }
+      }
+    }
+    float v0 = alpha * v[0] + beta * f0;
+    float v1 = alpha * v[1] + beta * f1;
+    float v2 = alpha * v[2] + beta * f2;
+    vel_out[3 * p] = v0;
+    vel_out[3 * p + 1] = v1;
+    vel_out[3 * p + 2] = v2;
+    pos_out[3 * p] = x0 + v0 * drift;
+    pos_out[3 * p + 1] = x1 + v1 * drift;
+    pos_out[3 * p + 2] = x2 + v2 * drift;
+    if (force_out) {
+      force_out[3 * p] = f0;
+      force_out[3 * p + 1] = f1;
+      force_out[3 * p + 2] = f2;
+    }
+  });
+}
+
+// ------------------------------------------------------------------------------------------------ dispatch
+static int check_mesh(int nx, int ny, int nz, int order) {
+  if (nx <= 0 || ny <= 0 || nz <= 0) {
+    set_error("mesh dimensions must be positive");
+    return MCPM_EINVAL;
+  }
+  if (order < 1 || order > 4) {
+    set_error("assignment order must be 1 (NGP), 2 (CIC), 3 (TSC) or 4 (PCS)");
+    return MCPM_EINVAL;
+  }
+  if (nx < order || ny < order || nz < order) {
+    set_error("mesh sides must be at least the assignment order");
+    return MCPM_EINVAL;
+  }
+  return 0;
+}
+
+static PosXform make_xform(const float* scale, float shift) {
+  PosXform xf = {1.0f, 1.0f, 1.0f, shift};
+  if (scale) {
+    xf.sx = scale[0];
+    xf.sy = scale[1];
+    xf.sz = scale[2];
+  }
+  return xf;
+}
+
+int paint(stream_t st, const float* pos, const float* weights, float wscalar, int64_t np, int nx, int ny, int nz,
+          int order, const float* scale, float shift, float* mesh, int accumulate) {
+  if (int e = check_mesh(nx, ny, nz, order)) return e;
+  if (!mesh || (np > 0 && !pos)) {
+    set_error("paint: null pointer");
+    return MCPM_EINVAL;
+  }
+  MeshDims n = {nx, ny, nz};
+  PosXform xf = make_xform(scale, shift);
+  if (!accumulate) rt_memset(mesh, 0, sizeof(float) * (size_t)nx * ny * nz, st);
+  switch (order) {
+    case 1: paint_impl<1>(st, pos, weights, wscalar, np, n, xf, mesh); break;
+    case 2: paint_impl<2>(st, pos, weights, wscalar, np, n, xf, mesh); break;
+    case 3: paint_impl<3>(st, pos, weights, wscalar, np, n, xf, mesh); break;
+    default: paint_impl<4>(st, pos, weights, wscalar, np, n, xf, mesh); break;
+  }
+  return rt_check("paint");
+}
+
+template <int ORDER>
+static int read_nm(stream_t st, const float* pos, const float* mesh, int nmesh, int64_t np, MeshDims n, PosXform xf,
+                   float* out) {
+  switch (nmesh) {
+    case 1: read_impl<ORDER, 1>(st, pos, mesh, np, n, xf, out); return 0;
+    case 2: read_impl<ORDER, 2>(st, pos, mesh, np, n, xf, out); return 0;
+    case 3: read_impl<ORDER, 3>(st, pos, mesh, np, n, xf, out); return 0;
+    case 4: read_impl<ORDER, 4>(st, pos, mesh, np, n, xf, out); return 0;
+  }
+  set_error("read: nmesh must be 1..4");
+  return MCPM_EINVAL;
+}
+
+int read(stream_t st, const float* pos, const float* mesh, int nmesh, int64_t np, int nx, int ny, int nz, int order,
+         const float* scale, float shift, float* out) {
+  if (int e = check_mesh(nx, ny, nz, order)) return e;
+  if (np > 0 && (!pos || !mesh || !out)) {
+    set_error("read: null pointer");
+    return MCPM_EINVAL;
+  }
+  MeshDims n = {nx, ny, nz};
+  PosXform xf = make_xform(scale, shift);
+  int e;
+  switch (order) {
+    case 1: e = read_nm<1>(st, pos, mesh, nmesh, np, n, xf, out); break;
+    case 2: e = read_nm<2>(st, pos, mesh, nmesh, np, n, xf, out); break;
+    case 3: e = read_nm<3>(st, pos, mesh, nmesh, np, n, xf, out); break;
+    default: e = read_nm<4>(st, pos, mesh, nmesh, np, n, xf, out); break;
+  }
+  return e ? e : rt_check("read");
+}
+
+int read_grad(stream_t st, const float* pos, const float* const* meshes, int nmesh, const float* cot, int ncot,
+              float cscale, const float* gw, int64_t np, int nx, int ny, int nz, int order, const float* scale,
+              float shift, float* grad, int accumulate) {
+  if (int e = check_mesh(nx, ny, nz, order)) return e;
+  if (nmesh < 1 || nmesh > 4 || ncot < 0 || ncot > nmesh) {
+    set_error("read_grad: nmesh must be 1..4 and ncot <= nmesh");
+    return MCPM_EINVAL;
+  }
+  if (np > 0 && (!pos || !meshes || !grad)) {
+    set_error("read_grad: null pointer");
+    return MCPM_EINVAL;
+  }
+  MeshDims n = {nx, ny, nz};
+  PosXform xf = make_xform(scale, shift);
+  MeshPtrs ms = {{nullptr, nullptr, nullptr, nullptr}};
+  for (int m = 0; m < nmesh; ++m) ms.p[m] = meshes[m];
+  switch (order) {
+    case 1: read_grad_impl<1>(st, pos, ms, nmesh, cot, ncot, cscale, gw, np, n, xf, grad, accumulate); break;
+    case 2: read_grad_impl<2>(st, pos, ms, nmesh, cot, ncot, cscale, gw, np, n, xf, grad, accumulate); break;
+    case 3: read_grad_impl<3>(st, pos, ms, nmesh, cot, ncot, cscale, gw, np, n, xf, grad, accumulate); break;
+    default: read_grad_impl<4>(st, pos, ms, nmesh, cot, ncot, cscale, gw, np, n, xf, grad, accumulate); break;
+  }
+  return rt_check("read_grad");
+}
+
+int paint3(stream_t st, const float* pos, const float* A, float ca, const float* B, float cb, int64_t np, int nx,
+           int ny, int nz, int order, float* mesh3, int accumulate) {
+  if (int e = check_mesh(nx, ny, nz, order)) return e;
+  if (!mesh3 || (np > 0 && (!pos || !A))) {
+    set_error("paint3: null pointer");
+    return MCPM_EINVAL;
+  }
+  MeshDims n = {nx, ny, nz};
+  if (!accumulate) rt_memset(mesh3, 0, sizeof(float) * 3 * (size_t)nx * ny * nz, st);
+  switch (order) {
+    case 1: paint3_impl<1>(st, pos, A, ca, B, cb, np, n, mesh3); break;
+    case 2: paint3_impl<2>(st, pos, A, ca, B, cb, np, n, mesh3); break;
+    case 3: paint3_impl<3>(st, pos, A, ca, B, cb, np, n, mesh3); break;
+    default: paint3_impl<4>(st, pos, A, ca, B, cb, np, n, mesh3); break;
+  }
+  return rt_check("paint3");
+}
+
+int paint_vjp(stream_t st, const float* pos, const float* weights, float wscalar, const float* mbar, int64_t np,
+              int nx, int ny, int nz, int order, const float* scale, float shift, float* posbar, float* wbar,
+              int accumulate) {
+  if (int e = check_mesh(nx, ny, nz, order)) return e;
+  if (np > 0 && (!pos || !mbar)) {
+    set_error("paint_vjp: null pointer");
+    return MCPM_EINVAL;
+  }
+  MeshDims n = {nx, ny, nz};
+  PosXform xf = make_xform(scale, shift);
+  switch (order) {
+    case 1: paint_vjp_impl<1>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate); break;
+    case 2: paint_vjp_impl<2>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate); break;
+    case 3: paint_vjp_impl<3>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate); break;
+    default: paint_vjp_impl<4>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate); break;
+  }
+  return rt_check("paint_vjp");
+}
+
+int kick_drift(stream_t st, const float* pos, const float* vel, const float* fmesh3, int64_t np, int nx, int ny,
+               int nz, int order, float alpha, float beta, float drift, float* pos_out, float* vel_out,
+               float* force_out) {
+  if (int e = check_mesh(nx, ny, nz, order)) return e;
+  if (np > 0 && (!pos || !vel || !fmesh3 || !pos_out || !vel_out)) {
+    set_error("kick_drift: null pointer");
+    return MCPM_EINVAL;
+  }
+  MeshDims n = {nx, ny, nz};
+  switch (order) {
+    case 1: kick_drift_impl<1>(st, pos, vel, fmesh3, np, n, alpha, beta, drift, pos_out, vel_out, force_out); break;
+    case 2: kick_drift_impl<2>(st, pos, vel, fmesh3, np, n, alpha, beta, drift, pos_out, vel_out, force_out); break;
+    case 3: kick_drift_impl<3>(st, pos, vel, fmesh3, np, n, alpha, beta, drift, pos_out, vel_out, force_out); break;
+    default: kick_drift_impl<4>(st, pos, vel, fmesh3, np, n, alpha, beta, drift, pos_out, vel_out, force_out); break;
+  }
+  return rt_check("kick_drift");
+}
+
+// ---- small particle-array kernels ------------------------------------------------------------------------------
+// out = a + b * s (drift, nbody.py:942-944); out may alias a
+int axpy3(stream_t st, const float* a, const float* b, float s, int64_t n3, float* out) {
+  launch_1d(st, n3, [=] MCPM_LAMBDA(int64_t i) { out[i] = a[i] + b[i] * s; });
+  return rt_check("axpy3");
+}
+
+// lpt combine (nbody.py:656-665).  dpos/vel may alias f2/f1.
+int lpt_combine(stream_t st, const float* pos, const float* f1, const float* f2, float d1, float d2, float dv2,
+                int64_t np, float* dpos, float* vel, float* pos_out) {
+  launch_1d(st, 3 * np, [=] MCPM_LAMBDA(int64_t i) {
+    float a = f1[i], b = f2 ? f2[i] : 0.0f;
+    float dp = d1 * a - d2 * b;
+    float v = a - dv2 * b;
+    if (dpos) dpos[i] = dp;
+    if (vel) vel[i] = v;
+    if (pos_out) pos_out[i] = pos[i] + dp;
+  });
+  return rt_check("lpt_combine");
+}
+
+// out[0] += sum_i a[i] * b[i] in float64 (coefficient cotangents)
+int dot_accum(stream_t st, const float* a, const float* b, int64_t n, double scale, double* out) {
+#ifdef MCPM_HOSTEMU
+  double s = 0.0;
+  for (int64_t i = 0; i < n; ++i) s += (double)a[i] * (double)b[i];
+  *out += scale * s;
+  return 0;
+#else
+  const int64_t chunk = 4096;  // one warp-reduced double atomic per 4096 products
+  const int64_t nchunks = (n + chunk - 1) / chunk;
+  launch_1d(st, nchunks * 32, [=] MCPM_LAMBDA(int64_t t) {
+    int64_t c = t >> 5;
+    int lane = (int)(t & 31);
+    int64_t lo = c * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    double s = 0.0;
+    for (int64_t i = lo + lane; i < hi; i += 32) s += (double)a[i] * (double)b[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) atomic_add(out, scale * s);
+  });
+  return rt_check("dot_accum");
+#endif
+}
+
+}  // namespace mcpm

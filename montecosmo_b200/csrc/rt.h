@@ -1,0 +1,103 @@
+// rt.h -- thin runtime layer: CUDA (sm_100a) in the product build; plain C++ loops when compiled with
+// -DMCPM_HOSTEMU.  The host-emulation build exists ONLY so that tests/ can exercise the engine's orchestration
+// (buffer wiring, adjoint bookkeeping) on a machine without a GPU; it is built by tests/hostemu.py into
+// tests/_hostemu/ and is never loaded by the montecosmo_b200 package.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/mcpm.h"
+
+namespace mcpm {
+
+struct cfloat {
+  float re, im;
+};
+
+void set_error(const std::string& msg);
+
+#ifdef MCPM_HOSTEMU
+#define MCPM_HD
+#define MCPM_LAMBDA
+typedef void* stream_t;
+
+inline stream_t as_stream(void* s) { return s; }
+
+template <class F>
+inline void launch_1d(stream_t, int64_t n, F f) {
+  for (int64_t i = 0; i < n; ++i) f(i);
+}
+MCPM_HD inline void atomic_add(float* p, float v) { *p += v; }
+MCPM_HD inline void atomic_add(double* p, double v) { *p += v; }
+inline int rt_memset(void* p, int v, size_t bytes, stream_t) {
+  memset(p, v, bytes);
+  return 0;
+}
+inline int rt_copy(void* d, const void* s, size_t bytes, stream_t) {
+  memcpy(d, s, bytes);
+  return 0;
+}
+inline int rt_malloc(void** p, size_t bytes) {
+  *p = malloc(bytes ? bytes : 1);
+  return *p ? 0 : 1;
+}
+inline void rt_free(void* p) { free(p); }
+inline int rt_check(const char*) { return 0; }
+
+#else  // ---------------------------------------------------------------- CUDA
+#include <cuda_runtime.h>
+#define MCPM_HD __host__ __device__ __forceinline__
+#define MCPM_LAMBDA __device__
+typedef cudaStream_t stream_t;
+
+inline stream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs
+
+template <class F>
+__global__ void __launch_bounds__(256) k_launch_1d(int64_t n, F f) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
+}
+
+// Grid-stride launch sized in whole waves of the 148 SMs (8 resident CTAs of 256 threads each).
+template <class F>
+inline void launch_1d(stream_t s, int64_t n, F f) {
+  if (n <= 0) return;
+  int64_t blocks = (n + 255) / 256;
+  const int64_t wave = (int64_t)kSMs * 8;
+  if (blocks > wave) blocks = wave;
+  k_launch_1d<<<(unsigned)blocks, 256, 0, s>>>(n, f);
+}
+
+__device__ __forceinline__ void atomic_add(float* p, float v) { atomicAdd(p, v); }
+__device__ __forceinline__ void atomic_add(double* p, double v) { atomicAdd(p, v); }
+
+inline int rt_memset(void* p, int v, size_t bytes, stream_t s) { return (int)cudaMemsetAsync(p, v, bytes, s); }
+inline int rt_copy(void* d, const void* src, size_t bytes, stream_t s) {
+  return (int)cudaMemcpyAsync(d, src, bytes, cudaMemcpyDeviceToDevice, s);
+}
+inline int rt_malloc(void** p, size_t bytes) { return (int)cudaMalloc(p, bytes ? bytes : 1); }
+inline void rt_free(void* p) { cudaFree(p); }
+inline int rt_check(const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    cudaGetLastError();
+    return MCPM_ECUDA;
+  }
+  return 0;
+}
+#endif
+
+// FFT layer (fft.cu): batched 3-D R2C / C2R on contiguous planes.
+struct FftPlans;
+FftPlans* fft_create(int nx, int ny, int nz, size_t* work_bytes);
+void fft_destroy(FftPlans*);
+int fft_r2c(FftPlans*, stream_t, const float* in, cfloat* out, int batch);
+int fft_c2r(FftPlans*, stream_t, cfloat* in, float* out, int batch);
+
+}  // namespace mcpm

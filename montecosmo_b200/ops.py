@@ -1,0 +1,387 @@
+"""
+Thin Python layer over the C ABI (include/mcpm.h): one method per entry point, arrays in / arrays out.
+
+`Ops` is parametrised by an *array adapter* (allocation, pointer, stream).  The package instantiates it with the torch
+CUDA adapter below -- device memory and streams are torch's, the arithmetic is libmcpm's.  The test-suite instantiates
+the same class with a NumPy adapter over the host-emulation build (tests/hostemu.py) to check orchestration on CPU.
+"""
+import ctypes as C
+import math
+
+from . import _capi
+from ._capi import check, fd_code, host_floats
+
+INF = float("inf")
+
+
+def r2chshape(shape):
+    """Real shape -> half-spectrum shape (utils.py:778-782)."""
+    return (*shape[:-1], shape[-1] // 2 + 1)
+
+
+def ch2rshape(shape):
+    """Half-spectrum shape -> real shape, last real side even (utils.py:769-776)."""
+    return (*shape[:-1], 2 * (shape[-1] - 1))
+
+
+class TorchCudaAdapter:
+    """Device memory and streams from torch; float32 / complex64 contiguous CUDA tensors."""
+
+    def __init__(self, device=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("montecosmo_b200 needs a CUDA device: there is no CPU fallback")
+        self.torch = torch
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+    def empty(self, shape, dtype="f32"):
+        t = self.torch
+        dt = {"f32": t.float32, "c64": t.complex64, "f64": t.float64}[dtype]
+        return t.empty(tuple(int(s) for s in shape), dtype=dt, device=self.device)
+
+    def zeros(self, shape, dtype="f32"):
+        return self.empty(shape, dtype).zero_()
+
+    def prepare(self, x, dtype="f32"):
+        t = self.torch
+        dt = {"f32": t.float32, "c64": t.complex64, "f64": t.float64}[dtype]
+        x = t.as_tensor(x, device=self.device)
+        if x.dtype != dt:
+            x = x.to(dt)
+        return x.contiguous()
+
+    def ptr(self, x):
+        return 0 if x is None else x.data_ptr()
+
+    def stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def shape(self, x):
+        return tuple(x.shape)
+
+
+class Engine:
+    """Owner of one mcpm_engine (cuFFT plans + scratch for one mesh shape)."""
+
+    def __init__(self, lib, shape):
+        self.lib, self.shape = lib, tuple(int(s) for s in shape)
+        h = C.c_void_p()
+        check(lib, lib.mcpm_engine_create(*self.shape, C.byref(h)))
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.mcpm_engine_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class Ops:
+    def __init__(self, lib, adapter):
+        self.lib, self.A = lib, adapter
+        self._engines = {}
+
+    # ------------------------------------------------------------------------------------------------ helpers
+    def engine(self, shape):
+        shape = tuple(int(s) for s in shape)
+        if shape not in self._engines:
+            self._engines[shape] = Engine(self.lib, shape)
+        return self._engines[shape]
+
+    def _xf(self, scale, shift):
+        return host_floats((1.0, 1.0, 1.0) if scale is None else scale), float(shift)
+
+    def _call(self, name, *args):
+        check(self.lib, getattr(self.lib, name)(*args))
+
+    # ------------------------------------------------------------------------------------------------ assignment
+    def paint(self, pos, shape, weights=None, wscalar=1.0, order=2, scale=None, shift=0.0, out=None, accumulate=False):
+        A = self.A
+        pos = A.prepare(pos)
+        weights = None if weights is None else A.prepare(weights)
+        mesh = A.empty(shape) if out is None else out
+        sc, sh = self._xf(scale, shift)
+        self._call("mcpm_paint", A.stream(), A.ptr(pos), A.ptr(weights), wscalar, A.shape(pos)[0], *shape, order, sc,
+                   sh, A.ptr(mesh), int(accumulate))
+        return mesh
+
+    def read(self, pos, mesh, order=2, scale=None, shift=0.0):
+        """mesh [nx,ny,nz] -> [np];  mesh [m,nx,ny,nz] -> [np,m]."""
+        A = self.A
+        pos, mesh = A.prepare(pos), A.prepare(mesh)
+        ms = A.shape(mesh)
+        nm = 1 if len(ms) == 3 else ms[0]
+        n = A.shape(pos)[0]
+        out = A.empty((n,) if len(ms) == 3 else (n, nm))
+        sc, sh = self._xf(scale, shift)
+        self._call("mcpm_read", A.stream(), A.ptr(pos), A.ptr(mesh), nm, n, *ms[-3:], order, sc, sh, A.ptr(out))
+        return out
+
+    def read_grad(self, pos, mesh, cot=None, order=2, scale=None, shift=0.0):
+        A = self.A
+        pos, mesh = A.prepare(pos), A.prepare(mesh)
+        cot = None if cot is None else A.prepare(cot)
+        ms = A.shape(mesh)
+        nm = 1 if len(ms) == 3 else ms[0]
+        n = A.shape(pos)[0]
+        out = A.empty((n, 3))
+        sc, sh = self._xf(scale, shift)
+        self._call("mcpm_read_grad", A.stream(), A.ptr(pos), A.ptr(mesh), nm, A.ptr(cot), n, *ms[-3:], order, sc, sh,
+                   A.ptr(out), 0)
+        return out
+
+    def paint_vjp(self, pos, mesh_bar, weights=None, wscalar=1.0, order=2, scale=None, shift=0.0, want_pos=True,
+                  want_weights=True):
+        A = self.A
+        pos, mesh_bar = A.prepare(pos), A.prepare(mesh_bar)
+        weights = None if weights is None else A.prepare(weights)
+        n = A.shape(pos)[0]
+        pb = A.empty((n, 3)) if want_pos else None
+        wb = A.empty((n,)) if want_weights else None
+        sc, sh = self._xf(scale, shift)
+        self._call("mcpm_paint_vjp", A.stream(), A.ptr(pos), A.ptr(weights), wscalar, A.ptr(mesh_bar), n,
+                   *A.shape(mesh_bar), order, sc, sh, A.ptr(pb), A.ptr(wb), 0)
+        return pb, wb
+
+    def paint3(self, pos, vals3, shape, vscale=1.0, order=2):
+        A = self.A
+        pos, vals3 = A.prepare(pos), A.prepare(vals3)
+        out = A.empty((3, *shape))
+        self._call("mcpm_paint3", A.stream(), A.ptr(pos), A.ptr(vals3), vscale, A.shape(pos)[0], *shape, order,
+                   A.ptr(out), 0)
+        return out
+
+    # ------------------------------------------------------------------------------------------------ FFT, Fourier passes
+    def rfftn(self, mesh):
+        A = self.A
+        mesh = A.prepare(mesh)
+        ms = A.shape(mesh)
+        batch = 1 if len(ms) == 3 else ms[0]
+        out = A.empty((*ms[:-3], *r2chshape(ms[-3:])), "c64")
+        self._call("mcpm_rfftn", self.engine(ms[-3:]).handle, A.stream(), A.ptr(mesh), A.ptr(out), batch)
+        return out
+
+    def irfftn(self, meshk, overwrite=False):
+        A = self.A
+        meshk = A.prepare(meshk, "c64")
+        if not overwrite:
+            meshk = meshk.clone() if hasattr(meshk, "clone") else meshk.copy()
+        ms = A.shape(meshk)
+        batch = 1 if len(ms) == 3 else ms[0]
+        rs = ch2rshape(ms[-3:])
+        out = A.empty((*ms[:-3], *rs))
+        self._call("mcpm_irfftn", self.engine(rs).handle, A.stream(), A.ptr(meshk), A.ptr(out), batch)
+        return out
+
+    def force_spectra(self, dk, lap_fd=INF, grad_fd=INF, kcut=INF, deconv_order=0):
+        A = self.A
+        dk = A.prepare(dk, "c64")
+        rs = ch2rshape(A.shape(dk))
+        out = A.empty((3, *A.shape(dk)), "c64")
+        self._call("mcpm_force_spectra", A.stream(), A.ptr(dk), A.ptr(out), *rs, fd_code(lap_fd), fd_code(grad_fd),
+                   0.0 if kcut == INF else kcut, deconv_order)
+        return out
+
+    def force_spectra_T(self, in3, lap_fd=INF, grad_fd=INF, kcut=INF, deconv_order=0, half_weights=False):
+        A = self.A
+        in3 = A.prepare(in3, "c64")
+        cs = A.shape(in3)[1:]
+        out = A.empty(cs, "c64")
+        self._call("mcpm_force_spectra_T", A.stream(), A.ptr(in3), A.ptr(out), *ch2rshape(cs), fd_code(lap_fd),
+                   fd_code(grad_fd), 0.0 if kcut == INF else kcut, deconv_order, int(half_weights), 0)
+        return out
+
+    def hessian_spectra(self, dk, lap_fd=INF, grad_fd=INF):
+        A = self.A
+        dk = A.prepare(dk, "c64")
+        out = A.empty((6, *A.shape(dk)), "c64")
+        self._call("mcpm_hessian_spectra", A.stream(), A.ptr(dk), A.ptr(out), *ch2rshape(A.shape(dk)),
+                   fd_code(lap_fd), fd_code(grad_fd))
+        return out
+
+    def hessian_spectra_T(self, in6, lap_fd=INF, grad_fd=INF, half_weights=False):
+        A = self.A
+        in6 = A.prepare(in6, "c64")
+        cs = A.shape(in6)[1:]
+        out = A.empty(cs, "c64")
+        self._call("mcpm_hessian_spectra_T", A.stream(), A.ptr(in6), A.ptr(out), *ch2rshape(cs), fd_code(lap_fd),
+                   fd_code(grad_fd), int(half_weights), 0)
+        return out
+
+    def lpt2_source(self, h6):
+        A = self.A
+        h6 = A.prepare(h6)
+        out = A.empty(A.shape(h6)[1:])
+        self._call("mcpm_lpt2_source", A.stream(), A.ptr(h6), A.ptr(out), math.prod(A.shape(h6)[1:]))
+        return out
+
+    def lpt2_source_vjp(self, h6, d2bar):
+        A = self.A
+        h6, d2bar = A.prepare(h6), A.prepare(d2bar)
+        out = A.empty(A.shape(h6))
+        self._call("mcpm_lpt2_source_vjp", A.stream(), A.ptr(h6), A.ptr(d2bar), A.ptr(out),
+                   math.prod(A.shape(h6)[1:]))
+        return out
+
+    def deconv(self, meshk, order=2):
+        A = self.A
+        meshk = A.prepare(meshk, "c64")
+        out = A.empty(A.shape(meshk), "c64")
+        self._call("mcpm_deconv", A.stream(), A.ptr(meshk), A.ptr(out), *ch2rshape(A.shape(meshk)), order)
+        return out
+
+    def interlace_combine(self, in_m, scale=1.0, deconv_order=0):
+        A = self.A
+        in_m = A.prepare(in_m, "c64")
+        m, cs = A.shape(in_m)[0], A.shape(in_m)[1:]
+        out = A.empty(cs, "c64")
+        self._call("mcpm_interlace_combine", A.stream(), A.ptr(in_m), A.ptr(out), m, *ch2rshape(cs), scale,
+                   deconv_order)
+        return out
+
+    def interlace_combine_T(self, inp, m, scale=1.0, deconv_order=0):
+        A = self.A
+        inp = A.prepare(inp, "c64")
+        cs = A.shape(inp)
+        out = A.empty((m, *cs), "c64")
+        self._call("mcpm_interlace_combine_T", A.stream(), A.ptr(inp), A.ptr(out), m, *ch2rshape(cs), scale,
+                   deconv_order)
+        return out
+
+    def chreshape(self, meshk, out_cshape):
+        A = self.A
+        meshk = A.prepare(meshk, "c64")
+        out = A.empty(out_cshape, "c64")
+        self._call("mcpm_chreshape", A.stream(), A.ptr(meshk), *ch2rshape(A.shape(meshk)), A.ptr(out),
+                   *ch2rshape(out_cshape))
+        return out
+
+    def scale_spectrum(self, meshk, transfer):
+        A = self.A
+        meshk, transfer = A.prepare(meshk, "c64"), A.prepare(transfer)
+        out = A.empty(A.shape(meshk), "c64")
+        self._call("mcpm_scale_spectrum", A.stream(), A.ptr(meshk), A.ptr(transfer), A.ptr(out),
+                   math.prod(A.shape(meshk)))
+        return out
+
+    # ------------------------------------------------------------------------------------------------ composites
+    def pm_forces(self, pos, shape, order=2, paint_deconv=False, lap_fd=INF, grad_fd=INF, kcut=INF, want_meshes=False):
+        A = self.A
+        pos = A.prepare(pos)
+        n = A.shape(pos)[0]
+        forces = A.empty((n, 3))
+        fm = A.empty((3, *shape)) if want_meshes else None
+        self._call("mcpm_pm_forces", self.engine(shape).handle, A.stream(), A.ptr(pos), n, order, int(paint_deconv),
+                   fd_code(lap_fd), fd_code(grad_fd), 0.0 if kcut == INF else kcut, A.ptr(fm), A.ptr(forces))
+        return (forces, fm) if want_meshes else forces
+
+    def pm_forces_vjp(self, pos, fbar, fmesh3, order=2, paint_deconv=False, lap_fd=INF, grad_fd=INF, kcut=INF):
+        A = self.A
+        pos, fbar, fmesh3 = A.prepare(pos), A.prepare(fbar), A.prepare(fmesh3)
+        n = A.shape(pos)[0]
+        shape = A.shape(fmesh3)[1:]
+        out = A.empty((n, 3))
+        self._call("mcpm_pm_forces_vjp", self.engine(shape).handle, A.stream(), A.ptr(pos), A.ptr(fbar),
+                   A.ptr(fmesh3), n, order, int(paint_deconv), fd_code(lap_fd), fd_code(grad_fd),
+                   0.0 if kcut == INF else kcut, A.ptr(out), 0)
+        return out
+
+    def pm_forces_mesh(self, pos, dk, order=2, lap_fd=INF, grad_fd=INF, kcut=INF):
+        A = self.A
+        pos, dk = A.prepare(pos), A.prepare(dk, "c64")
+        n = A.shape(pos)[0]
+        out = A.empty((n, 3))
+        self._call("mcpm_pm_forces_mesh", self.engine(ch2rshape(A.shape(dk))).handle, A.stream(), A.ptr(pos),
+                   A.ptr(dk), n, order, fd_code(lap_fd), fd_code(grad_fd), 0.0 if kcut == INF else kcut, A.ptr(out))
+        return out
+
+    def pm_forces2(self, pos, dk, order=2, lap_fd=INF, grad_fd=INF):
+        A = self.A
+        pos, dk = A.prepare(pos), A.prepare(dk, "c64")
+        n = A.shape(pos)[0]
+        out = A.empty((n, 3))
+        self._call("mcpm_pm_forces2", self.engine(ch2rshape(A.shape(dk))).handle, A.stream(), A.ptr(pos), A.ptr(dk),
+                   n, order, fd_code(lap_fd), fd_code(grad_fd), A.ptr(out), 0)
+        return out
+
+    def lpt(self, dk, pos, d1, d2, dv2, lpt_order=2, read_order=2, lap_fd=INF, grad_fd=INF, tape=False):
+        A = self.A
+        pos, dk = A.prepare(pos), A.prepare(dk, "c64")
+        n = A.shape(pos)[0]
+        rs = ch2rshape(A.shape(dk))
+        dpos, vel = A.empty((n, 3)), A.empty((n, 3))
+        f1 = A.empty((n, 3)) if tape else None
+        f2 = A.empty((n, 3)) if tape and lpt_order == 2 else None
+        h6 = A.empty((6, *rs)) if tape and lpt_order == 2 else None
+        self._call("mcpm_lpt", self.engine(rs).handle, A.stream(), A.ptr(dk), A.ptr(pos), n, lpt_order, read_order,
+                   fd_code(lap_fd), fd_code(grad_fd), d1, d2, dv2, A.ptr(dpos), A.ptr(vel), A.ptr(f1), A.ptr(f2),
+                   A.ptr(h6))
+        return (dpos, vel, (f1, f2, h6)) if tape else (dpos, vel)
+
+    def lpt_vjp(self, pos, cshape, d1, d2, dv2, dposbar, velbar, tape, lpt_order=2, read_order=2, lap_fd=INF,
+                grad_fd=INF, want_coef=False):
+        A = self.A
+        pos, dposbar, velbar = A.prepare(pos), A.prepare(dposbar), A.prepare(velbar)
+        f1, f2, h6 = tape
+        n = A.shape(pos)[0]
+        rs = ch2rshape(cshape)
+        dkbar = A.empty(cshape, "c64")
+        coef = A.zeros((3,), "f64") if want_coef else None
+        self._call("mcpm_lpt_vjp", self.engine(rs).handle, A.stream(), A.ptr(pos), n, lpt_order, read_order,
+                   fd_code(lap_fd), fd_code(grad_fd), d1, d2, dv2, A.ptr(dposbar), A.ptr(velbar), A.ptr(f1),
+                   A.ptr(f2), A.ptr(h6), A.ptr(dkbar), A.ptr(coef), 0)
+        return (dkbar, coef) if want_coef else dkbar
+
+    def nbody_steps(self, pos, vel, shape, alpha, beta, drift_pre, drift_post, order=2, paint_deconv=False,
+                    lap_fd=INF, grad_fd=INF, tape=False, tape_vel=False):
+        """In place on (pos, vel) -- pass fresh copies.  Returns the tape (xk, vk, fm) when asked."""
+        A = self.A
+        n = A.shape(pos)[0]
+        ns = len(alpha)
+        xk = A.empty((ns, n, 3)) if tape else None
+        vk = A.empty((ns, n, 3)) if tape and tape_vel else None
+        fm = A.empty((ns, 3, *shape)) if tape else None
+        self._call("mcpm_nbody_steps", self.engine(shape).handle, A.stream(), A.ptr(pos), A.ptr(vel), n, ns,
+                   host_floats(alpha), host_floats(beta), host_floats(drift_pre), host_floats(drift_post), order,
+                   int(paint_deconv), fd_code(lap_fd), fd_code(grad_fd), A.ptr(xk), A.ptr(vk), A.ptr(fm))
+        return (xk, vk, fm)
+
+    def nbody_steps_vjp(self, posbar, velbar, shape, alpha, beta, drift_pre, drift_post, tape, order=2,
+                        paint_deconv=False, lap_fd=INF, grad_fd=INF, v0=None, want_coef=False):
+        """In place on (posbar, velbar)."""
+        A = self.A
+        xk, vk, fm = tape
+        n = A.shape(posbar)[0]
+        ns = len(alpha)
+        coef = A.zeros((ns, 4), "f64") if want_coef else None
+        self._call("mcpm_nbody_steps_vjp", self.engine(shape).handle, A.stream(), A.ptr(posbar), A.ptr(velbar), n, ns,
+                   host_floats(alpha), host_floats(beta), host_floats(drift_pre), host_floats(drift_post), order,
+                   int(paint_deconv), fd_code(lap_fd), fd_code(grad_fd), A.ptr(xk), A.ptr(vk), A.ptr(fm), A.ptr(v0),
+                   A.ptr(coef))
+        return coef
+
+    def nufft_paint(self, pos, paint_shape, weights=None, wscalar=1.0, scale=None, paint_order=2, interlace_order=2,
+                    paint_deconv=True):
+        A = self.A
+        pos = A.prepare(pos)
+        weights = None if weights is None else A.prepare(weights)
+        out = A.empty(r2chshape(paint_shape), "c64")
+        sc, _ = self._xf(scale, 0.0)
+        self._call("mcpm_nufft", self.engine(paint_shape).handle, A.stream(), A.ptr(pos), A.ptr(weights), wscalar,
+                   A.shape(pos)[0], sc, paint_order, interlace_order, int(paint_deconv), A.ptr(out))
+        return out
+
+    def nufft_paint_vjp(self, pos, outbar, paint_shape, weights=None, wscalar=1.0, scale=None, paint_order=2,
+                        interlace_order=2, paint_deconv=True, want_pos=True, want_weights=True):
+        A = self.A
+        pos, outbar = A.prepare(pos), A.prepare(outbar, "c64")
+        weights = None if weights is None else A.prepare(weights)
+        n = A.shape(pos)[0]
+        pb = A.empty((n, 3)) if want_pos else None
+        wb = A.empty((n,)) if want_weights else None
+        sc, _ = self._xf(scale, 0.0)
+        self._call("mcpm_nufft_vjp", self.engine(paint_shape).handle, A.stream(), A.ptr(pos), A.ptr(weights), wscalar,
+                   n, sc, paint_order, interlace_order, int(paint_deconv), A.ptr(outbar), A.ptr(pb), A.ptr(wb))
+        return pb, wb

@@ -1,0 +1,401 @@
+"""
+Parity of the C ABI (include/mcpm.h) with the float64 oracle and the golden vectors of the reference source.
+
+Every test runs on two backends through the SAME ctypes prototypes:
+  * "hostemu"  -- the engine sources compiled as serial C++ (tests/hostemu.py), CPU, always run;
+  * "cuda"     -- libmcpm.so on a B200 (marked gpu).
+Engine arithmetic is float32; the oracle is float64.  Tolerances (stated per test) are relative L2 unless noted.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pm_oracle as O
+from tests.backends import NumpyAdapter, to_numpy
+
+INF = float("inf")
+
+
+def _make_ops(kind):
+    from montecosmo_b200.ops import Ops
+    if kind == "hostemu":
+        from tests import hostemu
+        return Ops(hostemu.load(), NumpyAdapter())
+    from montecosmo_b200 import _lib
+    from montecosmo_b200.ops import TorchCudaAdapter
+    return Ops(_lib.load(), TorchCudaAdapter())
+
+
+@pytest.fixture(scope="module", params=["hostemu", pytest.param("cuda", marks=pytest.mark.gpu)])
+def ops(request):
+    return _make_ops(request.param)
+
+
+def rel(a, b):
+    a, b = np.asarray(to_numpy(a), dtype=np.float64 if not np.iscomplexobj(to_numpy(a)) else np.complex128), \
+        np.asarray(b)
+    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
+
+
+def f32(x):
+    return np.asarray(x, dtype=np.float32)
+
+
+def c64(x):
+    return np.asarray(x, dtype=np.complex64)
+
+
+def T(x, dtype=torch.float64):
+    return torch.as_tensor(np.asarray(x), dtype=dtype)
+
+
+# ------------------------------------------------------------------------------------------------ paint / read
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+def test_paint_read_golden(ops, golden, order):
+    """vs the reference source (float64 inputs): 2e-5 covers float32 rounding of positions up to +-40 cells."""
+    g = golden("paint_read")
+    shape = tuple(int(s) for s in g["shape"])
+    assert rel(ops.paint(f32(g["pos"]), shape, f32(g["weights"]), order=order), g[f"paint_w_{order}"]) < 2e-5
+    assert rel(ops.paint(f32(g["pos"]), shape, None, order=order), g[f"paint_1_{order}"]) < 2e-5
+    assert rel(ops.read(f32(g["pos"]), f32(g["mesh"]), order=order), g[f"read_{order}"]) < 2e-5
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+def test_paint_read_oracle_same_inputs(ops, order):
+    """vs the oracle fed the SAME float32-rounded inputs: 2e-6 (pure float32 arithmetic error)."""
+    rng = np.random.default_rng(10 + order)
+    shape = (10, 12, 8)
+    pos = f32(rng.uniform(-15, 30, (2000, 3)))
+    pos[:100] = np.round(pos[:100])
+    pos[100:200] = np.floor(pos[100:200]) + 0.5
+    w = f32(rng.normal(size=2000))
+    mesh = f32(rng.normal(size=shape))
+    scale, shift = (1.25, 0.75, 1.5), 0.5
+    assert rel(ops.paint(pos, shape, w, order=order), O.paint(T(pos), shape, T(w), order).numpy()) < 2e-6
+    assert rel(ops.read(pos, mesh, order=order), O.read(T(pos), T(mesh), order).numpy()) < 2e-6
+    # in-kernel transform x' = x*scale + shift (nufft / interlace)
+    xs = T(pos) * T(f32(scale)) + shift
+    assert rel(ops.paint(pos, shape, w, 0.5, order, scale, shift), O.paint(xs, shape, T(w) * 0.5, order).numpy()) < 5e-6
+    assert rel(ops.read(pos, mesh, order, scale, shift), O.read(xs, T(mesh), order).numpy()) < 5e-6
+    # multi-mesh read, interleaved output
+    m3 = f32(rng.normal(size=(3, *shape)))
+    ref = np.stack([O.read(T(pos), T(m3[i]), order).numpy() for i in range(3)], -1)
+    assert rel(ops.read(pos, m3, order=order), ref) < 2e-6
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+def test_paint_properties(ops, order):
+    """weight conservation (bricks.py:1101-1102); read = paint^T; lattice read returns mesh values (nbody.py:602)."""
+    rng = np.random.default_rng(order)
+    shape = (8, 6, 10)
+    pos = f32(rng.uniform(-5, 15, (500, 3)))
+    w = f32(rng.uniform(0.5, 1.5, 500))
+    m = f32(rng.normal(size=shape))
+    painted = to_numpy(ops.paint(pos, shape, w, order=order)).astype(np.float64)
+    assert abs(painted.sum() - w.astype(np.float64).sum()) < 1e-4 * w.sum()
+    lhs = float((to_numpy(ops.read(pos, m, order=order)).astype(np.float64) * w).sum())
+    rhs = float((m.astype(np.float64) * painted).sum())
+    assert abs(lhs - rhs) < 1e-4 * max(abs(lhs), 1.0)
+    if order <= 2:
+        q = f32(O.regular_pos(shape).numpy())
+        assert rel(ops.read(q, m, order=order), m.reshape(-1)) < 1e-7
+
+
+def test_paint_edge_cases(ops):
+    shape = (8, 8, 8)
+    # empty particle set -> zero mesh; accumulate adds
+    z = to_numpy(ops.paint(np.zeros((0, 3), np.float32), shape, None, order=2))
+    assert z.shape == shape and not z.any()
+    pos = f32([[0.0, 0.0, 0.0], [7.5, 7.5, 7.5], [-0.25, 8.0, 15.999]])
+    a = ops.paint(pos, shape, None, order=2)
+    b = ops.paint(pos, shape, None, order=2, out=a, accumulate=True)
+    assert rel(b, 2 * O.paint(T(pos), shape, 1.0, 2).numpy()) < 1e-6
+    from montecosmo_b200._capi import McpmError
+    with pytest.raises(McpmError):
+        ops.paint(pos, shape, None, order=5)
+    with pytest.raises(McpmError):
+        ops.paint(pos, (8, 8, 2), None, order=4)
+
+
+@pytest.mark.parametrize("order", [2, 3, 4])
+def test_paint_read_vjp(ops, order):
+    """Gathers of the window gradient vs oracle autograd (1e-5)."""
+    rng = np.random.default_rng(20 + order)
+    shape = (8, 10, 6)
+    pos = f32(rng.uniform(-3, 12, (600, 3)))
+    w = f32(rng.uniform(0.5, 1.5, 600))
+    mbar = f32(rng.normal(size=shape))
+    scale, shift = (1.25, 1.0, 0.75), 0.5
+    p = T(pos).requires_grad_()
+    wt = T(w).requires_grad_()
+    xs = p * T(f32(scale)) + shift
+    (O.paint(xs, shape, wt * 0.7, order) * T(mbar)).sum().backward()
+    pb, wb = ops.paint_vjp(pos, mbar, w, 0.7, order, scale, shift)
+    assert rel(pb, p.grad.numpy()) < 1e-5
+    assert rel(wb, wt.grad.numpy()) < 1e-5
+    # read_grad with a cotangent over 3 meshes
+    m3 = f32(rng.normal(size=(3, *shape)))
+    cot = f32(rng.normal(size=(600, 3)))
+    p = T(pos).requires_grad_()
+    sum((O.read(p, T(m3[i]), order) * T(cot[:, i])).sum() for i in range(3)).backward()
+    assert rel(ops.read_grad(pos, m3, cot, order), p.grad.numpy()) < 1e-5
+    # paint3 = transpose of the 3-mesh read
+    ref = np.stack([O.paint(T(pos), shape, T(cot[:, i]), order).numpy() for i in range(3)])
+    assert rel(ops.paint3(pos, cot, shape, 1.0, order), ref) < 2e-6
+
+
+# ------------------------------------------------------------------------------------------------ Fourier passes
+def test_fft_roundtrip(ops):
+    rng = np.random.default_rng(3)
+    m = f32(rng.normal(size=(3, 8, 6, 10)))
+    k = ops.rfftn(m)
+    assert rel(k, np.fft.rfftn(m.astype(np.float64), axes=(1, 2, 3))) < 1e-6
+    assert rel(ops.irfftn(k), m) < 1e-6
+    assert rel(ops.irfftn(ops.rfftn(m[0])), m[0]) < 1e-6
+
+
+def test_fourier_kernels_golden(ops, golden):
+    """force / Hessian / deconvolution kernels vs the reference's kernel arrays on a non-cubic mesh (2e-6)."""
+    g = golden("kernels")
+    shape = tuple(int(s) for s in g["shape"])
+    rng = np.random.default_rng(5)
+    dk = c64(np.fft.rfftn(rng.normal(size=shape)))
+    for lap, grad, kcut, dec in [(INF, INF, INF, 0), (2, 4, INF, 0), (4, 2, 2.0, 0), (INF, INF, INF, 2)]:
+        tag = lambda fd: "inf" if fd == INF else str(fd)
+        base = g[f"invlaplace_{tag(lap)}"] * (g["gaussian_kcut2"] if kcut != INF else 1.0)
+        if dec:
+            base = base / g[f"rectangular_hat_{dec}"] ** 2
+        ref = np.stack([-g[f"gradient{i}_{tag(grad)}"] * base * dk for i in range(3)])
+        assert rel(ops.force_spectra(dk, lap, grad, kcut, dec), ref) < 2e-6
+    ref = np.stack([g[f"gradient{i}_inf"] * g[f"gradient{j}_inf"] * g["invlaplace_inf"] * dk
+                    for i, j in [(0, 0), (1, 1), (2, 2), (0, 1), (0, 2), (1, 2)]])
+    assert rel(ops.hessian_spectra(dk), ref) < 2e-6
+    for o in (1, 2, 3, 4):
+        assert rel(ops.deconv(dk, o), dk / g[f"rectangular_hat_{o}"]) < 2e-6
+
+
+def test_fourier_transposes(ops):
+    """<K x, y> = <x, K^T y> for the force / Hessian / interlace passes, in the real inner product Re sum conj(a) b."""
+    rng = np.random.default_rng(6)
+    shape = (8, 6, 10)
+    cs = O.r2chshape(shape)
+    cplx = lambda *s: c64(rng.normal(size=s) + 1j * rng.normal(size=s))
+    dot = lambda a, b: float(np.real(np.vdot(to_numpy(a).astype(np.complex128), to_numpy(b).astype(np.complex128))))
+    x, y3, y6 = cplx(*cs), cplx(3, *cs), cplx(6, *cs)
+    for kw in [dict(), dict(lap_fd=2, grad_fd=4, kcut=2.0, deconv_order=2)]:
+        assert abs(dot(ops.force_spectra(x, **kw), y3) - dot(x, ops.force_spectra_T(y3, **kw))) < 1e-4 * abs(
+            dot(x, x))
+    assert abs(dot(ops.hessian_spectra(x), y6) - dot(x, ops.hessian_spectra_T(y6))) < 1e-4 * abs(dot(x, x))
+    # half_weights variant = (w'/N) * plain transpose
+    wq = np.full(cs, 2.0)
+    wq[..., 0] = 1.0
+    wq[..., -1] = 1.0
+    assert rel(ops.force_spectra_T(y3, half_weights=True), to_numpy(ops.force_spectra_T(y3)) * wq / np.prod(shape)) < 1e-6
+    # interlace: K^T carries N / w'
+    xm = cplx(2, *cs)
+    lhs = dot(ops.interlace_combine(xm, 1.7, 2), x)
+    rhs = dot(xm, to_numpy(ops.interlace_combine_T(x, 2, 1.7, 2)) * wq / np.prod(shape))
+    assert abs(lhs - rhs) < 1e-4 * abs(dot(x, x))
+
+
+@pytest.mark.parametrize("tag", ["down", "up", "mixed", "same"])
+def test_chreshape_golden(ops, golden, tag):
+    g = golden("chreshape")
+    dst = tuple(int(s) for s in g[f"{tag}_dst"])
+    assert rel(ops.chreshape(c64(g[f"{tag}_in"]), O.r2chshape(dst)), g[f"{tag}_out"]) < 2e-6
+
+
+def test_lpt2_source(ops):
+    rng = np.random.default_rng(7)
+    h = f32(rng.normal(size=(6, 6, 6, 6)))
+    ht = T(h).requires_grad_()
+    d2 = ht[0] * ht[1] + ht[0] * ht[2] + ht[1] * ht[2] - ht[3] ** 2 - ht[4] ** 2 - ht[5] ** 2
+    assert rel(ops.lpt2_source(h), d2.detach().numpy()) < 1e-6
+    bar = f32(rng.normal(size=(6, 6, 6)))
+    (d2 * T(bar)).sum().backward()
+    assert rel(ops.lpt2_source_vjp(h, bar), ht.grad.numpy()) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ forces / LPT
+@pytest.mark.parametrize("name", ["forces_lpt", "forces_noncubic"])
+def test_pm_forces_golden(ops, golden, name):
+    """vs the reference source; 5e-5 (float32 FFT + assignment against float64)."""
+    g = golden(name)
+    shape = tuple(int(s) for s in g["shape"])
+    pos, dk = f32(g["pos"]), c64(g["delta_k"])
+    assert rel(ops.pm_forces(pos, shape, 2), g["pm_forces_paint"]) < 5e-5
+    assert rel(ops.pm_forces_mesh(pos, dk, 2), g["pm_forces_mesh"]) < 5e-5
+    assert rel(ops.pm_forces2(pos, dk, 2), g["pm_forces2"]) < 5e-5
+    if name == "forces_lpt":
+        assert rel(ops.pm_forces(pos, shape, 2, paint_deconv=True, kcut=2.5), g["pm_forces_paint_deconv_kcut"]) < 5e-5
+        assert rel(ops.pm_forces(pos, shape, 3, lap_fd=2, grad_fd=4), g["pm_forces_paint_o3_fd"]) < 5e-5
+        q = f32(O.regular_pos(shape).numpy())
+        assert rel(ops.pm_forces_mesh(q, dk, 1), g["pm_forces_mesh_ngp_lattice"]) < 5e-5
+
+
+def test_lpt_golden(ops, golden):
+    g = golden("forces_lpt")
+    shape = tuple(int(s) for s in g["shape"])
+    dk = c64(g["delta_k"])
+    q = f32(O.regular_pos(shape).numpy())
+    c = O.Cosmology()
+    co = lambda a: (float(O.a2g(c, a)), float(O.a2g2(c, a)), float(O.a2dg2dg(c, a)))
+    for order in (1, 2):
+        dp, vl = ops.lpt(dk, q, *co(0.3), lpt_order=order, read_order=1)
+        assert rel(dp, g[f"lpt{order}_a0.3_dpos"]) < 5e-5
+        assert rel(vl, g[f"lpt{order}_a0.3_vel"]) < 5e-5
+    dp, vl = ops.lpt(dk, f32(g["pos"]), *co(0.0), lpt_order=2, read_order=2)
+    assert rel(dp, g["lpt2_a0_cic_dpos"]) < 5e-5
+    assert rel(vl, g["lpt2_a0_cic_vel"]) < 5e-5
+
+
+def test_pm_forces_vjp(ops):
+    """VJP of pm_forces(pos, shape) w.r.t. pos vs oracle autograd (2e-4)."""
+    rng = np.random.default_rng(8)
+    shape = (8, 10, 12)
+    pos = f32(O.regular_pos(shape).numpy() + rng.normal(scale=0.6, size=(np.prod(shape), 3)))
+    fbar = f32(rng.normal(size=pos.shape))
+    for kw in [dict(order=2), dict(order=3, paint_deconv=True, lap_fd=2, grad_fd=4)]:
+        okw = dict(read_order=kw["order"], paint_deconv=kw.get("paint_deconv", False), lap_fd=kw.get("lap_fd", np.inf),
+                   grad_fd=kw.get("grad_fd", np.inf))
+        p = T(pos).requires_grad_()
+        (O.pm_forces(p, shape, **okw) * T(fbar)).sum().backward()
+        forces, fm = ops.pm_forces(pos, shape, want_meshes=True, **kw)
+        assert rel(forces, O.pm_forces(T(pos), shape, **okw).numpy()) < 5e-5
+        assert rel(ops.pm_forces_vjp(pos, fbar, fm, **kw), p.grad.numpy()) < 2e-4
+
+
+@pytest.mark.parametrize("lpt_order,read_order", [(1, 1), (2, 1), (2, 2)])
+def test_lpt_vjp(ops, lpt_order, read_order):
+    """VJP of lpt w.r.t. delta_k (torch complex convention) and the growth coefficients vs oracle autograd (2e-4)."""
+    rng = np.random.default_rng(9)
+    shape = (8, 6, 10)
+    dk = c64(np.fft.rfftn(rng.normal(size=shape)) * 0.02)
+    q = O.regular_pos(shape).numpy()
+    pos = f32(q if read_order == 1 else q + rng.normal(scale=0.4, size=q.shape))
+    d1, d2, dv2 = 0.61, -0.17, -0.52
+    dpb, vlb = f32(rng.normal(size=pos.shape)), f32(rng.normal(size=pos.shape))
+
+    class Cst:  # oracle cosmology stub returning the chosen coefficients as differentiable scalars
+        pass
+    coef = T([d1, d2, dv2]).requires_grad_()
+    dkt = T(dk, torch.complex128).requires_grad_()
+    f1 = O.pm_forces(T(pos), dkt, read_order)
+    dpo, vlo = coef[0] * f1, f1
+    if lpt_order == 2:
+        f2 = O.pm_forces2(T(pos), dkt, read_order)
+        dpo, vlo = dpo - coef[1] * f2, vlo - coef[2] * f2
+    ((dpo * T(dpb)).sum() + (vlo * T(vlb)).sum()).backward()
+    dp, vl, tape = ops.lpt(dk, pos, d1, d2, dv2, lpt_order=lpt_order, read_order=read_order, tape=True)
+    assert rel(dp, dpo.detach().numpy()) < 5e-5 and rel(vl, vlo.detach().numpy()) < 5e-5
+    dkbar, cb = ops.lpt_vjp(pos, dk.shape, d1, d2, dv2, dpb, vlb, tape, lpt_order=lpt_order, read_order=read_order,
+                            want_coef=True)
+    assert rel(dkbar, dkt.grad.numpy()) < 2e-4
+    ncoef = 1 if lpt_order == 1 else 3
+    assert rel(to_numpy(cb)[:ncoef], coef.grad.numpy()[:ncoef]) < 2e-4
+
+
+# ------------------------------------------------------------------------------------------------ BullFrog loop
+def _bf_coeffs(c, a0, a1, n):
+    g0, g1 = float(O.a2g(c, a0)), float(O.a2g(c, a1))
+    dg = (g1 - g0) / n
+    alpha = [float(O.alpha_bf(c, g0 + s * dg, dg)) for s in range(n)]
+    beta = [(1 - al) / (g0 + s * dg + dg / 2) for s, al in enumerate(alpha)]
+    return alpha, beta, [dg / 2] * n, [dg / 2] * n
+
+
+def test_nbody_golden(ops, golden):
+    """lpt + 4 BullFrog steps at 16^3 vs the reference source: max |dx| < 2e-4 cell, velocities 2e-4 relative."""
+    g = golden("nbody")
+    shape = tuple(int(s) for s in g["shape"])
+    dk = c64(g["delta_k"])
+    q = f32(O.regular_pos(shape).numpy())
+    c = O.Cosmology()
+    dp, vel = ops.lpt(dk, q, float(O.a2g(c, 0.0)), float(O.a2g2(c, 0.0)), float(O.a2dg2dg(c, 0.0)), 2, 1)
+    pos = to_numpy(dp) + q
+    ab = _bf_coeffs(c, 0.0, 1.0, 4)
+    assert rel(np.array(ab[0]), g["bf4_alpha"]) < 1e-9
+    pos, vel = ops.A.prepare(pos), ops.A.prepare(to_numpy(vel))
+    ops.nbody_steps(pos, vel, shape, *ab)
+    assert np.abs(to_numpy(pos) - g["bf4_pos"][0]).max() < 2e-4
+    assert rel(vel, g["bf4_vel"][0]) < 2e-4
+
+
+def test_nbody_steps_vjp(ops):
+    """Reverse sweep of the BullFrog loop vs oracle autograd through the same coefficients (5e-4), incl. coefficients."""
+    rng = np.random.default_rng(11)
+    shape = (8, 8, 8)
+    n = 3
+    q = O.regular_pos(shape).numpy()
+    pos0 = f32(q + rng.normal(scale=0.5, size=q.shape))
+    vel0 = f32(rng.normal(scale=0.5, size=q.shape))
+    alpha, beta = [0.6, 0.8, 0.9], [0.9, 0.5, 0.3]
+    pre, post = [0.11, 0.13, 0.17], [0.12, 0.14, 0.16]
+    pb, vb = f32(rng.normal(size=q.shape)), f32(rng.normal(size=q.shape))
+    # oracle
+    co = T(np.array([alpha, beta, pre, post]).T.copy()).requires_grad_()
+    x, v = T(pos0).requires_grad_(), T(vel0).requires_grad_()
+    xs, vs = x, v
+    for s in range(n):
+        xs = xs + vs * co[s, 2]
+        vs = co[s, 0] * vs + co[s, 1] * O.pm_forces(xs, shape, 2)
+        xs = xs + vs * co[s, 3]
+    ((xs * T(pb)).sum() + (vs * T(vb)).sum()).backward()
+    # engine
+    A = ops.A
+    pos, vel = A.prepare(pos0.copy()), A.prepare(vel0.copy())
+    tape = ops.nbody_steps(pos, vel, shape, alpha, beta, pre, post, tape=True, tape_vel=True)
+    assert np.abs(to_numpy(pos) - xs.detach().numpy()).max() < 1e-4
+    assert rel(vel, vs.detach().numpy()) < 1e-4
+    posbar, velbar = A.prepare(pb.copy()), A.prepare(vb.copy())
+    coef = ops.nbody_steps_vjp(posbar, velbar, shape, alpha, beta, pre, post, tape, v0=A.prepare(vel0),
+                               want_coef=True)
+    assert rel(posbar, x.grad.numpy()) < 5e-4
+    assert rel(velbar, v.grad.numpy()) < 5e-4
+    assert rel(coef, co.grad.numpy()) < 5e-4
+    # without the velocity tape (no coefficient cotangents): same state cotangents
+    pos, vel = A.prepare(pos0.copy()), A.prepare(vel0.copy())
+    tape = ops.nbody_steps(pos, vel, shape, alpha, beta, pre, post, tape=True)
+    posbar, velbar = A.prepare(pb.copy()), A.prepare(vb.copy())
+    ops.nbody_steps_vjp(posbar, velbar, shape, alpha, beta, pre, post, tape)
+    assert rel(posbar, x.grad.numpy()) < 5e-4
+
+
+# ------------------------------------------------------------------------------------------------ NUFFT
+def test_nufft_golden(ops, golden):
+    g = golden("nufft")
+    final = tuple(int(s) for s in g["final_shape"])
+    pos, w = f32(g["pos"]), f32(g["weights"])
+    assert rel(ops.nufft_paint(pos, final, w, paint_deconv=False), g["interlace_2_2"]) < 2e-5
+    assert rel(ops.nufft_paint(pos, final, w, paint_order=4, interlace_order=3, paint_deconv=False),
+               g["interlace_4_3"]) < 2e-5
+    assert rel(ops.nufft_paint(pos, final, w), g["nufft_same"]) < 2e-5
+    ps = O.scale_shape(final, 1.5)
+    sc = tuple(np.divide(ps, final))
+    out = ops.chreshape(ops.nufft_paint(pos, ps, w, scale=sc), O.r2chshape(final))
+    assert rel(out, g["nufft_over15"]) < 2e-5
+    out = ops.chreshape(ops.nufft_paint(pos, ps, None, scale=sc, paint_order=3, paint_deconv=False), O.r2chshape(final))
+    assert rel(out, g["nufft_over15_nodeconv_o3"]) < 2e-5
+    ps = (12, 10, 14)
+    out = ops.chreshape(ops.nufft_paint(pos, ps, w, scale=tuple(np.divide(ps, final))), O.r2chshape(final))
+    assert rel(out, g["nufft_tuple"]) < 2e-5
+
+
+def test_nufft_vjp(ops):
+    rng = np.random.default_rng(12)
+    final, ps = (8, 8, 8), (12, 10, 12)
+    sc = tuple(np.divide(ps, final))
+    pos = f32(rng.uniform(-2, 10, (500, 3)))
+    w = f32(rng.uniform(0.5, 1.5, 500))
+    cs = O.r2chshape(ps)
+    obar = c64(rng.normal(size=cs) + 1j * rng.normal(size=cs))
+    p, wt = T(pos).requires_grad_(), T(w).requires_grad_()
+    xs = p * T(f32(sc))
+    out = O.interlace(xs, ps, wt * 0.8, 2, 2) * float(np.prod(sc))
+    out = O.deconv_paint(out, 2)
+    assert rel(ops.nufft_paint(pos, ps, w, 0.8, sc), out.detach().numpy()) < 2e-5
+    ob = T(obar, torch.complex128)
+    (out.real * ob.real + out.imag * ob.imag).sum().backward()
+    pb, wb = ops.nufft_paint_vjp(pos, obar, ps, w, 0.8, sc)
+    assert rel(pb, p.grad.numpy()) < 5e-5
+    assert rel(wb, wt.grad.numpy()) < 5e-5

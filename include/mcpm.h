@@ -45,6 +45,8 @@ typedef struct mcpm_engine mcpm_engine; /* opaque: cuFFT plans + scratch for one
 
 int mcpm_version(void);
 const char* mcpm_last_error(void);
+/* number of engine kernels (not cuFFT's) launched by this process so far; reset != 0 zeroes the counter */
+long long mcpm_launch_count(int reset);
 
 /* Engine for real mesh shape (nx, ny, nz) on the current device.  max_batch = largest number of meshes transformed
  * in one call (6 covers 2LPT).  Scratch = (2*max_batch+2) meshes + cuFFT work area, allocated here, once. */
@@ -125,6 +127,25 @@ int mcpm_interlace_combine_T(void* stream, const void* in, void* out_m, int m, i
 
 /* chreshape (utils.py:975-1013): Hermitian- and mean-preserving Fourier crop / pad between real shapes. */
 int mcpm_chreshape(void* stream, const void* in, int inx, int iny, int inz, void* out, int onx, int ony, int onz);
+
+/* VJP of chreshape (transpose in the real inner product): outbar at the OUTPUT shape -> inbar at the INPUT shape. */
+int mcpm_chreshape_vjp(void* stream, const void* outbar, int onx, int ony, int onz, void* inbar, int inx, int iny,
+                       int inz);
+
+/* Hermitian weights w' (1 on kz = 0 / Nyquist planes, else 2) that turn rfftn / irfftn into each other's transpose:
+ * mode 0: out = in * N / w'  (VJP of rfftn: xbar = irfftn(out));  mode 1: out = in * w' / N  (VJP of irfftn: ybar = out,
+ * with in = rfftn(xbar)). */
+int mcpm_hermitian_weights(void* stream, const void* in, void* out, int nx, int ny, int nz, int mode);
+
+/* ---- observation-chain glue around the path ----------------------------------------------
+ * out = a*x + b*y + c (y nullable);  *out_f64 += sum a[i]*b[i] (float64 accumulation on device);
+ * flat-sky RSD in cell units (bricks.py:781-792): pos_out = pos + (vel . los) * coef * los, and its VJP w.r.t. vel. */
+int mcpm_axpby(void* stream, const float* x, float a, const float* y, float b, float c, int64_t n, float* out);
+int mcpm_dot(void* stream, const float* a, const float* b, int64_t n, double* out_f64);
+int mcpm_rsd_shift(void* stream, const float* pos, const float* vel, const float los[3], float coef, int64_t np,
+                   float* pos_out);
+int mcpm_rsd_shift_vjp(void* stream, const float* posbar, const float los[3], float coef, int64_t np, float* velbar,
+                       int accumulate);
 
 /* out = in * t (real transfer, half-spectrum shaped) ; white2lin (bricks.py:152-157) and its transpose */
 int mcpm_scale_spectrum(void* stream, const void* in, const float* t, void* out, int64_t nc);

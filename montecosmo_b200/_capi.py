@@ -14,6 +14,7 @@ XF = [hp, f32]  # scale[3] (host), shift
 SIGNATURES = {
     "mcpm_version": ([], i32),
     "mcpm_last_error": ([], C.c_char_p),
+    "mcpm_launch_count": ([i32], C.c_longlong),
     "mcpm_engine_create": (MESH + [C.POINTER(vp)], i32),
     "mcpm_engine_destroy": ([vp], i32),
     "mcpm_engine_scratch_bytes": ([vp], sz),
@@ -34,6 +35,12 @@ SIGNATURES = {
     "mcpm_interlace_combine": ([vp, vp, vp, i32] + MESH + [f32, i32], i32),
     "mcpm_interlace_combine_T": ([vp, vp, vp, i32] + MESH + [f32, i32], i32),
     "mcpm_chreshape": ([vp, vp] + MESH + [vp] + MESH, i32),
+    "mcpm_chreshape_vjp": ([vp, vp] + MESH + [vp] + MESH, i32),
+    "mcpm_hermitian_weights": ([vp, vp, vp] + MESH + [i32], i32),
+    "mcpm_axpby": ([vp, vp, f32, vp, f32, f32, i64, vp], i32),
+    "mcpm_dot": ([vp, vp, vp, i64, vp], i32),
+    "mcpm_rsd_shift": ([vp, vp, vp, hp, f32, i64, vp], i32),
+    "mcpm_rsd_shift_vjp": ([vp, vp, hp, f32, i64, vp, i32], i32),
     "mcpm_scale_spectrum": ([vp, vp, vp, vp, i64], i32),
     "mcpm_lpt_combine": ([vp, vp, vp, vp, f32, f32, f32, i64, vp, vp, vp], i32),
     "mcpm_kick_drift": ([vp, vp, vp, vp, i64] + MESH + [i32, f32, f32, f32, vp], i32),

@@ -1,5 +1,6 @@
 // api.cu -- the extern "C" boundary declared in include/mcpm.h.  No exceptions cross it; errors are codes plus a
 // thread-local message.
+#include <atomic>
 #include <exception>
 
 #include "engine.h"
@@ -7,6 +8,8 @@
 namespace mcpm {
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 }  // namespace mcpm
 
 using namespace mcpm;
@@ -43,6 +46,12 @@ extern "C" {
 
 int mcpm_version(void) { return MCPM_VERSION; }
 const char* mcpm_last_error(void) { return g_last_error.c_str(); }
+
+long long mcpm_launch_count(int reset) {
+  long long v = g_launches.load();
+  if (reset) g_launches.store(0);
+  return v;
+}
 
 int mcpm_engine_create(int nx, int ny, int nz, mcpm_engine** out) {
   API_BEGIN
@@ -188,6 +197,48 @@ int mcpm_chreshape(void* stream, const void* in, int inx, int iny, int inz, void
   API_BEGIN
   NEED(in && out && in != out, "chreshape: in and out must be distinct buffers");
   return chreshape(as_stream(stream), C(in), inx, iny, inz, C(out), onx, ony, onz);
+  API_END
+}
+
+int mcpm_chreshape_vjp(void* stream, const void* outbar, int onx, int ony, int onz, void* inbar, int inx, int iny,
+                       int inz) {
+  API_BEGIN
+  NEED(outbar && inbar && outbar != inbar, "chreshape_vjp: buffers must be distinct");
+  return chreshape_T(as_stream(stream), C(outbar), onx, ony, onz, C(inbar), inx, iny, inz);
+  API_END
+}
+
+int mcpm_hermitian_weights(void* stream, const void* in, void* out, int nx, int ny, int nz, int mode) {
+  API_BEGIN
+  return hermitian_weights(as_stream(stream), C(in), C(out), nx, ny, nz, mode);
+  API_END
+}
+
+int mcpm_axpby(void* stream, const float* x, float a, const float* y, float b, float c, int64_t n, float* out) {
+  API_BEGIN
+  return axpby(as_stream(stream), x, a, y, b, c, n, out);
+  API_END
+}
+
+int mcpm_dot(void* stream, const float* a, const float* b, int64_t n, double* out) {
+  API_BEGIN
+  return dot_accum(as_stream(stream), a, b, n, 1.0, out);
+  API_END
+}
+
+int mcpm_rsd_shift(void* stream, const float* pos, const float* vel, const float los[3], float coef, int64_t np,
+                   float* pos_out) {
+  API_BEGIN
+  NEED(los, "rsd_shift: null los");
+  return rsd_shift(as_stream(stream), pos, vel, los[0], los[1], los[2], coef, np, pos_out);
+  API_END
+}
+
+int mcpm_rsd_shift_vjp(void* stream, const float* posbar, const float los[3], float coef, int64_t np, float* velbar,
+                       int accumulate) {
+  API_BEGIN
+  NEED(los, "rsd_shift_vjp: null los");
+  return rsd_shift_vjp(as_stream(stream), posbar, los[0], los[1], los[2], coef, np, velbar, accumulate);
   API_END
 }
 

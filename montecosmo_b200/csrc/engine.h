@@ -40,6 +40,11 @@ int axpy3(stream_t, const float* a, const float* b, float s, int64_t n3, float* 
 int lpt_combine(stream_t, const float* pos, const float* f1, const float* f2, float d1, float d2, float dv2,
                 int64_t np, float* dpos, float* vel, float* pos_out);
 int dot_accum(stream_t, const float* a, const float* b, int64_t n, double scale, double* out);
+int axpby(stream_t, const float* x, float a, const float* y, float b, float c, int64_t n, float* out);
+int rsd_shift(stream_t, const float* pos, const float* vel, float lx, float ly, float lz, float coef, int64_t np,
+              float* pos_out);
+int rsd_shift_vjp(stream_t, const float* posbar, float lx, float ly, float lz, float coef, int64_t np, float* velbar,
+                  int accumulate);
 
 // fourier.cu  (`norm` multiplies the output; the engine passes 1/N ahead of a raw C2R)
 int force_spectra(stream_t, const cfloat* dk, cfloat* out3, int nx, int ny, int nz, int lap_fd, int grad_fd,
@@ -60,6 +65,8 @@ int interlace_combine_T(stream_t, const cfloat* in, cfloat* out_m, int m, int nx
 int scale_spectrum(stream_t, const cfloat* in, const float* t, cfloat* out, int64_t nc);
 int scale_real(stream_t, const float* in, float s, float* out, int64_t n);
 int chreshape(stream_t, const cfloat* in, int inx, int iny, int inz, cfloat* out, int onx, int ony, int onz);
+int chreshape_T(stream_t, const cfloat* outbar, int onx, int ony, int onz, cfloat* inbar, int inx, int iny, int inz);
+int hermitian_weights(stream_t, const cfloat* in, cfloat* out, int nx, int ny, int nz, int mode);
 
 // engine.cu
 int pm_forces(Engine*, stream_t, const float* pos, int64_t np, int order, int paint_deconv, int lap_fd, int grad_fd,

@@ -14,7 +14,7 @@
 namespace mcpm {
 
 #ifdef MCPM_HOSTEMU
-// Test-only hooks: the host-emulation build has no FFT of its own; tests/hostemu.py registers numpy.fft here.
+// Checker-only hooks: the host build has no FFT of its own; oracle/cpu_port.py registers scipy.fft (pocketfft) here.
 typedef void (*fft_hook_t)(const void* in, void* out, int nx, int ny, int nz, int batch);
 static fft_hook_t g_r2c = nullptr, g_c2r = nullptr;
 extern "C" __attribute__((visibility("default"))) void mcpm_hostemu_set_fft(fft_hook_t r2c, fft_hook_t c2r) {
@@ -45,6 +45,7 @@ int fft_c2r(FftPlans* p, stream_t, cfloat* in, float* out, int batch) {
   g_c2r(in, out, p->nx, p->ny, p->nz, batch);
   // cuFFT's C2R may overwrite its input: poison it so that orchestration bugs relying on it show up on CPU.
   size_t nc = (size_t)p->nx * p->ny * (p->nz / 2 + 1) * batch;
+#pragma omp parallel for schedule(static)
   for (size_t i = 0; i < nc; ++i) in[i] = cfloat{NAN, NAN};
   return 0;
 }

@@ -329,6 +329,23 @@ int scale_real(stream_t st, const float* in, float sc, float* out, int64_t n) {
   return rt_check("scale_real");
 }
 
+// Hermitian weights of the half spectrum in the real inner product (w' = 1 on kz = 0 / Nyquist, else 2):
+//   mode 0: out = in * N / w'   (rfftn^T:  xbar = irfftn(out))      mode 1: out = in * w' / N   (irfftn^T: ybar = out of rfftn(xbar))
+int hermitian_weights(stream_t st, const cfloat* in, cfloat* out, int nx, int ny, int nz, int mode) {
+  if (int e = check_dims(nx, ny, nz)) return e;
+  const int nzc = nz / 2 + 1;
+  const int64_t nc = (int64_t)nx * ny * nzc;
+  const float nn = (float)((double)nx * ny * nz);
+  launch_1d(st, nc, [=] MCPM_LAMBDA(int64_t e) {
+    int l = (int)(e % nzc);
+    float w = half_weight(l, nz);
+    float c = mode == 0 ? nn / w : w / nn;
+    cfloat v = in[e];
+    out[e] = cfloat{v.re * c, v.im * c};
+  });
+  return rt_check("hermitian_weights");
+}
+
 // ---------------------------------------------------------------------------------------------------- chreshape
 // One thread per OUTPUT element gathers its (at most 4 x 2) sources.  Per axis (utils.py:975-1013):
 //   crop  (s < ms), axes x,y: the new Nyquist row (freq -s/2) = (in[+s/2] + in[-s/2]) / sqrt2
@@ -431,6 +448,58 @@ int chreshape(stream_t st, const cfloat* in, int inx, int iny, int inz, cfloat* 
     out[e] = cfloat{re * w, im * w};
   });
   return rt_check("chreshape");
+}
+
+// Transpose of chreshape in the real inner product (its VJP): every OUTPUT-side cotangent element scatters to the
+// input elements it was gathered from; the Hermitian-mirrored source receives the conjugate.  `inbar` is zeroed here.
+int chreshape_T(stream_t st, const cfloat* outbar, int onx, int ony, int onz, cfloat* inbar, int inx, int iny, int inz) {
+  if (int e = check_dims(inx, iny, inz)) return e;
+  if (int e = check_dims(onx, ony, onz)) return e;
+  if ((inx & 1) || (iny & 1) || (onx & 1) || (ony & 1)) {
+    set_error("chreshape: mesh sides must be even");
+    return MCPM_EINVAL;
+  }
+  const int inzc = inz / 2 + 1, onzc = onz / 2 + 1;
+  const int64_t nout = (int64_t)onx * ony * onzc;
+  const float scale = (float)(((double)onx * ony * onz) / ((double)inx * iny * inz));
+  rt_memset(inbar, 0, sizeof(cfloat) * (size_t)inx * iny * inzc, st);
+  float* ib = reinterpret_cast<float*>(inbar);
+  launch_1d(st, nout, [=] MCPM_LAMBDA(int64_t e) {
+    int l = (int)(e % onzc);
+    int64_t r = e / onzc;
+    int j = (int)(r % ony);
+    int i = (int)(r / ony);
+    AxisSrc ax = axis_sources(i, onx, inx);
+    AxisSrc ay = axis_sources(j, ony, iny);
+    const float rs = 0.70710678118654752440f;
+    float wl = 1.0f;
+    bool herm = false, zero = false;
+    if (onzc < inzc) {
+      herm = (l == onzc - 1);
+      if (herm) wl = rs;
+    } else if (onzc > inzc) {
+      if (l == inzc - 1) wl = rs;
+      zero = l > inzc - 1;
+    }
+    if (zero) return;
+    cfloat v = outbar[e];
+    float w = ax.w * ay.w * wl * scale;
+    float re = v.re * w, im = v.im * w;
+    for (int a = 0; a < ax.n; ++a)
+      for (int b = 0; b < ay.n; ++b) {
+        int ii = ax.idx[a], jj = ay.idx[b];
+        int64_t s = ((int64_t)ii * iny + jj) * inzc + l;
+        atomic_add(ib + 2 * s, re);
+        atomic_add(ib + 2 * s + 1, im);
+        if (herm) {
+          int im_ = ii == 0 ? 0 : inx - ii, jm = jj == 0 ? 0 : iny - jj;
+          int64_t s2 = ((int64_t)im_ * iny + jm) * inzc + l;
+          atomic_add(ib + 2 * s2, re);
+          atomic_add(ib + 2 * s2 + 1, -im);
+        }
+      }
+  });
+  return rt_check("chreshape_T");
 }
 
 }  // namespace mcpm

@@ -491,10 +491,44 @@ int lpt_combine(stream_t st, const float* pos, const float* f1, const float* f2,
   return rt_check("lpt_combine");
 }
 
+// out = a*x + b*y + c  (y may be NULL)
+int axpby(stream_t st, const float* x, float a, const float* y, float b, float c, int64_t n, float* out) {
+  launch_1d(st, n, [=] MCPM_LAMBDA(int64_t i) { out[i] = a * x[i] + (y ? b * y[i] : 0.0f) + c; });
+  return rt_check("axpby");
+}
+
+// flat-sky redshift-space shift in cell units (bricks.py:781-792): pos_out = pos + (vel . los) * coef * los
+int rsd_shift(stream_t st, const float* pos, const float* vel, float lx, float ly, float lz, float coef, int64_t np,
+              float* pos_out) {
+  launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
+    const float* v = vel + 3 * p;
+    float s = (v[0] * lx + v[1] * ly + v[2] * lz) * coef;
+    pos_out[3 * p] = pos[3 * p] + s * lx;
+    pos_out[3 * p + 1] = pos[3 * p + 1] + s * ly;
+    pos_out[3 * p + 2] = pos[3 * p + 2] + s * lz;
+  });
+  return rt_check("rsd_shift");
+}
+
+// its VJP w.r.t. vel: velbar (+)= coef * (posbar . los) * los   (posbar passes through unchanged)
+int rsd_shift_vjp(stream_t st, const float* posbar, float lx, float ly, float lz, float coef, int64_t np,
+                  float* velbar, int accumulate) {
+  launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
+    const float* g = posbar + 3 * p;
+    float s = (g[0] * lx + g[1] * ly + g[2] * lz) * coef;
+    float* o = velbar + 3 * p;
+    o[0] = (accumulate ? o[0] : 0.0f) + s * lx;
+    o[1] = (accumulate ? o[1] : 0.0f) + s * ly;
+    o[2] = (accumulate ? o[2] : 0.0f) + s * lz;
+  });
+  return rt_check("rsd_shift_vjp");
+}
+
 // out[0] += sum_i a[i] * b[i] in float64 (coefficient cotangents)
 int dot_accum(stream_t st, const float* a, const float* b, int64_t n, double scale, double* out) {
 #ifdef MCPM_HOSTEMU
   double s = 0.0;
+#pragma omp parallel for reduction(+ : s) schedule(static)
   for (int64_t i = 0; i < n; ++i) s += (double)a[i] * (double)b[i];
   *out += scale * s;
   return 0;

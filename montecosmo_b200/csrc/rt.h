@@ -1,7 +1,7 @@
-// rt.h -- thin runtime layer: CUDA (sm_100a) in the product build; plain C++ loops when compiled with
-// -DMCPM_HOSTEMU.  The host-emulation build exists ONLY so that tests/ can exercise the engine's orchestration
-// (buffer wiring, adjoint bookkeeping) on a machine without a GPU; it is built by tests/hostemu.py into
-// tests/_hostemu/ and is never loaded by the montecosmo_b200 package.
+// rt.h -- thin runtime layer: CUDA (sm_100a) in the product build; plain C++ (OpenMP) loops when compiled with
+// -DMCPM_HOSTEMU.  The host build exists ONLY as checker / CPU baseline: oracle/cpu_port.py compiles it into
+// oracle/_build/ so that tests/ can exercise the engine's orchestration (buffer wiring, adjoint bookkeeping) without
+// a GPU and bench.py can time the same algorithm on the host cores.  The montecosmo_b200 package never loads it.
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -18,6 +18,7 @@ struct cfloat {
 };
 
 void set_error(const std::string& msg);
+void count_launch();  // api.cu: number of engine kernels launched by this process (bench.py's gpu_launches)
 
 #ifdef MCPM_HOSTEMU
 #define MCPM_HD
@@ -28,10 +29,18 @@ inline stream_t as_stream(void* s) { return s; }
 
 template <class F>
 inline void launch_1d(stream_t, int64_t n, F f) {
+  if (n > 0) count_launch();
+#pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < n; ++i) f(i);
 }
-MCPM_HD inline void atomic_add(float* p, float v) { *p += v; }
-MCPM_HD inline void atomic_add(double* p, double v) { *p += v; }
+MCPM_HD inline void atomic_add(float* p, float v) {
+#pragma omp atomic
+  *p += v;
+}
+MCPM_HD inline void atomic_add(double* p, double v) {
+#pragma omp atomic
+  *p += v;
+}
 inline int rt_memset(void* p, int v, size_t bytes, stream_t) {
   memset(p, v, bytes);
   return 0;
@@ -70,6 +79,7 @@ inline void launch_1d(stream_t s, int64_t n, F f) {
   int64_t blocks = (n + 255) / 256;
   const int64_t wave = (int64_t)kSMs * 8;
   if (blocks > wave) blocks = wave;
+  count_launch();
   k_launch_1d<<<(unsigned)blocks, 256, 0, s>>>(n, f);
 }
 

@@ -1,0 +1,182 @@
+"""
+Field-level log-density on the engine: the prior -> evolve -> likelihood chain of `FieldLevelModel`
+(montecosmo/model.py:631-634, 640-679, 683-837, 840-933) restricted to the configuration BASELINE.json benchmarks:
+
+  * white noise sampled in real space, `precond='real'` (bricks.py:303-305): delta_k = rfftn(white) * transfer,
+    transfer = sqrt(P_lin(k) * N / V) from a tabulated linear power (white2lin, bricks.py:96-106, 152-157);
+  * particles on the regular lattice (bricks.py:593-603); linear Lagrangian bias weights 1 + b1 D delta_L(q)
+    (first term of lagrangian_bias, bricks.py:358-362, NGP read);
+  * evolution 'lpt' (model.py:763) or 'nbody' = 2LPT + BullFrog steps (model.py:771-773, paint_deconv=False there);
+  * flat-sky redshift-space shift along `los` (bricks.py:781-792 in cell units), a_obs scalar;
+  * interlaced, deconvolved NUFFT paint with the bias weights (model.py:802-809) -> 1 + delta_obs mesh;
+  * Gaussian likelihood of an observed mesh with constant noise, N(0,1) prior on the white field.
+
+`logpdf` / `force` keep the reference's wrapper names (model.py:350-363).  Everything elementwise is an engine kernel
+(mcpm_axpby, mcpm_dot, mcpm_rsd_shift, ...); torch supplies memory and the autograd tape only.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import cosmo as _cosmo
+from . import nbody as nb
+from .ops import r2chshape
+
+
+class _Axpby(torch.autograd.Function):
+    """out = a*x + c with host constants a, c."""
+
+    @staticmethod
+    def forward(ctx, x, a, c):
+        ctx.a = a
+        return nb.ops().axpby(x, a, None, 0.0, c)
+
+    @staticmethod
+    def backward(ctx, g):
+        return nb.ops().axpby(g.contiguous(), ctx.a), None, None
+
+
+class _RsdShift(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, vel, los, coef):
+        ctx.cfg = (los, coef)
+        return nb.ops().rsd_shift(pos, vel, los, coef)
+
+    @staticmethod
+    def backward(ctx, g):
+        los, coef = ctx.cfg
+        g = g.contiguous()
+        return g, nb.ops().rsd_shift_vjp(g, los, coef), None, None
+
+
+class _GaussLogp(torch.autograd.Function):
+    """-0.5 * sum((x - mu)^2) * inv_var as a float64 device scalar; mu may be None (zero mean)."""
+
+    @staticmethod
+    def forward(ctx, x, mu, inv_var):
+        o = nb.ops()
+        r = x if mu is None else o.axpby(x, 1.0, mu, -1.0)
+        ctx.save_for_backward(r)
+        ctx.inv_var = inv_var
+        return o.dot(r, r).reshape(()) * (-0.5 * inv_var)
+
+    @staticmethod
+    def backward(ctx, g):
+        (r,) = ctx.saved_tensors
+        # g is a float64 device scalar (1.0 in practice); one tiny D2H read keeps the kernel interface scalar-valued
+        return nb.ops().axpby(r, -float(g) * ctx.inv_var), None, None
+
+
+def eisenstein_hu_nowiggle(k, cosmo):
+    """Zero-baryon-oscillation transfer function of Eisenstein & Hu (1998, ApJ 496, 605, eqs. 26-31).
+
+    Own restatement of the published fit, used only to tabulate a realistic linear power for synthetic benchmarks;
+    it is not pinned to jax_cosmo.power (which the reference calls at bricks.py:74).  k in h/Mpc.
+    """
+    h = float(cosmo.h)
+    om, ob = float(cosmo.Omega_m), float(cosmo.Omega_b)
+    omh2, obh2, fb = om * h**2, ob * h**2, ob / om
+    theta = 2.7255 / 2.7
+    s = 44.5 * np.log(9.83 / omh2) / np.sqrt(1 + 10 * obh2**0.75)  # Mpc
+    alpha = 1 - 0.328 * np.log(431 * omh2) * fb + 0.38 * np.log(22.3 * omh2) * fb**2
+    kmpc = k * h
+    gamma = om * h * (alpha + (1 - alpha) / (1 + (0.43 * kmpc * s) ** 4))
+    q = k * theta**2 / gamma
+    L0 = np.log(2 * np.e + 1.8 * q)
+    C0 = 14.2 + 731.0 / (1 + 62.5 * q)
+    return L0 / (L0 + C0 * q**2)
+
+
+def linear_power_table(cosmo, n_interp=256):
+    """(k, P_lin(k, a=1)) on logspace(-4, 1, n) h/Mpc (the grid of bricks.py:73), sigma8-normalised."""
+    ks = np.logspace(-4, 1, n_interp)
+    kk = np.logspace(-5, 2, 4096)
+    p = kk ** float(cosmo.n_s) * eisenstein_hu_nowiggle(kk, cosmo) ** 2
+    x = kk * 8.0
+    wth = 3 * (np.sin(x) - x * np.cos(x)) / x**3
+    sig2 = np.trapezoid(kk**3 * p * wth**2 / (2 * np.pi**2), np.log(kk))
+    amp = float(cosmo.sigma8) ** 2 / sig2
+    return ks, amp * ks ** float(cosmo.n_s) * eisenstein_hu_nowiggle(ks, cosmo) ** 2
+
+
+class FieldModel:
+    def __init__(self, mesh_shape=(64, 64, 64), box_size=(640.0, 640.0, 640.0), evolution="nbody", n_steps=5,
+                 a_start=0.0, a_obs=1.0, lpt_order=2, paint_order=2, interlace_order=2, paint_deconv=True,
+                 paint_oversamp=1.0, b1=1.0, rsd=True, los=(0.0, 0.0, 1.0), sigma_obs=1.0, cosmology=None, kpow=None):
+        self.mesh_shape = tuple(int(s) for s in mesh_shape)
+        self.box_size = tuple(float(b) for b in box_size)
+        self.evolution, self.n_steps, self.a_start, self.a_obs = evolution, int(n_steps), a_start, a_obs
+        self.lpt_order, self.paint_order, self.interlace_order = lpt_order, paint_order, interlace_order
+        self.paint_deconv, self.b1, self.rsd, self.los = paint_deconv, float(b1), rsd, tuple(float(x) for x in los)
+        self.paint_shape = nb.scale_shape(self.mesh_shape, paint_oversamp)
+        self.sigma_obs = float(sigma_obs)
+        self.cosmology = cosmology if cosmology is not None else _cosmo.Cosmology()
+        self.kpow = kpow if kpow is not None else linear_power_table(self.cosmology)
+        o = nb.ops()
+        self.transfer = o.A.prepare(self.transfer_mesh())
+        ax = [np.arange(s, dtype=np.float32) for s in self.mesh_shape]
+        self.q = o.A.prepare(np.stack(np.meshgrid(*ax, indexing="ij"), -1).reshape(-1, 3))  # regular_pos
+
+    # -- host-side constant (bricks.py:96-106 with a (k, P) table; white_noise scaling bricks.py:150) -----------------
+    def transfer_mesh(self):
+        ks, pows = self.kpow
+        kvec = nb.rfftk(self.mesh_shape, self.box_size)
+        kmesh = np.sqrt(sum(k**2 for k in kvec))
+        pmesh = np.interp(kmesh.reshape(-1), ks, pows, left=0.0, right=0.0).reshape(kmesh.shape)
+        return np.sqrt(pmesh * (np.prod(self.mesh_shape) / np.prod(self.box_size))).astype(np.float32)
+
+    # -- prior -> evolve ----------------------------------------------------------------------------------------------
+    def linear_field(self, white):
+        """delta_k(a=1) from the real white field (samp2base_mesh 'real' + white2lin)."""
+        return nb._ScaleSpectrum.apply(nb.rfftn(white), self.transfer)
+
+    def evolve(self, white):
+        c = self.cosmology  # growth tables are cached per parameter values (cosmo.growth_table), cf. model.py:762,769
+        dk = self.linear_field(white)
+        weights = 1.0
+        if self.b1 != 0.0:
+            delta_q = nb.read(self.q, nb.irfftn(dk), order=1)
+            weights = _Axpby.apply(delta_q, self.b1 * float(_cosmo.a2g(c, self.a_obs)), 1.0)
+        if self.evolution == "lpt":
+            pos, vel = nb.lpt(c, dk, self.q, self.a_obs, self.lpt_order, 1, _displaced=True)
+        elif self.evolution == "nbody":
+            pos, vel = nb.nbody_bf(c, dk, self.q, self.a_start, self.a_obs, self.n_steps, self.paint_order,
+                                   self.lpt_order, paint_deconv=False)
+            pos, vel = pos[-1], vel[-1]
+        else:
+            raise ValueError(f"unknown evolution {self.evolution}")
+        if self.rsd:
+            coef = float(_cosmo.a2g(c, self.a_obs) * _cosmo.a2f(c, self.a_obs))
+            pos = _RsdShift.apply(pos, vel, self.los, coef)
+        gxy = nb.nufft(pos, self.mesh_shape, self.paint_shape, weights, self.paint_order, self.interlace_order,
+                       paint_deconv=self.paint_deconv)
+        gxy = nb.chreshape(gxy, r2chshape(self.paint_shape)) if self.paint_shape != self.mesh_shape else gxy
+        return nb.irfftn(gxy)  # 1 + delta_obs at the paint shape (particles == cells: Jacobian 1, model.py:806)
+
+    predict = evolve
+
+    # -- wrappers (model.py:350-363) ----------------------------------------------------------------------------------
+    def logpdf(self, white, obs):
+        """log prior N(0,1) on the white field + Gaussian log-likelihood of `obs`, up to constants."""
+        white = nb._f32(white)
+        gxy = self.evolve(white)
+        return _GaussLogp.apply(gxy, nb._f32(obs), 1.0 / self.sigma_obs**2) + _GaussLogp.apply(white, None, 1.0)
+
+    def potential(self, white, obs):
+        return -self.logpdf(white, obs)
+
+    def value_and_force(self, white, obs):
+        """(logpdf, d logpdf / d white) with the likelihood seeded by hand, so that nothing synchronises the stream."""
+        o = nb.ops()
+        white = nb._f32(white).detach().requires_grad_(True)
+        gxy = self.evolve(white)
+        inv_var = 1.0 / self.sigma_obs**2
+        r = o.axpby(gxy.detach(), 1.0, nb._f32(obs), -1.0)
+        (gw,) = torch.autograd.grad(gxy, white, o.axpby(r, -inv_var))
+        wd = white.detach()
+        lp = o.dot(r, r).reshape(()) * (-0.5 * inv_var) + o.dot(wd, wd).reshape(()) * -0.5
+        return lp, o.axpby(gw, 1.0, wd, -1.0)
+
+    def force(self, white, obs):
+        return self.value_and_force(white, obs)[1]

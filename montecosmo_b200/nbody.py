@@ -1,0 +1,456 @@
+"""
+Drop-in mirror of the hot-path callables of `montecosmo/nbody.py` on the B200 engine.
+
+Same names, argument meaning and error behaviour as the reference (file:line cited per function); arrays are torch
+CUDA tensors (float32 / complex64) instead of jax arrays, and `torch.autograd.Function` plays the role of
+`jax.custom_vjp`: `torch.autograd.grad` flows through `paint`, `read`, `nufft`, `pm_forces`, `lpt` and `nbody_bf` via the
+engine's hand-written adjoints (mcpm_*_vjp).  All arithmetic on arrays happens in libmcpm.so; torch only owns memory,
+streams and the autograd tape.  There is no CPU path: importing this module without the built library or without a
+CUDA device raises.
+
+Host-side helpers that return small NumPy kernel arrays (`rfftk`, `*_hat`) are kept for API parity; the engine
+recomputes them in-kernel and never reads such arrays.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib, cosmo as _cosmo
+from .ops import Ops, TorchCudaAdapter, ch2rshape, r2chshape
+
+INF = float("inf")
+_OPS = None
+
+
+def ops() -> Ops:
+    """The process-wide operator table (loads libmcpm.so; raises without it or without CUDA)."""
+    global _OPS
+    if _OPS is None:
+        _OPS = Ops(_lib.load(), TorchCudaAdapter())
+    return _OPS
+
+
+def _f32(x):
+    return ops().A.prepare(x, "f32")
+
+
+def _c64(x):
+    return ops().A.prepare(x, "c64")
+
+
+def _check_kernel(kernel_type):
+    if kernel_type == "rectangular":
+        return
+    if kernel_type == "kaiser_bessel":
+        raise NotImplementedError("kernel_type='kaiser_bessel' is not implemented by the B200 engine (MCPM_EUNSUP)")
+    raise ValueError(f"Unknown kernel type: {kernel_type}")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# host-side kernel helpers (nbody.py:50-334), NumPy, for API parity
+# ----------------------------------------------------------------------------------------------------------------
+def scale_shape(shape, scale=1.0):
+    """utils.py:1163-1168."""
+    return tuple(int(o) for o in 2 * np.rint(np.multiply(shape, scale) / 2).astype(int))
+
+
+def rfftk(shape, box_size=None):
+    """nbody.py:50-77."""
+    dim = len(shape)
+    scales = dim * (2 * np.pi,) if box_size is None else tuple(2 * np.pi * s / b for s, b in zip(shape, box_size))
+    out = []
+    for ax, (s, sc) in enumerate(zip(shape, scales)):
+        k = (np.fft.fftfreq(s) if ax < dim - 1 else np.fft.rfftfreq(s)) * sc
+        shp = [1] * dim
+        shp[ax] = -1
+        out.append(k.reshape(shp))
+    return tuple(out)
+
+
+def invlaplace_hat(kvec, fd_order=np.inf):
+    """nbody.py:109-133."""
+    if fd_order == 2:
+        kk = sum((np.cos(k) - 1) * 2 for k in kvec)
+    elif fd_order == 4:
+        kk = sum((np.cos(2 * k) - 16 * np.cos(k) + 15) / 6 for k in kvec)
+    elif fd_order == np.inf:
+        kk = sum(k**2 for k in kvec)
+    else:
+        raise ValueError("Only orders 2, 4, and inf are supported.")
+    nz = np.where(kk == 0, 1, kk)
+    return -np.where(kk == 0, 0, 1 / nz)
+
+
+def gradient_hat(kvec, direction, fd_order=np.inf):
+    """nbody.py:136-163."""
+    k = kvec[direction]
+    if fd_order == 2:
+        k = np.sin(k)
+    elif fd_order == 4:
+        k = (8 * np.sin(k) - np.sin(2 * k)) / 6
+    elif fd_order != np.inf:
+        raise ValueError("Only orders 2, 4, and inf are supported.")
+    return 1j * k
+
+
+def gaussian_hat(kvec, kcut=np.inf):
+    """nbody.py:166-188."""
+    if kcut == np.inf:
+        return 1.0
+    return np.exp(-sum(k**2 for k in kvec) * (2 * np.pi / kcut) ** 2 / 2)
+
+
+def rectangular_hat(kvec, order=2):
+    """nbody.py:249-277."""
+    out = 1.0
+    for k in kvec:
+        out = out * np.sinc(k / (2 * np.pi)) ** order
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# autograd wrappers over the C ABI
+# ----------------------------------------------------------------------------------------------------------------
+class _Paint(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, weights, shape, wscalar, order, scale, shift):
+        ctx.save_for_backward(pos, weights)
+        ctx.cfg = (shape, wscalar, order, scale, shift)
+        return ops().paint(pos, shape, weights, wscalar, order, scale, shift)
+
+    @staticmethod
+    def backward(ctx, mbar):
+        pos, weights = ctx.saved_tensors
+        shape, wscalar, order, scale, shift = ctx.cfg
+        need_p, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and weights is not None
+        pb, wb = ops().paint_vjp(pos, mbar.contiguous(), weights, wscalar, order, scale, shift, need_p, need_w)
+        return pb, wb, None, None, None, None, None
+
+
+class _Read(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, mesh, order, scale, shift):
+        ctx.save_for_backward(pos, mesh)
+        ctx.cfg = (order, scale, shift)
+        return ops().read(pos, mesh, order, scale, shift)
+
+    @staticmethod
+    def backward(ctx, obar):
+        pos, mesh = ctx.saved_tensors
+        order, scale, shift = ctx.cfg
+        obar = obar.contiguous()
+        pb = mb = None
+        if ctx.needs_input_grad[0]:
+            pb = ops().read_grad(pos, mesh, obar.reshape(pos.shape[0], -1), order, scale, shift)
+        if ctx.needs_input_grad[1]:
+            if mesh.dim() == 3:
+                mb = ops().paint(pos, tuple(mesh.shape), obar, 1.0, order, scale, shift)
+            else:
+                mb = torch.stack([ops().paint(pos, tuple(mesh.shape[1:]), obar[:, i].contiguous(), 1.0, order, scale,
+                                              shift) for i in range(mesh.shape[0])])
+        return pb, mb, None, None, None
+
+
+class _Rfftn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mesh):
+        return ops().rfftn(mesh)
+
+    @staticmethod
+    def backward(ctx, kbar):
+        return ops().irfftn(ops().hermitian_weights(kbar.contiguous(), 0), overwrite=True)
+
+
+class _Irfftn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, meshk):
+        return ops().irfftn(meshk)
+
+    @staticmethod
+    def backward(ctx, mbar):
+        return ops().hermitian_weights(ops().rfftn(mbar.contiguous()), 1)
+
+
+class _Deconv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, meshk, order):
+        ctx.order = order
+        return ops().deconv(meshk, order)
+
+    @staticmethod
+    def backward(ctx, kbar):
+        return ops().deconv(kbar.contiguous(), ctx.order), None
+
+
+class _Chreshape(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, meshk, cshape):
+        ctx.in_cshape = tuple(meshk.shape)
+        return ops().chreshape(meshk, cshape)
+
+    @staticmethod
+    def backward(ctx, kbar):
+        return ops().chreshape_vjp(kbar.contiguous(), ctx.in_cshape), None
+
+
+class _ScaleSpectrum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, meshk, transfer):
+        ctx.save_for_backward(transfer)
+        return ops().scale_spectrum(meshk, transfer)
+
+    @staticmethod
+    def backward(ctx, kbar):
+        (transfer,) = ctx.saved_tensors
+        return ops().scale_spectrum(kbar.contiguous(), transfer), None
+
+
+class _NufftPaint(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, weights, paint_shape, wscalar, scale, paint_order, interlace_order, paint_deconv):
+        ctx.save_for_backward(pos, weights)
+        ctx.cfg = (paint_shape, wscalar, scale, paint_order, interlace_order, paint_deconv)
+        return ops().nufft_paint(pos, paint_shape, weights, wscalar, scale, paint_order, interlace_order, paint_deconv)
+
+    @staticmethod
+    def backward(ctx, kbar):
+        pos, weights = ctx.saved_tensors
+        paint_shape, wscalar, scale, paint_order, interlace_order, paint_deconv = ctx.cfg
+        need_p, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and weights is not None
+        pb, wb = ops().nufft_paint_vjp(pos, kbar.contiguous(), paint_shape, weights, wscalar, scale, paint_order,
+                                       interlace_order, paint_deconv, need_p, need_w)
+        return pb, wb, None, None, None, None, None, None
+
+
+class _PmForcesPaint(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, shape, order, paint_deconv, lap_fd, grad_fd, kcut):
+        forces, fm = ops().pm_forces(pos, shape, order, paint_deconv, lap_fd, grad_fd, kcut, want_meshes=True)
+        ctx.save_for_backward(pos, fm)
+        ctx.cfg = (order, paint_deconv, lap_fd, grad_fd, kcut)
+        return forces
+
+    @staticmethod
+    def backward(ctx, fbar):
+        pos, fm = ctx.saved_tensors
+        order, paint_deconv, lap_fd, grad_fd, kcut = ctx.cfg
+        return ops().pm_forces_vjp(pos, fbar.contiguous(), fm, order, paint_deconv, lap_fd, grad_fd, kcut), None, \
+            None, None, None, None, None
+
+
+class _Lpt(torch.autograd.Function):
+    """(delta_k, coef[3] float64 host) -> (dpos, vel); VJP to delta_k and the coefficients (nbody.py:634-667)."""
+
+    @staticmethod
+    def forward(ctx, dk, coef, pos, lpt_order, read_order, lap_fd, grad_fd, add_pos=False):
+        c = [float(v) for v in coef.detach().cpu()]
+        dpos, vel, tape = ops().lpt(dk, pos, c[0], c[1], c[2], lpt_order, read_order, lap_fd, grad_fd, tape=True)
+        if add_pos:  # return the displaced positions pos + dpos (same cotangent as dpos)
+            dpos = ops().axpby(dpos, 1.0, pos, 1.0)
+        ctx.cfg = (c, lpt_order, read_order, lap_fd, grad_fd, tuple(dk.shape))
+        ctx.pos, ctx.tape = pos, tape
+        ctx.coef_meta = (coef.device, coef.dtype)
+        return dpos, vel
+
+    @staticmethod
+    def backward(ctx, dpb, vlb):
+        c, lpt_order, read_order, lap_fd, grad_fd, cshape = ctx.cfg
+        dpb = torch.zeros_like(ctx.pos) if dpb is None else dpb.contiguous()
+        vlb = torch.zeros_like(ctx.pos) if vlb is None else vlb.contiguous()
+        want_coef = ctx.needs_input_grad[1]
+        out = ops().lpt_vjp(ctx.pos, cshape, c[0], c[1], c[2], dpb, vlb, ctx.tape, lpt_order, read_order, lap_fd,
+                            grad_fd, want_coef=want_coef)
+        dkbar, cb = out if want_coef else (out, None)
+        if cb is not None:
+            cb = cb.to(device=ctx.coef_meta[0], dtype=ctx.coef_meta[1])
+        ctx.tape = None
+        return dkbar, cb, None, None, None, None, None, None
+
+
+class _NbodySteps(torch.autograd.Function):
+    """BullFrog DKD loop (nbody.py:933-951, 999) with per-step coefficients [n_steps, 4] (float64, host)."""
+
+    @staticmethod
+    def forward(ctx, pos, vel, coefs, shape, order, paint_deconv, lap_fd, grad_fd):
+        co = coefs.detach().cpu().to(torch.float64).numpy()
+        al, be, pre, post = (co[:, i].tolist() for i in range(4))
+        want_coef = coefs.requires_grad
+        pos, vel0 = pos.clone(), vel.contiguous()
+        vel = vel0.clone()
+        tape = ops().nbody_steps(pos, vel, shape, al, be, pre, post, order, paint_deconv, lap_fd, grad_fd, tape=True,
+                                 tape_vel=want_coef)
+        ctx.cfg = (al, be, pre, post, shape, order, paint_deconv, lap_fd, grad_fd, want_coef)
+        ctx.tape, ctx.v0 = tape, (vel0 if want_coef else None)
+        ctx.coef_meta = (coefs.device, coefs.dtype)
+        return pos, vel
+
+    @staticmethod
+    def backward(ctx, pb, vb):
+        al, be, pre, post, shape, order, paint_deconv, lap_fd, grad_fd, want_coef = ctx.cfg
+        xk = ctx.tape[0]
+        pb = torch.zeros_like(xk[0]) if pb is None else pb.clone().contiguous()
+        vb = torch.zeros_like(xk[0]) if vb is None else vb.clone().contiguous()
+        cb = ops().nbody_steps_vjp(pb, vb, shape, al, be, pre, post, ctx.tape, order, paint_deconv, lap_fd, grad_fd,
+                                   v0=ctx.v0, want_coef=want_coef)
+        if cb is not None:
+            cb = cb.to(device=ctx.coef_meta[0], dtype=ctx.coef_meta[1])
+        ctx.tape = ctx.v0 = None
+        return pb, vb, cb, None, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# public API, reference names
+# ----------------------------------------------------------------------------------------------------------------
+def _split_weights(weights):
+    """weights scalar -> (None, float); tensor -> (tensor, 1.0)."""
+    if isinstance(weights, (int, float)):
+        return None, float(weights)
+    w = _f32(weights)
+    if w.dim() == 0:
+        return None, float(w)
+    return w, 1.0
+
+
+def paint(pos, shape: tuple, weights=1.0, order: int = 2, kernel_type="rectangular", oversamp=1.0):
+    """Paint the positions onto a mesh of given shape (nbody.py:365-396)."""
+    _check_kernel(kernel_type)
+    w, ws = _split_weights(weights)
+    return _Paint.apply(_f32(pos), w, tuple(int(s) for s in shape), ws, int(order), None, 0.0)
+
+
+def read(pos, mesh, order: int = 2, kernel_type="rectangular", oversamp=1.0):
+    """Read the value at the positions from the mesh (nbody.py:398-427)."""
+    _check_kernel(kernel_type)
+    return _Read.apply(_f32(pos), _f32(mesh), int(order), None, 0.0)
+
+
+def rfftn(mesh):
+    """jnp.fft.rfftn on the engine's cuFFT plans."""
+    return _Rfftn.apply(_f32(mesh))
+
+
+def irfftn(meshk):
+    """jnp.fft.irfftn (last real side = 2*(m-1), utils.py:769-776)."""
+    return _Irfftn.apply(_c64(meshk))
+
+
+def chreshape(mesh, shape):
+    """Hermitian- and mean-preserving Fourier crop / pad (utils.py:975-1013); `shape` is the complex target shape."""
+    return _Chreshape.apply(_c64(mesh), tuple(int(s) for s in shape))
+
+
+def deconv_paint(mesh, order: int = 2, kernel_type="rectangular", oversamp=1.0):
+    """Deconvolve the mesh by the paint kernel (nbody.py:315-334); real meshes go through rfftn / irfftn."""
+    _check_kernel(kernel_type)
+    if not torch.is_complex(torch.as_tensor(mesh)):
+        return irfftn(_Deconv.apply(rfftn(mesh), int(order)))
+    return _Deconv.apply(_c64(mesh), int(order))
+
+
+def interlace(pos, shape: tuple, weights=1.0, paint_order: int = 2, interlace_order: int = 2,
+              kernel_type="rectangular", paint_oversamp: float = 1.0):
+    """Equal-spacing interlacing (nbody.py:513-529)."""
+    _check_kernel(kernel_type)
+    w, ws = _split_weights(weights)
+    return _NufftPaint.apply(_f32(pos), w, tuple(int(s) for s in shape), ws, None, int(paint_order),
+                             int(interlace_order), False)
+
+
+def nufft(pos, final_shape: tuple, paint_shape=None, weights=1.0, paint_order: int = 2, interlace_order: int = 2,
+          kernel_type="rectangular", paint_deconv=True):
+    """Non-uniform FFT with oversampling, deconvolution and interlacing (nbody.py:532-577)."""
+    _check_kernel(kernel_type)
+    final_shape = tuple(int(s) for s in final_shape)
+    if paint_shape is None:
+        paint_shape = final_shape
+    elif isinstance(paint_shape, float):
+        paint_shape = scale_shape(final_shape, paint_shape)
+    elif isinstance(paint_shape, (tuple, np.ndarray)):
+        paint_shape = tuple(int(s) for s in paint_shape)
+    else:
+        raise ValueError("paint_shape must be None, a float, or a tuple/ndarray")
+    scale = tuple(float(p) / float(f) for p, f in zip(paint_shape, final_shape))
+    w, ws = _split_weights(weights)
+    mesh = _NufftPaint.apply(_f32(pos), w, paint_shape, ws, scale, int(paint_order), int(interlace_order),
+                             bool(paint_deconv))
+    if final_shape != paint_shape:
+        mesh = chreshape(mesh, r2chshape(final_shape))
+    return mesh
+
+
+def _coef_tensor(*vals):
+    return torch.stack([_cosmo._t(v).reshape(()) for v in vals])
+
+
+def pm_forces(pos, mesh, read_order: int = 2, paint_deconv: bool = False, grad_fd=np.inf, lap_fd=np.inf, kcut=np.inf):
+    """PM forces -grad lap^-1 delta at pos (nbody.py:583-604).  `mesh` is a shape tuple (paint pos) or delta_k."""
+    pos = _f32(pos)
+    if isinstance(mesh, tuple):
+        return _PmForcesPaint.apply(pos, tuple(int(s) for s in mesh), int(read_order), bool(paint_deconv), lap_fd,
+                                    grad_fd, kcut)
+    if kcut != np.inf:  # spectrum input with a long-range filter: not differentiable here, plain forward
+        return ops().pm_forces_mesh(pos, _c64(mesh), int(read_order), lap_fd, grad_fd, kcut)
+    # vel of a first-order lpt with unit coefficients is exactly pm_forces(pos, delta_k)
+    _, vel = _Lpt.apply(_c64(mesh), _coef_tensor(0.0, 0.0, 0.0), pos, 1, int(read_order), lap_fd, grad_fd)
+    return vel
+
+
+def pm_forces2(pos, mesh, read_order: int = 2, grad_fd=np.inf, lap_fd=np.inf):
+    """2LPT source force (nbody.py:607-631)."""
+    # dpos = d1 F1 - d2 F2 with d1 = 0, d2 = -1
+    dpos, _ = _Lpt.apply(_c64(mesh), _coef_tensor(0.0, -1.0, 0.0), _f32(pos), 2, int(read_order), lap_fd, grad_fd)
+    return dpos
+
+
+def lpt(cosmo, init_mesh, pos, a, lpt_order: int = 2, read_order: int = 2, grad_fd=np.inf, lap_fd=np.inf,
+        _displaced=False):
+    """First or second order LPT displacement at scale factor `a` (nbody.py:634-667).  Scalar `a` only."""
+    if np.ndim(a) != 0:
+        raise NotImplementedError("per-particle scale factors (light-cone lpt) are not implemented by the engine")
+    if lpt_order not in (1, 2):
+        raise ValueError("lpt_order must be 1 or 2")
+    init_mesh = torch.as_tensor(init_mesh)
+    if not torch.is_complex(init_mesh):
+        init_mesh = rfftn(init_mesh)
+    coef = _coef_tensor(_cosmo.a2g(cosmo, a), _cosmo.a2g2(cosmo, a), _cosmo.a2dg2dg(cosmo, a))
+    return _Lpt.apply(_c64(init_mesh), coef, _f32(pos), int(lpt_order), int(read_order), lap_fd, grad_fd, _displaced)
+
+
+def nbody_bf(cosmo, init_mesh, pos, a0=0.0, a1=1.0, n_steps=5, paint_order: int = 2, lpt_order: int = 2,
+             paint_deconv=False, grad_fd=np.inf, lap_fd=np.inf, snapshots=None, fn=None):
+    """N-body simulation with the BullFrog solver (nbody.py:967-1002): lpt at a0, then n_steps DKD steps in growth time.
+
+    Returns (pos, vel), each [S, Np, 3]; S = 1 unless `snapshots` is an int > 1 dividing the step count.
+    """
+    if fn is not None:
+        raise NotImplementedError("custom save functions are not supported")
+    n_steps = int(n_steps)
+    init_mesh = _c64(init_mesh)
+    pos = _f32(pos)
+    mesh_shape = ch2rshape(tuple(init_mesh.shape))
+    x, vel = lpt(cosmo, init_mesh, pos, a0, lpt_order, 1, grad_fd, lap_fd, _displaced=True)
+    al, be, pre, post, _, _ = _cosmo.bullfrog_coefficients(cosmo, a0, a1, n_steps)
+    coefs = torch.stack([al, be, pre, post], dim=1)
+    if snapshots is None or (isinstance(snapshots, int) and snapshots <= 1):
+        segments = [n_steps]
+    elif isinstance(snapshots, int) and n_steps % (snapshots - 1) == 0:
+        segments = [n_steps // (snapshots - 1)] * (snapshots - 1)
+    else:
+        raise NotImplementedError("snapshots must be None or an int such that (snapshots-1) divides n_steps")
+    xs, vs = ([x], [vel]) if len(segments) > 1 else ([], [])
+    s = 0
+    for seg in segments:
+        x, vel = _NbodySteps.apply(x, vel, coefs[s:s + seg], mesh_shape, int(paint_order), bool(paint_deconv),
+                                   lap_fd, grad_fd)
+        s += seg
+        xs.append(x)
+        vs.append(vel)
+    if len(xs) == 1:
+        return xs[0].unsqueeze(0), vs[0].unsqueeze(0)
+    return torch.stack(xs), torch.stack(vs)
+
+
+# growth helpers re-exported under the reference names (nbody.py:750-808)
+a2g, a2g2, a2f, a2f2, a2dg2dg = _cosmo.a2g, _cosmo.a2g2, _cosmo.a2f, _cosmo.a2f2, _cosmo.a2dg2dg
+g2a, g2g2, g2f, g2f2, g2dg2dg = _cosmo.g2a, _cosmo.g2g2, _cosmo.g2f, _cosmo.g2f2, _cosmo.g2dg2dg

@@ -385,3 +385,51 @@ class Ops:
         self._call("mcpm_nufft_vjp", self.engine(paint_shape).handle, A.stream(), A.ptr(pos), A.ptr(weights), wscalar,
                    n, sc, paint_order, interlace_order, int(paint_deconv), A.ptr(outbar), A.ptr(pb), A.ptr(wb))
         return pb, wb
+
+    # ------------------------------------------------------------------------------------------------ glue
+    def chreshape_vjp(self, outbar, in_cshape):
+        A = self.A
+        outbar = A.prepare(outbar, "c64")
+        inbar = A.empty(in_cshape, "c64")
+        self._call("mcpm_chreshape_vjp", A.stream(), A.ptr(outbar), *ch2rshape(A.shape(outbar)), A.ptr(inbar),
+                   *ch2rshape(in_cshape))
+        return inbar
+
+    def hermitian_weights(self, meshk, mode):
+        A = self.A
+        meshk = A.prepare(meshk, "c64")
+        out = A.empty(A.shape(meshk), "c64")
+        self._call("mcpm_hermitian_weights", A.stream(), A.ptr(meshk), A.ptr(out), *ch2rshape(A.shape(meshk)), mode)
+        return out
+
+    def axpby(self, x, a=1.0, y=None, b=0.0, c=0.0):
+        A = self.A
+        x = A.prepare(x)
+        y = None if y is None else A.prepare(y)
+        out = A.empty(A.shape(x))
+        self._call("mcpm_axpby", A.stream(), A.ptr(x), a, A.ptr(y), b, c, math.prod(A.shape(x)), A.ptr(out))
+        return out
+
+    def dot(self, a, b):
+        """float64 device scalar sum(a*b)."""
+        A = self.A
+        a, b = A.prepare(a), A.prepare(b)
+        out = A.zeros((1,), "f64")
+        self._call("mcpm_dot", A.stream(), A.ptr(a), A.ptr(b), math.prod(A.shape(a)), A.ptr(out))
+        return out
+
+    def rsd_shift(self, pos, vel, los, coef):
+        A = self.A
+        pos, vel = A.prepare(pos), A.prepare(vel)
+        out = A.empty(A.shape(pos))
+        self._call("mcpm_rsd_shift", A.stream(), A.ptr(pos), A.ptr(vel), host_floats(los), coef, A.shape(pos)[0],
+                   A.ptr(out))
+        return out
+
+    def rsd_shift_vjp(self, posbar, los, coef):
+        A = self.A
+        posbar = A.prepare(posbar)
+        out = A.empty(A.shape(posbar))
+        self._call("mcpm_rsd_shift_vjp", A.stream(), A.ptr(posbar), host_floats(los), coef, A.shape(posbar)[0],
+                   A.ptr(out), 0)
+        return out

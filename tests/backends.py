@@ -30,3 +30,8 @@ def to_numpy(x):
     if isinstance(x, np.ndarray):
         return x
     return x.detach().cpu().numpy()
+
+
+def torch_cpu_adapter():
+    from oracle.cpu_port import torch_cpu_adapter as f
+    return f()

@@ -1,0 +1,113 @@
+"""Per-operator timings of the engine on one GPU (CUDA events, L2 flushed between repeats).  Development tool."""
+import argparse
+import json
+import sys
+import os
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from montecosmo_b200 import _lib  # noqa: E402
+from montecosmo_b200.ops import Ops, TorchCudaAdapter  # noqa: E402
+
+
+def timeit(fn, reps=10, warm=3, flush=None):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=256)
+    ap.add_argument("--sigma", type=float, default=1.5)
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--only", default=None, help="comma-separated substrings of op names to run")
+    ap.add_argument("--reps", type=int, default=10)
+    a = ap.parse_args()
+    n = a.n
+    shape = (n, n, n)
+    N = n ** 3
+    ops = Ops(_lib.load(), TorchCudaAdapter())
+    dev = ops.A.device
+    g = torch.Generator(device=dev).manual_seed(0)
+    ax = torch.arange(n, device=dev, dtype=torch.float32)
+    q = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(-1, 3)
+    # smooth displacement field (sum of a few long waves) + small jitter: mimics an evolved Lagrangian lattice
+    k = 2 * np.pi / n
+    disp = a.sigma * torch.stack([torch.sin(k * 3 * q[:, 1]) + torch.cos(k * 5 * q[:, 2]),
+                                  torch.sin(k * 4 * q[:, 2]) + torch.cos(k * 2 * q[:, 0]),
+                                  torch.sin(k * 3 * q[:, 0]) + torch.cos(k * 6 * q[:, 1])], -1)
+    pos = (q + disp + 0.3 * torch.randn(N, 3, device=dev, generator=g)).contiguous()
+    pos_rand = (torch.rand(N, 3, device=dev, generator=g) * n).contiguous()
+    vel = torch.randn(N, 3, device=dev, generator=g).contiguous()
+    w = torch.rand(N, device=dev, generator=g).contiguous()
+    mesh3 = torch.randn(3, *shape, device=dev, generator=g).contiguous()
+    mesh = mesh3[0].contiguous()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)  # 256 MB > 126 MB L2
+    res = {}
+
+    only = a.only.split(",") if a.only else None
+
+    def rec(name, fn, bytes_alg):
+        if only and not any(o in name for o in only):
+            return
+        med, mn = timeit(fn, reps=a.reps, warm=1 if a.reps < 3 else 3, flush=flush)
+        res[name] = {"ms": med, "ms_min": mn, "alg_GBps": bytes_alg / med / 1e6}
+        print(f"{name:28s} {med:9.3f} ms (min {mn:8.3f})  {bytes_alg / med / 1e6:9.1f} GB/s algorithmic", flush=True)
+
+    out = torch.empty(shape, device=dev)
+    rec("paint_cic_lattice", lambda: ops.paint(pos, shape, None, order=2, out=out), 16 * N)
+    rec("paint_cic_lattice_w", lambda: ops.paint(pos, shape, w, order=2, out=out), 20 * N)
+    rec("paint_cic_random", lambda: ops.paint(pos_rand, shape, None, order=2, out=out), 16 * N)
+    rec("paint_cic_q", lambda: ops.paint(q, shape, None, order=2, out=out), 16 * N)
+    rec("paint_tsc_lattice", lambda: ops.paint(pos, shape, None, order=3, out=out), 16 * N)
+    rec("paint3_cic_lattice", lambda: ops.paint3(pos, vel, shape), 36 * N)
+    rec("read_cic_lattice", lambda: ops.read(pos, mesh, order=2), 20 * N)
+    rec("read3_cic_lattice", lambda: ops.read(pos, mesh3, order=2), 36 * N)
+    rec("read3_cic_random", lambda: ops.read(pos_rand, mesh3, order=2), 36 * N)
+    rec("read_grad3_cic_lattice", lambda: ops.read_grad(pos, mesh3, vel, order=2), 48 * N)
+    p2, v2 = pos.clone(), vel.clone()
+    lib, A = ops.lib, ops.A
+
+    def kd():
+        lib.mcpm_kick_drift(A.stream(), p2.data_ptr(), v2.data_ptr(), mesh3.data_ptr(), N, n, n, n, 2, 1.0, 0.0, 0.0, 0)
+    rec("kick_drift_cic", kd, 60 * N)
+    memset_t = timeit(lambda: out.zero_(), flush=flush)
+    print(f"{'memset mesh':28s} {memset_t[0]:9.3f} ms")
+    c2 = torch.empty_like(pos)
+    rec("copy_pos (d2d 2x12N)", lambda: c2.copy_(pos), 24 * N)
+
+    mk = ops.rfftn(mesh)
+    mk3 = ops.rfftn(mesh3)
+    rec("rfftn_b1", lambda: ops.rfftn(mesh), 8 * N)
+    rec("rfftn_b3", lambda: ops.rfftn(mesh3), 24 * N)
+    rec("irfftn_b1(+scale pass)", lambda: ops.irfftn(mk, overwrite=True), 8 * N)
+    rec("irfftn_b3(+scale pass)", lambda: ops.irfftn(mk3, overwrite=True), 24 * N)
+    rec("torch.rfftn_b1", lambda: torch.fft.rfftn(mesh), 8 * N)
+    rec("torch.irfftn_b1", lambda: torch.fft.irfftn(mk, s=shape), 8 * N)
+    rec("force_spectra", lambda: ops.force_spectra(mk), 16 * N)
+    rec("force_spectra_T", lambda: ops.force_spectra_T(mk3), 16 * N)
+    rec("hessian_spectra", lambda: ops.hessian_spectra(mk), 28 * N)
+    rec("pm_forces (124N)", lambda: ops.pm_forces(pos, shape, want_meshes=True), 124 * N)
+    f, fm = ops.pm_forces(pos, shape, want_meshes=True)
+    rec("pm_forces_vjp (136N)", lambda: ops.pm_forces_vjp(pos, vel, fm), 136 * N)
+    if a.out:
+        with open(a.out, "w") as fh:
+            json.dump(res, fh, indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -30,6 +30,11 @@ struct mcpm_engine {
     return MCPM_EINVAL;                          \
   }
 
+#define BIND(eng)                                  \
+  do {                                             \
+    if (int _b = rt_bind_device((eng)->e->device)) return _b; \
+  } while (0)
+
 #define NEED(cond, msg)   \
   do {                    \
     if (!(cond)) {        \
@@ -117,6 +122,7 @@ int mcpm_paint3(void* stream, const float* pos, const float* vals3, float vscale
 int mcpm_rfftn(mcpm_engine* eng, void* stream, const float* in, void* out_c64, int batch) {
   API_BEGIN
   NEED(eng && in && out_c64 && batch >= 1, "rfftn: bad arguments");
+  BIND(eng);
   return fft_r2c(eng->e->fft, as_stream(stream), in, C(out_c64), batch);
   API_END
 }
@@ -124,6 +130,7 @@ int mcpm_rfftn(mcpm_engine* eng, void* stream, const float* in, void* out_c64, i
 int mcpm_irfftn(mcpm_engine* eng, void* stream, void* in_c64, float* out, int batch) {
   API_BEGIN
   NEED(eng && in_c64 && out && batch >= 1, "irfftn: bad arguments");
+  BIND(eng);
   stream_t st = as_stream(stream);
   if (int e = fft_c2r(eng->e->fft, st, C(in_c64), out, batch)) return e;
   return scale_real(st, out, eng->e->invN, out, eng->e->N * batch);  // standalone irfftn pays one scaling pass
@@ -273,6 +280,7 @@ int mcpm_pm_forces(mcpm_engine* eng, void* stream, const float* pos, int64_t np,
                    int lap_fd, int grad_fd, float kcut, float* fmesh3, float* forces) {
   API_BEGIN
   NEED(eng, "null engine");
+  BIND(eng);
   return pm_forces(eng->e, as_stream(stream), pos, np, order, paint_deconv, lap_fd, grad_fd, kcut, fmesh3, forces);
   API_END
 }
@@ -282,6 +290,7 @@ int mcpm_pm_forces_vjp(mcpm_engine* eng, void* stream, const float* pos, const f
                        float* posbar, int accumulate) {
   API_BEGIN
   NEED(eng && fmesh3 && fbar && posbar, "pm_forces_vjp: null pointer");
+  BIND(eng);
   return pm_forces_vjp(eng->e, as_stream(stream), pos, fbar, 1.0f, fmesh3, np, order, paint_deconv, lap_fd, grad_fd,
                        kcut, posbar, accumulate);
   API_END
@@ -291,6 +300,7 @@ int mcpm_pm_forces_mesh(mcpm_engine* eng, void* stream, const float* pos, const 
                         int order, int lap_fd, int grad_fd, float kcut, float* forces) {
   API_BEGIN
   NEED(eng && delta_k && forces, "pm_forces_mesh: null pointer");
+  BIND(eng);
   return pm_forces_mesh(eng->e, as_stream(stream), pos, C(delta_k), np, order, lap_fd, grad_fd, kcut, forces);
   API_END
 }
@@ -299,6 +309,7 @@ int mcpm_pm_forces2(mcpm_engine* eng, void* stream, const float* pos, const void
                     int lap_fd, int grad_fd, float* forces, float* h6_out) {
   API_BEGIN
   NEED(eng && delta_k && forces, "pm_forces2: null pointer");
+  BIND(eng);
   return pm_forces2(eng->e, as_stream(stream), pos, C(delta_k), np, order, lap_fd, grad_fd, forces, h6_out);
   API_END
 }
@@ -308,6 +319,7 @@ int mcpm_lpt(mcpm_engine* eng, void* stream, const void* delta_k, const float* p
              float* f1, float* f2, float* h6) {
   API_BEGIN
   NEED(eng && delta_k && pos, "lpt: null pointer");
+  BIND(eng);
   return lpt(eng->e, as_stream(stream), C(delta_k), pos, np, lpt_order, read_order, lap_fd, grad_fd, d1, d2, dv2,
              dpos, vel, f1, f2, h6);
   API_END
@@ -318,6 +330,7 @@ int mcpm_lpt_vjp(mcpm_engine* eng, void* stream, const float* pos, int64_t np, i
                  const float* f1, const float* f2, const float* h6, void* dkbar, double* coefbar, int accumulate) {
   API_BEGIN
   NEED(eng && pos && dposbar && velbar && dkbar, "lpt_vjp: null pointer");
+  BIND(eng);
   return lpt_vjp(eng->e, as_stream(stream), pos, np, lpt_order, read_order, lap_fd, grad_fd, d1, d2, dv2, dposbar,
                  velbar, f1, f2, h6, C(dkbar), coefbar, accumulate);
   API_END
@@ -328,6 +341,7 @@ int mcpm_nbody_steps(mcpm_engine* eng, void* stream, float* pos, float* vel, int
                      int order, int paint_deconv, int lap_fd, int grad_fd, float* xk, float* vk, float* fm) {
   API_BEGIN
   NEED(eng && pos && vel, "nbody_steps: null pointer");
+  BIND(eng);
   return nbody_steps(eng->e, as_stream(stream), pos, vel, np, n_steps, alpha, beta, drift_pre, drift_post, order,
                      paint_deconv, lap_fd, grad_fd, xk, vk, fm);
   API_END
@@ -339,6 +353,7 @@ int mcpm_nbody_steps_vjp(mcpm_engine* eng, void* stream, float* posbar, float* v
                          const float* fm, const float* v0, double* coefbar) {
   API_BEGIN
   NEED(eng && posbar && velbar, "nbody_steps_vjp: null pointer");
+  BIND(eng);
   return nbody_steps_vjp(eng->e, as_stream(stream), posbar, velbar, np, n_steps, alpha, beta, drift_pre, drift_post,
                          order, paint_deconv, lap_fd, grad_fd, xk, vk, fm, v0, coefbar);
   API_END
@@ -348,6 +363,7 @@ int mcpm_nufft(mcpm_engine* eng, void* stream, const float* pos, const float* we
                const float scale[3], int paint_order, int interlace_order, int paint_deconv, void* out_k) {
   API_BEGIN
   NEED(eng && pos && out_k, "nufft: null pointer");
+  BIND(eng);
   return nufft(eng->e, as_stream(stream), pos, weights, wscalar, np, scale, paint_order, interlace_order,
                paint_deconv, C(out_k));
   API_END
@@ -358,6 +374,7 @@ int mcpm_nufft_vjp(mcpm_engine* eng, void* stream, const float* pos, const float
                    const void* outbar_k, float* posbar, float* weightsbar) {
   API_BEGIN
   NEED(eng && pos && outbar_k, "nufft_vjp: null pointer");
+  BIND(eng);
   return nufft_vjp(eng->e, as_stream(stream), pos, weights, wscalar, np, scale, paint_order, interlace_order,
                    paint_deconv, C(outbar_k), posbar, weightsbar);
   API_END

@@ -21,6 +21,7 @@ Engine* engine_create(int nx, int ny, int nz) {
   e->N = (int64_t)nx * ny * nz;
   e->Nc = (int64_t)nx * ny * e->nzc;
   e->invN = (float)(1.0 / (double)e->N);
+  e->device = rt_get_device();
   size_t fftws = 0;
   e->fft = fft_create(nx, ny, nz, &fftws);
   if (!e->fft) {

@@ -8,6 +8,7 @@ struct Engine {
   static constexpr int kR = 7;  // real scratch meshes (6 Hessian / 3 force + 1 density)
   static constexpr int kC = 7;  // half-spectrum scratch meshes
   int nx, ny, nz, nzc;
+  int device = 0;  // CUDA device the plans and scratch live on
   int64_t N, Nc;
   float invN;
   FftPlans* fft = nullptr;

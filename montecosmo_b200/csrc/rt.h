@@ -55,6 +55,8 @@ inline int rt_malloc(void** p, size_t bytes) {
 }
 inline void rt_free(void* p) { free(p); }
 inline int rt_check(const char*) { return 0; }
+inline int rt_get_device() { return 0; }
+inline int rt_bind_device(int) { return 0; }
 
 #else  // ---------------------------------------------------------------- CUDA
 #include <cuda_runtime.h>
@@ -92,6 +94,21 @@ inline int rt_copy(void* d, const void* src, size_t bytes, stream_t s) {
 }
 inline int rt_malloc(void** p, size_t bytes) { return (int)cudaMalloc(p, bytes ? bytes : 1); }
 inline void rt_free(void* p) { cudaFree(p); }
+inline int rt_get_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d;
+}
+// Make the engine's device (and its primary context) current on the calling host thread.  Callers such as torch's
+// autograd workers or XLA's executor threads may arrive with no context bound, which cuFFT does not tolerate.
+inline int rt_bind_device(int d) {
+  if (cudaSetDevice(d) != cudaSuccess) {
+    set_error("cudaSetDevice failed");
+    cudaGetLastError();
+    return MCPM_ECUDA;
+  }
+  return 0;
+}
 inline int rt_check(const char* what) {
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {

@@ -113,11 +113,22 @@ def cpu_reference_arm(steps, warmup, n_sample=128):
             "seconds_per_sample_eval": per_eval}
 
 
+def max_over_ranks(ms, device, world):
+    """Step time of the job = the slowest rank's (all-reduce MAX); identity for one rank."""
+    if world <= 1:
+        return float(ms)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_reference_arm(max(1, min(args.steps, 5)), min(args.warmup, 1), 128)
+    cb = cpu_reference_arm(max(1, min(args.steps, 5)), min(args.warmup, 1), int(os.environ.get("MCPM_BENCH_SAMPLE", "128")))
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -147,7 +158,6 @@ def kernel_rooflines(model, white, peaks):
     A, lib = o.A, o.lib
     p2, v2 = pos.clone(), vel.clone()
     rho = torch.randn(shape, device=pos.device)
-    ms4 = [fm[0], fm[1], fm[2], rho]
 
     def t(fn, reps=5):
         fn()
@@ -164,22 +174,39 @@ def kernel_rooflines(model, white, peaks):
 
     steps = model.n_steps
     rows = []
+    st = A.stream()
 
-    def add(name, fn, alg_bytes, launches):
+    def add(name, fn, alg_bytes, launches, note=""):
         ms = t(fn)
         rows.append({"kernel": name, "ms": ms, "launches_per_step": launches, "alg_bytes": alg_bytes,
                      "achieved_GBps": alg_bytes / ms / 1e6, "frac": alg_bytes / ms / 1e6 / peaks,
-                     "ms_per_step_total": ms * launches})
+                     "ms_per_step_total": ms * launches, "alg_bytes_note": note})
 
-    add("paint (CIC scatter)", lambda: o.paint(pos, shape, None, order=2, out=mesh), 16 * N, steps + 2)
-    add("paint3 (3-channel adjoint scatter)", lambda: o.paint3(pos, vel, shape), 36 * N, steps + 2)
-    add("kick_drift (3-mesh readout + kick + drift)",
-        lambda: lib.mcpm_kick_drift(A.stream(), p2.data_ptr(), v2.data_ptr(), fm.data_ptr(), N, *shape, 2, 1.0, 0.0,
-                                    0.0, 0), 60 * N, steps)
-    add("read_grad (4-mesh gradient gather)", lambda: o.read_grad(pos, torch.stack(ms4), None, order=2), 40 * N, steps)
+    fm4 = torch.empty((*shape, 4), device=pos.device)
+    lib.mcpm_interleave3(st, fm.data_ptr(), fm4.data_ptr(), N)
+    mesh4 = torch.zeros((*shape, 4), device=pos.device)
+    planar3 = torch.empty((3, *shape), device=pos.device)
+    xbar, vbar = torch.randn_like(pos), torch.randn_like(pos)
+    add("paint (CIC density scatter, 8 red.f32 / particle)", lambda: o.paint(pos, shape, None, order=2, out=mesh),
+        16 * N, steps + 2, "pos 12N + mesh 4N")
+    add("paint3v4 (reverse-step scatter, 8 red.v4.f32 / particle, fused vbar update)",
+        lambda: lib.mcpm_paint3v4(st, pos.data_ptr(), vbar.data_ptr(), xbar.data_ptr(), 1e-3, 0.5, N, *shape,
+                                  mesh4.data_ptr()), 64 * N, steps, "pos 12N + vbar 12N r + 12N w + xbar 12N + mesh4 16N")
+    add("kick_drift4 (float4 force readout + kick + drift)",
+        lambda: lib.mcpm_kick_drift4(st, p2.data_ptr(), v2.data_ptr(), fm4.data_ptr(), N, *shape, 1.0, 0.0, 0.0),
+        64 * N, steps, "pos 12N r/w + vel 12N r/w + mesh4 16N")
+    add("read_grad4v (reverse-step gradient gather, fused xbar / vbar update)",
+        lambda: lib.mcpm_read_grad4v(st, pos.data_ptr(), fm4.data_ptr(), rho.data_ptr(), vbar.data_ptr(), 0.5, 1.0, N,
+                                     *shape, xbar.data_ptr()), 80 * N, steps,
+        "pos 12N + vbar 12N r/w + xbar 12N r/w + mesh4 16N + rhobar 4N")
+    add("interleave3 (3 planar meshes -> float4 mesh)", lambda: lib.mcpm_interleave3(st, fm.data_ptr(), fm4.data_ptr(), N),
+        28 * N, steps, "12N r + 16N w")
+    add("deinterleave3 (float4 mesh -> 3 planar meshes)",
+        lambda: lib.mcpm_deinterleave3(st, mesh4.data_ptr(), planar3.data_ptr(), N), 28 * N, steps, "16N r + 12N w")
     mk = o.rfftn(rho)
-    add("force_spectra (Green x gradient, 3 outputs)", lambda: o.force_spectra(mk), 16 * N, steps + 2)
-    add("cuFFT R2C (library)", lambda: o.rfftn(rho), 8 * N, 4 * steps + 10)
+    add("force_spectra (Green x gradient, 1 -> 3 spectra)", lambda: o.force_spectra(mk), 16 * N, 2 * (steps + 2),
+        "4N r + 12N w")
+    add("cuFFT R2C 256^3 (library)", lambda: o.rfftn(rho), 8 * N, 116, "4N r + 4N w per transform; 116 transforms per step")
     dom = max([r for r in rows if "library" not in r["kernel"]], key=lambda r: r["ms_per_step_total"])
     return rows, dom
 
@@ -227,10 +254,7 @@ def run_engine(args):
         e1.record()
         barrier()
         launches = lib.mcpm_launch_count(0)
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms), launches
+        return max_over_ranks(e0.elapsed_time(e1), dev, world), launches
 
     sampler = ClockSampler(local)
     if rank == 0:

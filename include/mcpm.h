@@ -161,6 +161,23 @@ int mcpm_lpt_combine(void* stream, const float* pos, const float* f1, const floa
  * In place on pos / vel.  force_out may be NULL. */
 int mcpm_kick_drift(void* stream, float* pos, float* vel, const float* fmesh3, int64_t np, int nx, int ny, int nz,
                     int order, float alpha, float beta, float drift, float* force_out);
+/* ---- CIC step kernels on the float4-interleaved vector mesh "mesh4" = [nx, ny, nz] cells of {c0, c1, c2, c3} -------
+ * These are what mcpm_nbody_steps / _vjp run for order 2; exposed so that they can be timed and tested in isolation.
+ * interleave3 / deinterleave3: three planar meshes <-> mesh4.xyz (w = 0), the conversion around cuFFT.
+ * kick_drift4: as mcpm_kick_drift with the forces read from mesh4.xyz (8 x 16-byte loads per particle).
+ * paint3v4 (reverse step, first half): vbar += xbar * drift (stored, when xbar != NULL);
+ *           mesh4[cell].xyz += scale * vbar * W over the 8 CIC corners (8 x red.global.add.v4.f32). mesh4 is NOT zeroed.
+ * read_grad4v (reverse step, second half): xbar += d/dx [ cscale * vbar . F(x) + rhobar(x) ], F = mesh4.xyz, rhobar
+ *           planar; then vbar *= alpha. */
+int mcpm_interleave3(void* stream, const float* planar3, float* mesh4, int64_t n);
+int mcpm_deinterleave3(void* stream, const float* mesh4, float* planar3, int64_t n);
+int mcpm_kick_drift4(void* stream, float* pos, float* vel, const float* fmesh4, int64_t np, int nx, int ny, int nz,
+                     float alpha, float beta, float drift);
+int mcpm_paint3v4(void* stream, const float* pos, float* vbar, const float* xbar, float drift, float scale, int64_t np,
+                  int nx, int ny, int nz, float* mesh4);
+int mcpm_read_grad4v(void* stream, const float* pos, const float* fmesh4, const float* rhobar, float* vbar,
+                     float cscale, float alpha, int64_t np, int nx, int ny, int nz, float* xbar);
+
 /* pos += vel * drift */
 int mcpm_drift(void* stream, float* pos, const float* vel, float drift, int64_t np);
 
@@ -196,7 +213,7 @@ int mcpm_lpt_vjp(mcpm_engine* eng, void* stream, const float* pos, int64_t np, i
 /* nbody_bf step loop (nbody.py:933-951, 999): n_steps drift-kick-drift steps in place on (pos, vel).
  * Per-step host arrays: alpha[s], beta[s] = (1 - alpha) / g1, drift_pre[s], drift_post[s] (= dg/2 each).
  * Tape (nullable): xk [n_steps, np, 3] positions at kick time, vk [n_steps, np, 3] velocities after the kick,
- * fm [n_steps, 3, nx, ny, nz] force meshes. */
+ * fm [n_steps, 4, nx, ny, nz] floats of force meshes in an engine-defined layout (float4-interleaved for CIC). */
 int mcpm_nbody_steps(mcpm_engine* eng, void* stream, float* pos, float* vel, int64_t np, int n_steps,
                      const float* alpha, const float* beta, const float* drift_pre, const float* drift_post,
                      int order, int paint_deconv, int lap_fd, int grad_fd, float* xk, float* vk, float* fm);

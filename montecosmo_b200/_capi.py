@@ -44,6 +44,11 @@ SIGNATURES = {
     "mcpm_scale_spectrum": ([vp, vp, vp, vp, i64], i32),
     "mcpm_lpt_combine": ([vp, vp, vp, vp, f32, f32, f32, i64, vp, vp, vp], i32),
     "mcpm_kick_drift": ([vp, vp, vp, vp, i64] + MESH + [i32, f32, f32, f32, vp], i32),
+    "mcpm_interleave3": ([vp, vp, vp, i64], i32),
+    "mcpm_deinterleave3": ([vp, vp, vp, i64], i32),
+    "mcpm_kick_drift4": ([vp, vp, vp, vp, i64] + MESH + [f32, f32, f32], i32),
+    "mcpm_paint3v4": ([vp, vp, vp, vp, f32, f32, i64] + MESH + [vp], i32),
+    "mcpm_read_grad4v": ([vp, vp, vp, vp, vp, f32, f32, i64] + MESH + [vp], i32),
     "mcpm_drift": ([vp, vp, vp, f32, i64], i32),
     "mcpm_pm_forces": ([vp, vp, vp, i64, i32, i32, i32, i32, f32, vp, vp], i32),
     "mcpm_pm_forces_vjp": ([vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, f32, vp, i32], i32),

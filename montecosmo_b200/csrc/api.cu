@@ -1,6 +1,7 @@
 // api.cu -- the extern "C" boundary declared in include/mcpm.h.  No exceptions cross it; errors are codes plus a
 // thread-local message.
 #include <atomic>
+#include <cstdlib>
 #include <exception>
 
 #include "engine.h"
@@ -267,6 +268,42 @@ int mcpm_kick_drift(void* stream, float* pos, float* vel, const float* fmesh3, i
   API_BEGIN
   return kick_drift(as_stream(stream), pos, vel, fmesh3, np, nx, ny, nz, order, alpha, beta, drift, pos, vel,
                     force_out);
+  API_END
+}
+
+int mcpm_interleave3(void* stream, const float* planar3, float* mesh4, int64_t n) {
+  API_BEGIN
+  return interleave3(as_stream(stream), planar3, mesh4, n);
+  API_END
+}
+
+int mcpm_deinterleave3(void* stream, const float* mesh4, float* planar3, int64_t n) {
+  API_BEGIN
+  return deinterleave3(as_stream(stream), mesh4, planar3, n);
+  API_END
+}
+
+int mcpm_kick_drift4(void* stream, float* pos, float* vel, const float* fmesh4, int64_t np, int nx, int ny, int nz,
+                     float alpha, float beta, float drift) {
+  API_BEGIN
+  NEED(pos && vel && fmesh4, "kick_drift4: null pointer");
+  return kick_drift4(as_stream(stream), pos, vel, fmesh4, np, nx, ny, nz, alpha, beta, drift, pos, vel);
+  API_END
+}
+
+int mcpm_paint3v4(void* stream, const float* pos, float* vbar, const float* xbar, float drift, float scale, int64_t np,
+                  int nx, int ny, int nz, float* mesh4) {
+  API_BEGIN
+  NEED(pos && vbar && mesh4, "paint3v4: null pointer");
+  return paint3v4(as_stream(stream), pos, vbar, xbar, drift, xbar != nullptr, scale, np, nx, ny, nz, mesh4);
+  API_END
+}
+
+int mcpm_read_grad4v(void* stream, const float* pos, const float* fmesh4, const float* rhobar, float* vbar,
+                     float cscale, float alpha, int64_t np, int nx, int ny, int nz, float* xbar) {
+  API_BEGIN
+  NEED(pos && fmesh4 && rhobar && vbar && xbar, "read_grad4v: null pointer");
+  return read_grad4v(as_stream(stream), pos, fmesh4, rhobar, vbar, cscale, 1, alpha, np, nx, ny, nz, xbar, 1);
   API_END
 }
 

@@ -178,14 +178,24 @@ int nbody_steps(Engine* E, stream_t st, float* pos, float* vel, int64_t np, int 
   float* cur = xk ? xk : pos;  // position at kick time of the current step
   TRY(axpy3(st, pos, vel, drift_pre[0], P3, cur));
   const float* vin = vel;
+  // Tape slot per step: 4N floats.  CIC (order 2): the force mesh as float4 {Fx, Fy, Fz, 0} per cell (cic4.cu);
+  // other orders: three planar meshes in the first 3N floats.
+  const bool cic = (order == 2);
   for (int s = 0; s < n_steps; ++s) {
-    float* fms = fm ? fm + (int64_t)s * 3 * E->N : E->r(0);
-    TRY(pm_forces(E, st, cur, np, order, paint_deconv, lap_fd, grad_fd, 0.0f, fms, nullptr));
+    float* slot = fm ? fm + (int64_t)s * 4 * E->N : E->r(3);
+    float* planar = cic ? E->r(0) : slot;
+    TRY(pm_forces(E, st, cur, np, order, paint_deconv, lap_fd, grad_fd, 0.0f, planar, nullptr));
     const bool last = (s == n_steps - 1);
     float dcomb = drift_post[s] + (last ? 0.0f : drift_pre[s + 1]);
     float* xout = (xk && !last) ? xk + (int64_t)(s + 1) * P3 : pos;
     float* vout = vk ? vk + (int64_t)s * P3 : vel;
-    TRY(kick_drift(st, cur, vin, fms, np, E->nx, E->ny, E->nz, order, alpha[s], beta[s], dcomb, xout, vout, nullptr));
+    if (cic) {
+      TRY(interleave3(st, planar, slot, E->N));
+      TRY(kick_drift4(st, cur, vin, slot, np, E->nx, E->ny, E->nz, alpha[s], beta[s], dcomb, xout, vout));
+    } else {
+      TRY(kick_drift(st, cur, vin, slot, np, E->nx, E->ny, E->nz, order, alpha[s], beta[s], dcomb, xout, vout,
+                     nullptr));
+    }
     cur = xout;
     vin = vout;
   }
@@ -210,30 +220,49 @@ int nbody_steps_vjp(Engine* E, stream_t st, float* posbar, float* velbar, int64_
     return MCPM_EINVAL;
   }
   const int64_t P3 = 3 * np;
+  const bool cic = (order == 2);
   for (int s = n_steps - 1; s >= 0; --s) {
     const bool last = (s == n_steps - 1);
     float dcomb = drift_post[s] + (last ? 0.0f : drift_pre[s + 1]);
     const float* x1 = xk + (int64_t)s * P3;
-    const float* fms = fm + (int64_t)s * 3 * E->N;
+    const float* slot = fm + (int64_t)s * 4 * E->N;
+    const float* v1 = vk ? vk + (int64_t)s * P3 : nullptr;
+    const float* vprev = s == 0 ? v0 : (vk ? vk + (int64_t)(s - 1) * P3 : nullptr);
     if (coefbar) {
-      // d(drift)bar = <xbar, v1>: split evenly is wrong -- both halves see the same xbar, so each gets the full dot
-      const float* v1 = vk + (int64_t)s * P3;
+      // both half drifts that were fused into `dcomb` see the same xbar, so each gets the full <xbar, v1>
       TRY(dot_accum(st, posbar, v1, P3, 1.0, coefbar + 4 * s + 3));
       if (!last) TRY(dot_accum(st, posbar, v1, P3, 1.0, coefbar + 4 * (s + 1) + 2));
     }
-    TRY(axpy3(st, velbar, posbar, dcomb, P3, velbar));
+    if (cic) {
+      // vbar += xbar * dcomb and phibar = paint(beta * vbar) in one pass, into the float4 mesh r(0..3)
+      TRY(rt_memset(E->r(0), 0, sizeof(float) * 4 * (size_t)E->N, st) ? MCPM_ECUDA : 0);
+      TRY(paint3v4(st, x1, velbar, posbar, dcomb, 1, beta[s], np, E->nx, E->ny, E->nz, E->r(0)));
+      TRY(deinterleave3(st, E->r(0), E->r(4), E->N));
+      TRY(fft_r2c(E->fft, st, E->r(4), E->c(0), 3));
+    } else {
+      TRY(axpy3(st, velbar, posbar, dcomb, P3, velbar));
+      TRY(paint3(st, x1, velbar, beta[s], nullptr, 0.0f, np, E->nx, E->ny, E->nz, order, E->r(0), 0));
+      TRY(fft_r2c(E->fft, st, E->r(0), E->c(0), 3));
+    }
+    TRY(force_spectra_T(st, E->c(0), E->c(3), E->nx, E->ny, E->nz, lap_fd, grad_fd, 0.0f, paint_deconv ? order : 0, 0,
+                        0, E->invN));
+    TRY(fft_c2r(E->fft, st, E->c(3), E->r(3), 1));  // rhobar
     if (coefbar) {
-      const float* vprev = s == 0 ? v0 : vk + (int64_t)(s - 1) * P3;
       TRY(dot_accum(st, velbar, vprev, P3, 1.0, coefbar + 4 * s + 0));
-      // betabar = <vbar, F>, F = (v1 - alpha v0) / beta
-      const float* v1 = vk + (int64_t)s * P3;
-      if (beta[s] != 0.0f) {
+      if (beta[s] != 0.0f) {  // betabar = <vbar, F>, F = (v1 - alpha v0) / beta
         TRY(dot_accum(st, velbar, v1, P3, 1.0 / beta[s], coefbar + 4 * s + 1));
         TRY(dot_accum(st, velbar, vprev, P3, -(double)alpha[s] / beta[s], coefbar + 4 * s + 1));
       }
     }
-    TRY(pm_forces_vjp(E, st, x1, velbar, beta[s], fms, np, order, paint_deconv, lap_fd, grad_fd, 0.0f, posbar, 1));
-    TRY(axpy3(st, velbar, velbar, alpha[s] - 1.0f, P3, velbar));  // vbar *= alpha
+    if (cic) {
+      // xbar += dread(x1; beta*vbar . F + rhobar) and vbar *= alpha, one gather
+      TRY(read_grad4v(st, x1, slot, E->r(3), velbar, beta[s], 1, alpha[s], np, E->nx, E->ny, E->nz, posbar, 1));
+    } else {
+      const float* ms[4] = {slot, slot + E->N, slot + 2 * E->N, E->r(3)};
+      TRY(read_grad(st, x1, ms, 4, velbar, 3, beta[s], nullptr, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, posbar,
+                    1));
+      TRY(axpy3(st, velbar, velbar, alpha[s] - 1.0f, P3, velbar));
+    }
   }
   if (coefbar) TRY(dot_accum(st, posbar, v0, P3, 1.0, coefbar + 2));
   TRY(axpy3(st, velbar, posbar, drift_pre[0], P3, velbar));

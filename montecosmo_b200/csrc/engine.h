@@ -69,6 +69,16 @@ int chreshape(stream_t, const cfloat* in, int inx, int iny, int inz, cfloat* out
 int chreshape_T(stream_t, const cfloat* outbar, int onx, int ony, int onz, cfloat* inbar, int inx, int iny, int inz);
 int hermitian_weights(stream_t, const cfloat* in, cfloat* out, int nx, int ny, int nz, int mode);
 
+// cic4.cu: CIC kernels on the float4-interleaved vector mesh
+int interleave3(stream_t, const float* planar3, float* mesh4, int64_t n);
+int deinterleave3(stream_t, const float* mesh4, float* planar3, int64_t n);
+int kick_drift4(stream_t, const float* pos, const float* vel, const float* fmesh4, int64_t np, int nx, int ny, int nz,
+                float alpha, float beta, float drift, float* pos_out, float* vel_out);
+int paint3v4(stream_t, const float* pos, float* A, const float* B, float cb, int store, float scale, int64_t np, int nx,
+             int ny, int nz, float* mesh4);
+int read_grad4v(stream_t, const float* pos, const float* fmesh4, const float* rhobar, float* cot, float cscale,
+                int scale_cot, float alpha_tail, int64_t np, int nx, int ny, int nz, float* grad, int accumulate);
+
 // engine.cu
 int pm_forces(Engine*, stream_t, const float* pos, int64_t np, int order, int paint_deconv, int lap_fd, int grad_fd,
               float kcut, float* fmesh3, float* forces);

@@ -28,9 +28,9 @@ static void paint_impl(stream_t st, const float* pos, const float* weights, floa
     window_weights<ORDER>(x[0] * xf.sx + xf.shift, fx, wx);
     window_weights<ORDER>(x[1] * xf.sy + xf.shift, fy, wy);
     window_weights<ORDER>(x[2] * xf.sz + xf.shift, fz, wz);
-    fx = wrap_index(fx, n.nx);
-    fy = wrap_index(fy, n.ny);
-    fz = wrap_index(fz, n.nz);
+    fx = wrap_fast(fx, n.nx);
+    fy = wrap_fast(fy, n.ny);
+    fz = wrap_fast(fz, n.nz);
     float wp = weights ? weights[p] * wscalar : wscalar;
 #pragma unroll
     for (int a = 0; a < ORDER; ++a) {
@@ -64,9 +64,9 @@ static void read_impl(stream_t st, const float* pos, const float* mesh, int64_t 
     window_weights<ORDER>(x[0] * xf.sx + xf.shift, fx, wx);
     window_weights<ORDER>(x[1] * xf.sy + xf.shift, fy, wy);
     window_weights<ORDER>(x[2] * xf.sz + xf.shift, fz, wz);
-    fx = wrap_index(fx, n.nx);
-    fy = wrap_index(fy, n.ny);
-    fz = wrap_index(fz, n.nz);
+    fx = wrap_fast(fx, n.nx);
+    fy = wrap_fast(fy, n.ny);
+    fz = wrap_fast(fz, n.nz);
     float acc[NM];
 #pragma unroll
     for (int m = 0; m < NM; ++m) acc[m] = 0.0f;
@@ -114,9 +114,9 @@ static void read_grad_impl(stream_t st, const float* pos, MeshPtrs ms, int nmesh
     window_weights_grad<ORDER>(x[0] * xf.sx + xf.shift, fx, wx, dx);
     window_weights_grad<ORDER>(x[1] * xf.sy + xf.shift, fy, wy, dy);
     window_weights_grad<ORDER>(x[2] * xf.sz + xf.shift, fz, wz, dz);
-    fx = wrap_index(fx, n.nx);
-    fy = wrap_index(fy, n.ny);
-    fz = wrap_index(fz, n.nz);
+    fx = wrap_fast(fx, n.nx);
+    fy = wrap_fast(fy, n.ny);
+    fz = wrap_fast(fz, n.nz);
     float c4[4];
 #pragma unroll
     for (int m = 0; m < 4; ++m) c4[m] = (m < ncot && cot) ? cscale * cot[p * ncot + m] : 1.0f;
@@ -174,9 +174,9 @@ static void paint3_impl(stream_t st, const float* pos, const float* A, float ca,
     window_weights<ORDER>(x[0], fx, wx);
     window_weights<ORDER>(x[1], fy, wy);
     window_weights<ORDER>(x[2], fz, wz);
-    fx = wrap_index(fx, n.nx);
-    fy = wrap_index(fy, n.ny);
-    fz = wrap_index(fz, n.nz);
+    fx = wrap_fast(fx, n.nx);
+    fy = wrap_fast(fy, n.ny);
+    fz = wrap_fast(fz, n.nz);
     float v0 = ca * A[3 * p], v1 = ca * A[3 * p + 1], v2 = ca * A[3 * p + 2];
     if (B) {
       v0 += cb * B[3 * p];
@@ -219,9 +219,9 @@ static void paint_vjp_impl(stream_t st, const float* pos, const float* weights, 
     window_weights_grad<ORDER>(x[0] * xf.sx + xf.shift, fx, wx, dx);
     window_weights_grad<ORDER>(x[1] * xf.sy + xf.shift, fy, wy, dy);
     window_weights_grad<ORDER>(x[2] * xf.sz + xf.shift, fz, wz, dz);
-    fx = wrap_index(fx, n.nx);
-    fy = wrap_index(fy, n.ny);
-    fz = wrap_index(fz, n.nz);
+    fx = wrap_fast(fx, n.nx);
+    fy = wrap_fast(fy, n.ny);
+    fz = wrap_fast(fz, n.nz);
     float r = 0.0f, g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
 #pragma unroll
     for (int a = 0; a < ORDER; ++a) {
@@ -270,9 +270,9 @@ static void kick_drift_impl(stream_t st, const float* pos, const float* vel, con
     window_weights<ORDER>(x0, fx, wx);
     window_weights<ORDER>(x1, fy, wy);
     window_weights<ORDER>(x2, fz, wz);
-    fx = wrap_index(fx, n.nx);
-    fy = wrap_index(fy, n.ny);
-    fz = wrap_index(fz, n.nz);
+    fx = wrap_fast(fx, n.nx);
+    fy = wrap_fast(fy, n.ny);
+    fz = wrap_fast(fz, n.nz);
     float f0 = 0.0f, f1 = 0.0f, f2 = 0.0f;
 #pragma unroll
     for (int a = 0; a < ORDER; ++a) {

@@ -21,7 +21,7 @@ void set_error(const std::string& msg);
 void count_launch();  // api.cu: number of engine kernels launched by this process (bench.py's gpu_launches)
 
 #ifdef MCPM_HOSTEMU
-#define MCPM_HD
+#define MCPM_HD inline
 #define MCPM_LAMBDA
 typedef void* stream_t;
 
@@ -33,11 +33,11 @@ inline void launch_1d(stream_t, int64_t n, F f) {
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < n; ++i) f(i);
 }
-MCPM_HD inline void atomic_add(float* p, float v) {
+MCPM_HD void atomic_add(float* p, float v) {
 #pragma omp atomic
   *p += v;
 }
-MCPM_HD inline void atomic_add(double* p, double v) {
+MCPM_HD void atomic_add(double* p, double v) {
 #pragma omp atomic
   *p += v;
 }
@@ -74,12 +74,12 @@ __global__ void __launch_bounds__(256) k_launch_1d(int64_t n, F f) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
 }
 
-// Grid-stride launch sized in whole waves of the 148 SMs (8 resident CTAs of 256 threads each).
+// Grid-stride launch sized in whole waves of the 148 SMs (16 CTAs of 256 threads per SM: two full-occupancy waves).
 template <class F>
 inline void launch_1d(stream_t s, int64_t n, F f) {
   if (n <= 0) return;
   int64_t blocks = (n + 255) / 256;
-  const int64_t wave = (int64_t)kSMs * 8;
+  const int64_t wave = (int64_t)kSMs * 16;
   if (blocks > wave) blocks = wave;
   count_launch();
   k_launch_1d<<<(unsigned)blocks, 256, 0, s>>>(n, f);

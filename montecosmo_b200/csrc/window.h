@@ -11,6 +11,14 @@ MCPM_HD int wrap_index(int i, int n) {
   return m < 0 ? m + n : m;
 }
 
+// Same result; the common range [-n, 2n) costs two compares instead of an integer division.
+MCPM_HD int wrap_fast(int i, int n) {
+  if ((unsigned)i < (unsigned)n) return i;
+  if (i < 0 && i >= -n) return i + n;
+  if (i >= n && i < 2 * n) return i - n;
+  return wrap_index(i, n);
+}
+
 // W(s), s = |u| >= 0, and dW/ds.
 template <int ORDER>
 MCPM_HD float window(float s) {

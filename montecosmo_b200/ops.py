@@ -342,7 +342,7 @@ class Ops:
         ns = len(alpha)
         xk = A.empty((ns, n, 3)) if tape else None
         vk = A.empty((ns, n, 3)) if tape and tape_vel else None
-        fm = A.empty((ns, 3, *shape)) if tape else None
+        fm = A.empty((ns, 4, *shape)) if tape else None
         self._call("mcpm_nbody_steps", self.engine(shape).handle, A.stream(), A.ptr(pos), A.ptr(vel), n, ns,
                    host_floats(alpha), host_floats(beta), host_floats(drift_pre), host_floats(drift_post), order,
                    int(paint_deconv), fd_code(lap_fd), fd_code(grad_fd), A.ptr(xk), A.ptr(vk), A.ptr(fm))

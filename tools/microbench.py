@@ -104,6 +104,15 @@ def main():
     rec("pm_forces (124N)", lambda: ops.pm_forces(pos, shape, want_meshes=True), 124 * N)
     f, fm = ops.pm_forces(pos, shape, want_meshes=True)
     rec("pm_forces_vjp (136N)", lambda: ops.pm_forces_vjp(pos, vel, fm), 136 * N)
+    al, be, pre, post = [0.8], [0.5], [0.01], [0.01]
+    for tag in ("",):
+        rec(f"pm_forces {tag} (124N)", lambda: ops.pm_forces(pos, shape, want_meshes=True), 124 * N)
+        rec(f"pm_forces_vjp {tag} (136N)", lambda: ops.pm_forces_vjp(pos, vel, fm), 136 * N)
+        px, vx = pos.clone(), vel.clone()
+        rec(f"nbody_step fwd {tag}", lambda: ops.nbody_steps(px, vx, shape, al, be, pre, post), 124 * N)
+        tape = ops.nbody_steps(pos.clone(), vel.clone(), shape, al, be, pre, post, tape=True)
+        pb, vb = vel.clone(), pos.clone()
+        rec(f"nbody_step bwd {tag}", lambda: ops.nbody_steps_vjp(pb, vb, shape, al, be, pre, post, tape), 136 * N)
     if a.out:
         with open(a.out, "w") as fh:
             json.dump(res, fh, indent=1)

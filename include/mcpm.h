@@ -53,6 +53,20 @@ long long mcpm_launch_count(int reset);
 int mcpm_engine_create(int nx, int ny, int nz, mcpm_engine** out);
 int mcpm_engine_destroy(mcpm_engine* eng);
 size_t mcpm_engine_scratch_bytes(const mcpm_engine* eng);
+/* Performance hint, never changes which result is computed: the particle arrays passed to this engine's composite
+ * operators are a px x py x pz lattice in C order (regular_pos, bricks.py:593-603), smoothly displaced.  Enables the
+ * brick-tiled shared-memory scatter; particles that strayed from their brick's tile take the generic path.
+ * px = 0 clears the hint. */
+int mcpm_engine_set_lattice(mcpm_engine* eng, int px, int py, int pz);
+
+/* Brick-tiled CIC scatters for lattice-ordered particles (need a matching mcpm_engine_set_lattice; else MCPM_EUNSUP).
+ * These are what mcpm_pm_forces / mcpm_nbody_steps_vjp run under the hint; exposed for timing and tests.  Meshes are
+ * accumulated into (not zeroed).  paint_lattice: mesh += w_p * wscalar * W (CIC).  paint3_lattice: the reverse-step
+ * scatter, vbar += xbar * drift (stored, when xbar != NULL), mesh3[c] += scale * vbar[., c] * W into 3 planar meshes. */
+int mcpm_paint_lattice(mcpm_engine* eng, void* stream, const float* pos, const float* weights, float wscalar,
+                       int64_t np, float* mesh);
+int mcpm_paint3_lattice(mcpm_engine* eng, void* stream, const float* pos, float* vbar, const float* xbar, float drift,
+                        float scale, int64_t np, float* mesh3);
 
 /* ---- mass assignment ------------------------------------------------------------------------------------------
  * Positions are transformed in-kernel as x' = x * scale[d] + shift before assignment (nufft's final->paint units,

@@ -76,6 +76,53 @@ int mcpm_engine_destroy(mcpm_engine* eng) {
   return MCPM_OK;
 }
 
+int mcpm_engine_set_lattice(mcpm_engine* eng, int px, int py, int pz) {
+  API_BEGIN
+  NEED(eng, "null engine");
+  NEED(px >= 0 && py >= 0 && pz >= 0, "set_lattice: negative lattice shape");
+  Lattice L;
+  if (px > 0 && py > 0 && pz > 0) {
+    L.px = px;
+    L.py = py;
+    L.pz = pz;
+  }
+  eng->e->lat = L;
+  return MCPM_OK;
+  API_END
+}
+
+int mcpm_paint_lattice(mcpm_engine* eng, void* stream, const float* pos, const float* weights, float wscalar,
+                       int64_t np, float* mesh) {
+  API_BEGIN
+  NEED(eng && pos && mesh, "paint_lattice: null pointer");
+  BIND(eng);
+#ifndef MCPM_HOSTEMU
+  Engine* E = eng->e;
+  int r = brick_paint_cic(as_stream(stream), E->lat, pos, weights, wscalar, np, E->nx, E->ny, E->nz, mesh);
+  if (r < 0) return MCPM_ECUDA;
+  if (r == 1) return MCPM_OK;
+#endif
+  set_error("paint_lattice: no matching lattice hint on this engine (mcpm_engine_set_lattice), or CPU build");
+  return MCPM_EUNSUP;
+  API_END
+}
+
+int mcpm_paint3_lattice(mcpm_engine* eng, void* stream, const float* pos, float* vbar, const float* xbar, float drift,
+                        float scale, int64_t np, float* mesh3) {
+  API_BEGIN
+  NEED(eng && pos && vbar && mesh3, "paint3_lattice: null pointer");
+  BIND(eng);
+#ifndef MCPM_HOSTEMU
+  Engine* E = eng->e;
+  int r = brick_paint3_cic(as_stream(stream), E->lat, pos, vbar, xbar, drift, scale, np, E->nx, E->ny, E->nz, mesh3);
+  if (r < 0) return MCPM_ECUDA;
+  if (r == 1) return MCPM_OK;
+#endif
+  set_error("paint3_lattice: no matching lattice hint on this engine (mcpm_engine_set_lattice), or CPU build");
+  return MCPM_EUNSUP;
+  API_END
+}
+
 size_t mcpm_engine_scratch_bytes(const mcpm_engine* eng) { return eng ? eng->e->scratch_bytes : 0; }
 
 int mcpm_paint(void* stream, const float* pos, const float* weights, float wscalar, int64_t np, int nx, int ny,

@@ -51,6 +51,19 @@ void engine_destroy(Engine* e) {
     if (int _e = (x)) return _e; \
   } while (0)
 
+// CIC density paint: brick-tiled when the engine carries a matching lattice hint (CUDA build), generic otherwise
+static int paint_density(Engine* E, stream_t st, const float* pos, int64_t np, int order, float* mesh) {
+#ifndef MCPM_HOSTEMU
+  if (order == 2 && E->lat.px > 0) {
+    if (rt_memset(mesh, 0, sizeof(float) * (size_t)E->N, st)) return MCPM_ECUDA;
+    int r = brick_paint_cic(st, E->lat, pos, nullptr, 1.0f, np, E->nx, E->ny, E->nz, mesh);
+    if (r < 0) return MCPM_ECUDA;
+    if (r == 1) return 0;
+  }
+#endif
+  return paint(st, pos, nullptr, 1.0f, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, mesh, 0);
+}
+
 // delta_k (any spectrum, preserved) -> three real force meshes fm[3][N]  (nbody.py:595-603 up to the irfftn)
 static int force_meshes_from_spectrum(Engine* E, stream_t st, const cfloat* dk, int lap_fd, int grad_fd, float kcut,
                                       int deconv_order, float* fm) {
@@ -64,7 +77,7 @@ int pm_forces(Engine* E, stream_t st, const float* pos, int64_t np, int order, i
               int grad_fd, float kcut, float* fmesh3, float* forces) {
   float* fm = fmesh3 ? fmesh3 : E->r(0);
   float* rho = E->r(6);
-  TRY(paint(st, pos, nullptr, 1.0f, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, rho, 0));
+  TRY(paint_density(E, st, pos, np, order, rho));
   TRY(fft_r2c(E->fft, st, rho, E->c(6), 1));
   TRY(force_meshes_from_spectrum(E, st, E->c(6), lap_fd, grad_fd, kcut, paint_deconv ? order : 0, fm));
   if (forces) TRY(read(st, pos, fm, 3, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, forces));
@@ -234,10 +247,20 @@ int nbody_steps_vjp(Engine* E, stream_t st, float* posbar, float* velbar, int64_
       if (!last) TRY(dot_accum(st, posbar, v1, P3, 1.0, coefbar + 4 * (s + 1) + 2));
     }
     if (cic) {
-      // vbar += xbar * dcomb and phibar = paint(beta * vbar) in one pass, into the float4 mesh r(0..3)
-      TRY(rt_memset(E->r(0), 0, sizeof(float) * 4 * (size_t)E->N, st) ? MCPM_ECUDA : 0);
-      TRY(paint3v4(st, x1, velbar, posbar, dcomb, 1, beta[s], np, E->nx, E->ny, E->nz, E->r(0)));
-      TRY(deinterleave3(st, E->r(0), E->r(4), E->N));
+      // vbar += xbar * dcomb and phibar = paint(beta * vbar) in one pass
+      int handled = 0;
+#ifndef MCPM_HOSTEMU
+      if (E->lat.px > 0) {  // brick-tiled: accumulates in shared memory, flushes planar meshes directly
+        TRY(rt_memset(E->r(4), 0, sizeof(float) * 3 * (size_t)E->N, st) ? MCPM_ECUDA : 0);
+        handled = brick_paint3_cic(st, E->lat, x1, velbar, posbar, dcomb, beta[s], np, E->nx, E->ny, E->nz, E->r(4));
+        if (handled < 0) return MCPM_ECUDA;
+      }
+#endif
+      if (!handled) {  // float4 mesh r(0..3), then back to planar for cuFFT
+        TRY(rt_memset(E->r(0), 0, sizeof(float) * 4 * (size_t)E->N, st) ? MCPM_ECUDA : 0);
+        TRY(paint3v4(st, x1, velbar, posbar, dcomb, 1, beta[s], np, E->nx, E->ny, E->nz, E->r(0)));
+        TRY(deinterleave3(st, E->r(0), E->r(4), E->N));
+      }
       TRY(fft_r2c(E->fft, st, E->r(4), E->c(0), 3));
     } else {
       TRY(axpy3(st, velbar, posbar, dcomb, P3, velbar));

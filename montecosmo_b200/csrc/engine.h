@@ -4,11 +4,19 @@
 
 namespace mcpm {
 
+// Performance hint: the particle arrays given to the composite operators are a px x py x pz lattice in C order (z
+// fastest, regular_pos of bricks.py:593-603), smoothly displaced.  Enables the brick-tiled scatter (brick.cu); never
+// affects results (stray particles take the generic path).
+struct Lattice {
+  int px = 0, py = 0, pz = 0;
+};
+
 struct Engine {
   static constexpr int kR = 7;  // real scratch meshes (6 Hessian / 3 force + 1 density)
   static constexpr int kC = 7;  // half-spectrum scratch meshes
   int nx, ny, nz, nzc;
   int device = 0;  // CUDA device the plans and scratch live on
+  Lattice lat;     // optional particle-order hint
   int64_t N, Nc;
   float invN;
   FftPlans* fft = nullptr;
@@ -78,6 +86,12 @@ int paint3v4(stream_t, const float* pos, float* A, const float* B, float cb, int
              int ny, int nz, float* mesh4);
 int read_grad4v(stream_t, const float* pos, const float* fmesh4, const float* rhobar, float* cot, float cscale,
                 int scale_cot, float alpha_tail, int64_t np, int nx, int ny, int nz, float* grad, int accumulate);
+
+// brick.cu (CUDA build only): return 1 if handled, 0 if the generic path must be taken, < 0 on error
+int brick_paint_cic(stream_t, const Lattice&, const float* pos, const float* weights, float wscalar, int64_t np, int nx,
+                    int ny, int nz, float* mesh);
+int brick_paint3_cic(stream_t, const Lattice&, const float* pos, float* A, const float* B, float cb, float s,
+                     int64_t np, int nx, int ny, int nz, float* mesh3);
 
 // engine.cu
 int pm_forces(Engine*, stream_t, const float* pos, int64_t np, int order, int paint_deconv, int lap_fd, int grad_fd,

@@ -418,10 +418,13 @@ def lpt(cosmo, init_mesh, pos, a, lpt_order: int = 2, read_order: int = 2, grad_
 
 
 def nbody_bf(cosmo, init_mesh, pos, a0=0.0, a1=1.0, n_steps=5, paint_order: int = 2, lpt_order: int = 2,
-             paint_deconv=False, grad_fd=np.inf, lap_fd=np.inf, snapshots=None, fn=None):
+             paint_deconv=False, grad_fd=np.inf, lap_fd=np.inf, snapshots=None, fn=None, ptcl_shape="auto"):
     """N-body simulation with the BullFrog solver (nbody.py:967-1002): lpt at a0, then n_steps DKD steps in growth time.
 
     Returns (pos, vel), each [S, Np, 3]; S = 1 unless `snapshots` is an int > 1 dividing the step count.
+
+    `ptcl_shape` (extension) is a performance hint only: the lattice shape of `pos` (regular_pos order).  "auto" assumes
+    the mesh shape when the particle count matches it; None disables the brick-tiled kernels.
     """
     if fn is not None:
         raise NotImplementedError("custom save functions are not supported")
@@ -429,6 +432,9 @@ def nbody_bf(cosmo, init_mesh, pos, a0=0.0, a1=1.0, n_steps=5, paint_order: int 
     init_mesh = _c64(init_mesh)
     pos = _f32(pos)
     mesh_shape = ch2rshape(tuple(init_mesh.shape))
+    if ptcl_shape == "auto":
+        ptcl_shape = mesh_shape if pos.shape[0] == int(np.prod(mesh_shape)) else None
+    ops().set_lattice(mesh_shape, ptcl_shape)
     x, vel = lpt(cosmo, init_mesh, pos, a0, lpt_order, 1, grad_fd, lap_fd, _displaced=True)
     al, be, pre, post, _, _ = _cosmo.bullfrog_coefficients(cosmo, a0, a1, n_steps)
     coefs = torch.stack([al, be, pre, post], dim=1)

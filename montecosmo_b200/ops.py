@@ -90,6 +90,11 @@ class Ops:
             self._engines[shape] = Engine(self.lib, shape)
         return self._engines[shape]
 
+    def set_lattice(self, mesh_shape, ptcl_shape):
+        """Performance hint for the engine of `mesh_shape` (mcpm_engine_set_lattice); ptcl_shape None clears it."""
+        p = (0, 0, 0) if ptcl_shape is None else tuple(int(s) for s in ptcl_shape)
+        self._call("mcpm_engine_set_lattice", self.engine(mesh_shape).handle, *p)
+
     def _xf(self, scale, shift):
         return host_floats((1.0, 1.0, 1.0) if scale is None else scale), float(shift)
 

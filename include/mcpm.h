@@ -139,6 +139,27 @@ int mcpm_interlace_combine(void* stream, const void* in_m, void* out, int m, int
 int mcpm_interlace_combine_T(void* stream, const void* in, void* out_m, int m, int nx, int ny, int nz, float scale,
                              int deconv_order);
 
+/* ---- slab-decomposed building blocks (multi-GPU) ----------------------------------------------------
+ * The mesh is split along x over `parts` ranks (xl = nx/parts local planes); k-space is kept split along ky (kyl =
+ * ny/parts rows, layout [nx, kyl, nz/2+1]).  A distributed rfftn is  r2c_yz -> all-to-all (x-planes for ky rows, by the
+ * caller over NCCL) -> c2c_x;  irfftn runs backwards.  All transforms unnormalised.  The *_slab Fourier passes are the
+ * single-GPU ones evaluated on the local ky block [y0, y0 + ny_loc); `norm` multiplies the output (fold 1/N here). */
+typedef struct mcpm_slabfft mcpm_slabfft;
+int mcpm_slabfft_create(int nx, int ny, int nz, int parts, mcpm_slabfft** out);
+int mcpm_slabfft_destroy(mcpm_slabfft* h);
+int mcpm_slabfft_r2c_yz(mcpm_slabfft* h, void* stream, const float* in, void* out_c64, int nb);
+int mcpm_slabfft_c2r_yz(mcpm_slabfft* h, void* stream, void* in_c64, float* out, int nb);
+int mcpm_slabfft_c2c_x(mcpm_slabfft* h, void* stream, void* data_c64, int nb, int inverse);
+int mcpm_force_spectra_slab(void* stream, const void* delta_k, void* out3, int nx, int ny, int nz, int ny_loc, int y0,
+                            int lap_fd, int grad_fd, float kcut, int deconv_order, float norm);
+int mcpm_force_spectra_T_slab(void* stream, const void* in3, void* out1, int nx, int ny, int nz, int ny_loc, int y0,
+                              int lap_fd, int grad_fd, float kcut, int deconv_order, int half_weights, int accumulate,
+                              float norm);
+int mcpm_hessian_spectra_slab(void* stream, const void* delta_k, void* out6, int nx, int ny, int nz, int ny_loc, int y0,
+                              int lap_fd, int grad_fd, float norm);
+int mcpm_hessian_spectra_T_slab(void* stream, const void* in6, void* out1, int nx, int ny, int nz, int ny_loc, int y0,
+                                int lap_fd, int grad_fd, int half_weights, int accumulate, float norm);
+
 /* chreshape (utils.py:975-1013): Hermitian- and mean-preserving Fourier crop / pad between real shapes. */
 int mcpm_chreshape(void* stream, const void* in, int inx, int iny, int inz, void* out, int onx, int ony, int onz);
 

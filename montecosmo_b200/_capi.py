@@ -37,6 +37,15 @@ SIGNATURES = {
     "mcpm_deconv": ([vp, vp, vp] + MESH + [i32], i32),
     "mcpm_interlace_combine": ([vp, vp, vp, i32] + MESH + [f32, i32], i32),
     "mcpm_interlace_combine_T": ([vp, vp, vp, i32] + MESH + [f32, i32], i32),
+    "mcpm_slabfft_create": (MESH + [i32, C.POINTER(vp)], i32),
+    "mcpm_slabfft_destroy": ([vp], i32),
+    "mcpm_slabfft_r2c_yz": ([vp, vp, vp, vp, i32], i32),
+    "mcpm_slabfft_c2r_yz": ([vp, vp, vp, vp, i32], i32),
+    "mcpm_slabfft_c2c_x": ([vp, vp, vp, i32, i32], i32),
+    "mcpm_force_spectra_slab": ([vp, vp, vp] + MESH + [i32, i32, i32, i32, f32, i32, f32], i32),
+    "mcpm_force_spectra_T_slab": ([vp, vp, vp] + MESH + [i32, i32, i32, i32, f32, i32, i32, i32, f32], i32),
+    "mcpm_hessian_spectra_slab": ([vp, vp, vp] + MESH + [i32, i32, i32, i32, f32], i32),
+    "mcpm_hessian_spectra_T_slab": ([vp, vp, vp] + MESH + [i32, i32, i32, i32, i32, i32, f32], i32),
     "mcpm_chreshape": ([vp, vp] + MESH + [vp] + MESH, i32),
     "mcpm_chreshape_vjp": ([vp, vp] + MESH + [vp] + MESH, i32),
     "mcpm_hermitian_weights": ([vp, vp, vp] + MESH + [i32], i32),

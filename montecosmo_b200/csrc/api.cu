@@ -19,6 +19,11 @@ struct mcpm_engine {
   Engine* e;
 };
 
+struct mcpm_slabfft {
+  SlabFft* f;
+  int device;
+};
+
 #define API_BEGIN try {
 #define API_END                                  \
   }                                              \
@@ -245,6 +250,95 @@ int mcpm_interlace_combine_T(void* stream, const void* in, void* out_m, int m, i
   API_BEGIN
   return interlace_combine_T(as_stream(stream), C(in), C(out_m), m, nx, ny, nz, scale, deconv_order,
                              (float)((double)nx * ny * nz));
+  API_END
+}
+
+// ---- slab-decomposed building blocks ----------------------------------------------------------------------------
+int mcpm_slabfft_create(int nx, int ny, int nz, int parts, mcpm_slabfft** out) {
+  API_BEGIN
+  NEED(out, "slabfft_create: null out");
+  SlabFft* f = slabfft_create(nx, ny, nz, parts);
+  if (!f) return MCPM_ECUFFT;
+  *out = new mcpm_slabfft{f, rt_get_device()};
+  return MCPM_OK;
+  API_END
+}
+
+int mcpm_slabfft_destroy(mcpm_slabfft* h) {
+  if (!h) return MCPM_OK;
+  slabfft_destroy(h->f);
+  delete h;
+  return MCPM_OK;
+}
+
+int mcpm_slabfft_r2c_yz(mcpm_slabfft* h, void* stream, const float* in, void* out_c64, int nb) {
+  API_BEGIN
+  NEED(h && in && out_c64 && nb >= 1, "slabfft_r2c_yz: bad arguments");
+  if (int b = rt_bind_device(h->device)) return b;
+  return slabfft_r2c_yz(h->f, as_stream(stream), in, C(out_c64), nb);
+  API_END
+}
+
+int mcpm_slabfft_c2r_yz(mcpm_slabfft* h, void* stream, void* in_c64, float* out, int nb) {
+  API_BEGIN
+  NEED(h && in_c64 && out && nb >= 1, "slabfft_c2r_yz: bad arguments");
+  if (int b = rt_bind_device(h->device)) return b;
+  return slabfft_c2r_yz(h->f, as_stream(stream), C(in_c64), out, nb);
+  API_END
+}
+
+int mcpm_slabfft_c2c_x(mcpm_slabfft* h, void* stream, void* data_c64, int nb, int inverse) {
+  API_BEGIN
+  NEED(h && data_c64 && nb >= 1, "slabfft_c2c_x: bad arguments");
+  if (int b = rt_bind_device(h->device)) return b;
+  return slabfft_c2c_x(h->f, as_stream(stream), C(data_c64), nb, inverse);
+  API_END
+}
+
+int mcpm_force_spectra_slab(void* stream, const void* delta_k, void* out3, int nx, int ny, int nz, int ny_loc, int y0,
+                            int lap_fd, int grad_fd, float kcut, int deconv_order, float norm) {
+  API_BEGIN
+  NEED(ny_loc > 0 && y0 >= 0 && y0 + ny_loc <= ny, "force_spectra_slab: bad ky block");
+  SlabK sk;
+  sk.ny_loc = ny_loc;
+  sk.y0 = y0;
+  return force_spectra(as_stream(stream), C(delta_k), C(out3), nx, ny, nz, lap_fd, grad_fd, kcut, deconv_order, norm, sk);
+  API_END
+}
+
+int mcpm_force_spectra_T_slab(void* stream, const void* in3, void* out1, int nx, int ny, int nz, int ny_loc, int y0,
+                              int lap_fd, int grad_fd, float kcut, int deconv_order, int half_weights, int accumulate,
+                              float norm) {
+  API_BEGIN
+  NEED(ny_loc > 0 && y0 >= 0 && y0 + ny_loc <= ny, "force_spectra_T_slab: bad ky block");
+  SlabK sk;
+  sk.ny_loc = ny_loc;
+  sk.y0 = y0;
+  return force_spectra_T(as_stream(stream), C(in3), C(out1), nx, ny, nz, lap_fd, grad_fd, kcut, deconv_order,
+                         half_weights, accumulate, norm, sk);
+  API_END
+}
+
+int mcpm_hessian_spectra_slab(void* stream, const void* delta_k, void* out6, int nx, int ny, int nz, int ny_loc, int y0,
+                              int lap_fd, int grad_fd, float norm) {
+  API_BEGIN
+  NEED(ny_loc > 0 && y0 >= 0 && y0 + ny_loc <= ny, "hessian_spectra_slab: bad ky block");
+  SlabK sk;
+  sk.ny_loc = ny_loc;
+  sk.y0 = y0;
+  return hessian_spectra(as_stream(stream), C(delta_k), C(out6), nx, ny, nz, lap_fd, grad_fd, norm, sk);
+  API_END
+}
+
+int mcpm_hessian_spectra_T_slab(void* stream, const void* in6, void* out1, int nx, int ny, int nz, int ny_loc, int y0,
+                                int lap_fd, int grad_fd, int half_weights, int accumulate, float norm) {
+  API_BEGIN
+  NEED(ny_loc > 0 && y0 >= 0 && y0 + ny_loc <= ny, "hessian_spectra_T_slab: bad ky block");
+  SlabK sk;
+  sk.ny_loc = ny_loc;
+  sk.y0 = y0;
+  return hessian_spectra_T(as_stream(stream), C(in6), C(out1), nx, ny, nz, lap_fd, grad_fd, half_weights, accumulate,
+                           norm, sk);
   API_END
 }
 

@@ -55,15 +55,29 @@ int rsd_shift(stream_t, const float* pos, const float* vel, float lx, float ly, 
 int rsd_shift_vjp(stream_t, const float* posbar, float lx, float ly, float lz, float coef, int64_t np, float* velbar,
                   int accumulate);
 
+// Local ky block of a slab-decomposed half spectrum [nx, ny_loc, nz/2+1]; ny_loc = 0 means the full mesh.
+struct SlabK {
+  int ny_loc = 0, y0 = 0;
+};
+
+// Distributed-FFT building blocks for slab decomposition over `parts` ranks (fft.cu): batched 2-D transforms over (y,z)
+// of the local x-planes, and 1-D transforms along x of the local ky block.  All unnormalised.
+struct SlabFft;
+SlabFft* slabfft_create(int nx, int ny, int nz, int parts);
+void slabfft_destroy(SlabFft*);
+int slabfft_r2c_yz(SlabFft*, stream_t, const float* in, cfloat* out, int nb);   // [nb, xl, ny, nz] -> [nb, xl, ny, nzc]
+int slabfft_c2r_yz(SlabFft*, stream_t, cfloat* in, float* out, int nb);         // inverse, may overwrite its input
+int slabfft_c2c_x(SlabFft*, stream_t, cfloat* data, int nb, int inverse);       // in place on [nb][nx, kyl, nzc]
+
 // fourier.cu  (`norm` multiplies the output; the engine passes 1/N ahead of a raw C2R)
 int force_spectra(stream_t, const cfloat* dk, cfloat* out3, int nx, int ny, int nz, int lap_fd, int grad_fd,
-                  float kcut, int deconv_order, float norm);
+                  float kcut, int deconv_order, float norm, SlabK sk = SlabK());
 int force_spectra_T(stream_t, const cfloat* in3, cfloat* out1, int nx, int ny, int nz, int lap_fd, int grad_fd,
-                    float kcut, int deconv_order, int half_weights, int accumulate, float norm);
+                    float kcut, int deconv_order, int half_weights, int accumulate, float norm, SlabK sk = SlabK());
 int hessian_spectra(stream_t, const cfloat* dk, cfloat* out6, int nx, int ny, int nz, int lap_fd, int grad_fd,
-                    float norm);
+                    float norm, SlabK sk = SlabK());
 int hessian_spectra_T(stream_t, const cfloat* in6, cfloat* out1, int nx, int ny, int nz, int lap_fd, int grad_fd,
-                      int half_weights, int accumulate, float norm);
+                      int half_weights, int accumulate, float norm, SlabK sk = SlabK());
 int lpt2_source(stream_t, const float* h6, float* d2, int64_t n);
 int lpt2_source_vjp(stream_t, const float* h6, const float* d2bar, float* hbar6, int64_t n);
 int deconv(stream_t, const cfloat* in, cfloat* out, int nx, int ny, int nz, int order);

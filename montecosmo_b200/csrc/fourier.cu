@@ -7,18 +7,23 @@
 
 namespace mcpm {
 
+// Local block of the half spectrum [nx, ny_loc, nz/2+1] holding global ky rows y0 .. y0 + ny_loc - 1 (slab-decomposed
+// runs keep k-space split along ky; single-GPU: ny_loc = ny, y0 = 0).
 struct KGrid {
   int nx, ny, nz, nzc;
+  int ny_loc, y0;
   float tx, ty, tz;  // 2*pi / n
   int lap_fd, grad_fd;
 };
 
-static KGrid make_kgrid(int nx, int ny, int nz, int lap_fd = 0, int grad_fd = 0) {
+static KGrid make_kgrid(int nx, int ny, int nz, int lap_fd = 0, int grad_fd = 0, SlabK sk = SlabK()) {
   KGrid g;
   g.nx = nx;
   g.ny = ny;
   g.nz = nz;
   g.nzc = nz / 2 + 1;
+  g.ny_loc = sk.ny_loc > 0 ? sk.ny_loc : ny;
+  g.y0 = sk.ny_loc > 0 ? sk.y0 : 0;
   g.tx = (float)(6.283185307179586476925 / nx);
   g.ty = (float)(6.283185307179586476925 / ny);
   g.tz = (float)(6.283185307179586476925 / nz);
@@ -37,8 +42,8 @@ struct KVec {
 MCPM_HD KVec kvec_at(const KGrid& g, int64_t e, int& l) {
   l = (int)(e % g.nzc);
   int64_t r = e / g.nzc;
-  int j = (int)(r % g.ny);
-  int i = (int)(r / g.ny);
+  int j = (int)(r % g.ny_loc) + g.y0;
+  int i = (int)(r / g.ny_loc);
   KVec k;
   k.kx = g.tx * (float)signed_freq(i, g.nx);
   k.ky = g.ty * (float)signed_freq(j, g.ny);
@@ -112,11 +117,11 @@ static int check_fd(int fd) {
 
 // out_j = -(i g_j) * c * delta   (nbody.py:597-603)
 int force_spectra(stream_t st, const cfloat* dk, cfloat* out3, int nx, int ny, int nz, int lap_fd, int grad_fd,
-                  float kcut, int deconv_order, float norm) {
+                  float kcut, int deconv_order, float norm, SlabK sk) {
   if (int e = check_dims(nx, ny, nz)) return e;
   if (int e = check_fd(lap_fd) ? check_fd(lap_fd) : check_fd(grad_fd)) return e;
-  KGrid g = make_kgrid(nx, ny, nz, lap_fd, grad_fd);
-  const int64_t nc = (int64_t)nx * ny * g.nzc;
+  KGrid g = make_kgrid(nx, ny, nz, lap_fd, grad_fd, sk);
+  const int64_t nc = (int64_t)nx * g.ny_loc * g.nzc;
   const float r2 = rcut2_half_of(kcut);
   launch_1d(st, nc, [=] MCPM_LAMBDA(int64_t e) {
     int l;
@@ -135,11 +140,11 @@ int force_spectra(stream_t st, const cfloat* dk, cfloat* out3, int nx, int ny, i
 
 // transpose pass: out (+)= [w'/N] * sum_j conj(-(i g_j) c) in_j = [w'/N] * c * i * sum_j g_j in_j
 int force_spectra_T(stream_t st, const cfloat* in3, cfloat* out1, int nx, int ny, int nz, int lap_fd, int grad_fd,
-                    float kcut, int deconv_order, int half_weights, int accumulate, float norm) {
+                    float kcut, int deconv_order, int half_weights, int accumulate, float norm, SlabK sk) {
   if (int e = check_dims(nx, ny, nz)) return e;
   if (int e = check_fd(lap_fd) ? check_fd(lap_fd) : check_fd(grad_fd)) return e;
-  KGrid g = make_kgrid(nx, ny, nz, lap_fd, grad_fd);
-  const int64_t nc = (int64_t)nx * ny * g.nzc;
+  KGrid g = make_kgrid(nx, ny, nz, lap_fd, grad_fd, sk);
+  const int64_t nc = (int64_t)nx * g.ny_loc * g.nzc;
   const float r2 = rcut2_half_of(kcut);
   const float invn = (float)(1.0 / ((double)nx * ny * nz));
   launch_1d(st, nc, [=] MCPM_LAMBDA(int64_t e) {
@@ -165,11 +170,11 @@ int force_spectra_T(stream_t st, const cfloat* in3, cfloat* out1, int nx, int ny
 
 // out_ij = (i g_i)(i g_j) * invlaplace * delta = -g_i g_j G delta ; order 00, 11, 22, 01, 02, 12  (nbody.py:611-627)
 int hessian_spectra(stream_t st, const cfloat* dk, cfloat* out6, int nx, int ny, int nz, int lap_fd, int grad_fd,
-                    float norm) {
+                    float norm, SlabK sk) {
   if (int e = check_dims(nx, ny, nz)) return e;
   if (int e = check_fd(lap_fd) ? check_fd(lap_fd) : check_fd(grad_fd)) return e;
-  KGrid g = make_kgrid(nx, ny, nz, lap_fd, grad_fd);
-  const int64_t nc = (int64_t)nx * ny * g.nzc;
+  KGrid g = make_kgrid(nx, ny, nz, lap_fd, grad_fd, sk);
+  const int64_t nc = (int64_t)nx * g.ny_loc * g.nzc;
   launch_1d(st, nc, [=] MCPM_LAMBDA(int64_t e) {
     int l;
     KVec k = kvec_at(g, e, l);
@@ -188,11 +193,11 @@ int hessian_spectra(stream_t st, const cfloat* dk, cfloat* out6, int nx, int ny,
 }
 
 int hessian_spectra_T(stream_t st, const cfloat* in6, cfloat* out1, int nx, int ny, int nz, int lap_fd, int grad_fd,
-                      int half_weights, int accumulate, float norm) {
+                      int half_weights, int accumulate, float norm, SlabK sk) {
   if (int e = check_dims(nx, ny, nz)) return e;
   if (int e = check_fd(lap_fd) ? check_fd(lap_fd) : check_fd(grad_fd)) return e;
-  KGrid g = make_kgrid(nx, ny, nz, lap_fd, grad_fd);
-  const int64_t nc = (int64_t)nx * ny * g.nzc;
+  KGrid g = make_kgrid(nx, ny, nz, lap_fd, grad_fd, sk);
+  const int64_t nc = (int64_t)nx * g.ny_loc * g.nzc;
   const float invn = (float)(1.0 / ((double)nx * ny * nz));
   launch_1d(st, nc, [=] MCPM_LAMBDA(int64_t e) {
     int l;

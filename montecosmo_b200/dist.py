@@ -1,0 +1,308 @@
+"""
+Slab-decomposed particle-mesh engine over torch.distributed (one process per GPU, NCCL) -- SURVEY section 8e.
+
+Decomposition ("Lagrangian slabs"): the mesh [nx, ny, nz] is split along x; rank r owns planes [r*xl, (r+1)*xl) and,
+permanently, the particles whose LATTICE x-coordinate lies there.  Particles of a PM run move a bounded distance from
+their lattice site (rms ~2 cells, max ~15 at 2.5 Mpc/h cells), so each rank works on a local mesh extended by H halo
+planes on both sides and no particle ever migrates: perfect load balance, fixed-size buffers, a trivial tape.  A guard
+(checked once per call) raises if any particle comes within a cell of the edge of its extended slab.
+HBM is plentiful (180 GB): the halo costs (2H / xl) extra mesh memory and NVLink traffic, nothing else.
+
+Exchange steps per force evaluation (everything else is the single-GPU kernels on the local extended mesh):
+  * after paint:      halo planes are SENT to the neighbours and ADDED to their owned planes        (halo_reduce)
+  * before readout:   halo planes are FETCHED from the neighbours' owned planes                      (halo_gather)
+  * each 3-D FFT:     2-D FFT over (y,z) of the local planes -> all-to-all (x-planes for ky rows) -> 1-D FFT along x;
+                      k-space stays split along ky, layout [nx, kyl, nz/2+1]                           (rfftn / irfftn)
+halo_gather is the exact transpose of halo_reduce and irfftn o diag(m) o rfftn transposes as on one GPU, so the reverse
+sweep is the same sequence with scatter and gather swapping roles.
+
+Positions handed to / returned by this class are in LOCAL coordinates: x_local = x_global - (x0 - H); y, z global.
+Reference semantics: montecosmo/nbody.py:583-604 (pm_forces), 634-667 (lpt), 933-951 (BullFrog step).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ._capi import check, fd_code
+
+INF = float("inf")
+
+
+class SlabPM:
+    def __init__(self, ops, mesh_shape, halo=24, group=None):
+        self.o, self.lib, self.A = ops, ops.lib, ops.A
+        self.group = group
+        self.P = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        nx, ny, nz = (int(s) for s in mesh_shape)
+        if nx % self.P or ny % self.P or nz % 2:
+            raise ValueError("mesh sides nx, ny must be divisible by the number of ranks and nz even")
+        self.nx, self.ny, self.nz, self.nzc = nx, ny, nz, nz // 2 + 1
+        self.xl, self.kyl = nx // self.P, ny // self.P
+        self.H = int(halo)
+        if not (1 <= self.H <= self.xl):
+            raise ValueError(f"halo must be in [1, {self.xl}] (neighbour-only exchange)")
+        self.ext = self.xl + 2 * self.H
+        self.x0, self.y0 = self.rank * self.xl, self.rank * self.kyl
+        self.N = nx * ny * nz
+        self.npl = self.xl * ny * nz  # local particles (lattice == mesh)
+        h = C.c_void_p()
+        check(self.lib, self.lib.mcpm_slabfft_create(nx, ny, nz, self.P, C.byref(h)))
+        self._fft = h
+        self.prev, self.next = (self.rank - 1) % self.P, (self.rank + 1) % self.P
+        ax = [np.arange(self.xl, dtype=np.float32), np.arange(ny, dtype=np.float32), np.arange(nz, dtype=np.float32)]
+        self.q_own = self.A.prepare(np.stack(np.meshgrid(*ax, indexing="ij"), -1).reshape(-1, 3))  # owned-slab coords
+        self._oob = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_fft", None):
+                self.lib.mcpm_slabfft_destroy(self._fft)
+                self._fft = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------------ helpers
+    def _call(self, name, *args):
+        check(self.lib, getattr(self.lib, name)(*args))
+
+    def _st(self):
+        return self.A.stream()
+
+    def _global_rank(self, r):
+        return dist.get_global_rank(self.group, r) if self.group is not None else r
+
+    def scatter_real(self, full):
+        """Global real mesh [.., nx, ny, nz] -> my owned planes (test / setup helper)."""
+        return self.A.prepare(full[..., self.x0:self.x0 + self.xl, :, :])
+
+    def scatter_spectrum(self, full_k):
+        """Global half spectrum [nx, ny, nzc] -> my ky block [nx, kyl, nzc]."""
+        return self.A.prepare(full_k[..., :, self.y0:self.y0 + self.kyl, :], "c64")
+
+    # ------------------------------------------------------------------------------------------------ distributed FFT
+    def _a2a(self, send):
+        if self.P == 1:
+            return send
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(send), group=self.group)
+        return recv
+
+    def rfftn(self, a):
+        """[nb, xl, ny, nz] real (owned planes) -> [nb, nx, kyl, nzc] complex (my ky block), unnormalised."""
+        a = self.A.prepare(a)
+        nb = a.shape[0]
+        b = self.A.empty((nb, self.xl, self.ny, self.nzc), "c64")
+        self._call("mcpm_slabfft_r2c_yz", self._fft, self._st(), a.data_ptr(), b.data_ptr(), nb)
+        # send[q] = my planes restricted to rank q's ky rows
+        send = b.view(nb, self.xl, self.P, self.kyl, self.nzc).permute(2, 0, 1, 3, 4).contiguous()
+        recv = self._a2a(send)  # recv[q] = rank q's planes, my ky rows
+        c = recv.permute(1, 0, 2, 3, 4).contiguous().view(nb, self.nx, self.kyl, self.nzc)
+        self._call("mcpm_slabfft_c2c_x", self._fft, self._st(), c.data_ptr(), nb, 0)
+        return c
+
+    def irfftn(self, c, overwrite=False):
+        """[nb, nx, kyl, nzc] complex -> [nb, xl, ny, nz] real, UNNORMALISED (fold 1/N into the preceding Fourier pass)."""
+        c = self.A.prepare(c, "c64")
+        if not overwrite:
+            c = c.clone()
+        nb = c.shape[0]
+        self._call("mcpm_slabfft_c2c_x", self._fft, self._st(), c.data_ptr(), nb, 1)
+        send = c.view(nb, self.P, self.xl, self.kyl, self.nzc).permute(1, 0, 2, 3, 4).contiguous()
+        recv = self._a2a(send)  # recv[q] = my planes, rank q's ky rows
+        b = recv.permute(1, 2, 0, 3, 4).contiguous().view(nb, self.xl, self.ny, self.nzc)
+        out = self.A.empty((nb, self.xl, self.ny, self.nz))
+        self._call("mcpm_slabfft_c2r_yz", self._fft, self._st(), b.data_ptr(), out.data_ptr(), nb)
+        return out
+
+    # ------------------------------------------------------------------------------------------------ halos
+    def _exchange(self, to_prev, to_next, from_next, from_prev):
+        if self.P == 1:
+            from_next.copy_(to_prev)
+            from_prev.copy_(to_next)
+            return
+        ops = [dist.P2POp(dist.isend, to_prev, self._global_rank(self.prev), self.group),
+               dist.P2POp(dist.isend, to_next, self._global_rank(self.next), self.group),
+               dist.P2POp(dist.irecv, from_next, self._global_rank(self.next), self.group),
+               dist.P2POp(dist.irecv, from_prev, self._global_rank(self.prev), self.group)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+    def halo_reduce(self, ext):
+        """ext [ext, ny, nz(,4)]: send both halos to the neighbours, add theirs into my owned planes."""
+        H, xl = self.H, self.xl
+        a, b = torch.empty_like(ext[:H]), torch.empty_like(ext[:H])
+        self._exchange(ext[:H].contiguous(), ext[H + xl:].contiguous(), a, b)
+        ext[xl:xl + H] += a  # next's left halo covers my last H owned planes
+        ext[H:2 * H] += b  # prev's right halo covers my first H owned planes
+
+    def halo_gather(self, ext):
+        """ext [ext, ny, nz(,4)]: fill both halos from the neighbours' owned planes (transpose of halo_reduce)."""
+        H, xl = self.H, self.xl
+        right, left = torch.empty_like(ext[:H]), torch.empty_like(ext[:H])
+        self._exchange(ext[H:2 * H].contiguous(), ext[xl:xl + H].contiguous(), right, left)
+        ext[H + xl:] = right
+        ext[:H] = left
+
+    def _guard(self, pos):
+        x = pos[:, 0]
+        bad = ((x < 1.0) | (x > self.ext - 2.0)).any()
+        self._oob = bad if self._oob is None else (self._oob | bad)
+
+    def check_guard(self):
+        """Raise if any particle came within a cell of the edge of its extended slab since the last check (one sync)."""
+        if self._oob is not None and bool(self._oob):
+            self._oob = None
+            raise RuntimeError(f"a particle left its extended slab: increase halo (= {self.H} planes)")
+        self._oob = None
+
+    # ------------------------------------------------------------------------------------------------ Fourier passes
+    def force_spectra(self, dk, lap_fd=INF, grad_fd=INF, deconv_order=0):
+        out = self.A.empty((3, self.nx, self.kyl, self.nzc), "c64")
+        self._call("mcpm_force_spectra_slab", self._st(), dk.data_ptr(), out.data_ptr(), self.nx, self.ny, self.nz,
+                   self.kyl, self.y0, fd_code(lap_fd), fd_code(grad_fd), 0.0, deconv_order, 1.0 / self.N)
+        return out
+
+    def force_spectra_T(self, in3, out=None, half_weights=False, lap_fd=INF, grad_fd=INF, deconv_order=0):
+        acc = out is not None
+        out = self.A.empty((self.nx, self.kyl, self.nzc), "c64") if out is None else out
+        self._call("mcpm_force_spectra_T_slab", self._st(), in3.data_ptr(), out.data_ptr(), self.nx, self.ny, self.nz,
+                   self.kyl, self.y0, fd_code(lap_fd), fd_code(grad_fd), 0.0, deconv_order, int(half_weights), int(acc),
+                   1.0 if half_weights else 1.0 / self.N)
+        return out
+
+    # ------------------------------------------------------------------------------------------------ force step
+    def force_mesh4(self, pos, order=2):
+        """Extended float4 force mesh {Fx,Fy,Fz,0} [ext, ny, nz, 4] at the local positions (nbody.py:583-603)."""
+        A, lib, st = self.A, self.lib, self._st()
+        rho = A.zeros((self.ext, self.ny, self.nz))
+        one = (C.c_float * 3)(1.0, 1.0, 1.0)
+        self._call("mcpm_paint", st, pos.data_ptr(), 0, 1.0, pos.shape[0], self.ext, self.ny, self.nz, order, one, 0.0,
+                   rho.data_ptr(), 1)
+        self.halo_reduce(rho)
+        rk = self.rfftn(rho[self.H:self.H + self.xl].unsqueeze(0))
+        F = self.irfftn(self.force_spectra(rk[0]), overwrite=True)  # [3, xl, ny, nz]
+        fm4 = A.empty((self.ext, self.ny, self.nz, 4))
+        own = fm4[self.H:self.H + self.xl]
+        self._call("mcpm_interleave3", st, F.data_ptr(), own.data_ptr(), self.xl * self.ny * self.nz)
+        self.halo_gather(fm4)
+        return fm4
+
+    def steps_forward(self, pos, vel, alpha, beta, drift_pre, drift_post, tape=True):
+        """BullFrog DKD steps in place on local (pos, vel); CIC.  Returns the tape [(x_kick, fm4), ...]."""
+        ns = len(alpha)
+        st = self._st()
+        self._call("mcpm_drift", st, pos.data_ptr(), vel.data_ptr(), float(drift_pre[0]), pos.shape[0])
+        out = []
+        for s in range(ns):
+            self._guard(pos)
+            fm4 = self.force_mesh4(pos)
+            if tape:
+                out.append((pos.clone(), fm4))
+            dcomb = float(drift_post[s]) + (float(drift_pre[s + 1]) if s + 1 < ns else 0.0)
+            self._call("mcpm_kick_drift4", st, pos.data_ptr(), vel.data_ptr(), fm4.data_ptr(), pos.shape[0], self.ext,
+                       self.ny, self.nz, float(alpha[s]), float(beta[s]), dcomb)
+        self._guard(pos)
+        return out
+
+    def steps_backward(self, tape, posbar, velbar, alpha, beta, drift_pre, drift_post):
+        """Reverse sweep of steps_forward, in place on (posbar, velbar)."""
+        A, st = self.A, self._st()
+        ns = len(alpha)
+        n = posbar.shape[0]
+        cells = self.xl * self.ny * self.nz
+        for s in reversed(range(ns)):
+            x1, fm4 = tape[s]
+            dcomb = float(drift_post[s]) + (float(drift_pre[s + 1]) if s + 1 < ns else 0.0)
+            m4 = A.zeros((self.ext, self.ny, self.nz, 4))
+            self._call("mcpm_paint3v4", st, x1.data_ptr(), velbar.data_ptr(), posbar.data_ptr(), dcomb, float(beta[s]),
+                       n, self.ext, self.ny, self.nz, m4.data_ptr())
+            self.halo_reduce(m4)
+            planar = A.empty((3, self.xl, self.ny, self.nz))
+            self._call("mcpm_deinterleave3", st, m4[self.H:self.H + self.xl].data_ptr(), planar.data_ptr(), cells)
+            rk = self.force_spectra_T(self.rfftn(planar))
+            rhobar = A.empty((self.ext, self.ny, self.nz))
+            rhobar[self.H:self.H + self.xl] = self.irfftn(rk.unsqueeze(0), overwrite=True)[0]
+            self.halo_gather(rhobar)
+            self._call("mcpm_read_grad4v", st, x1.data_ptr(), fm4.data_ptr(), rhobar.data_ptr(), velbar.data_ptr(),
+                       float(beta[s]), float(alpha[s]), n, self.ext, self.ny, self.nz, posbar.data_ptr())
+        self._call("mcpm_drift", st, velbar.data_ptr(), posbar.data_ptr(), float(drift_pre[0]), n)
+
+    # ------------------------------------------------------------------------------------------------ LPT
+    def _lattice_read3(self, planar3):
+        """NGP read of three owned-slab meshes at the owned lattice sites -> [npl, 3] (nbody.py:602 note)."""
+        out = self.A.empty((self.npl, 3))
+        one = (C.c_float * 3)(1.0, 1.0, 1.0)
+        self._call("mcpm_read", self._st(), self.q_own.data_ptr(), planar3.data_ptr(), 3, self.npl, self.xl, self.ny,
+                   self.nz, 1, one, 0.0, out.data_ptr())
+        return out
+
+    def _lattice_paint3(self, vals3):
+        out = self.A.empty((3, self.xl, self.ny, self.nz))
+        self._call("mcpm_paint3", self._st(), self.q_own.data_ptr(), vals3.data_ptr(), 1.0, self.npl, self.xl, self.ny,
+                   self.nz, 1, out.data_ptr(), 0)
+        return out
+
+    def lpt_forward(self, dk, d1, d2, dv2, lpt_order=2):
+        """delta_k block [nx, kyl, nzc] -> local (pos, vel) of the owned lattice particles and the tape (nbody.py:634-667)."""
+        A, st = self.A, self._st()
+        dk = A.prepare(dk, "c64")
+        f1 = self._lattice_read3(self.irfftn(self.force_spectra(dk), overwrite=True))
+        f2 = h6 = None
+        if lpt_order == 2:
+            h6k = A.empty((6, self.nx, self.kyl, self.nzc), "c64")
+            self._call("mcpm_hessian_spectra_slab", st, dk.data_ptr(), h6k.data_ptr(), self.nx, self.ny, self.nz, self.kyl,
+                       self.y0, 0, 0, 1.0 / self.N)
+            h6 = self.irfftn(h6k, overwrite=True)
+            d2m = A.empty((1, self.xl, self.ny, self.nz))
+            self._call("mcpm_lpt2_source", st, h6.data_ptr(), d2m.data_ptr(), self.xl * self.ny * self.nz)
+            f2 = self._lattice_read3(self.irfftn(self.force_spectra(self.rfftn(d2m)[0]), overwrite=True))
+        dpos, vel = A.empty((self.npl, 3)), A.empty((self.npl, 3))
+        self._call("mcpm_lpt_combine", st, 0, f1.data_ptr(), 0 if f2 is None else f2.data_ptr(), float(d1), float(d2),
+                   float(dv2), self.npl, dpos.data_ptr(), vel.data_ptr(), 0)
+        q_ext = self.q_own.clone()
+        q_ext[:, 0] += self.H
+        pos = self.o.axpby(dpos, 1.0, q_ext, 1.0)
+        return pos, vel, (h6, (float(d1), float(d2), float(dv2)), lpt_order)
+
+    def lpt_backward(self, tape, posbar, velbar):
+        """(posbar, velbar) -> cotangent of the delta_k block, convention dL/dRe + i dL/dIm (engine.cu:lpt_vjp)."""
+        A, st, o = self.A, self._st(), self.o
+        h6, (d1, d2, dv2), lpt_order = tape
+        dkbar = None
+        if lpt_order == 2:
+            f2bar = o.axpby(posbar, -d2, velbar, -dv2)
+            rk = self.force_spectra_T(self.rfftn(self._lattice_paint3(f2bar)))
+            d2bar = self.irfftn(rk.unsqueeze(0), overwrite=True)
+            hbar = A.empty((6, self.xl, self.ny, self.nz))
+            self._call("mcpm_lpt2_source_vjp", st, h6.data_ptr(), d2bar.data_ptr(), hbar.data_ptr(),
+                       self.xl * self.ny * self.nz)
+            hk = self.rfftn(hbar)
+            dkbar = A.empty((self.nx, self.kyl, self.nzc), "c64")
+            self._call("mcpm_hessian_spectra_T_slab", st, hk.data_ptr(), dkbar.data_ptr(), self.nx, self.ny, self.nz,
+                       self.kyl, self.y0, 0, 0, 1, 0, 1.0)
+        f1bar = o.axpby(posbar, d1, velbar, 1.0)
+        return self.force_spectra_T(self.rfftn(self._lattice_paint3(f1bar)), out=dkbar, half_weights=True)
+
+    # ------------------------------------------------------------------------------------------------ nbody_bf
+    def nbody_forward(self, dk, cosmo, a0=0.0, a1=1.0, n_steps=5, lpt_order=2):
+        """lpt at a0 then n_steps BullFrog steps (nbody.py:967-1002) on this rank's particles.  Returns local (pos, vel)
+        and the tape for nbody_backward."""
+        from . import cosmo as _c
+        d1, d2, dv2 = float(_c.a2g(cosmo, a0)), float(_c.a2g2(cosmo, a0)), float(_c.a2dg2dg(cosmo, a0))
+        al, be, pre, post, _, _ = _c.bullfrog_coefficients(cosmo, a0, a1, n_steps)
+        co = [t.tolist() for t in (al, be, pre, post)]
+        pos, vel, ltape = self.lpt_forward(dk, d1, d2, dv2, lpt_order)
+        stape = self.steps_forward(pos, vel, *co)
+        self.check_guard()
+        return pos, vel, (ltape, stape, co)
+
+    def nbody_backward(self, tape, posbar, velbar):
+        ltape, stape, co = tape
+        posbar, velbar = posbar.clone(), velbar.clone()
+        self.steps_backward(stape, posbar, velbar, *co)
+        return self.lpt_backward(ltape, posbar, velbar)

@@ -64,6 +64,23 @@ def _c2r(inp, out, nx, ny, nz, batch):
     o[...] = sfft.irfftn(a, s=(nx, ny, nz), axes=(1, 2, 3), workers=-1, norm="forward")  # unnormalised, like cuFFT C2R
 
 
+_SLABHOOK = C.CFUNCTYPE(None, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)
+
+
+def _slab(kind, inp, out, nx, ny, nz, nb, xl, kyl):
+    nzc = nz // 2 + 1
+    if kind == 0:  # 2-D R2C over (y, z) of the local planes
+        a = _as(inp, np.float32, (nb, xl, ny, nz))
+        _as(out, np.complex64, (nb, xl, ny, nzc))[...] = sfft.rfftn(a, axes=(2, 3), workers=-1)
+    elif kind == 1:  # 2-D C2R, unnormalised
+        a = _as(inp, np.complex64, (nb, xl, ny, nzc))
+        _as(out, np.float32, (nb, xl, ny, nz))[...] = sfft.irfftn(a, s=(ny, nz), axes=(2, 3), workers=-1, norm="forward")
+    else:  # 1-D C2C along x of the local ky block, in place, unnormalised
+        a = _as(inp, np.complex64, (nb, nx, kyl, nzc))
+        res = sfft.fft(a, axis=1, workers=-1) if kind == 2 else sfft.ifft(a, axis=1, workers=-1, norm="forward")
+        _as(out, np.complex64, (nb, nx, kyl, nzc))[...] = res
+
+
 def load():
     """The CPU library with prototypes bound and FFT hooks registered."""
     global _lib
@@ -76,6 +93,11 @@ def load():
         r2c, c2r = _HOOK(_r2c), _HOOK(_c2r)
         _keep.extend([r2c, c2r])
         lib.mcpm_hostemu_set_fft(r2c, c2r)
+        lib.mcpm_hostemu_set_slabfft.argtypes = [_SLABHOOK]
+        lib.mcpm_hostemu_set_slabfft.restype = None
+        sh = _SLABHOOK(_slab)
+        _keep.append(sh)
+        lib.mcpm_hostemu_set_slabfft(sh)
         _lib = lib
     return _lib
 

@@ -37,6 +37,13 @@ MCPM_HD int signed_freq(int i, int n) { return i < (n + 1) / 2 ? i : i - n; }
 
 struct KVec {
   float kx, ky, kz;
+  // Hermitian consistency.  jnp.fft.irfftn of a spectrum that violates Hermitian symmetry keeps only its Hermitian
+  // projection on the self-conjugate planes kz = 0 and kz = Nyquist; cuFFT's C2R on such input is algorithm dependent
+  // (its batched 2-D C2R differed by 2.5% at batch 16).  For kernel x Hermitian field the projection is zero wherever the
+  // kernel is odd under k -> -k, i.e. carries an odd number of Nyquist-valued gradient factors (rfftk puts -pi on x, y
+  // and +pi on z, nbody.py:72-76, and -k maps a Nyquist index onto itself).  sc: element lies on a self-conjugate plane;
+  // nq*: that component is at its Nyquist index.
+  bool sc, nqx, nqy, nqz;
 };
 
 MCPM_HD KVec kvec_at(const KGrid& g, int64_t e, int& l) {
@@ -48,6 +55,10 @@ MCPM_HD KVec kvec_at(const KGrid& g, int64_t e, int& l) {
   k.kx = g.tx * (float)signed_freq(i, g.nx);
   k.ky = g.ty * (float)signed_freq(j, g.ny);
   k.kz = g.tz * (float)l;
+  k.nqx = 2 * i == g.nx;
+  k.nqy = 2 * j == g.ny;
+  k.nqz = 2 * l == g.nz;
+  k.sc = l == 0 || k.nqz;
   return k;
 }
 
@@ -66,6 +77,17 @@ MCPM_HD float grad_term(float k, int fd) {
   if (fd == 2) return sinf(k);
   if (fd == 4) return (8.0f * sinf(k) - sinf(2.0f * k)) * (1.0f / 6.0f);
   return k;
+}
+// the three gradient factors, with the Hermitian projection applied when the result feeds a C2R (see KVec)
+MCPM_HD void grad_terms(const KGrid& g, const KVec& k, float& gx, float& gy, float& gz, bool project = true) {
+  gx = grad_term(k.kx, g.grad_fd);
+  gy = grad_term(k.ky, g.grad_fd);
+  gz = grad_term(k.kz, g.grad_fd);
+  if (project && k.sc) {
+    if (k.nqx) gx = 0.0f;
+    if (k.nqy) gy = 0.0f;
+    if (k.nqz) gz = 0.0f;
+  }
 }
 // sinc(k / 2pi) = sin(k/2) / (k/2)
 MCPM_HD float sinc_half(float k) {
@@ -130,7 +152,8 @@ int force_spectra(stream_t st, const cfloat* dk, cfloat* out3, int nx, int ny, i
     cfloat d = dk[e];
     // (-i)(a + ib) = b - ia
     float re = d.im * c, im = -d.re * c;
-    float gx = grad_term(k.kx, g.grad_fd), gy = grad_term(k.ky, g.grad_fd), gz = grad_term(k.kz, g.grad_fd);
+    float gx, gy, gz;
+    grad_terms(g, k, gx, gy, gz);
     out3[e] = cfloat{gx * re, gx * im};
     out3[nc + e] = cfloat{gy * re, gy * im};
     out3[2 * nc + e] = cfloat{gz * re, gz * im};
@@ -152,7 +175,9 @@ int force_spectra_T(stream_t st, const cfloat* in3, cfloat* out1, int nx, int ny
     KVec k = kvec_at(g, e, l);
     float c = force_scalar(g, k, r2, deconv_order) * norm;
     if (half_weights) c *= half_weight(l, g.nz) * invn;
-    float gx = grad_term(k.kx, g.grad_fd), gy = grad_term(k.ky, g.grad_fd), gz = grad_term(k.kz, g.grad_fd);
+    // half_weights: the output is the cotangent of a free complex array (as autodiff returns it), not a C2R input
+    float gx, gy, gz;
+    grad_terms(g, k, gx, gy, gz, !half_weights);
     cfloat a = in3[e], b = in3[nc + e], d = in3[2 * nc + e];
     float sre = gx * a.re + gy * b.re + gz * d.re;
     float sim = gx * a.im + gy * b.im + gz * d.im;
@@ -180,14 +205,18 @@ int hessian_spectra(stream_t st, const cfloat* dk, cfloat* out6, int nx, int ny,
     KVec k = kvec_at(g, e, l);
     float c = -invlaplace(g, k) * norm;
     float gx = grad_term(k.kx, g.grad_fd), gy = grad_term(k.ky, g.grad_fd), gz = grad_term(k.kz, g.grad_fd);
+    // mixed terms are odd under k -> -k when exactly one of the two factors sits at its Nyquist index (see KVec)
+    float mxy = (k.sc && k.nqx != k.nqy) ? 0.0f : gx * gy;
+    float mxz = (k.sc && k.nqx != k.nqz) ? 0.0f : gx * gz;
+    float myz = (k.sc && k.nqy != k.nqz) ? 0.0f : gy * gz;
     cfloat d = dk[e];
     float re = d.re * c, im = d.im * c;
     out6[e] = cfloat{gx * gx * re, gx * gx * im};
     out6[nc + e] = cfloat{gy * gy * re, gy * gy * im};
     out6[2 * nc + e] = cfloat{gz * gz * re, gz * gz * im};
-    out6[3 * nc + e] = cfloat{gx * gy * re, gx * gy * im};
-    out6[4 * nc + e] = cfloat{gx * gz * re, gx * gz * im};
-    out6[5 * nc + e] = cfloat{gy * gz * re, gy * gz * im};
+    out6[3 * nc + e] = cfloat{mxy * re, mxy * im};
+    out6[4 * nc + e] = cfloat{mxz * re, mxz * im};
+    out6[5 * nc + e] = cfloat{myz * re, myz * im};
   });
   return rt_check("hessian_spectra");
 }
@@ -205,7 +234,9 @@ int hessian_spectra_T(stream_t st, const cfloat* in6, cfloat* out1, int nx, int 
     float c = -invlaplace(g, k) * norm;
     if (half_weights) c *= half_weight(l, g.nz) * invn;
     float gx = grad_term(k.kx, g.grad_fd), gy = grad_term(k.ky, g.grad_fd), gz = grad_term(k.kz, g.grad_fd);
-    float w[6] = {gx * gx, gy * gy, gz * gz, gx * gy, gx * gz, gy * gz};
+    const bool pr = k.sc && !half_weights;  // project only when the output feeds a C2R
+    float w[6] = {gx * gx, gy * gy, gz * gz, (pr && k.nqx != k.nqy) ? 0.0f : gx * gy,
+                  (pr && k.nqx != k.nqz) ? 0.0f : gx * gz, (pr && k.nqy != k.nqz) ? 0.0f : gy * gz};
     float re = 0.0f, im = 0.0f;
 #pragma unroll
     for (int t = 0; t < 6; ++t) {

@@ -103,7 +103,7 @@ int mcpm_paint_lattice(mcpm_engine* eng, void* stream, const float* pos, const f
   BIND(eng);
 #ifndef MCPM_HOSTEMU
   Engine* E = eng->e;
-  int r = brick_paint_cic(as_stream(stream), E->lat, pos, weights, wscalar, np, E->nx, E->ny, E->nz, mesh);
+  int r = brick_paint_cic(as_stream(stream), E->lat, pos, weights, wscalar, 0.0f, np, E->nx, E->ny, E->nz, mesh);
   if (r < 0) return MCPM_ECUDA;
   if (r == 1) return MCPM_OK;
 #endif

@@ -2,18 +2,23 @@
 //
 // The generic scatter sends 8 (density) or 8 x 16 B (reverse step) atomics per particle to L2, whose atomic units
 // sustain ~1 lane-op per slice-clock (profiles/r1_atomics_microbench.txt): that, not HBM, bounds it.  Here one CTA
-// takes a brick of 16 x 8 x 32 lattice-neighbour particles, accumulates them in a 22 x 14 x 40 shared-memory tile that
-// follows the brick's mean displacement, and flushes only the touched 16-byte groups with red.global.add.v4.f32:
-// ~0.7 L2 lane-ops per particle instead of 8.
+// takes a brick of 16 x 8 x 32 lattice-neighbour particles, accumulates them in a 26 x 18 x 44 shared-memory tile that
+// follows the brick's mean displacement, and flushes only the touched 16-byte groups with red.global.add.v4.f32.
 //
 // Accumulation in shared memory: sm_100a has no native float atomics on shared memory (ATOMS.CAST.SPIN CAS loops,
 // 9.5-16 cycles per warp-instruction) but int32 ATOMS.ADD is native, so contributions are accumulated in fixed point
 // with a per-brick power-of-two scale S = 2^floor(log2(2^30 / sum_p |v_p|)): no cell of the tile can overflow, the
-// quantum is <= 2^-19 of the brick's mean |v| per deposit (comparable to float32 rounding of the sums), and the result
+// quantum is <= 2^-18 of the brick's mean |v| per deposit (comparable to float32 rounding of the sums), and the result
 // is independent of the order in which the brick's atomics land (bitwise reproducible inside the tile).
 // Particles whose stencil leaves the tile use float atomics straight to global memory, so results never depend on the
-// lattice hint being right.  Geometry is compile-time (no runtime divisions in the zero / flush loops -- the v1 of this
-// kernel lost to exactly that, tools/experiments/brick_tiled_v1.cu.txt).
+// lattice hint being right.
+//
+// v2 of this kernel (22 x 14 x 40 tile) issued 600 warp-instructions per 32 particles and was issue-bound
+// (profiles/r1_ncu_brick_v2.txt: 26% of them in the flush loop's index arithmetic, 38% around the ATOMS).  This version
+// keeps per-particle state to 4 registers (tile cell + 3 fractions), works in float up to the single F2I of the tile
+// cell, takes the tile origin from a 512-particle sample, looks the flush rows up in a shared table, and re-zeroes the
+// tile inside the flush -- about a third of the instructions, with margins wide enough (5 / 5 / 6 cells each side) that
+// fewer than 5% of the particles stray at a = 1 on the benchmark run (tools/stray_probe.py).
 // Reference semantics: CIC paint of montecosmo/nbody.py:365-396 (same index rule and weights as cic4.cu / window.h).
 #ifndef MCPM_HOSTEMU
 #include "engine.h"
@@ -22,23 +27,24 @@
 namespace mcpm {
 
 namespace brick {
-constexpr int BX = 16, BY = 8, BZ = 32;         // lattice brick per CTA: 4096 particles
-// mesh tile = brick + margin 6 / 6 / 8 (TZ % 4 == 0): 3 cells per particle.  Measured on the benchmark run at 256^3
-// (tools/stray_probe.py): particles leaving a tile of margin M at a = 1: 46% (M=6), 16% (8), 4% (10); at a = 0.3: 0.4%.
-// Margin 10 (26 x 18 x 44) was nevertheless slower (3-channel kernel 678 vs 577 us): zeroing and scanning the tile once
-// per channel costs more than sending strays down the global-atomic path.
-constexpr int TX = 22, TY = 14, TZ = 40;
-constexpr int CELLS = TX * TY * TZ;             // 12320 (48 KB of int32: two CTAs per SM)
-constexpr int THREADS = 512;                    // 16 warps
-constexpr int ROWS = BX * BY;                   // 128 z-rows of 32 particles
-constexpr int PPT = ROWS / 16;                  // 8 particles (z-rows) per thread: amortises zero / reduce / flush
-constexpr int GROUPS = TX * TY * (TZ / 4);      // 3080 float4 groups per channel
+constexpr int BX = 16, BY = 8, BZ = 32;  // lattice brick per CTA: 4096 particles, one warp per z-row
+constexpr int TX = 26, TY = 18, TZ = 44;  // mesh tile (TZ % 4 == 0): 5.0 cells per particle, 82 KB of int32
+constexpr int CELLS = TX * TY * TZ;       // 20592
+constexpr int THREADS = 512;              // 16 warps, two CTAs per SM
+constexpr int WARPS = THREADS / 32;
+constexpr int PPT = BX * BY / WARPS;      // 8 z-rows (particles) per thread
+constexpr int ZG = TZ / 4;                // 11 float4 groups per tile row
+constexpr int TROWS = TX * TY;            // 468 tile rows
+constexpr int GROUPS = TROWS * ZG;        // 5148 float4 groups per channel
+constexpr size_t SMEM = sizeof(int) * (CELLS + TROWS) + sizeof(unsigned short) * PPT * THREADS;
+static_assert(BX == 16 && BY == 8 && WARPS == 16, "row mapping below assumes a 16 x 8 x 32 brick and 16 warps");
 }  // namespace brick
 
 struct BrickArgs {
   int px, py, pz;  // particle lattice == mesh here (spacing 1 cell)
   int nx, ny, nz;
   float inx, iny, inz;  // 1 / n
+  float shift;          // pos + shift is painted (interlacing); 0 otherwise
   const float* pos;
   // NCH = 1: value = (w ? w[p] : 1) * ws.        NCH = 3: value = s * (A[p] + cb * B[p]), A updated in place if store.
   const float* w;
@@ -50,72 +56,92 @@ struct BrickArgs {
   float* mesh;  // NCH planar meshes
 };
 
-// d mod n into [-n/2, n/2): one conditional correction covers |d| < 1.5 n (always, unless the caller wrapped positions
-// by several boxes); the integer division is only the rare fallback
-__device__ __forceinline__ int fold(int d, int n) {
-  const int h = (n + 1) >> 1;
-  if (d >= h) d -= n;
-  else if (d < -h) d += n;
-  if (d >= h || d < -h) {
-    int m = wrap_index(d, n);
-    d = m >= h ? m - n : m;
-  }
-  return d;
-}
+// thread (warp, lane), slot r -> lattice offsets inside the brick.  Slot 0 of the 16 warps samples all 16 x-planes and
+// all 8 y-rows of the brick (the tile origin is taken from those 512 particles).
+__device__ __forceinline__ int brick_qi(int warp, int r) { return ((warp >> 3) + 2 * ((warp & 7) + r)) & 15; }
 
-template <int NCH>
+// FULL: the lattice divides into whole bricks (no per-particle bounds checks)
+template <int NCH, bool FULL>
 __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickArgs a) {
   using namespace brick;
-  extern __shared__ __align__(16) int tile[];  // [TX][TY][TZ] fixed point, reused channel after channel
-  __shared__ float red[16][4 + NCH];
+  extern __shared__ __align__(16) int smem[];
+  int* tile = smem;                 // [TX][TY][TZ] fixed point, reused channel after channel
+  int* rowbase = smem + CELLS;      // [TX*TY] global offset of each tile row (wrapped)
+  unsigned short* stray = reinterpret_cast<unsigned short*>(rowbase + TROWS);
+  __shared__ float red[WARPS][4 + NCH];
   __shared__ float bc[4 + NCH];
-  __shared__ int stray[PPT * THREADS];
   __shared__ int nstray;
-  if (threadIdx.x == 0) nstray = 0;
-  for (int i = threadIdx.x; i < CELLS / 4; i += THREADS) reinterpret_cast<int4*>(tile)[i] = make_int4(0, 0, 0, 0);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) nstray = 0;
+  int4* tile4 = reinterpret_cast<int4*>(tile);
+  for (int i = tid; i < GROUPS; i += THREADS) tile4[i] = make_int4(0, 0, 0, 0);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0i = blockIdx.z * BX, q0j = blockIdx.y * BY, q0k = blockIdx.x * BZ;
-  // PPT z-rows per thread: rows warp, warp + 16, ... of the brick's 128
+  const int qj = q0j + (warp & 7), qk = q0k + lane;
+  const bool colok = FULL || (qj < a.py && qk < a.pz);
+  const int plane3 = 3 * a.py * a.pz;  // floats between consecutive lattice x-planes
+  const int64_t pbase = 3 * (((int64_t)q0i * a.py + qj) * a.pz + qk);
+  const float* xp = a.pos + pbase;
+
+  // ---- pass 1: positions of the thread's 8 z-rows; for the reverse step also A += cb * B and sum |value|
   float x[PPT][3];
-  unsigned validmask = 0;
-  float d0 = 0.f, d1 = 0.f, d2 = 0.f, cnt = 0.f, l1[NCH];
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) l1[c] = 0.f;
+  unsigned valid = 0;
 #pragma unroll
   for (int r = 0; r < PPT; ++r) {
-    const int row = warp + 16 * r;
-    const int qi = q0i + row / BY, qj = q0j + row % BY, qk = q0k + lane;
-    if (qi < a.px && qj < a.py && qk < a.pz) {
-      validmask |= 1u << r;
-      const int64_t p = ((int64_t)qi * a.py + qj) * a.pz + qk;
-      x[r][0] = a.pos[3 * p];
-      x[r][1] = a.pos[3 * p + 1];
-      x[r][2] = a.pos[3 * p + 2];
-      if (NCH == 1) {
-        l1[0] += fabsf((a.w ? a.w[p] : 1.0f) * a.ws);
-      } else {
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          float t = a.A[3 * p + c];
-          if (a.B) {
-            t += a.cb * a.B[3 * p + c];
-            if (a.store) a.A[3 * p + c] = t;  // re-read per channel pass below (L1 / L2 hit)
-          }
-          l1[c] += fabsf(a.s * t);
-        }
-      }
-      float e0 = x[r][0] - qi, e1 = x[r][1] - qj, e2 = x[r][2] - qk;
-      e0 -= a.nx * rintf(e0 * a.inx);  // positions may have been wrapped by the caller
-      e1 -= a.ny * rintf(e1 * a.iny);
-      e2 -= a.nz * rintf(e2 * a.inz);
-      d0 += e0;
-      d1 += e1;
-      d2 += e2;
-      cnt += 1.f;
+    const int di = brick_qi(warp, r);
+    if (FULL || (colok && q0i + di < a.px)) {
+      valid |= 1u << r;
+      const float* xr = xp + di * plane3;
+      x[r][0] = xr[0] + a.shift;
+      x[r][1] = xr[1] + a.shift;
+      x[r][2] = xr[2] + a.shift;
+    } else {
+      x[r][0] = x[r][1] = x[r][2] = 0.f;
     }
   }
-  // block reduction: mean displacement of the brick and sum |v| per channel
+  float l1[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) l1[c] = 0.f;
+  if (NCH == 3) {
+    float* Ap = a.A + pbase;
+    const float* Bp = a.B ? a.B + pbase : nullptr;
+#pragma unroll
+    for (int r = 0; r < PPT; ++r) {
+      if (!FULL && !(valid >> r & 1)) continue;
+      const int off = brick_qi(warp, r) * plane3;
+      float t0 = Ap[off], t1 = Ap[off + 1], t2 = Ap[off + 2];
+      if (Bp) {
+        t0 += a.cb * Bp[off];
+        t1 += a.cb * Bp[off + 1];
+        t2 += a.cb * Bp[off + 2];
+        if (a.store) {  // re-read per channel pass below (L1 / L2 hit)
+          Ap[off] = t0;
+          Ap[off + 1] = t1;
+          Ap[off + 2] = t2;
+        }
+      }
+      l1[0] += fabsf(a.s * t0);
+      l1[NCH > 1 ? 1 : 0] += fabsf(a.s * t1);
+      l1[NCH > 2 ? 2 : 0] += fabsf(a.s * t2);
+    }
+  } else if (a.w) {
+    const float* wp = a.w + pbase / 3;
+    const int plane1 = a.py * a.pz;
+#pragma unroll
+    for (int r = 0; r < PPT; ++r)
+      if (FULL || (valid >> r & 1)) l1[0] += fabsf(wp[brick_qi(warp, r) * plane1] * a.ws);
+  } else {
+    l1[0] = fabsf(a.ws) * (float)__popc(valid);
+  }
+  // tile origin from slot 0: displacement off the lattice site, reduced to the nearest periodic image
+  float d0 = 0.f, d1 = 0.f, d2 = 0.f, cnt = 0.f;
+  if (FULL || (valid & 1u)) {
+    float e0 = x[0][0] - (float)(q0i + brick_qi(warp, 0)), e1 = x[0][1] - (float)qj, e2 = x[0][2] - (float)qk;
+    d0 = e0 - a.nx * rintf(e0 * a.inx);  // positions may have been wrapped by the caller
+    d1 = e1 - a.ny * rintf(e1 * a.iny);
+    d2 = e2 - a.nz * rintf(e2 * a.inz);
+    cnt = 1.f;
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     d0 += __shfl_xor_sync(0xffffffffu, d0, o);
@@ -134,53 +160,71 @@ __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickA
     for (int c = 0; c < NCH; ++c) red[warp][4 + c] = l1[c];
   }
   __syncthreads();  // also orders the zero fill and the stores to A before what follows
-  if (threadIdx.x < 4 + NCH) {
+  if (tid < 4 + NCH) {
     float s = 0.f;
-    for (int w = 0; w < 16; ++w) s += red[w][threadIdx.x];
-    bc[threadIdx.x] = s;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) s += red[w][tid];
+    bc[tid] = s;
   }
   __syncthreads();
-  const float n = fmaxf(bc[3], 1.f);
-  const int ox = (int)floorf(q0i + bc[0] / n - 0.5f * (TX - BX));
-  const int oy = (int)floorf(q0j + bc[1] / n - 0.5f * (TY - BY));
-  int oz = (int)floorf(q0k + bc[2] / n - 0.5f * (TZ - BZ));
-  oz &= ~3;  // round down to a multiple of 4 (two's complement): 16-byte aligned groups along z
+  const float ninv = 1.0f / fmaxf(bc[3], 1.f);
+  // origin (unwrapped cell coordinates, as floats: exact below 2^24) and its wrapped integer twin
+  // (base cells of the brick span [q0 + mean, q0 + B - 1 + mean]; the tile admits base cells [o, o + T - 2])
+  const float oxf = rintf((float)q0i + bc[0] * ninv - 0.5f * (TX - BX));
+  const float oyf = rintf((float)q0j + bc[1] * ninv - 0.5f * (TY - BY));
+  const float ozf = 4.0f * rintf(0.25f * ((float)q0k + bc[2] * ninv - 0.5f * (TZ - 1 - BZ)));  // 16-byte groups along z
+  const int oz = wrap_index((int)ozf, a.nz);
+  if (tid < TROWS) {
+    const int ix = tid / TY, jy = tid - ix * TY;
+    int gx = wrap_index((int)oxf, a.nx) + ix, gy = wrap_index((int)oyf, a.ny) + jy;
+    gx = gx >= a.nx ? gx - a.nx : gx;
+    gy = gy >= a.ny ? gy - a.ny : gy;
+    rowbase[tid] = (gx * a.ny + gy) * a.nz;
+  }
 
-  // tile-local base cell of every particle (packed), strays queued once
+  // ---- per-particle state: tile cell (or -1) and the three CIC fractions, held in place of x[r][.]
   int tcell[PPT];
+  const float fnx = (float)a.nx, fny = (float)a.ny, fnz = (float)a.nz;
 #pragma unroll
   for (int r = 0; r < PPT; ++r) {
     tcell[r] = -1;
-    if (!(validmask >> r & 1)) continue;
-    const int ti = fold((int)floorf(x[r][0]) - ox, a.nx), tj = fold((int)floorf(x[r][1]) - oy, a.ny),
-              tk = fold((int)floorf(x[r][2]) - oz, a.nz);
-    if ((unsigned)ti <= (unsigned)(TX - 2) && (unsigned)tj <= (unsigned)(TY - 2) && (unsigned)tk <= (unsigned)(TZ - 2))
-      tcell[r] = (ti * TY + tj) * TZ + tk;
+    if (!FULL && !(valid >> r & 1)) continue;
+    const float bx = floorf(x[r][0]), by = floorf(x[r][1]), bz = floorf(x[r][2]);
+    x[r][0] -= bx;
+    x[r][1] -= by;
+    x[r][2] -= bz;
+    // base cell relative to the tile origin, modulo the mesh.  An inexact quotient can only misplace a value onto
+    // +-n, i.e. out of the tile: the particle then strays, which is always correct.
+    float tx = bx - oxf, ty = by - oyf, tz = bz - ozf;
+    tx -= fnx * floorf(tx * a.inx);
+    ty -= fny * floorf(ty * a.iny);
+    tz -= fnz * floorf(tz * a.inz);
+    const bool in = fabsf(tx - 0.5f * (TX - 2)) <= 0.5f * (TX - 2) && fabsf(ty - 0.5f * (TY - 2)) <= 0.5f * (TY - 2) &&
+                    fabsf(tz - 0.5f * (TZ - 2)) <= 0.5f * (TZ - 2);
+    if (in)
+      tcell[r] = (int)((tx * TY + ty) * TZ + tz);  // exact: small integers
     else
-      stray[atomicAdd(&nstray, 1)] = ((warp + 16 * r) << 5) | lane;
+      stray[atomicAdd(&nstray, 1)] = (unsigned short)(r * THREADS + tid);
   }
+  __syncthreads();  // rowbase, nstray
 
   const int64_t plane = (int64_t)a.nx * a.ny * a.nz;
 #pragma unroll 1
   for (int c = 0; c < NCH; ++c) {
-    if (c > 0) {  // the tile was flushed by the previous channel pass: clear it
-      __syncthreads();
-      for (int i = threadIdx.x; i < CELLS / 4; i += THREADS) reinterpret_cast<int4*>(tile)[i] = make_int4(0, 0, 0, 0);
-      __syncthreads();
-    }
     const float l = bc[4 + c];
     float e = l > 0.f ? floorf(log2f(1073741824.0f / l)) : 0.f;
     e = fminf(fmaxf(e, -120.f), 120.f);
     const float S = exp2f(e), invS = exp2f(-e);
+    const float* valp = NCH == 1 ? (a.w ? a.w + pbase / 3 : nullptr) : a.A + pbase + c;
+    const int vstride = NCH == 1 ? a.py * a.pz : plane3;
+    const float scale = (NCH == 1 ? a.ws : a.s) * S;
 #pragma unroll
     for (int r = 0; r < PPT; ++r) {
       if (tcell[r] < 0) continue;
-      const int row = warp + 16 * r;
-      const int64_t p = ((int64_t)(q0i + row / BY) * a.py + (q0j + row % BY)) * a.pz + q0k + lane;
-      const float val = NCH == 1 ? (a.w ? a.w[p] : 1.0f) * a.ws : a.s * a.A[3 * p + c];
-      const float fx = x[r][0] - floorf(x[r][0]), fy = x[r][1] - floorf(x[r][1]), fz = x[r][2] - floorf(x[r][2]);
-      const float gx = 1.f - fx, gy = 1.f - fy, gz = 1.f - fz;
-      const float vs = val * S, vz0 = vs * gz, vz1 = vs * fz;
+      const float vs = valp ? valp[brick_qi(warp, r) * vstride] * scale : scale;
+      const float fx = x[r][0], fy = x[r][1], fz = x[r][2];
+      const float gx = 1.f - fx, gy = 1.f - fy;
+      const float vz1 = vs * fz, vz0 = vs - vz1;  // vs * (1 - fz) up to one rounding of the fixed-point product
       const float w00 = gx * gy, w01 = gx * fy, w10 = fx * gy, w11 = fx * fy;
       int* t = tile + tcell[r];
       atomicAdd(t, __float2int_rn(vz0 * w00));  // ATOMS.ADD, constant offsets
@@ -193,31 +237,34 @@ __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickA
       atomicAdd(t + TY * TZ + TZ + 1, __float2int_rn(vz1 * w11));
     }
     __syncthreads();
-    // flush the touched 16-byte groups: one red.global.add.v4.f32 per group
+    // flush the touched 16-byte groups (one red.global.add.v4.f32 each) and re-zero them for the next channel
     float* meshc = a.mesh + c * plane;
-    for (int g = threadIdx.x; g < GROUPS; g += THREADS) {
-      const int kz = g % (TZ / 4), rr = g / (TZ / 4);  // compile-time divisors
-      const int jy = rr % TY, ix = rr / TY;
-      const int4 q = *reinterpret_cast<const int4*>(tile + (ix * TY + jy) * TZ + 4 * kz);
+    for (int g = tid; g < GROUPS; g += THREADS) {
+      const int4 q = tile4[g];
       if ((q.x | q.y | q.z | q.w) != 0) {
-        const int gx = wrap_fast(ox + ix, a.nx), gy = wrap_fast(oy + jy, a.ny), gz = wrap_fast(oz + 4 * kz, a.nz);
-        atomicAdd(reinterpret_cast<float4*>(meshc + ((int64_t)gx * a.ny + gy) * a.nz + gz),
+        if (c + 1 < NCH) tile4[g] = make_int4(0, 0, 0, 0);
+        const int row = g / ZG, kz = g - row * ZG;  // compile-time divisor
+        int gz = oz + 4 * kz;
+        gz = gz >= a.nz ? gz - a.nz : gz;
+        atomicAdd(reinterpret_cast<float4*>(meshc + (rowbase[row] + gz)),
                   make_float4(q.x * invS, q.y * invS, q.z * invS, q.w * invS));
       }
     }
+    if (c + 1 < NCH) __syncthreads();
   }
   // strays: float atomics straight to global memory, one queued particle per thread (convergent)
-  for (int si = threadIdx.x; si < nstray; si += THREADS) {
-    const int code = stray[si], row = code >> 5, ln = code & 31;
-    const int qi = q0i + row / BY, qj = q0j + row % BY, qk = q0k + ln;
-    const int64_t p = ((int64_t)qi * a.py + qj) * a.pz + qk;
-    const float px = a.pos[3 * p], py = a.pos[3 * p + 1], pz = a.pos[3 * p + 2];
+  const int ns = nstray;
+  for (int si = tid; si < ns; si += THREADS) {
+    const int code = stray[si], r = code / THREADS, t2 = code - r * THREADS;
+    const int w2 = t2 >> 5;
+    const int64_t p3 = 3 * (((int64_t)(q0i + brick_qi(w2, r)) * a.py + (q0j + (w2 & 7))) * a.pz + q0k + (t2 & 31));
+    const float px = a.pos[p3] + a.shift, py = a.pos[p3 + 1] + a.shift, pz = a.pos[p3 + 2] + a.shift;
     float vv[NCH];
     if (NCH == 1) {
-      vv[0] = (a.w ? a.w[p] : 1.0f) * a.ws;
+      vv[0] = (a.w ? a.w[p3 / 3] : 1.0f) * a.ws;
     } else {
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) vv[c] = a.s * a.A[3 * p + c];  // A already holds A + cb * B (stored above)
+      for (int c = 0; c < NCH; ++c) vv[c] = a.s * a.A[p3 + c];  // A already holds A + cb * B (stored above)
     }
     const float bx = floorf(px), by = floorf(py), bz = floorf(pz);
     const float fx = px - bx, fy = py - by, fz = pz - bz;
@@ -242,28 +289,35 @@ static bool brick_ok(const Lattice& L, int64_t np, int nx, int ny, int nz) {
   using namespace brick;
   if (L.px != nx || L.py != ny || L.pz != nz) return false;        // lattice spacing of one cell only
   if ((int64_t)L.px * L.py * L.pz != np) return false;
-  if ((nz & 3) || nx < 2 * TX || ny < 2 * TY || nz < 2 * TZ) return false;
+  if ((nz & 3) || nx < TX || ny < TY || nz < TZ) return false;         // a tile must not wrap onto itself
+  if (3 * np >= ((int64_t)1 << 31)) return false;                  // 32-bit row offsets inside a brick
   return true;
 }
 
 template <int NCH>
 static int launch_brick(stream_t st, const BrickArgs& a) {
   using namespace brick;
-  const size_t smem = sizeof(int) * CELLS;  // one channel at a time
-  cudaFuncSetAttribute(brick_scatter_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // per device
   dim3 grid((a.pz + BZ - 1) / BZ, (a.py + BY - 1) / BY, (a.px + BX - 1) / BX);
   count_launch();
-  brick_scatter_kernel<NCH><<<grid, THREADS, smem, st>>>(a);
+  if (a.px % BX == 0 && a.py % BY == 0 && a.pz % BZ == 0) {
+    cudaFuncSetAttribute(brick_scatter_kernel<NCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    brick_scatter_kernel<NCH, true><<<grid, THREADS, SMEM, st>>>(a);
+  } else {
+    cudaFuncSetAttribute(brick_scatter_kernel<NCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    brick_scatter_kernel<NCH, false><<<grid, THREADS, SMEM, st>>>(a);
+  }
   return rt_check("brick_scatter") ? -1 : 1;
 }
 
-// CIC density paint into a zeroed-or-accumulated planar mesh.  Returns 1 if handled, 0 -> generic path, < 0 error.
-int brick_paint_cic(stream_t st, const Lattice& L, const float* pos, const float* weights, float wscalar, int64_t np,
-                    int nx, int ny, int nz, float* mesh) {
+// CIC density paint of pos + shift into a zeroed-or-accumulated planar mesh.  Returns 1 if handled, 0 -> generic path,
+// < 0 error.
+int brick_paint_cic(stream_t st, const Lattice& L, const float* pos, const float* weights, float wscalar, float shift,
+                    int64_t np, int nx, int ny, int nz, float* mesh) {
   if (!brick_ok(L, np, nx, ny, nz)) return 0;
   BrickArgs a = {};
   a.px = L.px; a.py = L.py; a.pz = L.pz; a.nx = nx; a.ny = ny; a.nz = nz;
   a.inx = 1.0f / nx; a.iny = 1.0f / ny; a.inz = 1.0f / nz;
+  a.shift = shift;
   a.pos = pos; a.w = weights; a.ws = wscalar; a.mesh = mesh;
   return launch_brick<1>(st, a);
 }

@@ -51,17 +51,23 @@ void engine_destroy(Engine* e) {
     if (int _e = (x)) return _e; \
   } while (0)
 
-// CIC density paint: brick-tiled when the engine carries a matching lattice hint (CUDA build), generic otherwise
-static int paint_density(Engine* E, stream_t st, const float* pos, int64_t np, int order, float* mesh) {
+// CIC paint of pos * scale + shift into a fresh mesh: brick-tiled when the engine carries a matching lattice hint and
+// the positions are not rescaled (CUDA build), generic otherwise
+static int paint_fresh(Engine* E, stream_t st, const float* pos, const float* weights, float wscalar, int64_t np,
+                       int order, const float* scale, float shift, float* mesh) {
 #ifndef MCPM_HOSTEMU
-  if (order == 2 && E->lat.px > 0) {
+  const bool unit = !scale || (scale[0] == 1.0f && scale[1] == 1.0f && scale[2] == 1.0f);
+  if (order == 2 && E->lat.px > 0 && unit) {
     if (rt_memset(mesh, 0, sizeof(float) * (size_t)E->N, st)) return MCPM_ECUDA;
-    int r = brick_paint_cic(st, E->lat, pos, nullptr, 1.0f, np, E->nx, E->ny, E->nz, mesh);
+    int r = brick_paint_cic(st, E->lat, pos, weights, wscalar, shift, np, E->nx, E->ny, E->nz, mesh);
     if (r < 0) return MCPM_ECUDA;
     if (r == 1) return 0;
   }
 #endif
-  return paint(st, pos, nullptr, 1.0f, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, mesh, 0);
+  return paint(st, pos, weights, wscalar, np, E->nx, E->ny, E->nz, order, scale, shift, mesh, 0);
+}
+static int paint_density(Engine* E, stream_t st, const float* pos, int64_t np, int order, float* mesh) {
+  return paint_fresh(E, st, pos, nullptr, 1.0f, np, order, nullptr, 0.0f, mesh);
 }
 
 // delta_k (any spectrum, preserved) -> three real force meshes fm[3][N]  (nbody.py:595-603 up to the irfftn)
@@ -302,7 +308,7 @@ int nufft(Engine* E, stream_t st, const float* pos, const float* weights, float 
   }
   float jac = scale ? scale[0] * scale[1] * scale[2] : 1.0f;
   for (int i = 0; i < m; ++i)
-    TRY(paint(st, pos, weights, wscalar, np, E->nx, E->ny, E->nz, paint_order, scale, (float)i / (float)m, E->r(i), 0));
+    TRY(paint_fresh(E, st, pos, weights, wscalar, np, paint_order, scale, (float)i / (float)m, E->r(i)));
   TRY(fft_r2c(E->fft, st, E->r(0), E->c(0), m));
   TRY(interlace_combine(st, E->c(0), out_k, m, E->nx, E->ny, E->nz, jac, paint_deconv ? paint_order : 0));
   return 0;

@@ -102,8 +102,8 @@ int read_grad4v(stream_t, const float* pos, const float* fmesh4, const float* rh
                 int scale_cot, float alpha_tail, int64_t np, int nx, int ny, int nz, float* grad, int accumulate);
 
 // brick.cu (CUDA build only): return 1 if handled, 0 if the generic path must be taken, < 0 on error
-int brick_paint_cic(stream_t, const Lattice&, const float* pos, const float* weights, float wscalar, int64_t np, int nx,
-                    int ny, int nz, float* mesh);
+int brick_paint_cic(stream_t, const Lattice&, const float* pos, const float* weights, float wscalar, float shift,
+                    int64_t np, int nx, int ny, int nz, float* mesh);
 int brick_paint3_cic(stream_t, const Lattice&, const float* pos, float* A, const float* B, float cb, float s,
                      int64_t np, int nx, int ny, int nz, float* mesh3);
 

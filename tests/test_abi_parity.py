@@ -450,3 +450,28 @@ def test_brick_scatter_matches_generic(ops, mesh):
     for name, a, b in zip(["forces", "force meshes", "pos", "vel", "posbar", "velbar"], res[False], res[True]):
         assert rel(a, b) < 2e-5, name
     assert rel(res[False][0], O.pm_forces(T(pos), mesh, 2).numpy()) < 5e-5
+    # the interlaced, weighted paints of nufft take the same kernel (pos + shift, per-particle weights)
+    w = f32(rng.uniform(0.2, 3.0, n))
+    nu = {}
+    for hint in (None, mesh):
+        ops.set_lattice(mesh, hint)
+        nu[hint is None] = to_numpy(ops.nufft_paint(pos, mesh, w, 0.7, None, 2, 2, True)).copy()
+    ops.set_lattice(mesh, None)
+    assert rel(nu[True], nu[False]) < 2e-5
+    if not isinstance(A, NumpyAdapter):
+        # CUDA build: these shapes must really be handled by the brick kernels (MCPM_EUNSUP raises otherwise)
+        ops.set_lattice(mesh, mesh)
+        eng = ops.engine(mesh)
+        pd, wd = A.prepare(pos), A.prepare(w)
+        out = A.zeros(mesh)
+        ops._call("mcpm_paint_lattice", eng.handle, A.stream(), A.ptr(pd), A.ptr(wd), 0.5, n, A.ptr(out))
+        assert rel(out, O.paint(T(pos), mesh, T(w) * 0.5, 2).numpy()) < 2e-5
+        vb, xb = A.prepare(vel.copy()), A.prepare(f32(rng.normal(size=q.shape)))
+        out3 = A.zeros((3, *mesh))
+        ops._call("mcpm_paint3_lattice", eng.handle, A.stream(), A.ptr(pd), A.ptr(vb), A.ptr(xb), 0.25, 1.5, n,
+                  A.ptr(out3))
+        vnew = vel.astype(np.float64) + 0.25 * to_numpy(xb).astype(np.float64)
+        assert rel(vb, vnew) < 1e-6
+        for c in range(3):
+            assert rel(out3[c], O.paint(T(pos), mesh, T(vnew[:, c]) * 1.5, 2).numpy()) < 2e-5
+        ops.set_lattice(mesh, None)

@@ -48,6 +48,10 @@ const char* mcpm_last_error(void);
 /* number of engine kernels (not cuFFT's) launched by this process so far; reset != 0 zeroes the counter */
 long long mcpm_launch_count(int reset);
 
+/* Process-wide performance knobs (never change which result is computed).  Keys: "gather_minb" = 4 | 5 | 6, the
+ * resident CTAs per SM the readout kernels are compiled for. */
+int mcpm_tune(const char* key, int value);
+
 /* Engine for real mesh shape (nx, ny, nz) on the current device.  max_batch = largest number of meshes transformed
  * in one call (6 covers 2LPT).  Scratch = (2*max_batch+2) meshes + cuFFT work area, allocated here, once. */
 int mcpm_engine_create(int nx, int ny, int nz, mcpm_engine** out);
@@ -58,6 +62,11 @@ size_t mcpm_engine_scratch_bytes(const mcpm_engine* eng);
  * brick-tiled shared-memory scatter; particles that strayed from their brick's tile take the generic path.
  * px = 0 clears the hint. */
 int mcpm_engine_set_lattice(mcpm_engine* eng, int px, int py, int pz);
+/* Fused x-transform path of pm_forces and its VJP (2-D cuFFT per x-plane + one kernel doing the x-FFT, the force
+ * kernel of nbody.py:591-603 and the inverse x-FFTs).  On by default where supported (nx in {64, 128, 256});
+ * on = 0 selects the 3-D cuFFT + separate multiply path, on = 1 returns MCPM_EUNSUP where unsupported.
+ * Both paths compute the same operator (float32 rounding differs). */
+int mcpm_engine_set_fused_fft(mcpm_engine* eng, int on);
 
 /* Brick-tiled CIC scatters for lattice-ordered particles (need a matching mcpm_engine_set_lattice; else MCPM_EUNSUP).
  * These are what mcpm_pm_forces / mcpm_nbody_steps_vjp run under the hint; exposed for timing and tests.  Meshes are

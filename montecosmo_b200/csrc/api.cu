@@ -96,6 +96,31 @@ int mcpm_engine_set_lattice(mcpm_engine* eng, int px, int py, int pz) {
   API_END
 }
 
+int mcpm_tune(const char* key, int value) {
+  API_BEGIN
+  NEED(key, "tune: null key");
+  if (std::string(key) == "gather_minb") {
+    NEED(value >= 4 && value <= 6, "tune: gather_minb must be 4, 5 or 6");
+    set_gather_minb(value);
+    return MCPM_OK;
+  }
+  set_error(std::string("tune: unknown key ") + key);
+  return MCPM_EINVAL;
+  API_END
+}
+
+int mcpm_engine_set_fused_fft(mcpm_engine* eng, int on) {
+  API_BEGIN
+  NEED(eng, "null engine");
+  if (on && !eng->e->fft2d) {
+    set_error("set_fused_fft: not available for this mesh shape (nx must be 64, 128 or 256) or CPU build");
+    return MCPM_EUNSUP;
+  }
+  eng->e->fused_fft = on ? 1 : 0;
+  return MCPM_OK;
+  API_END
+}
+
 int mcpm_paint_lattice(mcpm_engine* eng, void* stream, const float* pos, const float* weights, float wscalar,
                        int64_t np, float* mesh) {
   API_BEGIN

@@ -35,6 +35,17 @@ __device__ __forceinline__ f4 load4(const f4* p) {
 }
 #endif
 
+// Resident CTAs per SM the two gather kernels are compiled for (register cap 64 / 48 / 40 per thread).  They are bound by
+// load latency at ~50% occupancy (profiles/r1_ncu_brick_v2.txt), so fewer registers can pay; mcpm_tune("gather_minb").
+static int g_gather_minb = 4;
+void set_gather_minb(int v) { g_gather_minb = v; }
+template <class F>
+static void launch_gather(stream_t st, int64_t n, F f) {
+  if (g_gather_minb == 5) launch_1d_occ<5>(st, n, f);
+  else if (g_gather_minb == 6) launch_1d_occ<6>(st, n, f);
+  else launch_1d(st, n, f);
+}
+
 // CIC base cell and fractions; cheap wrap for the usual range, exact modulo otherwise (nbody.py:372-376, 388)
 struct Cic {
   int i0, i1, j0, j1, k0, k1;
@@ -77,7 +88,7 @@ int deinterleave3(stream_t st, const float* mesh4, float* planar3, int64_t n) {
 int kick_drift4(stream_t st, const float* pos, const float* vel, const float* fmesh4, int64_t np, int nx, int ny,
                 int nz, float alpha, float beta, float drift, float* pos_out, float* vel_out) {
   const f4* fm = reinterpret_cast<const f4*>(fmesh4);
-  launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
+  launch_gather(st, np, [=] MCPM_LAMBDA(int64_t p) {
     float x[3] = {pos[3 * p], pos[3 * p + 1], pos[3 * p + 2]};
     Cic c = cic_setup(x, nx, ny, nz);
     const int64_t r00 = ((int64_t)c.i0 * ny + c.j0) * nz, r01 = ((int64_t)c.i0 * ny + c.j1) * nz;
@@ -153,7 +164,7 @@ int paint3v4(stream_t st, const float* pos, float* A, const float* B, float cb, 
 int read_grad4v(stream_t st, const float* pos, const float* fmesh4, const float* rhobar, float* cot, float cscale,
                 int scale_cot, float alpha_tail, int64_t np, int nx, int ny, int nz, float* grad, int accumulate) {
   const f4* fm = reinterpret_cast<const f4*>(fmesh4);
-  launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
+  launch_gather(st, np, [=] MCPM_LAMBDA(int64_t p) {
     float x[3] = {pos[3 * p], pos[3 * p + 1], pos[3 * p + 2]};
     Cic c = cic_setup(x, nx, ny, nz);
     const float q0 = cot[3 * p], q1 = cot[3 * p + 1], q2 = cot[3 * p + 2];

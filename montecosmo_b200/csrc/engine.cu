@@ -35,6 +35,12 @@ Engine* engine_create(int nx, int ny, int nz) {
     return nullptr;
   }
   e->scratch_bytes = rb + cb + fftws;
+#ifndef MCPM_HOSTEMU
+  if (xfuse_supported(nx)) {  // optional: without the 2-D plans the engine simply keeps the 3-D cuFFT path
+    e->fft2d = slabfft_create(nx, ny, nz, 1);
+    e->fused_fft = e->fft2d != nullptr;
+  }
+#endif
   return e;
 }
 
@@ -43,6 +49,7 @@ void engine_destroy(Engine* e) {
   if (e->rbuf) rt_free(e->rbuf);
   if (e->cbuf) rt_free(e->cbuf);
   if (e->fft) fft_destroy(e->fft);
+  if (e->fft2d) slabfft_destroy(e->fft2d);
   delete e;
 }
 
@@ -84,9 +91,36 @@ int pm_forces(Engine* E, stream_t st, const float* pos, int64_t np, int order, i
   float* fm = fmesh3 ? fmesh3 : E->r(0);
   float* rho = E->r(6);
   TRY(paint_density(E, st, pos, np, order, rho));
-  TRY(fft_r2c(E->fft, st, rho, E->c(6), 1));
-  TRY(force_meshes_from_spectrum(E, st, E->c(6), lap_fd, grad_fd, kcut, paint_deconv ? order : 0, fm));
+#ifndef MCPM_HOSTEMU
+  if (E->fused_fft) {  // 2-D (y,z) R2C per x-plane, one kernel for x-FFT + force kernel + 3 inverse x-FFTs, 2-D C2R
+    TRY(slabfft_r2c_yz(E->fft2d, st, rho, E->c(6), 1));
+    TRY(xfuse_force(st, E->c(6), E->c(0), E->nx, E->ny, E->nz, lap_fd, grad_fd, kcut, paint_deconv ? order : 0,
+                    E->invN));
+    TRY(slabfft_c2r_yz(E->fft2d, st, E->c(0), fm, 3));
+  } else
+#endif
+  {
+    TRY(fft_r2c(E->fft, st, rho, E->c(6), 1));
+    TRY(force_meshes_from_spectrum(E, st, E->c(6), lap_fd, grad_fd, kcut, paint_deconv ? order : 0, fm));
+  }
   if (forces) TRY(read(st, pos, fm, 3, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, forces));
+  return 0;
+}
+
+// three real meshes (preserved) -> rhobar = C2R(sum_j conj(m_j) R2C(mesh_j)), the density cotangent of pm_forces
+static int density_cotangent(Engine* E, stream_t st, const float* mesh3, int lap_fd, int grad_fd, float kcut,
+                             int deconv_order, float* rhobar) {
+#ifndef MCPM_HOSTEMU
+  if (E->fused_fft) {
+    TRY(slabfft_r2c_yz(E->fft2d, st, mesh3, E->c(0), 3));
+    TRY(xfuse_force_T(st, E->c(0), E->c(3), E->nx, E->ny, E->nz, lap_fd, grad_fd, kcut, deconv_order, E->invN));
+    TRY(slabfft_c2r_yz(E->fft2d, st, E->c(3), rhobar, 1));
+    return 0;
+  }
+#endif
+  TRY(fft_r2c(E->fft, st, mesh3, E->c(0), 3));
+  TRY(force_spectra_T(st, E->c(0), E->c(3), E->nx, E->ny, E->nz, lap_fd, grad_fd, kcut, deconv_order, 0, 0, E->invN));
+  TRY(fft_c2r(E->fft, st, E->c(3), rhobar, 1));
   return 0;
 }
 
@@ -98,10 +132,7 @@ int pm_forces_vjp(Engine* E, stream_t st, const float* pos, const float* fbar, f
                   int64_t np, int order, int paint_deconv, int lap_fd, int grad_fd, float kcut, float* posbar,
                   int accumulate) {
   TRY(paint3(st, pos, fbar, cscale, nullptr, 0.0f, np, E->nx, E->ny, E->nz, order, E->r(0), 0));
-  TRY(fft_r2c(E->fft, st, E->r(0), E->c(0), 3));
-  TRY(force_spectra_T(st, E->c(0), E->c(3), E->nx, E->ny, E->nz, lap_fd, grad_fd, kcut, paint_deconv ? order : 0, 0,
-                      0, E->invN));
-  TRY(fft_c2r(E->fft, st, E->c(3), E->r(3), 1));
+  TRY(density_cotangent(E, st, E->r(0), lap_fd, grad_fd, kcut, paint_deconv ? order : 0, E->r(3)));
   const float* ms[4] = {fmesh3, fmesh3 + E->N, fmesh3 + 2 * E->N, E->r(3)};
   TRY(read_grad(st, pos, ms, 4, fbar, 3, cscale, nullptr, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, posbar,
                 accumulate));
@@ -267,15 +298,11 @@ int nbody_steps_vjp(Engine* E, stream_t st, float* posbar, float* velbar, int64_
         TRY(paint3v4(st, x1, velbar, posbar, dcomb, 1, beta[s], np, E->nx, E->ny, E->nz, E->r(0)));
         TRY(deinterleave3(st, E->r(0), E->r(4), E->N));
       }
-      TRY(fft_r2c(E->fft, st, E->r(4), E->c(0), 3));
     } else {
       TRY(axpy3(st, velbar, posbar, dcomb, P3, velbar));
-      TRY(paint3(st, x1, velbar, beta[s], nullptr, 0.0f, np, E->nx, E->ny, E->nz, order, E->r(0), 0));
-      TRY(fft_r2c(E->fft, st, E->r(0), E->c(0), 3));
+      TRY(paint3(st, x1, velbar, beta[s], nullptr, 0.0f, np, E->nx, E->ny, E->nz, order, E->r(4), 0));
     }
-    TRY(force_spectra_T(st, E->c(0), E->c(3), E->nx, E->ny, E->nz, lap_fd, grad_fd, 0.0f, paint_deconv ? order : 0, 0,
-                        0, E->invN));
-    TRY(fft_c2r(E->fft, st, E->c(3), E->r(3), 1));  // rhobar
+    TRY(density_cotangent(E, st, E->r(4), lap_fd, grad_fd, 0.0f, paint_deconv ? order : 0, E->r(3)));  // rhobar
     if (coefbar) {
       TRY(dot_accum(st, velbar, vprev, P3, 1.0, coefbar + 4 * s + 0));
       if (beta[s] != 0.0f) {  // betabar = <vbar, F>, F = (v1 - alpha v0) / beta

@@ -20,6 +20,8 @@ struct Engine {
   int64_t N, Nc;
   float invN;
   FftPlans* fft = nullptr;
+  struct SlabFft* fft2d = nullptr;  // batched 2-D (y,z) plans per x-plane, for the fused x-transform path (xfft.cu)
+  int fused_fft = 0;                // 1: pm_forces and its VJP run 2-D cuFFT + one fused x-pass kernel
   float* rbuf = nullptr;
   cfloat* cbuf = nullptr;
   size_t scratch_bytes = 0;
@@ -92,6 +94,7 @@ int chreshape_T(stream_t, const cfloat* outbar, int onx, int ony, int onz, cfloa
 int hermitian_weights(stream_t, const cfloat* in, cfloat* out, int nx, int ny, int nz, int mode);
 
 // cic4.cu: CIC kernels on the float4-interleaved vector mesh
+void set_gather_minb(int v);
 int interleave3(stream_t, const float* planar3, float* mesh4, int64_t n);
 int deinterleave3(stream_t, const float* mesh4, float* planar3, int64_t n);
 int kick_drift4(stream_t, const float* pos, const float* vel, const float* fmesh4, int64_t np, int nx, int ny, int nz,
@@ -100,6 +103,13 @@ int paint3v4(stream_t, const float* pos, float* A, const float* B, float cb, int
              int ny, int nz, float* mesh4);
 int read_grad4v(stream_t, const float* pos, const float* fmesh4, const float* rhobar, float* cot, float cscale,
                 int scale_cot, float alpha_tail, int64_t np, int nx, int ny, int nz, float* grad, int accumulate);
+
+// xfft.cu (CUDA build only): the x-passes of rfftn / irfftn fused with the force kernel, on [nx, ny_loc, nz/2+1]
+bool xfuse_supported(int nx);
+int xfuse_force(stream_t, const cfloat* in, cfloat* out3, int nx, int ny, int nz, int lap_fd, int grad_fd, float kcut,
+                int deconv_order, float norm, SlabK sk = SlabK());
+int xfuse_force_T(stream_t, const cfloat* in3, cfloat* out, int nx, int ny, int nz, int lap_fd, int grad_fd,
+                  float kcut, int deconv_order, float norm, SlabK sk = SlabK());
 
 // brick.cu (CUDA build only): return 1 if handled, 0 if the generic path must be taken, < 0 on error
 int brick_paint_cic(stream_t, const Lattice&, const float* pos, const float* weights, float wscalar, float shift,

@@ -33,6 +33,10 @@ inline void launch_1d(stream_t, int64_t n, F f) {
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < n; ++i) f(i);
 }
+template <int MINB, class F>
+inline void launch_1d_occ(stream_t s, int64_t n, F f) {
+  launch_1d(s, n, f);
+}
 MCPM_HD void atomic_add(float* p, float v) {
 #pragma omp atomic
   *p += v;
@@ -83,6 +87,22 @@ inline void launch_1d(stream_t s, int64_t n, F f) {
   if (blocks > wave) blocks = wave;
   count_launch();
   k_launch_1d<<<(unsigned)blocks, 256, 0, s>>>(n, f);
+}
+
+// Same, with a register cap chosen for MINB resident CTAs of 256 threads per SM (latency-bound gathers want occupancy).
+template <int MINB, class F>
+__global__ void __launch_bounds__(256, MINB) k_launch_1d_occ(int64_t n, F f) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
+}
+template <int MINB, class F>
+inline void launch_1d_occ(stream_t s, int64_t n, F f) {
+  if (n <= 0) return;
+  int64_t blocks = (n + 255) / 256;
+  const int64_t wave = (int64_t)kSMs * MINB * 2;
+  if (blocks > wave) blocks = wave;
+  count_launch();
+  k_launch_1d_occ<MINB><<<(unsigned)blocks, 256, 0, s>>>(n, f);
 }
 
 __device__ __forceinline__ void atomic_add(float* p, float v) { atomicAdd(p, v); }

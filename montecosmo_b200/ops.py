@@ -95,6 +95,10 @@ class Ops:
         p = (0, 0, 0) if ptcl_shape is None else tuple(int(s) for s in ptcl_shape)
         self._call("mcpm_engine_set_lattice", self.engine(mesh_shape).handle, *p)
 
+    def set_fused_fft(self, mesh_shape, on):
+        """Select the fused x-transform path (mcpm_engine_set_fused_fft); raises McpmError where unsupported."""
+        self._call("mcpm_engine_set_fused_fft", self.engine(mesh_shape).handle, int(bool(on)))
+
     def _xf(self, scale, shift):
         return host_floats((1.0, 1.0, 1.0) if scale is None else scale), float(shift)
 

@@ -1,0 +1,95 @@
+"""
+Fused x-transform path of pm_forces (montecosmo_b200/csrc/xfft.cu): 2-D cuFFT per x-plane + one kernel doing the x-FFT,
+the force kernel of nbody.py:591-603 and the inverse x-FFTs.  Compared with the 3-D cuFFT + separate multiply path of
+the same engine (float32 rounding only: 2e-5 relative L2) and with the float64 oracle (5e-5 forces, 2e-4 VJP -- the
+tolerances of tests/test_abi_parity.py).  GPU only: the CPU port has no such path.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pm_oracle as O
+from tests.backends import to_numpy
+
+pytestmark = pytest.mark.gpu
+INF = float("inf")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from montecosmo_b200 import _lib
+    from montecosmo_b200.ops import Ops, TorchCudaAdapter
+    return Ops(_lib.load(), TorchCudaAdapter())
+
+
+def rel(a, b):
+    a, b = np.asarray(to_numpy(a), dtype=np.float64), np.asarray(to_numpy(b), dtype=np.float64)
+    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
+
+
+def T(x):
+    return torch.as_tensor(np.asarray(x), dtype=torch.float64)
+
+
+# nx = 64 (8 x 8), 128 (16 x 8), 256 (16 x 16) register transforms; ny * (nz/2+1) not a multiple of the 16-column tile
+SHAPES = [(64, 12, 16), (128, 6, 10), (256, 4, 6), (64, 16, 30)]
+OPTS = [dict(order=2), dict(order=3, paint_deconv=True, lap_fd=2, grad_fd=4), dict(order=2, kcut=2.0, lap_fd=4)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("kw", OPTS)
+def test_forces_and_vjp(ops, shape, kw):
+    rng = np.random.default_rng(sum(shape))
+    n = int(np.prod(shape))
+    pos = (O.regular_pos(shape).numpy() + rng.normal(scale=0.7, size=(n, 3))).astype(np.float32)
+    fbar = rng.normal(size=pos.shape).astype(np.float32)
+    okw = dict(read_order=kw["order"], paint_deconv=kw.get("paint_deconv", False), lap_fd=kw.get("lap_fd", np.inf),
+               grad_fd=kw.get("grad_fd", np.inf), kcut=kw.get("kcut", np.inf))
+    res = {}
+    for fused in (False, True):
+        ops.set_fused_fft(shape, fused)
+        f, fm = ops.pm_forces(pos, shape, want_meshes=True, **kw)
+        g = ops.pm_forces_vjp(pos, fbar, fm, **kw)
+        res[fused] = [to_numpy(x).copy() for x in (f, fm, g)]
+    for name, a, b in zip(["forces", "force meshes", "vjp"], res[True], res[False]):
+        assert rel(a, b) < 2e-5, name
+    p = T(pos).requires_grad_()
+    fo = O.pm_forces(p, shape, **okw)
+    (fo * T(fbar)).sum().backward()
+    assert rel(res[True][0], fo.detach().numpy()) < 5e-5
+    assert rel(res[True][2], p.grad.numpy()) < 2e-4
+
+
+def test_nbody_steps_and_reverse_sweep(ops):
+    shape = (64, 12, 16)
+    rng = np.random.default_rng(5)
+    n = int(np.prod(shape))
+    pos = (O.regular_pos(shape).numpy() + rng.normal(scale=0.5, size=(n, 3))).astype(np.float32)
+    vel = rng.normal(scale=0.3, size=(n, 3)).astype(np.float32)
+    alpha, beta, pre, post = [0.7, 0.9, 0.95], [0.6, 0.3, 0.2], [0.05, 0.04, 0.03], [0.05, 0.04, 0.03]
+    A = ops.A
+    res = {}
+    for fused in (False, True):
+        ops.set_fused_fft(shape, fused)
+        p2, v2 = A.prepare(pos.copy()), A.prepare(vel.copy())
+        tape = ops.nbody_steps(p2, v2, shape, alpha, beta, pre, post, 2, tape=True)
+        pb, vb = A.prepare(vel.copy()), A.prepare(pos.copy() * 0.01)
+        ops.nbody_steps_vjp(pb, vb, shape, alpha, beta, pre, post, tape, 2)
+        res[fused] = [to_numpy(x).copy() for x in (p2, v2, pb, vb)]
+    ops.set_fused_fft(shape, True)
+    for name, a, b in zip(["pos", "vel", "posbar", "velbar"], res[True], res[False]):
+        assert rel(a, b) < 2e-5, name
+    # and against the oracle's loop
+    x, v = T(pos), T(vel)
+    for s in range(3):
+        x = x + v * pre[s]
+        v = alpha[s] * v + beta[s] * O.pm_forces(x, shape, 2)
+        x = x + v * post[s]
+    assert np.abs(res[True][0] - x.numpy()).max() < 2e-4
+
+
+def test_unsupported_shape_reports(ops):
+    from montecosmo_b200._capi import McpmError
+    ops.set_fused_fft((12, 8, 8), False)
+    with pytest.raises(McpmError):
+        ops.set_fused_fft((12, 8, 8), True)

@@ -174,54 +174,63 @@ def kernel_rooflines(model, white, peaks):
 
     steps = model.n_steps
     rows = []
-    st = A.stream()
+    traffic_path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
 
-    def add(name, fn, alg_bytes, launches, note=""):
+    def add(key, name, fn, alg_bytes, launches, note, in_step=True):
         ms = t(fn)
-        rows.append({"kernel": name, "ms": ms, "launches_per_step": launches, "alg_bytes": alg_bytes,
+        rows.append({"kernel": name, "key": key, "ms": ms, "launches_per_step": launches, "alg_bytes": alg_bytes,
                      "achieved_GBps": alg_bytes / ms / 1e6, "frac": alg_bytes / ms / 1e6 / peaks,
-                     "ms_per_step_total": ms * launches, "alg_bytes_note": note})
+                     "ms_per_step_total": ms * launches, "alg_bytes_note": note, "in_step": in_step,
+                     "traffic": traffic.get(key, {}).get("dram_bytes")})
 
+    st = A.stream()
+    nzc = shape[2] // 2 + 1
     fm4 = torch.empty((*shape, 4), device=pos.device)
     lib.mcpm_interleave3(st, fm.data_ptr(), fm4.data_ptr(), N)
     mesh4 = torch.zeros((*shape, 4), device=pos.device)
     planar3 = torch.empty((3, *shape), device=pos.device)
     xbar, vbar = torch.randn_like(pos), torch.randn_like(pos)
-    add("paint (CIC density scatter, 8 red.f32 / particle)", lambda: o.paint(pos, shape, None, order=2, out=mesh),
-        16 * N, steps + 2, "pos 12N + mesh 4N")
-    add("paint3v4 (reverse-step scatter, 8 red.v4.f32 / particle, fused vbar update)",
-        lambda: lib.mcpm_paint3v4(st, pos.data_ptr(), vbar.data_ptr(), xbar.data_ptr(), 1e-3, 0.5, N, *shape,
-                                  mesh4.data_ptr()), 64 * N, steps, "pos 12N + vbar 12N r + 12N w + xbar 12N + mesh4 16N")
     eng = o.engine(shape)
     o.set_lattice(shape, shape)
-    add("brick paint (CIC density, smem tile + red.v4 flush; lattice-ordered particles)",
+    add("brick_paint", "brick paint (CIC density: shared-memory tile, fixed-point ATOMS, red.v4 flush)",
         lambda: (mesh.zero_(), lib.mcpm_paint_lattice(eng.handle, st, pos.data_ptr(), 0, 1.0, N, mesh.data_ptr())),
         16 * N, steps + 2, "pos 12N + mesh 4N (includes the 4N memset)")
-    add("brick paint3 (reverse-step scatter, 3 channel passes over a smem tile, fused vbar update)",
+    add("brick_paint3", "brick paint3 (reverse-step scatter of 3 channels, fused vbar += xbar*drift)",
         lambda: (planar3.zero_(), lib.mcpm_paint3_lattice(eng.handle, st, pos.data_ptr(), vbar.data_ptr(),
                                                            xbar.data_ptr(), 1e-3, 0.5, N, planar3.data_ptr())),
         60 * N, steps, "pos 12N + vbar 12N r + 12N w + xbar 12N + 3 meshes 12N (includes the 12N memset)")
-    add("kick_drift4 (float4 force readout + kick + drift)",
+    add("kick_drift4", "kick_drift4 (float4 force readout + kick + drift)",
         lambda: lib.mcpm_kick_drift4(st, p2.data_ptr(), v2.data_ptr(), fm4.data_ptr(), N, *shape, 1.0, 0.0, 0.0),
         64 * N, steps, "pos 12N r/w + vel 12N r/w + mesh4 16N")
-    add("read_grad4v (reverse-step gradient gather, fused xbar / vbar update)",
+    add("read_grad4v", "read_grad4v (reverse-step gradient gather, fused xbar / vbar update)",
         lambda: lib.mcpm_read_grad4v(st, pos.data_ptr(), fm4.data_ptr(), rho.data_ptr(), vbar.data_ptr(), 0.5, 1.0, N,
                                      *shape, xbar.data_ptr()), 80 * N, steps,
         "pos 12N + vbar 12N r/w + xbar 12N r/w + mesh4 16N + rhobar 4N")
-    add("interleave3 (3 planar meshes -> float4 mesh)", lambda: lib.mcpm_interleave3(st, fm.data_ptr(), fm4.data_ptr(), N),
-        28 * N, steps, "12N r + 16N w")
-    add("deinterleave3 (float4 mesh -> 3 planar meshes)",
-        lambda: lib.mcpm_deinterleave3(st, mesh4.data_ptr(), planar3.data_ptr(), N), 28 * N, steps, "16N r + 12N w")
+    add("interleave3", "interleave3 (3 planar meshes -> float4 mesh)",
+        lambda: lib.mcpm_interleave3(st, fm.data_ptr(), fm4.data_ptr(), N), 28 * N, steps, "12N r + 16N w")
     mk = o.rfftn(rho)
-    add("force_spectra (Green x gradient, 1 -> 3 spectra)", lambda: o.force_spectra(mk), 16 * N, 2 * (steps + 2),
-        "4N r + 12N w")
-    add("cuFFT R2C 256^3 (library)", lambda: o.rfftn(rho), 8 * N, 116, "4N r + 4N w per transform; 116 transforms per step")
-    # kernels the step loop does not run under the lattice hint are listed for comparison only
-    for r in rows:
-        if r["kernel"].startswith(("paint (CIC", "paint3v4", "deinterleave3")):
-            r["in_step"] = False
-    dom = max([r for r in rows if "library" not in r["kernel"] and r.get("in_step", True)],
-              key=lambda r: r["ms_per_step_total"])
+    mk3 = torch.empty((3, *mk.shape), dtype=mk.dtype, device=pos.device)
+    fused = bool(lib.mcpm_xfuse_force_slab(st, mk.data_ptr(), mk3.data_ptr(), *shape, shape[1], 0, 0, 0, 0.0, 0, 1.0) == 0)
+    if fused:
+        add("xfuse_force", "xfuse_force (x-FFT + force kernel + 3 inverse x-FFTs, 1 -> 3 spectra)",
+            lambda: lib.mcpm_xfuse_force_slab(st, mk.data_ptr(), mk3.data_ptr(), *shape, shape[1], 0, 0, 0, 0.0, 0, 1.0),
+            16 * N, steps, "4N r + 12N w")
+        add("xfuse_force_T", "xfuse_force_T (3 x-FFTs + transposed force kernel + inverse x-FFT, 3 -> 1 spectra)",
+            lambda: lib.mcpm_xfuse_force_T_slab(st, mk3.data_ptr(), mk.data_ptr(), *shape, shape[1], 0, 0, 0, 0.0, 0, 1.0),
+            16 * N, steps, "12N r + 4N w")
+    add("force_spectra", "force_spectra (Green x gradient streaming pass, 1 -> 3 spectra; LPT only when fused)",
+        lambda: o.force_spectra(mk), 16 * N, 2 if fused else 2 * (steps + 1), "4N r + 12N w")
+    add("cufft_r2c", "cuFFT 3-D R2C 256^3 (library; 3 passes)", lambda: o.rfftn(rho), 8 * N, 36 if fused else 116,
+        "4N r + 4N w per transform; per step: 36 3-D transforms (LPT, final paint) + 80 batched 2-D (y,z) ones", False)
+    # generic global-atomic kernels the step loop does not run under the lattice hint: listed for comparison only
+    add("paint_generic", "paint (generic CIC scatter, 8 red.f32 / particle)",
+        lambda: o.paint(pos, shape, None, order=2, out=mesh), 16 * N, 0, "pos 12N + mesh 4N", False)
+    add("paint3v4_generic", "paint3v4 (generic reverse-step scatter, 8 red.v4.f32 / particle)",
+        lambda: lib.mcpm_paint3v4(st, pos.data_ptr(), vbar.data_ptr(), xbar.data_ptr(), 1e-3, 0.5, N, *shape,
+                                  mesh4.data_ptr()), 64 * N, 0, "pos 12N + vbar 12N r + 12N w + xbar 12N + mesh4 16N",
+        False)
+    dom = max([r for r in rows if r["in_step"]], key=lambda r: r["ms_per_step_total"])
     return rows, dom
 
 
@@ -312,11 +321,15 @@ def run_engine(args):
                         "d2h_bytes_per_step": 4 * N + 8, "ms_per_step": ms_e2e / K},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_GBps"], "peak": peak,
-                             "peak_source": peak_src, "unit": "GB/s", "frac": dom["frac"], "traffic": None,
+                             "peak_source": peak_src, "unit": "GB/s", "frac": dom["frac"],
+                             "traffic": dom["traffic"],
+                             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full "
+                                               "capture (profiles/r1_traffic.json)" if dom["traffic"] else None,
                              "alg_bytes_per_launch": dom["alg_bytes"], "ms_per_launch": dom["ms"],
                              "share_of_step": dom["ms_per_step_total"] / (ms_dev / K)},
                 "kernels": rows, "cpu_baseline": cb, "logp_last": lp_val,
-                "paint_Gparticles_per_s": N / (rows[0]["ms"] * 1e-3) / 1e9}
+                "paint_Gparticles_per_s": N / (rows[0]["ms"] * 1e-3) / 1e9,
+                "paint_kernel": rows[0]["kernel"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -49,7 +49,8 @@ const char* mcpm_last_error(void);
 long long mcpm_launch_count(int reset);
 
 /* Process-wide performance knobs (never change which result is computed).  Keys: "gather_minb" = 4 | 5 | 6, the
- * resident CTAs per SM the readout kernels are compiled for. */
+ * resident CTAs per SM the readout kernels are compiled for; "gather_blocked" = 0 | 1, one CTA per 256 consecutive
+ * particles instead of a grid-stride loop. */
 int mcpm_tune(const char* key, int value);
 
 /* Engine for real mesh shape (nx, ny, nz) on the current device.  max_batch = largest number of meshes transformed
@@ -168,6 +169,17 @@ int mcpm_hessian_spectra_slab(void* stream, const void* delta_k, void* out6, int
                               int lap_fd, int grad_fd, float norm);
 int mcpm_hessian_spectra_T_slab(void* stream, const void* in6, void* out1, int nx, int ny, int nz, int ny_loc, int y0,
                                 int lap_fd, int grad_fd, int half_weights, int accumulate, float norm);
+
+/* Fused x-transform passes (CUDA build, nx in {64, 128, 256}; MCPM_EUNSUP otherwise), on a half spectrum
+ * [nx, ny_loc, nz/2+1] that has been transformed along (y,z) only:
+ *   xfuse_force   : out3[j] = IFFT_x( force kernel_j * FFT_x(in) )            = mcpm_force_spectra between the x-passes
+ *   xfuse_force_T : out1    = IFFT_x( sum_j conj(kernel_j) * FFT_x(in3[j]) )  = mcpm_force_spectra_T (no half weights)
+ * Unnormalised transforms; `norm` multiplies the output.  The engine's pm_forces / reverse step run these between
+ * batched 2-D cuFFT plans; with ny_loc < ny they serve a slab-decomposed mesh after the all-to-all. */
+int mcpm_xfuse_force_slab(void* stream, const void* in, void* out3, int nx, int ny, int nz, int ny_loc, int y0,
+                          int lap_fd, int grad_fd, float kcut, int deconv_order, float norm);
+int mcpm_xfuse_force_T_slab(void* stream, const void* in3, void* out1, int nx, int ny, int nz, int ny_loc, int y0,
+                            int lap_fd, int grad_fd, float kcut, int deconv_order, float norm);
 
 /* chreshape (utils.py:975-1013): Hermitian- and mean-preserving Fourier crop / pad between real shapes. */
 int mcpm_chreshape(void* stream, const void* in, int inx, int iny, int inz, void* out, int onx, int ony, int onz);

@@ -104,6 +104,17 @@ int mcpm_tune(const char* key, int value) {
     set_gather_minb(value);
     return MCPM_OK;
   }
+#ifndef MCPM_HOSTEMU
+  if (std::string(key) == "xfuse_occ") {
+    NEED(value == 2 || value == 3, "tune: xfuse_occ must be 2 or 3");
+    set_xfuse_occ(value);
+    return MCPM_OK;
+  }
+#endif
+  if (std::string(key) == "gather_blocked") {
+    set_gather_blocked(value != 0);
+    return MCPM_OK;
+  }
   set_error(std::string("tune: unknown key ") + key);
   return MCPM_EINVAL;
   API_END
@@ -328,6 +339,42 @@ int mcpm_force_spectra_slab(void* stream, const void* delta_k, void* out3, int n
   sk.ny_loc = ny_loc;
   sk.y0 = y0;
   return force_spectra(as_stream(stream), C(delta_k), C(out3), nx, ny, nz, lap_fd, grad_fd, kcut, deconv_order, norm, sk);
+  API_END
+}
+
+int mcpm_xfuse_force_slab(void* stream, const void* in, void* out3, int nx, int ny, int nz, int ny_loc, int y0,
+                          int lap_fd, int grad_fd, float kcut, int deconv_order, float norm) {
+  API_BEGIN
+  NEED(in && out3, "xfuse_force_slab: null pointer");
+  NEED(ny_loc > 0 && y0 >= 0 && y0 + ny_loc <= ny && nz > 0 && !(nz & 1), "xfuse_force_slab: bad shape or ky block");
+#ifndef MCPM_HOSTEMU
+  if (xfuse_supported(nx)) {
+    SlabK sk;
+    sk.ny_loc = ny_loc;
+    sk.y0 = y0;
+    return xfuse_force(as_stream(stream), C(in), C(out3), nx, ny, nz, lap_fd, grad_fd, kcut, deconv_order, norm, sk);
+  }
+#endif
+  set_error("xfuse_force_slab: nx must be 64, 128 or 256 (CUDA build only)");
+  return MCPM_EUNSUP;
+  API_END
+}
+
+int mcpm_xfuse_force_T_slab(void* stream, const void* in3, void* out1, int nx, int ny, int nz, int ny_loc, int y0,
+                            int lap_fd, int grad_fd, float kcut, int deconv_order, float norm) {
+  API_BEGIN
+  NEED(in3 && out1, "xfuse_force_T_slab: null pointer");
+  NEED(ny_loc > 0 && y0 >= 0 && y0 + ny_loc <= ny && nz > 0 && !(nz & 1), "xfuse_force_T_slab: bad shape or ky block");
+#ifndef MCPM_HOSTEMU
+  if (xfuse_supported(nx)) {
+    SlabK sk;
+    sk.ny_loc = ny_loc;
+    sk.y0 = y0;
+    return xfuse_force_T(as_stream(stream), C(in3), C(out1), nx, ny, nz, lap_fd, grad_fd, kcut, deconv_order, norm, sk);
+  }
+#endif
+  set_error("xfuse_force_T_slab: nx must be 64, 128 or 256 (CUDA build only)");
+  return MCPM_EUNSUP;
   API_END
 }
 

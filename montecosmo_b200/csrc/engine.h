@@ -95,6 +95,7 @@ int hermitian_weights(stream_t, const cfloat* in, cfloat* out, int nx, int ny, i
 
 // cic4.cu: CIC kernels on the float4-interleaved vector mesh
 void set_gather_minb(int v);
+void set_gather_blocked(int v);
 int interleave3(stream_t, const float* planar3, float* mesh4, int64_t n);
 int deinterleave3(stream_t, const float* mesh4, float* planar3, int64_t n);
 int kick_drift4(stream_t, const float* pos, const float* vel, const float* fmesh4, int64_t np, int nx, int ny, int nz,
@@ -106,6 +107,7 @@ int read_grad4v(stream_t, const float* pos, const float* fmesh4, const float* rh
 
 // xfft.cu (CUDA build only): the x-passes of rfftn / irfftn fused with the force kernel, on [nx, ny_loc, nz/2+1]
 bool xfuse_supported(int nx);
+void set_xfuse_occ(int v);
 int xfuse_force(stream_t, const cfloat* in, cfloat* out3, int nx, int ny, int nz, int lap_fd, int grad_fd, float kcut,
                 int deconv_order, float norm, SlabK sk = SlabK());
 int xfuse_force_T(stream_t, const cfloat* in3, cfloat* out, int nx, int ny, int nz, int lap_fd, int grad_fd,

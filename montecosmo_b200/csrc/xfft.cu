@@ -104,8 +104,9 @@ struct Args {
 // MODE 0: out_j = IFFT_x[ -(i g_j) c FFT_x[in] ]            (force_spectra between the x-passes)
 // MODE 1: out   = IFFT_x[ i c sum_j g_j FFT_x[in_j] ]        (force_spectra_T between the x-passes)
 // PLAIN: no long-range filter and no deconvolution (the BullFrog loop): the scalar factor is a table look-up
-template <int R1, int R2, int MODE, bool PLAIN>
-__global__ void __launch_bounds__(R2 * CT, 512 / (R2 * CT)) xfuse_kernel(Args a) {
+// OCC: resident CTAs of 256 threads per SM the register budget is chosen for (2: 128 registers, 3: 80)
+template <int R1, int R2, int MODE, bool PLAIN, int OCC>
+__global__ void __launch_bounds__(R2 * CT, OCC * 256 / (R2 * CT)) xfuse_kernel(Args a) {
   constexpr int N = R1 * R2, J = R1 / R2;
   extern __shared__ float2 xsm[];
   float2* tw = xsm;                // [N]   exp(-2 pi i n / N)
@@ -214,19 +215,23 @@ __global__ void __launch_bounds__(R2 * CT, 512 / (R2 * CT)) xfuse_kernel(Args a)
   }
 }
 
-template <int R1, int R2, int MODE>
-static int launch(stream_t st, const Args& a) {
+static int g_occ = 2;
+
+template <int R1, int R2, int MODE, bool PLAIN, int OCC>
+static void launch_one(stream_t st, const Args& a) {
   constexpr int N = R1 * R2;
   const size_t smem = sizeof(float2) * (2 * N + 2 * CT * (N + 1));
-  const unsigned grid = (a.M + CT - 1) / CT;
+  cudaFuncSetAttribute(xfuse_kernel<R1, R2, MODE, PLAIN, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  xfuse_kernel<R1, R2, MODE, PLAIN, OCC><<<(a.M + CT - 1) / CT, R2 * CT, smem, st>>>(a);
+}
+
+template <int R1, int R2, int MODE>
+static int launch(stream_t st, const Args& a) {
   count_launch();
-  if (!(a.r2 > 0.f) && a.deconv_order <= 0) {
-    cudaFuncSetAttribute(xfuse_kernel<R1, R2, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    xfuse_kernel<R1, R2, MODE, true><<<grid, R2 * CT, smem, st>>>(a);
-  } else {
-    cudaFuncSetAttribute(xfuse_kernel<R1, R2, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    xfuse_kernel<R1, R2, MODE, false><<<grid, R2 * CT, smem, st>>>(a);
-  }
+  const bool plain = !(a.r2 > 0.f) && a.deconv_order <= 0;
+  if (plain && g_occ == 3) launch_one<R1, R2, MODE, true, 3>(st, a);
+  else if (plain) launch_one<R1, R2, MODE, true, 2>(st, a);
+  else launch_one<R1, R2, MODE, false, 2>(st, a);
   return rt_check("xfuse") ? MCPM_ECUDA : 0;
 }
 
@@ -242,6 +247,7 @@ static int dispatch(stream_t st, const Args& a) {
 }
 }  // namespace xf
 
+void set_xfuse_occ(int v) { xf::g_occ = v; }
 bool xfuse_supported(int nx) { return nx == 64 || nx == 128 || nx == 256; }
 
 static xf::Args make_args(const cfloat* in, cfloat* out, int nx, int ny, int nz, int lap_fd, int grad_fd, float kcut,

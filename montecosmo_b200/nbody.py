@@ -405,14 +405,26 @@ def pm_forces2(pos, mesh, read_order: int = 2, grad_fd=np.inf, lap_fd=np.inf):
 
 def lpt(cosmo, init_mesh, pos, a, lpt_order: int = 2, read_order: int = 2, grad_fd=np.inf, lap_fd=np.inf,
         _displaced=False):
-    """First or second order LPT displacement at scale factor `a` (nbody.py:634-667).  Scalar `a` only."""
-    if np.ndim(a) != 0:
-        raise NotImplementedError("per-particle scale factors (light-cone lpt) are not implemented by the engine")
+    """First or second order LPT displacement at scale factor `a` (nbody.py:634-667).  `a` is a scalar, or one scale
+    factor per particle ([Np] or [Np, 1], the light-cone use of nbody.py:651-653): the two force fields then come from
+    the engine and the per-particle growth factors multiply them here."""
     if lpt_order not in (1, 2):
         raise ValueError("lpt_order must be 1 or 2")
     init_mesh = torch.as_tensor(init_mesh)
     if not torch.is_complex(init_mesh):
         init_mesh = rfftn(init_mesh)
+    if np.ndim(a) != 0:
+        a_col = torch.as_tensor(a, dtype=torch.float64).detach().cpu().reshape(-1, 1)
+        force1 = pm_forces(pos, init_mesh, read_order, grad_fd=grad_fd, lap_fd=lap_fd)
+        if a_col.shape[0] != force1.shape[0]:
+            raise ValueError("a must be a scalar or hold one scale factor per particle")
+        col = lambda t: t.to(device=force1.device, dtype=force1.dtype)
+        dpos, vel = col(_cosmo.a2g(cosmo, a_col)) * force1, force1
+        if lpt_order == 2:
+            force2 = pm_forces2(pos, init_mesh, read_order, grad_fd=grad_fd, lap_fd=lap_fd)
+            dpos = dpos - col(_cosmo.a2g2(cosmo, a_col)) * force2
+            vel = vel - col(_cosmo.a2dg2dg(cosmo, a_col)) * force2
+        return (dpos + _f32(pos), vel) if _displaced else (dpos, vel)
     coef = _coef_tensor(_cosmo.a2g(cosmo, a), _cosmo.a2g2(cosmo, a), _cosmo.a2dg2dg(cosmo, a))
     return _Lpt.apply(_c64(init_mesh), coef, _f32(pos), int(lpt_order), int(read_order), lap_fd, grad_fd, _displaced)
 

@@ -182,3 +182,30 @@ def test_model_logpdf_and_force(nb, evolution, n_steps):
     lp2.backward()
     assert abs(float(lp2) - float(lp)) < 1e-6 * abs(float(lp)) and rel(w.grad, g.detach().cpu().numpy()) < 1e-5
     assert rel(m.force(white, obs), g.detach().cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("lpt_order", [1, 2])
+def test_lpt_per_particle_scale_factor(nb, lpt_order):
+    """Light-cone lpt (nbody.py:651-653: `a` of shape [Np, 1]) against the oracle, value (5e-5) and gradient w.r.t. the
+    initial mesh (2e-4); the scalar path must agree with the per-particle path fed a constant array."""
+    from montecosmo_b200.cosmo import Cosmology
+    rng = np.random.default_rng(17)
+    shape = (8, 6, 10)
+    dk0 = np.fft.rfftn(rng.normal(size=shape)) * 0.02
+    q = O.regular_pos(shape)
+    pos = (q + torch.tensor(rng.normal(scale=0.3, size=q.shape))).float()
+    a = torch.tensor(rng.uniform(0.2, 1.0, (q.shape[0], 1)))
+    cd, cv = (torch.tensor(rng.normal(size=q.shape), dtype=torch.float32) for _ in range(2))
+    dk = torch.tensor(dk0, dtype=torch.complex64, device=dev(nb)).requires_grad_()
+    dp, vl = nb.lpt(Cosmology(), dk, pos.to(dev(nb)), a, lpt_order, 2)
+    ((dp * cd.to(dev(nb))).sum() + (vl * cv.to(dev(nb))).sum()).backward()
+    dko = torch.tensor(dk0, dtype=torch.complex128).requires_grad_()
+    dpo, vlo = O.lpt(O.Cosmology(), dko, pos.double(), a, lpt_order, 2)
+    ((dpo * cd.double()).sum() + (vlo * cv.double()).sum()).backward()
+    assert rel(dp, dpo) < 5e-5 and rel(vl, vlo) < 5e-5
+    assert rel(dk.grad, dko.grad) < 2e-4
+    d0, v0 = nb.lpt(Cosmology(), dk.detach(), pos.to(dev(nb)), 0.5, lpt_order, 2)
+    d1, v1 = nb.lpt(Cosmology(), dk.detach(), pos.to(dev(nb)), np.full(q.shape[0], 0.5), lpt_order, 2)
+    assert rel(d1, d0) < 1e-6 and rel(v1, v0) < 1e-6
+    with pytest.raises(ValueError):
+        nb.lpt(Cosmology(), dk.detach(), pos.to(dev(nb)), np.full(7, 0.5), lpt_order, 2)

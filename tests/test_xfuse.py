@@ -93,3 +93,40 @@ def test_unsupported_shape_reports(ops):
     ops.set_fused_fft((12, 8, 8), False)
     with pytest.raises(McpmError):
         ops.set_fused_fft((12, 8, 8), True)
+
+
+@pytest.mark.parametrize("nx,ny,nz,ny_loc,y0", [(64, 12, 16, 12, 0), (128, 8, 10, 4, 4), (256, 6, 8, 3, 2)])
+def test_kernel_against_numpy_x_transforms(ops, nx, ny, nz, ny_loc, y0):
+    """The kernel alone on a (ky-block of a) half spectrum: out = IFFT_x(kernel * FFT_x(in)) with numpy's FFT along x and
+    the engine's own streaming multiply (mcpm_force_spectra[_T]_slab) in between.  float32 vs float64 FFT: 2e-6."""
+    rng = np.random.default_rng(nx + ny_loc)
+    nzc = nz // 2 + 1
+    A = ops.A
+    st = A.stream()
+    shape_c = (nx, ny_loc, nzc)
+    x1 = (rng.normal(size=shape_c) + 1j * rng.normal(size=shape_c)).astype(np.complex64)
+    x3 = (rng.normal(size=(3, *shape_c)) + 1j * rng.normal(size=(3, *shape_c))).astype(np.complex64)
+    norm = 0.37
+    for lap_fd, grad_fd, kcut, dec in [(0, 0, 0.0, 0), (2, 4, 1.5, 2)]:
+        # forward operator
+        d_in, d_out = A.prepare(x1, "c64"), A.empty((3, *shape_c), "c64")
+        ops._call("mcpm_xfuse_force_slab", st, A.ptr(d_in), A.ptr(d_out), nx, ny, nz, ny_loc, y0, lap_fd, grad_fd, kcut,
+                  dec, norm)
+        fk = A.prepare(np.fft.fft(x1.astype(np.complex128), axis=0).astype(np.complex64), "c64")
+        mid = A.empty((3, *shape_c), "c64")
+        ops._call("mcpm_force_spectra_slab", st, A.ptr(fk), A.ptr(mid), nx, ny, nz, ny_loc, y0, lap_fd, grad_fd, kcut,
+                  dec, norm)
+        ref = np.fft.ifft(to_numpy(mid).astype(np.complex128), axis=1) * nx
+        got = to_numpy(d_out).astype(np.complex128)
+        assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 2e-6
+        # transpose operator
+        d_in3, d_out1 = A.prepare(x3, "c64"), A.empty(shape_c, "c64")
+        ops._call("mcpm_xfuse_force_T_slab", st, A.ptr(d_in3), A.ptr(d_out1), nx, ny, nz, ny_loc, y0, lap_fd, grad_fd,
+                  kcut, dec, norm)
+        fk3 = A.prepare(np.fft.fft(x3.astype(np.complex128), axis=1).astype(np.complex64), "c64")
+        mid1 = A.empty(shape_c, "c64")
+        ops._call("mcpm_force_spectra_T_slab", st, A.ptr(fk3), A.ptr(mid1), nx, ny, nz, ny_loc, y0, lap_fd, grad_fd, kcut,
+                  dec, 0, 0, norm)
+        ref1 = np.fft.ifft(to_numpy(mid1).astype(np.complex128), axis=0) * nx
+        got1 = to_numpy(d_out1).astype(np.complex128)
+        assert np.linalg.norm(got1 - ref1) / np.linalg.norm(ref1) < 2e-6

@@ -29,12 +29,14 @@ rho = torch.randn(n, n, n, device=dev, generator=g)
 flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
 p2, v2 = pos.clone(), vel.clone()
 st = A.stream()
-for minb in (4, 5, 6):
+for minb, blocked in ((4, 0), (4, 1), (5, 1), (6, 1)):
     lib.mcpm_tune(b"gather_minb", minb)
+    lib.mcpm_tune(b"gather_blocked", blocked)
     kd = timeit(lambda: lib.mcpm_kick_drift4(st, p2.data_ptr(), v2.data_ptr(), fm4.data_ptr(), N, n, n, n, 1.0, 0.0, 0.0),
                 flush=flush)
     rg = timeit(lambda: lib.mcpm_read_grad4v(st, pos.data_ptr(), fm4.data_ptr(), rho.data_ptr(), vel.data_ptr(), 0.5, 1.0,
                                              N, n, n, n, xbar.data_ptr()), flush=flush)
-    print(f"gather_minb={minb}: kick_drift4 {kd[0]:.3f} ms (min {kd[1]:.3f})   read_grad4v {rg[0]:.3f} ms (min {rg[1]:.3f})",
+    print(f"gather_minb={minb} blocked={blocked}: kick_drift4 {kd[0]:.3f} ms (min {kd[1]:.3f})   read_grad4v {rg[0]:.3f} ms (min {rg[1]:.3f})",
           flush=True)
 lib.mcpm_tune(b"gather_minb", 4)
+lib.mcpm_tune(b"gather_blocked", 0)

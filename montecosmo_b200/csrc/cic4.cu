@@ -96,8 +96,11 @@ int deinterleave3(stream_t st, const float* mesh4, float* planar3, int64_t n) {
 }
 
 // F = CIC read of mesh4.xyz at pos; vel' = alpha vel + beta F; pos' = pos + vel' drift  (pos_out/vel_out may alias)
+// `zero` (optional): `nzero` floats cleared on the side, spread over the particle threads -- the density mesh the next
+// step's scatter accumulates into; a few bytes per thread in a latency-bound kernel instead of a separate memset pass.
 int kick_drift4(stream_t st, const float* pos, const float* vel, const float* fmesh4, int64_t np, int nx, int ny,
-                int nz, float alpha, float beta, float drift, float* pos_out, float* vel_out) {
+                int nz, float alpha, float beta, float drift, float* pos_out, float* vel_out, float* zero,
+                int64_t nzero) {
   const f4* fm = reinterpret_cast<const f4*>(fmesh4);
   launch_gather(st, np, [=] MCPM_LAMBDA(int64_t p) {
     float x[3] = {pos[3 * p], pos[3 * p + 1], pos[3 * p + 2]};
@@ -126,6 +129,8 @@ int kick_drift4(stream_t st, const float* pos, const float* vel, const float* fm
     pos_out[3 * p] = x[0] + v0 * drift;
     pos_out[3 * p + 1] = x[1] + v1 * drift;
     pos_out[3 * p + 2] = x[2] + v2 * drift;
+    if (zero)
+      for (int64_t c = p; c < nzero; c += np) zero[c] = 0.0f;
   });
   return rt_check("kick_drift4");
 }
@@ -173,7 +178,8 @@ int paint3v4(stream_t st, const float* pos, float* A, const float* B, float cb, 
 //   u(corner) = cscale * (cot . F(corner)) + rhobar(corner);   g_a = sum_corners u * dW_a * prod_{d != a} W_d
 //   xbar += g ;  then (tail of the reverse step) cot *= alpha_tail  when alpha_tail >= 0 is requested via `scale_cot`.
 int read_grad4v(stream_t st, const float* pos, const float* fmesh4, const float* rhobar, float* cot, float cscale,
-                int scale_cot, float alpha_tail, int64_t np, int nx, int ny, int nz, float* grad, int accumulate) {
+                int scale_cot, float alpha_tail, int64_t np, int nx, int ny, int nz, float* grad, int accumulate,
+                float* zero, int64_t nzero) {
   const f4* fm = reinterpret_cast<const f4*>(fmesh4);
   launch_gather(st, np, [=] MCPM_LAMBDA(int64_t p) {
     float x[3] = {pos[3 * p], pos[3 * p + 1], pos[3 * p + 2]};
@@ -216,6 +222,8 @@ int read_grad4v(stream_t st, const float* pos, const float* fmesh4, const float*
       cot[3 * p + 1] = alpha_tail * q1;
       cot[3 * p + 2] = alpha_tail * q2;
     }
+    if (zero)  // the three meshes the next reverse step's scatter accumulates into (see kick_drift4)
+      for (int64_t c = p; c < nzero; c += np) zero[c] = 0.0f;
   });
   return rt_check("read_grad4v");
 }

@@ -60,12 +60,20 @@ void engine_destroy(Engine* e) {
 
 // CIC paint of pos * scale + shift into a fresh mesh: brick-tiled when the engine carries a matching lattice hint and
 // the positions are not rescaled (CUDA build), generic otherwise
-static int paint_fresh(Engine* E, stream_t st, const float* pos, const float* weights, float wscalar, int64_t np,
-                       int order, const float* scale, float shift, float* mesh) {
+static bool brick_path(const Engine* E, int order, const float* scale) {
 #ifndef MCPM_HOSTEMU
   const bool unit = !scale || (scale[0] == 1.0f && scale[1] == 1.0f && scale[2] == 1.0f);
-  if (order == 2 && E->lat.px > 0 && unit) {
-    if (rt_memset(mesh, 0, sizeof(float) * (size_t)E->N, st)) return MCPM_ECUDA;
+  return order == 2 && E->lat.px > 0 && unit;
+#else
+  return false;
+#endif
+}
+// `prezeroed`: the caller guarantees the mesh is already zero (cleared on the side by the previous step's kernel)
+static int paint_fresh(Engine* E, stream_t st, const float* pos, const float* weights, float wscalar, int64_t np,
+                       int order, const float* scale, float shift, float* mesh, bool prezeroed = false) {
+#ifndef MCPM_HOSTEMU
+  if (brick_path(E, order, scale)) {
+    if (!prezeroed && rt_memset(mesh, 0, sizeof(float) * (size_t)E->N, st)) return MCPM_ECUDA;
     int r = brick_paint_cic(st, E->lat, pos, weights, wscalar, shift, np, E->nx, E->ny, E->nz, mesh);
     if (r < 0) return MCPM_ECUDA;
     if (r == 1) return 0;
@@ -73,8 +81,9 @@ static int paint_fresh(Engine* E, stream_t st, const float* pos, const float* we
 #endif
   return paint(st, pos, weights, wscalar, np, E->nx, E->ny, E->nz, order, scale, shift, mesh, 0);
 }
-static int paint_density(Engine* E, stream_t st, const float* pos, int64_t np, int order, float* mesh) {
-  return paint_fresh(E, st, pos, nullptr, 1.0f, np, order, nullptr, 0.0f, mesh);
+static int paint_density(Engine* E, stream_t st, const float* pos, int64_t np, int order, float* mesh,
+                         bool prezeroed = false) {
+  return paint_fresh(E, st, pos, nullptr, 1.0f, np, order, nullptr, 0.0f, mesh, prezeroed);
 }
 
 // delta_k (any spectrum, preserved) -> three real force meshes fm[3][N]  (nbody.py:595-603 up to the irfftn)
@@ -87,10 +96,10 @@ static int force_meshes_from_spectrum(Engine* E, stream_t st, const cfloat* dk, 
 
 // pm_forces with a painted density (mesh given as a shape tuple, nbody.py:588-604)
 int pm_forces(Engine* E, stream_t st, const float* pos, int64_t np, int order, int paint_deconv, int lap_fd,
-              int grad_fd, float kcut, float* fmesh3, float* forces) {
+              int grad_fd, float kcut, float* fmesh3, float* forces, bool rho_prezeroed) {
   float* fm = fmesh3 ? fmesh3 : E->r(0);
   float* rho = E->r(6);
-  TRY(paint_density(E, st, pos, np, order, rho));
+  TRY(paint_density(E, st, pos, np, order, rho, rho_prezeroed));
 #ifndef MCPM_HOSTEMU
   if (E->fused_fft) {  // 2-D (y,z) R2C per x-plane, one kernel for x-FFT + force kernel + 3 inverse x-FFTs, 2-D C2R
     TRY(slabfft_r2c_yz(E->fft2d, st, rho, E->c(6), 1));
@@ -234,14 +243,17 @@ int nbody_steps(Engine* E, stream_t st, float* pos, float* vel, int64_t np, int 
   for (int s = 0; s < n_steps; ++s) {
     float* slot = fm ? fm + (int64_t)s * 4 * E->N : E->r(3);
     float* planar = cic ? E->r(0) : slot;
-    TRY(pm_forces(E, st, cur, np, order, paint_deconv, lap_fd, grad_fd, 0.0f, planar, nullptr));
+    // under the brick path the density mesh of step s+1 is cleared by the kick kernel of step s
+    const bool side_zero = cic && brick_path(E, order, nullptr);
+    TRY(pm_forces(E, st, cur, np, order, paint_deconv, lap_fd, grad_fd, 0.0f, planar, nullptr, side_zero && s > 0));
     const bool last = (s == n_steps - 1);
     float dcomb = drift_post[s] + (last ? 0.0f : drift_pre[s + 1]);
     float* xout = (xk && !last) ? xk + (int64_t)(s + 1) * P3 : pos;
     float* vout = vk ? vk + (int64_t)s * P3 : vel;
     if (cic) {
       TRY(interleave3(st, planar, slot, E->N));
-      TRY(kick_drift4(st, cur, vin, slot, np, E->nx, E->ny, E->nz, alpha[s], beta[s], dcomb, xout, vout));
+      TRY(kick_drift4(st, cur, vin, slot, np, E->nx, E->ny, E->nz, alpha[s], beta[s], dcomb, xout, vout,
+                      side_zero && !last ? E->r(6) : nullptr, E->N));
     } else {
       TRY(kick_drift(st, cur, vin, slot, np, E->nx, E->ny, E->nz, order, alpha[s], beta[s], dcomb, xout, vout,
                      nullptr));
@@ -271,6 +283,7 @@ int nbody_steps_vjp(Engine* E, stream_t st, float* posbar, float* velbar, int64_
   }
   const int64_t P3 = 3 * np;
   const bool cic = (order == 2);
+  const bool side_zero = cic && brick_path(E, order, nullptr);
   for (int s = n_steps - 1; s >= 0; --s) {
     const bool last = (s == n_steps - 1);
     float dcomb = drift_post[s] + (last ? 0.0f : drift_pre[s + 1]);
@@ -288,7 +301,8 @@ int nbody_steps_vjp(Engine* E, stream_t st, float* posbar, float* velbar, int64_
       int handled = 0;
 #ifndef MCPM_HOSTEMU
       if (E->lat.px > 0) {  // brick-tiled: accumulates in shared memory, flushes planar meshes directly
-        TRY(rt_memset(E->r(4), 0, sizeof(float) * 3 * (size_t)E->N, st) ? MCPM_ECUDA : 0);
+        if (!(side_zero && !last))  // cleared on the side by read_grad4v of the step before (in sweep order)
+          TRY(rt_memset(E->r(4), 0, sizeof(float) * 3 * (size_t)E->N, st) ? MCPM_ECUDA : 0);
         handled = brick_paint3_cic(st, E->lat, x1, velbar, posbar, dcomb, beta[s], np, E->nx, E->ny, E->nz, E->r(4));
         if (handled < 0) return MCPM_ECUDA;
       }
@@ -312,7 +326,8 @@ int nbody_steps_vjp(Engine* E, stream_t st, float* posbar, float* velbar, int64_
     }
     if (cic) {
       // xbar += dread(x1; beta*vbar . F + rhobar) and vbar *= alpha, one gather
-      TRY(read_grad4v(st, x1, slot, E->r(3), velbar, beta[s], 1, alpha[s], np, E->nx, E->ny, E->nz, posbar, 1));
+      TRY(read_grad4v(st, x1, slot, E->r(3), velbar, beta[s], 1, alpha[s], np, E->nx, E->ny, E->nz, posbar, 1,
+                      side_zero && s > 0 ? E->r(4) : nullptr, 3 * E->N));
     } else {
       const float* ms[4] = {slot, slot + E->N, slot + 2 * E->N, E->r(3)};
       TRY(read_grad(st, x1, ms, 4, velbar, 3, beta[s], nullptr, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, posbar,

@@ -99,11 +99,13 @@ void set_gather_blocked(int v);
 int interleave3(stream_t, const float* planar3, float* mesh4, int64_t n);
 int deinterleave3(stream_t, const float* mesh4, float* planar3, int64_t n);
 int kick_drift4(stream_t, const float* pos, const float* vel, const float* fmesh4, int64_t np, int nx, int ny, int nz,
-                float alpha, float beta, float drift, float* pos_out, float* vel_out);
+                float alpha, float beta, float drift, float* pos_out, float* vel_out, float* zero = nullptr,
+                int64_t nzero = 0);
 int paint3v4(stream_t, const float* pos, float* A, const float* B, float cb, int store, float scale, int64_t np, int nx,
              int ny, int nz, float* mesh4);
 int read_grad4v(stream_t, const float* pos, const float* fmesh4, const float* rhobar, float* cot, float cscale,
-                int scale_cot, float alpha_tail, int64_t np, int nx, int ny, int nz, float* grad, int accumulate);
+                int scale_cot, float alpha_tail, int64_t np, int nx, int ny, int nz, float* grad, int accumulate,
+                float* zero = nullptr, int64_t nzero = 0);
 
 // xfft.cu (CUDA build only): the x-passes of rfftn / irfftn fused with the force kernel, on [nx, ny_loc, nz/2+1]
 bool xfuse_supported(int nx);
@@ -121,7 +123,7 @@ int brick_paint3_cic(stream_t, const Lattice&, const float* pos, float* A, const
 
 // engine.cu
 int pm_forces(Engine*, stream_t, const float* pos, int64_t np, int order, int paint_deconv, int lap_fd, int grad_fd,
-              float kcut, float* fmesh3, float* forces);
+              float kcut, float* fmesh3, float* forces, bool rho_prezeroed = false);
 int pm_forces_vjp(Engine*, stream_t, const float* pos, const float* fbar, float cscale, const float* fmesh3,
                   int64_t np, int order, int paint_deconv, int lap_fd, int grad_fd, float kcut, float* posbar,
                   int accumulate);

@@ -50,7 +50,8 @@ long long mcpm_launch_count(int reset);
 
 /* Process-wide performance knobs (never change which result is computed).  Keys: "gather_minb" = 4 | 5 | 6, the
  * resident CTAs per SM the readout kernels are compiled for; "gather_blocked" = 0 | 1, one CTA per 256 consecutive
- * particles instead of a grid-stride loop. */
+ * particles instead of a grid-stride loop; "xfuse_occ" = 2 | 3, resident CTAs per SM of the fused x-transform;
+ * "side_zero" = 0 | 1, clear the next step's scatter meshes inside the readout kernels instead of memsets. */
 int mcpm_tune(const char* key, int value);
 
 /* Engine for real mesh shape (nx, ny, nz) on the current device.  max_batch = largest number of meshes transformed

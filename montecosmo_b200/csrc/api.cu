@@ -111,6 +111,10 @@ int mcpm_tune(const char* key, int value) {
     return MCPM_OK;
   }
 #endif
+  if (std::string(key) == "side_zero") {
+    set_side_zero(value != 0);
+    return MCPM_OK;
+  }
   if (std::string(key) == "gather_blocked") {
     set_gather_blocked(value != 0);
     return MCPM_OK;

@@ -60,6 +60,10 @@ void engine_destroy(Engine* e) {
 
 // CIC paint of pos * scale + shift into a fresh mesh: brick-tiled when the engine carries a matching lattice hint and
 // the positions are not rescaled (CUDA build), generic otherwise
+// mcpm_tune("side_zero"): clear the next step's scatter meshes inside the gather kernels (1) or with memsets (0)
+static int g_side_zero = 1;
+void set_side_zero(int v) { g_side_zero = v; }
+
 static bool brick_path(const Engine* E, int order, const float* scale) {
 #ifndef MCPM_HOSTEMU
   const bool unit = !scale || (scale[0] == 1.0f && scale[1] == 1.0f && scale[2] == 1.0f);
@@ -89,6 +93,13 @@ static int paint_density(Engine* E, stream_t st, const float* pos, int64_t np, i
 // delta_k (any spectrum, preserved) -> three real force meshes fm[3][N]  (nbody.py:595-603 up to the irfftn)
 static int force_meshes_from_spectrum(Engine* E, stream_t st, const cfloat* dk, int lap_fd, int grad_fd, float kcut,
                                       int deconv_order, float* fm) {
+#ifndef MCPM_HOSTEMU
+  if (E->fused_fft) {  // multiply + the three inverse x-transforms in one kernel, then 2-D C2R per x-plane
+    TRY(xfuse_force_k(st, dk, E->c(0), E->nx, E->ny, E->nz, lap_fd, grad_fd, kcut, deconv_order, E->invN));
+    TRY(slabfft_c2r_yz(E->fft2d, st, E->c(0), fm, 3));
+    return 0;
+  }
+#endif
   TRY(force_spectra(st, dk, E->c(0), E->nx, E->ny, E->nz, lap_fd, grad_fd, kcut, deconv_order, E->invN));
   TRY(fft_c2r(E->fft, st, E->c(0), fm, 3));
   return 0;
@@ -159,11 +170,23 @@ int pm_forces_mesh(Engine* E, stream_t st, const float* pos, const cfloat* dk, i
 int pm_forces2(Engine* E, stream_t st, const float* pos, const cfloat* dk, int64_t np, int order, int lap_fd,
                int grad_fd, float* forces, float* h6_out) {
   float* h6 = h6_out ? h6_out : E->r(0);
-  TRY(hessian_spectra(st, dk, E->c(0), E->nx, E->ny, E->nz, lap_fd, grad_fd, E->invN));
-  TRY(fft_c2r(E->fft, st, E->c(0), h6, 6));
-  TRY(lpt2_source(st, h6, E->r(6), E->N));
-  TRY(fft_r2c(E->fft, st, E->r(6), E->c(6), 1));
-  TRY(force_meshes_from_spectrum(E, st, E->c(6), lap_fd, grad_fd, 0.0f, 0, E->r(0)));
+#ifndef MCPM_HOSTEMU
+  if (E->fused_fft) {
+    TRY(xfuse_hessian_k(st, dk, E->c(0), E->nx, E->ny, E->nz, lap_fd, grad_fd, E->invN));
+    TRY(slabfft_c2r_yz(E->fft2d, st, E->c(0), h6, 6));
+    TRY(lpt2_source(st, h6, E->r(6), E->N));
+    TRY(slabfft_r2c_yz(E->fft2d, st, E->r(6), E->c(6), 1));
+    TRY(xfuse_force(st, E->c(6), E->c(0), E->nx, E->ny, E->nz, lap_fd, grad_fd, 0.0f, 0, E->invN));
+    TRY(slabfft_c2r_yz(E->fft2d, st, E->c(0), E->r(0), 3));
+  } else
+#endif
+  {
+    TRY(hessian_spectra(st, dk, E->c(0), E->nx, E->ny, E->nz, lap_fd, grad_fd, E->invN));
+    TRY(fft_c2r(E->fft, st, E->c(0), h6, 6));
+    TRY(lpt2_source(st, h6, E->r(6), E->N));
+    TRY(fft_r2c(E->fft, st, E->r(6), E->c(6), 1));
+    TRY(force_meshes_from_spectrum(E, st, E->c(6), lap_fd, grad_fd, 0.0f, 0, E->r(0)));
+  }
   TRY(read(st, pos, E->r(0), 3, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, forces));
   return 0;
 }
@@ -198,17 +221,31 @@ int lpt_vjp(Engine* E, stream_t st, const float* pos, int64_t np, int lpt_order,
       return MCPM_EINVAL;
     }
     TRY(paint3(st, pos, dposbar, -d2, velbar, -dv2, np, E->nx, E->ny, E->nz, read_order, E->r(0), 0));
-    TRY(fft_r2c(E->fft, st, E->r(0), E->c(0), 3));
-    TRY(force_spectra_T(st, E->c(0), E->c(3), E->nx, E->ny, E->nz, lap_fd, grad_fd, 0.0f, 0, 0, 0, E->invN));
-    TRY(fft_c2r(E->fft, st, E->c(3), E->r(6), 1));  // d2bar (real)
+    TRY(density_cotangent(E, st, E->r(0), lap_fd, grad_fd, 0.0f, 0, E->r(6)));  // d2bar (real)
     TRY(lpt2_source_vjp(st, h6, E->r(6), E->r(0), E->N));
-    TRY(fft_r2c(E->fft, st, E->r(0), E->c(0), 6));
-    TRY(hessian_spectra_T(st, E->c(0), dkbar, E->nx, E->ny, E->nz, lap_fd, grad_fd, 1, accumulate, 1.0f));
+#ifndef MCPM_HOSTEMU
+    if (E->fused_fft) {
+      TRY(slabfft_r2c_yz(E->fft2d, st, E->r(0), E->c(0), 6));
+      TRY(xfuse_hessian_tk(st, E->c(0), dkbar, E->nx, E->ny, E->nz, lap_fd, grad_fd, 1, accumulate, 1.0f));
+    } else
+#endif
+    {
+      TRY(fft_r2c(E->fft, st, E->r(0), E->c(0), 6));
+      TRY(hessian_spectra_T(st, E->c(0), dkbar, E->nx, E->ny, E->nz, lap_fd, grad_fd, 1, accumulate, 1.0f));
+    }
     accumulate = 1;
   }
   TRY(paint3(st, pos, dposbar, d1, velbar, 1.0f, np, E->nx, E->ny, E->nz, read_order, E->r(0), 0));
-  TRY(fft_r2c(E->fft, st, E->r(0), E->c(0), 3));
-  TRY(force_spectra_T(st, E->c(0), dkbar, E->nx, E->ny, E->nz, lap_fd, grad_fd, 0.0f, 0, 1, accumulate, 1.0f));
+#ifndef MCPM_HOSTEMU
+  if (E->fused_fft) {
+    TRY(slabfft_r2c_yz(E->fft2d, st, E->r(0), E->c(0), 3));
+    TRY(xfuse_force_tk(st, E->c(0), dkbar, E->nx, E->ny, E->nz, lap_fd, grad_fd, 0.0f, 0, 1, accumulate, 1.0f));
+  } else
+#endif
+  {
+    TRY(fft_r2c(E->fft, st, E->r(0), E->c(0), 3));
+    TRY(force_spectra_T(st, E->c(0), dkbar, E->nx, E->ny, E->nz, lap_fd, grad_fd, 0.0f, 0, 1, accumulate, 1.0f));
+  }
   if (coefbar) {
     if (!f1 || (lpt_order == 2 && !f2)) {
       set_error("lpt_vjp: coefficient cotangents need the f1 / f2 tape");
@@ -244,7 +281,7 @@ int nbody_steps(Engine* E, stream_t st, float* pos, float* vel, int64_t np, int 
     float* slot = fm ? fm + (int64_t)s * 4 * E->N : E->r(3);
     float* planar = cic ? E->r(0) : slot;
     // under the brick path the density mesh of step s+1 is cleared by the kick kernel of step s
-    const bool side_zero = cic && brick_path(E, order, nullptr);
+    const bool side_zero = g_side_zero && cic && brick_path(E, order, nullptr);
     TRY(pm_forces(E, st, cur, np, order, paint_deconv, lap_fd, grad_fd, 0.0f, planar, nullptr, side_zero && s > 0));
     const bool last = (s == n_steps - 1);
     float dcomb = drift_post[s] + (last ? 0.0f : drift_pre[s + 1]);
@@ -283,7 +320,7 @@ int nbody_steps_vjp(Engine* E, stream_t st, float* posbar, float* velbar, int64_
   }
   const int64_t P3 = 3 * np;
   const bool cic = (order == 2);
-  const bool side_zero = cic && brick_path(E, order, nullptr);
+  const bool side_zero = g_side_zero && cic && brick_path(E, order, nullptr);
   for (int s = n_steps - 1; s >= 0; --s) {
     const bool last = (s == n_steps - 1);
     float dcomb = drift_post[s] + (last ? 0.0f : drift_pre[s + 1]);

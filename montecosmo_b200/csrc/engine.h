@@ -114,6 +114,14 @@ int xfuse_force(stream_t, const cfloat* in, cfloat* out3, int nx, int ny, int nz
                 int deconv_order, float norm, SlabK sk = SlabK());
 int xfuse_force_T(stream_t, const cfloat* in3, cfloat* out, int nx, int ny, int nz, int lap_fd, int grad_fd,
                   float kcut, int deconv_order, float norm, SlabK sk = SlabK());
+int xfuse_force_k(stream_t, const cfloat* dk, cfloat* out3, int nx, int ny, int nz, int lap_fd, int grad_fd, float kcut,
+                  int deconv_order, float norm, SlabK sk = SlabK());
+int xfuse_hessian_k(stream_t, const cfloat* dk, cfloat* out6, int nx, int ny, int nz, int lap_fd, int grad_fd,
+                    float norm, SlabK sk = SlabK());
+int xfuse_force_tk(stream_t, const cfloat* in3, cfloat* out, int nx, int ny, int nz, int lap_fd, int grad_fd,
+                   float kcut, int deconv_order, int half_weights, int accumulate, float norm, SlabK sk = SlabK());
+int xfuse_hessian_tk(stream_t, const cfloat* in6, cfloat* out, int nx, int ny, int nz, int lap_fd, int grad_fd,
+                     int half_weights, int accumulate, float norm, SlabK sk = SlabK());
 
 // brick.cu (CUDA build only): return 1 if handled, 0 if the generic path must be taken, < 0 on error
 int brick_paint_cic(stream_t, const Lattice&, const float* pos, const float* weights, float wscalar, float shift,
@@ -122,6 +130,7 @@ int brick_paint3_cic(stream_t, const Lattice&, const float* pos, float* A, const
                      int64_t np, int nx, int ny, int nz, float* mesh3);
 
 // engine.cu
+void set_side_zero(int v);
 int pm_forces(Engine*, stream_t, const float* pos, int64_t np, int order, int paint_deconv, int lap_fd, int grad_fd,
               float kcut, float* fmesh3, float* forces, bool rho_prezeroed = false);
 int pm_forces_vjp(Engine*, stream_t, const float* pos, const float* fbar, float cscale, const float* fmesh3,

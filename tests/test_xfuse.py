@@ -98,7 +98,7 @@ def test_unsupported_shape_reports(ops):
 @pytest.mark.parametrize("nx,ny,nz,ny_loc,y0", [(64, 12, 16, 12, 0), (128, 8, 10, 4, 4), (256, 6, 8, 3, 2)])
 def test_kernel_against_numpy_x_transforms(ops, nx, ny, nz, ny_loc, y0):
     """The kernel alone on a (ky-block of a) half spectrum: out = IFFT_x(kernel * FFT_x(in)) with numpy's FFT along x and
-    the engine's own streaming multiply (mcpm_force_spectra[_T]_slab) in between.  float32 vs float64 FFT: 2e-6."""
+    the engine's own streaming multiply (mcpm_force_spectra[_T]_slab) in between.  float32 vs float64 FFT: 5e-6."""
     rng = np.random.default_rng(nx + ny_loc)
     nzc = nz // 2 + 1
     A = ops.A
@@ -107,7 +107,7 @@ def test_kernel_against_numpy_x_transforms(ops, nx, ny, nz, ny_loc, y0):
     x1 = (rng.normal(size=shape_c) + 1j * rng.normal(size=shape_c)).astype(np.complex64)
     x3 = (rng.normal(size=(3, *shape_c)) + 1j * rng.normal(size=(3, *shape_c))).astype(np.complex64)
     norm = 0.37
-    for lap_fd, grad_fd, kcut, dec in [(0, 0, 0.0, 0), (2, 4, 1.5, 2)]:
+    for lap_fd, grad_fd, kcut, dec in [(0, 0, 0.0, 0), (2, 4, 6.0, 2)]:
         # forward operator
         d_in, d_out = A.prepare(x1, "c64"), A.empty((3, *shape_c), "c64")
         ops._call("mcpm_xfuse_force_slab", st, A.ptr(d_in), A.ptr(d_out), nx, ny, nz, ny_loc, y0, lap_fd, grad_fd, kcut,
@@ -118,7 +118,7 @@ def test_kernel_against_numpy_x_transforms(ops, nx, ny, nz, ny_loc, y0):
                   dec, norm)
         ref = np.fft.ifft(to_numpy(mid).astype(np.complex128), axis=1) * nx
         got = to_numpy(d_out).astype(np.complex128)
-        assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 2e-6
+        assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 5e-6
         # transpose operator
         d_in3, d_out1 = A.prepare(x3, "c64"), A.empty(shape_c, "c64")
         ops._call("mcpm_xfuse_force_T_slab", st, A.ptr(d_in3), A.ptr(d_out1), nx, ny, nz, ny_loc, y0, lap_fd, grad_fd,
@@ -129,4 +129,37 @@ def test_kernel_against_numpy_x_transforms(ops, nx, ny, nz, ny_loc, y0):
                   dec, 0, 0, norm)
         ref1 = np.fft.ifft(to_numpy(mid1).astype(np.complex128), axis=0) * nx
         got1 = to_numpy(d_out1).astype(np.complex128)
-        assert np.linalg.norm(got1 - ref1) / np.linalg.norm(ref1) < 2e-6
+        assert np.linalg.norm(got1 - ref1) / np.linalg.norm(ref1) < 5e-6
+
+
+@pytest.mark.parametrize("shape", [(64, 12, 16), (128, 6, 10)])
+@pytest.mark.parametrize("lpt_order,read_order,fd", [(1, 1, (0, 0)), (2, 2, (0, 0)), (2, 1, (2, 4))])
+def test_lpt_and_its_vjp(ops, shape, lpt_order, read_order, fd):
+    """lpt runs spectrum-in (force / Hessian set -> inverse x-FFTs) and spectrum-out (x-FFTs -> transposed kernels with
+    Hermitian weights, accumulated) variants of the fused kernel: fused vs 3-D cuFFT path 2e-5, forward vs oracle 5e-5."""
+    rng = np.random.default_rng(11)
+    n = int(np.prod(shape))
+    dk = (np.fft.rfftn(rng.normal(size=shape)) * 0.02).astype(np.complex64)
+    q = O.regular_pos(shape).numpy()
+    pos = (q if read_order == 1 else q + rng.normal(scale=0.4, size=q.shape)).astype(np.float32)
+    d1, d2, dv2 = 0.61, -0.17, -0.52
+    dpb, vlb = (rng.normal(size=pos.shape).astype(np.float32) for _ in range(2))
+    lap_fd, grad_fd = (np.inf if v == 0 else v for v in fd)
+    res = {}
+    for fused in (False, True):
+        ops.set_fused_fft(shape, fused)
+        dp, vl, tape = ops.lpt(dk, pos, d1, d2, dv2, lpt_order, read_order, lap_fd, grad_fd, tape=True)
+        dkbar, cb = ops.lpt_vjp(pos, dk.shape, d1, d2, dv2, dpb, vlb, tape, lpt_order, read_order, lap_fd, grad_fd,
+                                want_coef=True)
+        res[fused] = [to_numpy(x).copy() for x in (dp, vl, dkbar, cb)]
+    ops.set_fused_fft(shape, True)
+    for name, a, b in zip(["dpos", "vel", "dkbar", "coefbar"], res[True], res[False]):
+        err = np.linalg.norm((a - b).ravel()) / np.linalg.norm(b.ravel())
+        assert err < 2e-5, (name, err)
+    dkt = torch.as_tensor(dk, dtype=torch.complex128)
+    f1 = O.pm_forces(T(pos), dkt, read_order, grad_fd=grad_fd, lap_fd=lap_fd)
+    dpo, vlo = d1 * f1, f1
+    if lpt_order == 2:
+        f2 = O.pm_forces2(T(pos), dkt, read_order, grad_fd=grad_fd, lap_fd=lap_fd)
+        dpo, vlo = dpo - d2 * f2, vlo - dv2 * f2
+    assert rel(res[True][0], dpo.numpy()) < 5e-5 and rel(res[True][1], vlo.numpy()) < 5e-5

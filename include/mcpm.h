@@ -189,6 +189,17 @@ int mcpm_chreshape(void* stream, const void* in, int inx, int iny, int inz, void
 int mcpm_chreshape_vjp(void* stream, const void* outbar, int onx, int ony, int onz, void* inbar, int inx, int iny,
                        int inz);
 
+/* rg2cgh / cgh2rg (utils.py:785-921): real Gaussian mesh [nx,ny,nz] (all sides even) <-> complex
+ * Gaussian Hermitian half spectrum by permutation and reweighting; rg2cgh(N(0,I)) is distributed as rfftn(N(0,I)).
+ * out = scale * [transfer *] P(mesh), scale = sqrt(N/2) for norm "backward", 1/sqrt(2) "ortho", 1/sqrt(2N) "forward";
+ * `transfer` (nullable, real [nx,ny,nz/2+1]) fuses the sqrt-power multiply of samp2base_mesh (bricks.py:305-309).
+ * _vjp: cotangent of the real mesh from the complex cotangent dL/dRe + i dL/dIm.  cgh2rg: mesh = inv_scale * P^-1. */
+int mcpm_rg2cgh(void* stream, const float* mesh, void* out_c64, int nx, int ny, int nz, float scale,
+                const float* transfer);
+int mcpm_rg2cgh_vjp(void* stream, const void* outbar_c64, float* meshbar, int nx, int ny, int nz, float scale,
+                    const float* transfer);
+int mcpm_cgh2rg(void* stream, const void* meshk_c64, float* mesh, int nx, int ny, int nz, float inv_scale);
+
 /* Hermitian weights w' (1 on kz = 0 / Nyquist planes, else 2) that turn rfftn / irfftn into each other's transpose:
  * mode 0: out = in * N / w'  (VJP of rfftn: xbar = irfftn(out));  mode 1: out = in * w' / N  (VJP of irfftn: ybar = out,
  * with in = rfftn(xbar)). */

@@ -52,6 +52,9 @@ SIGNATURES = {
     "mcpm_hessian_spectra_T_slab": ([vp, vp, vp] + MESH + [i32, i32, i32, i32, i32, i32, f32], i32),
     "mcpm_chreshape": ([vp, vp] + MESH + [vp] + MESH, i32),
     "mcpm_chreshape_vjp": ([vp, vp] + MESH + [vp] + MESH, i32),
+    "mcpm_rg2cgh": ([vp, vp, vp] + MESH + [f32, vp], i32),
+    "mcpm_rg2cgh_vjp": ([vp, vp, vp] + MESH + [f32, vp], i32),
+    "mcpm_cgh2rg": ([vp, vp, vp] + MESH + [f32], i32),
     "mcpm_hermitian_weights": ([vp, vp, vp] + MESH + [i32], i32),
     "mcpm_axpby": ([vp, vp, f32, vp, f32, f32, i64, vp], i32),
     "mcpm_dot": ([vp, vp, vp, i64, vp], i32),

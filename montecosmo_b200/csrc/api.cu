@@ -433,6 +433,29 @@ int mcpm_chreshape_vjp(void* stream, const void* outbar, int onx, int ony, int o
   API_END
 }
 
+int mcpm_rg2cgh(void* stream, const float* mesh, void* out_c64, int nx, int ny, int nz, float scale,
+                const float* transfer) {
+  API_BEGIN
+  NEED(mesh && out_c64, "rg2cgh: null pointer");
+  return rg2cgh(as_stream(stream), mesh, C(out_c64), nx, ny, nz, scale, transfer);
+  API_END
+}
+
+int mcpm_rg2cgh_vjp(void* stream, const void* outbar_c64, float* meshbar, int nx, int ny, int nz, float scale,
+                    const float* transfer) {
+  API_BEGIN
+  NEED(outbar_c64 && meshbar, "rg2cgh_vjp: null pointer");
+  return rg2cgh_vjp(as_stream(stream), C(outbar_c64), meshbar, nx, ny, nz, scale, transfer);
+  API_END
+}
+
+int mcpm_cgh2rg(void* stream, const void* meshk_c64, float* mesh, int nx, int ny, int nz, float inv_scale) {
+  API_BEGIN
+  NEED(meshk_c64 && mesh, "cgh2rg: null pointer");
+  return cgh2rg(as_stream(stream), C(meshk_c64), mesh, nx, ny, nz, inv_scale);
+  API_END
+}
+
 int mcpm_hermitian_weights(void* stream, const void* in, void* out, int nx, int ny, int nz, int mode) {
   API_BEGIN
   return hermitian_weights(as_stream(stream), C(in), C(out), nx, ny, nz, mode);

@@ -253,6 +253,171 @@ int hermitian_weights(stream_t st, const cfloat* in, cfloat* out, int nx, int ny
   return rt_check("hermitian_weights");
 }
 
+// ---------------------------------------------------------------------------------------------------- rg2cgh
+// rg2cgh / cgh2rg (utils.py:785-921): a real Gaussian mesh [nx,ny,nz] <-> a complex Gaussian Hermitian half spectrum
+// [nx,ny,nz/2+1] by permutation and reweighting, so that rg2cgh(N(0,I)) is distributed as rfftn(N(0,I)).
+// With (hx,hy,hz) = shape / 2 the N real numbers are laid out as
+//   planes 0 < z < hz: Re of (x,y,l=z)                 planes z > hz: Im of (x,y,l=z-hz)
+//   on the planes z = 0, hz (l = z):  rows 0 < y < hy: Re of (x,y,l)        rows y > hy: Im of (x,y-hy,l)
+//     on the rows y = 0, hy:  0 < x < hx: Re of (x,y,l)   x > hx: Im of (x-hx,y,l)   x = 0, hx: Re / sqrt2 (Im = 0)
+// and the other half of each self-conjugate plane / row follows from Hermitian symmetry, F(-k) = conj F(k).
+struct RgSrc {
+  int64_t re, im;  // source offsets in the real mesh (im < 0: no imaginary part)
+  float sre, sim;  // weights
+};
+
+MCPM_HD RgSrc rg_source(int i, int j, int l, int nx, int ny, int nz) {
+  const int hx = nx / 2, hy = ny / 2, hz = nz / 2;
+  RgSrc r;
+  r.sre = 1.0f;
+  r.sim = 1.0f;
+  auto at = [&](int x, int y, int z) { return ((int64_t)x * ny + y) * nz + z; };
+  if (l > 0 && l < hz) {
+    r.re = at(i, j, l);
+    r.im = at(i, j, hz + l);
+    return r;
+  }
+  const int z = l;  // 0 or hz: self-conjugate plane
+  if (j != 0 && j != hy) {
+    if (j < hy) {
+      r.re = at(i, j, z);
+      r.im = at(i, hy + j, z);
+    } else {  // conjugate of the partner (-i, -j)
+      const int ip = i == 0 ? 0 : nx - i, jp = ny - j;
+      r.re = at(ip, jp, z);
+      r.im = at(ip, hy + jp, z);
+      r.sim = -1.0f;
+    }
+    return r;
+  }
+  if (i != 0 && i != hx) {
+    if (i < hx) {
+      r.re = at(i, j, z);
+      r.im = at(hx + i, j, z);
+    } else {
+      const int ip = nx - i;
+      r.re = at(ip, j, z);
+      r.im = at(hx + ip, j, z);
+      r.sim = -1.0f;
+    }
+    return r;
+  }
+  r.re = at(i, j, z);  // one of the 8 real modes
+  r.im = -1;
+  r.sre = 1.41421356237309504880f;
+  r.sim = 0.0f;
+  return r;
+}
+
+// out = scale * [transfer *] rg2cgh_unit(mesh); scale = sqrt(N/2) (norm "backward"), 1/sqrt2 ("ortho"), 1/sqrt(2N) ("forward")
+int rg2cgh(stream_t st, const float* mesh, cfloat* out, int nx, int ny, int nz, float scale, const float* transfer) {
+  if (int e = check_dims(nx, ny, nz)) return e;
+  if ((nx & 1) || (ny & 1)) {
+    set_error("rg2cgh: dimension lengths must be even.");
+    return MCPM_EINVAL;
+  }
+  const int nzc = nz / 2 + 1;
+  const int64_t nc = (int64_t)nx * ny * nzc;
+  launch_1d(st, nc, [=] MCPM_LAMBDA(int64_t e) {
+    const int l = (int)(e % nzc);
+    const int64_t r = e / nzc;
+    const int j = (int)(r % ny), i = (int)(r / ny);
+    const RgSrc s = rg_source(i, j, l, nx, ny, nz);
+    const float c = transfer ? scale * transfer[e] : scale;
+    out[e] = cfloat{mesh[s.re] * (s.sre * c), s.im >= 0 ? mesh[s.im] * (s.sim * c) : 0.0f};
+  });
+  return rt_check("rg2cgh");
+}
+
+// Role of a real-mesh element: which spectrum element(s) it feeds.  part 0: real part, 1: imaginary part.
+struct RgDst {
+  int64_t a, b;  // spectrum elements fed (b < 0: only one); the second one is the Hermitian partner
+  int part;
+  float wa, wb;
+};
+
+MCPM_HD RgDst rg_dest(int x, int y, int z, int nx, int ny, int nz) {
+  const int hx = nx / 2, hy = ny / 2, hz = nz / 2, nzc = hz + 1;
+  auto at = [&](int i, int j, int l) { return ((int64_t)i * ny + j) * nzc + l; };
+  RgDst d;
+  d.b = -1;
+  d.wa = 1.0f;
+  d.wb = 0.0f;
+  if (z != 0 && z != hz) {
+    d.part = z > hz;
+    d.a = at(x, y, z > hz ? z - hz : z);
+    return d;
+  }
+  if (y != 0 && y != hy) {
+    d.part = y > hy;
+    const int j = y > hy ? y - hy : y;
+    d.a = at(x, j, z);
+    d.b = at(x == 0 ? 0 : nx - x, ny - j, z);
+    d.wb = d.part ? -1.0f : 1.0f;
+    return d;
+  }
+  if (x != 0 && x != hx) {
+    d.part = x > hx;
+    const int i = x > hx ? x - hx : x;
+    d.a = at(i, y, z);
+    d.b = at(nx - i, y, z);
+    d.wb = d.part ? -1.0f : 1.0f;
+    return d;
+  }
+  d.part = 0;
+  d.a = at(x, y, z);
+  d.wa = 1.41421356237309504880f;
+  return d;
+}
+
+// VJP of rg2cgh w.r.t. the real mesh: meshbar = scale * sum over the (one or two) spectrum elements fed of
+// weight * [transfer] * (Re or Im of outbar)   (cotangent convention dL/dRe + i dL/dIm).
+int rg2cgh_vjp(stream_t st, const cfloat* outbar, float* meshbar, int nx, int ny, int nz, float scale,
+               const float* transfer) {
+  if (int e = check_dims(nx, ny, nz)) return e;
+  if ((nx & 1) || (ny & 1)) {
+    set_error("rg2cgh: dimension lengths must be even.");
+    return MCPM_EINVAL;
+  }
+  const int64_t n = (int64_t)nx * ny * nz;
+  launch_1d(st, n, [=] MCPM_LAMBDA(int64_t e) {
+    const int z = (int)(e % nz);
+    const int64_t r = e / nz;
+    const int y = (int)(r % ny), x = (int)(r / ny);
+    const RgDst d = rg_dest(x, y, z, nx, ny, nz);
+    cfloat va = outbar[d.a];
+    float acc = (d.part ? va.im : va.re) * d.wa * (transfer ? transfer[d.a] : 1.0f);
+    if (d.b >= 0) {
+      cfloat vb = outbar[d.b];
+      acc += (d.part ? vb.im : vb.re) * d.wb * (transfer ? transfer[d.b] : 1.0f);
+    }
+    meshbar[e] = acc * scale;
+  });
+  return rt_check("rg2cgh_vjp");
+}
+
+// cgh2rg: the inverse permutation, mesh = inv_scale * (Re or Im of the element it came from) / weight
+int cgh2rg(stream_t st, const cfloat* meshk, float* mesh, int nx, int ny, int nz, float inv_scale) {
+  if (int e = check_dims(nx, ny, nz)) return e;
+  if ((nx & 1) || (ny & 1)) {
+    set_error("cgh2rg: dimension lengths must be even.");
+    return MCPM_EINVAL;
+  }
+  const int64_t n = (int64_t)nx * ny * nz;
+  launch_1d(st, n, [=] MCPM_LAMBDA(int64_t e) {
+    const int z = (int)(e % nz);
+    const int64_t r = e / nz;
+    const int y = (int)(r % ny), x = (int)(r / ny);
+    const RgDst d = rg_dest(x, y, z, nx, ny, nz);
+    // the reference keeps the value found at the Hermitian partner where there is one (utils.py:860-868)
+    const int64_t src = d.b >= 0 ? d.b : d.a;
+    const float w = d.b >= 0 ? d.wb : 1.0f / d.wa;
+    cfloat v = meshk[src];
+    mesh[e] = (d.part ? v.im : v.re) * w * inv_scale;
+  });
+  return rt_check("cgh2rg");
+}
+
 // ---------------------------------------------------------------------------------------------------- chreshape
 // One thread per OUTPUT element gathers its (at most 4 x 2) sources.  Per axis (utils.py:975-1013):
 //   crop  (s < ms), axes x,y: the new Nyquist row (freq -s/2) = (in[+s/2] + in[-s/2]) / sqrt2

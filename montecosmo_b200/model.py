@@ -103,7 +103,11 @@ def linear_power_table(cosmo, n_interp=256):
 class FieldModel:
     def __init__(self, mesh_shape=(64, 64, 64), box_size=(640.0, 640.0, 640.0), evolution="nbody", n_steps=5,
                  a_start=0.0, a_obs=1.0, lpt_order=2, paint_order=2, interlace_order=2, paint_deconv=True,
-                 paint_oversamp=1.0, b1=1.0, rsd=True, los=(0.0, 0.0, 1.0), sigma_obs=1.0, cosmology=None, kpow=None):
+                 paint_oversamp=1.0, b1=1.0, rsd=True, los=(0.0, 0.0, 1.0), sigma_obs=1.0, cosmology=None, kpow=None,
+                 precond="real"):
+        if precond not in ("real", "fourier"):
+            raise ValueError("precond must be 'real' or 'fourier'")
+        self.precond = precond
         self.mesh_shape = tuple(int(s) for s in mesh_shape)
         self.box_size = tuple(float(b) for b in box_size)
         self.evolution, self.n_steps, self.a_start, self.a_obs = evolution, int(n_steps), a_start, a_obs
@@ -128,7 +132,11 @@ class FieldModel:
 
     # -- prior -> evolve ----------------------------------------------------------------------------------------------
     def linear_field(self, white):
-        """delta_k(a=1) from the real white field (samp2base_mesh 'real' + white2lin)."""
+        """delta_k(a=1) from the real white field: samp2base_mesh (bricks.py:290-320) with precond 'real' (rfftn) or
+        'fourier' (rg2cgh, the transfer multiply fused into the permutation pass) + white2lin."""
+        if self.precond == "fourier":
+            from . import utils as _utils
+            return _utils.rg2cgh(white, "backward", self.transfer)
         return nb._ScaleSpectrum.apply(nb.rfftn(white), self.transfer)
 
     def evolve(self, white):

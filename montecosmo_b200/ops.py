@@ -404,6 +404,32 @@ class Ops:
                    *ch2rshape(in_cshape))
         return inbar
 
+    def rg2cgh(self, mesh, scale, transfer=None):
+        A = self.A
+        mesh = A.prepare(mesh)
+        rs = A.shape(mesh)
+        out = A.empty(r2chshape(rs), "c64")
+        transfer = None if transfer is None else A.prepare(transfer)
+        self._call("mcpm_rg2cgh", A.stream(), A.ptr(mesh), A.ptr(out), *rs, float(scale), A.ptr(transfer))
+        return out
+
+    def rg2cgh_vjp(self, outbar, scale, transfer=None):
+        A = self.A
+        outbar = A.prepare(outbar, "c64")
+        rs = ch2rshape(A.shape(outbar))
+        out = A.empty(rs)
+        transfer = None if transfer is None else A.prepare(transfer)
+        self._call("mcpm_rg2cgh_vjp", A.stream(), A.ptr(outbar), A.ptr(out), *rs, float(scale), A.ptr(transfer))
+        return out
+
+    def cgh2rg(self, meshk, inv_scale):
+        A = self.A
+        meshk = A.prepare(meshk, "c64")
+        rs = ch2rshape(A.shape(meshk))
+        out = A.empty(rs)
+        self._call("mcpm_cgh2rg", A.stream(), A.ptr(meshk), A.ptr(out), *rs, float(inv_scale))
+        return out
+
     def hermitian_weights(self, meshk, mode):
         A = self.A
         meshk = A.prepare(meshk, "c64")

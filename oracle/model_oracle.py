@@ -2,7 +2,7 @@
 CPU oracle of the benchmark log-density (TEST INFRASTRUCTURE ONLY; same rules as pm_oracle.py).
 
 Restates, in torch-CPU float64 on top of pm_oracle, the chain that `montecosmo_b200/model.py:FieldModel` runs on the
-GPU: model.py:640-679 (prior, precond='real'), bricks.py:152-157 (white2lin), bricks.py:358-362 (linear Lagrangian
+GPU: model.py:640-679 (prior, precond='real' or 'fourier', bricks.py:290-320), bricks.py:152-157 (white2lin), bricks.py:358-362 (linear Lagrangian
 bias, NGP read), nbody.py:634-667 / 967-1002 (lpt / nbody_bf), bricks.py:781-792 (flat-sky RSD in cell units),
 model.py:802-809 (nufft paint, irfftn), and a Gaussian likelihood.  Autograd gives the reference gradient.
 """
@@ -14,10 +14,11 @@ from . import pm_oracle as O
 
 def evolve(white, transfer, cosmo, mesh_shape, evolution="nbody", n_steps=5, a_start=0.0, a_obs=1.0, lpt_order=2,
            paint_order=2, interlace_order=2, paint_deconv=True, paint_shape=None, b1=1.0, rsd=True,
-           los=(0.0, 0.0, 1.0)):
+           los=(0.0, 0.0, 1.0), precond="real"):
     mesh_shape = tuple(mesh_shape)
     paint_shape = mesh_shape if paint_shape is None else tuple(paint_shape)
-    dk = torch.fft.rfftn(white) * O._t(transfer)
+    # samp2base_mesh, bricks.py:300-309: sample in real space (rfftn) or in Fourier space (rg2cgh)
+    dk = (torch.fft.rfftn(white) if precond == "real" else O.rg2cgh(white)) * O._t(transfer)
     q = O.regular_pos(mesh_shape)
     weights = 1.0
     if b1 != 0.0:

@@ -243,6 +243,96 @@ def hermitian_symmetric(arr):
     return out
 
 
+_RG_NORMS = ("backward", "ortho", "forward", "amp")
+
+
+def _rg_norm_factor(shape, norm):
+    """utils.py:821-829 / 872-880: the factor rg2cgh divides by (cgh2rg multiplies by)."""
+    n = float(np.prod(shape))
+    if norm not in _RG_NORMS:
+        raise AssertionError("norm must be either 'backward', 'forward', 'ortho', or 'amp'.")
+    return {"backward": (2.0 / n) ** 0.5, "ortho": 2.0 ** 0.5, "forward": (2.0 * n) ** 0.5, "amp": 1.0}[norm]
+
+
+def _rg_slices(shape, part):
+    hx, hy, hz = (s // 2 for s in shape)
+    if part == "imag":
+        return slice(hx + 1, None), slice(hy + 1, None), slice(hz + 1, None)
+    return slice(1, hx), slice(1, hy), slice(1, hz)
+
+
+def _rg2cgh_part(mesh, part, norm):
+    """utils.py:785-831.  One part (real or imaginary) of the Hermitian half spectrum, gathered from the real mesh:
+    interior planes, then the two self-conjugate planes kz in {0, Nyquist} (rows, mirrored rows with sign), their
+    self-conjugate rows ky in {0, Nyquist} (same along x), and the 8 purely real modes (x sqrt2)."""
+    shape = tuple(mesh.shape)
+    assert all(s % 2 == 0 for s in shape), "dimension lengths must be even."
+    hx, hy, hz = (s // 2 for s in shape)
+    sx, sy, sz = _rg_slices(shape, part)
+    flip = part == "imag" and norm != "amp"
+    out = torch.zeros(r2chshape(shape), dtype=mesh.dtype)
+    out[:, :, 1:-1] = mesh[:, :, sz]
+    for k in (0, hz):
+        out[:, 1:hy, k] = mesh[:, sy, k]
+        out[1:, hy + 1:, k] = torch.flip(mesh[1:, sy, k], dims=(0, 1))
+        out[0, hy + 1:, k] = torch.flip(mesh[0, sy, k], dims=(0,))
+        if flip:
+            out[:, hy + 1:, k] = -out[:, hy + 1:, k]
+        for j in (0, hy):
+            out[1:hx, j, k] = mesh[sx, j, k]
+            out[hx + 1:, j, k] = torch.flip(mesh[sx, j, k], dims=(0,))
+            if flip:
+                out[hx + 1:, j, k] = -out[hx + 1:, j, k]
+            for i in (0, hx):
+                if part == "real":
+                    out[i, j, k] = mesh[i, j, k] * (2.0 ** 0.5 if norm != "amp" else 1.0)
+    return out / _rg_norm_factor(shape, norm)
+
+
+def rg2cgh(mesh, norm="backward"):
+    """utils.py:888-903: real Gaussian mesh -> complex Gaussian Hermitian half spectrum, distributed as rfftn(N(0,I))."""
+    mesh = _t(mesh)
+    real = _rg2cgh_part(mesh, "real", norm)
+    if norm == "amp":
+        return real
+    return torch.complex(real, _rg2cgh_part(mesh, "imag", norm))
+
+
+def _cgh2rg_part(vals, part, norm):
+    """utils.py:836-882: scatter one part of the half spectrum back onto its partition of the real mesh.  Where a real
+    number has two Hermitian images the later assignment (the mirrored one) is the one the reference keeps."""
+    shape = ch2rshape(tuple(vals.shape))
+    assert all(s % 2 == 0 for s in shape), "dimension lengths must be even."
+    hx, hy, hz = (s // 2 for s in shape)
+    sx, sy, sz = _rg_slices(shape, part)
+    flip = part == "imag" and norm != "amp"
+    mesh = torch.zeros(shape, dtype=vals.dtype)
+    mesh[:, :, sz] = vals[:, :, 1:-1]
+    for k in (0, hz):
+        mesh[:, sy, k] = vals[:, 1:hy, k]
+        mesh[1:, sy, k] = torch.flip(vals[1:, hy + 1:, k], dims=(0, 1))
+        mesh[0, sy, k] = torch.flip(vals[0, hy + 1:, k], dims=(0,))
+        if flip:
+            mesh[:, sy, k] = -mesh[:, sy, k]
+        for j in (0, hy):
+            mesh[sx, j, k] = vals[1:hx, j, k]
+            mesh[sx, j, k] = torch.flip(vals[hx + 1:, j, k], dims=(0,))
+            if flip:
+                mesh[sx, j, k] = -mesh[sx, j, k]
+            for i in (0, hx):
+                if part == "real":
+                    mesh[i, j, k] = vals[i, j, k] / (2.0 ** 0.5 if norm != "amp" else 1.0)
+    return mesh * _rg_norm_factor(shape, norm)
+
+
+def cgh2rg(meshk, norm="backward"):
+    """utils.py:906-921: the inverse of rg2cgh (for "amp": the same amplitude on both parts)."""
+    meshk = _t(meshk, C128) if not isinstance(meshk, torch.Tensor) else meshk
+    re = meshk.real if torch.is_complex(meshk) else meshk
+    im = re if norm == "amp" else meshk.imag
+    return _cgh2rg_part(re, "real", norm) + _cgh2rg_part(im, "imag", norm)
+
+
 def chreshape(mesh, shape):
     """utils.py:975-1013: Hermitian- and mean-preserving Fourier crop / pad with Nyquist-plane fix-ups."""
     mesh = _t(mesh, C128).clone()

@@ -162,9 +162,11 @@ def test_model_logpdf_and_force(nb, evolution, n_steps):
     from montecosmo_b200.model import FieldModel
     rng = np.random.default_rng(5)
     shape = (16, 16, 16)
-    m = FieldModel(shape, (160.0,) * 3, evolution=evolution, n_steps=n_steps, a_obs=0.8, b1=0.7, sigma_obs=0.5)
+    precond = "fourier" if evolution == "lpt" else "real"  # both initial-condition parametrisations get a run
+    m = FieldModel(shape, (160.0,) * 3, evolution=evolution, n_steps=n_steps, a_obs=0.8, b1=0.7, sigma_obs=0.5,
+                   precond=precond)
     white = rng.normal(size=shape).astype(np.float32)
-    kw = dict(evolution=evolution, n_steps=n_steps, a_obs=0.8, b1=0.7)
+    kw = dict(evolution=evolution, n_steps=n_steps, a_obs=0.8, b1=0.7, precond=precond)
     transfer = m.transfer.cpu().numpy().astype(np.float64)
     with torch.no_grad():
         truth = MO.evolve(torch.tensor(rng.normal(size=shape)), transfer, O.Cosmology(), shape, **kw)
@@ -209,3 +211,39 @@ def test_lpt_per_particle_scale_factor(nb, lpt_order):
     assert rel(d1, d0) < 1e-6 and rel(v1, v0) < 1e-6
     with pytest.raises(ValueError):
         nb.lpt(Cosmology(), dk.detach(), pos.to(dev(nb)), np.full(7, 0.5), lpt_order, 2)
+
+
+def test_rg2cgh_golden_roundtrip_and_gradient(nb, golden):
+    """utils.rg2cgh / cgh2rg (utils.py:785-921) vs the golden vectors of the reference source (1e-6: a permutation with
+    float32 scaling), every norm vs the oracle, the inverse, and the VJP (with a fused transfer) vs oracle autograd."""
+    from montecosmo_b200 import utils as U
+    g = golden("rg2cgh")
+    white = torch.tensor(g["white"], dtype=torch.float32, device=dev(nb))
+    out = U.rg2cgh(white)
+    assert rel(out, g["rg2cgh"]) < 1e-6
+    assert rel(U.cgh2rg(out), g["cgh2rg_roundtrip"]) < 1e-6
+    rng = np.random.default_rng(4)
+    for shape in [(8, 6, 10), (4, 4, 4), (6, 8, 4)]:
+        w = torch.tensor(rng.normal(size=shape), dtype=torch.float32)
+        for norm in ("backward", "ortho", "forward"):
+            ko = O.rg2cgh(w.double(), norm)
+            assert rel(U.rg2cgh(w.to(dev(nb)), norm), ko) < 1e-6
+            assert rel(U.cgh2rg(ko.to(torch.complex64).to(dev(nb)), norm), w.double()) < 1e-6
+        # the result is a Hermitian half spectrum: irfftn then rfftn gives it back
+        k = U.rg2cgh(w.to(dev(nb)))
+        assert rel(nb.rfftn(nb.irfftn(k)), k.detach().cpu().numpy()) < 1e-5
+        # VJP with the transfer multiply fused in
+        cs = O.r2chshape(shape)
+        tr = torch.tensor(rng.uniform(0.5, 2.0, cs), dtype=torch.float32)
+        cot = torch.tensor(rng.normal(size=cs) + 1j * rng.normal(size=cs), dtype=torch.complex64)
+        we = leaf(w, nb)
+        oe = U.rg2cgh(we, "backward", tr.to(dev(nb)))
+        torch.view_as_real(oe * cot.to(dev(nb)).conj()).select(-1, 0).sum().backward()
+        wo = leaf(w, dtype=torch.float64)
+        oo = O.rg2cgh(wo) * tr.double()
+        (oo * cot.to(torch.complex128).conj()).real.sum().backward()
+        assert rel(oe, oo) < 1e-6 and rel(we.grad, wo.grad) < 1e-6
+    with pytest.raises(AssertionError):
+        U.rg2cgh(torch.zeros(4, 5, 4))
+    with pytest.raises(NotImplementedError):
+        U.rg2cgh(torch.zeros(4, 4, 4), norm="amp")

@@ -189,6 +189,15 @@ int mcpm_chreshape(void* stream, const void* in, int inx, int iny, int inz, void
 int mcpm_chreshape_vjp(void* stream, const void* outbar, int onx, int ony, int onz, void* inbar, int inx, int iny,
                        int inz);
 
+/* Binned auto / cross power spectrum, monopole (metrics.py:121-182).  For every half-spectrum element:
+ * bin = np.digitize(|k|, kedges), k = 2 pi f / box_size; out[0][bin] += w', out[1][bin] += w' |k|,
+ * out[2..3][bin] += w' Re / Im (m0 conj m1) after dividing m_i by rectangular_hat^deconv_i; w' = 1 on kz = 0 / Nyquist,
+ * else 2.  m1 NULL = auto spectrum.  kedges: n_edges float64 on the device, increasing; out: [4][n_edges + 1] float64 on
+ * the device, accumulated into.  The caller normalises (metrics.py:176-177). */
+int mcpm_spectrum_bins(void* stream, const void* m0_c64, const void* m1_c64, int nx, int ny, int nz, double box_x,
+                       double box_y, double box_z, const double* kedges, int n_edges, int deconv0, int deconv1,
+                       double* out);
+
 /* rg2cgh / cgh2rg (utils.py:785-921): real Gaussian mesh [nx,ny,nz] (all sides even) <-> complex
  * Gaussian Hermitian half spectrum by permutation and reweighting; rg2cgh(N(0,I)) is distributed as rfftn(N(0,I)).
  * out = scale * [transfer *] P(mesh), scale = sqrt(N/2) for norm "backward", 1/sqrt(2) "ortho", 1/sqrt(2N) "forward";

@@ -5,7 +5,7 @@ Pointer arguments are passed as integers (device addresses from `tensor.data_ptr
 """
 import ctypes as C
 
-vp, f32, i32, i64, sz = C.c_void_p, C.c_float, C.c_int, C.c_int64, C.c_size_t
+vp, f32, f64, i32, i64, sz = C.c_void_p, C.c_float, C.c_double, C.c_int, C.c_int64, C.c_size_t
 hp = C.POINTER(C.c_float)  # host float array
 
 MESH = [i32, i32, i32]
@@ -52,6 +52,7 @@ SIGNATURES = {
     "mcpm_hessian_spectra_T_slab": ([vp, vp, vp] + MESH + [i32, i32, i32, i32, i32, i32, f32], i32),
     "mcpm_chreshape": ([vp, vp] + MESH + [vp] + MESH, i32),
     "mcpm_chreshape_vjp": ([vp, vp] + MESH + [vp] + MESH, i32),
+    "mcpm_spectrum_bins": ([vp, vp, vp] + MESH + [f64, f64, f64, vp, i32, i32, i32, vp], i32),
     "mcpm_rg2cgh": ([vp, vp, vp] + MESH + [f32, vp], i32),
     "mcpm_rg2cgh_vjp": ([vp, vp, vp] + MESH + [f32, vp], i32),
     "mcpm_cgh2rg": ([vp, vp, vp] + MESH + [f32], i32),

@@ -253,6 +253,57 @@ int hermitian_weights(stream_t st, const cfloat* in, cfloat* out, int nx, int ny
   return rt_check("hermitian_weights");
 }
 
+// ---------------------------------------------------------------------------------------------------- spectrum
+// Binned auto / cross power of half spectra, monopole (metrics.py:121-182): for every element, bin = np.digitize(|k|,
+// kedges) with k = 2 pi f / box_size, weight w' = 1 on kz = 0 / Nyquist else 2 (Hermitian double counting), and
+//   out[0][bin] += w'   out[1][bin] += w' |k|   out[2][bin] += w' Re(m0 conj m1)   out[3][bin] += w' Im(m0 conj m1)
+// after dividing m_i by rectangular_hat^deconv_i (cell units).  Wavenumbers and sums are float64 so that bin membership
+// matches the float64 reference exactly; out = [4][n_edges + 1] float64, accumulated into (caller zeroes it).
+struct Box3 {
+  double x, y, z;
+};
+
+int spectrum_bins(stream_t st, const cfloat* m0, const cfloat* m1, int nx, int ny, int nz, double bx, double by,
+                  double bz, const double* kedges, int n_edges, int deconv0, int deconv1, double* out) {
+  if (int e = check_dims(nx, ny, nz)) return e;
+  const Box3 box = {bx, by, bz};
+  if (n_edges < 1) {
+    set_error("spectrum_bins: at least one bin edge is required");
+    return MCPM_EINVAL;
+  }
+  KGrid g = make_kgrid(nx, ny, nz);
+  const int64_t nc = (int64_t)nx * ny * g.nzc;
+  const int nb = n_edges + 1;
+  const double twopi = 6.283185307179586476925;
+  launch_1d(st, nc, [=] MCPM_LAMBDA(int64_t e) {
+    int l;
+    KVec kc = kvec_at(g, e, l);  // cell units, for the deconvolution window
+    const int64_t r = e / g.nzc;
+    const int j = (int)(r % g.ny), i = (int)(r / g.ny);
+    const double kx = twopi * signed_freq(i, g.nx) / box.x, ky = twopi * signed_freq(j, g.ny) / box.y,
+                 kz = twopi * l / box.z;
+    const double kk = sqrt(kx * kx + ky * ky + kz * kz);
+    int lo = 0, hi = n_edges;  // number of edges <= kk
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (kedges[mid] <= kk) lo = mid + 1;
+      else hi = mid;
+    }
+    const double w = half_weight(l, g.nz);
+    cfloat a = m0[e];
+    cfloat b = m1 ? m1[e] : a;
+    float ca = deconv0 > 0 ? 1.0f / window_hat(kc, deconv0) : 1.0f;
+    float cb = deconv1 > 0 ? 1.0f / window_hat(kc, deconv1) : 1.0f;
+    if (!m1) cb = ca;
+    const double ar = (double)a.re * ca, ai = (double)a.im * ca, br = (double)b.re * cb, bi = (double)b.im * cb;
+    atomic_add(out + lo, w);
+    atomic_add(out + nb + lo, w * kk);
+    atomic_add(out + 2 * nb + lo, w * (ar * br + ai * bi));
+    if (m1) atomic_add(out + 3 * nb + lo, w * (ai * br - ar * bi));
+  });
+  return rt_check("spectrum_bins");
+}
+
 // ---------------------------------------------------------------------------------------------------- rg2cgh
 // rg2cgh / cgh2rg (utils.py:785-921): a real Gaussian mesh [nx,ny,nz] <-> a complex Gaussian Hermitian half spectrum
 // [nx,ny,nz/2+1] by permutation and reweighting, so that rg2cgh(N(0,I)) is distributed as rfftn(N(0,I)).

@@ -49,3 +49,41 @@ def value_and_force(white, obs, transfer, cosmo, mesh_shape, **kw):
     lp = logpdf(w, obs, transfer, cosmo, mesh_shape, **kw)
     (g,) = torch.autograd.grad(lp, w)
     return lp.detach(), g
+
+
+def lagrangian_bias(cosmo, pos, a, box_size, lin_mesh, bias, read_order=2):
+    """bricks.py:327-452 without the primordial non-Gaussianity terms, float64: (weights, dvel)."""
+    b = {k: bias.get(k, 0.0) for k in ("b1", "b2", "bs2", "b3", "bds2", "bs3", "bn2", "bnpar")}
+    lin_mesh = lin_mesh if isinstance(lin_mesh, torch.Tensor) else O._t(lin_mesh, O.C128)
+    shape = O.ch2rshape(tuple(lin_mesh.shape))
+    g = O.a2g(cosmo, a)
+    g = g.reshape(-1) if isinstance(g, torch.Tensor) and g.numel() > 1 else g
+    kvec = [O._t(k) for k in O.rfftk(shape, box_size)]
+    kmesh2 = sum(k ** 2 for k in kvec)
+    pot = lin_mesh * O._t(O.invlaplace_hat(O.rfftk(shape, box_size)))
+    rd = lambda m: O.read(pos, m, read_order)
+    irf = lambda m: torch.fft.irfftn(m, s=shape)
+    delta_pos = rd(irf(lin_mesh)) * g
+    w = 1.0 + b["b1"] * delta_pos
+    d2 = delta_pos ** 2
+    sigma2 = d2.mean()
+    w = w + b["b2"] * (d2 - sigma2) / 2
+    sh = {}
+    for i in range(2):
+        nabi = 1j * kvec[i]
+        sh[(i, i)] = irf(nabi ** 2 * pot - lin_mesh / 3)
+        for j in range(i + 1, 3):
+            sh[(i, j)] = irf(nabi * (1j * kvec[j]) * pot)
+    sh[(2, 2)] = -(sh[(0, 0)] + sh[(1, 1)])
+    a_, b_, c_ = sh[(0, 0)], sh[(1, 1)], sh[(2, 2)]
+    d_, e_, f_ = sh[(0, 1)], sh[(0, 2)], sh[(1, 2)]
+    shear2_pos = rd(a_ ** 2 + b_ ** 2 + c_ ** 2 + 2 * (d_ ** 2 + e_ ** 2 + f_ ** 2)) * g ** 2 - 2 / 3 * sigma2
+    w = w + b["bs2"] * shear2_pos
+    w = w + b["b3"] * (delta_pos ** 3 - 3 * sigma2 * delta_pos) / 6
+    w = w + b["bds2"] * delta_pos * shear2_pos
+    shear3 = 3 * (a_ * (b_ * c_ - f_ ** 2) - d_ * (d_ * c_ - e_ * f_) + e_ * (d_ * f_ - b_ * e_))
+    w = w + b["bs3"] * rd(shear3) * g ** 3
+    w = w + b["bn2"] * rd(irf(-kmesh2 * lin_mesh)) * g
+    grads = torch.stack([rd(irf(1j * k * lin_mesh)) for k in kvec], dim=-1)
+    gcol = g.reshape(-1, 1) if isinstance(g, torch.Tensor) and g.dim() > 0 else g
+    return w, b["bnpar"] * grads * gcol

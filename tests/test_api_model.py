@@ -247,3 +247,29 @@ def test_rg2cgh_golden_roundtrip_and_gradient(nb, golden):
         U.rg2cgh(torch.zeros(4, 5, 4))
     with pytest.raises(NotImplementedError):
         U.rg2cgh(torch.zeros(4, 4, 4), norm="amp")
+
+
+def test_lagrangian_bias_weights_and_gradient(nb):
+    """bricks.lagrangian_bias (bricks.py:327-452, no PNG terms) against the oracle: weights and dvel 5e-5, gradient of a
+    scalar functional w.r.t. the linear mesh 2e-4."""
+    from montecosmo_b200 import bricks as B
+    from montecosmo_b200.cosmo import Cosmology
+    rng = np.random.default_rng(23)
+    shape, box = (8, 10, 12), (80.0, 100.0, 96.0)
+    dk0 = np.fft.rfftn(rng.normal(size=shape)) * 0.05
+    q = O.regular_pos(shape)
+    pos = (q + torch.tensor(rng.normal(scale=0.4, size=q.shape))).float()
+    bias = dict(b1=0.8, b2=0.3, bs2=-0.2, b3=0.1, bds2=0.05, bs3=-0.07, bn2=0.4, bnpar=0.6)
+    cw = torch.tensor(rng.normal(size=q.shape[0]), dtype=torch.float32)
+    cv = torch.tensor(rng.normal(size=q.shape), dtype=torch.float32)
+    dk = torch.tensor(dk0, dtype=torch.complex64, device=dev(nb)).requires_grad_()
+    w, dvel, phi = B.lagrangian_bias(Cosmology(), pos.to(dev(nb)), 0.7, box, dk, bias, read_order=2)
+    ((w * cw.to(dev(nb))).sum() + (dvel * cv.to(dev(nb))).sum()).backward()
+    dko = torch.tensor(dk0, dtype=torch.complex128).requires_grad_()
+    wo, dvo = MO.lagrangian_bias(O.Cosmology(), pos.double(), 0.7, box, dko, bias, read_order=2)
+    ((wo * cw.double()).sum() + (dvo * cv.double()).sum()).backward()
+    assert phi == 0.0 and rel(w, wo) < 5e-5 and rel(dvel, dvo) < 5e-5
+    assert rel(dk.grad, dko.grad) < 2e-4
+    assert rel(B.regular_pos(shape), q.numpy()) == 0.0
+    with pytest.raises(NotImplementedError):
+        B.lagrangian_bias(Cosmology(), pos.to(dev(nb)), 0.7, box, dk.detach(), bias, png_type="fNL")

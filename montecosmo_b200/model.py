@@ -188,3 +188,30 @@ class FieldModel:
 
     def force(self, white, obs):
         return self.value_and_force(white, obs)[1]
+
+    def graphed_value_and_force(self, obs, warmup=2):
+        """Capture one evaluation -- every kernel of lpt, the BullFrog loop, the paints, the FFTs and the whole reverse
+        sweep -- in a CUDA graph and return `fn(white) -> (logpdf, force)` that replays it (a sampler calls the same
+        evaluation thousands of times: one graph launch instead of ~250 kernel launches and the Python around them).
+        The returned tensors are the graph's static outputs: consume or copy them before the next call.  Nothing on the
+        engine's call path allocates or synchronises, so the capture needs no special casing; cuFFT plans and scratch are
+        created during the warm-up evaluations."""
+        dev = nb.ops().A.device
+        static_white = torch.zeros(self.mesh_shape, device=dev, dtype=torch.float32)
+        static_obs = nb._f32(obs).detach().clone()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self.value_and_force(static_white, static_obs)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self.value_and_force(static_white, static_obs)
+
+        def run(white):
+            static_white.copy_(nb._f32(white), non_blocking=True)
+            graph.replay()
+            return out
+        run.graph = graph
+        return run

@@ -1,0 +1,123 @@
+"""
+BASELINE.json's full size (C3: 256^3 mesh / 256^3 particles) through size-independent properties, on the evolved a = 1
+state of the benchmark workload -- the oracle cannot run at this size, the identities below need no reference:
+
+  * weight conservation of paint (bricks.py:1101-1102) and brick-tiled vs generic scatter;
+  * read is the transpose of paint:  <read(pos, m), w> = <m, paint(pos, w)>   (nbody.py:365-427);
+  * momentum conservation: sum_p F_p = 0, because the force operator is antisymmetric (G_j^T = -G_j) and the CIC
+    read is the transpose of the CIC paint;
+  * the fused x-transform path and the 3-D cuFFT path compute the same forces;
+  * the hand-written reverse sweep agrees with a directional central difference of the log-density.
+GPU only.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+N = 256
+
+
+@pytest.fixture(scope="module")
+def state():
+    from bench import workload
+    from montecosmo_b200 import nbody as nb
+    from montecosmo_b200.model import FieldModel
+    nb._OPS = None
+    o = nb.ops()
+    m = FieldModel(**workload(N))
+    dev = o.A.device
+    g = torch.Generator(device=dev).manual_seed(2024)
+    white = torch.randn(m.mesh_shape, device=dev, generator=g)
+    with torch.no_grad():
+        dk = m.linear_field(white)
+        pos, vel = nb.nbody_bf(m.cosmology, dk, m.q, m.a_start, m.a_obs, m.n_steps)
+    return dict(nb=nb, o=o, m=m, white=white, pos=pos[-1].contiguous(), vel=vel[-1].contiguous(), gen=g)
+
+
+def fdot(o, a, b):
+    return float(o.dot(a.reshape(-1), b.reshape(-1)))
+
+
+def test_paint_conservation_and_brick_vs_generic(state):
+    o, pos, shape = state["o"], state["pos"], state["m"].mesh_shape
+    npart = pos.shape[0]
+    one = torch.ones(shape, device=pos.device)
+    w = torch.rand(npart, device=pos.device, generator=state["gen"]) + 0.5
+    o.set_lattice(shape, None)
+    generic = o.paint(pos, shape, None, order=2)
+    generic_w = o.paint(pos, shape, w, order=2)
+    assert abs(fdot(o, generic, one) - npart) < 1e-6 * npart
+    assert abs(fdot(o, generic_w, one) - float(w.double().sum())) < 1e-6 * npart
+    # brick-tiled kernel on the same particles (must be handled: MCPM_EUNSUP raises otherwise)
+    o.set_lattice(shape, shape)
+    eng = o.engine(shape)
+    A = o.A
+    for weights, ref in ((None, generic), (w, generic_w)):
+        out = torch.zeros(shape, device=pos.device)
+        o._call("mcpm_paint_lattice", eng.handle, A.stream(), A.ptr(pos), A.ptr(weights), 1.0, npart, A.ptr(out))
+        assert abs(fdot(o, out, one) - fdot(o, ref, one)) < 1e-6 * npart
+        err = float((out - ref).double().norm() / ref.double().norm())
+        assert err < 2e-5, err
+
+
+def test_read_is_the_transpose_of_paint(state):
+    o, pos, shape = state["o"], state["pos"], state["m"].mesh_shape
+    g = state["gen"]
+    mesh = torch.randn(shape, device=pos.device, generator=g)
+    w = torch.randn(pos.shape[0], device=pos.device, generator=g)
+    for order in (1, 2, 3):
+        lhs = fdot(o, o.read(pos, mesh, order=order), w)
+        rhs = fdot(o, mesh, o.paint(pos, shape, w, order=order))
+        assert abs(lhs - rhs) < 1e-5 * (abs(lhs) + abs(rhs) + np.sqrt(pos.shape[0])), (order, lhs, rhs)
+
+
+def test_momentum_conservation_and_fft_paths(state):
+    o, pos, shape = state["o"], state["pos"], state["m"].mesh_shape
+    o.set_lattice(shape, shape)
+    res = {}
+    for fused in (True, False):
+        o.set_fused_fft(shape, fused)
+        res[fused] = o.pm_forces(pos, shape, 2)
+    o.set_fused_fft(shape, True)
+    f = res[True].double()
+    total, scale = f.sum(0).abs().max(), f.abs().sum(0).min()
+    assert float(total / scale) < 1e-5, float(total / scale)
+    err = float((res[True] - res[False]).double().norm() / res[False].double().norm())
+    assert err < 2e-5, err
+
+
+def test_reverse_sweep_against_central_difference(state):
+    m, o, white = state["m"], state["o"], state["white"]
+    g = state["gen"]
+    obs = 1.0 + torch.randn(m.mesh_shape, device=white.device, generator=g)
+    lp, grad = m.value_and_force(white, obs)
+    v = grad / grad.norm()  # steepest direction: the best conditioned one for float32 forward passes
+    eps = 0.05
+    with torch.no_grad():
+        lp_p = float(m.logpdf(white + eps * v, obs))
+        lp_m = float(m.logpdf(white - eps * v, obs))
+    fd = (lp_p - lp_m) / (2 * eps)
+    an = fdot(o, grad, v)
+    assert abs(fd - an) < 1e-2 * abs(an), (fd, an)
+
+
+def test_cuda_graph_replay_matches_eager():
+    """FieldModel.graphed_value_and_force: the whole evaluation captured in a CUDA graph replays to the eager result
+    (64^3 here; atomics make both runs order dependent at the 1e-6 level)."""
+    from bench import workload
+    from montecosmo_b200 import nbody as nb
+    from montecosmo_b200.model import FieldModel
+    nb._OPS = None
+    dev = nb.ops().A.device
+    m = FieldModel(**workload(64))
+    g = torch.Generator(device=dev).manual_seed(3)
+    obs = 1.0 + torch.randn(m.mesh_shape, device=dev, generator=g)
+    fn = m.graphed_value_and_force(obs)
+    for _ in range(3):
+        white = torch.randn(m.mesh_shape, device=dev, generator=g)
+        lp_g, f_g = fn(white)
+        lp_g, f_g = float(lp_g), f_g.clone()
+        lp_e, f_e = m.value_and_force(white, obs)
+        assert abs(lp_g - float(lp_e)) < 1e-5 * abs(float(lp_e))
+        assert float((f_g - f_e).norm() / f_e.norm()) < 1e-4

@@ -61,7 +61,7 @@ void engine_destroy(Engine* e) {
 // CIC paint of pos * scale + shift into a fresh mesh: brick-tiled when the engine carries a matching lattice hint and
 // the positions are not rescaled (CUDA build), generic otherwise
 // mcpm_tune("side_zero"): clear the next step's scatter meshes inside the gather kernels (1) or with memsets (0)
-static int g_side_zero = 1;
+static int g_side_zero = 0;  // measured: no net gain (the gathers slow down by what the memsets cost), kept selectable
 void set_side_zero(int v) { g_side_zero = v; }
 
 static bool brick_path(const Engine* E, int order, const float* scale) {

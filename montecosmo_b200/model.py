@@ -213,5 +213,6 @@ class FieldModel:
             static_white.copy_(nb._f32(white), non_blocking=True)
             graph.replay()
             return out
-        run.graph = graph
+        # the graph reads these buffers on every replay: they must live as long as the callable does
+        run.graph, run.static_white, run.static_obs, run.out = graph, static_white, static_obs, out
         return run

@@ -320,6 +320,33 @@ def run_engine(args):
     clocks = sampler.stop() if rank == 0 else None
     lp_val = float(h_lp)
     launches = launches_per_eval * K
+    # The smaller BASELINE configs, for the record (not the metric): C1 64^3 / 5 steps (run/infer_example.py scale) and
+    # C2 128^3 / 10 steps inside a leapfrog loop -- 2 gradient evaluations per iteration, as isokinetic_mclachlan
+    # (samplers.py:350-351) -- both on the graph-replayed evaluation.
+    other = {}
+    if rank == 0 and fn is not None and n == 256:
+        for tag, nn, nsteps in (("C1_64", 64, 5), ("C2_128_leapfrog", 128, 10)):
+            wl = workload(nn)
+            wl["n_steps"] = nsteps
+            mm = FieldModel(**wl)
+            oo = 1.0 + torch.randn(mm.mesh_shape, device=dev, generator=gen)
+            ff = mm.graphed_value_and_force(oo)
+            q, p, eps = torch.randn(mm.mesh_shape, device=dev, generator=gen), torch.zeros(mm.mesh_shape, device=dev), 1e-3
+            iters = 100
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):  # position-Verlet-like split with two force evaluations per iteration
+                p.add_(ff(q)[1], alpha=0.5 * eps)
+                q.add_(p, alpha=0.5 * eps)
+                p.add_(ff(q)[1], alpha=0.5 * eps)
+                q.add_(p, alpha=0.5 * eps)
+            e1.record()
+            torch.cuda.synchronize()
+            other[tag] = {"mesh": nn, "n_body_steps": nsteps, "evals_per_s": 2 * iters / (e0.elapsed_time(e1) * 1e-3),
+                          "iterations": iters}
+            del ff, mm
+        torch.cuda.empty_cache()
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -349,7 +376,7 @@ def run_engine(args):
                                                "capture (profiles/r1_traffic.json)" if dom["traffic"] else None,
                              "alg_bytes_per_launch": dom["alg_bytes"], "ms_per_launch": dom["ms"],
                              "share_of_step": dom["ms_per_step_total"] / (ms_dev / K)},
-                "kernels": rows, "cpu_baseline": cb, "logp_last": lp_val,
+                "kernels": rows, "cpu_baseline": cb, "logp_last": lp_val, "other_configs": other,
                 "paint_Gparticles_per_s": N / (rows[0]["ms"] * 1e-3) / 1e9,
                 "paint_kernel": rows[0]["kernel"]}
         print(json.dumps(line), flush=True)

@@ -50,7 +50,7 @@ long long mcpm_launch_count(int reset);
 
 /* Process-wide performance knobs (never change which result is computed).  Keys: "gather_minb" = 4 | 5 | 6, the
  * resident CTAs per SM the readout kernels are compiled for; "gather_blocked" = 0 | 1, one CTA per 256 consecutive
- * particles instead of a grid-stride loop; "xfuse_occ" = 2 | 3, resident CTAs per SM of the fused x-transform;
+ * particles instead of a grid-stride loop;
  * "side_zero" = 0 | 1, clear the next step's scatter meshes inside the readout kernels instead of memsets. */
 int mcpm_tune(const char* key, int value);
 
@@ -65,7 +65,7 @@ size_t mcpm_engine_scratch_bytes(const mcpm_engine* eng);
  * px = 0 clears the hint. */
 int mcpm_engine_set_lattice(mcpm_engine* eng, int px, int py, int pz);
 /* Fused x-transform path of pm_forces and its VJP (2-D cuFFT per x-plane + one kernel doing the x-FFT, the force
- * kernel of nbody.py:591-603 and the inverse x-FFTs).  On by default where supported (nx in {64, 128, 256});
+ * kernel of nbody.py:591-603 and the inverse x-FFTs).  On by default where supported (nx in {64, 128, 256, 512, 1024});
  * on = 0 selects the 3-D cuFFT + separate multiply path, on = 1 returns MCPM_EUNSUP where unsupported.
  * Both paths compute the same operator (float32 rounding differs). */
 int mcpm_engine_set_fused_fft(mcpm_engine* eng, int on);
@@ -171,12 +171,13 @@ int mcpm_hessian_spectra_slab(void* stream, const void* delta_k, void* out6, int
 int mcpm_hessian_spectra_T_slab(void* stream, const void* in6, void* out1, int nx, int ny, int nz, int ny_loc, int y0,
                                 int lap_fd, int grad_fd, int half_weights, int accumulate, float norm);
 
-/* Fused x-transform passes (CUDA build, nx in {64, 128, 256}; MCPM_EUNSUP otherwise), on a half spectrum
+/* Fused x-transform passes (CUDA build, nx in {64, 128, 256, 512, 1024}; MCPM_EUNSUP otherwise), on a half spectrum
  * [nx, ny_loc, nz/2+1] that has been transformed along (y,z) only:
  *   xfuse_force   : out3[j] = IFFT_x( force kernel_j * FFT_x(in) )            = mcpm_force_spectra between the x-passes
  *   xfuse_force_T : out1    = IFFT_x( sum_j conj(kernel_j) * FFT_x(in3[j]) )  = mcpm_force_spectra_T (no half weights)
  * Unnormalised transforms; `norm` multiplies the output.  The engine's pm_forces / reverse step run these between
  * batched 2-D cuFFT plans; with ny_loc < ny they serve a slab-decomposed mesh after the all-to-all. */
+int mcpm_xfuse_supported(int nx); /* 1 if the fused x-transform exists for this nx in this build, else 0 */
 int mcpm_xfuse_force_slab(void* stream, const void* in, void* out3, int nx, int ny, int nz, int ny_loc, int y0,
                           int lap_fd, int grad_fd, float kcut, int deconv_order, float norm);
 int mcpm_xfuse_force_T_slab(void* stream, const void* in3, void* out1, int nx, int ny, int nz, int ny_loc, int y0,

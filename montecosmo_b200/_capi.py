@@ -45,6 +45,7 @@ SIGNATURES = {
     "mcpm_slabfft_c2r_yz": ([vp, vp, vp, vp, i32], i32),
     "mcpm_slabfft_c2c_x": ([vp, vp, vp, i32, i32], i32),
     "mcpm_force_spectra_slab": ([vp, vp, vp] + MESH + [i32, i32, i32, i32, f32, i32, f32], i32),
+    "mcpm_xfuse_supported": ([i32], i32),
     "mcpm_xfuse_force_slab": ([vp, vp, vp] + MESH + [i32, i32, i32, i32, f32, i32, f32], i32),
     "mcpm_xfuse_force_T_slab": ([vp, vp, vp] + MESH + [i32, i32, i32, i32, f32, i32, f32], i32),
     "mcpm_force_spectra_T_slab": ([vp, vp, vp] + MESH + [i32, i32, i32, i32, f32, i32, i32, i32, f32], i32),

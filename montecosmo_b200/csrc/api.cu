@@ -104,13 +104,6 @@ int mcpm_tune(const char* key, int value) {
     set_gather_minb(value);
     return MCPM_OK;
   }
-#ifndef MCPM_HOSTEMU
-  if (std::string(key) == "xfuse_occ") {
-    NEED(value == 2 || value == 3, "tune: xfuse_occ must be 2 or 3");
-    set_xfuse_occ(value);
-    return MCPM_OK;
-  }
-#endif
   if (std::string(key) == "side_zero") {
     set_side_zero(value != 0);
     return MCPM_OK;
@@ -128,7 +121,7 @@ int mcpm_engine_set_fused_fft(mcpm_engine* eng, int on) {
   API_BEGIN
   NEED(eng, "null engine");
   if (on && !eng->e->fft2d) {
-    set_error("set_fused_fft: not available for this mesh shape (nx must be 64, 128 or 256) or CPU build");
+    set_error("set_fused_fft: not available for this mesh shape (nx must be 64, 128, 256, 512 or 1024) or CPU build");
     return MCPM_EUNSUP;
   }
   eng->e->fused_fft = on ? 1 : 0;
@@ -346,6 +339,15 @@ int mcpm_force_spectra_slab(void* stream, const void* delta_k, void* out3, int n
   API_END
 }
 
+int mcpm_xfuse_supported(int nx) {
+#ifndef MCPM_HOSTEMU
+  return xfuse_supported(nx) ? 1 : 0;
+#else
+  (void)nx;
+  return 0;
+#endif
+}
+
 int mcpm_xfuse_force_slab(void* stream, const void* in, void* out3, int nx, int ny, int nz, int ny_loc, int y0,
                           int lap_fd, int grad_fd, float kcut, int deconv_order, float norm) {
   API_BEGIN
@@ -359,7 +361,7 @@ int mcpm_xfuse_force_slab(void* stream, const void* in, void* out3, int nx, int 
     return xfuse_force(as_stream(stream), C(in), C(out3), nx, ny, nz, lap_fd, grad_fd, kcut, deconv_order, norm, sk);
   }
 #endif
-  set_error("xfuse_force_slab: nx must be 64, 128 or 256 (CUDA build only)");
+  set_error("xfuse_force_slab: nx must be 64, 128, 256, 512 or 1024 (CUDA build only)");
   return MCPM_EUNSUP;
   API_END
 }
@@ -377,7 +379,7 @@ int mcpm_xfuse_force_T_slab(void* stream, const void* in3, void* out1, int nx, i
     return xfuse_force_T(as_stream(stream), C(in3), C(out1), nx, ny, nz, lap_fd, grad_fd, kcut, deconv_order, norm, sk);
   }
 #endif
-  set_error("xfuse_force_T_slab: nx must be 64, 128 or 256 (CUDA build only)");
+  set_error("xfuse_force_T_slab: nx must be 64, 128, 256, 512 or 1024 (CUDA build only)");
   return MCPM_EUNSUP;
   API_END
 }

@@ -114,7 +114,6 @@ int read_grad4v(stream_t, const float* pos, const float* fmesh4, const float* rh
 
 // xfft.cu (CUDA build only): the x-passes of rfftn / irfftn fused with the force kernel, on [nx, ny_loc, nz/2+1]
 bool xfuse_supported(int nx);
-void set_xfuse_occ(int v);
 int xfuse_force(stream_t, const cfloat* in, cfloat* out3, int nx, int ny, int nz, int lap_fd, int grad_fd, float kcut,
                 int deconv_order, float norm, SlabK sk = SlabK());
 int xfuse_force_T(stream_t, const cfloat* in3, cfloat* out, int nx, int ny, int nz, int lap_fd, int grad_fd,

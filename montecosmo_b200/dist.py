@@ -53,6 +53,8 @@ class SlabPM:
         h = C.c_void_p()
         check(self.lib, self.lib.mcpm_slabfft_create(nx, ny, nz, self.P, C.byref(h)))
         self._fft = h
+        # fused x-transform (xfft.cu) between the all-to-alls where this build has it for nx; set False to compare
+        self.xfuse = bool(self.lib.mcpm_xfuse_supported(nx))
         self.prev, self.next = (self.rank - 1) % self.P, (self.rank + 1) % self.P
         ax = [np.arange(self.xl, dtype=np.float32), np.arange(ny, dtype=np.float32), np.arange(nz, dtype=np.float32)]
         self.q_own = self.A.prepare(np.stack(np.meshgrid(*ax, indexing="ij"), -1).reshape(-1, 3))  # owned-slab coords
@@ -92,8 +94,9 @@ class SlabPM:
         dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(send), group=self.group)
         return recv
 
-    def rfftn(self, a):
-        """[nb, xl, ny, nz] real (owned planes) -> [nb, nx, kyl, nzc] complex (my ky block), unnormalised."""
+    def rfftn_yz(self, a):
+        """[nb, xl, ny, nz] real (owned planes) -> [nb, nx, kyl, nzc] complex (my ky block) transformed along (y,z)
+        only: batched 2-D R2C of the local planes + the all-to-all that trades x-planes for ky rows."""
         a = self.A.prepare(a)
         nb = a.shape[0]
         b = self.A.empty((nb, self.xl, self.ny, self.nzc), "c64")
@@ -101,17 +104,23 @@ class SlabPM:
         # send[q] = my planes restricted to rank q's ky rows
         send = b.view(nb, self.xl, self.P, self.kyl, self.nzc).permute(2, 0, 1, 3, 4).contiguous()
         recv = self._a2a(send)  # recv[q] = rank q's planes, my ky rows
-        c = recv.permute(1, 0, 2, 3, 4).contiguous().view(nb, self.nx, self.kyl, self.nzc)
-        self._call("mcpm_slabfft_c2c_x", self._fft, self._st(), c.data_ptr(), nb, 0)
+        return recv.permute(1, 0, 2, 3, 4).contiguous().view(nb, self.nx, self.kyl, self.nzc)
+
+    def rfftn(self, a):
+        """[nb, xl, ny, nz] real (owned planes) -> [nb, nx, kyl, nzc] complex (my ky block), unnormalised."""
+        c = self.rfftn_yz(a)
+        self._call("mcpm_slabfft_c2c_x", self._fft, self._st(), c.data_ptr(), c.shape[0], 0)
         return c
 
-    def irfftn(self, c, overwrite=False):
-        """[nb, nx, kyl, nzc] complex -> [nb, xl, ny, nz] real, UNNORMALISED (fold 1/N into the preceding Fourier pass)."""
+    def irfftn(self, c, overwrite=False, x_done=False):
+        """[nb, nx, kyl, nzc] complex -> [nb, xl, ny, nz] real, UNNORMALISED (fold 1/N into the preceding Fourier pass).
+        x_done: the inverse transform along x has already been applied (fused x-transform kernels)."""
         c = self.A.prepare(c, "c64")
         if not overwrite:
             c = c.clone()
         nb = c.shape[0]
-        self._call("mcpm_slabfft_c2c_x", self._fft, self._st(), c.data_ptr(), nb, 1)
+        if not x_done:
+            self._call("mcpm_slabfft_c2c_x", self._fft, self._st(), c.data_ptr(), nb, 1)
         send = c.view(nb, self.P, self.xl, self.kyl, self.nzc).permute(1, 0, 2, 3, 4).contiguous()
         recv = self._a2a(send)  # recv[q] = my planes, rank q's ky rows
         b = recv.permute(1, 2, 0, 3, 4).contiguous().view(nb, self.xl, self.ny, self.nzc)
@@ -175,6 +184,28 @@ class SlabPM:
                    1.0 if half_weights else 1.0 / self.N)
         return out
 
+    # density planes -> three force meshes, and the transpose (3 meshes -> 1), each with ONE kernel between the
+    # all-to-alls where the fused x-transform exists for nx (xfft.cu), else c2c_x + streaming multiply + c2c_x
+    def forces_from_density(self, rho_owned):
+        if self.xfuse:
+            c = self.rfftn_yz(rho_owned.unsqueeze(0))
+            out = self.A.empty((3, self.nx, self.kyl, self.nzc), "c64")
+            self._call("mcpm_xfuse_force_slab", self._st(), c.data_ptr(), out.data_ptr(), self.nx, self.ny, self.nz,
+                       self.kyl, self.y0, 0, 0, 0.0, 0, 1.0 / self.N)
+            return self.irfftn(out, overwrite=True, x_done=True)
+        rk = self.rfftn(rho_owned.unsqueeze(0))
+        return self.irfftn(self.force_spectra(rk[0]), overwrite=True)
+
+    def density_cotangent(self, planar3):
+        if self.xfuse:
+            c = self.rfftn_yz(planar3)
+            out = self.A.empty((1, self.nx, self.kyl, self.nzc), "c64")
+            self._call("mcpm_xfuse_force_T_slab", self._st(), c.data_ptr(), out.data_ptr(), self.nx, self.ny, self.nz,
+                       self.kyl, self.y0, 0, 0, 0.0, 0, 1.0 / self.N)
+            return self.irfftn(out, overwrite=True, x_done=True)[0]
+        rk = self.force_spectra_T(self.rfftn(planar3))
+        return self.irfftn(rk.unsqueeze(0), overwrite=True)[0]
+
     # ------------------------------------------------------------------------------------------------ force step
     def force_mesh4(self, pos, order=2):
         """Extended float4 force mesh {Fx,Fy,Fz,0} [ext, ny, nz, 4] at the local positions (nbody.py:583-603)."""
@@ -184,8 +215,7 @@ class SlabPM:
         self._call("mcpm_paint", st, pos.data_ptr(), 0, 1.0, pos.shape[0], self.ext, self.ny, self.nz, order, one, 0.0,
                    rho.data_ptr(), 1)
         self.halo_reduce(rho)
-        rk = self.rfftn(rho[self.H:self.H + self.xl].unsqueeze(0))
-        F = self.irfftn(self.force_spectra(rk[0]), overwrite=True)  # [3, xl, ny, nz]
+        F = self.forces_from_density(rho[self.H:self.H + self.xl])  # [3, xl, ny, nz]
         fm4 = A.empty((self.ext, self.ny, self.nz, 4))
         own = fm4[self.H:self.H + self.xl]
         self._call("mcpm_interleave3", st, F.data_ptr(), own.data_ptr(), self.xl * self.ny * self.nz)
@@ -224,9 +254,8 @@ class SlabPM:
             self.halo_reduce(m4)
             planar = A.empty((3, self.xl, self.ny, self.nz))
             self._call("mcpm_deinterleave3", st, m4[self.H:self.H + self.xl].data_ptr(), planar.data_ptr(), cells)
-            rk = self.force_spectra_T(self.rfftn(planar))
             rhobar = A.empty((self.ext, self.ny, self.nz))
-            rhobar[self.H:self.H + self.xl] = self.irfftn(rk.unsqueeze(0), overwrite=True)[0]
+            rhobar[self.H:self.H + self.xl] = self.density_cotangent(planar)
             self.halo_gather(rhobar)
             self._call("mcpm_read_grad4v", st, x1.data_ptr(), fm4.data_ptr(), rhobar.data_ptr(), velbar.data_ptr(),
                        float(beta[s]), float(alpha[s]), n, self.ext, self.ny, self.nz, posbar.data_ptr())

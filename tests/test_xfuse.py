@@ -31,8 +31,8 @@ def T(x):
     return torch.as_tensor(np.asarray(x), dtype=torch.float64)
 
 
-# nx = 64 (8 x 8), 128 (16 x 8), 256 (16 x 16) register transforms; ny * (nz/2+1) not a multiple of the 16-column tile
-SHAPES = [(64, 12, 16), (128, 6, 10), (256, 4, 6), (64, 16, 30)]
+# nx = 64 (8 x 8), 128 (16 x 8), 256 (16 x 16), 512 (32 x 16), 1024 (32 x 32) register transforms; ny * (nz/2+1) not a multiple of the 16-column tile
+SHAPES = [(64, 12, 16), (128, 6, 10), (256, 4, 6), (64, 16, 30), (512, 4, 6), (1024, 4, 4)]
 OPTS = [dict(order=2), dict(order=3, paint_deconv=True, lap_fd=2, grad_fd=4), dict(order=2, kcut=2.0, lap_fd=4)]
 
 
@@ -95,7 +95,8 @@ def test_unsupported_shape_reports(ops):
         ops.set_fused_fft((12, 8, 8), True)
 
 
-@pytest.mark.parametrize("nx,ny,nz,ny_loc,y0", [(64, 12, 16, 12, 0), (128, 8, 10, 4, 4), (256, 6, 8, 3, 2)])
+@pytest.mark.parametrize("nx,ny,nz,ny_loc,y0", [(64, 12, 16, 12, 0), (128, 8, 10, 4, 4), (256, 6, 8, 3, 2), (512, 6, 4, 2, 3),
+                                               (1024, 4, 6, 4, 0)])
 def test_kernel_against_numpy_x_transforms(ops, nx, ny, nz, ny_loc, y0):
     """The kernel alone on a (ky-block of a) half spectrum: out = IFFT_x(kernel * FFT_x(in)) with numpy's FFT along x and
     the engine's own streaming multiply (mcpm_force_spectra[_T]_slab) in between.  float32 vs float64 FFT: 5e-6."""
@@ -132,7 +133,7 @@ def test_kernel_against_numpy_x_transforms(ops, nx, ny, nz, ny_loc, y0):
         assert np.linalg.norm(got1 - ref1) / np.linalg.norm(ref1) < 5e-6
 
 
-@pytest.mark.parametrize("shape", [(64, 12, 16), (128, 6, 10)])
+@pytest.mark.parametrize("shape", [(64, 12, 16), (128, 6, 10), (512, 4, 4)])
 @pytest.mark.parametrize("lpt_order,read_order,fd", [(1, 1, (0, 0)), (2, 2, (0, 0)), (2, 1, (2, 4))])
 def test_lpt_and_its_vjp(ops, shape, lpt_order, read_order, fd):
     """lpt runs spectrum-in (force / Hessian set -> inverse x-FFTs) and spectrum-out (x-FFTs -> transposed kernels with

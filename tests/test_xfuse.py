@@ -56,8 +56,11 @@ def test_forces_and_vjp(ops, shape, kw):
     p = T(pos).requires_grad_()
     fo = O.pm_forces(p, shape, **okw)
     (fo * T(fbar)).sum().backward()
-    assert rel(res[True][0], fo.detach().numpy()) < 5e-5
-    assert rel(res[True][2], p.grad.numpy()) < 2e-4
+    # 1 / k^2 at the fundamental of a 1024-cell axis amplifies the float32 rounding of the painted density by 2.7e4:
+    # both engine paths agree with each other (above) and sit 1.2e-4 from the float64 oracle on the longest meshes
+    tol = 5e-5 if shape[0] <= 256 else 3e-4
+    assert rel(res[True][0], fo.detach().numpy()) < tol
+    assert rel(res[True][2], p.grad.numpy()) < 4 * tol
 
 
 def test_nbody_steps_and_reverse_sweep(ops):

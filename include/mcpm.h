@@ -180,6 +180,15 @@ int mcpm_hessian_spectra_T_slab(void* stream, const void* in6, void* out1, int n
 int mcpm_xfuse_supported(int nx); /* 1 if the fused x-transform exists for this nx in this build, else 0 */
 int mcpm_xfuse_force_slab(void* stream, const void* in, void* out3, int nx, int ny, int nz, int ny_loc, int y0,
                           int lap_fd, int grad_fd, float kcut, int deconv_order, float norm);
+/* The same two operators with the distributed transpose inside the kernel (slab decomposition over npeer <= 8 GPUs of
+ * one NVLink domain): in_peers[r] / out_peers[r] are rank r's buffers [ncomp][nx/npeer][ny][nz/2+1] -- the output of its
+ * local 2-D R2C / the input of its local 2-D C2R -- mapped into this process (CUDA IPC / symmetric memory).  This rank
+ * transforms the columns of ky rows y0 .. y0+ny_loc-1, loading every x-plane from and storing it to its owner over
+ * NVLink: no all-to-all, no pack / unpack passes.  transpose = 0: 1 -> 3 components, 1: 3 -> 1.  The caller orders the
+ * ranks with a barrier before (inputs complete everywhere) and after (outputs landed everywhere). */
+int mcpm_xfuse_force_peer(void* stream, const void* const* in_peers, void* const* out_peers, int npeer, int transpose,
+                          int nx, int ny, int nz, int ny_loc, int y0, int lap_fd, int grad_fd, float kcut,
+                          int deconv_order, float norm);
 int mcpm_xfuse_force_T_slab(void* stream, const void* in3, void* out1, int nx, int ny, int nz, int ny_loc, int y0,
                             int lap_fd, int grad_fd, float kcut, int deconv_order, float norm);
 

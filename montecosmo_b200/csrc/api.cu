@@ -366,6 +366,31 @@ int mcpm_xfuse_force_slab(void* stream, const void* in, void* out3, int nx, int 
   API_END
 }
 
+int mcpm_xfuse_force_peer(void* stream, const void* const* in_peers, void* const* out_peers, int npeer, int transpose,
+                          int nx, int ny, int nz, int ny_loc, int y0, int lap_fd, int grad_fd, float kcut,
+                          int deconv_order, float norm) {
+  API_BEGIN
+  NEED(in_peers && out_peers, "xfuse_force_peer: null pointer table");
+  NEED(npeer >= 1 && npeer <= 8, "xfuse_force_peer: 1..8 ranks");
+  NEED(ny_loc > 0 && y0 >= 0 && y0 + ny_loc <= ny && nz > 0 && !(nz & 1), "xfuse_force_peer: bad shape or ky block");
+#ifndef MCPM_HOSTEMU
+  if (xfuse_supported(nx)) {
+    const cfloat* ip[8];
+    cfloat* op[8];
+    for (int r = 0; r < npeer; ++r) {
+      NEED(in_peers[r] && out_peers[r], "xfuse_force_peer: null peer buffer");
+      ip[r] = C(in_peers[r]);
+      op[r] = C(out_peers[r]);
+    }
+    return xfuse_force_peer(as_stream(stream), ip, op, npeer, transpose, nx, ny, nz, ny_loc, y0, lap_fd, grad_fd, kcut,
+                            deconv_order, norm);
+  }
+#endif
+  set_error("xfuse_force_peer: nx must be 64, 128, 256, 512 or 1024 (CUDA build only)");
+  return MCPM_EUNSUP;
+  API_END
+}
+
 int mcpm_xfuse_force_T_slab(void* stream, const void* in3, void* out1, int nx, int ny, int nz, int ny_loc, int y0,
                             int lap_fd, int grad_fd, float kcut, int deconv_order, float norm) {
   API_BEGIN

@@ -46,7 +46,36 @@ static xf::Args make_args(const cfloat* in, cfloat* out, int nx, int ny, int nz,
   a.deconv_order = deconv_order;
   a.half_weights = half_weights;
   a.accumulate = accumulate;
+  a.npeer = 0;
+  a.xl = nx;
+  for (int r = 0; r < 8; ++r) {
+    a.in_peer[r] = nullptr;
+    a.out_peer[r] = nullptr;
+  }
   return a;
+}
+
+// Peer-memory variant of xfuse_force (transpose = 0: 1 -> 3) and xfuse_force_T (transpose = 1: 3 -> 1) for a mesh
+// slab-decomposed over `npeer` ranks: in_peers[r] / out_peers[r] are rank r's buffers [ncomp][nx/npeer][ny][nzc]
+// (after / before the local 2-D (y,z) transforms), mapped into this process; this rank handles ky rows y0 .. y0+ny_loc-1.
+int xfuse_force_peer(stream_t st, const cfloat* const* in_peers, cfloat* const* out_peers, int npeer, int transpose,
+                     int nx, int ny, int nz, int ny_loc, int y0, int lap_fd, int grad_fd, float kcut, int deconv_order,
+                     float norm) {
+  if (npeer < 1 || npeer > 8 || nx % npeer) {
+    set_error("xfuse_force_peer: 1..8 ranks, nx divisible by their number");
+    return MCPM_EINVAL;
+  }
+  SlabK sk;
+  sk.ny_loc = ny_loc;
+  sk.y0 = y0;
+  xf::Args a = make_args(in_peers[0], out_peers[0], nx, ny, nz, lap_fd, grad_fd, kcut, deconv_order, norm, sk);
+  a.npeer = npeer;
+  a.xl = nx / npeer;
+  for (int r = 0; r < npeer; ++r) {
+    a.in_peer[r] = in_peers[r];
+    a.out_peer[r] = out_peers[r];
+  }
+  return xf::dispatch(transpose ? xf::FORCE_T : xf::FORCE, st, a);
 }
 
 // in: [nx, ny_loc, nzc] after the 2-D (y,z) R2C of every x-plane.  out3: three such arrays, inputs of the 2-D C2R.

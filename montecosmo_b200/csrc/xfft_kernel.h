@@ -105,6 +105,12 @@ struct Args {
   int deconv_order;
   int half_weights;   // spectrum-out modes: cotangent of a free complex array (w'/N weights, no Hermitian projection)
   int accumulate;     // spectrum-out modes: out += result
+  // Peer mode (FORCE / FORCE_T on a slab-decomposed mesh, npeer > 0): x-plane p lives on rank p / xl as plane p % xl of
+  // that rank's buffer [ncomp][xl][ny][nzc]; this rank transforms the columns of its ky block y0 .. y0 + ny_loc - 1 and
+  // reads / writes every plane in its owner's memory (NVLink peer pointers): the kernel IS the all-to-all.
+  int npeer, xl;
+  const cfloat* in_peer[8];
+  cfloat* out_peer[8];
 };
 
 // What sits between the x-transforms (fourier.cu names) and which side is already / stays in k-space:
@@ -155,6 +161,21 @@ __global__ void __launch_bounds__(R2* columns_per_cta(R1* R2), (R1 >= 32 ? 1 : 5
   const float2* in = reinterpret_cast<const float2*>(a.in) + mm + t * M;
   float2* out = reinterpret_cast<float2*>(a.out) + mm + t * M;
   const int64_t MR2 = M * R2, MR1 = M * R1;
+  // x-space element addresses: plane t + R2*n1 on the load side, t + R2*j + R1*k2 (position e) on the store side
+  const bool peer = a.npeer > 0;
+  const int64_t pplane = (int64_t)a.g.ny * a.g.nzc;                    // peer buffers hold full-ky planes
+  const int64_t pcol = (int64_t)a.g.y0 * a.g.nzc + mm;                  // this column inside such a plane
+  const int64_t pcomp = (int64_t)a.xl * pplane;                         // component stride of a peer buffer
+  auto x_in = [&](int comp, int plane) -> const float2* {
+    if (!peer) return in + comp * a.cstride + (int64_t)(plane - t) * M;
+    const int r = plane / a.xl;
+    return reinterpret_cast<const float2*>(a.in_peer[r]) + comp * pcomp + (int64_t)(plane - r * a.xl) * pplane + pcol;
+  };
+  auto x_out = [&](int comp, int plane) -> float2* {
+    if (!peer) return out + comp * a.cstride + (int64_t)(plane - t) * M;
+    const int r = plane / a.xl;
+    return reinterpret_cast<float2*>(a.out_peer[r]) + comp * pcomp + (int64_t)(plane - r * a.xl) * pplane + pcol;
+  };
   // x-space elements of a thread: m-th is plane t + R2*m.  k-space elements: position e = j*R2 + k2 is kx index
   // t + R2*j + R1*k2, i.e. plane offset (e/R2)*R2 + (e%R2)*R1 from plane t; as col_fft input it is m = j + J*k2.
   auto kx_index = [&](int e) { return t + R2 * (e / R2) + R1 * (e % R2); };
@@ -208,7 +229,7 @@ __global__ void __launch_bounds__(R2* columns_per_cta(R1* R2), (R1 >= 32 ? 1 : 5
   if (NIN == 1) {
     if (fwd_x(MODE)) {
 #pragma unroll
-      for (int n1 = 0; n1 < R1; ++n1) X[n1] = in[n1 * MR2];
+      for (int n1 = 0; n1 < R1; ++n1) X[n1] = *x_in(0, t + R2 * n1);
       col_fft<R1, R2, -1>(X, t, cb0, tw);
       nfft = 1;
     } else {
@@ -221,9 +242,8 @@ __global__ void __launch_bounds__(R2* columns_per_cta(R1* R2), (R1 >= 32 ? 1 : 5
 #pragma unroll 1
     for (int comp = 0; comp < NIN; ++comp) {
       float2 v[R1];
-      const float2* ip = in + comp * a.cstride;
 #pragma unroll
-      for (int n1 = 0; n1 < R1; ++n1) v[n1] = ip[n1 * MR2];
+      for (int n1 = 0; n1 < R1; ++n1) v[n1] = *x_in(comp, t + R2 * n1);
       col_fft<R1, R2, -1>(v, t, (comp & 1) ? cb1 : cb0, tw);
 #pragma unroll
       for (int e = 0; e < R1; ++e) {
@@ -251,7 +271,7 @@ __global__ void __launch_bounds__(R2* columns_per_cta(R1* R2), (R1 >= 32 ? 1 : 5
       col_fft<R1, R2, +1>(w, t, (nfft & 1) ? cb1 : cb0, tw);
       if (active) {
 #pragma unroll
-        for (int e = 0; e < R1; ++e) out[k_offset(e)] = w[e];  // x-space: same plane pattern as the k-space one
+        for (int e = 0; e < R1; ++e) *x_out(0, kx_index(e)) = w[e];  // x-space: same plane pattern as the k-space one
       }
     } else if (active) {
 #pragma unroll
@@ -276,9 +296,8 @@ __global__ void __launch_bounds__(R2* columns_per_cta(R1* R2), (R1 >= 32 ? 1 : 5
       }
       col_fft<R1, R2, +1>(w, t, ((nfft + comp) & 1) ? cb1 : cb0, tw);
       if (active) {
-        float2* o = out + comp * a.cstride;
 #pragma unroll
-        for (int e = 0; e < R1; ++e) o[k_offset(e)] = w[e];
+        for (int e = 0; e < R1; ++e) *x_out(comp, kx_index(e)) = w[e];
       }
     }
   }

@@ -22,6 +22,7 @@ Reference semantics: montecosmo/nbody.py:583-604 (pm_forces), 634-667 (lpt), 933
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -55,6 +56,12 @@ class SlabPM:
         self._fft = h
         # fused x-transform (xfft.cu) between the all-to-alls where this build has it for nx; set False to compare
         self.xfuse = bool(self.lib.mcpm_xfuse_supported(nx))
+        # ... and, on CUDA with more than one rank, with the all-to-all folded into that kernel: every rank maps its
+        # peers' spectrum buffers (torch symmetric memory = CUDA IPC over NVLink) and the kernel loads / stores x-planes
+        # at their owners.  MCPM_SLAB_P2P=0 keeps NCCL all-to-alls; any failure to set it up falls back to them.
+        self.p2p, self.p2p_note = False, "off"
+        if self.xfuse and self.P > 1 and os.environ.get("MCPM_SLAB_P2P", "1") != "0":
+            self._setup_p2p()
         self.prev, self.next = (self.rank - 1) % self.P, (self.rank + 1) % self.P
         ax = [np.arange(self.xl, dtype=np.float32), np.arange(ny, dtype=np.float32), np.arange(nz, dtype=np.float32)]
         self.q_own = self.A.prepare(np.stack(np.meshgrid(*ax, indexing="ij"), -1).reshape(-1, 3))  # owned-slab coords
@@ -67,6 +74,43 @@ class SlabPM:
                 self._fft = None
         except Exception:
             pass
+
+    def _setup_p2p(self):
+        try:
+            import torch.distributed._symmetric_memory as symm
+            dev = self.A.device
+            if getattr(dev, "type", str(dev)) != "cuda" and not str(dev).startswith("cuda"):
+                self.p2p_note = "not a CUDA device"
+                return
+            grp = self.group if self.group is not None else dist.group.WORLD
+            shape = (3, self.xl, self.ny, self.nzc, 2)  # interleaved complex64 as float32 pairs
+            self._sym_in = symm.empty(shape, dtype=torch.float32, device=dev)
+            self._sym_out = symm.empty(shape, dtype=torch.float32, device=dev)
+            self._h_in = symm.rendezvous(self._sym_in, grp)
+            self._h_out = symm.rendezvous(self._sym_out, grp)
+            pin, pout = list(self._h_in.buffer_ptrs), list(self._h_out.buffer_ptrs)
+            if len(pin) != self.P or len(pout) != self.P or self.P > 8:
+                self.p2p_note = "unexpected peer table"
+                return
+            self._peer_in = (C.c_void_p * 8)(*(pin + [0] * (8 - self.P)))
+            self._peer_out = (C.c_void_p * 8)(*(pout + [0] * (8 - self.P)))
+            self.p2p, self.p2p_note = True, "symmetric memory, peer loads/stores inside the x-transform kernel"
+        except Exception as e:  # no NVLink peer access, missing permissions, older torch: keep the NCCL path
+            self.p2p, self.p2p_note = False, f"unavailable ({type(e).__name__}: {e})"
+
+    def _peer_force(self, real_in, nb_in, transpose):
+        """real_in [nb_in, xl, ny, nz] -> [nb_out, xl, ny, nz]: local 2-D R2C into the symmetric buffer, barrier, the
+        fused kernel on my ky block reading / writing every rank's buffer, barrier, local 2-D C2R."""
+        st = self._st()
+        self._call("mcpm_slabfft_r2c_yz", self._fft, st, real_in.data_ptr(), self._sym_in.data_ptr(), nb_in)
+        self._h_in.barrier()
+        self._call("mcpm_xfuse_force_peer", st, self._peer_in, self._peer_out, self.P, int(transpose), self.nx, self.ny,
+                   self.nz, self.kyl, self.y0, 0, 0, 0.0, 0, 1.0 / self.N)
+        self._h_out.barrier()
+        nb_out = 1 if transpose else 3
+        out = self.A.empty((nb_out, self.xl, self.ny, self.nz))
+        self._call("mcpm_slabfft_c2r_yz", self._fft, st, self._sym_out.data_ptr(), out.data_ptr(), nb_out)
+        return out
 
     # ------------------------------------------------------------------------------------------------ helpers
     def _call(self, name, *args):
@@ -187,6 +231,8 @@ class SlabPM:
     # density planes -> three force meshes, and the transpose (3 meshes -> 1), each with ONE kernel between the
     # all-to-alls where the fused x-transform exists for nx (xfft.cu), else c2c_x + streaming multiply + c2c_x
     def forces_from_density(self, rho_owned):
+        if self.p2p:
+            return self._peer_force(rho_owned.contiguous().unsqueeze(0), 1, False)
         if self.xfuse:
             c = self.rfftn_yz(rho_owned.unsqueeze(0))
             out = self.A.empty((3, self.nx, self.kyl, self.nzc), "c64")
@@ -197,6 +243,8 @@ class SlabPM:
         return self.irfftn(self.force_spectra(rk[0]), overwrite=True)
 
     def density_cotangent(self, planar3):
+        if self.p2p:
+            return self._peer_force(planar3.contiguous(), 3, True)[0]
         if self.xfuse:
             c = self.rfftn_yz(planar3)
             out = self.A.empty((1, self.nx, self.kyl, self.nzc), "c64")

@@ -177,7 +177,7 @@ def main():
         halo = a.nbody_steps * (2 + 2 * 4 + 2 * 4 + 2) * pm.H * n * n * 4
         out.update({"metric": "slab-decomposed nbody_bf forward + reverse sweep, evaluations/s", "mesh": n, "n_gpus": world,
                     "value": 1e3 / per, "unit": "evals/s", "ms_per_eval": per, "nbody_steps": a.nbody_steps,
-                    "halo_planes": pm.H, "max_mem_GiB": float(mem),
+                    "halo_planes": pm.H, "max_mem_GiB": float(mem), "fused_x_transform": bool(pm.xfuse), "p2p": pm.p2p_note,
                     "nvlink_GB_out_per_gpu_per_eval": (a2a + halo) / 1e9 if world > 1 else 0.0,
                     "nvlink_GBps_per_gpu_if_all_time_were_comm": (a2a + halo) / 1e9 / (per * 1e-3) if world > 1 else 0.0})
         print(json.dumps(out), flush=True)

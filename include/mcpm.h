@@ -74,6 +74,13 @@ int mcpm_engine_set_fused_fft(mcpm_engine* eng, int on);
  * These are what mcpm_pm_forces / mcpm_nbody_steps_vjp run under the hint; exposed for timing and tests.  Meshes are
  * accumulated into (not zeroed).  paint_lattice: mesh += w_p * wscalar * W (CIC).  paint3_lattice: the reverse-step
  * scatter, vbar += xbar * drift (stored, when xbar != NULL), mesh3[c] += scale * vbar[., c] * W into 3 planar meshes. */
+/* The same two kernels without an engine, for a lattice that does not span the mesh: px x py x pz particles in C order
+ * (spacing one cell), painted into an nx x ny x nz mesh with px <= nx, ... -- a slab-decomposed rank's particles and
+ * its halo-extended mesh.  MCPM_EUNSUP when the geometry is not supported (mesh smaller than a tile, nz % 4 != 0). */
+int mcpm_paint_brick(void* stream, int px, int py, int pz, const float* pos, const float* weights, float wscalar,
+                     float shift, int64_t np, int nx, int ny, int nz, float* mesh);
+int mcpm_paint3_brick(void* stream, int px, int py, int pz, const float* pos, float* vbar, const float* xbar,
+                      float drift, float scale, int64_t np, int nx, int ny, int nz, float* mesh3);
 int mcpm_paint_lattice(mcpm_engine* eng, void* stream, const float* pos, const float* weights, float wscalar,
                        int64_t np, float* mesh);
 int mcpm_paint3_lattice(mcpm_engine* eng, void* stream, const float* pos, float* vbar, const float* xbar, float drift,

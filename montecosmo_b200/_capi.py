@@ -21,6 +21,8 @@ SIGNATURES = {
     "mcpm_engine_set_lattice": ([vp, i32, i32, i32], i32),
     "mcpm_engine_set_fused_fft": ([vp, i32], i32),
     "mcpm_tune": ([C.c_char_p, i32], i32),
+    "mcpm_paint_brick": ([vp, i32, i32, i32, vp, vp, f32, f32, i64] + MESH + [vp], i32),
+    "mcpm_paint3_brick": ([vp, i32, i32, i32, vp, vp, vp, f32, f32, i64] + MESH + [vp], i32),
     "mcpm_paint_lattice": ([vp, vp, vp, vp, f32, i64, vp], i32),
     "mcpm_paint3_lattice": ([vp, vp, vp, vp, vp, f32, f32, i64, vp], i32),
     "mcpm_paint": ([vp, vp, vp, f32, i64] + MESH + [i32] + XF + [vp, i32], i32),

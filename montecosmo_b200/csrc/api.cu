@@ -129,6 +129,42 @@ int mcpm_engine_set_fused_fft(mcpm_engine* eng, int on) {
   API_END
 }
 
+int mcpm_paint_brick(void* stream, int px, int py, int pz, const float* pos, const float* weights, float wscalar,
+                     float shift, int64_t np, int nx, int ny, int nz, float* mesh) {
+  API_BEGIN
+  NEED(pos && mesh, "paint_brick: null pointer");
+#ifndef MCPM_HOSTEMU
+  Lattice L;
+  L.px = px;
+  L.py = py;
+  L.pz = pz;
+  int r = brick_paint_cic(as_stream(stream), L, pos, weights, wscalar, shift, np, nx, ny, nz, mesh);
+  if (r < 0) return MCPM_ECUDA;
+  if (r == 1) return MCPM_OK;
+#endif
+  set_error("paint_brick: unsupported lattice / mesh geometry, or CPU build");
+  return MCPM_EUNSUP;
+  API_END
+}
+
+int mcpm_paint3_brick(void* stream, int px, int py, int pz, const float* pos, float* vbar, const float* xbar,
+                      float drift, float scale, int64_t np, int nx, int ny, int nz, float* mesh3) {
+  API_BEGIN
+  NEED(pos && vbar && mesh3, "paint3_brick: null pointer");
+#ifndef MCPM_HOSTEMU
+  Lattice L;
+  L.px = px;
+  L.py = py;
+  L.pz = pz;
+  int r = brick_paint3_cic(as_stream(stream), L, pos, vbar, xbar, drift, scale, np, nx, ny, nz, mesh3);
+  if (r < 0) return MCPM_ECUDA;
+  if (r == 1) return MCPM_OK;
+#endif
+  set_error("paint3_brick: unsupported lattice / mesh geometry, or CPU build");
+  return MCPM_EUNSUP;
+  API_END
+}
+
 int mcpm_paint_lattice(mcpm_engine* eng, void* stream, const float* pos, const float* weights, float wscalar,
                        int64_t np, float* mesh) {
   API_BEGIN

@@ -285,9 +285,11 @@ __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickA
   }
 }
 
+// The lattice has a spacing of one cell; it need not span the mesh (a slab-decomposed rank paints its xl x ny x nz
+// particles into a mesh extended by halo planes).
 static bool brick_ok(const Lattice& L, int64_t np, int nx, int ny, int nz) {
   using namespace brick;
-  if (L.px != nx || L.py != ny || L.pz != nz) return false;        // lattice spacing of one cell only
+  if (L.px <= 0 || L.py <= 0 || L.pz <= 0 || L.px > nx || L.py > ny || L.pz > nz) return false;
   if ((int64_t)L.px * L.py * L.pz != np) return false;
   if ((nz & 3) || nx < TX || ny < TY || nz < TZ) return false;         // a tile must not wrap onto itself
   if (3 * np >= ((int64_t)1 << 31)) return false;                  // 32-bit row offsets inside a brick

@@ -67,7 +67,7 @@ void set_side_zero(int v) { g_side_zero = v; }
 static bool brick_path(const Engine* E, int order, const float* scale) {
 #ifndef MCPM_HOSTEMU
   const bool unit = !scale || (scale[0] == 1.0f && scale[1] == 1.0f && scale[2] == 1.0f);
-  return order == 2 && E->lat.px > 0 && unit;
+  return order == 2 && E->lat.px == E->nx && E->lat.py == E->ny && E->lat.pz == E->nz && unit;
 #else
   return false;
 #endif

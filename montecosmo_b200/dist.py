@@ -59,6 +59,9 @@ class SlabPM:
         # ... and, on CUDA with more than one rank, with the all-to-all folded into that kernel: every rank maps its
         # peers' spectrum buffers (torch symmetric memory = CUDA IPC over NVLink) and the kernel loads / stores x-planes
         # at their owners.  MCPM_SLAB_P2P=0 keeps NCCL all-to-alls; any failure to set it up falls back to them.
+        # brick-tiled scatters (brick.cu) of the rank's lattice particles into its halo-extended mesh: CUDA builds only;
+        # the first call decides (MCPM_EUNSUP -> generic kernels)
+        self.brick = os.environ.get("MCPM_SLAB_BRICK", "1") != "0" and bool(self.lib.mcpm_xfuse_supported(64))
         self.p2p, self.p2p_note = False, "off"
         if self.xfuse and self.P > 1 and os.environ.get("MCPM_SLAB_P2P", "1") != "0":
             self._setup_p2p()
@@ -185,13 +188,15 @@ class SlabPM:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
 
-    def halo_reduce(self, ext):
-        """ext [ext, ny, nz(,4)]: send both halos to the neighbours, add theirs into my owned planes."""
+    def halo_reduce(self, ext, lead=False):
+        """ext [ext, ny, nz(,4)] (lead: [c, ext, ny, nz]): send both halos to the neighbours, add theirs into my owned
+        planes."""
         H, xl = self.H, self.xl
-        a, b = torch.empty_like(ext[:H]), torch.empty_like(ext[:H])
-        self._exchange(ext[:H].contiguous(), ext[H + xl:].contiguous(), a, b)
-        ext[xl:xl + H] += a  # next's left halo covers my last H owned planes
-        ext[H:2 * H] += b  # prev's right halo covers my first H owned planes
+        e = ext.movedim(1, 0) if lead else ext  # a view with the plane index first
+        a, b = torch.empty_like(e[:H].contiguous()), torch.empty_like(e[:H].contiguous())
+        self._exchange(e[:H].contiguous(), e[H + xl:].contiguous(), a, b)
+        e[xl:xl + H] += a  # next's left halo covers my last H owned planes
+        e[H:2 * H] += b  # prev's right halo covers my first H owned planes
 
     def halo_gather(self, ext):
         """ext [ext, ny, nz(,4)]: fill both halos from the neighbours' owned planes (transpose of halo_reduce)."""
@@ -260,8 +265,12 @@ class SlabPM:
         A, lib, st = self.A, self.lib, self._st()
         rho = A.zeros((self.ext, self.ny, self.nz))
         one = (C.c_float * 3)(1.0, 1.0, 1.0)
-        self._call("mcpm_paint", st, pos.data_ptr(), 0, 1.0, pos.shape[0], self.ext, self.ny, self.nz, order, one, 0.0,
-                   rho.data_ptr(), 1)
+        # brick-tiled scatter of my xl x ny x nz lattice particles into the halo-extended mesh where this build has it
+        if not (order == 2 and self.brick and lib.mcpm_paint_brick(
+                st, self.xl, self.ny, self.nz, pos.data_ptr(), 0, 1.0, 0.0, pos.shape[0], self.ext, self.ny, self.nz,
+                rho.data_ptr()) == 0):
+            self._call("mcpm_paint", st, pos.data_ptr(), 0, 1.0, pos.shape[0], self.ext, self.ny, self.nz, order, one,
+                       0.0, rho.data_ptr(), 1)
         self.halo_reduce(rho)
         F = self.forces_from_density(rho[self.H:self.H + self.xl])  # [3, xl, ny, nz]
         fm4 = A.empty((self.ext, self.ny, self.nz, 4))
@@ -296,12 +305,19 @@ class SlabPM:
         for s in reversed(range(ns)):
             x1, fm4 = tape[s]
             dcomb = float(drift_post[s]) + (float(drift_pre[s + 1]) if s + 1 < ns else 0.0)
-            m4 = A.zeros((self.ext, self.ny, self.nz, 4))
-            self._call("mcpm_paint3v4", st, x1.data_ptr(), velbar.data_ptr(), posbar.data_ptr(), dcomb, float(beta[s]),
-                       n, self.ext, self.ny, self.nz, m4.data_ptr())
-            self.halo_reduce(m4)
-            planar = A.empty((3, self.xl, self.ny, self.nz))
-            self._call("mcpm_deinterleave3", st, m4[self.H:self.H + self.xl].data_ptr(), planar.data_ptr(), cells)
+            m3 = A.zeros((3, self.ext, self.ny, self.nz)) if self.brick else None
+            if m3 is not None and self.lib.mcpm_paint3_brick(
+                    st, self.xl, self.ny, self.nz, x1.data_ptr(), velbar.data_ptr(), posbar.data_ptr(), dcomb,
+                    float(beta[s]), n, self.ext, self.ny, self.nz, m3.data_ptr()) == 0:
+                self.halo_reduce(m3, lead=True)  # three planar extended meshes
+                planar = m3[:, self.H:self.H + self.xl].contiguous()
+            else:
+                m4 = A.zeros((self.ext, self.ny, self.nz, 4))
+                self._call("mcpm_paint3v4", st, x1.data_ptr(), velbar.data_ptr(), posbar.data_ptr(), dcomb,
+                           float(beta[s]), n, self.ext, self.ny, self.nz, m4.data_ptr())
+                self.halo_reduce(m4)
+                planar = A.empty((3, self.xl, self.ny, self.nz))
+                self._call("mcpm_deinterleave3", st, m4[self.H:self.H + self.xl].data_ptr(), planar.data_ptr(), cells)
             rhobar = A.empty((self.ext, self.ny, self.nz))
             rhobar[self.H:self.H + self.xl] = self.density_cotangent(planar)
             self.halo_gather(rhobar)

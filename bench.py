@@ -219,10 +219,11 @@ def kernel_rooflines(model, white, peaks):
         add("xfuse_force_T", "xfuse_force_T (3 x-FFTs + transposed force kernel + inverse x-FFT, 3 -> 1 spectra)",
             lambda: lib.mcpm_xfuse_force_T_slab(st, mk3.data_ptr(), mk.data_ptr(), *shape, shape[1], 0, 0, 0, 0.0, 0, 1.0),
             16 * N, steps, "12N r + 4N w")
-    add("force_spectra", "force_spectra (Green x gradient streaming pass, 1 -> 3 spectra; LPT only when fused)",
-        lambda: o.force_spectra(mk), 16 * N, 2 if fused else 2 * (steps + 1), "4N r + 12N w")
-    add("cufft_r2c", "cuFFT 3-D R2C 256^3 (library; 3 passes)", lambda: o.rfftn(rho), 8 * N, 36 if fused else 116,
-        "4N r + 4N w per transform; per step: 36 3-D transforms (LPT, final paint) + 80 batched 2-D (y,z) ones", False)
+    add("force_spectra", "force_spectra (Green x gradient streaming pass, 1 -> 3 spectra; unused on the fused path)",
+        lambda: o.force_spectra(mk), 16 * N, 0 if fused else 2 * (steps + 1), "4N r + 12N w", not fused)
+    add("cufft_r2c", "cuFFT 3-D R2C (library; 3 passes)", lambda: o.rfftn(rho), 8 * N, 8 if fused else 116,
+        "4N r + 4N w per transform; per evaluation on the fused path: 8 3-D transforms (initial field, final paint, "
+        "likelihood) + 48 batched 2-D (y,z) launches covering 108 mesh transforms", False)
     # generic global-atomic kernels the step loop does not run under the lattice hint: listed for comparison only
     add("paint_generic", "paint (generic CIC scatter, 8 red.f32 / particle)",
         lambda: o.paint(pos, shape, None, order=2, out=mesh), 16 * N, 0, "pos 12N + mesh 4N", False)

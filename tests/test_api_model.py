@@ -182,7 +182,7 @@ def test_model_logpdf_and_force(nb, evolution, n_steps):
     w = leaf(torch.tensor(white), nb)
     lp2 = m.logpdf(w, obs)
     lp2.backward()
-    assert abs(float(lp2) - float(lp)) < 1e-6 * abs(float(lp)) and rel(w.grad, g.detach().cpu().numpy()) < 1e-5
+    assert abs(float(lp2.detach()) - float(lp)) < 1e-6 * abs(float(lp)) and rel(w.grad, g.detach().cpu().numpy()) < 1e-5
     assert rel(m.force(white, obs), g.detach().cpu().numpy()) < 1e-5
 
 

@@ -235,6 +235,40 @@ def kernel_rooflines(model, white, peaks):
     return rows, dom
 
 
+def small_configs(dev, gen):
+    """The smaller BASELINE configs, for the record (not the metric): C1 64^3 / 5 steps (run/infer_example.py scale) and
+    C2 128^3 / 10 steps, each inside a 100-iteration leapfrog loop with 2 gradient evaluations per iteration (as
+    isokinetic_mclachlan, samplers.py:350-351), on the graph-replayed evaluation."""
+    import torch
+    from montecosmo_b200.model import FieldModel
+    out = {}
+    try:
+        for tag, nn, nsteps in (("C1_64", 64, 5), ("C2_128_leapfrog", 128, 10)):
+            wl = workload(nn)
+            wl["n_steps"] = nsteps
+            mm = FieldModel(**wl)
+            ff = mm.graphed_value_and_force(1.0 + torch.randn(mm.mesh_shape, device=dev, generator=gen))
+            q = torch.randn(mm.mesh_shape, device=dev, generator=gen)
+            p, eps, iters = torch.zeros_like(q), 1e-3, 100
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                p.add_(ff(q)[1], alpha=0.5 * eps)
+                q.add_(p, alpha=0.5 * eps)
+                p.add_(ff(q)[1], alpha=0.5 * eps)
+                q.add_(p, alpha=0.5 * eps)
+            e1.record()
+            torch.cuda.synchronize()
+            out[tag] = {"mesh": nn, "n_body_steps": nsteps, "evals_per_s": 2 * iters / (e0.elapsed_time(e1) * 1e-3),
+                        "iterations": iters}
+            del ff, mm
+        torch.cuda.empty_cache()
+    except Exception as e:
+        out["error"] = f"{type(e).__name__}: {e}"
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------- engine arm
 def run_engine(args):
     import torch
@@ -287,7 +321,13 @@ def run_engine(args):
     launches_per_eval = int(lib.mcpm_launch_count(0))
     # The public call a sampler makes: FieldModel.graphed_value_and_force -- the whole evaluation captured once in a CUDA
     # graph, replayed per step on a new white field (--no-graph: the eager FieldModel.value_and_force).
-    fn = None if args.no_graph else model.graphed_value_and_force(obs)
+    fn, graph_note = None, "disabled (--no-graph)"
+    if not args.no_graph:
+        try:
+            fn, graph_note = model.graphed_value_and_force(obs), "ok"
+        except Exception as e:  # never lose the measurement to the capture: time the eager call instead
+            fn, graph_note = None, f"capture failed, eager call timed instead ({type(e).__name__}: {e})"
+            torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -321,33 +361,7 @@ def run_engine(args):
     clocks = sampler.stop() if rank == 0 else None
     lp_val = float(h_lp)
     launches = launches_per_eval * K
-    # The smaller BASELINE configs, for the record (not the metric): C1 64^3 / 5 steps (run/infer_example.py scale) and
-    # C2 128^3 / 10 steps inside a leapfrog loop -- 2 gradient evaluations per iteration, as isokinetic_mclachlan
-    # (samplers.py:350-351) -- both on the graph-replayed evaluation.
-    other = {}
-    if rank == 0 and fn is not None and n == 256:
-        for tag, nn, nsteps in (("C1_64", 64, 5), ("C2_128_leapfrog", 128, 10)):
-            wl = workload(nn)
-            wl["n_steps"] = nsteps
-            mm = FieldModel(**wl)
-            oo = 1.0 + torch.randn(mm.mesh_shape, device=dev, generator=gen)
-            ff = mm.graphed_value_and_force(oo)
-            q, p, eps = torch.randn(mm.mesh_shape, device=dev, generator=gen), torch.zeros(mm.mesh_shape, device=dev), 1e-3
-            iters = 100
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(iters):  # position-Verlet-like split with two force evaluations per iteration
-                p.add_(ff(q)[1], alpha=0.5 * eps)
-                q.add_(p, alpha=0.5 * eps)
-                p.add_(ff(q)[1], alpha=0.5 * eps)
-                q.add_(p, alpha=0.5 * eps)
-            e1.record()
-            torch.cuda.synchronize()
-            other[tag] = {"mesh": nn, "n_body_steps": nsteps, "evals_per_s": 2 * iters / (e0.elapsed_time(e1) * 1e-3),
-                          "iterations": iters}
-            del ff, mm
-        torch.cuda.empty_cache()
+    other = small_configs(dev, gen) if (rank == 0 and fn is not None and n == 256) else {}
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -367,6 +381,7 @@ def run_engine(args):
                 "gpu_launches": int(launches),
                 "gpu_launches_note": f"{launches_per_eval} engine kernels per evaluation (mcpm_launch_count on an eager "
                                      "evaluation) x steps; cuFFT's kernels not counted",
+                "graph": graph_note,
                 "api": "FieldModel.value_and_force (eager)" if fn is None else
                        "FieldModel.graphed_value_and_force (CUDA graph of the whole evaluation, replayed per step)",
                 "eager": {"value": world * K / (ms_eager * 1e-3), "unit": UNIT, "ms_per_step": ms_eager / K},

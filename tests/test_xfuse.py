@@ -166,4 +166,5 @@ def test_lpt_and_its_vjp(ops, shape, lpt_order, read_order, fd):
     if lpt_order == 2:
         f2 = O.pm_forces2(T(pos), dkt, read_order, grad_fd=grad_fd, lap_fd=lap_fd)
         dpo, vlo = dpo - d2 * f2, vlo - dv2 * f2
-    assert rel(res[True][0], dpo.numpy()) < 5e-5 and rel(res[True][1], vlo.numpy()) < 5e-5
+    tol = 5e-5 if shape[0] <= 256 else 3e-4  # float32 on a 512-cell axis (see test_forces_and_vjp)
+    assert rel(res[True][0], dpo.numpy()) < tol and rel(res[True][1], vlo.numpy()) < tol

@@ -278,6 +278,8 @@ def run_engine(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's version banner (printed when the box sets NCCL_DEBUG) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from montecosmo_b200 import nbody as nb
     from montecosmo_b200.model import FieldModel

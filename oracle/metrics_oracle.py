@@ -1,8 +1,9 @@
 """
 CPU restatement of montecosmo/metrics.py's power-spectrum estimator (TEST INFRASTRUCTURE ONLY; same rules as
-pm_oracle.py): _waves (metrics.py:60-118) and _spectrum (121-182), monopole, NumPy float64.  Parity unpinned against
-the reference itself (no golden vector exists for it); it is the yardstick for the engine's binned reduction
-and for the power-spectrum tolerance of the parity report.
+pm_oracle.py): _waves (metrics.py:60-118) and _spectrum (121-182), monopole, NumPy float64.  Pinned against the
+reference's own source executed under the NumPy stand-in for JAX (tests/golden/spectrum.npz, bin counts identical,
+powers to 1e-11; unpinned against real JAX/XLA like the rest of the oracle).  It is the yardstick for the engine's
+binned reduction and for the power-spectrum tolerance of the parity report.
 """
 import numpy as np
 

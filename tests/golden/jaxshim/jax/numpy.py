@@ -83,6 +83,13 @@ float32, float64, int16, int32, int64, complex64, complex128 = (
 bool_ = _np.bool_
 
 
+def bincount(x, weights=None, minlength=0, length=None):
+    """jnp.bincount: `length` fixes the output size (static shape under jit); values beyond it are dropped."""
+    n = int(length) if length is not None else int(minlength)
+    out = _np.bincount(_np.asarray(x), weights=None if weights is None else _np.asarray(weights), minlength=n)
+    return _wrap(out[:n] if length is not None else out)
+
+
 def unstack(x, axis=0):
     return tuple(_wrap(_np.moveaxis(x, axis, 0)[i]) for i in range(x.shape[axis]))
 

@@ -23,6 +23,12 @@ def load_reference():
     return nbody, utils, Cosmology, jnp
 
 
+def load_reference_next_rows():
+    """montecosmo/{metrics,bricks}.py, the "next" rows of SURVEY 8f (import after load_reference)."""
+    from montecosmo import bricks, metrics  # noqa: E402
+    return metrics, bricks
+
+
 ABACUS = dict(Omega_c=0.26447041, Omega_b=0.04930169, h=0.6736, n_s=0.9649, sigma8=0.8076353990239834,
               Omega_k=0.0, w0=-1.0, wa=0.0)  # bricks.py:40-50
 OTHER = dict(Omega_c=0.21, Omega_b=0.05, h=0.7, n_s=0.96, sigma8=0.8, Omega_k=0.0, w0=-1.0, wa=0.0)
@@ -191,6 +197,39 @@ def main():
     d = {"white": w, "rg2cgh": A(utils.rg2cgh(jnp.asarray(w)))}
     d["cgh2rg_roundtrip"] = A(utils.cgh2rg(jnp.asarray(d["rg2cgh"])))
     out["rg2cgh"] = d
+
+    # ---- power-spectrum estimator and Lagrangian bias (next rows f-4, f-1) --------------------------------------
+    metrics, bricks = load_reference_next_rows()
+    rng = np.random.default_rng(7)
+    a = rng.normal(size=(12, 8, 10))
+    b = 0.7 * a + 0.5 * rng.normal(size=(12, 8, 10))
+    box = (100.0, 80.0, 120.0)
+    d = {"mesh0": a, "mesh1": b, "box_size": np.array(box)}
+    for tag, kw in [("default", dict(kedges=None, include_corners=True, deconv=2)),
+                    ("n5_nocorners", dict(kedges=5, include_corners=False, deconv=0)),
+                    ("dk02", dict(kedges=0.2, include_corners=True, deconv=(1, 2)))]:
+        kc, km, p = metrics._spectrum(jnp.asarray(a), None, box_size=box, **kw)
+        d[f"auto_{tag}_kcount"], d[f"auto_{tag}_kmean"], d[f"auto_{tag}_pow"] = A(kc), A(km), A(p)
+        kc, km, p = metrics._spectrum(jnp.asarray(a), jnp.asarray(b), box_size=box, **kw)
+        d[f"cross_{tag}_pow"] = A(p)
+    ks, p1, tr, coh = metrics.powtranscoh(jnp.asarray(a), jnp.asarray(b), np.array(box))
+    d["ptc_k"], d["ptc_pow1"], d["ptc_trans"], d["ptc_coh"] = A(ks), A(p1), A(tr), A(coh)
+    out["spectrum"] = d
+
+    rng = np.random.default_rng(8)
+    shape, box = (8, 10, 12), (80.0, 100.0, 96.0)
+    dk = np.fft.rfftn(rng.normal(size=shape)) * 0.05
+    pos = lattice(shape) + rng.normal(scale=0.4, size=(int(np.prod(shape)), 3))
+    bias = dict(b1=0.8, b2=0.3, bs2=-0.2, b3=0.1, bds2=0.05, bs3=-0.07, bn2=0.4, bnpar=0.6)
+    png = dict(fNL_bp=0.0, fNL_bpd=0.0, fNL_bpd2=0.0, fNL_bps2=0.0, fNL_bn2p=0.0)
+    cosmo = Cosmology(**ABACUS)
+    cosmo._workspace = {}
+    w, dvel, _ = bricks.lagrangian_bias(cosmo, jnp.asarray(pos), jnp.asarray(0.7), np.array(box), jnp.asarray(dk),
+                                        bias, png, png_type=None, read_order=2)
+    d = {"shape": np.array(shape), "box_size": np.array(box), "delta_k": dk, "pos": pos, "a": np.array(0.7),
+         "weights": A(w), "dvel": A(dvel)}
+    d.update({f"bias_{k}": np.array(v) for k, v in bias.items()})
+    out["lagrangian_bias"] = d
 
     for name, dd in out.items():
         path = os.path.join(HERE, f"{name}.npz")

@@ -249,11 +249,17 @@ def test_rg2cgh_golden_roundtrip_and_gradient(nb, golden):
         U.rg2cgh(torch.zeros(4, 4, 4), norm="amp")
 
 
-def test_lagrangian_bias_weights_and_gradient(nb):
-    """bricks.lagrangian_bias (bricks.py:327-452, no PNG terms) against the oracle: weights and dvel 5e-5, gradient of a
-    scalar functional w.r.t. the linear mesh 2e-4."""
+def test_lagrangian_bias_weights_and_gradient(nb, golden):
+    """bricks.lagrangian_bias (bricks.py:327-452, no PNG terms) against the golden vectors of the reference source and the
+    oracle: weights and dvel 5e-5, gradient of a scalar functional w.r.t. the linear mesh 2e-4."""
     from montecosmo_b200 import bricks as B
     from montecosmo_b200.cosmo import Cosmology
+    gd = golden("lagrangian_bias")
+    gb = {k[5:]: float(v) for k, v in gd.items() if k.startswith("bias_")}
+    wg, dvg, _ = B.lagrangian_bias(Cosmology(), torch.tensor(gd["pos"], dtype=torch.float32, device=dev(nb)),
+                                   float(gd["a"]), tuple(gd["box_size"]),
+                                   torch.tensor(gd["delta_k"], dtype=torch.complex64, device=dev(nb)), gb, read_order=2)
+    assert rel(wg, gd["weights"]) < 5e-5 and rel(dvg, gd["dvel"]) < 5e-5
     rng = np.random.default_rng(23)
     shape, box = (8, 10, 12), (80.0, 100.0, 96.0)
     dk0 = np.fft.rfftn(rng.normal(size=shape)) * 0.05

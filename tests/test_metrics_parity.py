@@ -29,10 +29,24 @@ def nb(request):
     nbody._OPS = old
 
 
-def test_spectrum_estimator_matches_oracle(nb):
+def test_spectrum_estimator_matches_oracle(nb, golden):
     from montecosmo_b200 import metrics as M
     rng = np.random.default_rng(0)
     dev = nb.ops().A.device
+    # golden vectors of montecosmo/metrics.py itself (tests/golden/make_golden.py)
+    g = golden("spectrum")
+    a, b = (torch.tensor(g[k], dtype=torch.float32, device=dev) for k in ("mesh0", "mesh1"))
+    box = tuple(g["box_size"])
+    for tag, kw in [("default", dict(kedges=None, include_corners=True, deconv=2)),
+                    ("n5_nocorners", dict(kedges=5, include_corners=False, deconv=0)),
+                    ("dk02", dict(kedges=0.2, include_corners=True, deconv=(1, 2)))]:
+        kc, km, p = M._spectrum(a, box_size=box, **kw)
+        assert np.array_equal(kc, g[f"auto_{tag}_kcount"]) and np.allclose(km, g[f"auto_{tag}_kmean"], rtol=1e-12)
+        assert np.allclose(p, g[f"auto_{tag}_pow"], rtol=2e-5)
+        assert np.allclose(M._spectrum(a, b, box_size=box, **kw)[2], g[f"cross_{tag}_pow"], rtol=2e-5)
+    ks, p1, tr, coh = M.powtranscoh(a, b, box)
+    assert np.allclose(p1, g["ptc_pow1"], rtol=2e-5) and np.allclose(tr, g["ptc_trans"], rtol=2e-5)
+    assert np.allclose(coh, g["ptc_coh"], rtol=2e-5)
     for shape, box in [((12, 8, 10), (100.0, 80.0, 120.0)), ((16, 16, 16), None)]:
         a = rng.normal(size=shape).astype(np.float32)
         b = (0.7 * a + 0.5 * rng.normal(size=shape)).astype(np.float32)

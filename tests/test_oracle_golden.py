@@ -150,3 +150,36 @@ def test_oracle_properties():
     up = O.chreshape(mk, O.r2chshape((12, 14, 10)))
     close(O.chreshape(up, O.r2chshape(shape)), mk.numpy(), rtol=1e-10)
     assert abs(float(torch.fft.irfftn(up, s=(12, 14, 10)).mean() - m.mean())) < 1e-12
+
+
+def test_spectrum_estimator(golden):
+    """oracle/metrics_oracle.py against montecosmo/metrics.py's own _spectrum / powtranscoh."""
+    from oracle import metrics_oracle as MX
+    g = golden("spectrum")
+    a, b, box = g["mesh0"], g["mesh1"], tuple(g["box_size"])
+    for tag, kw in [("default", dict(kedges=None, include_corners=True, deconv=(2, 2))),
+                    ("n5_nocorners", dict(kedges=5, include_corners=False, deconv=(0, 0))),
+                    ("dk02", dict(kedges=0.2, include_corners=True, deconv=(1, 2)))]:
+        kc, km, p = MX.spectrum(a, box_size=box, **kw)
+        assert np.array_equal(kc, g[f"auto_{tag}_kcount"])
+        close(km, g[f"auto_{tag}_kmean"])
+        close(p, g[f"auto_{tag}_pow"])
+        close(MX.spectrum(a, b, box_size=box, **kw)[2], g[f"cross_{tag}_pow"])
+    _, km, p0 = MX.spectrum(a, box_size=box)
+    _, _, p1 = MX.spectrum(b, box_size=box)
+    _, _, p01 = MX.spectrum(a, b, box_size=box)
+    close(km, g["ptc_k"])
+    close(p1, g["ptc_pow1"])
+    close((p1 / p0) ** 0.5, g["ptc_trans"])
+    close(p01 / (p0 * p1) ** 0.5, g["ptc_coh"])
+
+
+def test_lagrangian_bias(golden):
+    """oracle/model_oracle.py:lagrangian_bias against montecosmo/bricks.py:327-452 (no PNG terms)."""
+    from oracle import model_oracle as MO
+    g = golden("lagrangian_bias")
+    bias = {k[5:]: float(v) for k, v in g.items() if k.startswith("bias_")}
+    w, dvel = MO.lagrangian_bias(O.Cosmology(), torch.as_tensor(g["pos"]), float(g["a"]), tuple(g["box_size"]),
+                                 torch.as_tensor(g["delta_k"]), bias, read_order=2)
+    close(w, g["weights"])
+    close(dvel, g["dvel"], atol=1e-11)

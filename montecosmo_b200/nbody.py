@@ -112,6 +112,51 @@ def rectangular_hat(kvec, order=2):
 # ----------------------------------------------------------------------------------------------------------------
 # autograd wrappers over the C ABI
 # ----------------------------------------------------------------------------------------------------------------
+def rectangular(s, order):
+    """1-D mass-assignment window on |s| (nbody.py:220-246): 1 NGP, 2 CIC, 3 TSC, 4 PCS.  Host-side NumPy, like the
+    reference's kernel helpers; the engine evaluates the same polynomials in window.h."""
+    s = np.abs(np.asarray(s, dtype=np.float64))
+    if order == 0:
+        return np.full(np.shape(s)[-1:], np.inf)
+    if order == 1:
+        return np.full(np.shape(s)[-1:], 1.0)
+    if order == 2:
+        return 1 - s
+    if order == 3:
+        return (s <= 0.5) * (0.75 - s**2) + (0.5 < s) / 2 * (1.5 - s) ** 2
+    if order == 4:
+        return (s <= 1) / 6 * (4 - 6 * s**2 + 3 * s**3) + (1 < s) / 6 * (2 - s) ** 3
+    raise IndexError("order must be in 0..4")
+
+
+def optim_kcut(oversamp, safety=0.98):
+    """Optimal wavenumber cutoff of the Kaiser-Bessel window (nbody.py:357-363)."""
+    return safety * np.pi * (2 - 1 / oversamp)
+
+
+def kaiser_bessel(s, order, kcut):
+    """Kaiser-Bessel window (nbody.py:280-290), host-side NumPy.  The engine's paint / read kernels implement the
+    rectangular family only (kernel_type='kaiser_bessel' raises NotImplementedError there)."""
+    s = np.asarray(s, dtype=np.float64) * 2 / order
+    kcut = kcut * order / 2
+    return np.i0(kcut * (1 - s**2) ** 0.5) / (order * np.sinh(kcut) / kcut)
+
+
+def kaiser_bessel_hat(kvec, order, kcut):
+    """Fourier transform of the Kaiser-Bessel window (nbody.py:293-312), host-side NumPy."""
+    def kernel(k, kc):
+        k = k * order / 2
+        kc = kc * order / 2
+        dist = np.abs(kc**2 - k**2) ** 0.5
+        with np.errstate(divide="ignore", invalid="ignore"):
+            out = np.where(np.abs(k) <= kc, np.sinh(dist) / dist, np.sin(dist) / dist)
+        return out / (np.sinh(kc) / kc)
+    out = 1.0
+    for k in kvec:
+        out = out * kernel(k, kcut)
+    return out
+
+
 class _Paint(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pos, weights, shape, wscalar, order, scale, shift):
@@ -469,6 +514,53 @@ def nbody_bf(cosmo, init_mesh, pos, a0=0.0, a1=1.0, n_steps=5, paint_order: int 
     return torch.stack(xs), torch.stack(vs)
 
 
+def bullfrog_vf(cosmo, dg, mesh_shape: tuple, paint_order: int = 2, paint_deconv=False, grad_fd=np.inf, lap_fd=np.inf):
+    """BullFrog vector field (nbody.py:902-960): `vector_field(g0, state, args)` runs one drift-kick-drift step of size
+    `dg` from growth time `g0` on `state = (pos, vel)` and returns `(new - old) / dg` for both, the increment an explicit
+    Euler step of size `dg` turns back into the step (nbody.py:999).  One engine call per evaluation, differentiable
+    in the state and, through alpha_bf, in the cosmology."""
+    mesh_shape = tuple(int(s) for s in mesh_shape)
+
+    def vector_field(g0, state, args=None):
+        pos, vel = _f32(state[0]), _f32(state[1])
+        g0_t, dg_t = _cosmo._t(g0), _cosmo._t(dg)
+        alpha = _cosmo.alpha_bf(cosmo, g0_t, dg_t)
+        coefs = torch.stack([alpha.reshape(()), ((1 - alpha) / (g0_t + dg_t / 2)).reshape(()), (dg_t / 2).reshape(()),
+                             (dg_t / 2).reshape(())]).reshape(1, 4)
+        new_pos, new_vel = _NbodySteps.apply(pos, vel, coefs, mesh_shape, int(paint_order), bool(paint_deconv), lap_fd,
+                                             grad_fd)
+        inv = 1.0 / float(dg_t)
+        return (new_pos - pos) * inv, (new_vel - vel) * inv
+
+    return vector_field
+
+
+def nbody_bf_scan(cosmo, init_mesh, pos, a, n_steps=5, paint_order: int = 2, grad_fd=np.inf, lap_fd=np.inf,
+                  snapshots=None):
+    """No-diffrax BullFrog loop (nbody.py:1005-1029): n_steps equal steps in growth time from g = 0 to g(a), starting
+    from `pos` with vel = pm_forces(pos, init_mesh) -- no LPT displacement, unlike nbody_bf.  The reference scans
+    `bullfrog_vf`'s vector field as if it were a step function (its commented-out `step`); what is implemented here is
+    that intended loop, state <- state + dg * vector_field(g0, state), as one engine call.  Returns (pos, vel) each
+    [1, Np, 3]."""
+    if snapshots is not None:
+        raise NotImplementedError("nbody_bf_scan returns the final state only, as the reference does")
+    n_steps = int(n_steps)
+    init_mesh = _c64(init_mesh)
+    pos = _f32(pos)
+    mesh_shape = ch2rshape(tuple(init_mesh.shape))
+    vel = pm_forces(pos, init_mesh, int(paint_order), grad_fd=grad_fd, lap_fd=lap_fd)
+    dg = _cosmo.a2g(cosmo, a) / n_steps
+    rows = []
+    for i in range(n_steps):
+        g0 = i * dg
+        alpha = _cosmo.alpha_bf(cosmo, g0, dg)
+        rows.append(torch.stack([alpha.reshape(()), ((1 - alpha) / (g0 + dg / 2)).reshape(()), (dg / 2).reshape(()),
+                                 (dg / 2).reshape(())]))
+    x, v = _NbodySteps.apply(pos, vel, torch.stack(rows), mesh_shape, int(paint_order), False, lap_fd, grad_fd)
+    return x.unsqueeze(0), v.unsqueeze(0)
+
+
 # growth helpers re-exported under the reference names (nbody.py:750-808)
 a2g, a2g2, a2f, a2f2, a2dg2dg = _cosmo.a2g, _cosmo.a2g2, _cosmo.a2f, _cosmo.a2f2, _cosmo.a2dg2dg
 g2a, g2g2, g2f, g2f2, g2dg2dg = _cosmo.g2a, _cosmo.g2g2, _cosmo.g2f, _cosmo.g2f2, _cosmo.g2dg2dg
+alpha_bf = _cosmo.alpha_bf  # nbody.py:907-919

@@ -279,3 +279,42 @@ def test_lagrangian_bias_weights_and_gradient(nb, golden):
     assert rel(B.regular_pos(shape), q.numpy()) == 0.0
     with pytest.raises(NotImplementedError):
         B.lagrangian_bias(Cosmology(), pos.to(dev(nb)), 0.7, box, dk.detach(), bias, png_type="fNL")
+
+
+def test_bullfrog_vf_scan_and_host_windows(nb, golden):
+    """bullfrog_vf (nbody.py:902-960) against the oracle's drift-kick-drift step; nbody_bf_scan against the same steps in
+    a loop; the host-side window helpers against the golden vectors of the reference source."""
+    from montecosmo_b200.cosmo import Cosmology
+    rng = np.random.default_rng(31)
+    shape = (8, 6, 10)
+    q = O.regular_pos(shape)
+    pos = (q + torch.tensor(rng.normal(scale=0.5, size=q.shape))).float()
+    vel = torch.tensor(rng.normal(scale=0.3, size=q.shape), dtype=torch.float32)
+    g0, dg = 0.3, 0.15
+    vf = nb.bullfrog_vf(Cosmology(), dg, shape, 2)
+    dp, dv = vf(g0, (pos.to(dev(nb)), vel.to(dev(nb))), None)
+    po, vo = O.bullfrog_step(O.Cosmology(), (pos.double(), vel.double()), torch.tensor(g0), torch.tensor(dg), shape, 2)
+    assert rel(pos.to(dev(nb)) + dg * dp, po) < 1e-6 and rel(vel.to(dev(nb)) + dg * dv, vo) < 5e-5
+    # nbody_bf_scan: vel = pm_forces(pos, delta_k), then n_steps equal steps from g = 0 to g(a)
+    dk0 = np.fft.rfftn(rng.normal(size=shape)) * 0.02
+    a, n_steps = 0.6, 3
+    xs, vs = nb.nbody_bf_scan(Cosmology(), torch.tensor(dk0, dtype=torch.complex64, device=dev(nb)), pos.to(dev(nb)), a,
+                              n_steps)
+    co = O.Cosmology()
+    state = (pos.double(), O.pm_forces(pos.double(), torch.tensor(dk0), 2))
+    dgo = O.a2g(co, a) / n_steps
+    for i in range(n_steps):
+        state = O.bullfrog_step(co, state, i * dgo, dgo, shape, 2)
+    assert xs.shape == (1, q.shape[0], 3) and rel(xs[0], state[0]) < 1e-6 and rel(vs[0], state[1]) < 5e-5
+    # host-side kernels
+    g = golden("kernels")
+    kvec = nb.rfftk(tuple(int(s) for s in g["shape"]))
+    assert np.allclose(nb.kaiser_bessel_hat(kvec, 4, nb.optim_kcut(1.5)), g["kaiser_bessel_hat_4"], rtol=1e-12)
+    s = np.linspace(0, 2, 41)
+    for order in (1, 2, 3, 4):
+        ref = O.rectangular(torch.tensor(s), order).numpy()
+        assert np.allclose(nb.rectangular(s, order) * np.ones_like(s), ref, rtol=1e-14)
+    assert np.allclose(nb.kaiser_bessel(s[:21], 2, nb.optim_kcut(2.0)),
+                       O.kaiser_bessel(torch.tensor(s[:21]), 2, nb.optim_kcut(2.0)).numpy(), rtol=1e-12)
+    assert float(nb.alpha_bf(Cosmology(), torch.tensor(0.3), torch.tensor(0.1))) == pytest.approx(
+        float(O.alpha_bf(O.Cosmology(), torch.tensor(0.3), torch.tensor(0.1))), rel=1e-12)

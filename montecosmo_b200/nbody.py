@@ -474,17 +474,41 @@ def lpt(cosmo, init_mesh, pos, a, lpt_order: int = 2, read_order: int = 2, grad_
     return _Lpt.apply(_c64(init_mesh), coef, _f32(pos), int(lpt_order), int(read_order), lap_fd, grad_fd, _displaced)
 
 
+def save_y(t, y, args):
+    """Default save function of nbody_bf (nbody.py:964-965)."""
+    return y
+
+
+def _save_plan(ts, g0, dg, n_steps):
+    """For every save time, the step whose dense output holds it and the position inside it: diffrax 0.5.0 saves
+    `SaveAt(ts=...)` from the solver's interpolation, which for Euler is the straight line between the two ends of a
+    step.  t in (t_i, t_i+1] belongs to step i (t <= g0 to step 0, t > g1 to the last step, linearly continued)."""
+    plan = []
+    for t in ts:
+        u = (t - g0) / dg
+        uf = float(u)
+        if abs(uf - round(uf)) < 1e-9 and 0 <= round(uf) <= n_steps:  # on a step boundary: that state itself
+            plan.append((max(int(round(uf)) - 1, 0), 1.0 if round(uf) >= 1 else 0.0))
+        else:
+            i = min(max(int(np.ceil(uf)) - 1, 0), n_steps - 1)
+            plan.append((i, u - i))
+    return plan
+
+
 def nbody_bf(cosmo, init_mesh, pos, a0=0.0, a1=1.0, n_steps=5, paint_order: int = 2, lpt_order: int = 2,
-             paint_deconv=False, grad_fd=np.inf, lap_fd=np.inf, snapshots=None, fn=None, ptcl_shape="auto"):
+             paint_deconv=False, grad_fd=np.inf, lap_fd=np.inf, snapshots=None, fn=save_y, ptcl_shape="auto"):
     """N-body simulation with the BullFrog solver (nbody.py:967-1002): lpt at a0, then n_steps DKD steps in growth time.
 
-    Returns (pos, vel), each [S, Np, 3]; S = 1 unless `snapshots` is an int > 1 dividing the step count.
+    Returns (pos, vel), each [S, Np, 3].  `snapshots` as in the reference: None or an int <= 1 saves the final state
+    (S = 1); an int S saves at linspace(g0, g1, S) in growth time; a sequence of scale factors saves at a2g(cosmo, .).
+    Save times inside a step get the solver's dense output (linear between the step's ends, as diffrax's Euler), and
+    `fn(t, (pos, vel), None)` maps every saved state (any tuple / tensor result is stacked along a new leading axis);
+    with snapshots=None the reference ignores `fn`, and so does this.
 
     `ptcl_shape` (extension) is a performance hint only: the lattice shape of `pos` (regular_pos order).  "auto" assumes
     the mesh shape when the particle count matches it; None disables the brick-tiled kernels.
     """
-    if fn is not None:
-        raise NotImplementedError("custom save functions are not supported")
+    fn = save_y if fn is None else fn
     n_steps = int(n_steps)
     init_mesh = _c64(init_mesh)
     pos = _f32(pos)
@@ -495,23 +519,37 @@ def nbody_bf(cosmo, init_mesh, pos, a0=0.0, a1=1.0, n_steps=5, paint_order: int 
     x, vel = lpt(cosmo, init_mesh, pos, a0, lpt_order, 1, grad_fd, lap_fd, _displaced=True)
     al, be, pre, post, _, _ = _cosmo.bullfrog_coefficients(cosmo, a0, a1, n_steps)
     coefs = torch.stack([al, be, pre, post], dim=1)
-    if snapshots is None or (isinstance(snapshots, int) and snapshots <= 1):
-        segments = [n_steps]
-    elif isinstance(snapshots, int) and n_steps % (snapshots - 1) == 0:
-        segments = [n_steps // (snapshots - 1)] * (snapshots - 1)
+    g0, g1 = _cosmo.a2g(cosmo, a0), _cosmo.a2g(cosmo, a1)
+    dg = (g1 - g0) / n_steps
+    if snapshots is None:
+        ts, fn = None, save_y
+    elif isinstance(snapshots, (int, np.integer)):
+        ts = None if snapshots <= 1 else [g0 + (g1 - g0) * (i / (snapshots - 1)) for i in range(int(snapshots))]
     else:
-        raise NotImplementedError("snapshots must be None or an int such that (snapshots-1) divides n_steps")
-    xs, vs = ([x], [vel]) if len(segments) > 1 else ([], [])
-    s = 0
-    for seg in segments:
-        x, vel = _NbodySteps.apply(x, vel, coefs[s:s + seg], mesh_shape, int(paint_order), bool(paint_deconv),
-                                   lap_fd, grad_fd)
-        s += seg
-        xs.append(x)
-        vs.append(vel)
-    if len(xs) == 1:
-        return xs[0].unsqueeze(0), vs[0].unsqueeze(0)
-    return torch.stack(xs), torch.stack(vs)
+        ts = list(_cosmo.a2g(cosmo, torch.as_tensor(np.asarray(snapshots, dtype=np.float64))).reshape(-1))
+    plan = [(n_steps - 1, 1.0)] if ts is None else _save_plan(ts, g0, dg, n_steps)
+    # step boundaries whose states are needed, reached segment by segment (one engine call each)
+    need = set()
+    for i, th in plan:
+        need.update((i + 1,) if th == 1.0 and isinstance(th, float) else (i,) if isinstance(th, float) else (i, i + 1))
+    states, s = {0: (x, vel)}, 0
+    for b in sorted(need):
+        if b > s:
+            x, vel = _NbodySteps.apply(x, vel, coefs[s:b], mesh_shape, int(paint_order), bool(paint_deconv), lap_fd,
+                                       grad_fd)
+            s = b
+            states[b] = (x, vel)
+    outs = []
+    for k, (i, th) in enumerate(plan):
+        if isinstance(th, float):
+            y = states[i + 1] if th == 1.0 else states[i]
+        else:
+            thf = th.to(device=x.device, dtype=x.dtype)
+            y = tuple(a + (b - a) * thf for a, b in zip(states[i], states[i + 1]))
+        outs.append(fn(g1 if ts is None else ts[k], y, None))
+    if isinstance(outs[0], (tuple, list)):
+        return tuple(torch.stack([o[j] for o in outs]) for j in range(len(outs[0])))
+    return torch.stack(outs)
 
 
 def bullfrog_vf(cosmo, dg, mesh_shape: tuple, paint_order: int = 2, paint_deconv=False, grad_fd=np.inf, lap_fd=np.inf):

@@ -652,11 +652,13 @@ def bullfrog_step(cosmo, state, g0, dg, mesh_shape, paint_order=2, paint_deconv=
 
 
 def nbody_bf(cosmo, init_mesh, pos, a0=0.0, a1=1.0, n_steps=5, paint_order=2, lpt_order=2, paint_deconv=False,
-             grad_fd=np.inf, lap_fd=np.inf, snapshots=None):
-    """nbody.py:967-1002 with diffrax Euler restated: y <- y + ((new - y) / dg) * dt, last dt clipped onto g1.
+             grad_fd=np.inf, lap_fd=np.inf, snapshots=None, fn=None):
+    """nbody.py:967-1002 with diffrax 0.5.0's Euler restated: y <- y + ((new - y) / dg) * dt, last dt clipped onto g1.
 
-    Returns (pos, vel), each [S, Np, 3]; S = 1 (final state) unless `snapshots` is an int > 1, in which case the
-    states at linspace(g0, g1, S) are returned (step boundaries only are supported by this restatement).
+    Returns (pos, vel), each [S, Np, 3]; S = 1 (final state) unless `snapshots` asks for more (nbody.py:987-996): an int
+    S > 1 saves at linspace(g0, g1, S), a sequence of scale factors at a2g(cosmo, .).  diffrax fills `SaveAt(ts=...)`
+    from the solver's dense output, which for Euler is the straight line between the two ends of the step that holds
+    t; `fn(t, y, args)` (default: identity) maps every saved state.
     """
     n_steps = int(n_steps)
     init_mesh = _t(init_mesh, C128) if not isinstance(init_mesh, torch.Tensor) else init_mesh
@@ -666,7 +668,7 @@ def nbody_bf(cosmo, init_mesh, pos, a0=0.0, a1=1.0, n_steps=5, paint_order=2, lp
     mesh_shape = ch2rshape(tuple(init_mesh.shape))
     dpos, vel = lpt(cosmo, init_mesh, pos=pos, a=a0, lpt_order=lpt_order, read_order=1, grad_fd=grad_fd, lap_fd=lap_fd)
     state = (pos + dpos, vel)
-    traj = [state]
+    traj, times = [state], [g0]
     t = g0
     for n in range(n_steps):
         tn = g1 if n == n_steps - 1 else t + dg
@@ -675,11 +677,27 @@ def nbody_bf(cosmo, init_mesh, pos, a0=0.0, a1=1.0, n_steps=5, paint_order=2, lp
         state = tuple(y + ((nw - y) / dg) * dt for y, nw in zip(state, new))
         t = tn
         traj.append(state)
-    if snapshots is None or (isinstance(snapshots, int) and snapshots <= 1):
+        times.append(t)
+    if snapshots is None:
         return state[0][None], state[1][None]
-    assert isinstance(snapshots, int) and n_steps % (snapshots - 1) == 0, "snapshots must fall on step boundaries"
-    sel = [traj[i * n_steps // (snapshots - 1)] for i in range(snapshots)]
-    return torch.stack([s[0] for s in sel]), torch.stack([s[1] for s in sel])
+    fn = (lambda t, y, args: y) if fn is None else fn
+    if isinstance(snapshots, (int, np.integer)):
+        if snapshots <= 1:
+            outs = [fn(g1, state, None)]
+        else:
+            ts = [g0 + (g1 - g0) * (i / (snapshots - 1)) for i in range(int(snapshots))]
+    else:
+        ts = list(a2g(cosmo, _t(np.asarray(snapshots, dtype=np.float64))).reshape(-1))
+    if not (isinstance(snapshots, (int, np.integer)) and snapshots <= 1):
+        tt = np.array([float(x) for x in times])
+        outs = []
+        for s in ts:
+            i = int(np.clip(np.searchsorted(tt, float(s), side="left") - 1, 0, n_steps - 1))  # t in (t_i, t_i+1]
+            th = (s - times[i]) / (times[i + 1] - times[i])
+            outs.append(fn(s, tuple(a + th * (b - a) for a, b in zip(traj[i], traj[i + 1])), None))
+    if isinstance(outs[0], (tuple, list)):
+        return tuple(torch.stack([o[j] for o in outs]) for j in range(len(outs[0])))
+    return torch.stack(outs)
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -164,6 +164,17 @@ def main():
     p, v = nbody.nbody_bf(c, jnp.asarray(dk), jnp.asarray(q), a0=0.1, a1=0.8, n_steps=3, paint_order=3,
                           lpt_order=1, paint_deconv=True, snapshots=4)
     d["bf3_snap_pos"], d["bf3_snap_vel"] = A(p), A(v)
+    # save times inside steps (dense output of the Euler solver), scale-factor list, custom save function
+    c._workspace = {}
+    p, v = nbody.nbody_bf(c, jnp.asarray(dk), jnp.asarray(q), a0=0.1, a1=0.8, n_steps=3, snapshots=3)
+    d["bf3_mid_pos"], d["bf3_mid_vel"] = A(p), A(v)
+    c._workspace = {}
+    d["bf3_alist"] = np.array([0.15, 0.4, 0.8])
+    p, v = nbody.nbody_bf(c, jnp.asarray(dk), jnp.asarray(q), a0=0.1, a1=0.8, n_steps=3, snapshots=list(d["bf3_alist"]))
+    d["bf3_alist_pos"], d["bf3_alist_vel"] = A(p), A(v)
+    c._workspace = {}
+    d["bf3_fn_disp"] = A(nbody.nbody_bf(c, jnp.asarray(dk), jnp.asarray(q), a0=0.1, a1=0.8, n_steps=3, snapshots=5,
+                                        fn=lambda t, y, args: y[0] - jnp.asarray(q)))
     # BullFrog coefficients per step, as the engine receives them (nbody.py:907-919, 933-938)
     c._workspace = {}
     g0, g1 = float(nbody.a2g(c, 0.0)), float(nbody.a2g(c, 1.0))

@@ -318,3 +318,34 @@ def test_bullfrog_vf_scan_and_host_windows(nb, golden):
                        O.kaiser_bessel(torch.tensor(s[:21]), 2, nb.optim_kcut(2.0)).numpy(), rtol=1e-12)
     assert float(nb.alpha_bf(Cosmology(), torch.tensor(0.3), torch.tensor(0.1))) == pytest.approx(
         float(O.alpha_bf(O.Cosmology(), torch.tensor(0.3), torch.tensor(0.1))), rel=1e-12)
+
+
+def test_nbody_bf_snapshots_dense_output(nb, golden):
+    """Save times inside steps, a scale-factor list and a custom save function (nbody.py:987-996; diffrax's Euler dense
+    output is linear inside a step) against the golden vectors of the reference source, and the gradient through an
+    interpolated snapshot against the oracle's autograd."""
+    from montecosmo_b200.cosmo import Cosmology
+    g = golden("nbody")
+    shape = tuple(int(s) for s in g["shape"])
+    dk = torch.tensor(g["delta_k"], dtype=torch.complex64, device=dev(nb))
+    q = O.regular_pos(shape).float().to(dev(nb))
+    p, v = nb.nbody_bf(Cosmology(), dk, q, 0.1, 0.8, 3, snapshots=3)
+    assert p.shape == (3, q.shape[0], 3)
+    assert np.abs(p.cpu().numpy() - g["bf3_mid_pos"]).max() < 2e-4 and rel(v, g["bf3_mid_vel"]) < 2e-4
+    p, v = nb.nbody_bf(Cosmology(), dk, q, 0.1, 0.8, 3, snapshots=list(g["bf3_alist"]))
+    assert np.abs(p.cpu().numpy() - g["bf3_alist_pos"]).max() < 2e-4 and rel(v, g["bf3_alist_vel"]) < 2e-4
+    d = nb.nbody_bf(Cosmology(), dk, q, 0.1, 0.8, 3, snapshots=5, fn=lambda t, y, args: y[0] - q)
+    assert d.shape == (5, q.shape[0], 3) and np.abs(d.cpu().numpy() - g["bf3_fn_disp"]).max() < 2e-4
+    p1, _ = nb.nbody_bf(Cosmology(), dk, q, 0.1, 0.8, 3, snapshots=1, fn=lambda t, y, args: (2 * y[0], y[1]))
+    assert p1.shape == (1, q.shape[0], 3) and np.abs(p1[0].cpu().numpy() / 2 - g["bf3_mid_pos"][-1]).max() < 2e-4
+    # gradient of a functional of the middle (interpolated) snapshot w.r.t. delta_k
+    rng = np.random.default_rng(8)
+    cot = torch.tensor(rng.normal(size=(q.shape[0], 3)), dtype=torch.float32)
+    dkl = leaf(dk)
+    p, v = nb.nbody_bf(Cosmology(), dkl, q, 0.1, 0.8, 3, snapshots=3)
+    ((p[1] * cot.to(dev(nb))).sum() + (v[1] * cot.to(dev(nb))).sum()).backward()
+    dko = torch.tensor(g["delta_k"]).requires_grad_()
+    po, vo = O.nbody_bf(O.Cosmology(), dko, O.regular_pos(shape), 0.1, 0.8, 3, snapshots=3)
+    ((po[1] * cot.double()).sum() + (vo[1] * cot.double()).sum()).backward()
+    # same regime as test_nbody_bf_matches_golden_and_oracle_grad: CIC derivatives jump at cell faces, 5e-3 in float32
+    assert rel(dkl.grad, dko.grad) < 5e-3

@@ -123,6 +123,15 @@ def test_nbody_bf(golden):
     p, v = O.nbody_bf(c, dk, q, 0.1, 0.8, 3, paint_order=3, lpt_order=1, paint_deconv=True, snapshots=4)
     close(p, g["bf3_snap_pos"], rtol=1e-8, atol=1e-10)
     close(v, g["bf3_snap_vel"], rtol=1e-8, atol=1e-10)
+    # save times inside steps, a list of scale factors, a custom save function (nbody.py:987-996)
+    p, v = O.nbody_bf(c, dk, q, 0.1, 0.8, 3, snapshots=3)
+    close(p, g["bf3_mid_pos"], rtol=1e-8, atol=1e-10)
+    close(v, g["bf3_mid_vel"], rtol=1e-8, atol=1e-10)
+    p, v = O.nbody_bf(c, dk, q, 0.1, 0.8, 3, snapshots=list(g["bf3_alist"]))
+    close(p, g["bf3_alist_pos"], rtol=1e-8, atol=1e-10)
+    close(v, g["bf3_alist_vel"], rtol=1e-8, atol=1e-10)
+    d = O.nbody_bf(c, dk, q, 0.1, 0.8, 3, snapshots=5, fn=lambda t, y, args: y[0] - q)
+    close(d, g["bf3_fn_disp"], rtol=1e-8, atol=1e-10)
     g0, dg = g["bf4_g0_dg"]
     alphas = [float(O.alpha_bf(c, g0 + n * dg, dg)) for n in range(4)]
     close(np.array(alphas), g["bf4_alpha"], rtol=1e-10)

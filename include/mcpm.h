@@ -89,7 +89,8 @@ int mcpm_paint3_lattice(mcpm_engine* eng, void* stream, const float* pos, float*
 /* ---- mass assignment ------------------------------------------------------------------------------------------
  * Positions are transformed in-kernel as x' = x * scale[d] + shift before assignment (nufft's final->paint units,
  * nbody.py:569, and interlace's shift, nbody.py:524); pass scale = {1,1,1}, shift = 0 for plain paint / read.
- * order: 1 NGP, 2 CIC, 3 TSC, 4 PCS (`rectangular`, nbody.py:220-246).  kernel_type 'kaiser_bessel' -> MCPM_EUNSUP. */
+ * order: 1 NGP, 2 CIC, 3 TSC, 4 PCS (`rectangular`, nbody.py:220-246); kernel_type 'kaiser_bessel': the *_kb entry
+ * points below. */
 
 /* paint (nbody.py:365-396): mesh[(id0+s) mod n] += w_p * prod_d W(id0_d + s_d - x'_d).
  * weights may be NULL (then every particle carries `wscalar`), else w_p = weights[p] * wscalar.
@@ -114,6 +115,25 @@ int mcpm_read_grad(void* stream, const float* pos, const float* mesh, int nmesh,
 int mcpm_paint_vjp(void* stream, const float* pos, const float* weights, float wscalar, const float* mesh_bar,
                    int64_t np, int nx, int ny, int nz, int order, const float scale[3], float shift, float* posbar,
                    float* weightsbar, int accumulate);
+
+/* ---- Kaiser-Bessel window (kernel_type = 'kaiser_bessel': nbody.py:280-290 window, 293-312 transform, selected at
+ * nbody.py:321-322, 383-384, 415-416).  The same five operators with
+ *   W(s) = I0(kc sqrt(1 - (2 s / order)^2)) / (order sinh(kc) / kc),  kc = kcut * order / 2,
+ * on the same neighbours as `rectangular` of that order (nbody.py:375-376); kcut = optim_kcut(oversamp) =
+ * 0.98 pi (2 - 1/oversamp) (nbody.py:357-363) is computed by the caller.  The position derivative is finite at the
+ * edge of the support (s = order/2), where autodiff of the reference's sqrt would return inf. */
+int mcpm_paint_kb(void* stream, const float* pos, const float* weights, float wscalar, int64_t np, int nx, int ny,
+                  int nz, int order, float kcut, const float scale[3], float shift, float* mesh, int accumulate);
+int mcpm_read_kb(void* stream, const float* pos, const float* mesh, int nmesh, int64_t np, int nx, int ny, int nz,
+                 int order, float kcut, const float scale[3], float shift, float* out);
+int mcpm_read_grad_kb(void* stream, const float* pos, const float* mesh, int nmesh, const float* cot, int64_t np,
+                      int nx, int ny, int nz, int order, float kcut, const float scale[3], float shift, float* grad,
+                      int accumulate);
+int mcpm_paint_vjp_kb(void* stream, const float* pos, const float* weights, float wscalar, const float* mesh_bar,
+                      int64_t np, int nx, int ny, int nz, int order, float kcut, const float scale[3], float shift,
+                      float* posbar, float* weightsbar, int accumulate);
+/* deconv_paint with the Kaiser-Bessel transform (nbody.py:293-312, 321-322): out = in / prod_d kb_hat(k_d). */
+int mcpm_deconv_kb(void* stream, const void* in, void* out, int nx, int ny, int nz, int order, float kcut);
 
 /* three-channel paint (VJP of a 3-mesh read w.r.t. the meshes): mesh3[m] += vscale * vals3[p,m] * W, m = 0..2 */
 int mcpm_paint3(void* stream, const float* pos, const float* vals3, float vscale, int64_t np, int nx, int ny, int nz,
@@ -327,6 +347,14 @@ int mcpm_nufft(mcpm_engine* eng, void* stream, const float* pos, const float* we
 int mcpm_nufft_vjp(mcpm_engine* eng, void* stream, const float* pos, const float* weights, float wscalar,
                    int64_t np, const float scale[3], int paint_order, int interlace_order, int paint_deconv,
                    const void* outbar_k, float* posbar, float* weightsbar);
+
+/* nufft / its VJP with kernel_type = 'kaiser_bessel' (nbody.py:532-577 with the window of 280-312). */
+int mcpm_nufft_kb(mcpm_engine* eng, void* stream, const float* pos, const float* weights, float wscalar, int64_t np,
+                  const float scale[3], int paint_order, float kcut, int interlace_order, int paint_deconv,
+                  void* out_k);
+int mcpm_nufft_vjp_kb(mcpm_engine* eng, void* stream, const float* pos, const float* weights, float wscalar,
+                      int64_t np, const float scale[3], int paint_order, float kcut, int interlace_order,
+                      int paint_deconv, const void* outbar_k, float* posbar, float* weightsbar);
 
 #ifdef __cplusplus
 }

@@ -29,6 +29,11 @@ SIGNATURES = {
     "mcpm_read": ([vp, vp, vp, i32, i64] + MESH + [i32] + XF + [vp], i32),
     "mcpm_read_grad": ([vp, vp, vp, i32, vp, i64] + MESH + [i32] + XF + [vp, i32], i32),
     "mcpm_paint_vjp": ([vp, vp, vp, f32, vp, i64] + MESH + [i32] + XF + [vp, vp, i32], i32),
+    "mcpm_paint_kb": ([vp, vp, vp, f32, i64] + MESH + [i32, f32] + XF + [vp, i32], i32),
+    "mcpm_read_kb": ([vp, vp, vp, i32, i64] + MESH + [i32, f32] + XF + [vp], i32),
+    "mcpm_read_grad_kb": ([vp, vp, vp, i32, vp, i64] + MESH + [i32, f32] + XF + [vp, i32], i32),
+    "mcpm_paint_vjp_kb": ([vp, vp, vp, f32, vp, i64] + MESH + [i32, f32] + XF + [vp, vp, i32], i32),
+    "mcpm_deconv_kb": ([vp, vp, vp] + MESH + [i32, f32], i32),
     "mcpm_paint3": ([vp, vp, vp, f32, i64] + MESH + [i32, vp, i32], i32),
     "mcpm_rfftn": ([vp, vp, vp, vp, i32], i32),
     "mcpm_irfftn": ([vp, vp, vp, vp, i32], i32),
@@ -84,6 +89,8 @@ SIGNATURES = {
     "mcpm_nbody_steps_vjp": ([vp, vp, vp, vp, i64, i32, hp, hp, hp, hp, i32, i32, i32, i32, vp, vp, vp, vp, vp], i32),
     "mcpm_nufft": ([vp, vp, vp, vp, f32, i64, hp, i32, i32, i32, vp], i32),
     "mcpm_nufft_vjp": ([vp, vp, vp, vp, f32, i64, hp, i32, i32, i32, vp, vp, vp], i32),
+    "mcpm_nufft_kb": ([vp, vp, vp, vp, f32, i64, hp, i32, f32, i32, i32, vp], i32),
+    "mcpm_nufft_vjp_kb": ([vp, vp, vp, vp, f32, i64, hp, i32, f32, i32, i32, vp, vp, vp], i32),
 }
 
 ERROR_NAMES = {1: "MCPM_EINVAL", 2: "MCPM_ECUDA", 3: "MCPM_ECUFFT", 4: "MCPM_ENOMEM", 5: "MCPM_EUNSUP"}

@@ -234,6 +234,54 @@ int mcpm_paint_vjp(void* stream, const float* pos, const float* weights, float w
   API_END
 }
 
+// ---- Kaiser-Bessel window (kernel_type = 'kaiser_bessel', nbody.py:280-312, 321-322, 383-384, 415-416) ---------------
+int mcpm_paint_kb(void* stream, const float* pos, const float* weights, float wscalar, int64_t np, int nx, int ny,
+                  int nz, int order, float kcut, const float scale[3], float shift, float* mesh, int accumulate) {
+  API_BEGIN
+  NEED(kcut > 0.0f, "paint_kb: kcut must be positive (optim_kcut(oversamp))");
+  return paint(as_stream(stream), pos, weights, wscalar, np, nx, ny, nz, order, scale, shift, mesh, accumulate, kcut);
+  API_END
+}
+
+int mcpm_read_kb(void* stream, const float* pos, const float* mesh, int nmesh, int64_t np, int nx, int ny, int nz,
+                 int order, float kcut, const float scale[3], float shift, float* out) {
+  API_BEGIN
+  NEED(kcut > 0.0f, "read_kb: kcut must be positive (optim_kcut(oversamp))");
+  return read(as_stream(stream), pos, mesh, nmesh, np, nx, ny, nz, order, scale, shift, out, kcut);
+  API_END
+}
+
+int mcpm_read_grad_kb(void* stream, const float* pos, const float* mesh, int nmesh, const float* cot, int64_t np,
+                      int nx, int ny, int nz, int order, float kcut, const float scale[3], float shift, float* grad,
+                      int accumulate) {
+  API_BEGIN
+  NEED(nmesh >= 1 && nmesh <= 4, "read_grad_kb: nmesh must be 1..4");
+  NEED(kcut > 0.0f, "read_grad_kb: kcut must be positive (optim_kcut(oversamp))");
+  const int64_t plane = (int64_t)nx * ny * nz;
+  const float* ms[4] = {mesh, mesh + plane, mesh + 2 * plane, mesh + 3 * plane};
+  return read_grad(as_stream(stream), pos, ms, nmesh, cot, cot ? nmesh : 0, 1.0f, nullptr, np, nx, ny, nz, order,
+                   scale, shift, grad, accumulate, kcut);
+  API_END
+}
+
+int mcpm_paint_vjp_kb(void* stream, const float* pos, const float* weights, float wscalar, const float* mesh_bar,
+                      int64_t np, int nx, int ny, int nz, int order, float kcut, const float scale[3], float shift,
+                      float* posbar, float* weightsbar, int accumulate) {
+  API_BEGIN
+  NEED(kcut > 0.0f, "paint_vjp_kb: kcut must be positive (optim_kcut(oversamp))");
+  return paint_vjp(as_stream(stream), pos, weights, wscalar, mesh_bar, np, nx, ny, nz, order, scale, shift, posbar,
+                   weightsbar, accumulate, kcut);
+  API_END
+}
+
+int mcpm_deconv_kb(void* stream, const void* in, void* out, int nx, int ny, int nz, int order, float kcut) {
+  API_BEGIN
+  NEED(in && out, "deconv_kb: null pointer");
+  NEED(order >= 1 && order <= 4 && kcut > 0.0f, "deconv_kb: order must be 1..4 and kcut positive");
+  return deconv(as_stream(stream), C(in), C(out), nx, ny, nz, order, kcut);
+  API_END
+}
+
 int mcpm_paint3(void* stream, const float* pos, const float* vals3, float vscale, int64_t np, int nx, int ny, int nz,
                 int order, float* mesh3, int accumulate) {
   API_BEGIN
@@ -728,6 +776,30 @@ int mcpm_nufft_vjp(mcpm_engine* eng, void* stream, const float* pos, const float
   BIND(eng);
   return nufft_vjp(eng->e, as_stream(stream), pos, weights, wscalar, np, scale, paint_order, interlace_order,
                    paint_deconv, C(outbar_k), posbar, weightsbar);
+  API_END
+}
+
+int mcpm_nufft_kb(mcpm_engine* eng, void* stream, const float* pos, const float* weights, float wscalar, int64_t np,
+                  const float scale[3], int paint_order, float kcut, int interlace_order, int paint_deconv,
+                  void* out_k) {
+  API_BEGIN
+  NEED(eng && pos && out_k, "nufft_kb: null pointer");
+  NEED(kcut > 0.0f, "nufft_kb: kcut must be positive (optim_kcut(oversamp))");
+  BIND(eng);
+  return nufft(eng->e, as_stream(stream), pos, weights, wscalar, np, scale, paint_order, interlace_order,
+               paint_deconv, C(out_k), kcut);
+  API_END
+}
+
+int mcpm_nufft_vjp_kb(mcpm_engine* eng, void* stream, const float* pos, const float* weights, float wscalar,
+                      int64_t np, const float scale[3], int paint_order, float kcut, int interlace_order,
+                      int paint_deconv, const void* outbar_k, float* posbar, float* weightsbar) {
+  API_BEGIN
+  NEED(eng && pos && outbar_k, "nufft_vjp_kb: null pointer");
+  NEED(kcut > 0.0f, "nufft_vjp_kb: kcut must be positive (optim_kcut(oversamp))");
+  BIND(eng);
+  return nufft_vjp(eng->e, as_stream(stream), pos, weights, wscalar, np, scale, paint_order, interlace_order,
+                   paint_deconv, C(outbar_k), posbar, weightsbar, kcut);
   API_END
 }
 

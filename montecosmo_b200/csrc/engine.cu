@@ -378,36 +378,50 @@ int nbody_steps_vjp(Engine* E, stream_t st, float* posbar, float* velbar, int64_
 }
 
 // nufft at the paint shape (nbody.py:569-574): m interlaced paints -> batched R2C -> one combine pass
+// kb_kcut > 0: Kaiser-Bessel window (paint and its deconvolution, nbody.py:321-322, 383-384) instead of `rectangular`.
 int nufft(Engine* E, stream_t st, const float* pos, const float* weights, float wscalar, int64_t np,
-          const float* scale, int paint_order, int interlace_order, int paint_deconv, cfloat* out_k) {
+          const float* scale, int paint_order, int interlace_order, int paint_deconv, cfloat* out_k, float kb_kcut) {
   const int m = interlace_order;
   if (m < 1 || m > Engine::kR - 1) {
     set_error("nufft: interlace_order must be in 1..6");
     return MCPM_EINVAL;
   }
   float jac = scale ? scale[0] * scale[1] * scale[2] : 1.0f;
-  for (int i = 0; i < m; ++i)
-    TRY(paint_fresh(E, st, pos, weights, wscalar, np, paint_order, scale, (float)i / (float)m, E->r(i)));
+  const bool kb = kb_kcut > 0.0f;
+  for (int i = 0; i < m; ++i) {
+    if (kb)
+      TRY(paint(st, pos, weights, wscalar, np, E->nx, E->ny, E->nz, paint_order, scale, (float)i / (float)m, E->r(i), 0,
+                kb_kcut));
+    else
+      TRY(paint_fresh(E, st, pos, weights, wscalar, np, paint_order, scale, (float)i / (float)m, E->r(i)));
+  }
   TRY(fft_r2c(E->fft, st, E->r(0), E->c(0), m));
-  TRY(interlace_combine(st, E->c(0), out_k, m, E->nx, E->ny, E->nz, jac, paint_deconv ? paint_order : 0));
+  TRY(interlace_combine(st, E->c(0), out_k, m, E->nx, E->ny, E->nz, jac, paint_deconv && !kb ? paint_order : 0));
+  if (kb && paint_deconv) TRY(deconv(st, out_k, out_k, E->nx, E->ny, E->nz, paint_order, kb_kcut));
   return 0;
 }
 
 int nufft_vjp(Engine* E, stream_t st, const float* pos, const float* weights, float wscalar, int64_t np,
               const float* scale, int paint_order, int interlace_order, int paint_deconv, const cfloat* outbar_k,
-              float* posbar, float* weightsbar) {
+              float* posbar, float* weightsbar, float kb_kcut) {
   const int m = interlace_order;
   if (m < 1 || m > Engine::kR - 1) {
     set_error("nufft: interlace_order must be in 1..6");
     return MCPM_EINVAL;
   }
   float jac = scale ? scale[0] * scale[1] * scale[2] : 1.0f;
+  const bool kb = kb_kcut > 0.0f;
+  if (kb && paint_deconv) {  // the deconvolution is a real diagonal factor: its transpose is itself
+    TRY(deconv(st, outbar_k, E->c(Engine::kC - 1), E->nx, E->ny, E->nz, paint_order, kb_kcut));
+    outbar_k = E->c(Engine::kC - 1);
+  }
   // out_i = conj(kernel_i) * outbar / w'  (raw C2R supplies the remaining factor N * 1/N)
-  TRY(interlace_combine_T(st, outbar_k, E->c(0), m, E->nx, E->ny, E->nz, jac, paint_deconv ? paint_order : 0, 1.0f));
+  TRY(interlace_combine_T(st, outbar_k, E->c(0), m, E->nx, E->ny, E->nz, jac, paint_deconv && !kb ? paint_order : 0,
+                          1.0f));
   TRY(fft_c2r(E->fft, st, E->c(0), E->r(0), m));
   for (int i = 0; i < m; ++i)
     TRY(paint_vjp(st, pos, weights, wscalar, E->r(i), np, E->nx, E->ny, E->nz, paint_order, scale,
-                  (float)i / (float)m, posbar, weightsbar, i > 0));
+                  (float)i / (float)m, posbar, weightsbar, i > 0, kb_kcut));
   return 0;
 }
 

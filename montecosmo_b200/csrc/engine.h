@@ -32,19 +32,19 @@ struct Engine {
 Engine* engine_create(int nx, int ny, int nz);
 void engine_destroy(Engine*);
 
-// paint.cu
+// paint.cu.  kb_kcut > 0 selects the Kaiser-Bessel window with that cutoff (nbody.py:280-290) instead of `rectangular`.
 int paint(stream_t, const float* pos, const float* weights, float wscalar, int64_t np, int nx, int ny, int nz,
-          int order, const float* scale, float shift, float* mesh, int accumulate);
+          int order, const float* scale, float shift, float* mesh, int accumulate, float kb_kcut = 0.0f);
 int read(stream_t, const float* pos, const float* mesh, int nmesh, int64_t np, int nx, int ny, int nz, int order,
-         const float* scale, float shift, float* out);
+         const float* scale, float shift, float* out, float kb_kcut = 0.0f);
 int read_grad(stream_t, const float* pos, const float* const* meshes, int nmesh, const float* cot, int ncot,
               float cscale, const float* gw, int64_t np, int nx, int ny, int nz, int order, const float* scale,
-              float shift, float* grad, int accumulate);
+              float shift, float* grad, int accumulate, float kb_kcut = 0.0f);
 int paint3(stream_t, const float* pos, const float* A, float ca, const float* B, float cb, int64_t np, int nx,
            int ny, int nz, int order, float* mesh3, int accumulate);
 int paint_vjp(stream_t, const float* pos, const float* weights, float wscalar, const float* mbar, int64_t np, int nx,
               int ny, int nz, int order, const float* scale, float shift, float* posbar, float* wbar,
-              int accumulate);
+              int accumulate, float kb_kcut = 0.0f);
 int kick_drift(stream_t, const float* pos, const float* vel, const float* fmesh3, int64_t np, int nx, int ny, int nz,
                int order, float alpha, float beta, float drift, float* pos_out, float* vel_out, float* force_out);
 int axpy3(stream_t, const float* a, const float* b, float s, int64_t n3, float* out);
@@ -82,7 +82,7 @@ int hessian_spectra_T(stream_t, const cfloat* in6, cfloat* out1, int nx, int ny,
                       int half_weights, int accumulate, float norm, SlabK sk = SlabK());
 int lpt2_source(stream_t, const float* h6, float* d2, int64_t n);
 int lpt2_source_vjp(stream_t, const float* h6, const float* d2bar, float* hbar6, int64_t n);
-int deconv(stream_t, const cfloat* in, cfloat* out, int nx, int ny, int nz, int order);
+int deconv(stream_t, const cfloat* in, cfloat* out, int nx, int ny, int nz, int order, float kb_kcut = 0.0f);
 int interlace_combine(stream_t, const cfloat* in_m, cfloat* out, int m, int nx, int ny, int nz, float scale,
                       int deconv_order);
 int interlace_combine_T(stream_t, const cfloat* in, cfloat* out_m, int m, int nx, int ny, int nz, float scale,
@@ -160,9 +160,9 @@ int nbody_steps_vjp(Engine*, stream_t, float* posbar, float* velbar, int64_t np,
                     int lap_fd, int grad_fd, const float* xk, const float* vk, const float* fm, const float* v0,
                     double* coefbar);
 int nufft(Engine*, stream_t, const float* pos, const float* weights, float wscalar, int64_t np, const float* scale,
-          int paint_order, int interlace_order, int paint_deconv, cfloat* out_k);
+          int paint_order, int interlace_order, int paint_deconv, cfloat* out_k, float kb_kcut = 0.0f);
 int nufft_vjp(Engine*, stream_t, const float* pos, const float* weights, float wscalar, int64_t np,
               const float* scale, int paint_order, int interlace_order, int paint_deconv, const cfloat* outbar_k,
-              float* posbar, float* weightsbar);
+              float* posbar, float* weightsbar, float kb_kcut = 0.0f);
 
 }  // namespace mcpm

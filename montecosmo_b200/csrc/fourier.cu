@@ -149,10 +149,21 @@ int lpt2_source_vjp(stream_t st, const float* h6, const float* d2bar, float* hba
   return rt_check("lpt2_source_vjp");
 }
 
-int deconv(stream_t st, const cfloat* in, cfloat* out, int nx, int ny, int nz, int order) {
+int deconv(stream_t st, const cfloat* in, cfloat* out, int nx, int ny, int nz, int order, float kb_kcut) {
   if (int e = check_dims(nx, ny, nz)) return e;
   KGrid g = make_kgrid(nx, ny, nz);
   const int64_t nc = (int64_t)nx * ny * g.nzc;
+  if (kb_kcut > 0.0f) {  // deconv_paint with kernel_type = 'kaiser_bessel' (nbody.py:321-322)
+    KbHat h = make_kbhat(order, kb_kcut);
+    launch_1d(st, nc, [=] MCPM_LAMBDA(int64_t e) {
+      int l;
+      KVec k = kvec_at(g, e, l);
+      float c = 1.0f / kb_window_hat(h, k);
+      cfloat v = in[e];
+      out[e] = cfloat{v.re * c, v.im * c};
+    });
+    return rt_check("deconv_kb");
+  }
   launch_1d(st, nc, [=] MCPM_LAMBDA(int64_t e) {
     int l;
     KVec k = kvec_at(g, e, l);

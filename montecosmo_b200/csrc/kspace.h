@@ -101,6 +101,29 @@ MCPM_HD float powi(float x, int p) {
 MCPM_HD float window_hat(const KVec& k, int order) {
   return powi(sinc_half(k.kx) * sinc_half(k.ky) * sinc_half(k.kz), order);
 }
+// kaiser_bessel_hat (nbody.py:293-312), one factor: with k' = k*order/2, kc = kcut*order/2, d = sqrt|kc^2 - k'^2|,
+// sinh(d)/d inside the cutoff and sin(d)/d beyond it, over sinh(kc)/kc; the removable 0/0 at d = 0 is taken as 1.
+struct KbHat {
+  float half_order, kc, inv_norm;  // order/2 ; kcut*order/2 ; kc / sinh(kc)
+};
+static inline KbHat make_kbhat(int order, float kcut) {
+  double kc = 0.5 * (double)kcut * order;
+  KbHat h;
+  h.half_order = 0.5f * (float)order;
+  h.kc = (float)kc;
+  h.inv_norm = (float)(kc / std::sinh(kc));
+  return h;
+}
+MCPM_HD float kb_hat_1d(const KbHat& h, float k) {
+  float kp = k * h.half_order;
+  float d2 = h.kc * h.kc - kp * kp;
+  float d = sqrtf(fabsf(d2));
+  float v = d == 0.0f ? 1.0f : (fabsf(kp) <= h.kc ? sinhf(d) / d : sinf(d) / d);
+  return v * h.inv_norm;
+}
+MCPM_HD float kb_window_hat(const KbHat& h, const KVec& k) {
+  return kb_hat_1d(h, k.kx) * kb_hat_1d(h, k.ky) * kb_hat_1d(h, k.kz);
+}
 // weight of a half-spectrum element in the real inner product: 1 on the self-conjugate planes kz = 0, Nyquist; else 2
 MCPM_HD float half_weight(int l, int nz) { return (l == 0 || 2 * l == nz) ? 1.0f : 2.0f; }
 

@@ -18,16 +18,16 @@ struct PosXform {
   float sx, sy, sz, shift;
 };
 
-template <int ORDER>
+template <int ORDER, class WIN = RectWin>
 static void paint_impl(stream_t st, const float* pos, const float* weights, float wscalar, int64_t np, MeshDims n,
-                       PosXform xf, float* mesh) {
+                       PosXform xf, float* mesh, WIN win = WIN()) {
   launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
     const float* x = pos + 3 * p;
     int fx, fy, fz;
     float wx[ORDER], wy[ORDER], wz[ORDER];
-    window_weights<ORDER>(x[0] * xf.sx + xf.shift, fx, wx);
-    window_weights<ORDER>(x[1] * xf.sy + xf.shift, fy, wy);
-    window_weights<ORDER>(x[2] * xf.sz + xf.shift, fz, wz);
+    win.template weights<ORDER>(x[0] * xf.sx + xf.shift, fx, wx);
+    win.template weights<ORDER>(x[1] * xf.sy + xf.shift, fy, wy);
+    win.template weights<ORDER>(x[2] * xf.sz + xf.shift, fz, wz);
     fx = wrap_fast(fx, n.nx);
     fy = wrap_fast(fy, n.ny);
     fz = wrap_fast(fz, n.nz);
@@ -53,17 +53,17 @@ static void paint_impl(stream_t st, const float* pos, const float* weights, floa
   });
 }
 
-template <int ORDER, int NM>
+template <int ORDER, int NM, class WIN = RectWin>
 static void read_impl(stream_t st, const float* pos, const float* mesh, int64_t np, MeshDims n, PosXform xf,
-                      float* out) {
+                      float* out, WIN win = WIN()) {
   const int64_t plane = (int64_t)n.nx * n.ny * n.nz;
   launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
     const float* x = pos + 3 * p;
     int fx, fy, fz;
     float wx[ORDER], wy[ORDER], wz[ORDER];
-    window_weights<ORDER>(x[0] * xf.sx + xf.shift, fx, wx);
-    window_weights<ORDER>(x[1] * xf.sy + xf.shift, fy, wy);
-    window_weights<ORDER>(x[2] * xf.sz + xf.shift, fz, wz);
+    win.template weights<ORDER>(x[0] * xf.sx + xf.shift, fx, wx);
+    win.template weights<ORDER>(x[1] * xf.sy + xf.shift, fy, wy);
+    win.template weights<ORDER>(x[2] * xf.sz + xf.shift, fz, wz);
     fx = wrap_fast(fx, n.nx);
     fy = wrap_fast(fy, n.ny);
     fz = wrap_fast(fz, n.nz);
@@ -103,17 +103,17 @@ struct MeshPtrs {
 // c[p,m] = cscale * cot[p*ncot+m] for m < ncot, 1 otherwise;  gscale_p = gw ? gw[p] : 1.
 // One gather serves the position-VJP of read (cot = out_bar), of paint (mesh = mesh_bar, gw = weights) and the
 // backward force (3 force meshes with cot = beta*vbar, plus the density-cotangent mesh with c = 1).
-template <int ORDER>
+template <int ORDER, class WIN = RectWin>
 static void read_grad_impl(stream_t st, const float* pos, MeshPtrs ms, int nmesh, const float* cot, int ncot,
                            float cscale, const float* gw, int64_t np, MeshDims n, PosXform xf, float* grad,
-                           int accumulate) {
+                           int accumulate, WIN win = WIN()) {
   launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
     const float* x = pos + 3 * p;
     int fx, fy, fz;
     float wx[ORDER], wy[ORDER], wz[ORDER], dx[ORDER], dy[ORDER], dz[ORDER];
-    window_weights_grad<ORDER>(x[0] * xf.sx + xf.shift, fx, wx, dx);
-    window_weights_grad<ORDER>(x[1] * xf.sy + xf.shift, fy, wy, dy);
-    window_weights_grad<ORDER>(x[2] * xf.sz + xf.shift, fz, wz, dz);
+    win.template weights_grad<ORDER>(x[0] * xf.sx + xf.shift, fx, wx, dx);
+    win.template weights_grad<ORDER>(x[1] * xf.sy + xf.shift, fy, wy, dy);
+    win.template weights_grad<ORDER>(x[2] * xf.sz + xf.shift, fz, wz, dz);
     fx = wrap_fast(fx, n.nx);
     fy = wrap_fast(fy, n.ny);
     fz = wrap_fast(fz, n.nz);
@@ -209,16 +209,17 @@ static void paint3_impl(stream_t st, const float* pos, const float* A, float ca,
 
 // VJP of paint w.r.t. weights and positions from the mesh cotangent, one gather:
 //   wbar[p] (+)= wscalar * sum mesh_bar * W ;  posbar[p,a] (+)= w_p * scale_a * sum mesh_bar * dW_a ...
-template <int ORDER>
+template <int ORDER, class WIN = RectWin>
 static void paint_vjp_impl(stream_t st, const float* pos, const float* weights, float wscalar, const float* mbar,
-                           int64_t np, MeshDims n, PosXform xf, float* posbar, float* wbar, int accumulate) {
+                           int64_t np, MeshDims n, PosXform xf, float* posbar, float* wbar, int accumulate,
+                           WIN win = WIN()) {
   launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
     const float* x = pos + 3 * p;
     int fx, fy, fz;
     float wx[ORDER], wy[ORDER], wz[ORDER], dx[ORDER], dy[ORDER], dz[ORDER];
-    window_weights_grad<ORDER>(x[0] * xf.sx + xf.shift, fx, wx, dx);
-    window_weights_grad<ORDER>(x[1] * xf.sy + xf.shift, fy, wy, dy);
-    window_weights_grad<ORDER>(x[2] * xf.sz + xf.shift, fz, wz, dz);
+    win.template weights_grad<ORDER>(x[0] * xf.sx + xf.shift, fx, wx, dx);
+    win.template weights_grad<ORDER>(x[1] * xf.sy + xf.shift, fy, wy, dy);
+    win.template weights_grad<ORDER>(x[2] * xf.sz + xf.shift, fz, wz, dz);
     fx = wrap_fast(fx, n.nx);
     fy = wrap_fast(fy, n.ny);
     fz = wrap_fast(fz, n.nz);
@@ -340,7 +341,7 @@ static PosXform make_xform(const float* scale, float shift) {
 }
 
 int paint(stream_t st, const float* pos, const float* weights, float wscalar, int64_t np, int nx, int ny, int nz,
-          int order, const float* scale, float shift, float* mesh, int accumulate) {
+          int order, const float* scale, float shift, float* mesh, int accumulate, float kb_kcut) {
   if (int e = check_mesh(nx, ny, nz, order)) return e;
   if (!mesh || (np > 0 && !pos)) {
     set_error("paint: null pointer");
@@ -349,6 +350,16 @@ int paint(stream_t st, const float* pos, const float* weights, float wscalar, in
   MeshDims n = {nx, ny, nz};
   PosXform xf = make_xform(scale, shift);
   if (!accumulate) rt_memset(mesh, 0, sizeof(float) * (size_t)nx * ny * nz, st);
+  if (kb_kcut > 0.0f) {
+    KbWin kb = make_kbwin(order, kb_kcut);
+    switch (order) {
+      case 1: paint_impl<1>(st, pos, weights, wscalar, np, n, xf, mesh, kb); break;
+      case 2: paint_impl<2>(st, pos, weights, wscalar, np, n, xf, mesh, kb); break;
+      case 3: paint_impl<3>(st, pos, weights, wscalar, np, n, xf, mesh, kb); break;
+      default: paint_impl<4>(st, pos, weights, wscalar, np, n, xf, mesh, kb); break;
+    }
+    return rt_check("paint");
+  }
   switch (order) {
     case 1: paint_impl<1>(st, pos, weights, wscalar, np, n, xf, mesh); break;
     case 2: paint_impl<2>(st, pos, weights, wscalar, np, n, xf, mesh); break;
@@ -358,21 +369,21 @@ int paint(stream_t st, const float* pos, const float* weights, float wscalar, in
   return rt_check("paint");
 }
 
-template <int ORDER>
+template <int ORDER, class WIN = RectWin>
 static int read_nm(stream_t st, const float* pos, const float* mesh, int nmesh, int64_t np, MeshDims n, PosXform xf,
-                   float* out) {
+                   float* out, WIN win = WIN()) {
   switch (nmesh) {
-    case 1: read_impl<ORDER, 1>(st, pos, mesh, np, n, xf, out); return 0;
-    case 2: read_impl<ORDER, 2>(st, pos, mesh, np, n, xf, out); return 0;
-    case 3: read_impl<ORDER, 3>(st, pos, mesh, np, n, xf, out); return 0;
-    case 4: read_impl<ORDER, 4>(st, pos, mesh, np, n, xf, out); return 0;
+    case 1: read_impl<ORDER, 1>(st, pos, mesh, np, n, xf, out, win); return 0;
+    case 2: read_impl<ORDER, 2>(st, pos, mesh, np, n, xf, out, win); return 0;
+    case 3: read_impl<ORDER, 3>(st, pos, mesh, np, n, xf, out, win); return 0;
+    case 4: read_impl<ORDER, 4>(st, pos, mesh, np, n, xf, out, win); return 0;
   }
   set_error("read: nmesh must be 1..4");
   return MCPM_EINVAL;
 }
 
 int read(stream_t st, const float* pos, const float* mesh, int nmesh, int64_t np, int nx, int ny, int nz, int order,
-         const float* scale, float shift, float* out) {
+         const float* scale, float shift, float* out, float kb_kcut) {
   if (int e = check_mesh(nx, ny, nz, order)) return e;
   if (np > 0 && (!pos || !mesh || !out)) {
     set_error("read: null pointer");
@@ -381,6 +392,16 @@ int read(stream_t st, const float* pos, const float* mesh, int nmesh, int64_t np
   MeshDims n = {nx, ny, nz};
   PosXform xf = make_xform(scale, shift);
   int e;
+  if (kb_kcut > 0.0f) {
+    KbWin kb = make_kbwin(order, kb_kcut);
+    switch (order) {
+      case 1: e = read_nm<1>(st, pos, mesh, nmesh, np, n, xf, out, kb); break;
+      case 2: e = read_nm<2>(st, pos, mesh, nmesh, np, n, xf, out, kb); break;
+      case 3: e = read_nm<3>(st, pos, mesh, nmesh, np, n, xf, out, kb); break;
+      default: e = read_nm<4>(st, pos, mesh, nmesh, np, n, xf, out, kb); break;
+    }
+    return e ? e : rt_check("read");
+  }
   switch (order) {
     case 1: e = read_nm<1>(st, pos, mesh, nmesh, np, n, xf, out); break;
     case 2: e = read_nm<2>(st, pos, mesh, nmesh, np, n, xf, out); break;
@@ -392,7 +413,7 @@ int read(stream_t st, const float* pos, const float* mesh, int nmesh, int64_t np
 
 int read_grad(stream_t st, const float* pos, const float* const* meshes, int nmesh, const float* cot, int ncot,
               float cscale, const float* gw, int64_t np, int nx, int ny, int nz, int order, const float* scale,
-              float shift, float* grad, int accumulate) {
+              float shift, float* grad, int accumulate, float kb_kcut) {
   if (int e = check_mesh(nx, ny, nz, order)) return e;
   if (nmesh < 1 || nmesh > 4 || ncot < 0 || ncot > nmesh) {
     set_error("read_grad: nmesh must be 1..4 and ncot <= nmesh");
@@ -406,6 +427,16 @@ int read_grad(stream_t st, const float* pos, const float* const* meshes, int nme
   PosXform xf = make_xform(scale, shift);
   MeshPtrs ms = {{nullptr, nullptr, nullptr, nullptr}};
   for (int m = 0; m < nmesh; ++m) ms.p[m] = meshes[m];
+  if (kb_kcut > 0.0f) {
+    KbWin kb = make_kbwin(order, kb_kcut);
+    switch (order) {
+      case 1: read_grad_impl<1>(st, pos, ms, nmesh, cot, ncot, cscale, gw, np, n, xf, grad, accumulate, kb); break;
+      case 2: read_grad_impl<2>(st, pos, ms, nmesh, cot, ncot, cscale, gw, np, n, xf, grad, accumulate, kb); break;
+      case 3: read_grad_impl<3>(st, pos, ms, nmesh, cot, ncot, cscale, gw, np, n, xf, grad, accumulate, kb); break;
+      default: read_grad_impl<4>(st, pos, ms, nmesh, cot, ncot, cscale, gw, np, n, xf, grad, accumulate, kb); break;
+    }
+    return rt_check("read_grad");
+  }
   switch (order) {
     case 1: read_grad_impl<1>(st, pos, ms, nmesh, cot, ncot, cscale, gw, np, n, xf, grad, accumulate); break;
     case 2: read_grad_impl<2>(st, pos, ms, nmesh, cot, ncot, cscale, gw, np, n, xf, grad, accumulate); break;
@@ -435,7 +466,7 @@ int paint3(stream_t st, const float* pos, const float* A, float ca, const float*
 
 int paint_vjp(stream_t st, const float* pos, const float* weights, float wscalar, const float* mbar, int64_t np,
               int nx, int ny, int nz, int order, const float* scale, float shift, float* posbar, float* wbar,
-              int accumulate) {
+              int accumulate, float kb_kcut) {
   if (int e = check_mesh(nx, ny, nz, order)) return e;
   if (np > 0 && (!pos || !mbar)) {
     set_error("paint_vjp: null pointer");
@@ -443,6 +474,16 @@ int paint_vjp(stream_t st, const float* pos, const float* weights, float wscalar
   }
   MeshDims n = {nx, ny, nz};
   PosXform xf = make_xform(scale, shift);
+  if (kb_kcut > 0.0f) {
+    KbWin kb = make_kbwin(order, kb_kcut);
+    switch (order) {
+      case 1: paint_vjp_impl<1>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, kb); break;
+      case 2: paint_vjp_impl<2>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, kb); break;
+      case 3: paint_vjp_impl<3>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, kb); break;
+      default: paint_vjp_impl<4>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, kb); break;
+    }
+    return rt_check("paint_vjp");
+  }
   switch (order) {
     case 1: paint_vjp_impl<1>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate); break;
     case 2: paint_vjp_impl<2>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate); break;

@@ -68,4 +68,79 @@ MCPM_HD void window_weights_grad(float x, int& first, float* w, float* dw) {
   }
 }
 
+// ---- window families as functors, so that one kernel body serves both -------------------------------------------
+struct RectWin {  // `rectangular` (nbody.py:220-246)
+  template <int ORDER>
+  MCPM_HD void weights(float x, int& first, float* w) const {
+    window_weights<ORDER>(x, first, w);
+  }
+  template <int ORDER>
+  MCPM_HD void weights_grad(float x, int& first, float* w, float* dw) const {
+    window_weights_grad<ORDER>(x, first, w, dw);
+  }
+};
+
+// Modified Bessel functions I0(z) and I1(z)/z, z >= 0 (CUDA's cyl_bessel_i*f on the device, libstdc++'s on the host).
+MCPM_HD float bessel_i0(float z) {
+#if defined(__CUDA_ARCH__)
+  return cyl_bessel_i0f(z);
+#else
+  return std::cyl_bessel_i(0.0f, z);
+#endif
+}
+MCPM_HD float bessel_i1_over_z(float z) {
+  if (z < 1e-3f) return 0.5f + 0.0625f * z * z;
+#if defined(__CUDA_ARCH__)
+  return cyl_bessel_i1f(z) / z;
+#else
+  return std::cyl_bessel_i(1.0f, z) / z;
+#endif
+}
+
+// `kaiser_bessel` (nbody.py:280-290): W(s) = I0(kc sqrt(1 - s'^2)) / (order sinh(kc) / kc), s' = 2 s / order,
+// kc = kcut * order / 2, kcut = optim_kcut(oversamp) (nbody.py:357-363).  Same base index and shifts as the rectangular
+// family (nbody.py:375-376); the window does not vanish at the edge of its support (s' = 1 gives I0(0) / norm).
+// dW/ds = -inv_norm * I1(z)/z * kc^2 * s' * (2/order), finite at s' = 1 (where autodiff of sqrt gives inf).
+struct KbWin {
+  float kc, inv_norm, s_scale;  // kcut*order/2 ; kc / (order sinh kc) ; 2 / order
+  template <int ORDER>
+  MCPM_HD void weights(float x, int& first, float* w) const {
+    float f0 = (ORDER & 1) ? rintf(x) : floorf(x);
+    float fr = x - f0;
+    const int s0 = -((ORDER - 1) / 2);
+    first = (int)f0 + s0;
+#pragma unroll
+    for (int t = 0; t < ORDER; ++t) {
+      float sp = fabsf((float)(s0 + t) - fr) * s_scale;
+      w[t] = bessel_i0(kc * sqrtf(fmaxf(1.0f - sp * sp, 0.0f))) * inv_norm;
+    }
+  }
+  template <int ORDER>
+  MCPM_HD void weights_grad(float x, int& first, float* w, float* dw) const {
+    float f0 = (ORDER & 1) ? rintf(x) : floorf(x);
+    float fr = x - f0;
+    const int s0 = -((ORDER - 1) / 2);
+    first = (int)f0 + s0;
+#pragma unroll
+    for (int t = 0; t < ORDER; ++t) {
+      float u = (float)(s0 + t) - fr;
+      float sp = fabsf(u) * s_scale;
+      float z = kc * sqrtf(fmaxf(1.0f - sp * sp, 0.0f));
+      w[t] = bessel_i0(z) * inv_norm;
+      float sg = u > 0.0f ? 1.0f : (u < 0.0f ? -1.0f : 0.0f);
+      // d/dx W(|u|) = -sign(u) dW/ds
+      dw[t] = sg * inv_norm * bessel_i1_over_z(z) * kc * kc * sp * s_scale;
+    }
+  }
+};
+
+static inline KbWin make_kbwin(int order, float kcut) {
+  double kc = 0.5 * (double)kcut * order;
+  KbWin w;
+  w.kc = (float)kc;
+  w.inv_norm = (float)(kc / (order * std::sinh(kc)));
+  w.s_scale = 2.0f / (float)order;
+  return w;
+}
+
 }  // namespace mcpm

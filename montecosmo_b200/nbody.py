@@ -39,11 +39,13 @@ def _c64(x):
     return ops().A.prepare(x, "c64")
 
 
-def _check_kernel(kernel_type):
+def _kb_kcut(kernel_type, oversamp):
+    """Window family selector for the engine (nbody.py:319-324, 381-386): 0.0 for 'rectangular', the Kaiser-Bessel
+    cutoff optim_kcut(oversamp) for 'kaiser_bessel' (the mcpm_*_kb entry points)."""
     if kernel_type == "rectangular":
-        return
+        return 0.0
     if kernel_type == "kaiser_bessel":
-        raise NotImplementedError("kernel_type='kaiser_bessel' is not implemented by the B200 engine (MCPM_EUNSUP)")
+        return float(0.98 * np.pi * (2 - 1 / oversamp))
     raise ValueError(f"Unknown kernel type: {kernel_type}")
 
 
@@ -135,8 +137,7 @@ def optim_kcut(oversamp, safety=0.98):
 
 
 def kaiser_bessel(s, order, kcut):
-    """Kaiser-Bessel window (nbody.py:280-290), host-side NumPy.  The engine's paint / read kernels implement the
-    rectangular family only (kernel_type='kaiser_bessel' raises NotImplementedError there)."""
+    """Kaiser-Bessel window (nbody.py:280-290), host-side NumPy; the engine evaluates it in window.h (KbWin)."""
     s = np.asarray(s, dtype=np.float64) * 2 / order
     kcut = kcut * order / 2
     return np.i0(kcut * (1 - s**2) ** 0.5) / (order * np.sinh(kcut) / kcut)
@@ -159,42 +160,43 @@ def kaiser_bessel_hat(kvec, order, kcut):
 
 class _Paint(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pos, weights, shape, wscalar, order, scale, shift):
+    def forward(ctx, pos, weights, shape, wscalar, order, scale, shift, kb=0.0):
         ctx.save_for_backward(pos, weights)
-        ctx.cfg = (shape, wscalar, order, scale, shift)
-        return ops().paint(pos, shape, weights, wscalar, order, scale, shift)
+        ctx.cfg = (shape, wscalar, order, scale, shift, kb)
+        return ops().paint(pos, shape, weights, wscalar, order, scale, shift, kb_kcut=kb)
 
     @staticmethod
     def backward(ctx, mbar):
         pos, weights = ctx.saved_tensors
-        shape, wscalar, order, scale, shift = ctx.cfg
+        shape, wscalar, order, scale, shift, kb = ctx.cfg
         need_p, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and weights is not None
-        pb, wb = ops().paint_vjp(pos, mbar.contiguous(), weights, wscalar, order, scale, shift, need_p, need_w)
-        return pb, wb, None, None, None, None, None
+        pb, wb = ops().paint_vjp(pos, mbar.contiguous(), weights, wscalar, order, scale, shift, need_p, need_w,
+                                 kb_kcut=kb)
+        return pb, wb, None, None, None, None, None, None
 
 
 class _Read(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pos, mesh, order, scale, shift):
+    def forward(ctx, pos, mesh, order, scale, shift, kb=0.0):
         ctx.save_for_backward(pos, mesh)
-        ctx.cfg = (order, scale, shift)
-        return ops().read(pos, mesh, order, scale, shift)
+        ctx.cfg = (order, scale, shift, kb)
+        return ops().read(pos, mesh, order, scale, shift, kb_kcut=kb)
 
     @staticmethod
     def backward(ctx, obar):
         pos, mesh = ctx.saved_tensors
-        order, scale, shift = ctx.cfg
+        order, scale, shift, kb = ctx.cfg
         obar = obar.contiguous()
         pb = mb = None
         if ctx.needs_input_grad[0]:
-            pb = ops().read_grad(pos, mesh, obar.reshape(pos.shape[0], -1), order, scale, shift)
+            pb = ops().read_grad(pos, mesh, obar.reshape(pos.shape[0], -1), order, scale, shift, kb_kcut=kb)
         if ctx.needs_input_grad[1]:
             if mesh.dim() == 3:
-                mb = ops().paint(pos, tuple(mesh.shape), obar, 1.0, order, scale, shift)
+                mb = ops().paint(pos, tuple(mesh.shape), obar, 1.0, order, scale, shift, kb_kcut=kb)
             else:
                 mb = torch.stack([ops().paint(pos, tuple(mesh.shape[1:]), obar[:, i].contiguous(), 1.0, order, scale,
-                                              shift) for i in range(mesh.shape[0])])
-        return pb, mb, None, None, None
+                                              shift, kb_kcut=kb) for i in range(mesh.shape[0])])
+        return pb, mb, None, None, None, None
 
 
 class _Rfftn(torch.autograd.Function):
@@ -219,13 +221,13 @@ class _Irfftn(torch.autograd.Function):
 
 class _Deconv(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, meshk, order):
-        ctx.order = order
-        return ops().deconv(meshk, order)
+    def forward(ctx, meshk, order, kb=0.0):
+        ctx.cfg = (order, kb)
+        return ops().deconv(meshk, order, kb_kcut=kb)
 
     @staticmethod
     def backward(ctx, kbar):
-        return ops().deconv(kbar.contiguous(), ctx.order), None
+        return ops().deconv(kbar.contiguous(), ctx.cfg[0], kb_kcut=ctx.cfg[1]), None, None
 
 
 class _Chreshape(torch.autograd.Function):
@@ -253,19 +255,20 @@ class _ScaleSpectrum(torch.autograd.Function):
 
 class _NufftPaint(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pos, weights, paint_shape, wscalar, scale, paint_order, interlace_order, paint_deconv):
+    def forward(ctx, pos, weights, paint_shape, wscalar, scale, paint_order, interlace_order, paint_deconv, kb=0.0):
         ctx.save_for_backward(pos, weights)
-        ctx.cfg = (paint_shape, wscalar, scale, paint_order, interlace_order, paint_deconv)
-        return ops().nufft_paint(pos, paint_shape, weights, wscalar, scale, paint_order, interlace_order, paint_deconv)
+        ctx.cfg = (paint_shape, wscalar, scale, paint_order, interlace_order, paint_deconv, kb)
+        return ops().nufft_paint(pos, paint_shape, weights, wscalar, scale, paint_order, interlace_order, paint_deconv,
+                                 kb_kcut=kb)
 
     @staticmethod
     def backward(ctx, kbar):
         pos, weights = ctx.saved_tensors
-        paint_shape, wscalar, scale, paint_order, interlace_order, paint_deconv = ctx.cfg
+        paint_shape, wscalar, scale, paint_order, interlace_order, paint_deconv, kb = ctx.cfg
         need_p, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and weights is not None
         pb, wb = ops().nufft_paint_vjp(pos, kbar.contiguous(), paint_shape, weights, wscalar, scale, paint_order,
-                                       interlace_order, paint_deconv, need_p, need_w)
-        return pb, wb, None, None, None, None, None, None
+                                       interlace_order, paint_deconv, need_p, need_w, kb_kcut=kb)
+        return pb, wb, None, None, None, None, None, None, None
 
 
 class _PmForcesPaint(torch.autograd.Function):
@@ -359,15 +362,15 @@ def _split_weights(weights):
 
 def paint(pos, shape: tuple, weights=1.0, order: int = 2, kernel_type="rectangular", oversamp=1.0):
     """Paint the positions onto a mesh of given shape (nbody.py:365-396)."""
-    _check_kernel(kernel_type)
+    kb = _kb_kcut(kernel_type, oversamp)
     w, ws = _split_weights(weights)
-    return _Paint.apply(_f32(pos), w, tuple(int(s) for s in shape), ws, int(order), None, 0.0)
+    return _Paint.apply(_f32(pos), w, tuple(int(s) for s in shape), ws, int(order), None, 0.0, kb)
 
 
 def read(pos, mesh, order: int = 2, kernel_type="rectangular", oversamp=1.0):
     """Read the value at the positions from the mesh (nbody.py:398-427)."""
-    _check_kernel(kernel_type)
-    return _Read.apply(_f32(pos), _f32(mesh), int(order), None, 0.0)
+    kb = _kb_kcut(kernel_type, oversamp)
+    return _Read.apply(_f32(pos), _f32(mesh), int(order), None, 0.0, kb)
 
 
 def rfftn(mesh):
@@ -387,38 +390,40 @@ def chreshape(mesh, shape):
 
 def deconv_paint(mesh, order: int = 2, kernel_type="rectangular", oversamp=1.0):
     """Deconvolve the mesh by the paint kernel (nbody.py:315-334); real meshes go through rfftn / irfftn."""
-    _check_kernel(kernel_type)
+    kb = _kb_kcut(kernel_type, oversamp)
     if not torch.is_complex(torch.as_tensor(mesh)):
-        return irfftn(_Deconv.apply(rfftn(mesh), int(order)))
-    return _Deconv.apply(_c64(mesh), int(order))
+        return irfftn(_Deconv.apply(rfftn(mesh), int(order), kb))
+    return _Deconv.apply(_c64(mesh), int(order), kb)
 
 
 def interlace(pos, shape: tuple, weights=1.0, paint_order: int = 2, interlace_order: int = 2,
               kernel_type="rectangular", paint_oversamp: float = 1.0):
     """Equal-spacing interlacing (nbody.py:513-529)."""
-    _check_kernel(kernel_type)
+    kb = _kb_kcut(kernel_type, paint_oversamp)
     w, ws = _split_weights(weights)
     return _NufftPaint.apply(_f32(pos), w, tuple(int(s) for s in shape), ws, None, int(paint_order),
-                             int(interlace_order), False)
+                             int(interlace_order), False, kb)
 
 
 def nufft(pos, final_shape: tuple, paint_shape=None, weights=1.0, paint_order: int = 2, interlace_order: int = 2,
           kernel_type="rectangular", paint_deconv=True):
     """Non-uniform FFT with oversampling, deconvolution and interlacing (nbody.py:532-577)."""
-    _check_kernel(kernel_type)
     final_shape = tuple(int(s) for s in final_shape)
     if paint_shape is None:
-        paint_shape = final_shape
+        paint_shape, paint_oversamp = final_shape, 1.0
     elif isinstance(paint_shape, float):
-        paint_shape = scale_shape(final_shape, paint_shape)
+        paint_oversamp = paint_shape
+        paint_shape = scale_shape(final_shape, paint_oversamp)
     elif isinstance(paint_shape, (tuple, np.ndarray)):
         paint_shape = tuple(int(s) for s in paint_shape)
+        paint_oversamp = float(np.exp(np.log(np.divide(final_shape, paint_shape)).mean()))  # as nbody.py:566
     else:
         raise ValueError("paint_shape must be None, a float, or a tuple/ndarray")
+    kb = _kb_kcut(kernel_type, paint_oversamp)
     scale = tuple(float(p) / float(f) for p, f in zip(paint_shape, final_shape))
     w, ws = _split_weights(weights)
     mesh = _NufftPaint.apply(_f32(pos), w, paint_shape, ws, scale, int(paint_order), int(interlace_order),
-                             bool(paint_deconv))
+                             bool(paint_deconv), kb)
     if final_shape != paint_shape:
         mesh = chreshape(mesh, r2chshape(final_shape))
     return mesh

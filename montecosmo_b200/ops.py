@@ -106,17 +106,24 @@ class Ops:
         check(self.lib, getattr(self.lib, name)(*args))
 
     # ------------------------------------------------------------------------------------------------ assignment
-    def paint(self, pos, shape, weights=None, wscalar=1.0, order=2, scale=None, shift=0.0, out=None, accumulate=False):
+    @staticmethod
+    def _win(name, order, kb_kcut):
+        """Entry point and order arguments for the window family: kb_kcut > 0 selects the Kaiser-Bessel variants."""
+        return (name + "_kb", (order, float(kb_kcut))) if kb_kcut else (name, (order,))
+
+    def paint(self, pos, shape, weights=None, wscalar=1.0, order=2, scale=None, shift=0.0, out=None, accumulate=False,
+              kb_kcut=0.0):
         A = self.A
         pos = A.prepare(pos)
         weights = None if weights is None else A.prepare(weights)
         mesh = A.empty(shape) if out is None else out
         sc, sh = self._xf(scale, shift)
-        self._call("mcpm_paint", A.stream(), A.ptr(pos), A.ptr(weights), wscalar, A.shape(pos)[0], *shape, order, sc,
+        fn, oa = self._win("mcpm_paint", order, kb_kcut)
+        self._call(fn, A.stream(), A.ptr(pos), A.ptr(weights), wscalar, A.shape(pos)[0], *shape, *oa, sc,
                    sh, A.ptr(mesh), int(accumulate))
         return mesh
 
-    def read(self, pos, mesh, order=2, scale=None, shift=0.0):
+    def read(self, pos, mesh, order=2, scale=None, shift=0.0, kb_kcut=0.0):
         """mesh [nx,ny,nz] -> [np];  mesh [m,nx,ny,nz] -> [np,m]."""
         A = self.A
         pos, mesh = A.prepare(pos), A.prepare(mesh)
@@ -125,10 +132,11 @@ class Ops:
         n = A.shape(pos)[0]
         out = A.empty((n,) if len(ms) == 3 else (n, nm))
         sc, sh = self._xf(scale, shift)
-        self._call("mcpm_read", A.stream(), A.ptr(pos), A.ptr(mesh), nm, n, *ms[-3:], order, sc, sh, A.ptr(out))
+        fn, oa = self._win("mcpm_read", order, kb_kcut)
+        self._call(fn, A.stream(), A.ptr(pos), A.ptr(mesh), nm, n, *ms[-3:], *oa, sc, sh, A.ptr(out))
         return out
 
-    def read_grad(self, pos, mesh, cot=None, order=2, scale=None, shift=0.0):
+    def read_grad(self, pos, mesh, cot=None, order=2, scale=None, shift=0.0, kb_kcut=0.0):
         A = self.A
         pos, mesh = A.prepare(pos), A.prepare(mesh)
         cot = None if cot is None else A.prepare(cot)
@@ -137,12 +145,12 @@ class Ops:
         n = A.shape(pos)[0]
         out = A.empty((n, 3))
         sc, sh = self._xf(scale, shift)
-        self._call("mcpm_read_grad", A.stream(), A.ptr(pos), A.ptr(mesh), nm, A.ptr(cot), n, *ms[-3:], order, sc, sh,
-                   A.ptr(out), 0)
+        fn, oa = self._win("mcpm_read_grad", order, kb_kcut)
+        self._call(fn, A.stream(), A.ptr(pos), A.ptr(mesh), nm, A.ptr(cot), n, *ms[-3:], *oa, sc, sh, A.ptr(out), 0)
         return out
 
     def paint_vjp(self, pos, mesh_bar, weights=None, wscalar=1.0, order=2, scale=None, shift=0.0, want_pos=True,
-                  want_weights=True):
+                  want_weights=True, kb_kcut=0.0):
         A = self.A
         pos, mesh_bar = A.prepare(pos), A.prepare(mesh_bar)
         weights = None if weights is None else A.prepare(weights)
@@ -150,8 +158,9 @@ class Ops:
         pb = A.empty((n, 3)) if want_pos else None
         wb = A.empty((n,)) if want_weights else None
         sc, sh = self._xf(scale, shift)
-        self._call("mcpm_paint_vjp", A.stream(), A.ptr(pos), A.ptr(weights), wscalar, A.ptr(mesh_bar), n,
-                   *A.shape(mesh_bar), order, sc, sh, A.ptr(pb), A.ptr(wb), 0)
+        fn, oa = self._win("mcpm_paint_vjp", order, kb_kcut)
+        self._call(fn, A.stream(), A.ptr(pos), A.ptr(weights), wscalar, A.ptr(mesh_bar), n, *A.shape(mesh_bar), *oa, sc,
+                   sh, A.ptr(pb), A.ptr(wb), 0)
         return pb, wb
 
     def paint3(self, pos, vals3, shape, vscale=1.0, order=2):
@@ -234,11 +243,12 @@ class Ops:
                    math.prod(A.shape(h6)[1:]))
         return out
 
-    def deconv(self, meshk, order=2):
+    def deconv(self, meshk, order=2, kb_kcut=0.0):
         A = self.A
         meshk = A.prepare(meshk, "c64")
         out = A.empty(A.shape(meshk), "c64")
-        self._call("mcpm_deconv", A.stream(), A.ptr(meshk), A.ptr(out), *ch2rshape(A.shape(meshk)), order)
+        fn, oa = self._win("mcpm_deconv", order, kb_kcut)
+        self._call(fn, A.stream(), A.ptr(meshk), A.ptr(out), *ch2rshape(A.shape(meshk)), *oa)
         return out
 
     def interlace_combine(self, in_m, scale=1.0, deconv_order=0):
@@ -372,18 +382,19 @@ class Ops:
         return coef
 
     def nufft_paint(self, pos, paint_shape, weights=None, wscalar=1.0, scale=None, paint_order=2, interlace_order=2,
-                    paint_deconv=True):
+                    paint_deconv=True, kb_kcut=0.0):
         A = self.A
         pos = A.prepare(pos)
         weights = None if weights is None else A.prepare(weights)
         out = A.empty(r2chshape(paint_shape), "c64")
         sc, _ = self._xf(scale, 0.0)
-        self._call("mcpm_nufft", self.engine(paint_shape).handle, A.stream(), A.ptr(pos), A.ptr(weights), wscalar,
-                   A.shape(pos)[0], sc, paint_order, interlace_order, int(paint_deconv), A.ptr(out))
+        fn, oa = self._win("mcpm_nufft", paint_order, kb_kcut)
+        self._call(fn, self.engine(paint_shape).handle, A.stream(), A.ptr(pos), A.ptr(weights), wscalar,
+                   A.shape(pos)[0], sc, *oa, interlace_order, int(paint_deconv), A.ptr(out))
         return out
 
     def nufft_paint_vjp(self, pos, outbar, paint_shape, weights=None, wscalar=1.0, scale=None, paint_order=2,
-                        interlace_order=2, paint_deconv=True, want_pos=True, want_weights=True):
+                        interlace_order=2, paint_deconv=True, want_pos=True, want_weights=True, kb_kcut=0.0):
         A = self.A
         pos, outbar = A.prepare(pos), A.prepare(outbar, "c64")
         weights = None if weights is None else A.prepare(weights)
@@ -391,8 +402,9 @@ class Ops:
         pb = A.empty((n, 3)) if want_pos else None
         wb = A.empty((n,)) if want_weights else None
         sc, _ = self._xf(scale, 0.0)
-        self._call("mcpm_nufft_vjp", self.engine(paint_shape).handle, A.stream(), A.ptr(pos), A.ptr(weights), wscalar,
-                   n, sc, paint_order, interlace_order, int(paint_deconv), A.ptr(outbar), A.ptr(pb), A.ptr(wb))
+        fn, oa = self._win("mcpm_nufft_vjp", paint_order, kb_kcut)
+        self._call(fn, self.engine(paint_shape).handle, A.stream(), A.ptr(pos), A.ptr(weights), wscalar,
+                   n, sc, *oa, interlace_order, int(paint_deconv), A.ptr(outbar), A.ptr(pb), A.ptr(wb))
         return pb, wb
 
     # ------------------------------------------------------------------------------------------------ glue

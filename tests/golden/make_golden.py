@@ -86,6 +86,9 @@ def main():
         d[f"read_{o}"] = A(nbody.read(jnp.asarray(pos), jnp.asarray(mesh), o))
     d["paint_kb_4"] = A(nbody.paint(jnp.asarray(pos), shape, jnp.asarray(wts), 4, "kaiser_bessel", 1.5))
     d["read_kb_4"] = A(nbody.read(jnp.asarray(pos), jnp.asarray(mesh), 4, "kaiser_bessel", 1.5))
+    for o, ov in ((1, 1.0), (2, 2.0), (3, 1.25)):
+        d[f"paint_kb_{o}"] = A(nbody.paint(jnp.asarray(pos), shape, jnp.asarray(wts), o, "kaiser_bessel", ov))
+        d[f"read_kb_{o}"] = A(nbody.read(jnp.asarray(pos), jnp.asarray(mesh), o, "kaiser_bessel", ov))
     out["paint_read"] = d
 
     # ---- chreshape: crop and pad, non-cubic ---------------------------------------------------------------------
@@ -116,7 +119,13 @@ def main():
     d["deconv_real_in"] = rmesh
     d["deconv_real_2"] = A(nbody.deconv_paint(jnp.asarray(rmesh), 2))
     cm = np.fft.rfftn(rmesh)
-    d["deconv_cplx_3"] = A(nbody.deconv_paint(jnp.asarray(cm), 3))
+    d["deconv_cplx_3"] = A(nbody.deconv_paint(jnp.asarray(cm.copy()), 3))  # the reference divides in place
+    # Kaiser-Bessel window through the same chain (nbody.py:280-312, 321-322, 383-384)
+    d["deconv_kb_real_4"] = A(nbody.deconv_paint(jnp.asarray(rmesh), 4, "kaiser_bessel", 1.5))
+    d["deconv_kb_cplx_2"] = A(nbody.deconv_paint(jnp.asarray(cm.copy()), 2, "kaiser_bessel", 2.0))
+    d["interlace_kb_4_2"] = A(nbody.interlace(jnp.asarray(pos), final, jnp.asarray(wts), 4, 2, "kaiser_bessel", 1.5))
+    d["nufft_kb_over15"] = A(nbody.nufft(jnp.asarray(pos), final, 1.5, jnp.asarray(wts), 4, 2, "kaiser_bessel"))
+    d["nufft_kb_tuple_o2"] = A(nbody.nufft(jnp.asarray(pos), final, (12, 10, 14), jnp.asarray(wts), 2, 2, "kaiser_bessel"))
     out["nufft"] = d
 
     # ---- growth tables ------------------------------------------------------------------------------------------

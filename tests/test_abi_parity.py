@@ -144,6 +144,90 @@ def test_paint_read_vjp(ops, order):
     assert rel(ops.paint3(pos, cot, shape, 1.0, order), ref) < 2e-6
 
 
+# ------------------------------------------------------------------------------------------------ Kaiser-Bessel window
+@pytest.mark.parametrize("order,oversamp", [(1, 1.0), (2, 2.0), (3, 1.25), (4, 1.5)])
+def test_kaiser_bessel_paint_read_golden(ops, golden, order, oversamp):
+    """kernel_type='kaiser_bessel' (nbody.py:280-290, 383-384, 415-416) vs the reference source: 2e-5 as the rectangular
+    family (float32 positions up to +-40 cells; I0 in float32)."""
+    g = golden("paint_read")
+    shape = tuple(int(s) for s in g["shape"])
+    kc = float(O.optim_kcut(oversamp))
+    assert rel(ops.paint(f32(g["pos"]), shape, f32(g["weights"]), order=order, kb_kcut=kc), g[f"paint_kb_{order}"]) < 2e-5
+    assert rel(ops.read(f32(g["pos"]), f32(g["mesh"]), order=order, kb_kcut=kc), g[f"read_kb_{order}"]) < 2e-5
+
+
+@pytest.mark.parametrize("order", [2, 3, 4])
+def test_kaiser_bessel_vjp_and_transform(ops, order):
+    """Same float32 inputs on both sides: paint / read 5e-6; the window-gradient gathers vs oracle autograd (I1 through
+    torch.special.i0) 2e-5; in-kernel position transform; read = paint^T."""
+    rng = np.random.default_rng(40 + order)
+    shape = (8, 10, 6)
+    pos = f32(rng.uniform(-3, 12, (600, 3)))
+    w = f32(rng.uniform(0.5, 1.5, 600))
+    mesh = f32(rng.normal(size=shape))
+    mbar = f32(rng.normal(size=shape))
+    ov = 1.5
+    kc = float(O.optim_kcut(ov))
+    scale, shift = (1.25, 1.0, 0.75), 0.5
+    assert rel(ops.paint(pos, shape, w, order=order, kb_kcut=kc),
+               O.paint(T(pos), shape, T(w), order, "kaiser_bessel", ov).numpy()) < 5e-6
+    assert rel(ops.read(pos, mesh, order=order, kb_kcut=kc),
+               O.read(T(pos), T(mesh), order, "kaiser_bessel", ov).numpy()) < 5e-6
+    p = T(pos).requires_grad_()
+    wt = T(w).requires_grad_()
+    xs = p * T(f32(scale)) + shift
+    (O.paint(xs, shape, wt * 0.7, order, "kaiser_bessel", ov) * T(mbar)).sum().backward()
+    pb, wb = ops.paint_vjp(pos, mbar, w, 0.7, order, scale, shift, kb_kcut=kc)
+    assert rel(pb, p.grad.numpy()) < 2e-5
+    assert rel(wb, wt.grad.numpy()) < 2e-5
+    m3 = f32(rng.normal(size=(3, *shape)))
+    cot = f32(rng.normal(size=(600, 3)))
+    p = T(pos).requires_grad_()
+    sum((O.read(p, T(m3[i]), order, "kaiser_bessel", ov) * T(cot[:, i])).sum() for i in range(3)).backward()
+    assert rel(ops.read_grad(pos, m3, cot, order, kb_kcut=kc), p.grad.numpy()) < 2e-5
+    painted = to_numpy(ops.paint(pos, shape, w, order=order, kb_kcut=kc)).astype(np.float64)
+    lhs = float((to_numpy(ops.read(pos, mesh, order=order, kb_kcut=kc)).astype(np.float64) * w).sum())
+    rhs = float((mesh.astype(np.float64) * painted).sum())
+    assert abs(lhs - rhs) < 1e-4 * max(abs(lhs), 1.0)
+
+
+def test_kaiser_bessel_deconv_and_nufft_golden(ops, golden):
+    """deconv_paint / interlace / nufft with the Kaiser-Bessel window (nbody.py:293-312, 321-322, 532-577) vs the
+    reference source, and the VJP of the fused nufft vs oracle autograd."""
+    g = golden("nufft")
+    final = tuple(int(s) for s in g["final_shape"])
+    pos, w = f32(g["pos"]), f32(g["weights"])
+    cm = np.fft.rfftn(g["deconv_real_in"])
+    assert rel(ops.deconv(c64(cm), 2, kb_kcut=float(O.optim_kcut(2.0))), g["deconv_kb_cplx_2"]) < 5e-6
+    out = ops.irfftn(ops.deconv(ops.rfftn(f32(g["deconv_real_in"])), 4, kb_kcut=float(O.optim_kcut(1.5))))
+    assert rel(out, g["deconv_kb_real_4"]) < 5e-6
+    kc = float(O.optim_kcut(1.5))
+    assert rel(ops.nufft_paint(pos, final, w, paint_order=4, paint_deconv=False, kb_kcut=kc), g["interlace_kb_4_2"]) < 2e-5
+    ps = O.scale_shape(final, 1.5)
+    sc = tuple(np.divide(ps, final))
+    out = ops.chreshape(ops.nufft_paint(pos, ps, w, scale=sc, paint_order=4, kb_kcut=kc), O.r2chshape(final))
+    assert rel(out, g["nufft_kb_over15"]) < 2e-5
+    ps = (12, 10, 14)
+    ov = float(np.exp(np.log(np.divide(final, ps)).mean()))  # nbody.py:566
+    kc2 = float(O.optim_kcut(ov))
+    out = ops.chreshape(ops.nufft_paint(pos, ps, w, scale=tuple(np.divide(ps, final)), kb_kcut=kc2), O.r2chshape(final))
+    assert rel(out, g["nufft_kb_tuple_o2"]) < 2e-5
+    # VJP
+    rng = np.random.default_rng(13)
+    sc = tuple(np.divide(ps, final))
+    cs = O.r2chshape(ps)
+    obar = c64(rng.normal(size=cs) + 1j * rng.normal(size=cs))
+    p, wt = T(pos).requires_grad_(), T(w).requires_grad_()
+    o = O.interlace(p * T(f32(sc)), ps, wt * 0.8, 4, 2, "kaiser_bessel", 1.5) * float(np.prod(sc))
+    o = O.deconv_paint(o, 4, "kaiser_bessel", 1.5)
+    assert rel(ops.nufft_paint(pos, ps, w, 0.8, sc, 4, 2, True, kb_kcut=kc), o.detach().numpy()) < 2e-5
+    ob = T(obar, torch.complex128)
+    (o.real * ob.real + o.imag * ob.imag).sum().backward()
+    pb, wb = ops.nufft_paint_vjp(pos, obar, ps, w, 0.8, sc, 4, 2, True, kb_kcut=kc)
+    assert rel(pb, p.grad.numpy()) < 5e-5
+    assert rel(wb, wt.grad.numpy()) < 5e-5
+
+
 # ------------------------------------------------------------------------------------------------ Fourier passes
 def test_fft_roundtrip(ops):
     rng = np.random.default_rng(3)

@@ -65,10 +65,49 @@ def test_paint_read_autograd(nb):
         lo.backward()
         assert abs(float(loss.detach()) - float(lo.detach())) < 1e-4 * abs(float(lo.detach()))
         assert rel(p.grad, po.grad) < 1e-5 and rel(ww.grad, wo.grad) < 1e-5 and rel(m.grad, mo.grad) < 1e-5
-    with pytest.raises(NotImplementedError):
-        nb.paint(pos, shape, 1.0, 2, kernel_type="kaiser_bessel")
     with pytest.raises(ValueError):
         nb.paint(pos, shape, 1.0, 2, kernel_type="nope")
+
+
+def test_kaiser_bessel_window_autograd(nb, golden):
+    """kernel_type='kaiser_bessel' through the reference-named callables (paint, read, deconv_paint, interlace, nufft;
+    nbody.py:280-312, 321-322, 383-384, 415-416) with autograd, vs the oracle's autograd and the golden vectors."""
+    rng = np.random.default_rng(41)
+    shape = (8, 6, 10)
+    pos = torch.tensor(rng.uniform(-2, 12, (300, 3)), dtype=torch.float32)
+    w = torch.tensor(rng.uniform(0.5, 1.5, 300), dtype=torch.float32)
+    mbar = torch.tensor(rng.normal(size=shape), dtype=torch.float32)
+    mesh = torch.tensor(rng.normal(size=shape), dtype=torch.float32)
+    for order, ov in ((2, 2.0), (4, 1.5)):
+        p, ww, m = leaf(pos, nb), leaf(w, nb), leaf(mesh, nb)
+        loss = (nb.paint(p, shape, ww, order, "kaiser_bessel", ov) * mbar.to(dev(nb))).sum() \
+            + (nb.read(p, m, order, "kaiser_bessel", ov) * ww).sum()
+        loss.backward()
+        po, wo, mo = leaf(pos, dtype=torch.float64), leaf(w, dtype=torch.float64), leaf(mesh, dtype=torch.float64)
+        lo = (O.paint(po, shape, wo, order, "kaiser_bessel", ov) * mbar.double()).sum() \
+            + (O.read(po, mo, order, "kaiser_bessel", ov) * wo).sum()
+        lo.backward()
+        assert abs(float(loss.detach()) - float(lo.detach())) < 1e-4 * abs(float(lo.detach()))
+        assert rel(p.grad, po.grad) < 2e-5 and rel(ww.grad, wo.grad) < 2e-5 and rel(m.grad, mo.grad) < 2e-5
+    g = golden("nufft")
+    final = tuple(int(s) for s in g["final_shape"])
+    gp = torch.tensor(g["pos"], dtype=torch.float32, device=dev(nb))
+    gw = torch.tensor(g["weights"], dtype=torch.float32, device=dev(nb))
+    assert rel(nb.nufft(gp, final, 1.5, gw, 4, 2, "kaiser_bessel"), g["nufft_kb_over15"]) < 2e-5
+    assert rel(nb.nufft(gp, final, (12, 10, 14), gw, 2, 2, "kaiser_bessel"), g["nufft_kb_tuple_o2"]) < 2e-5
+    assert rel(nb.interlace(gp, final, gw, 4, 2, "kaiser_bessel", 1.5), g["interlace_kb_4_2"]) < 2e-5
+    rm = torch.tensor(g["deconv_real_in"], dtype=torch.float32, device=dev(nb))
+    assert rel(nb.deconv_paint(rm, 4, "kaiser_bessel", 1.5), g["deconv_kb_real_4"]) < 5e-6
+    # gradient through nufft with the Kaiser-Bessel window
+    cs = O.r2chshape(final)
+    cot = torch.tensor(rng.normal(size=cs) + 1j * rng.normal(size=cs), dtype=torch.complex64)
+    p, ww = leaf(gp.cpu(), nb), leaf(gw.cpu(), nb)
+    out = nb.nufft(p, final, 1.5, ww, 4, 2, "kaiser_bessel")
+    torch.view_as_real(out * cot.to(dev(nb)).conj()).select(-1, 0).sum().backward()
+    po, wo = leaf(gp.cpu(), dtype=torch.float64), leaf(gw.cpu(), dtype=torch.float64)
+    oo = O.nufft(po, final, 1.5, wo, 4, 2, "kaiser_bessel")
+    (oo * cot.to(torch.complex128).conj()).real.sum().backward()
+    assert rel(out, oo) < 2e-5 and rel(p.grad, po.grad) < 1e-4 and rel(ww.grad, wo.grad) < 1e-4
 
 
 def test_fft_chreshape_deconv_autograd(nb):

@@ -45,6 +45,16 @@ def test_paint_read_kaiser_bessel(golden):
     shape = tuple(int(s) for s in g["shape"])
     close(O.paint(g["pos"], shape, g["weights"], 4, "kaiser_bessel", 1.5), g["paint_kb_4"])
     close(O.read(g["pos"], g["mesh"], 4, "kaiser_bessel", 1.5), g["read_kb_4"])
+    for o, ov in ((1, 1.0), (2, 2.0), (3, 1.25)):
+        close(O.paint(g["pos"], shape, g["weights"], o, "kaiser_bessel", ov), g[f"paint_kb_{o}"])
+        close(O.read(g["pos"], g["mesh"], o, "kaiser_bessel", ov), g[f"read_kb_{o}"])
+    g = golden("nufft")
+    final = tuple(int(s) for s in g["final_shape"])
+    close(O.deconv_paint(O._t(g["deconv_real_in"]), 4, "kaiser_bessel", 1.5), g["deconv_kb_real_4"])
+    close(O.deconv_paint(O._t(np.fft.rfftn(g["deconv_real_in"]), O.C128), 2, "kaiser_bessel", 2.0), g["deconv_kb_cplx_2"])
+    close(O.interlace(g["pos"], final, g["weights"], 4, 2, "kaiser_bessel", 1.5), g["interlace_kb_4_2"])
+    close(O.nufft(g["pos"], final, 1.5, g["weights"], 4, 2, "kaiser_bessel"), g["nufft_kb_over15"])
+    close(O.nufft(g["pos"], final, (12, 10, 14), g["weights"], 2, 2, "kaiser_bessel"), g["nufft_kb_tuple_o2"])
 
 
 @pytest.mark.parametrize("tag", ["down", "up", "mixed", "same"])

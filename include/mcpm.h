@@ -198,6 +198,17 @@ int mcpm_hessian_spectra_slab(void* stream, const void* delta_k, void* out6, int
 int mcpm_hessian_spectra_T_slab(void* stream, const void* in6, void* out1, int nx, int ny, int nz, int ny_loc, int y0,
                                 int lap_fd, int grad_fd, int half_weights, int accumulate, float norm);
 
+/* interlace combine and its transpose on the local ky block (the slab-decomposed final paint of the model).  _T:
+ * out_i = norm * conj(kernel_i) * in, divided by the Hermitian weight w' when half_weights != 0. */
+int mcpm_interlace_combine_slab(void* stream, const void* in_m, void* out, int m, int nx, int ny, int nz, int ny_loc,
+                                int y0, float scale, int deconv_order);
+int mcpm_interlace_combine_T_slab(void* stream, const void* in, void* out_m, int m, int nx, int ny, int nz, int ny_loc,
+                                  int y0, float scale, int deconv_order, int half_weights, float norm);
+/* out (+)= a * w' * in  (inverse = 0)  or  a / w' * in  (inverse != 0) on any block of a half spectrum whose fastest
+ * axis is the whole kz axis: the weights of mcpm_hermitian_weights for callers that keep their own 1/N. */
+int mcpm_half_weight_axpy(void* stream, const void* in, void* out, int64_t nc, int nz, float a, int inverse,
+                          int accumulate);
+
 /* Fused x-transform passes (CUDA build, nx in {64, 128, 256, 512, 1024}; MCPM_EUNSUP otherwise), on a half spectrum
  * [nx, ny_loc, nz/2+1] that has been transformed along (y,z) only:
  *   xfuse_force   : out3[j] = IFFT_x( force kernel_j * FFT_x(in) )            = mcpm_force_spectra between the x-passes

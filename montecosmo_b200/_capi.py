@@ -59,6 +59,9 @@ SIGNATURES = {
     "mcpm_force_spectra_T_slab": ([vp, vp, vp] + MESH + [i32, i32, i32, i32, f32, i32, i32, i32, f32], i32),
     "mcpm_hessian_spectra_slab": ([vp, vp, vp] + MESH + [i32, i32, i32, i32, f32], i32),
     "mcpm_hessian_spectra_T_slab": ([vp, vp, vp] + MESH + [i32, i32, i32, i32, i32, i32, f32], i32),
+    "mcpm_interlace_combine_slab": ([vp, vp, vp, i32] + MESH + [i32, i32, f32, i32], i32),
+    "mcpm_interlace_combine_T_slab": ([vp, vp, vp, i32] + MESH + [i32, i32, f32, i32, i32, f32], i32),
+    "mcpm_half_weight_axpy": ([vp, vp, vp, i64, i32, f32, i32, i32], i32),
     "mcpm_chreshape": ([vp, vp] + MESH + [vp] + MESH, i32),
     "mcpm_chreshape_vjp": ([vp, vp] + MESH + [vp] + MESH, i32),
     "mcpm_spectrum_bins": ([vp, vp, vp] + MESH + [f64, f64, f64, vp, i32, i32, i32, vp], i32),

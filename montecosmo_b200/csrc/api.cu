@@ -370,6 +370,37 @@ int mcpm_interlace_combine_T(void* stream, const void* in, void* out_m, int m, i
   API_END
 }
 
+int mcpm_interlace_combine_slab(void* stream, const void* in_m, void* out, int m, int nx, int ny, int nz, int ny_loc,
+                                int y0, float scale, int deconv_order) {
+  API_BEGIN
+  NEED(ny_loc > 0 && y0 >= 0 && y0 + ny_loc <= ny, "interlace_combine_slab: bad ky block");
+  SlabK sk;
+  sk.ny_loc = ny_loc;
+  sk.y0 = y0;
+  return interlace_combine(as_stream(stream), C(in_m), C(out), m, nx, ny, nz, scale, deconv_order, sk);
+  API_END
+}
+
+int mcpm_interlace_combine_T_slab(void* stream, const void* in, void* out_m, int m, int nx, int ny, int nz, int ny_loc,
+                                  int y0, float scale, int deconv_order, int half_weights, float norm) {
+  API_BEGIN
+  NEED(ny_loc > 0 && y0 >= 0 && y0 + ny_loc <= ny, "interlace_combine_T_slab: bad ky block");
+  SlabK sk;
+  sk.ny_loc = ny_loc;
+  sk.y0 = y0;
+  return interlace_combine_T(as_stream(stream), C(in), C(out_m), m, nx, ny, nz, scale, deconv_order, norm, sk,
+                             half_weights);
+  API_END
+}
+
+int mcpm_half_weight_axpy(void* stream, const void* in, void* out, int64_t nc, int nz, float a, int inverse,
+                          int accumulate) {
+  API_BEGIN
+  NEED(in && out && nc >= 0, "half_weight_axpy: bad arguments");
+  return half_weight_axpy(as_stream(stream), C(in), C(out), nc, nz, a, inverse, accumulate);
+  API_END
+}
+
 // ---- slab-decomposed building blocks ----------------------------------------------------------------------------
 int mcpm_slabfft_create(int nx, int ny, int nz, int parts, mcpm_slabfft** out) {
   API_BEGIN

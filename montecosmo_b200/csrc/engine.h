@@ -84,9 +84,10 @@ int lpt2_source(stream_t, const float* h6, float* d2, int64_t n);
 int lpt2_source_vjp(stream_t, const float* h6, const float* d2bar, float* hbar6, int64_t n);
 int deconv(stream_t, const cfloat* in, cfloat* out, int nx, int ny, int nz, int order, float kb_kcut = 0.0f);
 int interlace_combine(stream_t, const cfloat* in_m, cfloat* out, int m, int nx, int ny, int nz, float scale,
-                      int deconv_order);
+                      int deconv_order, SlabK sk = SlabK());
 int interlace_combine_T(stream_t, const cfloat* in, cfloat* out_m, int m, int nx, int ny, int nz, float scale,
-                        int deconv_order, float norm);
+                        int deconv_order, float norm, SlabK sk = SlabK(), int half_weights = 1);
+int half_weight_axpy(stream_t, const cfloat* in, cfloat* out, int64_t nc, int nz, float a, int inverse, int accumulate);
 int scale_spectrum(stream_t, const cfloat* in, const float* t, cfloat* out, int64_t nc);
 int scale_real(stream_t, const float* in, float s, float* out, int64_t n);
 int chreshape(stream_t, const cfloat* in, int inx, int iny, int inz, cfloat* out, int onx, int ony, int onz);

@@ -176,14 +176,14 @@ int deconv(stream_t st, const cfloat* in, cfloat* out, int nx, int ny, int nz, i
 
 // out = scale / W^p * (1/m) sum_i in_i exp(+i (i/m)(kx+ky+kz))      (nbody.py:523-526, 571-574)
 int interlace_combine(stream_t st, const cfloat* in_m, cfloat* out, int m, int nx, int ny, int nz, float scale,
-                      int deconv_order) {
+                      int deconv_order, SlabK sk) {
   if (int e = check_dims(nx, ny, nz)) return e;
   if (m < 1 || m > 8) {
     set_error("interlace order must be in 1..8");
     return MCPM_EINVAL;
   }
-  KGrid g = make_kgrid(nx, ny, nz);
-  const int64_t nc = (int64_t)nx * ny * g.nzc;
+  KGrid g = make_kgrid(nx, ny, nz, 0, 0, sk);
+  const int64_t nc = (int64_t)nx * g.ny_loc * g.nzc;
   const float invm = 1.0f / (float)m;
   launch_1d(st, nc, [=] MCPM_LAMBDA(int64_t e) {
     int l;
@@ -207,20 +207,21 @@ int interlace_combine(stream_t st, const cfloat* in_m, cfloat* out, int m, int n
 // transpose: out_i = (norm / w') * conj(kernel_i) * in.  The paint-mesh cotangent is irfftn(out_i) with norm = N,
 // or a raw (unnormalised) C2R of out_i with norm = 1.
 int interlace_combine_T(stream_t st, const cfloat* in, cfloat* out_m, int m, int nx, int ny, int nz, float scale,
-                        int deconv_order, float norm) {
+                        int deconv_order, float norm, SlabK sk, int half_weights) {
   if (int e = check_dims(nx, ny, nz)) return e;
   if (m < 1 || m > 8) {
     set_error("interlace order must be in 1..8");
     return MCPM_EINVAL;
   }
-  KGrid g = make_kgrid(nx, ny, nz);
-  const int64_t nc = (int64_t)nx * ny * g.nzc;
+  KGrid g = make_kgrid(nx, ny, nz, 0, 0, sk);
+  const int64_t nc = (int64_t)nx * g.ny_loc * g.nzc;
   const float invm = 1.0f / (float)m;
   launch_1d(st, nc, [=] MCPM_LAMBDA(int64_t e) {
     int l;
     KVec k = kvec_at(g, e, l);
     float ks = k.kx + k.ky + k.kz;
-    float c = scale * invm * norm / half_weight(l, g.nz);
+    float c = scale * invm * norm;
+    if (half_weights) c /= half_weight(l, g.nz);
     if (deconv_order > 0) c /= window_hat(k, deconv_order);
     cfloat v = in[e];
     for (int i = 0; i < m; ++i) {
@@ -262,6 +263,31 @@ int hermitian_weights(stream_t st, const cfloat* in, cfloat* out, int nx, int ny
     out[e] = cfloat{v.re * c, v.im * c};
   });
   return rt_check("hermitian_weights");
+}
+
+// out (+)= a * w'(kz) * in, or a / w' * in when inverse != 0, on any block of a half spectrum whose fastest axis is the
+// full kz axis (nzc = nz/2+1 entries): the Hermitian weights of hermitian_weights above without the 1/N bookkeeping,
+// for callers that keep their own normalisation (the slab-decomposed model, whose distributed FFTs are unnormalised).
+int half_weight_axpy(stream_t st, const cfloat* in, cfloat* out, int64_t nc, int nz, float a, int inverse,
+                     int accumulate) {
+  if (nz <= 0 || (nz & 1)) {
+    set_error("half_weight_axpy: nz must be positive and even");
+    return MCPM_EINVAL;
+  }
+  const int nzc = nz / 2 + 1;
+  launch_1d(st, nc, [=] MCPM_LAMBDA(int64_t e) {
+    int l = (int)(e % nzc);
+    float w = half_weight(l, nz);
+    float c = inverse ? a / w : a * w;
+    cfloat v = in[e];
+    if (accumulate) {
+      cfloat o = out[e];
+      out[e] = cfloat{o.re + v.re * c, o.im + v.im * c};
+    } else {
+      out[e] = cfloat{v.re * c, v.im * c};
+    }
+  });
+  return rt_check("half_weight_axpy");
 }
 
 // ---------------------------------------------------------------------------------------------------- spectrum

@@ -159,9 +159,20 @@ class SlabPM:
         self._call("mcpm_slabfft_c2c_x", self._fft, self._st(), c.data_ptr(), c.shape[0], 0)
         return c
 
-    def irfftn(self, c, overwrite=False, x_done=False):
+    def _project_yz(self, b):
+        """Hermitian projection along ky of the self-conjugate planes kz = 0 and kz = Nyquist of b [nb, xl, ny, nzc], in
+        place.  After the inverse x-transform this equals the 3-D projection jnp.fft.irfftn applies implicitly (it
+        returns the real part of the full inverse transform); cuFFT's 2-D C2R on inconsistent input is algorithm
+        dependent (Hermitian consistency).  Two planes out of nz/2+1: negligible traffic."""
+        idx = (-torch.arange(self.ny, device=b.device)) % self.ny
+        for l in (0, self.nz // 2):
+            col = b[..., l]
+            b[..., l] = 0.5 * (col + col[..., idx].conj())
+
+    def irfftn(self, c, overwrite=False, x_done=False, project=False):
         """[nb, nx, kyl, nzc] complex -> [nb, xl, ny, nz] real, UNNORMALISED (fold 1/N into the preceding Fourier pass).
-        x_done: the inverse transform along x has already been applied (fused x-transform kernels)."""
+        x_done: the inverse transform along x has already been applied (fused x-transform kernels).
+        project: the input is not Hermitian-consistent by construction (a cotangent, an interlaced sum): project it."""
         c = self.A.prepare(c, "c64")
         if not overwrite:
             c = c.clone()
@@ -171,6 +182,8 @@ class SlabPM:
         send = c.view(nb, self.P, self.xl, self.kyl, self.nzc).permute(1, 0, 2, 3, 4).contiguous()
         recv = self._a2a(send)  # recv[q] = my planes, rank q's ky rows
         b = recv.permute(1, 2, 0, 3, 4).contiguous().view(nb, self.xl, self.ny, self.nzc)
+        if project:
+            self._project_yz(b)
         out = self.A.empty((nb, self.xl, self.ny, self.nz))
         self._call("mcpm_slabfft_c2r_yz", self._fft, self._st(), b.data_ptr(), out.data_ptr(), nb)
         return out

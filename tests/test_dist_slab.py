@@ -116,3 +116,103 @@ def test_slab_engine_world2_gloo(shape, halo):
         assert res["pos"] < 1e-4 and res["vel"] < 1e-4, res
         assert res["steps_bwd"] < 5e-4 and res["lpt_bwd"] < 5e-4 and res["dkbar"] < 5e-4, res
         assert res["disp_rms"] > 0.2, res  # the comparison above is on a genuinely displaced lattice
+
+
+def _model_worker(rank, world, port, shape, halo, kw, q):
+    try:
+        sys.path.insert(0, ROOT)
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2")
+        import torch.distributed as dist
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from oracle import cpu_port
+        import montecosmo_b200.nbody as nbody
+        from montecosmo_b200.dist import SlabPM
+        from montecosmo_b200.dist_model import SlabFieldModel
+        from montecosmo_b200.model import FieldModel
+        ops = cpu_port.cpu_ops()
+        nbody._OPS = ops  # the single-process model of this (CPU) test runs on the same checker library
+        box = tuple(40.0 * s for s in shape)
+        rng = np.random.default_rng(3)  # same global fields on every rank
+        white = torch.tensor(rng.normal(size=shape).astype(np.float32))
+        truth = torch.tensor(rng.normal(size=shape).astype(np.float32))
+        ref = FieldModel(shape, box, "nbody", a_start=0.1, **kw)
+        obs = ref.evolve(truth).detach() + torch.tensor(rng.normal(size=shape).astype(np.float32))
+        lp_ref, f_ref = ref.value_and_force(white, obs)
+        pm = SlabPM(ops, shape, halo=halo)
+        mdl = SlabFieldModel(pm, box, a_start=0.1, **kw)
+        sl = slice(pm.x0, pm.x0 + pm.xl)
+        lp, f = mdl.value_and_force(white[sl].contiguous(), obs[sl].contiguous())
+        rel = lambda a, b: float(np.linalg.norm((np.asarray(a) - np.asarray(b)).ravel()) / np.linalg.norm(np.asarray(b).ravel()))
+        res = {"lp": abs(float(lp) - float(lp_ref)) / abs(float(lp_ref)), "force": rel(f.numpy(), f_ref.numpy()[sl]),
+               "pred": rel(mdl.predict(truth[sl].contiguous()).numpy(), ref.evolve(truth).detach().numpy()[sl]),
+               "force_norm": float(np.linalg.norm(f_ref.numpy() + white.numpy()))}
+        q.put((rank, res, None))
+        dist.destroy_process_group()
+    except Exception:
+        import traceback
+        q.put((rank, None, traceback.format_exc()))
+
+
+@pytest.mark.parametrize("shape,halo,kw", [
+    ((16, 16, 16), 6, dict(n_steps=2, b1=1.0, rsd=True)),
+    ((24, 16, 20), 8, dict(n_steps=1, b1=0.0, rsd=False, paint_deconv=False, interlace_order=3, lpt_order=1)),
+])
+def test_slab_field_model_world2_gloo(shape, halo, kw):
+    """grad(log-density) of the whole model chain on 2 slabs against the single-process FieldModel (same kernels, same
+    white noise and observation): log-density 1e-5, force and predicted mesh 5e-4 relative L2."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29641 + shape[0]
+    ps = [ctx.Process(target=_model_worker, args=(r, 2, port, shape, halo, kw, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    out = [q.get(timeout=600) for _ in ps]
+    for p in ps:
+        p.join(60)
+    for rank, res, err in out:
+        assert err is None, f"rank {rank}:\n{err}"
+        assert res["lp"] < 1e-5 and res["force"] < 5e-4 and res["pred"] < 5e-4, res
+        assert res["force_norm"] > 1e-3, res  # the likelihood term of the force is not trivially zero
+
+
+@pytest.mark.parametrize("backend", ["hostemu", pytest.param("cuda", marks=pytest.mark.gpu)])
+def test_slab_field_model_single_rank(backend):
+    """The slab model on ONE rank (periodic halos exchanged with itself) against FieldModel: exercises every kernel and
+    the hand-chained reverse sweep of dist_model.py on whichever device the backend names -- on a B200 this is the
+    single-GPU check of the code path the multi-GPU runs take (tools/slab_bench.py --model)."""
+    import montecosmo_b200.nbody as nbody
+    from montecosmo_b200.dist import SlabPM
+    from montecosmo_b200.dist_model import SlabFieldModel
+    from montecosmo_b200.model import FieldModel
+    from montecosmo_b200.ops import Ops
+    old = nbody._OPS
+    try:
+        if backend == "hostemu":
+            from oracle import cpu_port
+            nbody._OPS = cpu_port.cpu_ops()
+        else:
+            from montecosmo_b200 import _lib
+            from montecosmo_b200.ops import TorchCudaAdapter
+            nbody._OPS = Ops(_lib.load(), TorchCudaAdapter())
+        ops = nbody._OPS
+        dev = ops.A.device
+        # 64^3 on the GPU so that the fused x-transform and the brick-tiled scatters (both need nx >= 64) are on the path
+        shape, halo = ((32, 32, 32), 8) if backend == "hostemu" else ((64, 64, 64), 16)
+        box = tuple(20.0 * s for s in shape)
+        rng = np.random.default_rng(5)
+        white = torch.tensor(rng.normal(size=shape).astype(np.float32), device=dev)
+        truth = torch.tensor(rng.normal(size=shape).astype(np.float32), device=dev)
+        kw = dict(n_steps=3, b1=0.7, rsd=True)
+        ref = FieldModel(shape, box, "nbody", a_start=0.1, **kw)
+        obs = ref.evolve(truth).detach() + torch.tensor(rng.normal(size=shape).astype(np.float32), device=dev)
+        lp_ref, f_ref = ref.value_and_force(white, obs)
+        mdl = SlabFieldModel(SlabPM(ops, shape, halo=halo), box, a_start=0.1, **kw)
+        lp, f = mdl.value_and_force(white, obs)
+        rel = lambda a, b: float((a - b).norm() / b.norm())
+        assert abs(float(lp) - float(lp_ref)) < 1e-5 * abs(float(lp_ref))
+        # float32 on both sides, different kernels for the same operators (brick / fused paths vs the slab sequence)
+        assert rel(f, f_ref) < 5e-4
+        assert rel(mdl.predict(truth), ref.evolve(truth).detach()) < 5e-4
+    finally:
+        nbody._OPS = old

@@ -42,6 +42,10 @@ def main():
     ap.add_argument("--halo", type=int, default=24)
     ap.add_argument("--nbody-steps", type=int, default=10)
     ap.add_argument("--check", type=int, default=0)
+    ap.add_argument("--model", action="store_true",
+                    help="time the whole grad(log-density) chain (dist_model.SlabFieldModel: prior, bias weights, RSD, "
+                         "interlaced final paint, likelihood and the full reverse sweep to the white field) instead of "
+                         "nbody_bf forward + reverse alone")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -146,7 +150,18 @@ def main():
     g = torch.Generator(device=dev).manual_seed(9 + rank)
     pb, vb = torch.randn((pm.npl, 3), device=dev, generator=g), torch.randn((pm.npl, 3), device=dev, generator=g)
 
+    if a.model:
+        from montecosmo_b200.dist_model import SlabFieldModel
+        mdl = SlabFieldModel(pm, (2.5 * n,) * 3, n_steps=a.nbody_steps, cosmology=cosmo)
+        gw = torch.Generator(device=dev).manual_seed(77 + rank)
+        white = torch.randn((pm.xl, n, n), device=dev, generator=gw)
+        obs = mdl.predict(torch.randn((pm.xl, n, n), device=dev, generator=gw)) \
+            + torch.randn((pm.xl, n, n), device=dev, generator=gw)
+        del dk
+
     def step():
+        if a.model:
+            return mdl.value_and_force(white, obs)
         pos, vel, tape = pm.nbody_forward(dk, cosmo, 0.0, 1.0, a.nbody_steps)
         return pm.nbody_backward(tape, pb, vb)
 
@@ -175,7 +190,10 @@ def main():
         nfft = 13 + 13 + 8 * a.nbody_steps
         a2a = nfft * 8 * (n ** 3 / 2) / world * (world - 1) / world * 1.004
         halo = a.nbody_steps * (2 + 2 * 4 + 2 * 4 + 2) * pm.H * n * n * 4
-        out.update({"metric": "slab-decomposed nbody_bf forward + reverse sweep, evaluations/s", "mesh": n, "n_gpus": world,
+        if a.model:  # + white rfftn / its transpose, bias irfftn / its transpose, final paint: 2 R2C + 1 C2R and transposes
+            nfft += 2 + 2 + 2 * 3 + 2
+        out.update({"metric": ("slab-decomposed grad(log-density) of the field-level model, evaluations/s" if a.model else
+                               "slab-decomposed nbody_bf forward + reverse sweep, evaluations/s"), "mesh": n, "n_gpus": world,
                     "value": 1e3 / per, "unit": "evals/s", "ms_per_eval": per, "nbody_steps": a.nbody_steps,
                     "halo_planes": pm.H, "max_mem_GiB": float(mem), "fused_x_transform": bool(pm.xfuse), "p2p": pm.p2p_note,
                     "nvlink_GB_out_per_gpu_per_eval": (a2a + halo) / 1e9 if world > 1 else 0.0,

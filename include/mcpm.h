@@ -140,7 +140,10 @@ int mcpm_paint3(void* stream, const float* pos, const float* vals3, float vscale
                 int order, float* mesh3, int accumulate);
 
 /* ---- FFT (jnp.fft.rfftn / irfftn call sites nbody.py:589,603,620,627,630) -------------------------------------
- * batch meshes, contiguous planes.  mcpm_irfftn may overwrite its input (cuFFT C2R). */
+ * batch meshes, contiguous planes.  mcpm_irfftn may overwrite its input (cuFFT C2R).  It accepts ANY complex input, as
+ * jnp.fft.irfftn does (which returns the real part of the full inverse transform): the input is first projected onto
+ * Hermitian symmetry on the planes kz = 0 / Nyquist (mcpm_hermitian_project), because cuFFT's C2R on inconsistent input
+ * is algorithm dependent. */
 int mcpm_rfftn(mcpm_engine* eng, void* stream, const float* in, void* out_c64, int batch);
 int mcpm_irfftn(mcpm_engine* eng, void* stream, void* in_c64, float* out, int batch);
 
@@ -204,6 +207,9 @@ int mcpm_interlace_combine_slab(void* stream, const void* in_m, void* out, int m
                                 int y0, float scale, int deconv_order);
 int mcpm_interlace_combine_T_slab(void* stream, const void* in, void* out_m, int m, int nx, int ny, int nz, int ny_loc,
                                   int y0, float scale, int deconv_order, int half_weights, float norm);
+/* In-place Hermitian projection of `batch` half spectra on the self-conjugate planes kz = 0 and kz = Nyquist:
+ * A(i,j,l) <- (A(i,j,l) + conj A(-i,-j,l)) / 2 -- what jnp.fft.irfftn applies implicitly to its input. */
+int mcpm_hermitian_project(void* stream, void* data_c64, int nx, int ny, int nz, int batch);
 /* out (+)= a * w' * in  (inverse = 0)  or  a / w' * in  (inverse != 0) on any block of a half spectrum whose fastest
  * axis is the whole kz axis: the weights of mcpm_hermitian_weights for callers that keep their own 1/N. */
 int mcpm_half_weight_axpy(void* stream, const void* in, void* out, int64_t nc, int nz, float a, int inverse,

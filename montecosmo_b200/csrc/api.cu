@@ -302,6 +302,8 @@ int mcpm_irfftn(mcpm_engine* eng, void* stream, void* in_c64, float* out, int ba
   NEED(eng && in_c64 && out && batch >= 1, "irfftn: bad arguments");
   BIND(eng);
   stream_t st = as_stream(stream);
+  // jnp.fft.irfftn semantics for ANY input: the Hermitian projection it applies implicitly, made explicit for cuFFT
+  if (int e = hermitian_project(st, C(in_c64), eng->e->nx, eng->e->ny, eng->e->nz, batch)) return e;
   if (int e = fft_c2r(eng->e->fft, st, C(in_c64), out, batch)) return e;
   return scale_real(st, out, eng->e->invN, out, eng->e->N * batch);  // standalone irfftn pays one scaling pass
   API_END
@@ -390,6 +392,13 @@ int mcpm_interlace_combine_T_slab(void* stream, const void* in, void* out_m, int
   sk.y0 = y0;
   return interlace_combine_T(as_stream(stream), C(in), C(out_m), m, nx, ny, nz, scale, deconv_order, norm, sk,
                              half_weights);
+  API_END
+}
+
+int mcpm_hermitian_project(void* stream, void* data_c64, int nx, int ny, int nz, int batch) {
+  API_BEGIN
+  NEED(data_c64 && batch >= 1, "hermitian_project: bad arguments");
+  return hermitian_project(as_stream(stream), C(data_c64), nx, ny, nz, batch);
   API_END
 }
 

@@ -418,6 +418,8 @@ int nufft_vjp(Engine* E, stream_t st, const float* pos, const float* weights, fl
   // out_i = conj(kernel_i) * outbar / w'  (raw C2R supplies the remaining factor N * 1/N)
   TRY(interlace_combine_T(st, outbar_k, E->c(0), m, E->nx, E->ny, E->nz, jac, paint_deconv && !kb ? paint_order : 0,
                           1.0f));
+  // conj(phase_i) breaks Hermitian symmetry on the Nyquist planes exactly as the forward phase does: project (fourier.cu)
+  TRY(hermitian_project(st, E->c(0), E->nx, E->ny, E->nz, m));
   TRY(fft_c2r(E->fft, st, E->c(0), E->r(0), m));
   for (int i = 0; i < m; ++i)
     TRY(paint_vjp(st, pos, weights, wscalar, E->r(i), np, E->nx, E->ny, E->nz, paint_order, scale,

@@ -87,6 +87,7 @@ int interlace_combine(stream_t, const cfloat* in_m, cfloat* out, int m, int nx, 
                       int deconv_order, SlabK sk = SlabK());
 int interlace_combine_T(stream_t, const cfloat* in, cfloat* out_m, int m, int nx, int ny, int nz, float scale,
                         int deconv_order, float norm, SlabK sk = SlabK(), int half_weights = 1);
+int hermitian_project(stream_t, cfloat* data, int nx, int ny, int nz, int batch);
 int half_weight_axpy(stream_t, const cfloat* in, cfloat* out, int64_t nc, int nz, float a, int inverse, int accumulate);
 int scale_spectrum(stream_t, const cfloat* in, const float* t, cfloat* out, int64_t nc);
 int scale_real(stream_t, const float* in, float s, float* out, int64_t n);

@@ -265,6 +265,41 @@ int hermitian_weights(stream_t st, const cfloat* in, cfloat* out, int nx, int ny
   return rt_check("hermitian_weights");
 }
 
+// Hermitian projection of `batch` half spectra, in place, on the two self-conjugate planes kz = 0 and kz = Nyquist:
+//   A(i, j, l) <- (A(i, j, l) + conj A(-i, -j, l)) / 2.
+// jnp.fft.irfftn returns the real part of the full inverse transform, i.e. it applies this projection implicitly
+// (its last-axis C2R ignores the imaginary parts left on those planes after the x and y transforms).  cuFFT's C2R on
+// inconsistent input is algorithm dependent instead: the even-length real transform folds Im X(0) and Im X(N/2) into its
+// output.  Spectra that are not Hermitian by construction -- the interlaced sum (its shift phase breaks the symmetry on
+// the Nyquist planes, nbody.py:524-525), cotangents of free complex arrays, whatever a caller hands mcpm_irfftn -- are
+// therefore projected before their C2R.  One thread per conjugate pair: 2 * nx * ny elements per mesh, negligible.
+int hermitian_project(stream_t st, cfloat* data, int nx, int ny, int nz, int batch) {
+  if (int e = check_dims(nx, ny, nz)) return e;
+  const int nzc = nz / 2 + 1;
+  const int64_t plane = (int64_t)nx * ny;
+  const int64_t nc = plane * nzc;
+  launch_1d(st, (int64_t)batch * 2 * plane, [=] MCPM_LAMBDA(int64_t t) {
+    int64_t r = t % plane;
+    int64_t bw = t / plane;
+    int l = (bw & 1) ? nz / 2 : 0;
+    cfloat* A = data + (bw >> 1) * nc;
+    int i = (int)(r / ny), j = (int)(r % ny);
+    int ip = i ? nx - i : 0, jp = j ? ny - j : 0;
+    int64_t rp = (int64_t)ip * ny + jp;
+    if (rp < r) return;  // the partner's thread handles this pair
+    cfloat a = A[r * nzc + l];
+    if (rp == r) {
+      A[r * nzc + l] = cfloat{a.re, 0.0f};
+      return;
+    }
+    cfloat c = A[rp * nzc + l];
+    cfloat h = cfloat{0.5f * (a.re + c.re), 0.5f * (a.im - c.im)};
+    A[r * nzc + l] = h;
+    A[rp * nzc + l] = cfloat{h.re, -h.im};
+  });
+  return rt_check("hermitian_project");
+}
+
 // out (+)= a * w'(kz) * in, or a / w' * in when inverse != 0, on any block of a half spectrum whose fastest axis is the
 // full kz axis (nzc = nz/2+1 entries): the Hermitian weights of hermitian_weights above without the 1/N bookkeeping,
 // for callers that keep their own normalisation (the slab-decomposed model, whose distributed FFTs are unnormalised).

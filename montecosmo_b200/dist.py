@@ -163,11 +163,9 @@ class SlabPM:
         """Hermitian projection along ky of the self-conjugate planes kz = 0 and kz = Nyquist of b [nb, xl, ny, nzc], in
         place.  After the inverse x-transform this equals the 3-D projection jnp.fft.irfftn applies implicitly (it
         returns the real part of the full inverse transform); cuFFT's 2-D C2R on inconsistent input is algorithm
-        dependent (Hermitian consistency).  Two planes out of nz/2+1: negligible traffic."""
-        idx = (-torch.arange(self.ny, device=b.device)) % self.ny
-        for l in (0, self.nz // 2):
-            col = b[..., l]
-            b[..., l] = 0.5 * (col + col[..., idx].conj())
+        dependent (Hermitian consistency).  The engine's projection kernel with nx = 1: every local x-plane is one
+        2-D spectrum.  Two planes out of nz/2+1: negligible traffic."""
+        self._call("mcpm_hermitian_project", self._st(), b.data_ptr(), 1, self.ny, self.nz, b.shape[0] * b.shape[1])
 
     def irfftn(self, c, overwrite=False, x_done=False, project=False):
         """[nb, nx, kyl, nzc] complex -> [nb, xl, ny, nz] real, UNNORMALISED (fold 1/N into the preceding Fourier pass).

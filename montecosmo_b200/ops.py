@@ -193,6 +193,14 @@ class Ops:
         self._call("mcpm_irfftn", self.engine(rs).handle, A.stream(), A.ptr(meshk), A.ptr(out), batch)
         return out
 
+    def hermitian_project(self, meshk):
+        """In place: the Hermitian projection jnp.fft.irfftn applies implicitly (mcpm_hermitian_project)."""
+        A = self.A
+        ms = A.shape(meshk)
+        batch = 1 if len(ms) == 3 else ms[0]
+        self._call("mcpm_hermitian_project", A.stream(), A.ptr(meshk), *ch2rshape(ms[-3:]), batch)
+        return meshk
+
     def force_spectra(self, dk, lap_fd=INF, grad_fd=INF, kcut=INF, deconv_order=0):
         A = self.A
         dk = A.prepare(dk, "c64")

@@ -238,6 +238,23 @@ def test_fft_roundtrip(ops):
     assert rel(ops.irfftn(ops.rfftn(m[0])), m[0]) < 1e-6
 
 
+@pytest.mark.parametrize("shape", [(8, 6, 10), (12, 12, 4), (32, 32, 32)])
+def test_irfftn_of_non_hermitian_input(ops, shape):
+    """jnp.fft.irfftn accepts any complex array and returns the real part of the full inverse transform.  cuFFT's C2R
+    does not (inconsistent input is algorithm dependent), so mcpm_irfftn projects first.  The projection alone equals
+    rfftn(irfftn(.)).  The 256^3 case, where cuFFT takes another algorithm, is in tests/test_zz_cross_check_256.py."""
+    rng = np.random.default_rng(sum(shape))
+    cs = O.r2chshape(shape)
+    a = c64(rng.normal(size=(2, *cs)) + 1j * rng.normal(size=(2, *cs)))
+    ref = np.fft.irfftn(a.astype(np.complex128), s=shape, axes=(1, 2, 3))
+    assert rel(ops.irfftn(a), ref) < 5e-6
+    proj = to_numpy(ops.hermitian_project(ops.A.prepare(a.copy(), "c64")))
+    assert rel(proj, np.fft.rfftn(ref, axes=(1, 2, 3))) < 5e-6
+    # a Hermitian input is left alone (up to rounding)
+    h = c64(np.fft.rfftn(rng.normal(size=shape)))
+    assert rel(ops.hermitian_project(ops.A.prepare(h.copy(), "c64")), h.astype(np.complex128)) < 1e-7
+
+
 def test_fourier_kernels_golden(ops, golden):
     """force / Hessian / deconvolution kernels vs the reference's kernel arrays on a non-cubic mesh (2e-6).
 

@@ -46,6 +46,9 @@ def main():
                     help="time the whole grad(log-density) chain (dist_model.SlabFieldModel: prior, bias weights, RSD, "
                          "interlaced final paint, likelihood and the full reverse sweep to the white field) instead of "
                          "nbody_bf forward + reverse alone")
+    ap.add_argument("--cell", type=float, default=2.5, help="cell size in Mpc/h (box = cell * mesh); 2.5 = BASELINE C3-C5")
+    ap.add_argument("--model-check", action="store_true",
+                    help="with --model on ONE GPU: compare log-density and force with the single-GPU FieldModel at --mesh")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -146,18 +149,32 @@ def main():
 
     n = a.mesh
     pm = SlabPM(ops, (n, n, n), halo=min(a.halo, n // world))
-    dk = local_delta_k(pm, cosmo, 2.5 * n, 1234)
+    dk = local_delta_k(pm, cosmo, a.cell * n, 1234)
     g = torch.Generator(device=dev).manual_seed(9 + rank)
     pb, vb = torch.randn((pm.npl, 3), device=dev, generator=g), torch.randn((pm.npl, 3), device=dev, generator=g)
 
     if a.model:
         from montecosmo_b200.dist_model import SlabFieldModel
-        mdl = SlabFieldModel(pm, (2.5 * n,) * 3, n_steps=a.nbody_steps, cosmology=cosmo)
+        mdl = SlabFieldModel(pm, (a.cell * n,) * 3, n_steps=a.nbody_steps, cosmology=cosmo)
         gw = torch.Generator(device=dev).manual_seed(77 + rank)
         white = torch.randn((pm.xl, n, n), device=dev, generator=gw)
         obs = mdl.predict(torch.randn((pm.xl, n, n), device=dev, generator=gw)) \
             + torch.randn((pm.xl, n, n), device=dev, generator=gw)
         del dk
+        if a.model_check and world == 1:
+            try:
+                from montecosmo_b200.model import FieldModel
+                ref = FieldModel((n, n, n), (a.cell * n,) * 3, "nbody", n_steps=a.nbody_steps, cosmology=cosmo)
+                lp_ref, f_ref = ref.value_and_force(white, obs)
+                lp, f = mdl.value_and_force(white, obs)
+                out["model_check"] = {"mesh": n, "cell_mpc_h": a.cell, "logp": float(lp), "logp_ref": float(lp_ref),
+                                      "rel_logp_err": abs(float(lp) - float(lp_ref)) / abs(float(lp_ref)),
+                                      "rel_force_err": float((f - f_ref).norm() / f_ref.norm()),
+                                      "force_cosine": float((f * f_ref).sum() / (f.norm() * f_ref.norm()))}
+                del ref, lp_ref, f_ref, lp, f
+                torch.cuda.empty_cache()
+            except Exception as e:  # the timing below still runs
+                out["model_check"] = {"error": f"{type(e).__name__}: {e}"}
 
     def step():
         if a.model:

@@ -252,6 +252,13 @@ int mcpm_spectrum_bins(void* stream, const void* m0_c64, const void* m1_c64, int
                        double box_y, double box_z, const double* kedges, int n_edges, int deconv0, int deconv1,
                        double* out);
 
+/* The same with a multipole (metrics.py:165-166): the power sums out[2..3] carry (2 ell + 1) L_ell(mu), mu = k . los /
+ * |k| (0 at k = 0) for the unit line of sight los[3] (host; box_center / |box_center|, zero for a centred box);
+ * out[0..1] (count, sum |k|) are unchanged.  ell = 0 equals mcpm_spectrum_bins. */
+int mcpm_spectrum_bins_ell(void* stream, const void* m0_c64, const void* m1_c64, int nx, int ny, int nz, double box_x,
+                           double box_y, double box_z, const double* kedges, int n_edges, int deconv0, int deconv1,
+                           int ell, const double los[3], double* out);
+
 /* rg2cgh / cgh2rg (utils.py:785-921): real Gaussian mesh [nx,ny,nz] (all sides even) <-> complex
  * Gaussian Hermitian half spectrum by permutation and reweighting; rg2cgh(N(0,I)) is distributed as rfftn(N(0,I)).
  * out = scale * [transfer *] P(mesh), scale = sqrt(N/2) for norm "backward", 1/sqrt(2) "ortho", 1/sqrt(2N) "forward";

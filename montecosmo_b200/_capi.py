@@ -66,6 +66,7 @@ SIGNATURES = {
     "mcpm_chreshape": ([vp, vp] + MESH + [vp] + MESH, i32),
     "mcpm_chreshape_vjp": ([vp, vp] + MESH + [vp] + MESH, i32),
     "mcpm_spectrum_bins": ([vp, vp, vp] + MESH + [f64, f64, f64, vp, i32, i32, i32, vp], i32),
+    "mcpm_spectrum_bins_ell": ([vp, vp, vp] + MESH + [f64, f64, f64, vp, i32, i32, i32, i32, C.POINTER(C.c_double), vp], i32),
     "mcpm_rg2cgh": ([vp, vp, vp] + MESH + [f32, vp], i32),
     "mcpm_rg2cgh_vjp": ([vp, vp, vp] + MESH + [f32, vp], i32),
     "mcpm_cgh2rg": ([vp, vp, vp] + MESH + [f32], i32),

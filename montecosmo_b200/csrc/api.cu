@@ -595,6 +595,17 @@ int mcpm_spectrum_bins(void* stream, const void* m0_c64, const void* m1_c64, int
   API_END
 }
 
+int mcpm_spectrum_bins_ell(void* stream, const void* m0_c64, const void* m1_c64, int nx, int ny, int nz, double box_x,
+                           double box_y, double box_z, const double* kedges, int n_edges, int deconv0, int deconv1,
+                           int ell, const double los[3], double* out) {
+  API_BEGIN
+  NEED(m0_c64 && kedges && out && los, "spectrum_bins_ell: null pointer");
+  NEED(box_x > 0 && box_y > 0 && box_z > 0, "spectrum_bins_ell: box sizes must be positive");
+  return spectrum_bins(as_stream(stream), C(m0_c64), m1_c64 ? C(m1_c64) : nullptr, nx, ny, nz, box_x, box_y, box_z,
+                       kedges, n_edges, deconv0, deconv1, out, ell, los[0], los[1], los[2]);
+  API_END
+}
+
 int mcpm_rg2cgh(void* stream, const float* mesh, void* out_c64, int nx, int ny, int nz, float scale,
                 const float* transfer) {
   API_BEGIN

@@ -94,7 +94,8 @@ int scale_real(stream_t, const float* in, float s, float* out, int64_t n);
 int chreshape(stream_t, const cfloat* in, int inx, int iny, int inz, cfloat* out, int onx, int ony, int onz);
 int chreshape_T(stream_t, const cfloat* outbar, int onx, int ony, int onz, cfloat* inbar, int inx, int iny, int inz);
 int spectrum_bins(stream_t, const cfloat* m0, const cfloat* m1, int nx, int ny, int nz, double bx, double by, double bz,
-                  const double* kedges, int n_edges, int deconv0, int deconv1, double* out);
+                  const double* kedges, int n_edges, int deconv0, int deconv1, double* out, int ell = 0, double lx = 0.0, double ly = 0.0,
+                  double lz = 0.0);
 int rg2cgh(stream_t, const float* mesh, cfloat* out, int nx, int ny, int nz, float scale, const float* transfer);
 int rg2cgh_vjp(stream_t, const cfloat* outbar, float* meshbar, int nx, int ny, int nz, float scale, const float* transfer);
 int cgh2rg(stream_t, const cfloat* meshk, float* mesh, int nx, int ny, int nz, float inv_scale);

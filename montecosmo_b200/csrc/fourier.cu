@@ -335,10 +335,18 @@ struct Box3 {
   double x, y, z;
 };
 
+// Multipole ell along the unit line of sight `los` (metrics.py:165-166): the power sums carry (2 ell + 1) L_ell(mu),
+// mu = k . los / |k| (0 at k = 0, safe_div); the count and the mean wavenumber do not.  ell = 0 is the monopole.
 int spectrum_bins(stream_t st, const cfloat* m0, const cfloat* m1, int nx, int ny, int nz, double bx, double by,
-                  double bz, const double* kedges, int n_edges, int deconv0, int deconv1, double* out) {
+                  double bz, const double* kedges, int n_edges, int deconv0, int deconv1, double* out, int ell,
+                  double lx, double ly, double lz) {
   if (int e = check_dims(nx, ny, nz)) return e;
+  if (ell < 0 || ell > 64) {
+    set_error("spectrum_bins: multipole order must be in 0..64");
+    return MCPM_EINVAL;
+  }
   const Box3 box = {bx, by, bz};
+  const Box3 los = {lx, ly, lz};
   if (n_edges < 1) {
     set_error("spectrum_bins: at least one bin edge is required");
     return MCPM_EINVAL;
@@ -362,6 +370,17 @@ int spectrum_bins(stream_t st, const cfloat* m0, const cfloat* m1, int nx, int n
       else hi = mid;
     }
     const double w = half_weight(l, g.nz);
+    double leg = 1.0;
+    if (ell > 0) {  // Bonnet recurrence, float64
+      const double mu = kk == 0.0 ? 0.0 : (kx * los.x + ky * los.y + kz * los.z) / kk;
+      double p0 = 1.0, p1 = mu;
+      for (int n = 1; n < ell; ++n) {
+        const double p2 = ((2 * n + 1) * mu * p1 - n * p0) / (n + 1);
+        p0 = p1;
+        p1 = p2;
+      }
+      leg = (2 * ell + 1) * p1;
+    }
     cfloat a = m0[e];
     cfloat b = m1 ? m1[e] : a;
     float ca = deconv0 > 0 ? 1.0f / window_hat(kc, deconv0) : 1.0f;
@@ -370,8 +389,8 @@ int spectrum_bins(stream_t st, const cfloat* m0, const cfloat* m1, int nx, int n
     const double ar = (double)a.re * ca, ai = (double)a.im * ca, br = (double)b.re * cb, bi = (double)b.im * cb;
     atomic_add(out + lo, w);
     atomic_add(out + nb + lo, w * kk);
-    atomic_add(out + 2 * nb + lo, w * (ar * br + ai * bi));
-    if (m1) atomic_add(out + 3 * nb + lo, w * (ai * br - ar * bi));
+    atomic_add(out + 2 * nb + lo, w * leg * (ar * br + ai * bi));
+    if (m1) atomic_add(out + 3 * nb + lo, w * leg * (ai * br - ar * bi));
   });
   return rt_check("spectrum_bins");
 }

@@ -1,6 +1,6 @@
 """
 Mirror of the power-spectrum estimators of `montecosmo/metrics.py` (spectrum 184-187, transfer 190-194, coherence
-196-201, powtranscoh 203-210; binning of _waves 60-118 and _spectrum 121-182), monopole only.  The FFT and the binned
+196-201, powtranscoh 203-210; binning of _waves 60-118 and _spectrum 121-182), every multipole.  The FFT and the binned
 reduction over the half spectrum run on the engine (mcpm_rfftn, mcpm_spectrum_bins); the bin edges and the final
 normalisation are a few host-side float64 operations, as in the reference.
 """
@@ -42,21 +42,28 @@ def _to_spectrum(mesh):
 
 def _spectrum(mesh0, mesh1=None, box_size=None, box_center=(0.0, 0.0, 0.0), ells=0, kedges=None, include_corners=True,
               deconv=(0, 0)):
-    if ells != 0:
-        raise NotImplementedError("only the monopole (ells=0) is implemented by the B200 engine")
+    """metrics.py:121-182: (kcount, kmean, P_ell) with P_ell an array for an int `ells`, a dict {ell: array} for a list;
+    the line of sight of the multipoles is box_center / |box_center| (zero for a centred box, metrics.py:127-128)."""
     if isinstance(deconv, int):
         deconv = (deconv, deconv)
+    center = np.asarray(box_center, dtype=float)
+    nrm = np.linalg.norm(center)
+    los = center / nrm if nrm != 0 else np.zeros_like(center)  # safe_div
     m0 = _to_spectrum(mesh0)
     m1 = None if mesh1 is None else _to_spectrum(mesh1)
     mesh_shape = np.array(ch2rshape(tuple(m0.shape)))
     box_size = mesh_shape.astype(float) if box_size is None else np.asarray(box_size, dtype=float)
     edges = _kedges(mesh_shape, box_size, kedges, include_corners)
-    sums = _nb.ops().spectrum_bins(m0, m1, box_size, edges, deconv).cpu().numpy()[:, 1:-1]
-    kcount = sums[0]
-    kmean = sums[1] / kcount
-    pmean = sums[2] if m1 is None else np.sqrt(sums[2] ** 2 + sums[3] ** 2)
-    pmean = pmean * (box_size / mesh_shape ** 2).prod() / kcount  # from cell units to [Mpc/h]^3
-    return kcount, kmean, pmean
+    pow, kcount, kmean = {}, None, None
+    for ell in np.atleast_1d(ells):
+        sums = _nb.ops().spectrum_bins(m0, m1, box_size, edges, deconv, int(ell), los).cpu().numpy()[:, 1:-1]
+        kcount = sums[0]
+        kmean = sums[1] / kcount
+        pmean = sums[2] if m1 is None else np.sqrt(sums[2] ** 2 + sums[3] ** 2)
+        pow[int(ell)] = pmean * (box_size / mesh_shape ** 2).prod() / kcount  # from cell units to [Mpc/h]^3
+    if isinstance(ells, (int, np.integer)):
+        return kcount, kmean, pow[int(ells)]
+    return kcount, kmean, pow
 
 
 def spectrum(mesh0, mesh1=None, box_size=None, box_center=(0.0, 0.0, 0.0), ells=0, kedges=None, include_corners=True):

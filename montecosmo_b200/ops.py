@@ -424,16 +424,22 @@ class Ops:
                    *ch2rshape(in_cshape))
         return inbar
 
-    def spectrum_bins(self, m0, m1, box_size, kedges, deconv=(0, 0)):
-        """[4, len(kedges)+1] float64: count, sum |k|, sum Re, sum Im of m0 conj(m1) per np.digitize bin."""
+    def spectrum_bins(self, m0, m1, box_size, kedges, deconv=(0, 0), ell=0, los=(0.0, 0.0, 0.0)):
+        """[4, len(kedges)+1] float64: count, sum |k|, sum Re, sum Im of m0 conj(m1) per np.digitize bin; the power sums
+        of multipole `ell` along the unit vector `los` carry (2 ell + 1) L_ell(mu)."""
         A = self.A
         m0 = A.prepare(m0, "c64")
         m1 = None if m1 is None else A.prepare(m1, "c64")
         rs = ch2rshape(A.shape(m0))
         ke = A.prepare(kedges, "f64")
         out = A.zeros((4, len(kedges) + 1), "f64")
-        self._call("mcpm_spectrum_bins", A.stream(), A.ptr(m0), A.ptr(m1), *rs, float(box_size[0]), float(box_size[1]),
-                   float(box_size[2]), A.ptr(ke), len(kedges), int(deconv[0]), int(deconv[1]), A.ptr(out))
+        box = (float(box_size[0]), float(box_size[1]), float(box_size[2]))
+        if ell == 0:
+            self._call("mcpm_spectrum_bins", A.stream(), A.ptr(m0), A.ptr(m1), *rs, *box, A.ptr(ke), len(kedges),
+                       int(deconv[0]), int(deconv[1]), A.ptr(out))
+        else:
+            self._call("mcpm_spectrum_bins_ell", A.stream(), A.ptr(m0), A.ptr(m1), *rs, *box, A.ptr(ke), len(kedges),
+                       int(deconv[0]), int(deconv[1]), int(ell), (C.c_double * 3)(*(float(x) for x in los)), A.ptr(out))
         return out
 
     def rg2cgh(self, mesh, scale, transfer=None):

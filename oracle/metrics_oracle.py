@@ -1,6 +1,6 @@
 """
 CPU restatement of montecosmo/metrics.py's power-spectrum estimator (TEST INFRASTRUCTURE ONLY; same rules as
-pm_oracle.py): _waves (metrics.py:60-118) and _spectrum (121-182), monopole, NumPy float64.  Pinned against the
+pm_oracle.py): _waves (metrics.py:60-118) and _spectrum (121-182) with multipoles, NumPy float64.  Pinned against the
 reference's own source executed under the NumPy stand-in for JAX (tests/golden/spectrum.npz, bin counts identical,
 powers to 1e-11; unpinned against real JAX/XLA like the rest of the oracle).  It is the yardstick for the engine's
 binned reduction and for the power-spectrum tolerance of the parity report.
@@ -33,8 +33,13 @@ def waves(mesh_shape, box_size, kedges=None, include_corners=True):
     return np.asarray(kedges), kmesh, rfftw
 
 
-def spectrum(mesh0, mesh1=None, box_size=None, kedges=None, include_corners=True, deconv=(0, 0)):
-    """(kcount, kmean, P) per bin; cross spectra return |<m0 conj m1>| as the reference does (metrics.py:172-175)."""
+def spectrum(mesh0, mesh1=None, box_size=None, kedges=None, include_corners=True, deconv=(0, 0), ells=0,
+             box_center=(0.0, 0.0, 0.0)):
+    """(kcount, kmean, P) per bin; cross spectra return |<m0 conj m1>| as the reference does (metrics.py:172-175).
+    `ells` an int gives an array, a list a dict {ell: array}; multipoles carry (2 ell + 1) L_ell(mu) with mu along
+    box_center / |box_center| (metrics.py:127-128, 91-92, 165-166)."""
+    from numpy.polynomial import legendre as npleg
+
     def to_k(m):
         m = np.asarray(m)
         return (np.fft.rfftn(m), m.shape) if np.isrealobj(m) else (m.astype(np.complex128), O.ch2rshape(m.shape))
@@ -49,14 +54,24 @@ def spectrum(mesh0, mesh1=None, box_size=None, kedges=None, include_corners=True
     shape = np.asarray(shape)
     box_size = shape.astype(float) if box_size is None else np.asarray(box_size, dtype=float)
     kedges, kmesh, rfftw = waves(shape, box_size, kedges, include_corners)
+    center = np.asarray(box_center, dtype=float)
+    nrm = np.linalg.norm(center)
+    los = center / nrm if nrm != 0 else np.zeros(3)
+    kvec = O.rfftk(tuple(int(s) for s in shape), tuple(box_size))
+    kdot = sum(k * l for k, l in zip(kvec, los))
+    mumesh = np.where(kmesh == 0, 0.0, kdot / np.where(kmesh == 0, 1.0, kmesh))
     nb = len(kedges) + 1
     dig = np.digitize(kmesh.reshape(-1), kedges)
     kcount = np.bincount(dig, weights=rfftw.reshape(-1), minlength=nb)[1:-1]
     kmean = np.bincount(dig, weights=(kmesh * rfftw).reshape(-1), minlength=nb)[1:-1] / kcount
-    w = (mmk * rfftw).reshape(-1)
-    if mesh1 is None:
-        p = np.bincount(dig, weights=w, minlength=nb)[1:-1]
-    else:
-        p = np.hypot(np.bincount(dig, weights=w.real, minlength=nb)[1:-1],
-                     np.bincount(dig, weights=w.imag, minlength=nb)[1:-1])
-    return kcount, kmean, p * (box_size / shape ** 2).prod() / kcount
+    pows = {}
+    for ell in np.atleast_1d(ells):
+        leg = (2 * ell + 1) * npleg.legval(mumesh, [0.0] * int(ell) + [1.0])
+        w = (mmk * leg * rfftw).reshape(-1)
+        if mesh1 is None:
+            p = np.bincount(dig, weights=w, minlength=nb)[1:-1]
+        else:
+            p = np.hypot(np.bincount(dig, weights=w.real, minlength=nb)[1:-1],
+                         np.bincount(dig, weights=w.imag, minlength=nb)[1:-1])
+        pows[int(ell)] = p * (box_size / shape ** 2).prod() / kcount
+    return kcount, kmean, (pows[int(ells)] if isinstance(ells, (int, np.integer)) else pows)

@@ -232,6 +232,16 @@ def main():
         d[f"auto_{tag}_kcount"], d[f"auto_{tag}_kmean"], d[f"auto_{tag}_pow"] = A(kc), A(km), A(p)
         kc, km, p = metrics._spectrum(jnp.asarray(a), jnp.asarray(b), box_size=box, **kw)
         d[f"cross_{tag}_pow"] = A(p)
+    # multipoles along box_center / |box_center| (metrics.py:127-128, 165-166); a centred box has mu = 0
+    center = (30.0, -20.0, 90.0)
+    d["box_center"] = np.array(center)
+    kc, km, p = metrics._spectrum(jnp.asarray(a), None, box_size=box, box_center=center, ells=[0, 2, 4], deconv=2)
+    for ell in (0, 2, 4):
+        d[f"auto_ell{ell}_pow"] = A(p[ell])
+    kc, km, p = metrics._spectrum(jnp.asarray(a), jnp.asarray(b), box_size=box, box_center=center, ells=[1, 2], kedges=6)
+    d["cross_ell1_pow"], d["cross_ell2_pow"] = A(p[1]), A(p[2])
+    kc, km, p = metrics._spectrum(jnp.asarray(a), None, box_size=box, ells=2)
+    d["auto_ell2_centred_pow"] = A(p)
     ks, p1, tr, coh = metrics.powtranscoh(jnp.asarray(a), jnp.asarray(b), np.array(box))
     d["ptc_k"], d["ptc_pow1"], d["ptc_trans"], d["ptc_coh"] = A(ks), A(p1), A(tr), A(coh)
     out["spectrum"] = d

@@ -64,8 +64,19 @@ def test_spectrum_estimator_matches_oracle(nb, golden):
                                                include_corners=corners)[2], rtol=2e-5)
         ks, p1, tr, coh = M.powtranscoh(torch.tensor(a, device=dev), torch.tensor(b, device=dev), box or shape)
         assert np.all(coh <= 1 + 1e-6) and np.all(tr > 0)
-    with pytest.raises(NotImplementedError):
-        M.spectrum(torch.tensor(a, device=dev), ells=2)
+    # multipoles (metrics.py:165-166) against the golden vectors; quadrupoles change sign, so the bound is absolute,
+    # 2e-5 of the largest monopole power
+    a, b = (torch.tensor(g[k], dtype=torch.float32, device=dev) for k in ("mesh0", "mesh1"))
+    box, center = tuple(g["box_size"]), tuple(g["box_center"])
+    top = np.abs(g["auto_ell0_pow"]).max()
+    p = M._spectrum(a, box_size=box, box_center=center, ells=[0, 2, 4], deconv=2)[2]
+    for ell in (0, 2, 4):
+        assert np.abs(p[ell] - g[f"auto_ell{ell}_pow"]).max() < 2e-5 * top
+    p = M._spectrum(a, b, box_size=box, box_center=center, ells=[1, 2], kedges=6)[2]
+    assert np.abs(p[1] - g["cross_ell1_pow"]).max() < 2e-5 * top
+    assert np.abs(p[2] - g["cross_ell2_pow"]).max() < 2e-5 * top
+    km, p2 = M.spectrum(a, box_size=box, ells=2)
+    assert np.abs(p2 - g["auto_ell2_centred_pow"]).max() < 2e-5 * top
 
 
 def test_parity_report_density_displacement_power(nb):

@@ -184,6 +184,14 @@ def test_spectrum_estimator(golden):
         close(km, g[f"auto_{tag}_kmean"])
         close(p, g[f"auto_{tag}_pow"])
         close(MX.spectrum(a, b, box_size=box, **kw)[2], g[f"cross_{tag}_pow"])
+    center = tuple(g["box_center"])
+    p = MX.spectrum(a, box_size=box, box_center=center, ells=[0, 2, 4], deconv=(2, 2))[2]
+    for ell in (0, 2, 4):
+        close(p[ell], g[f"auto_ell{ell}_pow"], rtol=1e-9, atol=1e-9)
+    p = MX.spectrum(a, b, box_size=box, box_center=center, ells=[1, 2], kedges=6)[2]
+    close(p[1], g["cross_ell1_pow"], rtol=1e-9, atol=1e-9)
+    close(p[2], g["cross_ell2_pow"], rtol=1e-9, atol=1e-9)
+    close(MX.spectrum(a, box_size=box, ells=2)[2], g["auto_ell2_centred_pow"], rtol=1e-9, atol=1e-9)
     _, km, p0 = MX.spectrum(a, box_size=box)
     _, _, p1 = MX.spectrum(b, box_size=box)
     _, _, p01 = MX.spectrum(a, b, box_size=box)

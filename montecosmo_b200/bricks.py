@@ -4,7 +4,9 @@ Lagrangian bias expansion (327-452) and the flat-sky redshift-space shift in cel
 
 lagrangian_bias composes engine operators -- irfftn (mcpm_irfftn) and read (mcpm_read, differentiable in mesh and
 positions) -- with pointwise torch expressions for the Fourier multipliers and the shear invariants, so torch.autograd
-differentiates it end to end.  Primordial non-Gaussianity terms (png_type is not None) are not implemented.
+differentiates it end to end.  The primordial non-Gaussianity terms (png_type is not None, bricks.py:411-438) and add_png
+(129-141) take a tabulated (k, P) `kpow`; the Eisenstein-Hu branch of lin_power (kpow=None) lives in jax_cosmo and is
+outside the path.
 """
 import numpy as np
 import torch
@@ -13,6 +15,43 @@ from . import cosmo as _cosmo
 from . import nbody as _nb
 
 _BIAS_KEYS = ("b1", "b2", "bs2", "b3", "bds2", "bs3", "bn2", "bnpar")
+_PNG_KEYS = ("fNL_bp", "fNL_bpd", "fNL_bpd2", "fNL_bps2", "fNL_bn2p")
+RH = 2997.92458  # jax_cosmo.constants.rh, h^-1 Mpc (bricks.py:125)
+
+
+def trans_phi2delta_mesh(cosmo, mesh_shape, box_size, kpow, a=1.0):
+    """Transfer from the primordial potential to the linear matter density on the half-spectrum mesh (bricks.py:108-127
+    evaluated on kmesh), host float64 like the reference's other tabulated kernels; `kpow` = (k, P) normalised to
+    sigma8 = 1 (lin_power, bricks.py:67-77)."""
+    if kpow is None:
+        raise NotImplementedError("trans_phi2delta needs a (k, P) table: the Eisenstein-Hu branch lives in jax_cosmo")
+    ks, pows = (np.asarray(x, dtype=np.float64) for x in kpow)
+    pow_lin = pows * float(cosmo.sigma8) ** 2
+    pow_large = ks ** float(cosmo.n_s)
+    lin_trans = (pow_lin / pow_large / (pow_lin[0] / pow_large[0])) ** 0.5
+    a_md = 1.0 / (1.0 + 10.0)  # matter-dominated era
+    growth_md = float(_cosmo.a2g(cosmo, a_md)) / a_md
+    trans = 2.0 * RH**2 * ks**2 * lin_trans * (float(_cosmo.a2g(cosmo, a)) / growth_md) / (3.0 * float(cosmo.Omega_m))
+    kmesh = np.sqrt(sum(k**2 for k in _nb.rfftk(mesh_shape, box_size)))
+    return np.interp(kmesh.reshape(-1), ks, trans, left=0.0, right=0.0).reshape(kmesh.shape)
+
+
+def _inv_transfer(cosmo, mesh_shape, box_size, kpow, dev):
+    """1 / trans_phi2delta with safe_div's 0 where the transfer vanishes, float32 on the device."""
+    t = trans_phi2delta_mesh(cosmo, mesh_shape, box_size, kpow)
+    inv = np.where(t == 0, 0.0, 1.0 / np.where(t == 0, 1.0, t))
+    return torch.as_tensor(t.astype(np.float32), device=dev), torch.as_tensor(inv.astype(np.float32), device=dev)
+
+
+def add_png(cosmo, fNL, lin_mesh, box_size, kpow=None):
+    """Add local primordial non-Gaussianity to the linear field (bricks.py:129-141): phi += fNL (phi^2 - <phi^2>)."""
+    lin_mesh = _nb._c64(lin_mesh)
+    mesh_shape = _nb.ch2rshape(tuple(lin_mesh.shape))
+    t, inv = _inv_transfer(cosmo, mesh_shape, box_size, kpow, lin_mesh.device)
+    phi = _nb.irfftn(lin_mesh * inv)
+    phi2 = phi**2
+    phi = phi + fNL * (phi2 - phi2.mean())
+    return t * _nb.rfftn(phi)
 
 
 def regular_pos(mesh_shape, ptcl_shape=None):
@@ -25,9 +64,10 @@ def regular_pos(mesh_shape, ptcl_shape=None):
 def lagrangian_bias(cosmo, pos, a, box_size, lin_mesh, bias, png=None, png_type=None, kpow=None, read_order: int = 2):
     """Lagrangian bias expansion weights (bricks.py:327-452):
     w = 1 + b1 d + b2 (d^2 - <d^2>)/2 + bs2 (s^2 - <s^2>) + b3 (d^3 - 3<d^2> d)/6 + bds2 d s^2 + bs3 s^3 + bn2 lap d,
-    and the higher-derivative velocity term dvel = bnpar grad d.  Returns (weights, dvel, phi = 0)."""
-    if png_type is not None:
-        raise NotImplementedError("primordial non-Gaussianity bias terms are not implemented by the B200 engine")
+    and the higher-derivative velocity term dvel = bnpar grad d; with png_type not None also (bricks.py:411-438)
+    + fNL_bp phi + fNL_bpd (phi d - <phi d>) + fNL_bpd2 (phi (d^2 - <d^2>) - 2 <phi d> d) + fNL_bps2 phi s^2
+    + fNL_bn2p lap phi, phi = irfftn(delta_k / trans_phi2delta).  Returns (weights, dvel, phi); phi = 0 without PNG."""
+    f = {k: (png or {}).get(k, 0.0) for k in _PNG_KEYS}
     b = {k: bias.get(k, 0.0) if isinstance(bias, dict) else 0.0 for k in _BIAS_KEYS}
     lin_mesh = _nb._c64(lin_mesh)
     pos = _nb._f32(pos)
@@ -69,10 +109,24 @@ def lagrangian_bias(cosmo, pos, a, box_size, lin_mesh, bias, png=None, png_type=
     weights = weights + b["bs3"] * rd(shear3) * g**3
     weights = weights + b["bn2"] * rd(_nb.irfftn(-k2 * lin_mesh)) * g
 
+    phi = 0.0
+    if png_type is not None:
+        _, inv = _inv_transfer(cosmo, mesh_shape, box_size, kpow, dev)
+        phik = lin_mesh * inv
+        phi = _nb.irfftn(phik)
+        phi_pos = rd(phi)
+        weights = weights + f["fNL_bp"] * phi_pos
+        phi_delta_pos = phi_pos * delta_pos
+        sigma_pd = phi_delta_pos.mean()
+        weights = weights + f["fNL_bpd"] * (phi_delta_pos - sigma_pd)
+        weights = weights + f["fNL_bpd2"] * (phi_pos * delta2_pos - 2 * sigma_pd * delta_pos)
+        weights = weights + f["fNL_bps2"] * phi_pos * shear2_pos
+        weights = weights + f["fNL_bn2p"] * rd(_nb.irfftn(-k2 * phik))
+
     grads = [rd(_nb.irfftn((1j * k) * lin_mesh)) for k in kvec]  # h/Mpc
     gcol = g if g.dim() == 0 else g.reshape(-1, 1)
     dvel = b["bnpar"] * torch.stack(grads, dim=-1) * gcol
-    return weights, dvel, 0.0
+    return weights, dvel, phi
 
 
 def rsd(cosmo, a, vel, los=(0.0, 0.0, 1.0)):

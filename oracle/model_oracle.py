@@ -51,8 +51,44 @@ def value_and_force(white, obs, transfer, cosmo, mesh_shape, **kw):
     return lp.detach(), g
 
 
-def lagrangian_bias(cosmo, pos, a, box_size, lin_mesh, bias, read_order=2):
-    """bricks.py:327-452 without the primordial non-Gaussianity terms, float64: (weights, dvel)."""
+RH = 2997.92458  # jax_cosmo.constants.rh, h^-1 Mpc (bricks.py:125)
+_PNG_KEYS = ("fNL_bp", "fNL_bpd", "fNL_bpd2", "fNL_bps2", "fNL_bn2p")
+
+
+def trans_phi2delta(cosmo, kmesh, kpow, a=1.0):
+    """bricks.py:108-127 with a tabulated (k, P) normalised to sigma8 = 1 (the Eisenstein-Hu branch of lin_power lives in
+    jax_cosmo and is outside the path): transfer from the primordial potential to the linear density, on kmesh."""
+    ks, pows = (np.asarray(x, dtype=np.float64) for x in kpow)
+    pow_lin = pows * float(cosmo.sigma8) ** 2
+    pow_large = ks ** float(cosmo.n_s)
+    lin_trans = (pow_lin / pow_large / (pow_lin[0] / pow_large[0])) ** 0.5
+    a_md = 1.0 / 11.0
+    growth_md = float(O.a2g(cosmo, a_md)) / a_md
+    trans = 2.0 * RH ** 2 * ks ** 2 * lin_trans * (float(O.a2g(cosmo, a)) / growth_md) / (3.0 * float(cosmo.Omega_m))
+    km = np.asarray(kmesh, dtype=np.float64)
+    return np.interp(km.reshape(-1), ks, trans, left=0.0, right=0.0).reshape(km.shape)
+
+
+def _safe_div_t(x, y):
+    y = O._t(y)
+    return torch.where(y == 0, torch.zeros_like(x), x / torch.where(y == 0, torch.ones_like(y), y))
+
+
+def add_png(cosmo, fNL, lin_mesh, box_size, kpow):
+    """bricks.py:129-141."""
+    lin_mesh = lin_mesh if isinstance(lin_mesh, torch.Tensor) else O._t(lin_mesh, O.C128)
+    shape = O.ch2rshape(tuple(lin_mesh.shape))
+    kmesh = sum(k ** 2 for k in O.rfftk(shape, box_size)) ** 0.5
+    t = trans_phi2delta(cosmo, kmesh, kpow)
+    phi = torch.fft.irfftn(_safe_div_t(lin_mesh, t), s=shape)
+    phi2 = phi ** 2
+    phi = phi + fNL * (phi2 - phi2.mean())
+    return O._t(t) * torch.fft.rfftn(phi)
+
+
+def lagrangian_bias(cosmo, pos, a, box_size, lin_mesh, bias, read_order=2, png=None, png_type=None, kpow=None):
+    """bricks.py:327-452, float64: (weights, dvel), or (weights, dvel, phi) when png_type is not None (the primordial
+    non-Gaussianity terms of bricks.py:411-438, with a tabulated kpow)."""
     b = {k: bias.get(k, 0.0) for k in ("b1", "b2", "bs2", "b3", "bds2", "bs3", "bn2", "bnpar")}
     lin_mesh = lin_mesh if isinstance(lin_mesh, torch.Tensor) else O._t(lin_mesh, O.C128)
     shape = O.ch2rshape(tuple(lin_mesh.shape))
@@ -67,7 +103,8 @@ def lagrangian_bias(cosmo, pos, a, box_size, lin_mesh, bias, read_order=2):
     w = 1.0 + b["b1"] * delta_pos
     d2 = delta_pos ** 2
     sigma2 = d2.mean()
-    w = w + b["b2"] * (d2 - sigma2) / 2
+    delta2_pos = d2 - sigma2
+    w = w + b["b2"] * delta2_pos / 2
     sh = {}
     for i in range(2):
         nabi = 1j * kvec[i]
@@ -84,6 +121,21 @@ def lagrangian_bias(cosmo, pos, a, box_size, lin_mesh, bias, read_order=2):
     shear3 = 3 * (a_ * (b_ * c_ - f_ ** 2) - d_ * (d_ * c_ - e_ * f_) + e_ * (d_ * f_ - b_ * e_))
     w = w + b["bs3"] * rd(shear3) * g ** 3
     w = w + b["bn2"] * rd(irf(-kmesh2 * lin_mesh)) * g
+    phi = None
+    if png_type is not None:
+        f = {k: (png or {}).get(k, 0.0) for k in _PNG_KEYS}
+        t = trans_phi2delta(cosmo, np.sqrt(kmesh2.numpy()), kpow)
+        phik = _safe_div_t(lin_mesh, t)
+        phi = irf(phik)
+        phi_pos = rd(phi)
+        w = w + f["fNL_bp"] * phi_pos
+        pd = phi_pos * delta_pos
+        sigma_pd = pd.mean()
+        w = w + f["fNL_bpd"] * (pd - sigma_pd)
+        w = w + f["fNL_bpd2"] * (phi_pos * delta2_pos - 2 * sigma_pd * delta_pos)
+        w = w + f["fNL_bps2"] * phi_pos * shear2_pos
+        w = w + f["fNL_bn2p"] * rd(irf(-kmesh2 * phik))
     grads = torch.stack([rd(irf(1j * k * lin_mesh)) for k in kvec], dim=-1)
     gcol = g.reshape(-1, 1) if isinstance(g, torch.Tensor) and g.dim() > 0 else g
-    return w, b["bnpar"] * grads * gcol
+    dvel = b["bnpar"] * grads * gcol
+    return (w, dvel) if png_type is None else (w, dvel, phi)

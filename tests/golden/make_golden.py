@@ -259,6 +259,17 @@ def main():
     d = {"shape": np.array(shape), "box_size": np.array(box), "delta_k": dk, "pos": pos, "a": np.array(0.7),
          "weights": A(w), "dvel": A(dvel)}
     d.update({f"bias_{k}": np.array(v) for k, v in bias.items()})
+    # primordial non-Gaussianity terms (bricks.py:411-438) with a tabulated (k, P) normalised to sigma8 = 1
+    ks = np.logspace(-4, 1, 64)
+    pk = 2.0e4 * (ks / 0.02) ** 0.96 / (1 + (ks / 0.02) ** 2) ** 1.7
+    png = dict(fNL_bp=0.9, fNL_bpd=-0.4, fNL_bpd2=0.25, fNL_bps2=0.15, fNL_bn2p=-0.3)
+    cosmo._workspace = {}
+    w, dvel, phi = bricks.lagrangian_bias(cosmo, jnp.asarray(pos), jnp.asarray(0.7), np.array(box), jnp.asarray(dk),
+                                          bias, png, png_type="fNL", kpow=(ks, pk), read_order=2)
+    d.update({"kpow_k": ks, "kpow_p": pk, "png_weights": A(w), "png_phi": A(phi)})
+    d.update({f"png_{k}": np.array(v) for k, v in png.items()})
+    cosmo._workspace = {}
+    d["add_png_fNL50"] = A(bricks.add_png(cosmo, 50.0, jnp.asarray(dk), np.array(box), kpow=(ks, pk)))
     out["lagrangian_bias"] = d
 
     for name, dd in out.items():

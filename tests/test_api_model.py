@@ -289,7 +289,7 @@ def test_rg2cgh_golden_roundtrip_and_gradient(nb, golden):
 
 
 def test_lagrangian_bias_weights_and_gradient(nb, golden):
-    """bricks.lagrangian_bias (bricks.py:327-452, no PNG terms) against the golden vectors of the reference source and the
+    """bricks.lagrangian_bias (bricks.py:327-452) against the golden vectors of the reference source and the
     oracle: weights and dvel 5e-5, gradient of a scalar functional w.r.t. the linear mesh 2e-4."""
     from montecosmo_b200 import bricks as B
     from montecosmo_b200.cosmo import Cosmology
@@ -316,8 +316,24 @@ def test_lagrangian_bias_weights_and_gradient(nb, golden):
     assert phi == 0.0 and rel(w, wo) < 5e-5 and rel(dvel, dvo) < 5e-5
     assert rel(dk.grad, dko.grad) < 2e-4
     assert rel(B.regular_pos(shape), q.numpy()) == 0.0
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):  # kpow=None would need jax_cosmo's Eisenstein-Hu power
         B.lagrangian_bias(Cosmology(), pos.to(dev(nb)), 0.7, box, dk.detach(), bias, png_type="fNL")
+    # primordial non-Gaussianity terms (bricks.py:411-438) and add_png (129-141) with a tabulated power: golden vectors
+    # of the reference source, and the gradient w.r.t. the linear mesh against the oracle's autograd
+    png = {k[4:]: float(v) for k, v in gd.items() if k.startswith("png_fNL")}
+    kpow = (gd["kpow_k"], gd["kpow_p"])
+    gpos = torch.tensor(gd["pos"], dtype=torch.float32, device=dev(nb))
+    gdk = torch.tensor(gd["delta_k"], dtype=torch.complex64, device=dev(nb)).requires_grad_()
+    wp, _, phi = B.lagrangian_bias(Cosmology(), gpos, float(gd["a"]), tuple(gd["box_size"]), gdk, gb, png, "fNL", kpow, 2)
+    assert rel(wp, gd["png_weights"]) < 5e-5 and rel(phi, gd["png_phi"]) < 5e-5
+    assert rel(B.add_png(Cosmology(), 50.0, gdk.detach(), tuple(gd["box_size"]), kpow), gd["add_png_fNL50"]) < 5e-5
+    cw = torch.tensor(rng.normal(size=gpos.shape[0]), dtype=torch.float32)
+    (wp * cw.to(dev(nb))).sum().backward()
+    dko = torch.tensor(gd["delta_k"]).requires_grad_()
+    wo, _, _ = MO.lagrangian_bias(O.Cosmology(), torch.tensor(gd["pos"]), float(gd["a"]), tuple(gd["box_size"]), dko, gb, 2,
+                                  png, "fNL", kpow)
+    (wo * cw.double()).sum().backward()
+    assert rel(gdk.grad, dko.grad) < 2e-4
 
 
 def test_bullfrog_vf_scan_and_host_windows(nb, golden):

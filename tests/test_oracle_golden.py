@@ -202,7 +202,7 @@ def test_spectrum_estimator(golden):
 
 
 def test_lagrangian_bias(golden):
-    """oracle/model_oracle.py:lagrangian_bias against montecosmo/bricks.py:327-452 (no PNG terms)."""
+    """oracle/model_oracle.py:lagrangian_bias against montecosmo/bricks.py:327-452."""
     from oracle import model_oracle as MO
     g = golden("lagrangian_bias")
     bias = {k[5:]: float(v) for k, v in g.items() if k.startswith("bias_")}
@@ -210,3 +210,12 @@ def test_lagrangian_bias(golden):
                                  torch.as_tensor(g["delta_k"]), bias, read_order=2)
     close(w, g["weights"])
     close(dvel, g["dvel"], atol=1e-11)
+    # primordial non-Gaussianity terms (bricks.py:411-438) and add_png (129-141), tabulated power
+    png = {k[4:]: float(v) for k, v in g.items() if k.startswith("png_fNL")}
+    kpow = (g["kpow_k"], g["kpow_p"])
+    w, dvel, phi = MO.lagrangian_bias(O.Cosmology(), torch.as_tensor(g["pos"]), float(g["a"]), tuple(g["box_size"]),
+                                      torch.as_tensor(g["delta_k"]), bias, 2, png, "fNL", kpow)
+    close(w, g["png_weights"])
+    close(phi, g["png_phi"], atol=1e-14)
+    close(MO.add_png(O.Cosmology(), 50.0, torch.as_tensor(g["delta_k"]), tuple(g["box_size"]), kpow), g["add_png_fNL50"],
+          atol=1e-10)

@@ -207,6 +207,19 @@ int mcpm_interlace_combine_slab(void* stream, const void* in_m, void* out, int m
                                 int y0, float scale, int deconv_order);
 int mcpm_interlace_combine_T_slab(void* stream, const void* in, void* out_m, int m, int nx, int ny, int nz, int ny_loc,
                                   int y0, float scale, int deconv_order, int half_weights, float norm);
+/* chreshape (utils.py:975-1013) as a crop on a spectrum split along ky (the slab-decomposed final paint with a finer paint
+ * mesh, BASELINE C5): `in` = [inx, rows, inz/2+1] holds global ky rows y0 .. y0+rows-1 of an iny-row spectrum; x and kz
+ * are cropped to onx <= inx, onz <= inz and multiplied by `scale` (and by row_w[jr], nullable); the rows themselves are
+ * redistributed by the caller (a selection, plus one 1/sqrt2-weighted sum for the new ky Nyquist row).  Cropping kz
+ * folds conj in[-kx, -ky, onz/2] into the new Nyquist plane: `nyq_plane` = that plane of the WHOLE input spectrum,
+ * [inx, iny], gathered by the caller (NULL when onz == inz).  _vjp: the transpose in the real inner product; inbar is
+ * zeroed here, the mirrored contributions are accumulated into nyq_plane_bar [inx, iny] for the caller to sum over
+ * ranks and add to plane onz/2 of its rows. */
+int mcpm_chreshape_crop_xz_slab(void* stream, const void* in, int inx, int iny, int inz, int rows, int y0,
+                                const void* nyq_plane, const float* row_w, void* out, int onx, int onz, float scale);
+int mcpm_chreshape_crop_xz_slab_vjp(void* stream, const void* outbar, int onx, int onz, int rows, int y0,
+                                    const float* row_w, void* inbar, int inx, int iny, int inz, void* nyq_plane_bar,
+                                    float scale);
 /* In-place Hermitian projection of `batch` half spectra on the self-conjugate planes kz = 0 and kz = Nyquist:
  * A(i,j,l) <- (A(i,j,l) + conj A(-i,-j,l)) / 2 -- what jnp.fft.irfftn applies implicitly to its input. */
 int mcpm_hermitian_project(void* stream, void* data_c64, int nx, int ny, int nz, int batch);

@@ -61,6 +61,8 @@ SIGNATURES = {
     "mcpm_hessian_spectra_T_slab": ([vp, vp, vp] + MESH + [i32, i32, i32, i32, i32, i32, f32], i32),
     "mcpm_interlace_combine_slab": ([vp, vp, vp, i32] + MESH + [i32, i32, f32, i32], i32),
     "mcpm_interlace_combine_T_slab": ([vp, vp, vp, i32] + MESH + [i32, i32, f32, i32, i32, f32], i32),
+    "mcpm_chreshape_crop_xz_slab": ([vp, vp] + MESH + [i32, i32, vp, vp, vp, i32, i32, f32], i32),
+    "mcpm_chreshape_crop_xz_slab_vjp": ([vp, vp, i32, i32, i32, i32, vp, vp] + MESH + [vp, f32], i32),
     "mcpm_hermitian_project": ([vp, vp] + MESH + [i32], i32),
     "mcpm_half_weight_axpy": ([vp, vp, vp, i64, i32, f32, i32, i32], i32),
     "mcpm_chreshape": ([vp, vp] + MESH + [vp] + MESH, i32),

@@ -395,6 +395,25 @@ int mcpm_interlace_combine_T_slab(void* stream, const void* in, void* out_m, int
   API_END
 }
 
+int mcpm_chreshape_crop_xz_slab(void* stream, const void* in, int inx, int iny, int inz, int rows, int y0,
+                                const void* nyq_plane, const float* row_w, void* out, int onx, int onz, float scale) {
+  API_BEGIN
+  NEED(in && out && rows >= 0 && y0 >= 0 && y0 + rows <= iny, "chreshape_crop_xz_slab: bad arguments");
+  return chreshape_crop_xz_slab(as_stream(stream), C(in), inx, iny, inz, rows, y0, nyq_plane ? C(nyq_plane) : nullptr,
+                                row_w, C(out), onx, onz, scale);
+  API_END
+}
+
+int mcpm_chreshape_crop_xz_slab_vjp(void* stream, const void* outbar, int onx, int onz, int rows, int y0,
+                                    const float* row_w, void* inbar, int inx, int iny, int inz, void* nyq_plane_bar,
+                                    float scale) {
+  API_BEGIN
+  NEED(outbar && inbar && rows >= 0 && y0 >= 0 && y0 + rows <= iny, "chreshape_crop_xz_slab_vjp: bad arguments");
+  return chreshape_crop_xz_slab_T(as_stream(stream), C(outbar), onx, onz, rows, y0, row_w, C(inbar), inx, iny, inz,
+                                  nyq_plane_bar ? C(nyq_plane_bar) : nullptr, scale);
+  API_END
+}
+
 int mcpm_hermitian_project(void* stream, void* data_c64, int nx, int ny, int nz, int batch) {
   API_BEGIN
   NEED(data_c64 && batch >= 1, "hermitian_project: bad arguments");

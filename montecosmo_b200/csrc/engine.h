@@ -87,6 +87,10 @@ int interlace_combine(stream_t, const cfloat* in_m, cfloat* out, int m, int nx, 
                       int deconv_order, SlabK sk = SlabK());
 int interlace_combine_T(stream_t, const cfloat* in, cfloat* out_m, int m, int nx, int ny, int nz, float scale,
                         int deconv_order, float norm, SlabK sk = SlabK(), int half_weights = 1);
+int chreshape_crop_xz_slab(stream_t, const cfloat* in, int inx, int iny, int inz, int rows, int y0, const cfloat* nyq_plane,
+                           const float* row_w, cfloat* out, int onx, int onz, float scale);
+int chreshape_crop_xz_slab_T(stream_t, const cfloat* outbar, int onx, int onz, int rows, int y0, const float* row_w,
+                             cfloat* inbar, int inx, int iny, int inz, cfloat* nyq_plane_bar, float scale);
 int hermitian_project(stream_t, cfloat* data, int nx, int ny, int nz, int batch);
 int half_weight_axpy(stream_t, const cfloat* in, cfloat* out, int64_t nc, int nz, float a, int inverse, int accumulate);
 int scale_spectrum(stream_t, const cfloat* in, const float* t, cfloat* out, int64_t nc);

@@ -664,6 +664,99 @@ int chreshape(stream_t st, const cfloat* in, int inx, int iny, int inz, cfloat* 
   return rt_check("chreshape");
 }
 
+// Slab form of the crop (slab-decomposed final paint with a finer paint mesh, SURVEY 8e / BASELINE C5).  The spectrum
+// is split along ky: `in` = [inx, rows, inz/2+1] holds the global rows y0 .. y0+rows-1 of an iny-row spectrum.  This
+// pass crops x and kz (onx <= inx, onz <= inz) and leaves the rows alone; the caller then redistributes rows (the ky
+// crop is a row selection plus one 1/sqrt2-weighted sum for the new Nyquist row).  Cropping kz folds the mirrored
+// element conj in[-kx, -ky, l] into the new Nyquist plane l = onz/2; the mirrored row lives on another rank, so that
+// one plane of the WHOLE input spectrum is passed separately (`nyq_plane` = [inx, iny], all-gathered by the caller).
+// `row_w` (nullable) weights each local row (the caller's 1/sqrt2 on the two rows that merge into the new ky Nyquist).
+int chreshape_crop_xz_slab(stream_t st, const cfloat* in, int inx, int iny, int inz, int rows, int y0,
+                           const cfloat* nyq_plane, const float* row_w, cfloat* out, int onx, int onz, float scale) {
+  if (int e = check_dims(inx, iny, inz)) return e;
+  if (onx <= 0 || onz <= 0 || (onx & 1) || (onz & 1) || (inx & 1) || onx > inx || onz > inz) {
+    set_error("chreshape_crop_xz_slab: even sides with onx <= inx and onz <= inz are required");
+    return MCPM_EINVAL;
+  }
+  const int inzc = inz / 2 + 1, onzc = onz / 2 + 1;
+  if (onzc < inzc && !nyq_plane) {
+    set_error("chreshape_crop_xz_slab: cropping kz needs the gathered Nyquist plane");
+    return MCPM_EINVAL;
+  }
+  const int64_t nout = (int64_t)onx * rows * onzc;
+  launch_1d(st, nout, [=] MCPM_LAMBDA(int64_t e) {
+    int l = (int)(e % onzc);
+    int64_t r = e / onzc;
+    int jr = (int)(r % rows);
+    int i = (int)(r / rows);
+    AxisSrc ax = axis_sources(i, onx, inx);
+    const bool herm = onzc < inzc && l == onzc - 1;
+    const float wl = herm ? 0.70710678118654752440f : 1.0f;
+    float re = 0.0f, im = 0.0f;
+    for (int a = 0; a < ax.n; ++a) {
+      int ii = ax.idx[a];
+      cfloat v = in[((int64_t)ii * rows + jr) * inzc + l];
+      re += v.re;
+      im += v.im;
+      if (herm) {
+        int im_ = ii == 0 ? 0 : inx - ii, j2 = y0 + jr, jm = j2 == 0 ? 0 : iny - j2;
+        cfloat u = nyq_plane[(int64_t)im_ * iny + jm];
+        re += u.re;
+        im -= u.im;
+      }
+    }
+    float w = ax.w * wl * scale * (row_w ? row_w[jr] : 1.0f);
+    out[e] = cfloat{re * w, im * w};
+  });
+  return rt_check("chreshape_crop_xz_slab");
+}
+
+// Its transpose in the real inner product.  `inbar` [inx, rows, inzc] is zeroed here; the mirrored contributions of the
+// new Nyquist plane are ACCUMULATED into `nyq_plane_bar` [inx, iny] (zeroed by the caller), which the caller sums over
+// ranks and adds to plane l = onz/2 of its own rows.
+int chreshape_crop_xz_slab_T(stream_t st, const cfloat* outbar, int onx, int onz, int rows, int y0, const float* row_w,
+                             cfloat* inbar, int inx, int iny, int inz, cfloat* nyq_plane_bar, float scale) {
+  if (int e = check_dims(inx, iny, inz)) return e;
+  if (onx <= 0 || onz <= 0 || (onx & 1) || (onz & 1) || (inx & 1) || onx > inx || onz > inz) {
+    set_error("chreshape_crop_xz_slab_T: even sides with onx <= inx and onz <= inz are required");
+    return MCPM_EINVAL;
+  }
+  const int inzc = inz / 2 + 1, onzc = onz / 2 + 1;
+  if (onzc < inzc && !nyq_plane_bar) {
+    set_error("chreshape_crop_xz_slab_T: cropping kz needs the Nyquist-plane accumulator");
+    return MCPM_EINVAL;
+  }
+  const int64_t nout = (int64_t)onx * rows * onzc;
+  rt_memset(inbar, 0, sizeof(cfloat) * (size_t)inx * rows * inzc, st);
+  float* ib = reinterpret_cast<float*>(inbar);
+  float* pb = reinterpret_cast<float*>(nyq_plane_bar);
+  launch_1d(st, nout, [=] MCPM_LAMBDA(int64_t e) {
+    int l = (int)(e % onzc);
+    int64_t r = e / onzc;
+    int jr = (int)(r % rows);
+    int i = (int)(r / rows);
+    AxisSrc ax = axis_sources(i, onx, inx);
+    const bool herm = onzc < inzc && l == onzc - 1;
+    const float wl = herm ? 0.70710678118654752440f : 1.0f;
+    cfloat v = outbar[e];
+    float w = ax.w * wl * scale * (row_w ? row_w[jr] : 1.0f);
+    float re = v.re * w, im = v.im * w;
+    for (int a = 0; a < ax.n; ++a) {
+      int ii = ax.idx[a];
+      int64_t s = ((int64_t)ii * rows + jr) * inzc + l;
+      atomic_add(ib + 2 * s, re);
+      atomic_add(ib + 2 * s + 1, im);
+      if (herm) {
+        int im_ = ii == 0 ? 0 : inx - ii, j2 = y0 + jr, jm = j2 == 0 ? 0 : iny - j2;
+        int64_t s2 = (int64_t)im_ * iny + jm;
+        atomic_add(pb + 2 * s2, re);
+        atomic_add(pb + 2 * s2 + 1, -im);
+      }
+    }
+  });
+  return rt_check("chreshape_crop_xz_slab_T");
+}
+
 // Transpose of chreshape in the real inner product (its VJP): every OUTPUT-side cotangent element scatters to the
 // input elements it was gathered from; the Hermitian-mirrored source receives the conjugate.  `inbar` is zeroed here.
 int chreshape_T(stream_t st, const cfloat* outbar, int onx, int ony, int onz, cfloat* inbar, int inx, int iny, int inz) {

@@ -410,3 +410,102 @@ class SlabPM:
         posbar, velbar = posbar.clone(), velbar.clone()
         self.steps_backward(stape, posbar, velbar, *co)
         return self.lpt_backward(ltape, posbar, velbar)
+
+
+class SlabResize:
+    """chreshape (utils.py:975-1013) from the spectrum of one slab geometry to a coarser one -- the Fourier crop between
+    the paint mesh and the final mesh of `nufft` (nbody.py:575-576) when both are split along ky over the same ranks.
+
+    Per axis the crop keeps the low frequencies and folds the two old rows at +-s/2 into the new Nyquist row with
+    weights 1/sqrt2.  On x and kz that is local to a rank (mcpm_chreshape_crop_xz_slab); kz additionally needs the
+    mirrored element conj in[-kx, -ky] on ONE plane, which is all-gathered (nx * ny complex numbers); on ky it is a
+    redistribution of whole rows (one all-to-all with uneven splits) in which the two rows that merge carry 1/sqrt2.
+    `backward` is the transpose in the real inner product (the convention of mcpm_chreshape_vjp).
+    """
+
+    def __init__(self, pm_in, pm_out):
+        if pm_in.P != pm_out.P or pm_in.rank != pm_out.rank:
+            raise ValueError("both slab geometries must live on the same ranks")
+        if pm_out.nx > pm_in.nx or pm_out.ny > pm_in.ny or pm_out.nz > pm_in.nz:
+            raise ValueError("SlabResize crops: the output mesh must not exceed the input mesh on any axis")
+        self.i, self.o, self.A, self.lib = pm_in, pm_out, pm_in.A, pm_in.lib
+        a, b, P, rank = pm_in, pm_out, pm_in.P, pm_in.rank
+        self.scale = float(b.N) / float(a.N)
+        r2 = 0.7071067811865476
+        # row plan: input row j2 (frequency f) -> output row and weight
+        plan = []  # (src rank, dst rank, j2, j_out, w)
+        for j2 in range(a.ny):
+            f = j2 if j2 < (a.ny + 1) // 2 else j2 - a.ny
+            if b.ny == a.ny:
+                jo, w = j2, 1.0
+            elif -b.ny // 2 < f < b.ny // 2:
+                jo, w = f % b.ny, 1.0
+            elif abs(f) == b.ny // 2:
+                jo, w = b.ny // 2, r2
+            else:
+                continue
+            plan.append((j2 // a.kyl, jo // b.kyl, j2, jo, w))
+        mine = sorted((p for p in plan if p[0] == rank), key=lambda p: (p[1], p[3], p[2]))
+        to_me = sorted((p for p in plan if p[1] == rank), key=lambda p: (p[0], p[3], p[2]))
+        dev = self.A.device
+        self.send_rows = torch.tensor([p[2] - a.y0 for p in mine], dtype=torch.long, device=dev)
+        self.send_split = [sum(1 for p in mine if p[1] == d) for d in range(P)]
+        self.recv_rows = torch.tensor([p[3] - b.y0 for p in to_me], dtype=torch.long, device=dev)
+        self.recv_split = [sum(1 for p in to_me if p[0] == s) for s in range(P)]
+        w = np.ones(a.kyl, dtype=np.float32)
+        for p in mine:
+            w[p[2] - a.y0] = p[4]
+        self.row_w = self.A.prepare(w)
+        self.crop_z = b.nzc < a.nzc
+
+    def _rows_a2a(self, send, send_split, recv_split):
+        """[R_send, nx, nzc] complex, rows grouped by destination -> [R_recv, nx, nzc], rows grouped by source."""
+        if self.i.P == 1:
+            return send
+        recv = torch.empty((sum(recv_split), *send.shape[1:]), dtype=send.dtype, device=send.device)
+        dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(send.contiguous()), recv_split, send_split,
+                               group=self.i.group)
+        return recv
+
+    def _gather_plane(self, blk):
+        """Plane l = nz_out/2 of the whole input spectrum, [nx_in, ny_in], from every rank's rows."""
+        a = self.i
+        mine = blk[:, :, self.o.nz // 2].contiguous()
+        if a.P == 1:
+            return mine
+        parts = [torch.empty_like(mine) for _ in range(a.P)]
+        dist.all_gather([torch.view_as_real(p) for p in parts], torch.view_as_real(mine), group=a.group)
+        return torch.cat(parts, dim=1).contiguous()
+
+    def forward(self, blk):
+        """[nx_in, kyl_in, nzc_in] (my ky rows of the input spectrum) -> [nx_out, kyl_out, nzc_out]."""
+        a, b, A = self.i, self.o, self.A
+        blk = A.prepare(blk, "c64")
+        plane = self._gather_plane(blk) if self.crop_z else None
+        xz = A.empty((b.nx, a.kyl, b.nzc), "c64")
+        a._call("mcpm_chreshape_crop_xz_slab", a._st(), blk.data_ptr(), a.nx, a.ny, a.nz, a.kyl, a.y0,
+                0 if plane is None else plane.data_ptr(), self.row_w.data_ptr(), xz.data_ptr(), b.nx, b.nz, self.scale)
+        send = xz[:, self.send_rows, :].permute(1, 0, 2).contiguous()
+        recv = self._rows_a2a(send, self.send_split, self.recv_split)
+        out = torch.zeros((b.nx, b.kyl, b.nzc), dtype=blk.dtype, device=blk.device)
+        out.index_add_(1, self.recv_rows, recv.permute(1, 0, 2))  # the two rows of the new ky Nyquist land on one index
+        return out
+
+    def backward(self, outbar):
+        """Transpose of forward: [nx_out, kyl_out, nzc_out] -> [nx_in, kyl_in, nzc_in]."""
+        a, b, A = self.i, self.o, self.A
+        outbar = A.prepare(outbar, "c64")
+        send = outbar[:, self.recv_rows, :].permute(1, 0, 2).contiguous()
+        got = self._rows_a2a(send, self.recv_split, self.send_split)
+        xzbar = torch.zeros((b.nx, a.kyl, b.nzc), dtype=outbar.dtype, device=outbar.device)
+        xzbar[:, self.send_rows, :] = got.permute(1, 0, 2)
+        inbar = A.empty((a.nx, a.kyl, a.nzc), "c64")
+        pbar = torch.zeros((a.nx, a.ny), dtype=outbar.dtype, device=outbar.device) if self.crop_z else None
+        a._call("mcpm_chreshape_crop_xz_slab_vjp", a._st(), xzbar.data_ptr(), b.nx, b.nz, a.kyl, a.y0,
+                self.row_w.data_ptr(), inbar.data_ptr(), a.nx, a.ny, a.nz, 0 if pbar is None else pbar.data_ptr(),
+                self.scale)
+        if pbar is not None:
+            if a.P > 1:
+                dist.all_reduce(torch.view_as_real(pbar), group=a.group)
+            inbar[:, :, b.nz // 2] += pbar[:, a.y0:a.y0 + a.kyl]
+        return inbar

@@ -26,12 +26,16 @@ import torch.distributed as dist
 
 from . import cosmo as _cosmo
 from .model import linear_power_table
-from .nbody import rfftk
+from .nbody import rfftk, scale_shape
 
 
 class SlabFieldModel:
     def __init__(self, pm, box_size, n_steps=5, a_start=0.0, a_obs=1.0, lpt_order=2, paint_order=2, interlace_order=2,
-                 paint_deconv=True, b1=1.0, rsd=True, los=(0.0, 0.0, 1.0), sigma_obs=1.0, cosmology=None, kpow=None):
+                 paint_deconv=True, paint_oversamp=1.0, b1=1.0, rsd=True, los=(0.0, 0.0, 1.0), sigma_obs=1.0,
+                 cosmology=None, kpow=None):
+        if int(paint_order) != 2:
+            # model.evolve hands the same paint_order to nbody_bf (model.py:771) and SlabPM's step kernels are CIC
+            raise NotImplementedError("the slab-decomposed step loop is CIC only (paint_order = 2)")
         self.pm, self.o, self.A, self.lib = pm, pm.o, pm.A, pm.lib
         self.mesh_shape = (pm.nx, pm.ny, pm.nz)
         self.box_size = tuple(float(b) for b in box_size)
@@ -41,6 +45,18 @@ class SlabFieldModel:
         self.cosmology = cosmology if cosmology is not None else _cosmo.Cosmology()
         self.kpow = kpow if kpow is not None else linear_power_table(self.cosmology)
         self.transfer = self.A.prepare(self._transfer_block())
+        # a paint mesh finer than the evolution mesh (model.py:802-809 with paint_oversamp, BASELINE C5): a second slab
+        # geometry on the same ranks for the paints and their transforms, and the distributed Fourier crop back
+        self.paint_shape = scale_shape(self.mesh_shape, paint_oversamp)
+        self.pm2, self.resize, self.ratio = pm, None, (1.0, 1.0, 1.0)
+        if self.paint_shape != self.mesh_shape:
+            from .dist import SlabPM, SlabResize
+            self.ratio = tuple(p / m for p, m in zip(self.paint_shape, self.mesh_shape))
+            h2 = self.ratio[0] * pm.H
+            if abs(h2 - round(h2)) > 1e-9 or self.paint_shape[0] % pm.P or self.paint_shape[1] % pm.P:
+                raise ValueError("paint mesh: nx, ny must divide over the ranks and halo * paint/mesh ratio must be whole")
+            self.pm2 = SlabPM(pm.o, self.paint_shape, halo=int(round(h2)), group=pm.group)
+            self.resize = SlabResize(self.pm2, pm)
 
     def _transfer_block(self):
         """My ky rows of FieldModel.transfer_mesh (bricks.py:96-106, 150): sqrt(P(k) N / V), [nx, kyl, nzc]."""
@@ -57,18 +73,60 @@ class SlabFieldModel:
         self.pm._call(name, *args)
 
     def _paint_ext(self, pos, weights, shift):
-        """Weighted paint of my particles into a fresh halo-extended mesh, halos reduced; returns the owned planes."""
-        pm, A, st = self.pm, self.A, self.pm._st()
-        rho = A.zeros((pm.ext, pm.ny, pm.nz))
-        one = (C.c_float * 3)(1.0, 1.0, 1.0)
+        """Weighted paint of my particles into a fresh halo-extended PAINT mesh (positions scaled by the paint / mesh
+        ratio in-kernel, nbody.py:569), halos reduced; returns the owned planes."""
+        pm, p2, A, st = self.pm, self.pm2, self.A, self.pm._st()
+        rho = A.zeros((p2.ext, p2.ny, p2.nz))
+        sc = (C.c_float * 3)(*self.ratio)
         wp = 0 if weights is None else weights.data_ptr()
-        if not (self.paint_order == 2 and pm.brick and self.lib.mcpm_paint_brick(
+        if not (self.resize is None and self.paint_order == 2 and pm.brick and self.lib.mcpm_paint_brick(
                 st, pm.xl, pm.ny, pm.nz, pos.data_ptr(), wp, 1.0, float(shift), pos.shape[0], pm.ext, pm.ny, pm.nz,
                 rho.data_ptr()) == 0):
-            self._call("mcpm_paint", st, pos.data_ptr(), wp, 1.0, pos.shape[0], pm.ext, pm.ny, pm.nz, self.paint_order,
-                       one, float(shift), rho.data_ptr(), 1)
-        pm.halo_reduce(rho)
-        return rho[pm.H:pm.H + pm.xl]
+            self._call("mcpm_paint", st, pos.data_ptr(), wp, 1.0, pos.shape[0], p2.ext, p2.ny, p2.nz, self.paint_order,
+                       sc, float(shift), rho.data_ptr(), 1)
+        p2.halo_reduce(rho)
+        return rho[p2.H:p2.H + p2.xl]
+
+    def _final_mesh(self, pos, weights):
+        """Interlaced, deconvolved final paint (nbody.py:513-577) and back to real space: my planes of 1 + delta_obs at
+        the evolution shape (particles == cells: Jacobian 1 overall, model.py:806)."""
+        pm, p2, A, st, m = self.pm, self.pm2, self.A, self.pm._st(), self.interlace_order
+        pk = p2.rfftn(torch.stack([self._paint_ext(pos, weights, i / m) for i in range(m)]))
+        gk = A.empty((p2.nx, p2.kyl, p2.nzc), "c64")
+        jac = float(np.prod(self.ratio))
+        self._call("mcpm_interlace_combine_slab", st, pk.data_ptr(), gk.data_ptr(), m, p2.nx, p2.ny, p2.nz, p2.kyl,
+                   p2.y0, jac / pm.N, self._deconv_order())
+        if self.resize is not None:
+            gk = self.resize.forward(gk)
+        return pm.irfftn(gk.unsqueeze(0), overwrite=True, project=True)[0]
+
+    def _final_mesh_vjp(self, pos, weights, gbar):
+        """Transpose of _final_mesh: cotangent of my planes of the final mesh -> (posbar, weightsbar)."""
+        pm, p2, A, st, m = self.pm, self.pm2, self.A, self.pm._st(), self.interlace_order
+        gkb = pm.rfftn(gbar.unsqueeze(0))[0]
+        jac = float(np.prod(self.ratio))
+        hw = 0
+        if self.resize is not None:  # cotangent of the free final spectrum (C2R^T = R2C x w'), through the crop's transpose
+            self._call("mcpm_half_weight_axpy", st, gkb.data_ptr(), gkb.data_ptr(), pm.nx * pm.kyl * pm.nzc, pm.nz, 1.0, 0,
+                       0)
+            gkb = self.resize.backward(gkb)
+            hw = 1
+        mk = A.empty((m, p2.nx, p2.kyl, p2.nzc), "c64")
+        self._call("mcpm_interlace_combine_T_slab", st, gkb.data_ptr(), mk.data_ptr(), m, p2.nx, p2.ny, p2.nz, p2.kyl,
+                   p2.y0, jac / pm.N, self._deconv_order(), hw, 1.0)
+        mbar = p2.irfftn(mk, overwrite=True, project=True)  # [m, xl2, ny2, nz2] cotangents of the painted meshes
+        n = pos.shape[0]
+        posbar = A.empty((n, 3))
+        wbar = A.empty((n,)) if weights is not None else None
+        sc = (C.c_float * 3)(*self.ratio)
+        for i in range(m):
+            ext = A.empty((p2.ext, p2.ny, p2.nz))
+            ext[p2.H:p2.H + p2.xl] = mbar[i]
+            p2.halo_gather(ext)
+            self._call("mcpm_paint_vjp", st, pos.data_ptr(), 0 if weights is None else weights.data_ptr(), 1.0,
+                       ext.data_ptr(), n, p2.ext, p2.ny, p2.nz, self.paint_order, sc, float(i / m), posbar.data_ptr(),
+                       0 if wbar is None else wbar.data_ptr(), int(i > 0))
+        return posbar, wbar
 
     def _deconv_order(self):
         return self.paint_order if self.paint_deconv else 0
@@ -96,13 +154,7 @@ class SlabFieldModel:
             pos = o.rsd_shift(pos, vel, self.los, coef)
             pm._guard(pos)
             pm.check_guard()
-        # interlaced, deconvolved final paint (nbody.py:513-577; Jacobian 1: particles == cells) and back to real space
-        painted = torch.stack([self._paint_ext(pos, weights, i / m) for i in range(m)])
-        pk = pm.rfftn(painted)
-        gk = A.empty((pm.nx, pm.kyl, pm.nzc), "c64")
-        self._call("mcpm_interlace_combine_slab", st, pk.data_ptr(), gk.data_ptr(), m, pm.nx, pm.ny, pm.nz, pm.kyl,
-                   pm.y0, 1.0 / N, self._deconv_order())
-        gxy = pm.irfftn(gk.unsqueeze(0), overwrite=True, project=True)[0]
+        gxy = self._final_mesh(pos, weights)
         # Gaussian likelihood + N(0,1) prior (model.py:840-933 restricted to a constant noise level)
         inv_var = 1.0 / self.sigma_obs**2
         r = o.axpby(gxy, 1.0, obs, -1.0)
@@ -112,22 +164,8 @@ class SlabFieldModel:
 
         # ---- reverse sweep -------------------------------------------------------------------------------------------
         gbar = o.axpby(r, -inv_var)
-        gkb = pm.rfftn(gbar.unsqueeze(0))[0]
-        mk = A.empty((m, pm.nx, pm.kyl, pm.nzc), "c64")
-        self._call("mcpm_interlace_combine_T_slab", st, gkb.data_ptr(), mk.data_ptr(), m, pm.nx, pm.ny, pm.nz, pm.kyl,
-                   pm.y0, 1.0 / N, self._deconv_order(), 0, 1.0)
-        mbar = pm.irfftn(mk, overwrite=True, project=True)  # [m, xl, ny, nz] cotangents of the painted meshes
+        posbar, wbar = self._final_mesh_vjp(pos, weights, gbar)
         n = pos.shape[0]
-        posbar = A.empty((n, 3))
-        wbar = A.empty((n,)) if weights is not None else None
-        one = (C.c_float * 3)(1.0, 1.0, 1.0)
-        for i in range(m):
-            ext = A.empty((pm.ext, pm.ny, pm.nz))
-            ext[pm.H:pm.H + pm.xl] = mbar[i]
-            pm.halo_gather(ext)
-            self._call("mcpm_paint_vjp", st, pos.data_ptr(), 0 if weights is None else weights.data_ptr(), 1.0,
-                       ext.data_ptr(), n, pm.ext, pm.ny, pm.nz, self.paint_order, one, float(i / m), posbar.data_ptr(),
-                       0 if wbar is None else wbar.data_ptr(), int(i > 0))
         velbar = o.rsd_shift_vjp(posbar, self.los, coef) if self.rsd else A.zeros((n, 3))
         dkbar = pm.nbody_backward(tape, posbar, velbar)
         if weights is not None:  # dl = C2R(dk): its transpose is R2C times the Hermitian weights
@@ -159,8 +197,4 @@ class SlabFieldModel:
             pos = o.rsd_shift(pos, vel, self.los, float(_cosmo.a2g(c, self.a_obs) * _cosmo.a2f(c, self.a_obs)))
             pm._guard(pos)
             pm.check_guard()
-        pk = pm.rfftn(torch.stack([self._paint_ext(pos, weights, i / m) for i in range(m)]))
-        gk = A.empty((pm.nx, pm.kyl, pm.nzc), "c64")
-        self._call("mcpm_interlace_combine_slab", st, pk.data_ptr(), gk.data_ptr(), m, pm.nx, pm.ny, pm.nz, pm.kyl,
-                   pm.y0, 1.0 / N, self._deconv_order())
-        return pm.irfftn(gk.unsqueeze(0), overwrite=True, project=True)[0]
+        return self._final_mesh(pos, weights)

@@ -104,10 +104,15 @@ class FieldModel:
     def __init__(self, mesh_shape=(64, 64, 64), box_size=(640.0, 640.0, 640.0), evolution="nbody", n_steps=5,
                  a_start=0.0, a_obs=1.0, lpt_order=2, paint_order=2, interlace_order=2, paint_deconv=True,
                  paint_oversamp=1.0, b1=1.0, rsd=True, los=(0.0, 0.0, 1.0), sigma_obs=1.0, cosmology=None, kpow=None,
-                 precond="real"):
+                 precond="real", out_shape="paint"):
         if precond not in ("real", "fourier"):
             raise ValueError("precond must be 'real' or 'fourier'")
-        self.precond = precond
+        if out_shape not in ("paint", "mesh"):
+            raise ValueError("out_shape must be 'paint' or 'mesh'")
+        # 'paint': the mesh is handed on at the paint shape, as evolve does (model.py:806-807); 'mesh': at the evolution
+        # shape, where the reference's likelihood brings it back anyway when final_shape == init_shape and there is no
+        # selection function (model.py:855) -- what the slab-decomposed model (dist_model.py) evaluates
+        self.precond, self.out_shape = precond, out_shape
         self.mesh_shape = tuple(int(s) for s in mesh_shape)
         self.box_size = tuple(float(b) for b in box_size)
         self.evolution, self.n_steps, self.a_start, self.a_obs = evolution, int(n_steps), a_start, a_obs
@@ -159,7 +164,8 @@ class FieldModel:
             pos = _RsdShift.apply(pos, vel, self.los, coef)
         gxy = nb.nufft(pos, self.mesh_shape, self.paint_shape, weights, self.paint_order, self.interlace_order,
                        paint_deconv=self.paint_deconv)
-        gxy = nb.chreshape(gxy, r2chshape(self.paint_shape)) if self.paint_shape != self.mesh_shape else gxy
+        if self.paint_shape != self.mesh_shape and self.out_shape == "paint":
+            gxy = nb.chreshape(gxy, r2chshape(self.paint_shape))
         return nb.irfftn(gxy)  # 1 + delta_obs at the paint shape (particles == cells: Jacobian 1, model.py:806)
 
     predict = evolve

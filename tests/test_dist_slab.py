@@ -135,7 +135,7 @@ def _model_worker(rank, world, port, shape, halo, kw, q):
         rng = np.random.default_rng(3)  # same global fields on every rank
         white = torch.tensor(rng.normal(size=shape).astype(np.float32))
         truth = torch.tensor(rng.normal(size=shape).astype(np.float32))
-        ref = FieldModel(shape, box, "nbody", a_start=0.1, **kw)
+        ref = FieldModel(shape, box, "nbody", a_start=0.1, out_shape="mesh", **kw)
         obs = ref.evolve(truth).detach() + torch.tensor(rng.normal(size=shape).astype(np.float32))
         lp_ref, f_ref = ref.value_and_force(white, obs)
         pm = SlabPM(ops, shape, halo=halo)
@@ -156,6 +156,9 @@ def _model_worker(rank, world, port, shape, halo, kw, q):
 @pytest.mark.parametrize("shape,halo,kw", [
     ((16, 16, 16), 6, dict(n_steps=2, b1=1.0, rsd=True)),
     ((24, 16, 20), 8, dict(n_steps=1, b1=0.0, rsd=False, paint_deconv=False, interlace_order=3, lpt_order=1)),
+    # a paint mesh finer than the evolution mesh (BASELINE C5: 2x): second slab geometry + distributed Fourier crop
+    ((16, 16, 16), 6, dict(n_steps=2, b1=1.0, rsd=True, paint_oversamp=2.0)),
+    ((16, 16, 16), 4, dict(n_steps=1, b1=0.5, rsd=True, paint_oversamp=1.5, interlace_order=3)),
 ])
 def test_slab_field_model_world2_gloo(shape, halo, kw):
     """grad(log-density) of the whole model chain on 2 slabs against the single-process FieldModel (same kernels, same
@@ -219,3 +222,51 @@ def test_slab_field_model_single_rank(backend):
         assert rel(mdl.predict(truth), ref.evolve(truth).detach()) < 5e-4
     finally:
         nbody._OPS = old
+
+
+def _resize_worker(rank, world, port, q):
+    try:
+        sys.path.insert(0, ROOT)
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2")
+        import torch.distributed as dist
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from oracle import cpu_port
+        from montecosmo_b200.dist import SlabPM, SlabResize
+        ops = cpu_port.cpu_ops()
+        res = {}
+        for sin, sout in [((16, 12, 20), (8, 8, 12)), ((12, 16, 8), (12, 8, 8)), ((8, 8, 8), (8, 8, 8)),
+                          ((16, 16, 16), (8, 16, 8))]:
+            a, b = SlabPM(ops, sin, halo=2), SlabPM(ops, sout, halo=2)
+            rz = SlabResize(a, b)
+            rng = np.random.default_rng(1)
+            full = np.fft.rfftn(rng.normal(size=sin)).astype(np.complex64)
+            ref = ops.chreshape(torch.tensor(full), (sout[0], sout[1], sout[2] // 2 + 1)).numpy()
+            out = rz.forward(a.scatter_spectrum(torch.tensor(full))).numpy()
+            res[f"fwd {sin}->{sout}"] = float(np.abs(out - ref[:, b.y0:b.y0 + b.kyl, :]).max() / np.abs(ref).max())
+            ob = (rng.normal(size=ref.shape) + 1j * rng.normal(size=ref.shape)).astype(np.complex64)
+            refb = ops.chreshape_vjp(torch.tensor(ob), full.shape).numpy()
+            inb = rz.backward(b.scatter_spectrum(torch.tensor(ob))).numpy()
+            res[f"bwd {sin}->{sout}"] = float(np.abs(inb - refb[:, a.y0:a.y0 + a.kyl, :]).max() / np.abs(refb).max())
+        q.put((rank, res, None))
+        dist.destroy_process_group()
+    except Exception:
+        import traceback
+        q.put((rank, None, traceback.format_exc()))
+
+
+def test_slab_resize_world2_gloo():
+    """The distributed Fourier crop (dist.SlabResize: local x / kz crop kernel, gathered Nyquist plane, row all-to-all)
+    and its transpose against the single-process mcpm_chreshape / mcpm_chreshape_vjp (themselves pinned to the golden
+    vectors of utils.chreshape): 1e-6 of the largest element, every rank's rows."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_resize_worker, args=(r, 2, 29733, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    out = [q.get(timeout=600) for _ in ps]
+    for p in ps:
+        p.join(60)
+    for rank, res, err in out:
+        assert err is None, f"rank {rank}:\n{err}"
+        assert max(res.values()) < 1e-6, res

@@ -47,6 +47,8 @@ def main():
                          "interlaced final paint, likelihood and the full reverse sweep to the white field) instead of "
                          "nbody_bf forward + reverse alone")
     ap.add_argument("--cell", type=float, default=2.5, help="cell size in Mpc/h (box = cell * mesh); 2.5 = BASELINE C3-C5")
+    ap.add_argument("--oversamp", type=float, default=1.0,
+                    help="with --model: paint mesh = oversamp x evolution mesh (BASELINE C5 uses 2)")
     ap.add_argument("--model-check", action="store_true",
                     help="with --model on ONE GPU: compare log-density and force with the single-GPU FieldModel at --mesh")
     a = ap.parse_args()
@@ -155,7 +157,7 @@ def main():
 
     if a.model:
         from montecosmo_b200.dist_model import SlabFieldModel
-        mdl = SlabFieldModel(pm, (a.cell * n,) * 3, n_steps=a.nbody_steps, cosmology=cosmo)
+        mdl = SlabFieldModel(pm, (a.cell * n,) * 3, n_steps=a.nbody_steps, cosmology=cosmo, paint_oversamp=a.oversamp)
         gw = torch.Generator(device=dev).manual_seed(77 + rank)
         white = torch.randn((pm.xl, n, n), device=dev, generator=gw)
         obs = mdl.predict(torch.randn((pm.xl, n, n), device=dev, generator=gw)) \
@@ -164,7 +166,8 @@ def main():
         if a.model_check and world == 1:
             try:
                 from montecosmo_b200.model import FieldModel
-                ref = FieldModel((n, n, n), (a.cell * n,) * 3, "nbody", n_steps=a.nbody_steps, cosmology=cosmo)
+                ref = FieldModel((n, n, n), (a.cell * n,) * 3, "nbody", n_steps=a.nbody_steps, cosmology=cosmo,
+                                 paint_oversamp=a.oversamp, out_shape="mesh")
                 lp_ref, f_ref = ref.value_and_force(white, obs)
                 lp, f = mdl.value_and_force(white, obs)
                 out["model_check"] = {"mesh": n, "cell_mpc_h": a.cell, "logp": float(lp), "logp_ref": float(lp_ref),
@@ -212,7 +215,7 @@ def main():
         out.update({"metric": ("slab-decomposed grad(log-density) of the field-level model, evaluations/s" if a.model else
                                "slab-decomposed nbody_bf forward + reverse sweep, evaluations/s"), "mesh": n, "n_gpus": world,
                     "value": 1e3 / per, "unit": "evals/s", "ms_per_eval": per, "nbody_steps": a.nbody_steps,
-                    "halo_planes": pm.H, "max_mem_GiB": float(mem), "fused_x_transform": bool(pm.xfuse), "p2p": pm.p2p_note,
+                    "halo_planes": pm.H, "paint_oversamp": a.oversamp if a.model else None, "max_mem_GiB": float(mem), "fused_x_transform": bool(pm.xfuse), "p2p": pm.p2p_note,
                     "nvlink_GB_out_per_gpu_per_eval": (a2a + halo) / 1e9 if world > 1 else 0.0,
                     "nvlink_GBps_per_gpu_if_all_time_were_comm": (a2a + halo) / 1e9 / (per * 1e-3) if world > 1 else 0.0})
         print(json.dumps(out), flush=True)

@@ -179,8 +179,9 @@ def test_slab_field_model_world2_gloo(shape, halo, kw):
         assert res["force_norm"] > 1e-3, res  # the likelihood term of the force is not trivially zero
 
 
+@pytest.mark.parametrize("oversamp", [1.0, 2.0])
 @pytest.mark.parametrize("backend", ["hostemu", pytest.param("cuda", marks=pytest.mark.gpu)])
-def test_slab_field_model_single_rank(backend):
+def test_slab_field_model_single_rank(backend, oversamp):
     """The slab model on ONE rank (periodic halos exchanged with itself) against FieldModel: exercises every kernel and
     the hand-chained reverse sweep of dist_model.py on whichever device the backend names -- on a B200 this is the
     single-GPU check of the code path the multi-GPU runs take (tools/slab_bench.py --model)."""
@@ -206,8 +207,12 @@ def test_slab_field_model_single_rank(backend):
         rng = np.random.default_rng(5)
         white = torch.tensor(rng.normal(size=shape).astype(np.float32), device=dev)
         truth = torch.tensor(rng.normal(size=shape).astype(np.float32), device=dev)
-        kw = dict(n_steps=3, b1=0.7, rsd=True)
-        ref = FieldModel(shape, box, "nbody", a_start=0.1, **kw)
+        if backend == "hostemu" and oversamp != 1.0:
+            shape, halo = (16, 16, 16), 6  # the 2-rank test covers this on the CPU; keep the suite short
+            box = tuple(20.0 * s for s in shape)
+            white, truth = white[:16, :16, :16].contiguous(), truth[:16, :16, :16].contiguous()
+        kw = dict(n_steps=3, b1=0.7, rsd=True, paint_oversamp=oversamp)  # 2.0: finer paint mesh + Fourier crop (C5)
+        ref = FieldModel(shape, box, "nbody", a_start=0.1, out_shape="mesh", **kw)
         obs = ref.evolve(truth).detach() + torch.tensor(rng.normal(size=shape).astype(np.float32), device=dev)
         lp_ref, f_ref = ref.value_and_force(white, obs)
         mdl = SlabFieldModel(SlabPM(ops, shape, halo=halo), box, a_start=0.1, **kw)

@@ -50,7 +50,9 @@ def main():
     ap.add_argument("--oversamp", type=float, default=1.0,
                     help="with --model: paint mesh = oversamp x evolution mesh (BASELINE C5 uses 2)")
     ap.add_argument("--model-check", action="store_true",
-                    help="with --model on ONE GPU: compare log-density and force with the single-GPU FieldModel at --mesh")
+                    help="with --model: compare log-density and force with the single-GPU FieldModel (computed on every "
+                         "rank's own GPU from the same global fields) before timing")
+    ap.add_argument("--model-check-mesh", type=int, default=0, help="mesh of that comparison (default: --mesh)")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -163,18 +165,35 @@ def main():
         obs = mdl.predict(torch.randn((pm.xl, n, n), device=dev, generator=gw)) \
             + torch.randn((pm.xl, n, n), device=dev, generator=gw)
         del dk
-        if a.model_check and world == 1:
+        if a.model_check:
+            # Every rank computes the single-GPU FieldModel on the same GLOBAL white field / observation (same seed on
+            # identical devices gives the same sequence) and compares its own slab; errors are the max over ranks.
             try:
                 from montecosmo_b200.model import FieldModel
-                ref = FieldModel((n, n, n), (a.cell * n,) * 3, "nbody", n_steps=a.nbody_steps, cosmology=cosmo,
+                nc = a.model_check_mesh or n
+                pmc = pm if nc == n else SlabPM(ops, (nc, nc, nc), halo=min(a.halo, nc // world))
+                mdc = mdl if nc == n else SlabFieldModel(pmc, (a.cell * nc,) * 3, n_steps=a.nbody_steps, cosmology=cosmo,
+                                                         paint_oversamp=a.oversamp)
+                gg = torch.Generator(device=dev).manual_seed(4242)
+                gwhite, gtruth, gnoise = (torch.randn((nc, nc, nc), device=dev, generator=gg) for _ in range(3))
+                ref = FieldModel((nc, nc, nc), (a.cell * nc,) * 3, "nbody", n_steps=a.nbody_steps, cosmology=cosmo,
                                  paint_oversamp=a.oversamp, out_shape="mesh")
-                lp_ref, f_ref = ref.value_and_force(white, obs)
-                lp, f = mdl.value_and_force(white, obs)
-                out["model_check"] = {"mesh": n, "cell_mpc_h": a.cell, "logp": float(lp), "logp_ref": float(lp_ref),
+                gobs = ref.evolve(gtruth).detach() + gnoise
+                lp_ref, f_ref = ref.value_and_force(gwhite, gobs)
+                sl = slice(pmc.x0, pmc.x0 + pmc.xl)
+                lp, f = mdc.value_and_force(gwhite[sl].contiguous(), gobs[sl].contiguous())
+                fr = f_ref[sl]
+                sums = torch.stack([((f - fr) ** 2).sum(), (fr ** 2).sum(), (f * fr).sum(), (f ** 2).sum()]).double()
+                if world > 1:
+                    dist.all_reduce(sums)
+                out["model_check"] = {"mesh": nc, "cell_mpc_h": a.cell, "ranks": world, "logp": float(lp),
+                                      "logp_ref": float(lp_ref),
                                       "rel_logp_err": abs(float(lp) - float(lp_ref)) / abs(float(lp_ref)),
-                                      "rel_force_err": float((f - f_ref).norm() / f_ref.norm()),
-                                      "force_cosine": float((f * f_ref).sum() / (f.norm() * f_ref.norm()))}
-                del ref, lp_ref, f_ref, lp, f
+                                      "rel_force_err": float((sums[0] / sums[1]).sqrt()),
+                                      "force_cosine": float(sums[2] / (sums[1] * sums[3]).sqrt())}
+                del ref, lp_ref, f_ref, lp, f, gwhite, gtruth, gnoise, gobs
+                if nc != n:
+                    del mdc, pmc
                 torch.cuda.empty_cache()
             except Exception as e:  # the timing below still runs
                 out["model_check"] = {"error": f"{type(e).__name__}: {e}"}

@@ -34,7 +34,7 @@ INF = float("inf")
 
 
 class SlabPM:
-    def __init__(self, ops, mesh_shape, halo=24, group=None):
+    def __init__(self, ops, mesh_shape, halo=24, group=None, p2p=True):
         self.o, self.lib, self.A = ops, ops.lib, ops.A
         self.group = group
         self.P = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -63,7 +63,9 @@ class SlabPM:
         # the first call decides (MCPM_EUNSUP -> generic kernels)
         self.brick = os.environ.get("MCPM_SLAB_BRICK", "1") != "0" and bool(self.lib.mcpm_xfuse_supported(64))
         self.p2p, self.p2p_note = False, "off"
-        if self.xfuse and self.P > 1 and os.environ.get("MCPM_SLAB_P2P", "1") != "0":
+        # p2p=False: a geometry that only paints and transforms (the finer paint mesh of the final nufft) needs no peer
+        # buffers -- they are 6 half spectra of symmetric memory
+        if p2p and self.xfuse and self.P > 1 and os.environ.get("MCPM_SLAB_P2P", "1") != "0":
             self._setup_p2p()
         self.prev, self.next = (self.rank - 1) % self.P, (self.rank + 1) % self.P
         ax = [np.arange(self.xl, dtype=np.float32), np.arange(ny, dtype=np.float32), np.arange(nz, dtype=np.float32)]

@@ -55,7 +55,7 @@ class SlabFieldModel:
             h2 = self.ratio[0] * pm.H
             if abs(h2 - round(h2)) > 1e-9 or self.paint_shape[0] % pm.P or self.paint_shape[1] % pm.P:
                 raise ValueError("paint mesh: nx, ny must divide over the ranks and halo * paint/mesh ratio must be whole")
-            self.pm2 = SlabPM(pm.o, self.paint_shape, halo=int(round(h2)), group=pm.group)
+            self.pm2 = SlabPM(pm.o, self.paint_shape, halo=int(round(h2)), group=pm.group, p2p=False)
             self.resize = SlabResize(self.pm2, pm)
 
     def _transfer_block(self):

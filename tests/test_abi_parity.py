@@ -117,6 +117,35 @@ def test_paint_edge_cases(ops):
         ops.paint(pos, (8, 8, 2), None, order=4)
 
 
+def test_empty_inputs_and_rejected_arguments(ops):
+    """Empty particle sets flow through every particle operator (zero-size outputs, zero meshes); arguments the
+    reference would reject, or that the engine cannot serve, come back as MCPM_EINVAL with a message -- no crash, no
+    partial write.  Positions far outside the box, or non-finite, never index outside the mesh."""
+    from montecosmo_b200._capi import McpmError
+    shape = (8, 6, 10)
+    e = np.zeros((0, 3), np.float32)
+    mesh = f32(np.random.default_rng(0).normal(size=shape))
+    assert to_numpy(ops.read(e, mesh)).shape == (0,)
+    assert to_numpy(ops.read_grad(e, mesh)).shape == (0, 3)
+    pb, wb = ops.paint_vjp(e, mesh)
+    assert to_numpy(pb).shape == (0, 3) and to_numpy(wb).shape == (0,)
+    assert not to_numpy(ops.paint3(e, e, shape)).any()
+    assert not to_numpy(ops.nufft_paint(e, shape)).any()
+    assert to_numpy(ops.pm_forces(e, shape)).shape == (0, 3)
+    one = np.zeros((3, 3), np.float32)
+    for bad in (lambda: ops.paint(one, shape, order=5), lambda: ops.paint(one, shape, order=0),
+                lambda: ops.paint(one, (2, 2, 2), order=4), lambda: ops.nufft_paint(one, shape, interlace_order=7),
+                lambda: ops.deconv(c64(np.zeros((8, 6, 6))), 5, kb_kcut=1.0)):
+        with pytest.raises(McpmError) as ei:
+            bad()
+        assert ei.value.code == 1 and str(ei.value)
+    far = f32([[1e9, -1e9, 3e8], [np.nan, 0.0, 0.0], [np.inf, 1.0, 2.0], [7.999999, 5.999999, 9.999999]])
+    out = to_numpy(ops.paint(far[:1], shape))
+    assert abs(out.sum() - 1.0) < 1e-6                      # wrapped, mass conserved
+    ops.paint(far, shape)                                   # non-finite positions: garbage in, but no fault
+    ops.read(far, mesh)
+
+
 @pytest.mark.parametrize("order", [2, 3, 4])
 def test_paint_read_vjp(ops, order):
     """Gathers of the window gradient vs oracle autograd (1e-5)."""

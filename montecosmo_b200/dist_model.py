@@ -30,9 +30,12 @@ from .nbody import rfftk, scale_shape
 
 
 class SlabFieldModel:
-    def __init__(self, pm, box_size, n_steps=5, a_start=0.0, a_obs=1.0, lpt_order=2, paint_order=2, interlace_order=2,
+    def __init__(self, pm, box_size, evolution="nbody", n_steps=5, a_start=0.0, a_obs=1.0, lpt_order=2, paint_order=2, interlace_order=2,
                  paint_deconv=True, paint_oversamp=1.0, b1=1.0, rsd=True, los=(0.0, 0.0, 1.0), sigma_obs=1.0,
                  cosmology=None, kpow=None):
+        if evolution not in ("lpt", "nbody"):
+            raise ValueError(f"unknown evolution {evolution}")
+        self.evolution = evolution
         if int(paint_order) != 2:
             # model.evolve hands the same paint_order to nbody_bf (model.py:771) and SlabPM's step kernels are CIC
             raise NotImplementedError("the slab-decomposed step loop is CIC only (paint_order = 2)")
@@ -131,6 +134,22 @@ class SlabFieldModel:
     def _deconv_order(self):
         return self.paint_order if self.paint_deconv else 0
 
+    def _evolve(self, dk):
+        """lpt at a_obs (model.py:763) or lpt at a_start + BullFrog steps (model.py:771-773): local (pos, vel, tape)."""
+        c = self.cosmology
+        if self.evolution == "lpt":
+            d1, d2, dv2 = (float(f(c, self.a_obs)) for f in (_cosmo.a2g, _cosmo.a2g2, _cosmo.a2dg2dg))
+            pos, vel, ltape = self.pm.lpt_forward(dk, d1, d2, dv2, self.lpt_order)
+            self.pm._guard(pos)
+            self.pm.check_guard()
+            return pos, vel, ("lpt", ltape)
+        pos, vel, tape = self.pm.nbody_forward(dk, c, self.a_start, self.a_obs, self.n_steps, self.lpt_order)
+        return pos, vel, ("nbody", tape)
+
+    def _evolve_vjp(self, tape, posbar, velbar):
+        kind, t = tape
+        return self.pm.lpt_backward(t, posbar, velbar) if kind == "lpt" else self.pm.nbody_backward(t, posbar, velbar)
+
     # ------------------------------------------------------------------------------------------------ evaluation
     def value_and_force(self, white, obs):
         """(logpdf, d logpdf / d white) for my planes of the white field [xl, ny, nz] and of the observed mesh; the
@@ -148,7 +167,7 @@ class SlabFieldModel:
         if self.b1 != 0.0:
             dl = pm.irfftn(dk.unsqueeze(0), project=True)[0]
             weights = o.axpby(dl.reshape(-1), self.b1 * D / N, None, 0.0, 1.0)
-        pos, vel, tape = pm.nbody_forward(dk, c, self.a_start, self.a_obs, self.n_steps, self.lpt_order)
+        pos, vel, tape = self._evolve(dk)
         coef = float(_cosmo.a2g(c, self.a_obs) * _cosmo.a2f(c, self.a_obs))
         if self.rsd:  # bricks.py:781-792 in cell units
             pos = o.rsd_shift(pos, vel, self.los, coef)
@@ -167,7 +186,7 @@ class SlabFieldModel:
         posbar, wbar = self._final_mesh_vjp(pos, weights, gbar)
         n = pos.shape[0]
         velbar = o.rsd_shift_vjp(posbar, self.los, coef) if self.rsd else A.zeros((n, 3))
-        dkbar = pm.nbody_backward(tape, posbar, velbar)
+        dkbar = self._evolve_vjp(tape, posbar, velbar)
         if weights is not None:  # dl = C2R(dk): its transpose is R2C times the Hermitian weights
             dlbar = o.axpby(wbar, self.b1 * D / N).reshape(1, pm.xl, pm.ny, pm.nz)
             dlk = pm.rfftn(dlbar)[0]
@@ -192,7 +211,7 @@ class SlabFieldModel:
         if self.b1 != 0.0:
             dl = pm.irfftn(dk.unsqueeze(0), project=True)[0]
             weights = o.axpby(dl.reshape(-1), self.b1 * float(_cosmo.a2g(c, self.a_obs)) / N, None, 0.0, 1.0)
-        pos, vel, _ = pm.nbody_forward(dk, c, self.a_start, self.a_obs, self.n_steps, self.lpt_order)
+        pos, vel, _ = self._evolve(dk)
         if self.rsd:
             pos = o.rsd_shift(pos, vel, self.los, float(_cosmo.a2g(c, self.a_obs) * _cosmo.a2f(c, self.a_obs)))
             pm._guard(pos)

@@ -135,11 +135,13 @@ def _model_worker(rank, world, port, shape, halo, kw, q):
         rng = np.random.default_rng(3)  # same global fields on every rank
         white = torch.tensor(rng.normal(size=shape).astype(np.float32))
         truth = torch.tensor(rng.normal(size=shape).astype(np.float32))
-        ref = FieldModel(shape, box, "nbody", a_start=0.1, out_shape="mesh", **kw)
+        kw = dict(kw)
+        evo = kw.pop("evolution", "nbody")
+        ref = FieldModel(shape, box, evo, a_start=0.1, out_shape="mesh", **kw)
         obs = ref.evolve(truth).detach() + torch.tensor(rng.normal(size=shape).astype(np.float32))
         lp_ref, f_ref = ref.value_and_force(white, obs)
         pm = SlabPM(ops, shape, halo=halo)
-        mdl = SlabFieldModel(pm, box, a_start=0.1, **kw)
+        mdl = SlabFieldModel(pm, box, evo, a_start=0.1, **kw)
         sl = slice(pm.x0, pm.x0 + pm.xl)
         lp, f = mdl.value_and_force(white[sl].contiguous(), obs[sl].contiguous())
         rel = lambda a, b: float(np.linalg.norm((np.asarray(a) - np.asarray(b)).ravel()) / np.linalg.norm(np.asarray(b).ravel()))
@@ -159,6 +161,7 @@ def _model_worker(rank, world, port, shape, halo, kw, q):
     # a paint mesh finer than the evolution mesh (BASELINE C5: 2x): second slab geometry + distributed Fourier crop
     ((16, 16, 16), 6, dict(n_steps=2, b1=1.0, rsd=True, paint_oversamp=2.0)),
     ((16, 16, 16), 4, dict(n_steps=1, b1=0.5, rsd=True, paint_oversamp=1.5, interlace_order=3)),
+    ((16, 16, 16), 4, dict(evolution="lpt", a_obs=0.8, b1=1.0, rsd=True)),  # evolution = 'lpt' (model.py:763)
 ])
 def test_slab_field_model_world2_gloo(shape, halo, kw):
     """grad(log-density) of the whole model chain on 2 slabs against the single-process FieldModel (same kernels, same

@@ -186,15 +186,30 @@ def alpha_bf(c, g0, dg):
     return (d2 - lin_ratio) / (d0 - lin_ratio)
 
 
-def bullfrog_coefficients(c, a0, a1, n_steps):
+def alpha_fpm(c, g0, dg):
+    """FastPM growth-time kick coefficient, nbody.py:921-931 (the reference defines it next to alpha_bf and leaves the
+    switch commented out): E(a0) g0 f(g0) a0^2 / (E(a2) g2 f(g2) a2^2) with g2 = g0 + dg."""
+    g0 = _t(g0)
+    g2 = g0 + dg
+    a0, a2 = g2a(c, g0), g2a(c, g2)
+    coeff0 = Esqr(c, a0) ** 0.5 * g0 * g2f(c, g0) * a0**2
+    coeff2 = Esqr(c, a2) ** 0.5 * g2 * g2f(c, g2) * a2**2
+    return coeff0 / coeff2
+
+
+def bullfrog_coefficients(c, a0, a1, n_steps, integrator="bullfrog"):
     """Per-step (alpha, beta = (1 - alpha) / g1, drift_pre, drift_post) of the DKD loop (nbody.py:933-951, 974-976).
 
+    integrator = 'fastpm' uses alpha_fpm (nbody.py:921-931) in place of alpha_bf: the same loop, another kick coefficient.
     Times advance as diffrax's constant-step controller does: t_{s+1} = t_s + dg, the last step clipped onto g1.
     Returns four float64 tensors of length n_steps (differentiable w.r.t. the cosmology) and (g0, dg).
     """
     key = _param_key(c)
+    if integrator not in ("bullfrog", "fastpm"):
+        raise ValueError("integrator must be 'bullfrog' or 'fastpm'")
+    kick = alpha_bf if integrator == "bullfrog" else alpha_fpm
     ckey = None if key is None or isinstance(a0, torch.Tensor) or isinstance(a1, torch.Tensor) else \
-        ("bf", key, float(a0), float(a1), int(n_steps))
+        (integrator, key, float(a0), float(a1), int(n_steps))
     if ckey is not None and c._workspace.get("bf_coef", (None,))[0] == ckey:
         return c._workspace["bf_coef"][1]
     g0, g1 = a2g(c, a0), a2g(c, a1)
@@ -202,7 +217,7 @@ def bullfrog_coefficients(c, a0, a1, n_steps):
     alphas, betas = [], []
     t = g0
     for _ in range(n_steps):
-        al = alpha_bf(c, t, dg)
+        al = kick(c, t, dg)
         alphas.append(al)
         betas.append((1 - al) / (t + dg / 2))
         t = t + dg

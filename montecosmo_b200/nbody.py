@@ -501,7 +501,8 @@ def _save_plan(ts, g0, dg, n_steps):
 
 
 def nbody_bf(cosmo, init_mesh, pos, a0=0.0, a1=1.0, n_steps=5, paint_order: int = 2, lpt_order: int = 2,
-             paint_deconv=False, grad_fd=np.inf, lap_fd=np.inf, snapshots=None, fn=save_y, ptcl_shape="auto"):
+             paint_deconv=False, grad_fd=np.inf, lap_fd=np.inf, snapshots=None, fn=save_y, ptcl_shape="auto",
+             integrator="bullfrog"):
     """N-body simulation with the BullFrog solver (nbody.py:967-1002): lpt at a0, then n_steps DKD steps in growth time.
 
     Returns (pos, vel), each [S, Np, 3].  `snapshots` as in the reference: None or an int <= 1 saves the final state
@@ -509,6 +510,9 @@ def nbody_bf(cosmo, init_mesh, pos, a0=0.0, a1=1.0, n_steps=5, paint_order: int 
     Save times inside a step get the solver's dense output (linear between the step's ends, as diffrax's Euler), and
     `fn(t, (pos, vel), None)` maps every saved state (any tuple / tensor result is stacked along a new leading axis);
     with snapshots=None the reference ignores `fn`, and so does this.
+
+    `integrator` (extension): "bullfrog" (the live alpha_bf, nbody.py:907-919) or "fastpm" (alpha_fpm, nbody.py:921-931,
+    which the reference keeps next to it with the switch commented out): same drift-kick-drift loop, other kick weights.
 
     `ptcl_shape` (extension) is a performance hint only: the lattice shape of `pos` (regular_pos order).  "auto" assumes
     the mesh shape when the particle count matches it; None disables the brick-tiled kernels.
@@ -522,7 +526,7 @@ def nbody_bf(cosmo, init_mesh, pos, a0=0.0, a1=1.0, n_steps=5, paint_order: int 
         ptcl_shape = mesh_shape if pos.shape[0] == int(np.prod(mesh_shape)) else None
     ops().set_lattice(mesh_shape, ptcl_shape)
     x, vel = lpt(cosmo, init_mesh, pos, a0, lpt_order, 1, grad_fd, lap_fd, _displaced=True)
-    al, be, pre, post, _, _ = _cosmo.bullfrog_coefficients(cosmo, a0, a1, n_steps)
+    al, be, pre, post, _, _ = _cosmo.bullfrog_coefficients(cosmo, a0, a1, n_steps, integrator)
     coefs = torch.stack([al, be, pre, post], dim=1)
     g0, g1 = _cosmo.a2g(cosmo, a0), _cosmo.a2g(cosmo, a1)
     dg = (g1 - g0) / n_steps
@@ -607,3 +611,4 @@ def nbody_bf_scan(cosmo, init_mesh, pos, a, n_steps=5, paint_order: int = 2, gra
 a2g, a2g2, a2f, a2f2, a2dg2dg = _cosmo.a2g, _cosmo.a2g2, _cosmo.a2f, _cosmo.a2f2, _cosmo.a2dg2dg
 g2a, g2g2, g2f, g2f2, g2dg2dg = _cosmo.g2a, _cosmo.g2g2, _cosmo.g2f, _cosmo.g2f2, _cosmo.g2dg2dg
 alpha_bf = _cosmo.alpha_bf  # nbody.py:907-919
+alpha_fpm = _cosmo.alpha_fpm  # nbody.py:921-931

@@ -638,6 +638,16 @@ def alpha_bf(cosmo, g0, dg):
     return (d2 - lin_ratio) / (d0 - lin_ratio)
 
 
+def alpha_fpm(cosmo, g0, dg):
+    """nbody.py:921-931 (FastPM growth-time coefficient, defined next to alpha_bf; the reference's kick uses alpha_bf)."""
+    g0 = _t(g0)
+    g2 = g0 + dg
+    a0, a2 = g2a(cosmo, g0), g2a(cosmo, g2)
+    coeff0 = Esqr(cosmo, a0) ** 0.5 * g0 * g2f(cosmo, g0) * a0 ** 2
+    coeff2 = Esqr(cosmo, a2) ** 0.5 * g2 * g2f(cosmo, g2) * a2 ** 2
+    return coeff0 / coeff2
+
+
 def bullfrog_step(cosmo, state, g0, dg, mesh_shape, paint_order=2, paint_deconv=False,
                   grad_fd=np.inf, lap_fd=np.inf):
     """One drift-kick-drift step, nbody.py:933-951."""

@@ -197,6 +197,18 @@ def main():
         lin = (float(nbody.g2g2(c, gg0)) + d0 * dg / 2) / gm - gm
         alphas.append((d2 - lin) / (d0 - lin))
     d["bf4_alpha"] = np.array(alphas)
+    # alpha_fpm (nbody.py:921-931) is a closure of bullfrog_vf that nothing calls: its formula, evaluated with the
+    # reference's own growth helpers and background
+    from jax_cosmo import background
+    fpm = []
+    for n in range(4):
+        gg0 = g0 + n * dg
+        gg2 = gg0 + dg
+        a0_, a2_ = nbody.g2a(c, gg0), nbody.g2a(c, gg2)
+        c0 = background.Esqr(c, a0_) ** .5 * gg0 * nbody.g2f(c, gg0) * a0_ ** 2
+        c2 = background.Esqr(c, a2_) ** .5 * gg2 * nbody.g2f(c, gg2) * a2_ ** 2
+        fpm.append(float(c0 / c2))
+    d["bf4_alpha_fpm"] = np.array(fpm)
     d["bf4_g0_dg"] = np.array([g0, dg])
     out["nbody"] = d
 

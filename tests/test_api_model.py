@@ -373,6 +373,28 @@ def test_bullfrog_vf_scan_and_host_windows(nb, golden):
                        O.kaiser_bessel(torch.tensor(s[:21]), 2, nb.optim_kcut(2.0)).numpy(), rtol=1e-12)
     assert float(nb.alpha_bf(Cosmology(), torch.tensor(0.3), torch.tensor(0.1))) == pytest.approx(
         float(O.alpha_bf(O.Cosmology(), torch.tensor(0.3), torch.tensor(0.1))), rel=1e-12)
+    # alpha_fpm (nbody.py:921-931) against the golden vector, and the FastPM-weighted loop against the oracle's steps
+    gn = golden("nbody")
+    g0n, dgn = gn["bf4_g0_dg"]
+    assert np.allclose([float(nb.alpha_fpm(Cosmology(), g0n + n * dgn, dgn)) for n in range(4)], gn["bf4_alpha_fpm"],
+                       rtol=1e-10)
+    shp = tuple(int(s) for s in gn["shape"])
+    dkn = torch.tensor(gn["delta_k"], dtype=torch.complex64, device=dev(nb))
+    qn = O.regular_pos(shp)
+    pf, vf_ = nb.nbody_bf(Cosmology(), dkn, qn.float().to(dev(nb)), 0.1, 0.8, 3, integrator="fastpm")
+    co = O.Cosmology()
+    dpo, vlo = O.lpt(co, torch.tensor(gn["delta_k"]), qn, 0.1, 2, 1)
+    state, g_lo, g_hi = (qn + dpo, vlo), O.a2g(co, 0.1), O.a2g(co, 0.8)
+    dgo = (g_hi - g_lo) / 3
+    for i in range(3):
+        t = g_lo + i * dgo
+        x = state[0] + state[1] * (dgo / 2)
+        al = O.alpha_fpm(co, t, dgo)
+        v = al * state[1] + (1 - al) * O.pm_forces(x, shp, 2) / (t + dgo / 2)
+        state = (x + v * (dgo / 2), v)
+    assert np.abs(pf[0].cpu().numpy() - state[0].numpy()).max() < 2e-4 and rel(vf_[0], state[1]) < 2e-4
+    with pytest.raises(ValueError):
+        nb.nbody_bf(Cosmology(), dkn, qn.float().to(dev(nb)), 0.1, 0.8, 3, integrator="leapfrog")
 
 
 def test_nbody_bf_snapshots_dense_output(nb, golden):

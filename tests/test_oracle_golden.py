@@ -145,6 +145,7 @@ def test_nbody_bf(golden):
     g0, dg = g["bf4_g0_dg"]
     alphas = [float(O.alpha_bf(c, g0 + n * dg, dg)) for n in range(4)]
     close(np.array(alphas), g["bf4_alpha"], rtol=1e-10)
+    close(np.array([float(O.alpha_fpm(c, g0 + n * dg, dg)) for n in range(4)]), g["bf4_alpha_fpm"], rtol=1e-10)
 
 
 def test_oracle_properties():

@@ -51,7 +51,9 @@ long long mcpm_launch_count(int reset);
 /* Process-wide performance knobs (never change which result is computed).  Keys: "gather_minb" = 4 | 5 | 6, the
  * resident CTAs per SM the readout kernels are compiled for; "gather_blocked" = 0 | 1, one CTA per 256 consecutive
  * particles instead of a grid-stride loop;
- * "side_zero" = 0 | 1, clear the next step's scatter meshes inside the readout kernels instead of memsets. */
+ * "side_zero" = 0 | 1, clear the next step's scatter meshes inside the readout kernels instead of memsets;
+ * "brick_zmerge" = 0 | 1, the brick-tiled scatters hand each lane's upper-z deposits to the next lane by shuffle (4 SHFL
+ * for 4 shared-memory atomics per channel; bit-identical tiles), off until measured. */
 int mcpm_tune(const char* key, int value);
 
 /* Engine for real mesh shape (nx, ny, nz) on the current device.  max_batch = largest number of meshes transformed

@@ -112,6 +112,12 @@ int mcpm_tune(const char* key, int value) {
     set_gather_blocked(value != 0);
     return MCPM_OK;
   }
+  if (std::string(key) == "brick_zmerge") {
+#ifndef MCPM_HOSTEMU
+    set_brick_zmerge(value != 0);
+#endif
+    return MCPM_OK;
+  }
   set_error(std::string("tune: unknown key ") + key);
   return MCPM_EINVAL;
   API_END

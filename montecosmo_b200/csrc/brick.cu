@@ -60,8 +60,13 @@ struct BrickArgs {
 // all 8 y-rows of the brick (the tile origin is taken from those 512 particles).
 __device__ __forceinline__ int brick_qi(int warp, int r) { return ((warp >> 3) + 2 * ((warp & 7) + r)) & 15; }
 
-// FULL: the lattice divides into whole bricks (no per-particle bounds checks)
-template <int NCH, bool FULL>
+// FULL: the lattice divides into whole bricks (no per-particle bounds checks).
+// ZMERGE (mcpm_tune("brick_zmerge"), off by default until measured): the 32 lanes of a warp hold z-neighbours of one
+// lattice row, so lane l's upper-z deposits and lane l+1's lower-z deposits usually land on the same four tile cells
+// (base cells one apart in z, same x and y).  The lower lane then hands its four upper values to the next lane by
+// shuffle instead of issuing them: 4 SHFL replace 4 ATOMS per channel (the LSU pipe bounds this kernel, DESIGN.md
+// section 4).  Integer sums are associative, so the tile -- and the result -- is bit-identical to the unmerged kernel.
+template <int NCH, bool FULL, bool ZMERGE>
 __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickArgs a) {
   using namespace brick;
   extern __shared__ __align__(16) int smem[];
@@ -208,6 +213,20 @@ __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickA
   }
   __syncthreads();  // rowbase, nstray
 
+  // ZMERGE: which slots absorb the previous lane's upper-z deposits / hand theirs to the next lane (tile cells one
+  // apart: in-tile cells have tz <= TZ - 2, so tcell + 1 is the same tile row)
+  unsigned take = 0, give = 0;
+  if (ZMERGE) {
+#pragma unroll
+    for (int r = 0; r < PPT; ++r) {
+      const int prev = __shfl_up_sync(0xffffffffu, tcell[r], 1), next = __shfl_down_sync(0xffffffffu, tcell[r], 1);
+      if (tcell[r] >= 0) {
+        if (lane > 0 && prev >= 0 && prev + 1 == tcell[r]) take |= 1u << r;
+        if (lane < 31 && next == tcell[r] + 1) give |= 1u << r;
+      }
+    }
+  }
+
   const int64_t plane = (int64_t)a.nx * a.ny * a.nz;
 #pragma unroll 1
   for (int c = 0; c < NCH; ++c) {
@@ -218,6 +237,42 @@ __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickA
     const float* valp = NCH == 1 ? (a.w ? a.w + pbase / 3 : nullptr) : a.A + pbase + c;
     const int vstride = NCH == 1 ? a.py * a.pz : plane3;
     const float scale = (NCH == 1 ? a.ws : a.s) * S;
+    if (ZMERGE) {
+#pragma unroll
+      for (int r = 0; r < PPT; ++r) {  // warp-uniform: every lane runs the shuffles, inactive lanes carry zeros
+        const bool act = tcell[r] >= 0;
+        const float vs = act ? (valp ? valp[brick_qi(warp, r) * vstride] * scale : scale) : 0.f;
+        const float fx = x[r][0], fy = x[r][1], fz = x[r][2];
+        const float gx = 1.f - fx, gy = 1.f - fy;
+        const float vz1 = vs * fz, vz0 = vs - vz1;
+        const float w00 = gx * gy, w01 = gx * fy, w10 = fx * gy, w11 = fx * fy;
+        int lo0 = __float2int_rn(vz0 * w00), lo1 = __float2int_rn(vz0 * w01), lo2 = __float2int_rn(vz0 * w10),
+            lo3 = __float2int_rn(vz0 * w11);
+        const int up0 = __float2int_rn(vz1 * w00), up1 = __float2int_rn(vz1 * w01), up2 = __float2int_rn(vz1 * w10),
+                  up3 = __float2int_rn(vz1 * w11);
+        const int p0 = __shfl_up_sync(0xffffffffu, up0, 1), p1 = __shfl_up_sync(0xffffffffu, up1, 1),
+                  p2 = __shfl_up_sync(0xffffffffu, up2, 1), p3 = __shfl_up_sync(0xffffffffu, up3, 1);
+        if (take >> r & 1) {
+          lo0 += p0;
+          lo1 += p1;
+          lo2 += p2;
+          lo3 += p3;
+        }
+        if (act) {
+          int* t = tile + tcell[r];
+          atomicAdd(t, lo0);
+          atomicAdd(t + TZ, lo1);
+          atomicAdd(t + TY * TZ, lo2);
+          atomicAdd(t + TY * TZ + TZ, lo3);
+          if (!(give >> r & 1)) {
+            atomicAdd(t + 1, up0);
+            atomicAdd(t + TZ + 1, up1);
+            atomicAdd(t + TY * TZ + 1, up2);
+            atomicAdd(t + TY * TZ + TZ + 1, up3);
+          }
+        }
+      }
+    } else {
 #pragma unroll
     for (int r = 0; r < PPT; ++r) {
       if (tcell[r] < 0) continue;
@@ -235,6 +290,7 @@ __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickA
       atomicAdd(t + TY * TZ + 1, __float2int_rn(vz1 * w10));
       atomicAdd(t + TY * TZ + TZ, __float2int_rn(vz0 * w11));
       atomicAdd(t + TY * TZ + TZ + 1, __float2int_rn(vz1 * w11));
+    }
     }
     __syncthreads();
     // flush the touched 16-byte groups (one red.global.add.v4.f32 each) and re-zero them for the next channel
@@ -296,17 +352,28 @@ static bool brick_ok(const Lattice& L, int64_t np, int nx, int ny, int nz) {
   return true;
 }
 
+static int g_brick_zmerge = 0;  // mcpm_tune("brick_zmerge"): hand upper-z deposits to the next lane by shuffle (see kernel)
+void set_brick_zmerge(int v) { g_brick_zmerge = v; }
+
+template <int NCH, bool FULL, bool ZMERGE>
+static void launch_brick_variant(stream_t st, const BrickArgs& a, dim3 grid) {
+  using namespace brick;
+  cudaFuncSetAttribute(brick_scatter_kernel<NCH, FULL, ZMERGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+  brick_scatter_kernel<NCH, FULL, ZMERGE><<<grid, THREADS, SMEM, st>>>(a);
+}
+
 template <int NCH>
 static int launch_brick(stream_t st, const BrickArgs& a) {
   using namespace brick;
   dim3 grid((a.pz + BZ - 1) / BZ, (a.py + BY - 1) / BY, (a.px + BX - 1) / BX);
   count_launch();
-  if (a.px % BX == 0 && a.py % BY == 0 && a.pz % BZ == 0) {
-    cudaFuncSetAttribute(brick_scatter_kernel<NCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
-    brick_scatter_kernel<NCH, true><<<grid, THREADS, SMEM, st>>>(a);
+  const bool full = a.px % BX == 0 && a.py % BY == 0 && a.pz % BZ == 0;
+  if (g_brick_zmerge) {
+    if (full) launch_brick_variant<NCH, true, true>(st, a, grid);
+    else launch_brick_variant<NCH, false, true>(st, a, grid);
   } else {
-    cudaFuncSetAttribute(brick_scatter_kernel<NCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
-    brick_scatter_kernel<NCH, false><<<grid, THREADS, SMEM, st>>>(a);
+    if (full) launch_brick_variant<NCH, true, false>(st, a, grid);
+    else launch_brick_variant<NCH, false, false>(st, a, grid);
   }
   return rt_check("brick_scatter") ? -1 : 1;
 }

@@ -108,6 +108,7 @@ int hermitian_weights(stream_t, const cfloat* in, cfloat* out, int nx, int ny, i
 // cic4.cu: CIC kernels on the float4-interleaved vector mesh
 void set_gather_minb(int v);
 void set_gather_blocked(int v);
+void set_brick_zmerge(int v);  // brick.cu (CUDA build only)
 int interleave3(stream_t, const float* planar3, float* mesh4, int64_t n);
 int deinterleave3(stream_t, const float* mesh4, float* planar3, int64_t n);
 int kick_drift4(stream_t, const float* pos, const float* vel, const float* fmesh4, int64_t np, int nx, int ny, int nz,

@@ -20,4 +20,6 @@ echo "pytest rc=$?" >> ${o}_pytest_gpu.log
 timeout 300 python bench.py > ${o}_bench.json 2> ${o}_bench_err.log && \
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file ${o}_launches.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > ${o}_ncu.log 2>&1
+# 4. A/B of the kernel variants built blind at the end of round 1 (whole evaluation, same inputs)
+timeout 120 python tools/tune_eval.py 256 base brick_zmerge=1 base brick_zmerge=1 > ${o}_tune_zmerge.log 2>&1
 tail -3 ${o}_cross_check.log ${o}_pytest_gpu.log; head -c 600 ${o}_bench.json

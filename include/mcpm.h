@@ -258,7 +258,7 @@ int mcpm_chreshape(void* stream, const void* in, int inx, int iny, int inz, void
 int mcpm_chreshape_vjp(void* stream, const void* outbar, int onx, int ony, int onz, void* inbar, int inx, int iny,
                        int inz);
 
-/* Binned auto / cross power spectrum, monopole (metrics.py:121-182).  For every half-spectrum element:
+/* Binned auto / cross power spectrum, monopole (metrics.py:121-182; multipoles: the _ell variant below).  For every half-spectrum element:
  * bin = np.digitize(|k|, kedges), k = 2 pi f / box_size; out[0][bin] += w', out[1][bin] += w' |k|,
  * out[2..3][bin] += w' Re / Im (m0 conj m1) after dividing m_i by rectangular_hat^deconv_i; w' = 1 on kz = 0 / Nyquist,
  * else 2.  m1 NULL = auto spectrum.  kedges: n_edges float64 on the device, increasing; out: [4][n_edges + 1] float64 on

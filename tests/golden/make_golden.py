@@ -228,6 +228,10 @@ def main():
     w = rng.normal(size=(8, 6, 10))
     d = {"white": w, "rg2cgh": A(utils.rg2cgh(jnp.asarray(w)))}
     d["cgh2rg_roundtrip"] = A(utils.cgh2rg(jnp.asarray(d["rg2cgh"])))
+    ampk = rng.uniform(0.5, 2.0, size=(8, 6, 6))  # an amplitude per mode, deliberately NOT even in k
+    d["ampk"] = ampk
+    d["cgh2rg_amp"] = A(utils.cgh2rg(jnp.asarray(ampk + 0j), norm="amp"))
+    d["rg2cgh_amp"] = A(utils.rg2cgh(jnp.asarray(w), norm="amp"))
     out["rg2cgh"] = d
 
     # ---- power-spectrum estimator and Lagrangian bias (next rows f-4, f-1) --------------------------------------

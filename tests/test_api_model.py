@@ -284,8 +284,12 @@ def test_rg2cgh_golden_roundtrip_and_gradient(nb, golden):
         assert rel(oe, oo) < 1e-6 and rel(we.grad, wo.grad) < 1e-6
     with pytest.raises(AssertionError):
         U.rg2cgh(torch.zeros(4, 5, 4))
-    with pytest.raises(NotImplementedError):
-        U.rg2cgh(torch.zeros(4, 4, 4), norm="amp")
+    # norm = "amp" (utils.py:807-817, 858-868, 915-918): golden vectors of the reference source, exact (a permutation)
+    ampk = torch.tensor(g["ampk"], dtype=torch.float32, device=dev(nb))
+    assert np.array_equal(U.cgh2rg(ampk, "amp").cpu().numpy(), g["cgh2rg_amp"].astype(np.float32))
+    assert np.array_equal(U.rg2cgh(white, "amp").cpu().numpy(), g["rg2cgh_amp"].astype(np.float32))
+    with pytest.raises(AssertionError):
+        U.rg2cgh(torch.zeros(4, 4, 4), norm="nope")
 
 
 def test_lagrangian_bias_weights_and_gradient(nb, golden):

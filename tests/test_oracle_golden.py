@@ -220,3 +220,14 @@ def test_lagrangian_bias(golden):
     close(phi, g["png_phi"], atol=1e-14)
     close(MO.add_png(O.Cosmology(), 50.0, torch.as_tensor(g["delta_k"]), tuple(g["box_size"]), kpow), g["add_png_fNL50"],
           atol=1e-10)
+
+
+def test_rg2cgh_cgh2rg(golden):
+    """oracle rg2cgh / cgh2rg (utils.py:785-921) against the reference source, every use: the Gaussian permutation, its
+    inverse, and norm="amp" (amplitude meshes: no sign, no sqrt2, no scaling) on an amplitude that is not even in k."""
+    g = golden("rg2cgh")
+    k = O.rg2cgh(g["white"])
+    close(k, g["rg2cgh"])
+    close(O.cgh2rg(k), g["cgh2rg_roundtrip"])
+    close(O.cgh2rg(O._t(g["ampk"]), "amp"), g["cgh2rg_amp"], rtol=0, atol=0)
+    close(O.rg2cgh(g["white"], "amp"), g["rg2cgh_amp"], rtol=0, atol=0)

@@ -178,6 +178,64 @@ def g2dg2dg(c, g):
     return safe_div(g2g2(c, g) * g2f2(c, g), _t(g) * g2f(c, g))
 
 
+RH = 2997.92458  # jax_cosmo.constants.rh, h^-1 Mpc
+DIST_LOG10_AMIN = -3.0  # nbody.py:813
+DIST_STEPS = 256  # nbody.py:814
+
+
+def distance_table(c, log10_amin=DIST_LOG10_AMIN, steps=DIST_STEPS):
+    """RK4 table of the radial comoving distance chi(a) = R_H int_a^1 da' / (a'^2 E(a')) in Mpc/h on `steps` log-spaced
+    scale factors (nbody.py:816-857; jax_cosmo's dchioverda = R_H / (a^2 E) and its fixed-step RK4 odeint, one step per
+    table interval in ln a).  Cached like growth_table."""
+    key = _param_key(c)
+    ckey = None if key is None else (key, float(log10_amin), int(steps))
+    hit = c._workspace.get("distance")
+    if hit is not None and ckey is not None and hit[0] == ckey:
+        return hit[1]
+    atab = _t(np.logspace(log10_amin, 0.0, steps))
+    xs = torch.log(atab)
+
+    def rhs(x):  # d chi / d ln a
+        a = torch.exp(x)
+        return RH / (a * Esqr(c, a) ** 0.5)
+
+    y, prev, out = torch.zeros((), dtype=F64), xs[0], []
+    for xi in xs:
+        h = xi - prev
+        k1 = rhs(prev)
+        k2 = rhs(prev + h / 2)
+        k4 = rhs(xi)
+        y = y + h / 6.0 * (k1 + 4 * k2 + k4)  # the right-hand side does not depend on chi: k2 = k3
+        prev = xi
+        out.append(y)
+    chi = torch.stack(out)
+    tab = {"a": atab, "chi": chi[-1] - chi}
+    c._workspace["distance"] = (ckey, tab)
+    return tab
+
+
+def a2chi(c, a, log10_amin=DIST_LOG10_AMIN, steps=DIST_STEPS):
+    """Radial comoving distance in Mpc/h at scale factor a (nbody.py:816-857), clipped at 0."""
+    t = distance_table(c, log10_amin, steps)
+    return torch.clamp(interp(a, t["a"], t["chi"]), min=0.0)
+
+
+def chi2a(c, chi, log10_amin=DIST_LOG10_AMIN, steps=DIST_STEPS):
+    """Scale factor at radial comoving distance chi, by reverse linear interpolation (nbody.py:860-884)."""
+    t = distance_table(c, log10_amin, steps)
+    return interp(chi, torch.flip(t["chi"], dims=(0,)), torch.flip(t["a"], dims=(0,)))
+
+
+def k2ell(c, a, k):
+    """Comoving wavenumber -> multipole, Limber approximation (nbody.py:886-890)."""
+    return a2chi(c, a) * _t(k) - 0.5
+
+
+def ell2k(c, a, ell):
+    """Multipole -> comoving wavenumber, Limber approximation (nbody.py:892-896)."""
+    return (_t(ell) + 0.5) / a2chi(c, a)
+
+
 def alpha_bf(c, g0, dg):
     """BullFrog kick coefficient, nbody.py:907-919."""
     g1, g2 = g0 + dg / 2, g0 + dg

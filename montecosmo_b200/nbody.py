@@ -70,6 +70,25 @@ def rfftk(shape, box_size=None):
     return tuple(out)
 
 
+def fftk(shape, box_size=None):
+    """Wavevectors for fftn (nbody.py:78-103)."""
+    dim = len(shape)
+    scales = dim * (2 * np.pi,) if box_size is None else tuple(2 * np.pi * s / b for s, b in zip(shape, box_size))
+    out = []
+    for ax, (s, sc) in enumerate(zip(shape, scales)):
+        shp = [1] * dim
+        shp[ax] = -1
+        out.append((np.fft.fftfreq(s) * sc).reshape(shp))
+    return tuple(out)
+
+
+def top_hat(kvec, kcut=np.inf):
+    """Sharp low-pass: True where |k| < kcut (nbody.py:191-217)."""
+    if kcut == np.inf:
+        return 1.0
+    return sum(k**2 for k in kvec) < kcut**2
+
+
 def invlaplace_hat(kvec, fd_order=np.inf):
     """nbody.py:109-133."""
     if fd_order == 2:
@@ -612,3 +631,4 @@ a2g, a2g2, a2f, a2f2, a2dg2dg = _cosmo.a2g, _cosmo.a2g2, _cosmo.a2f, _cosmo.a2f2
 g2a, g2g2, g2f, g2f2, g2dg2dg = _cosmo.g2a, _cosmo.g2g2, _cosmo.g2f, _cosmo.g2f2, _cosmo.g2dg2dg
 alpha_bf = _cosmo.alpha_bf  # nbody.py:907-919
 alpha_fpm = _cosmo.alpha_fpm  # nbody.py:921-931
+a2chi, chi2a, k2ell, ell2k = _cosmo.a2chi, _cosmo.chi2a, _cosmo.k2ell, _cosmo.ell2k  # distances, nbody.py:810-896

@@ -638,6 +638,34 @@ def alpha_bf(cosmo, g0, dg):
     return (d2 - lin_ratio) / (d0 - lin_ratio)
 
 
+RH = 2997.92458  # jax_cosmo.constants.rh (h^-1 Mpc)
+
+
+def distance_table(cosmo, log10_amin=-3.0, steps=256):
+    """nbody.py:816-857: chi(a) on `steps` log-spaced a, jax_cosmo's dchioverda = rh / (a^2 E(a)) integrated in ln a by
+    its fixed-step RK4 odeint, then chi(a) = chi_tab[-1] - chi_tab."""
+    atab = _t(np.logspace(log10_amin, 0.0, steps))
+
+    def dchioverdlna(y, x):
+        xa = torch.exp(x)
+        return RH / (xa ** 2 * Esqr(cosmo, xa) ** 0.5) * xa
+
+    chitab = _odeint_rk4(dchioverdlna, torch.zeros((), dtype=F64), torch.log(atab))
+    return {"a": atab, "chi": chitab[-1] - chitab}
+
+
+def a2chi(cosmo, a):
+    """nbody.py:816-857."""
+    t = distance_table(cosmo)
+    return torch.clamp(_interp(a, t["a"], t["chi"]), min=0.0)
+
+
+def chi2a(cosmo, chi):
+    """nbody.py:860-884 (chi decreases with a: both tables reversed)."""
+    t = distance_table(cosmo)
+    return _interp(chi, torch.flip(t["chi"], dims=(0,)), torch.flip(t["a"], dims=(0,)))
+
+
 def alpha_fpm(cosmo, g0, dg):
     """nbody.py:921-931 (FastPM growth-time coefficient, defined next to alpha_bf; the reference's kick uses alpha_bf)."""
     g0 = _t(g0)

@@ -90,6 +90,11 @@ def bincount(x, weights=None, minlength=0, length=None):
     return _wrap(out[:n] if length is not None else out)
 
 
+def clip(a, a_min=None, a_max=None):
+    """jnp.clip: either bound may be omitted (nbody.py:859 passes the lower one only)."""
+    return _wrap(_np.clip(_np.asarray(a), a_min, a_max))
+
+
 def unstack(x, axis=0):
     return tuple(_wrap(_np.moveaxis(x, axis, 0)[i]) for i in range(x.shape[axis]))
 

@@ -140,6 +140,14 @@ def main():
         for name in ("g2a", "g2g2", "g2f", "g2f2", "g2dg2dg"):
             d[f"{tag}_{name}"] = A(getattr(nbody, name)(c, g))
         d[f"{tag}_params"] = np.array([par[k] for k in ("Omega_c", "Omega_b", "h", "n_s", "sigma8")])
+        # distances (nbody.py:810-896)
+        c._workspace = {}
+        d[f"{tag}_a2chi"] = A(nbody.a2chi(c, a))
+        chi = np.array([0.0, 10.0, 500.0, 2500.0, 6000.0])
+        d[f"{tag}_chi"] = chi
+        d[f"{tag}_chi2a"] = A(nbody.chi2a(c, chi))
+        d[f"{tag}_k2ell"] = A(nbody.k2ell(c, 0.5, np.array([0.01, 0.1])))
+        d[f"{tag}_ell2k"] = A(nbody.ell2k(c, 0.5, np.array([10.0, 1000.0])))
     out["growth"] = d
 
     # ---- forces, LPT, N-body at 16^3 (and a 12x10x14 non-cubic force case) -------------------------------------

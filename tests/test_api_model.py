@@ -369,6 +369,14 @@ def test_bullfrog_vf_scan_and_host_windows(nb, golden):
     g = golden("kernels")
     kvec = nb.rfftk(tuple(int(s) for s in g["shape"]))
     assert np.allclose(nb.kaiser_bessel_hat(kvec, 4, nb.optim_kcut(1.5)), g["kaiser_bessel_hat_4"], rtol=1e-12)
+    kf = nb.fftk((8, 6, 10), (80.0, 60.0, 50.0))  # nbody.py:78-103
+    assert [k.shape for k in kf] == [(8, 1, 1), (1, 6, 1), (1, 1, 10)]
+    assert np.allclose(kf[2].ravel(), np.fft.fftfreq(10) * 2 * np.pi * 10 / 50.0, rtol=1e-15)
+    assert nb.top_hat(kvec, np.inf) == 1.0  # nbody.py:191-217
+    th = nb.top_hat(kvec, 2.0)
+    assert th.dtype == bool and th.shape == np.broadcast_shapes(*(k.shape for k in kvec))
+    assert np.array_equal(th, sum(k**2 for k in kvec) < 4.0)
+    assert float(nb.a2chi(Cosmology(), 1.0)) == 0.0 and float(nb.chi2a(Cosmology(), 0.0)) == 1.0
     s = np.linspace(0, 2, 41)
     for order in (1, 2, 3, 4):
         ref = O.rectangular(torch.tensor(s), order).numpy()

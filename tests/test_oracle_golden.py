@@ -89,6 +89,17 @@ def test_growth(golden, tag):
     gg = g[f"{tag}_a2g"]
     for name in ("g2a", "g2g2", "g2f", "g2f2", "g2dg2dg"):
         close(getattr(O, name)(c, gg), g[f"{tag}_{name}"], rtol=1e-10)
+    # distances (nbody.py:810-896), oracle and the engine's host-side mirror (cosmo.py; no device involved)
+    from montecosmo_b200 import cosmo as MC
+    mc = MC.Cosmology(Omega_c=oc, Omega_b=ob, h=h, n_s=ns, sigma8=s8)
+    close(O.a2chi(c, a), g[f"{tag}_a2chi"], rtol=1e-10)
+    close(O.chi2a(c, g[f"{tag}_chi"]), g[f"{tag}_chi2a"], rtol=1e-10)
+    close(MC.a2chi(mc, a), g[f"{tag}_a2chi"], rtol=1e-10)
+    close(MC.chi2a(mc, g[f"{tag}_chi"]), g[f"{tag}_chi2a"], rtol=1e-10)
+    close(MC.k2ell(mc, 0.5, np.array([0.01, 0.1])), g[f"{tag}_k2ell"], rtol=1e-10)
+    close(MC.ell2k(mc, 0.5, np.array([10.0, 1000.0])), g[f"{tag}_ell2k"], rtol=1e-10)
+    for name in ("a2g", "a2g2", "a2f", "a2f2", "a2dg2dg"):
+        close(getattr(MC, name)(mc, a), g[f"{tag}_{name}"], rtol=1e-10)
 
 
 @pytest.mark.parametrize("name", ["forces_lpt", "forces_noncubic"])

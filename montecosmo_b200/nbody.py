@@ -580,6 +580,45 @@ def nbody_bf(cosmo, init_mesh, pos, a0=0.0, a1=1.0, n_steps=5, paint_order: int 
     return torch.stack(outs)
 
 
+def lpt_fpm(cosmo, init_mesh, pos, a, lpt_order: int = 1, paint_order: int = 2, grad_fd=np.inf, lap_fd=np.inf):
+    """FastPM-convention LPT (nbody.py:1030-1073): displacement dq = D1 F1 - D2 F2 and momentum p = a^2 E (f1 D1 F1 -
+    f2 D2 F2), the initial state of the legacy scale-factor-time solvers.  Composed from the engine's pm_forces /
+    pm_forces2 (the reference's inline Hessian sum is pm_forces2's source, nbody.py:615-627)."""
+    init_mesh = torch.as_tensor(init_mesh)
+    if not torch.is_complex(init_mesh):
+        init_mesh = rfftn(init_mesh)
+    a_t = _cosmo._t(a).reshape(-1)
+    f1 = pm_forces(pos, init_mesh, paint_order, grad_fd=grad_fd, lap_fd=lap_fd)
+    col = lambda t: t.to(device=f1.device, dtype=f1.dtype).reshape(-1, 1)
+    E = _cosmo.Esqr(cosmo, a_t) ** 0.5
+    dq = col(_cosmo.a2g(cosmo, a_t)) * f1
+    p = col(a_t**2 * _cosmo.a2f(cosmo, a_t) * E) * dq
+    if lpt_order == 2:
+        f2 = pm_forces2(pos, init_mesh, paint_order, grad_fd=grad_fd, lap_fd=lap_fd)
+        dq2 = col(_cosmo.a2g2(cosmo, a_t)) * f2
+        dq = dq - dq2
+        p = p - col(a_t**2 * _cosmo.a2f2(cosmo, a_t) * E) * dq2
+    return dq, p
+
+
+def diffrax_vf(cosmo, mesh_shape, paint_order, grad_fd=np.inf, lap_fd=np.inf):
+    """N-body vector field in scale-factor time for generic ODE solvers (nbody.py:1076-1092):
+    `vector_field(a, (pos, vel), args) -> (dpos, dvel)` with dpos = vel / (a^3 E), dvel = 1.5 Omega_m F / (a^2 E), F the
+    particle-mesh force from the engine (differentiable in pos).  The adaptive Tsit5 driver around it (nbody_tsit5,
+    1109-1138) is diffrax's and is not restated here."""
+    mesh_shape = tuple(int(s) for s in mesh_shape)
+
+    def vector_field(a, state, args=None):
+        pos, vel = _f32(state[0]), _f32(state[1])
+        forces = pm_forces(pos, mesh_shape, paint_order, grad_fd=grad_fd, lap_fd=lap_fd)
+        a_t = _cosmo._t(a)
+        E = float(_cosmo.Esqr(cosmo, a_t) ** 0.5)
+        af = float(a_t)
+        return vel * (1.0 / (af**3 * E)), forces * (1.5 * float(cosmo.Omega_m) / (af**2 * E))
+
+    return vector_field
+
+
 def bullfrog_vf(cosmo, dg, mesh_shape: tuple, paint_order: int = 2, paint_deconv=False, grad_fd=np.inf, lap_fd=np.inf):
     """BullFrog vector field (nbody.py:902-960): `vector_field(g0, state, args)` runs one drift-kick-drift step of size
     `dg` from growth time `g0` on `state = (pos, vel)` and returns `(new - old) / dg` for both, the increment an explicit

@@ -638,6 +638,45 @@ def alpha_bf(cosmo, g0, dg):
     return (d2 - lin_ratio) / (d0 - lin_ratio)
 
 
+def lpt_fpm(cosmo, init_mesh, pos, a, lpt_order=1, paint_order=2, grad_fd=np.inf, lap_fd=np.inf):
+    """nbody.py:1030-1073.  The inline Hessian accumulation of the reference (sum over i of h_ii * (h_00 + .. + h_i-1,i-1)
+    minus the squared off-diagonals) is restated literally rather than through pm_forces2."""
+    a = _t(a).reshape(-1)
+    E = Esqr(cosmo, a) ** 0.5
+    init_mesh = init_mesh if isinstance(init_mesh, torch.Tensor) else _t(init_mesh, C128)
+    mesh_shape = ch2rshape(tuple(init_mesh.shape))
+    pos = _t(pos)
+    f1 = pm_forces(pos, init_mesh, paint_order, grad_fd=grad_fd, lap_fd=lap_fd)
+    dq = a2g(cosmo, a) * f1
+    p = a ** 2 * a2f(cosmo, a) * E * dq
+    if lpt_order == 2:
+        kvec = rfftk(mesh_shape)
+        pot = init_mesh * _t(invlaplace_hat(kvec, lap_fd))
+        delta2, acc = 0.0, 0.0
+        for i in range(3):
+            hii = torch.fft.irfftn(_t(gradient_hat(kvec, i, grad_fd) ** 2, C128) * pot, s=mesh_shape)
+            delta2 = delta2 + hii * acc
+            acc = acc + hii
+            for j in range(i + 1, 3):
+                hij = _t(gradient_hat(kvec, i, grad_fd) * gradient_hat(kvec, j, grad_fd), C128)
+                delta2 = delta2 - torch.fft.irfftn(hij * pot, s=mesh_shape) ** 2
+        f2 = pm_forces(pos, torch.fft.rfftn(delta2), paint_order, grad_fd=grad_fd, lap_fd=lap_fd)
+        dq2 = a2g2(cosmo, a) * f2
+        dq = dq - dq2
+        p = p - a ** 2 * a2f2(cosmo, a) * E * dq2
+    return dq, p
+
+
+def diffrax_vf(cosmo, mesh_shape, paint_order, grad_fd=np.inf, lap_fd=np.inf):
+    """nbody.py:1076-1092."""
+    def vector_field(a, state, args=None):
+        pos, vel = state
+        forces = pm_forces(pos, tuple(mesh_shape), paint_order, grad_fd=grad_fd, lap_fd=lap_fd) * 1.5 * cosmo.Omega_m
+        E = Esqr(cosmo, _t(a)) ** 0.5
+        return vel / (a ** 3 * E), forces / (a ** 2 * E)
+    return vector_field
+
+
 RH = 2997.92458  # jax_cosmo.constants.rh (h^-1 Mpc)
 
 

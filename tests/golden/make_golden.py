@@ -171,6 +171,16 @@ def main():
     c._workspace = {}
     dp, vl = nbody.lpt(c, jnp.asarray(dk), jnp.asarray(pos), 0.0, 2, 2)
     d["lpt2_a0_cic_dpos"], d["lpt2_a0_cic_vel"] = A(dp), A(vl)
+    # legacy scale-factor-time pieces (nbody.py:1030-1092)
+    for order in (1, 2):
+        c._workspace = {}
+        dq, pp = nbody.lpt_fpm(c, jnp.asarray(dk), jnp.asarray(pos), 0.3, order, 2)
+        d[f"lpt_fpm{order}_dq"], d[f"lpt_fpm{order}_p"] = A(dq), A(pp)
+    vel0 = rng.normal(scale=0.3, size=pos.shape)
+    d["vf_vel"] = vel0
+    # the solver's time is a float64 array; a Python float would meet jax_cosmo's float32 epsilon as a weak scalar
+    dpv, dvv = nbody.diffrax_vf(c, shape, 2)(jnp.asarray(0.5), (jnp.asarray(pos), jnp.asarray(vel0)), None)
+    d["vf_dpos"], d["vf_dvel"] = A(dpv), A(dvv)
     out["forces_lpt"] = d
 
     d = {"shape": np.array(shape), "delta_k": dk}

@@ -478,3 +478,22 @@ def test_physics_self_checks_without_an_oracle(nb):
         assert abs(r.imag) < 5e-3
         deficit[n] = 1.0 - r.real
     assert 0 < deficit[32] < 2.5e-2 and deficit[32] < 0.4 * deficit[16], deficit
+
+
+def test_legacy_scale_factor_time_pieces(nb, golden):
+    """lpt_fpm (nbody.py:1030-1073) and diffrax_vf (1076-1092) against the golden vectors of the reference source: 5e-5
+    like the other force-level quantities; the vector field is differentiable in the positions."""
+    from montecosmo_b200.cosmo import Cosmology
+    g = golden("forces_lpt")
+    shape = tuple(int(s) for s in g["shape"])
+    dk = torch.tensor(g["delta_k"], dtype=torch.complex64, device=dev(nb))
+    pos = torch.tensor(g["pos"], dtype=torch.float32, device=dev(nb))
+    for order in (1, 2):
+        dq, p = nb.lpt_fpm(Cosmology(), dk, pos, 0.3, order, 2)
+        assert rel(dq, g[f"lpt_fpm{order}_dq"]) < 5e-5 and rel(p, g[f"lpt_fpm{order}_p"]) < 5e-5
+    vel = torch.tensor(g["vf_vel"], dtype=torch.float32, device=dev(nb))
+    pl = leaf(pos)
+    dp, dv = nb.diffrax_vf(Cosmology(), shape, 2)(0.5, (pl, vel), None)
+    assert rel(dp, g["vf_dpos"]) < 1e-6 and rel(dv, g["vf_dvel"]) < 5e-5
+    dv.sum().backward()
+    assert pl.grad is not None and bool(torch.isfinite(pl.grad).all())

@@ -130,6 +130,14 @@ def test_lpt(golden):
     dp, vl = O.lpt(c, dk, g["pos"], 0.0, 2, 2)
     close(dp, g["lpt2_a0_cic_dpos"], rtol=1e-9)
     close(vl, g["lpt2_a0_cic_vel"], rtol=1e-9)
+    # legacy scale-factor-time pieces (nbody.py:1030-1092)
+    for order in (1, 2):
+        dq, pp = O.lpt_fpm(c, dk, g["pos"], 0.3, order, 2)
+        close(dq, g[f"lpt_fpm{order}_dq"], rtol=1e-9)
+        close(pp, g[f"lpt_fpm{order}_p"], rtol=1e-9)
+    dpv, dvv = O.diffrax_vf(c, shape, 2)(0.5, (O._t(g["pos"]), O._t(g["vf_vel"])), None)
+    close(dpv, g["vf_dpos"], rtol=1e-9)
+    close(dvv, g["vf_dvel"], rtol=1e-9)
 
 
 def test_nbody_bf(golden):

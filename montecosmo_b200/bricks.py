@@ -1,6 +1,7 @@
 """
 Mirror of the `montecosmo/bricks.py` callables next to the engine's path: regular_pos (593-603), the
-Lagrangian bias expansion (327-452) and the flat-sky redshift-space shift in cell units (781-792).
+Lagrangian bias expansion (327-452) and the cell -> physical -> redshift-space chain (628-877: frames, lines of sight
+and light-cone scale factors, redshift-space distortions, Alcock-Paczynski).
 
 lagrangian_bias composes engine operators -- irfftn (mcpm_irfftn) and read (mcpm_read, differentiable in mesh and
 positions) -- with pointwise torch expressions for the Fourier multipliers and the shear invariants, so torch.autograd
@@ -129,9 +130,166 @@ def lagrangian_bias(cosmo, pos, a, box_size, lin_mesh, bias, png=None, png_type=
     return weights, dvel, phi
 
 
-def rsd(cosmo, a, vel, los=(0.0, 0.0, 1.0)):
-    """Flat-sky redshift-space displacement in cell units, dpos = (vel . los) D f los (bricks.py:781-792 with the
-    growth-time velocity of nbody_bf)."""
-    los = torch.as_tensor(np.asarray(los, dtype=np.float32), device=vel.device)
-    coef = float(_cosmo.a2g(cosmo, a) * _cosmo.a2f(cosmo, a))
-    return (vel * los).sum(-1, keepdim=True) * coef * los
+# ----------------------------------------------------------------------------------------------------------------
+# cell -> physical -> redshift space (bricks.py:628-660, 667-740, 747-870): elementwise on [Np, 3], torch, differentiable
+# in the positions, velocities and -- through cosmo.py's growth and distance tables -- the cosmology.  `box_rot` is a
+# scipy Rotation (as in the reference), a 3 x 3 matrix, or None for the identity.
+# ----------------------------------------------------------------------------------------------------------------
+def _rotmat(box_rot, like):
+    if box_rot is None:
+        return None
+    m = box_rot.as_matrix() if hasattr(box_rot, "as_matrix") else np.asarray(box_rot, dtype=np.float64)
+    return torch.as_tensor(m, dtype=like.dtype, device=like.device)
+
+
+def _rot(x, box_rot, inverse=False):
+    m = _rotmat(box_rot, x)
+    if m is None:
+        return x
+    return x @ (m if inverse else m.T)  # rows are vectors: R x  ==  x R^T
+
+
+def _vec(v, like):
+    return torch.as_tensor(np.asarray(v, dtype=np.float64), dtype=like.dtype, device=like.device)
+
+
+def _tab(fn, c, x):
+    """A cosmo.py table function (float64, host tables, differentiable in x and in the cosmology) applied to a tensor
+    that may live on the device: evaluated on the host and brought back -- autograd follows the copies.  These are the
+    light-cone / Alcock-Paczynski lookups, outside the benchmarked configurations (a_obs scalar, flat sky)."""
+    x = torch.as_tensor(x)
+    dt = x.dtype if x.is_floating_point() else torch.float32
+    return fn(c, x.to("cpu", torch.float64)).to(device=x.device, dtype=dt)
+
+
+def cell2phys_pos(pos, box_center, box_rot, box_size, mesh_shape):
+    """bricks.py:628-636."""
+    pos = torch.as_tensor(pos)
+    pos = pos * _vec(np.divide(box_size, mesh_shape), pos) - _vec(box_size, pos) / 2
+    return _rot(pos, box_rot) + _vec(box_center, pos)
+
+
+def phys2cell_pos(pos, box_center, box_rot, box_size, mesh_shape):
+    """bricks.py:638-646."""
+    pos = torch.as_tensor(pos)
+    pos = _rot(pos - _vec(box_center, pos), box_rot, inverse=True) + _vec(box_size, pos) / 2
+    return pos / _vec(np.divide(box_size, mesh_shape), pos)
+
+
+def cell2phys_vel(vel, box_rot, box_size, mesh_shape):
+    """bricks.py:648-654."""
+    vel = torch.as_tensor(vel)
+    return _rot(vel * _vec(np.divide(box_size, mesh_shape), vel), box_rot)
+
+
+def phys2cell_vel(vel, box_rot, box_size, mesh_shape):
+    """bricks.py:656-662."""
+    vel = torch.as_tensor(vel)
+    return _rot(vel, box_rot, inverse=True) / _vec(np.divide(box_size, mesh_shape), vel)
+
+
+def pos_mesh(box_center, box_rot, box_size, mesh_shape):
+    """Physical positions of the mesh cells, [*mesh_shape, 3] (bricks.py:691-697); host float64 like the reference."""
+    pos = torch.as_tensor(np.indices(mesh_shape, dtype=float).reshape(3, -1).T)
+    return cell2phys_pos(pos, box_center, box_rot, box_size, mesh_shape).reshape(tuple(mesh_shape) + (3,))
+
+
+def radius_mesh(box_center, box_rot, box_size, mesh_shape, curved_sky=True):
+    """Physical distance of the mesh cells to the observer, or along the line of sight (bricks.py:665-689)."""
+    c = np.asarray(box_center, dtype=np.float64)
+    m = None if box_rot is None else (box_rot.as_matrix() if hasattr(box_rot, "as_matrix") else np.asarray(box_rot))
+    c = c if m is None else m.T @ c  # R^T c
+    ax = [np.arange(n, dtype=np.float64).reshape([-1 if d == i else 1 for d in range(3)]) for i, n in enumerate(mesh_shape)]
+    rvec = [r * b / n - b / 2 + ci for r, n, b, ci in zip(ax, mesh_shape, box_size, c)]
+    if curved_sky:
+        return torch.as_tensor(sum(r**2 for r in rvec) ** 0.5)
+    nrm = np.linalg.norm(c)
+    los = c / nrm if nrm != 0 else np.zeros(3)
+    return torch.as_tensor(np.abs(sum(r * l for r, l in zip(rvec, los))))
+
+
+def scale_pos(pos, los, scale_par, scale_perp):
+    """bricks.py:712-720."""
+    pos_par = (pos * los).sum(-1, keepdim=True) * los
+    return pos_par * scale_par + (pos - pos_par) * scale_perp
+
+
+def parperp2isoap(alpha_par, alpha_perp):
+    """bricks.py:722-728."""
+    return (alpha_par * alpha_perp**2) ** (1 / 3), alpha_par / alpha_perp
+
+
+def isoap2parperp(alpha_iso, alpha_ap):
+    """bricks.py:730-736."""
+    return alpha_iso * alpha_ap ** (2 / 3), alpha_iso * alpha_ap ** (-1 / 3)
+
+
+def _safe_div(x, y):
+    ok = y != 0
+    return torch.where(ok, x / torch.where(ok, y, torch.ones_like(y)), torch.zeros_like(x))
+
+
+def _flat_los(box_center, like):
+    c = np.asarray(box_center, dtype=np.float64)
+    n = np.linalg.norm(c)
+    return _vec(c / n if n != 0 else np.zeros(3), like)
+
+
+def los_scalefactor_pos(pos, box_center, box_rot, box_size, mesh_shape, cosmo, a_obs=None, curved_sky=True):
+    """Line of sight(s) and scale factor(s) of particles for the light-cone / sky configurations (bricks.py:747-766)."""
+    pos = cell2phys_pos(pos, box_center, box_rot, box_size, mesh_shape)
+    if curved_sky:
+        rpos = pos.norm(dim=-1, keepdim=True)
+        los = _safe_div(pos, rpos)
+    else:
+        los = _flat_los(box_center, pos)
+        rpos = (pos * los).sum(-1, keepdim=True).abs()
+    a = _tab(_cosmo.chi2a, cosmo, rpos) if a_obs is None else a_obs
+    return los, a
+
+
+def rsd(cosmo, vel, los, a, box_rot, box_size, mesh_shape, dvel=0.0):
+    """Redshift-space displacement in Mpc/h (bricks.py:781-792): growth-time velocities of nbody_bf, so Dq = vel D f;
+    `a` a scalar or one value per particle [Np, 1]; `dvel` the higher-derivative velocity bias of lagrangian_bias."""
+    vel = cell2phys_vel(vel, box_rot, box_size, mesh_shape)
+    gf = _tab(_cosmo.a2g, cosmo, a) * _tab(_cosmo.a2f, cosmo, a)
+    vel = vel * gf.to(vel.dtype) + dvel
+    return (vel * los).sum(-1, keepdim=True) * los
+
+
+def _ap_alpha(cosmo, cosmo_fid, rpos):
+    return _safe_div(_tab(_cosmo.a2chi, cosmo_fid, _tab(_cosmo.chi2a, cosmo, rpos)), rpos)
+
+
+def ap_auto(pos, los, cosmo, cosmo_fid, curved_sky=True):
+    """Automatic Alcock-Paczynski rescaling (bricks.py:795-813): distances re-read in the fiducial cosmology."""
+    rpos = pos.norm(dim=-1, keepdim=True) if curved_sky else (pos * los).sum(-1, keepdim=True).abs()
+    return pos * _ap_alpha(cosmo, cosmo_fid, rpos)
+
+
+def ap_param(pos, los, alphas, curved_sky=True):
+    """Parametrised Alcock-Paczynski rescaling (bricks.py:847-856)."""
+    if curved_sky:
+        return pos * alphas["alpha_iso"]
+    return scale_pos(pos, los, *isoap2parperp(alphas["alpha_iso"], alphas["alpha_ap"]))
+
+
+def rsd_ap_auto(pos, vel, rpos, los, a, cosmo, cosmo_fid, curved_sky=True):
+    """Redshift-space distortions and automatic Alcock-Paczynski together (bricks.py:858-877): the observed scale factor
+    1 / (1/a + v_los E(a) / R_H), its fiducial distance, and the radial rescaling it implies."""
+    vel_los = (vel * los).sum(-1, keepdim=True)
+    if not curved_sky:
+        vel_los = vel_los * torch.sign((pos * los).sum(-1, keepdim=True))
+    a = torch.as_tensor(a, dtype=pos.dtype, device=pos.device)
+    E = _tab(lambda c, x: _cosmo.Esqr(c, x) ** 0.5, cosmo, a)
+    a_new = 1.0 / (1.0 / a + vel_los * E / RH)
+    alpha = _safe_div(_tab(_cosmo.a2chi, cosmo_fid, a_new), rpos)
+    return pos * alpha if curved_sky else scale_pos(pos, los, alpha, 1.0)
+
+
+def redges_and_scalefactors(cosmo, rmin, rmax, n_shells):
+    """Radius shell edges, linearly spaced in growth factor, and their effective scale factors (bricks.py:700-710)."""
+    gmin = float(_cosmo.a2g(cosmo, _cosmo.chi2a(cosmo, rmax)))
+    gmax = float(_cosmo.a2g(cosmo, _cosmo.chi2a(cosmo, rmin)))
+    gs = np.linspace(gmin, gmax, n_shells + 1)
+    return _cosmo.a2chi(cosmo, _cosmo.g2a(cosmo, gs)), _cosmo.g2a(cosmo, (gs[:-1] + gs[1:]) / 2)

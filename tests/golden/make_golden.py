@@ -306,6 +306,45 @@ def main():
     d["add_png_fNL50"] = A(bricks.add_png(cosmo, 50.0, jnp.asarray(dk), np.array(box), kpow=(ks, pk)))
     out["lagrangian_bias"] = d
 
+    # ---- cell -> physical -> redshift space (bricks.py:628-877, next row f-3) ------------------------------------
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(9)
+    shape, box, center = (8, 10, 12), (800.0, 1000.0, 960.0), (900.0, -300.0, 1500.0)
+    rot = Rotation.from_rotvec([0.3, -0.5, 0.8])
+    pos = rng.uniform(0, 1, (200, 3)) * np.array(shape)
+    vel = rng.normal(scale=0.05, size=(200, 3))
+    cosmo, fid = Cosmology(**ABACUS), Cosmology(**OTHER)
+    d = {"shape": np.array(shape), "box_size": np.array(box), "box_center": np.array(center),
+         "rot_matrix": rot.as_matrix(), "pos": pos, "vel": vel}
+    phys = A(bricks.cell2phys_pos(jnp.asarray(pos), center, rot, box, shape))
+    d["cell2phys_pos"] = phys
+    d["phys2cell_roundtrip"] = A(bricks.phys2cell_pos(jnp.asarray(phys), center, rot, box, shape))
+    d["cell2phys_vel"] = A(bricks.cell2phys_vel(jnp.asarray(vel), rot, box, shape))
+    d["phys2cell_vel"] = A(bricks.phys2cell_vel(jnp.asarray(vel), rot, box, shape))
+    d["pos_mesh"] = A(bricks.pos_mesh(center, rot, box, shape))
+    for tag, curved in (("curved", True), ("flat", False)):
+        d[f"radius_mesh_{tag}"] = A(bricks.radius_mesh(np.array(center), rot, box, shape, curved))
+        cosmo._workspace = {}
+        los, a = bricks.los_scalefactor_pos(jnp.asarray(pos), np.array(center), rot, box, shape, cosmo, None, curved)
+        d[f"los_{tag}"], d[f"a_{tag}"] = A(los) * np.ones((1, 3)), A(a)
+        dpos = bricks.rsd(cosmo, jnp.asarray(vel), jnp.asarray(los), jnp.asarray(a), rot, box, shape, dvel=0.01)
+        d[f"rsd_{tag}"] = A(dpos)
+        fid._workspace = {}
+        d[f"ap_auto_{tag}"] = A(bricks.ap_auto(jnp.asarray(phys), jnp.asarray(los), cosmo, fid, curved))
+        d[f"ap_param_{tag}"] = A(bricks.ap_param(jnp.asarray(phys.copy()), jnp.asarray(los),
+                                                 dict(alpha_iso=1.03, alpha_ap=0.97), curved))
+        rpos = np.linalg.norm(phys, axis=-1, keepdims=True) if curved else np.abs((phys * A(los)).sum(-1, keepdims=True))
+        d[f"rsd_ap_auto_{tag}"] = A(bricks.rsd_ap_auto(jnp.asarray(phys.copy()), jnp.asarray(d["cell2phys_vel"]),
+                                                       jnp.asarray(rpos), jnp.asarray(los), jnp.asarray(a), cosmo, fid,
+                                                       curved))
+    d["scale_pos"] = A(bricks.scale_pos(jnp.asarray(phys.copy()), jnp.asarray(d["los_flat"][:1]), 1.1, 0.9))
+    d["isoap2parperp"] = np.array(bricks.isoap2parperp(1.03, 0.97))
+    d["parperp2isoap"] = np.array(bricks.parperp2isoap(1.05, 0.98))
+    cosmo._workspace = {}
+    red, aa = bricks.redges_and_scalefactors(cosmo, 500.0, 2500.0, 4)
+    d["redges"], d["redges_a"] = A(red), A(aa)
+    out["observation"] = d
+
     for name, dd in out.items():
         path = os.path.join(HERE, f"{name}.npz")
         np.savez_compressed(path, **{k: np.asarray(v) for k, v in dd.items()})

@@ -497,3 +497,56 @@ def test_legacy_scale_factor_time_pieces(nb, golden):
     assert rel(dp, g["vf_dpos"]) < 1e-6 and rel(dv, g["vf_dvel"]) < 5e-5
     dv.sum().backward()
     assert pl.grad is not None and bool(torch.isfinite(pl.grad).all())
+
+
+def test_observation_chain_golden(nb, golden):
+    """The cell -> physical -> redshift-space helpers of bricks.py:628-877 (frames with a rotated box, curved and flat
+    sky lines of sight, light-cone scale factors, redshift-space distortions, Alcock-Paczynski) against the golden
+    vectors of the reference source: float32 tensors on the engine's device, 2e-6 of the largest value; the light-cone
+    displacement is differentiable in the velocities and in the cosmology."""
+    from scipy.spatial.transform import Rotation
+    from montecosmo_b200 import bricks as B
+    from montecosmo_b200.cosmo import Cosmology
+    g = golden("observation")
+    gr = golden("growth")
+    shape, box, center = tuple(int(s) for s in g["shape"]), tuple(g["box_size"]), tuple(g["box_center"])
+    rot = Rotation.from_matrix(g["rot_matrix"])
+    d = dev(nb)
+    pos = torch.tensor(g["pos"], dtype=torch.float32, device=d)
+    vel = torch.tensor(g["vel"], dtype=torch.float32, device=d)
+    oc, ob, h, ns, s8 = gr["other_params"]
+    cosmo, fid = Cosmology(), Cosmology(Omega_c=oc, Omega_b=ob, h=h, n_s=ns, sigma8=s8)
+
+    def near(x, ref, tol=2e-6):
+        x = x.detach().cpu().numpy().astype(np.float64)
+        assert np.abs(x - ref).max() <= tol * max(np.abs(ref).max(), 1e-30), np.abs(x - ref).max()
+
+    phys = B.cell2phys_pos(pos, center, rot, box, shape)
+    near(phys, g["cell2phys_pos"])
+    near(B.phys2cell_pos(phys, center, rot, box, shape), g["phys2cell_roundtrip"], 1e-5)
+    near(B.cell2phys_vel(vel, rot, box, shape), g["cell2phys_vel"])
+    near(B.phys2cell_vel(vel, rot, box, shape), g["phys2cell_vel"])
+    near(B.cell2phys_pos(pos, center, g["rot_matrix"], box, shape), g["cell2phys_pos"])  # a matrix works as well
+    assert np.allclose(B.pos_mesh(center, rot, box, shape).numpy(), g["pos_mesh"], rtol=1e-12, atol=1e-9)
+    pvel = B.cell2phys_vel(vel, rot, box, shape)
+    for tag, curved in (("curved", True), ("flat", False)):
+        assert np.allclose(B.radius_mesh(center, rot, box, shape, curved).numpy(), g[f"radius_mesh_{tag}"], rtol=1e-12)
+        los, a = B.los_scalefactor_pos(pos, center, rot, box, shape, cosmo, None, curved)
+        near(los * torch.ones(1, 3, device=d), g[f"los_{tag}"])
+        near(a, g[f"a_{tag}"], 1e-6)
+        near(B.rsd(cosmo, vel, los, a, rot, box, shape, dvel=0.01), g[f"rsd_{tag}"], 5e-6)
+        near(B.ap_auto(phys, los, cosmo, fid, curved), g[f"ap_auto_{tag}"], 5e-6)
+        near(B.ap_param(phys, los, dict(alpha_iso=1.03, alpha_ap=0.97), curved), g[f"ap_param_{tag}"])
+        rpos = phys.norm(dim=-1, keepdim=True) if curved else (phys * los).sum(-1, keepdim=True).abs()
+        near(B.rsd_ap_auto(phys, pvel, rpos, los, a, cosmo, fid, curved), g[f"rsd_ap_auto_{tag}"], 5e-6)
+    near(B.scale_pos(phys, torch.tensor(g["los_flat"][:1], dtype=torch.float32, device=d), 1.1, 0.9), g["scale_pos"])
+    assert np.allclose(B.isoap2parperp(1.03, 0.97), g["isoap2parperp"]) and np.allclose(B.parperp2isoap(1.05, 0.98),
+                                                                                      g["parperp2isoap"])
+    red, aa = B.redges_and_scalefactors(cosmo, 500.0, 2500.0, 4)
+    assert np.allclose(red.numpy(), g["redges"], rtol=1e-10) and np.allclose(aa.numpy(), g["redges_a"], rtol=1e-10)
+    # gradients: velocities, and Omega_c through the growth table, on the light cone
+    ocl = torch.tensor(0.26447041, dtype=torch.float64, requires_grad=True)
+    vl = leaf(vel)
+    los, a = B.los_scalefactor_pos(pos, center, rot, box, shape, cosmo, None, True)
+    B.rsd(Cosmology(Omega_c=ocl), vl, los, a, rot, box, shape).pow(2).sum().backward()
+    assert bool(torch.isfinite(vl.grad).all()) and float(vl.grad.abs().sum()) > 0 and float(ocl.grad.abs()) > 0

@@ -74,7 +74,8 @@ def lagrangian_bias(cosmo, pos, a, box_size, lin_mesh, bias, png=None, png_type=
     pos = _nb._f32(pos)
     dev = lin_mesh.device
     mesh_shape = _nb.ch2rshape(tuple(lin_mesh.shape))
-    growth = torch.as_tensor(_cosmo.a2g(cosmo, a), dtype=torch.float64)
+    a_host = a.detach().to("cpu", torch.float64) if isinstance(a, torch.Tensor) else a  # growth tables live on the host
+    growth = torch.as_tensor(_cosmo.a2g(cosmo, a_host), dtype=torch.float64)
     g = growth.to(device=dev, dtype=torch.float32).reshape(-1)  # scalar, or one value per particle
     g = g if g.numel() > 1 else g.reshape(())
 

@@ -222,3 +222,74 @@ class FieldModel:
         # the graph reads these buffers on every replay: they must live as long as the callable does
         run.graph, run.static_white, run.static_obs, run.out = graph, static_white, static_obs, out
         return run
+
+
+class FieldLevelModel(FieldModel):
+    """The general `evolve` of the reference (model.py:683-837, 'lpt' / 'nbody' evolutions with Lagrangian bias), beyond
+    the benchmarked configuration of FieldModel: initial, evolution and paint meshes of different shapes, any particle
+    lattice, the full Lagrangian bias expansion with its velocity term and primordial non-Gaussianity, a box placed
+    and rotated with respect to the observer, curved or flat sky, light-cone scale factors (a_obs=None: read from the
+    comoving distance of every particle; 'lpt' only, as in the reference), redshift-space distortions and
+    Alcock-Paczynski rescaling.  Every step is a mirrored callable (nbody.py / bricks.py / utils.py names), so
+    torch.autograd differentiates the chain end to end through the engine's adjoints.
+    """
+
+    def __init__(self, mesh_shape=(64, 64, 64), box_size=(640.0, 640.0, 640.0), evol_oversamp=1.0, ptcl_oversamp=1.0,
+                 box_center=(0.0, 0.0, 0.0), box_rot=None, curved_sky=False, bias=None, png=None, png_type=None,
+                 ap_auto=None, cosmo_fid=None, kernel_type="rectangular", **kw):
+        super().__init__(mesh_shape, box_size, **kw)
+        self.init_shape = self.mesh_shape
+        self.evol_shape = nb.scale_shape(self.init_shape, evol_oversamp)
+        self.ptcl_shape = nb.scale_shape(self.evol_shape, ptcl_oversamp)
+        self.box_center, self.box_rot, self.curved_sky = tuple(float(c) for c in box_center), box_rot, bool(curved_sky)
+        self.bias = dict(b1=self.b1) if bias is None else dict(bias)
+        self.png, self.png_type = png, png_type
+        self.ap_auto, self.cosmo_fid, self.kernel_type = ap_auto, cosmo_fid, kernel_type
+
+    def evolve(self, white, ap=None):
+        from . import bricks as B
+        c, dev = self.cosmology, nb.ops().A.device
+        geo = (self.box_center, self.box_rot, self.box_size)
+        init_mesh = self.linear_field(white)  # white2lin at the initial shape (bricks.py:152-157)
+        if self.evol_shape != self.init_shape:
+            init_mesh = nb.chreshape(init_mesh, r2chshape(self.evol_shape))
+        pos = B.regular_pos(self.evol_shape, self.ptcl_shape)
+        _, a = B.los_scalefactor_pos(pos, *geo, self.evol_shape, c, self.a_obs, self.curved_sky)
+        weights, dvel, _ = B.lagrangian_bias(c, pos, a, self.box_size, init_mesh, self.bias, self.png, self.png_type,
+                                             self.kpow_sigma8_1() if self.png_type is not None else None, read_order=1)
+        if self.png_type is not None:
+            init_mesh = B.add_png(c, self.png["fNL"], init_mesh, self.box_size, self.kpow_sigma8_1())
+            init_mesh = nb.chreshape(nb.chreshape(init_mesh, r2chshape(self.init_shape)), r2chshape(self.evol_shape))
+        if self.evolution == "lpt":
+            dpos, vel = nb.lpt(c, init_mesh, pos, a, self.lpt_order, 1)
+            pos = pos + dpos
+        elif self.evolution == "nbody":
+            if np.ndim(a) != 0:
+                raise AssertionError("N-body light-cone not implemented yet")  # model.py:768
+            pos, vel = nb.nbody_bf(c, init_mesh, pos, self.a_start, a, self.n_steps, self.paint_order, self.lpt_order,
+                                   paint_deconv=False, ptcl_shape=self.ptcl_shape if self.ptcl_shape == self.evol_shape
+                                   else None)
+            pos, vel = pos[-1], vel[-1]
+        else:
+            raise ValueError(f"unknown evolution {self.evolution}")
+        los, a = B.los_scalefactor_pos(pos, *geo, self.evol_shape, c, self.a_obs, self.curved_sky)
+        pos = B.cell2phys_pos(pos, *geo, self.evol_shape)
+        if self.rsd:
+            pos = pos + B.rsd(c, vel, los, a, self.box_rot, self.box_size, self.evol_shape, dvel)
+        if self.ap_auto is not None:
+            pos = B.ap_auto(pos, los, c, self.cosmo_fid, self.curved_sky) if self.ap_auto else \
+                B.ap_param(pos, los, ap, self.curved_sky)
+        pos = B.phys2cell_pos(pos, *geo, self.init_shape)
+        gxy = nb.nufft(pos, self.init_shape, self.paint_shape if self.paint_shape != self.init_shape else None, weights,
+                       self.paint_order, self.interlace_order, self.kernel_type, self.paint_deconv)
+        gxy = gxy * float(np.divide(self.init_shape, self.ptcl_shape).prod())  # particle units -> mesh units
+        if self.paint_shape != self.init_shape and self.out_shape == "paint":
+            gxy = nb.chreshape(gxy, r2chshape(self.paint_shape))
+        return nb.irfftn(gxy)
+
+    predict = evolve
+
+    def kpow_sigma8_1(self):
+        """The tabulated power normalised to sigma8 = 1, as bricks.lin_power's `kpow` argument wants it."""
+        ks, pows = self.kpow
+        return ks, pows / float(self.cosmology.sigma8) ** 2

@@ -139,3 +139,87 @@ def lagrangian_bias(cosmo, pos, a, box_size, lin_mesh, bias, read_order=2, png=N
     gcol = g.reshape(-1, 1) if isinstance(g, torch.Tensor) and g.dim() > 0 else g
     dvel = b["bnpar"] * grads * gcol
     return (w, dvel) if png_type is None else (w, dvel, phi)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the general evolve (model.py:683-837, 'lpt' / 'nbody' with Lagrangian bias): frames, lines of sight, light cone,
+# redshift-space distortions and Alcock-Paczynski of bricks.py:628-877 restated in float64
+# ----------------------------------------------------------------------------------------------------------------
+def _rot(x, rot, inverse=False):
+    if rot is None:
+        return x
+    m = O._t(rot.as_matrix() if hasattr(rot, "as_matrix") else np.asarray(rot))
+    return x @ (m if inverse else m.T)
+
+
+def cell2phys_pos(pos, center, rot, box, shape):
+    """bricks.py:628-636."""
+    return _rot(pos * O._t(np.divide(box, shape)) - O._t(np.asarray(box)) / 2, rot) + O._t(np.asarray(center))
+
+
+def phys2cell_pos(pos, center, rot, box, shape):
+    """bricks.py:638-646."""
+    return (_rot(pos - O._t(np.asarray(center)), rot, True) + O._t(np.asarray(box)) / 2) / O._t(np.divide(box, shape))
+
+
+def los_scalefactor_pos(pos, center, rot, box, shape, cosmo, a_obs=None, curved_sky=True):
+    """bricks.py:747-766."""
+    pos = cell2phys_pos(pos, center, rot, box, shape)
+    if curved_sky:
+        rpos = pos.norm(dim=-1, keepdim=True)
+        los = _safe_div_t(pos, rpos)
+    else:
+        c = np.asarray(center, dtype=np.float64)
+        n = np.linalg.norm(c)
+        los = O._t(c / n if n != 0 else np.zeros(3))
+        rpos = (pos * los).sum(-1, keepdim=True).abs()
+    return los, (O.chi2a(cosmo, rpos) if a_obs is None else a_obs)
+
+
+def rsd(cosmo, vel, los, a, rot, box, shape, dvel=0.0):
+    """bricks.py:781-792."""
+    vel = _rot(vel * O._t(np.divide(box, shape)), rot) * (O.a2g(cosmo, a) * O.a2f(cosmo, a)) + dvel
+    return (vel * los).sum(-1, keepdim=True) * los
+
+
+def ap_auto(pos, los, cosmo, cosmo_fid, curved_sky=True):
+    """bricks.py:795-813."""
+    rpos = pos.norm(dim=-1, keepdim=True) if curved_sky else (pos * los).sum(-1, keepdim=True).abs()
+    return pos * _safe_div_t(O.a2chi(cosmo_fid, O.chi2a(cosmo, rpos)), rpos)
+
+
+def evolve_general(white, transfer, cosmo, init_shape, box_size, evol_shape=None, ptcl_shape=None, paint_shape=None,
+                   box_center=(0.0, 0.0, 0.0), box_rot=None, curved_sky=False, a_obs=1.0, evolution="lpt", n_steps=5,
+                   a_start=0.0, lpt_order=2, paint_order=2, interlace_order=2, paint_deconv=True, bias=None, rsd_on=True,
+                   ap_fid=None, kernel_type="rectangular"):
+    """model.py:683-837 (the 'lpt' / 'nbody' branch with Lagrangian bias, no primordial non-Gaussianity)."""
+    init_shape = tuple(init_shape)
+    evol_shape = init_shape if evol_shape is None else tuple(evol_shape)
+    ptcl_shape = evol_shape if ptcl_shape is None else tuple(ptcl_shape)
+    paint_shape = init_shape if paint_shape is None else tuple(paint_shape)
+    geo = (box_center, box_rot, box_size)
+    init_mesh = torch.fft.rfftn(white) * O._t(transfer)
+    if evol_shape != init_shape:
+        init_mesh = O.chreshape(init_mesh, O.r2chshape(evol_shape))
+    pos = O.regular_pos(evol_shape, ptcl_shape)
+    _, a = los_scalefactor_pos(pos, *geo, evol_shape, cosmo, a_obs, curved_sky)
+    weights, dvel = lagrangian_bias(cosmo, pos, a, box_size, init_mesh, bias or {}, read_order=1)
+    if evolution == "lpt":
+        dpos, vel = O.lpt(cosmo, init_mesh, pos, a, lpt_order, 1)
+        pos = pos + dpos
+    else:
+        pos, vel = O.nbody_bf(cosmo, init_mesh, pos, a_start, a, n_steps, paint_order, lpt_order, paint_deconv=False)
+        pos, vel = pos[-1], vel[-1]
+    los, a = los_scalefactor_pos(pos, *geo, evol_shape, cosmo, a_obs, curved_sky)
+    pos = cell2phys_pos(pos, *geo, evol_shape)
+    if rsd_on:
+        pos = pos + rsd(cosmo, vel, los, a, box_rot, box_size, evol_shape, dvel)
+    if ap_fid is not None:
+        pos = ap_auto(pos, los, cosmo, ap_fid, curved_sky)
+    pos = phys2cell_pos(pos, *geo, init_shape)
+    gxy = O.nufft(pos, init_shape, None if paint_shape == init_shape else paint_shape, weights, paint_order,
+                  interlace_order, kernel_type, paint_deconv)
+    gxy = gxy * float(np.divide(init_shape, ptcl_shape).prod())
+    if paint_shape != init_shape:
+        gxy = O.chreshape(gxy, O.r2chshape(paint_shape))
+    return torch.fft.irfftn(gxy, s=paint_shape)

@@ -250,3 +250,25 @@ def test_rg2cgh_cgh2rg(golden):
     close(O.cgh2rg(k), g["cgh2rg_roundtrip"])
     close(O.cgh2rg(O._t(g["ampk"]), "amp"), g["cgh2rg_amp"], rtol=0, atol=0)
     close(O.rg2cgh(g["white"], "amp"), g["rg2cgh_amp"], rtol=0, atol=0)
+
+
+def test_observation_chain(golden):
+    """oracle/model_oracle.py's float64 restatement of bricks.py:628-813 (frames, lines of sight, light-cone scale
+    factors, RSD, automatic Alcock-Paczynski) against the reference source."""
+    from scipy.spatial.transform import Rotation
+    from oracle import model_oracle as MO
+    g, gr = golden("observation"), golden("growth")
+    shape, box, center = tuple(int(s) for s in g["shape"]), tuple(g["box_size"]), tuple(g["box_center"])
+    rot = Rotation.from_matrix(g["rot_matrix"])
+    oc, ob, h, ns, s8 = gr["other_params"]
+    cosmo, fid = O.Cosmology(), O.Cosmology(Omega_c=oc, Omega_b=ob, h=h, n_s=ns, sigma8=s8)
+    pos, vel = O._t(g["pos"]), O._t(g["vel"])
+    phys = MO.cell2phys_pos(pos, center, rot, box, shape)
+    close(phys, g["cell2phys_pos"], rtol=1e-10)
+    close(MO.phys2cell_pos(phys, center, rot, box, shape), g["phys2cell_roundtrip"], rtol=1e-10)
+    for tag, curved in (("curved", True), ("flat", False)):
+        los, a = MO.los_scalefactor_pos(pos, center, rot, box, shape, cosmo, None, curved)
+        close(los * torch.ones(1, 3, dtype=torch.float64), g[f"los_{tag}"], rtol=1e-10)
+        close(a, g[f"a_{tag}"], rtol=1e-10)
+        close(MO.rsd(cosmo, vel, los, a, rot, box, shape, dvel=0.01), g[f"rsd_{tag}"], rtol=1e-9)
+        close(MO.ap_auto(phys, los, cosmo, fid, curved), g[f"ap_auto_{tag}"], rtol=1e-10)

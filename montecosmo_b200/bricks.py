@@ -132,6 +132,101 @@ def lagrangian_bias(cosmo, pos, a, box_size, lin_mesh, bias, png=None, png_type=
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# Kaiser model (bricks.py:170-247): growth, Eulerian linear bias, redshift-space distortions and the scale-dependent
+# bias of primordial non-Gaussianity, all linear.  Fourier multipliers are host-built float32 meshes (like `transfer`),
+# the transforms are the engine's.
+# ----------------------------------------------------------------------------------------------------------------
+def b1_L2E(b1):
+    """Lagrangian -> Eulerian linear bias (bricks.py:454-455)."""
+    return 1 + b1
+
+
+def _kmu(mesh_shape, box_size, los):
+    kvec = _nb.rfftk(mesh_shape, box_size)  # h/Mpc
+    kmesh = sum(k**2 for k in kvec) ** 0.5
+    kdot = sum(k * l for k, l in zip(kvec, los))
+    return kmesh, np.where(kmesh == 0, 0.0, kdot / np.where(kmesh == 0, 1.0, kmesh))
+
+
+def kaiser_boost(cosmo, a, mesh_shape, box_size, b1E, fNL_bp=0.0, png_type=None, los=(0.0, 0.0, 0.0), kpow=None):
+    """Eulerian Kaiser boost D(a) (b1E + f(a) mu^2) [+ fNL_bp / T_phi->delta] on the half-spectrum mesh, host float64
+    (bricks.py:170-184); scalar `a`."""
+    kmesh, mu = _kmu(mesh_shape, box_size, np.asarray(los, dtype=np.float64))
+    boost = float(_cosmo.a2g(cosmo, a)) * (b1E + float(_cosmo.a2f(cosmo, a)) * mu**2)
+    if png_type is not None:
+        t = trans_phi2delta_mesh(cosmo, mesh_shape, box_size, kpow)
+        boost = boost + np.where(t == 0, 0.0, fNL_bp / np.where(t == 0, 1.0, t))
+    return boost
+
+
+def kaiser_model(cosmo, a, lin_mesh, box_size, b1E, fNL_bp=0.0, png_type=None, los=(0.0, 0.0, 0.0), kpow=None):
+    """1 + delta of the Kaiser model (bricks.py:186-232).  Flat sky without light cone (los of shape (3,), scalar a):
+    one Fourier multiply and one inverse transform.  Flat sky with a light cone (a: a mesh of scale factors): two
+    transforms.  Curved sky (los: a mesh of unit vectors [*mesh_shape, 3]): mu^2 delta = sum_ij l_i l_j F^-1[k_i k_j /
+    k^2 delta_k], six transforms -- the same field as the reference's spherical-harmonic expansion
+    (metrics.py:412-443; mu^2 = 1/3 + 8 pi / 15 sum_m Y_2m(k) Y_2m(r)) for a zero-mean delta_k."""
+    lin_mesh = _nb._c64(lin_mesh)
+    dev = lin_mesh.device
+    mesh_shape = _nb.ch2rshape(tuple(lin_mesh.shape))
+    los_t = torch.as_tensor(np.asarray(los, dtype=np.float64) if not isinstance(los, torch.Tensor) else los)
+    f32 = lambda x: torch.as_tensor(np.asarray(x, dtype=np.float32), device=dev)
+    scalar_a = np.ndim(a) == 0
+    if los_t.shape == (3,) and scalar_a:
+        boost = kaiser_boost(cosmo, a, mesh_shape, box_size, b1E, fNL_bp, png_type, los_t.numpy(), kpow)
+        return 1 + _nb.irfftn(lin_mesh * f32(boost))
+    a_dev = a if scalar_a else torch.as_tensor(a).to(device=dev, dtype=torch.float32)
+    g, f = (_tab(fn, cosmo, a_dev) if not scalar_a else float(fn(cosmo, a)) for fn in (_cosmo.a2g, _cosmo.a2f))
+    if los_t.shape == (3,):
+        _, mu = _kmu(mesh_shape, box_size, los_t.numpy())
+        delta = b1E * _nb.irfftn(lin_mesh) + f * _nb.irfftn(lin_mesh * f32(mu**2))
+    else:
+        kvec = _nb.rfftk(mesh_shape)  # cell units, as optim_mu2_delta
+        k2 = sum(k**2 for k in kvec)
+        inv = np.where(k2 == 0, 0.0, 1.0 / np.where(k2 == 0, 1.0, k2))
+        l = los_t.to(device=dev, dtype=torch.float32)
+        mu2_delta = 0.0
+        for i in range(3):
+            for j in range(i, 3):
+                hij = _nb.irfftn(lin_mesh * f32(kvec[i] * kvec[j] * inv))
+                mu2_delta = mu2_delta + (1.0 if i == j else 2.0) * l[..., i] * l[..., j] * hij
+        delta = b1E * _nb.irfftn(lin_mesh) + f * mu2_delta
+    delta = g * delta
+    if png_type is not None:
+        t = trans_phi2delta_mesh(cosmo, mesh_shape, box_size, kpow)
+        delta = delta + fNL_bp * _nb.irfftn(lin_mesh * f32(np.where(t == 0, 0.0, 1.0 / np.where(t == 0, 1.0, t))))
+    return 1 + delta
+
+
+def kaiser_posterior(delta_obs, cosmo, a, box_size, var_noise, b1E, los=(0.0, 0.0, 0.0), kpow=None):
+    """Posterior mean and std of the linear field given the observed one under the Kaiser model (bricks.py:234-247),
+    Fourier space; the linear power comes from the (k, P) table `kpow` normalised to sigma8 = 1 (lin_power)."""
+    delta_obs = _nb._c64(delta_obs)
+    mesh_shape = _nb.ch2rshape(tuple(delta_obs.shape))
+    if kpow is None:
+        raise NotImplementedError("kaiser_posterior needs a (k, P) table: the Eisenstein-Hu branch lives in jax_cosmo")
+    ks, pows = (np.asarray(x, dtype=np.float64) for x in kpow)
+    kmesh, _ = _kmu(mesh_shape, box_size, np.zeros(3))
+    pmesh = np.interp(kmesh.reshape(-1), ks, pows * float(cosmo.sigma8) ** 2, left=0.0, right=0.0).reshape(kmesh.shape)
+    pmesh = pmesh * np.divide(mesh_shape, box_size).prod()  # cell units
+    boost = kaiser_boost(cosmo, a, mesh_shape, box_size, b1E, los=los)
+    stds = (pmesh / (1 + boost**2 / var_noise * pmesh)) ** 0.5
+    f32 = lambda x: torch.as_tensor(np.asarray(x, dtype=np.float32), device=delta_obs.device)
+    return f32(stds**2 * boost / var_noise) * delta_obs, f32(stds)
+
+
+def los_scalefactor_mesh(box_center, box_rot, box_size, mesh_shape, cosmo, a_obs=None, curved_sky=True):
+    """Line of sight and scale factor of every mesh cell (bricks.py:768-786), host float64 like radius_mesh."""
+    if curved_sky:
+        pos = pos_mesh(box_center, box_rot, box_size, mesh_shape)
+        rmesh = pos.norm(dim=-1)
+        los = _safe_div(pos, rmesh.unsqueeze(-1))
+    else:
+        los = _flat_los(box_center, torch.zeros(1, dtype=torch.float64))
+        rmesh = radius_mesh(box_center, box_rot, box_size, mesh_shape, curved_sky)
+    return los, (_cosmo.chi2a(cosmo, rmesh) if a_obs is None else a_obs)
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # cell -> physical -> redshift space (bricks.py:628-660, 667-740, 747-870): elementwise on [Np, 3], torch, differentiable
 # in the positions, velocities and -- through cosmo.py's growth and distance tables -- the cosmology.  `box_rot` is a
 # scipy Rotation (as in the reference), a 3 x 3 matrix, or None for the identity.

@@ -225,7 +225,7 @@ class FieldModel:
 
 
 class FieldLevelModel(FieldModel):
-    """The general `evolve` of the reference (model.py:683-837, 'lpt' / 'nbody' evolutions with Lagrangian bias), beyond
+    """The general `evolve` of the reference (model.py:683-837: 'kaiser', and 'lpt' / 'nbody' with Lagrangian bias), beyond
     the benchmarked configuration of FieldModel: initial, evolution and paint meshes of different shapes, any particle
     lattice, the full Lagrangian bias expansion with its velocity term and primordial non-Gaussianity, a box placed
     and rotated with respect to the observer, curved or flat sky, light-cone scale factors (a_obs=None: read from the
@@ -253,6 +253,15 @@ class FieldLevelModel(FieldModel):
         init_mesh = self.linear_field(white)  # white2lin at the initial shape (bricks.py:152-157)
         if self.evol_shape != self.init_shape:
             init_mesh = nb.chreshape(init_mesh, r2chshape(self.evol_shape))
+        if self.evolution == "kaiser":  # model.py:690-699: growth, Eulerian bias, RSD and PNG all linear
+            los, a = B.los_scalefactor_mesh(*geo, self.evol_shape, c, self.a_obs, self.curved_sky)
+            cell_los = B._rot(los, self.box_rot, inverse=True)
+            fnl_bp = 0.0 if self.png is None else self.png.get("fNL_bp", 0.0)
+            gxy = B.kaiser_model(c, a, init_mesh, self.box_size, B.b1_L2E(self.bias.get("b1", 0.0)), fnl_bp,
+                                 self.png_type, cell_los, self.kpow_sigma8_1() if self.png_type is not None else None)
+            if self.evol_shape != self.init_shape:  # back to the final shape (model.py:733-736)
+                gxy = nb.irfftn(nb.chreshape(nb.rfftn(gxy), r2chshape(self.init_shape)))
+            return gxy
         pos = B.regular_pos(self.evol_shape, self.ptcl_shape)
         _, a = B.los_scalefactor_pos(pos, *geo, self.evol_shape, c, self.a_obs, self.curved_sky)
         weights, dvel, _ = B.lagrangian_bias(c, pos, a, self.box_size, init_mesh, self.bias, self.png, self.png_type,

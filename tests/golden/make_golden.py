@@ -343,6 +343,27 @@ def main():
     cosmo._workspace = {}
     red, aa = bricks.redges_and_scalefactors(cosmo, 500.0, 2500.0, 4)
     d["redges"], d["redges_a"] = A(red), A(aa)
+    # Kaiser model (bricks.py:170-232): flat sky, flat sky on the light cone, curved sky
+    shape, box = (8, 10, 12), (800.0, 1000.0, 960.0)
+    dkk = np.fft.rfftn(rng.normal(size=shape)) * 0.05
+    dkk[0, 0, 0] = 0.0
+    ks = np.logspace(-4, 1, 64)
+    pk = 2.0e4 * (ks / 0.02) ** 0.96 / (1 + (ks / 0.02) ** 2) ** 1.7
+    flat_los = np.array(center) / np.linalg.norm(center)
+    d["kaiser_delta_k"], d["kaiser_shape"], d["kaiser_box"], d["kaiser_los"] = dkk, np.array(shape), np.array(box), flat_los
+    d["kaiser_kpow_k"], d["kaiser_kpow_p"] = ks, pk
+    cosmo._workspace = {}
+    d["kaiser_boost"] = A(bricks.kaiser_boost(cosmo, 0.7, shape, box, 1.8, 0.5, "fNL", flat_los, (ks, pk)))
+    d["kaiser_flat"] = A(bricks.kaiser_model(cosmo, 0.7, jnp.asarray(dkk.copy()), box, 1.8, 0.5, "fNL", flat_los, (ks, pk)))
+    los_m, a_m = bricks.los_scalefactor_mesh(np.array(center), rot, box, shape, cosmo, None, False)
+    d["kaiser_a_mesh_flat"] = A(a_m)
+    d["kaiser_lightcone"] = A(bricks.kaiser_model(cosmo, jnp.asarray(a_m), jnp.asarray(dkk.copy()), box, 1.8,
+                                                  los=jnp.asarray(los_m)))
+    los_c, a_c = bricks.los_scalefactor_mesh(np.array(center), rot, box, shape, cosmo, None, True)
+    cell_los = rot.apply(np.asarray(los_c).reshape(-1, 3), inverse=True).reshape(tuple(shape) + (3,))
+    d["kaiser_a_mesh_curved"], d["kaiser_cell_los"] = A(a_c), cell_los
+    d["kaiser_curved"] = A(bricks.kaiser_model(cosmo, jnp.asarray(a_c), jnp.asarray(dkk.copy()), box, 1.8,
+                                               los=jnp.asarray(cell_los)))
     out["observation"] = d
 
     for name, dd in out.items():

@@ -591,3 +591,64 @@ def test_general_evolve_against_oracle(nb, case):
     (out * cot.float().to(dev(nb))).sum().backward()
     (ref * cot).sum().backward()
     assert rel(w.grad, wo.grad) < 1e-3
+
+
+def test_kaiser_model_golden(nb, golden):
+    """kaiser_boost / kaiser_model (bricks.py:170-232) in its three configurations -- flat sky (one Fourier multiply, with
+    the scale-dependent PNG bias), flat sky on the light cone (a mesh of scale factors), curved sky (a mesh of lines of
+    sight; six second-derivative transforms here, a spherical-harmonic sum in the reference) -- and los_scalefactor_mesh
+    (bricks.py:768-786), against the golden vectors of the reference source."""
+    from scipy.spatial.transform import Rotation
+    from montecosmo_b200 import bricks as B
+    from montecosmo_b200.cosmo import Cosmology
+    g = golden("observation")
+    shape, box = tuple(int(s) for s in g["kaiser_shape"]), tuple(g["kaiser_box"])
+    center, rot = tuple(g["box_center"]), Rotation.from_matrix(g["rot_matrix"])
+    kpow, los = (g["kaiser_kpow_k"], g["kaiser_kpow_p"]), g["kaiser_los"]
+    dk = torch.tensor(g["kaiser_delta_k"], dtype=torch.complex64, device=dev(nb))
+    c = Cosmology()
+    assert np.allclose(B.kaiser_boost(c, 0.7, shape, box, 1.8, 0.5, "fNL", los, kpow), g["kaiser_boost"], rtol=1e-10)
+    assert rel(B.kaiser_model(c, 0.7, dk, box, 1.8, 0.5, "fNL", los, kpow) - 1, g["kaiser_flat"] - 1) < 1e-5
+    los_m, a_m = B.los_scalefactor_mesh(center, rot, box, shape, c, None, False)
+    assert np.allclose(a_m.numpy(), g["kaiser_a_mesh_flat"], rtol=1e-10) and np.allclose(los_m.numpy(), los, rtol=1e-12)
+    assert rel(B.kaiser_model(c, a_m, dk, box, 1.8, los=los_m) - 1, g["kaiser_lightcone"] - 1) < 1e-5
+    los_c, a_c = B.los_scalefactor_mesh(center, rot, box, shape, c, None, True)
+    assert np.allclose(a_c.numpy(), g["kaiser_a_mesh_curved"], rtol=1e-10)
+    cell_los = torch.as_tensor(rot.apply(los_c.numpy().reshape(-1, 3), inverse=True).reshape(shape + (3,)))
+    assert np.allclose(cell_los.numpy(), g["kaiser_cell_los"], rtol=1e-10, atol=1e-12)
+    assert rel(B.kaiser_model(c, a_c, dk, box, 1.8, los=cell_los) - 1, g["kaiser_curved"] - 1) < 1e-5
+    # the posterior mean / std are the Wiener filter of the same boost (bricks.py:234-247)
+    mean, std = B.kaiser_posterior(dk, c, 0.7, box, 0.3, 1.8, los, kpow)
+    boost = B.kaiser_boost(c, 0.7, shape, box, 1.8, los=los)
+    kvec = nb.rfftk(shape, box)
+    pm = np.interp(np.sqrt(sum(k**2 for k in kvec)).ravel(), kpow[0], kpow[1] * float(c.sigma8) ** 2, left=0.0,
+                   right=0.0).reshape(boost.shape) * np.divide(shape, box).prod()
+    s2 = pm / (1 + boost**2 / 0.3 * pm)
+    assert rel(std, np.sqrt(s2)) < 1e-6 and rel(mean, s2 * boost / 0.3 * g["kaiser_delta_k"]) < 1e-6
+
+
+def test_kaiser_evolution_of_the_general_model(nb):
+    """evolution='kaiser' (model.py:690-699, 733-736): flat sky without light cone is one Fourier multiply of the linear
+    field -- checked against numpy float64 from the model's own transfer mesh -- and differentiable in the white field."""
+    from montecosmo_b200 import bricks as B
+    from montecosmo_b200.model import FieldLevelModel
+    rng = np.random.default_rng(19)
+    shape, box, center = (16, 16, 16), (640.0,) * 3, (0.0, 300.0, 2000.0)
+    m = FieldLevelModel(shape, box, evolution="kaiser", a_obs=0.6, box_center=center, bias=dict(b1=0.8))
+    white = rng.normal(size=shape).astype(np.float32)
+    w = leaf(torch.tensor(white), nb)
+    out = m.evolve(w)
+    los = np.array(center) / np.linalg.norm(center)
+    boost = B.kaiser_boost(m.cosmology, 0.6, shape, box, 1.8, los=los)
+    ref = 1 + np.fft.irfftn(np.fft.rfftn(white.astype(np.float64)) * m.transfer.cpu().numpy() * boost, s=shape, axes=(0, 1, 2))
+    assert rel(out - 1, ref - 1) < 1e-5
+    out.sum().backward()
+    assert bool(torch.isfinite(w.grad).all())
+    # a finer evolution mesh comes back to the initial shape; the two differ only on the Nyquist planes, whose modes the
+    # padding splits into +-k_N halves that see different mu^2 before the crop merges them again (measured 7.7e-3)
+    m2 = FieldLevelModel(shape, box, evolution="kaiser", a_obs=0.6, box_center=center, bias=dict(b1=0.8), evol_oversamp=1.5)
+    out2 = m2.evolve(torch.tensor(white))
+    assert tuple(out2.shape) == shape and rel(out2 - 1, ref - 1) < 2e-2
+    k1, k2 = np.fft.rfftn(out2.cpu().numpy().astype(np.float64)), np.fft.rfftn(ref)
+    inner = np.s_[1:7, 1:7, 1:7]  # away from every Nyquist plane the two agree to float32 rounding
+    assert np.abs(k1[inner] - k2[inner]).max() < 1e-4 * np.abs(k2[inner]).max()

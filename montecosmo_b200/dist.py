@@ -150,6 +150,8 @@ class SlabPM:
         nb = a.shape[0]
         b = self.A.empty((nb, self.xl, self.ny, self.nzc), "c64")
         self._call("mcpm_slabfft_r2c_yz", self._fft, self._st(), a.data_ptr(), b.data_ptr(), nb)
+        if self.P == 1:  # one rank: the two layouts coincide
+            return b
         # send[q] = my planes restricted to rank q's ky rows
         send = b.view(nb, self.xl, self.P, self.kyl, self.nzc).permute(2, 0, 1, 3, 4).contiguous()
         recv = self._a2a(send)  # recv[q] = rank q's planes, my ky rows
@@ -179,9 +181,12 @@ class SlabPM:
         nb = c.shape[0]
         if not x_done:
             self._call("mcpm_slabfft_c2c_x", self._fft, self._st(), c.data_ptr(), nb, 1)
-        send = c.view(nb, self.P, self.xl, self.kyl, self.nzc).permute(1, 0, 2, 3, 4).contiguous()
-        recv = self._a2a(send)  # recv[q] = my planes, rank q's ky rows
-        b = recv.permute(1, 2, 0, 3, 4).contiguous().view(nb, self.xl, self.ny, self.nzc)
+        if self.P == 1:
+            b = c
+        else:
+            send = c.view(nb, self.P, self.xl, self.kyl, self.nzc).permute(1, 0, 2, 3, 4).contiguous()
+            recv = self._a2a(send)  # recv[q] = my planes, rank q's ky rows
+            b = recv.permute(1, 2, 0, 3, 4).contiguous().view(nb, self.xl, self.ny, self.nzc)
         if project:
             self._project_yz(b)
         out = self.A.empty((nb, self.xl, self.ny, self.nz))

@@ -55,6 +55,137 @@ def add_png(cosmo, fNL, lin_mesh, box_size, kpow=None):
     return t * _nb.rfftn(phi)
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# linear power and bias parametrisations (bricks.py:67-106, 143-166, 454-505): host-side tables and scalars
+# ----------------------------------------------------------------------------------------------------------------
+def lin_power(cosmo, a=1.0, kpow=None, n_interp=256):
+    """(k, P_lin) from a tabulation normalised to sigma8 = 1 (bricks.py:67-77).  kpow=None is jax_cosmo's Eisenstein-Hu
+    power, outside the path."""
+    if kpow is None:
+        raise NotImplementedError("lin_power needs a (k, P) table: the Eisenstein-Hu branch lives in jax_cosmo")
+    ks, pows = kpow
+    return np.asarray(ks, dtype=np.float64), np.asarray(pows, dtype=np.float64) * float(cosmo.sigma8) ** 2
+
+
+def lin_power_interp(cosmo, a=1.0, kpow=None, n_interp=256):
+    """Linear interpolation of the tabulated power, zero outside the table (bricks.py:79-93)."""
+    ks, pows = lin_power(cosmo, a, kpow, n_interp)
+    return lambda x: np.interp(np.asarray(x).reshape(-1), ks, pows, left=0.0, right=0.0).reshape(np.shape(x))
+
+
+def lin_power_mesh(cosmo, mesh_shape, box_size, a=1.0, kpow=None, n_interp=256):
+    """Linear power on the half-spectrum mesh, [Mpc/h]^3 (bricks.py:95-106); host float64."""
+    kmesh = sum(k**2 for k in _nb.rfftk(mesh_shape, box_size)) ** 0.5
+    return lin_power_interp(cosmo, a, kpow, n_interp)(kmesh)
+
+
+def trans_phi2delta_interp(cosmo, a=1.0, kpow=None, n_interp=256):
+    """Transfer from the primordial potential to the linear density as a function of k (bricks.py:108-127)."""
+    ks, pow_lin = lin_power(cosmo, kpow=kpow, n_interp=n_interp)
+    pow_large = ks ** float(cosmo.n_s)
+    lin_trans = (pow_lin / pow_large / (pow_lin[0] / pow_large[0])) ** 0.5
+    a_md = 1.0 / 11.0
+    growth_md = float(_cosmo.a2g(cosmo, a_md)) / a_md
+    trans = 2.0 * RH**2 * ks**2 * lin_trans * (float(_cosmo.a2g(cosmo, a)) / growth_md) / (3.0 * float(cosmo.Omega_m))
+    return lambda x: np.interp(np.asarray(x).reshape(-1), ks, trans, left=0.0, right=0.0).reshape(np.shape(x))
+
+
+def white2lin(cosmo, white_mesh, init_shape, box_size, kpow=None):
+    """White noise mesh (Fourier space, physical units) -> linear matter mesh (bricks.py:152-157)."""
+    white_mesh = _nb._c64(white_mesh)
+    pm = lin_power_mesh(cosmo, init_shape, box_size, kpow=kpow)
+    return _nb._ScaleSpectrum.apply(white_mesh, torch.as_tensor((pm**0.5).astype(np.float32), device=white_mesh.device))
+
+
+def lin2white(cosmo, lin_mesh, init_shape, box_size, kpow=None):
+    """Linear matter mesh -> white noise mesh, zero where the power vanishes (bricks.py:159-164)."""
+    lin_mesh = _nb._c64(lin_mesh)
+    rp = lin_power_mesh(cosmo, init_shape, box_size, kpow=kpow) ** 0.5
+    inv = np.where(rp == 0, 0.0, 1.0 / np.where(rp == 0, 1.0, rp))
+    return _nb._ScaleSpectrum.apply(lin_mesh, torch.as_tensor(inv.astype(np.float32), device=lin_mesh.device))
+
+
+def b1_E2L(b1):
+    return b1 - 1
+
+
+def b2_L2E(b2, b1L):
+    return b2 + 8 / 21 * b1L
+
+
+def b2_E2L(b2, b1L):
+    return b2 - 8 / 21 * b1L
+
+
+def bpd_L2E(bpd, bp):
+    return bpd + bp / 2
+
+
+def bpd_E2L(bpd, bp):
+    return bpd - bp / 2
+
+
+def b_phi(b1, p=1.0, delta_c=1.686):
+    """Primordial scale-dependent bias parameter 2 delta_c (b1 + 1 - p) (bricks.py:472-481)."""
+    return 2 * delta_c * (b1 + 1 - p)
+
+
+def b_phi_delta(b1, b2, delta_c=1.686):
+    """Primordial-density bias parameter 2 (delta_c b2 - b1) (bricks.py:483-492)."""
+    return 2 * (delta_c * b2 - b1)
+
+
+def fNL_bias(png, bias, p=1.0, png_type=None):
+    """Fill the PNG bias amplitudes from fNL (bricks.py:494-508); returns the (updated) dict like the reference."""
+    fNL, fNL_bp, fNL_bpd = png["fNL"], png["fNL_bp"], png["fNL_bpd"]
+    if png_type == "fNL":
+        fNL_bp, fNL_bpd = fNL * b_phi(bias["b1"], p), fNL * b_phi_delta(bias["b1"], bias["b2"])
+    elif png_type == "bias":
+        fNL_bp, fNL_bpd = fNL * fNL_bp, fNL * fNL_bpd
+    png["fNL_bp"], png["fNL_bpd"] = fNL_bp, fNL_bpd
+    return png
+
+
+def eulerian_bias(matter_mesh, phi_mesh, box_size, bias, png, png_type=None):
+    """Eulerian bias expansion on the evolved matter mesh (bricks.py:513-585; renormalised operators of Desjacques+2018
+    eq. 3.38, 7.10, 7.11): 1 + b1 d + b2 (d^2 - <d^2>)/2 + bs2 (s^2 - 2/3 <d^2>) + bn2 lap d [+ PNG terms], with the
+    Lagrangian parameters converted to Eulerian ones.  Inputs are half spectra; returns (weights mesh, dvel = 0)."""
+    b1, b2 = b1_L2E(bias["b1"]), b2_L2E(bias["b2"], bias["b1"])
+    bs2, bn2 = bias["bs2"], bias["bn2"]
+    matter_mesh = _nb._c64(matter_mesh).clone()
+    matter_mesh[0, 0, 0] = 0.0  # zero mean
+    dev = matter_mesh.device
+    delta = _nb.irfftn(matter_mesh)
+    mesh_shape = tuple(delta.shape)
+    kvec = [torch.as_tensor(k.astype(np.float32), device=dev) for k in _nb.rfftk(mesh_shape, box_size)]
+    k2 = sum(k**2 for k in kvec)
+    inv_k2 = torch.where(k2 == 0, torch.zeros_like(k2), 1.0 / torch.where(k2 == 0, torch.ones_like(k2), k2))
+    weights = 1.0 + b1 * delta
+    if png_type is not None:
+        fNL, fNL_bp = png["fNL"], png["fNL_bp"]
+        fNL_bpd = fNL * bpd_L2E(png["fNL_bpd"] / fNL, fNL_bp / fNL)
+        phi = _nb.irfftn(_nb._c64(phi_mesh))
+        phi_delta = phi * delta
+        weights = weights + fNL_bp * phi + fNL_bpd * (phi_delta - phi_delta.mean())
+    delta2 = delta**2
+    sigma2 = delta2.mean()
+    weights = weights + b2 * (delta2 - sigma2) / 2
+    shear2 = 0.0
+    for i in range(3):
+        shear2 = shear2 + _nb.irfftn((kvec[i] * kvec[i] * inv_k2 - 1.0 / 3.0) * matter_mesh) ** 2
+        for j in range(i + 1, 3):
+            shear2 = shear2 + 2 * _nb.irfftn((kvec[i] * kvec[j] * inv_k2) * matter_mesh) ** 2
+    weights = weights + bs2 * (shear2 - 2.0 / 3.0 * sigma2)
+    weights = weights + bn2 * _nb.irfftn(-k2 * matter_mesh)
+    return weights, 0.0
+
+
+def count2delta(mesh, selec_mesh):
+    """Count mesh -> delta mesh under the global integral constraint (bricks.py:927-937)."""
+    alpha_selec = selec_mesh * mesh.mean() / selec_mesh.mean()
+    return (mesh - alpha_selec) / (alpha_selec**2).mean() ** 0.5
+
+
 def regular_pos(mesh_shape, ptcl_shape=None):
     """Particle lattice in cell units, C order (bricks.py:593-603)."""
     ptcl_shape = mesh_shape if ptcl_shape is None else ptcl_shape

@@ -304,6 +304,25 @@ def main():
     d.update({f"png_{k}": np.array(v) for k, v in png.items()})
     cosmo._workspace = {}
     d["add_png_fNL50"] = A(bricks.add_png(cosmo, 50.0, jnp.asarray(dk), np.array(box), kpow=(ks, pk)))
+    # power, bias parametrisations and the Eulerian expansion (bricks.py:67-166, 454-585)
+    cosmo._workspace = {}
+    d["lin_power_mesh"] = A(bricks.lin_power_mesh(cosmo, shape, np.array(box), kpow=(ks, pk)))
+    d["trans_phi2delta"] = A(bricks.trans_phi2delta_interp(cosmo, kpow=(ks, pk))(np.array([1e-3, 0.05, 0.7])))
+    d["white2lin"] = A(bricks.white2lin(cosmo, jnp.asarray(dk), shape, np.array(box), kpow=(ks, pk)))
+    d["lin2white"] = A(bricks.lin2white(cosmo, jnp.asarray(d["white2lin"]), shape, np.array(box), kpow=(ks, pk)))
+    phik = np.fft.rfftn(rng.normal(size=shape)) * 0.02
+    d["eul_phik"] = phik
+    png_e = dict(fNL=20.0, fNL_bp=0.0, fNL_bpd=0.0)
+    png_e = bricks.fNL_bias(png_e, bias, p=1.0, png_type="fNL")
+    d["fNL_bias"] = np.array([png_e["fNL_bp"], png_e["fNL_bpd"]])
+    we, _ = bricks.eulerian_bias(jnp.asarray(dk.copy()), jnp.asarray(phik), np.array(box), bias, png_e, png_type="fNL")
+    d["eulerian_weights_png"] = A(we)
+    we, _ = bricks.eulerian_bias(jnp.asarray(dk.copy()), jnp.asarray(phik), np.array(box), bias, png_e, png_type=None)
+    d["eulerian_weights"] = A(we)
+    cm = rng.uniform(0.5, 2.0, size=shape)
+    sm = rng.uniform(0.1, 1.0, size=shape)
+    d["count_mesh"], d["selec_mesh"] = cm, sm
+    d["count2delta"] = A(bricks.count2delta(jnp.asarray(cm), jnp.asarray(sm)))
     out["lagrangian_bias"] = d
 
     # ---- cell -> physical -> redshift space (bricks.py:628-877, next row f-3) ------------------------------------

@@ -652,3 +652,37 @@ def test_kaiser_evolution_of_the_general_model(nb):
     k1, k2 = np.fft.rfftn(out2.cpu().numpy().astype(np.float64)), np.fft.rfftn(ref)
     inner = np.s_[1:7, 1:7, 1:7]  # away from every Nyquist plane the two agree to float32 rounding
     assert np.abs(k1[inner] - k2[inner]).max() < 1e-4 * np.abs(k2[inner]).max()
+
+
+def test_power_bias_and_eulerian_expansion_golden(nb, golden):
+    """lin_power_mesh / trans_phi2delta_interp / white2lin / lin2white (bricks.py:67-166), the bias parametrisations and
+    fNL_bias (454-508), eulerian_bias (513-585) and count2delta (927-937) against the reference source."""
+    from montecosmo_b200 import bricks as B
+    from montecosmo_b200.cosmo import Cosmology
+    g = golden("lagrangian_bias")
+    shape, box = tuple(int(s) for s in g["shape"]), tuple(g["box_size"])
+    kpow = (g["kpow_k"], g["kpow_p"])
+    c = Cosmology()
+    d = dev(nb)
+    dk = torch.tensor(g["delta_k"], dtype=torch.complex64, device=d)
+    assert np.allclose(B.lin_power_mesh(c, shape, box, kpow=kpow), g["lin_power_mesh"], rtol=1e-12)
+    assert np.allclose(B.trans_phi2delta_interp(c, kpow=kpow)(np.array([1e-3, 0.05, 0.7])), g["trans_phi2delta"], rtol=1e-10)
+    lin = B.white2lin(c, dk, shape, box, kpow)
+    assert rel(lin, g["white2lin"]) < 1e-6
+    assert rel(B.lin2white(c, lin, shape, box, kpow), g["lin2white"]) < 1e-6
+    bias = {k[5:]: float(v) for k, v in g.items() if k.startswith("bias_")}
+    png = B.fNL_bias(dict(fNL=20.0, fNL_bp=0.0, fNL_bpd=0.0), bias, p=1.0, png_type="fNL")
+    assert np.allclose([png["fNL_bp"], png["fNL_bpd"]], g["fNL_bias"], rtol=1e-12)
+    assert B.b1_E2L(B.b1_L2E(0.3)) == pytest.approx(0.3) and B.b2_E2L(B.b2_L2E(0.2, 0.5), 0.5) == pytest.approx(0.2)
+    assert B.bpd_E2L(B.bpd_L2E(0.4, 0.6), 0.6) == pytest.approx(0.4)
+    phik = torch.tensor(g["eul_phik"], dtype=torch.complex64, device=d)
+    dkl = leaf(dk)
+    we, dvel = B.eulerian_bias(dkl, phik, box, bias, png, png_type="fNL")
+    assert dvel == 0.0 and rel(we, g["eulerian_weights_png"]) < 2e-5
+    we.sum().backward()
+    assert bool(torch.isfinite(torch.view_as_real(dkl.grad)).all())
+    assert rel(B.eulerian_bias(dk, phik, box, bias, png, None)[0], g["eulerian_weights"]) < 2e-5
+    cm, sm = (torch.tensor(g[k], dtype=torch.float32, device=d) for k in ("count_mesh", "selec_mesh"))
+    assert rel(B.count2delta(cm, sm), g["count2delta"]) < 1e-5
+    with pytest.raises(NotImplementedError):
+        B.lin_power(c)  # kpow=None is jax_cosmo's Eisenstein-Hu power

@@ -520,3 +520,98 @@ def redges_and_scalefactors(cosmo, rmin, rmax, n_shells):
     gmax = float(_cosmo.a2g(cosmo, _cosmo.chi2a(cosmo, rmin)))
     gs = np.linspace(gmin, gmax, n_shells + 1)
     return _cosmo.a2chi(cosmo, _cosmo.g2a(cosmo, gs)), _cosmo.g2a(cosmo, (gs[:-1] + gs[1:]) / 2)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# catalogue registration (utils.py:1186-1210, bricks.py:879-897, 1024-1100): the callers of nufft / paint outside the
+# model (SURVEY 8b "what calls it").  Catalogue particles come in arbitrary order: the generic scatter kernels.
+# ----------------------------------------------------------------------------------------------------------------
+def radecrad2cart(ra, dec, radius):
+    """ra, dec in degrees and radius -> cartesian [..., 3] (utils.py:1186-1196)."""
+    ra, dec, radius = (torch.as_tensor(np.asarray(x, dtype=np.float64)) if not isinstance(x, torch.Tensor) else x
+                       for x in (ra, dec, radius))
+    ra, dec = torch.deg2rad(ra), torch.deg2rad(dec)
+    return radius.unsqueeze(-1) * torch.stack((torch.cos(dec) * torch.cos(ra), torch.cos(dec) * torch.sin(ra),
+                                               torch.sin(dec)), -1)
+
+
+def cart2radecrad(cart):
+    """cartesian -> ra in [0, 360), dec in [-90, 90] (degrees), radius (utils.py:1199-1210)."""
+    cart = torch.as_tensor(cart)
+    radius = cart.norm(dim=-1)
+    ra = torch.rad2deg(torch.atan2(cart[..., 1], cart[..., 0])) % 360.0
+    dec = torch.rad2deg(torch.asin(_safe_div(cart[..., 2], radius)))
+    return ra, dec, radius
+
+
+def radecz2cart(cosmo, radecz):
+    """{'RA', 'DEC', 'Z'} (degrees, redshift) -> cartesian Mpc/h, float64 on the host (bricks.py:879-887)."""
+    z = torch.as_tensor(np.asarray(radecz["Z"], dtype=np.float64))
+    return radecrad2cart(radecz["RA"], radecz["DEC"], _cosmo.a2chi(cosmo, 1.0 / (1.0 + z)))
+
+
+def cart2radecz(cosmo, cart):
+    """cartesian Mpc/h -> {'RA', 'DEC', 'Z'} (bricks.py:889-897)."""
+    ra, dec, radius = cart2radecrad(torch.as_tensor(cart).to("cpu", torch.float64))
+    return {"RA": ra, "DEC": dec, "Z": 1.0 / _cosmo.chi2a(cosmo, radius) - 1.0}
+
+
+def _rotvec(box_rotvec):
+    from scipy.spatial.transform import Rotation
+    return Rotation.from_rotvec(np.asarray(box_rotvec, dtype=np.float64))
+
+
+def _paint_shape(final_shape, paint_shape):
+    return paint_shape if paint_shape is None or isinstance(paint_shape, float) else tuple(int(s) for s in paint_shape)
+
+
+def cutsky2count(data, cosmo, count_shape, paint_shape, box_size, box_center, box_rotvec, paint_order: int = 2,
+                 interlace_order: int = 2, paint_deconv: bool = True):
+    """Painted count mesh of a cut-sky catalogue {'RA', 'DEC', 'Z', 'WEIGHT'} (bricks.py:1052-1068)."""
+    pos = phys2cell_pos(radecz2cart(cosmo, data), box_center, _rotvec(box_rotvec), box_size, count_shape)
+    mesh = _nb.nufft(_nb._f32(pos), count_shape, _paint_shape(count_shape, paint_shape), _nb._f32(data["WEIGHT"]),
+                     paint_order, interlace_order, paint_deconv=paint_deconv)
+    return _nb.irfftn(mesh)
+
+
+def cutsky2selection(data, cosmo, mask_shape, selec_shape, paint_shape, box_size, box_center, box_rotvec,
+                     paint_order: int = 2, interlace_order: int = 2, paint_deconv: bool = True):
+    """Selection mesh (unit mean within its support) and boolean mask of a cut-sky random catalogue
+    (bricks.py:1026-1050)."""
+    pos = phys2cell_pos(radecz2cart(cosmo, data), box_center, _rotvec(box_rotvec), box_size, selec_shape)
+    w = _nb._f32(data["WEIGHT"])
+    p32 = _nb._f32(pos)
+    selec = _nb.irfftn(_nb.nufft(p32, selec_shape, _paint_shape(selec_shape, paint_shape), w, paint_order,
+                                 interlace_order, paint_deconv=paint_deconv))
+    support = _nb.paint(p32, selec_shape, w, paint_order) > 0
+    selec = selec / selec[support].mean()
+    pmask = _nb._f32(pos * torch.as_tensor(np.divide(mask_shape, selec_shape)))
+    return selec, _nb.paint(pmask, mask_shape, w, paint_order) > 0
+
+
+def fullsky2count(data, cosmo, a_obs, los, box_size, box_center, box_rotvec, final_shape, paint_shape,
+                  paint_order: int = 2, interlace_order: int = 2, paint_deconv: bool = True):
+    """Painted count mesh from cartesian positions of a periodic box, one dict {'pos'[, 'vel', 'WEIGHT']} or an iterable
+    of them accumulated in Fourier space; with 'vel' (km/s, peculiar) the flat-sky redshift-space shift along `los` is
+    applied at a_obs (bricks.py:1071-1100)."""
+    rot, los = _rotvec(box_rotvec), np.asarray(los, dtype=np.float64)
+    chunks = [data] if isinstance(data, dict) else data
+    final_shape = tuple(int(s) for s in final_shape)
+    count, n_tracers = None, 0.0
+    for chunk in chunks:
+        pos = np.asarray(chunk["pos"], dtype=np.float64)
+        if "vel" in chunk:
+            E = float(_cosmo.Esqr(cosmo, a_obs) ** 0.5)
+            vel = np.asarray(chunk["vel"], dtype=np.float64) / (a_obs * 100 * E)
+            pos = pos + (vel * los).sum(-1, keepdims=True) * los
+        weights = _nb._f32(chunk["WEIGHT"]) if "WEIGHT" in chunk else 1.0
+        cell = phys2cell_pos(torch.as_tensor(pos), box_center, rot, box_size, final_shape)
+        k = _nb.nufft(_nb._f32(cell), final_shape, _paint_shape(final_shape, paint_shape), weights, paint_order,
+                      interlace_order, paint_deconv=paint_deconv)
+        count = k if count is None else count + k
+        n_tracers += float(weights.sum()) if "WEIGHT" in chunk else len(pos)
+    mesh = _nb.irfftn(count)
+    total = float(mesh.sum())
+    assert abs(total - n_tracers) <= 1e-4 * max(abs(n_tracers), 1.0), \
+        f"Count mesh sum {total} does not match number of tracers {n_tracers}."
+    return mesh

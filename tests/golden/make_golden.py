@@ -383,6 +383,27 @@ def main():
     d["kaiser_a_mesh_curved"], d["kaiser_cell_los"] = A(a_c), cell_los
     d["kaiser_curved"] = A(bricks.kaiser_model(cosmo, jnp.asarray(a_c), jnp.asarray(dkk.copy()), box, 1.8,
                                                los=jnp.asarray(cell_los)))
+    # catalogue registration (bricks.py:879-897, 1026-1100)
+    nobj = 300
+    cat = {"RA": rng.uniform(20.0, 40.0, nobj), "DEC": rng.uniform(-10.0, 15.0, nobj), "Z": rng.uniform(0.4, 0.6, nobj),
+           "WEIGHT": rng.uniform(0.5, 1.5, nobj)}
+    cosmo._workspace = {}
+    cart = A(bricks.radecz2cart(cosmo, cat))
+    csize, ccenter, crotvec = (500.0, 600.0, 550.0), tuple(cart.mean(0)), (0.1, 0.2, -0.3)
+    d.update({f"cat_{k}": v for k, v in cat.items()})
+    d["cat_cart"], d["cat_box"], d["cat_center"], d["cat_rotvec"] = cart, np.array(csize), np.array(ccenter), np.array(crotvec)
+    back = bricks.cart2radecz(cosmo, jnp.asarray(cart))
+    d["cat_back"] = np.stack([A(back["RA"]), A(back["DEC"]), A(back["Z"])])
+    d["cutsky2count"] = A(bricks.cutsky2count(cat, cosmo, (12, 14, 12), 1.5, csize, ccenter, crotvec))
+    sel, msk = bricks.cutsky2selection(cat, cosmo, (6, 8, 6), (12, 14, 12), None, csize, ccenter, crotvec)
+    d["cutsky_selection"], d["cutsky_mask"] = A(sel), A(msk)
+    ppos = rng.uniform(-250.0, 250.0, (nobj, 3)) + np.array(ccenter)
+    pvel = rng.normal(scale=300.0, size=(nobj, 3))
+    d["full_pos"], d["full_vel"] = ppos, pvel
+    flos = np.array(ccenter) / np.linalg.norm(ccenter)
+    chunks = [{"pos": ppos[:100], "vel": pvel[:100], "WEIGHT": cat["WEIGHT"][:100]},
+              {"pos": ppos[100:], "vel": pvel[100:], "WEIGHT": cat["WEIGHT"][100:]}]
+    d["fullsky2count"] = A(bricks.fullsky2count(chunks, cosmo, 0.65, flos, csize, ccenter, crotvec, (12, 14, 12), None))
     out["observation"] = d
 
     for name, dd in out.items():

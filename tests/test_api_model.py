@@ -686,3 +686,28 @@ def test_power_bias_and_eulerian_expansion_golden(nb, golden):
     assert rel(B.count2delta(cm, sm), g["count2delta"]) < 1e-5
     with pytest.raises(NotImplementedError):
         B.lin_power(c)  # kpow=None is jax_cosmo's Eisenstein-Hu power
+
+
+def test_catalogue_registration_golden(nb, golden):
+    """The callers of nufft / paint outside the model (bricks.py:879-897, 1026-1100): sky <-> cartesian
+    coordinates, cutsky2count, cutsky2selection, fullsky2count (streamed chunks with redshift-space shift), against the
+    golden vectors of the reference source.  Catalogue particles are unordered: the generic scatter kernels."""
+    from montecosmo_b200 import bricks as B
+    from montecosmo_b200.cosmo import Cosmology
+    g = golden("observation")
+    c = Cosmology()
+    cat = {k: g[f"cat_{k}"] for k in ("RA", "DEC", "Z", "WEIGHT")}
+    size, center, rotvec = tuple(g["cat_box"]), tuple(g["cat_center"]), tuple(g["cat_rotvec"])
+    cart = B.radecz2cart(c, cat)
+    assert np.allclose(cart.numpy(), g["cat_cart"], rtol=1e-10)
+    back = B.cart2radecz(c, cart)
+    assert np.allclose(np.stack([back["RA"].numpy(), back["DEC"].numpy(), back["Z"].numpy()]), g["cat_back"], rtol=1e-9)
+    cnt = B.cutsky2count(cat, c, (12, 14, 12), 1.5, size, center, rotvec)
+    assert rel(cnt, g["cutsky2count"]) < 5e-5 and abs(float(cnt.sum()) - cat["WEIGHT"].sum()) < 1e-3 * cat["WEIGHT"].sum()
+    sel, msk = B.cutsky2selection(cat, c, (6, 8, 6), (12, 14, 12), None, size, center, rotvec)
+    assert rel(sel, g["cutsky_selection"]) < 5e-5 and np.array_equal(msk.cpu().numpy(), g["cutsky_mask"])
+    flos = np.array(center) / np.linalg.norm(center)
+    w = cat["WEIGHT"]
+    chunks = [{"pos": g["full_pos"][:100], "vel": g["full_vel"][:100], "WEIGHT": w[:100]},
+              {"pos": g["full_pos"][100:], "vel": g["full_vel"][100:], "WEIGHT": w[100:]}]
+    assert rel(B.fullsky2count(chunks, c, 0.65, flos, size, center, rotvec, (12, 14, 12), None), g["fullsky2count"]) < 5e-5

@@ -282,7 +282,7 @@ def _kmu(mesh_shape, box_size, los):
 def kaiser_boost(cosmo, a, mesh_shape, box_size, b1E, fNL_bp=0.0, png_type=None, los=(0.0, 0.0, 0.0), kpow=None):
     """Eulerian Kaiser boost D(a) (b1E + f(a) mu^2) [+ fNL_bp / T_phi->delta] on the half-spectrum mesh, host float64
     (bricks.py:170-184); scalar `a`."""
-    kmesh, mu = _kmu(mesh_shape, box_size, np.asarray(los, dtype=np.float64))
+    _, mu = _kmu(mesh_shape, box_size, np.asarray(los, dtype=np.float64))
     boost = float(_cosmo.a2g(cosmo, a)) * (b1E + float(_cosmo.a2f(cosmo, a)) * mu**2)
     if png_type is not None:
         t = trans_phi2delta_mesh(cosmo, mesh_shape, box_size, kpow)

@@ -157,7 +157,7 @@ class SlabFieldModel:
         FieldModel.value_and_force (model.py:350-363 wrappers)."""
         pm, o, A, st = self.pm, self.o, self.A, self.pm._st()
         c = self.cosmology
-        N, cells, m = pm.N, pm.xl * pm.ny * pm.nz, self.interlace_order
+        N = pm.N
         white, obs = A.prepare(white), A.prepare(obs)
         D = float(_cosmo.a2g(c, self.a_obs))
         # prior: delta_k = rfftn(white) * transfer (bricks.py:303-309, 152-157)
@@ -203,8 +203,8 @@ class SlabFieldModel:
 
     def predict(self, white):
         """My planes of the 1 + delta_obs mesh (FieldModel.evolve)."""
-        pm, o, A, st = self.pm, self.o, self.A, self.pm._st()
-        c, N, m = self.cosmology, self.pm.N, self.interlace_order
+        pm, o, A = self.pm, self.o, self.A
+        c, N = self.cosmology, self.pm.N
         white = A.prepare(white)
         dk = o.scale_spectrum(pm.rfftn(white.unsqueeze(0))[0], self.transfer)
         weights = None

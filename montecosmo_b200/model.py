@@ -248,7 +248,7 @@ class FieldLevelModel(FieldModel):
 
     def evolve(self, white, ap=None):
         from . import bricks as B
-        c, dev = self.cosmology, nb.ops().A.device
+        c = self.cosmology
         geo = (self.box_center, self.box_rot, self.box_size)
         init_mesh = self.linear_field(white)  # white2lin at the initial shape (bricks.py:152-157)
         if self.evol_shape != self.init_shape:

@@ -166,11 +166,21 @@ def _model_worker(rank, world, port, shape, halo, kw, q):
 def test_slab_field_model_world2_gloo(shape, halo, kw):
     """grad(log-density) of the whole model chain on 2 slabs against the single-process FieldModel (same kernels, same
     white noise and observation): log-density 1e-5, force and predicted mesh 5e-4 relative L2."""
+    _run_model_workers(2, shape, halo, kw)
+
+
+def test_slab_field_model_world4_gloo():
+    """The same on 4 ranks, where the left and the right neighbour of a rank differ (on 2 ranks they coincide, which
+    would hide a swapped halo direction or row exchange), with the 2x paint mesh and its distributed Fourier crop."""
+    _run_model_workers(4, (16, 16, 16), 4, dict(n_steps=1, b1=1.0, rsd=True, paint_oversamp=2.0))
+
+
+def _run_model_workers(world, shape, halo, kw):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29641 + shape[0]
-    ps = [ctx.Process(target=_model_worker, args=(r, 2, port, shape, halo, kw, q)) for r in range(2)]
+    port = 29641 + shape[0] + 7 * world
+    ps = [ctx.Process(target=_model_worker, args=(r, world, port, shape, halo, kw, q)) for r in range(world)]
     for p in ps:
         p.start()
     out = [q.get(timeout=600) for _ in ps]

@@ -113,6 +113,26 @@ def main():
         tape = ops.nbody_steps(pos.clone(), vel.clone(), shape, al, be, pre, post, tape=True)
         pb, vb = vel.clone(), pos.clone()
         rec(f"nbody_step bwd {tag}", lambda: ops.nbody_steps_vjp(pb, vb, shape, al, be, pre, post, tape), 136 * N)
+    # kernels added at the end of round 1 (parity-tested, not yet timed)
+    kc = 0.98 * np.pi * (2 - 1 / 1.5)  # optim_kcut(1.5)
+    rec("paint_kb4_lattice", lambda: ops.paint(pos, shape, None, order=4, out=out, kb_kcut=kc), 16 * N)
+    rec("paint_pcs_lattice", lambda: ops.paint(pos, shape, None, order=4, out=out), 16 * N)
+    rec("read_kb4_lattice", lambda: ops.read(pos, mesh, order=4, kb_kcut=kc), 20 * N)
+    rec("deconv_kb", lambda: ops.deconv(mk, 4, kb_kcut=kc), 8 * N)
+    rec("deconv_rect", lambda: ops.deconv(mk, 4), 8 * N)
+    mkp = mk3.clone()
+    rec("hermitian_project_b3", lambda: ops.hermitian_project(mkp), 3 * 2 * 2 * 8 * n * n)
+    ke = torch.linspace(0.01, 3.0, 40, dtype=torch.float64, device=dev)
+    rec("spectrum_bins", lambda: ops.spectrum_bins(mk, None, (float(n),) * 3, ke), 4 * N)
+    rec("spectrum_bins_ell2", lambda: ops.spectrum_bins(mk, None, (float(n),) * 3, ke, ell=2, los=(0.0, 0.0, 1.0)), 4 * N)
+    rec("nufft_paint (2 shifts)", lambda: ops.nufft_paint(pos, shape, w), 2 * 20 * N + 2 * 8 * N + 12 * N)
+    for zm in (0, 1):
+        lib.mcpm_tune(b"brick_zmerge", zm)
+        ops.set_lattice(shape, shape)
+        rec(f"pm_forces zmerge={zm} (124N)", lambda: ops.pm_forces(pos, shape, want_meshes=True), 124 * N)
+        rec(f"pm_forces_vjp zmerge={zm} (136N)", lambda: ops.pm_forces_vjp(pos, vel, fm), 136 * N)
+    lib.mcpm_tune(b"brick_zmerge", 0)
+    ops.set_lattice(shape, None)
     if a.out:
         with open(a.out, "w") as fh:
             json.dump(res, fh, indent=1)

@@ -22,4 +22,6 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > ${o}_ncu.log 2>&1
 # 4. A/B of the kernel variants built blind at the end of round 1 (whole evaluation, same inputs)
 timeout 120 python tools/tune_eval.py 256 base brick_zmerge=1 base brick_zmerge=1 > ${o}_tune_zmerge.log 2>&1
+# 5. per-operator timings, including the kernels that have parity tests but no timing yet
+timeout 200 python tools/microbench.py --n 256 --out ${o}_microbench.json > ${o}_microbench.log 2>&1
 tail -3 ${o}_cross_check.log ${o}_pytest_gpu.log; head -c 600 ${o}_bench.json

@@ -711,3 +711,29 @@ def test_catalogue_registration_golden(nb, golden):
     chunks = [{"pos": g["full_pos"][:100], "vel": g["full_vel"][:100], "WEIGHT": w[:100]},
               {"pos": g["full_pos"][100:], "vel": g["full_vel"][100:], "WEIGHT": w[100:]}]
     assert rel(B.fullsky2count(chunks, c, 0.65, flos, size, center, rotvec, (12, 14, 12), None), g["fullsky2count"]) < 5e-5
+
+
+def test_baseline_config_c1_full_size(nb):
+    """BASELINE.json configs[0] at its full size -- 64^3 mesh / 64^3 particles, 640 Mpc/h box, 2LPT + 5 BullFrog steps
+    to a = 1, linear bias + flat-sky RSD, interlaced deconvolved paint, Gaussian likelihood -- against the float64 oracle:
+    log-density 1e-5, grad(log-density) cosine >= 0.9999 and relative L2 <= 3e-3.  SURVEY 8c proposed 1e-3 for the
+    latter; at this size and depth (a = 1, 10 Mpc/h cells) float32 positions put a few particles on the other side of
+    a cell face, where the CIC derivative jumps, and the measured value scatters with the white-noise seed: 7.0e-4
+    (this seed), 9.1e-4, 1.2e-3, 1.6e-3 on the CPU port; the log-density agrees to 2.8e-7, the cosine to 1 - 2.5e-7."""
+    from montecosmo_b200.model import FieldModel
+    rng = np.random.default_rng(0)
+    shape = (64, 64, 64)
+    m = FieldModel(shape, (640.0,) * 3, evolution="nbody", n_steps=5, a_obs=1.0, b1=1.0, sigma_obs=1.0)
+    kw = dict(evolution="nbody", n_steps=5, a_obs=1.0, b1=1.0)
+    white = rng.normal(size=shape).astype(np.float32)
+    transfer = m.transfer.cpu().numpy().astype(np.float64)
+    with torch.no_grad():
+        truth = MO.evolve(torch.tensor(rng.normal(size=shape)), transfer, O.Cosmology(), shape, **kw)
+    obs = (truth.numpy() + rng.normal(size=shape)).astype(np.float32)
+    lp, g = m.value_and_force(white, obs)
+    lpo, go = MO.value_and_force(white.astype(np.float64), obs.astype(np.float64), transfer, O.Cosmology(), shape,
+                                 sigma_obs=1.0, **kw)
+    assert abs(float(lp) - float(lpo)) < 1e-5 * abs(float(lpo))
+    gn, gon = g.detach().cpu().numpy().ravel().astype(np.float64), go.numpy().ravel()
+    assert np.linalg.norm(gn - gon) <= 3e-3 * np.linalg.norm(gon)
+    assert gn @ gon / np.linalg.norm(gn) / np.linalg.norm(gon) >= 0.9999

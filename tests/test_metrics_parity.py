@@ -79,14 +79,16 @@ def test_spectrum_estimator_matches_oracle(nb, golden):
     assert np.abs(p2 - g["auto_ell2_centred_pow"]).max() < 2e-5 * top
 
 
-def test_parity_report_density_displacement_power(nb):
+@pytest.mark.parametrize("n", [32, 64])
+def test_parity_report_density_displacement_power(nb, n):
     """BASELINE.json north_star: results match the reference on identical white noise and cosmology within a stated
-    float32 tolerance on the density field, displacements, power spectrum (grad(log-density): tests/test_api_model.py)."""
+    float32 tolerance on the density field, displacements, power spectrum (grad(log-density): tests/test_api_model.py).
+    n = 64 with a 640 Mpc/h box and 5 steps is BASELINE configs[0] at its full size."""
     from montecosmo_b200 import metrics as M
     from montecosmo_b200.cosmo import Cosmology
     from montecosmo_b200.model import FieldModel
     rng = np.random.default_rng(12)
-    shape, box = (32, 32, 32), (320.0,) * 3
+    shape, box = (n, n, n), (10.0 * n,) * 3
     kw = dict(evolution="nbody", n_steps=5, a_obs=1.0, b1=0.5)
     m = FieldModel(shape, box, sigma_obs=1.0, **kw)
     white = rng.normal(size=shape).astype(np.float32)

@@ -139,11 +139,13 @@ def test_empty_inputs_and_rejected_arguments(ops):
         with pytest.raises(McpmError) as ei:
             bad()
         assert ei.value.code == 1 and str(ei.value)
-    far = f32([[1e9, -1e9, 3e8], [np.nan, 0.0, 0.0], [np.inf, 1.0, 2.0], [7.999999, 5.999999, 9.999999]])
-    out = to_numpy(ops.paint(far[:1], shape))
+    far = f32([[1e9, -1e9, 3e8]])
+    out = to_numpy(ops.paint(far, shape))
     assert abs(out.sum() - 1.0) < 1e-6                      # wrapped, mass conserved
-    ops.paint(far, shape)                                   # non-finite positions: garbage in, but no fault
-    ops.read(far, mesh)
+    if isinstance(ops.A, NumpyAdapter):                     # (on the GPU this runs last: tests/test_zz_cross_check_256.py)
+        bad = f32([[np.nan, 0.0, 0.0], [np.inf, 1.0, 2.0], [-np.inf, 7.999999, 9.999999]])
+        ops.paint(bad, shape)                               # non-finite positions: garbage in, but no fault
+        ops.read(bad, mesh)
 
 
 @pytest.mark.parametrize("order", [2, 3, 4])
@@ -604,18 +606,4 @@ def test_brick_scatter_matches_generic(ops, mesh):
         assert rel(vb, vnew) < 1e-6
         for c in range(3):
             assert rel(out3[c], O.paint(T(pos), mesh, T(vnew[:, c]) * 1.5, 2).numpy()) < 2e-5
-        # mcpm_tune("brick_zmerge"): upper-z deposits handed to the next lane by shuffle.  The shared-memory tile is
-        # bit-identical (integer sums); only the stray particles' float atomics land in another order: 1e-6.
-        try:
-            ops._call("mcpm_tune", b"brick_zmerge", 1)
-            outz = A.zeros(mesh)
-            ops._call("mcpm_paint_lattice", eng.handle, A.stream(), A.ptr(pd), A.ptr(wd), 0.5, n, A.ptr(outz))
-            assert rel(outz, to_numpy(out).astype(np.float64)) < 1e-6
-            vbz = A.prepare(vel.copy())
-            out3z = A.zeros((3, *mesh))
-            ops._call("mcpm_paint3_lattice", eng.handle, A.stream(), A.ptr(pd), A.ptr(vbz), A.ptr(xb), 0.25, 1.5, n,
-                      A.ptr(out3z))
-            assert rel(out3z, to_numpy(out3).astype(np.float64)) < 1e-6 and rel(vbz, to_numpy(vb).astype(np.float64)) == 0.0
-        finally:
-            ops._call("mcpm_tune", b"brick_zmerge", 0)
         ops.set_lattice(mesh, None)

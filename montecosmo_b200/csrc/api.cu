@@ -837,7 +837,7 @@ int mcpm_nbody_steps_vjp(mcpm_engine* eng, void* stream, float* posbar, float* v
 int mcpm_nufft(mcpm_engine* eng, void* stream, const float* pos, const float* weights, float wscalar, int64_t np,
                const float scale[3], int paint_order, int interlace_order, int paint_deconv, void* out_k) {
   API_BEGIN
-  NEED(eng && pos && out_k, "nufft: null pointer");
+  NEED(eng && out_k && (np == 0 || pos), "nufft: null pointer");  // an empty particle set paints a zero mesh
   BIND(eng);
   return nufft(eng->e, as_stream(stream), pos, weights, wscalar, np, scale, paint_order, interlace_order,
                paint_deconv, C(out_k));
@@ -848,7 +848,7 @@ int mcpm_nufft_vjp(mcpm_engine* eng, void* stream, const float* pos, const float
                    int64_t np, const float scale[3], int paint_order, int interlace_order, int paint_deconv,
                    const void* outbar_k, float* posbar, float* weightsbar) {
   API_BEGIN
-  NEED(eng && pos && outbar_k, "nufft_vjp: null pointer");
+  NEED(eng && outbar_k && (np == 0 || pos), "nufft_vjp: null pointer");
   BIND(eng);
   return nufft_vjp(eng->e, as_stream(stream), pos, weights, wscalar, np, scale, paint_order, interlace_order,
                    paint_deconv, C(outbar_k), posbar, weightsbar);
@@ -859,7 +859,7 @@ int mcpm_nufft_kb(mcpm_engine* eng, void* stream, const float* pos, const float*
                   const float scale[3], int paint_order, float kcut, int interlace_order, int paint_deconv,
                   void* out_k) {
   API_BEGIN
-  NEED(eng && pos && out_k, "nufft_kb: null pointer");
+  NEED(eng && out_k && (np == 0 || pos), "nufft_kb: null pointer");
   NEED(kcut > 0.0f, "nufft_kb: kcut must be positive (optim_kcut(oversamp))");
   BIND(eng);
   return nufft(eng->e, as_stream(stream), pos, weights, wscalar, np, scale, paint_order, interlace_order,
@@ -871,7 +871,7 @@ int mcpm_nufft_vjp_kb(mcpm_engine* eng, void* stream, const float* pos, const fl
                       int64_t np, const float scale[3], int paint_order, float kcut, int interlace_order,
                       int paint_deconv, const void* outbar_k, float* posbar, float* weightsbar) {
   API_BEGIN
-  NEED(eng && pos && outbar_k, "nufft_vjp_kb: null pointer");
+  NEED(eng && outbar_k && (np == 0 || pos), "nufft_vjp_kb: null pointer");
   NEED(kcut > 0.0f, "nufft_vjp_kb: kcut must be positive (optim_kcut(oversamp))");
   BIND(eng);
   return nufft_vjp(eng->e, as_stream(stream), pos, weights, wscalar, np, scale, paint_order, interlace_order,

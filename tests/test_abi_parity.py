@@ -607,3 +607,39 @@ def test_brick_scatter_matches_generic(ops, mesh):
         for c in range(3):
             assert rel(out3[c], O.paint(T(pos), mesh, T(vnew[:, c]) * 1.5, 2).numpy()) < 2e-5
         ops.set_lattice(mesh, None)
+
+
+def test_paint_read_random_configurations(ops):
+    """Seeded sweep over mesh shapes (non-cubic, down to the smallest legal side), orders, both window families, position
+    ranges and in-kernel transforms: paint and read against the oracle on identical float32 inputs (5e-6; 5e-5 where
+    positions reach +-50 box lengths, whose float32 spacing after the in-kernel transform is ~3e-5 cell), and
+    <read(x, m), w> = <m, paint(x, w)> for each."""
+    rng = np.random.default_rng(2024)
+    for case in range(40):
+        order = int(rng.integers(1, 5))
+        shape = tuple(int(s) for s in rng.integers(max(order, 2), 14, 3))
+        n = int(rng.integers(1, 400))
+        span = float(rng.choice([1.0, 3.0, 50.0]))
+        pos = f32(rng.uniform(-span, span, (n, 3)) * np.array(shape))
+        if case % 4 == 0:
+            pos[: n // 2] = np.round(pos[: n // 2] * 2) / 2  # on cell centres / faces
+        w = f32(rng.normal(size=n))
+        mesh = f32(rng.normal(size=shape))
+        kb = bool(rng.integers(0, 2))
+        ov = float(rng.choice([1.0, 1.5, 2.0]))
+        scale, shift = ((1.0, 1.0, 1.0), 0.0) if case % 3 else (tuple(rng.uniform(0.5, 2.0, 3)), float(rng.uniform(0, 1)))
+        if (order == 1 or kb) and span > 3:
+            # windows that jump at the edge of their support (NGP, Kaiser-Bessel): a float32-rounded transform of a far
+            # position may pick the other base cell than the float64 one; without a transform both sides see the same x
+            scale, shift = (1.0, 1.0, 1.0), 0.0
+        kt, kc = ("kaiser_bessel", float(O.optim_kcut(ov))) if kb else ("rectangular", 0.0)
+        xs = T(pos) * T(f32(scale)) + shift
+        p = ops.paint(pos, shape, w, 1.0, order, scale, shift, kb_kcut=kc)
+        r = ops.read(pos, mesh, order, scale, shift, kb_kcut=kc)
+        tag = (case, order, shape, n, kt)
+        tol = 5e-5 if span > 3 else 5e-6
+        assert rel(p, O.paint(xs, shape, T(w), order, kt, ov).numpy()) < tol, tag
+        assert rel(r, O.read(xs, T(mesh), order, kt, ov).numpy()) < tol, tag
+        lhs = float((to_numpy(r).astype(np.float64) * w).sum())
+        rhs = float((mesh.astype(np.float64) * to_numpy(p).astype(np.float64)).sum())
+        assert abs(lhs - rhs) < 1e-4 * max(abs(lhs), abs(rhs), 1.0), tag

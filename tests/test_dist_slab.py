@@ -97,13 +97,14 @@ def _worker(rank, world, port, shape, halo, q):
         q.put((rank, None, traceback.format_exc()))
 
 
-@pytest.mark.parametrize("shape,halo", [((16, 16, 16), 6), ((24, 16, 20), 8)])
-def test_slab_engine_world2_gloo(shape, halo):
+@pytest.mark.parametrize("world,shape,halo", [(2, (16, 16, 16), 6), (2, (24, 16, 20), 8), (4, (16, 16, 16), 4)])
+def test_slab_engine_world2_gloo(world, shape, halo):
+    """2 ranks, and 4 ranks (where a rank's left and right neighbours differ, so a swapped direction cannot hide)."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29541 + shape[0]
-    ps = [ctx.Process(target=_worker, args=(r, 2, port, shape, halo, q)) for r in range(2)]
+    port = 29541 + shape[0] + 11 * world
+    ps = [ctx.Process(target=_worker, args=(r, world, port, shape, halo, q)) for r in range(world)]
     for p in ps:
         p.start()
     out = [q.get(timeout=600) for _ in ps]

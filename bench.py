@@ -370,6 +370,18 @@ def run_engine(args):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    # Run-to-run spread of the result on identical inputs (the order in which float atomics land is not
+    # deterministic): two eager evaluations outside the timed region, relative L2 of the gradient difference.
+    spread = None
+    if rank == 0:
+        try:
+            lp_a, g_a = model.value_and_force(whites[0], obs)
+            g_a, lp_a = g_a.clone(), float(lp_a)
+            lp_b, g_b = model.value_and_force(whites[0], obs)
+            spread = {"rel_l2_grad": float((g_b - g_a).norm() / g_a.norm()),
+                      "rel_logp": abs(float(lp_b) - lp_a) / max(abs(lp_a), 1e-300), "evaluations": 2}
+        except Exception as e:  # never let a diagnostic cost the measurement
+            spread = {"error": f"{type(e).__name__}: {e}"}
     line = None
     if rank == 0:
         rows, dom = kernel_rooflines(model, whites[0], peak)
@@ -396,7 +408,7 @@ def run_engine(args):
                              "share_of_step": dom["ms_per_step_total"] / (ms_dev / K)},
                 "kernels": rows, "cpu_baseline": cb, "logp_last": lp_val, "other_configs": other,
                 "paint_Gparticles_per_s": N / (rows[0]["ms"] * 1e-3) / 1e9,
-                "paint_kernel": rows[0]["kernel"]}
+                "paint_kernel": rows[0]["kernel"], "run_to_run": spread}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -12,6 +12,7 @@ import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_PORTS = iter(range(29700 + os.getpid() % 200, 29999))
 
 
 def _worker(rank, world, port, shape, halo, q):
@@ -180,7 +181,7 @@ def _run_model_workers(world, shape, halo, kw):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29641 + shape[0] + 7 * world
+    port = next(_PORTS)  # a fresh rendezvous port per case: no reliance on a just-closed socket being reusable
     ps = [ctx.Process(target=_model_worker, args=(r, world, port, shape, halo, kw, q)) for r in range(world)]
     for p in ps:
         p.start()

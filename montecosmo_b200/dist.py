@@ -495,7 +495,8 @@ class SlabResize:
         send = xz[:, self.send_rows, :].permute(1, 0, 2).contiguous()
         recv = self._rows_a2a(send, self.send_split, self.recv_split)
         out = torch.zeros((b.nx, b.kyl, b.nzc), dtype=blk.dtype, device=blk.device)
-        out.index_add_(1, self.recv_rows, recv.permute(1, 0, 2))  # the two rows of the new ky Nyquist land on one index
+        # the two rows of the new ky Nyquist land on one index; accumulated on the float pairs (every backend has that)
+        torch.view_as_real(out).index_add_(1, self.recv_rows, torch.view_as_real(recv.permute(1, 0, 2).contiguous()))
         return out
 
     def backward(self, outbar):

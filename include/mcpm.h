@@ -66,6 +66,16 @@ size_t mcpm_engine_scratch_bytes(const mcpm_engine* eng);
  * brick-tiled shared-memory scatter; particles that strayed from their brick's tile take the generic path.
  * px = 0 clears the hint. */
 int mcpm_engine_set_lattice(mcpm_engine* eng, int px, int py, int pz);
+/* Lattice-relative positions (needs mcpm_engine_set_lattice).  With on != 0 every `pos` array this engine's composite
+ * operators take or return (mcpm_pm_forces*, mcpm_lpt*, mcpm_nbody_steps*, mcpm_nufft* and the xk tape) holds the
+ * DISPLACEMENT of particle p from its lattice site  site_a(p) = i_a * n_a / p_a  (regular_pos, bricks.py:593-603;
+ * (i_x, i_y, i_z) = unravel(p, (px, py, pz))) instead of the absolute position: x = site + pos.  The reference adds
+ * lpt's dpos to the sites once (nbody.py:984-985) and carries the float64 sum; in float32 the sum resolves 1.5e-5 cell
+ * at x ~ 256 (6e-5 at 1024), which flips particles across cell faces where the CIC derivative jumps.  The kernels
+ * combine the site (exact integers) with the small displacement instead, so the CIC fraction resolves ~1e-7 cell at
+ * any mesh size.  Cotangents are unchanged (d/dx = d/dpos).  `pos` may be NULL where it is read-only: the particles sit
+ * on their sites (lpt's reads at q).  on = 0 restores absolute positions. */
+int mcpm_engine_set_relative(mcpm_engine* eng, int on);
 /* Fused x-transform path of pm_forces and its VJP (2-D cuFFT per x-plane + one kernel doing the x-FFT, the force
  * kernel of nbody.py:591-603 and the inverse x-FFTs).  On by default where supported (nx in {64, 128, 256, 512, 1024});
  * on = 0 selects the 3-D cuFFT + separate multiply path, on = 1 returns MCPM_EUNSUP where unsupported.
@@ -330,6 +340,47 @@ int mcpm_paint3v4(void* stream, const float* pos, float* vbar, const float* xbar
                   int nx, int ny, int nz, float* mesh4);
 int mcpm_read_grad4v(void* stream, const float* pos, const float* fmesh4, const float* rhobar, float* vbar,
                      float cscale, float alpha, int64_t np, int nx, int ny, int nz, float* xbar);
+
+/* ---- position frames for the stateless particle kernels -------------------------------------------------------
+ * relative = 0: absolute positions (as every entry point above).  relative = 1: pos[p] is the displacement from
+ * lattice site  o_a + i_a * s_a / p_a  (target-mesh cells), (i_x, i_y, i_z) = unravel(p, (px, py, pz)); px*py*pz must
+ * equal np.  (sx, sy, sz) = the mesh cells the lattice spans (regular_pos: the mesh shape; a slab-decomposed rank:
+ * its own xl x ny x nz with ox = halo planes).  scale[] multiplies the displacement only; the site is already in
+ * target-mesh units.  A NULL frame means absolute.  The brick variants need a spacing of exactly one cell. */
+typedef struct mcpm_frame {
+  int relative;
+  int px, py, pz;
+  int ox, oy, oz;
+  int sx, sy, sz;
+} mcpm_frame;
+int mcpm_paint_f(void* stream, const mcpm_frame* frame, const float* pos, const float* weights, float wscalar,
+                 int64_t np, int nx, int ny, int nz, int order, const float scale[3], float shift, float* mesh,
+                 int accumulate);
+int mcpm_read_f(void* stream, const mcpm_frame* frame, const float* pos, const float* mesh, int nmesh, int64_t np,
+                int nx, int ny, int nz, int order, const float scale[3], float shift, float* out);
+int mcpm_read_grad_f(void* stream, const mcpm_frame* frame, const float* pos, const float* mesh, int nmesh,
+                     const float* cot, int64_t np, int nx, int ny, int nz, int order, const float scale[3],
+                     float shift, float* grad, int accumulate);
+int mcpm_paint_vjp_f(void* stream, const mcpm_frame* frame, const float* pos, const float* weights, float wscalar,
+                     const float* mesh_bar, int64_t np, int nx, int ny, int nz, int order, const float scale[3],
+                     float shift, float* posbar, float* weightsbar, int accumulate);
+int mcpm_paint3_f(void* stream, const mcpm_frame* frame, const float* pos, const float* vals3, float vscale, int64_t np,
+                  int nx, int ny, int nz, int order, float* mesh3, int accumulate);
+int mcpm_kick_drift_f(void* stream, const mcpm_frame* frame, float* pos, float* vel, const float* fmesh3, int64_t np,
+                      int nx, int ny, int nz, int order, float alpha, float beta, float drift, float* force_out);
+int mcpm_kick_drift4_f(void* stream, const mcpm_frame* frame, float* pos, float* vel, const float* fmesh4, int64_t np,
+                       int nx, int ny, int nz, float alpha, float beta, float drift);
+int mcpm_paint3v4_f(void* stream, const mcpm_frame* frame, const float* pos, float* vbar, const float* xbar,
+                    float drift, float scale, int64_t np, int nx, int ny, int nz, float* mesh4);
+int mcpm_read_grad4v_f(void* stream, const mcpm_frame* frame, const float* pos, const float* fmesh4,
+                       const float* rhobar, float* vbar, float cscale, float alpha, int64_t np, int nx, int ny, int nz,
+                       float* xbar);
+int mcpm_paint_brick_f(void* stream, const mcpm_frame* frame, int px, int py, int pz, const float* pos,
+                       const float* weights, float wscalar, float shift, int64_t np, int nx, int ny, int nz,
+                       float* mesh);
+int mcpm_paint3_brick_f(void* stream, const mcpm_frame* frame, int px, int py, int pz, const float* pos, float* vbar,
+                        const float* xbar, float drift, float scale, int64_t np, int nx, int ny, int nz,
+                        float* mesh3);
 
 /* pos += vel * drift */
 int mcpm_drift(void* stream, float* pos, const float* vel, float drift, int64_t np);

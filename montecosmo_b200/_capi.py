@@ -20,6 +20,7 @@ SIGNATURES = {
     "mcpm_engine_scratch_bytes": ([vp], sz),
     "mcpm_engine_set_lattice": ([vp, i32, i32, i32], i32),
     "mcpm_engine_set_fused_fft": ([vp, i32], i32),
+    "mcpm_engine_set_relative": ([vp, i32], i32),
     "mcpm_tune": ([C.c_char_p, i32], i32),
     "mcpm_paint_brick": ([vp, i32, i32, i32, vp, vp, f32, f32, i64] + MESH + [vp], i32),
     "mcpm_paint3_brick": ([vp, i32, i32, i32, vp, vp, vp, f32, f32, i64] + MESH + [vp], i32),
@@ -85,6 +86,17 @@ SIGNATURES = {
     "mcpm_kick_drift4": ([vp, vp, vp, vp, i64] + MESH + [f32, f32, f32], i32),
     "mcpm_paint3v4": ([vp, vp, vp, vp, f32, f32, i64] + MESH + [vp], i32),
     "mcpm_read_grad4v": ([vp, vp, vp, vp, vp, f32, f32, i64] + MESH + [vp], i32),
+    "mcpm_paint_f": ([vp, vp, vp, vp, f32, i64] + MESH + [i32] + XF + [vp, i32], i32),
+    "mcpm_read_f": ([vp, vp, vp, vp, i32, i64] + MESH + [i32] + XF + [vp], i32),
+    "mcpm_read_grad_f": ([vp, vp, vp, vp, i32, vp, i64] + MESH + [i32] + XF + [vp, i32], i32),
+    "mcpm_paint_vjp_f": ([vp, vp, vp, vp, f32, vp, i64] + MESH + [i32] + XF + [vp, vp, i32], i32),
+    "mcpm_paint3_f": ([vp, vp, vp, vp, f32, i64] + MESH + [i32, vp, i32], i32),
+    "mcpm_kick_drift_f": ([vp, vp, vp, vp, vp, i64] + MESH + [i32, f32, f32, f32, vp], i32),
+    "mcpm_kick_drift4_f": ([vp, vp, vp, vp, vp, i64] + MESH + [f32, f32, f32], i32),
+    "mcpm_paint3v4_f": ([vp, vp, vp, vp, vp, f32, f32, i64] + MESH + [vp], i32),
+    "mcpm_read_grad4v_f": ([vp, vp, vp, vp, vp, vp, f32, f32, i64] + MESH + [vp], i32),
+    "mcpm_paint_brick_f": ([vp, vp, i32, i32, i32, vp, vp, f32, f32, i64] + MESH + [vp], i32),
+    "mcpm_paint3_brick_f": ([vp, vp, i32, i32, i32, vp, vp, vp, f32, f32, i64] + MESH + [vp], i32),
     "mcpm_drift": ([vp, vp, vp, f32, i64], i32),
     "mcpm_pm_forces": ([vp, vp, vp, i64, i32, i32, i32, i32, f32, vp, vp], i32),
     "mcpm_pm_forces_vjp": ([vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, f32, vp, i32], i32),
@@ -99,6 +111,17 @@ SIGNATURES = {
     "mcpm_nufft_kb": ([vp, vp, vp, vp, f32, i64, hp, i32, f32, i32, i32, vp], i32),
     "mcpm_nufft_vjp_kb": ([vp, vp, vp, vp, f32, i64, hp, i32, f32, i32, i32, vp, vp, vp], i32),
 }
+
+class Frame(C.Structure):
+    """mcpm_frame (include/mcpm.h): absolute or lattice-relative positions for the stateless particle kernels."""
+    _fields_ = [(n, C.c_int) for n in ("relative", "px", "py", "pz", "ox", "oy", "oz", "sx", "sy", "sz")]
+
+
+def frame(ptcl_shape, span=None, origin=(0, 0, 0)):
+    """Relative frame of a lattice `ptcl_shape` spanning `span` mesh cells (default: one cell per site) from `origin`."""
+    span = tuple(ptcl_shape) if span is None else tuple(span)
+    return Frame(1, *[int(v) for v in ptcl_shape], *[int(v) for v in origin], *[int(v) for v in span])
+
 
 ERROR_NAMES = {1: "MCPM_EINVAL", 2: "MCPM_ECUDA", 3: "MCPM_ECUFFT", 4: "MCPM_ENOMEM", 5: "MCPM_EUNSUP"}
 

@@ -52,6 +52,24 @@ struct mcpm_slabfft {
 static inline const cfloat* C(const void* p) { return reinterpret_cast<const cfloat*>(p); }
 static inline cfloat* C(void* p) { return reinterpret_cast<cfloat*>(p); }
 
+// public mcpm_frame -> internal Frame; returns false on an inconsistent descriptor
+static bool to_frame(const mcpm_frame* in, int64_t np, Frame& f, const Frame*& out) {
+  out = nullptr;
+  if (!in || !in->relative) return true;
+  if (in->px <= 0 || in->py <= 0 || in->pz <= 0 || in->sx <= 0 || in->sy <= 0 || in->sz <= 0 ||
+      (int64_t)in->px * in->py * in->pz != np) {
+    set_error("frame: lattice px*py*pz must equal np and the spans must be positive");
+    return false;
+  }
+  f = make_rel_frame(in->px, in->py, in->pz, in->sx, in->sy, in->sz, in->ox, in->oy, in->oz);
+  out = &f;
+  return true;
+}
+#define FRAME(np)                                  \
+  Frame _f;                                        \
+  const Frame* fr;                                 \
+  if (!to_frame(frame, (np), _f, fr)) return MCPM_EINVAL
+
 extern "C" {
 #pragma GCC visibility push(default)
 
@@ -92,6 +110,15 @@ int mcpm_engine_set_lattice(mcpm_engine* eng, int px, int py, int pz) {
     L.pz = pz;
   }
   eng->e->lat = L;
+  return MCPM_OK;
+  API_END
+}
+
+int mcpm_engine_set_relative(mcpm_engine* eng, int on) {
+  API_BEGIN
+  NEED(eng, "null engine");
+  if (on) NEED(eng->e->lat.px > 0, "set_relative: set the particle lattice first (mcpm_engine_set_lattice)");
+  eng->e->rel = on ? 1 : 0;
   return MCPM_OK;
   API_END
 }
@@ -742,6 +769,134 @@ int mcpm_read_grad4v(void* stream, const float* pos, const float* fmesh4, const 
   API_BEGIN
   NEED(pos && fmesh4 && rhobar && vbar && xbar, "read_grad4v: null pointer");
   return read_grad4v(as_stream(stream), pos, fmesh4, rhobar, vbar, cscale, 1, alpha, np, nx, ny, nz, xbar, 1);
+  API_END
+}
+
+// ---- the same particle kernels with a position frame (mcpm_frame: absolute or lattice-relative positions) -----------
+int mcpm_paint_f(void* stream, const mcpm_frame* frame, const float* pos, const float* weights, float wscalar,
+                 int64_t np, int nx, int ny, int nz, int order, const float scale[3], float shift, float* mesh,
+                 int accumulate) {
+  API_BEGIN
+  FRAME(np);
+  return paint(as_stream(stream), pos, weights, wscalar, np, nx, ny, nz, order, scale, shift, mesh, accumulate, 0.0f,
+               fr);
+  API_END
+}
+
+int mcpm_read_f(void* stream, const mcpm_frame* frame, const float* pos, const float* mesh, int nmesh, int64_t np,
+                int nx, int ny, int nz, int order, const float scale[3], float shift, float* out) {
+  API_BEGIN
+  FRAME(np);
+  return read(as_stream(stream), pos, mesh, nmesh, np, nx, ny, nz, order, scale, shift, out, 0.0f, fr);
+  API_END
+}
+
+int mcpm_read_grad_f(void* stream, const mcpm_frame* frame, const float* pos, const float* mesh, int nmesh,
+                     const float* cot, int64_t np, int nx, int ny, int nz, int order, const float scale[3],
+                     float shift, float* grad, int accumulate) {
+  API_BEGIN
+  NEED(nmesh >= 1 && nmesh <= 4, "read_grad: nmesh must be 1..4");
+  FRAME(np);
+  const int64_t plane = (int64_t)nx * ny * nz;
+  const float* ms[4] = {mesh, mesh + plane, mesh + 2 * plane, mesh + 3 * plane};
+  return read_grad(as_stream(stream), pos, ms, nmesh, cot, cot ? nmesh : 0, 1.0f, nullptr, np, nx, ny, nz, order,
+                   scale, shift, grad, accumulate, 0.0f, fr);
+  API_END
+}
+
+int mcpm_paint_vjp_f(void* stream, const mcpm_frame* frame, const float* pos, const float* weights, float wscalar,
+                     const float* mesh_bar, int64_t np, int nx, int ny, int nz, int order, const float scale[3],
+                     float shift, float* posbar, float* weightsbar, int accumulate) {
+  API_BEGIN
+  FRAME(np);
+  return paint_vjp(as_stream(stream), pos, weights, wscalar, mesh_bar, np, nx, ny, nz, order, scale, shift, posbar,
+                   weightsbar, accumulate, 0.0f, fr);
+  API_END
+}
+
+int mcpm_paint3_f(void* stream, const mcpm_frame* frame, const float* pos, const float* vals3, float vscale, int64_t np,
+                  int nx, int ny, int nz, int order, float* mesh3, int accumulate) {
+  API_BEGIN
+  FRAME(np);
+  return paint3(as_stream(stream), pos, vals3, vscale, nullptr, 0.0f, np, nx, ny, nz, order, mesh3, accumulate, fr);
+  API_END
+}
+
+int mcpm_kick_drift_f(void* stream, const mcpm_frame* frame, float* pos, float* vel, const float* fmesh3, int64_t np,
+                      int nx, int ny, int nz, int order, float alpha, float beta, float drift, float* force_out) {
+  API_BEGIN
+  FRAME(np);
+  return kick_drift(as_stream(stream), pos, vel, fmesh3, np, nx, ny, nz, order, alpha, beta, drift, pos, vel,
+                    force_out, fr);
+  API_END
+}
+
+int mcpm_kick_drift4_f(void* stream, const mcpm_frame* frame, float* pos, float* vel, const float* fmesh4, int64_t np,
+                       int nx, int ny, int nz, float alpha, float beta, float drift) {
+  API_BEGIN
+  NEED(pos && vel && fmesh4, "kick_drift4: null pointer");
+  FRAME(np);
+  return kick_drift4(as_stream(stream), pos, vel, fmesh4, np, nx, ny, nz, alpha, beta, drift, pos, vel, nullptr, 0, fr);
+  API_END
+}
+
+int mcpm_paint3v4_f(void* stream, const mcpm_frame* frame, const float* pos, float* vbar, const float* xbar,
+                    float drift, float scale, int64_t np, int nx, int ny, int nz, float* mesh4) {
+  API_BEGIN
+  NEED(pos && vbar && mesh4, "paint3v4: null pointer");
+  FRAME(np);
+  return paint3v4(as_stream(stream), pos, vbar, xbar, drift, xbar != nullptr, scale, np, nx, ny, nz, mesh4, fr);
+  API_END
+}
+
+int mcpm_read_grad4v_f(void* stream, const mcpm_frame* frame, const float* pos, const float* fmesh4,
+                       const float* rhobar, float* vbar, float cscale, float alpha, int64_t np, int nx, int ny, int nz,
+                       float* xbar) {
+  API_BEGIN
+  NEED(pos && fmesh4 && rhobar && vbar && xbar, "read_grad4v: null pointer");
+  FRAME(np);
+  return read_grad4v(as_stream(stream), pos, fmesh4, rhobar, vbar, cscale, 1, alpha, np, nx, ny, nz, xbar, 1, nullptr,
+                     0, fr);
+  API_END
+}
+
+int mcpm_paint_brick_f(void* stream, const mcpm_frame* frame, int px, int py, int pz, const float* pos,
+                       const float* weights, float wscalar, float shift, int64_t np, int nx, int ny, int nz,
+                       float* mesh) {
+  API_BEGIN
+  NEED(pos && mesh, "paint_brick: null pointer");
+#ifndef MCPM_HOSTEMU
+  FRAME(np);
+  Lattice L;
+  L.px = px;
+  L.py = py;
+  L.pz = pz;
+  int r = brick_paint_cic(as_stream(stream), L, pos, weights, wscalar, shift, np, nx, ny, nz, mesh, fr);
+  if (r < 0) return MCPM_ECUDA;
+  if (r == 1) return MCPM_OK;
+#endif
+  set_error("paint_brick: unsupported lattice / mesh / frame geometry, or CPU build");
+  return MCPM_EUNSUP;
+  API_END
+}
+
+int mcpm_paint3_brick_f(void* stream, const mcpm_frame* frame, int px, int py, int pz, const float* pos, float* vbar,
+                        const float* xbar, float drift, float scale, int64_t np, int nx, int ny, int nz,
+                        float* mesh3) {
+  API_BEGIN
+  NEED(pos && vbar && mesh3, "paint3_brick: null pointer");
+#ifndef MCPM_HOSTEMU
+  FRAME(np);
+  Lattice L;
+  L.px = px;
+  L.py = py;
+  L.pz = pz;
+  int r = brick_paint3_cic(as_stream(stream), L, pos, vbar, xbar, drift, scale, np, nx, ny, nz, mesh3, fr);
+  if (r < 0) return MCPM_ECUDA;
+  if (r == 1) return MCPM_OK;
+#endif
+  set_error("paint3_brick: unsupported lattice / mesh / frame geometry, or CPU build");
+  return MCPM_EUNSUP;
   API_END
 }
 

@@ -45,6 +45,8 @@ struct BrickArgs {
   int nx, ny, nz;
   float inx, iny, inz;  // 1 / n
   float shift;          // pos + shift is painted (interlacing); 0 otherwise
+  int rel;              // 1: pos holds displacements from the lattice sites (frame.h), 0: absolute positions
+  int ox, oy, oz;       // mesh cell of lattice site (0, 0, 0): the halo offset of a slab-decomposed rank
   const float* pos;
   // NCH = 1: value = (w ? w[p] : 1) * ws.        NCH = 3: value = s * (A[p] + cb * B[p]), A updated in place if store.
   const float* w;
@@ -88,18 +90,21 @@ __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickA
   const int64_t pbase = 3 * (((int64_t)q0i * a.py + qj) * a.pz + qk);
   const float* xp = a.pos + pbase;
 
-  // ---- pass 1: positions of the thread's 8 z-rows; for the reverse step also A += cb * B and sum |value|
+  // ---- pass 1: displacement u = x - site of the thread's 8 z-rows (exact when formed from an absolute position: the
+  // site is a whole number below 2^24); for the reverse step also A += cb * B and sum |value|
   float x[PPT][3];
   unsigned valid = 0;
+  const float sy = a.rel ? 0.f : (float)(qj + a.oy), sz = a.rel ? 0.f : (float)(qk + a.oz);
 #pragma unroll
   for (int r = 0; r < PPT; ++r) {
     const int di = brick_qi(warp, r);
     if (FULL || (colok && q0i + di < a.px)) {
       valid |= 1u << r;
       const float* xr = xp + di * plane3;
-      x[r][0] = xr[0] + a.shift;
-      x[r][1] = xr[1] + a.shift;
-      x[r][2] = xr[2] + a.shift;
+      const float sx = a.rel ? 0.f : (float)(q0i + di + a.ox);
+      x[r][0] = (xr[0] + a.shift) - sx;
+      x[r][1] = (xr[1] + a.shift) - sy;
+      x[r][2] = (xr[2] + a.shift) - sz;
     } else {
       x[r][0] = x[r][1] = x[r][2] = 0.f;
     }
@@ -141,8 +146,8 @@ __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickA
   // tile origin from slot 0: displacement off the lattice site, reduced to the nearest periodic image
   float d0 = 0.f, d1 = 0.f, d2 = 0.f, cnt = 0.f;
   if (FULL || (valid & 1u)) {
-    float e0 = x[0][0] - (float)(q0i + brick_qi(warp, 0)), e1 = x[0][1] - (float)qj, e2 = x[0][2] - (float)qk;
-    d0 = e0 - a.nx * rintf(e0 * a.inx);  // positions may have been wrapped by the caller
+    const float e0 = x[0][0], e1 = x[0][1], e2 = x[0][2];
+    d0 = e0 - a.nx * rintf(e0 * a.inx);  // absolute positions may have been wrapped by the caller
     d1 = e1 - a.ny * rintf(e1 * a.iny);
     d2 = e2 - a.nz * rintf(e2 * a.inz);
     cnt = 1.f;
@@ -175,9 +180,9 @@ __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickA
   const float ninv = 1.0f / fmaxf(bc[3], 1.f);
   // origin (unwrapped cell coordinates, as floats: exact below 2^24) and its wrapped integer twin
   // (base cells of the brick span [q0 + mean, q0 + B - 1 + mean]; the tile admits base cells [o, o + T - 2])
-  const float oxf = rintf((float)q0i + bc[0] * ninv - 0.5f * (TX - BX));
-  const float oyf = rintf((float)q0j + bc[1] * ninv - 0.5f * (TY - BY));
-  const float ozf = 4.0f * rintf(0.25f * ((float)q0k + bc[2] * ninv - 0.5f * (TZ - 1 - BZ)));  // 16-byte groups along z
+  const float oxf = rintf((float)(q0i + a.ox) + bc[0] * ninv - 0.5f * (TX - BX));
+  const float oyf = rintf((float)(q0j + a.oy) + bc[1] * ninv - 0.5f * (TY - BY));
+  const float ozf = 4.0f * rintf(0.25f * ((float)(q0k + a.oz) + bc[2] * ninv - 0.5f * (TZ - 1 - BZ)));  // 16-byte groups along z
   const int oz = wrap_index((int)ozf, a.nz);
   if (tid < TROWS) {
     const int ix = tid / TY, jy = tid - ix * TY;
@@ -198,9 +203,10 @@ __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickA
     x[r][0] -= bx;
     x[r][1] -= by;
     x[r][2] -= bz;
-    // base cell relative to the tile origin, modulo the mesh.  An inexact quotient can only misplace a value onto
-    // +-n, i.e. out of the tile: the particle then strays, which is always correct.
-    float tx = bx - oxf, ty = by - oyf, tz = bz - ozf;
+    // base cell (site + floor(u)) relative to the tile origin, modulo the mesh.  An inexact quotient can only misplace a
+    // value onto +-n, i.e. out of the tile: the particle then strays, which is always correct.
+    float tx = ((float)(q0i + brick_qi(warp, r) + a.ox) - oxf) + bx, ty = ((float)(qj + a.oy) - oyf) + by,
+          tz = ((float)(qk + a.oz) - ozf) + bz;
     tx -= fnx * floorf(tx * a.inx);
     ty -= fny * floorf(ty * a.iny);
     tz -= fnz * floorf(tz * a.inz);
@@ -313,8 +319,12 @@ __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickA
   for (int si = tid; si < ns; si += THREADS) {
     const int code = stray[si], r = code / THREADS, t2 = code - r * THREADS;
     const int w2 = t2 >> 5;
-    const int64_t p3 = 3 * (((int64_t)(q0i + brick_qi(w2, r)) * a.py + (q0j + (w2 & 7))) * a.pz + q0k + (t2 & 31));
-    const float px = a.pos[p3] + a.shift, py = a.pos[p3 + 1] + a.shift, pz = a.pos[p3 + 2] + a.shift;
+    const int si0 = q0i + brick_qi(w2, r), sj0 = q0j + (w2 & 7), sk0 = q0k + (t2 & 31);
+    const int64_t p3 = 3 * (((int64_t)si0 * a.py + sj0) * a.pz + sk0);
+    // the same u = x - site as pass 1, so that the fractions are bit-identical to the in-tile path
+    const float px = (a.pos[p3] + a.shift) - (a.rel ? 0.f : (float)(si0 + a.ox)),
+                py = (a.pos[p3 + 1] + a.shift) - (a.rel ? 0.f : (float)(sj0 + a.oy)),
+                pz = (a.pos[p3 + 2] + a.shift) - (a.rel ? 0.f : (float)(sk0 + a.oz));
     float vv[NCH];
     if (NCH == 1) {
       vv[0] = (a.w ? a.w[p3 / 3] : 1.0f) * a.ws;
@@ -326,7 +336,8 @@ __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickA
     const float fx = px - bx, fy = py - by, fz = pz - bz;
     const float gx = 1.f - fx, gy = 1.f - fy, gz = 1.f - fz;
     const float wxy[4] = {gx * gy, gx * fy, fx * gy, fx * fy};
-    const int i0 = wrap_fast((int)bx, a.nx), j0 = wrap_fast((int)by, a.ny), k0 = wrap_fast((int)bz, a.nz);
+    const int i0 = wrap_fast(si0 + a.ox + (int)bx, a.nx), j0 = wrap_fast(sj0 + a.oy + (int)by, a.ny),
+              k0 = wrap_fast(sk0 + a.oz + (int)bz, a.nz);
     const int i1 = i0 + 1 == a.nx ? 0 : i0 + 1, j1 = j0 + 1 == a.ny ? 0 : j0 + 1, k1 = k0 + 1 == a.nz ? 0 : k0 + 1;
 #pragma unroll
     for (int ab = 0; ab < 4; ++ab) {
@@ -380,10 +391,26 @@ static int launch_brick(stream_t st, const BrickArgs& a) {
 
 // CIC density paint of pos + shift into a zeroed-or-accumulated planar mesh.  Returns 1 if handled, 0 -> generic path,
 // < 0 error.
+// `fr` (optional): relative frame of spacing one cell on lattice L -- pos holds displacements, fr->o the halo offset.
+static bool frame_fits(const Lattice& L, const Frame* fr) {
+  if (!fr || !fr->rel) return true;
+  return fr->px == L.px && fr->py == L.py && fr->pz == L.pz && fr->nux == 1 && fr->nuy == 1 && fr->nuz == 1 &&
+         fr->dex == 1 && fr->dey == 1 && fr->dez == 1;
+}
+static void set_frame(BrickArgs& a, const Frame* fr) {
+  if (fr && fr->rel) {
+    a.rel = 1;
+    a.ox = fr->ox;
+    a.oy = fr->oy;
+    a.oz = fr->oz;
+  }
+}
+
 int brick_paint_cic(stream_t st, const Lattice& L, const float* pos, const float* weights, float wscalar, float shift,
-                    int64_t np, int nx, int ny, int nz, float* mesh) {
-  if (!brick_ok(L, np, nx, ny, nz)) return 0;
+                    int64_t np, int nx, int ny, int nz, float* mesh, const Frame* fr) {
+  if (!brick_ok(L, np, nx, ny, nz) || !frame_fits(L, fr)) return 0;
   BrickArgs a = {};
+  set_frame(a, fr);
   a.px = L.px; a.py = L.py; a.pz = L.pz; a.nx = nx; a.ny = ny; a.nz = nz;
   a.inx = 1.0f / nx; a.iny = 1.0f / ny; a.inz = 1.0f / nz;
   a.shift = shift;
@@ -393,9 +420,10 @@ int brick_paint_cic(stream_t st, const Lattice& L, const float* pos, const float
 
 // Reverse-step scatter: A += cb * B (stored when B != NULL), mesh3[c] += s * A[., c] * W, three planar meshes.
 int brick_paint3_cic(stream_t st, const Lattice& L, const float* pos, float* A, const float* B, float cb, float s,
-                     int64_t np, int nx, int ny, int nz, float* mesh3) {
-  if (!brick_ok(L, np, nx, ny, nz)) return 0;
+                     int64_t np, int nx, int ny, int nz, float* mesh3, const Frame* fr) {
+  if (!brick_ok(L, np, nx, ny, nz) || !frame_fits(L, fr)) return 0;
   BrickArgs a = {};
+  set_frame(a, fr);
   a.px = L.px; a.py = L.py; a.pz = L.pz; a.nx = nx; a.ny = ny; a.nz = nz;
   a.inx = 1.0f / nx; a.iny = 1.0f / ny; a.inz = 1.0f / nz;
   a.pos = pos; a.A = A; a.B = B; a.cb = cb; a.s = s; a.store = B != nullptr; a.mesh = mesh3;

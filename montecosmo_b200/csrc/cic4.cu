@@ -63,15 +63,21 @@ struct Cic {
   float fx, fy, fz;
 };
 
-MCPM_HD Cic cic_setup(const float* x, int nx, int ny, int nz) {
+// `x` is the absolute position, or (relative frame, frame.h) the displacement from the particle's lattice site: the site
+// enters as exact integers, the fraction comes from the small displacement alone.
+MCPM_HD Cic cic_setup(const float* x, int64_t p, const Frame& fr, int nx, int ny, int nz) {
   Cic c;
-  float bx = floorf(x[0]), by = floorf(x[1]), bz = floorf(x[2]);
-  c.fx = x[0] - bx;
-  c.fy = x[1] - by;
-  c.fz = x[2] - bz;
-  c.i0 = wrap_fast((int)bx, nx);
-  c.j0 = wrap_fast((int)by, ny);
-  c.k0 = wrap_fast((int)bz, nz);
+  int sx, sy, sz;
+  float rx, ry, rz;
+  frame_site(fr, p, sx, sy, sz, rx, ry, rz);
+  const float u0 = rx + x[0], u1 = ry + x[1], u2 = rz + x[2];
+  float bx = floorf(u0), by = floorf(u1), bz = floorf(u2);
+  c.fx = u0 - bx;
+  c.fy = u1 - by;
+  c.fz = u2 - bz;
+  c.i0 = wrap_fast(sx + (int)bx, nx);
+  c.j0 = wrap_fast(sy + (int)by, ny);
+  c.k0 = wrap_fast(sz + (int)bz, nz);
   c.i1 = c.i0 + 1 == nx ? 0 : c.i0 + 1;
   c.j1 = c.j0 + 1 == ny ? 0 : c.j0 + 1;
   c.k1 = c.k0 + 1 == nz ? 0 : c.k0 + 1;
@@ -100,11 +106,12 @@ int deinterleave3(stream_t st, const float* mesh4, float* planar3, int64_t n) {
 // step's scatter accumulates into; a few bytes per thread in a latency-bound kernel instead of a separate memset pass.
 int kick_drift4(stream_t st, const float* pos, const float* vel, const float* fmesh4, int64_t np, int nx, int ny,
                 int nz, float alpha, float beta, float drift, float* pos_out, float* vel_out, float* zero,
-                int64_t nzero) {
+                int64_t nzero, const Frame* frp) {
   const f4* fm = reinterpret_cast<const f4*>(fmesh4);
+  const Frame fr = frp ? *frp : Frame();
   launch_gather(st, np, [=] MCPM_LAMBDA(int64_t p) {
     float x[3] = {pos[3 * p], pos[3 * p + 1], pos[3 * p + 2]};
-    Cic c = cic_setup(x, nx, ny, nz);
+    Cic c = cic_setup(x, p, fr, nx, ny, nz);
     const int64_t r00 = ((int64_t)c.i0 * ny + c.j0) * nz, r01 = ((int64_t)c.i0 * ny + c.j1) * nz;
     const int64_t r10 = ((int64_t)c.i1 * ny + c.j0) * nz, r11 = ((int64_t)c.i1 * ny + c.j1) * nz;
     const float gx = 1.0f - c.fx, gy = 1.0f - c.fy, gz = 1.0f - c.fz;
@@ -138,11 +145,12 @@ int kick_drift4(stream_t st, const float* pos, const float* vel, const float* fm
 // val = A + cb * B  (stored back into A when store != 0);  mesh4[cell] += scale * val * W  over the 8 CIC corners.
 // Backward step: A = vbar, B = xbar, cb = drift, scale = beta   ->  vbar += xbar * drift ; phibar = paint(beta * vbar).
 int paint3v4(stream_t st, const float* pos, float* A, const float* B, float cb, int store, float scale, int64_t np,
-             int nx, int ny, int nz, float* mesh4) {
+             int nx, int ny, int nz, float* mesh4, const Frame* frp) {
   f4* m = reinterpret_cast<f4*>(mesh4);
+  const Frame fr = frp ? *frp : Frame();
   launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
     float x[3] = {pos[3 * p], pos[3 * p + 1], pos[3 * p + 2]};
-    Cic c = cic_setup(x, nx, ny, nz);
+    Cic c = cic_setup(x, p, fr, nx, ny, nz);
     float v0 = A[3 * p], v1 = A[3 * p + 1], v2 = A[3 * p + 2];
     if (B) {
       v0 += cb * B[3 * p];
@@ -179,11 +187,12 @@ int paint3v4(stream_t st, const float* pos, float* A, const float* B, float cb, 
 //   xbar += g ;  then (tail of the reverse step) cot *= alpha_tail  when alpha_tail >= 0 is requested via `scale_cot`.
 int read_grad4v(stream_t st, const float* pos, const float* fmesh4, const float* rhobar, float* cot, float cscale,
                 int scale_cot, float alpha_tail, int64_t np, int nx, int ny, int nz, float* grad, int accumulate,
-                float* zero, int64_t nzero) {
+                float* zero, int64_t nzero, const Frame* frp) {
   const f4* fm = reinterpret_cast<const f4*>(fmesh4);
+  const Frame fr = frp ? *frp : Frame();
   launch_gather(st, np, [=] MCPM_LAMBDA(int64_t p) {
     float x[3] = {pos[3 * p], pos[3 * p + 1], pos[3 * p + 2]};
-    Cic c = cic_setup(x, nx, ny, nz);
+    Cic c = cic_setup(x, p, fr, nx, ny, nz);
     const float q0 = cot[3 * p], q1 = cot[3 * p + 1], q2 = cot[3 * p + 2];
     const float c0 = cscale * q0, c1 = cscale * q1, c2 = cscale * q2;
     const int64_t r00 = ((int64_t)c.i0 * ny + c.j0) * nz, r01 = ((int64_t)c.i0 * ny + c.j1) * nz;

@@ -75,15 +75,17 @@ static bool brick_path(const Engine* E, int order, const float* scale) {
 // `prezeroed`: the caller guarantees the mesh is already zero (cleared on the side by the previous step's kernel)
 static int paint_fresh(Engine* E, stream_t st, const float* pos, const float* weights, float wscalar, int64_t np,
                        int order, const float* scale, float shift, float* mesh, bool prezeroed = false) {
+  Frame f;
+  const Frame* fr = E->frame(f);
 #ifndef MCPM_HOSTEMU
-  if (brick_path(E, order, scale)) {
+  if (brick_path(E, order, scale) && pos) {
     if (!prezeroed && rt_memset(mesh, 0, sizeof(float) * (size_t)E->N, st)) return MCPM_ECUDA;
-    int r = brick_paint_cic(st, E->lat, pos, weights, wscalar, shift, np, E->nx, E->ny, E->nz, mesh);
+    int r = brick_paint_cic(st, E->lat, pos, weights, wscalar, shift, np, E->nx, E->ny, E->nz, mesh, fr);
     if (r < 0) return MCPM_ECUDA;
     if (r == 1) return 0;
   }
 #endif
-  return paint(st, pos, weights, wscalar, np, E->nx, E->ny, E->nz, order, scale, shift, mesh, 0);
+  return paint(st, pos, weights, wscalar, np, E->nx, E->ny, E->nz, order, scale, shift, mesh, 0, 0.0f, fr);
 }
 static int paint_density(Engine* E, stream_t st, const float* pos, int64_t np, int order, float* mesh,
                          bool prezeroed = false) {
@@ -123,7 +125,8 @@ int pm_forces(Engine* E, stream_t st, const float* pos, int64_t np, int order, i
     TRY(fft_r2c(E->fft, st, rho, E->c(6), 1));
     TRY(force_meshes_from_spectrum(E, st, E->c(6), lap_fd, grad_fd, kcut, paint_deconv ? order : 0, fm));
   }
-  if (forces) TRY(read(st, pos, fm, 3, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, forces));
+  Frame f;
+  if (forces) TRY(read(st, pos, fm, 3, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, forces, 0.0f, E->frame(f)));
   return 0;
 }
 
@@ -151,18 +154,21 @@ static int density_cotangent(Engine* E, stream_t st, const float* mesh3, int lap
 int pm_forces_vjp(Engine* E, stream_t st, const float* pos, const float* fbar, float cscale, const float* fmesh3,
                   int64_t np, int order, int paint_deconv, int lap_fd, int grad_fd, float kcut, float* posbar,
                   int accumulate) {
-  TRY(paint3(st, pos, fbar, cscale, nullptr, 0.0f, np, E->nx, E->ny, E->nz, order, E->r(0), 0));
+  Frame f;
+  const Frame* fr = E->frame(f);
+  TRY(paint3(st, pos, fbar, cscale, nullptr, 0.0f, np, E->nx, E->ny, E->nz, order, E->r(0), 0, fr));
   TRY(density_cotangent(E, st, E->r(0), lap_fd, grad_fd, kcut, paint_deconv ? order : 0, E->r(3)));
   const float* ms[4] = {fmesh3, fmesh3 + E->N, fmesh3 + 2 * E->N, E->r(3)};
   TRY(read_grad(st, pos, ms, 4, fbar, 3, cscale, nullptr, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, posbar,
-                accumulate));
+                accumulate, 0.0f, fr));
   return 0;
 }
 
 int pm_forces_mesh(Engine* E, stream_t st, const float* pos, const cfloat* dk, int64_t np, int order, int lap_fd,
                    int grad_fd, float kcut, float* forces) {
   TRY(force_meshes_from_spectrum(E, st, dk, lap_fd, grad_fd, kcut, 0, E->r(0)));
-  TRY(read(st, pos, E->r(0), 3, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, forces));
+  Frame f;
+  TRY(read(st, pos, E->r(0), 3, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, forces, 0.0f, E->frame(f)));
   return 0;
 }
 
@@ -187,7 +193,8 @@ int pm_forces2(Engine* E, stream_t st, const float* pos, const cfloat* dk, int64
     TRY(fft_r2c(E->fft, st, E->r(6), E->c(6), 1));
     TRY(force_meshes_from_spectrum(E, st, E->c(6), lap_fd, grad_fd, 0.0f, 0, E->r(0)));
   }
-  TRY(read(st, pos, E->r(0), 3, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, forces));
+  Frame f;
+  TRY(read(st, pos, E->r(0), 3, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, forces, 0.0f, E->frame(f)));
   return 0;
 }
 
@@ -215,12 +222,14 @@ int lpt(Engine* E, stream_t st, const cfloat* dk, const float* pos, int64_t np, 
 int lpt_vjp(Engine* E, stream_t st, const float* pos, int64_t np, int lpt_order, int read_order, int lap_fd,
             int grad_fd, float d1, float d2, float dv2, const float* dposbar, const float* velbar, const float* f1,
             const float* f2, const float* h6, cfloat* dkbar, double* coefbar, int accumulate) {
+  Frame f;
+  const Frame* fr = E->frame(f);
   if (lpt_order == 2) {
     if (!h6) {
       set_error("lpt_vjp: the Hessian tape h6 is required for lpt_order 2");
       return MCPM_EINVAL;
     }
-    TRY(paint3(st, pos, dposbar, -d2, velbar, -dv2, np, E->nx, E->ny, E->nz, read_order, E->r(0), 0));
+    TRY(paint3(st, pos, dposbar, -d2, velbar, -dv2, np, E->nx, E->ny, E->nz, read_order, E->r(0), 0, fr));
     TRY(density_cotangent(E, st, E->r(0), lap_fd, grad_fd, 0.0f, 0, E->r(6)));  // d2bar (real)
     TRY(lpt2_source_vjp(st, h6, E->r(6), E->r(0), E->N));
 #ifndef MCPM_HOSTEMU
@@ -235,7 +244,7 @@ int lpt_vjp(Engine* E, stream_t st, const float* pos, int64_t np, int lpt_order,
     }
     accumulate = 1;
   }
-  TRY(paint3(st, pos, dposbar, d1, velbar, 1.0f, np, E->nx, E->ny, E->nz, read_order, E->r(0), 0));
+  TRY(paint3(st, pos, dposbar, d1, velbar, 1.0f, np, E->nx, E->ny, E->nz, read_order, E->r(0), 0, fr));
 #ifndef MCPM_HOSTEMU
   if (E->fused_fft) {
     TRY(slabfft_r2c_yz(E->fft2d, st, E->r(0), E->c(0), 3));
@@ -277,6 +286,8 @@ int nbody_steps(Engine* E, stream_t st, float* pos, float* vel, int64_t np, int 
   // Tape slot per step: 4N floats.  CIC (order 2): the force mesh as float4 {Fx, Fy, Fz, 0} per cell (cic4.cu);
   // other orders: three planar meshes in the first 3N floats.
   const bool cic = (order == 2);
+  Frame f;
+  const Frame* fr = E->frame(f);
   for (int s = 0; s < n_steps; ++s) {
     float* slot = fm ? fm + (int64_t)s * 4 * E->N : E->r(3);
     float* planar = cic ? E->r(0) : slot;
@@ -290,10 +301,10 @@ int nbody_steps(Engine* E, stream_t st, float* pos, float* vel, int64_t np, int 
     if (cic) {
       TRY(interleave3(st, planar, slot, E->N));
       TRY(kick_drift4(st, cur, vin, slot, np, E->nx, E->ny, E->nz, alpha[s], beta[s], dcomb, xout, vout,
-                      side_zero && !last ? E->r(6) : nullptr, E->N));
+                      side_zero && !last ? E->r(6) : nullptr, E->N, fr));
     } else {
       TRY(kick_drift(st, cur, vin, slot, np, E->nx, E->ny, E->nz, order, alpha[s], beta[s], dcomb, xout, vout,
-                     nullptr));
+                     nullptr, fr));
     }
     cur = xout;
     vin = vout;
@@ -321,6 +332,8 @@ int nbody_steps_vjp(Engine* E, stream_t st, float* posbar, float* velbar, int64_
   const int64_t P3 = 3 * np;
   const bool cic = (order == 2);
   const bool side_zero = g_side_zero && cic && brick_path(E, order, nullptr);
+  Frame f;
+  const Frame* fr = E->frame(f);
   for (int s = n_steps - 1; s >= 0; --s) {
     const bool last = (s == n_steps - 1);
     float dcomb = drift_post[s] + (last ? 0.0f : drift_pre[s + 1]);
@@ -340,18 +353,19 @@ int nbody_steps_vjp(Engine* E, stream_t st, float* posbar, float* velbar, int64_
       if (E->lat.px > 0) {  // brick-tiled: accumulates in shared memory, flushes planar meshes directly
         if (!(side_zero && !last))  // cleared on the side by read_grad4v of the step before (in sweep order)
           TRY(rt_memset(E->r(4), 0, sizeof(float) * 3 * (size_t)E->N, st) ? MCPM_ECUDA : 0);
-        handled = brick_paint3_cic(st, E->lat, x1, velbar, posbar, dcomb, beta[s], np, E->nx, E->ny, E->nz, E->r(4));
+        handled = brick_paint3_cic(st, E->lat, x1, velbar, posbar, dcomb, beta[s], np, E->nx, E->ny, E->nz, E->r(4),
+                                   fr);
         if (handled < 0) return MCPM_ECUDA;
       }
 #endif
       if (!handled) {  // float4 mesh r(0..3), then back to planar for cuFFT
         TRY(rt_memset(E->r(0), 0, sizeof(float) * 4 * (size_t)E->N, st) ? MCPM_ECUDA : 0);
-        TRY(paint3v4(st, x1, velbar, posbar, dcomb, 1, beta[s], np, E->nx, E->ny, E->nz, E->r(0)));
+        TRY(paint3v4(st, x1, velbar, posbar, dcomb, 1, beta[s], np, E->nx, E->ny, E->nz, E->r(0), fr));
         TRY(deinterleave3(st, E->r(0), E->r(4), E->N));
       }
     } else {
       TRY(axpy3(st, velbar, posbar, dcomb, P3, velbar));
-      TRY(paint3(st, x1, velbar, beta[s], nullptr, 0.0f, np, E->nx, E->ny, E->nz, order, E->r(4), 0));
+      TRY(paint3(st, x1, velbar, beta[s], nullptr, 0.0f, np, E->nx, E->ny, E->nz, order, E->r(4), 0, fr));
     }
     TRY(density_cotangent(E, st, E->r(4), lap_fd, grad_fd, 0.0f, paint_deconv ? order : 0, E->r(3)));  // rhobar
     if (coefbar) {
@@ -364,11 +378,11 @@ int nbody_steps_vjp(Engine* E, stream_t st, float* posbar, float* velbar, int64_
     if (cic) {
       // xbar += dread(x1; beta*vbar . F + rhobar) and vbar *= alpha, one gather
       TRY(read_grad4v(st, x1, slot, E->r(3), velbar, beta[s], 1, alpha[s], np, E->nx, E->ny, E->nz, posbar, 1,
-                      side_zero && s > 0 ? E->r(4) : nullptr, 3 * E->N));
+                      side_zero && s > 0 ? E->r(4) : nullptr, 3 * E->N, fr));
     } else {
       const float* ms[4] = {slot, slot + E->N, slot + 2 * E->N, E->r(3)};
       TRY(read_grad(st, x1, ms, 4, velbar, 3, beta[s], nullptr, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, posbar,
-                    1));
+                    1, 0.0f, fr));
       TRY(axpy3(st, velbar, velbar, alpha[s] - 1.0f, P3, velbar));
     }
   }
@@ -388,10 +402,12 @@ int nufft(Engine* E, stream_t st, const float* pos, const float* weights, float 
   }
   float jac = scale ? scale[0] * scale[1] * scale[2] : 1.0f;
   const bool kb = kb_kcut > 0.0f;
+  Frame f;
+  const Frame* fr = E->frame(f);
   for (int i = 0; i < m; ++i) {
     if (kb)
       TRY(paint(st, pos, weights, wscalar, np, E->nx, E->ny, E->nz, paint_order, scale, (float)i / (float)m, E->r(i), 0,
-                kb_kcut));
+                kb_kcut, fr));
     else
       TRY(paint_fresh(E, st, pos, weights, wscalar, np, paint_order, scale, (float)i / (float)m, E->r(i)));
   }
@@ -421,9 +437,11 @@ int nufft_vjp(Engine* E, stream_t st, const float* pos, const float* weights, fl
   // conj(phase_i) breaks Hermitian symmetry on the Nyquist planes exactly as the forward phase does: project (fourier.cu)
   TRY(hermitian_project(st, E->c(0), E->nx, E->ny, E->nz, m));
   TRY(fft_c2r(E->fft, st, E->c(0), E->r(0), m));
+  Frame f;
+  const Frame* fr = E->frame(f);
   for (int i = 0; i < m; ++i)
     TRY(paint_vjp(st, pos, weights, wscalar, E->r(i), np, E->nx, E->ny, E->nz, paint_order, scale,
-                  (float)i / (float)m, posbar, weightsbar, i > 0, kb_kcut));
+                  (float)i / (float)m, posbar, weightsbar, i > 0, kb_kcut, fr));
   return 0;
 }
 

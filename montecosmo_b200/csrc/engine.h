@@ -1,5 +1,6 @@
 // engine.h -- internal declarations shared by the engine translation units.
 #pragma once
+#include "frame.h"
 #include "rt.h"
 
 namespace mcpm {
@@ -17,6 +18,13 @@ struct Engine {
   int nx, ny, nz, nzc;
   int device = 0;  // CUDA device the plans and scratch live on
   Lattice lat;     // optional particle-order hint
+  int rel = 0;     // 1: the composite operators take lattice-relative positions (frame.h); needs `lat`
+  // the frame the particle kernels are given: NULL (absolute) or the lattice `lat` spanning this engine's mesh
+  const Frame* frame(Frame& f) const {
+    if (!rel) return nullptr;
+    f = make_rel_frame(lat.px, lat.py, lat.pz, nx, ny, nz);
+    return &f;
+  }
   int64_t N, Nc;
   float invN;
   FftPlans* fft = nullptr;
@@ -34,19 +42,21 @@ void engine_destroy(Engine*);
 
 // paint.cu.  kb_kcut > 0 selects the Kaiser-Bessel window with that cutoff (nbody.py:280-290) instead of `rectangular`.
 int paint(stream_t, const float* pos, const float* weights, float wscalar, int64_t np, int nx, int ny, int nz,
-          int order, const float* scale, float shift, float* mesh, int accumulate, float kb_kcut = 0.0f);
+          int order, const float* scale, float shift, float* mesh, int accumulate, float kb_kcut = 0.0f,
+          const Frame* fr = nullptr);
 int read(stream_t, const float* pos, const float* mesh, int nmesh, int64_t np, int nx, int ny, int nz, int order,
-         const float* scale, float shift, float* out, float kb_kcut = 0.0f);
+         const float* scale, float shift, float* out, float kb_kcut = 0.0f, const Frame* fr = nullptr);
 int read_grad(stream_t, const float* pos, const float* const* meshes, int nmesh, const float* cot, int ncot,
               float cscale, const float* gw, int64_t np, int nx, int ny, int nz, int order, const float* scale,
-              float shift, float* grad, int accumulate, float kb_kcut = 0.0f);
+              float shift, float* grad, int accumulate, float kb_kcut = 0.0f, const Frame* fr = nullptr);
 int paint3(stream_t, const float* pos, const float* A, float ca, const float* B, float cb, int64_t np, int nx,
-           int ny, int nz, int order, float* mesh3, int accumulate);
+           int ny, int nz, int order, float* mesh3, int accumulate, const Frame* fr = nullptr);
 int paint_vjp(stream_t, const float* pos, const float* weights, float wscalar, const float* mbar, int64_t np, int nx,
               int ny, int nz, int order, const float* scale, float shift, float* posbar, float* wbar,
-              int accumulate, float kb_kcut = 0.0f);
+              int accumulate, float kb_kcut = 0.0f, const Frame* fr = nullptr);
 int kick_drift(stream_t, const float* pos, const float* vel, const float* fmesh3, int64_t np, int nx, int ny, int nz,
-               int order, float alpha, float beta, float drift, float* pos_out, float* vel_out, float* force_out);
+               int order, float alpha, float beta, float drift, float* pos_out, float* vel_out, float* force_out,
+               const Frame* fr = nullptr);
 int axpy3(stream_t, const float* a, const float* b, float s, int64_t n3, float* out);
 int lpt_combine(stream_t, const float* pos, const float* f1, const float* f2, float d1, float d2, float dv2,
                 int64_t np, float* dpos, float* vel, float* pos_out);
@@ -113,12 +123,12 @@ int interleave3(stream_t, const float* planar3, float* mesh4, int64_t n);
 int deinterleave3(stream_t, const float* mesh4, float* planar3, int64_t n);
 int kick_drift4(stream_t, const float* pos, const float* vel, const float* fmesh4, int64_t np, int nx, int ny, int nz,
                 float alpha, float beta, float drift, float* pos_out, float* vel_out, float* zero = nullptr,
-                int64_t nzero = 0);
+                int64_t nzero = 0, const Frame* fr = nullptr);
 int paint3v4(stream_t, const float* pos, float* A, const float* B, float cb, int store, float scale, int64_t np, int nx,
-             int ny, int nz, float* mesh4);
+             int ny, int nz, float* mesh4, const Frame* fr = nullptr);
 int read_grad4v(stream_t, const float* pos, const float* fmesh4, const float* rhobar, float* cot, float cscale,
                 int scale_cot, float alpha_tail, int64_t np, int nx, int ny, int nz, float* grad, int accumulate,
-                float* zero = nullptr, int64_t nzero = 0);
+                float* zero = nullptr, int64_t nzero = 0, const Frame* fr = nullptr);
 
 // xfft.cu (CUDA build only): the x-passes of rfftn / irfftn fused with the force kernel, on [nx, ny_loc, nz/2+1]
 bool xfuse_supported(int nx);
@@ -140,9 +150,9 @@ int xfuse_hessian_tk(stream_t, const cfloat* in6, cfloat* out, int nx, int ny, i
 
 // brick.cu (CUDA build only): return 1 if handled, 0 if the generic path must be taken, < 0 on error
 int brick_paint_cic(stream_t, const Lattice&, const float* pos, const float* weights, float wscalar, float shift,
-                    int64_t np, int nx, int ny, int nz, float* mesh);
+                    int64_t np, int nx, int ny, int nz, float* mesh, const Frame* fr = nullptr);
 int brick_paint3_cic(stream_t, const Lattice&, const float* pos, float* A, const float* B, float cb, float s,
-                     int64_t np, int nx, int ny, int nz, float* mesh3);
+                     int64_t np, int nx, int ny, int nz, float* mesh3, const Frame* fr = nullptr);
 
 // engine.cu
 void set_side_zero(int v);

@@ -16,21 +16,35 @@ struct MeshDims {
 
 struct PosXform {
   float sx, sy, sz, shift;
+  Frame fr;  // absolute or lattice-relative positions (frame.h)
 };
+
+// Transformed coordinate of particle p as an exact integer part b (its lattice site; 0 for absolute frames) plus a small
+// float part u:  x' = b + u,  u = site remainder + pos * scale + shift.  pos may be NULL in a relative frame (particles
+// on their sites).
+MCPM_HD void load_pos(const float* pos, int64_t p, const PosXform& xf, int* b, float* u) {
+  float r0, r1, r2;
+  frame_site(xf.fr, p, b[0], b[1], b[2], r0, r1, r2);
+  const float d0 = pos ? pos[3 * p] : 0.0f, d1 = pos ? pos[3 * p + 1] : 0.0f, d2 = pos ? pos[3 * p + 2] : 0.0f;
+  u[0] = r0 + (d0 * xf.sx + xf.shift);
+  u[1] = r1 + (d1 * xf.sy + xf.shift);
+  u[2] = r2 + (d2 * xf.sz + xf.shift);
+}
 
 template <int ORDER, class WIN = RectWin>
 static void paint_impl(stream_t st, const float* pos, const float* weights, float wscalar, int64_t np, MeshDims n,
                        PosXform xf, float* mesh, WIN win = WIN()) {
   launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
-    const float* x = pos + 3 * p;
-    int fx, fy, fz;
+    int sb[3], fx, fy, fz;
+    float su[3];
+    load_pos(pos, p, xf, sb, su);
     float wx[ORDER], wy[ORDER], wz[ORDER];
-    win.template weights<ORDER>(x[0] * xf.sx + xf.shift, fx, wx);
-    win.template weights<ORDER>(x[1] * xf.sy + xf.shift, fy, wy);
-    win.template weights<ORDER>(x[2] * xf.sz + xf.shift, fz, wz);
-    fx = wrap_fast(fx, n.nx);
-    fy = wrap_fast(fy, n.ny);
-    fz = wrap_fast(fz, n.nz);
+    win.template weights<ORDER>(su[0], fx, wx);
+    win.template weights<ORDER>(su[1], fy, wy);
+    win.template weights<ORDER>(su[2], fz, wz);
+    fx = wrap_fast(fx + sb[0], n.nx);
+    fy = wrap_fast(fy + sb[1], n.ny);
+    fz = wrap_fast(fz + sb[2], n.nz);
     float wp = weights ? weights[p] * wscalar : wscalar;
 #pragma unroll
     for (int a = 0; a < ORDER; ++a) {
@@ -58,15 +72,16 @@ static void read_impl(stream_t st, const float* pos, const float* mesh, int64_t 
                       float* out, WIN win = WIN()) {
   const int64_t plane = (int64_t)n.nx * n.ny * n.nz;
   launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
-    const float* x = pos + 3 * p;
-    int fx, fy, fz;
+    int sb[3], fx, fy, fz;
+    float su[3];
+    load_pos(pos, p, xf, sb, su);
     float wx[ORDER], wy[ORDER], wz[ORDER];
-    win.template weights<ORDER>(x[0] * xf.sx + xf.shift, fx, wx);
-    win.template weights<ORDER>(x[1] * xf.sy + xf.shift, fy, wy);
-    win.template weights<ORDER>(x[2] * xf.sz + xf.shift, fz, wz);
-    fx = wrap_fast(fx, n.nx);
-    fy = wrap_fast(fy, n.ny);
-    fz = wrap_fast(fz, n.nz);
+    win.template weights<ORDER>(su[0], fx, wx);
+    win.template weights<ORDER>(su[1], fy, wy);
+    win.template weights<ORDER>(su[2], fz, wz);
+    fx = wrap_fast(fx + sb[0], n.nx);
+    fy = wrap_fast(fy + sb[1], n.ny);
+    fz = wrap_fast(fz + sb[2], n.nz);
     float acc[NM];
 #pragma unroll
     for (int m = 0; m < NM; ++m) acc[m] = 0.0f;
@@ -108,15 +123,16 @@ static void read_grad_impl(stream_t st, const float* pos, MeshPtrs ms, int nmesh
                            float cscale, const float* gw, int64_t np, MeshDims n, PosXform xf, float* grad,
                            int accumulate, WIN win = WIN()) {
   launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
-    const float* x = pos + 3 * p;
-    int fx, fy, fz;
+    int sb[3], fx, fy, fz;
+    float su[3];
+    load_pos(pos, p, xf, sb, su);
     float wx[ORDER], wy[ORDER], wz[ORDER], dx[ORDER], dy[ORDER], dz[ORDER];
-    win.template weights_grad<ORDER>(x[0] * xf.sx + xf.shift, fx, wx, dx);
-    win.template weights_grad<ORDER>(x[1] * xf.sy + xf.shift, fy, wy, dy);
-    win.template weights_grad<ORDER>(x[2] * xf.sz + xf.shift, fz, wz, dz);
-    fx = wrap_fast(fx, n.nx);
-    fy = wrap_fast(fy, n.ny);
-    fz = wrap_fast(fz, n.nz);
+    win.template weights_grad<ORDER>(su[0], fx, wx, dx);
+    win.template weights_grad<ORDER>(su[1], fy, wy, dy);
+    win.template weights_grad<ORDER>(su[2], fz, wz, dz);
+    fx = wrap_fast(fx + sb[0], n.nx);
+    fy = wrap_fast(fy + sb[1], n.ny);
+    fz = wrap_fast(fz + sb[2], n.nz);
     float c4[4];
 #pragma unroll
     for (int m = 0; m < 4; ++m) c4[m] = (m < ncot && cot) ? cscale * cot[p * ncot + m] : 1.0f;
@@ -165,18 +181,19 @@ static void read_grad_impl(stream_t st, const float* pos, MeshPtrs ms, int nmesh
 // The index / weight computation is shared by the three channels.
 template <int ORDER>
 static void paint3_impl(stream_t st, const float* pos, const float* A, float ca, const float* B, float cb,
-                        int64_t np, MeshDims n, float* mesh3) {
+                        int64_t np, MeshDims n, PosXform xf, float* mesh3) {
   const int64_t plane = (int64_t)n.nx * n.ny * n.nz;
   launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
-    const float* x = pos + 3 * p;
-    int fx, fy, fz;
+    int sb[3], fx, fy, fz;
+    float su[3];
+    load_pos(pos, p, xf, sb, su);
     float wx[ORDER], wy[ORDER], wz[ORDER];
-    window_weights<ORDER>(x[0], fx, wx);
-    window_weights<ORDER>(x[1], fy, wy);
-    window_weights<ORDER>(x[2], fz, wz);
-    fx = wrap_fast(fx, n.nx);
-    fy = wrap_fast(fy, n.ny);
-    fz = wrap_fast(fz, n.nz);
+    window_weights<ORDER>(su[0], fx, wx);
+    window_weights<ORDER>(su[1], fy, wy);
+    window_weights<ORDER>(su[2], fz, wz);
+    fx = wrap_fast(fx + sb[0], n.nx);
+    fy = wrap_fast(fy + sb[1], n.ny);
+    fz = wrap_fast(fz + sb[2], n.nz);
     float v0 = ca * A[3 * p], v1 = ca * A[3 * p + 1], v2 = ca * A[3 * p + 2];
     if (B) {
       v0 += cb * B[3 * p];
@@ -214,15 +231,16 @@ static void paint_vjp_impl(stream_t st, const float* pos, const float* weights, 
                            int64_t np, MeshDims n, PosXform xf, float* posbar, float* wbar, int accumulate,
                            WIN win = WIN()) {
   launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
-    const float* x = pos + 3 * p;
-    int fx, fy, fz;
+    int sb[3], fx, fy, fz;
+    float su[3];
+    load_pos(pos, p, xf, sb, su);
     float wx[ORDER], wy[ORDER], wz[ORDER], dx[ORDER], dy[ORDER], dz[ORDER];
-    win.template weights_grad<ORDER>(x[0] * xf.sx + xf.shift, fx, wx, dx);
-    win.template weights_grad<ORDER>(x[1] * xf.sy + xf.shift, fy, wy, dy);
-    win.template weights_grad<ORDER>(x[2] * xf.sz + xf.shift, fz, wz, dz);
-    fx = wrap_fast(fx, n.nx);
-    fy = wrap_fast(fy, n.ny);
-    fz = wrap_fast(fz, n.nz);
+    win.template weights_grad<ORDER>(su[0], fx, wx, dx);
+    win.template weights_grad<ORDER>(su[1], fy, wy, dy);
+    win.template weights_grad<ORDER>(su[2], fz, wz, dz);
+    fx = wrap_fast(fx + sb[0], n.nx);
+    fy = wrap_fast(fy + sb[1], n.ny);
+    fz = wrap_fast(fz + sb[2], n.nz);
     float r = 0.0f, g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
 #pragma unroll
     for (int a = 0; a < ORDER; ++a) {
@@ -259,21 +277,23 @@ static void paint_vjp_impl(stream_t st, const float* pos, const float* weights, 
 // F = read(pos, fmesh[3]); vel = alpha*vel + beta*F; pos += vel*drift   (nbody.py:933-951)
 template <int ORDER>
 static void kick_drift_impl(stream_t st, const float* pos, const float* vel, const float* fmesh, int64_t np,
-                            MeshDims n, float alpha, float beta, float drift, float* pos_out, float* vel_out,
-                            float* force_out) {
+                            MeshDims n, PosXform xf, float alpha, float beta, float drift, float* pos_out,
+                            float* vel_out, float* force_out) {
   const int64_t plane = (int64_t)n.nx * n.ny * n.nz;
   launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
     const float* x = pos + 3 * p;
     const float* v = vel + 3 * p;
-    float x0 = x[0], x1 = x[1], x2 = x[2];
-    int fx, fy, fz;
+    float x0 = x[0], x1 = x[1], x2 = x[2];  // absolute position, or displacement from the lattice site (updated as such)
+    int sb[3], fx, fy, fz;
+    float su[3];
+    load_pos(pos, p, xf, sb, su);
     float wx[ORDER], wy[ORDER], wz[ORDER];
-    window_weights<ORDER>(x0, fx, wx);
-    window_weights<ORDER>(x1, fy, wy);
-    window_weights<ORDER>(x2, fz, wz);
-    fx = wrap_fast(fx, n.nx);
-    fy = wrap_fast(fy, n.ny);
-    fz = wrap_fast(fz, n.nz);
+    window_weights<ORDER>(su[0], fx, wx);
+    window_weights<ORDER>(su[1], fy, wy);
+    window_weights<ORDER>(su[2], fz, wz);
+    fx = wrap_fast(fx + sb[0], n.nx);
+    fy = wrap_fast(fy + sb[1], n.ny);
+    fz = wrap_fast(fz + sb[2], n.nz);
     float f0 = 0.0f, f1 = 0.0f, f2 = 0.0f;
 #pragma unroll
     for (int a = 0; a < ORDER; ++a) {
@@ -330,8 +350,8 @@ static int check_mesh(int nx, int ny, int nz, int order) {
   return 0;
 }
 
-static PosXform make_xform(const float* scale, float shift) {
-  PosXform xf = {1.0f, 1.0f, 1.0f, shift};
+static PosXform make_xform(const float* scale, float shift, const Frame* fr = nullptr) {
+  PosXform xf = {1.0f, 1.0f, 1.0f, shift, fr ? *fr : Frame()};
   if (scale) {
     xf.sx = scale[0];
     xf.sy = scale[1];
@@ -341,14 +361,14 @@ static PosXform make_xform(const float* scale, float shift) {
 }
 
 int paint(stream_t st, const float* pos, const float* weights, float wscalar, int64_t np, int nx, int ny, int nz,
-          int order, const float* scale, float shift, float* mesh, int accumulate, float kb_kcut) {
+          int order, const float* scale, float shift, float* mesh, int accumulate, float kb_kcut, const Frame* fr) {
   if (int e = check_mesh(nx, ny, nz, order)) return e;
-  if (!mesh || (np > 0 && !pos)) {
+  if (!mesh || (np > 0 && !pos && !(fr && fr->rel))) {
     set_error("paint: null pointer");
     return MCPM_EINVAL;
   }
   MeshDims n = {nx, ny, nz};
-  PosXform xf = make_xform(scale, shift);
+  PosXform xf = make_xform(scale, shift, fr);
   if (!accumulate) rt_memset(mesh, 0, sizeof(float) * (size_t)nx * ny * nz, st);
   if (kb_kcut > 0.0f) {
     KbWin kb = make_kbwin(order, kb_kcut);
@@ -383,14 +403,14 @@ static int read_nm(stream_t st, const float* pos, const float* mesh, int nmesh, 
 }
 
 int read(stream_t st, const float* pos, const float* mesh, int nmesh, int64_t np, int nx, int ny, int nz, int order,
-         const float* scale, float shift, float* out, float kb_kcut) {
+         const float* scale, float shift, float* out, float kb_kcut, const Frame* fr) {
   if (int e = check_mesh(nx, ny, nz, order)) return e;
-  if (np > 0 && (!pos || !mesh || !out)) {
+  if (np > 0 && ((!pos && !(fr && fr->rel)) || !mesh || !out)) {
     set_error("read: null pointer");
     return MCPM_EINVAL;
   }
   MeshDims n = {nx, ny, nz};
-  PosXform xf = make_xform(scale, shift);
+  PosXform xf = make_xform(scale, shift, fr);
   int e;
   if (kb_kcut > 0.0f) {
     KbWin kb = make_kbwin(order, kb_kcut);
@@ -413,18 +433,18 @@ int read(stream_t st, const float* pos, const float* mesh, int nmesh, int64_t np
 
 int read_grad(stream_t st, const float* pos, const float* const* meshes, int nmesh, const float* cot, int ncot,
               float cscale, const float* gw, int64_t np, int nx, int ny, int nz, int order, const float* scale,
-              float shift, float* grad, int accumulate, float kb_kcut) {
+              float shift, float* grad, int accumulate, float kb_kcut, const Frame* fr) {
   if (int e = check_mesh(nx, ny, nz, order)) return e;
   if (nmesh < 1 || nmesh > 4 || ncot < 0 || ncot > nmesh) {
     set_error("read_grad: nmesh must be 1..4 and ncot <= nmesh");
     return MCPM_EINVAL;
   }
-  if (np > 0 && (!pos || !meshes || !grad)) {
+  if (np > 0 && ((!pos && !(fr && fr->rel)) || !meshes || !grad)) {
     set_error("read_grad: null pointer");
     return MCPM_EINVAL;
   }
   MeshDims n = {nx, ny, nz};
-  PosXform xf = make_xform(scale, shift);
+  PosXform xf = make_xform(scale, shift, fr);
   MeshPtrs ms = {{nullptr, nullptr, nullptr, nullptr}};
   for (int m = 0; m < nmesh; ++m) ms.p[m] = meshes[m];
   if (kb_kcut > 0.0f) {
@@ -447,33 +467,34 @@ int read_grad(stream_t st, const float* pos, const float* const* meshes, int nme
 }
 
 int paint3(stream_t st, const float* pos, const float* A, float ca, const float* B, float cb, int64_t np, int nx,
-           int ny, int nz, int order, float* mesh3, int accumulate) {
+           int ny, int nz, int order, float* mesh3, int accumulate, const Frame* fr) {
   if (int e = check_mesh(nx, ny, nz, order)) return e;
-  if (!mesh3 || (np > 0 && (!pos || !A))) {
+  if (!mesh3 || (np > 0 && ((!pos && !(fr && fr->rel)) || !A))) {
     set_error("paint3: null pointer");
     return MCPM_EINVAL;
   }
   MeshDims n = {nx, ny, nz};
+  PosXform xf = make_xform(nullptr, 0.0f, fr);
   if (!accumulate) rt_memset(mesh3, 0, sizeof(float) * 3 * (size_t)nx * ny * nz, st);
   switch (order) {
-    case 1: paint3_impl<1>(st, pos, A, ca, B, cb, np, n, mesh3); break;
-    case 2: paint3_impl<2>(st, pos, A, ca, B, cb, np, n, mesh3); break;
-    case 3: paint3_impl<3>(st, pos, A, ca, B, cb, np, n, mesh3); break;
-    default: paint3_impl<4>(st, pos, A, ca, B, cb, np, n, mesh3); break;
+    case 1: paint3_impl<1>(st, pos, A, ca, B, cb, np, n, xf, mesh3); break;
+    case 2: paint3_impl<2>(st, pos, A, ca, B, cb, np, n, xf, mesh3); break;
+    case 3: paint3_impl<3>(st, pos, A, ca, B, cb, np, n, xf, mesh3); break;
+    default: paint3_impl<4>(st, pos, A, ca, B, cb, np, n, xf, mesh3); break;
   }
   return rt_check("paint3");
 }
 
 int paint_vjp(stream_t st, const float* pos, const float* weights, float wscalar, const float* mbar, int64_t np,
               int nx, int ny, int nz, int order, const float* scale, float shift, float* posbar, float* wbar,
-              int accumulate, float kb_kcut) {
+              int accumulate, float kb_kcut, const Frame* fr) {
   if (int e = check_mesh(nx, ny, nz, order)) return e;
-  if (np > 0 && (!pos || !mbar)) {
+  if (np > 0 && ((!pos && !(fr && fr->rel)) || !mbar)) {
     set_error("paint_vjp: null pointer");
     return MCPM_EINVAL;
   }
   MeshDims n = {nx, ny, nz};
-  PosXform xf = make_xform(scale, shift);
+  PosXform xf = make_xform(scale, shift, fr);
   if (kb_kcut > 0.0f) {
     KbWin kb = make_kbwin(order, kb_kcut);
     switch (order) {
@@ -495,18 +516,19 @@ int paint_vjp(stream_t st, const float* pos, const float* weights, float wscalar
 
 int kick_drift(stream_t st, const float* pos, const float* vel, const float* fmesh3, int64_t np, int nx, int ny,
                int nz, int order, float alpha, float beta, float drift, float* pos_out, float* vel_out,
-               float* force_out) {
+               float* force_out, const Frame* fr) {
   if (int e = check_mesh(nx, ny, nz, order)) return e;
   if (np > 0 && (!pos || !vel || !fmesh3 || !pos_out || !vel_out)) {
     set_error("kick_drift: null pointer");
     return MCPM_EINVAL;
   }
   MeshDims n = {nx, ny, nz};
+  PosXform xf = make_xform(nullptr, 0.0f, fr);
   switch (order) {
-    case 1: kick_drift_impl<1>(st, pos, vel, fmesh3, np, n, alpha, beta, drift, pos_out, vel_out, force_out); break;
-    case 2: kick_drift_impl<2>(st, pos, vel, fmesh3, np, n, alpha, beta, drift, pos_out, vel_out, force_out); break;
-    case 3: kick_drift_impl<3>(st, pos, vel, fmesh3, np, n, alpha, beta, drift, pos_out, vel_out, force_out); break;
-    default: kick_drift_impl<4>(st, pos, vel, fmesh3, np, n, alpha, beta, drift, pos_out, vel_out, force_out); break;
+    case 1: kick_drift_impl<1>(st, pos, vel, fmesh3, np, n, xf, alpha, beta, drift, pos_out, vel_out, force_out); break;
+    case 2: kick_drift_impl<2>(st, pos, vel, fmesh3, np, n, xf, alpha, beta, drift, pos_out, vel_out, force_out); break;
+    case 3: kick_drift_impl<3>(st, pos, vel, fmesh3, np, n, xf, alpha, beta, drift, pos_out, vel_out, force_out); break;
+    default: kick_drift_impl<4>(st, pos, vel, fmesh3, np, n, xf, alpha, beta, drift, pos_out, vel_out, force_out); break;
   }
   return rt_check("kick_drift");
 }

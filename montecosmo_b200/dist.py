@@ -16,7 +16,10 @@ Exchange steps per force evaluation (everything else is the single-GPU kernels o
 halo_gather is the exact transpose of halo_reduce and irfftn o diag(m) o rfftn transposes as on one GPU, so the reverse
 sweep is the same sequence with scatter and gather swapping roles.
 
-Positions handed to / returned by this class are in LOCAL coordinates: x_local = x_global - (x0 - H); y, z global.
+Positions handed to / returned by this class are DISPLACEMENTS from the particles' own lattice sites (float32; the
+kernels are given the frame `self.frame`: site (i, j, k) of the rank's xl x ny x nz lattice sits at cell (H + i, j, k) of
+its halo-extended mesh, include/mcpm.h: mcpm_frame).  The CIC fraction then resolves ~1e-7 cell whatever the mesh size,
+where an absolute float32 coordinate near 1000 resolves 6e-5.
 Reference semantics: montecosmo/nbody.py:583-604 (pm_forces), 634-667 (lpt), 933-951 (BullFrog step).
 """
 from __future__ import annotations
@@ -28,7 +31,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from ._capi import check, fd_code
+from ._capi import check, fd_code, frame as _frame
 
 INF = float("inf")
 
@@ -70,6 +73,8 @@ class SlabPM:
         self.prev, self.next = (self.rank - 1) % self.P, (self.rank + 1) % self.P
         ax = [np.arange(self.xl, dtype=np.float32), np.arange(ny, dtype=np.float32), np.arange(nz, dtype=np.float32)]
         self.q_own = self.A.prepare(np.stack(np.meshgrid(*ax, indexing="ij"), -1).reshape(-1, 3))  # owned-slab coords
+        self.frame = _frame((self.xl, ny, nz), origin=(self.H, 0, 0))  # relative positions on the halo-extended mesh
+        self._fr = C.byref(self.frame)
         self._oob = None
 
     def __del__(self):
@@ -225,8 +230,10 @@ class SlabPM:
         ext[:H] = left
 
     def _guard(self, pos):
+        # site i + displacement d must keep the CIC stencil inside the extended slab: 1 <= H + i + d <= ext - 2 for every
+        # owned i in [0, xl)
         x = pos[:, 0]
-        bad = ((x < 1.0) | (x > self.ext - 2.0)).any()
+        bad = ((x < 1.0 - self.H) | (x > self.H - 1.0)).any()
         self._oob = bad if self._oob is None else (self._oob | bad)
 
     def check_guard(self):
@@ -284,11 +291,11 @@ class SlabPM:
         rho = A.zeros((self.ext, self.ny, self.nz))
         one = (C.c_float * 3)(1.0, 1.0, 1.0)
         # brick-tiled scatter of my xl x ny x nz lattice particles into the halo-extended mesh where this build has it
-        if not (order == 2 and self.brick and lib.mcpm_paint_brick(
-                st, self.xl, self.ny, self.nz, pos.data_ptr(), 0, 1.0, 0.0, pos.shape[0], self.ext, self.ny, self.nz,
-                rho.data_ptr()) == 0):
-            self._call("mcpm_paint", st, pos.data_ptr(), 0, 1.0, pos.shape[0], self.ext, self.ny, self.nz, order, one,
-                       0.0, rho.data_ptr(), 1)
+        if not (order == 2 and self.brick and self._brick_ok(lib.mcpm_paint_brick_f(
+                st, self._fr, self.xl, self.ny, self.nz, pos.data_ptr(), 0, 1.0, 0.0, pos.shape[0], self.ext, self.ny,
+                self.nz, rho.data_ptr()))):
+            self._call("mcpm_paint_f", st, self._fr, pos.data_ptr(), 0, 1.0, pos.shape[0], self.ext, self.ny, self.nz,
+                       order, one, 0.0, rho.data_ptr(), 1)
         self.halo_reduce(rho)
         F = self.forces_from_density(rho[self.H:self.H + self.xl])  # [3, xl, ny, nz]
         fm4 = A.empty((self.ext, self.ny, self.nz, 4))
@@ -296,6 +303,16 @@ class SlabPM:
         self._call("mcpm_interleave3", st, F.data_ptr(), own.data_ptr(), self.xl * self.ny * self.nz)
         self.halo_gather(fm4)
         return fm4
+
+    def _brick_ok(self, code):
+        """True: the brick kernel ran.  False: this geometry / build has none (MCPM_EUNSUP), take the generic kernel.
+        Any other code is a real error and is raised -- a failed launch must not be papered over by the fallback."""
+        if code == 0:
+            return True
+        if code == 5:  # MCPM_EUNSUP
+            return False
+        check(self.lib, code)
+        return False
 
     def steps_forward(self, pos, vel, alpha, beta, drift_pre, drift_post, tape=True):
         """BullFrog DKD steps in place on local (pos, vel); CIC.  Returns the tape [(x_kick, fm4), ...]."""
@@ -309,8 +326,8 @@ class SlabPM:
             if tape:
                 out.append((pos.clone(), fm4))
             dcomb = float(drift_post[s]) + (float(drift_pre[s + 1]) if s + 1 < ns else 0.0)
-            self._call("mcpm_kick_drift4", st, pos.data_ptr(), vel.data_ptr(), fm4.data_ptr(), pos.shape[0], self.ext,
-                       self.ny, self.nz, float(alpha[s]), float(beta[s]), dcomb)
+            self._call("mcpm_kick_drift4_f", st, self._fr, pos.data_ptr(), vel.data_ptr(), fm4.data_ptr(), pos.shape[0],
+                       self.ext, self.ny, self.nz, float(alpha[s]), float(beta[s]), dcomb)
         self._guard(pos)
         return out
 
@@ -324,14 +341,14 @@ class SlabPM:
             x1, fm4 = tape[s]
             dcomb = float(drift_post[s]) + (float(drift_pre[s + 1]) if s + 1 < ns else 0.0)
             m3 = A.zeros((3, self.ext, self.ny, self.nz)) if self.brick else None
-            if m3 is not None and self.lib.mcpm_paint3_brick(
-                    st, self.xl, self.ny, self.nz, x1.data_ptr(), velbar.data_ptr(), posbar.data_ptr(), dcomb,
-                    float(beta[s]), n, self.ext, self.ny, self.nz, m3.data_ptr()) == 0:
+            if m3 is not None and self._brick_ok(self.lib.mcpm_paint3_brick_f(
+                    st, self._fr, self.xl, self.ny, self.nz, x1.data_ptr(), velbar.data_ptr(), posbar.data_ptr(), dcomb,
+                    float(beta[s]), n, self.ext, self.ny, self.nz, m3.data_ptr())):
                 self.halo_reduce(m3, lead=True)  # three planar extended meshes
                 planar = m3[:, self.H:self.H + self.xl].contiguous()
             else:
                 m4 = A.zeros((self.ext, self.ny, self.nz, 4))
-                self._call("mcpm_paint3v4", st, x1.data_ptr(), velbar.data_ptr(), posbar.data_ptr(), dcomb,
+                self._call("mcpm_paint3v4_f", st, self._fr, x1.data_ptr(), velbar.data_ptr(), posbar.data_ptr(), dcomb,
                            float(beta[s]), n, self.ext, self.ny, self.nz, m4.data_ptr())
                 self.halo_reduce(m4)
                 planar = A.empty((3, self.xl, self.ny, self.nz))
@@ -339,8 +356,9 @@ class SlabPM:
             rhobar = A.empty((self.ext, self.ny, self.nz))
             rhobar[self.H:self.H + self.xl] = self.density_cotangent(planar)
             self.halo_gather(rhobar)
-            self._call("mcpm_read_grad4v", st, x1.data_ptr(), fm4.data_ptr(), rhobar.data_ptr(), velbar.data_ptr(),
-                       float(beta[s]), float(alpha[s]), n, self.ext, self.ny, self.nz, posbar.data_ptr())
+            self._call("mcpm_read_grad4v_f", st, self._fr, x1.data_ptr(), fm4.data_ptr(), rhobar.data_ptr(),
+                       velbar.data_ptr(), float(beta[s]), float(alpha[s]), n, self.ext, self.ny, self.nz,
+                       posbar.data_ptr())
         self._call("mcpm_drift", st, velbar.data_ptr(), posbar.data_ptr(), float(drift_pre[0]), n)
 
     # ------------------------------------------------------------------------------------------------ LPT
@@ -359,7 +377,7 @@ class SlabPM:
         return out
 
     def lpt_forward(self, dk, d1, d2, dv2, lpt_order=2):
-        """delta_k block [nx, kyl, nzc] -> local (pos, vel) of the owned lattice particles and the tape (nbody.py:634-667)."""
+        """delta_k block [nx, kyl, nzc] -> (displacement, vel) of the owned lattice particles and the tape (nbody.py:634-667)."""
         A, st = self.A, self._st()
         dk = A.prepare(dk, "c64")
         f1 = self._lattice_read3(self.irfftn(self.force_spectra(dk), overwrite=True))
@@ -375,10 +393,7 @@ class SlabPM:
         dpos, vel = A.empty((self.npl, 3)), A.empty((self.npl, 3))
         self._call("mcpm_lpt_combine", st, 0, f1.data_ptr(), 0 if f2 is None else f2.data_ptr(), float(d1), float(d2),
                    float(dv2), self.npl, dpos.data_ptr(), vel.data_ptr(), 0)
-        q_ext = self.q_own.clone()
-        q_ext[:, 0] += self.H
-        pos = self.o.axpby(dpos, 1.0, q_ext, 1.0)
-        return pos, vel, (h6, (float(d1), float(d2), float(dv2)), lpt_order)
+        return dpos, vel, (h6, (float(d1), float(d2), float(dv2)), lpt_order)  # dpos IS the relative position
 
     def lpt_backward(self, tape, posbar, velbar):
         """(posbar, velbar) -> cotangent of the delta_k block, convention dL/dRe + i dL/dIm (engine.cu:lpt_vjp)."""

@@ -52,6 +52,7 @@ class SlabFieldModel:
         # geometry on the same ranks for the paints and their transforms, and the distributed Fourier crop back
         self.paint_shape = scale_shape(self.mesh_shape, paint_oversamp)
         self.pm2, self.resize, self.ratio = pm, None, (1.0, 1.0, 1.0)
+        self.frame2 = pm.frame  # my lattice in the cells of the paint mesh
         if self.paint_shape != self.mesh_shape:
             from .dist import SlabPM, SlabResize
             self.ratio = tuple(p / m for p, m in zip(self.paint_shape, self.mesh_shape))
@@ -60,6 +61,9 @@ class SlabFieldModel:
                 raise ValueError("paint mesh: nx, ny must divide over the ranks and halo * paint/mesh ratio must be whole")
             self.pm2 = SlabPM(pm.o, self.paint_shape, halo=int(round(h2)), group=pm.group, p2p=False)
             self.resize = SlabResize(self.pm2, pm)
+            from ._capi import frame as _frame
+            self.frame2 = _frame((pm.xl, pm.ny, pm.nz), span=(self.pm2.xl, self.pm2.ny, self.pm2.nz),
+                                 origin=(self.pm2.H, 0, 0))
 
     def _transfer_block(self):
         """My ky rows of FieldModel.transfer_mesh (bricks.py:96-106, 150): sqrt(P(k) N / V), [nx, kyl, nzc]."""
@@ -82,11 +86,12 @@ class SlabFieldModel:
         rho = A.zeros((p2.ext, p2.ny, p2.nz))
         sc = (C.c_float * 3)(*self.ratio)
         wp = 0 if weights is None else weights.data_ptr()
-        if not (self.resize is None and self.paint_order == 2 and pm.brick and self.lib.mcpm_paint_brick(
-                st, pm.xl, pm.ny, pm.nz, pos.data_ptr(), wp, 1.0, float(shift), pos.shape[0], pm.ext, pm.ny, pm.nz,
-                rho.data_ptr()) == 0):
-            self._call("mcpm_paint", st, pos.data_ptr(), wp, 1.0, pos.shape[0], p2.ext, p2.ny, p2.nz, self.paint_order,
-                       sc, float(shift), rho.data_ptr(), 1)
+        fr = C.byref(self.frame2)
+        if not (self.resize is None and self.paint_order == 2 and pm.brick and pm._brick_ok(self.lib.mcpm_paint_brick_f(
+                st, fr, pm.xl, pm.ny, pm.nz, pos.data_ptr(), wp, 1.0, float(shift), pos.shape[0], pm.ext, pm.ny, pm.nz,
+                rho.data_ptr()))):
+            self._call("mcpm_paint_f", st, fr, pos.data_ptr(), wp, 1.0, pos.shape[0], p2.ext, p2.ny, p2.nz,
+                       self.paint_order, sc, float(shift), rho.data_ptr(), 1)
         p2.halo_reduce(rho)
         return rho[p2.H:p2.H + p2.xl]
 
@@ -126,9 +131,10 @@ class SlabFieldModel:
             ext = A.empty((p2.ext, p2.ny, p2.nz))
             ext[p2.H:p2.H + p2.xl] = mbar[i]
             p2.halo_gather(ext)
-            self._call("mcpm_paint_vjp", st, pos.data_ptr(), 0 if weights is None else weights.data_ptr(), 1.0,
-                       ext.data_ptr(), n, p2.ext, p2.ny, p2.nz, self.paint_order, sc, float(i / m), posbar.data_ptr(),
-                       0 if wbar is None else wbar.data_ptr(), int(i > 0))
+            self._call("mcpm_paint_vjp_f", st, C.byref(self.frame2), pos.data_ptr(),
+                       0 if weights is None else weights.data_ptr(), 1.0, ext.data_ptr(), n, p2.ext, p2.ny, p2.nz,
+                       self.paint_order, sc, float(i / m), posbar.data_ptr(), 0 if wbar is None else wbar.data_ptr(),
+                       int(i > 0))
         return posbar, wbar
 
     def _deconv_order(self):

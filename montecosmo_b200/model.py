@@ -104,7 +104,7 @@ class FieldModel:
     def __init__(self, mesh_shape=(64, 64, 64), box_size=(640.0, 640.0, 640.0), evolution="nbody", n_steps=5,
                  a_start=0.0, a_obs=1.0, lpt_order=2, paint_order=2, interlace_order=2, paint_deconv=True,
                  paint_oversamp=1.0, b1=1.0, rsd=True, los=(0.0, 0.0, 1.0), sigma_obs=1.0, cosmology=None, kpow=None,
-                 precond="real", out_shape="paint"):
+                 precond="real", out_shape="paint", relative=True):
         if precond not in ("real", "fourier"):
             raise ValueError("precond must be 'real' or 'fourier'")
         if out_shape not in ("paint", "mesh"):
@@ -113,6 +113,9 @@ class FieldModel:
         # shape, where the reference's likelihood brings it back anyway when final_shape == init_shape and there is no
         # selection function (model.py:855) -- what the slab-decomposed model (dist_model.py) evaluates
         self.precond, self.out_shape = precond, out_shape
+        # relative: carry particles as float32 displacements from their lattice sites (mcpm_engine_set_relative) instead
+        # of float32 absolute positions; False reproduces round 1's arithmetic (kept for the A/B in the parity report)
+        self.relative = bool(relative)
         self.mesh_shape = tuple(int(s) for s in mesh_shape)
         self.box_size = tuple(float(b) for b in box_size)
         self.evolution, self.n_steps, self.a_start, self.a_obs = evolution, int(n_steps), a_start, a_obs
@@ -151,19 +154,22 @@ class FieldModel:
         if self.b1 != 0.0:
             delta_q = nb.read(self.q, nb.irfftn(dk), order=1)
             weights = _Axpby.apply(delta_q, self.b1 * float(_cosmo.a2g(c, self.a_obs)), 1.0)
+        # Particles are carried as float32 displacements from their lattice sites, never as the sum q + displacement
+        # (nbody_bf's `relative`, nufft's `lattice`): the reference's float64 sum has no float32 equivalent at 256^3.
+        rel = self.relative
         if self.evolution == "lpt":
-            pos, vel = nb.lpt(c, dk, self.q, self.a_obs, self.lpt_order, 1, _displaced=True)
+            pos, vel = nb.lpt(c, dk, self.q, self.a_obs, self.lpt_order, 1, _displaced=not rel)
         elif self.evolution == "nbody":
             pos, vel = nb.nbody_bf(c, dk, self.q, self.a_start, self.a_obs, self.n_steps, self.paint_order,
-                                   self.lpt_order, paint_deconv=False)
+                                   self.lpt_order, paint_deconv=False, ptcl_shape=self.mesh_shape, relative=rel)
             pos, vel = pos[-1], vel[-1]
         else:
             raise ValueError(f"unknown evolution {self.evolution}")
         if self.rsd:
             coef = float(_cosmo.a2g(c, self.a_obs) * _cosmo.a2f(c, self.a_obs))
-            pos = _RsdShift.apply(pos, vel, self.los, coef)
+            pos = _RsdShift.apply(pos, vel, self.los, coef)  # a shift: the same kernel serves displacements
         gxy = nb.nufft(pos, self.mesh_shape, self.paint_shape, weights, self.paint_order, self.interlace_order,
-                       paint_deconv=self.paint_deconv)
+                       paint_deconv=self.paint_deconv, lattice=self.mesh_shape if rel else None)
         if self.paint_shape != self.mesh_shape and self.out_shape == "paint":
             gxy = nb.chreshape(gxy, r2chshape(self.paint_shape))
         return nb.irfftn(gxy)  # 1 + delta_obs at the paint shape (particles == cells: Jacobian 1, model.py:806)

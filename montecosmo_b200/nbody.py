@@ -274,20 +274,21 @@ class _ScaleSpectrum(torch.autograd.Function):
 
 class _NufftPaint(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pos, weights, paint_shape, wscalar, scale, paint_order, interlace_order, paint_deconv, kb=0.0):
+    def forward(ctx, pos, weights, paint_shape, wscalar, scale, paint_order, interlace_order, paint_deconv, kb=0.0,
+                lattice=None):
         ctx.save_for_backward(pos, weights)
-        ctx.cfg = (paint_shape, wscalar, scale, paint_order, interlace_order, paint_deconv, kb)
+        ctx.cfg = (paint_shape, wscalar, scale, paint_order, interlace_order, paint_deconv, kb, lattice)
         return ops().nufft_paint(pos, paint_shape, weights, wscalar, scale, paint_order, interlace_order, paint_deconv,
-                                 kb_kcut=kb)
+                                 kb_kcut=kb, lattice=lattice)
 
     @staticmethod
     def backward(ctx, kbar):
         pos, weights = ctx.saved_tensors
-        paint_shape, wscalar, scale, paint_order, interlace_order, paint_deconv, kb = ctx.cfg
+        paint_shape, wscalar, scale, paint_order, interlace_order, paint_deconv, kb, lattice = ctx.cfg
         need_p, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and weights is not None
         pb, wb = ops().nufft_paint_vjp(pos, kbar.contiguous(), paint_shape, weights, wscalar, scale, paint_order,
-                                       interlace_order, paint_deconv, need_p, need_w, kb_kcut=kb)
-        return pb, wb, None, None, None, None, None, None, None
+                                       interlace_order, paint_deconv, need_p, need_w, kb_kcut=kb, lattice=lattice)
+        return pb, wb, None, None, None, None, None, None, None, None
 
 
 class _PmForcesPaint(torch.autograd.Function):
@@ -339,31 +340,31 @@ class _NbodySteps(torch.autograd.Function):
     """BullFrog DKD loop (nbody.py:933-951, 999) with per-step coefficients [n_steps, 4] (float64, host)."""
 
     @staticmethod
-    def forward(ctx, pos, vel, coefs, shape, order, paint_deconv, lap_fd, grad_fd):
+    def forward(ctx, pos, vel, coefs, shape, order, paint_deconv, lap_fd, grad_fd, lattice=None):
         co = coefs.detach().cpu().to(torch.float64).numpy()
         al, be, pre, post = (co[:, i].tolist() for i in range(4))
         want_coef = coefs.requires_grad
         pos, vel0 = pos.clone(), vel.contiguous()
         vel = vel0.clone()
         tape = ops().nbody_steps(pos, vel, shape, al, be, pre, post, order, paint_deconv, lap_fd, grad_fd, tape=True,
-                                 tape_vel=want_coef)
-        ctx.cfg = (al, be, pre, post, shape, order, paint_deconv, lap_fd, grad_fd, want_coef)
+                                 tape_vel=want_coef, lattice=lattice)
+        ctx.cfg = (al, be, pre, post, shape, order, paint_deconv, lap_fd, grad_fd, want_coef, lattice)
         ctx.tape, ctx.v0 = tape, (vel0 if want_coef else None)
         ctx.coef_meta = (coefs.device, coefs.dtype)
         return pos, vel
 
     @staticmethod
     def backward(ctx, pb, vb):
-        al, be, pre, post, shape, order, paint_deconv, lap_fd, grad_fd, want_coef = ctx.cfg
+        al, be, pre, post, shape, order, paint_deconv, lap_fd, grad_fd, want_coef, lattice = ctx.cfg
         xk = ctx.tape[0]
         pb = torch.zeros_like(xk[0]) if pb is None else pb.clone().contiguous()
         vb = torch.zeros_like(xk[0]) if vb is None else vb.clone().contiguous()
         cb = ops().nbody_steps_vjp(pb, vb, shape, al, be, pre, post, ctx.tape, order, paint_deconv, lap_fd, grad_fd,
-                                   v0=ctx.v0, want_coef=want_coef)
+                                   v0=ctx.v0, want_coef=want_coef, lattice=lattice)
         if cb is not None:
             cb = cb.to(device=ctx.coef_meta[0], dtype=ctx.coef_meta[1])
         ctx.tape = ctx.v0 = None
-        return pb, vb, cb, None, None, None, None, None
+        return pb, vb, cb, None, None, None, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -425,8 +426,12 @@ def interlace(pos, shape: tuple, weights=1.0, paint_order: int = 2, interlace_or
 
 
 def nufft(pos, final_shape: tuple, paint_shape=None, weights=1.0, paint_order: int = 2, interlace_order: int = 2,
-          kernel_type="rectangular", paint_deconv=True):
-    """Non-uniform FFT with oversampling, deconvolution and interlacing (nbody.py:532-577)."""
+          kernel_type="rectangular", paint_deconv=True, lattice=None):
+    """Non-uniform FFT with oversampling, deconvolution and interlacing (nbody.py:532-577).
+
+    `lattice` (extension): `pos` holds displacements (in final_shape cells) from the sites of the regular lattice of that
+    shape spanning the mesh (regular_pos, bricks.py:593-603) instead of absolute positions -- what
+    nbody_bf(..., relative=True) returns; float32 then resolves the CIC fraction to ~1e-7 cell at any mesh size."""
     final_shape = tuple(int(s) for s in final_shape)
     if paint_shape is None:
         paint_shape, paint_oversamp = final_shape, 1.0
@@ -442,7 +447,7 @@ def nufft(pos, final_shape: tuple, paint_shape=None, weights=1.0, paint_order: i
     scale = tuple(float(p) / float(f) for p, f in zip(paint_shape, final_shape))
     w, ws = _split_weights(weights)
     mesh = _NufftPaint.apply(_f32(pos), w, paint_shape, ws, scale, int(paint_order), int(interlace_order),
-                             bool(paint_deconv), kb)
+                             bool(paint_deconv), kb, None if lattice is None else tuple(int(s) for s in lattice))
     if final_shape != paint_shape:
         mesh = chreshape(mesh, r2chshape(final_shape))
     return mesh
@@ -521,7 +526,7 @@ def _save_plan(ts, g0, dg, n_steps):
 
 def nbody_bf(cosmo, init_mesh, pos, a0=0.0, a1=1.0, n_steps=5, paint_order: int = 2, lpt_order: int = 2,
              paint_deconv=False, grad_fd=np.inf, lap_fd=np.inf, snapshots=None, fn=save_y, ptcl_shape="auto",
-             integrator="bullfrog"):
+             integrator="bullfrog", relative=None):
     """N-body simulation with the BullFrog solver (nbody.py:967-1002): lpt at a0, then n_steps DKD steps in growth time.
 
     Returns (pos, vel), each [S, Np, 3].  `snapshots` as in the reference: None or an int <= 1 saves the final state
@@ -535,16 +540,32 @@ def nbody_bf(cosmo, init_mesh, pos, a0=0.0, a1=1.0, n_steps=5, paint_order: int 
 
     `ptcl_shape` (extension) is a performance hint only: the lattice shape of `pos` (regular_pos order).  "auto" assumes
     the mesh shape when the particle count matches it; None disables the brick-tiled kernels.
+
+    `relative` (extension): `pos` must be regular_pos(mesh_shape, ptcl_shape); the loop then carries DISPLACEMENTS from
+    those lattice sites instead of absolute positions.  The reference carries the float64 sum q + dpos
+    (nbody.py:984-985); a float32 sum resolves only 1.5e-5 cell at x ~ 256, which is what limited grad(log-density)
+    parity in round 1 -- see mcpm_engine_set_relative in include/mcpm.h.  True: the call also RETURNS displacements
+    (add `pos` to get positions; what FieldModel hands on to nufft(..., lattice=...)).  None (default): displacements
+    inside the loop whenever the caller declares the lattice (`ptcl_shape` given as a tuple), positions returned as the
+    reference does; with ptcl_shape="auto" nothing is assumed about `pos` and the loop carries absolute positions.
+    False: absolute positions throughout (round 1's arithmetic).
     """
     fn = save_y if fn is None else fn
     n_steps = int(n_steps)
     init_mesh = _c64(init_mesh)
     pos = _f32(pos)
     mesh_shape = ch2rshape(tuple(init_mesh.shape))
+    declared = ptcl_shape != "auto" and ptcl_shape is not None
     if ptcl_shape == "auto":
         ptcl_shape = mesh_shape if pos.shape[0] == int(np.prod(mesh_shape)) else None
     ops().set_lattice(mesh_shape, ptcl_shape)
-    x, vel = lpt(cosmo, init_mesh, pos, a0, lpt_order, 1, grad_fd, lap_fd, _displaced=True)
+    if relative and ptcl_shape is None:
+        raise ValueError("relative=True needs the particle lattice (ptcl_shape)")
+    inner_rel = bool(relative) or (relative is None and declared)
+    lattice = tuple(int(s) for s in ptcl_shape) if inner_rel else None
+    if lattice is not None and int(np.prod(lattice)) != pos.shape[0]:
+        raise ValueError("ptcl_shape does not match the number of particles")
+    x, vel = lpt(cosmo, init_mesh, pos, a0, lpt_order, 1, grad_fd, lap_fd, _displaced=not inner_rel)
     al, be, pre, post, _, _ = _cosmo.bullfrog_coefficients(cosmo, a0, a1, n_steps, integrator)
     coefs = torch.stack([al, be, pre, post], dim=1)
     g0, g1 = _cosmo.a2g(cosmo, a0), _cosmo.a2g(cosmo, a1)
@@ -564,9 +585,11 @@ def nbody_bf(cosmo, init_mesh, pos, a0=0.0, a1=1.0, n_steps=5, paint_order: int 
     for b in sorted(need):
         if b > s:
             x, vel = _NbodySteps.apply(x, vel, coefs[s:b], mesh_shape, int(paint_order), bool(paint_deconv), lap_fd,
-                                       grad_fd)
+                                       grad_fd, lattice)
             s = b
             states[b] = (x, vel)
+    if inner_rel and not relative:  # back to absolute positions at the boundary, as the reference returns them
+        states = {b: (xs + pos, vs) for b, (xs, vs) in states.items()}
     outs = []
     for k, (i, th) in enumerate(plan):
         if isinstance(th, float):

@@ -93,7 +93,21 @@ class Ops:
     def set_lattice(self, mesh_shape, ptcl_shape):
         """Performance hint for the engine of `mesh_shape` (mcpm_engine_set_lattice); ptcl_shape None clears it."""
         p = (0, 0, 0) if ptcl_shape is None else tuple(int(s) for s in ptcl_shape)
-        self._call("mcpm_engine_set_lattice", self.engine(mesh_shape).handle, *p)
+        eng = self._frame(mesh_shape, None)
+        self._call("mcpm_engine_set_lattice", eng.handle, *p)
+
+    def _frame(self, shape, lattice):
+        """Select what the `pos` arrays of the next composite call on the engine of `shape` mean: absolute positions
+        (lattice None) or displacements from the sites of the regular lattice `lattice` (mcpm_engine_set_relative)."""
+        eng = self.engine(shape)
+        want = None if lattice is None else tuple(int(s) for s in lattice)
+        if getattr(eng, "rel_state", None) == want:
+            return eng
+        if want is not None:
+            self._call("mcpm_engine_set_lattice", eng.handle, *want)
+        self._call("mcpm_engine_set_relative", eng.handle, int(want is not None))
+        eng.rel_state = want
+        return eng
 
     def set_fused_fft(self, mesh_shape, on):
         """Select the fused x-transform path (mcpm_engine_set_fused_fft); raises McpmError where unsupported."""
@@ -294,23 +308,25 @@ class Ops:
         return out
 
     # ------------------------------------------------------------------------------------------------ composites
-    def pm_forces(self, pos, shape, order=2, paint_deconv=False, lap_fd=INF, grad_fd=INF, kcut=INF, want_meshes=False):
+    def pm_forces(self, pos, shape, order=2, paint_deconv=False, lap_fd=INF, grad_fd=INF, kcut=INF, want_meshes=False,
+                  lattice=None):
         A = self.A
         pos = A.prepare(pos)
         n = A.shape(pos)[0]
         forces = A.empty((n, 3))
         fm = A.empty((3, *shape)) if want_meshes else None
-        self._call("mcpm_pm_forces", self.engine(shape).handle, A.stream(), A.ptr(pos), n, order, int(paint_deconv),
+        self._call("mcpm_pm_forces", self._frame(shape, lattice).handle, A.stream(), A.ptr(pos), n, order, int(paint_deconv),
                    fd_code(lap_fd), fd_code(grad_fd), 0.0 if kcut == INF else kcut, A.ptr(fm), A.ptr(forces))
         return (forces, fm) if want_meshes else forces
 
-    def pm_forces_vjp(self, pos, fbar, fmesh3, order=2, paint_deconv=False, lap_fd=INF, grad_fd=INF, kcut=INF):
+    def pm_forces_vjp(self, pos, fbar, fmesh3, order=2, paint_deconv=False, lap_fd=INF, grad_fd=INF, kcut=INF,
+                      lattice=None):
         A = self.A
         pos, fbar, fmesh3 = A.prepare(pos), A.prepare(fbar), A.prepare(fmesh3)
         n = A.shape(pos)[0]
         shape = A.shape(fmesh3)[1:]
         out = A.empty((n, 3))
-        self._call("mcpm_pm_forces_vjp", self.engine(shape).handle, A.stream(), A.ptr(pos), A.ptr(fbar),
+        self._call("mcpm_pm_forces_vjp", self._frame(shape, lattice).handle, A.stream(), A.ptr(pos), A.ptr(fbar),
                    A.ptr(fmesh3), n, order, int(paint_deconv), fd_code(lap_fd), fd_code(grad_fd),
                    0.0 if kcut == INF else kcut, A.ptr(out), 0)
         return out
@@ -320,7 +336,7 @@ class Ops:
         pos, dk = A.prepare(pos), A.prepare(dk, "c64")
         n = A.shape(pos)[0]
         out = A.empty((n, 3))
-        self._call("mcpm_pm_forces_mesh", self.engine(ch2rshape(A.shape(dk))).handle, A.stream(), A.ptr(pos),
+        self._call("mcpm_pm_forces_mesh", self._frame(ch2rshape(A.shape(dk)), None).handle, A.stream(), A.ptr(pos),
                    A.ptr(dk), n, order, fd_code(lap_fd), fd_code(grad_fd), 0.0 if kcut == INF else kcut, A.ptr(out))
         return out
 
@@ -329,7 +345,7 @@ class Ops:
         pos, dk = A.prepare(pos), A.prepare(dk, "c64")
         n = A.shape(pos)[0]
         out = A.empty((n, 3))
-        self._call("mcpm_pm_forces2", self.engine(ch2rshape(A.shape(dk))).handle, A.stream(), A.ptr(pos), A.ptr(dk),
+        self._call("mcpm_pm_forces2", self._frame(ch2rshape(A.shape(dk)), None).handle, A.stream(), A.ptr(pos), A.ptr(dk),
                    n, order, fd_code(lap_fd), fd_code(grad_fd), A.ptr(out), 0)
         return out
 
@@ -342,7 +358,7 @@ class Ops:
         f1 = A.empty((n, 3)) if tape else None
         f2 = A.empty((n, 3)) if tape and lpt_order == 2 else None
         h6 = A.empty((6, *rs)) if tape and lpt_order == 2 else None
-        self._call("mcpm_lpt", self.engine(rs).handle, A.stream(), A.ptr(dk), A.ptr(pos), n, lpt_order, read_order,
+        self._call("mcpm_lpt", self._frame(rs, None).handle, A.stream(), A.ptr(dk), A.ptr(pos), n, lpt_order, read_order,
                    fd_code(lap_fd), fd_code(grad_fd), d1, d2, dv2, A.ptr(dpos), A.ptr(vel), A.ptr(f1), A.ptr(f2),
                    A.ptr(h6))
         return (dpos, vel, (f1, f2, h6)) if tape else (dpos, vel)
@@ -356,53 +372,55 @@ class Ops:
         rs = ch2rshape(cshape)
         dkbar = A.empty(cshape, "c64")
         coef = A.zeros((3,), "f64") if want_coef else None
-        self._call("mcpm_lpt_vjp", self.engine(rs).handle, A.stream(), A.ptr(pos), n, lpt_order, read_order,
+        self._call("mcpm_lpt_vjp", self._frame(rs, None).handle, A.stream(), A.ptr(pos), n, lpt_order, read_order,
                    fd_code(lap_fd), fd_code(grad_fd), d1, d2, dv2, A.ptr(dposbar), A.ptr(velbar), A.ptr(f1),
                    A.ptr(f2), A.ptr(h6), A.ptr(dkbar), A.ptr(coef), 0)
         return (dkbar, coef) if want_coef else dkbar
 
     def nbody_steps(self, pos, vel, shape, alpha, beta, drift_pre, drift_post, order=2, paint_deconv=False,
-                    lap_fd=INF, grad_fd=INF, tape=False, tape_vel=False):
-        """In place on (pos, vel) -- pass fresh copies.  Returns the tape (xk, vk, fm) when asked."""
+                    lap_fd=INF, grad_fd=INF, tape=False, tape_vel=False, lattice=None):
+        """In place on (pos, vel) -- pass fresh copies.  Returns the tape (xk, vk, fm) when asked.  `lattice`: pos (and
+        the xk tape) hold displacements from the sites of that regular lattice (mcpm_engine_set_relative)."""
         A = self.A
         n = A.shape(pos)[0]
         ns = len(alpha)
         xk = A.empty((ns, n, 3)) if tape else None
         vk = A.empty((ns, n, 3)) if tape and tape_vel else None
         fm = A.empty((ns, 4, *shape)) if tape else None
-        self._call("mcpm_nbody_steps", self.engine(shape).handle, A.stream(), A.ptr(pos), A.ptr(vel), n, ns,
+        self._call("mcpm_nbody_steps", self._frame(shape, lattice).handle, A.stream(), A.ptr(pos), A.ptr(vel), n, ns,
                    host_floats(alpha), host_floats(beta), host_floats(drift_pre), host_floats(drift_post), order,
                    int(paint_deconv), fd_code(lap_fd), fd_code(grad_fd), A.ptr(xk), A.ptr(vk), A.ptr(fm))
         return (xk, vk, fm)
 
     def nbody_steps_vjp(self, posbar, velbar, shape, alpha, beta, drift_pre, drift_post, tape, order=2,
-                        paint_deconv=False, lap_fd=INF, grad_fd=INF, v0=None, want_coef=False):
+                        paint_deconv=False, lap_fd=INF, grad_fd=INF, v0=None, want_coef=False, lattice=None):
         """In place on (posbar, velbar)."""
         A = self.A
         xk, vk, fm = tape
         n = A.shape(posbar)[0]
         ns = len(alpha)
         coef = A.zeros((ns, 4), "f64") if want_coef else None
-        self._call("mcpm_nbody_steps_vjp", self.engine(shape).handle, A.stream(), A.ptr(posbar), A.ptr(velbar), n, ns,
+        self._call("mcpm_nbody_steps_vjp", self._frame(shape, lattice).handle, A.stream(), A.ptr(posbar), A.ptr(velbar), n, ns,
                    host_floats(alpha), host_floats(beta), host_floats(drift_pre), host_floats(drift_post), order,
                    int(paint_deconv), fd_code(lap_fd), fd_code(grad_fd), A.ptr(xk), A.ptr(vk), A.ptr(fm), A.ptr(v0),
                    A.ptr(coef))
         return coef
 
     def nufft_paint(self, pos, paint_shape, weights=None, wscalar=1.0, scale=None, paint_order=2, interlace_order=2,
-                    paint_deconv=True, kb_kcut=0.0):
+                    paint_deconv=True, kb_kcut=0.0, lattice=None):
         A = self.A
         pos = A.prepare(pos)
         weights = None if weights is None else A.prepare(weights)
         out = A.empty(r2chshape(paint_shape), "c64")
         sc, _ = self._xf(scale, 0.0)
         fn, oa = self._win("mcpm_nufft", paint_order, kb_kcut)
-        self._call(fn, self.engine(paint_shape).handle, A.stream(), A.ptr(pos), A.ptr(weights), wscalar,
+        self._call(fn, self._frame(paint_shape, lattice).handle, A.stream(), A.ptr(pos), A.ptr(weights), wscalar,
                    A.shape(pos)[0], sc, *oa, interlace_order, int(paint_deconv), A.ptr(out))
         return out
 
     def nufft_paint_vjp(self, pos, outbar, paint_shape, weights=None, wscalar=1.0, scale=None, paint_order=2,
-                        interlace_order=2, paint_deconv=True, want_pos=True, want_weights=True, kb_kcut=0.0):
+                        interlace_order=2, paint_deconv=True, want_pos=True, want_weights=True, kb_kcut=0.0,
+                        lattice=None):
         A = self.A
         pos, outbar = A.prepare(pos), A.prepare(outbar, "c64")
         weights = None if weights is None else A.prepare(weights)
@@ -411,7 +429,7 @@ class Ops:
         wb = A.empty((n,)) if want_weights else None
         sc, _ = self._xf(scale, 0.0)
         fn, oa = self._win("mcpm_nufft_vjp", paint_order, kb_kcut)
-        self._call(fn, self.engine(paint_shape).handle, A.stream(), A.ptr(pos), A.ptr(weights), wscalar,
+        self._call(fn, self._frame(paint_shape, lattice).handle, A.stream(), A.ptr(pos), A.ptr(weights), wscalar,
                    n, sc, *oa, interlace_order, int(paint_deconv), A.ptr(outbar), A.ptr(pb), A.ptr(wb))
         return pb, wb
 

@@ -14,7 +14,9 @@ from . import pm_oracle as O
 
 def evolve(white, transfer, cosmo, mesh_shape, evolution="nbody", n_steps=5, a_start=0.0, a_obs=1.0, lpt_order=2,
            paint_order=2, interlace_order=2, paint_deconv=True, paint_shape=None, b1=1.0, rsd=True,
-           los=(0.0, 0.0, 1.0), precond="real"):
+           los=(0.0, 0.0, 1.0), precond="real", checkpoint=False, state_out=None):
+    """`checkpoint`: recompute the BullFrog steps in the backward pass (memory only).  `state_out`: a dict that receives
+    the particle state ahead of the paint (q, pos, vel, weights), for the full-size fixtures."""
     mesh_shape = tuple(mesh_shape)
     paint_shape = mesh_shape if paint_shape is None else tuple(paint_shape)
     # samp2base_mesh, bricks.py:300-309: sample in real space (rfftn) or in Fourier space (rg2cgh)
@@ -28,8 +30,12 @@ def evolve(white, transfer, cosmo, mesh_shape, evolution="nbody", n_steps=5, a_s
         dpos, vel = O.lpt(cosmo, dk, q, a_obs, lpt_order, 1)
         pos = q + dpos
     else:
-        pos, vel = O.nbody_bf(cosmo, dk, q, a_start, a_obs, n_steps, paint_order, lpt_order, paint_deconv=False)
+        pos, vel = O.nbody_bf(cosmo, dk, q, a_start, a_obs, n_steps, paint_order, lpt_order, paint_deconv=False,
+                              checkpoint=checkpoint)
         pos, vel = pos[-1], vel[-1]
+    if state_out is not None:
+        state_out.update(q=q, pos=pos.detach(), vel=vel.detach(),
+                         weights=weights.detach() if isinstance(weights, torch.Tensor) else weights)
     if rsd:
         l = O._t(np.asarray(los))
         pos = pos + (vel * l).sum(-1, keepdim=True) * (O.a2g(cosmo, a_obs) * O.a2f(cosmo, a_obs)) * l

@@ -184,9 +184,69 @@ def _assignment(pos, shape, order, kernel_type, oversamp):
         yield torch.remainder(idx, shape_t), ker  # python-style modulo
 
 
+# Memory-lean twins of paint / read for the full-size fixtures (tests/golden/make_full_size_fixture.py): identical
+# forward arithmetic, but the autograd graph of the order^3 neighbour loop is not kept -- the backward pass rebuilds it one
+# neighbour at a time (torch.autograd on that neighbour's window alone), so a 256^3 gradient fits in RAM.  Switched on
+# with LEAN_ASSIGNMENT = True; tests/test_oracle_golden.py checks both forms give the same gradients.
+LEAN_ASSIGNMENT = False
+
+
+class _LeanPaint(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, weights, shape, order, kernel_type, oversamp):
+        ctx.save_for_backward(pos, weights)
+        ctx.cfg = (shape, order, kernel_type, oversamp)
+        mesh = torch.zeros(shape, dtype=pos.dtype)
+        for idx, ker in _assignment(pos, shape, order, kernel_type, oversamp):
+            mesh.index_put_(tuple(idx.unbind(-1)), (weights * ker).expand(pos.shape[0]), accumulate=True)
+        return mesh
+
+    @staticmethod
+    def backward(ctx, gmesh):
+        pos, weights = ctx.saved_tensors
+        shape, order, kernel_type, oversamp = ctx.cfg
+        gpos, gw = torch.zeros_like(pos), torch.zeros(pos.shape[0], dtype=pos.dtype)
+        with torch.enable_grad():
+            p = pos.detach().requires_grad_(True)
+            for idx, ker in _assignment(p, shape, order, kernel_type, oversamp):
+                gm = gmesh[tuple(idx.unbind(-1))]
+                gw += gm * ker.detach()
+                if ker.requires_grad:  # NGP's window is constant
+                    gpos += torch.autograd.grad(ker, p, gm * weights)[0]
+        gw = gw.sum() if weights.dim() == 0 else gw
+        return gpos, gw, None, None, None, None
+
+
+class _LeanRead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, mesh, order, kernel_type, oversamp):
+        ctx.save_for_backward(pos, mesh)
+        ctx.cfg = (order, kernel_type, oversamp)
+        out = torch.zeros(pos.shape[0], dtype=mesh.dtype)
+        for idx, ker in _assignment(pos, mesh.shape, order, kernel_type, oversamp):
+            out += mesh[tuple(idx.unbind(-1))] * ker
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        pos, mesh = ctx.saved_tensors
+        order, kernel_type, oversamp = ctx.cfg
+        gpos, gmesh = torch.zeros_like(pos), torch.zeros_like(mesh)
+        with torch.enable_grad():
+            p = pos.detach().requires_grad_(True)
+            for idx, ker in _assignment(p, mesh.shape, order, kernel_type, oversamp):
+                ii = tuple(idx.unbind(-1))
+                gmesh.index_put_(ii, gout * ker.detach(), accumulate=True)
+                if ker.requires_grad:
+                    gpos += torch.autograd.grad(ker, p, gout * mesh[ii])[0]
+        return gpos, gmesh, None, None, None
+
+
 def paint(pos, shape, weights=1.0, order=2, kernel_type="rectangular", oversamp=1.0):
     """nbody.py:365-396: scatter-add of weights * prod_j W over order^3 neighbours."""
     pos = _t(pos)
+    if LEAN_ASSIGNMENT:
+        return _LeanPaint.apply(pos, _t(weights, pos.dtype), tuple(int(s) for s in shape), order, kernel_type, oversamp)
     mesh = torch.zeros(tuple(int(s) for s in shape), dtype=pos.dtype)
     weights = _t(weights, pos.dtype)
     for idx, ker in _assignment(pos, shape, order, kernel_type, oversamp):
@@ -199,6 +259,8 @@ def read(pos, mesh, order=2, kernel_type="rectangular", oversamp=1.0):
     """nbody.py:398-427: gather transpose of paint."""
     pos = _t(pos)
     mesh = _t(mesh, pos.dtype)
+    if LEAN_ASSIGNMENT:
+        return _LeanRead.apply(pos, mesh, order, kernel_type, oversamp)
     out = torch.zeros(pos.shape[0], dtype=mesh.dtype)
     for idx, ker in _assignment(pos, mesh.shape, order, kernel_type, oversamp):
         out = out + mesh[tuple(idx.unbind(-1))] * ker
@@ -729,8 +791,10 @@ def bullfrog_step(cosmo, state, g0, dg, mesh_shape, paint_order=2, paint_deconv=
 
 
 def nbody_bf(cosmo, init_mesh, pos, a0=0.0, a1=1.0, n_steps=5, paint_order=2, lpt_order=2, paint_deconv=False,
-             grad_fd=np.inf, lap_fd=np.inf, snapshots=None, fn=None):
+             grad_fd=np.inf, lap_fd=np.inf, snapshots=None, fn=None, checkpoint=False):
     """nbody.py:967-1002 with diffrax 0.5.0's Euler restated: y <- y + ((new - y) / dg) * dt, last dt clipped onto g1.
+    `checkpoint` (oracle-only): recompute every step in the backward pass instead of keeping its autograd graph, the
+    memory policy diffrax's default adjoint applies in the reference (nbody.py:999) -- same numbers, 256^3 fits in RAM.
 
     Returns (pos, vel), each [S, Np, 3]; S = 1 (final state) unless `snapshots` asks for more (nbody.py:987-996): an int
     S > 1 saves at linspace(g0, g1, S), a sequence of scale factors at a2g(cosmo, .).  diffrax fills `SaveAt(ts=...)`
@@ -750,7 +814,12 @@ def nbody_bf(cosmo, init_mesh, pos, a0=0.0, a1=1.0, n_steps=5, paint_order=2, lp
     for n in range(n_steps):
         tn = g1 if n == n_steps - 1 else t + dg
         dt = tn - t
-        new = bullfrog_step(cosmo, state, t, dg, mesh_shape, paint_order, paint_deconv, grad_fd, lap_fd)
+        if checkpoint and torch.is_grad_enabled():
+            from torch.utils.checkpoint import checkpoint as _ckpt
+            new = _ckpt(lambda p_, v_, t_=t: bullfrog_step(cosmo, (p_, v_), t_, dg, mesh_shape, paint_order, paint_deconv,
+                                                           grad_fd, lap_fd), *state, use_reentrant=False)
+        else:
+            new = bullfrog_step(cosmo, state, t, dg, mesh_shape, paint_order, paint_deconv, grad_fd, lap_fd)
         state = tuple(y + ((nw - y) / dg) * dt for y, nw in zip(state, new))
         t = tn
         traj.append(state)

@@ -172,8 +172,18 @@ def test_nbody_bf_matches_golden_and_oracle_grad(nb, golden):
     po, vo = O.nbody_bf(O.Cosmology(), dko, O.regular_pos(shape), 0.0, 1.0, 4)
     ((po[0] * cp.double()).sum() + (vo[0] * cv.double()).sum()).backward()
     # a0 = 0 -> a = 1 in 4 steps is strongly non-linear at this amplitude: CIC derivatives are discontinuous at cell
-    # faces, so float32 rounding of positions moves a few particles across them; 5e-3 here, 1e-3 at model level below
+    # faces, so float32 rounding of ABSOLUTE positions moves a few particles across them (5e-3; measured 1.9e-3) ...
     assert rel(dk.grad, dko.grad) < 5e-3
+    # ... which is why the loop carries displacements from the lattice sites once the caller declares the lattice
+    # (ptcl_shape; mcpm_engine_set_relative): same API, same returned positions, measured 5.8e-7
+    dk2 = leaf(dk)
+    pos2, vel2 = nb.nbody_bf(Cosmology(), dk2, q, 0.0, 1.0, 4, ptcl_shape=shape)
+    assert np.abs(pos2[0].detach().cpu().numpy() - g["bf4_pos"][0]).max() < 2e-4
+    ((pos2[0] * cp.to(dev(nb))).sum() + (vel2[0] * cv.to(dev(nb))).sum()).backward()
+    assert rel(dk2.grad, dko.grad) < 1e-4
+    # relative=True returns the displacements themselves
+    d3, v3 = nb.nbody_bf(Cosmology(), dk.detach(), q, 0.0, 1.0, 4, ptcl_shape=shape, relative=True)
+    assert np.abs((d3[0] + q).cpu().numpy() - g["bf4_pos"][0]).max() < 2e-4 and rel(v3[0], g["bf4_vel"][0]) < 2e-4
 
 
 def test_cosmology_gradient_through_engine(nb):
@@ -716,10 +726,10 @@ def test_catalogue_registration_golden(nb, golden):
 def test_baseline_config_c1_full_size(nb):
     """BASELINE.json configs[0] at its full size -- 64^3 mesh / 64^3 particles, 640 Mpc/h box, 2LPT + 5 BullFrog steps
     to a = 1, linear bias + flat-sky RSD, interlaced deconvolved paint, Gaussian likelihood -- against the float64 oracle:
-    log-density 1e-5, grad(log-density) cosine >= 0.9999 and relative L2 <= 3e-3.  SURVEY 8c proposed 1e-3 for the
-    latter; at this size and depth (a = 1, 10 Mpc/h cells) float32 positions put a few particles on the other side of
-    a cell face, where the CIC derivative jumps, and the measured value scatters with the white-noise seed: 7.0e-4
-    (this seed), 9.1e-4, 1.2e-3, 1.6e-3 on the CPU port; the log-density agrees to 2.8e-7, the cosine to 1 - 2.5e-7."""
+    log-density 1e-5, grad(log-density) cosine >= 0.9999 and relative L2 <= 1e-3.  Round 1 needed 3e-3 here:
+    absolute float32 positions put particles on the other side of a cell face, where the CIC derivative jumps (9.6e-4,
+    1.3e-3, 8.2e-4, 1.3e-3 for white-noise seeds 0-3 on the CPU port).  FieldModel now carries displacements from the
+    lattice sites (mcpm_engine_set_relative): 2.9e-5, 2.2e-5, 5.5e-5, 2.8e-4 for the same seeds."""
     from montecosmo_b200.model import FieldModel
     rng = np.random.default_rng(0)
     shape = (64, 64, 64)
@@ -735,5 +745,5 @@ def test_baseline_config_c1_full_size(nb):
                                  sigma_obs=1.0, **kw)
     assert abs(float(lp) - float(lpo)) < 1e-5 * abs(float(lpo))
     gn, gon = g.detach().cpu().numpy().ravel().astype(np.float64), go.numpy().ravel()
-    assert np.linalg.norm(gn - gon) <= 3e-3 * np.linalg.norm(gon)
+    assert np.linalg.norm(gn - gon) <= 1e-3 * np.linalg.norm(gon)
     assert gn @ gon / np.linalg.norm(gn) / np.linalg.norm(gon) >= 0.9999

@@ -70,18 +70,17 @@ def _worker(rank, world, port, shape, halo, q):
         al, be, pre, post, _, _ = bullfrog_coefficients(c, a0, a1, ns)
         co = [t.tolist() for t in (al, be, pre, post)]
         dp, vl, ltape = ops.lpt(dk, qfull, d1, d2, dv2, 2, 1, tape=True)
-        pfull, vfull = (dp + torch.tensor(qfull)).contiguous(), vl.clone()
-        stape = ops.nbody_steps(pfull, vfull, shape, *co, tape=True)
+        # both engines carry displacements from the lattice sites (mcpm_engine_set_relative / mcpm_frame)
+        pfull, vfull = dp.clone().contiguous(), vl.clone()
+        stape = ops.nbody_steps(pfull, vfull, shape, *co, tape=True, lattice=shape)
         sl = slice(rank * pm.npl, (rank + 1) * pm.npl)  # lattice order is x-major: a slab is a contiguous range
-        mypos = pos.numpy().copy()
-        mypos[:, 0] += pm.x0 - pm.H
-        res["pos"] = float(np.abs(mypos - pfull.numpy()[sl]).max())
+        res["pos"] = float(np.abs(pos.numpy() - pfull.numpy()[sl]).max())
         res["vel"] = rel(vel.numpy(), vfull.numpy()[sl])
-        res["disp_rms"] = float((pfull.numpy() - qfull).std())
+        res["disp_rms"] = float(pfull.numpy().std())
         pb = rng.normal(size=qfull.shape).astype(np.float32)
         vb = rng.normal(size=qfull.shape).astype(np.float32)
         pbf, vbf = torch.tensor(pb.copy()), torch.tensor(vb.copy())
-        ops.nbody_steps_vjp(pbf, vbf, shape, *co, stape)
+        ops.nbody_steps_vjp(pbf, vbf, shape, *co, stape, lattice=shape)
         ref = ops.lpt_vjp(qfull, dk.shape, d1, d2, dv2, pbf, vbf, ltape, 2, 1)
         # the two halves of the reverse sweep separately, then together
         pl, vl_ = torch.tensor(pb[sl].copy()), torch.tensor(vb[sl].copy())
@@ -234,11 +233,11 @@ def test_slab_field_model_single_rank(backend, oversamp):
         lp, f = mdl.value_and_force(white, obs)
         rel = lambda a, b: float((a - b).norm() / b.norm())
         assert abs(float(lp) - float(lp_ref)) < 1e-5 * abs(float(lp_ref))
-        # float32 on both sides, different kernels for the same operators (brick / fused paths vs the slab sequence) and
-        # particle x kept in two different frames (global vs halo-shifted): each side is within the 1e-3 the model
-        # gradient is held to against the float64 oracle, so 2e-3 between them.  Measured: 2e-6 on the CPU
-        # port (same kernels both sides), 8.1e-4 on a B200 at 64^3 (gpurun_out/r1w_pytest_gpu.log).
-        assert rel(f, f_ref) < 2e-3
+        # float32 on both sides, different kernels for the same operators (brick / fused paths vs the slab sequence).
+        # Round 1 held this to 2e-3 (8.1e-4 measured on a B200): particle x was an absolute float32 coordinate kept in
+        # two different frames (global vs halo-shifted).  Both engines now carry displacements from the lattice sites
+        # (mcpm_engine_set_relative / mcpm_frame), the frame no longer enters the rounding, and the bound is back to 5e-4.
+        assert rel(f, f_ref) < 5e-4
         assert rel(mdl.predict(truth), ref.evolve(truth).detach()) < 5e-4
     finally:
         nbody._OPS = old

@@ -1,0 +1,124 @@
+"""
+The benchmarked configurations against the float64 oracle AT THEIR FULL SIZE (VERDICT r1 "what's missing" #2).
+
+Fixtures `tests/golden/c2_128.npz` (BASELINE configs[1]: 128^3) and `c3_256.npz` (configs[2]: 256^3, the configuration
+bench.py's metric is quoted on) hold the oracle's forward results and its autograd gradient on the bench workload
+(generator: tests/golden/make_full_size_fixture.py; inputs regenerated here from the same seeds).  The engine's
+`FieldModel` is compared with the tolerances SURVEY.md 8c states for a float32 engine against the float64 reference:
+
+    log-density                        relative 1e-5
+    density field (32^3 block, and every cell through the 32^3 block average)      relative L2 1e-4
+    displacement after 10 steps        rms <= 1e-3 cell
+    power spectrum, reference binning  ratio within 1 +- 1e-4 below k_Nyq / 2, 1 +- 1e-3 up to k_Nyq
+    grad(log-density)                  relative L2 <= 1e-3 and cosine >= 0.9999 (on the stored strided subsample
+                                       [::4, ::4, ::4], the [0:32]^3 block, the norm and three directional derivatives)
+
+128^3 also runs on the CPU port (the same kernel sources as OpenMP loops) so that the check exists without a GPU; 256^3
+needs the B200.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import make_full_size_fixture as FX  # noqa: E402
+
+
+@pytest.fixture(scope="module", params=["hostemu", pytest.param("cuda", marks=pytest.mark.gpu)])
+def nb(request):
+    import montecosmo_b200.nbody as nbody
+    from montecosmo_b200.ops import Ops
+    old = nbody._OPS
+    if request.param == "hostemu":
+        from tests import hostemu
+        from tests.backends import torch_cpu_adapter
+        nbody._OPS = Ops(hostemu.load(), torch_cpu_adapter())
+    else:
+        nbody._OPS = None
+        nbody.ops()
+    nbody._backend = request.param
+    yield nbody
+    nbody._OPS = old
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64).ravel(), np.asarray(b, dtype=np.float64).ravel()
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def _cos(a, b):
+    a, b = np.asarray(a, dtype=np.float64).ravel(), np.asarray(b, dtype=np.float64).ravel()
+    return float(a @ b / np.linalg.norm(a) / np.linalg.norm(b))
+
+
+def check_against_fixture(nb, fx, report=None):
+    from montecosmo_b200 import metrics as M
+    from montecosmo_b200.model import FieldModel
+    n = int(fx["n"])
+    shape, white, obs = FX.inputs(n, int(fx["seed"]))
+    assert abs(white.sum() - float(fx["white_sum"])) < 1e-6 and abs(obs.sum() - float(fx["obs_sum"])) < 1e-6
+    box = (float(fx["box"]),) * 3
+    m = FieldModel(shape, box, evolution="nbody", n_steps=int(fx["n_steps"]), a_start=0.0, a_obs=1.0, b1=1.0,
+                   sigma_obs=1.0)
+    dev = nb.ops().A.device
+    w = torch.tensor(white, dtype=torch.float32, device=dev)
+    o = torch.tensor(obs, dtype=torch.float32, device=dev)
+    out = {}
+    # forward pieces: displacement / velocity ahead of RSD, the painted mesh, its spectrum
+    with torch.no_grad():
+        dk = m.linear_field(w)
+        disp, vel = nb.nbody_bf(m.cosmology, dk, m.q, m.a_start, m.a_obs, m.n_steps, m.paint_order, m.lpt_order,
+                                paint_deconv=False, ptcl_shape=shape, relative=True)
+        stride = int(fx["stride"])
+        d = disp[-1][::stride].cpu().numpy().astype(np.float64) - fx["disp_sub"]
+        out["disp_rms"], out["disp_max"] = float(np.sqrt((d ** 2).mean())), float(np.abs(d).max())
+        out["vel_rel"] = _rel(vel[-1][::stride].cpu().numpy(), fx["vel_sub"])
+        del disp, vel, dk
+        mesh = m.evolve(w)
+        mn = mesh.cpu().numpy().astype(np.float64)
+        c = n // 32
+        out["mesh_block_rel"] = _rel(mn[:32, :32, :32], fx["mesh_block"])
+        out["mesh_coarse_rel"] = _rel(mn.reshape(32, c, 32, c, 32, c).mean(axis=(1, 3, 5)), fx["mesh_coarse"])
+        kc, km, pk = M._spectrum(mesh, box_size=box)
+        assert np.array_equal(kc, fx["pk_count"])
+        ratio = np.asarray(pk) / fx["pk"]
+        knyq = np.pi * n / box[0]
+        lo = fx["pk_kmean"] < knyq / 2
+        out["pk_lo"], out["pk_hi"] = float(np.abs(ratio[lo] - 1).max()), float(np.abs(ratio[fx["pk_kmean"] < knyq] - 1).max())
+        del mesh, mn
+    lp, g = m.value_and_force(w, o)
+    out["logp_rel"] = abs(float(lp) - float(fx["logp"])) / abs(float(fx["logp"]))
+    gn = g.detach().cpu().numpy().astype(np.float64)
+    out["grad_sub_rel"], out["grad_sub_cos"] = _rel(gn[::4, ::4, ::4], fx["grad_sub"]), _cos(gn[::4, ::4, ::4], fx["grad_sub"])
+    out["grad_block_rel"] = _rel(gn[:32, :32, :32], fx["grad_block"])
+    out["grad_norm_rel"] = abs(np.linalg.norm(gn) - float(fx["grad_norm"])) / float(fx["grad_norm"])
+    dots = np.array([float((gn * v).sum()) for v in FX.directions(shape)])
+    out["grad_dot_rel"] = float(np.abs(dots / fx["grad_dot"] - 1).max())
+    if report is not None:
+        report.update(out)
+    print({k: f"{v:.2e}" for k, v in out.items()})
+    assert out["logp_rel"] < 1e-5
+    assert out["mesh_block_rel"] < 1e-4 and out["mesh_coarse_rel"] < 1e-4
+    assert out["disp_rms"] < 1e-3
+    assert out["pk_lo"] < 1e-4 and out["pk_hi"] < 1e-3
+    assert out["grad_sub_rel"] <= 1e-3 and out["grad_sub_cos"] >= 0.9999
+    assert out["grad_block_rel"] <= 1e-3 and out["grad_norm_rel"] < 1e-3 and out["grad_dot_rel"] < 1e-3
+    return out
+
+
+def test_c2_128_against_oracle(nb, golden):
+    """BASELINE configs[1]: 128^3 mesh / particles, 640 Mpc/h, 2LPT + 10 BullFrog steps, bias + RSD + interlaced paint."""
+    check_against_fixture(nb, golden("c2_128"))
+
+
+@pytest.mark.gpu
+def test_c3_256_against_oracle(nb, golden):
+    """BASELINE configs[2], the benchmarked configuration, at its full size."""
+    if getattr(nb, "_backend", "") != "cuda":
+        pytest.skip("256^3 runs on the GPU only")
+    if not os.path.exists(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c3_256.npz")):
+        pytest.skip("fixture tests/golden/c3_256.npz not generated")
+    check_against_fixture(nb, golden("c3_256"))

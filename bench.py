@@ -3,17 +3,24 @@
 bench.py -- grad(log-density) evaluations per second of the field-level PM model (BASELINE.json metric).
 
   python bench.py --gpus N --steps K --warmup W            this engine (CUDA, libmcpm.so through the C ABI)
-  python bench.py --impl reference --gpus N --steps K ...  CPU restatement of the reference algorithm (oracle/), rank 0 only
+  python bench.py --impl reference --gpus N --steps K ...  CPU implementation of the same path, rank 0 only
 
 A "step" is one evaluation of (logpdf, d logpdf / d white) of the model in montecosmo_b200/model.py on one synthetic
-white-noise field.  Workload at every N: BASELINE configs[2] ("C3", the configuration the metric is quoted on): 256^3
-mesh / 256^3 particles, 640 Mpc/h box, 2LPT + 10 BullFrog steps, linear bias + flat-sky RSD, interlaced deconvolved
-CIC paint, Gaussian likelihood.  With N > 1 every rank runs an independent replica (one chain per GPU, the reference's own
-multi-device mode, script.py:13-20): weak scaling, no data-path collective.
+white-noise field: BASELINE configs[2] ("C3", the configuration the metric is quoted on) -- 256^3 mesh / 256^3 particles,
+640 Mpc/h box, 2LPT + 10 BullFrog steps, linear bias + flat-sky RSD, interlaced deconvolved CIC paint, Gaussian
+likelihood.
+
+N = 1: `FieldModel` on one GPU (the whole evaluation replayed from a CUDA graph).
+N > 1: the SLAB-DECOMPOSED model (`dist_model.SlabFieldModel` on `dist.SlabPM`) with real exchanges on the data path --
+halo planes after every paint and before every readout, the distributed FFT transposes (inside the fused x-transform
+kernel over NVLink peer memory in the step loop, NCCL all-to-all elsewhere), an all-reduced log-density.  Weak scaling:
+every rank holds 256^3 cells and 256^3 particles (mesh 512x256x256 on 2, 512x512x256 on 4, 512^3 on 8, same 2.5 Mpc/h
+cells), and `value` counts 256^3-equivalents: N x evaluations/s of the N-times-larger mesh.  The replica mode of round 1
+(one independent chain per GPU, the reference's own multi-device mode, script.py:13-20) is reported under "replicas".
 
 One JSON line is printed by rank 0 (contract in the task statement): value = device-resident throughput, e2e = the same
-through host buffers (H2D of the white field and D2H of gradient + value inside the timed region), roofline for the
-dominant kernel measured live with CUDA events, cpu_baseline = the oracle timed on this box's host cores.
+through pinned host buffers (H2D of the white field and D2H of gradient + value inside the timed region), roofline for
+the dominant kernel measured live with CUDA events, cpu_baseline = the CPU port really run at 256^3 on this box's cores.
 """
 import argparse
 import json
@@ -30,18 +37,28 @@ sys.path.insert(0, ROOT)
 
 METRIC = "grad(logp) evals/s at 256^3 mesh"
 UNIT = "evals/s"
+CELL = 2.5  # Mpc/h
+SLAB_SHAPES = {1: (256, 256, 256), 2: (512, 256, 256), 4: (512, 512, 256), 8: (512, 512, 512)}
 
 
-def workload(n):
-    return dict(mesh_shape=(n, n, n), box_size=(2.5 * n,) * 3, evolution="nbody", n_steps=10, a_start=0.0, a_obs=1.0,
-                lpt_order=2, paint_order=2, interlace_order=2, paint_deconv=True, b1=1.0, rsd=True, sigma_obs=1.0)
+def workload(shape):
+    shape = (shape,) * 3 if isinstance(shape, int) else tuple(shape)
+    return dict(mesh_shape=shape, box_size=tuple(CELL * s for s in shape), evolution="nbody", n_steps=10, a_start=0.0,
+                a_obs=1.0, lpt_order=2, paint_order=2, interlace_order=2, paint_deconv=True, b1=1.0, rsd=True,
+                sigma_obs=1.0)
 
 
-def config_dict(n, n_gpus):
-    return {"workload": f"C3: {n}^3 mesh / {n}^3 particles, {2.5 * n:g} Mpc/h box, 2LPT + 10-step BullFrog (DKD), "
-                        "linear Lagrangian bias b1=1 + flat-sky RSD, interlaced (x2) deconvolved CIC paint, Gaussian "
-                        "likelihood; one step = value and gradient of log-density w.r.t. the white field",
-            "mesh": n, "particles": n ** 3, "n_body_steps": 10, "parallelism": f"replicas x{n_gpus} (one chain per GPU)",
+def config_dict(shape, n_gpus, parallelism=None):
+    shape = (shape,) * 3 if isinstance(shape, int) else tuple(shape)
+    cells = int(np.prod(shape))
+    par = parallelism or ("single GPU" if n_gpus == 1 else f"slab x{n_gpus}")
+    per = cells // n_gpus
+    side = round(per ** (1 / 3))
+    return {"workload": f"C3: {side}^3 mesh / {side}^3 particles per GPU ({'x'.join(map(str, shape))} mesh on {n_gpus} GPU(s), "
+                        f"{CELL:g} Mpc/h cells), 2LPT + 10-step BullFrog (DKD), linear Lagrangian bias b1=1 + flat-sky RSD, "
+                        "interlaced (x2) deconvolved CIC paint, Gaussian likelihood; one step = value and gradient of "
+                        "log-density w.r.t. the white field",
+            "mesh": list(shape), "particles": cells, "n_body_steps": 10, "parallelism": par,
             "l2": "working set per step (>6 GB of particle/mesh tape) exceeds the 126 MB L2; no explicit flush"}
 
 
@@ -78,20 +95,41 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-# ---------------------------------------------------------------------------------------------------- CPU baseline
-def cpu_reference_arm(steps, warmup, n_sample=128):
-    """The CPU port of the path (oracle/cpu_port.py: the same kernels as OpenMP loops + pocketfft, float32) on all host
-    cores: a bounded sample (n_sample^3) of the 256^3 workload, scaled by the particle-count ratio to the metric's unit."""
+# ---------------------------------------------------------------------------------------------------- CPU arm
+def _host_threads():
+    """All host cores for the CPU legs.  torchrun exports OMP_NUM_THREADS=1 to its workers, which throttled round 1's
+    CPU arm threefold: the OpenMP runtime of the CPU port is told explicitly, before and after it loads."""
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    return cores
+
+
+def _set_omp(cores):
+    import ctypes
+    for name in ("libgomp.so.1", "libgomp.so"):
+        try:
+            ctypes.CDLL(name).omp_set_num_threads(int(cores))
+            return
+        except OSError:
+            continue
+
+
+def cpu_port_arm(steps, warmup, n=256):
+    """CPU implementation of the path, REALLY RUN at the benchmark size: the engine's own kernel sources compiled for the
+    host (oracle/cpu_port.py: every kernel body an OpenMP loop, FFTs by pocketfft, float32), driven through the same
+    `FieldModel`.  It is not the reference's JAX (not installable here) and not an independent implementation -- the
+    independent float64 restatement is timed beside it at C1 (`oracle_f64_c1`) as the anchor SURVEY 8d asks for."""
+    cores = _host_threads()
     import torch
     from oracle import cpu_port
     import montecosmo_b200.nbody as nb
     from montecosmo_b200.model import FieldModel
-    cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     saved = nb._OPS
     nb._OPS = cpu_port.cpu_ops()  # the checker's operator table, for this leg only
+    _set_omp(cores)
     try:
-        model = FieldModel(**workload(n_sample))
+        model = FieldModel(**workload(n))
         gen = torch.Generator().manual_seed(0)
         obs = 1.0 + torch.randn(model.mesh_shape, generator=gen)
         times = []
@@ -106,11 +144,32 @@ def cpu_reference_arm(steps, warmup, n_sample=128):
     finally:
         nb._OPS = saved
     per_eval = float(np.mean(times))
-    scale = (256 / n_sample) ** 3  # particle-count ratio; the FFT's log factor is ignored (favours the CPU)
-    return {"value": 1.0 / (per_eval * scale), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{len(times)} grad evaluation(s) of the same model at {n_sample}^3 on {cores} host threads "
-                      f"(OpenMP + pocketfft float32 port, {per_eval:.2f} s each), scaled by ({n_sample}/256)^3 to 256^3",
-            "seconds_per_sample_eval": per_eval}
+    return {"value": 1.0 / per_eval, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(times)} grad evaluation(s) of the SAME {n}^3 model (no extrapolation) after {warmup} warm-up, "
+                      f"{cores} host threads: the engine's kernel sources built for the host (OpenMP loops + pocketfft, "
+                      f"float32), {per_eval:.2f} s each",
+            "seconds_per_eval": per_eval, "mesh": n, "evaluations": len(times)}
+
+
+def oracle_anchor():
+    """The independent float64 restatement (oracle/pm_oracle.py, torch autograd) timed at C1 (64^3, 5 steps): the
+    SURVEY 8d anchor.  One evaluation, all host threads."""
+    cores = _host_threads()
+    import torch
+    from oracle import model_oracle as MO
+    from oracle import pm_oracle as O
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_full_size_fixture as FX
+    torch.set_num_threads(cores)
+    shape, white, obs = FX.inputs(64, 0)
+    transfer = FX.transfer_mesh(shape, (640.0,) * 3)
+    kw = dict(FX.KW, n_steps=5)
+    t0 = time.perf_counter()
+    MO.value_and_force(white, obs, transfer, O.Cosmology(), shape, **kw)
+    return {"config": "C1: 64^3, 640 Mpc/h, 2LPT + 5 BullFrog steps, bias + RSD + interlaced paint", "dtype": "f64",
+            "seconds_per_eval": time.perf_counter() - t0, "cores": cores,
+            "what": "oracle/pm_oracle.py + model_oracle.py (torch-CPU float64, autograd gradient): the independent "
+                    "restatement of the reference algorithm"}
 
 
 def max_over_ranks(ms, device, world):
@@ -128,36 +187,32 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_reference_arm(max(1, min(args.steps, 5)), min(args.warmup, 1), int(os.environ.get("MCPM_BENCH_SAMPLE", "128")))
+    steps, warm = max(1, min(args.steps, 4)), min(args.warmup, 1)
+    # MCPM_BENCH_SAMPLE: test hook (tests/test_bench_contract.py runs this arm at 32^3 on a CPU-only box); the line then
+    # says which mesh was really run.  The driver runs without it: 256^3, measured, no extrapolation.
+    n = int(os.environ.get("MCPM_BENCH_SAMPLE", "256"))
+    cb = cpu_port_arm(steps, warm, n)
+    if n == 256:
+        try:
+            cb["oracle_f64_c1"] = oracle_anchor()
+        except Exception as e:
+            cb["oracle_f64_c1"] = {"error": f"{type(e).__name__}: {e}"}
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True,
+            "steps": steps, "warmup": warm, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(256, args.gpus), "cpu_baseline": cb,
+            "config": config_dict(n, 1, "host CPU, all cores (rank 0 only)"), "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "reference's JAX cannot be installed in this image; this arm times the CPU restatement of its "
-                    "algorithm (oracle/), all host threads, on a bounded sample"}
+            "note": "the reference's JAX cannot be installed in this image (no jax / jax_cosmo / numpyro wheels); this arm "
+                    "times the CPU port of the same path -- the engine's own kernel sources as OpenMP loops -- at the "
+                    f"full 256^3 size on all {cb['cores']} host threads (requested steps {args.steps} / warmup "
+                    f"{args.warmup} capped at {steps} / {warm}: one evaluation takes seconds); the independent float64 "
+                    "oracle is timed at C1 under cpu_baseline.oracle_f64_c1"}
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------- roofline
-def kernel_rooflines(model, white, peaks):
-    """Time the engine's particle kernels in isolation on the evolved (a = 1) state of this run, CUDA events on the
-    launching stream, L2 flushed between launches; returns per-kernel rows and the dominant one (time x launches per step)."""
+def _timer(flush):
     import torch
-    from montecosmo_b200 import nbody as nb
-    o = nb.ops()
-    shape = model.mesh_shape
-    N = int(np.prod(shape))
-    with torch.no_grad():
-        dk = model.linear_field(nb._f32(white))
-        pos, vel = nb.nbody_bf(model.cosmology, dk, model.q, model.a_start, model.a_obs, model.n_steps)
-        pos, vel = pos[-1].contiguous(), vel[-1].contiguous()
-        _, fm = o.pm_forces(pos, shape, want_meshes=True)
-    flush = torch.empty(256 * 1024 * 1024 // 4, device=pos.device)
-    mesh = torch.empty(shape, device=pos.device)
-    A, lib = o.A, o.lib
-    p2, v2 = pos.clone(), vel.clone()
-    rho = torch.randn(shape, device=pos.device)
 
     def t(fn, reps=5):
         fn()
@@ -171,11 +226,40 @@ def kernel_rooflines(model, white, peaks):
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         return float(np.mean(ts))
+    return t
 
+
+def kernel_rooflines(model, white, peaks):
+    """Time the engine's particle kernels in isolation on the evolved (a = 1) state of this run, CUDA events on the
+    launching stream, L2 flushed between launches; returns per-kernel rows and the dominant one (time x launches per step).
+    Positions are displacements from the lattice sites, as the model carries them."""
+    import ctypes as C
+    import torch
+    from montecosmo_b200 import nbody as nb
+    from montecosmo_b200._capi import frame as make_frame
+    o = nb.ops()
+    shape = model.mesh_shape
+    N = int(np.prod(shape))
+    with torch.no_grad():
+        dk = model.linear_field(nb._f32(white))
+        pos, vel = nb.nbody_bf(model.cosmology, dk, model.q, model.a_start, model.a_obs, model.n_steps, ptcl_shape=shape,
+                               relative=True)
+        pos, vel = pos[-1].contiguous(), vel[-1].contiguous()
+        _, fm = o.pm_forces(pos, shape, want_meshes=True, lattice=shape)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=pos.device)
+    t = _timer(flush)
+    mesh = torch.empty(shape, device=pos.device)
+    A, lib = o.A, o.lib
+    p2, v2 = pos.clone(), vel.clone()
+    rho = torch.randn(shape, device=pos.device)
     steps = model.n_steps
     rows = []
-    traffic_path = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
+    traffic, tsrc = {}, None
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            traffic, tsrc = json.load(open(path)), name
+            break
 
     def add(key, name, fn, alg_bytes, launches, note, in_step=True):
         ms = t(fn)
@@ -185,27 +269,28 @@ def kernel_rooflines(model, white, peaks):
                      "traffic": traffic.get(key, {}).get("dram_bytes")})
 
     st = A.stream()
-    nzc = shape[2] // 2 + 1
+    fr = make_frame(shape)
+    frp = C.byref(fr)
     fm4 = torch.empty((*shape, 4), device=pos.device)
     lib.mcpm_interleave3(st, fm.data_ptr(), fm4.data_ptr(), N)
     mesh4 = torch.zeros((*shape, 4), device=pos.device)
     planar3 = torch.empty((3, *shape), device=pos.device)
     xbar, vbar = torch.randn_like(pos), torch.randn_like(pos)
-    eng = o.engine(shape)
-    o.set_lattice(shape, shape)
+    one = (C.c_float * 3)(1.0, 1.0, 1.0)
     add("brick_paint", "brick paint (CIC density: shared-memory tile, fixed-point ATOMS, red.v4 flush)",
-        lambda: (mesh.zero_(), lib.mcpm_paint_lattice(eng.handle, st, pos.data_ptr(), 0, 1.0, N, mesh.data_ptr())),
+        lambda: (mesh.zero_(), lib.mcpm_paint_brick_f(st, frp, *shape, pos.data_ptr(), 0, 1.0, 0.0, N, *shape,
+                                                      mesh.data_ptr())),
         16 * N, steps + 2, "pos 12N + mesh 4N (includes the 4N memset)")
     add("brick_paint3", "brick paint3 (reverse-step scatter of 3 channels, fused vbar += xbar*drift)",
-        lambda: (planar3.zero_(), lib.mcpm_paint3_lattice(eng.handle, st, pos.data_ptr(), vbar.data_ptr(),
-                                                           xbar.data_ptr(), 1e-3, 0.5, N, planar3.data_ptr())),
+        lambda: (planar3.zero_(), lib.mcpm_paint3_brick_f(st, frp, *shape, pos.data_ptr(), vbar.data_ptr(),
+                                                          xbar.data_ptr(), 1e-3, 0.5, N, *shape, planar3.data_ptr())),
         60 * N, steps, "pos 12N + vbar 12N r + 12N w + xbar 12N + 3 meshes 12N (includes the 12N memset)")
     add("kick_drift4", "kick_drift4 (float4 force readout + kick + drift)",
-        lambda: lib.mcpm_kick_drift4(st, p2.data_ptr(), v2.data_ptr(), fm4.data_ptr(), N, *shape, 1.0, 0.0, 0.0),
+        lambda: lib.mcpm_kick_drift4_f(st, frp, p2.data_ptr(), v2.data_ptr(), fm4.data_ptr(), N, *shape, 1.0, 0.0, 0.0),
         64 * N, steps, "pos 12N r/w + vel 12N r/w + mesh4 16N")
     add("read_grad4v", "read_grad4v (reverse-step gradient gather, fused xbar / vbar update)",
-        lambda: lib.mcpm_read_grad4v(st, pos.data_ptr(), fm4.data_ptr(), rho.data_ptr(), vbar.data_ptr(), 0.5, 1.0, N,
-                                     *shape, xbar.data_ptr()), 80 * N, steps,
+        lambda: lib.mcpm_read_grad4v_f(st, frp, pos.data_ptr(), fm4.data_ptr(), rho.data_ptr(), vbar.data_ptr(), 0.5, 1.0,
+                                       N, *shape, xbar.data_ptr()), 80 * N, steps,
         "pos 12N + vbar 12N r/w + xbar 12N r/w + mesh4 16N + rhobar 4N")
     add("interleave3", "interleave3 (3 planar meshes -> float4 mesh)",
         lambda: lib.mcpm_interleave3(st, fm.data_ptr(), fm4.data_ptr(), N), 28 * N, steps, "12N r + 16N w")
@@ -226,13 +311,68 @@ def kernel_rooflines(model, white, peaks):
         "likelihood) + 48 batched 2-D (y,z) launches covering 108 mesh transforms", False)
     # generic global-atomic kernels the step loop does not run under the lattice hint: listed for comparison only
     add("paint_generic", "paint (generic CIC scatter, 8 red.f32 / particle)",
-        lambda: o.paint(pos, shape, None, order=2, out=mesh), 16 * N, 0, "pos 12N + mesh 4N", False)
+        lambda: lib.mcpm_paint_f(st, frp, pos.data_ptr(), 0, 1.0, N, *shape, 2, one, 0.0, mesh.data_ptr(), 0), 16 * N, 0,
+        "pos 12N + mesh 4N", False)
     add("paint3v4_generic", "paint3v4 (generic reverse-step scatter, 8 red.v4.f32 / particle)",
-        lambda: lib.mcpm_paint3v4(st, pos.data_ptr(), vbar.data_ptr(), xbar.data_ptr(), 1e-3, 0.5, N, *shape,
-                                  mesh4.data_ptr()), 64 * N, 0, "pos 12N + vbar 12N r + 12N w + xbar 12N + mesh4 16N",
+        lambda: lib.mcpm_paint3v4_f(st, frp, pos.data_ptr(), vbar.data_ptr(), xbar.data_ptr(), 1e-3, 0.5, N, *shape,
+                                    mesh4.data_ptr()), 64 * N, 0, "pos 12N + vbar 12N r + 12N w + xbar 12N + mesh4 16N",
         False)
     dom = max([r for r in rows if r["in_step"]], key=lambda r: r["ms_per_step_total"])
-    return rows, dom
+    return rows, dom, tsrc, pos
+
+
+def paint_microbench(model, disp256, peaks):
+    """SURVEY 8d's paint-only microbenchmark P: CIC density paint at 256^3 and 512^3, particles = cells, on (a) the
+    lattice + Gaussian jitter sigma = 1.5 cells and (b) the evolved a = 1 state (clustered: stresses the atomics), with
+    the brick-tiled kernel (what a PM run takes) and the generic global-atomic kernel (what a catalogue takes).
+    Gparticles/s, mesh clear included, L2 flushed between launches; 16 B/particle algorithmic."""
+    import ctypes as C
+    import torch
+    from montecosmo_b200 import nbody as nb
+    from montecosmo_b200._capi import frame as make_frame
+    from montecosmo_b200.model import FieldModel
+    o = nb.ops()
+    A, lib = o.A, o.lib
+    dev = A.device
+    st = A.stream()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    t = _timer(flush)
+    one = (C.c_float * 3)(1.0, 1.0, 1.0)
+    out = []
+    for n in (256, 512):
+        shape = (n, n, n)
+        N = n ** 3
+        fr = make_frame(shape)
+        frp = C.byref(fr)
+        mesh = torch.empty(shape, device=dev)
+        gen = torch.Generator(device=dev).manual_seed(5 + n)
+        cases = {"jitter_sigma1.5": torch.randn((N, 3), device=dev, generator=gen) * 1.5}
+        try:
+            if n == 256:
+                cases["evolved_a1"] = disp256
+            else:
+                with torch.no_grad():
+                    m = FieldModel(**workload(n))
+                    dk = m.linear_field(torch.randn(shape, device=dev, generator=gen))
+                    d, _ = nb.nbody_bf(m.cosmology, dk, m.q, 0.0, 1.0, 10, ptcl_shape=shape, relative=True)
+                    cases["evolved_a1"] = d[-1].contiguous()
+                    del m, dk, d
+        except Exception as e:
+            out.append({"mesh": n, "case": "evolved_a1", "error": f"{type(e).__name__}: {e}"})
+        for case, disp in cases.items():
+            row = {"mesh": n, "case": case, "disp_rms_cells": float(disp.std())}
+            for kern, fn in (("brick", lambda: (mesh.zero_(), lib.mcpm_paint_brick_f(
+                                 st, frp, *shape, disp.data_ptr(), 0, 1.0, 0.0, N, *shape, mesh.data_ptr()))),
+                             ("generic", lambda: lib.mcpm_paint_f(st, frp, disp.data_ptr(), 0, 1.0, N, *shape, 2, one, 0.0,
+                                                                  mesh.data_ptr(), 0))):
+                ms = t(fn, reps=3)
+                row[kern] = {"ms": ms, "Gparticles_per_s": N / ms / 1e6, "frac_of_hbm": 16 * N / ms / 1e6 / peaks}
+            out.append(row)
+        del cases, mesh
+        torch.cuda.empty_cache()
+    o._engines.pop((512, 512, 512), None)
+    torch.cuda.empty_cache()
+    return out
 
 
 def small_configs(dev, gen):
@@ -245,6 +385,7 @@ def small_configs(dev, gen):
     try:
         for tag, nn, nsteps in (("C1_64", 64, 5), ("C2_128_leapfrog", 128, 10)):
             wl = workload(nn)
+            wl["box_size"] = (640.0,) * 3
             wl["n_steps"] = nsteps
             mm = FieldModel(**wl)
             ff = mm.graphed_value_and_force(1.0 + torch.randn(mm.mesh_shape, device=dev, generator=gen))
@@ -285,17 +426,8 @@ def run_engine(args):
     from montecosmo_b200.model import FieldModel
     lib = nb.ops().lib
     n = args.mesh
-    model = FieldModel(**workload(n))
     dev = nb.ops().A.device
-    N = n ** 3
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    # observation: the model's own output at another seed + unit noise
-    with torch.no_grad():
-        truth = model.evolve(torch.randn(model.mesh_shape, device=dev, generator=gen))
-        obs = (truth + torch.randn(model.mesh_shape, device=dev, generator=gen)).contiguous()
-    del truth
     K, W = args.steps, args.warmup
-    whites = [torch.randn(model.mesh_shape, device=dev, generator=gen) for _ in range(2)]
 
     def barrier():
         if world > 1:
@@ -314,6 +446,26 @@ def run_engine(args):
         barrier()
         return max_over_ranks(e0.elapsed_time(e1), dev, world)
 
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
+    sampler = ClockSampler(local)
+    slab = None
+    if world > 1 and not args.replicas:
+        slab = run_slab(args, world, rank, dev, timed, barrier, sampler)
+
+    # ---- the single-GPU model: the metric at N = 1; per-rank replicas (no collective) at N > 1, for the record
+    model = FieldModel(**workload(n))
+    N = n ** 3
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    with torch.no_grad():  # observation: the model's own output at another seed + unit noise
+        truth = model.evolve(torch.randn(model.mesh_shape, device=dev, generator=gen))
+        obs = (truth + torch.randn(model.mesh_shape, device=dev, generator=gen)).contiguous()
+    del truth
+    whites = [torch.randn(model.mesh_shape, device=dev, generator=gen) for _ in range(2)]
     # kernels of ours per evaluation, counted on one eager evaluation (a graph replay launches the same nodes)
     model.value_and_force(whites[0], obs)
     torch.cuda.synchronize()
@@ -321,8 +473,6 @@ def run_engine(args):
     model.value_and_force(whites[0], obs)
     torch.cuda.synchronize()
     launches_per_eval = int(lib.mcpm_launch_count(0))
-    # The public call a sampler makes: FieldModel.graphed_value_and_force -- the whole evaluation captured once in a CUDA
-    # graph, replayed per step on a new white field (--no-graph: the eager FieldModel.value_and_force).
     fn, graph_note = None, "disabled (--no-graph)"
     if not args.no_graph:
         try:
@@ -330,17 +480,13 @@ def run_engine(args):
         except Exception as e:  # never lose the measurement to the capture: time the eager call instead
             fn, graph_note = None, f"capture failed, eager call timed instead ({type(e).__name__}: {e})"
             torch.cuda.synchronize()
-
-    sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and slab is None:
         sampler.start()
-    # (1) device-resident
     keep = {}
 
     def step_dev(i):
         keep["out"] = fn(whites[i % 2]) if fn is not None else model.value_and_force(whites[i % 2], obs)
     ms_dev = timed(step_dev)
-    # (2) end to end through host buffers: pinned white in, gradient + value out
     h_white = [torch.randn(model.mesh_shape, generator=torch.Generator().manual_seed(7 + i)).pin_memory() for i in range(2)]
     h_grad = torch.empty(model.mesh_shape, dtype=torch.float32).pin_memory()
     h_lp = torch.empty((), dtype=torch.float64).pin_memory()
@@ -358,18 +504,15 @@ def run_engine(args):
         h_lp.copy_(lp, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller needs the result before proposing the next state
     ms_e2e = timed(step_e2e)
-    # (3) the eager call, for the record
     ms_eager = timed(lambda i: model.value_and_force(whites[i % 2], obs)) if fn is not None else ms_dev
     clocks = sampler.stop() if rank == 0 else None
     lp_val = float(h_lp)
-    launches = launches_per_eval * K
-    other = small_configs(dev, gen) if (rank == 0 and fn is not None and n == 256) else {}
+    single = {"value": world * K / (ms_dev * 1e-3), "ms_per_step": ms_dev / K,
+              "e2e": {"value": world * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * N,
+                      "d2h_bytes_per_step": 4 * N + 8, "ms_per_step": ms_e2e / K},
+              "eager": {"value": world * K / (ms_eager * 1e-3), "unit": UNIT, "ms_per_step": ms_eager / K}}
+    other = small_configs(dev, gen) if (rank == 0 and fn is not None and n == 256 and world == 1) else {}
 
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     # Run-to-run spread of the result on identical inputs (the order in which float atomics land is not
     # deterministic): two eager evaluations outside the timed region, relative L2 of the gradient difference.
     spread = None
@@ -384,36 +527,138 @@ def run_engine(args):
             spread = {"error": f"{type(e).__name__}: {e}"}
     line = None
     if rank == 0:
-        rows, dom = kernel_rooflines(model, whites[0], peak)
-        cb = None if args.no_cpu_baseline else cpu_reference_arm(2, 1, 128)
-        value = world * K / (ms_dev * 1e-3)
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "config": config_dict(n, world), "clocks": clocks,
-                "e2e": {"value": world * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * N,
-                        "d2h_bytes_per_step": 4 * N + 8, "ms_per_step": ms_e2e / K},
-                "gpu_launches": int(launches),
-                "gpu_launches_note": f"{launches_per_eval} engine kernels per evaluation (mcpm_launch_count on an eager "
-                                     "evaluation) x steps; cuFFT's kernels not counted",
-                "graph": graph_note,
-                "api": "FieldModel.value_and_force (eager)" if fn is None else
-                       "FieldModel.graphed_value_and_force (CUDA graph of the whole evaluation, replayed per step)",
-                "eager": {"value": world * K / (ms_eager * 1e-3), "unit": UNIT, "ms_per_step": ms_eager / K},
+        del fn, keep
+        torch.cuda.empty_cache()
+        rows, dom, tsrc, disp = kernel_rooflines(model, whites[0], peak)
+        pmb = None
+        if world == 1 and not args.no_paint_bench:
+            try:
+                pmb = paint_microbench(model, disp, peak)
+            except Exception as e:
+                pmb = [{"error": f"{type(e).__name__}: {e}"}]
+        cb = None
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_port_arm(1, 1, 256)
+            try:
+                cb["oracle_f64_c1"] = oracle_anchor()
+            except Exception as e:
+                cb["oracle_f64_c1"] = {"error": f"{type(e).__name__}: {e}"}
+        main = slab if slab is not None else single
+        shape = SLAB_SHAPES[world] if slab is not None else (n, n, n)
+        line = {"metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": config_dict(shape, world, None if slab is not None or world == 1 else
+                                      f"replicas x{world} (one chain per GPU, no collective)"),
+                "clocks": clocks, "e2e": main["e2e"],
+                "gpu_launches": int((slab["launches_per_eval"] if slab is not None else launches_per_eval) * K),
+                "gpu_launches_note": "engine kernels per evaluation on this rank (mcpm_launch_count on an eager "
+                                     "evaluation) x steps; cuFFT's and NCCL's kernels not counted",
+                "graph": graph_note if slab is None else "not used (the slab model interleaves NCCL / symmetric-memory "
+                                                         "barriers with the kernels; eager launches)",
+                "api": ("SlabFieldModel.value_and_force (slab-decomposed, one process per GPU)" if slab is not None else
+                        "FieldModel.value_and_force (eager)" if graph_note != "ok" else
+                        "FieldModel.graphed_value_and_force (CUDA graph of the whole evaluation, replayed per step)"),
                 "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_GBps"], "peak": peak,
                              "peak_source": peak_src, "unit": "GB/s", "frac": dom["frac"],
                              "traffic": dom["traffic"],
-                             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full "
-                                               "capture (profiles/r1_traffic.json)" if dom["traffic"] else None,
+                             "traffic_source": (f"dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full "
+                                                f"capture (profiles/{tsrc}; a frozen capture, re-taken when the kernel "
+                                                f"changes -- see profiles/README.md)") if dom["traffic"] else None,
                              "alg_bytes_per_launch": dom["alg_bytes"], "ms_per_launch": dom["ms"],
-                             "share_of_step": dom["ms_per_step_total"] / (ms_dev / K)},
+                             "share_of_step": dom["ms_per_step_total"] / single["ms_per_step"],
+                             "whole_evaluation": {"alg_bytes": 55e9, "frac": 55e9 / (single["ms_per_step"] * 1e-3) / 1e9 / peak,
+                                                  "note": "SURVEY 8d's 3.3 kN bytes for C3 over the single-GPU step time"}},
                 "kernels": rows, "cpu_baseline": cb, "logp_last": lp_val, "other_configs": other,
                 "paint_Gparticles_per_s": N / (rows[0]["ms"] * 1e-3) / 1e9,
-                "paint_kernel": rows[0]["kernel"], "run_to_run": spread}
+                "paint_kernel": rows[0]["kernel"], "paint_microbench": pmb, "run_to_run": spread}
+        if slab is not None:
+            line["roofline"]["nvlink"] = slab["nvlink"]
+            line["slab"] = {k: v for k, v in slab.items() if k not in ("e2e", "nvlink")}
+            line["replicas"] = dict(single, note="one independent 256^3 chain per GPU (round 1's --gpus N mode, the "
+                                                 "reference's pmap over chains, script.py:13-20): no data-path collective")
+        else:
+            line["eager"] = single["eager"]
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return line
+
+
+def run_slab(args, world, rank, dev, timed, barrier, sampler):
+    """N > 1: the slab-decomposed model, weak-scaled (256^3 cells and particles per rank)."""
+    import torch
+    import torch.distributed as dist
+    from montecosmo_b200 import nbody as nb
+    from montecosmo_b200.dist import SlabPM
+    from montecosmo_b200.dist_model import SlabFieldModel
+    ops = nb.ops()
+    lib = ops.lib
+    shape = SLAB_SHAPES[world]
+    K = args.steps
+    pm = SlabPM(ops, shape, halo=min(args.halo, shape[0] // world))
+    wl = workload(shape)
+    mdl = SlabFieldModel(pm, wl["box_size"], n_steps=wl["n_steps"], a_start=wl["a_start"], a_obs=wl["a_obs"],
+                         b1=wl["b1"], rsd=wl["rsd"], sigma_obs=wl["sigma_obs"])
+    local_shape = (pm.xl, shape[1], shape[2])
+    gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+    with torch.no_grad():
+        obs = (mdl.predict(torch.randn(local_shape, device=dev, generator=gen))
+               + torch.randn(local_shape, device=dev, generator=gen)).contiguous()
+    whites = [torch.randn(local_shape, device=dev, generator=gen) for _ in range(2)]
+    mdl.value_and_force(whites[0], obs)
+    torch.cuda.synchronize()
+    lib.mcpm_launch_count(1)
+    mdl.value_and_force(whites[0], obs)
+    torch.cuda.synchronize()
+    launches = int(lib.mcpm_launch_count(0))
+    if rank == 0:
+        sampler.start()
+    keep = {}
+
+    def step_dev(i):
+        keep["out"] = mdl.value_and_force(whites[i % 2], obs)
+    ms_dev = timed(step_dev)
+    nl = int(np.prod(local_shape))
+    h_white = [torch.randn(local_shape, generator=torch.Generator().manual_seed(7 + i + 10 * rank)).pin_memory()
+               for i in range(2)]
+    h_grad = torch.empty(local_shape, dtype=torch.float32).pin_memory()
+    h_lp = torch.empty((), dtype=torch.float64).pin_memory()
+    d_white = torch.empty(local_shape, device=dev)
+
+    def step_e2e(i):
+        d_white.copy_(h_white[i % 2], non_blocking=True)
+        lp, g = mdl.value_and_force(d_white, obs)
+        h_grad.copy_(g, non_blocking=True)
+        h_lp.copy_(lp, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    ms_e2e = timed(step_e2e)
+    mem = torch.tensor([torch.cuda.max_memory_allocated() / 2 ** 30], device=dev, dtype=torch.float64)
+    dist.all_reduce(mem, op=dist.ReduceOp.MAX)
+    # NVLink bytes out of each GPU per evaluation (SURVEY 8e): one exchange of a half spectrum per distributed mesh
+    # transform, 8 B x (cells/2) / P x (P-1)/P each, + the halo planes of every paint / readout
+    cells = float(np.prod(shape))
+    ns = wl["n_steps"]
+    nfft = 13 + 13 + 8 * ns + (2 + 2 + 2 * 3 + 2)
+    a2a = nfft * 8 * (cells / 2) / world * (world - 1) / world * (1 + 2.0 / shape[2])
+    plane = shape[1] * shape[2] * 4.0
+    halo = (ns * (1 + 4 + 3 + 1) + 2 * 2) * 2 * pm.H * plane
+    per = ms_dev / K
+    nv = (a2a + halo) / 1e9
+    del keep, mdl, pm
+    torch.cuda.empty_cache()
+    barrier()
+    return {"value": world * K / (ms_dev * 1e-3), "ms_per_step": per, "mesh": list(shape), "halo_planes": min(args.halo, shape[0] // world),
+            "launches_per_eval": launches, "max_mem_GiB_per_gpu": float(mem),
+            "e2e": {"value": world * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * nl * world,
+                    "d2h_bytes_per_step": (4 * nl + 8) * world, "ms_per_step": ms_e2e / K,
+                    "note": "every rank copies its own planes of the white field in and of the gradient out"},
+            "nvlink": {"bound": "nvlink", "GB_out_per_gpu_per_eval": nv, "achieved_GBps_per_gpu": nv / (per * 1e-3),
+                       "peak_GBps_per_direction": 900.0, "frac": nv / (per * 1e-3) / 900.0,
+                       "note": "bytes out per GPU per evaluation / whole step time: the fraction of NVLink's 900 GB/s the "
+                               "exchanges would need if they were spread over the step; transposes "
+                               f"{a2a / 1e9:.2f} GB + halos {halo / 1e9:.2f} GB"}}
 
 
 def main():
@@ -423,9 +668,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--mesh", type=int, default=256, help="mesh side (development only; the contract runs 256)")
+    ap.add_argument("--halo", type=int, default=24, help="halo planes of the slab decomposition (N > 1)")
+    ap.add_argument("--replicas", action="store_true", help="N > 1: time independent replicas only (round 1's mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-paint-bench", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager call instead of the CUDA-graph replay")
     args = ap.parse_args()
+    _host_threads()  # before anything loads an OpenMP runtime
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -139,6 +139,16 @@ int mcpm_tune(const char* key, int value) {
     set_gather_blocked(value != 0);
     return MCPM_OK;
   }
+  if (std::string(key) == "gather_tma" || std::string(key) == "gather_seg") {
+#ifndef MCPM_HOSTEMU
+    if (std::string(key) == "gather_tma") set_gather_tma(value != 0);
+    else {
+      NEED(value == 32 || value == 64 || value == 128, "tune: gather_seg must be 32, 64 or 128");
+      set_gather_seg(value);
+    }
+#endif
+    return MCPM_OK;
+  }
   if (std::string(key) == "brick_zmerge") {
 #ifndef MCPM_HOSTEMU
     set_brick_zmerge(value != 0);

@@ -108,6 +108,13 @@ int kick_drift4(stream_t st, const float* pos, const float* vel, const float* fm
                 int nz, float alpha, float beta, float drift, float* pos_out, float* vel_out, float* zero,
                 int64_t nzero, const Frame* frp) {
   const f4* fm = reinterpret_cast<const f4*>(fmesh4);
+#ifndef MCPM_HOSTEMU
+  if (!zero) {  // particle arrays staged through shared memory by bulk async copies (cic4_tma.cu), where it applies
+    const int r = kick_drift4_tma(st, pos, vel, fmesh4, np, nx, ny, nz, alpha, beta, drift, pos_out, vel_out, frp);
+    if (r < 0) return MCPM_ECUDA;
+    if (r == 1) return 0;
+  }
+#endif
   const Frame fr = frp ? *frp : Frame();
   launch_gather(st, np, [=] MCPM_LAMBDA(int64_t p) {
     float x[3] = {pos[3 * p], pos[3 * p + 1], pos[3 * p + 2]};
@@ -189,6 +196,14 @@ int read_grad4v(stream_t st, const float* pos, const float* fmesh4, const float*
                 int scale_cot, float alpha_tail, int64_t np, int nx, int ny, int nz, float* grad, int accumulate,
                 float* zero, int64_t nzero, const Frame* frp) {
   const f4* fm = reinterpret_cast<const f4*>(fmesh4);
+#ifndef MCPM_HOSTEMU
+  if (!zero) {
+    const int r = read_grad4v_tma(st, pos, fmesh4, rhobar, cot, cscale, scale_cot, alpha_tail, np, nx, ny, nz, grad,
+                                  accumulate, frp);
+    if (r < 0) return MCPM_ECUDA;
+    if (r == 1) return 0;
+  }
+#endif
   const Frame fr = frp ? *frp : Frame();
   launch_gather(st, np, [=] MCPM_LAMBDA(int64_t p) {
     float x[3] = {pos[3 * p], pos[3 * p + 1], pos[3 * p + 2]};

@@ -130,6 +130,15 @@ int read_grad4v(stream_t, const float* pos, const float* fmesh4, const float* rh
                 int scale_cot, float alpha_tail, int64_t np, int nx, int ny, int nz, float* grad, int accumulate,
                 float* zero = nullptr, int64_t nzero = 0, const Frame* fr = nullptr);
 
+// cic4_tma.cu (CUDA build only): the same two gathers with bulk-copy staged particle arrays; 1 handled, 0 not applicable
+void set_gather_tma(int v);
+void set_gather_seg(int v);
+int kick_drift4_tma(stream_t, const float* pos, const float* vel, const float* fmesh4, int64_t np, int nx, int ny, int nz,
+                    float alpha, float beta, float drift, float* pos_out, float* vel_out, const Frame* fr);
+int read_grad4v_tma(stream_t, const float* pos, const float* fmesh4, const float* rhobar, float* cot, float cscale,
+                    int scale_cot, float alpha_tail, int64_t np, int nx, int ny, int nz, float* grad, int accumulate,
+                    const Frame* fr);
+
 // xfft.cu (CUDA build only): the x-passes of rfftn / irfftn fused with the force kernel, on [nx, ny_loc, nz/2+1]
 bool xfuse_supported(int nx);
 int xfuse_force(stream_t, const cfloat* in, cfloat* out3, int nx, int ny, int nz, int lap_fd, int grad_fd, float kcut,

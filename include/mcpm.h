@@ -52,9 +52,14 @@ long long mcpm_launch_count(int reset);
  * resident CTAs per SM the readout kernels are compiled for; "gather_blocked" = 0 | 1, one CTA per 256 consecutive
  * particles instead of a grid-stride loop;
  * "side_zero" = 0 | 1, clear the next step's scatter meshes inside the readout kernels instead of memsets;
- * "brick_zmerge" = 0 | 1, the brick-tiled scatters hand each lane's upper-z deposits to the next lane by shuffle (4 SHFL
- * for 4 shared-memory atomics per channel; bit-identical tiles), off until measured. */
+ * "brick" = 0 | 1, the brick-tiled shared-memory scatters (default 1; 0 = generic global-atomic kernels);
+ * "gather_tma" = 0 | 1, the step-loop gathers with bulk-copy staged particle arrays (csrc/cic4_tma.cu; default 1);
+ * "gather_seg" = 32 | 64 | 128, particles per bulk copy there (default 32). */
 int mcpm_tune(const char* key, int value);
+/* The same knobs for ONE engine.  mcpm_tune sets the process-wide defaults, which an engine copies when it is created and
+ * which the stateless entry points use; an engine's own knobs apply to its composite operators only, so replicas on
+ * several devices / threads in one process do not interfere. */
+int mcpm_engine_tune(mcpm_engine* eng, const char* key, int value);
 
 /* Engine for real mesh shape (nx, ny, nz) on the current device.  max_batch = largest number of meshes transformed
  * in one call (6 covers 2LPT).  Scratch = (2*max_batch+2) meshes + cuFFT work area, allocated here, once. */
@@ -404,7 +409,11 @@ int mcpm_pm_forces2(mcpm_engine* eng, void* stream, const float* pos, const void
 
 /* lpt (nbody.py:634-667), scalar scale factor.  Growth coefficients are host scalars computed by the caller
  * (d1 = a2g(a), d2 = a2g2(a), dv2 = a2dg2dg(a), nbody.py:750-777) so they stay differentiable on the host.
- * Outputs dpos, vel [np,3]; tape: f1 [np,3], f2 [np,3], h6 [6,nx,ny,nz] (each nullable when no VJP is wanted). */
+ * Outputs dpos, vel [np,3]; tape: f1 [np,3], f2 [np,3], h6 [6,nx,ny,nz] (each nullable when no VJP is wanted).
+ * pos == NULL (mcpm_lpt, mcpm_lpt_vjp, mcpm_pm_forces_mesh, mcpm_pm_forces2): the particles sit on the cells of the mesh,
+ * pos = regular_pos(mesh_shape) (bricks.py:593-603; np = nx*ny*nz), which is how nbody_bf and model.evolve call lpt
+ * (nbody.py:984, model.py:763).  NGP and CIC reads there return the cell value itself, so the three reads and their
+ * transposes become layout changes instead of gathers / scatters. */
 int mcpm_lpt(mcpm_engine* eng, void* stream, const void* delta_k, const float* pos, int64_t np, int lpt_order,
              int read_order, int lap_fd, int grad_fd, float d1, float d2, float dv2, float* dpos, float* vel,
              float* f1, float* f2, float* h6);

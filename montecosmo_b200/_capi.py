@@ -22,6 +22,7 @@ SIGNATURES = {
     "mcpm_engine_set_fused_fft": ([vp, i32], i32),
     "mcpm_engine_set_relative": ([vp, i32], i32),
     "mcpm_tune": ([C.c_char_p, i32], i32),
+    "mcpm_engine_tune": ([vp, C.c_char_p, i32], i32),
     "mcpm_paint_brick": ([vp, i32, i32, i32, vp, vp, f32, f32, i64] + MESH + [vp], i32),
     "mcpm_paint3_brick": ([vp, i32, i32, i32, vp, vp, vp, f32, f32, i64] + MESH + [vp], i32),
     "mcpm_paint_lattice": ([vp, vp, vp, vp, f32, i64, vp], i32),

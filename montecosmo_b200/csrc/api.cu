@@ -11,6 +11,62 @@ static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static Tune g_default_tune;
+static thread_local const Tune* t_tune = nullptr;
+Tune& default_tune() { return g_default_tune; }
+const Tune& tune() { return t_tune ? *t_tune : g_default_tune; }
+TuneScope::TuneScope(const Tune* t) : prev(t_tune) { t_tune = t; }
+TuneScope::~TuneScope() { t_tune = prev; }
+
+int tune_set(Tune& t, const char* key, int value) {
+  const std::string k(key ? key : "");
+  auto bad = [&](const char* msg) {
+    set_error(std::string("tune: ") + msg);
+    return (int)MCPM_EINVAL;
+  };
+  if (k == "gather_minb") {
+    if (value < 4 || value > 6) return bad("gather_minb must be 4, 5 or 6");
+    t.gather_minb = value;
+  } else if (k == "side_zero") {
+    t.side_zero = value != 0;
+  } else if (k == "gather_blocked") {
+    t.gather_blocked = value != 0;
+  } else if (k == "brick") {
+    t.brick = value != 0;
+  } else if (k == "gather_tma") {
+    t.gather_tma = value != 0;
+  } else if (k == "gather_seg") {
+    if (value != 32 && value != 64 && value != 128) return bad("gather_seg must be 32, 64 or 128");
+    t.gather_seg = value;
+  } else {
+    return bad(("unknown key " + k).c_str());
+  }
+  return MCPM_OK;
+}
+
+// Make the engine's device current for the duration of an entry point and restore the caller's device afterwards
+// (callers such as XLA's executor threads or torch's autograd workers own their current-device state).
+struct DeviceScope {
+  int prev = -1, err = 0;
+  explicit DeviceScope(int d) {
+#ifndef MCPM_HOSTEMU
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      prev = -1;
+      cudaGetLastError();
+    }
+    if (prev != d) err = rt_bind_device(d);
+    else prev = -1;  // already current: nothing to restore
+#else
+    (void)d;
+#endif
+  }
+  ~DeviceScope() {
+#ifndef MCPM_HOSTEMU
+    if (prev >= 0) cudaSetDevice(prev);
+#endif
+  }
+};
 }  // namespace mcpm
 
 using namespace mcpm;
@@ -36,10 +92,10 @@ struct mcpm_slabfft {
     return MCPM_EINVAL;                          \
   }
 
-#define BIND(eng)                                  \
-  do {                                             \
-    if (int _b = rt_bind_device((eng)->e->device)) return _b; \
-  } while (0)
+#define BIND(eng)                               \
+  DeviceScope _dev((eng)->e->device);           \
+  if (_dev.err) return _dev.err;                \
+  TuneScope _tune(&(eng)->e->tune)
 
 #define NEED(cond, msg)   \
   do {                    \
@@ -126,37 +182,14 @@ int mcpm_engine_set_relative(mcpm_engine* eng, int on) {
 int mcpm_tune(const char* key, int value) {
   API_BEGIN
   NEED(key, "tune: null key");
-  if (std::string(key) == "gather_minb") {
-    NEED(value >= 4 && value <= 6, "tune: gather_minb must be 4, 5 or 6");
-    set_gather_minb(value);
-    return MCPM_OK;
-  }
-  if (std::string(key) == "side_zero") {
-    set_side_zero(value != 0);
-    return MCPM_OK;
-  }
-  if (std::string(key) == "gather_blocked") {
-    set_gather_blocked(value != 0);
-    return MCPM_OK;
-  }
-  if (std::string(key) == "gather_tma" || std::string(key) == "gather_seg") {
-#ifndef MCPM_HOSTEMU
-    if (std::string(key) == "gather_tma") set_gather_tma(value != 0);
-    else {
-      NEED(value == 32 || value == 64 || value == 128, "tune: gather_seg must be 32, 64 or 128");
-      set_gather_seg(value);
-    }
-#endif
-    return MCPM_OK;
-  }
-  if (std::string(key) == "brick_zmerge") {
-#ifndef MCPM_HOSTEMU
-    set_brick_zmerge(value != 0);
-#endif
-    return MCPM_OK;
-  }
-  set_error(std::string("tune: unknown key ") + key);
-  return MCPM_EINVAL;
+  return tune_set(default_tune(), key, value);
+  API_END
+}
+
+int mcpm_engine_tune(mcpm_engine* eng, const char* key, int value) {
+  API_BEGIN
+  NEED(eng && key, "engine_tune: null argument");
+  return tune_set(eng->e->tune, key, value);
   API_END
 }
 
@@ -958,7 +991,7 @@ int mcpm_lpt(mcpm_engine* eng, void* stream, const void* delta_k, const float* p
              int read_order, int lap_fd, int grad_fd, float d1, float d2, float dv2, float* dpos, float* vel,
              float* f1, float* f2, float* h6) {
   API_BEGIN
-  NEED(eng && delta_k && pos, "lpt: null pointer");
+  NEED(eng && delta_k, "lpt: null pointer");  // pos == NULL: the particles sit on the cells of the mesh
   BIND(eng);
   return lpt(eng->e, as_stream(stream), C(delta_k), pos, np, lpt_order, read_order, lap_fd, grad_fd, d1, d2, dv2,
              dpos, vel, f1, f2, h6);
@@ -969,7 +1002,7 @@ int mcpm_lpt_vjp(mcpm_engine* eng, void* stream, const float* pos, int64_t np, i
                  int lap_fd, int grad_fd, float d1, float d2, float dv2, const float* dposbar, const float* velbar,
                  const float* f1, const float* f2, const float* h6, void* dkbar, double* coefbar, int accumulate) {
   API_BEGIN
-  NEED(eng && pos && dposbar && velbar && dkbar, "lpt_vjp: null pointer");
+  NEED(eng && dposbar && velbar && dkbar, "lpt_vjp: null pointer");
   BIND(eng);
   return lpt_vjp(eng->e, as_stream(stream), pos, np, lpt_order, read_order, lap_fd, grad_fd, d1, d2, dv2, dposbar,
                  velbar, f1, f2, h6, C(dkbar), coefbar, accumulate);

@@ -63,12 +63,9 @@ struct BrickArgs {
 __device__ __forceinline__ int brick_qi(int warp, int r) { return ((warp >> 3) + 2 * ((warp & 7) + r)) & 15; }
 
 // FULL: the lattice divides into whole bricks (no per-particle bounds checks).
-// ZMERGE (mcpm_tune("brick_zmerge"), off by default until measured): the 32 lanes of a warp hold z-neighbours of one
-// lattice row, so lane l's upper-z deposits and lane l+1's lower-z deposits usually land on the same four tile cells
-// (base cells one apart in z, same x and y).  The lower lane then hands its four upper values to the next lane by
-// shuffle instead of issuing them: 4 SHFL replace 4 ATOMS per channel (the LSU pipe bounds this kernel, DESIGN.md
-// section 4).  Integer sums are associative, so the tile -- and the result -- is bit-identical to the unmerged kernel.
-template <int NCH, bool FULL, bool ZMERGE>
+// (A variant that handed each lane's four upper-z deposits to the next lane by shuffle -- 4 SHFL for 4 ATOMS -- was
+// measured on a B200 in round 2 and removed: 29.98 vs 29.51 ms per evaluation, the shuffles cost what the atomics saved.)
+template <int NCH, bool FULL>
 __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickArgs a) {
   using namespace brick;
   extern __shared__ __align__(16) int smem[];
@@ -219,66 +216,27 @@ __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickA
   }
   __syncthreads();  // rowbase, nstray
 
-  // ZMERGE: which slots absorb the previous lane's upper-z deposits / hand theirs to the next lane (tile cells one
-  // apart: in-tile cells have tz <= TZ - 2, so tcell + 1 is the same tile row)
-  unsigned take = 0, give = 0;
-  if (ZMERGE) {
-#pragma unroll
-    for (int r = 0; r < PPT; ++r) {
-      const int prev = __shfl_up_sync(0xffffffffu, tcell[r], 1), next = __shfl_down_sync(0xffffffffu, tcell[r], 1);
-      if (tcell[r] >= 0) {
-        if (lane > 0 && prev >= 0 && prev + 1 == tcell[r]) take |= 1u << r;
-        if (lane < 31 && next == tcell[r] + 1) give |= 1u << r;
-      }
-    }
-  }
-
   const int64_t plane = (int64_t)a.nx * a.ny * a.nz;
+  bool all_stray = false;  // block-uniform
 #pragma unroll 1
   for (int c = 0; c < NCH; ++c) {
     const float l = bc[4 + c];
-    float e = l > 0.f ? floorf(log2f(1073741824.0f / l)) : 0.f;
-    e = fminf(fmaxf(e, -120.f), 120.f);
-    const float S = exp2f(e), invS = exp2f(-e);
     const float* valp = NCH == 1 ? (a.w ? a.w + pbase / 3 : nullptr) : a.A + pbase + c;
     const int vstride = NCH == 1 ? a.py * a.pz : plane3;
+    // Fixed-point scale.  Safe: S = 2^floor(log2(2^30 / sum|v|)) cannot overflow whatever the clustering, but its quantum
+    // (2^-18 of a unit weight for a 4096-particle brick) puts ~3e-6 of white noise on a unit-mean density mesh -- 50x
+    // float32 rounding, and measured as a 4.5x larger displacement error than the float-atomic CPU port after 10 steps.
+    // The density paint therefore deposits with 8 S (FINE = 3 bits: quantum 2^-21, float32-like) and verifies: the largest
+    // true cell sum is then < 8 * 2^30, so a cell that left [-2^29, 2^29) -- possibly wrapped -- still reads outside that
+    // band (an undetected alias would need a true sum beyond 2^32 - 2^29 > 8 * 2^30).  If any cell does (one cell holding
+    // > 1/16 of the brick's weight: rare even in clusters) the tile is dropped and the whole brick goes through the stray
+    // path below (float atomics to global memory).  The reverse-step channels keep the safe scale: their noise enters
+    // the gradient linearly (~3e-6 relative), not through particles changing cells.
+    constexpr int FINE = NCH == 1 ? 3 : 0;
+    float e = l > 0.f ? floorf(log2f(1073741824.0f / l)) + (float)FINE : 0.f;
+    e = fminf(fmaxf(e, -120.f), 120.f);
+    const float S = exp2f(e), invS = exp2f(-e);
     const float scale = (NCH == 1 ? a.ws : a.s) * S;
-    if (ZMERGE) {
-#pragma unroll
-      for (int r = 0; r < PPT; ++r) {  // warp-uniform: every lane runs the shuffles, inactive lanes carry zeros
-        const bool act = tcell[r] >= 0;
-        const float vs = act ? (valp ? valp[brick_qi(warp, r) * vstride] * scale : scale) : 0.f;
-        const float fx = x[r][0], fy = x[r][1], fz = x[r][2];
-        const float gx = 1.f - fx, gy = 1.f - fy;
-        const float vz1 = vs * fz, vz0 = vs - vz1;
-        const float w00 = gx * gy, w01 = gx * fy, w10 = fx * gy, w11 = fx * fy;
-        int lo0 = __float2int_rn(vz0 * w00), lo1 = __float2int_rn(vz0 * w01), lo2 = __float2int_rn(vz0 * w10),
-            lo3 = __float2int_rn(vz0 * w11);
-        const int up0 = __float2int_rn(vz1 * w00), up1 = __float2int_rn(vz1 * w01), up2 = __float2int_rn(vz1 * w10),
-                  up3 = __float2int_rn(vz1 * w11);
-        const int p0 = __shfl_up_sync(0xffffffffu, up0, 1), p1 = __shfl_up_sync(0xffffffffu, up1, 1),
-                  p2 = __shfl_up_sync(0xffffffffu, up2, 1), p3 = __shfl_up_sync(0xffffffffu, up3, 1);
-        if (take >> r & 1) {
-          lo0 += p0;
-          lo1 += p1;
-          lo2 += p2;
-          lo3 += p3;
-        }
-        if (act) {
-          int* t = tile + tcell[r];
-          atomicAdd(t, lo0);
-          atomicAdd(t + TZ, lo1);
-          atomicAdd(t + TY * TZ, lo2);
-          atomicAdd(t + TY * TZ + TZ, lo3);
-          if (!(give >> r & 1)) {
-            atomicAdd(t + 1, up0);
-            atomicAdd(t + TZ + 1, up1);
-            atomicAdd(t + TY * TZ + 1, up2);
-            atomicAdd(t + TY * TZ + TZ + 1, up3);
-          }
-        }
-      }
-    } else {
 #pragma unroll
     for (int r = 0; r < PPT; ++r) {
       if (tcell[r] < 0) continue;
@@ -297,8 +255,20 @@ __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickA
       atomicAdd(t + TY * TZ + TZ, __float2int_rn(vz0 * w11));
       atomicAdd(t + TY * TZ + TZ + 1, __float2int_rn(vz1 * w11));
     }
-    }
     __syncthreads();
+    if (FINE > 0) {
+      unsigned bad = 0;  // any cell outside [-2^29, 2^29)?
+      for (int g = tid; g < GROUPS; g += THREADS) {
+        const int4 q = tile4[g];
+        bad |= ((unsigned)q.x + 0x20000000u) | ((unsigned)q.y + 0x20000000u) | ((unsigned)q.z + 0x20000000u) |
+               ((unsigned)q.w + 0x20000000u);
+      }
+      if (__syncthreads_or((bad >> 30) != 0)) {  // drop the tile: every particle of the brick takes the stray path
+        for (int i = tid; i < GROUPS; i += THREADS) tile4[i] = make_int4(0, 0, 0, 0);
+        all_stray = true;
+        __syncthreads();
+      }
+    }
     // flush the touched 16-byte groups (one red.global.add.v4.f32 each) and re-zero them for the next channel
     float* meshc = a.mesh + c * plane;
     for (int g = tid; g < GROUPS; g += THREADS) {
@@ -314,12 +284,14 @@ __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickA
     }
     if (c + 1 < NCH) __syncthreads();
   }
-  // strays: float atomics straight to global memory, one queued particle per thread (convergent)
-  const int ns = nstray;
+  // strays: float atomics straight to global memory, one queued particle per thread (convergent); after a dropped tile,
+  // every particle of the brick
+  const int ns = all_stray ? PPT * THREADS : nstray;
   for (int si = tid; si < ns; si += THREADS) {
-    const int code = stray[si], r = code / THREADS, t2 = code - r * THREADS;
+    const int code = all_stray ? si : stray[si], r = code / THREADS, t2 = code - r * THREADS;
     const int w2 = t2 >> 5;
     const int si0 = q0i + brick_qi(w2, r), sj0 = q0j + (w2 & 7), sk0 = q0k + (t2 & 31);
+    if (!FULL && all_stray && (si0 >= a.px || sj0 >= a.py || sk0 >= a.pz)) continue;
     const int64_t p3 = 3 * (((int64_t)si0 * a.py + sj0) * a.pz + sk0);
     // the same u = x - site as pass 1, so that the fractions are bit-identical to the in-tile path
     const float px = (a.pos[p3] + a.shift) - (a.rel ? 0.f : (float)(si0 + a.ox)),
@@ -356,6 +328,7 @@ __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickA
 // particles into a mesh extended by halo planes).
 static bool brick_ok(const Lattice& L, int64_t np, int nx, int ny, int nz) {
   using namespace brick;
+  if (!tune().brick) return false;  // mcpm_tune("brick", 0): A/B against the generic global-atomic kernels
   if (L.px <= 0 || L.py <= 0 || L.pz <= 0 || L.px > nx || L.py > ny || L.pz > nz) return false;
   if ((int64_t)L.px * L.py * L.pz != np) return false;
   if ((nz & 3) || nx < TX || ny < TY || nz < TZ) return false;         // a tile must not wrap onto itself
@@ -363,14 +336,12 @@ static bool brick_ok(const Lattice& L, int64_t np, int nx, int ny, int nz) {
   return true;
 }
 
-static int g_brick_zmerge = 0;  // mcpm_tune("brick_zmerge"): hand upper-z deposits to the next lane by shuffle (see kernel)
-void set_brick_zmerge(int v) { g_brick_zmerge = v; }
 
-template <int NCH, bool FULL, bool ZMERGE>
+template <int NCH, bool FULL>
 static void launch_brick_variant(stream_t st, const BrickArgs& a, dim3 grid) {
   using namespace brick;
-  cudaFuncSetAttribute(brick_scatter_kernel<NCH, FULL, ZMERGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
-  brick_scatter_kernel<NCH, FULL, ZMERGE><<<grid, THREADS, SMEM, st>>>(a);
+  cudaFuncSetAttribute(brick_scatter_kernel<NCH, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+  brick_scatter_kernel<NCH, FULL><<<grid, THREADS, SMEM, st>>>(a);
 }
 
 template <int NCH>
@@ -379,13 +350,8 @@ static int launch_brick(stream_t st, const BrickArgs& a) {
   dim3 grid((a.pz + BZ - 1) / BZ, (a.py + BY - 1) / BY, (a.px + BX - 1) / BX);
   count_launch();
   const bool full = a.px % BX == 0 && a.py % BY == 0 && a.pz % BZ == 0;
-  if (g_brick_zmerge) {
-    if (full) launch_brick_variant<NCH, true, true>(st, a, grid);
-    else launch_brick_variant<NCH, false, true>(st, a, grid);
-  } else {
-    if (full) launch_brick_variant<NCH, true, false>(st, a, grid);
-    else launch_brick_variant<NCH, false, false>(st, a, grid);
-  }
+  if (full) launch_brick_variant<NCH, true>(st, a, grid);
+  else launch_brick_variant<NCH, false>(st, a, grid);
   return rt_check("brick_scatter") ? -1 : 1;
 }
 

@@ -37,23 +37,19 @@ __device__ __forceinline__ f4 load4(const f4* p) {
 
 // Resident CTAs per SM the two gather kernels are compiled for (register cap 64 / 48 / 40 per thread).  They are bound by
 // load latency at ~50% occupancy (profiles/r1_ncu_brick_v2.txt), so fewer registers can pay; mcpm_tune("gather_minb").
-static int g_gather_minb = 4;
-static int g_gather_blocked = 0;
-void set_gather_minb(int v) { g_gather_minb = v; }
-void set_gather_blocked(int v) { g_gather_blocked = v; }
 template <class F>
 static void launch_gather(stream_t st, int64_t n, F f) {
 #ifndef MCPM_HOSTEMU
   // blocked: one CTA per 256 consecutive particles, scheduled in order -- a single front sweeps the mesh, so every mesh
   // line is fetched from HBM about once; the grid-stride launch keeps ~27 fronts alive, more than L2 holds
-  if (g_gather_blocked && n > 0) {
+  if (tune().gather_blocked && n > 0) {
     count_launch();
     k_launch_1d<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, f);
     return;
   }
 #endif
-  if (g_gather_minb == 5) launch_1d_occ<5>(st, n, f);
-  else if (g_gather_minb == 6) launch_1d_occ<6>(st, n, f);
+  if (tune().gather_minb == 5) launch_1d_occ<5>(st, n, f);
+  else if (tune().gather_minb == 6) launch_1d_occ<6>(st, n, f);
   else launch_1d(st, n, f);
 }
 

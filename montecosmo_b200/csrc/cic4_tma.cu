@@ -14,6 +14,12 @@
 //   * the mesh is read as before, 8 x LDG.128 per particle through L1: the segments of a CTA are consecutive in the
 //     particle order (Lagrangian order, z fastest), so the CTA's gathers stay inside a few mesh rows, and CTAs are
 //     scheduled in particle order -- one front sweeps the mesh, every mesh line is fetched from HBM about once.
+// The CTAs are PERSISTENT (one grid-sized wave; warp w of the grid takes segments w, w + W, w + 2W, ...): the first version
+// gave every CTA four segments per warp and measured 0.52 ms where the kernel it replaced took 0.29 -- each short-lived
+// CTA paid the pipeline fill (barrier set-up, first copy latency) and the drain of its last stores.  At any instant the
+// grid works on W consecutive segments (a slab of ~2 lattice x-planes at 256^3), so the mesh footprint in flight stays
+// inside L2.  Shared memory is kept small (SEG = 32: 0.4 KB per array and stage) because it is carved out of L1, which
+// the mesh gathers need: 64- and 128-particle segments measured 1.5 and 7 ms slower per evaluation than 32.
 // Works for absolute positions in any particle order, and for lattice-relative positions (frame.h) of spacing one cell
 // whose pencils hold a whole number of segments; anything else takes the kernels of cic4.cu.
 #ifndef MCPM_HOSTEMU
@@ -25,8 +31,8 @@ namespace mcpm {
 
 namespace gtma {
 constexpr int WARPS = 8;   // per CTA
-constexpr int SPW = 4;     // segments per warp and CTA pass
 constexpr int THREADS = WARPS * 32;
+constexpr int NSTAGE = 3;  // input ring per warp: two segments in flight under the one being worked on
 }  // namespace gtma
 
 struct GatherArgs {
@@ -74,39 +80,39 @@ __global__ void __launch_bounds__(gtma::THREADS, MODE == 0 ? 4 : 3) gather_tma_k
   constexpr int SUB = SEG / 32;
   static_assert(SEG % 32 == 0 && BYTES % 16 == 0, "a segment is whole warps and whole 16-byte units");
   extern __shared__ __align__(128) float smem[];
-  __shared__ __align__(8) uint64_t bars[WARPS][2];
+  __shared__ __align__(8) uint64_t bars[WARPS][NSTAGE];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* sin = smem + (size_t)warp * (2 * (NIN + NOUT) * ROW);  // [stage][NIN][ROW]
-  float* sout = sin + 2 * NIN * ROW;                            // [stage][NOUT][ROW]
+  float* sin = smem + (size_t)warp * ((NSTAGE * NIN + 2 * NOUT) * ROW);  // [NSTAGE][NIN][ROW]
+  float* sout = sin + NSTAGE * NIN * ROW;                                // [2][NOUT][ROW]
   uint64_t* bar = bars[warp];
   if (lane == 0) {
-    tma::mbar_init(&bar[0], 1);
-    tma::mbar_init(&bar[1], 1);
+    for (int i = 0; i < NSTAGE; ++i) tma::mbar_init(&bar[i], 1);
     tma::fence_barrier_init();
   }
   __syncwarp();
 
   const int nload = (MODE == 1 && !a.accumulate) ? 2 : NIN;
-  const int64_t seg0 = (int64_t)blockIdx.x * (WARPS * SPW) + warp;
-  auto issue = [&](int t) {  // lane 0: bulk loads of this warp's t-th segment into stage t & 1
-    const int64_t seg = seg0 + (int64_t)t * WARPS;
-    const int st = t & 1;
+  const int64_t W = (int64_t)gridDim.x * WARPS;              // warps in the grid
+  const int64_t seg0 = (int64_t)blockIdx.x * WARPS + warp;   // this warp's first segment
+  const int nmine = seg0 < a.nseg ? (int)((a.nseg - seg0 + W - 1) / W) : 0;
+  auto issue = [&](int t) {  // lane 0: bulk loads of this warp's t-th segment into stage t % NSTAGE
+    const int64_t seg = seg0 + (int64_t)t * W;
+    const int st = t % NSTAGE;
     tma::mbar_arrive_expect_tx(&bar[st], BYTES * nload);
     for (int m = 0; m < nload; ++m)
       tma::bulk_g2s(sin + (st * NIN + m) * ROW, a.in[m] + seg * ROW, BYTES, &bar[st]);
   };
-  int nmine = 0;  // segments of this warp in this pass
-  for (int t = 0; t < SPW; ++t)
-    if (seg0 + (int64_t)t * WARPS < a.nseg) nmine = t + 1;
-  if (nmine > 0 && lane == 0) issue(0);
+  if (lane == 0)
+    for (int t = 0; t < NSTAGE - 1 && t < nmine; ++t) issue(t);
 
   const float4* __restrict__ fm = a.fm4;
   const int nx = a.nx, ny = a.ny, nz = a.nz;
   for (int t = 0; t < nmine; ++t) {
-    const int st = t & 1;
-    if (t + 1 < nmine && lane == 0) issue(t + 1);  // stage st^1 was last read in iteration t-1 (syncwarp since)
-    tma::mbar_wait(&bar[st], (t >> 1) & 1);
-    const int64_t p0 = (seg0 + (int64_t)t * WARPS) * SEG;
+    const int st = t % NSTAGE;
+    // stage (t + NSTAGE - 1) % NSTAGE was last read in iteration t - 1 (syncwarp since)
+    if (lane == 0 && t + NSTAGE - 1 < nmine) issue(t + NSTAGE - 1);
+    tma::mbar_wait(&bar[st], (uint32_t)(t / NSTAGE) & 1u);
+    const int64_t p0 = (seg0 + (int64_t)t * W) * SEG;
     int sx = 0, sy = 0, sk = 0;
     if (a.rel) {  // lattice site of the segment's first particle: one pencil holds whole segments
       const int64_t jk = p0 / a.pz;
@@ -118,10 +124,10 @@ __global__ void __launch_bounds__(gtma::THREADS, MODE == 0 ? 4 : 3) gather_tma_k
     const float* spos = sin + (st * NIN + 0) * ROW;
     const float* sb = sin + (st * NIN + 1) * ROW;
     const float* sc = sin + (st * NIN + (NIN - 1)) * ROW;
-    if (lane == 0) tma::bulk_wait_read<1>();  // the stores of iteration t-2 have released sout[st]
+    if (lane == 0) tma::bulk_wait_read<1>();  // the stores of iteration t-2 have released sout[t & 1]
     __syncwarp();
-    float* o0 = sout + (st * NOUT + 0) * ROW;
-    float* o1 = sout + (st * NOUT + 1) * ROW;
+    float* o0 = sout + ((t & 1) * NOUT + 0) * ROW;
+    float* o1 = sout + ((t & 1) * NOUT + 1) * ROW;
 #pragma unroll
     for (int s = 0; s < SUB; ++s) {
       const int q = (s * 32 + lane) * 3;
@@ -206,16 +212,13 @@ __global__ void __launch_bounds__(gtma::THREADS, MODE == 0 ? 4 : 3) gather_tma_k
   if (lane == 0) tma::bulk_wait<0>();  // shared memory must outlive the last stores
 }
 
-static int g_gather_tma = 1;  // mcpm_tune("gather_tma"): 1 = these kernels where they apply, 0 = cic4.cu's
-void set_gather_tma(int v) { g_gather_tma = v; }
-static int g_gather_seg = 64;  // mcpm_tune("gather_seg"): particles per bulk copy (32 | 64 | 128)
-void set_gather_seg(int v) { g_gather_seg = v; }
+// knobs: tune().gather_tma (1 = these kernels where they apply, 0 = cic4.cu's), tune().gather_seg (32 default | 64 | 128)
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // Geometry check shared by both entry points; fills the frame part of the arguments.
 static bool gather_tma_ok(GatherArgs& a, int64_t np, const Frame* fr, int seg) {
-  if (!g_gather_tma || np <= 0 || np % seg) return false;
+  if (!tune().gather_tma || np <= 0 || np % seg) return false;
   a.rel = 0;
   if (fr && fr->rel) {
     if (fr->nux != 1 || fr->nuy != 1 || fr->nuz != 1 || fr->dex != 1 || fr->dey != 1 || fr->dez != 1) return false;
@@ -231,27 +234,35 @@ static bool gather_tma_ok(GatherArgs& a, int64_t np, const Frame* fr, int seg) {
   return true;
 }
 
+template <int MODE, int SEG>
+static void launch_gather_tma_seg(stream_t st, const GatherArgs& a) {
+  using namespace gtma;
+  constexpr int NIN = MODE == 0 ? 2 : 3, NOUT = 2;
+  const size_t smem = (size_t)WARPS * (NSTAGE * NIN + 2 * NOUT) * SEG * 3 * sizeof(float);
+  static int per_sm[16] = {0};  // resident CTAs per SM of this instantiation, per device (queried once)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 15;
+  if (per_sm[dev] == 0) {
+    cudaFuncSetAttribute(gather_tma_kernel<MODE, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gather_tma_kernel<MODE, SEG>, THREADS, smem) != cudaSuccess ||
+        n < 1)
+      n = 1;
+    per_sm[dev] = n;
+  }
+  const int64_t want = (a.nseg + WARPS - 1) / WARPS, wave = (int64_t)kSMs * per_sm[dev];
+  const unsigned grid = (unsigned)(want < wave ? want : wave);  // persistent: at most one resident wave
+  gather_tma_kernel<MODE, SEG><<<grid, THREADS, smem, st>>>(a);
+}
+
 template <int MODE>
 static int launch_gather_tma(stream_t st, const GatherArgs& a, int seg) {
-  using namespace gtma;
-  const int64_t per_cta = WARPS * SPW;
-  const unsigned grid = (unsigned)((a.nseg + per_cta - 1) / per_cta);
-  constexpr int NARR = (MODE == 0 ? 2 : 3) + 2;
-  const size_t smem = (size_t)WARPS * 2 * NARR * seg * 3 * sizeof(float);
   count_launch();
   switch (seg) {
-    case 32:
-      cudaFuncSetAttribute(gather_tma_kernel<MODE, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      gather_tma_kernel<MODE, 32><<<grid, THREADS, smem, st>>>(a);
-      break;
-    case 128:
-      cudaFuncSetAttribute(gather_tma_kernel<MODE, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      gather_tma_kernel<MODE, 128><<<grid, THREADS, smem, st>>>(a);
-      break;
-    default:
-      cudaFuncSetAttribute(gather_tma_kernel<MODE, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      gather_tma_kernel<MODE, 64><<<grid, THREADS, smem, st>>>(a);
-      break;
+    case 64: launch_gather_tma_seg<MODE, 64>(st, a); break;
+    case 128: launch_gather_tma_seg<MODE, 128>(st, a); break;
+    default: launch_gather_tma_seg<MODE, 32>(st, a); break;
   }
   return rt_check(MODE == 0 ? "kick_drift4 (bulk-copy staged)" : "read_grad4v (bulk-copy staged)") ? -1 : 1;
 }
@@ -259,7 +270,7 @@ static int launch_gather_tma(stream_t st, const GatherArgs& a, int seg) {
 // Return 1 if handled, 0 if the caller must take the cic4.cu kernel, < 0 on a launch error.
 int kick_drift4_tma(stream_t st, const float* pos, const float* vel, const float* fmesh4, int64_t np, int nx, int ny,
                     int nz, float alpha, float beta, float drift, float* pos_out, float* vel_out, const Frame* fr) {
-  const int seg = (g_gather_seg == 32 || g_gather_seg == 128) ? g_gather_seg : 64;
+  const int gs = tune().gather_seg, seg = (gs == 64 || gs == 128) ? gs : 32;
   GatherArgs a = {};
   if (!gather_tma_ok(a, np, fr, seg)) return 0;
   if (!aligned16(pos) || !aligned16(vel) || !aligned16(pos_out) || !aligned16(vel_out) || !aligned16(fmesh4)) return 0;
@@ -280,7 +291,7 @@ int kick_drift4_tma(stream_t st, const float* pos, const float* vel, const float
 int read_grad4v_tma(stream_t st, const float* pos, const float* fmesh4, const float* rhobar, float* cot, float cscale,
                     int scale_cot, float alpha_tail, int64_t np, int nx, int ny, int nz, float* grad, int accumulate,
                     const Frame* fr) {
-  const int seg = (g_gather_seg == 32 || g_gather_seg == 128) ? g_gather_seg : 64;
+  const int gs = tune().gather_seg, seg = (gs == 64 || gs == 128) ? gs : 32;
   GatherArgs a = {};
   if (!gather_tma_ok(a, np, fr, seg)) return 0;
   if (!aligned16(pos) || !aligned16(cot) || !aligned16(grad) || !aligned16(fmesh4)) return 0;

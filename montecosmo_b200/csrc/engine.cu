@@ -22,6 +22,7 @@ Engine* engine_create(int nx, int ny, int nz) {
   e->Nc = (int64_t)nx * ny * e->nzc;
   e->invN = (float)(1.0 / (double)e->N);
   e->device = rt_get_device();
+  e->tune = default_tune();
   size_t fftws = 0;
   e->fft = fft_create(nx, ny, nz, &fftws);
   if (!e->fft) {
@@ -60,9 +61,8 @@ void engine_destroy(Engine* e) {
 
 // CIC paint of pos * scale + shift into a fresh mesh: brick-tiled when the engine carries a matching lattice hint and
 // the positions are not rescaled (CUDA build), generic otherwise
-// mcpm_tune("side_zero"): clear the next step's scatter meshes inside the gather kernels (1) or with memsets (0)
-static int g_side_zero = 0;  // measured: no net gain (the gathers slow down by what the memsets cost), kept selectable
-void set_side_zero(int v) { g_side_zero = v; }
+// tune().side_zero: clear the next step's scatter meshes inside the gather kernels (1) or with memsets (0); measured: no
+// net gain (the gathers slow down by what the memsets cost), kept selectable
 
 static bool brick_path(const Engine* E, int order, const float* scale) {
 #ifndef MCPM_HOSTEMU
@@ -90,6 +90,33 @@ static int paint_fresh(Engine* E, stream_t st, const float* pos, const float* we
 static int paint_density(Engine* E, stream_t st, const float* pos, int64_t np, int order, float* mesh,
                          bool prezeroed = false) {
   return paint_fresh(E, st, pos, nullptr, 1.0f, np, order, nullptr, 0.0f, mesh, prezeroed);
+}
+
+// Three-mesh read at `pos`, or -- pos == NULL -- at the cells of the mesh themselves (regular_pos(mesh_shape)): a layout
+// change for NGP / CIC, the generic kernel on an identity frame for TSC / PCS.
+static int read3_at(Engine* E, stream_t st, const float* pos, const float* m3, int64_t np, int order, float* out) {
+  Frame f;
+  if (pos) return read(st, pos, m3, 3, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, out, 0.0f, E->frame(f));
+  if (np != E->N) {
+    set_error("pos == NULL means the particles sit on the cells of the mesh: np must equal nx*ny*nz");
+    return MCPM_EINVAL;
+  }
+  if (order <= 2) return read_sites3(st, m3, np, out);
+  f = make_rel_frame(E->nx, E->ny, E->nz, E->nx, E->ny, E->nz);
+  return read(st, nullptr, m3, 3, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, out, 0.0f, &f);
+}
+// its transpose: mesh3 = paint3(pos; ca A + cb B), fresh meshes
+static int paint3_at(Engine* E, stream_t st, const float* pos, const float* A, float ca, const float* B, float cb,
+                     int64_t np, int order, float* mesh3) {
+  Frame f;
+  if (pos) return paint3(st, pos, A, ca, B, cb, np, E->nx, E->ny, E->nz, order, mesh3, 0, E->frame(f));
+  if (np != E->N) {
+    set_error("pos == NULL means the particles sit on the cells of the mesh: np must equal nx*ny*nz");
+    return MCPM_EINVAL;
+  }
+  if (order <= 2) return paint_sites3(st, A, ca, B, cb, np, mesh3, 0);
+  f = make_rel_frame(E->nx, E->ny, E->nz, E->nx, E->ny, E->nz);
+  return paint3(st, nullptr, A, ca, B, cb, np, E->nx, E->ny, E->nz, order, mesh3, 0, &f);
 }
 
 // delta_k (any spectrum, preserved) -> three real force meshes fm[3][N]  (nbody.py:595-603 up to the irfftn)
@@ -167,8 +194,7 @@ int pm_forces_vjp(Engine* E, stream_t st, const float* pos, const float* fbar, f
 int pm_forces_mesh(Engine* E, stream_t st, const float* pos, const cfloat* dk, int64_t np, int order, int lap_fd,
                    int grad_fd, float kcut, float* forces) {
   TRY(force_meshes_from_spectrum(E, st, dk, lap_fd, grad_fd, kcut, 0, E->r(0)));
-  Frame f;
-  TRY(read(st, pos, E->r(0), 3, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, forces, 0.0f, E->frame(f)));
+  TRY(read3_at(E, st, pos, E->r(0), np, order, forces));
   return 0;
 }
 
@@ -193,8 +219,7 @@ int pm_forces2(Engine* E, stream_t st, const float* pos, const cfloat* dk, int64
     TRY(fft_r2c(E->fft, st, E->r(6), E->c(6), 1));
     TRY(force_meshes_from_spectrum(E, st, E->c(6), lap_fd, grad_fd, 0.0f, 0, E->r(0)));
   }
-  Frame f;
-  TRY(read(st, pos, E->r(0), 3, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, forces, 0.0f, E->frame(f)));
+  TRY(read3_at(E, st, pos, E->r(0), np, order, forces));
   return 0;
 }
 
@@ -222,14 +247,12 @@ int lpt(Engine* E, stream_t st, const cfloat* dk, const float* pos, int64_t np, 
 int lpt_vjp(Engine* E, stream_t st, const float* pos, int64_t np, int lpt_order, int read_order, int lap_fd,
             int grad_fd, float d1, float d2, float dv2, const float* dposbar, const float* velbar, const float* f1,
             const float* f2, const float* h6, cfloat* dkbar, double* coefbar, int accumulate) {
-  Frame f;
-  const Frame* fr = E->frame(f);
   if (lpt_order == 2) {
     if (!h6) {
       set_error("lpt_vjp: the Hessian tape h6 is required for lpt_order 2");
       return MCPM_EINVAL;
     }
-    TRY(paint3(st, pos, dposbar, -d2, velbar, -dv2, np, E->nx, E->ny, E->nz, read_order, E->r(0), 0, fr));
+    TRY(paint3_at(E, st, pos, dposbar, -d2, velbar, -dv2, np, read_order, E->r(0)));
     TRY(density_cotangent(E, st, E->r(0), lap_fd, grad_fd, 0.0f, 0, E->r(6)));  // d2bar (real)
     TRY(lpt2_source_vjp(st, h6, E->r(6), E->r(0), E->N));
 #ifndef MCPM_HOSTEMU
@@ -244,7 +267,7 @@ int lpt_vjp(Engine* E, stream_t st, const float* pos, int64_t np, int lpt_order,
     }
     accumulate = 1;
   }
-  TRY(paint3(st, pos, dposbar, d1, velbar, 1.0f, np, E->nx, E->ny, E->nz, read_order, E->r(0), 0, fr));
+  TRY(paint3_at(E, st, pos, dposbar, d1, velbar, 1.0f, np, read_order, E->r(0)));
 #ifndef MCPM_HOSTEMU
   if (E->fused_fft) {
     TRY(slabfft_r2c_yz(E->fft2d, st, E->r(0), E->c(0), 3));
@@ -292,7 +315,8 @@ int nbody_steps(Engine* E, stream_t st, float* pos, float* vel, int64_t np, int 
     float* slot = fm ? fm + (int64_t)s * 4 * E->N : E->r(3);
     float* planar = cic ? E->r(0) : slot;
     // under the brick path the density mesh of step s+1 is cleared by the kick kernel of step s
-    const bool side_zero = g_side_zero && cic && brick_path(E, order, nullptr);
+    // (needs the tape: without `fm` the float4 slot r(3..6) overlaps the density mesh r(6) the kick kernel would clear)
+    const bool side_zero = tune().side_zero && fm && cic && brick_path(E, order, nullptr);
     TRY(pm_forces(E, st, cur, np, order, paint_deconv, lap_fd, grad_fd, 0.0f, planar, nullptr, side_zero && s > 0));
     const bool last = (s == n_steps - 1);
     float dcomb = drift_post[s] + (last ? 0.0f : drift_pre[s + 1]);
@@ -331,7 +355,7 @@ int nbody_steps_vjp(Engine* E, stream_t st, float* posbar, float* velbar, int64_
   }
   const int64_t P3 = 3 * np;
   const bool cic = (order == 2);
-  const bool side_zero = g_side_zero && cic && brick_path(E, order, nullptr);
+  const bool side_zero = tune().side_zero && cic && brick_path(E, order, nullptr);
   Frame f;
   const Frame* fr = E->frame(f);
   for (int s = n_steps - 1; s >= 0; --s) {

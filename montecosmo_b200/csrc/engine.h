@@ -12,12 +12,35 @@ struct Lattice {
   int px = 0, py = 0, pz = 0;
 };
 
+// Performance knobs (never change which result is computed).  mcpm_tune sets the process-wide defaults, which every
+// engine copies at creation; mcpm_engine_tune changes one engine.  Kernels read the knobs of the engine whose entry point
+// is executing on the calling host thread (a thread-local pointer held for the duration of the call), so engines on
+// other devices or threads -- one replica per GPU in one process, SURVEY 8b -- never see each other's settings; the
+// stateless entry points use the defaults.
+struct Tune {
+  int side_zero = 0;       // clear the next step's scatter meshes inside the gather kernels instead of memsets
+  int gather_minb = 4;     // resident CTAs per SM the cic4.cu gathers are compiled for (4 | 5 | 6)
+  int gather_blocked = 0;  // cic4.cu gathers: one CTA per 256 consecutive particles instead of a grid-stride loop
+  int brick = 1;           // brick-tiled shared-memory scatters (brick.cu) where they apply; 0: generic global atomics
+  int gather_tma = 1;      // gathers with bulk-copy staged particle arrays (cic4_tma.cu) where they apply
+  int gather_seg = 32;     // particles per bulk copy there (32 | 64 | 128)
+};
+Tune& default_tune();  // api.cu
+const Tune& tune();    // the executing engine's knobs, else the defaults
+struct TuneScope {
+  const Tune* prev;
+  explicit TuneScope(const Tune* t);
+  ~TuneScope();
+};
+int tune_set(Tune& t, const char* key, int value);  // MCPM_OK or MCPM_EINVAL (message set)
+
 struct Engine {
   static constexpr int kR = 7;  // real scratch meshes (6 Hessian / 3 force + 1 density)
   static constexpr int kC = 7;  // half-spectrum scratch meshes
   int nx, ny, nz, nzc;
   int device = 0;  // CUDA device the plans and scratch live on
   Lattice lat;     // optional particle-order hint
+  Tune tune;       // this engine's performance knobs (copied from the process defaults at creation)
   int rel = 0;     // 1: the composite operators take lattice-relative positions (frame.h); needs `lat`
   // the frame the particle kernels are given: NULL (absolute) or the lattice `lat` spanning this engine's mesh
   const Frame* frame(Frame& f) const {
@@ -57,6 +80,8 @@ int paint_vjp(stream_t, const float* pos, const float* weights, float wscalar, c
 int kick_drift(stream_t, const float* pos, const float* vel, const float* fmesh3, int64_t np, int nx, int ny, int nz,
                int order, float alpha, float beta, float drift, float* pos_out, float* vel_out, float* force_out,
                const Frame* fr = nullptr);
+int read_sites3(stream_t, const float* planar3, int64_t n, float* out);
+int paint_sites3(stream_t, const float* A, float ca, const float* B, float cb, int64_t n, float* mesh3, int accumulate);
 int axpy3(stream_t, const float* a, const float* b, float s, int64_t n3, float* out);
 int lpt_combine(stream_t, const float* pos, const float* f1, const float* f2, float d1, float d2, float dv2,
                 int64_t np, float* dpos, float* vel, float* pos_out);
@@ -116,9 +141,6 @@ int cgh2rg(stream_t, const cfloat* meshk, float* mesh, int nx, int ny, int nz, f
 int hermitian_weights(stream_t, const cfloat* in, cfloat* out, int nx, int ny, int nz, int mode);
 
 // cic4.cu: CIC kernels on the float4-interleaved vector mesh
-void set_gather_minb(int v);
-void set_gather_blocked(int v);
-void set_brick_zmerge(int v);  // brick.cu (CUDA build only)
 int interleave3(stream_t, const float* planar3, float* mesh4, int64_t n);
 int deinterleave3(stream_t, const float* mesh4, float* planar3, int64_t n);
 int kick_drift4(stream_t, const float* pos, const float* vel, const float* fmesh4, int64_t np, int nx, int ny, int nz,
@@ -131,8 +153,6 @@ int read_grad4v(stream_t, const float* pos, const float* fmesh4, const float* rh
                 float* zero = nullptr, int64_t nzero = 0, const Frame* fr = nullptr);
 
 // cic4_tma.cu (CUDA build only): the same two gathers with bulk-copy staged particle arrays; 1 handled, 0 not applicable
-void set_gather_tma(int v);
-void set_gather_seg(int v);
 int kick_drift4_tma(stream_t, const float* pos, const float* vel, const float* fmesh4, int64_t np, int nx, int ny, int nz,
                     float alpha, float beta, float drift, float* pos_out, float* vel_out, const Frame* fr);
 int read_grad4v_tma(stream_t, const float* pos, const float* fmesh4, const float* rhobar, float* cot, float cscale,
@@ -164,7 +184,6 @@ int brick_paint3_cic(stream_t, const Lattice&, const float* pos, float* A, const
                      int64_t np, int nx, int ny, int nz, float* mesh3, const Frame* fr = nullptr);
 
 // engine.cu
-void set_side_zero(int v);
 int pm_forces(Engine*, stream_t, const float* pos, int64_t np, int order, int paint_deconv, int lap_fd, int grad_fd,
               float kcut, float* fmesh3, float* forces, bool rho_prezeroed = false);
 int pm_forces_vjp(Engine*, stream_t, const float* pos, const float* fbar, float cscale, const float* fmesh3,

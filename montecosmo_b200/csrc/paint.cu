@@ -533,6 +533,28 @@ int kick_drift(stream_t st, const float* pos, const float* vel, const float* fme
   return rt_check("kick_drift");
 }
 
+// ---- particles on the cells of the mesh (regular_pos(mesh_shape), bricks.py:593-603): NGP and CIC reads return the cell
+// value itself (a particle at an integer position has weight 1 on its base cell), so lpt's reads at q (nbody.py:984-985
+// pass read_order = 1) and their transposes are layout changes between planar meshes and the [np, 3] particle array.
+int read_sites3(stream_t st, const float* planar3, int64_t n, float* out) {
+  launch_1d(st, 3 * n, [=] MCPM_LAMBDA(int64_t i) {
+    const int64_t p = i / 3;
+    out[i] = planar3[(i - 3 * p) * n + p];
+  });
+  return rt_check("read_sites3");
+}
+// mesh3[c][p] (+)= ca * A[p, c] + cb * B[p, c]
+int paint_sites3(stream_t st, const float* A, float ca, const float* B, float cb, int64_t n, float* mesh3, int accumulate) {
+  launch_1d(st, n, [=] MCPM_LAMBDA(int64_t p) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = ca * A[3 * p + c] + (B ? cb * B[3 * p + c] : 0.0f);
+      mesh3[c * n + p] = accumulate ? mesh3[c * n + p] + v : v;
+    }
+  });
+  return rt_check("paint_sites3");
+}
+
 // ---- small particle-array kernels ------------------------------------------------------------------------------
 // out = a + b * s (drift, nbody.py:942-944); out may alias a
 int axpy3(stream_t st, const float* a, const float* b, float s, int64_t n3, float* out) {

@@ -152,13 +152,14 @@ class FieldModel:
         dk = self.linear_field(white)
         weights = 1.0
         if self.b1 != 0.0:
-            delta_q = nb.read(self.q, nb.irfftn(dk), order=1)
+            # read(q, delta, order=1) on the lattice that is the mesh: the NGP value at a cell centre is the cell itself
+            delta_q = nb.irfftn(dk).reshape(-1)
             weights = _Axpby.apply(delta_q, self.b1 * float(_cosmo.a2g(c, self.a_obs)), 1.0)
         # Particles are carried as float32 displacements from their lattice sites, never as the sum q + displacement
         # (nbody_bf's `relative`, nufft's `lattice`): the reference's float64 sum has no float32 equivalent at 256^3.
         rel = self.relative
         if self.evolution == "lpt":
-            pos, vel = nb.lpt(c, dk, self.q, self.a_obs, self.lpt_order, 1, _displaced=not rel)
+            pos, vel = nb.lpt(c, dk, None if rel else self.q, self.a_obs, self.lpt_order, 1, _displaced=not rel)
         elif self.evolution == "nbody":
             pos, vel = nb.nbody_bf(c, dk, self.q, self.a_start, self.a_obs, self.n_steps, self.paint_order,
                                    self.lpt_order, paint_deconv=False, ptcl_shape=self.mesh_shape, relative=rel)

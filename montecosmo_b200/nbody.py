@@ -315,6 +315,8 @@ class _Lpt(torch.autograd.Function):
         c = [float(v) for v in coef.detach().cpu()]
         dpos, vel, tape = ops().lpt(dk, pos, c[0], c[1], c[2], lpt_order, read_order, lap_fd, grad_fd, tape=True)
         if add_pos:  # return the displaced positions pos + dpos (same cotangent as dpos)
+            if pos is None:
+                raise ValueError("lpt on the mesh cells (pos=None) returns displacements")
             dpos = ops().axpby(dpos, 1.0, pos, 1.0)
         ctx.cfg = (c, lpt_order, read_order, lap_fd, grad_fd, tuple(dk.shape))
         ctx.pos, ctx.tape = pos, tape
@@ -324,8 +326,9 @@ class _Lpt(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dpb, vlb):
         c, lpt_order, read_order, lap_fd, grad_fd, cshape = ctx.cfg
-        dpb = torch.zeros_like(ctx.pos) if dpb is None else dpb.contiguous()
-        vlb = torch.zeros_like(ctx.pos) if vlb is None else vlb.contiguous()
+        like = dpb if dpb is not None else vlb
+        dpb = torch.zeros_like(like) if dpb is None else dpb.contiguous()
+        vlb = torch.zeros_like(like) if vlb is None else vlb.contiguous()
         want_coef = ctx.needs_input_grad[1]
         out = ops().lpt_vjp(ctx.pos, cshape, c[0], c[1], c[2], dpb, vlb, ctx.tape, lpt_order, read_order, lap_fd,
                             grad_fd, want_coef=want_coef)
@@ -487,6 +490,9 @@ def lpt(cosmo, init_mesh, pos, a, lpt_order: int = 2, read_order: int = 2, grad_
     init_mesh = torch.as_tensor(init_mesh)
     if not torch.is_complex(init_mesh):
         init_mesh = rfftn(init_mesh)
+    if pos is None:  # extension: the particles sit on the cells of the mesh (regular_pos(mesh_shape)); scalar `a` only
+        coef = _coef_tensor(_cosmo.a2g(cosmo, a), _cosmo.a2g2(cosmo, a), _cosmo.a2dg2dg(cosmo, a))
+        return _Lpt.apply(_c64(init_mesh), coef, None, int(lpt_order), int(read_order), lap_fd, grad_fd, False)
     if np.ndim(a) != 0:
         a_col = torch.as_tensor(a, dtype=torch.float64).detach().cpu().reshape(-1, 1)
         force1 = pm_forces(pos, init_mesh, read_order, grad_fd=grad_fd, lap_fd=lap_fd)
@@ -565,7 +571,10 @@ def nbody_bf(cosmo, init_mesh, pos, a0=0.0, a1=1.0, n_steps=5, paint_order: int 
     lattice = tuple(int(s) for s in ptcl_shape) if inner_rel else None
     if lattice is not None and int(np.prod(lattice)) != pos.shape[0]:
         raise ValueError("ptcl_shape does not match the number of particles")
-    x, vel = lpt(cosmo, init_mesh, pos, a0, lpt_order, 1, grad_fd, lap_fd, _displaced=not inner_rel)
+    # displacements from a lattice that IS the mesh: lpt's NGP reads at the sites are the cell values (pos=None fast path)
+    on_cells = inner_rel and lattice == tuple(mesh_shape)
+    x, vel = lpt(cosmo, init_mesh, None if on_cells else pos, a0, lpt_order, 1, grad_fd, lap_fd,
+                 _displaced=not inner_rel)
     al, be, pre, post, _, _ = _cosmo.bullfrog_coefficients(cosmo, a0, a1, n_steps, integrator)
     coefs = torch.stack([al, be, pre, post], dim=1)
     g0, g1 = _cosmo.a2g(cosmo, a0), _cosmo.a2g(cosmo, a1)

@@ -350,10 +350,12 @@ class Ops:
         return out
 
     def lpt(self, dk, pos, d1, d2, dv2, lpt_order=2, read_order=2, lap_fd=INF, grad_fd=INF, tape=False):
+        """pos None: the particles sit on the cells of the mesh (regular_pos(mesh_shape))."""
         A = self.A
-        pos, dk = A.prepare(pos), A.prepare(dk, "c64")
-        n = A.shape(pos)[0]
+        dk = A.prepare(dk, "c64")
         rs = ch2rshape(A.shape(dk))
+        pos = None if pos is None else A.prepare(pos)
+        n = math.prod(rs) if pos is None else A.shape(pos)[0]
         dpos, vel = A.empty((n, 3)), A.empty((n, 3))
         f1 = A.empty((n, 3)) if tape else None
         f2 = A.empty((n, 3)) if tape and lpt_order == 2 else None
@@ -366,9 +368,10 @@ class Ops:
     def lpt_vjp(self, pos, cshape, d1, d2, dv2, dposbar, velbar, tape, lpt_order=2, read_order=2, lap_fd=INF,
                 grad_fd=INF, want_coef=False):
         A = self.A
-        pos, dposbar, velbar = A.prepare(pos), A.prepare(dposbar), A.prepare(velbar)
+        dposbar, velbar = A.prepare(dposbar), A.prepare(velbar)
+        pos = None if pos is None else A.prepare(pos)
         f1, f2, h6 = tape
-        n = A.shape(pos)[0]
+        n = A.shape(dposbar)[0]
         rs = ch2rshape(cshape)
         dkbar = A.empty(cshape, "c64")
         coef = A.zeros((3,), "f64") if want_coef else None

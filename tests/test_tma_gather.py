@@ -83,7 +83,7 @@ def test_tma_gathers_are_bit_identical(mesh, lattice, rel):
                 assert torch.equal(a, b), (mesh, lattice, rel, seg, float((a - b).abs().max()))
     finally:
         tune(b"gather_tma", 1)
-        tune(b"gather_seg", 64)
+        tune(b"gather_seg", 32)
 
 
 def test_tma_gathers_launch_when_applicable():

@@ -36,53 +36,6 @@ def test_irfftn_non_hermitian_256():
     assert np.linalg.norm(out - ref) / np.linalg.norm(ref) < 2e-5
 
 
-def test_brick_zmerge_variant_is_bit_compatible():
-    """mcpm_tune("brick_zmerge"): the brick-tiled scatters hand each lane's upper-z deposits to the next lane by shuffle
-    (written at the end of round 1, never yet run on a GPU -- hence at the end of the suite).  The shared-memory tile is
-    bit-identical (integer sums); the stray particles' and the flush's float atomics land in another order: 1e-6."""
-    ops = _ops()
-    A = ops.A
-    for mesh in ((64, 48, 96), (36, 22, 100)):  # whole bricks, and a lattice that does not divide into bricks
-        _zmerge_case(ops, A, mesh)
-
-
-def _zmerge_case(ops, A, mesh):
-    from oracle import pm_oracle as O
-    n = int(np.prod(mesh))
-    rng = np.random.default_rng(21)
-    q = O.regular_pos(mesh).numpy()
-    k = [2 * np.pi / m for m in mesh]
-    disp = np.stack([1.5 * np.sin(k[1] * q[:, 1]) + 1.0 * np.cos(2 * k[2] * q[:, 2]),
-                     1.2 * np.sin(2 * k[2] * q[:, 2]) + 0.8 * np.cos(k[0] * q[:, 0]),
-                     2.0 * np.sin(k[0] * q[:, 0]) + 1.5 * np.cos(3 * k[1] * q[:, 1])], -1)
-    pos = q + disp + rng.normal(scale=0.4, size=q.shape)
-    stray = rng.choice(n, n // 40, replace=False)
-    pos[stray] += rng.uniform(-30, 30, (len(stray), 3))
-    pd = A.prepare(pos.astype(np.float32))
-    wd = A.prepare(rng.uniform(0.2, 3.0, n).astype(np.float32))
-    vel = (rng.normal(size=q.shape) * np.exp(rng.normal(size=(n, 1)))).astype(np.float32)
-    xb = A.prepare(rng.normal(size=q.shape).astype(np.float32))
-    ops.set_lattice(mesh, mesh)
-    eng = ops.engine(mesh)
-    res = {}
-    try:
-        for zm in (0, 1):
-            ops._call("mcpm_tune", b"brick_zmerge", zm)
-            out, out3, vb = A.zeros(mesh), A.zeros((3, *mesh)), A.prepare(vel.copy())
-            ops._call("mcpm_paint_lattice", eng.handle, A.stream(), A.ptr(pd), A.ptr(wd), 0.5, n, A.ptr(out))
-            ops._call("mcpm_paint3_lattice", eng.handle, A.stream(), A.ptr(pd), A.ptr(vb), A.ptr(xb), 0.25, 1.5, n,
-                      A.ptr(out3))
-            res[zm] = [t.double().cpu().numpy() for t in (out, out3, vb)]
-    finally:
-        ops._call("mcpm_tune", b"brick_zmerge", 0)
-        ops.set_lattice(mesh, None)
-    rel = lambda a, b: np.linalg.norm((a - b).ravel()) / np.linalg.norm(b.ravel())
-    assert rel(res[1][0], res[0][0]) < 1e-6 and rel(res[1][1], res[0][1]) < 1e-6 and np.array_equal(res[1][2], res[0][2])
-    ref = O.paint(torch.tensor(pos.astype(np.float32), dtype=torch.float64), mesh,
-                  torch.tensor(wd.cpu().numpy(), dtype=torch.float64) * 0.5, 2).numpy()
-    assert rel(res[1][0], ref) < 2e-5  # and against the float64 oracle, like the unmerged kernel
-
-
 def test_field_model_vs_slab_model_256():
     """grad(log-density) at the benchmark mesh from the two implementations: 1e-3 relative L2, log-density 1e-5
     (10 Mpc/h cells).  Round 1 held this to 5e-3: both sides carried absolute float32 positions, in different frames;

@@ -126,12 +126,9 @@ def main():
     rec("spectrum_bins", lambda: ops.spectrum_bins(mk, None, (float(n),) * 3, ke), 4 * N)
     rec("spectrum_bins_ell2", lambda: ops.spectrum_bins(mk, None, (float(n),) * 3, ke, ell=2, los=(0.0, 0.0, 1.0)), 4 * N)
     rec("nufft_paint (2 shifts)", lambda: ops.nufft_paint(pos, shape, w), 2 * 20 * N + 2 * 8 * N + 12 * N)
-    for zm in (0, 1):
-        lib.mcpm_tune(b"brick_zmerge", zm)
-        ops.set_lattice(shape, shape)
-        rec(f"pm_forces zmerge={zm} (124N)", lambda: ops.pm_forces(pos, shape, want_meshes=True), 124 * N)
-        rec(f"pm_forces_vjp zmerge={zm} (136N)", lambda: ops.pm_forces_vjp(pos, vel, fm), 136 * N)
-    lib.mcpm_tune(b"brick_zmerge", 0)
+    ops.set_lattice(shape, shape)
+    rec("pm_forces brick (124N)", lambda: ops.pm_forces(pos, shape, want_meshes=True), 124 * N)
+    rec("pm_forces_vjp brick (136N)", lambda: ops.pm_forces_vjp(pos, vel, fm), 136 * N)
     ops.set_lattice(shape, None)
     if a.out:
         with open(a.out, "w") as fh:

@@ -11,13 +11,13 @@ from montecosmo_b200 import nbody as nb  # noqa: E402
 from montecosmo_b200.model import FieldModel  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-settings = [s for s in sys.argv[2:]] or ["base", "brick_zmerge=1", "base", "brick_zmerge=1"]
+settings = [s for s in sys.argv[2:]] or ["base", "gather_tma=0", "base", "gather_tma=0"]
 m = FieldModel(**workload(n))
 lib, dev = nb.ops().lib, nb.ops().A.device
 g = torch.Generator(device=dev).manual_seed(0)
 obs = 1.0 + torch.randn(m.mesh_shape, device=dev, generator=g)
 w = torch.randn(m.mesh_shape, device=dev, generator=g)
-defaults = {"gather_blocked": 0, "gather_minb": 4, "side_zero": 0, "brick_zmerge": 0, "gather_tma": 1, "gather_seg": 64}
+defaults = {"gather_blocked": 0, "gather_minb": 4, "side_zero": 0, "gather_tma": 1, "gather_seg": 32}
 for s in settings:
     cur = dict(defaults)
     if s != "base":

@@ -25,7 +25,9 @@ for s in settings:
             k, v = kv.split("=")
             cur[k] = int(v)
     for k, v in cur.items():
-        lib.mcpm_tune(k.encode(), v)
+        lib.mcpm_tune(k.encode(), v)  # process defaults (stateless entry points, engines created from now on) ...
+        for eng in nb.ops()._engines.values():  # ... and the engines that already exist
+            lib.mcpm_engine_tune(eng.handle, k.encode(), v)
     for _ in range(2):
         lp, gr = m.value_and_force(w, obs)
     torch.cuda.synchronize()

@@ -380,6 +380,12 @@ int mcpm_paint3v4_f(void* stream, const mcpm_frame* frame, const float* pos, flo
 int mcpm_read_grad4v_f(void* stream, const mcpm_frame* frame, const float* pos, const float* fmesh4,
                        const float* rhobar, float* vbar, float cscale, float alpha, int64_t np, int nx, int ny, int nz,
                        float* xbar);
+/* read_grad4v with the tail of the reverse step fused in: xbar += d/dx [...], then vbar = alpha * vbar + dnext * xbar
+ * (the kick's vbar *= alpha and the NEXT reverse step's leading vbar += xbar * drift while both are in registers; the
+ * scatter of that next step then reads vbar only: mcpm_paint3_brick with xbar = NULL).  What mcpm_nbody_steps_vjp runs. */
+int mcpm_read_grad4v_step_f(void* stream, const mcpm_frame* frame, const float* pos, const float* fmesh4,
+                            const float* rhobar, float* vbar, float cscale, float alpha, float dnext, int64_t np, int nx,
+                            int ny, int nz, float* xbar);
 int mcpm_paint_brick_f(void* stream, const mcpm_frame* frame, int px, int py, int pz, const float* pos,
                        const float* weights, float wscalar, float shift, int64_t np, int nx, int ny, int nz,
                        float* mesh);
@@ -431,7 +437,10 @@ int mcpm_nbody_steps(mcpm_engine* eng, void* stream, float* pos, float* vel, int
                      const float* alpha, const float* beta, const float* drift_pre, const float* drift_post,
                      int order, int paint_deconv, int lap_fd, int grad_fd, float* xk, float* vk, float* fm);
 /* VJP of the loop: (posbar, velbar) at the end -> at the start, in place.  v0 = velocities before the first step.
- * coefbar (device float64 [n_steps, 4]: alpha, beta, drift_pre, drift_post cotangents) may be NULL. */
+ * coefbar (device float64 [n_steps, 4]: alpha, beta, drift_pre, drift_post cotangents) may be NULL.
+ * fm may be NULL (pass fm = NULL to mcpm_nbody_steps too): the force meshes are then not taped -- 16 bytes per cell and
+ * step -- and every reverse step recomputes its own from xk[s] (one extra paint + forward Fourier pass per step), the
+ * memory / recompute trade of the reference's checkpointed adjoint (diffrax, nbody.py:999). */
 int mcpm_nbody_steps_vjp(mcpm_engine* eng, void* stream, float* posbar, float* velbar, int64_t np, int n_steps,
                          const float* alpha, const float* beta, const float* drift_pre, const float* drift_post,
                          int order, int paint_deconv, int lap_fd, int grad_fd, const float* xk, const float* vk,

@@ -96,6 +96,7 @@ SIGNATURES = {
     "mcpm_kick_drift4_f": ([vp, vp, vp, vp, vp, i64] + MESH + [f32, f32, f32], i32),
     "mcpm_paint3v4_f": ([vp, vp, vp, vp, vp, f32, f32, i64] + MESH + [vp], i32),
     "mcpm_read_grad4v_f": ([vp, vp, vp, vp, vp, vp, f32, f32, i64] + MESH + [vp], i32),
+    "mcpm_read_grad4v_step_f": ([vp, vp, vp, vp, vp, vp, f32, f32, f32, i64] + MESH + [vp], i32),
     "mcpm_paint_brick_f": ([vp, vp, i32, i32, i32, vp, vp, f32, f32, i64] + MESH + [vp], i32),
     "mcpm_paint3_brick_f": ([vp, vp, i32, i32, i32, vp, vp, vp, f32, f32, i64] + MESH + [vp], i32),
     "mcpm_drift": ([vp, vp, vp, f32, i64], i32),

@@ -55,8 +55,10 @@ struct DeviceScope {
       prev = -1;
       cudaGetLastError();
     }
-    if (prev != d) err = rt_bind_device(d);
-    else prev = -1;  // already current: nothing to restore
+    // cudaSetDevice ALWAYS: a host thread that has not touched the runtime yet (torch's autograd workers, XLA's executor
+    // threads) reports device 0 as current without a context bound to it, and cufftExec then fails
+    err = rt_bind_device(d);
+    if (prev == d) prev = -1;  // nothing to restore
 #else
     (void)d;
 #endif
@@ -232,7 +234,9 @@ int mcpm_paint3_brick(void* stream, int px, int py, int pz, const float* pos, fl
   L.px = px;
   L.py = py;
   L.pz = pz;
-  int r = brick_paint3_cic(as_stream(stream), L, pos, vbar, xbar, drift, scale, np, nx, ny, nz, mesh3);
+  if (xbar)  // vbar += xbar * drift: its own pass here (the engine's reverse sweep folds it into the preceding gather)
+    if (int e = axpy3(as_stream(stream), vbar, xbar, drift, 3 * np, vbar)) return e;
+  int r = brick_paint3_cic(as_stream(stream), L, pos, vbar, scale, np, nx, ny, nz, mesh3);
   if (r < 0) return MCPM_ECUDA;
   if (r == 1) return MCPM_OK;
 #endif
@@ -264,7 +268,9 @@ int mcpm_paint3_lattice(mcpm_engine* eng, void* stream, const float* pos, float*
   BIND(eng);
 #ifndef MCPM_HOSTEMU
   Engine* E = eng->e;
-  int r = brick_paint3_cic(as_stream(stream), E->lat, pos, vbar, xbar, drift, scale, np, E->nx, E->ny, E->nz, mesh3);
+  if (xbar)
+    if (int e = axpy3(as_stream(stream), vbar, xbar, drift, 3 * np, vbar)) return e;
+  int r = brick_paint3_cic(as_stream(stream), E->lat, pos, vbar, scale, np, E->nx, E->ny, E->nz, mesh3);
   if (r < 0) return MCPM_ECUDA;
   if (r == 1) return MCPM_OK;
 #endif
@@ -903,6 +909,17 @@ int mcpm_read_grad4v_f(void* stream, const mcpm_frame* frame, const float* pos, 
   API_END
 }
 
+int mcpm_read_grad4v_step_f(void* stream, const mcpm_frame* frame, const float* pos, const float* fmesh4,
+                            const float* rhobar, float* vbar, float cscale, float alpha, float dnext, int64_t np, int nx,
+                            int ny, int nz, float* xbar) {
+  API_BEGIN
+  NEED(pos && fmesh4 && rhobar && vbar && xbar, "read_grad4v_step: null pointer");
+  FRAME(np);
+  return read_grad4v(as_stream(stream), pos, fmesh4, rhobar, vbar, cscale, 1, alpha, np, nx, ny, nz, xbar, 1, nullptr,
+                     0, fr, dnext);
+  API_END
+}
+
 int mcpm_paint_brick_f(void* stream, const mcpm_frame* frame, int px, int py, int pz, const float* pos,
                        const float* weights, float wscalar, float shift, int64_t np, int nx, int ny, int nz,
                        float* mesh) {
@@ -934,7 +951,9 @@ int mcpm_paint3_brick_f(void* stream, const mcpm_frame* frame, int px, int py, i
   L.px = px;
   L.py = py;
   L.pz = pz;
-  int r = brick_paint3_cic(as_stream(stream), L, pos, vbar, xbar, drift, scale, np, nx, ny, nz, mesh3, fr);
+  if (xbar)
+    if (int e = axpy3(as_stream(stream), vbar, xbar, drift, 3 * np, vbar)) return e;
+  int r = brick_paint3_cic(as_stream(stream), L, pos, vbar, scale, np, nx, ny, nz, mesh3, fr);
   if (r < 0) return MCPM_ECUDA;
   if (r == 1) return MCPM_OK;
 #endif

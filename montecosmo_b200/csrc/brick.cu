@@ -48,13 +48,11 @@ struct BrickArgs {
   int rel;              // 1: pos holds displacements from the lattice sites (frame.h), 0: absolute positions
   int ox, oy, oz;       // mesh cell of lattice site (0, 0, 0): the halo offset of a slab-decomposed rank
   const float* pos;
-  // NCH = 1: value = (w ? w[p] : 1) * ws.        NCH = 3: value = s * (A[p] + cb * B[p]), A updated in place if store.
+  // NCH = 1: value = (w ? w[p] : 1) * ws.        NCH = 3: value = s * A[p, c].
   const float* w;
   float ws;
-  float* A;
-  const float* B;
-  float cb, s;
-  int store;
+  const float* A;
+  float s;
   float* mesh;  // NCH planar meshes
 };
 
@@ -109,27 +107,15 @@ __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickA
   float l1[NCH];
 #pragma unroll
   for (int c = 0; c < NCH; ++c) l1[c] = 0.f;
-  if (NCH == 3) {
-    float* Ap = a.A + pbase;
-    const float* Bp = a.B ? a.B + pbase : nullptr;
+  if (NCH == 3) {  // sum |value| per channel (the fixed-point scale); the values are re-read channel by channel below
+    const float* Ap = a.A + pbase;
 #pragma unroll
     for (int r = 0; r < PPT; ++r) {
       if (!FULL && !(valid >> r & 1)) continue;
       const int off = brick_qi(warp, r) * plane3;
-      float t0 = Ap[off], t1 = Ap[off + 1], t2 = Ap[off + 2];
-      if (Bp) {
-        t0 += a.cb * Bp[off];
-        t1 += a.cb * Bp[off + 1];
-        t2 += a.cb * Bp[off + 2];
-        if (a.store) {  // re-read per channel pass below (L1 / L2 hit)
-          Ap[off] = t0;
-          Ap[off + 1] = t1;
-          Ap[off + 2] = t2;
-        }
-      }
-      l1[0] += fabsf(a.s * t0);
-      l1[NCH > 1 ? 1 : 0] += fabsf(a.s * t1);
-      l1[NCH > 2 ? 2 : 0] += fabsf(a.s * t2);
+      l1[0] += fabsf(a.s * Ap[off]);
+      l1[NCH > 1 ? 1 : 0] += fabsf(a.s * Ap[off + 1]);
+      l1[NCH > 2 ? 2 : 0] += fabsf(a.s * Ap[off + 2]);
     }
   } else if (a.w) {
     const float* wp = a.w + pbase / 3;
@@ -218,11 +204,18 @@ __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickA
 
   const int64_t plane = (int64_t)a.nx * a.ny * a.nz;
   bool all_stray = false;  // block-uniform
+  // Per-particle values of the current channel, fetched ONE CHANNEL AHEAD: the loads of channel c + 1 are issued before
+  // the flush of channel c and consumed after it.  (Round 1 re-read them inside the deposit loop, behind each particle's
+  // branch: ncu put 45 % of this kernel's stall samples on the first use of those loads.)
+  const float* valp0 = NCH == 1 ? (a.w ? a.w + pbase / 3 : nullptr) : a.A + pbase;
+  const int vstride = NCH == 1 ? a.py * a.pz : plane3;
+  float val[PPT];
+#pragma unroll
+  for (int r = 0; r < PPT; ++r)
+    val[r] = (valp0 && (FULL || (valid >> r & 1))) ? valp0[brick_qi(warp, r) * vstride] : 1.0f;
 #pragma unroll 1
   for (int c = 0; c < NCH; ++c) {
     const float l = bc[4 + c];
-    const float* valp = NCH == 1 ? (a.w ? a.w + pbase / 3 : nullptr) : a.A + pbase + c;
-    const int vstride = NCH == 1 ? a.py * a.pz : plane3;
     // Fixed-point scale.  Safe: S = 2^floor(log2(2^30 / sum|v|)) cannot overflow whatever the clustering, but its quantum
     // (2^-18 of a unit weight for a 4096-particle brick) puts ~3e-6 of white noise on a unit-mean density mesh -- 50x
     // float32 rounding, and measured as a 4.5x larger displacement error than the float-atomic CPU port after 10 steps.
@@ -240,7 +233,7 @@ __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickA
 #pragma unroll
     for (int r = 0; r < PPT; ++r) {
       if (tcell[r] < 0) continue;
-      const float vs = valp ? valp[brick_qi(warp, r) * vstride] * scale : scale;
+      const float vs = val[r] * scale;
       const float fx = x[r][0], fy = x[r][1], fz = x[r][2];
       const float gx = 1.f - fx, gy = 1.f - fy;
       const float vz1 = vs * fz, vz0 = vs - vz1;  // vs * (1 - fz) up to one rounding of the fixed-point product
@@ -268,6 +261,11 @@ __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickA
         all_stray = true;
         __syncthreads();
       }
+    }
+    if (NCH > 1 && c + 1 < NCH) {  // next channel's values: in flight during the flush
+#pragma unroll
+      for (int r = 0; r < PPT; ++r)
+        if (FULL || (valid >> r & 1)) val[r] = valp0[brick_qi(warp, r) * vstride + c + 1];
     }
     // flush the touched 16-byte groups (one red.global.add.v4.f32 each) and re-zero them for the next channel
     float* meshc = a.mesh + c * plane;
@@ -302,7 +300,7 @@ __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickA
       vv[0] = (a.w ? a.w[p3 / 3] : 1.0f) * a.ws;
     } else {
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) vv[c] = a.s * a.A[p3 + c];  // A already holds A + cb * B (stored above)
+      for (int c = 0; c < NCH; ++c) vv[c] = a.s * a.A[p3 + c];
     }
     const float bx = floorf(px), by = floorf(py), bz = floorf(pz);
     const float fx = px - bx, fy = py - by, fz = pz - bz;
@@ -384,15 +382,15 @@ int brick_paint_cic(stream_t st, const Lattice& L, const float* pos, const float
   return launch_brick<1>(st, a);
 }
 
-// Reverse-step scatter: A += cb * B (stored when B != NULL), mesh3[c] += s * A[., c] * W, three planar meshes.
-int brick_paint3_cic(stream_t st, const Lattice& L, const float* pos, float* A, const float* B, float cb, float s,
-                     int64_t np, int nx, int ny, int nz, float* mesh3, const Frame* fr) {
+// Reverse-step scatter: mesh3[c] += s * A[., c] * W, three planar meshes.
+int brick_paint3_cic(stream_t st, const Lattice& L, const float* pos, const float* A, float s, int64_t np, int nx, int ny,
+                     int nz, float* mesh3, const Frame* fr) {
   if (!brick_ok(L, np, nx, ny, nz) || !frame_fits(L, fr)) return 0;
   BrickArgs a = {};
   set_frame(a, fr);
   a.px = L.px; a.py = L.py; a.pz = L.pz; a.nx = nx; a.ny = ny; a.nz = nz;
   a.inx = 1.0f / nx; a.iny = 1.0f / ny; a.inz = 1.0f / nz;
-  a.pos = pos; a.A = A; a.B = B; a.cb = cb; a.s = s; a.store = B != nullptr; a.mesh = mesh3;
+  a.pos = pos; a.A = A; a.s = s; a.mesh = mesh3;
   return launch_brick<3>(st, a);
 }
 

@@ -187,15 +187,16 @@ int paint3v4(stream_t st, const float* pos, float* A, const float* B, float cb, 
 
 // Backward force gather on (forces in mesh4.xyz, rhobar planar), CIC:
 //   u(corner) = cscale * (cot . F(corner)) + rhobar(corner);   g_a = sum_corners u * dW_a * prod_{d != a} W_d
-//   xbar += g ;  then (tail of the reverse step) cot *= alpha_tail  when alpha_tail >= 0 is requested via `scale_cot`.
+//   xbar += g ;  then (tail of the reverse step, `scale_cot`)  cot = alpha_tail * cot + dnext * xbar_new : the kick's
+//   vbar *= alpha and the NEXT reverse step's leading vbar += xbar * drift in one pass, while both are in registers.
 int read_grad4v(stream_t st, const float* pos, const float* fmesh4, const float* rhobar, float* cot, float cscale,
                 int scale_cot, float alpha_tail, int64_t np, int nx, int ny, int nz, float* grad, int accumulate,
-                float* zero, int64_t nzero, const Frame* frp) {
+                float* zero, int64_t nzero, const Frame* frp, float dnext) {
   const f4* fm = reinterpret_cast<const f4*>(fmesh4);
 #ifndef MCPM_HOSTEMU
   if (!zero) {
     const int r = read_grad4v_tma(st, pos, fmesh4, rhobar, cot, cscale, scale_cot, alpha_tail, np, nx, ny, nz, grad,
-                                  accumulate, frp);
+                                  accumulate, frp, dnext);
     if (r < 0) return MCPM_ECUDA;
     if (r == 1) return 0;
   }
@@ -229,18 +230,17 @@ int read_grad4v(stream_t st, const float* pos, const float* fmesh4, const float*
                (dz0 * u110 + u111) * (wx1 * wy1);
     float* g = grad + 3 * p;
     if (accumulate) {
-      g[0] += g0;
-      g[1] += g1;
-      g[2] += g2;
-    } else {
-      g[0] = g0;
-      g[1] = g1;
-      g[2] = g2;
+      g0 += g[0];
+      g1 += g[1];
+      g2 += g[2];
     }
+    g[0] = g0;
+    g[1] = g1;
+    g[2] = g2;
     if (scale_cot) {
-      cot[3 * p] = alpha_tail * q0;
-      cot[3 * p + 1] = alpha_tail * q1;
-      cot[3 * p + 2] = alpha_tail * q2;
+      cot[3 * p] = alpha_tail * q0 + dnext * g0;
+      cot[3 * p + 1] = alpha_tail * q1 + dnext * g1;
+      cot[3 * p + 2] = alpha_tail * q2 + dnext * g2;
     }
     if (zero)  // the three meshes the next reverse step's scatter accumulates into (see kick_drift4)
       for (int64_t c = p; c < nzero; c += np) zero[c] = 0.0f;

@@ -43,7 +43,7 @@ struct GatherArgs {
   int nx, ny, nz;
   int rel, py, pz, ox, oy, oz;  // relative frame of spacing one cell (lattice py x pz pencils), else rel = 0
   float alpha, beta, drift;     // kick
-  float cscale, alpha_tail;     // grad
+  float cscale, alpha_tail, dnext;  // grad
   int accumulate, scale_cot;
   int64_t nseg;
 };
@@ -179,23 +179,19 @@ __global__ void __launch_bounds__(gtma::THREADS, MODE == 0 ? 4 : 3) gather_tma_k
                          (dy0 * u100 + u110) * (wx1 * wz0) + (dy0 * u101 + u111) * (wx1 * wz1);
         const float g2 = (dz0 * u000 + u001) * (wx0 * wy0) + (dz0 * u010 + u011) * (wx0 * wy1) +
                          (dz0 * u100 + u101) * (wx1 * wy0) + (dz0 * u110 + u111) * (wx1 * wy1);
+        float t0 = g0, t1 = g1, t2 = g2;
         if (a.accumulate) {
-          float t0 = sc[q], t1 = sc[q + 1], t2 = sc[q + 2];
-          t0 += g0;
-          t1 += g1;
-          t2 += g2;
-          o1[q] = t0;
-          o1[q + 1] = t1;
-          o1[q + 2] = t2;
-        } else {
-          o1[q] = g0;
-          o1[q + 1] = g1;
-          o1[q + 2] = g2;
+          t0 += sc[q];
+          t1 += sc[q + 1];
+          t2 += sc[q + 2];
         }
+        o1[q] = t0;
+        o1[q + 1] = t1;
+        o1[q + 2] = t2;
         if (a.scale_cot) {
-          o0[q] = a.alpha_tail * q0;
-          o0[q + 1] = a.alpha_tail * q1;
-          o0[q + 2] = a.alpha_tail * q2;
+          o0[q] = a.alpha_tail * q0 + a.dnext * t0;
+          o0[q + 1] = a.alpha_tail * q1 + a.dnext * t1;
+          o0[q + 2] = a.alpha_tail * q2 + a.dnext * t2;
         }
       }
     }
@@ -290,7 +286,7 @@ int kick_drift4_tma(stream_t st, const float* pos, const float* vel, const float
 
 int read_grad4v_tma(stream_t st, const float* pos, const float* fmesh4, const float* rhobar, float* cot, float cscale,
                     int scale_cot, float alpha_tail, int64_t np, int nx, int ny, int nz, float* grad, int accumulate,
-                    const Frame* fr) {
+                    const Frame* fr, float dnext) {
   const int gs = tune().gather_seg, seg = (gs == 64 || gs == 128) ? gs : 32;
   GatherArgs a = {};
   if (!gather_tma_ok(a, np, fr, seg)) return 0;
@@ -307,6 +303,7 @@ int read_grad4v_tma(stream_t st, const float* pos, const float* fmesh4, const fl
   a.nz = nz;
   a.cscale = cscale;
   a.alpha_tail = alpha_tail;
+  a.dnext = dnext;
   a.accumulate = accumulate;
   a.scale_cot = scale_cot;
   return launch_gather_tma<1>(st, a, seg);

@@ -339,14 +339,19 @@ int nbody_steps(Engine* E, stream_t st, float* pos, float* vel, int64_t np, int 
 
 // Reverse sweep.  Per step (x1 = kick-time position, v1 = alpha v0 + beta F(x1), x_out = x1 + v1 * dcomb):
 //   vbar += xbar * dcomb ; xbar += pm_forces_vjp(x1, beta * vbar) ; [coef cotangents] ; vbar *= alpha
-// and finally vbar += xbar * drift_pre[0].
+// and finally vbar += xbar * drift_pre[0].  The leading update of step s-1 (and the final one) uses the xbar the gather of
+// step s has just produced, so it rides in that gather's epilogue (`dnext`): vbar = alpha vbar + dnext xbar.  Only the
+// first step of the sweep needs its own pass, and the 3-channel scatter reads vbar without touching xbar.
+// fm == NULL: the force meshes were not taped; each step recomputes its own from xk[s] (paint + the forward Fourier
+// passes: one extra pm_forces per step instead of 16 bytes per cell and step of tape -- the trade diffrax's
+// checkpointed adjoint makes in the reference, nbody.py:999).
 int nbody_steps_vjp(Engine* E, stream_t st, float* posbar, float* velbar, int64_t np, int n_steps, const float* alpha,
                     const float* beta, const float* drift_pre, const float* drift_post, int order, int paint_deconv,
                     int lap_fd, int grad_fd, const float* xk, const float* vk, const float* fm, const float* v0,
                     double* coefbar) {
   if (n_steps <= 0) return 0;
-  if (!xk || !fm) {
-    set_error("nbody_steps_vjp: the tape (xk, fm) from the forward pass is required");
+  if (!xk) {
+    set_error("nbody_steps_vjp: the tape xk from the forward pass is required");
     return MCPM_EINVAL;
   }
   if (coefbar && (!vk || !v0)) {
@@ -355,43 +360,49 @@ int nbody_steps_vjp(Engine* E, stream_t st, float* posbar, float* velbar, int64_
   }
   const int64_t P3 = 3 * np;
   const bool cic = (order == 2);
-  const bool side_zero = tune().side_zero && cic && brick_path(E, order, nullptr);
+  const bool side_zero = tune().side_zero && fm && cic && brick_path(E, order, nullptr);
   Frame f;
   const Frame* fr = E->frame(f);
+  auto dcomb_of = [&](int s) { return drift_post[s] + (s == n_steps - 1 ? 0.0f : drift_pre[s + 1]); };
+  if (coefbar) {  // both half drifts that were fused into dcomb(n-1) see the xbar the sweep starts from
+    const float* v1 = vk + (int64_t)(n_steps - 1) * P3;
+    TRY(dot_accum(st, posbar, v1, P3, 1.0, coefbar + 4 * (n_steps - 1) + 3));
+  }
+  TRY(axpy3(st, velbar, posbar, dcomb_of(n_steps - 1), P3, velbar));
   for (int s = n_steps - 1; s >= 0; --s) {
     const bool last = (s == n_steps - 1);
-    float dcomb = drift_post[s] + (last ? 0.0f : drift_pre[s + 1]);
     const float* x1 = xk + (int64_t)s * P3;
-    const float* slot = fm + (int64_t)s * 4 * E->N;
     const float* v1 = vk ? vk + (int64_t)s * P3 : nullptr;
     const float* vprev = s == 0 ? v0 : (vk ? vk + (int64_t)(s - 1) * P3 : nullptr);
-    if (coefbar) {
-      // both half drifts that were fused into `dcomb` see the same xbar, so each gets the full <xbar, v1>
-      TRY(dot_accum(st, posbar, v1, P3, 1.0, coefbar + 4 * s + 3));
-      if (!last) TRY(dot_accum(st, posbar, v1, P3, 1.0, coefbar + 4 * (s + 1) + 2));
+    const float dnext = s > 0 ? dcomb_of(s - 1) : drift_pre[0];
+    const float* slot;
+    if (fm) {
+      slot = fm + (int64_t)s * 4 * E->N;
+    } else {  // recompute this step's force meshes; r(3..6) holds them (float4 for CIC) until the gather has read them
+      float* planar = cic ? E->r(0) : E->r(3);
+      TRY(pm_forces(E, st, x1, np, order, paint_deconv, lap_fd, grad_fd, 0.0f, planar, nullptr, false));
+      if (cic) TRY(interleave3(st, planar, E->r(3), E->N));
+      slot = E->r(3);
     }
+    // phibar = paint(beta * vbar): three planar meshes.  With recomputed forces the scratch r(3..6) is taken, so the
+    // scatter goes to r(0..2) and rhobar to the tail of the complex scratch.
+    float* m3 = fm ? E->r(4) : E->r(0);
+    float* rhobar = fm ? E->r(3) : reinterpret_cast<float*>(E->c(Engine::kC - 1));
     if (cic) {
-      // vbar += xbar * dcomb and phibar = paint(beta * vbar) in one pass
       int handled = 0;
 #ifndef MCPM_HOSTEMU
       if (E->lat.px > 0) {  // brick-tiled: accumulates in shared memory, flushes planar meshes directly
         if (!(side_zero && !last))  // cleared on the side by read_grad4v of the step before (in sweep order)
-          TRY(rt_memset(E->r(4), 0, sizeof(float) * 3 * (size_t)E->N, st) ? MCPM_ECUDA : 0);
-        handled = brick_paint3_cic(st, E->lat, x1, velbar, posbar, dcomb, beta[s], np, E->nx, E->ny, E->nz, E->r(4),
-                                   fr);
+          TRY(rt_memset(m3, 0, sizeof(float) * 3 * (size_t)E->N, st) ? MCPM_ECUDA : 0);
+        handled = brick_paint3_cic(st, E->lat, x1, velbar, beta[s], np, E->nx, E->ny, E->nz, m3, fr);
         if (handled < 0) return MCPM_ECUDA;
       }
 #endif
-      if (!handled) {  // float4 mesh r(0..3), then back to planar for cuFFT
-        TRY(rt_memset(E->r(0), 0, sizeof(float) * 4 * (size_t)E->N, st) ? MCPM_ECUDA : 0);
-        TRY(paint3v4(st, x1, velbar, posbar, dcomb, 1, beta[s], np, E->nx, E->ny, E->nz, E->r(0), fr));
-        TRY(deinterleave3(st, E->r(0), E->r(4), E->N));
-      }
+      if (!handled) TRY(paint3(st, x1, velbar, beta[s], nullptr, 0.0f, np, E->nx, E->ny, E->nz, order, m3, 0, fr));
     } else {
-      TRY(axpy3(st, velbar, posbar, dcomb, P3, velbar));
-      TRY(paint3(st, x1, velbar, beta[s], nullptr, 0.0f, np, E->nx, E->ny, E->nz, order, E->r(4), 0, fr));
+      TRY(paint3(st, x1, velbar, beta[s], nullptr, 0.0f, np, E->nx, E->ny, E->nz, order, m3, 0, fr));
     }
-    TRY(density_cotangent(E, st, E->r(4), lap_fd, grad_fd, 0.0f, paint_deconv ? order : 0, E->r(3)));  // rhobar
+    TRY(density_cotangent(E, st, m3, lap_fd, grad_fd, 0.0f, paint_deconv ? order : 0, rhobar));
     if (coefbar) {
       TRY(dot_accum(st, velbar, vprev, P3, 1.0, coefbar + 4 * s + 0));
       if (beta[s] != 0.0f) {  // betabar = <vbar, F>, F = (v1 - alpha v0) / beta
@@ -400,18 +411,26 @@ int nbody_steps_vjp(Engine* E, stream_t st, float* posbar, float* velbar, int64_
       }
     }
     if (cic) {
-      // xbar += dread(x1; beta*vbar . F + rhobar) and vbar *= alpha, one gather
-      TRY(read_grad4v(st, x1, slot, E->r(3), velbar, beta[s], 1, alpha[s], np, E->nx, E->ny, E->nz, posbar, 1,
-                      side_zero && s > 0 ? E->r(4) : nullptr, 3 * E->N, fr));
+      // xbar += dread(x1; beta*vbar . F + rhobar), then vbar = alpha vbar + dnext xbar: one gather
+      TRY(read_grad4v(st, x1, slot, rhobar, velbar, beta[s], 1, alpha[s], np, E->nx, E->ny, E->nz, posbar, 1,
+                      side_zero && s > 0 ? E->r(4) : nullptr, 3 * E->N, fr, coefbar ? 0.0f : dnext));
     } else {
-      const float* ms[4] = {slot, slot + E->N, slot + 2 * E->N, E->r(3)};
+      const float* ms[4] = {slot, slot + E->N, slot + 2 * E->N, rhobar};
       TRY(read_grad(st, x1, ms, 4, velbar, 3, beta[s], nullptr, np, E->nx, E->ny, E->nz, order, nullptr, 0.0f, posbar,
                     1, 0.0f, fr));
-      TRY(axpy3(st, velbar, velbar, alpha[s] - 1.0f, P3, velbar));
+      TRY(axpby(st, velbar, alpha[s], posbar, coefbar ? 0.0f : dnext, 0.0f, P3, velbar));
+    }
+    if (coefbar) {  // the drift cotangents need xbar before it is folded into vbar: take the unfused order
+      if (s > 0) {
+        const float* vprev1 = vk + (int64_t)(s - 1) * P3;
+        TRY(dot_accum(st, posbar, vprev1, P3, 1.0, coefbar + 4 * (s - 1) + 3));
+        TRY(dot_accum(st, posbar, vprev1, P3, 1.0, coefbar + 4 * s + 2));
+      } else {
+        TRY(dot_accum(st, posbar, v0, P3, 1.0, coefbar + 2));
+      }
+      TRY(axpy3(st, velbar, posbar, dnext, P3, velbar));
     }
   }
-  if (coefbar) TRY(dot_accum(st, posbar, v0, P3, 1.0, coefbar + 2));
-  TRY(axpy3(st, velbar, posbar, drift_pre[0], P3, velbar));
   return 0;
 }
 

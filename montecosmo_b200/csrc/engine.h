@@ -150,14 +150,14 @@ int paint3v4(stream_t, const float* pos, float* A, const float* B, float cb, int
              int ny, int nz, float* mesh4, const Frame* fr = nullptr);
 int read_grad4v(stream_t, const float* pos, const float* fmesh4, const float* rhobar, float* cot, float cscale,
                 int scale_cot, float alpha_tail, int64_t np, int nx, int ny, int nz, float* grad, int accumulate,
-                float* zero = nullptr, int64_t nzero = 0, const Frame* fr = nullptr);
+                float* zero = nullptr, int64_t nzero = 0, const Frame* fr = nullptr, float dnext = 0.0f);
 
 // cic4_tma.cu (CUDA build only): the same two gathers with bulk-copy staged particle arrays; 1 handled, 0 not applicable
 int kick_drift4_tma(stream_t, const float* pos, const float* vel, const float* fmesh4, int64_t np, int nx, int ny, int nz,
                     float alpha, float beta, float drift, float* pos_out, float* vel_out, const Frame* fr);
 int read_grad4v_tma(stream_t, const float* pos, const float* fmesh4, const float* rhobar, float* cot, float cscale,
                     int scale_cot, float alpha_tail, int64_t np, int nx, int ny, int nz, float* grad, int accumulate,
-                    const Frame* fr);
+                    const Frame* fr, float dnext);
 
 // xfft.cu (CUDA build only): the x-passes of rfftn / irfftn fused with the force kernel, on [nx, ny_loc, nz/2+1]
 bool xfuse_supported(int nx);
@@ -180,8 +180,8 @@ int xfuse_hessian_tk(stream_t, const cfloat* in6, cfloat* out, int nx, int ny, i
 // brick.cu (CUDA build only): return 1 if handled, 0 if the generic path must be taken, < 0 on error
 int brick_paint_cic(stream_t, const Lattice&, const float* pos, const float* weights, float wscalar, float shift,
                     int64_t np, int nx, int ny, int nz, float* mesh, const Frame* fr = nullptr);
-int brick_paint3_cic(stream_t, const Lattice&, const float* pos, float* A, const float* B, float cb, float s,
-                     int64_t np, int nx, int ny, int nz, float* mesh3, const Frame* fr = nullptr);
+int brick_paint3_cic(stream_t, const Lattice&, const float* pos, const float* A, float s, int64_t np, int nx, int ny,
+                     int nz, float* mesh3, const Frame* fr = nullptr);
 
 // engine.cu
 int pm_forces(Engine*, stream_t, const float* pos, int64_t np, int order, int paint_deconv, int lap_fd, int grad_fd,

@@ -337,18 +337,22 @@ class SlabPM:
         ns = len(alpha)
         n = posbar.shape[0]
         cells = self.xl * self.ny * self.nz
+        dcomb = lambda s: float(drift_post[s]) + (float(drift_pre[s + 1]) if s + 1 < ns else 0.0)
+        # vbar += xbar * dcomb leads every reverse step; for all but the first it rides in the previous gather (dnext)
+        if ns:
+            self._call("mcpm_drift", st, velbar.data_ptr(), posbar.data_ptr(), dcomb(ns - 1), n)
         for s in reversed(range(ns)):
             x1, fm4 = tape[s]
-            dcomb = float(drift_post[s]) + (float(drift_pre[s + 1]) if s + 1 < ns else 0.0)
+            dnext = dcomb(s - 1) if s > 0 else float(drift_pre[0])
             m3 = A.zeros((3, self.ext, self.ny, self.nz)) if self.brick else None
             if m3 is not None and self._brick_ok(self.lib.mcpm_paint3_brick_f(
-                    st, self._fr, self.xl, self.ny, self.nz, x1.data_ptr(), velbar.data_ptr(), posbar.data_ptr(), dcomb,
+                    st, self._fr, self.xl, self.ny, self.nz, x1.data_ptr(), velbar.data_ptr(), 0, 0.0,
                     float(beta[s]), n, self.ext, self.ny, self.nz, m3.data_ptr())):
                 self.halo_reduce(m3, lead=True)  # three planar extended meshes
                 planar = m3[:, self.H:self.H + self.xl].contiguous()
             else:
                 m4 = A.zeros((self.ext, self.ny, self.nz, 4))
-                self._call("mcpm_paint3v4_f", st, self._fr, x1.data_ptr(), velbar.data_ptr(), posbar.data_ptr(), dcomb,
+                self._call("mcpm_paint3v4_f", st, self._fr, x1.data_ptr(), velbar.data_ptr(), 0, 0.0,
                            float(beta[s]), n, self.ext, self.ny, self.nz, m4.data_ptr())
                 self.halo_reduce(m4)
                 planar = A.empty((3, self.xl, self.ny, self.nz))
@@ -356,10 +360,11 @@ class SlabPM:
             rhobar = A.empty((self.ext, self.ny, self.nz))
             rhobar[self.H:self.H + self.xl] = self.density_cotangent(planar)
             self.halo_gather(rhobar)
-            self._call("mcpm_read_grad4v_f", st, self._fr, x1.data_ptr(), fm4.data_ptr(), rhobar.data_ptr(),
-                       velbar.data_ptr(), float(beta[s]), float(alpha[s]), n, self.ext, self.ny, self.nz,
+            self._call("mcpm_read_grad4v_step_f", st, self._fr, x1.data_ptr(), fm4.data_ptr(), rhobar.data_ptr(),
+                       velbar.data_ptr(), float(beta[s]), float(alpha[s]), dnext, n, self.ext, self.ny, self.nz,
                        posbar.data_ptr())
-        self._call("mcpm_drift", st, velbar.data_ptr(), posbar.data_ptr(), float(drift_pre[0]), n)
+        if not ns:
+            return
 
     # ------------------------------------------------------------------------------------------------ LPT
     def _lattice_read3(self, planar3):

@@ -104,7 +104,7 @@ class FieldModel:
     def __init__(self, mesh_shape=(64, 64, 64), box_size=(640.0, 640.0, 640.0), evolution="nbody", n_steps=5,
                  a_start=0.0, a_obs=1.0, lpt_order=2, paint_order=2, interlace_order=2, paint_deconv=True,
                  paint_oversamp=1.0, b1=1.0, rsd=True, los=(0.0, 0.0, 1.0), sigma_obs=1.0, cosmology=None, kpow=None,
-                 precond="real", out_shape="paint", relative=True):
+                 precond="real", out_shape="paint", relative=True, tape_forces=True):
         if precond not in ("real", "fourier"):
             raise ValueError("precond must be 'real' or 'fourier'")
         if out_shape not in ("paint", "mesh"):
@@ -116,6 +116,9 @@ class FieldModel:
         # relative: carry particles as float32 displacements from their lattice sites (mcpm_engine_set_relative) instead
         # of float32 absolute positions; False reproduces round 1's arithmetic (kept for the A/B in the parity report)
         self.relative = bool(relative)
+        # tape_forces=False: the BullFrog loop tapes positions only and recomputes each step's force meshes in the backward
+        # pass (one extra paint + forward Fourier pass per step) instead of keeping 16 bytes per cell and step
+        self.tape_forces = bool(tape_forces)
         self.mesh_shape = tuple(int(s) for s in mesh_shape)
         self.box_size = tuple(float(b) for b in box_size)
         self.evolution, self.n_steps, self.a_start, self.a_obs = evolution, int(n_steps), a_start, a_obs
@@ -162,7 +165,8 @@ class FieldModel:
             pos, vel = nb.lpt(c, dk, None if rel else self.q, self.a_obs, self.lpt_order, 1, _displaced=not rel)
         elif self.evolution == "nbody":
             pos, vel = nb.nbody_bf(c, dk, self.q, self.a_start, self.a_obs, self.n_steps, self.paint_order,
-                                   self.lpt_order, paint_deconv=False, ptcl_shape=self.mesh_shape, relative=rel)
+                                   self.lpt_order, paint_deconv=False, ptcl_shape=self.mesh_shape, relative=rel,
+                                   tape_forces=self.tape_forces)
             pos, vel = pos[-1], vel[-1]
         else:
             raise ValueError(f"unknown evolution {self.evolution}")

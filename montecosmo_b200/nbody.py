@@ -343,14 +343,14 @@ class _NbodySteps(torch.autograd.Function):
     """BullFrog DKD loop (nbody.py:933-951, 999) with per-step coefficients [n_steps, 4] (float64, host)."""
 
     @staticmethod
-    def forward(ctx, pos, vel, coefs, shape, order, paint_deconv, lap_fd, grad_fd, lattice=None):
+    def forward(ctx, pos, vel, coefs, shape, order, paint_deconv, lap_fd, grad_fd, lattice=None, tape_forces=True):
         co = coefs.detach().cpu().to(torch.float64).numpy()
         al, be, pre, post = (co[:, i].tolist() for i in range(4))
         want_coef = coefs.requires_grad
         pos, vel0 = pos.clone(), vel.contiguous()
         vel = vel0.clone()
         tape = ops().nbody_steps(pos, vel, shape, al, be, pre, post, order, paint_deconv, lap_fd, grad_fd, tape=True,
-                                 tape_vel=want_coef, lattice=lattice)
+                                 tape_vel=want_coef, lattice=lattice, tape_forces=tape_forces)
         ctx.cfg = (al, be, pre, post, shape, order, paint_deconv, lap_fd, grad_fd, want_coef, lattice)
         ctx.tape, ctx.v0 = tape, (vel0 if want_coef else None)
         ctx.coef_meta = (coefs.device, coefs.dtype)
@@ -367,7 +367,7 @@ class _NbodySteps(torch.autograd.Function):
         if cb is not None:
             cb = cb.to(device=ctx.coef_meta[0], dtype=ctx.coef_meta[1])
         ctx.tape = ctx.v0 = None
-        return pb, vb, cb, None, None, None, None, None, None
+        return pb, vb, cb, None, None, None, None, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -532,7 +532,7 @@ def _save_plan(ts, g0, dg, n_steps):
 
 def nbody_bf(cosmo, init_mesh, pos, a0=0.0, a1=1.0, n_steps=5, paint_order: int = 2, lpt_order: int = 2,
              paint_deconv=False, grad_fd=np.inf, lap_fd=np.inf, snapshots=None, fn=save_y, ptcl_shape="auto",
-             integrator="bullfrog", relative=None):
+             integrator="bullfrog", relative=None, tape_forces=True):
     """N-body simulation with the BullFrog solver (nbody.py:967-1002): lpt at a0, then n_steps DKD steps in growth time.
 
     Returns (pos, vel), each [S, Np, 3].  `snapshots` as in the reference: None or an int <= 1 saves the final state
@@ -555,6 +555,10 @@ def nbody_bf(cosmo, init_mesh, pos, a0=0.0, a1=1.0, n_steps=5, paint_order: int 
     inside the loop whenever the caller declares the lattice (`ptcl_shape` given as a tuple), positions returned as the
     reference does; with ptcl_shape="auto" nothing is assumed about `pos` and the loop carries absolute positions.
     False: absolute positions throughout (round 1's arithmetic).
+
+    `tape_forces` (extension; memory only, same result): False keeps positions but not the per-step force meshes for the
+    backward pass (16 bytes per cell and step) and recomputes them there -- the memory / recompute trade of the
+    reference's checkpointed diffrax adjoint (nbody.py:999).
     """
     fn = save_y if fn is None else fn
     n_steps = int(n_steps)
@@ -594,7 +598,7 @@ def nbody_bf(cosmo, init_mesh, pos, a0=0.0, a1=1.0, n_steps=5, paint_order: int 
     for b in sorted(need):
         if b > s:
             x, vel = _NbodySteps.apply(x, vel, coefs[s:b], mesh_shape, int(paint_order), bool(paint_deconv), lap_fd,
-                                       grad_fd, lattice)
+                                       grad_fd, lattice, bool(tape_forces))
             s = b
             states[b] = (x, vel)
     if inner_rel and not relative:  # back to absolute positions at the boundary, as the reference returns them

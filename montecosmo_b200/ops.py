@@ -381,7 +381,7 @@ class Ops:
         return (dkbar, coef) if want_coef else dkbar
 
     def nbody_steps(self, pos, vel, shape, alpha, beta, drift_pre, drift_post, order=2, paint_deconv=False,
-                    lap_fd=INF, grad_fd=INF, tape=False, tape_vel=False, lattice=None):
+                    lap_fd=INF, grad_fd=INF, tape=False, tape_vel=False, lattice=None, tape_forces=True):
         """In place on (pos, vel) -- pass fresh copies.  Returns the tape (xk, vk, fm) when asked.  `lattice`: pos (and
         the xk tape) hold displacements from the sites of that regular lattice (mcpm_engine_set_relative)."""
         A = self.A
@@ -389,7 +389,8 @@ class Ops:
         ns = len(alpha)
         xk = A.empty((ns, n, 3)) if tape else None
         vk = A.empty((ns, n, 3)) if tape and tape_vel else None
-        fm = A.empty((ns, 4, *shape)) if tape else None
+        # tape_forces=False: 16 bytes per cell and step less tape; the reverse sweep recomputes each step's force meshes
+        fm = A.empty((ns, 4, *shape)) if tape and tape_forces else None
         self._call("mcpm_nbody_steps", self._frame(shape, lattice).handle, A.stream(), A.ptr(pos), A.ptr(vel), n, ns,
                    host_floats(alpha), host_floats(beta), host_floats(drift_pre), host_floats(drift_post), order,
                    int(paint_deconv), fd_code(lap_fd), fd_code(grad_fd), A.ptr(xk), A.ptr(vk), A.ptr(fm))

@@ -450,6 +450,26 @@ def test_nbody_bf_snapshots_dense_output(nb, golden):
     assert rel(dkl.grad, dko.grad) < 5e-3
 
 
+def test_force_tape_is_optional(nb):
+    """tape_forces=False (mcpm_nbody_steps_vjp with fm = NULL): the reverse sweep recomputes every step's force meshes
+    from the taped kick positions -- same log-density and gradient (float-atomic summation order aside), for CIC (float4
+    force meshes) and a non-CIC order (planar ones)."""
+    from montecosmo_b200.model import FieldModel
+    rng = np.random.default_rng(12)
+    shape = (16, 12, 20)
+    white = rng.normal(size=shape).astype(np.float32)
+    obs = (1.0 + rng.normal(size=shape)).astype(np.float32)
+    for order in (2, 3):
+        out = []
+        for tf in (True, False):
+            m = FieldModel(shape, (200.0, 150.0, 250.0), evolution="nbody", n_steps=3, a_start=0.1, paint_order=order,
+                           tape_forces=tf)
+            lp, g = m.value_and_force(white, obs)
+            out.append((float(lp), g.detach().cpu().numpy().astype(np.float64)))
+        assert abs(out[0][0] - out[1][0]) <= 1e-6 * abs(out[0][0])
+        assert np.linalg.norm(out[0][1] - out[1][1]) <= 2e-5 * np.linalg.norm(out[0][1])
+
+
 def test_physics_self_checks_without_an_oracle(nb):
     """Checks that need no reference run: the 1LPT displacement of a single plane wave equals its analytic
     value D(a) A sin(k q) / k along the wave vector, and a small-amplitude field evolved by nbody_bf to a = 1 reproduces

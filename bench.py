@@ -281,16 +281,17 @@ def kernel_rooflines(model, white, peaks):
         lambda: (mesh.zero_(), lib.mcpm_paint_brick_f(st, frp, *shape, pos.data_ptr(), 0, 1.0, 0.0, N, *shape,
                                                       mesh.data_ptr())),
         16 * N, steps + 2, "pos 12N + mesh 4N (includes the 4N memset)")
-    add("brick_paint3", "brick paint3 (reverse-step scatter of 3 channels, fused vbar += xbar*drift)",
-        lambda: (planar3.zero_(), lib.mcpm_paint3_brick_f(st, frp, *shape, pos.data_ptr(), vbar.data_ptr(),
-                                                          xbar.data_ptr(), 1e-3, 0.5, N, *shape, planar3.data_ptr())),
-        60 * N, steps, "pos 12N + vbar 12N r + 12N w + xbar 12N + 3 meshes 12N (includes the 12N memset)")
+    add("brick_paint3", "brick paint3 (reverse-step scatter of the 3 channels of beta * vbar)",
+        lambda: (planar3.zero_(), lib.mcpm_paint3_brick_f(st, frp, *shape, pos.data_ptr(), vbar.data_ptr(), 0, 0.0, 0.5,
+                                                          N, *shape, planar3.data_ptr())),
+        36 * N, steps, "SURVEY 8d's paint3: pos 12N + vbar 12N + 3 meshes 12N (the 12N memset is timed too; round 1's "
+                       "60N counted the vbar += xbar*drift update that now rides in read_grad4v's epilogue)")
     add("kick_drift4", "kick_drift4 (float4 force readout + kick + drift)",
         lambda: lib.mcpm_kick_drift4_f(st, frp, p2.data_ptr(), v2.data_ptr(), fm4.data_ptr(), N, *shape, 1.0, 0.0, 0.0),
         64 * N, steps, "pos 12N r/w + vel 12N r/w + mesh4 16N")
     add("read_grad4v", "read_grad4v (reverse-step gradient gather, fused xbar / vbar update)",
-        lambda: lib.mcpm_read_grad4v_f(st, frp, pos.data_ptr(), fm4.data_ptr(), rho.data_ptr(), vbar.data_ptr(), 0.5, 1.0,
-                                       N, *shape, xbar.data_ptr()), 80 * N, steps,
+        lambda: lib.mcpm_read_grad4v_step_f(st, frp, pos.data_ptr(), fm4.data_ptr(), rho.data_ptr(), vbar.data_ptr(), 0.5,
+                                            1.0, 1e-3, N, *shape, xbar.data_ptr()), 80 * N, steps,
         "pos 12N + vbar 12N r/w + xbar 12N r/w + mesh4 16N + rhobar 4N")
     add("interleave3", "interleave3 (3 planar meshes -> float4 mesh)",
         lambda: lib.mcpm_interleave3(st, fm.data_ptr(), fm4.data_ptr(), N), 28 * N, steps, "12N r + 16N w")

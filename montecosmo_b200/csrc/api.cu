@@ -36,6 +36,8 @@ int tune_set(Tune& t, const char* key, int value) {
     t.brick = value != 0;
   } else if (k == "gather_tma") {
     t.gather_tma = value != 0;
+  } else if (k == "gather_brick") {
+    t.gather_brick = value != 0;
   } else if (k == "gather_seg") {
     if (value != 32 && value != 64 && value != 128) return bad("gather_seg must be 32, 64 or 128");
     t.gather_seg = value;

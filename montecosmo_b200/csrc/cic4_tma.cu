@@ -42,6 +42,12 @@ struct GatherArgs {
   const float* rhobar;
   int nx, ny, nz;
   int rel, py, pz, ox, oy, oz;  // relative frame of spacing one cell (lattice py x pz pencils), else rel = 0
+  // Brick-ordered work assignment (lat != 0: the particle order is a known px x py x pz lattice, relative or not): the 8
+  // warps of a CTA take the 8 segments of a 2 (x) x 4 (y) patch of lattice rows at one z-segment, so every mesh line is
+  // read by up to 8 rows of the same CTA at the same time instead of 2 (L1 hit rate ~50 % -> ~75 %).  spp = segments
+  // per pencil, tiles = (px/2) * (py/4) * spp.  lat == 0: segments in linear order (any particle order).
+  int lat, lpy, spp;
+  unsigned ntiles;
   float alpha, beta, drift;     // kick
   float cscale, alpha_tail, dnext;  // grad
   int accumulate, scale_cot;
@@ -92,15 +98,32 @@ __global__ void __launch_bounds__(gtma::THREADS, MODE == 0 ? 4 : 3) gather_tma_k
   __syncwarp();
 
   const int nload = (MODE == 1 && !a.accumulate) ? 2 : NIN;
-  const int64_t W = (int64_t)gridDim.x * WARPS;              // warps in the grid
-  const int64_t seg0 = (int64_t)blockIdx.x * WARPS + warp;   // this warp's first segment
-  const int nmine = seg0 < a.nseg ? (int)((a.nseg - seg0 + W - 1) / W) : 0;
+  // 32-bit index arithmetic throughout: nseg < 2^31 (checked by the host side)
+  const unsigned ntile = a.lat ? a.ntiles : (unsigned)((a.nseg + WARPS - 1) / WARPS);  // units of 8 segments
+  const int nmine = blockIdx.x < ntile ? (int)((ntile - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  const unsigned hj = (unsigned)a.lpy >> 2;  // y-patches per x-pair (lat mode)
+  auto seg_of = [&](int t, unsigned& seg, unsigned& li, unsigned& lj, unsigned& ks) -> bool {
+    const unsigned T = blockIdx.x + (unsigned)t * gridDim.x;
+    if (a.lat) {  // tile T = (i2 * hj + j4) * spp + ks; warp (di, dj) = (warp >> 2, warp & 3)
+      const unsigned ij = T / (unsigned)a.spp;
+      ks = T - ij * (unsigned)a.spp;
+      const unsigned i2 = ij / hj, j4 = ij - i2 * hj;
+      li = 2 * i2 + (warp >> 2);
+      lj = 4 * j4 + (warp & 3);
+      seg = (li * (unsigned)a.lpy + lj) * (unsigned)a.spp + ks;
+      return true;
+    }
+    seg = T * WARPS + warp;
+    li = lj = ks = 0;
+    return seg < (unsigned)a.nseg;
+  };
   auto issue = [&](int t) {  // lane 0: bulk loads of this warp's t-th segment into stage t % NSTAGE
-    const int64_t seg = seg0 + (int64_t)t * W;
+    unsigned seg, li, lj, ks;
+    if (!seg_of(t, seg, li, lj, ks)) return;
     const int st = t % NSTAGE;
     tma::mbar_arrive_expect_tx(&bar[st], BYTES * nload);
     for (int m = 0; m < nload; ++m)
-      tma::bulk_g2s(sin + (st * NIN + m) * ROW, a.in[m] + seg * ROW, BYTES, &bar[st]);
+      tma::bulk_g2s(sin + (st * NIN + m) * ROW, a.in[m] + (size_t)seg * ROW, BYTES, &bar[st]);
   };
   if (lane == 0)
     for (int t = 0; t < NSTAGE - 1 && t < nmine; ++t) issue(t);
@@ -111,15 +134,21 @@ __global__ void __launch_bounds__(gtma::THREADS, MODE == 0 ? 4 : 3) gather_tma_k
     const int st = t % NSTAGE;
     // stage (t + NSTAGE - 1) % NSTAGE was last read in iteration t - 1 (syncwarp since)
     if (lane == 0 && t + NSTAGE - 1 < nmine) issue(t + NSTAGE - 1);
+    unsigned seg, li, lj, ks;
+    if (!seg_of(t, seg, li, lj, ks)) break;  // linear mode: the last unit of 8 segments may be partial (warp-uniform)
     tma::mbar_wait(&bar[st], (uint32_t)(t / NSTAGE) & 1u);
-    const int64_t p0 = (seg0 + (int64_t)t * W) * SEG;
+    const size_t p0 = (size_t)seg * SEG;
     int sx = 0, sy = 0, sk = 0;
     if (a.rel) {  // lattice site of the segment's first particle: one pencil holds whole segments
-      const int64_t jk = p0 / a.pz;
-      sk = (int)(p0 - jk * a.pz) + a.oz;
-      const int i = (int)(jk / a.py);
-      sx = i + a.ox;
-      sy = (int)(jk - (int64_t)i * a.py) + a.oy;
+      if (!a.lat) {
+        const unsigned spp = (unsigned)a.pz / SEG, jk = seg / spp;
+        ks = seg - jk * spp;
+        li = jk / (unsigned)a.py;
+        lj = jk - li * (unsigned)a.py;
+      }
+      sx = (int)li + a.ox;
+      sy = (int)lj + a.oy;
+      sk = (int)(ks * SEG) + a.oz;
     }
     const float* spos = sin + (st * NIN + 0) * ROW;
     const float* sb = sin + (st * NIN + 1) * ROW;
@@ -198,7 +227,7 @@ __global__ void __launch_bounds__(gtma::THREADS, MODE == 0 ? 4 : 3) gather_tma_k
     tma::fence_async_smem();  // every lane: its shared-memory writes before the bulk stores that read them
     __syncwarp();
     if (lane == 0) {
-      const int64_t off = p0 * 3;
+      const size_t off = p0 * 3;
       if (MODE == 0 || a.scale_cot) tma::bulk_s2g(a.out[0] + off, o0, BYTES);
       tma::bulk_s2g(a.out[1] + off, o1, BYTES);
       tma::bulk_commit();
@@ -214,8 +243,9 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 // Geometry check shared by both entry points; fills the frame part of the arguments.
 static bool gather_tma_ok(GatherArgs& a, int64_t np, const Frame* fr, int seg) {
-  if (!tune().gather_tma || np <= 0 || np % seg) return false;
+  if (!tune().gather_tma || np <= 0 || np % seg || np / seg >= ((int64_t)1 << 31)) return false;
   a.rel = 0;
+  a.lat = 0;
   if (fr && fr->rel) {
     if (fr->nux != 1 || fr->nuy != 1 || fr->nuz != 1 || fr->dex != 1 || fr->dey != 1 || fr->dez != 1) return false;
     if (fr->pz % seg) return false;
@@ -225,6 +255,13 @@ static bool gather_tma_ok(GatherArgs& a, int64_t np, const Frame* fr, int seg) {
     a.ox = fr->ox;
     a.oy = fr->oy;
     a.oz = fr->oz;
+    // brick-ordered assignment when the lattice divides into 2 x 4 patches of rows
+    if (fr->px % 2 == 0 && fr->py % 4 == 0 && tune().gather_brick) {
+      a.lat = 1;
+      a.lpy = fr->py;
+      a.spp = fr->pz / seg;
+      a.ntiles = (unsigned)((int64_t)(fr->px / 2) * (fr->py / 4) * a.spp);
+    }
   }
   a.nseg = np / seg;
   return true;
@@ -247,7 +284,7 @@ static void launch_gather_tma_seg(stream_t st, const GatherArgs& a) {
       n = 1;
     per_sm[dev] = n;
   }
-  const int64_t want = (a.nseg + WARPS - 1) / WARPS, wave = (int64_t)kSMs * per_sm[dev];
+  const int64_t want = a.lat ? (int64_t)a.ntiles : (a.nseg + WARPS - 1) / WARPS, wave = (int64_t)kSMs * per_sm[dev];
   const unsigned grid = (unsigned)(want < wave ? want : wave);  // persistent: at most one resident wave
   gather_tma_kernel<MODE, SEG><<<grid, THREADS, smem, st>>>(a);
 }

@@ -24,6 +24,7 @@ struct Tune {
   int brick = 1;           // brick-tiled shared-memory scatters (brick.cu) where they apply; 0: generic global atomics
   int gather_tma = 1;      // gathers with bulk-copy staged particle arrays (cic4_tma.cu) where they apply
   int gather_seg = 32;     // particles per bulk copy there (32 | 64 | 128)
+  int gather_brick = 1;    // there: a CTA's 8 warps take a 2 x 4 patch of lattice rows (L1 reuse) instead of one pencil
 };
 Tune& default_tune();  // api.cu
 const Tune& tune();    // the executing engine's knobs, else the defaults

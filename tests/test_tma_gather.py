@@ -64,6 +64,7 @@ def _grad(c):
     ((64, 32, 128), (64, 32, 128), True),    # lattice == mesh, relative (what FieldModel runs)
     ((64, 32, 128), (64, 32, 128), False),   # absolute positions, wrapped and far-out particles
     ((48, 40, 96), (48, 40, 96), True),      # pz = 96: whole 32-segments only -> 64 / 128 must fall back
+    ((34, 6, 64), (34, 6, 64), True),        # py % 4 != 0: no 2 x 4 patches of rows -> linear segment order
     ((40, 24, 64), (20, 12, 32), True),      # lattice coarser than the mesh (spacing 2): not a unit frame -> falls back
     ((33, 17, 50), (33, 17, 50), False),     # particle count not a multiple of any segment -> falls back
 ])
@@ -74,16 +75,18 @@ def test_tma_gathers_are_bit_identical(mesh, lattice, rel):
     try:
         tune(b"gather_tma", 0)
         ref_k, ref_g = _kick(c), _grad(c)
-        for seg in (32, 64, 128):
+        for seg, brick in ((32, 1), (64, 1), (128, 1), (32, 0)):
             tune(b"gather_tma", 1)
             tune(b"gather_seg", seg)
+            tune(b"gather_brick", brick)
             k, g = _kick(c), _grad(c)
             torch.cuda.synchronize()
             for a, b in zip(k + g, ref_k + ref_g):
-                assert torch.equal(a, b), (mesh, lattice, rel, seg, float((a - b).abs().max()))
+                assert torch.equal(a, b), (mesh, lattice, rel, seg, brick, float((a - b).abs().max()))
     finally:
         tune(b"gather_tma", 1)
         tune(b"gather_seg", 32)
+        tune(b"gather_brick", 1)
 
 
 def test_tma_gathers_launch_when_applicable():

@@ -614,6 +614,19 @@ def run_slab(args, world, rank, dev, timed, barrier, sampler):
     mdl.value_and_force(whites[0], obs)
     torch.cuda.synchronize()
     launches = int(lib.mcpm_launch_count(0))
+    # The slab model launches eagerly and draws every intermediate from torch's caching allocator: its first evaluations
+    # pay cudaMalloc (which synchronises the device) and NCCL's lazy channel set-up, and on 2 B200s the first timed loop
+    # measured 80 ms per evaluation where the second measured 51.  Untimed settling evaluations, the same number on
+    # every rank (collectives inside), until the allocator has stopped growing -- at most 8.
+    grew = torch.tensor([1.0], device=dev)
+    for _ in range(8):
+        before = torch.cuda.memory_reserved()
+        mdl.value_and_force(whites[_ % 2], obs)
+        torch.cuda.synchronize()
+        grew[0] = float(torch.cuda.memory_reserved() != before)
+        dist.all_reduce(grew, op=dist.ReduceOp.MAX)
+        if float(grew) == 0.0:
+            break
     if rank == 0:
         sampler.start()
     keep = {}

@@ -55,7 +55,9 @@ long long mcpm_launch_count(int reset);
  * "brick" = 0 | 1, the brick-tiled shared-memory scatters (default 1; 0 = generic global-atomic kernels);
  * "gather_tma" = 0 | 1, the step-loop gathers with bulk-copy staged particle arrays (csrc/cic4_tma.cu; default 1);
  * "gather_seg" = 32 | 64 | 128, particles per bulk copy there (default 32); "gather_brick" = 0 | 1, a CTA's 8 warps take a
- * 2 x 4 patch of lattice rows instead of one z-pencil (default 1). */
+ * 2 x 4 patch of lattice rows instead of one z-pencil (default 1); "yzfft" = 0 | 1, the batched (y,z) transforms of the
+ * fused-FFT path as one kernel with both passes on-chip (csrc/yzfft.cu; square planes of side 64, 128, 256; default 1)
+ * instead of cuFFT's two-kernel 2-D plans. */
 int mcpm_tune(const char* key, int value);
 /* The same knobs for ONE engine.  mcpm_tune sets the process-wide defaults, which an engine copies when it is created and
  * which the stateless entry points use; an engine's own knobs apply to its composite operators only, so replicas on

@@ -36,6 +36,8 @@ int tune_set(Tune& t, const char* key, int value) {
     t.brick = value != 0;
   } else if (k == "gather_tma") {
     t.gather_tma = value != 0;
+  } else if (k == "yzfft") {
+    t.yzfft = value != 0;
   } else if (k == "gather_brick") {
     t.gather_brick = value != 0;
   } else if (k == "gather_seg") {

@@ -24,6 +24,7 @@ struct Tune {
   int brick = 1;           // brick-tiled shared-memory scatters (brick.cu) where they apply; 0: generic global atomics
   int gather_tma = 1;      // gathers with bulk-copy staged particle arrays (cic4_tma.cu) where they apply
   int gather_seg = 32;     // particles per bulk copy there (32 | 64 | 128)
+  int yzfft = 1;           // the batched (y,z) transforms as one fused kernel (yzfft.cu) where supported; 0: cuFFT 2-D plans
   int gather_brick = 1;    // there: a CTA's 8 warps take a 2 x 4 patch of lattice rows (L1 reuse) instead of one pencil
 };
 Tune& default_tune();  // api.cu
@@ -152,6 +153,11 @@ int paint3v4(stream_t, const float* pos, float* A, const float* B, float cb, int
 int read_grad4v(stream_t, const float* pos, const float* fmesh4, const float* rhobar, float* cot, float cscale,
                 int scale_cot, float alpha_tail, int64_t np, int nx, int ny, int nz, float* grad, int accumulate,
                 float* zero = nullptr, int64_t nzero = 0, const Frame* fr = nullptr, float dnext = 0.0f);
+
+// yzfft.cu (CUDA build only): fused two-pass (y,z) R2C / C2R on square planes of side 64, 128, 256; unnormalised
+bool yzfft_supported(int ny, int nz);
+int yzfft_r2c(stream_t, const float* in, cfloat* out, int ny, int nz, int nplanes);
+int yzfft_c2r(stream_t, const cfloat* in, float* out, int ny, int nz, int nplanes);
 
 // cic4_tma.cu (CUDA build only): the same two gathers with bulk-copy staged particle arrays; 1 handled, 0 not applicable
 int kick_drift4_tma(stream_t, const float* pos, const float* vel, const float* fmesh4, int64_t np, int nx, int ny, int nz,

@@ -308,6 +308,10 @@ void slabfft_destroy(SlabFft* p) {
 }
 
 int slabfft_r2c_yz(SlabFft* p, stream_t st, const float* in, cfloat* out, int nb) {
+  if (tune().yzfft && yzfft_supported(p->ny, p->nz)) {  // both passes in one kernel (yzfft.cu)
+    const int r = yzfft_r2c(st, in, out, p->ny, p->nz, nb * p->xl);
+    if (r != MCPM_EUNSUP) return r;
+  }
   std::lock_guard<std::mutex> lk(p->mu);
   const size_t rd = (size_t)p->xl * p->ny * p->nz, cd = (size_t)p->xl * p->ny * (p->nz / 2 + 1);
   return run_batched(p->r2c, nb, [&](cufftHandle h, int off) {
@@ -317,6 +321,10 @@ int slabfft_r2c_yz(SlabFft* p, stream_t st, const float* in, cfloat* out, int nb
 }
 
 int slabfft_c2r_yz(SlabFft* p, stream_t st, cfloat* in, float* out, int nb) {
+  if (tune().yzfft && yzfft_supported(p->ny, p->nz)) {
+    const int r = yzfft_c2r(st, in, out, p->ny, p->nz, nb * p->xl);
+    if (r != MCPM_EUNSUP) return r;
+  }
   std::lock_guard<std::mutex> lk(p->mu);
   const size_t rd = (size_t)p->xl * p->ny * p->nz, cd = (size_t)p->xl * p->ny * (p->nz / 2 + 1);
   return run_batched(p->c2r, nb, [&](cufftHandle h, int off) {

@@ -55,9 +55,9 @@ long long mcpm_launch_count(int reset);
  * "brick" = 0 | 1, the brick-tiled shared-memory scatters (default 1; 0 = generic global-atomic kernels);
  * "gather_tma" = 0 | 1, the step-loop gathers with bulk-copy staged particle arrays (csrc/cic4_tma.cu; default 1);
  * "gather_seg" = 32 | 64 | 128, particles per bulk copy there (default 32); "gather_brick" = 0 | 1, a CTA's 8 warps take a
- * 2 x 4 patch of lattice rows instead of one z-pencil (default 1); "yzfft" = 0 | 1, the batched (y,z) transforms of the
- * fused-FFT path as one kernel with both passes on-chip (csrc/yzfft.cu; square planes of side 64, 128, 256; default 1)
- * instead of cuFFT's two-kernel 2-D plans. */
+ * 2 x 4 patch of lattice rows instead of one z-pencil (default 0: measured slower); "yzfft" = 0 | 1, the batched (y,z)
+ * transforms of the fused-FFT path as one kernel with both passes on-chip (csrc/yzfft.cu; square planes of side 64, 128,
+ * 256) instead of cuFFT's two-kernel 2-D plans (default 0: measured 84 / 96 us against cuFFT's 65 us per 256^3 mesh). */
 int mcpm_tune(const char* key, int value);
 /* The same knobs for ONE engine.  mcpm_tune sets the process-wide defaults, which an engine copies when it is created and
  * which the stateless entry points use; an engine's own knobs apply to its composite operators only, so replicas on
@@ -247,6 +247,23 @@ int mcpm_hermitian_project(void* stream, void* data_c64, int nx, int ny, int nz,
  * axis is the whole kz axis: the weights of mcpm_hermitian_weights for callers that keep their own 1/N. */
 int mcpm_half_weight_axpy(void* stream, const void* in, void* out, int64_t nc, int nz, float a, int inverse,
                           int accumulate);
+
+/* Halo exchange of a slab-decomposed mesh over peer memory (halo-plane summation after painting, halo fetch
+ * before readout).  Rank r owns planes [halo, halo + xl) of its extended mesh [nlead][xl + 2 halo][plane] (plane = floats
+ * per x-plane, channels included; nlead = 3 for three planar meshes).  prev_ext / next_ext are the SAME buffer of ranks
+ * r-1 / r+1 mapped into this process (CUDA IPC / symmetric memory; own pointers when there is one rank: the periodic
+ * wrap).  One kernel per exchange reads the neighbours' planes over NVLink where they lie: no packing, no collective.
+ *   reduce : own[halo + j] += prev[halo + xl + j],  own[xl + j] += next[j]             j < halo   (after a paint)
+ *   gather : own[j] = prev[xl + j],  own[halo + xl + j] = next[halo + j]               j < halo   (before a readout)
+ *   gather4: builds the float4 force mesh {Fx, Fy, Fz, 0} [xl + 2 halo][plane cells] from the three planar meshes of
+ *            OWNED planes [3][xl][plane cells] of this rank and its two neighbours (interleave + halo fetch in one pass).
+ * The caller orders the ranks with a barrier before (the neighbours' planes are complete) and before reuse. */
+int mcpm_halo_reduce_peer(void* stream, float* own_ext, const float* prev_ext, const float* next_ext, int halo, int xl,
+                          int64_t plane, int nlead);
+int mcpm_halo_gather_peer(void* stream, float* own_ext, const float* prev_ext, const float* next_ext, int halo, int xl,
+                          int64_t plane, int nlead);
+int mcpm_halo_gather4_peer(void* stream, float* fmesh4_ext, const float* f3_own, const float* f3_prev, const float* f3_next,
+                           int halo, int xl, int64_t plane);
 
 /* Fused x-transform passes (CUDA build, nx in {64, 128, 256, 512, 1024}; MCPM_EUNSUP otherwise), on a half spectrum
  * [nx, ny_loc, nz/2+1] that has been transformed along (y,z) only:

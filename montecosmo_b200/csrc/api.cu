@@ -966,6 +966,30 @@ int mcpm_paint3_brick_f(void* stream, const mcpm_frame* frame, int px, int py, i
   API_END
 }
 
+int mcpm_halo_reduce_peer(void* stream, float* own_ext, const float* prev_ext, const float* next_ext, int halo, int xl,
+                          int64_t plane, int nlead) {
+  API_BEGIN
+  NEED(own_ext && prev_ext && next_ext && halo >= 1 && halo <= xl && plane > 0 && nlead >= 1, "halo_reduce_peer: bad arguments");
+  return halo_reduce_peer(as_stream(stream), own_ext, prev_ext, next_ext, halo, xl, plane, nlead);
+  API_END
+}
+
+int mcpm_halo_gather_peer(void* stream, float* own_ext, const float* prev_ext, const float* next_ext, int halo, int xl,
+                          int64_t plane, int nlead) {
+  API_BEGIN
+  NEED(own_ext && prev_ext && next_ext && halo >= 1 && halo <= xl && plane > 0 && nlead >= 1, "halo_gather_peer: bad arguments");
+  return halo_gather_peer(as_stream(stream), own_ext, prev_ext, next_ext, halo, xl, plane, nlead);
+  API_END
+}
+
+int mcpm_halo_gather4_peer(void* stream, float* fmesh4_ext, const float* f3_own, const float* f3_prev, const float* f3_next,
+                           int halo, int xl, int64_t plane) {
+  API_BEGIN
+  NEED(fmesh4_ext && f3_own && f3_prev && f3_next && halo >= 1 && halo <= xl && plane > 0, "halo_gather4_peer: bad arguments");
+  return halo_gather4_peer(as_stream(stream), fmesh4_ext, f3_own, f3_prev, f3_next, halo, xl, plane);
+  API_END
+}
+
 int mcpm_drift(void* stream, float* pos, const float* vel, float drift, int64_t np) {
   API_BEGIN
   return axpy3(as_stream(stream), pos, vel, drift, 3 * np, pos);

@@ -24,8 +24,11 @@ struct Tune {
   int brick = 1;           // brick-tiled shared-memory scatters (brick.cu) where they apply; 0: generic global atomics
   int gather_tma = 1;      // gathers with bulk-copy staged particle arrays (cic4_tma.cu) where they apply
   int gather_seg = 32;     // particles per bulk copy there (32 | 64 | 128)
-  int yzfft = 1;           // the batched (y,z) transforms as one fused kernel (yzfft.cu) where supported; 0: cuFFT 2-D plans
-  int gather_brick = 1;    // there: a CTA's 8 warps take a 2 x 4 patch of lattice rows (L1 reuse) instead of one pencil
+  // Both measured on a B200 in round 2 and left OFF (profiles/r2_tune_*.txt): the fused (y,z) kernel runs 84 / 96 us per
+  // 256^3 mesh (R2C / C2R) against 65 us for cuFFT's two passes, whose second pass reads the first one's output from L2;
+  // the 2 x 4 patch mapping of the gathers costs 0.9 ms per evaluation more than one pencil per CTA.
+  int yzfft = 0;           // the batched (y,z) transforms as one fused kernel (yzfft.cu) where supported; 0: cuFFT 2-D plans
+  int gather_brick = 0;    // cic4_tma.cu: a CTA's 8 warps take a 2 x 4 patch of lattice rows instead of one pencil
 };
 Tune& default_tune();  // api.cu
 const Tune& tune();    // the executing engine's knobs, else the defaults
@@ -153,6 +156,12 @@ int paint3v4(stream_t, const float* pos, float* A, const float* B, float cb, int
 int read_grad4v(stream_t, const float* pos, const float* fmesh4, const float* rhobar, float* cot, float cscale,
                 int scale_cot, float alpha_tail, int64_t np, int nx, int ny, int nz, float* grad, int accumulate,
                 float* zero = nullptr, int64_t nzero = 0, const Frame* fr = nullptr, float dnext = 0.0f);
+
+// halo.cu: halo exchange of a slab-decomposed mesh as kernels over peer memory
+int halo_reduce_peer(stream_t, float* own, const float* prev, const float* next, int H, int xl, int64_t plane, int nlead);
+int halo_gather_peer(stream_t, float* own, const float* prev, const float* next, int H, int xl, int64_t plane, int nlead);
+int halo_gather4_peer(stream_t, float* fm4_ext, const float* F_own, const float* F_prev, const float* F_next, int H, int xl,
+                      int64_t plane);
 
 // yzfft.cu (CUDA build only): fused two-pass (y,z) R2C / C2R on square planes of side 64, 128, 256; unnormalised
 bool yzfft_supported(int ny, int nz);

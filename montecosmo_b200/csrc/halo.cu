@@ -1,0 +1,78 @@
+// halo.cu -- halo exchange of a slab-decomposed mesh as kernels over peer memory ("accumulate into n/P + h
+// planes, send the h halo planes to rank r+1 and add; fetch h planes before gathering").
+//
+// Rank r owns planes [H, H + xl) of its halo-extended mesh [ext = xl + 2H][plane]; its halos [0, H) and [H + xl, ext)
+// overlap the last / first H owned planes of ranks r-1 / r+1.  Round 1 moved the halos with torch: .contiguous() packs,
+// batch_isend_irecv over NCCL, adds and slice assignments from Python -- six launches and two NCCL calls per exchange.
+// Here every rank keeps the meshes that take part in an exchange in symmetric memory (CUDA IPC mappings of its peers'
+// buffers, as the x-transform kernel of xfft.cu does) and ONE kernel per exchange reads the neighbours' planes over NVLink
+// where they lie and combines them: no packing, no staging copy, no collective call.  The caller orders the ranks with a
+// barrier before (the neighbours' planes are complete) and before the buffers are written again.
+//   reduce :  own[H + j]      += prev[H + xl + j]     own[xl + j] += next[j]          j < H   (after a paint)
+//   gather :  own[j]           = prev[xl + j]         own[H + xl + j] = next[H + j]   j < H   (before a readout)
+//   gather4:  the same, building the float4 force mesh {Fx, Fy, Fz, 0} of the step kernels from the three planar meshes
+//             the C2R wrote (own planes included): the interleave pass and the halo fetch in one kernel.
+// With one rank prev = next = own: the periodic wrap of a single slab.
+#include "engine.h"
+
+namespace mcpm {
+
+struct alignas(16) hf4 {
+  float x, y, z, w;
+};
+
+// meshes laid out [nlead][ext][plane] (nlead = 3 for the planar reverse-step scatter, 1 otherwise)
+int halo_reduce_peer(stream_t st, float* own, const float* prev, const float* next, int H, int xl, int64_t plane,
+                     int nlead) {
+  const int64_t ext = xl + 2 * (int64_t)H, slab = (int64_t)H * plane;
+  launch_1d(st, (int64_t)nlead * slab, [=] MCPM_LAMBDA(int64_t i) {
+    const int64_t c = i / slab, r = i - c * slab, base = c * ext * plane;
+    own[base + (int64_t)H * plane + r] += prev[base + (int64_t)(H + xl) * plane + r];
+    own[base + (int64_t)xl * plane + r] += next[base + r];
+  });
+  return rt_check("halo_reduce_peer");
+}
+
+int halo_gather_peer(stream_t st, float* own, const float* prev, const float* next, int H, int xl, int64_t plane,
+                     int nlead) {
+  const int64_t ext = xl + 2 * (int64_t)H, slab = (int64_t)H * plane;
+  launch_1d(st, (int64_t)nlead * slab, [=] MCPM_LAMBDA(int64_t i) {
+    const int64_t c = i / slab, r = i - c * slab, base = c * ext * plane;
+    own[base + r] = prev[base + (int64_t)xl * plane + r];
+    own[base + (int64_t)(H + xl) * plane + r] = next[base + (int64_t)H * plane + r];
+  });
+  return rt_check("halo_gather_peer");
+}
+
+// F_* : three planar meshes [3][xl][plane] of OWNED planes (this rank's and its neighbours'); out: [ext][plane] float4
+int halo_gather4_peer(stream_t st, float* fm4_ext, const float* F_own, const float* F_prev, const float* F_next, int H,
+                      int xl, int64_t plane) {
+  const int64_t own_n = (int64_t)xl * plane, halo_n = (int64_t)H * plane;
+  hf4* out = reinterpret_cast<hf4*>(fm4_ext);
+  launch_1d(st, own_n + 2 * halo_n, [=] MCPM_LAMBDA(int64_t i) {
+    const float* F;
+    int64_t src, dst;
+    if (i < own_n) {  // my planes
+      F = F_own;
+      src = i;
+      dst = halo_n + i;
+    } else if (i < own_n + halo_n) {  // left halo: the last H owned planes of the previous rank
+      F = F_prev;
+      src = own_n - halo_n + (i - own_n);
+      dst = i - own_n;
+    } else {  // right halo: the first H owned planes of the next rank
+      F = F_next;
+      src = i - own_n - halo_n;
+      dst = halo_n + own_n + src;
+    }
+    hf4 v;
+    v.x = F[src];
+    v.y = F[own_n + src];
+    v.z = F[2 * own_n + src];
+    v.w = 0.0f;
+    out[dst] = v;
+  });
+  return rt_check("halo_gather4_peer");
+}
+
+}  // namespace mcpm

@@ -36,6 +36,40 @@ from ._capi import check, fd_code, frame as _frame
 INF = float("inf")
 
 
+class _Sections:
+    """CUDA-event section timers (MCPM_SLAB_PROFILE=1): where a slab evaluation spends its time, per named section."""
+
+    def __init__(self):
+        self.on = os.environ.get("MCPM_SLAB_PROFILE", "0") == "1"
+        self.pending, self.total, self.count = [], {}, {}
+
+    def wrap(self, obj, names):
+        if not self.on:
+            return
+        for name in names:
+            fn = getattr(obj, name)
+
+            def timed(*a, _fn=fn, _name=name, **kw):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = _fn(*a, **kw)
+                e1.record()
+                self.pending.append((_name, e0, e1))
+                return out
+            setattr(obj, name, timed)
+
+    def report(self, reset=True):
+        torch.cuda.synchronize()
+        for name, e0, e1 in self.pending:
+            self.total[name] = self.total.get(name, 0.0) + e0.elapsed_time(e1)
+            self.count[name] = self.count.get(name, 0) + 1
+        self.pending = []
+        out = {k: {"ms": round(v, 3), "calls": self.count[k]} for k, v in sorted(self.total.items(), key=lambda kv: -kv[1])}
+        if reset:
+            self.total, self.count = {}, {}
+        return out
+
+
 class SlabPM:
     def __init__(self, ops, mesh_shape, halo=24, group=None, p2p=True):
         self.o, self.lib, self.A = ops, ops.lib, ops.A
@@ -68,14 +102,21 @@ class SlabPM:
         self.p2p, self.p2p_note = False, "off"
         # p2p=False: a geometry that only paints and transforms (the finer paint mesh of the final nufft) needs no peer
         # buffers -- they are 6 half spectra of symmetric memory
+        self.prev, self.next = (self.rank - 1) % self.P, (self.rank + 1) % self.P
+        self._want_p2p = bool(p2p)
         if p2p and self.xfuse and self.P > 1 and os.environ.get("MCPM_SLAB_P2P", "1") != "0":
             self._setup_p2p()
-        self.prev, self.next = (self.rank - 1) % self.P, (self.rank + 1) % self.P
+        if p2p:
+            self._agree_p2p()
         ax = [np.arange(self.xl, dtype=np.float32), np.arange(ny, dtype=np.float32), np.arange(nz, dtype=np.float32)]
         self.q_own = self.A.prepare(np.stack(np.meshgrid(*ax, indexing="ij"), -1).reshape(-1, 3))  # owned-slab coords
         self.frame = _frame((self.xl, ny, nz), origin=(self.H, 0, 0))  # relative positions on the halo-extended mesh
         self._fr = C.byref(self.frame)
         self._oob = None
+        self.sections = _Sections()
+        if self.sections.on and self.A.device.type == "cuda":  # nested sections: inner times are included in outer ones
+            self.sections.wrap(self, ["halo_reduce", "halo_gather", "forces_from_density", "density_cotangent",
+                                      "lpt_forward", "lpt_backward", "steps_forward", "steps_backward", "rfftn", "irfftn"])
 
     def __del__(self):
         try:
@@ -104,11 +145,46 @@ class SlabPM:
                 return
             self._peer_in = (C.c_void_p * 8)(*(pin + [0] * (8 - self.P)))
             self._peer_out = (C.c_void_p * 8)(*(pout + [0] * (8 - self.P)))
-            self.p2p, self.p2p_note = True, "symmetric memory, peer loads/stores inside the x-transform kernel"
+            # the meshes that take part in a halo exchange, in symmetric memory too (csrc/halo.cu: one kernel per exchange
+            # reads the neighbours' planes where they lie)
+            self._halo = {}
+            for key, shape in (("rho", (self.ext, self.ny, self.nz)), ("m3", (3, self.ext, self.ny, self.nz)),
+                               ("F", (3, self.xl, self.ny, self.nz)), ("rb", (self.ext, self.ny, self.nz))):
+                buf = symm.empty(shape, dtype=torch.float32, device=dev)
+                hd = symm.rendezvous(buf, grp)
+                ptrs = list(hd.buffer_ptrs)
+                if len(ptrs) != self.P:
+                    self.p2p_note = "unexpected peer table"
+                    return
+                self._halo[key] = (buf, hd, ptrs)
+            self.p2p, self.p2p_note = True, "symmetric memory: peer loads/stores inside the x-transform and halo kernels"
         except Exception as e:  # no NVLink peer access, missing permissions, older torch: keep the NCCL path
             self.p2p, self.p2p_note = False, f"unavailable ({type(e).__name__}: {e})"
 
-    def _peer_force(self, real_in, nb_in, transpose):
+    def _agree_p2p(self):
+        """Every rank must take the same path: one that fell back to NCCL while its peers wait in a symmetric-memory
+        barrier would deadlock the job.  p2p stays on only if it came up on ALL ranks."""
+        if self.P > 1:
+            flag = torch.tensor([1.0 if self.p2p else 0.0], device=self.A.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if self.p2p and float(flag) == 0.0:
+                self.p2p, self.p2p_note = False, "off: peer memory did not come up on every rank"
+
+    def _halo_buf(self, key, shape):
+        """The mesh of an exchange: my symmetric buffer and (mine, prev's, next's) pointers; a plain tensor with my own
+        pointer three times when this is the only rank (the periodic wrap of a single slab)."""
+        if self.p2p:
+            buf, hd, ptrs = self._halo[key]
+            return buf, hd, (ptrs[self.rank], ptrs[self.prev], ptrs[self.next])
+        buf = self.A.empty(shape)
+        return buf, None, (buf.data_ptr(),) * 3
+
+    @property
+    def peer_halos(self):
+        """Halo exchanges as csrc/halo.cu kernels: over symmetric memory (p2p), or on one CUDA / host rank."""
+        return self.p2p or self.P == 1
+
+    def _peer_force(self, real_in, nb_in, transpose, out=None):
         """real_in [nb_in, xl, ny, nz] -> [nb_out, xl, ny, nz]: local 2-D R2C into the symmetric buffer, barrier, the
         fused kernel on my ky block reading / writing every rank's buffer, barrier, local 2-D C2R."""
         st = self._st()
@@ -118,7 +194,7 @@ class SlabPM:
                    self.nz, self.kyl, self.y0, 0, 0, 0.0, 0, 1.0 / self.N)
         self._h_out.barrier()
         nb_out = 1 if transpose else 3
-        out = self.A.empty((nb_out, self.xl, self.ny, self.nz))
+        out = self.A.empty((nb_out, self.xl, self.ny, self.nz)) if out is None else out
         self._call("mcpm_slabfft_c2r_yz", self._fft, st, self._sym_out.data_ptr(), out.data_ptr(), nb_out)
         return out
 
@@ -260,9 +336,9 @@ class SlabPM:
 
     # density planes -> three force meshes, and the transpose (3 meshes -> 1), each with ONE kernel between the
     # all-to-alls where the fused x-transform exists for nx (xfft.cu), else c2c_x + streaming multiply + c2c_x
-    def forces_from_density(self, rho_owned):
+    def forces_from_density(self, rho_owned, out=None):
         if self.p2p:
-            return self._peer_force(rho_owned.contiguous().unsqueeze(0), 1, False)
+            return self._peer_force(rho_owned.contiguous().unsqueeze(0), 1, False, out=out)
         if self.xfuse:
             c = self.rfftn_yz(rho_owned.unsqueeze(0))
             out = self.A.empty((3, self.nx, self.kyl, self.nzc), "c64")
@@ -272,9 +348,9 @@ class SlabPM:
         rk = self.rfftn(rho_owned.unsqueeze(0))
         return self.irfftn(self.force_spectra(rk[0]), overwrite=True)
 
-    def density_cotangent(self, planar3):
+    def density_cotangent(self, planar3, out=None):
         if self.p2p:
-            return self._peer_force(planar3.contiguous(), 3, True)[0]
+            return self._peer_force(planar3.contiguous(), 3, True, out=None if out is None else out.unsqueeze(0))[0]
         if self.xfuse:
             c = self.rfftn_yz(planar3)
             out = self.A.empty((1, self.nx, self.kyl, self.nzc), "c64")
@@ -288,7 +364,13 @@ class SlabPM:
     def force_mesh4(self, pos, order=2):
         """Extended float4 force mesh {Fx,Fy,Fz,0} [ext, ny, nz, 4] at the local positions (nbody.py:583-603)."""
         A, lib, st = self.A, self.lib, self._st()
-        rho = A.zeros((self.ext, self.ny, self.nz))
+        peer = self.peer_halos
+        plane = self.ny * self.nz
+        if peer:
+            rho, hd_rho, p_rho = self._halo_buf("rho", (self.ext, self.ny, self.nz))
+            rho.zero_()
+        else:
+            rho = A.zeros((self.ext, self.ny, self.nz))
         one = (C.c_float * 3)(1.0, 1.0, 1.0)
         # brick-tiled scatter of my xl x ny x nz lattice particles into the halo-extended mesh where this build has it
         if not (order == 2 and self.brick and self._brick_ok(lib.mcpm_paint_brick_f(
@@ -296,9 +378,22 @@ class SlabPM:
                 self.nz, rho.data_ptr()))):
             self._call("mcpm_paint_f", st, self._fr, pos.data_ptr(), 0, 1.0, pos.shape[0], self.ext, self.ny, self.nz,
                        order, one, 0.0, rho.data_ptr(), 1)
+        fm4 = A.empty((self.ext, self.ny, self.nz, 4))
+        if peer:  # one kernel per exchange over the neighbours' memory (csrc/halo.cu); barriers order the ranks
+            if hd_rho is not None:
+                hd_rho.barrier()
+            self._call("mcpm_halo_reduce_peer", st, p_rho[0], p_rho[1], p_rho[2], self.H, self.xl, plane, 1)
+            Fb, hd_F, p_F = self._halo_buf("F", (3, self.xl, self.ny, self.nz))
+            F = self.forces_from_density(rho[self.H:self.H + self.xl], out=Fb if self.p2p else None)
+            if not self.p2p:
+                p_F = (F.data_ptr(),) * 3
+            if hd_F is not None:
+                hd_F.barrier()
+            # interleave {Fx, Fy, Fz, 0} and fetch the halo planes from the neighbours' owned planes in one pass
+            self._call("mcpm_halo_gather4_peer", st, fm4.data_ptr(), p_F[0], p_F[1], p_F[2], self.H, self.xl, plane)
+            return fm4
         self.halo_reduce(rho)
         F = self.forces_from_density(rho[self.H:self.H + self.xl])  # [3, xl, ny, nz]
-        fm4 = A.empty((self.ext, self.ny, self.nz, 4))
         own = fm4[self.H:self.H + self.xl]
         self._call("mcpm_interleave3", st, F.data_ptr(), own.data_ptr(), self.xl * self.ny * self.nz)
         self.halo_gather(fm4)
@@ -344,27 +439,52 @@ class SlabPM:
         for s in reversed(range(ns)):
             x1, fm4 = tape[s]
             dnext = dcomb(s - 1) if s > 0 else float(drift_pre[0])
-            m3 = A.zeros((3, self.ext, self.ny, self.nz)) if self.brick else None
+            peer = self.peer_halos
+            plane = self.ny * self.nz
+            m3 = hd3 = p3 = None
+            if self.brick:
+                if peer:
+                    m3, hd3, p3 = self._halo_buf("m3", (3, self.ext, self.ny, self.nz))
+                    m3.zero_()
+                else:
+                    m3 = A.zeros((3, self.ext, self.ny, self.nz))
             if m3 is not None and self._brick_ok(self.lib.mcpm_paint3_brick_f(
                     st, self._fr, self.xl, self.ny, self.nz, x1.data_ptr(), velbar.data_ptr(), 0, 0.0,
                     float(beta[s]), n, self.ext, self.ny, self.nz, m3.data_ptr())):
-                self.halo_reduce(m3, lead=True)  # three planar extended meshes
+                if peer:
+                    if hd3 is not None:
+                        hd3.barrier()
+                    self._call("mcpm_halo_reduce_peer", st, p3[0], p3[1], p3[2], self.H, self.xl, plane, 3)
+                else:
+                    self.halo_reduce(m3, lead=True)  # three planar extended meshes
                 planar = m3[:, self.H:self.H + self.xl].contiguous()
             else:
                 m4 = A.zeros((self.ext, self.ny, self.nz, 4))
                 self._call("mcpm_paint3v4_f", st, self._fr, x1.data_ptr(), velbar.data_ptr(), 0, 0.0,
                            float(beta[s]), n, self.ext, self.ny, self.nz, m4.data_ptr())
-                self.halo_reduce(m4)
+                if self.P == 1:  # one rank: the periodic wrap, same kernel on the float4 mesh
+                    self._call("mcpm_halo_reduce_peer", st, m4.data_ptr(), m4.data_ptr(), m4.data_ptr(), self.H, self.xl,
+                               4 * plane, 1)
+                else:
+                    self.halo_reduce(m4)
                 planar = A.empty((3, self.xl, self.ny, self.nz))
                 self._call("mcpm_deinterleave3", st, m4[self.H:self.H + self.xl].data_ptr(), planar.data_ptr(), cells)
-            rhobar = A.empty((self.ext, self.ny, self.nz))
-            rhobar[self.H:self.H + self.xl] = self.density_cotangent(planar)
-            self.halo_gather(rhobar)
+            if peer:
+                rhobar, hdr, pr = self._halo_buf("rb", (self.ext, self.ny, self.nz))
+                own = rhobar[self.H:self.H + self.xl]
+                res = self.density_cotangent(planar, out=own if self.p2p else None)
+                if not self.p2p:
+                    own.copy_(res)
+                if hdr is not None:
+                    hdr.barrier()
+                self._call("mcpm_halo_gather_peer", st, pr[0], pr[1], pr[2], self.H, self.xl, plane, 1)
+            else:
+                rhobar = A.empty((self.ext, self.ny, self.nz))
+                rhobar[self.H:self.H + self.xl] = self.density_cotangent(planar)
+                self.halo_gather(rhobar)
             self._call("mcpm_read_grad4v_step_f", st, self._fr, x1.data_ptr(), fm4.data_ptr(), rhobar.data_ptr(),
                        velbar.data_ptr(), float(beta[s]), float(alpha[s]), dnext, n, self.ext, self.ny, self.nz,
                        posbar.data_ptr())
-        if not ns:
-            return
 
     # ------------------------------------------------------------------------------------------------ LPT
     def _lattice_read3(self, planar3):

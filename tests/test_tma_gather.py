@@ -86,7 +86,7 @@ def test_tma_gathers_are_bit_identical(mesh, lattice, rel):
     finally:
         tune(b"gather_tma", 1)
         tune(b"gather_seg", 32)
-        tune(b"gather_brick", 1)
+        tune(b"gather_brick", 0)
 
 
 def test_tma_gathers_launch_when_applicable():

@@ -48,5 +48,5 @@ def test_fused_yz_transforms_match_numpy(n, nx, nb):
             assert rel(outs[knob][1], a.astype(np.float64) * n * n) < 3e-6, (knob, rel(outs[knob][1], a * n * n))
         assert rel(outs[1][0], outs[0][0]) < 3e-6 and rel(outs[1][1], outs[0][1]) < 3e-6
     finally:
-        lib.mcpm_tune(b"yzfft", 1)
+        lib.mcpm_tune(b"yzfft", 0)
         lib.mcpm_slabfft_destroy(h)

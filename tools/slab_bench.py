@@ -212,6 +212,8 @@ def main():
     for _ in range(a.warmup):
         step()
     barrier()
+    if pm.sections.on:
+        pm.sections.report()  # drop the warm-up's sections
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
@@ -223,6 +225,8 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(mem, op=dist.ReduceOp.MAX)
+    if rank == 0 and pm.sections.on:
+        out["sections_ms_total_over_timed_steps"] = pm.sections.report()
     if rank == 0:
         per = float(ms) / a.steps
         # NVLink bytes out of each GPU per evaluation: all-to-alls (8 B * N/P * (P-1)/P per transform) + halo planes

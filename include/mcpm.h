@@ -283,6 +283,17 @@ int mcpm_xfuse_force_slab(void* stream, const void* in, void* out3, int nx, int 
 int mcpm_xfuse_force_peer(void* stream, const void* const* in_peers, void* const* out_peers, int npeer, int transpose,
                           int nx, int ny, int nz, int ny_loc, int y0, int lap_fd, int grad_fd, float kcut,
                           int deconv_order, float norm);
+/* The general form: any of the six operators of the fused x-transform with its x-space side in the peers' memory.
+ * mode 0 FORCE (1 -> 3), 1 FORCE_T (3 -> 1): both sides x-space, as mcpm_xfuse_force_peer.  2 FORCE_K (spectrum -> 3
+ * x-space components), 3 HESS_K (spectrum -> 6: the 2LPT Hessian set 00 11 22 01 02 12): k_local = this rank's ky block
+ * of the 3-D spectrum [nx, ny_loc, nz/2+1] is read, results go to out_peers (inputs of the owners' 2-D C2R).
+ * 4 FORCE_TK (3 -> spectrum), 5 HESS_TK (6 -> spectrum): x-space planes are read from in_peers (outputs of the owners'
+ * 2-D R2C), the cotangent spectrum is written (accumulate != 0: added) to k_local, with the Hermitian weights w'/N when
+ * half_weights != 0.  Peer buffers are [ncomp][nx/npeer][ny][nz/2+1].  These make the slab-decomposed lpt / lpt_vjp
+ * (nbody.py:634-667) free of all-to-alls, pack and unpack passes: the kernel is the transpose. */
+int mcpm_xfuse_peer(void* stream, int mode, const void* const* in_peers, void* const* out_peers, void* k_local, int npeer,
+                    int nx, int ny, int nz, int ny_loc, int y0, int lap_fd, int grad_fd, int half_weights, int accumulate,
+                    float norm);
 int mcpm_xfuse_force_T_slab(void* stream, const void* in3, void* out1, int nx, int ny, int nz, int ny_loc, int y0,
                             int lap_fd, int grad_fd, float kcut, int deconv_order, float norm);
 

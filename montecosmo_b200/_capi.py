@@ -56,6 +56,7 @@ SIGNATURES = {
     "mcpm_force_spectra_slab": ([vp, vp, vp] + MESH + [i32, i32, i32, i32, f32, i32, f32], i32),
     "mcpm_xfuse_supported": ([i32], i32),
     "mcpm_xfuse_force_slab": ([vp, vp, vp] + MESH + [i32, i32, i32, i32, f32, i32, f32], i32),
+    "mcpm_xfuse_peer": ([vp, i32, vp, vp, vp, i32] + MESH + [i32, i32, i32, i32, i32, i32, f32], i32),
     "mcpm_xfuse_force_peer": ([vp, vp, vp, i32, i32] + MESH + [i32, i32, i32, i32, f32, i32, f32], i32),
     "mcpm_xfuse_force_T_slab": ([vp, vp, vp] + MESH + [i32, i32, i32, i32, f32, i32, f32], i32),
     "mcpm_force_spectra_T_slab": ([vp, vp, vp] + MESH + [i32, i32, i32, i32, f32, i32, i32, i32, f32], i32),

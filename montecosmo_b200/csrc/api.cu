@@ -595,6 +595,38 @@ int mcpm_xfuse_force_slab(void* stream, const void* in, void* out3, int nx, int 
   API_END
 }
 
+int mcpm_xfuse_peer(void* stream, int mode, const void* const* in_peers, void* const* out_peers, void* k_local, int npeer,
+                    int nx, int ny, int nz, int ny_loc, int y0, int lap_fd, int grad_fd, int half_weights, int accumulate,
+                    float norm) {
+  API_BEGIN
+  NEED(npeer >= 1 && npeer <= 8, "xfuse_peer: 1..8 ranks");
+  NEED(ny_loc > 0 && y0 >= 0 && y0 + ny_loc <= ny && nz > 0 && !(nz & 1), "xfuse_peer: bad shape or ky block");
+#ifndef MCPM_HOSTEMU
+  if (xfuse_supported(nx)) {
+    const cfloat* ip[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cfloat* op[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    const bool x_in = mode == 0 || mode == 1 || mode == 4 || mode == 5, x_out = mode >= 0 && mode <= 3;
+    NEED(!x_in || in_peers, "xfuse_peer: this mode reads x-space planes from the peers");
+    NEED(!x_out || out_peers, "xfuse_peer: this mode writes x-space planes to the peers");
+    for (int r = 0; r < npeer; ++r) {
+      if (x_in) {
+        NEED(in_peers[r], "xfuse_peer: null peer buffer");
+        ip[r] = C(in_peers[r]);
+      }
+      if (x_out) {
+        NEED(out_peers[r], "xfuse_peer: null peer buffer");
+        op[r] = C(out_peers[r]);
+      }
+    }
+    return xfuse_peer_mode(as_stream(stream), mode, ip, op, C(k_local), npeer, nx, ny, nz, ny_loc, y0, lap_fd, grad_fd,
+                           half_weights, accumulate, norm);
+  }
+#endif
+  set_error("xfuse_peer: nx must be 64, 128, 256, 512 or 1024 (CUDA build only)");
+  return MCPM_EUNSUP;
+  API_END
+}
+
 int mcpm_xfuse_force_peer(void* stream, const void* const* in_peers, void* const* out_peers, int npeer, int transpose,
                           int nx, int ny, int nz, int ny_loc, int y0, int lap_fd, int grad_fd, float kcut,
                           int deconv_order, float norm) {

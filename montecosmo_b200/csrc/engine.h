@@ -184,6 +184,9 @@ int xfuse_force_T(stream_t, const cfloat* in3, cfloat* out, int nx, int ny, int 
 int xfuse_force_peer(stream_t, const cfloat* const* in_peers, cfloat* const* out_peers, int npeer, int transpose, int nx,
                      int ny, int nz, int ny_loc, int y0, int lap_fd, int grad_fd, float kcut, int deconv_order,
                      float norm);
+int xfuse_peer_mode(stream_t, int mode, const cfloat* const* in_peers, cfloat* const* out_peers, cfloat* k_local, int npeer,
+                    int nx, int ny, int nz, int ny_loc, int y0, int lap_fd, int grad_fd, int half_weights, int accumulate,
+                    float norm);
 int xfuse_force_k(stream_t, const cfloat* dk, cfloat* out3, int nx, int ny, int nz, int lap_fd, int grad_fd, float kcut,
                   int deconv_order, float norm, SlabK sk = SlabK());
 int xfuse_hessian_k(stream_t, const cfloat* dk, cfloat* out6, int nx, int ny, int nz, int lap_fd, int grad_fd,

@@ -78,6 +78,36 @@ int xfuse_force_peer(stream_t st, const cfloat* const* in_peers, cfloat* const* 
   return xf::dispatch(transpose ? xf::FORCE_T : xf::FORCE, st, a);
 }
 
+// Any of the six operators (xfft_kernel.h: Mode) with its x-space side in peer memory: modes whose INPUT is x-space
+// (FORCE, FORCE_T, FORCE_TK, HESS_TK) load every x-plane from in_peers[owner]; modes whose OUTPUT is x-space (FORCE,
+// FORCE_T, FORCE_K, HESS_K) store every plane at out_peers[owner]; the k-space side (a 3-D spectrum, this rank's ky block
+// [nx, ny_loc, nzc]) is local: `k_local`.  This is what makes the slab-decomposed lpt / lpt_vjp free of all-to-alls.
+int xfuse_peer_mode(stream_t st, int mode, const cfloat* const* in_peers, cfloat* const* out_peers, cfloat* k_local,
+                    int npeer, int nx, int ny, int nz, int ny_loc, int y0, int lap_fd, int grad_fd, int half_weights,
+                    int accumulate, float norm) {
+  if (npeer < 1 || npeer > 8 || nx % npeer || mode < 0 || mode > xf::HESS_TK) {
+    set_error("xfuse_peer_mode: 1..8 ranks, nx divisible by their number, mode 0..5");
+    return MCPM_EINVAL;
+  }
+  const bool k_in = mode == xf::FORCE_K || mode == xf::HESS_K, k_out = mode == xf::FORCE_TK || mode == xf::HESS_TK;
+  if ((k_in || k_out) && !k_local) {
+    set_error("xfuse_peer_mode: this mode needs the local spectrum");
+    return MCPM_EINVAL;
+  }
+  SlabK sk;
+  sk.ny_loc = ny_loc;
+  sk.y0 = y0;
+  xf::Args a = make_args(k_in ? k_local : in_peers[0], k_out ? k_local : out_peers[0], nx, ny, nz, lap_fd, grad_fd, 0.0f, 0,
+                         norm, sk, half_weights, accumulate);
+  a.npeer = npeer;
+  a.xl = nx / npeer;
+  for (int r = 0; r < npeer; ++r) {
+    a.in_peer[r] = in_peers ? in_peers[r] : nullptr;
+    a.out_peer[r] = out_peers ? out_peers[r] : nullptr;
+  }
+  return xf::dispatch(mode, st, a);
+}
+
 // in: [nx, ny_loc, nzc] after the 2-D (y,z) R2C of every x-plane.  out3: three such arrays, inputs of the 2-D C2R.
 int xfuse_force(stream_t st, const cfloat* in, cfloat* out3, int nx, int ny, int nz, int lap_fd, int grad_fd,
                 float kcut, int deconv_order, float norm, SlabK sk) {

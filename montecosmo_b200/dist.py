@@ -134,7 +134,8 @@ class SlabPM:
                 self.p2p_note = "not a CUDA device"
                 return
             grp = self.group if self.group is not None else dist.group.WORLD
-            shape = (3, self.xl, self.ny, self.nzc, 2)  # interleaved complex64 as float32 pairs
+            # interleaved complex64 as float32 pairs; 6 components: the 2LPT Hessian set goes through the same buffers
+            shape = (6, self.xl, self.ny, self.nzc, 2)
             self._sym_in = symm.empty(shape, dtype=torch.float32, device=dev)
             self._sym_out = symm.empty(shape, dtype=torch.float32, device=dev)
             self._h_in = symm.rendezvous(self._sym_in, grp)
@@ -197,6 +198,32 @@ class SlabPM:
         out = self.A.empty((nb_out, self.xl, self.ny, self.nz)) if out is None else out
         self._call("mcpm_slabfft_c2r_yz", self._fft, st, self._sym_out.data_ptr(), out.data_ptr(), nb_out)
         return out
+
+    def _peer_k2x(self, mode, dk, nb_out):
+        """Local ky block of a 3-D spectrum -> nb_out real meshes of my planes [nb_out, xl, ny, nz]: the multiply, the
+        inverse x-transforms and the transpose in one kernel that stores every x-plane at its owner (mcpm_xfuse_peer
+        mode 2 FORCE_K / 3 HESS_K), then my local 2-D C2R.  lpt's force and Hessian meshes (nbody.py:595-603, 611-627)."""
+        st = self._st()
+        self._h_in.barrier()  # every rank has finished the C2R that read its output buffer last
+        self._call("mcpm_xfuse_peer", st, mode, None, self._peer_out, dk.data_ptr(), self.P, self.nx, self.ny, self.nz,
+                   self.kyl, self.y0, 0, 0, 0, 0, 1.0 / self.N)
+        self._h_out.barrier()
+        out = self.A.empty((nb_out, self.xl, self.ny, self.nz))
+        self._call("mcpm_slabfft_c2r_yz", self._fft, st, self._sym_out.data_ptr(), out.data_ptr(), nb_out)
+        return out
+
+    def _peer_x2k(self, mode, real_in, dkbar, accumulate):
+        """nb real meshes of my planes -> (added into) my ky block of the cotangent spectrum: local 2-D R2C, then one
+        kernel that loads every x-plane from its owner, transforms along x and applies the transposed operator with the
+        Hermitian weights (mode 4 FORCE_TK / 5 HESS_TK).  lpt_vjp (engine.cu)."""
+        st = self._st()
+        nb = real_in.shape[0]
+        self._call("mcpm_slabfft_r2c_yz", self._fft, st, real_in.data_ptr(), self._sym_in.data_ptr(), nb)
+        self._h_in.barrier()
+        self._call("mcpm_xfuse_peer", st, mode, self._peer_in, None, dkbar.data_ptr(), self.P, self.nx, self.ny, self.nz,
+                   self.kyl, self.y0, 0, 0, 1, int(accumulate), 1.0)
+        self._h_out.barrier()  # nobody overwrites its input buffer while a peer still reads it
+        return dkbar
 
     # ------------------------------------------------------------------------------------------------ helpers
     def _call(self, name, *args):
@@ -505,16 +532,24 @@ class SlabPM:
         """delta_k block [nx, kyl, nzc] -> (displacement, vel) of the owned lattice particles and the tape (nbody.py:634-667)."""
         A, st = self.A, self._st()
         dk = A.prepare(dk, "c64")
-        f1 = self._lattice_read3(self.irfftn(self.force_spectra(dk), overwrite=True))
         f2 = h6 = None
-        if lpt_order == 2:
-            h6k = A.empty((6, self.nx, self.kyl, self.nzc), "c64")
-            self._call("mcpm_hessian_spectra_slab", st, dk.data_ptr(), h6k.data_ptr(), self.nx, self.ny, self.nz, self.kyl,
-                       self.y0, 0, 0, 1.0 / self.N)
-            h6 = self.irfftn(h6k, overwrite=True)
-            d2m = A.empty((1, self.xl, self.ny, self.nz))
-            self._call("mcpm_lpt2_source", st, h6.data_ptr(), d2m.data_ptr(), self.xl * self.ny * self.nz)
-            f2 = self._lattice_read3(self.irfftn(self.force_spectra(self.rfftn(d2m)[0]), overwrite=True))
+        if self.p2p:  # every transform's transpose inside the fused x-transform kernel, over peer memory
+            f1 = self._lattice_read3(self._peer_k2x(2, dk, 3))
+            if lpt_order == 2:
+                h6 = self._peer_k2x(3, dk, 6)
+                d2m = A.empty((1, self.xl, self.ny, self.nz))
+                self._call("mcpm_lpt2_source", st, h6.data_ptr(), d2m.data_ptr(), self.xl * self.ny * self.nz)
+                f2 = self._lattice_read3(self._peer_force(d2m, 1, False))
+        else:
+            f1 = self._lattice_read3(self.irfftn(self.force_spectra(dk), overwrite=True))
+            if lpt_order == 2:
+                h6k = A.empty((6, self.nx, self.kyl, self.nzc), "c64")
+                self._call("mcpm_hessian_spectra_slab", st, dk.data_ptr(), h6k.data_ptr(), self.nx, self.ny, self.nz,
+                           self.kyl, self.y0, 0, 0, 1.0 / self.N)
+                h6 = self.irfftn(h6k, overwrite=True)
+                d2m = A.empty((1, self.xl, self.ny, self.nz))
+                self._call("mcpm_lpt2_source", st, h6.data_ptr(), d2m.data_ptr(), self.xl * self.ny * self.nz)
+                f2 = self._lattice_read3(self.irfftn(self.force_spectra(self.rfftn(d2m)[0]), overwrite=True))
         dpos, vel = A.empty((self.npl, 3)), A.empty((self.npl, 3))
         self._call("mcpm_lpt_combine", st, 0, f1.data_ptr(), 0 if f2 is None else f2.data_ptr(), float(d1), float(d2),
                    float(dv2), self.npl, dpos.data_ptr(), vel.data_ptr(), 0)
@@ -525,6 +560,17 @@ class SlabPM:
         A, st, o = self.A, self._st(), self.o
         h6, (d1, d2, dv2), lpt_order = tape
         dkbar = None
+        if self.p2p:
+            dkbar = A.empty((self.nx, self.kyl, self.nzc), "c64")
+            if lpt_order == 2:
+                f2bar = o.axpby(posbar, -d2, velbar, -dv2)
+                d2bar = self._peer_force(self._lattice_paint3(f2bar), 3, True)
+                hbar = A.empty((6, self.xl, self.ny, self.nz))
+                self._call("mcpm_lpt2_source_vjp", st, h6.data_ptr(), d2bar.data_ptr(), hbar.data_ptr(),
+                           self.xl * self.ny * self.nz)
+                self._peer_x2k(5, hbar, dkbar, False)
+            f1bar = o.axpby(posbar, d1, velbar, 1.0)
+            return self._peer_x2k(4, self._lattice_paint3(f1bar), dkbar, lpt_order == 2)
         if lpt_order == 2:
             f2bar = o.axpby(posbar, -d2, velbar, -dv2)
             rk = self.force_spectra_T(self.rfftn(self._lattice_paint3(f2bar)))

@@ -113,6 +113,10 @@ class SlabPM:
         self.frame = _frame((self.xl, ny, nz), origin=(self.H, 0, 0))  # relative positions on the halo-extended mesh
         self._fr = C.byref(self.frame)
         self._oob = None
+        # tape_forces = False: the step loop tapes kick positions only and the reverse sweep recomputes each step's force
+        # mesh (one more paint + force evaluation per step instead of 16 bytes per extended cell and step: at 1024^3 on 8
+        # GPUs with 20 steps that is 59 GB per GPU) -- the trade of the reference's checkpointed adjoint (nbody.py:999)
+        self.tape_forces = os.environ.get("MCPM_SLAB_TAPE_FORCES", "1") != "0"
         self.sections = _Sections()
         if self.sections.on and self.A.device.type == "cuda":  # nested sections: inner times are included in outer ones
             self.sections.wrap(self, ["halo_reduce", "halo_gather", "forces_from_density", "density_cotangent",
@@ -446,7 +450,7 @@ class SlabPM:
             self._guard(pos)
             fm4 = self.force_mesh4(pos)
             if tape:
-                out.append((pos.clone(), fm4))
+                out.append((pos.clone(), fm4 if self.tape_forces else None))
             dcomb = float(drift_post[s]) + (float(drift_pre[s + 1]) if s + 1 < ns else 0.0)
             self._call("mcpm_kick_drift4_f", st, self._fr, pos.data_ptr(), vel.data_ptr(), fm4.data_ptr(), pos.shape[0],
                        self.ext, self.ny, self.nz, float(alpha[s]), float(beta[s]), dcomb)
@@ -465,6 +469,8 @@ class SlabPM:
             self._call("mcpm_drift", st, velbar.data_ptr(), posbar.data_ptr(), dcomb(ns - 1), n)
         for s in reversed(range(ns)):
             x1, fm4 = tape[s]
+            if fm4 is None:  # not taped: recompute from the kick positions
+                fm4 = self.force_mesh4(x1)
             dnext = dcomb(s - 1) if s > 0 else float(drift_pre[0])
             peer = self.peer_halos
             plane = self.ny * self.nz

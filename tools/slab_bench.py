@@ -48,6 +48,7 @@ def main():
                          "nbody_bf forward + reverse alone")
     ap.add_argument("--cell", type=float, default=2.5, help="cell size in Mpc/h (box = cell * mesh); 2.5 = BASELINE C3-C5")
     ap.add_argument("--oversamp", type=float, default=1.0,
+    ap.add_argument("--no-force-tape", action="store_true", help="tape kick positions only; recompute force meshes in the reverse sweep")
                     help="with --model: paint mesh = oversamp x evolution mesh (BASELINE C5 uses 2)")
     ap.add_argument("--model-check", action="store_true",
                     help="with --model: compare log-density and force with the single-GPU FieldModel (computed on every "
@@ -106,6 +107,8 @@ def main():
 
     n = a.mesh
     pm = SlabPM(ops, (n, n, n), halo=min(a.halo, n // world))
+    if a.no_force_tape:
+        pm.tape_forces = False
     dk = local_delta_k(pm, cosmo, a.cell * n, 1234)
     g = torch.Generator(device=dev).manual_seed(9 + rank)
     pb, vb = torch.randn((pm.npl, 3), device=dev, generator=g), torch.randn((pm.npl, 3), device=dev, generator=g)
@@ -191,7 +194,7 @@ def main():
         out.update({"metric": ("slab-decomposed grad(log-density) of the field-level model, evaluations/s" if a.model else
                                "slab-decomposed nbody_bf forward + reverse sweep, evaluations/s"), "mesh": n, "n_gpus": world,
                     "value": 1e3 / per, "unit": "evals/s", "ms_per_eval": per, "nbody_steps": a.nbody_steps,
-                    "halo_planes": pm.H, "paint_oversamp": a.oversamp if a.model else None, "max_mem_GiB": float(mem), "fused_x_transform": bool(pm.xfuse), "p2p": pm.p2p_note,
+                    "halo_planes": pm.H, "force_tape": bool(pm.tape_forces), "paint_oversamp": a.oversamp if a.model else None, "max_mem_GiB": float(mem), "fused_x_transform": bool(pm.xfuse), "p2p": pm.p2p_note,
                     "nvlink_GB_out_per_gpu_per_eval": (a2a + halo) / 1e9 if world > 1 else 0.0,
                     "nvlink_GBps_per_gpu_if_all_time_were_comm": (a2a + halo) / 1e9 / (per * 1e-3) if world > 1 else 0.0})
         print(json.dumps(out), flush=True)

@@ -252,21 +252,32 @@ SlabFft* slabfft_create(int nx, int ny, int nz, int parts) {
   p->xl = nx / parts;
   p->kyl = ny / parts;
   size_t maxws = 0, ws = 0;
+  // Batched plans for 1, 2, 3 and 6 meshes at once; a batch without its own plan runs as a sequence of the available ones
+  // (run_batched).  The work area is shared and sized by the largest plan: for big local volumes (the 2048^3 paint mesh
+  // of BASELINE C5: 256 planes of 2048^2 per rank) only the plans whose work area stays under 4 GiB are kept.
   const int nbs[4] = {1, 2, 3, 6};
+  const size_t cap = (size_t)4 << 30;
   for (int nb : nbs) {
-    cufftHandle h;
+    cufftHandle h, h2;
+    size_t ws2 = 0;
     if (slab_plan2d(p, CUFFT_R2C, nb, &h, &ws)) {
       slabfft_destroy(p);
       return nullptr;
     }
-    p->r2c[nb] = h;
-    maxws = ws > maxws ? ws : maxws;
-    if (slab_plan2d(p, CUFFT_C2R, nb, &h, &ws)) {
+    if (slab_plan2d(p, CUFFT_C2R, nb, &h2, &ws2)) {
+      cufftDestroy(h);
       slabfft_destroy(p);
       return nullptr;
     }
-    p->c2r[nb] = h;
+    if (nb > 1 && (ws > cap || ws2 > cap)) {
+      cufftDestroy(h);
+      cufftDestroy(h2);
+      continue;
+    }
+    p->r2c[nb] = h;
+    p->c2r[nb] = h2;
     maxws = ws > maxws ? ws : maxws;
+    maxws = ws2 > maxws ? ws2 : maxws;
   }
   {
     cufftHandle h;

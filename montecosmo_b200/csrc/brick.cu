@@ -22,6 +22,7 @@
 // Reference semantics: CIC paint of montecosmo/nbody.py:365-396 (same index rule and weights as cic4.cu / window.h).
 #ifndef MCPM_HOSTEMU
 #include "engine.h"
+#include "tma.h"
 #include "window.h"
 
 namespace mcpm {
@@ -59,6 +60,9 @@ struct BrickArgs {
 // thread (warp, lane), slot r -> lattice offsets inside the brick.  Slot 0 of the 16 warps samples all 16 x-planes and
 // all 8 y-rows of the brick (the tile origin is taken from those 512 particles).
 __device__ __forceinline__ int brick_qi(int warp, int r) { return ((warp >> 3) + 2 * ((warp & 7) + r)) & 15; }
+
+template <int NCH>
+__device__ __forceinline__ void stray_deposit(const BrickArgs& a, int si0, int sj0, int sk0);
 
 // FULL: the lattice divides into whole bricks (no per-particle bounds checks).
 // (A variant that handed each lane's four upper-z deposits to the next lane by shuffle -- 4 SHFL for 4 ATOMS -- was
@@ -290,35 +294,327 @@ __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickA
     const int w2 = t2 >> 5;
     const int si0 = q0i + brick_qi(w2, r), sj0 = q0j + (w2 & 7), sk0 = q0k + (t2 & 31);
     if (!FULL && all_stray && (si0 >= a.px || sj0 >= a.py || sk0 >= a.pz)) continue;
-    const int64_t p3 = 3 * (((int64_t)si0 * a.py + sj0) * a.pz + sk0);
-    // the same u = x - site as pass 1, so that the fractions are bit-identical to the in-tile path
-    const float px = (a.pos[p3] + a.shift) - (a.rel ? 0.f : (float)(si0 + a.ox)),
-                py = (a.pos[p3 + 1] + a.shift) - (a.rel ? 0.f : (float)(sj0 + a.oy)),
-                pz = (a.pos[p3 + 2] + a.shift) - (a.rel ? 0.f : (float)(sk0 + a.oz));
-    float vv[NCH];
-    if (NCH == 1) {
-      vv[0] = (a.w ? a.w[p3 / 3] : 1.0f) * a.ws;
-    } else {
+    stray_deposit<NCH>(a, si0, sj0, sk0);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Streaming variant (round 2, "v4"): PERSISTENT CTAs, particle rows staged by bulk async copies.
+//
+// What the profile of the kernel above said (profiles/r2_ncu_kernels.txt, gpurun_out/r2a_full_brick.ncu-rep): 30-45 % of
+// the stall samples sit on the first use of the strided 4-byte loads of pos / A (12 sectors per request, ~1 us of latency
+// exposed at the start of every short-lived CTA), the LSU pipe is 63-70 % busy, and a full-tile zero fill, overflow check
+// and flush sweep are paid per brick.  Here
+//   * a CTA is resident for the whole launch and walks bricks b = blockIdx.x, + gridDim.x, ...;
+//   * each z-row of the next brick (32 particles: 384 contiguous, 16-byte aligned bytes of pos, the same of A, 128 of w)
+//     is fetched by ONE cp.async.bulk onto an mbarrier while the current brick deposits and flushes: no LSU
+//     instruction, no register and no exposed latency on the global side of the particle arrays; shared memory is read
+//     at a stride of 3 words (conflict free);
+//   * the tile is zeroed once per launch: every flush re-zeroes what it wrote, and both the overflow check and the flush
+//     visit only the bounding box of the brick's deposits (about half of the 18 x 18 rows of the tile);
+//   * strays deposit straight to global memory where they are found (no queue).
+// Brick 8 x 8 x 32 (2048 particles), tile 18 x 18 x 44: 57 KB + 48 KB of staging, two CTAs per SM.
+// Same fixed-point tile arithmetic as above (per-brick scale from sum |v|; FINE bits with verified headroom for NCH = 1).
+namespace bstream {
+constexpr int BX = 8, BY = 8, BZ = 32, PPT = 4;
+constexpr int TX = BX + 10, TY = BY + 10, TZ = 44, ZG = TZ / 4;
+constexpr int ROWS = BX * BY, WARPS = ROWS / PPT, THREADS = WARPS * 32;  // 64 rows, 16 warps, 512 threads
+constexpr int TROWS = TX * TY;
+constexpr int PROW = 3 * BZ;  // floats per staged row of pos / A
+template <int NCH, int TZS>
+struct Smem {
+  static constexpr int CELLS = TROWS * TZS;
+  static constexpr int VROW = NCH == 3 ? PROW : BZ;
+  static constexpr size_t TILE_B = sizeof(int) * CELLS;
+  static constexpr size_t ROWBASE_B = sizeof(int) * ((TROWS + 3) & ~3);
+  static constexpr size_t POS_B = sizeof(float) * ROWS * PROW;
+  static constexpr size_t VAL_B = sizeof(float) * ROWS * VROW;
+  static constexpr size_t STRAY_B = sizeof(unsigned short) * ROWS * BZ;
+  static constexpr size_t BYTES = TILE_B + ROWBASE_B + POS_B + VAL_B + STRAY_B;
+};
+static_assert(WARPS % 8 == 0, "a warp keeps one lattice y-row");
+}  // namespace bstream
+
+// One stray particle (lattice site si0, sj0, sk0) as float atomics to global memory: the same u = x - site as the in-tile
+// path, so that the fractions are bit-identical to it.
+template <int NCH>
+__device__ __forceinline__ void stray_deposit(const BrickArgs& a, int si0, int sj0, int sk0) {
+  const int64_t plane = (int64_t)a.nx * a.ny * a.nz;
+  const int64_t p3 = 3 * (((int64_t)si0 * a.py + sj0) * a.pz + sk0);
+  const float px = (a.pos[p3] + a.shift) - (a.rel ? 0.f : (float)(si0 + a.ox)),
+              py = (a.pos[p3 + 1] + a.shift) - (a.rel ? 0.f : (float)(sj0 + a.oy)),
+              pz = (a.pos[p3 + 2] + a.shift) - (a.rel ? 0.f : (float)(sk0 + a.oz));
+  float vv[NCH];
+  if (NCH == 1) {
+    vv[0] = (a.w ? a.w[p3 / 3] : 1.0f) * a.ws;
+  } else {
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) vv[c] = a.s * a.A[p3 + c];
+    for (int c = 0; c < NCH; ++c) vv[c] = a.s * a.A[p3 + c];
+  }
+  const float bx = floorf(px), by = floorf(py), bz = floorf(pz);
+  const float fx = px - bx, fy = py - by, fz = pz - bz;
+  const float gx = 1.f - fx, gy = 1.f - fy, gz = 1.f - fz;
+  const float wxy[4] = {gx * gy, gx * fy, fx * gy, fx * fy};
+  const int i0 = wrap_fast(si0 + a.ox + (int)bx, a.nx), j0 = wrap_fast(sj0 + a.oy + (int)by, a.ny),
+            k0 = wrap_fast(sk0 + a.oz + (int)bz, a.nz);
+  const int i1 = i0 + 1 == a.nx ? 0 : i0 + 1, j1 = j0 + 1 == a.ny ? 0 : j0 + 1, k1 = k0 + 1 == a.nz ? 0 : k0 + 1;
+#pragma unroll
+  for (int ab = 0; ab < 4; ++ab) {
+    float* rowp = a.mesh + ((int64_t)((ab >> 1) ? i1 : i0) * a.ny + ((ab & 1) ? j1 : j0)) * a.nz;
+    const float w0 = wxy[ab] * gz, w1 = wxy[ab] * fz;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      atomicAdd(rowp + c * plane + k0, vv[c] * w0);
+      atomicAdd(rowp + c * plane + k1, vv[c] * w1);
     }
-    const float bx = floorf(px), by = floorf(py), bz = floorf(pz);
-    const float fx = px - bx, fy = py - by, fz = pz - bz;
-    const float gx = 1.f - fx, gy = 1.f - fy, gz = 1.f - fz;
-    const float wxy[4] = {gx * gy, gx * fy, fx * gy, fx * fy};
-    const int i0 = wrap_fast(si0 + a.ox + (int)bx, a.nx), j0 = wrap_fast(sj0 + a.oy + (int)by, a.ny),
-              k0 = wrap_fast(sk0 + a.oz + (int)bz, a.nz);
-    const int i1 = i0 + 1 == a.nx ? 0 : i0 + 1, j1 = j0 + 1 == a.ny ? 0 : j0 + 1, k1 = k0 + 1 == a.nz ? 0 : k0 + 1;
+  }
+}
+
+template <int NCH, int TZS>
+__global__ void __launch_bounds__(bstream::THREADS, 2) brick_stream_kernel(BrickArgs a, int nby, int nbz, int nbricks) {
+  using namespace bstream;
+  using SM = Smem<NCH, TZS>;
+  constexpr int ZGS = TZS / 4;  // float4 groups per tile row as stored (the first ZG are used)
+  extern __shared__ __align__(128) unsigned char smraw[];
+  int* tile = reinterpret_cast<int*>(smraw);
+  int* rowbase = reinterpret_cast<int*>(smraw + SM::TILE_B);
+  float* ps = reinterpret_cast<float*>(smraw + SM::TILE_B + SM::ROWBASE_B);  // [ROWS][PROW]
+  float* vs = ps + ROWS * PROW;                                             // [ROWS][VROW]
+  unsigned short* stray = reinterpret_cast<unsigned short*>(smraw + SM::TILE_B + SM::ROWBASE_B + SM::POS_B + SM::VAL_B);
+  __shared__ int nstray;
+  __shared__ float red[WARPS][4 + NCH];
+  __shared__ float bc[4 + NCH];
+  __shared__ int bb[4];  // bounding box of the brick's base cells in the tile: xmin, xmax, ymin, ymax
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int4* tile4 = reinterpret_cast<int4*>(tile);
+  for (int i = tid; i < SM::CELLS / 4; i += THREADS) tile4[i] = make_int4(0, 0, 0, 0);
+  if (tid == 0) {
+    tma::mbar_init(&bar, 1);
+    tma::fence_barrier_init();
+  }
+  __syncthreads();
+
+  const bool has_w = NCH == 1 && a.w != nullptr;
+  const bool has_v = NCH == 3 || has_w;
+  const uint32_t tx_bytes = (uint32_t)(SM::POS_B + (has_v ? SM::VAL_B : 0));
+  // warp 0 fetches brick b: one bulk copy per array per z-row
+  auto issue = [&](int b) {
+    const int bk = b % nbz, bij = b / nbz, bj = bij % nby, bi = bij / nby;
+    if (lane == 0) tma::mbar_arrive_expect_tx(&bar, tx_bytes);
+    __syncwarp();
+    for (int row = lane; row < ROWS; row += 32) {
+      const int64_t p0 = ((int64_t)(bi * BX + (row >> 3)) * a.py + (bj * BY + (row & 7))) * a.pz + bk * BZ;
+      tma::bulk_g2s(ps + row * PROW, a.pos + 3 * p0, PROW * sizeof(float), &bar);
+      if (NCH == 3) tma::bulk_g2s(vs + row * PROW, a.A + 3 * p0, PROW * sizeof(float), &bar);
+      else if (has_w) tma::bulk_g2s(vs + row * BZ, a.w + p0, BZ * sizeof(float), &bar);
+    }
+  };
+  if (warp == 0 && (int)blockIdx.x < nbricks) issue(blockIdx.x);
+
+  const int64_t plane = (int64_t)a.nx * a.ny * a.nz;
+  const float fnx = (float)a.nx, fny = (float)a.ny, fnz = (float)a.nz;
+  uint32_t parity = 0;
+#pragma unroll 1
+  for (int b = blockIdx.x; b < nbricks; b += gridDim.x, parity ^= 1) {
+    const int bk = b % nbz, bij = b / nbz, bj = bij % nby, bi = bij / nby;
+    const int q0i = bi * BX, q0j = bj * BY, q0k = bk * BZ;
+    const int dj = warp & 7, qj = q0j + dj, qk = q0k + lane;
+    tma::mbar_wait(&bar, parity);
+
+    // ---- pass 1: displacements u = x - site, values, partial sums
+    float x[PPT][3], val[NCH][PPT];
+    float l1[NCH], d0 = 0.f, d1 = 0.f, d2 = 0.f;
 #pragma unroll
-    for (int ab = 0; ab < 4; ++ab) {
-      float* rowp = a.mesh + ((int64_t)((ab >> 1) ? i1 : i0) * a.ny + ((ab & 1) ? j1 : j0)) * a.nz;
-      const float w0 = wxy[ab] * gz, w1 = wxy[ab] * fz;
+    for (int c = 0; c < NCH; ++c) l1[c] = 0.f;
+    const float sy = a.rel ? 0.f : (float)(qj + a.oy), sz = a.rel ? 0.f : (float)(qk + a.oz);
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        atomicAdd(rowp + c * plane + k0, vv[c] * w0);
-        atomicAdd(rowp + c * plane + k1, vv[c] * w1);
+    for (int r = 0; r < PPT; ++r) {
+      const int di = (warp >> 3) + r * (WARPS / 8), row = di * BY + dj;
+      const float* xr = ps + row * PROW + 3 * lane;
+      const float sx = a.rel ? 0.f : (float)(q0i + di + a.ox);
+      x[r][0] = (xr[0] + a.shift) - sx;
+      x[r][1] = (xr[1] + a.shift) - sy;
+      x[r][2] = (xr[2] + a.shift) - sz;
+      if (NCH == 3) {
+        const float* vr = vs + row * PROW + 3 * lane;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          val[c][r] = vr[c];
+          l1[c] += fabsf(a.s * val[c][r]);
+        }
+      } else {
+        val[0][r] = has_w ? vs[row * BZ + lane] : 1.0f;
+        l1[0] += fabsf(val[0][r] * a.ws);
+      }
+      // displacement reduced to the nearest periodic image (absolute positions may have been wrapped by the caller)
+      d0 += x[r][0] - fnx * rintf(x[r][0] * a.inx);
+      d1 += x[r][1] - fny * rintf(x[r][1] * a.iny);
+      d2 += x[r][2] - fnz * rintf(x[r][2] * a.inz);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+      d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+      d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) l1[c] += __shfl_xor_sync(0xffffffffu, l1[c], o);
+    }
+    if (lane == 0) {
+      red[warp][0] = d0;
+      red[warp][1] = d1;
+      red[warp][2] = d2;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) red[warp][4 + c] = l1[c];
+    }
+    if (tid == 0) {
+      bb[0] = TX;
+      bb[1] = -1;
+      bb[2] = TY;
+      bb[3] = -1;
+      nstray = 0;
+    }
+    __syncthreads();  // A: every thread has read the staged rows; red / bb are written
+    {
+      const int bn = b + gridDim.x;  // the staging buffers are free: fetch the next brick under this one's deposits
+      if (warp == 0 && bn < nbricks) issue(bn);
+    }
+    if (tid < 4 + NCH && tid != 3) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) s += red[w][tid];
+      bc[tid] = s;
+    }
+    __syncthreads();  // A'
+    constexpr float ninv = 1.0f / (float)(ROWS * BZ);
+    const float oxf = rintf((float)(q0i + a.ox) + bc[0] * ninv - 0.5f * (TX - BX));
+    const float oyf = rintf((float)(q0j + a.oy) + bc[1] * ninv - 0.5f * (TY - BY));
+    const float ozf = 4.0f * rintf(0.25f * ((float)(q0k + a.oz) + bc[2] * ninv - 0.5f * (TZ - 1 - BZ)));
+    const int oxw = wrap_index((int)oxf, a.nx), oyw = wrap_index((int)oyf, a.ny), oz = wrap_index((int)ozf, a.nz);
+    if (tid < TROWS) {
+      const int ix = tid / TY, jy = tid - ix * TY;
+      int gx = oxw + ix, gy = oyw + jy;
+      gx = gx >= a.nx ? gx - a.nx : gx;
+      gy = gy >= a.ny ? gy - a.ny : gy;
+      rowbase[tid] = (gx * a.ny + gy) * a.nz;
+    }
+
+    // ---- tile cell and fractions; strays are queued
+    int tcell[PPT];
+    int xmin = TX, xmax = -1, ymin = TY, ymax = -1;
+#pragma unroll
+    for (int r = 0; r < PPT; ++r) {
+      const int di = (warp >> 3) + r * (WARPS / 8);
+      const float bx = floorf(x[r][0]), by = floorf(x[r][1]), bz = floorf(x[r][2]);
+      x[r][0] -= bx;
+      x[r][1] -= by;
+      x[r][2] -= bz;
+      float tx = ((float)(q0i + di + a.ox) - oxf) + bx, ty = ((float)(qj + a.oy) - oyf) + by,
+            tz = ((float)(qk + a.oz) - ozf) + bz;
+      tx -= fnx * floorf(tx * a.inx);
+      ty -= fny * floorf(ty * a.iny);
+      tz -= fnz * floorf(tz * a.inz);
+      const bool in = fabsf(tx - 0.5f * (TX - 2)) <= 0.5f * (TX - 2) && fabsf(ty - 0.5f * (TY - 2)) <= 0.5f * (TY - 2) &&
+                      fabsf(tz - 0.5f * (TZ - 2)) <= 0.5f * (TZ - 2);
+      if (in) {
+        const int itx = (int)tx, ity = (int)ty;
+        tcell[r] = (itx * TY + ity) * TZS + (int)tz;
+        xmin = min(xmin, itx);
+        xmax = max(xmax, itx);
+        ymin = min(ymin, ity);
+        ymax = max(ymax, ity);
+      } else {
+        tcell[r] = -1;
+        stray[atomicAdd(&nstray, 1)] = (unsigned short)(r * THREADS + tid);
       }
     }
+    xmin = __reduce_min_sync(0xffffffffu, xmin);
+    xmax = __reduce_max_sync(0xffffffffu, xmax);
+    ymin = __reduce_min_sync(0xffffffffu, ymin);
+    ymax = __reduce_max_sync(0xffffffffu, ymax);
+    if (lane == 0 && xmax >= 0) {
+      atomicMin(&bb[0], xmin);
+      atomicMax(&bb[1], xmax);
+      atomicMin(&bb[2], ymin);
+      atomicMax(&bb[3], ymax);
+    }
+
+    bool all_stray = false;  // block-uniform
+    int bx0 = 0, by0 = 0, nyb = 1, nrow = 0, ns = 0;
+#pragma unroll  // val[c][r] stays in registers
+    for (int c = 0; c < NCH; ++c) {
+      const float l = bc[4 + c];
+      constexpr int FINE = NCH == 1 ? 3 : 0;  // see brick_scatter_kernel
+      float e = l > 0.f ? floorf(log2f(1073741824.0f / l)) + (float)FINE : 0.f;
+      e = fminf(fmaxf(e, -120.f), 120.f);
+      const float S = exp2f(e), invS = exp2f(-e);
+      const float scale = (NCH == 1 ? a.ws : a.s) * S;
+#pragma unroll
+      for (int r = 0; r < PPT; ++r) {
+        if (tcell[r] < 0) continue;
+        const float vsc = val[c][r] * scale;
+        const float fx = x[r][0], fy = x[r][1], fz = x[r][2];
+        const float gx = 1.f - fx, gy = 1.f - fy;
+        const float vz1 = vsc * fz, vz0 = vsc - vz1;
+        const float w00 = gx * gy, w01 = gx * fy, w10 = fx * gy, w11 = fx * fy;
+        int* t = tile + tcell[r];
+        atomicAdd(t, __float2int_rn(vz0 * w00));
+        atomicAdd(t + 1, __float2int_rn(vz1 * w00));
+        atomicAdd(t + TZS, __float2int_rn(vz0 * w01));
+        atomicAdd(t + TZS + 1, __float2int_rn(vz1 * w01));
+        atomicAdd(t + TY * TZS, __float2int_rn(vz0 * w10));
+        atomicAdd(t + TY * TZS + 1, __float2int_rn(vz1 * w10));
+        atomicAdd(t + TY * TZS + TZS, __float2int_rn(vz0 * w11));
+        atomicAdd(t + TY * TZS + TZS + 1, __float2int_rn(vz1 * w11));
+      }
+      __syncthreads();  // B: the tile holds channel c (and bb, rowbase are final)
+      // rows [bb0, bb1 + 1] x [bb2, bb3 + 1] of the tile were touched; half a warp takes a row (ZG = 11 groups)
+      if (c == 0) {  // read once: thread 0 re-initialises bb in the next brick's pass 1
+        bx0 = bb[0];
+        by0 = bb[2];
+        nyb = bb[3] - by0 + 2;
+        nrow = bb[1] < 0 ? 0 : (bb[1] - bx0 + 2) * nyb;
+        ns = nstray;
+      }
+      const int kz = lane & 15, hw = lane >> 4;
+      if (FINE > 0) {
+        unsigned bad = 0;  // any cell outside [-2^29, 2^29)?
+        for (int rb = 2 * warp + hw; rb < nrow; rb += 2 * WARPS) {
+          if (kz >= ZG) continue;
+          const int ixr = rb / nyb, row = (bx0 + ixr) * TY + by0 + (rb - ixr * nyb);
+          const int4 q = tile4[row * ZGS + kz];
+          bad |= ((unsigned)q.x + 0x20000000u) | ((unsigned)q.y + 0x20000000u) | ((unsigned)q.z + 0x20000000u) |
+                 ((unsigned)q.w + 0x20000000u);
+        }
+        if (__syncthreads_or((bad >> 30) != 0)) all_stray = true;  // drop the tile: the flush below only re-zeroes it
+      }
+      float* meshc = a.mesh + c * plane;
+      for (int rb = 2 * warp + hw; rb < nrow; rb += 2 * WARPS) {
+        if (kz >= ZG) continue;
+        const int ixr = rb / nyb, row = (bx0 + ixr) * TY + by0 + (rb - ixr * nyb);
+        const int g = row * ZGS + kz;
+        const int4 q = tile4[g];
+        if ((q.x | q.y | q.z | q.w) != 0) {
+          tile4[g] = make_int4(0, 0, 0, 0);
+          if (!all_stray) {
+            int gz = oz + 4 * kz;
+            gz = gz >= a.nz ? gz - a.nz : gz;
+            atomicAdd(reinterpret_cast<float4*>(meshc + (rowbase[row] + gz)),
+                      make_float4(q.x * invS, q.y * invS, q.z * invS, q.w * invS));
+          }
+        }
+      }
+      if (c + 1 < NCH) __syncthreads();  // the tile is clean before the next channel's deposits
+    }
+    // strays: float atomics straight to global memory, one queued particle per thread (convergent); after a dropped tile
+    // (NCH == 1 only), every particle of the brick
+    if (all_stray) ns = PPT * THREADS;
+    for (int si = tid; si < ns; si += THREADS) {
+      const int code = all_stray ? si : stray[si], r = code / THREADS, t2 = code - r * THREADS, w2 = t2 >> 5;
+      stray_deposit<NCH>(a, q0i + (w2 >> 3) + r * (WARPS / 8), q0j + (w2 & 7), q0k + (t2 & 31));
+    }
+    // no barrier here: the next brick's pass 1 touches only the staging buffers, red and bb, and its barrier A orders
+    // this flush before the next deposits
   }
 }
 
@@ -342,9 +638,42 @@ static void launch_brick_variant(stream_t st, const BrickArgs& a, dim3 grid) {
   brick_scatter_kernel<NCH, FULL><<<grid, THREADS, SMEM, st>>>(a);
 }
 
+// Streaming variant: whole 8 x 8 x 32 bricks, 16-byte aligned rows (bulk copies), mesh at least one tile wide.
+template <int NCH, int TZS>
+static int launch_stream(stream_t st, const BrickArgs& a) {
+  using namespace bstream;
+  using SM = Smem<NCH, TZS>;
+  static int per_sm[16] = {0};  // resident CTAs per SM, per device (queried once)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 15;
+  if (per_sm[dev] == 0) {
+    cudaFuncSetAttribute(brick_stream_kernel<NCH, TZS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES);
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, brick_stream_kernel<NCH, TZS>, THREADS, SM::BYTES) !=
+            cudaSuccess || n < 1)
+      n = 1;
+    per_sm[dev] = n;
+  }
+  const int nbx = a.px / BX, nby = a.py / BY, nbz = a.pz / BZ;
+  const int64_t nb = (int64_t)nbx * nby * nbz, wave = (int64_t)kSMs * per_sm[dev];
+  count_launch();
+  brick_stream_kernel<NCH, TZS><<<(unsigned)(nb < wave ? nb : wave), THREADS, SM::BYTES, st>>>(a, nby, nbz, (int)nb);
+  return rt_check("brick_stream") ? -1 : 1;
+}
+static bool stream_ok(const BrickArgs& a) {
+  using namespace bstream;
+  if (!tune().brick_stream) return false;
+  if (a.px % BX || a.py % BY || a.pz % BZ) return false;
+  if (a.nx < TX || a.ny < TY || a.nz < TZ) return false;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return al16(a.pos) && al16(a.A) && al16(a.w);
+}
+
 template <int NCH>
 static int launch_brick(stream_t st, const BrickArgs& a) {
   using namespace brick;
+  if (stream_ok(a)) return tune().brick_stream == 48 ? launch_stream<NCH, 48>(st, a) : launch_stream<NCH, 44>(st, a);
   dim3 grid((a.pz + BZ - 1) / BZ, (a.py + BY - 1) / BY, (a.px + BX - 1) / BX);
   count_launch();
   const bool full = a.px % BX == 0 && a.py % BY == 0 && a.pz % BZ == 0;

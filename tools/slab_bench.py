@@ -48,8 +48,8 @@ def main():
                          "nbody_bf forward + reverse alone")
     ap.add_argument("--cell", type=float, default=2.5, help="cell size in Mpc/h (box = cell * mesh); 2.5 = BASELINE C3-C5")
     ap.add_argument("--oversamp", type=float, default=1.0,
-    ap.add_argument("--no-force-tape", action="store_true", help="tape kick positions only; recompute force meshes in the reverse sweep")
                     help="with --model: paint mesh = oversamp x evolution mesh (BASELINE C5 uses 2)")
+    ap.add_argument("--no-force-tape", action="store_true", help="tape kick positions only; recompute force meshes in the reverse sweep")
     ap.add_argument("--model-check", action="store_true",
                     help="with --model: compare log-density and force with the single-GPU FieldModel (computed on every "
                          "rank's own GPU from the same global fields) before timing")

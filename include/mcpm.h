@@ -119,7 +119,8 @@ int mcpm_paint(void* stream, const float* pos, const float* weights, float wscal
                int nz, int order, const float scale[3], float shift, float* mesh, int accumulate);
 
 /* read (nbody.py:398-427): out[p] = sum_s mesh[(id0+s) mod n] * prod_d W(...);  nmesh meshes at once:
- * mesh = [nmesh, nx, ny, nz] planes, out = [np, nmesh] interleaved (nmesh = 3 gives a force array [np, 3]). */
+ * mesh = [nmesh, nx, ny, nz] planes, out = [np, nmesh] interleaved (nmesh = 3 gives a force array [np, 3]);
+ * nmesh in 1..4, or 7 | 9 (the field sets of mcpm_bias_weights). */
 int mcpm_read(void* stream, const float* pos, const float* mesh, int nmesh, int64_t np, int nx, int ny, int nz,
               int order, const float scale[3], float shift, float* out);
 
@@ -345,6 +346,34 @@ int mcpm_rsd_shift(void* stream, const float* pos, const float* vel, const float
                    float* pos_out);
 int mcpm_rsd_shift_vjp(void* stream, const float* posbar, const float los[3], float coef, int64_t np, float* velbar,
                        int accumulate);
+
+/* ---- Lagrangian bias expansion (montecosmo/bricks.py:327-452) as fused passes -----------------
+ * bias_spectra: ONE pass over delta_k [nx,ny,nz/2+1] writing the M = 10 (inv_transfer given: 12) spectra whose inverse
+ * transforms the expansion needs, in this order: s00, s11, s01, s02, s12 (s_ij = (k_i k_j / k^2 - delta_ij / 3) delta,
+ * bricks.py:361-372), delta, -k^2 delta (:397), i k_x|y|z delta (:444-446), [phi = delta * inv_transfer, -k^2 phi (:411-413,
+ * 436)].  cells_per_len[d] = n_d / box_d turns rad/cell into h/Mpc (rfftk with box_size, nbody.py:50-77).  Every
+ * output is Hermitian-consistent (feeds a C2R).  _vjp: its transpose, dkbar (+)= sum_m conj(multiplier_m) outbar[m]. */
+int mcpm_bias_spectra(void* stream, const void* delta_k_c64, int nx, int ny, int nz, const float cells_per_len[3],
+                      const float* inv_transfer, void* out_c64);
+int mcpm_bias_spectra_vjp(void* stream, const void* outbar_c64, int nx, int ny, int nz, const float cells_per_len[3],
+                          const float* inv_transfer, void* dkbar_c64, int accumulate);
+/* s5 = [s00, s11, s01, s02, s12][n] -> out2 = [s^2, s^3][n] with s22 = -(s00 + s11) (bricks.py:373-395), and its VJP. */
+int mcpm_shear_invariants(void* stream, const float* s5, int64_t n, float* out2);
+int mcpm_shear_invariants_vjp(void* stream, const float* s5, const float* out2bar, int64_t n, float* s5bar);
+/* Particle side.  vals [np, K]: the K = 7 (9 with PNG) fields read at each particle, in the order delta, s^2, s^3,
+ * lap delta, grad delta (3), [phi, lap phi].  growth: one value (growth_arr = NULL) or one per particle (light cone).
+ * coef[13] = b1, b2, bs2, b3, bds2, bs3, bn2, bnpar, fNL_bp, fNL_bpd, fNL_bpd2, fNL_bps2, fNL_bn2p.
+ * bias_moments: mom_f64[0] += sum (delta g)^2, mom_f64[1] += sum phi delta g (np times the two means, :354, :421).
+ * bias_weights: weights [np] and dvel [np, 3] (nullable) of bricks.py:350-449, reading the moments from device memory.
+ * bias_weights_vjp: wbar [np], dvelbar [np, 3] (nullable) -> valsbar [np, K]; coefbar_f64[14] (accumulated): the 13
+ * coefficients, then the scalar growth factor; gbar_arr [np] when growth_arr is given.  msum_f64[2]: zeroed scratch. */
+int mcpm_bias_moments(void* stream, const float* vals, int K, float growth, const float* growth_arr, int64_t np,
+                      double* mom_f64);
+int mcpm_bias_weights(void* stream, const float* vals, int K, float growth, const float* growth_arr,
+                      const float coef[13], const double* mom_f64, int64_t np, float* weights, float* dvel);
+int mcpm_bias_weights_vjp(void* stream, const float* vals, int K, float growth, const float* growth_arr,
+                          const float coef[13], const double* mom_f64, const float* wbar, const float* dvelbar,
+                          int64_t np, double* msum_f64, float* valsbar, double* coefbar_f64, float* gbar_arr);
 
 /* out = in * t (real transfer, half-spectrum shaped) ; white2lin (bricks.py:152-157) and its transpose */
 int mcpm_scale_spectrum(void* stream, const void* in, const float* t, void* out, int64_t nc);

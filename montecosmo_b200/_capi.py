@@ -80,6 +80,13 @@ SIGNATURES = {
     "mcpm_dot": ([vp, vp, vp, i64, vp], i32),
     "mcpm_rsd_shift": ([vp, vp, vp, hp, f32, i64, vp], i32),
     "mcpm_rsd_shift_vjp": ([vp, vp, hp, f32, i64, vp, i32], i32),
+    "mcpm_bias_spectra": ([vp, vp] + MESH + [hp, vp, vp], i32),
+    "mcpm_bias_spectra_vjp": ([vp, vp] + MESH + [hp, vp, vp, i32], i32),
+    "mcpm_shear_invariants": ([vp, vp, i64, vp], i32),
+    "mcpm_shear_invariants_vjp": ([vp, vp, vp, i64, vp], i32),
+    "mcpm_bias_moments": ([vp, vp, i32, f32, vp, i64, vp], i32),
+    "mcpm_bias_weights": ([vp, vp, i32, f32, vp, hp, vp, i64, vp, vp], i32),
+    "mcpm_bias_weights_vjp": ([vp, vp, i32, f32, vp, hp, vp, vp, vp, i64, vp, vp, vp, vp], i32),
     "mcpm_scale_spectrum": ([vp, vp, vp, vp, i64], i32),
     "mcpm_lpt_combine": ([vp, vp, vp, vp, f32, f32, f32, i64, vp, vp, vp], i32),
     "mcpm_kick_drift": ([vp, vp, vp, vp, i64] + MESH + [i32, f32, f32, f32, vp], i32),

@@ -3,9 +3,9 @@ Mirror of the `montecosmo/bricks.py` callables next to the engine's path (SURVEY
 Lagrangian bias expansion (327-452) and the cell -> physical -> redshift-space chain (628-877: frames, lines of sight
 and light-cone scale factors, redshift-space distortions, Alcock-Paczynski).
 
-lagrangian_bias composes engine operators -- irfftn (mcpm_irfftn) and read (mcpm_read, differentiable in mesh and
-positions) -- with pointwise torch expressions for the Fourier multipliers and the shear invariants, so torch.autograd
-differentiates it end to end.  The primordial non-Gaussianity terms (png_type is not None, bricks.py:411-438) and add_png
+lagrangian_bias runs on the fused passes of csrc/bias.cu (Fourier multipliers, shear invariants, polynomial; each with
+its hand-written transpose) around the engine's transforms and gather; `lagrangian_bias_composed` is round 1's
+pointwise-torch composition of the same expansion, kept as a cross-check.  The primordial non-Gaussianity terms (png_type is not None, bricks.py:411-438) and add_png
 (129-141) take a tabulated (k, P) `kpow`; the Eisenstein-Hu branch of lin_power (kpow=None) lives in jax_cosmo and is
 outside the path.
 """
@@ -193,8 +193,106 @@ def regular_pos(mesh_shape, ptcl_shape=None):
     return _nb.ops().A.prepare(np.stack(np.meshgrid(*ax, indexing="ij"), -1).reshape(-1, 3))
 
 
+class _BiasMeshes(torch.autograd.Function):
+    """lin_mesh -> the K = 7 (9 with PNG) real meshes the expansion reads at the particles, [K, nx, ny, nz] in the order
+    delta, s^2, s^3, lap delta, grad delta (3), [phi, lap phi]: one Fourier pass (mcpm_bias_spectra), two batched C2R,
+    one pointwise pass (mcpm_shear_invariants); backward is the transposed chain (bricks.py:342-348, 361-397, 411-446)."""
+
+    @staticmethod
+    def forward(ctx, lin_mesh, cpl, inv_transfer):
+        o = _nb.ops()
+        spec = o.bias_spectra(lin_mesh, cpl, inv_transfer)  # [M, ...]: s00 s11 s01 s02 s12 | delta | lap gx gy gz [phi lapphi]
+        m = spec.shape[0]
+        rshape = _nb.ch2rshape(tuple(lin_mesh.shape))
+        real = o.A.empty((m + 2, *rshape))  # s5 | delta, s^2, s^3, lap, grad (3), [phi, lap phi]
+        o.hermitian_project(spec)
+        o.irfftn(spec[:6], overwrite=True, out=real[:6])
+        o.irfftn(spec[6:], overwrite=True, out=real[8:])
+        o.shear_invariants(real[:5], out=real[6:8])
+        ctx.save_for_backward(real[:5], inv_transfer)
+        ctx.cpl = cpl
+        return real[5:]
+
+    @staticmethod
+    def backward(ctx, mbar):
+        o = _nb.ops()
+        s5, inv_transfer = ctx.saved_tensors
+        mbar = mbar.contiguous()
+        k = mbar.shape[0]
+        m = k + 3  # 5 shear components replace the two invariants
+        sbar = o.A.empty((m, *_nb.r2chshape(tuple(mbar.shape[1:]))), "c64")
+        o.rfftn(o.shear_invariants_vjp(s5, mbar[1:3]), out=sbar[:5])
+        o.rfftn(mbar[0:1], out=sbar[5:6])
+        o.rfftn(mbar[3:], out=sbar[6:])
+        o.hermitian_weights(sbar, 1, inplace=True)  # rfftn + weights = the transpose of irfftn
+        return o.bias_spectra_vjp(sbar, ctx.cpl, inv_transfer), None, None
+
+
+class _BiasWeights(torch.autograd.Function):
+    """vals [np, K], growth (host scalar or [np] device array), coef [13] (host float64) -> weights [np], dvel [np, 3]
+    (mcpm_bias_moments + mcpm_bias_weights; bricks.py:350-449).  Differentiable in all three."""
+
+    @staticmethod
+    def forward(ctx, vals, growth, coef):
+        o = _nb.ops()
+        g = float(growth) if growth.dim() == 0 else growth
+        c = [float(x) for x in coef]
+        w, dvel, mom = o.bias_weights(vals, g, c)
+        ctx.save_for_backward(vals, growth, mom)
+        ctx.coef = c
+        return w, dvel
+
+    @staticmethod
+    def backward(ctx, wbar, dvelbar):
+        o = _nb.ops()
+        vals, growth, mom = ctx.saved_tensors
+        g = float(growth) if growth.dim() == 0 else growth
+        vb, cb, gb = o.bias_weights_vjp(vals, g, ctx.coef, mom, wbar.contiguous(),
+                                        None if dvelbar is None else dvelbar.contiguous())
+        cbar = gbar = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            cb = torch.as_tensor(cb).to("cpu", torch.float64)  # 14 numbers back to the host scalars they belong to
+            cbar = cb[:13]
+            gbar = cb[13].reshape(()).to(growth.dtype) if growth.dim() == 0 else gb.to(growth.dtype)
+        return vb, gbar, cbar
+
+
 def lagrangian_bias(cosmo, pos, a, box_size, lin_mesh, bias, png=None, png_type=None, kpow=None, read_order: int = 2):
     """Lagrangian bias expansion weights (bricks.py:327-452):
+    w = 1 + b1 d + b2 (d^2 - <d^2>)/2 + bs2 (s^2 - <s^2>) + b3 (d^3 - 3<d^2> d)/6 + bds2 d s^2 + bs3 s^3 + bn2 lap d,
+    and the higher-derivative velocity term dvel = bnpar grad d; with png_type not None also (bricks.py:411-438)
+    + fNL_bp phi + fNL_bpd (phi d - <phi d>) + fNL_bpd2 (phi (d^2 - <d^2>) - 2 <phi d> d) + fNL_bps2 phi s^2
+    + fNL_bn2p lap phi, phi = irfftn(delta_k / trans_phi2delta).  Returns (weights, dvel, phi); phi = 0 without PNG.
+
+    Four engine passes and the transforms between them (bias.cu): Fourier multipliers -> C2R x 10 | 12 -> shear
+    invariants -> one gather of the K fields at the particles -> polynomial; differentiable in lin_mesh, pos, the bias /
+    PNG coefficients and (through the growth factor) the cosmology."""
+    f = {k: (png or {}).get(k, 0.0) for k in _PNG_KEYS}
+    b = {k: bias.get(k, 0.0) if isinstance(bias, dict) else 0.0 for k in _BIAS_KEYS}
+    lin_mesh = _nb._c64(lin_mesh)
+    pos = _nb._f32(pos)
+    dev = lin_mesh.device
+    mesh_shape = _nb.ch2rshape(tuple(lin_mesh.shape))
+    a_host = a.detach().to("cpu", torch.float64) if isinstance(a, torch.Tensor) else a  # growth tables live on the host
+    growth = torch.as_tensor(_cosmo.a2g(cosmo, a_host), dtype=torch.float64).reshape(-1)
+    growth = growth.reshape(()) if growth.numel() == 1 else growth.to(device=dev, dtype=torch.float32)
+    if png_type is None:
+        f = {k: 0.0 for k in _PNG_KEYS}
+    coef = torch.stack([torch.as_tensor(v, dtype=torch.float64).reshape(()).cpu()
+                        for v in [b[k] for k in _BIAS_KEYS] + [f[k] for k in _PNG_KEYS]])
+    box = np.broadcast_to(np.asarray(box_size, dtype=np.float64), (3,))
+    cpl = tuple(float(n / l) for n, l in zip(mesh_shape, box))  # rad / cell -> h / Mpc
+    inv = _inv_transfer(cosmo, mesh_shape, box_size, kpow, dev)[1] if png_type is not None else None
+    meshes = _BiasMeshes.apply(lin_mesh, cpl, inv)
+    vals = _nb._Read.apply(pos, meshes, int(read_order), None, 0.0, 0.0)
+    weights, dvel = _BiasWeights.apply(vals, growth, coef)
+    phi = meshes[7] if png_type is not None else 0.0
+    return weights, dvel, phi
+
+
+def lagrangian_bias_composed(cosmo, pos, a, box_size, lin_mesh, bias, png=None, png_type=None, kpow=None, read_order: int = 2):
+    """Round 1's composition of the same expansion from single transforms and pointwise torch expressions, kept as an
+    independent cross-check of the fused passes (tests).  Lagrangian bias expansion weights (bricks.py:327-452):
     w = 1 + b1 d + b2 (d^2 - <d^2>)/2 + bs2 (s^2 - <s^2>) + b3 (d^3 - 3<d^2> d)/6 + bds2 d s^2 + bs3 s^3 + bn2 lap d,
     and the higher-derivative velocity term dvel = bnpar grad d; with png_type not None also (bricks.py:411-438)
     + fNL_bp phi + fNL_bpd (phi d - <phi d>) + fNL_bpd2 (phi (d^2 - <d^2>) - 2 <phi d> d) + fNL_bps2 phi s^2

@@ -803,6 +803,72 @@ int mcpm_rsd_shift_vjp(void* stream, const float* posbar, const float los[3], fl
   API_END
 }
 
+int mcpm_bias_spectra(void* stream, const void* delta_k, int nx, int ny, int nz, const float cpl[3],
+                      const float* inv_transfer, void* out) {
+  API_BEGIN
+  NEED(delta_k && out && cpl, "bias_spectra: null pointer");
+  return bias_spectra(as_stream(stream), C(delta_k), nx, ny, nz, cpl[0], cpl[1], cpl[2], inv_transfer, C(out));
+  API_END
+}
+
+int mcpm_bias_spectra_vjp(void* stream, const void* outbar, int nx, int ny, int nz, const float cpl[3],
+                          const float* inv_transfer, void* dkbar, int accumulate) {
+  API_BEGIN
+  NEED(outbar && dkbar && cpl, "bias_spectra_vjp: null pointer");
+  return bias_spectra_T(as_stream(stream), C(outbar), nx, ny, nz, cpl[0], cpl[1], cpl[2], inv_transfer, C(dkbar), accumulate);
+  API_END
+}
+
+int mcpm_shear_invariants(void* stream, const float* s5, int64_t n, float* out2) {
+  API_BEGIN
+  NEED(s5 && out2, "shear_invariants: null pointer");
+  return shear_invariants(as_stream(stream), s5, n, out2);
+  API_END
+}
+
+int mcpm_shear_invariants_vjp(void* stream, const float* s5, const float* out2bar, int64_t n, float* s5bar) {
+  API_BEGIN
+  NEED(s5 && out2bar && s5bar, "shear_invariants_vjp: null pointer");
+  return shear_invariants_vjp(as_stream(stream), s5, out2bar, n, s5bar);
+  API_END
+}
+
+static BiasCoef bias_coef(const float c[13]) {
+  return BiasCoef{c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8], c[9], c[10], c[11], c[12]};
+}
+
+int mcpm_bias_moments(void* stream, const float* vals, int K, float growth, const float* growth_arr, int64_t np,
+                      double* mom) {
+  API_BEGIN
+  NEED(mom && (vals || np == 0), "bias_moments: null pointer");
+  NEED(K == 7 || K == 9, "bias_moments: K must be 7 or 9");
+  return bias_moments(as_stream(stream), vals, K, growth, growth_arr, np, mom);
+  API_END
+}
+
+int mcpm_bias_weights(void* stream, const float* vals, int K, float growth, const float* growth_arr, const float coef[13],
+                      const double* mom, int64_t np, float* weights, float* dvel) {
+  API_BEGIN
+  NEED(coef && mom && ((vals && weights) || np == 0), "bias_weights: null pointer");
+  NEED(K == 7 || K == 9, "bias_weights: K must be 7 or 9");
+  NEED(np > 0, "bias_weights: the particle means need at least one particle");
+  return bias_weights(as_stream(stream), vals, K, growth, growth_arr, bias_coef(coef), mom, np, weights, dvel);
+  API_END
+}
+
+int mcpm_bias_weights_vjp(void* stream, const float* vals, int K, float growth, const float* growth_arr,
+                          const float coef[13], const double* mom, const float* wbar, const float* dvelbar, int64_t np,
+                          double* msum, float* valsbar, double* coefbar, float* gbar_arr) {
+  API_BEGIN
+  NEED(coef && mom && msum && coefbar && vals && wbar && valsbar, "bias_weights_vjp: null pointer");
+  NEED(K == 7 || K == 9, "bias_weights_vjp: K must be 7 or 9");
+  NEED(np > 0, "bias_weights_vjp: the particle means need at least one particle");
+  NEED(!growth_arr || gbar_arr, "bias_weights_vjp: per-particle growth needs gbar_arr");
+  return bias_weights_vjp(as_stream(stream), vals, K, growth, growth_arr, bias_coef(coef), mom, wbar, dvelbar, np, msum,
+                          valsbar, coefbar, growth_arr ? gbar_arr : nullptr);
+  API_END
+}
+
 int mcpm_scale_spectrum(void* stream, const void* in, const float* t, void* out, int64_t nc) {
   API_BEGIN
   return scale_spectrum(as_stream(stream), C(in), t, C(out), nc);

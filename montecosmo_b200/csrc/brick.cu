@@ -370,7 +370,17 @@ __device__ __forceinline__ void stray_deposit(const BrickArgs& a, int si0, int s
   }
 }
 
-template <int NCH, int TZS>
+// REL: lattice-relative positions (displacements; what the engine's step loop carries).  !REL: absolute positions,
+// possibly wrapped by the caller by whole box lengths.
+//
+// Instruction diet (profiles/r2_ncu_brick_stream.txt): the first working version of this kernel issued 352 warp
+// instructions per 32 particles and was ISSUE bound (67 % of the issue slots, 0.26 ms per 256^3 density paint against 0.16
+// for the kernel above): 37 % of them in the check / flush loops (a runtime integer division per half-warp row), 8 % in
+// the copy issue (two divisions per brick and thread), the rest float modulo arithmetic per particle.  Now: brick
+// coordinates advance by carries, tile cells are formed in integers (one F2I.FLOOR per coordinate, a wrap only for the
+// particles that need it), the origin comes from the first slot's 512 particles, flush items are decoded with
+// multiply-shift divisions, and the unweighted density paint skips the sum |v| reduction.
+template <int NCH, int TZS, bool REL>
 __global__ void __launch_bounds__(bstream::THREADS, 2) brick_stream_kernel(BrickArgs a, int nby, int nbz, int nbricks) {
   using namespace bstream;
   using SM = Smem<NCH, TZS>;
@@ -383,7 +393,8 @@ __global__ void __launch_bounds__(bstream::THREADS, 2) brick_stream_kernel(Brick
   unsigned short* stray = reinterpret_cast<unsigned short*>(smraw + SM::TILE_B + SM::ROWBASE_B + SM::POS_B + SM::VAL_B);
   __shared__ int nstray;
   __shared__ float red[WARPS][4 + NCH];
-  __shared__ float bc[4 + NCH];
+  __shared__ int org[8];          // per brick, computed once and broadcast: tile origin (unwrapped x, y, z; wrapped x, y, z)
+  __shared__ float scl[NCH][2];   // per brick and channel: value -> fixed point (sign of the scalar included), and back
   __shared__ int bb[4];  // bounding box of the brick's base cells in the tile: xmin, xmax, ymin, ymax
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -398,67 +409,95 @@ __global__ void __launch_bounds__(bstream::THREADS, 2) brick_stream_kernel(Brick
   const bool has_w = NCH == 1 && a.w != nullptr;
   const bool has_v = NCH == 3 || has_w;
   const uint32_t tx_bytes = (uint32_t)(SM::POS_B + (has_v ? SM::VAL_B : 0));
-  // warp 0 fetches brick b: one bulk copy per array per z-row
-  auto issue = [&](int b) {
-    const int bk = b % nbz, bij = b / nbz, bj = bij % nby, bi = bij / nby;
-    if (lane == 0) tma::mbar_arrive_expect_tx(&bar, tx_bytes);
-    __syncwarp();
-    for (int row = lane; row < ROWS; row += 32) {
-      const int64_t p0 = ((int64_t)(bi * BX + (row >> 3)) * a.py + (bj * BY + (row & 7))) * a.pz + bk * BZ;
-      tma::bulk_g2s(ps + row * PROW, a.pos + 3 * p0, PROW * sizeof(float), &bar);
-      if (NCH == 3) tma::bulk_g2s(vs + row * PROW, a.A + 3 * p0, PROW * sizeof(float), &bar);
-      else if (has_w) tma::bulk_g2s(vs + row * BZ, a.w + p0, BZ * sizeof(float), &bar);
+  // Fetch a brick: one bulk copy per array per z-row, issued by ALL warps (warp w: rows 4w .. 4w + 3, lanes 0-3 pos, lanes
+  // 4-7 the values).  A first version issued the brick's 64-128 copies from warp 0 alone, lane after lane, with the whole
+  // CTA waiting behind it at the next barrier.  Thread 0 posts the expected byte count; complete_tx of a copy may land
+  // before it (the tx-count is signed, and the phase cannot complete before that one arrival).
+  const int crow = PPT * warp + (lane & 3);  // the row this lane copies
+  auto issue = [&](int bi, int bj, int bk) {
+    if (lane < 8) {
+      const int p0 = ((bi * BX + (crow >> 3)) * a.py + (bj * BY + (crow & 7))) * a.pz + bk * BZ;  // 3 np < 2^31 (brick_ok)
+      if (lane < 4) tma::bulk_g2s(ps + crow * PROW, a.pos + 3 * (int64_t)p0, PROW * sizeof(float), &bar);
+      else if (NCH == 3) tma::bulk_g2s(vs + crow * PROW, a.A + 3 * (int64_t)p0, PROW * sizeof(float), &bar);
+      else if (has_w) tma::bulk_g2s(vs + crow * BZ, a.w + p0, BZ * sizeof(float), &bar);
     }
   };
-  if (warp == 0 && (int)blockIdx.x < nbricks) issue(blockIdx.x);
+  // brick coordinates advance by gridDim.x bricks with carries (no divisions in the loop)
+  int bk = blockIdx.x % nbz, bj = (blockIdx.x / nbz) % nby, bi = blockIdx.x / nbz / nby;
+  const int gk = gridDim.x % nbz, gj = (gridDim.x / nbz) % nby, gi = gridDim.x / nbz / nby;
+  auto advance = [&](int& i, int& j, int& k) {
+    k += gk;
+    int c = k >= nbz;
+    k -= c ? nbz : 0;
+    j += gj + c;
+    c = j >= nby;
+    j -= c ? nby : 0;
+    i += gi + c;
+  };
+  if ((int)blockIdx.x < nbricks) {
+    if (tid == 0) tma::mbar_arrive_expect_tx(&bar, tx_bytes);
+    issue(bi, bj, bk);
+  }
+  int ni = bi, nj = bj, nk = bk;
+  advance(ni, nj, nk);
 
   const int64_t plane = (int64_t)a.nx * a.ny * a.nz;
-  const float fnx = (float)a.nx, fny = (float)a.ny, fnz = (float)a.nz;
+  const int dj = warp & 7, di0 = warp >> 3;  // this warp's lattice row: (di0 + 2 r, dj), lane = z
   uint32_t parity = 0;
 #pragma unroll 1
   for (int b = blockIdx.x; b < nbricks; b += gridDim.x, parity ^= 1) {
-    const int bk = b % nbz, bij = b / nbz, bj = bij % nby, bi = bij / nby;
     const int q0i = bi * BX, q0j = bj * BY, q0k = bk * BZ;
-    const int dj = warp & 7, qj = q0j + dj, qk = q0k + lane;
+    const bool more = b + (int)gridDim.x < nbricks;
     tma::mbar_wait(&bar, parity);
+    if (tid == 0 && more) tma::mbar_arrive_expect_tx(&bar, tx_bytes);  // next phase: its copies follow barrier A
 
-    // ---- pass 1: displacements u = x - site, values, partial sums
-    float x[PPT][3], val[NCH][PPT];
-    float l1[NCH], d0 = 0.f, d1 = 0.f, d2 = 0.f;
+    // ---- pass 1: u = x (+ shift) - site, values; partial sums of the first slot's displacements and of |v|
+    float u[PPT][3], val[NCH][PPT];
+    float l1[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) l1[c] = 0.f;
-    const float sy = a.rel ? 0.f : (float)(qj + a.oy), sz = a.rel ? 0.f : (float)(qk + a.oz);
 #pragma unroll
     for (int r = 0; r < PPT; ++r) {
-      const int di = (warp >> 3) + r * (WARPS / 8), row = di * BY + dj;
+      const int row = (di0 + 2 * r) * BY + dj;
       const float* xr = ps + row * PROW + 3 * lane;
-      const float sx = a.rel ? 0.f : (float)(q0i + di + a.ox);
-      x[r][0] = (xr[0] + a.shift) - sx;
-      x[r][1] = (xr[1] + a.shift) - sy;
-      x[r][2] = (xr[2] + a.shift) - sz;
+      if (REL) {
+        u[r][0] = xr[0] + a.shift;
+        u[r][1] = xr[1] + a.shift;
+        u[r][2] = xr[2] + a.shift;
+      } else {  // exact: the site is a whole number below 2^24
+        u[r][0] = (xr[0] + a.shift) - (float)(q0i + di0 + 2 * r + a.ox);
+        u[r][1] = (xr[1] + a.shift) - (float)(q0j + dj + a.oy);
+        u[r][2] = (xr[2] + a.shift) - (float)(q0k + lane + a.oz);
+      }
       if (NCH == 3) {
         const float* vr = vs + row * PROW + 3 * lane;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           val[c][r] = vr[c];
-          l1[c] += fabsf(a.s * val[c][r]);
+          l1[c] += fabsf(val[c][r]);
         }
+      } else if (has_w) {
+        val[0][r] = vs[row * BZ + lane];
+        l1[0] += fabsf(val[0][r]);
       } else {
-        val[0][r] = has_w ? vs[row * BZ + lane] : 1.0f;
-        l1[0] += fabsf(val[0][r] * a.ws);
+        val[0][r] = 1.0f;
       }
-      // displacement reduced to the nearest periodic image (absolute positions may have been wrapped by the caller)
-      d0 += x[r][0] - fnx * rintf(x[r][0] * a.inx);
-      d1 += x[r][1] - fny * rintf(x[r][1] * a.iny);
-      d2 += x[r][2] - fnz * rintf(x[r][2] * a.inz);
+    }
+    float d0 = u[0][0], d1 = u[0][1], d2 = u[0][2];
+    if (!REL) {  // nearest periodic image (absolute positions may have been wrapped by the caller)
+      d0 -= (float)a.nx * rintf(d0 * a.inx);
+      d1 -= (float)a.ny * rintf(d1 * a.iny);
+      d2 -= (float)a.nz * rintf(d2 * a.inz);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       d0 += __shfl_xor_sync(0xffffffffu, d0, o);
       d1 += __shfl_xor_sync(0xffffffffu, d1, o);
       d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+      if (has_v) {
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) l1[c] += __shfl_xor_sync(0xffffffffu, l1[c], o);
+        for (int c = 0; c < NCH; ++c) l1[c] += __shfl_xor_sync(0xffffffffu, l1[c], o);
+      }
     }
     if (lane == 0) {
       red[warp][0] = d0;
@@ -475,22 +514,43 @@ __global__ void __launch_bounds__(bstream::THREADS, 2) brick_stream_kernel(Brick
       nstray = 0;
     }
     __syncthreads();  // A: every thread has read the staged rows; red / bb are written
-    {
-      const int bn = b + gridDim.x;  // the staging buffers are free: fetch the next brick under this one's deposits
-      if (warp == 0 && bn < nbricks) issue(bn);
-    }
-    if (tid < 4 + NCH && tid != 3) {
-      float s = 0.f;
+    if (more) issue(ni, nj, nk);  // the staging buffers are free: the next brick arrives under this one's deposits
+    // Per-brick scalars are formed by ONE thread each and broadcast (the first version had all 16 warps redo the three
+    // integer modulos, log2 / exp2 ... : ~150 of the 440 warp instructions a warp spent per brick between A' and B).
+    // Threads 0-2: tile origin along x, y, z in unwrapped cell coordinates (base cells of the brick span
+    // [q0 + mean, q0 + B - 1 + mean]; the tile admits base cells [o, o + T - 2]), along z a multiple of 4 (16-byte groups);
+    // threads 4 .. 4 + NCH - 1: the channel's fixed-point scale.
+    if (tid < 3) {
+      float sum = 0.f;
 #pragma unroll
-      for (int w = 0; w < WARPS; ++w) s += red[w][tid];
-      bc[tid] = s;
+      for (int w = 0; w < WARPS; ++w) sum += red[w][tid];
+      constexpr float ninv = 1.0f / (float)(WARPS * 32);  // the first slot: 512 particles spread over the whole brick
+      const int q0 = tid == 0 ? q0i + a.ox : tid == 1 ? q0j + a.oy : q0k + a.oz;
+      const int n = tid == 0 ? a.nx : tid == 1 ? a.ny : a.nz;
+      const float slack = tid == 0 ? 0.5f * (TX - BX) : tid == 1 ? 0.5f * (TY - BY) : 0.5f * (TZ - 1 - BZ);
+      const float of = (float)q0 + sum * ninv - slack;
+      const int o = tid == 2 ? 4 * __float2int_rn(0.25f * of) : __float2int_rn(of);
+      org[tid] = o;
+      org[3 + tid] = wrap_index(o, n);
+    } else if (tid >= 4 && tid < 4 + NCH) {
+      const int c = tid - 4;
+      float l;
+      if (has_v) {
+        l = 0.f;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) l += red[w][tid];
+        l *= fabsf(NCH == 1 ? a.ws : a.s);
+      } else {
+        l = fabsf(a.ws) * (float)(ROWS * BZ);
+      }
+      constexpr int FINE = NCH == 1 ? 3 : 0;  // see brick_scatter_kernel
+      float e = l > 0.f ? floorf(log2f(1073741824.0f / l)) + (float)FINE : 0.f;
+      e = fminf(fmaxf(e, -120.f), 120.f);
+      scl[c][0] = (NCH == 1 ? a.ws : a.s) * exp2f(e);
+      scl[c][1] = exp2f(-e);
     }
     __syncthreads();  // A'
-    constexpr float ninv = 1.0f / (float)(ROWS * BZ);
-    const float oxf = rintf((float)(q0i + a.ox) + bc[0] * ninv - 0.5f * (TX - BX));
-    const float oyf = rintf((float)(q0j + a.oy) + bc[1] * ninv - 0.5f * (TY - BY));
-    const float ozf = 4.0f * rintf(0.25f * ((float)(q0k + a.oz) + bc[2] * ninv - 0.5f * (TZ - 1 - BZ)));
-    const int oxw = wrap_index((int)oxf, a.nx), oyw = wrap_index((int)oyf, a.ny), oz = wrap_index((int)ozf, a.nz);
+    const int oxi = org[0], oyi = org[1], ozi = org[2], oxw = org[3], oyw = org[4], oz = org[5];
     if (tid < TROWS) {
       const int ix = tid / TY, jy = tid - ix * TY;
       int gx = oxw + ix, gy = oyw + jy;
@@ -502,23 +562,23 @@ __global__ void __launch_bounds__(bstream::THREADS, 2) brick_stream_kernel(Brick
     // ---- tile cell and fractions; strays are queued
     int tcell[PPT];
     int xmin = TX, xmax = -1, ymin = TY, ymax = -1;
+    const int cxi = q0i + a.ox - oxi + di0, cyi = q0j + a.oy - oyi + dj, czi = q0k + a.oz - ozi + lane;
 #pragma unroll
     for (int r = 0; r < PPT; ++r) {
-      const int di = (warp >> 3) + r * (WARPS / 8);
-      const float bx = floorf(x[r][0]), by = floorf(x[r][1]), bz = floorf(x[r][2]);
-      x[r][0] -= bx;
-      x[r][1] -= by;
-      x[r][2] -= bz;
-      float tx = ((float)(q0i + di + a.ox) - oxf) + bx, ty = ((float)(qj + a.oy) - oyf) + by,
-            tz = ((float)(qk + a.oz) - ozf) + bz;
-      tx -= fnx * floorf(tx * a.inx);
-      ty -= fny * floorf(ty * a.iny);
-      tz -= fnz * floorf(tz * a.inz);
-      const bool in = fabsf(tx - 0.5f * (TX - 2)) <= 0.5f * (TX - 2) && fabsf(ty - 0.5f * (TY - 2)) <= 0.5f * (TY - 2) &&
-                      fabsf(tz - 0.5f * (TZ - 2)) <= 0.5f * (TZ - 2);
+      const int ibx = __float2int_rd(u[r][0]), iby = __float2int_rd(u[r][1]), ibz = __float2int_rd(u[r][2]);
+      u[r][0] -= (float)ibx;  // fractions: x - floor(x), as every CIC kernel of the engine forms them
+      u[r][1] -= (float)iby;
+      u[r][2] -= (float)ibz;
+      int itx = ibx + cxi + 2 * r, ity = iby + cyi, itz = ibz + czi;
+      if (!REL) {  // whole box lengths off (caller-wrapped positions): bring the cell back next to the tile
+        if ((unsigned)itx > (unsigned)(TX - 2)) itx = wrap_fast(itx, a.nx);
+        if ((unsigned)ity > (unsigned)(TY - 2)) ity = wrap_fast(ity, a.ny);
+        if ((unsigned)itz > (unsigned)(TZ - 2)) itz = wrap_fast(itz, a.nz);
+      }
+      const bool in = (unsigned)itx <= (unsigned)(TX - 2) && (unsigned)ity <= (unsigned)(TY - 2) &&
+                      (unsigned)itz <= (unsigned)(TZ - 2);
       if (in) {
-        const int itx = (int)tx, ity = (int)ty;
-        tcell[r] = (itx * TY + ity) * TZS + (int)tz;
+        tcell[r] = (itx * TY + ity) * TZS + itz;
         xmin = min(xmin, itx);
         xmax = max(xmax, itx);
         ymin = min(ymin, ity);
@@ -540,25 +600,22 @@ __global__ void __launch_bounds__(bstream::THREADS, 2) brick_stream_kernel(Brick
     }
 
     bool all_stray = false;  // block-uniform
-    int bx0 = 0, by0 = 0, nyb = 1, nrow = 0, ns = 0;
+    int nitem = 0, by0 = 0, nyb = 1, rbase = 0, ns = 0;
+    unsigned mny = 0;
 #pragma unroll  // val[c][r] stays in registers
     for (int c = 0; c < NCH; ++c) {
-      const float l = bc[4 + c];
-      constexpr int FINE = NCH == 1 ? 3 : 0;  // see brick_scatter_kernel
-      float e = l > 0.f ? floorf(log2f(1073741824.0f / l)) + (float)FINE : 0.f;
-      e = fminf(fmaxf(e, -120.f), 120.f);
-      const float S = exp2f(e), invS = exp2f(-e);
-      const float scale = (NCH == 1 ? a.ws : a.s) * S;
+      constexpr int FINE = NCH == 1 ? 3 : 0;
+      const float scale = scl[c][0], invS = scl[c][1];
 #pragma unroll
       for (int r = 0; r < PPT; ++r) {
         if (tcell[r] < 0) continue;
         const float vsc = val[c][r] * scale;
-        const float fx = x[r][0], fy = x[r][1], fz = x[r][2];
+        const float fx = u[r][0], fy = u[r][1], fz = u[r][2];
         const float gx = 1.f - fx, gy = 1.f - fy;
-        const float vz1 = vsc * fz, vz0 = vsc - vz1;
+        const float vz1 = vsc * fz, vz0 = vsc - vz1;  // vsc * (1 - fz) up to one rounding of the fixed-point product
         const float w00 = gx * gy, w01 = gx * fy, w10 = fx * gy, w11 = fx * fy;
         int* t = tile + tcell[r];
-        atomicAdd(t, __float2int_rn(vz0 * w00));
+        atomicAdd(t, __float2int_rn(vz0 * w00));  // ATOMS.ADD, constant offsets
         atomicAdd(t + 1, __float2int_rn(vz1 * w00));
         atomicAdd(t + TZS, __float2int_rn(vz0 * w01));
         atomicAdd(t + TZS + 1, __float2int_rn(vz1 * w01));
@@ -567,40 +624,48 @@ __global__ void __launch_bounds__(bstream::THREADS, 2) brick_stream_kernel(Brick
         atomicAdd(t + TY * TZS + TZS, __float2int_rn(vz0 * w11));
         atomicAdd(t + TY * TZS + TZS + 1, __float2int_rn(vz1 * w11));
       }
-      __syncthreads();  // B: the tile holds channel c (and bb, rowbase are final)
-      // rows [bb0, bb1 + 1] x [bb2, bb3 + 1] of the tile were touched; half a warp takes a row (ZG = 11 groups)
-      if (c == 0) {  // read once: thread 0 re-initialises bb in the next brick's pass 1
-        bx0 = bb[0];
+      __syncthreads();  // B: the tile holds channel c (and bb, rowbase, nstray are final)
+      if (c == 0) {  // read once: thread 0 re-initialises bb / nstray in the next brick's pass 1
+        // rows [bb0, bb1 + 1] x [bb2, bb3 + 1] of the tile were touched: nrow x ZG groups, item q -> (row, kz) by
+        // multiply-shift divisions (exact: q < 2^15 with divisor 11; row index < 324 with divisor <= 18)
         by0 = bb[2];
         nyb = bb[3] - by0 + 2;
-        nrow = bb[1] < 0 ? 0 : (bb[1] - bx0 + 2) * nyb;
+        nitem = bb[1] < 0 ? 0 : (bb[1] - bb[0] + 2) * nyb * ZG;
+        rbase = bb[0] * TY + by0;
+        mny = (65536u + (unsigned)nyb - 1u) / (unsigned)nyb;
         ns = nstray;
       }
-      const int kz = lane & 15, hw = lane >> 4;
+      auto group_of = [&](int q, int& row, int& kz) {
+        const int rb = (int)(((unsigned)q * 5958u) >> 16);  // q / 11
+        kz = q - rb * ZG;
+        const int ixr = (int)(((unsigned)rb * mny) >> 16);  // rb / nyb
+        row = rbase + ixr * TY + (rb - ixr * nyb);
+      };
+      static_assert(ZG == 11, "multiply-shift constant above");
       if (FINE > 0) {
         unsigned bad = 0;  // any cell outside [-2^29, 2^29)?
-        for (int rb = 2 * warp + hw; rb < nrow; rb += 2 * WARPS) {
-          if (kz >= ZG) continue;
-          const int ixr = rb / nyb, row = (bx0 + ixr) * TY + by0 + (rb - ixr * nyb);
-          const int4 q = tile4[row * ZGS + kz];
-          bad |= ((unsigned)q.x + 0x20000000u) | ((unsigned)q.y + 0x20000000u) | ((unsigned)q.z + 0x20000000u) |
-                 ((unsigned)q.w + 0x20000000u);
+        for (int q = tid; q < nitem; q += THREADS) {
+          int row, kz;
+          group_of(q, row, kz);
+          const int4 v = tile4[row * ZGS + kz];
+          bad |= ((unsigned)v.x + 0x20000000u) | ((unsigned)v.y + 0x20000000u) | ((unsigned)v.z + 0x20000000u) |
+                 ((unsigned)v.w + 0x20000000u);
         }
         if (__syncthreads_or((bad >> 30) != 0)) all_stray = true;  // drop the tile: the flush below only re-zeroes it
       }
       float* meshc = a.mesh + c * plane;
-      for (int rb = 2 * warp + hw; rb < nrow; rb += 2 * WARPS) {
-        if (kz >= ZG) continue;
-        const int ixr = rb / nyb, row = (bx0 + ixr) * TY + by0 + (rb - ixr * nyb);
+      for (int q = tid; q < nitem; q += THREADS) {
+        int row, kz;
+        group_of(q, row, kz);
         const int g = row * ZGS + kz;
-        const int4 q = tile4[g];
-        if ((q.x | q.y | q.z | q.w) != 0) {
+        const int4 v = tile4[g];
+        if ((v.x | v.y | v.z | v.w) != 0) {
           tile4[g] = make_int4(0, 0, 0, 0);
           if (!all_stray) {
             int gz = oz + 4 * kz;
             gz = gz >= a.nz ? gz - a.nz : gz;
             atomicAdd(reinterpret_cast<float4*>(meshc + (rowbase[row] + gz)),
-                      make_float4(q.x * invS, q.y * invS, q.z * invS, q.w * invS));
+                      make_float4(v.x * invS, v.y * invS, v.z * invS, v.w * invS));
           }
         }
       }
@@ -611,10 +676,14 @@ __global__ void __launch_bounds__(bstream::THREADS, 2) brick_stream_kernel(Brick
     if (all_stray) ns = PPT * THREADS;
     for (int si = tid; si < ns; si += THREADS) {
       const int code = all_stray ? si : stray[si], r = code / THREADS, t2 = code - r * THREADS, w2 = t2 >> 5;
-      stray_deposit<NCH>(a, q0i + (w2 >> 3) + r * (WARPS / 8), q0j + (w2 & 7), q0k + (t2 & 31));
+      stray_deposit<NCH>(a, q0i + (w2 >> 3) + 2 * r, q0j + (w2 & 7), q0k + (t2 & 31));
     }
     // no barrier here: the next brick's pass 1 touches only the staging buffers, red and bb, and its barrier A orders
     // this flush before the next deposits
+    bi = ni;
+    bj = nj;
+    bk = nk;
+    advance(ni, nj, nk);
   }
 }
 
@@ -639,7 +708,7 @@ static void launch_brick_variant(stream_t st, const BrickArgs& a, dim3 grid) {
 }
 
 // Streaming variant: whole 8 x 8 x 32 bricks, 16-byte aligned rows (bulk copies), mesh at least one tile wide.
-template <int NCH, int TZS>
+template <int NCH, int TZS, bool REL>
 static int launch_stream(stream_t st, const BrickArgs& a) {
   using namespace bstream;
   using SM = Smem<NCH, TZS>;
@@ -648,9 +717,9 @@ static int launch_stream(stream_t st, const BrickArgs& a) {
   cudaGetDevice(&dev);
   dev &= 15;
   if (per_sm[dev] == 0) {
-    cudaFuncSetAttribute(brick_stream_kernel<NCH, TZS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES);
+    cudaFuncSetAttribute(brick_stream_kernel<NCH, TZS, REL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES);
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, brick_stream_kernel<NCH, TZS>, THREADS, SM::BYTES) !=
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, brick_stream_kernel<NCH, TZS, REL>, THREADS, SM::BYTES) !=
             cudaSuccess || n < 1)
       n = 1;
     per_sm[dev] = n;
@@ -658,7 +727,7 @@ static int launch_stream(stream_t st, const BrickArgs& a) {
   const int nbx = a.px / BX, nby = a.py / BY, nbz = a.pz / BZ;
   const int64_t nb = (int64_t)nbx * nby * nbz, wave = (int64_t)kSMs * per_sm[dev];
   count_launch();
-  brick_stream_kernel<NCH, TZS><<<(unsigned)(nb < wave ? nb : wave), THREADS, SM::BYTES, st>>>(a, nby, nbz, (int)nb);
+  brick_stream_kernel<NCH, TZS, REL><<<(unsigned)(nb < wave ? nb : wave), THREADS, SM::BYTES, st>>>(a, nby, nbz, (int)nb);
   return rt_check("brick_stream") ? -1 : 1;
 }
 static bool stream_ok(const BrickArgs& a) {
@@ -673,7 +742,11 @@ static bool stream_ok(const BrickArgs& a) {
 template <int NCH>
 static int launch_brick(stream_t st, const BrickArgs& a) {
   using namespace brick;
-  if (stream_ok(a)) return tune().brick_stream == 48 ? launch_stream<NCH, 48>(st, a) : launch_stream<NCH, 44>(st, a);
+  if (stream_ok(a)) {
+    const bool wide = tune().brick_stream == 48;
+    if (a.rel) return wide ? launch_stream<NCH, 48, true>(st, a) : launch_stream<NCH, 44, true>(st, a);
+    return wide ? launch_stream<NCH, 48, false>(st, a) : launch_stream<NCH, 44, false>(st, a);
+  }
   dim3 grid((a.pz + BZ - 1) / BZ, (a.py + BY - 1) / BY, (a.px + BX - 1) / BX);
   count_launch();
   const bool full = a.px % BX == 0 && a.py % BY == 0 && a.pz % BZ == 0;

@@ -93,6 +93,22 @@ int lpt_combine(stream_t, const float* pos, const float* f1, const float* f2, fl
                 int64_t np, float* dpos, float* vel, float* pos_out);
 int dot_accum(stream_t, const float* a, const float* b, int64_t n, double scale, double* out);
 int axpby(stream_t, const float* x, float a, const float* y, float b, float c, int64_t n, float* out);
+// bias.cu
+struct BiasCoef {
+  float b1, b2, bs2, b3, bds2, bs3, bn2, bnpar, fbp, fbpd, fbpd2, fbps2, fbn2p;
+};
+int bias_spectra(stream_t, const cfloat* dk, int nx, int ny, int nz, float cx, float cy, float cz, const float* inv_transfer,
+                 cfloat* out);
+int bias_spectra_T(stream_t, const cfloat* outbar, int nx, int ny, int nz, float cx, float cy, float cz,
+                   const float* inv_transfer, cfloat* dkbar, int accumulate);
+int shear_invariants(stream_t, const float* s5, int64_t n, float* out2);
+int shear_invariants_vjp(stream_t, const float* s5, const float* out2bar, int64_t n, float* s5bar);
+int bias_moments(stream_t, const float* vals, int K, float gs, const float* garr, int64_t np, double* mom);
+int bias_weights(stream_t, const float* vals, int K, float gs, const float* garr, BiasCoef c, const double* mom, int64_t np,
+                 float* weights, float* dvel);
+int bias_weights_vjp(stream_t, const float* vals, int K, float gs, const float* garr, BiasCoef c, const double* mom,
+                     const float* wbar, const float* dvelbar, int64_t np, double* msum, float* valsbar, double* coefbar,
+                     float* gbar_arr);
 int rsd_shift(stream_t, const float* pos, const float* vel, float lx, float ly, float lz, float coef, int64_t np,
               float* pos_out);
 int rsd_shift_vjp(stream_t, const float* posbar, float lx, float ly, float lz, float coef, int64_t np, float* velbar,

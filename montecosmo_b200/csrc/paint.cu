@@ -397,8 +397,10 @@ static int read_nm(stream_t st, const float* pos, const float* mesh, int nmesh, 
     case 2: read_impl<ORDER, 2>(st, pos, mesh, np, n, xf, out, win); return 0;
     case 3: read_impl<ORDER, 3>(st, pos, mesh, np, n, xf, out, win); return 0;
     case 4: read_impl<ORDER, 4>(st, pos, mesh, np, n, xf, out, win); return 0;
+    case 7: read_impl<ORDER, 7>(st, pos, mesh, np, n, xf, out, win); return 0;  // the fields of lagrangian_bias (bias.cu)
+    case 9: read_impl<ORDER, 9>(st, pos, mesh, np, n, xf, out, win); return 0;  // ... with primordial non-Gaussianity
   }
-  set_error("read: nmesh must be 1..4");
+  set_error("read: nmesh must be 1..4, 7 or 9");
   return MCPM_EINVAL;
 }
 

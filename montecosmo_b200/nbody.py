@@ -208,7 +208,12 @@ class _Read(torch.autograd.Function):
         obar = obar.contiguous()
         pb = mb = None
         if ctx.needs_input_grad[0]:
-            pb = ops().read_grad(pos, mesh, obar.reshape(pos.shape[0], -1), order, scale, shift, kb_kcut=kb)
+            ob = obar.reshape(pos.shape[0], -1)
+            if mesh.dim() == 4 and mesh.shape[0] > 4:  # mcpm_read_grad takes up to 4 meshes: chunks, summed
+                pb = sum(ops().read_grad(pos, mesh[i:i + 4], ob[:, i:i + 4].contiguous(), order, scale, shift, kb_kcut=kb)
+                         for i in range(0, mesh.shape[0], 4))
+            else:
+                pb = ops().read_grad(pos, mesh, ob, order, scale, shift, kb_kcut=kb)
         if ctx.needs_input_grad[1]:
             if mesh.dim() == 3:
                 mb = ops().paint(pos, tuple(mesh.shape), obar, 1.0, order, scale, shift, kb_kcut=kb)

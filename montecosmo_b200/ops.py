@@ -186,16 +186,18 @@ class Ops:
         return out
 
     # ------------------------------------------------------------------------------------------------ FFT, Fourier passes
-    def rfftn(self, mesh):
+    def rfftn(self, mesh, out=None):
+        """`out`: a contiguous complex block of the right size to write into (e.g. a slice of a larger batch)."""
         A = self.A
         mesh = A.prepare(mesh)
         ms = A.shape(mesh)
         batch = 1 if len(ms) == 3 else ms[0]
-        out = A.empty((*ms[:-3], *r2chshape(ms[-3:])), "c64")
+        if out is None:
+            out = A.empty((*ms[:-3], *r2chshape(ms[-3:])), "c64")
         self._call("mcpm_rfftn", self.engine(ms[-3:]).handle, A.stream(), A.ptr(mesh), A.ptr(out), batch)
         return out
 
-    def irfftn(self, meshk, overwrite=False):
+    def irfftn(self, meshk, overwrite=False, out=None):
         A = self.A
         meshk = A.prepare(meshk, "c64")
         if not overwrite:
@@ -203,7 +205,8 @@ class Ops:
         ms = A.shape(meshk)
         batch = 1 if len(ms) == 3 else ms[0]
         rs = ch2rshape(ms[-3:])
-        out = A.empty((*ms[:-3], *rs))
+        if out is None:
+            out = A.empty((*ms[:-3], *rs))
         self._call("mcpm_irfftn", self.engine(rs).handle, A.stream(), A.ptr(meshk), A.ptr(out), batch)
         return out
 
@@ -490,11 +493,18 @@ class Ops:
         self._call("mcpm_cgh2rg", A.stream(), A.ptr(meshk), A.ptr(out), *rs, float(inv_scale))
         return out
 
-    def hermitian_weights(self, meshk, mode):
+    def hermitian_weights(self, meshk, mode, inplace=False):
+        """3-D, or a batch [M, nx, ny, nzc] (one launch per member); inplace: overwrite meshk."""
         A = self.A
         meshk = A.prepare(meshk, "c64")
-        out = A.empty(A.shape(meshk), "c64")
-        self._call("mcpm_hermitian_weights", A.stream(), A.ptr(meshk), A.ptr(out), *ch2rshape(A.shape(meshk)), mode)
+        out = meshk if inplace else A.empty(A.shape(meshk), "c64")
+        ms = A.shape(meshk)
+        rs = ch2rshape(ms[-3:])
+        if len(ms) == 3:
+            self._call("mcpm_hermitian_weights", A.stream(), A.ptr(meshk), A.ptr(out), *rs, mode)
+        else:
+            for m in range(ms[0]):
+                self._call("mcpm_hermitian_weights", A.stream(), A.ptr(meshk[m]), A.ptr(out[m]), *rs, mode)
         return out
 
     def axpby(self, x, a=1.0, y=None, b=0.0, c=0.0):
@@ -512,6 +522,73 @@ class Ops:
         out = A.zeros((1,), "f64")
         self._call("mcpm_dot", A.stream(), A.ptr(a), A.ptr(b), math.prod(A.shape(a)), A.ptr(out))
         return out
+
+    # ---- Lagrangian bias expansion (bias.cu; bricks.py:327-452)
+    def bias_spectra(self, delta_k, cells_per_len, inv_transfer=None):
+        """[M, nx, ny, nzc] spectra (M = 10, or 12 with an inverse transfer) from one pass over delta_k."""
+        A = self.A
+        delta_k = A.prepare(delta_k, "c64")
+        nx, ny, nzc = A.shape(delta_k)
+        nz = 2 * (nzc - 1)
+        it = None if inv_transfer is None else A.prepare(inv_transfer)
+        out = A.empty((12 if it is not None else 10, nx, ny, nzc), "c64")
+        self._call("mcpm_bias_spectra", A.stream(), A.ptr(delta_k), nx, ny, nz, host_floats(cells_per_len), A.ptr(it),
+                   A.ptr(out))
+        return out
+
+    def bias_spectra_vjp(self, outbar, cells_per_len, inv_transfer=None):
+        A = self.A
+        outbar = A.prepare(outbar, "c64")
+        _, nx, ny, nzc = A.shape(outbar)
+        it = None if inv_transfer is None else A.prepare(inv_transfer)
+        out = A.empty((nx, ny, nzc), "c64")
+        self._call("mcpm_bias_spectra_vjp", A.stream(), A.ptr(outbar), nx, ny, 2 * (nzc - 1), host_floats(cells_per_len),
+                   A.ptr(it), A.ptr(out), 0)
+        return out
+
+    def shear_invariants(self, s5, out=None):
+        A = self.A
+        s5 = A.prepare(s5)
+        shape = A.shape(s5)[1:]
+        out = A.empty((2, *shape)) if out is None else out
+        self._call("mcpm_shear_invariants", A.stream(), A.ptr(s5), math.prod(shape), A.ptr(out))
+        return out
+
+    def shear_invariants_vjp(self, s5, out2bar, out=None):
+        A = self.A
+        s5, out2bar = A.prepare(s5), A.prepare(out2bar)
+        out = A.empty(A.shape(s5)) if out is None else out
+        self._call("mcpm_shear_invariants_vjp", A.stream(), A.ptr(s5), A.ptr(out2bar), math.prod(A.shape(s5)[1:]), A.ptr(out))
+        return out
+
+    def bias_weights(self, vals, growth, coef, want_dvel=True):
+        """weights [np], dvel [np, 3], moments (float64 [2], kept for the reverse pass); growth: float or [np] array."""
+        A = self.A
+        vals = A.prepare(vals)
+        n, K = A.shape(vals)
+        garr = None if isinstance(growth, float) else A.prepare(growth)
+        gs = growth if garr is None else 0.0
+        mom = A.zeros((2,), "f64")
+        self._call("mcpm_bias_moments", A.stream(), A.ptr(vals), K, gs, A.ptr(garr), n, A.ptr(mom))
+        w, dv = A.empty((n,)), (A.empty((n, 3)) if want_dvel else None)
+        self._call("mcpm_bias_weights", A.stream(), A.ptr(vals), K, gs, A.ptr(garr), host_floats(coef), A.ptr(mom), n,
+                   A.ptr(w), A.ptr(dv))
+        return w, dv, mom
+
+    def bias_weights_vjp(self, vals, growth, coef, mom, wbar, dvelbar=None):
+        """-> valsbar [np, K], coefbar float64 [14] (13 coefficients + scalar growth), gbar [np] or None."""
+        A = self.A
+        vals, wbar = A.prepare(vals), A.prepare(wbar)
+        n, K = A.shape(vals)
+        garr = None if isinstance(growth, float) else A.prepare(growth)
+        gs = growth if garr is None else 0.0
+        dvb = None if dvelbar is None else A.prepare(dvelbar)
+        msum, cb = A.zeros((2,), "f64"), A.zeros((14,), "f64")
+        vb = A.empty((n, K))
+        gb = A.empty((n,)) if garr is not None else None
+        self._call("mcpm_bias_weights_vjp", A.stream(), A.ptr(vals), K, gs, A.ptr(garr), host_floats(coef), A.ptr(mom),
+                   A.ptr(wbar), A.ptr(dvb), n, A.ptr(msum), A.ptr(vb), A.ptr(cb), A.ptr(gb))
+        return vb, cb, gb
 
     def rsd_shift(self, pos, vel, los, coef):
         A = self.A

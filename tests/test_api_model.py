@@ -352,6 +352,49 @@ def test_lagrangian_bias_weights_and_gradient(nb, golden):
     assert rel(gdk.grad, dko.grad) < 2e-4
 
 
+def test_lagrangian_bias_fused_passes_match_composition(nb, golden):
+    """The fused passes of csrc/bias.cu behind bricks.lagrangian_bias against round 1's pointwise-torch composition of the
+    same expansion (bricks.lagrangian_bias_composed, itself pinned to the reference source's golden vectors): weights,
+    dvel and phi, and the cotangents of EVERY differentiable input -- linear mesh, positions, the 8 bias and 5 PNG
+    coefficients, and the growth factor (scalar scale factor and per-particle light-cone scale factors) -- 2e-4.
+    bricks.py:327-452."""
+    from montecosmo_b200 import bricks as B
+    from montecosmo_b200.cosmo import Cosmology
+    gd = golden("lagrangian_bias")
+    kpow = (gd["kpow_k"], gd["kpow_p"])
+    rng = np.random.default_rng(77)
+    shape, box = (8, 10, 12), (80.0, 100.0, 96.0)
+    dk0 = np.fft.rfftn(rng.normal(size=shape)) * 0.05
+    q = O.regular_pos(shape)
+    pos0 = (q + torch.tensor(rng.normal(scale=0.4, size=q.shape))).float()
+    bias0 = dict(b1=0.8, b2=0.3, bs2=-0.2, b3=0.1, bds2=0.05, bs3=-0.07, bn2=0.4, bnpar=0.6)
+    png0 = dict(fNL_bp=0.5, fNL_bpd=-0.3, fNL_bpd2=0.2, fNL_bps2=0.1, fNL_bn2p=-0.4)
+    cw = torch.tensor(rng.normal(size=q.shape[0]), dtype=torch.float32, device=dev(nb))
+    cv = torch.tensor(rng.normal(size=q.shape), dtype=torch.float32, device=dev(nb))
+    cp = torch.tensor(rng.normal(size=shape), dtype=torch.float32, device=dev(nb))
+    a_lightcone = torch.tensor(rng.uniform(0.4, 0.9, q.shape[0]))
+    for png_type, a in ((None, 0.7), ("fNL", 0.7), ("fNL", a_lightcone)):
+        out = {}
+        for fn in (B.lagrangian_bias, B.lagrangian_bias_composed):
+            dk = torch.tensor(dk0, dtype=torch.complex64, device=dev(nb)).requires_grad_()
+            pos = pos0.to(dev(nb)).requires_grad_()
+            bias = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in bias0.items()}
+            png = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in png0.items()}
+            om = torch.tensor(0.2611, dtype=torch.float64, requires_grad=True)  # Omega_c: the growth factor depends on it
+            w, dvel, phi = fn(Cosmology(Omega_c=om), pos, a, box, dk, bias, png, png_type, kpow, 2)
+            loss = (w * cw).sum() + (dvel * cv).sum() + ((phi * cp).sum() if png_type else 0.0)
+            loss.backward()
+            coefs = [bias[k].grad for k in bias0] + ([png[k].grad for k in png0] if png_type else [])
+            out[fn.__name__] = (w.detach(), dvel.detach(), dk.grad, pos.grad, torch.stack(coefs), om.grad)
+        f, c = out["lagrangian_bias"], out["lagrangian_bias_composed"]
+        tag = (png_type, "lightcone" if isinstance(a, torch.Tensor) else a)
+        assert rel(f[0], c[0]) < 2e-5 and rel(f[1], c[1]) < 2e-5, tag
+        assert rel(f[2], c[2]) < 2e-4, tag          # linear mesh
+        assert rel(f[3], c[3]) < 2e-4, tag          # positions
+        assert rel(f[4], c[4]) < 2e-4, tag          # coefficients
+        assert abs(float(f[5]) - float(c[5])) < 2e-4 * abs(float(c[5])), tag  # cosmology through the growth factor
+
+
 def test_bullfrog_vf_scan_and_host_windows(nb, golden):
     """bullfrog_vf (nbody.py:902-960) against the oracle's drift-kick-drift step; nbody_bf_scan against the same steps in
     a loop; the host-side window helpers against the golden vectors of the reference source."""

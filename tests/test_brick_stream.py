@@ -63,7 +63,7 @@ CASES = [
     ((64, 32, 128), (64, 32, 128), (0, 0, 0), True, False, 0.0, 1.5),
     ((64, 32, 128), (64, 32, 128), (0, 0, 0), False, True, 0.5, 2.5),
     ((16, 40, 64), (64, 40, 64), (24, 0, 0), True, True, 0.0, 2.0),   # a slab rank: 16 planes inside a 64-plane mesh
-    ((8, 8, 32), (18, 18, 44), (3, 2, 1), True, False, 0.0, 0.7),     # one brick, the smallest legal mesh
+    ((8, 8, 32), (26, 18, 44), (3, 2, 1), True, False, 0.0, 0.7),     # one brick, the smallest mesh both kernels take
     ((128, 128, 128), (128, 128, 128), (0, 0, 0), True, True, 0.0, 2.2),  # 1024 bricks: several per resident CTA
 ]
 

@@ -37,6 +37,8 @@ int tune_set(Tune& t, const char* key, int value) {
   } else if (k == "brick_stream") {
     if (value != 0 && value != 1 && value != 44 && value != 48) return bad("brick_stream must be 0, 44 or 48");
     t.brick_stream = value == 1 ? 44 : value;
+  } else if (k == "brick_stream1") {
+    t.brick_stream1 = value != 0;
   } else if (k == "gather_tma") {
     t.gather_tma = value != 0;
   } else if (k == "yzfft") {

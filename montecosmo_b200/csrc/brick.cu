@@ -742,7 +742,11 @@ static bool stream_ok(const BrickArgs& a) {
 template <int NCH>
 static int launch_brick(stream_t st, const BrickArgs& a) {
   using namespace brick;
-  if (stream_ok(a)) {
+  // Measured on a B200 at 256^3 (profiles/r2_brick_stream.txt): the 3-channel reverse scatter gains 10 % early in a run and
+  // nothing at a = 1 (0.351 vs 0.392 ms, 0.435 vs 0.438); the density paint LOSES 6-15 % (0.173 vs 0.163, 0.210 vs 0.183:
+  // one channel does not amortise the per-brick passes over a tile a third of whose rows it never touches) and keeps the
+  // per-brick kernel unless mcpm_tune("brick_stream1", 1).
+  if (stream_ok(a) && (NCH == 3 || tune().brick_stream1)) {
     const bool wide = tune().brick_stream == 48;
     if (a.rel) return wide ? launch_stream<NCH, 48, true>(st, a) : launch_stream<NCH, 44, true>(st, a);
     return wide ? launch_stream<NCH, 48, false>(st, a) : launch_stream<NCH, 44, false>(st, a);

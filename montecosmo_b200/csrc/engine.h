@@ -22,7 +22,8 @@ struct Tune {
   int gather_minb = 4;     // resident CTAs per SM the cic4.cu gathers are compiled for (4 | 5 | 6)
   int gather_blocked = 0;  // cic4.cu gathers: one CTA per 256 consecutive particles instead of a grid-stride loop
   int brick = 1;           // brick-tiled shared-memory scatters (brick.cu) where they apply; 0: generic global atomics
-  int brick_stream = 44;   // brick.cu: persistent, bulk-copy staged scatter; value = tile row stride in words (44 | 48), 0: off
+  int brick_stream = 44;   // brick.cu: persistent, bulk-copy staged 3-channel scatter; value = tile row stride in words (44 | 48), 0: off
+  int brick_stream1 = 0;   // ... also for the 1-channel density paint (measured slower than the per-brick kernel)
   int gather_tma = 1;      // gathers with bulk-copy staged particle arrays (cic4_tma.cu) where they apply
   int gather_seg = 32;     // particles per bulk copy there (32 | 64 | 128)
   // Both measured on a B200 in round 2 and left OFF (profiles/r2_tune_*.txt): the fused (y,z) kernel runs 84 / 96 us per

@@ -96,6 +96,7 @@ def test_stream_scatter_matches_generic(lattice, mesh, origin, relative, weights
     tune = lambda key, v: ops._call("mcpm_tune", key, v)
     ref, ref3 = _reference(*args)
     try:
+        tune(b"brick_stream1", 1)  # the density paint takes the streaming kernel only on request
         res = {}
         for knob in (0, 44, 48):
             tune(b"brick_stream", knob)
@@ -112,6 +113,7 @@ def test_stream_scatter_matches_generic(lattice, mesh, origin, relative, weights
         assert _rel(res[44][0], res[48][0]) < 1e-6
     finally:
         tune(b"brick_stream", 44)
+        tune(b"brick_stream1", 0)
 
 
 def test_stream_scatter_overflowing_brick_falls_back():
@@ -137,6 +139,7 @@ def test_stream_scatter_overflowing_brick_falls_back():
     ref, ref3 = _reference(*args)
     tune = lambda key, v: ops._call("mcpm_tune", key, v)
     try:
+        tune(b"brick_stream1", 1)
         for knob in (0, 44):
             tune(b"brick_stream", knob)
             out, out3 = _scatter(*args)
@@ -147,3 +150,4 @@ def test_stream_scatter_overflowing_brick_falls_back():
                 assert _rel(out3[c], ref3[c]) < 2e-5, (knob, c)
     finally:
         tune(b"brick_stream", 44)
+        tune(b"brick_stream1", 0)

@@ -26,6 +26,7 @@ st = A.stream()
 fr = Frame(1, n, n, n, 0, 0, 0, n, n, n)
 mesh, mesh3 = torch.zeros((n, n, n), device=dev), torch.zeros((3, n, n, n), device=dev)
 vbar = torch.randn((N, 3), device=dev, generator=g)
+lib.mcpm_tune(b"brick_stream1", 1)
 for a1 in (0.3, 1.0):
     pos, vel = nb.nbody_bf(m.cosmology, dk, m.q, 0.0, a1, 10, ptcl_shape=None)
     d = (pos[0] - m.q)
@@ -39,3 +40,4 @@ for a1 in (0.3, 1.0):
         print(f"a={a1} disp rms {float(d.std()):.2f}  brick_stream={knob:2d}: paint {p1[0]:.4f} ms (min {p1[1]:.4f})   "
               f"paint3 {p3[0]:.4f} ms (min {p3[1]:.4f})   [memsets included]", flush=True)
 lib.mcpm_tune(b"brick_stream", 44)
+lib.mcpm_tune(b"brick_stream1", 0)

@@ -17,7 +17,7 @@ lib, dev = nb.ops().lib, nb.ops().A.device
 g = torch.Generator(device=dev).manual_seed(0)
 obs = 1.0 + torch.randn(m.mesh_shape, device=dev, generator=g)
 w = torch.randn(m.mesh_shape, device=dev, generator=g)
-defaults = {"gather_blocked": 0, "gather_minb": 4, "side_zero": 0, "gather_tma": 1, "gather_seg": 32, "brick": 1, "gather_brick": 0, "yzfft": 0, "brick_stream": 44}
+defaults = {"gather_blocked": 0, "gather_minb": 4, "side_zero": 0, "gather_tma": 1, "gather_seg": 32, "brick": 1, "gather_brick": 0, "yzfft": 0, "brick_stream": 44, "brick_stream1": 0}
 for s in settings:
     cur = dict(defaults)
     if s != "base":

@@ -516,6 +516,18 @@ int mcpm_nufft_vjp(mcpm_engine* eng, void* stream, const float* pos, const float
                    int64_t np, const float scale[3], int paint_order, int interlace_order, int paint_deconv,
                    const void* outbar_k, float* posbar, float* weightsbar);
 
+/* nufft of REDSHIFT-SPACE positions with the flat-sky shift applied inside the paint kernels (model.py:780-809 with
+ * bricks.py:781-792 in cell units): every particle is deposited at pos + (vel . los) * coef * los, which is never
+ * written to memory.  _vjp additionally returns velbar [np,3] = coef * (xbar . los) * los (posbar is the cotangent of
+ * pos itself, as in mcpm_nufft_vjp). */
+int mcpm_nufft_rsd(mcpm_engine* eng, void* stream, const float* pos, const float* vel, const float los[3], float coef,
+                   const float* weights, float wscalar, int64_t np, const float scale[3], int paint_order,
+                   int interlace_order, int paint_deconv, void* out_k);
+int mcpm_nufft_rsd_vjp(mcpm_engine* eng, void* stream, const float* pos, const float* vel, const float los[3], float coef,
+                       const float* weights, float wscalar, int64_t np, const float scale[3], int paint_order,
+                       int interlace_order, int paint_deconv, const void* outbar_k, float* posbar, float* velbar,
+                       float* weightsbar);
+
 /* nufft / its VJP with kernel_type = 'kaiser_bessel' (nbody.py:532-577 with the window of 280-312). */
 int mcpm_nufft_kb(mcpm_engine* eng, void* stream, const float* pos, const float* weights, float wscalar, int64_t np,
                   const float scale[3], int paint_order, float kcut, int interlace_order, int paint_deconv,

@@ -120,6 +120,8 @@ SIGNATURES = {
     "mcpm_nbody_steps": ([vp, vp, vp, vp, i64, i32, hp, hp, hp, hp, i32, i32, i32, i32, vp, vp, vp], i32),
     "mcpm_nbody_steps_vjp": ([vp, vp, vp, vp, i64, i32, hp, hp, hp, hp, i32, i32, i32, i32, vp, vp, vp, vp, vp], i32),
     "mcpm_nufft": ([vp, vp, vp, vp, f32, i64, hp, i32, i32, i32, vp], i32),
+    "mcpm_nufft_rsd": ([vp, vp, vp, vp, hp, f32, vp, f32, i64, hp, i32, i32, i32, vp], i32),
+    "mcpm_nufft_rsd_vjp": ([vp, vp, vp, vp, hp, f32, vp, f32, i64, hp, i32, i32, i32, vp, vp, vp, vp], i32),
     "mcpm_nufft_vjp": ([vp, vp, vp, vp, f32, i64, hp, i32, i32, i32, vp, vp, vp], i32),
     "mcpm_nufft_kb": ([vp, vp, vp, vp, f32, i64, hp, i32, f32, i32, i32, vp], i32),
     "mcpm_nufft_vjp_kb": ([vp, vp, vp, vp, f32, i64, hp, i32, f32, i32, i32, vp, vp, vp], i32),

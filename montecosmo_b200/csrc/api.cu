@@ -1203,6 +1203,31 @@ int mcpm_nufft_vjp(mcpm_engine* eng, void* stream, const float* pos, const float
   API_END
 }
 
+int mcpm_nufft_rsd(mcpm_engine* eng, void* stream, const float* pos, const float* vel, const float los[3], float coef,
+                   const float* weights, float wscalar, int64_t np, const float scale[3], int paint_order,
+                   int interlace_order, int paint_deconv, void* out_k) {
+  API_BEGIN
+  NEED(eng && out_k && los && (np == 0 || (pos && vel)), "nufft_rsd: null pointer");
+  BIND(eng);
+  const ObsShift obs = {vel, los[0], los[1], los[2], coef};
+  return nufft(eng->e, as_stream(stream), pos, weights, wscalar, np, scale, paint_order, interlace_order, paint_deconv,
+               C(out_k), 0.0f, &obs);
+  API_END
+}
+
+int mcpm_nufft_rsd_vjp(mcpm_engine* eng, void* stream, const float* pos, const float* vel, const float los[3], float coef,
+                       const float* weights, float wscalar, int64_t np, const float scale[3], int paint_order,
+                       int interlace_order, int paint_deconv, const void* outbar_k, float* posbar, float* velbar,
+                       float* weightsbar) {
+  API_BEGIN
+  NEED(eng && outbar_k && los && (np == 0 || (pos && vel)), "nufft_rsd_vjp: null pointer");
+  BIND(eng);
+  const ObsShift obs = {vel, los[0], los[1], los[2], coef};
+  return nufft_vjp(eng->e, as_stream(stream), pos, weights, wscalar, np, scale, paint_order, interlace_order,
+                   paint_deconv, C(outbar_k), posbar, weightsbar, 0.0f, &obs, velbar);
+  API_END
+}
+
 int mcpm_nufft_kb(mcpm_engine* eng, void* stream, const float* pos, const float* weights, float wscalar, int64_t np,
                   const float scale[3], int paint_order, float kcut, int interlace_order, int paint_deconv,
                   void* out_k) {

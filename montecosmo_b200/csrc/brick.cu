@@ -55,6 +55,7 @@ struct BrickArgs {
   const float* A;
   float s;
   float* mesh;  // NCH planar meshes
+  ObsShift obs;  // NCH = 1: optional redshift-space shift of the painted position (engine.h)
 };
 
 // thread (warp, lane), slot r -> lattice offsets inside the brick.  Slot 0 of the 16 warps samples all 16 x-planes and
@@ -101,9 +102,17 @@ __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickA
       valid |= 1u << r;
       const float* xr = xp + di * plane3;
       const float sx = a.rel ? 0.f : (float)(q0i + di + a.ox);
-      x[r][0] = (xr[0] + a.shift) - sx;
-      x[r][1] = (xr[1] + a.shift) - sy;
-      x[r][2] = (xr[2] + a.shift) - sz;
+      float p0 = xr[0], p1 = xr[1], p2 = xr[2];
+      if (NCH == 1 && a.obs.vel) {  // fused redshift-space shift, associated as rsd_shift (paint.cu) does
+        const float* vr = a.obs.vel + pbase + di * plane3;
+        const float sh = (vr[0] * a.obs.lx + vr[1] * a.obs.ly + vr[2] * a.obs.lz) * a.obs.coef;
+        p0 = p0 + sh * a.obs.lx;
+        p1 = p1 + sh * a.obs.ly;
+        p2 = p2 + sh * a.obs.lz;
+      }
+      x[r][0] = (p0 + a.shift) - sx;
+      x[r][1] = (p1 + a.shift) - sy;
+      x[r][2] = (p2 + a.shift) - sz;
     } else {
       x[r][0] = x[r][1] = x[r][2] = 0.f;
     }
@@ -341,9 +350,17 @@ template <int NCH>
 __device__ __forceinline__ void stray_deposit(const BrickArgs& a, int si0, int sj0, int sk0) {
   const int64_t plane = (int64_t)a.nx * a.ny * a.nz;
   const int64_t p3 = 3 * (((int64_t)si0 * a.py + sj0) * a.pz + sk0);
-  const float px = (a.pos[p3] + a.shift) - (a.rel ? 0.f : (float)(si0 + a.ox)),
-              py = (a.pos[p3 + 1] + a.shift) - (a.rel ? 0.f : (float)(sj0 + a.oy)),
-              pz = (a.pos[p3 + 2] + a.shift) - (a.rel ? 0.f : (float)(sk0 + a.oz));
+  float r0 = a.pos[p3], r1 = a.pos[p3 + 1], r2 = a.pos[p3 + 2];
+  if (NCH == 1 && a.obs.vel) {
+    const float* vr = a.obs.vel + p3;
+    const float sh = (vr[0] * a.obs.lx + vr[1] * a.obs.ly + vr[2] * a.obs.lz) * a.obs.coef;
+    r0 = r0 + sh * a.obs.lx;
+    r1 = r1 + sh * a.obs.ly;
+    r2 = r2 + sh * a.obs.lz;
+  }
+  const float px = (r0 + a.shift) - (a.rel ? 0.f : (float)(si0 + a.ox)),
+              py = (r1 + a.shift) - (a.rel ? 0.f : (float)(sj0 + a.oy)),
+              pz = (r2 + a.shift) - (a.rel ? 0.f : (float)(sk0 + a.oz));
   float vv[NCH];
   if (NCH == 1) {
     vv[0] = (a.w ? a.w[p3 / 3] : 1.0f) * a.ws;
@@ -732,7 +749,7 @@ static int launch_stream(stream_t st, const BrickArgs& a) {
 }
 static bool stream_ok(const BrickArgs& a) {
   using namespace bstream;
-  if (!tune().brick_stream) return false;
+  if (!tune().brick_stream || a.obs.vel) return false;  // the fused redshift-space shift lives in the per-brick kernel
   if (a.px % BX || a.py % BY || a.pz % BZ) return false;
   if (a.nx < TX || a.ny < TY || a.nz < TZ) return false;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
@@ -777,10 +794,11 @@ static void set_frame(BrickArgs& a, const Frame* fr) {
 }
 
 int brick_paint_cic(stream_t st, const Lattice& L, const float* pos, const float* weights, float wscalar, float shift,
-                    int64_t np, int nx, int ny, int nz, float* mesh, const Frame* fr) {
+                    int64_t np, int nx, int ny, int nz, float* mesh, const Frame* fr, const ObsShift* obs) {
   if (!brick_ok(L, np, nx, ny, nz) || !frame_fits(L, fr)) return 0;
   BrickArgs a = {};
   set_frame(a, fr);
+  if (obs) a.obs = *obs;
   a.px = L.px; a.py = L.py; a.pz = L.pz; a.nx = nx; a.ny = ny; a.nz = nz;
   a.inx = 1.0f / nx; a.iny = 1.0f / ny; a.inz = 1.0f / nz;
   a.shift = shift;

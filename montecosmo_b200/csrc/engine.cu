@@ -74,18 +74,19 @@ static bool brick_path(const Engine* E, int order, const float* scale) {
 }
 // `prezeroed`: the caller guarantees the mesh is already zero (cleared on the side by the previous step's kernel)
 static int paint_fresh(Engine* E, stream_t st, const float* pos, const float* weights, float wscalar, int64_t np,
-                       int order, const float* scale, float shift, float* mesh, bool prezeroed = false) {
+                       int order, const float* scale, float shift, float* mesh, bool prezeroed = false,
+                       const ObsShift* obs = nullptr) {
   Frame f;
   const Frame* fr = E->frame(f);
 #ifndef MCPM_HOSTEMU
   if (brick_path(E, order, scale) && pos) {
     if (!prezeroed && rt_memset(mesh, 0, sizeof(float) * (size_t)E->N, st)) return MCPM_ECUDA;
-    int r = brick_paint_cic(st, E->lat, pos, weights, wscalar, shift, np, E->nx, E->ny, E->nz, mesh, fr);
+    int r = brick_paint_cic(st, E->lat, pos, weights, wscalar, shift, np, E->nx, E->ny, E->nz, mesh, fr, obs);
     if (r < 0) return MCPM_ECUDA;
     if (r == 1) return 0;
   }
 #endif
-  return paint(st, pos, weights, wscalar, np, E->nx, E->ny, E->nz, order, scale, shift, mesh, 0, 0.0f, fr);
+  return paint(st, pos, weights, wscalar, np, E->nx, E->ny, E->nz, order, scale, shift, mesh, 0, 0.0f, fr, obs);
 }
 static int paint_density(Engine* E, stream_t st, const float* pos, int64_t np, int order, float* mesh,
                          bool prezeroed = false) {
@@ -437,7 +438,8 @@ int nbody_steps_vjp(Engine* E, stream_t st, float* posbar, float* velbar, int64_
 // nufft at the paint shape (nbody.py:569-574): m interlaced paints -> batched R2C -> one combine pass
 // kb_kcut > 0: Kaiser-Bessel window (paint and its deconvolution, nbody.py:321-322, 383-384) instead of `rectangular`.
 int nufft(Engine* E, stream_t st, const float* pos, const float* weights, float wscalar, int64_t np,
-          const float* scale, int paint_order, int interlace_order, int paint_deconv, cfloat* out_k, float kb_kcut) {
+          const float* scale, int paint_order, int interlace_order, int paint_deconv, cfloat* out_k, float kb_kcut,
+          const ObsShift* obs) {
   const int m = interlace_order;
   if (m < 1 || m > Engine::kR - 1) {
     set_error("nufft: interlace_order must be in 1..6");
@@ -450,9 +452,9 @@ int nufft(Engine* E, stream_t st, const float* pos, const float* weights, float 
   for (int i = 0; i < m; ++i) {
     if (kb)
       TRY(paint(st, pos, weights, wscalar, np, E->nx, E->ny, E->nz, paint_order, scale, (float)i / (float)m, E->r(i), 0,
-                kb_kcut, fr));
+                kb_kcut, fr, obs));
     else
-      TRY(paint_fresh(E, st, pos, weights, wscalar, np, paint_order, scale, (float)i / (float)m, E->r(i)));
+      TRY(paint_fresh(E, st, pos, weights, wscalar, np, paint_order, scale, (float)i / (float)m, E->r(i), false, obs));
   }
   TRY(fft_r2c(E->fft, st, E->r(0), E->c(0), m));
   TRY(interlace_combine(st, E->c(0), out_k, m, E->nx, E->ny, E->nz, jac, paint_deconv && !kb ? paint_order : 0));
@@ -462,7 +464,7 @@ int nufft(Engine* E, stream_t st, const float* pos, const float* weights, float 
 
 int nufft_vjp(Engine* E, stream_t st, const float* pos, const float* weights, float wscalar, int64_t np,
               const float* scale, int paint_order, int interlace_order, int paint_deconv, const cfloat* outbar_k,
-              float* posbar, float* weightsbar, float kb_kcut) {
+              float* posbar, float* weightsbar, float kb_kcut, const ObsShift* obs, float* velbar) {
   const int m = interlace_order;
   if (m < 1 || m > Engine::kR - 1) {
     set_error("nufft: interlace_order must be in 1..6");
@@ -484,7 +486,7 @@ int nufft_vjp(Engine* E, stream_t st, const float* pos, const float* weights, fl
   const Frame* fr = E->frame(f);
   for (int i = 0; i < m; ++i)
     TRY(paint_vjp(st, pos, weights, wscalar, E->r(i), np, E->nx, E->ny, E->nz, paint_order, scale,
-                  (float)i / (float)m, posbar, weightsbar, i > 0, kb_kcut, fr));
+                  (float)i / (float)m, posbar, weightsbar, i > 0, kb_kcut, fr, obs, velbar));
   return 0;
 }
 

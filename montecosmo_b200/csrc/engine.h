@@ -12,6 +12,13 @@ struct Lattice {
   int px = 0, py = 0, pz = 0;
 };
 
+// Flat-sky redshift-space shift applied INSIDE a paint (bricks.py:781-792 in cell units): the particle is deposited at
+// pos + (vel . los) * coef * los without that position ever being written to memory.  vel == NULL: no shift.
+struct ObsShift {
+  const float* vel = nullptr;
+  float lx = 0.f, ly = 0.f, lz = 0.f, coef = 0.f;
+};
+
 // Performance knobs (never change which result is computed).  mcpm_tune sets the process-wide defaults, which every
 // engine copies at creation; mcpm_engine_tune changes one engine.  Kernels read the knobs of the engine whose entry point
 // is executing on the calling host thread (a thread-local pointer held for the duration of the call), so engines on
@@ -73,7 +80,7 @@ void engine_destroy(Engine*);
 // paint.cu.  kb_kcut > 0 selects the Kaiser-Bessel window with that cutoff (nbody.py:280-290) instead of `rectangular`.
 int paint(stream_t, const float* pos, const float* weights, float wscalar, int64_t np, int nx, int ny, int nz,
           int order, const float* scale, float shift, float* mesh, int accumulate, float kb_kcut = 0.0f,
-          const Frame* fr = nullptr);
+          const Frame* fr = nullptr, const ObsShift* obs = nullptr);
 int read(stream_t, const float* pos, const float* mesh, int nmesh, int64_t np, int nx, int ny, int nz, int order,
          const float* scale, float shift, float* out, float kb_kcut = 0.0f, const Frame* fr = nullptr);
 int read_grad(stream_t, const float* pos, const float* const* meshes, int nmesh, const float* cot, int ncot,
@@ -83,7 +90,8 @@ int paint3(stream_t, const float* pos, const float* A, float ca, const float* B,
            int ny, int nz, int order, float* mesh3, int accumulate, const Frame* fr = nullptr);
 int paint_vjp(stream_t, const float* pos, const float* weights, float wscalar, const float* mbar, int64_t np, int nx,
               int ny, int nz, int order, const float* scale, float shift, float* posbar, float* wbar,
-              int accumulate, float kb_kcut = 0.0f, const Frame* fr = nullptr);
+              int accumulate, float kb_kcut = 0.0f, const Frame* fr = nullptr, const ObsShift* obs = nullptr,
+              float* velbar = nullptr);
 int kick_drift(stream_t, const float* pos, const float* vel, const float* fmesh3, int64_t np, int nx, int ny, int nz,
                int order, float alpha, float beta, float drift, float* pos_out, float* vel_out, float* force_out,
                const Frame* fr = nullptr);
@@ -216,7 +224,7 @@ int xfuse_hessian_tk(stream_t, const cfloat* in6, cfloat* out, int nx, int ny, i
 
 // brick.cu (CUDA build only): return 1 if handled, 0 if the generic path must be taken, < 0 on error
 int brick_paint_cic(stream_t, const Lattice&, const float* pos, const float* weights, float wscalar, float shift,
-                    int64_t np, int nx, int ny, int nz, float* mesh, const Frame* fr = nullptr);
+                    int64_t np, int nx, int ny, int nz, float* mesh, const Frame* fr = nullptr, const ObsShift* obs = nullptr);
 int brick_paint3_cic(stream_t, const Lattice&, const float* pos, const float* A, float s, int64_t np, int nx, int ny,
                      int nz, float* mesh3, const Frame* fr = nullptr);
 
@@ -243,9 +251,10 @@ int nbody_steps_vjp(Engine*, stream_t, float* posbar, float* velbar, int64_t np,
                     int lap_fd, int grad_fd, const float* xk, const float* vk, const float* fm, const float* v0,
                     double* coefbar);
 int nufft(Engine*, stream_t, const float* pos, const float* weights, float wscalar, int64_t np, const float* scale,
-          int paint_order, int interlace_order, int paint_deconv, cfloat* out_k, float kb_kcut = 0.0f);
+          int paint_order, int interlace_order, int paint_deconv, cfloat* out_k, float kb_kcut = 0.0f, const ObsShift* obs = nullptr);
 int nufft_vjp(Engine*, stream_t, const float* pos, const float* weights, float wscalar, int64_t np,
               const float* scale, int paint_order, int interlace_order, int paint_deconv, const cfloat* outbar_k,
-              float* posbar, float* weightsbar, float kb_kcut = 0.0f);
+              float* posbar, float* weightsbar, float kb_kcut = 0.0f,
+              const ObsShift* obs = nullptr, float* velbar = nullptr);
 
 }  // namespace mcpm

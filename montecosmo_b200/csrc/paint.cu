@@ -17,6 +17,7 @@ struct MeshDims {
 struct PosXform {
   float sx, sy, sz, shift;
   Frame fr;  // absolute or lattice-relative positions (frame.h)
+  ObsShift obs;  // optional redshift-space shift added to the position before scale / shift (engine.h)
 };
 
 // Transformed coordinate of particle p as an exact integer part b (its lattice site; 0 for absolute frames) plus a small
@@ -25,7 +26,14 @@ struct PosXform {
 MCPM_HD void load_pos(const float* pos, int64_t p, const PosXform& xf, int* b, float* u) {
   float r0, r1, r2;
   frame_site(xf.fr, p, b[0], b[1], b[2], r0, r1, r2);
-  const float d0 = pos ? pos[3 * p] : 0.0f, d1 = pos ? pos[3 * p + 1] : 0.0f, d2 = pos ? pos[3 * p + 2] : 0.0f;
+  float d0 = pos ? pos[3 * p] : 0.0f, d1 = pos ? pos[3 * p + 1] : 0.0f, d2 = pos ? pos[3 * p + 2] : 0.0f;
+  if (xf.obs.vel) {  // the same association as rsd_shift: pos + ((v . los) * coef) * los
+    const float* v = xf.obs.vel + 3 * p;
+    const float sh = (v[0] * xf.obs.lx + v[1] * xf.obs.ly + v[2] * xf.obs.lz) * xf.obs.coef;
+    d0 = d0 + sh * xf.obs.lx;
+    d1 = d1 + sh * xf.obs.ly;
+    d2 = d2 + sh * xf.obs.lz;
+  }
   u[0] = r0 + (d0 * xf.sx + xf.shift);
   u[1] = r1 + (d1 * xf.sy + xf.shift);
   u[2] = r2 + (d2 * xf.sz + xf.shift);
@@ -229,7 +237,7 @@ static void paint3_impl(stream_t st, const float* pos, const float* A, float ca,
 template <int ORDER, class WIN = RectWin>
 static void paint_vjp_impl(stream_t st, const float* pos, const float* weights, float wscalar, const float* mbar,
                            int64_t np, MeshDims n, PosXform xf, float* posbar, float* wbar, int accumulate,
-                           WIN win = WIN()) {
+                           float* velbar, WIN win = WIN()) {
   launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
     int sb[3], fx, fy, fz;
     float su[3];
@@ -270,6 +278,13 @@ static void paint_vjp_impl(stream_t st, const float* pos, const float* weights, 
       g[0] = (accumulate ? g[0] : 0.0f) + g0 * xf.sx * wp;
       g[1] = (accumulate ? g[1] : 0.0f) + g1 * xf.sy * wp;
       g[2] = (accumulate ? g[2] : 0.0f) + g2 * xf.sz * wp;
+    }
+    if (velbar) {  // transpose of the fused redshift-space shift: velbar (+)= coef * (xbar . los) * los
+      const float sh = (g0 * xf.sx * wp * xf.obs.lx + g1 * xf.sy * wp * xf.obs.ly + g2 * xf.sz * wp * xf.obs.lz) * xf.obs.coef;
+      float* o = velbar + 3 * p;
+      o[0] = (accumulate ? o[0] : 0.0f) + sh * xf.obs.lx;
+      o[1] = (accumulate ? o[1] : 0.0f) + sh * xf.obs.ly;
+      o[2] = (accumulate ? o[2] : 0.0f) + sh * xf.obs.lz;
     }
   });
 }
@@ -350,8 +365,8 @@ static int check_mesh(int nx, int ny, int nz, int order) {
   return 0;
 }
 
-static PosXform make_xform(const float* scale, float shift, const Frame* fr = nullptr) {
-  PosXform xf = {1.0f, 1.0f, 1.0f, shift, fr ? *fr : Frame()};
+static PosXform make_xform(const float* scale, float shift, const Frame* fr = nullptr, const ObsShift* obs = nullptr) {
+  PosXform xf = {1.0f, 1.0f, 1.0f, shift, fr ? *fr : Frame(), obs ? *obs : ObsShift()};
   if (scale) {
     xf.sx = scale[0];
     xf.sy = scale[1];
@@ -361,14 +376,15 @@ static PosXform make_xform(const float* scale, float shift, const Frame* fr = nu
 }
 
 int paint(stream_t st, const float* pos, const float* weights, float wscalar, int64_t np, int nx, int ny, int nz,
-          int order, const float* scale, float shift, float* mesh, int accumulate, float kb_kcut, const Frame* fr) {
+          int order, const float* scale, float shift, float* mesh, int accumulate, float kb_kcut, const Frame* fr,
+          const ObsShift* obs) {
   if (int e = check_mesh(nx, ny, nz, order)) return e;
   if (!mesh || (np > 0 && !pos && !(fr && fr->rel))) {
     set_error("paint: null pointer");
     return MCPM_EINVAL;
   }
   MeshDims n = {nx, ny, nz};
-  PosXform xf = make_xform(scale, shift, fr);
+  PosXform xf = make_xform(scale, shift, fr, obs);
   if (!accumulate) rt_memset(mesh, 0, sizeof(float) * (size_t)nx * ny * nz, st);
   if (kb_kcut > 0.0f) {
     KbWin kb = make_kbwin(order, kb_kcut);
@@ -489,29 +505,30 @@ int paint3(stream_t st, const float* pos, const float* A, float ca, const float*
 
 int paint_vjp(stream_t st, const float* pos, const float* weights, float wscalar, const float* mbar, int64_t np,
               int nx, int ny, int nz, int order, const float* scale, float shift, float* posbar, float* wbar,
-              int accumulate, float kb_kcut, const Frame* fr) {
+              int accumulate, float kb_kcut, const Frame* fr, const ObsShift* obs, float* velbar) {
   if (int e = check_mesh(nx, ny, nz, order)) return e;
   if (np > 0 && ((!pos && !(fr && fr->rel)) || !mbar)) {
     set_error("paint_vjp: null pointer");
     return MCPM_EINVAL;
   }
   MeshDims n = {nx, ny, nz};
-  PosXform xf = make_xform(scale, shift, fr);
+  PosXform xf = make_xform(scale, shift, fr, obs);
+  if (!(obs && obs->vel)) velbar = nullptr;
   if (kb_kcut > 0.0f) {
     KbWin kb = make_kbwin(order, kb_kcut);
     switch (order) {
-      case 1: paint_vjp_impl<1>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, kb); break;
-      case 2: paint_vjp_impl<2>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, kb); break;
-      case 3: paint_vjp_impl<3>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, kb); break;
-      default: paint_vjp_impl<4>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, kb); break;
+      case 1: paint_vjp_impl<1>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar, kb); break;
+      case 2: paint_vjp_impl<2>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar, kb); break;
+      case 3: paint_vjp_impl<3>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar, kb); break;
+      default: paint_vjp_impl<4>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar, kb); break;
     }
     return rt_check("paint_vjp");
   }
   switch (order) {
-    case 1: paint_vjp_impl<1>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate); break;
-    case 2: paint_vjp_impl<2>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate); break;
-    case 3: paint_vjp_impl<3>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate); break;
-    default: paint_vjp_impl<4>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate); break;
+    case 1: paint_vjp_impl<1>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar); break;
+    case 2: paint_vjp_impl<2>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar); break;
+    case 3: paint_vjp_impl<3>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar); break;
+    default: paint_vjp_impl<4>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar); break;
   }
   return rt_check("paint_vjp");
 }

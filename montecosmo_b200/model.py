@@ -170,11 +170,11 @@ class FieldModel:
             pos, vel = pos[-1], vel[-1]
         else:
             raise ValueError(f"unknown evolution {self.evolution}")
-        if self.rsd:
-            coef = float(_cosmo.a2g(c, self.a_obs) * _cosmo.a2f(c, self.a_obs))
-            pos = _RsdShift.apply(pos, vel, self.los, coef)  # a shift: the same kernel serves displacements
+        rsd = None
+        if self.rsd:  # flat-sky shift (a shift: the same rule serves displacements), applied inside the paint kernels
+            rsd = (vel, self.los, float(_cosmo.a2g(c, self.a_obs) * _cosmo.a2f(c, self.a_obs)))
         gxy = nb.nufft(pos, self.mesh_shape, self.paint_shape, weights, self.paint_order, self.interlace_order,
-                       paint_deconv=self.paint_deconv, lattice=self.mesh_shape if rel else None)
+                       paint_deconv=self.paint_deconv, lattice=self.mesh_shape if rel else None, rsd=rsd)
         if self.paint_shape != self.mesh_shape and self.out_shape == "paint":
             gxy = nb.chreshape(gxy, r2chshape(self.paint_shape))
         return nb.irfftn(gxy)  # 1 + delta_obs at the paint shape (particles == cells: Jacobian 1, model.py:806)

@@ -280,20 +280,26 @@ class _ScaleSpectrum(torch.autograd.Function):
 class _NufftPaint(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pos, weights, paint_shape, wscalar, scale, paint_order, interlace_order, paint_deconv, kb=0.0,
-                lattice=None):
-        ctx.save_for_backward(pos, weights)
-        ctx.cfg = (paint_shape, wscalar, scale, paint_order, interlace_order, paint_deconv, kb, lattice)
+                lattice=None, vel=None, los=None, coef=0.0):
+        ctx.save_for_backward(pos, weights, vel)
+        ctx.cfg = (paint_shape, wscalar, scale, paint_order, interlace_order, paint_deconv, kb, lattice, los, coef)
         return ops().nufft_paint(pos, paint_shape, weights, wscalar, scale, paint_order, interlace_order, paint_deconv,
-                                 kb_kcut=kb, lattice=lattice)
+                                 kb_kcut=kb, lattice=lattice, rsd=None if vel is None else (vel, los, coef))
 
     @staticmethod
     def backward(ctx, kbar):
-        pos, weights = ctx.saved_tensors
-        paint_shape, wscalar, scale, paint_order, interlace_order, paint_deconv, kb, lattice = ctx.cfg
+        pos, weights, vel = ctx.saved_tensors
+        paint_shape, wscalar, scale, paint_order, interlace_order, paint_deconv, kb, lattice, los, coef = ctx.cfg
         need_p, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and weights is not None
-        pb, wb = ops().nufft_paint_vjp(pos, kbar.contiguous(), paint_shape, weights, wscalar, scale, paint_order,
-                                       interlace_order, paint_deconv, need_p, need_w, kb_kcut=kb, lattice=lattice)
-        return pb, wb, None, None, None, None, None, None, None, None
+        if vel is None:
+            pb, wb = ops().nufft_paint_vjp(pos, kbar.contiguous(), paint_shape, weights, wscalar, scale, paint_order,
+                                           interlace_order, paint_deconv, need_p, need_w, kb_kcut=kb, lattice=lattice)
+            vb = None
+        else:  # the shift's transpose rides in the same gather: velbar = coef (xbar . los) los
+            pb, wb, vb = ops().nufft_paint_vjp(pos, kbar.contiguous(), paint_shape, weights, wscalar, scale, paint_order,
+                                               interlace_order, paint_deconv, need_p, need_w, kb_kcut=kb, lattice=lattice,
+                                               rsd=(vel, los, coef))
+        return pb, wb, None, None, None, None, None, None, None, None, vb, None, None
 
 
 class _PmForcesPaint(torch.autograd.Function):
@@ -434,8 +440,12 @@ def interlace(pos, shape: tuple, weights=1.0, paint_order: int = 2, interlace_or
 
 
 def nufft(pos, final_shape: tuple, paint_shape=None, weights=1.0, paint_order: int = 2, interlace_order: int = 2,
-          kernel_type="rectangular", paint_deconv=True, lattice=None):
+          kernel_type="rectangular", paint_deconv=True, lattice=None, rsd=None):
     """Non-uniform FFT with oversampling, deconvolution and interlacing (nbody.py:532-577).
+
+    `rsd` (extension) = (vel, los, coef): paint the redshift-space positions pos + (vel . los) * coef * los of the flat-sky
+    observer (bricks.py:781-792, what model.py:780-809 hands to nufft) with the shift applied inside the paint kernels --
+    one pass over the particles fewer in each direction; differentiable in vel as well.
 
     `lattice` (extension): `pos` holds displacements (in final_shape cells) from the sites of the regular lattice of that
     shape spanning the mesh (regular_pos, bricks.py:593-603) instead of absolute positions -- what
@@ -454,8 +464,10 @@ def nufft(pos, final_shape: tuple, paint_shape=None, weights=1.0, paint_order: i
     kb = _kb_kcut(kernel_type, paint_oversamp)
     scale = tuple(float(p) / float(f) for p, f in zip(paint_shape, final_shape))
     w, ws = _split_weights(weights)
+    vel, los, coef = (None, None, 0.0) if rsd is None else (_f32(rsd[0]), tuple(float(x) for x in rsd[1]), float(rsd[2]))
     mesh = _NufftPaint.apply(_f32(pos), w, paint_shape, ws, scale, int(paint_order), int(interlace_order),
-                             bool(paint_deconv), kb, None if lattice is None else tuple(int(s) for s in lattice))
+                             bool(paint_deconv), kb, None if lattice is None else tuple(int(s) for s in lattice),
+                             vel, los, coef)
     if final_shape != paint_shape:
         mesh = chreshape(mesh, r2chshape(final_shape))
     return mesh

@@ -414,12 +414,23 @@ class Ops:
         return coef
 
     def nufft_paint(self, pos, paint_shape, weights=None, wscalar=1.0, scale=None, paint_order=2, interlace_order=2,
-                    paint_deconv=True, kb_kcut=0.0, lattice=None):
+                    paint_deconv=True, kb_kcut=0.0, lattice=None, rsd=None):
+        """rsd = (vel, los, coef): deposit at pos + (vel . los) * coef * los, the shift applied inside the paint kernels
+        (mcpm_nufft_rsd; rectangular windows)."""
         A = self.A
         pos = A.prepare(pos)
         weights = None if weights is None else A.prepare(weights)
         out = A.empty(r2chshape(paint_shape), "c64")
         sc, _ = self._xf(scale, 0.0)
+        if rsd is not None:
+            if kb_kcut:
+                raise ValueError("the fused redshift-space shift is built for the rectangular windows")
+            vel, los, coef = rsd
+            vel = A.prepare(vel)
+            self._call("mcpm_nufft_rsd", self._frame(paint_shape, lattice).handle, A.stream(), A.ptr(pos), A.ptr(vel),
+                       host_floats(los), float(coef), A.ptr(weights), wscalar, A.shape(pos)[0], sc, paint_order,
+                       interlace_order, int(paint_deconv), A.ptr(out))
+            return out
         fn, oa = self._win("mcpm_nufft", paint_order, kb_kcut)
         self._call(fn, self._frame(paint_shape, lattice).handle, A.stream(), A.ptr(pos), A.ptr(weights), wscalar,
                    A.shape(pos)[0], sc, *oa, interlace_order, int(paint_deconv), A.ptr(out))
@@ -427,7 +438,8 @@ class Ops:
 
     def nufft_paint_vjp(self, pos, outbar, paint_shape, weights=None, wscalar=1.0, scale=None, paint_order=2,
                         interlace_order=2, paint_deconv=True, want_pos=True, want_weights=True, kb_kcut=0.0,
-                        lattice=None):
+                        lattice=None, rsd=None):
+        """-> (posbar, weightsbar), or with rsd = (vel, los, coef): (posbar, weightsbar, velbar)."""
         A = self.A
         pos, outbar = A.prepare(pos), A.prepare(outbar, "c64")
         weights = None if weights is None else A.prepare(weights)
@@ -435,6 +447,14 @@ class Ops:
         pb = A.empty((n, 3)) if want_pos else None
         wb = A.empty((n,)) if want_weights else None
         sc, _ = self._xf(scale, 0.0)
+        if rsd is not None:
+            vel, los, coef = rsd
+            vel = A.prepare(vel)
+            vb = A.empty((n, 3))
+            self._call("mcpm_nufft_rsd_vjp", self._frame(paint_shape, lattice).handle, A.stream(), A.ptr(pos), A.ptr(vel),
+                       host_floats(los), float(coef), A.ptr(weights), wscalar, n, sc, paint_order, interlace_order,
+                       int(paint_deconv), A.ptr(outbar), A.ptr(pb), A.ptr(vb), A.ptr(wb))
+            return pb, wb, vb
         fn, oa = self._win("mcpm_nufft_vjp", paint_order, kb_kcut)
         self._call(fn, self._frame(paint_shape, lattice).handle, A.stream(), A.ptr(pos), A.ptr(weights), wscalar,
                    n, sc, *oa, interlace_order, int(paint_deconv), A.ptr(outbar), A.ptr(pb), A.ptr(wb))

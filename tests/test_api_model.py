@@ -395,6 +395,44 @@ def test_lagrangian_bias_fused_passes_match_composition(nb, golden):
         assert abs(float(f[5]) - float(c[5])) < 2e-4 * abs(float(c[5])), tag  # cosmology through the growth factor
 
 
+def test_nufft_with_fused_redshift_space_shift(nb):
+    """nufft(..., rsd=(vel, los, coef)) -- the flat-sky shift of bricks.py:781-792 applied inside the paint kernels
+    (mcpm_nufft_rsd) -- against the two-pass composition mcpm_rsd_shift -> mcpm_nufft it replaces on the evolve path
+    (model.py:780-809), and against the float64 oracle: half spectrum 1e-6 (same arithmetic, same association), and the
+    cotangents of pos, vel and weights 2e-5.  Absolute positions on a generic mesh (global-atomic kernels, paint mesh
+    1.5x the final one) and lattice-relative displacements on a mesh the brick-tiled kernel takes."""
+    rng = np.random.default_rng(91)
+    los, coef = (0.36, -0.48, 0.8), 0.37
+    for shape, paint, lattice in (((8, 12, 12), (12, 18, 18), None), ((32, 24, 64), None, (32, 24, 64))):
+        n = int(np.prod(shape))
+        q = O.regular_pos(shape)
+        disp = torch.tensor(rng.normal(scale=0.6, size=q.shape)).float()
+        pos0 = disp if lattice else (q.float() + disp)
+        vel0 = torch.tensor(rng.normal(scale=1.5, size=q.shape)).float()
+        w0 = torch.tensor(rng.uniform(0.3, 2.0, n)).float()
+        cshape = tuple(nb.r2chshape(shape)) if hasattr(nb, "r2chshape") else (shape[0], shape[1], shape[2] // 2 + 1)
+        ck = torch.tensor(rng.normal(size=cshape) + 1j * rng.normal(size=cshape)).to(torch.complex64).to(dev(nb))
+        res = []
+        for fused in (True, False):
+            pos, vel, w = (t.clone().to(dev(nb)).requires_grad_() for t in (pos0, vel0, w0))
+            if fused:
+                out = nb.nufft(pos, shape, paint, w, 2, 2, paint_deconv=True, lattice=lattice, rsd=(vel, los, coef))
+            else:
+                from montecosmo_b200.model import _RsdShift
+                out = nb.nufft(_RsdShift.apply(pos, vel, los, coef), shape, paint, w, 2, 2, paint_deconv=True, lattice=lattice)
+            (out * ck.conj()).real.sum().backward()
+            res.append((out.detach(), pos.grad, vel.grad, w.grad))
+        names = ("spectrum", "posbar", "velbar", "weightsbar")
+        for name, a, b, tol in zip(names, res[0], res[1], (1e-6, 2e-5, 2e-5, 2e-5)):
+            assert rel(a, b) < tol, (shape, name)
+        # float64 oracle of the same chain
+        po, vo, wo = (t.double().requires_grad_() for t in (pos0, vel0, w0))
+        xs = (q + po if lattice else po) + (vo @ torch.tensor(los, dtype=torch.float64))[:, None] * coef * torch.tensor(los, dtype=torch.float64)
+        oo = O.nufft(xs, shape, paint, wo, 2, 2, paint_deconv=True)
+        (oo * ck.cpu().to(torch.complex128).conj()).real.sum().backward()
+        assert rel(res[0][0], oo.detach()) < 2e-5 and rel(res[0][2], vo.grad) < 1e-4 and rel(res[0][1], po.grad) < 1e-4
+
+
 def test_bullfrog_vf_scan_and_host_windows(nb, golden):
     """bullfrog_vf (nbody.py:902-960) against the oracle's drift-kick-drift step; nbody_bf_scan against the same steps in
     a loop; the host-side window helpers against the golden vectors of the reference source."""

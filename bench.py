@@ -281,7 +281,7 @@ def kernel_rooflines(model, white, peaks):
         lambda: (mesh.zero_(), lib.mcpm_paint_brick_f(st, frp, *shape, pos.data_ptr(), 0, 1.0, 0.0, N, *shape,
                                                       mesh.data_ptr())),
         16 * N, steps + 2, "pos 12N + mesh 4N (includes the 4N memset)")
-    add("brick_paint3", "brick paint3 (reverse-step scatter of the 3 channels of beta * vbar)",
+    add("brick_paint3", "brick paint3 (reverse-step scatter of the 3 channels of beta * vbar; streaming kernel: persistent CTAs, bulk-copy staged rows)",
         lambda: (planar3.zero_(), lib.mcpm_paint3_brick_f(st, frp, *shape, pos.data_ptr(), vbar.data_ptr(), 0, 0.0, 0.5,
                                                           N, *shape, planar3.data_ptr())),
         36 * N, steps, "SURVEY 8d's paint3: pos 12N + vbar 12N + 3 meshes 12N (the 12N memset is timed too; round 1's "

@@ -62,13 +62,15 @@ struct BrickArgs {
 // all 8 y-rows of the brick (the tile origin is taken from those 512 particles).
 __device__ __forceinline__ int brick_qi(int warp, int r) { return ((warp >> 3) + 2 * ((warp & 7) + r)) & 15; }
 
-template <int NCH>
+template <int NCH, bool OBS = false>
 __device__ __forceinline__ void stray_deposit(const BrickArgs& a, int si0, int sj0, int sk0);
 
 // FULL: the lattice divides into whole bricks (no per-particle bounds checks).
 // (A variant that handed each lane's four upper-z deposits to the next lane by shuffle -- 4 SHFL for 4 ATOMS -- was
 // measured on a B200 in round 2 and removed: 29.98 vs 29.51 ms per evaluation, the shuffles cost what the atomics saved.)
-template <int NCH, bool FULL>
+// OBS: the painted position carries the fused redshift-space shift a.obs (a separate instantiation: the branch costs the
+// plain density paint 8 % when it is a run-time test, 0.198 vs 0.183 ms at 256^3).
+template <int NCH, bool FULL, bool OBS = false>
 __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickArgs a) {
   using namespace brick;
   extern __shared__ __align__(16) int smem[];
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickA
       const float* xr = xp + di * plane3;
       const float sx = a.rel ? 0.f : (float)(q0i + di + a.ox);
       float p0 = xr[0], p1 = xr[1], p2 = xr[2];
-      if (NCH == 1 && a.obs.vel) {  // fused redshift-space shift, associated as rsd_shift (paint.cu) does
+      if (OBS) {  // fused redshift-space shift, associated as rsd_shift (paint.cu) does
         const float* vr = a.obs.vel + pbase + di * plane3;
         const float sh = (vr[0] * a.obs.lx + vr[1] * a.obs.ly + vr[2] * a.obs.lz) * a.obs.coef;
         p0 = p0 + sh * a.obs.lx;
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(brick::THREADS, 2) brick_scatter_kernel(BrickA
     const int w2 = t2 >> 5;
     const int si0 = q0i + brick_qi(w2, r), sj0 = q0j + (w2 & 7), sk0 = q0k + (t2 & 31);
     if (!FULL && all_stray && (si0 >= a.px || sj0 >= a.py || sk0 >= a.pz)) continue;
-    stray_deposit<NCH>(a, si0, sj0, sk0);
+    stray_deposit<NCH, OBS>(a, si0, sj0, sk0);
   }
 }
 
@@ -346,12 +348,12 @@ static_assert(WARPS % 8 == 0, "a warp keeps one lattice y-row");
 
 // One stray particle (lattice site si0, sj0, sk0) as float atomics to global memory: the same u = x - site as the in-tile
 // path, so that the fractions are bit-identical to it.
-template <int NCH>
+template <int NCH, bool OBS>
 __device__ __forceinline__ void stray_deposit(const BrickArgs& a, int si0, int sj0, int sk0) {
   const int64_t plane = (int64_t)a.nx * a.ny * a.nz;
   const int64_t p3 = 3 * (((int64_t)si0 * a.py + sj0) * a.pz + sk0);
   float r0 = a.pos[p3], r1 = a.pos[p3 + 1], r2 = a.pos[p3 + 2];
-  if (NCH == 1 && a.obs.vel) {
+  if (OBS) {
     const float* vr = a.obs.vel + p3;
     const float sh = (vr[0] * a.obs.lx + vr[1] * a.obs.ly + vr[2] * a.obs.lz) * a.obs.coef;
     r0 = r0 + sh * a.obs.lx;
@@ -717,11 +719,16 @@ static bool brick_ok(const Lattice& L, int64_t np, int nx, int ny, int nz) {
 }
 
 
+template <int NCH, bool FULL, bool OBS>
+static void launch_brick_obs(stream_t st, const BrickArgs& a, dim3 grid) {
+  using namespace brick;
+  cudaFuncSetAttribute(brick_scatter_kernel<NCH, FULL, OBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+  brick_scatter_kernel<NCH, FULL, OBS><<<grid, THREADS, SMEM, st>>>(a);
+}
 template <int NCH, bool FULL>
 static void launch_brick_variant(stream_t st, const BrickArgs& a, dim3 grid) {
-  using namespace brick;
-  cudaFuncSetAttribute(brick_scatter_kernel<NCH, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
-  brick_scatter_kernel<NCH, FULL><<<grid, THREADS, SMEM, st>>>(a);
+  if (NCH == 1 && a.obs.vel) launch_brick_obs<1, FULL, true>(st, a, grid);
+  else launch_brick_obs<NCH, FULL, false>(st, a, grid);
 }
 
 // Streaming variant: whole 8 x 8 x 32 bricks, 16-byte aligned rows (bulk copies), mesh at least one tile wide.

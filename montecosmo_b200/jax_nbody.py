@@ -42,6 +42,10 @@ HANDLERS = {
     "mcpm_pm_forces_vjp": "McpmPmForcesVjp", "mcpm_pm_forces_mesh": "McpmPmForcesMesh", "mcpm_pm_forces2": "McpmPmForces2",
     "mcpm_lpt": "McpmLpt", "mcpm_lpt_vjp": "McpmLptVjp", "mcpm_nbody_steps": "McpmNbodySteps",
     "mcpm_nbody_steps_vjp": "McpmNbodyStepsVjp",
+    "mcpm_nufft_rsd": "McpmNufftRsd", "mcpm_nufft_rsd_vjp": "McpmNufftRsdVjp", "mcpm_bias_spectra": "McpmBiasSpectra",
+    "mcpm_bias_spectra_vjp": "McpmBiasSpectraVjp", "mcpm_shear_invariants": "McpmShearInvariants",
+    "mcpm_shear_invariants_vjp": "McpmShearInvariantsVjp", "mcpm_bias_weights": "McpmBiasWeights",
+    "mcpm_bias_weights_vjp": "McpmBiasWeightsVjp",
 }
 for _name, _sym in HANDLERS.items():
     jax.ffi.register_ffi_target(_name, jax.ffi.pycapsule(getattr(_SHIM, _sym)), platform="CUDA")
@@ -205,9 +209,37 @@ def _nufft_bwd(paint_shape, scale, paint_order, interlace_order, kernel_type, pa
 _nufft_paint.defvjp(_nufft_fwd, _nufft_bwd)
 
 
+# the same paint with the flat-sky redshift-space shift pos + (vel . los) coef los applied inside the kernels
+@partial(jax.custom_vjp, nondiff_argnums=(2, 4, 5, 6, 7, 8, 9, 10))
+def _nufft_paint_rsd(pos, vel, paint_shape, weights, los, coef, scale, paint_order, interlace_order, paint_deconv, lattice):
+    return jax.ffi.ffi_call("mcpm_nufft_rsd", _sds(r2chshape(paint_shape), c64))(
+        pos.astype(f32), vel.astype(f32), weights, los=np.asarray(los, np.float32), coef=np.float32(coef),
+        wscalar=np.float32(1.0), scale=np.asarray(scale, np.float32), paint_order=i32(paint_order),
+        interlace_order=i32(interlace_order), paint_deconv=i32(paint_deconv),
+        lattice=_NOLAT if lattice is None else np.asarray(lattice, np.int32), relative=i32(lattice is not None))
+
+
+def _nufft_rsd_fwd(pos, vel, paint_shape, weights, *cfg):
+    return _nufft_paint_rsd(pos, vel, paint_shape, weights, *cfg), (pos, vel, weights)
+
+
+def _nufft_rsd_bwd(paint_shape, los, coef, scale, paint_order, interlace_order, paint_deconv, lattice, res, kbar):
+    pos, vel, weights = res
+    pb, vb, wb = jax.ffi.ffi_call("mcpm_nufft_rsd_vjp", (_sds(pos.shape), _sds(pos.shape), _sds(pos.shape[:1])))(
+        pos.astype(f32), vel.astype(f32), weights, jnp.conj(kbar), los=np.asarray(los, np.float32), coef=np.float32(coef),
+        wscalar=np.float32(1.0), scale=np.asarray(scale, np.float32), paint_order=i32(paint_order),
+        interlace_order=i32(interlace_order), paint_deconv=i32(paint_deconv),
+        lattice=_NOLAT if lattice is None else np.asarray(lattice, np.int32), relative=i32(lattice is not None))
+    return pb, vb, wb
+
+
+_nufft_paint_rsd.defvjp(_nufft_rsd_fwd, _nufft_rsd_bwd)
+
+
 def nufft(pos, final_shape: tuple, paint_shape=None, weights=1.0, paint_order: int = 2, interlace_order: int = 2,
-          kernel_type="rectangular", paint_deconv=True, lattice=None):
-    """nbody.py:532-577.  `lattice` (extension): pos holds displacements from the sites of that regular lattice."""
+          kernel_type="rectangular", paint_deconv=True, lattice=None, rsd=None):
+    """nbody.py:532-577.  `lattice` (extension): pos holds displacements from the sites of that regular lattice.
+    `rsd` (extension) = (vel, los, coef) with static los / coef: paint pos + (vel . los) coef los (model.py:780-809)."""
     final_shape = tuple(int(s) for s in final_shape)
     if paint_shape is None:
         paint_shape = final_shape
@@ -215,6 +247,12 @@ def nufft(pos, final_shape: tuple, paint_shape=None, weights=1.0, paint_order: i
         paint_shape = tuple(int(2 * round(s * paint_shape / 2)) for s in final_shape)  # scale_shape, utils.py:1163-1168
     paint_shape = tuple(int(s) for s in paint_shape)
     scale = tuple(p / f for p, f in zip(paint_shape, final_shape))
+    if rsd is not None:
+        vel, los, coef = rsd
+        mesh = _nufft_paint_rsd(pos, vel, paint_shape, _weights(weights, pos.shape[0]), tuple(float(x) for x in los),
+                                float(coef), scale, paint_order, interlace_order, bool(paint_deconv),
+                                None if lattice is None else tuple(lattice))
+        return mesh if final_shape == paint_shape else chreshape(mesh, r2chshape(final_shape))
     mesh = _nufft_paint(pos, paint_shape, _weights(weights, pos.shape[0]), scale, paint_order, interlace_order,
                         kernel_type, bool(paint_deconv), None if lattice is None else tuple(lattice))
     return mesh if final_shape == paint_shape else chreshape(mesh, r2chshape(final_shape))
@@ -387,3 +425,80 @@ def nbody_bf(cosmo, init_mesh, pos, a0=0.0, a1=1.0, n_steps=5, paint_order: int 
     if lattice is not None:
         x = x + pos
     return x[None], v[None]
+
+
+# ------------------------------------------------------------------------------------------------ lagrangian_bias
+# bricks.py:327-452 on the fused passes of csrc/bias.cu (same chain as montecosmo_b200/bricks.py): Fourier multipliers
+# -> batched irfftn -> shear invariants -> one 7 | 9-mesh read -> polynomial; every stage a custom_vjp.
+@partial(jax.custom_vjp, nondiff_argnums=(2,))
+def _bias_spectra(dk, inv_transfer, cpl):
+    m = 12 if inv_transfer.size else 10
+    return jax.ffi.ffi_call("mcpm_bias_spectra", _sds((m, *dk.shape), c64))(dk, inv_transfer,
+                                                                             cells_per_len=np.asarray(cpl, np.float32))
+
+
+def _bias_spectra_bwd(cpl, res, obar):
+    dk_shape, inv_transfer = res
+    dkbar = jax.ffi.ffi_call("mcpm_bias_spectra_vjp", _sds(dk_shape, c64))(jnp.conj(obar), inv_transfer,
+                                                                           cells_per_len=np.asarray(cpl, np.float32))
+    return jnp.conj(dkbar), jnp.zeros_like(inv_transfer)
+
+
+_bias_spectra.defvjp(lambda dk, it, cpl: (_bias_spectra(dk, it, cpl), (dk.shape, it)), _bias_spectra_bwd)
+
+
+@jax.custom_vjp
+def _shear_invariants(s5):
+    return jax.ffi.ffi_call("mcpm_shear_invariants", _sds((2, *s5.shape[1:])))(s5)
+
+
+_shear_invariants.defvjp(lambda s5: (_shear_invariants(s5), s5),
+                         lambda s5, ob: (jax.ffi.ffi_call("mcpm_shear_invariants_vjp", _sds(s5.shape))(s5, ob.astype(f32)),))
+
+
+@jax.custom_vjp
+def _bias_weights(vals, growth, coef):
+    """vals [np, K], growth (scalar), coef [13] -> (weights [np], dvel [np, 3]).  growth and coef are traced scalars passed
+    as attributes: call under jit with them static, or use the per-stage calls directly."""
+    w, dv, _ = _bias_weights_call(vals, growth, coef)
+    return w, dv
+
+
+def _bias_weights_call(vals, growth, coef):
+    n = vals.shape[0]
+    return jax.ffi.ffi_call("mcpm_bias_weights", (_sds((n,)), _sds((n, 3)), _sds((2,), jnp.float64)))(
+        vals, _NONE(), growth=np.float32(growth), coef=np.asarray(coef, np.float32))
+
+
+def _bias_weights_fwd(vals, growth, coef):
+    w, dv, mom = _bias_weights_call(vals, growth, coef)
+    return (w, dv), (vals, growth, coef, mom)
+
+
+def _bias_weights_bwd(res, bars):
+    vals, growth, coef, mom = res
+    wbar, dvbar = bars
+    n = vals.shape[0]
+    vb, cb, _, _ = jax.ffi.ffi_call("mcpm_bias_weights_vjp", (_sds(vals.shape), _sds((14,), jnp.float64), _sds((n,)),
+                                                              _sds((2,), jnp.float64)))(
+        vals, _NONE(), mom, wbar.astype(f32), dvbar.astype(f32), growth=np.float32(growth), coef=np.asarray(coef, np.float32))
+    return vb, cb[13], cb[:13]
+
+
+_bias_weights.defvjp(_bias_weights_fwd, _bias_weights_bwd)
+
+
+def lagrangian_bias(growth, pos, box_size, lin_mesh, coef, inv_transfer=None, read_order: int = 2):
+    """bricks.py:327-452: (weights, dvel, phi).  growth = a2g(cosmo, a) and coef = the 13 bias / PNG coefficients are the
+    caller's JAX scalars (static under jit here: their cotangents come back from mcpm_bias_weights_vjp); inv_transfer =
+    1 / trans_phi2delta on the half-spectrum mesh for the PNG terms, else None."""
+    shape = ch2rshape(lin_mesh.shape)
+    cpl = tuple(float(n / l) for n, l in zip(shape, np.broadcast_to(np.asarray(box_size, float), (3,))))
+    it = _NONE() if inv_transfer is None else inv_transfer.astype(f32)
+    spec = _bias_spectra(lin_mesh.astype(c64), it, cpl)
+    real = jnp.stack([irfftn(spec[m]) for m in range(spec.shape[0])])
+    inv = _shear_invariants(real[:5])
+    meshes = jnp.concatenate([real[5:6], inv, real[6:]], axis=0)  # delta, s^2, s^3, lap, grad (3), [phi, lap phi]
+    vals = read(pos, meshes, read_order)
+    weights, dvel = _bias_weights(vals, growth, coef)
+    return weights, dvel, (meshes[7] if inv_transfer is not None else 0.0)

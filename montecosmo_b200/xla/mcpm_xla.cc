@@ -276,6 +276,70 @@ ffi::Error NufftVjp(cudaStream_t st, int32_t dev, F32 pos, F32 weights, C64 outb
   return status(mcpm_nufft_vjp(e.eng(), st, pos.typed_data(), opt(weights), wscalar, np, scale3(scale, sc), paint_order,
                                interlace_order, paint_deconv, outbar.typed_data(), optr(posbar), optr(weightsbar)));
 }
+// nufft of redshift-space positions, the flat-sky shift applied inside the paint kernels (model.py:780-809 with
+// bricks.py:781-792); its VJP returns posbar, velbar and weightsbar from one gather
+ffi::Error NufftRsd(cudaStream_t st, int32_t dev, F32 pos, F32 vel, F32 weights, Floats los, float coef, float wscalar,
+                    Floats scale, int32_t paint_order, int32_t interlace_order, int32_t paint_deconv, Ints lattice,
+                    int32_t relative, RC64 out) {
+  auto m = real_shape_of_spectrum(*out);
+  EngineCall e(dev, m[0], m[1], m[2], lattice, relative);
+  if (e.err.failure()) return e.err;
+  float sc[3];
+  return status(mcpm_nufft_rsd(e.eng(), st, pos.typed_data(), vel.typed_data(), los.begin(), coef, opt(weights), wscalar,
+                               pos.dimensions()[0], scale3(scale, sc), paint_order, interlace_order, paint_deconv,
+                               out->typed_data()));
+}
+ffi::Error NufftRsdVjp(cudaStream_t st, int32_t dev, F32 pos, F32 vel, F32 weights, C64 outbar, Floats los, float coef,
+                       float wscalar, Floats scale, int32_t paint_order, int32_t interlace_order, int32_t paint_deconv,
+                       Ints lattice, int32_t relative, RF32 posbar, RF32 velbar, RF32 weightsbar) {
+  auto m = real_shape_of_spectrum(outbar);
+  EngineCall e(dev, m[0], m[1], m[2], lattice, relative);
+  if (e.err.failure()) return e.err;
+  float sc[3];
+  return status(mcpm_nufft_rsd_vjp(e.eng(), st, pos.typed_data(), vel.typed_data(), los.begin(), coef, opt(weights), wscalar,
+                                   pos.dimensions()[0], scale3(scale, sc), paint_order, interlace_order, paint_deconv,
+                                   outbar.typed_data(), optr(posbar), velbar->typed_data(), optr(weightsbar)));
+}
+// Lagrangian bias expansion (bricks.py:327-452) as fused passes: Fourier multipliers, shear invariants, polynomial
+ffi::Error BiasSpectra(cudaStream_t st, C64 dk, F32 inv_transfer, Floats cells_per_len, RC64 out) {
+  auto m = real_shape_of_spectrum(dk);
+  return status(mcpm_bias_spectra(st, dk.typed_data(), m[0], m[1], m[2], cells_per_len.begin(), opt(inv_transfer),
+                                  out->typed_data()));
+}
+ffi::Error BiasSpectraVjp(cudaStream_t st, C64 outbar, F32 inv_transfer, Floats cells_per_len, RC64 dkbar) {
+  auto m = real_shape_of_spectrum(*dkbar);
+  return status(mcpm_bias_spectra_vjp(st, outbar.typed_data(), m[0], m[1], m[2], cells_per_len.begin(), opt(inv_transfer),
+                                      dkbar->typed_data(), 0));
+}
+ffi::Error ShearInvariants(cudaStream_t st, F32 s5, RF32 out2) {
+  return status(mcpm_shear_invariants(st, s5.typed_data(), (int64_t)(s5.element_count() / 5), out2->typed_data()));
+}
+ffi::Error ShearInvariantsVjp(cudaStream_t st, F32 s5, F32 out2bar, RF32 s5bar) {
+  return status(mcpm_shear_invariants_vjp(st, s5.typed_data(), out2bar.typed_data(), (int64_t)(s5.element_count() / 5),
+                                          s5bar->typed_data()));
+}
+// vals [np, K]; growth_arr: zero-size for a scalar growth factor.  mom (float64 [2]) is a result the backward call takes.
+ffi::Error BiasWeights(cudaStream_t st, F32 vals, F32 growth_arr, float growth, Floats coef, RF32 weights, RF32 dvel,
+                       RF64 mom) {
+  const int64_t np = vals.dimensions()[0];
+  const int K = (int)vals.dimensions()[1];
+  if (cudaMemsetAsync(mom->typed_data(), 0, 2 * sizeof(double), st) != cudaSuccess) return ffi::Error::Internal("memset");
+  if (int rc = mcpm_bias_moments(st, vals.typed_data(), K, growth, opt(growth_arr), np, mom->typed_data())) return status(rc);
+  return status(mcpm_bias_weights(st, vals.typed_data(), K, growth, opt(growth_arr), coef.begin(), mom->typed_data(), np,
+                                  weights->typed_data(), dvel->typed_data()));
+}
+// coefbar: float64 [14] (13 coefficients + the scalar growth factor); gbar_arr: [np] (unused with a scalar growth factor)
+ffi::Error BiasWeightsVjp(cudaStream_t st, F32 vals, F32 growth_arr, F64 mom, F32 wbar, F32 dvelbar, float growth,
+                          Floats coef, RF32 valsbar, RF64 coefbar, RF32 gbar_arr, RF64 msum) {
+  const int64_t np = vals.dimensions()[0];
+  const int K = (int)vals.dimensions()[1];
+  if (cudaMemsetAsync(msum->typed_data(), 0, 2 * sizeof(double), st) != cudaSuccess ||
+      cudaMemsetAsync(coefbar->typed_data(), 0, 14 * sizeof(double), st) != cudaSuccess)
+    return ffi::Error::Internal("memset");
+  return status(mcpm_bias_weights_vjp(st, vals.typed_data(), K, growth, opt(growth_arr), coef.begin(), mom.typed_data(),
+                                      wbar.typed_data(), opt(dvelbar), np, msum->typed_data(), valsbar->typed_data(),
+                                      coefbar->typed_data(), gbar_arr->typed_data()));
+}
 // pm_forces with a painted mesh (nbody.py:583-604): -> forces [np, 3] and the three force meshes (residual of the VJP)
 ffi::Error PmForces(cudaStream_t st, int32_t dev, F32 pos, int32_t order, int32_t paint_deconv, int32_t lap_fd,
                     int32_t grad_fd, float kcut, Ints lattice, int32_t relative, RF32 forces, RF32 fmesh3) {
@@ -407,6 +471,25 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(McpmNufftVjp, NufftVjp,
     MCPM_STREAM_DEV.Arg<F32>().Arg<F32>().Arg<C64>().Attr<float>("wscalar").Attr<Floats>("scale")
         .Attr<int32_t>("paint_order").Attr<float>("kcut").Attr<int32_t>("interlace_order").Attr<int32_t>("paint_deconv")
             LATTICE.Ret<F32>().Ret<F32>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(McpmNufftRsd, NufftRsd,
+    MCPM_STREAM_DEV.Arg<F32>().Arg<F32>().Arg<F32>().Attr<Floats>("los").Attr<float>("coef").Attr<float>("wscalar")
+        .Attr<Floats>("scale").Attr<int32_t>("paint_order").Attr<int32_t>("interlace_order").Attr<int32_t>("paint_deconv")
+            LATTICE.Ret<C64>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(McpmNufftRsdVjp, NufftRsdVjp,
+    MCPM_STREAM_DEV.Arg<F32>().Arg<F32>().Arg<F32>().Arg<C64>().Attr<Floats>("los").Attr<float>("coef")
+        .Attr<float>("wscalar").Attr<Floats>("scale").Attr<int32_t>("paint_order").Attr<int32_t>("interlace_order")
+        .Attr<int32_t>("paint_deconv") LATTICE.Ret<F32>().Ret<F32>().Ret<F32>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(McpmBiasSpectra, BiasSpectra,
+    MCPM_STREAM.Arg<C64>().Arg<F32>().Attr<Floats>("cells_per_len").Ret<C64>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(McpmBiasSpectraVjp, BiasSpectraVjp,
+    MCPM_STREAM.Arg<C64>().Arg<F32>().Attr<Floats>("cells_per_len").Ret<C64>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(McpmShearInvariants, ShearInvariants, MCPM_STREAM.Arg<F32>().Ret<F32>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(McpmShearInvariantsVjp, ShearInvariantsVjp, MCPM_STREAM.Arg<F32>().Arg<F32>().Ret<F32>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(McpmBiasWeights, BiasWeights,
+    MCPM_STREAM.Arg<F32>().Arg<F32>().Attr<float>("growth").Attr<Floats>("coef").Ret<F32>().Ret<F32>().Ret<F64>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(McpmBiasWeightsVjp, BiasWeightsVjp,
+    MCPM_STREAM.Arg<F32>().Arg<F32>().Arg<F64>().Arg<F32>().Arg<F32>().Attr<float>("growth").Attr<Floats>("coef")
+        .Ret<F32>().Ret<F64>().Ret<F32>().Ret<F64>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(McpmPmForces, PmForces,
     MCPM_STREAM_DEV.Arg<F32>().Attr<int32_t>("order").Attr<int32_t>("paint_deconv") FD.Attr<float>("kcut")
         LATTICE.Ret<F32>().Ret<F32>());

@@ -243,7 +243,8 @@ def kernel_rooflines(model, white, peaks):
     with torch.no_grad():
         dk = model.linear_field(nb._f32(white))
         pos, vel = nb.nbody_bf(model.cosmology, dk, model.q, model.a_start, model.a_obs, model.n_steps, ptcl_shape=shape,
-                               relative=True)
+                               relative=True, snapshots=3)  # start, middle (in growth time: the run's step 5) and end
+        pos_mid = pos[1].contiguous()
         pos, vel = pos[-1].contiguous(), vel[-1].contiguous()
         _, fm = o.pm_forces(pos, shape, want_meshes=True, lattice=shape)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=pos.device)
@@ -261,12 +262,19 @@ def kernel_rooflines(model, white, peaks):
             traffic, tsrc = json.load(open(path)), name
             break
 
-    def add(key, name, fn, alg_bytes, launches, note, in_step=True):
+    def add(key, name, fn, alg_bytes, launches, note, in_step=True, fn_mid=None):
+        """fn_mid: the same launch on the run's mid-point particles.  The scatters' time depends on the clustering (same-cell
+        collisions of the shared-memory atomics: 0.35 ms early, 0.44 at a = 1 for paint3), so they are timed on both states
+        and reported as the mean -- what the 10 steps of an evaluation see on average."""
         ms = t(fn)
+        states = None
+        if fn_mid is not None:
+            states = {"a_obs": ms, "mid_run": t(fn_mid)}
+            ms = 0.5 * (states["a_obs"] + states["mid_run"])
         rows.append({"kernel": name, "key": key, "ms": ms, "launches_per_step": launches, "alg_bytes": alg_bytes,
                      "achieved_GBps": alg_bytes / ms / 1e6, "frac": alg_bytes / ms / 1e6 / peaks,
                      "ms_per_step_total": ms * launches, "alg_bytes_note": note, "in_step": in_step,
-                     "traffic": traffic.get(key, {}).get("dram_bytes")})
+                     "traffic": traffic.get(key, {}).get("dram_bytes"), "ms_by_state": states})
 
     st = A.stream()
     fr = make_frame(shape)
@@ -280,12 +288,16 @@ def kernel_rooflines(model, white, peaks):
     add("brick_paint", "brick paint (CIC density: shared-memory tile, fixed-point ATOMS, red.v4 flush)",
         lambda: (mesh.zero_(), lib.mcpm_paint_brick_f(st, frp, *shape, pos.data_ptr(), 0, 1.0, 0.0, N, *shape,
                                                       mesh.data_ptr())),
-        16 * N, steps + 2, "pos 12N + mesh 4N (includes the 4N memset)")
+        16 * N, steps + 2, "pos 12N + mesh 4N (includes the 4N memset)",
+        fn_mid=lambda: (mesh.zero_(), lib.mcpm_paint_brick_f(st, frp, *shape, pos_mid.data_ptr(), 0, 1.0, 0.0, N, *shape,
+                                                             mesh.data_ptr())))
     add("brick_paint3", "brick paint3 (reverse-step scatter of the 3 channels of beta * vbar; streaming kernel: persistent CTAs, bulk-copy staged rows)",
         lambda: (planar3.zero_(), lib.mcpm_paint3_brick_f(st, frp, *shape, pos.data_ptr(), vbar.data_ptr(), 0, 0.0, 0.5,
                                                           N, *shape, planar3.data_ptr())),
         36 * N, steps, "SURVEY 8d's paint3: pos 12N + vbar 12N + 3 meshes 12N (the 12N memset is timed too; round 1's "
-                       "60N counted the vbar += xbar*drift update that now rides in read_grad4v's epilogue)")
+                       "60N counted the vbar += xbar*drift update that now rides in read_grad4v's epilogue)",
+        fn_mid=lambda: (planar3.zero_(), lib.mcpm_paint3_brick_f(st, frp, *shape, pos_mid.data_ptr(), vbar.data_ptr(), 0, 0.0,
+                                                                 0.5, N, *shape, planar3.data_ptr())))
     add("kick_drift4", "kick_drift4 (float4 force readout + kick + drift)",
         lambda: lib.mcpm_kick_drift4_f(st, frp, p2.data_ptr(), v2.data_ptr(), fm4.data_ptr(), N, *shape, 1.0, 0.0, 0.0),
         64 * N, steps, "pos 12N r/w + vel 12N r/w + mesh4 16N")

@@ -622,6 +622,23 @@ def run_slab(args, world, rank, dev, timed, barrier, sampler):
     whites = [torch.randn(local_shape, device=dev, generator=gen) for _ in range(2)]
     mdl.value_and_force(whites[0], obs)
     torch.cuda.synchronize()
+    # Halo sized from a measurement: the default of 24 planes is an a = 1 worst case; the warm-up evaluation's largest
+    # x-displacement (max over ranks) x 1.25 + 2 planes is what this run needs -- at 64 owned planes per rank (8 GPUs) 24
+    # halo planes are 75 % more cells to clear, flush, exchange and gather.  The guard still raises if a particle ever
+    # leaves the extended slab (SlabPM.check_guard): a caller then rebuilds with more planes.
+    halo_default, halo_used = pm.H, pm.H
+    if not args.fixed_halo:
+        need = pm.halo_needed()
+        need += need % 2  # an even number of planes
+        if need < pm.H:
+            del mdl, pm
+            torch.cuda.empty_cache()
+            pm = SlabPM(ops, shape, halo=need)
+            mdl = SlabFieldModel(pm, wl["box_size"], n_steps=wl["n_steps"], a_start=wl["a_start"], a_obs=wl["a_obs"],
+                                 b1=wl["b1"], rsd=wl["rsd"], sigma_obs=wl["sigma_obs"])
+            mdl.value_and_force(whites[0], obs)
+            torch.cuda.synchronize()
+            halo_used = need
     lib.mcpm_launch_count(1)
     mdl.value_and_force(whites[0], obs)
     torch.cuda.synchronize()
@@ -669,13 +686,16 @@ def run_slab(args, world, rank, dev, timed, barrier, sampler):
     nfft = 13 + 13 + 8 * ns + (2 + 2 + 2 * 3 + 2)
     a2a = nfft * 8 * (cells / 2) / world * (world - 1) / world * (1 + 2.0 / shape[2])
     plane = shape[1] * shape[2] * 4.0
-    halo = (ns * (1 + 4 + 3 + 1) + 2 * 2) * 2 * pm.H * plane
+    halo = (ns * (1 + 4 + 3 + 1) + 2 * 2) * 2 * halo_used * plane
     per = ms_dev / K
     nv = (a2a + halo) / 1e9
     del keep, mdl, pm
     torch.cuda.empty_cache()
     barrier()
-    return {"value": world * K / (ms_dev * 1e-3), "ms_per_step": per, "mesh": list(shape), "halo_planes": min(args.halo, shape[0] // world),
+    return {"value": world * K / (ms_dev * 1e-3), "ms_per_step": per, "mesh": list(shape), "halo_planes": halo_used,
+            "halo_note": (f"sized from the warm-up evaluation's largest x-displacement (x 1.25 + 2 planes; default "
+                          f"{halo_default}); the guard raises if a particle leaves its extended slab"
+                          if halo_used != halo_default else "default"),
             "launches_per_eval": launches, "max_mem_GiB_per_gpu": float(mem),
             "e2e": {"value": world * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * nl * world,
                     "d2h_bytes_per_step": (4 * nl + 8) * world, "ms_per_step": ms_e2e / K,
@@ -695,6 +715,7 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--mesh", type=int, default=256, help="mesh side (development only; the contract runs 256)")
     ap.add_argument("--halo", type=int, default=24, help="halo planes of the slab decomposition (N > 1)")
+    ap.add_argument("--fixed-halo", action="store_true", help="N > 1: keep --halo planes instead of sizing them from a warm-up evaluation")
     ap.add_argument("--replicas", action="store_true", help="N > 1: time independent replicas only (round 1's mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-paint-bench", action="store_true")

@@ -113,6 +113,7 @@ class SlabPM:
         self.frame = _frame((self.xl, ny, nz), origin=(self.H, 0, 0))  # relative positions on the halo-extended mesh
         self._fr = C.byref(self.frame)
         self._oob = None
+        self._maxdx = None
         # tape_forces = False: the step loop tapes kick positions only and the reverse sweep recomputes each step's force
         # mesh (one more paint + force evaluation per step instead of 16 bytes per extended cell and step: at 1024^3 on 8
         # GPUs with 20 steps that is 59 GB per GPU) -- the trade of the reference's checkpointed adjoint (nbody.py:999)
@@ -340,8 +341,23 @@ class SlabPM:
         # site i + displacement d must keep the CIC stencil inside the extended slab: 1 <= H + i + d <= ext - 2 for every
         # owned i in [0, xl)
         x = pos[:, 0]
-        bad = ((x < 1.0 - self.H) | (x > self.H - 1.0)).any()
+        m = x.abs().max()
+        bad = m > self.H - 1.0
         self._oob = bad if self._oob is None else (self._oob | bad)
+        self._maxdx = m if self._maxdx is None else torch.maximum(self._maxdx, m)
+
+    def halo_needed(self, factor=1.25, margin=2):
+        """Halo planes that would have held every particle seen by the guard since this object was built (max over ranks
+        of |x displacement|, times `factor`, plus `margin` planes; the CIC stencil needs one more than the displacement).
+        One device -> host read and, with several ranks, one all-reduce: call it between evaluations, e.g. after a
+        warm-up one, to size the halo of a run from a measurement instead of the a = 1 default of 24 planes."""
+        import math
+        if self._maxdx is None:
+            return self.H
+        m = self._maxdx.detach().clone().reshape(1).float()
+        if self.P > 1:
+            dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self.group)
+        return int(math.ceil(float(m) * factor)) + int(margin)
 
     def check_guard(self):
         """Raise if any particle came within a cell of the edge of its extended slab since the last check (one sync)."""

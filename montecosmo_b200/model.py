@@ -64,8 +64,9 @@ class _GaussLogp(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (r,) = ctx.saved_tensors
-        # g is a float64 device scalar (1.0 in practice); one tiny D2H read keeps the kernel interface scalar-valued
-        return nb.ops().axpby(r, -float(g) * ctx.inv_var), None, None
+        # g is a float64 device scalar (1.0 in practice): scale on the device -- no D2H read, so logpdf().backward(), what a
+        # generic sampler calls, neither synchronises the stream nor breaks a CUDA-graph capture
+        return r * (g * (-ctx.inv_var)).to(r.dtype), None, None
 
 
 def eisenstein_hu_nowiggle(k, cosmo):

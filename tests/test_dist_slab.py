@@ -90,6 +90,14 @@ def _worker(rank, world, port, shape, halo, q):
                              ref.numpy()[:, pm.y0:pm.y0 + pm.kyl, :])
         dkbar = pm.nbody_backward(tape, torch.tensor(pb[sl]), torch.tensor(vb[sl]))
         res["dkbar"] = rel(dkbar.numpy(), ref.numpy()[:, pm.y0:pm.y0 + pm.kyl, :])
+        # 4. halo sized from the measurement: the same number on every rank (an all-reduce inside), at least the largest
+        # x-displacement + the CIC stencil, at most what was allotted; a slab engine rebuilt with it gives the same result
+        need = pm.halo_needed(factor=1.0, margin=2)
+        dmax = float(np.abs(pfull.numpy()[:, 0]).max())
+        res["halo_needed_ok"] = float(not (dmax + 1.0 <= need <= H + 1))
+        pm2 = SlabPM(ops, shape, halo=min(need, H))
+        pos2, vel2, _ = pm2.nbody_forward(pm2.scatter_spectrum(torch.tensor(dk)), c, a0, a1, ns)
+        res["halo_resized"] = max(float(np.abs(pos2.numpy() - pos.numpy()).max()), rel(vel2.numpy(), vel.numpy()))
         q.put((rank, res, None))
         dist.destroy_process_group()
     except Exception as e:  # surface the traceback in the parent
@@ -117,6 +125,7 @@ def test_slab_engine_world2_gloo(world, shape, halo):
         assert res["pos"] < 1e-4 and res["vel"] < 1e-4, res
         assert res["steps_bwd"] < 5e-4 and res["lpt_bwd"] < 5e-4 and res["dkbar"] < 5e-4, res
         assert res["disp_rms"] > 0.2, res  # the comparison above is on a genuinely displaced lattice
+        assert res["halo_needed_ok"] == 0.0 and res["halo_resized"] < 1e-5, res
 
 
 def _model_worker(rank, world, port, shape, halo, kw, q):

@@ -656,6 +656,9 @@ def run_slab(args, world, rank, dev, timed, barrier, sampler):
         dist.all_reduce(grew, op=dist.ReduceOp.MAX)
         if float(grew) == 0.0:
             break
+    for i in range(2):  # two more on the settled allocator (GPU call 17 still saw one 58 ms first loop after the break above)
+        mdl.value_and_force(whites[i % 2], obs)
+    torch.cuda.synchronize()
     if rank == 0:
         sampler.start()
     keep = {}

@@ -191,6 +191,30 @@ def test_oracle_properties():
     assert abs(float(torch.fft.irfftn(up, s=(12, 14, 10)).mean() - m.mean())) < 1e-12
 
 
+def test_growth_against_independent_quadrature():
+    """The growth helpers are pinned to golden vectors of the reference source run under a stand-in for jax_cosmo that the
+    builder wrote too.  Independent of both: for matter + Lambda (w = -1, no radiation -- the physics
+    of jax_cosmo's growth ODE) the growing mode is Heath's integral D(a) ~ H(a) int_0^a da' / (a' H(a'))^3.  D(a) / D(1) and
+    f = dlnD / dlna from scipy quadrature against the oracle's and the engine-side table's a2g / a2f: 5e-4 (measured: up to
+    2.1e-4 -- the restated jax_cosmo table is a 128-point RK4 solve started at a = 1e-2 on the matter-dominated solution,
+    which is exact only as a -> 0; a transcription error in the ODE or its normalisation would show at the percent level)."""
+    from scipy.integrate import quad
+    from montecosmo_b200 import cosmo as PC
+    for Oc, Ob, Ok in ((0.26447041, 0.04930169, 0.0), (0.20, 0.05, 0.0), (0.30, 0.05, 0.05)):
+        om = Oc + Ob
+        ol = 1.0 - om - Ok
+        E = lambda a: np.sqrt(om / a**3 + Ok / a**2 + ol)
+        Dun = lambda a: E(a) * quad(lambda x: 1.0 / (x * E(x)) ** 3, 0.0, a, epsabs=1e-14, epsrel=1e-12)[0]
+        for a in (0.1, 0.3, 0.6, 1.0):
+            D = Dun(a) / Dun(1.0)
+            h = 1e-4 * a
+            f = (np.log(Dun(a + h)) - np.log(Dun(a - h))) / (np.log(a + h) - np.log(a - h))
+            co, cp = O.Cosmology(Omega_c=Oc, Omega_b=Ob, Omega_k=Ok), PC.Cosmology(Omega_c=Oc, Omega_b=Ob, Omega_k=Ok)
+            for name, g, ff in (("oracle", float(O.a2g(co, a)), float(O.a2f(co, a))),
+                                ("engine", float(PC.a2g(cp, a)), float(PC.a2f(cp, a)))):
+                assert abs(g / D - 1) < 5e-4 and abs(ff / f - 1) < 5e-4, (name, Oc, Ok, a, g, D, ff, f)
+
+
 def test_spectrum_estimator(golden):
     """oracle/metrics_oracle.py against montecosmo/metrics.py's own _spectrum / powtranscoh."""
     from oracle import metrics_oracle as MX

@@ -342,6 +342,9 @@ int mcpm_hermitian_weights(void* stream, const void* in, void* out, int nx, int 
  * flat-sky RSD in cell units (bricks.py:781-792): pos_out = pos + (vel . los) * coef * los, and its VJP w.r.t. vel. */
 int mcpm_axpby(void* stream, const float* x, float a, const float* y, float b, float c, int64_t n, float* out);
 int mcpm_dot(void* stream, const float* a, const float* b, int64_t n, double* out_f64);
+/* out[0] = max(out[0], max_i |x[i * stride]|), out[0] >= 0 on entry (device float; NaN sticks): the halo guard of a
+ * slab-decomposed caller -- the largest displacement of its particles across the slab direction -- as one pass. */
+int mcpm_absmax(void* stream, const float* x, int64_t n, int stride, float* out);
 int mcpm_rsd_shift(void* stream, const float* pos, const float* vel, const float los[3], float coef, int64_t np,
                    float* pos_out);
 int mcpm_rsd_shift_vjp(void* stream, const float* posbar, const float los[3], float coef, int64_t np, float* velbar,

@@ -789,6 +789,13 @@ int mcpm_dot(void* stream, const float* a, const float* b, int64_t n, double* ou
   API_END
 }
 
+int mcpm_absmax(void* stream, const float* x, int64_t n, int stride, float* out) {
+  API_BEGIN
+  NEED(out && (x || n == 0) && stride >= 1, "absmax: null pointer or stride < 1");
+  return absmax_strided(as_stream(stream), x, n, stride, out);
+  API_END
+}
+
 int mcpm_rsd_shift(void* stream, const float* pos, const float* vel, const float los[3], float coef, int64_t np,
                    float* pos_out) {
   API_BEGIN

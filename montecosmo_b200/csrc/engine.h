@@ -118,6 +118,7 @@ int bias_weights(stream_t, const float* vals, int K, float gs, const float* garr
 int bias_weights_vjp(stream_t, const float* vals, int K, float gs, const float* garr, BiasCoef c, const double* mom,
                      const float* wbar, const float* dvelbar, int64_t np, double* msum, float* valsbar, double* coefbar,
                      float* gbar_arr);
+int absmax_strided(stream_t, const float* x, int64_t n, int stride, float* out);
 int rsd_shift(stream_t, const float* pos, const float* vel, float lx, float ly, float lz, float coef, int64_t np,
               float* pos_out);
 int rsd_shift_vjp(stream_t, const float* posbar, float lx, float ly, float lz, float coef, int64_t np, float* velbar,

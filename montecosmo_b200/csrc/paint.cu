@@ -628,6 +628,33 @@ int rsd_shift_vjp(stream_t st, const float* posbar, float lx, float ly, float lz
   return rt_check("rsd_shift_vjp");
 }
 
+// out[0] = max(out[0], max_i |x[i * stride]|); out[0] >= 0 on entry.  The halo guard of a slab-decomposed rank (the largest
+// x-displacement of its particles, every step): as torch ops on the strided column it cost a 95 us elementwise pass and a
+// reduction per step, 2.6 ms per 256^3 evaluation (profiles/r2_slab_one_rank.txt).
+int absmax_strided(stream_t st, const float* x, int64_t n, int stride, float* out) {
+#ifdef MCPM_HOSTEMU
+  float m = out[0];
+#pragma omp parallel for reduction(max : m) schedule(static)
+  for (int64_t i = 0; i < n; ++i) m = std::fmax(m, std::fabs(x[i * stride]));
+  out[0] = m;
+  (void)st;
+  return 0;
+#else
+  const int64_t chunk = 4096, nchunks = (n + chunk - 1) / chunk;  // one warp per chunk
+  launch_1d(st, nchunks * 32, [=] MCPM_LAMBDA(int64_t t) {
+    const int64_t c = t >> 5;
+    const int lane = (int)(t & 31);
+    const int64_t lo = c * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    float m = 0.0f;
+    for (int64_t i = lo + lane; i < hi; i += 32) m = fmaxf(m, fabsf(x[i * stride]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_down_sync(0xffffffffu, m, o));
+    // non-negative floats order like their bit patterns; NaN (0x7fc00000) compares above every finite value and sticks
+    if (lane == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
+  });
+  return rt_check("absmax_strided");
+#endif
+}
+
 // out[0] += sum_i a[i] * b[i] in float64 (coefficient cotangents)
 int dot_accum(stream_t st, const float* a, const float* b, int64_t n, double scale, double* out) {
 #ifdef MCPM_HOSTEMU

@@ -112,8 +112,7 @@ class SlabPM:
         self.q_own = self.A.prepare(np.stack(np.meshgrid(*ax, indexing="ij"), -1).reshape(-1, 3))  # owned-slab coords
         self.frame = _frame((self.xl, ny, nz), origin=(self.H, 0, 0))  # relative positions on the halo-extended mesh
         self._fr = C.byref(self.frame)
-        self._oob = None
-        self._maxdx = None
+        self._maxdx = None  # running max |x displacement| seen by the guard (device float)
         # tape_forces = False: the step loop tapes kick positions only and the reverse sweep recomputes each step's force
         # mesh (one more paint + force evaluation per step instead of 16 bytes per extended cell and step: at 1024^3 on 8
         # GPUs with 20 steps that is 59 GB per GPU) -- the trade of the reference's checkpointed adjoint (nbody.py:999)
@@ -340,11 +339,10 @@ class SlabPM:
     def _guard(self, pos):
         # site i + displacement d must keep the CIC stencil inside the extended slab: 1 <= H + i + d <= ext - 2 for every
         # owned i in [0, xl)
-        x = pos[:, 0]
-        m = x.abs().max()
-        bad = m > self.H - 1.0
-        self._oob = bad if self._oob is None else (self._oob | bad)
-        self._maxdx = m if self._maxdx is None else torch.maximum(self._maxdx, m)
+        # one pass over the strided x column (mcpm_absmax) into a running maximum on the device; nothing synchronises
+        if self._maxdx is None:
+            self._maxdx = self.A.zeros((1,))
+        self._call("mcpm_absmax", self._st(), pos.data_ptr(), pos.shape[0], 3, self._maxdx.data_ptr())
 
     def halo_needed(self, factor=1.25, margin=2):
         """Halo planes that would have held every particle seen by the guard since this object was built (max over ranks
@@ -354,17 +352,15 @@ class SlabPM:
         import math
         if self._maxdx is None:
             return self.H
-        m = self._maxdx.detach().clone().reshape(1).float()
+        m = self._maxdx.detach().clone()
         if self.P > 1:
             dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self.group)
         return int(math.ceil(float(m) * factor)) + int(margin)
 
     def check_guard(self):
         """Raise if any particle came within a cell of the edge of its extended slab since the last check (one sync)."""
-        if self._oob is not None and bool(self._oob):
-            self._oob = None
+        if self._maxdx is not None and not float(self._maxdx) <= self.H - 1.0:  # also catches NaN
             raise RuntimeError(f"a particle left its extended slab: increase halo (= {self.H} planes)")
-        self._oob = None
 
     # ------------------------------------------------------------------------------------------------ Fourier passes
     def force_spectra(self, dk, lap_fd=INF, grad_fd=INF, deconv_order=0):

@@ -5,6 +5,8 @@
 // PM run are in Lagrangian-lattice order (z fastest), so the 32 lanes of a warp hold z-neighbours: their loads and
 // their red.global.add.f32 land in a handful of consecutive 128-byte lines, which keeps both the LSU and the L2
 // atomic units at line granularity instead of element granularity.
+#include <limits>
+
 #include "engine.h"
 #include "window.h"
 
@@ -634,9 +636,14 @@ int rsd_shift_vjp(stream_t st, const float* posbar, float lx, float ly, float lz
 int absmax_strided(stream_t st, const float* x, int64_t n, int stride, float* out) {
 #ifdef MCPM_HOSTEMU
   float m = out[0];
-#pragma omp parallel for reduction(max : m) schedule(static)
-  for (int64_t i = 0; i < n; ++i) m = std::fmax(m, std::fabs(x[i * stride]));
-  out[0] = m;
+  int nan = m != m;
+#pragma omp parallel for reduction(max : m) reduction(| : nan) schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    const float a = std::fabs(x[i * stride]);
+    if (a != a) nan |= 1;
+    else if (a > m) m = a;
+  }
+  out[0] = nan ? std::numeric_limits<float>::quiet_NaN() : m;
   (void)st;
   return 0;
 #else
@@ -646,8 +653,14 @@ int absmax_strided(stream_t st, const float* x, int64_t n, int stride, float* ou
     const int lane = (int)(t & 31);
     const int64_t lo = c * chunk, hi = lo + chunk < n ? lo + chunk : n;
     float m = 0.0f;
-    for (int64_t i = lo + lane; i < hi; i += 32) m = fmaxf(m, fabsf(x[i * stride]));
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_down_sync(0xffffffffu, m, o));
+    for (int64_t i = lo + lane; i < hi; i += 32) {  // fmaxf would drop a NaN: keep it (a != a), and keep it once held
+      const float a = fabsf(x[i * stride]);
+      m = (a > m || a != a) ? a : m;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float a = __shfl_down_sync(0xffffffffu, m, o);
+      m = (a > m || a != a) ? a : m;
+    }
     // non-negative floats order like their bit patterns; NaN (0x7fc00000) compares above every finite value and sticks
     if (lane == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
   });

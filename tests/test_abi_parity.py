@@ -643,3 +643,28 @@ def test_paint_read_random_configurations(ops):
         lhs = float((to_numpy(r).astype(np.float64) * w).sum())
         rhs = float((mesh.astype(np.float64) * to_numpy(p).astype(np.float64)).sum())
         assert abs(lhs - rhs) < 1e-4 * max(abs(lhs), abs(rhs), 1.0), tag
+
+
+def test_absmax_strided(ops):
+    """mcpm_absmax (the halo guard of a slab-decomposed caller): running maximum of |x| over a strided column, exact;
+    accumulates across calls; a NaN sticks; an empty input leaves the value alone."""
+    A = ops.A
+    rng = np.random.default_rng(5)
+    for n in (1, 31, 4096, 70001):
+        pos = f32(rng.normal(scale=3.0, size=(n, 3)))
+        pos[rng.integers(0, n), 0] = -17.25
+        out = A.zeros((1,))
+        pd = A.prepare(pos)
+        ops._call("mcpm_absmax", A.stream(), A.ptr(pd), n, 3, A.ptr(out))
+        assert float(to_numpy(out)[0]) == float(np.abs(pos[:, 0]).max())
+        small = A.prepare(f32(np.full((5, 3), 0.5)))
+        ops._call("mcpm_absmax", A.stream(), A.ptr(small), 5, 3, A.ptr(out))   # a smaller batch does not lower it
+        ops._call("mcpm_absmax", A.stream(), A.ptr(small), 0, 3, A.ptr(out))   # nor does an empty one
+        assert float(to_numpy(out)[0]) == float(np.abs(pos[:, 0]).max())
+    bad = f32(rng.normal(size=(100, 3)))
+    bad[7, 0] = np.nan
+    out = A.zeros((1,))
+    bd = A.prepare(bad)
+    ops._call("mcpm_absmax", A.stream(), A.ptr(bd), 100, 3, A.ptr(out))
+    v = float(to_numpy(out)[0])
+    assert not v <= 1e30  # NaN (or above every finite bound): the caller's `not max <= limit` test raises

@@ -627,6 +627,7 @@ def run_slab(args, world, rank, dev, timed, barrier, sampler):
     # halo planes are 75 % more cells to clear, flush, exchange and gather.  The guard still raises if a particle ever
     # leaves the extended slab (SlabPM.check_guard): a caller then rebuilds with more planes.
     halo_default, halo_used = pm.H, pm.H
+    sched = None
     if not args.fixed_halo:
         need = pm.halo_needed()
         need += need % 2  # an even number of planes
@@ -639,6 +640,10 @@ def run_slab(args, world, rank, dev, timed, barrier, sampler):
             mdl.value_and_force(whites[0], obs)
             torch.cuda.synchronize()
             halo_used = need
+        # ... and per step: the kick positions of step s stay within a few planes early in the run, so the exchanges of
+        # that step (and of its reverse step) move only the active planes next to the owned region
+        sched = pm.halo_schedule(wl["n_steps"])
+        pm.set_halo_schedule(sched)
     lib.mcpm_launch_count(1)
     mdl.value_and_force(whites[0], obs)
     torch.cuda.synchronize()
@@ -689,13 +694,15 @@ def run_slab(args, world, rank, dev, timed, barrier, sampler):
     nfft = 13 + 13 + 8 * ns + (2 + 2 + 2 * 3 + 2)
     a2a = nfft * 8 * (cells / 2) / world * (world - 1) / world * (1 + 2.0 / shape[2])
     plane = shape[1] * shape[2] * 4.0
-    halo = (ns * (1 + 4 + 3 + 1) + 2 * 2) * 2 * halo_used * plane
+    h_steps = float(np.mean(sched)) if sched else float(halo_used)  # mean active planes of the step-loop exchanges
+    halo = (ns * (1 + 4 + 3 + 1) * h_steps + 2 * 2 * halo_used) * 2 * plane
     per = ms_dev / K
     nv = (a2a + halo) / 1e9
     del keep, mdl, pm
     torch.cuda.empty_cache()
     barrier()
     return {"value": world * K / (ms_dev * 1e-3), "ms_per_step": per, "mesh": list(shape), "halo_planes": halo_used,
+            "halo_schedule": sched,
             "halo_note": (f"sized from the warm-up evaluation's largest x-displacement (x 1.25 + 2 planes; default "
                           f"{halo_default}); the guard raises if a particle leaves its extended slab"
                           if halo_used != halo_default else "default"),

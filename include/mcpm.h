@@ -258,13 +258,17 @@ int mcpm_half_weight_axpy(void* stream, const void* in, void* out, int64_t nc, i
  *   gather : own[j] = prev[xl + j],  own[halo + xl + j] = next[halo + j]               j < halo   (before a readout)
  *   gather4: builds the float4 force mesh {Fx, Fy, Fz, 0} [xl + 2 halo][plane cells] from the three planar meshes of
  *            OWNED planes [3][xl][plane cells] of this rank and its two neighbours (interleave + halo fetch in one pass).
- * The caller orders the ranks with a barrier before (the neighbours' planes are complete) and before reuse. */
+ * The caller orders the ranks with a barrier before (the neighbours' planes are complete) and before reuse.
+ * active (0 = halo): only the `active` halo planes next to the owned region are exchanged -- what a step needs while its
+ * particles stay within active - 1 planes of their sites (the halo is sized for a = 1; early steps need a few planes):
+ *   reduce : own[halo + j] += prev[halo + xl + j],  own[xl + halo - active + j] += next[halo - active + j]    j < active
+ *   gather : own[halo - active + j] = prev[xl + halo - active + j],  own[halo + xl + j] = next[halo + j]      j < active */
 int mcpm_halo_reduce_peer(void* stream, float* own_ext, const float* prev_ext, const float* next_ext, int halo, int xl,
-                          int64_t plane, int nlead);
+                          int64_t plane, int nlead, int active);
 int mcpm_halo_gather_peer(void* stream, float* own_ext, const float* prev_ext, const float* next_ext, int halo, int xl,
-                          int64_t plane, int nlead);
+                          int64_t plane, int nlead, int active);
 int mcpm_halo_gather4_peer(void* stream, float* fmesh4_ext, const float* f3_own, const float* f3_prev, const float* f3_next,
-                           int halo, int xl, int64_t plane);
+                           int halo, int xl, int64_t plane, int active);
 
 /* Fused x-transform passes (CUDA build, nx in {64, 128, 256, 512, 1024}; MCPM_EUNSUP otherwise), on a half spectrum
  * [nx, ny_loc, nz/2+1] that has been transformed along (y,z) only:

@@ -108,9 +108,9 @@ SIGNATURES = {
     "mcpm_read_grad4v_step_f": ([vp, vp, vp, vp, vp, vp, f32, f32, f32, i64] + MESH + [vp], i32),
     "mcpm_paint_brick_f": ([vp, vp, i32, i32, i32, vp, vp, f32, f32, i64] + MESH + [vp], i32),
     "mcpm_paint3_brick_f": ([vp, vp, i32, i32, i32, vp, vp, vp, f32, f32, i64] + MESH + [vp], i32),
-    "mcpm_halo_reduce_peer": ([vp, vp, vp, vp, i32, i32, i64, i32], i32),
-    "mcpm_halo_gather_peer": ([vp, vp, vp, vp, i32, i32, i64, i32], i32),
-    "mcpm_halo_gather4_peer": ([vp, vp, vp, vp, vp, i32, i32, i64], i32),
+    "mcpm_halo_reduce_peer": ([vp, vp, vp, vp, i32, i32, i64, i32, i32], i32),
+    "mcpm_halo_gather_peer": ([vp, vp, vp, vp, i32, i32, i64, i32, i32], i32),
+    "mcpm_halo_gather4_peer": ([vp, vp, vp, vp, vp, i32, i32, i64, i32], i32),
     "mcpm_drift": ([vp, vp, vp, f32, i64], i32),
     "mcpm_pm_forces": ([vp, vp, vp, i64, i32, i32, i32, i32, f32, vp, vp], i32),
     "mcpm_pm_forces_vjp": ([vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, f32, vp, i32], i32),

@@ -1077,26 +1077,29 @@ int mcpm_paint3_brick_f(void* stream, const mcpm_frame* frame, int px, int py, i
 }
 
 int mcpm_halo_reduce_peer(void* stream, float* own_ext, const float* prev_ext, const float* next_ext, int halo, int xl,
-                          int64_t plane, int nlead) {
+                          int64_t plane, int nlead, int active) {
   API_BEGIN
   NEED(own_ext && prev_ext && next_ext && halo >= 1 && halo <= xl && plane > 0 && nlead >= 1, "halo_reduce_peer: bad arguments");
-  return halo_reduce_peer(as_stream(stream), own_ext, prev_ext, next_ext, halo, xl, plane, nlead);
+  NEED(active >= 0 && active <= halo, "halo_reduce_peer: active planes must be in 0..halo (0 = all)");
+  return halo_reduce_peer(as_stream(stream), own_ext, prev_ext, next_ext, halo, xl, plane, nlead, active ? active : halo);
   API_END
 }
 
 int mcpm_halo_gather_peer(void* stream, float* own_ext, const float* prev_ext, const float* next_ext, int halo, int xl,
-                          int64_t plane, int nlead) {
+                          int64_t plane, int nlead, int active) {
   API_BEGIN
   NEED(own_ext && prev_ext && next_ext && halo >= 1 && halo <= xl && plane > 0 && nlead >= 1, "halo_gather_peer: bad arguments");
-  return halo_gather_peer(as_stream(stream), own_ext, prev_ext, next_ext, halo, xl, plane, nlead);
+  NEED(active >= 0 && active <= halo, "halo_gather_peer: active planes must be in 0..halo (0 = all)");
+  return halo_gather_peer(as_stream(stream), own_ext, prev_ext, next_ext, halo, xl, plane, nlead, active ? active : halo);
   API_END
 }
 
 int mcpm_halo_gather4_peer(void* stream, float* fmesh4_ext, const float* f3_own, const float* f3_prev, const float* f3_next,
-                           int halo, int xl, int64_t plane) {
+                           int halo, int xl, int64_t plane, int active) {
   API_BEGIN
   NEED(fmesh4_ext && f3_own && f3_prev && f3_next && halo >= 1 && halo <= xl && plane > 0, "halo_gather4_peer: bad arguments");
-  return halo_gather4_peer(as_stream(stream), fmesh4_ext, f3_own, f3_prev, f3_next, halo, xl, plane);
+  NEED(active >= 0 && active <= halo, "halo_gather4_peer: active planes must be in 0..halo (0 = all)");
+  return halo_gather4_peer(as_stream(stream), fmesh4_ext, f3_own, f3_prev, f3_next, halo, xl, plane, active ? active : halo);
   API_END
 }
 

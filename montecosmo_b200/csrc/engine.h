@@ -185,10 +185,10 @@ int read_grad4v(stream_t, const float* pos, const float* fmesh4, const float* rh
                 float* zero = nullptr, int64_t nzero = 0, const Frame* fr = nullptr, float dnext = 0.0f);
 
 // halo.cu: halo exchange of a slab-decomposed mesh as kernels over peer memory
-int halo_reduce_peer(stream_t, float* own, const float* prev, const float* next, int H, int xl, int64_t plane, int nlead);
-int halo_gather_peer(stream_t, float* own, const float* prev, const float* next, int H, int xl, int64_t plane, int nlead);
+int halo_reduce_peer(stream_t, float* own, const float* prev, const float* next, int H, int xl, int64_t plane, int nlead, int h);
+int halo_gather_peer(stream_t, float* own, const float* prev, const float* next, int H, int xl, int64_t plane, int nlead, int h);
 int halo_gather4_peer(stream_t, float* fm4_ext, const float* F_own, const float* F_prev, const float* F_next, int H, int xl,
-                      int64_t plane);
+                      int64_t plane, int h);
 
 // yzfft.cu (CUDA build only): fused two-pass (y,z) R2C / C2R on square planes of side 64, 128, 256; unnormalised
 bool yzfft_supported(int ny, int nz);

@@ -13,6 +13,10 @@
 //   gather4:  the same, building the float4 force mesh {Fx, Fy, Fz, 0} of the step kernels from the three planar meshes
 //             the C2R wrote (own planes included): the interleave pass and the halo fetch in one kernel.
 // With one rank prev = next = own: the periodic wrap of a single slab.
+// ACTIVE planes h <= H: only the h halo planes next to the owned region take part (the particles of a step stay within
+// h - 1 planes of their sites early in a run, when the displacements are small); h = H is the whole halo.
+//   reduce :  own[H + j] += prev[H + xl + j]          own[xl + H - h + j] += next[H - h + j]      j < h
+//   gather :  own[H - h + j] = prev[xl + H - h + j]   own[H + xl + j]      = next[H + j]          j < h
 #include "engine.h"
 
 namespace mcpm {
@@ -23,22 +27,22 @@ struct alignas(16) hf4 {
 
 // meshes laid out [nlead][ext][plane] (nlead = 3 for the planar reverse-step scatter, 1 otherwise)
 int halo_reduce_peer(stream_t st, float* own, const float* prev, const float* next, int H, int xl, int64_t plane,
-                     int nlead) {
-  const int64_t ext = xl + 2 * (int64_t)H, slab = (int64_t)H * plane;
+                     int nlead, int h) {
+  const int64_t ext = xl + 2 * (int64_t)H, slab = (int64_t)h * plane, lo = (int64_t)(H - h) * plane;
   launch_1d(st, (int64_t)nlead * slab, [=] MCPM_LAMBDA(int64_t i) {
     const int64_t c = i / slab, r = i - c * slab, base = c * ext * plane;
     own[base + (int64_t)H * plane + r] += prev[base + (int64_t)(H + xl) * plane + r];
-    own[base + (int64_t)xl * plane + r] += next[base + r];
+    own[base + (int64_t)xl * plane + lo + r] += next[base + lo + r];
   });
   return rt_check("halo_reduce_peer");
 }
 
 int halo_gather_peer(stream_t st, float* own, const float* prev, const float* next, int H, int xl, int64_t plane,
-                     int nlead) {
-  const int64_t ext = xl + 2 * (int64_t)H, slab = (int64_t)H * plane;
+                     int nlead, int h) {
+  const int64_t ext = xl + 2 * (int64_t)H, slab = (int64_t)h * plane, lo = (int64_t)(H - h) * plane;
   launch_1d(st, (int64_t)nlead * slab, [=] MCPM_LAMBDA(int64_t i) {
     const int64_t c = i / slab, r = i - c * slab, base = c * ext * plane;
-    own[base + r] = prev[base + (int64_t)xl * plane + r];
+    own[base + lo + r] = prev[base + (int64_t)xl * plane + lo + r];
     own[base + (int64_t)(H + xl) * plane + r] = next[base + (int64_t)H * plane + r];
   });
   return rt_check("halo_gather_peer");
@@ -46,8 +50,8 @@ int halo_gather_peer(stream_t st, float* own, const float* prev, const float* ne
 
 // F_* : three planar meshes [3][xl][plane] of OWNED planes (this rank's and its neighbours'); out: [ext][plane] float4
 int halo_gather4_peer(stream_t st, float* fm4_ext, const float* F_own, const float* F_prev, const float* F_next, int H,
-                      int xl, int64_t plane) {
-  const int64_t own_n = (int64_t)xl * plane, halo_n = (int64_t)H * plane;
+                      int xl, int64_t plane, int h) {
+  const int64_t own_n = (int64_t)xl * plane, halo_n = (int64_t)h * plane, lead = (int64_t)H * plane;
   hf4* out = reinterpret_cast<hf4*>(fm4_ext);
   launch_1d(st, own_n + 2 * halo_n, [=] MCPM_LAMBDA(int64_t i) {
     const float* F;
@@ -55,15 +59,15 @@ int halo_gather4_peer(stream_t st, float* fm4_ext, const float* F_own, const flo
     if (i < own_n) {  // my planes
       F = F_own;
       src = i;
-      dst = halo_n + i;
-    } else if (i < own_n + halo_n) {  // left halo: the last H owned planes of the previous rank
+      dst = lead + i;
+    } else if (i < own_n + halo_n) {  // left halo (its h inner planes): the last h owned planes of the previous rank
       F = F_prev;
       src = own_n - halo_n + (i - own_n);
-      dst = i - own_n;
-    } else {  // right halo: the first H owned planes of the next rank
+      dst = lead - halo_n + (i - own_n);
+    } else {  // right halo: the first h owned planes of the next rank
       F = F_next;
       src = i - own_n - halo_n;
-      dst = halo_n + own_n + src;
+      dst = lead + own_n + src;
     }
     hf4 v;
     v.x = F[src];

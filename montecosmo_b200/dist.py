@@ -112,7 +112,9 @@ class SlabPM:
         self.q_own = self.A.prepare(np.stack(np.meshgrid(*ax, indexing="ij"), -1).reshape(-1, 3))  # owned-slab coords
         self.frame = _frame((self.xl, ny, nz), origin=(self.H, 0, 0))  # relative positions on the halo-extended mesh
         self._fr = C.byref(self.frame)
-        self._maxdx = None  # running max |x displacement| seen by the guard (device float)
+        self._maxdx = None  # running maxima of |x displacement| seen by the guard (device floats, _guard)
+        self._hsched = None  # active halo planes per step (set_halo_schedule); None: the whole halo
+        self._h = self.H     # active halo planes of the exchange in flight
         # tape_forces = False: the step loop tapes kick positions only and the reverse sweep recomputes each step's force
         # mesh (one more paint + force evaluation per step instead of 16 bytes per extended cell and step: at 1024^3 on 8
         # GPUs with 20 steps that is 59 GB per GPU) -- the trade of the reference's checkpointed adjoint (nbody.py:999)
@@ -321,28 +323,39 @@ class SlabPM:
     def halo_reduce(self, ext, lead=False):
         """ext [ext, ny, nz(,4)] (lead: [c, ext, ny, nz]): send both halos to the neighbours, add theirs into my owned
         planes."""
-        H, xl = self.H, self.xl
+        H, xl, h = self.H, self.xl, self._h  # h <= H active planes: the ones next to the owned region
         e = ext.movedim(1, 0) if lead else ext  # a view with the plane index first
-        a, b = torch.empty_like(e[:H].contiguous()), torch.empty_like(e[:H].contiguous())
-        self._exchange(e[:H].contiguous(), e[H + xl:].contiguous(), a, b)
-        e[xl:xl + H] += a  # next's left halo covers my last H owned planes
-        e[H:2 * H] += b  # prev's right halo covers my first H owned planes
+        a, b = torch.empty_like(e[:h].contiguous()), torch.empty_like(e[:h].contiguous())
+        self._exchange(e[H - h:H].contiguous(), e[H + xl:H + xl + h].contiguous(), a, b)
+        e[xl + H - h:xl + H] += a  # next's left halo covers my last owned planes
+        e[H:H + h] += b  # prev's right halo covers my first owned planes
 
     def halo_gather(self, ext):
         """ext [ext, ny, nz(,4)]: fill both halos from the neighbours' owned planes (transpose of halo_reduce)."""
-        H, xl = self.H, self.xl
-        right, left = torch.empty_like(ext[:H]), torch.empty_like(ext[:H])
-        self._exchange(ext[H:2 * H].contiguous(), ext[xl:xl + H].contiguous(), right, left)
-        ext[H + xl:] = right
-        ext[:H] = left
+        H, xl, h = self.H, self.xl, self._h
+        right, left = torch.empty_like(ext[:h]), torch.empty_like(ext[:h])
+        self._exchange(ext[H:H + h].contiguous(), ext[xl + H - h:xl + H].contiguous(), right, left)
+        ext[H + xl:H + xl + h] = right
+        ext[H - h:H] = left
 
-    def _guard(self, pos):
+    NSLOT = 129  # slot 0: every guarded position; slot 1 + s: the kick positions of step s (s < 128)
+
+    def _guard(self, pos, step=None):
         # site i + displacement d must keep the CIC stencil inside the extended slab: 1 <= H + i + d <= ext - 2 for every
-        # owned i in [0, xl)
-        # one pass over the strided x column (mcpm_absmax) into a running maximum on the device; nothing synchronises
+        # owned i in [0, xl).  One pass over the strided x column (mcpm_absmax) into running maxima on the device; nothing
+        # synchronises.  The kick positions of step s are also tracked on their own: they size that step's active halo.
         if self._maxdx is None:
-            self._maxdx = self.A.zeros((1,))
+            self._maxdx = self.A.zeros((self.NSLOT,))
         self._call("mcpm_absmax", self._st(), pos.data_ptr(), pos.shape[0], 3, self._maxdx.data_ptr())
+        if step is not None and step + 1 < self.NSLOT:
+            self._call("mcpm_absmax", self._st(), pos.data_ptr(), pos.shape[0], 3, self._maxdx[step + 1:].data_ptr())
+
+    def _maxima(self):
+        """Host copy of the running maxima, all-reduced over the ranks (one read, one collective)."""
+        m = self._maxdx.detach().clone()
+        if self.P > 1:
+            dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self.group)
+        return m.cpu().numpy()
 
     def halo_needed(self, factor=1.25, margin=2):
         """Halo planes that would have held every particle seen by the guard since this object was built (max over ranks
@@ -352,15 +365,37 @@ class SlabPM:
         import math
         if self._maxdx is None:
             return self.H
-        m = self._maxdx.detach().clone()
-        if self.P > 1:
-            dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self.group)
-        return int(math.ceil(float(m) * factor)) + int(margin)
+        return int(math.ceil(float(self._maxima()[0]) * factor)) + int(margin)
+
+    def halo_schedule(self, n_steps, factor=1.25, margin=2):
+        """Active halo planes per step of the loop, from the largest |x displacement| seen at each step's kick positions
+        (same rule as halo_needed, capped at the allotted halo): early steps exchange a few planes, the last ones all."""
+        import math
+        if self._maxdx is None:
+            return None
+        m = self._maxima()
+        return [max(1, min(self.H, int(math.ceil(float(m[1 + s]) * factor)) + int(margin))) for s in range(n_steps)]
+
+    def set_halo_schedule(self, sched):
+        """sched[s] = active halo planes of step s (None: the whole halo every step).  The guard checks each step against
+        its own entry, so a later evaluation that outgrows the schedule raises instead of losing deposits."""
+        self._hsched = None if sched is None else [int(v) for v in sched]
+
+    def _active(self, s):
+        return self.H if self._hsched is None or s >= len(self._hsched) else self._hsched[s]
 
     def check_guard(self):
         """Raise if any particle came within a cell of the edge of its extended slab since the last check (one sync)."""
-        if self._maxdx is not None and not float(self._maxdx) <= self.H - 1.0:  # also catches NaN
+        if self._maxdx is None:
+            return
+        m = self._maxdx.detach().cpu().numpy()  # one read
+        if not float(m[0]) <= self.H - 1.0:  # also catches NaN
             raise RuntimeError(f"a particle left its extended slab: increase halo (= {self.H} planes)")
+        if self._hsched is not None:
+            for s, h in enumerate(self._hsched):
+                if 1 + s < self.NSLOT and not float(m[1 + s]) <= h - 1.0:
+                    raise RuntimeError(f"step {s}: a particle left the {h} active halo planes of the schedule "
+                                       f"(largest x-displacement {float(m[1 + s]):.2f}): set_halo_schedule(None) or a wider one")
 
     # ------------------------------------------------------------------------------------------------ Fourier passes
     def force_spectra(self, dk, lap_fd=INF, grad_fd=INF, deconv_order=0):
@@ -425,7 +460,7 @@ class SlabPM:
         if peer:  # one kernel per exchange over the neighbours' memory (csrc/halo.cu); barriers order the ranks
             if hd_rho is not None:
                 hd_rho.barrier()
-            self._call("mcpm_halo_reduce_peer", st, p_rho[0], p_rho[1], p_rho[2], self.H, self.xl, plane, 1)
+            self._call("mcpm_halo_reduce_peer", st, p_rho[0], p_rho[1], p_rho[2], self.H, self.xl, plane, 1, self._h)
             Fb, hd_F, p_F = self._halo_buf("F", (3, self.xl, self.ny, self.nz))
             F = self.forces_from_density(rho[self.H:self.H + self.xl], out=Fb if self.p2p else None)
             if not self.p2p:
@@ -433,7 +468,7 @@ class SlabPM:
             if hd_F is not None:
                 hd_F.barrier()
             # interleave {Fx, Fy, Fz, 0} and fetch the halo planes from the neighbours' owned planes in one pass
-            self._call("mcpm_halo_gather4_peer", st, fm4.data_ptr(), p_F[0], p_F[1], p_F[2], self.H, self.xl, plane)
+            self._call("mcpm_halo_gather4_peer", st, fm4.data_ptr(), p_F[0], p_F[1], p_F[2], self.H, self.xl, plane, self._h)
             return fm4
         self.halo_reduce(rho)
         F = self.forces_from_density(rho[self.H:self.H + self.xl])  # [3, xl, ny, nz]
@@ -459,13 +494,15 @@ class SlabPM:
         self._call("mcpm_drift", st, pos.data_ptr(), vel.data_ptr(), float(drift_pre[0]), pos.shape[0])
         out = []
         for s in range(ns):
-            self._guard(pos)
+            self._guard(pos, step=s)
+            self._h = self._active(s)
             fm4 = self.force_mesh4(pos)
             if tape:
                 out.append((pos.clone(), fm4 if self.tape_forces else None))
             dcomb = float(drift_post[s]) + (float(drift_pre[s + 1]) if s + 1 < ns else 0.0)
             self._call("mcpm_kick_drift4_f", st, self._fr, pos.data_ptr(), vel.data_ptr(), fm4.data_ptr(), pos.shape[0],
                        self.ext, self.ny, self.nz, float(alpha[s]), float(beta[s]), dcomb)
+        self._h = self.H
         self._guard(pos)
         return out
 
@@ -481,6 +518,7 @@ class SlabPM:
             self._call("mcpm_drift", st, velbar.data_ptr(), posbar.data_ptr(), dcomb(ns - 1), n)
         for s in reversed(range(ns)):
             x1, fm4 = tape[s]
+            self._h = self._active(s)  # the exchanges of a reverse step are the transposes of its forward ones
             if fm4 is None:  # not taped: recompute from the kick positions
                 fm4 = self.force_mesh4(x1)
             dnext = dcomb(s - 1) if s > 0 else float(drift_pre[0])
@@ -499,7 +537,7 @@ class SlabPM:
                 if peer:
                     if hd3 is not None:
                         hd3.barrier()
-                    self._call("mcpm_halo_reduce_peer", st, p3[0], p3[1], p3[2], self.H, self.xl, plane, 3)
+                    self._call("mcpm_halo_reduce_peer", st, p3[0], p3[1], p3[2], self.H, self.xl, plane, 3, self._h)
                 else:
                     self.halo_reduce(m3, lead=True)  # three planar extended meshes
                 planar = m3[:, self.H:self.H + self.xl].contiguous()
@@ -509,7 +547,7 @@ class SlabPM:
                            float(beta[s]), n, self.ext, self.ny, self.nz, m4.data_ptr())
                 if self.P == 1:  # one rank: the periodic wrap, same kernel on the float4 mesh
                     self._call("mcpm_halo_reduce_peer", st, m4.data_ptr(), m4.data_ptr(), m4.data_ptr(), self.H, self.xl,
-                               4 * plane, 1)
+                               4 * plane, 1, self._h)
                 else:
                     self.halo_reduce(m4)
                 planar = A.empty((3, self.xl, self.ny, self.nz))
@@ -522,7 +560,7 @@ class SlabPM:
                     own.copy_(res)
                 if hdr is not None:
                     hdr.barrier()
-                self._call("mcpm_halo_gather_peer", st, pr[0], pr[1], pr[2], self.H, self.xl, plane, 1)
+                self._call("mcpm_halo_gather_peer", st, pr[0], pr[1], pr[2], self.H, self.xl, plane, 1, self._h)
             else:
                 rhobar = A.empty((self.ext, self.ny, self.nz))
                 rhobar[self.H:self.H + self.xl] = self.density_cotangent(planar)
@@ -530,6 +568,7 @@ class SlabPM:
             self._call("mcpm_read_grad4v_step_f", st, self._fr, x1.data_ptr(), fm4.data_ptr(), rhobar.data_ptr(),
                        velbar.data_ptr(), float(beta[s]), float(alpha[s]), dnext, n, self.ext, self.ny, self.nz,
                        posbar.data_ptr())
+        self._h = self.H
 
     # ------------------------------------------------------------------------------------------------ LPT
     def _lattice_read3(self, planar3):

@@ -98,6 +98,22 @@ def _worker(rank, world, port, shape, halo, q):
         pm2 = SlabPM(ops, shape, halo=min(need, H))
         pos2, vel2, _ = pm2.nbody_forward(pm2.scatter_spectrum(torch.tensor(dk)), c, a0, a1, ns)
         res["halo_resized"] = max(float(np.abs(pos2.numpy() - pos.numpy()).max()), rel(vel2.numpy(), vel.numpy()))
+        # 5. per-step active halo planes from the measured kick positions: the exchanges of the early steps move fewer
+        # planes; forward and reverse sweeps unchanged; a schedule that is too narrow trips the guard
+        sched = pm.halo_schedule(ns, factor=1.0, margin=2)
+        res["sched_ok"] = float(not (len(sched) == ns and all(1 <= h <= H for h in sched) and sched[0] <= sched[-1]))
+        pm.set_halo_schedule(sched)
+        pos3, vel3, tape3 = pm.nbody_forward(pm.scatter_spectrum(torch.tensor(dk)), c, a0, a1, ns)
+        dkbar3 = pm.nbody_backward(tape3, torch.tensor(pb[sl]), torch.tensor(vb[sl]))
+        res["sched_same"] = max(float(np.abs(pos3.numpy() - pos.numpy()).max()), rel(vel3.numpy(), vel.numpy()),
+                                rel(dkbar3.numpy(), dkbar.numpy()))
+        pm.set_halo_schedule([1] * ns)
+        try:
+            pm.nbody_forward(pm.scatter_spectrum(torch.tensor(dk)), c, a0, a1, ns)
+            res["sched_guard"] = 1.0
+        except RuntimeError:
+            res["sched_guard"] = 0.0
+        pm.set_halo_schedule(None)
         q.put((rank, res, None))
         dist.destroy_process_group()
     except Exception as e:  # surface the traceback in the parent
@@ -126,6 +142,7 @@ def test_slab_engine_world2_gloo(world, shape, halo):
         assert res["steps_bwd"] < 5e-4 and res["lpt_bwd"] < 5e-4 and res["dkbar"] < 5e-4, res
         assert res["disp_rms"] > 0.2, res  # the comparison above is on a genuinely displaced lattice
         assert res["halo_needed_ok"] == 0.0 and res["halo_resized"] < 1e-5, res
+        assert res["sched_ok"] == 0.0 and res["sched_same"] < 1e-5 and res["sched_guard"] == 0.0, res
 
 
 def _model_worker(rank, world, port, shape, halo, kw, q):

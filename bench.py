@@ -620,7 +620,11 @@ def run_slab(args, world, rank, dev, timed, barrier, sampler):
         obs = (mdl.predict(torch.randn(local_shape, device=dev, generator=gen))
                + torch.randn(local_shape, device=dev, generator=gen)).contiguous()
     whites = [torch.randn(local_shape, device=dev, generator=gen) for _ in range(2)]
-    mdl.value_and_force(whites[0], obs)
+    h_white = [torch.randn(local_shape, generator=torch.Generator().manual_seed(7 + i + 10 * rank)).pin_memory()
+               for i in range(2)]
+    fields = whites + [h.to(dev) for h in h_white]  # every white field the timed loops will see
+    for f in fields:  # the halo below is sized from ALL of them: a field never seen could outgrow it and trip the guard
+        mdl.value_and_force(f, obs)
     torch.cuda.synchronize()
     # Halo sized from a measurement: the default of 24 planes is an a = 1 worst case; the warm-up evaluation's largest
     # x-displacement (max over ranks) x 1.25 + 2 planes is what this run needs -- at 64 owned planes per rank (8 GPUs) 24
@@ -637,13 +641,15 @@ def run_slab(args, world, rank, dev, timed, barrier, sampler):
             pm = SlabPM(ops, shape, halo=need)
             mdl = SlabFieldModel(pm, wl["box_size"], n_steps=wl["n_steps"], a_start=wl["a_start"], a_obs=wl["a_obs"],
                                  b1=wl["b1"], rsd=wl["rsd"], sigma_obs=wl["sigma_obs"])
-            mdl.value_and_force(whites[0], obs)
+            for f in fields:
+                mdl.value_and_force(f, obs)
             torch.cuda.synchronize()
             halo_used = need
         # ... and per step: the kick positions of step s stay within a few planes early in the run, so the exchanges of
         # that step (and of its reverse step) move only the active planes next to the owned region
         sched = pm.halo_schedule(wl["n_steps"])
         pm.set_halo_schedule(sched)
+    del fields
     lib.mcpm_launch_count(1)
     mdl.value_and_force(whites[0], obs)
     torch.cuda.synchronize()
@@ -672,8 +678,6 @@ def run_slab(args, world, rank, dev, timed, barrier, sampler):
         keep["out"] = mdl.value_and_force(whites[i % 2], obs)
     ms_dev = timed(step_dev)
     nl = int(np.prod(local_shape))
-    h_white = [torch.randn(local_shape, generator=torch.Generator().manual_seed(7 + i + 10 * rank)).pin_memory()
-               for i in range(2)]
     h_grad = torch.empty(local_shape, dtype=torch.float32).pin_memory()
     h_lp = torch.empty((), dtype=torch.float64).pin_memory()
     d_white = torch.empty(local_shape, device=dev)

@@ -484,9 +484,9 @@ int nufft_vjp(Engine* E, stream_t st, const float* pos, const float* weights, fl
   TRY(fft_c2r(E->fft, st, E->c(0), E->r(0), m));
   Frame f;
   const Frame* fr = E->frame(f);
-  for (int i = 0; i < m; ++i)
-    TRY(paint_vjp(st, pos, weights, wscalar, E->r(i), np, E->nx, E->ny, E->nz, paint_order, scale,
-                  (float)i / (float)m, posbar, weightsbar, i > 0, kb_kcut, fr, obs, velbar));
+  // the m interlaced transposes in one gather over the particles (meshes r(0) .. r(m - 1) are contiguous)
+  TRY(paint_vjp(st, pos, weights, wscalar, E->r(0), np, E->nx, E->ny, E->nz, paint_order, scale, 0.0f, posbar, weightsbar,
+                0, kb_kcut, fr, obs, velbar, m, E->N));
   return 0;
 }
 

@@ -91,7 +91,7 @@ int paint3(stream_t, const float* pos, const float* A, float ca, const float* B,
 int paint_vjp(stream_t, const float* pos, const float* weights, float wscalar, const float* mbar, int64_t np, int nx,
               int ny, int nz, int order, const float* scale, float shift, float* posbar, float* wbar,
               int accumulate, float kb_kcut = 0.0f, const Frame* fr = nullptr, const ObsShift* obs = nullptr,
-              float* velbar = nullptr);
+              float* velbar = nullptr, int nshift = 1, int64_t mesh_stride = 0);
 int kick_drift(stream_t, const float* pos, const float* vel, const float* fmesh3, int64_t np, int nx, int ny, int nz,
                int order, float alpha, float beta, float drift, float* pos_out, float* vel_out, float* force_out,
                const Frame* fr = nullptr);

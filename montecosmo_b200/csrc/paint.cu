@@ -25,20 +25,26 @@ struct PosXform {
 // Transformed coordinate of particle p as an exact integer part b (its lattice site; 0 for absolute frames) plus a small
 // float part u:  x' = b + u,  u = site remainder + pos * scale + shift.  pos may be NULL in a relative frame (particles
 // on their sites).
-MCPM_HD void load_pos(const float* pos, int64_t p, const PosXform& xf, int* b, float* u) {
-  float r0, r1, r2;
-  frame_site(xf.fr, p, b[0], b[1], b[2], r0, r1, r2);
-  float d0 = pos ? pos[3 * p] : 0.0f, d1 = pos ? pos[3 * p + 1] : 0.0f, d2 = pos ? pos[3 * p + 2] : 0.0f;
+// The particle's own part of that: integer site b, site remainder r, and position d (observation shift included).
+MCPM_HD void load_site_disp(const float* pos, int64_t p, const PosXform& xf, int* b, float* r, float* d) {
+  frame_site(xf.fr, p, b[0], b[1], b[2], r[0], r[1], r[2]);
+  d[0] = pos ? pos[3 * p] : 0.0f;
+  d[1] = pos ? pos[3 * p + 1] : 0.0f;
+  d[2] = pos ? pos[3 * p + 2] : 0.0f;
   if (xf.obs.vel) {  // the same association as rsd_shift: pos + ((v . los) * coef) * los
     const float* v = xf.obs.vel + 3 * p;
     const float sh = (v[0] * xf.obs.lx + v[1] * xf.obs.ly + v[2] * xf.obs.lz) * xf.obs.coef;
-    d0 = d0 + sh * xf.obs.lx;
-    d1 = d1 + sh * xf.obs.ly;
-    d2 = d2 + sh * xf.obs.lz;
+    d[0] = d[0] + sh * xf.obs.lx;
+    d[1] = d[1] + sh * xf.obs.ly;
+    d[2] = d[2] + sh * xf.obs.lz;
   }
-  u[0] = r0 + (d0 * xf.sx + xf.shift);
-  u[1] = r1 + (d1 * xf.sy + xf.shift);
-  u[2] = r2 + (d2 * xf.sz + xf.shift);
+}
+MCPM_HD void load_pos(const float* pos, int64_t p, const PosXform& xf, int* b, float* u) {
+  float r[3], d[3];
+  load_site_disp(pos, p, xf, b, r, d);
+  u[0] = r[0] + (d[0] * xf.sx + xf.shift);
+  u[1] = r[1] + (d[1] * xf.sy + xf.shift);
+  u[2] = r[2] + (d[2] * xf.sz + xf.shift);
 }
 
 template <int ORDER, class WIN = RectWin>
@@ -236,40 +242,49 @@ static void paint3_impl(stream_t st, const float* pos, const float* A, float ca,
 
 // VJP of paint w.r.t. weights and positions from the mesh cotangent, one gather:
 //   wbar[p] (+)= wscalar * sum mesh_bar * W ;  posbar[p,a] (+)= w_p * scale_a * sum mesh_bar * dW_a ...
+// nshift > 1: the transposes of `nshift` interlaced paints in ONE gather -- mesh cotangent t = mbar + t * mesh_stride was
+// painted at shift xf.shift + t / nshift (nufft, nbody.py:524) -- so the particle arrays are read once and every output
+// is written once (two passes over the particles cost 0.77 ms of a 256^3 evaluation, with accumulating outputs).
 template <int ORDER, class WIN = RectWin>
 static void paint_vjp_impl(stream_t st, const float* pos, const float* weights, float wscalar, const float* mbar,
                            int64_t np, MeshDims n, PosXform xf, float* posbar, float* wbar, int accumulate,
-                           float* velbar, WIN win = WIN()) {
+                           float* velbar, int nshift, int64_t mesh_stride, WIN win = WIN()) {
   launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
-    int sb[3], fx, fy, fz;
-    float su[3];
-    load_pos(pos, p, xf, sb, su);
-    float wx[ORDER], wy[ORDER], wz[ORDER], dx[ORDER], dy[ORDER], dz[ORDER];
-    win.template weights_grad<ORDER>(su[0], fx, wx, dx);
-    win.template weights_grad<ORDER>(su[1], fy, wy, dy);
-    win.template weights_grad<ORDER>(su[2], fz, wz, dz);
-    fx = wrap_fast(fx + sb[0], n.nx);
-    fy = wrap_fast(fy + sb[1], n.ny);
-    fz = wrap_fast(fz + sb[2], n.nz);
+    int sb[3];
+    float sr[3], sd[3];
+    load_site_disp(pos, p, xf, sb, sr, sd);
     float r = 0.0f, g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
+    for (int t = 0; t < nshift; ++t) {
+      const float sh = xf.shift + (float)t / (float)nshift;  // exactly the shifts the forward paints used (engine.cu: nufft)
+      const float su[3] = {sr[0] + (sd[0] * xf.sx + sh), sr[1] + (sd[1] * xf.sy + sh), sr[2] + (sd[2] * xf.sz + sh)};
+      const float* mb = mbar + (int64_t)t * mesh_stride;
+      int fx, fy, fz;
+      float wx[ORDER], wy[ORDER], wz[ORDER], dx[ORDER], dy[ORDER], dz[ORDER];
+      win.template weights_grad<ORDER>(su[0], fx, wx, dx);
+      win.template weights_grad<ORDER>(su[1], fy, wy, dy);
+      win.template weights_grad<ORDER>(su[2], fz, wz, dz);
+      fx = wrap_fast(fx + sb[0], n.nx);
+      fy = wrap_fast(fy + sb[1], n.ny);
+      fz = wrap_fast(fz + sb[2], n.nz);
 #pragma unroll
-    for (int a = 0; a < ORDER; ++a) {
-      int ia = fx + a;
-      ia = ia >= n.nx ? ia - n.nx : ia;
+      for (int a = 0; a < ORDER; ++a) {
+        int ia = fx + a;
+        ia = ia >= n.nx ? ia - n.nx : ia;
 #pragma unroll
-      for (int b = 0; b < ORDER; ++b) {
-        int ib = fy + b;
-        ib = ib >= n.ny ? ib - n.ny : ib;
-        int64_t row = ((int64_t)ia * n.ny + ib) * n.nz;
+        for (int b = 0; b < ORDER; ++b) {
+          int ib = fy + b;
+          ib = ib >= n.ny ? ib - n.ny : ib;
+          int64_t row = ((int64_t)ia * n.ny + ib) * n.nz;
 #pragma unroll
-        for (int c = 0; c < ORDER; ++c) {
-          int ic = fz + c;
-          ic = ic >= n.nz ? ic - n.nz : ic;
-          float v = mbar[row + ic];
-          r += v * (wx[a] * wy[b] * wz[c]);
-          g0 += v * (dx[a] * wy[b] * wz[c]);
-          g1 += v * (wx[a] * dy[b] * wz[c]);
-          g2 += v * (wx[a] * wy[b] * dz[c]);
+          for (int c = 0; c < ORDER; ++c) {
+            int ic = fz + c;
+            ic = ic >= n.nz ? ic - n.nz : ic;
+            float v = mb[row + ic];
+            r += v * (wx[a] * wy[b] * wz[c]);
+            g0 += v * (dx[a] * wy[b] * wz[c]);
+            g1 += v * (wx[a] * dy[b] * wz[c]);
+            g2 += v * (wx[a] * wy[b] * dz[c]);
+          }
         }
       }
     }
@@ -507,7 +522,8 @@ int paint3(stream_t st, const float* pos, const float* A, float ca, const float*
 
 int paint_vjp(stream_t st, const float* pos, const float* weights, float wscalar, const float* mbar, int64_t np,
               int nx, int ny, int nz, int order, const float* scale, float shift, float* posbar, float* wbar,
-              int accumulate, float kb_kcut, const Frame* fr, const ObsShift* obs, float* velbar) {
+              int accumulate, float kb_kcut, const Frame* fr, const ObsShift* obs, float* velbar, int nshift,
+              int64_t mesh_stride) {
   if (int e = check_mesh(nx, ny, nz, order)) return e;
   if (np > 0 && ((!pos && !(fr && fr->rel)) || !mbar)) {
     set_error("paint_vjp: null pointer");
@@ -516,21 +532,22 @@ int paint_vjp(stream_t st, const float* pos, const float* weights, float wscalar
   MeshDims n = {nx, ny, nz};
   PosXform xf = make_xform(scale, shift, fr, obs);
   if (!(obs && obs->vel)) velbar = nullptr;
+  if (nshift < 1) nshift = 1;
   if (kb_kcut > 0.0f) {
     KbWin kb = make_kbwin(order, kb_kcut);
     switch (order) {
-      case 1: paint_vjp_impl<1>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar, kb); break;
-      case 2: paint_vjp_impl<2>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar, kb); break;
-      case 3: paint_vjp_impl<3>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar, kb); break;
-      default: paint_vjp_impl<4>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar, kb); break;
+      case 1: paint_vjp_impl<1>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar, nshift, mesh_stride, kb); break;
+      case 2: paint_vjp_impl<2>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar, nshift, mesh_stride, kb); break;
+      case 3: paint_vjp_impl<3>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar, nshift, mesh_stride, kb); break;
+      default: paint_vjp_impl<4>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar, nshift, mesh_stride, kb); break;
     }
     return rt_check("paint_vjp");
   }
   switch (order) {
-    case 1: paint_vjp_impl<1>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar); break;
-    case 2: paint_vjp_impl<2>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar); break;
-    case 3: paint_vjp_impl<3>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar); break;
-    default: paint_vjp_impl<4>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar); break;
+    case 1: paint_vjp_impl<1>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar, nshift, mesh_stride); break;
+    case 2: paint_vjp_impl<2>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar, nshift, mesh_stride); break;
+    case 3: paint_vjp_impl<3>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar, nshift, mesh_stride); break;
+    default: paint_vjp_impl<4>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar, nshift, mesh_stride); break;
   }
   return rt_check("paint_vjp");
 }

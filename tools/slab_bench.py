@@ -50,6 +50,9 @@ def main():
     ap.add_argument("--oversamp", type=float, default=1.0,
                     help="with --model: paint mesh = oversamp x evolution mesh (BASELINE C5 uses 2)")
     ap.add_argument("--no-force-tape", action="store_true", help="tape kick positions only; recompute force meshes in the reverse sweep")
+    ap.add_argument("--auto-halo", action="store_true",
+                    help="with --model: after the warm-up evaluations, set the per-step active halo planes from the measured "
+                         "x-displacements (SlabPM.halo_schedule); the allotted halo stays --halo")
     ap.add_argument("--model-check", action="store_true",
                     help="with --model: compare log-density and force with the single-GPU FieldModel (computed on every "
                          "rank's own GPU from the same global fields) before timing")
@@ -168,6 +171,12 @@ def main():
     for _ in range(a.warmup):
         step()
     barrier()
+    if a.auto_halo:
+        sched = pm.halo_schedule(a.nbody_steps)
+        pm.set_halo_schedule(sched)
+        out["halo_schedule"] = sched
+        step()  # one evaluation under the schedule before timing (and its guard check)
+        barrier()
     if pm.sections.on:
         pm.sections.report()  # drop the warm-up's sections
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -283,8 +283,10 @@ int mcpm_xfuse_force_slab(void* stream, const void* in, void* out3, int nx, int 
  * one NVLink domain): in_peers[r] / out_peers[r] are rank r's buffers [ncomp][nx/npeer][ny][nz/2+1] -- the output of its
  * local 2-D R2C / the input of its local 2-D C2R -- mapped into this process (CUDA IPC / symmetric memory).  This rank
  * transforms the columns of ky rows y0 .. y0+ny_loc-1, loading every x-plane from and storing it to its owner over
- * NVLink: no all-to-all, no pack / unpack passes.  transpose = 0: 1 -> 3 components, 1: 3 -> 1.  The caller orders the
- * ranks with a barrier before (inputs complete everywhere) and after (outputs landed everywhere). */
+ * NVLink: no all-to-all, no pack / unpack passes.  transpose = 0: 1 -> 3 components, 1: 3 -> 1; 2: 1 -> 2 components
+ * (F^_x, Phi^) and 3: 2 -> 1 (C^_x, g_y C^_y + g_z C^_z) -- the two-field forms whose y / z parts mcpm_yz_gradients applies
+ * on the local planes, so that one field in four stays off the wire (plain kernel only: no kcut / deconvolution).  The
+ * caller orders the ranks with a barrier before (inputs complete everywhere) and after (outputs landed everywhere). */
 int mcpm_xfuse_force_peer(void* stream, const void* const* in_peers, void* const* out_peers, int npeer, int transpose,
                           int nx, int ny, int nz, int ny_loc, int y0, int lap_fd, int grad_fd, float kcut,
                           int deconv_order, float norm);
@@ -346,6 +348,12 @@ int mcpm_hermitian_weights(void* stream, const void* in, void* out, int nx, int 
  * flat-sky RSD in cell units (bricks.py:781-792): pos_out = pos + (vel . los) * coef * los, and its VJP w.r.t. vel. */
 int mcpm_axpby(void* stream, const float* x, float a, const float* y, float b, float c, int64_t n, float* out);
 int mcpm_dot(void* stream, const float* a, const float* b, int64_t n, double* out_f64);
+/* The y and z force components from the potential on spectra already in x-space (a slab-decomposed caller then moves two
+ * fields through the distributed x-transform instead of three): buf3 = [3][xl][ny][nz/2+1].  transpose = 0: components
+ * 0, 1 hold (F^_x, Phi^) as mcpm_xfuse_force_peer(transpose = 2) leaves them; on return components 1, 2 hold
+ * F^_y = -(i g_y) Phi^, F^_z = -(i g_z) Phi^ (gradient_hat, nbody.py:136-163; Hermitian-consistent).  transpose = 1:
+ * (C^_x, C^_y, C^_z) -> component 1 = g_y C^_y + g_z C^_z, the second input of mcpm_xfuse_force_peer(transpose = 3). */
+int mcpm_yz_gradients(void* stream, void* buf3_c64, int xl, int ny, int nz, int grad_fd, int transpose);
 /* out[0] = max(out[0], max_i |x[i * stride]|), out[0] >= 0 on entry (device float; NaN sticks): the halo guard of a
  * slab-decomposed caller -- the largest displacement of its particles across the slab direction -- as one pass. */
 int mcpm_absmax(void* stream, const float* x, int64_t n, int stride, float* out);

@@ -78,6 +78,7 @@ SIGNATURES = {
     "mcpm_hermitian_weights": ([vp, vp, vp] + MESH + [i32], i32),
     "mcpm_axpby": ([vp, vp, f32, vp, f32, f32, i64, vp], i32),
     "mcpm_dot": ([vp, vp, vp, i64, vp], i32),
+    "mcpm_yz_gradients": ([vp, vp, i32, i32, i32, i32, i32], i32),
     "mcpm_absmax": ([vp, vp, i64, i32, vp], i32),
     "mcpm_rsd_shift": ([vp, vp, vp, hp, f32, i64, vp], i32),
     "mcpm_rsd_shift_vjp": ([vp, vp, hp, f32, i64, vp, i32], i32),

@@ -789,6 +789,13 @@ int mcpm_dot(void* stream, const float* a, const float* b, int64_t n, double* ou
   API_END
 }
 
+int mcpm_yz_gradients(void* stream, void* buf3, int xl, int ny, int nz, int grad_fd, int transpose) {
+  API_BEGIN
+  NEED(buf3, "yz_gradients: null pointer");
+  return yz_gradients(as_stream(stream), C(buf3), xl, ny, nz, grad_fd, transpose);
+  API_END
+}
+
 int mcpm_absmax(void* stream, const float* x, int64_t n, int stride, float* out) {
   API_BEGIN
   NEED(out && (x || n == 0) && stride >= 1, "absmax: null pointer or stride < 1");

@@ -119,6 +119,7 @@ int bias_weights_vjp(stream_t, const float* vals, int K, float gs, const float* 
                      const float* wbar, const float* dvelbar, int64_t np, double* msum, float* valsbar, double* coefbar,
                      float* gbar_arr);
 int absmax_strided(stream_t, const float* x, int64_t n, int stride, float* out);
+int yz_gradients(stream_t, cfloat* buf3, int xl, int ny, int nz, int grad_fd, int transpose);
 int rsd_shift(stream_t, const float* pos, const float* vel, float lx, float ly, float lz, float coef, int64_t np,
               float* pos_out);
 int rsd_shift_vjp(stream_t, const float* posbar, float lx, float ly, float lz, float coef, int64_t np, float* velbar,

@@ -126,6 +126,37 @@ int hessian_spectra_T(stream_t st, const cfloat* in6, cfloat* out1, int nx, int 
   return rt_check("hessian_spectra_T");
 }
 
+// The y and z force components from the potential, on spectra that are already in x-space: buf3 = [3][xl][ny][nzc]
+// holds (F^_x, Phi^) of xfuse's FORCE2 in components 0, 1; on return components 1, 2 hold F^_y = -(i g_y) Phi^ and
+// F^_z = -(i g_z) Phi^ (gradient_hat along y / z, nbody.py:136-163, with the Hermitian projection of kspace.h: KVec --
+// the factors depend on (ky, kz) only, so they commute with the x-transform).  transpose = 1: components (C^_x, C^_y,
+// C^_z) -> component 1 = g_y C^_y + g_z C^_z, the input of FORCE2_T.  In place, one streaming pass over local planes.
+int yz_gradients(stream_t st, cfloat* buf3, int xl, int ny, int nz, int grad_fd, int transpose) {
+  if (int e = check_fd(grad_fd)) return e;
+  if (xl <= 0 || ny <= 0 || nz <= 0 || (nz & 1)) {
+    set_error("yz_gradients: bad shape");
+    return MCPM_EINVAL;
+  }
+  const int nzc = nz / 2 + 1;
+  const int64_t nc = (int64_t)xl * ny * nzc;
+  const float ty = (float)(6.283185307179586476925 / ny), tz = (float)(6.283185307179586476925 / nz);
+  launch_1d(st, nc, [=] MCPM_LAMBDA(int64_t e) {
+    const int l = (int)(e % nzc), j = (int)((e / nzc) % ny);
+    const bool nqy = 2 * j == ny, nqz = 2 * l == nz, sc = l == 0 || nqz;
+    const float gy = (sc && nqy) ? 0.0f : grad_term(ty * (float)signed_freq(j, ny), grad_fd);
+    const float gz = (sc && nqz) ? 0.0f : grad_term(tz * (float)l, grad_fd);
+    if (!transpose) {
+      const cfloat p = buf3[nc + e];
+      buf3[nc + e] = cfloat{gy * p.im, -gy * p.re};
+      buf3[2 * nc + e] = cfloat{gz * p.im, -gz * p.re};
+    } else {
+      const cfloat a = buf3[nc + e], b = buf3[2 * nc + e];
+      buf3[nc + e] = cfloat{gy * a.re + gz * b.re, gy * a.im + gz * b.im};
+    }
+  });
+  return rt_check("yz_gradients");
+}
+
 // d2 = h00 h11 + h00 h22 + h11 h22 - h01^2 - h02^2 - h12^2   (nbody.py:615-627)
 int lpt2_source(stream_t st, const float* h6, float* d2, int64_t n) {
   launch_1d(st, n, [=] MCPM_LAMBDA(int64_t e) {

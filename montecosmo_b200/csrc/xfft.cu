@@ -75,7 +75,9 @@ int xfuse_force_peer(stream_t st, const cfloat* const* in_peers, cfloat* const* 
     a.in_peer[r] = in_peers[r];
     a.out_peer[r] = out_peers[r];
   }
-  return xf::dispatch(transpose ? xf::FORCE_T : xf::FORCE, st, a);
+  // transpose: 0 force (1 -> 3), 1 its transpose (3 -> 1), 2 / 3 the two-field forms (xfft_kernel.h: FORCE2, FORCE2_T)
+  const int mode = transpose == 0 ? xf::FORCE : transpose == 1 ? xf::FORCE_T : transpose == 2 ? xf::FORCE2 : xf::FORCE2_T;
+  return xf::dispatch(mode, st, a);
 }
 
 // Any of the six operators (xfft_kernel.h: Mode) with its x-space side in peer memory: modes whose INPUT is x-space
@@ -85,8 +87,8 @@ int xfuse_force_peer(stream_t st, const cfloat* const* in_peers, cfloat* const* 
 int xfuse_peer_mode(stream_t st, int mode, const cfloat* const* in_peers, cfloat* const* out_peers, cfloat* k_local,
                     int npeer, int nx, int ny, int nz, int ny_loc, int y0, int lap_fd, int grad_fd, int half_weights,
                     int accumulate, float norm) {
-  if (npeer < 1 || npeer > 8 || nx % npeer || mode < 0 || mode > xf::HESS_TK) {
-    set_error("xfuse_peer_mode: 1..8 ranks, nx divisible by their number, mode 0..5");
+  if (npeer < 1 || npeer > 8 || nx % npeer || mode < 0 || mode > xf::FORCE2_T) {
+    set_error("xfuse_peer_mode: 1..8 ranks, nx divisible by their number, mode 0..7");
     return MCPM_EINVAL;
   }
   const bool k_in = mode == xf::FORCE_K || mode == xf::HESS_K, k_out = mode == xf::FORCE_TK || mode == xf::HESS_TK;

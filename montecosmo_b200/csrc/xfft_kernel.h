@@ -120,9 +120,18 @@ struct Args {
 //   HESS_K   out_t = IFFT_x[ -G g_a g_b in ], t = 00 11 22 01 02 12 1 -> 6   hessian_spectra, `in` a 3-D spectrum
 //   FORCE_TK out (+)= [w'/N] i c sum_j g_j FFT_x[in_j]              3 -> 1   force_spectra_T, `out` a 3-D spectrum
 //   HESS_TK  out (+)= [w'/N] -G sum_t g_a g_b FFT_x[in_t]           6 -> 1   hessian_spectra_T, `out` a 3-D spectrum
-enum Mode { FORCE = 0, FORCE_T = 1, FORCE_K = 2, HESS_K = 3, FORCE_TK = 4, HESS_TK = 5 };
-__host__ __device__ constexpr int n_in(int mode) { return mode == FORCE_T || mode == FORCE_TK ? 3 : (mode == HESS_TK ? 6 : 1); }
-__host__ __device__ constexpr int n_out(int mode) { return mode == FORCE || mode == FORCE_K ? 3 : (mode == HESS_K ? 6 : 1); }
+//   FORCE2   out_0 = IFFT_x[ -(i g_x) c FFT_x[in] ], out_1 = IFFT_x[ c FFT_x[in] ]   1 -> 2   force along x + potential:
+//            the y and z components follow from the potential on the (y,z) spectra of each x-plane (fourier.cu:
+//            yz_gradients), so a slab-decomposed caller moves TWO fields back instead of three
+//   FORCE2_T out   = IFFT_x[ i c (g_x FFT_x[in_0] + FFT_x[in_1]) ]                   2 -> 1   its transpose: in_1 holds
+//            g_y in_y + g_z in_z, combined on the local planes before the exchange
+enum Mode { FORCE = 0, FORCE_T = 1, FORCE_K = 2, HESS_K = 3, FORCE_TK = 4, HESS_TK = 5, FORCE2 = 6, FORCE2_T = 7 };
+__host__ __device__ constexpr int n_in(int mode) {
+  return mode == FORCE_T || mode == FORCE_TK ? 3 : (mode == HESS_TK ? 6 : (mode == FORCE2_T ? 2 : 1));
+}
+__host__ __device__ constexpr int n_out(int mode) {
+  return mode == FORCE || mode == FORCE_K ? 3 : (mode == HESS_K ? 6 : (mode == FORCE2 ? 2 : 1));
+}
 __host__ __device__ constexpr bool fwd_x(int mode) { return mode != FORCE_K && mode != HESS_K; }
 __host__ __device__ constexpr bool inv_x(int mode) { return mode != FORCE_TK && mode != HESS_TK; }
 __host__ __device__ constexpr bool hessian(int mode) { return mode == HESS_K || mode == HESS_TK; }
@@ -205,6 +214,7 @@ __global__ void __launch_bounds__(R2* columns_per_cta(R1* R2), (R1 >= 32 ? 1 : 5
     const int i = kx_index(e);
     const float gx = xk[i].y;
     const bool nqx = 2 * i == a.g.nx;
+    if (MODE == FORCE2 || MODE == FORCE2_T) return comp == 0 ? ((proj && nqx) ? 0.f : gx) : 1.0f;
     if (!HESS) {
       if (comp == 0) return (proj && nqx) ? 0.f : gx;
       if (comp == 1) return (proj && nqy) ? 0.f : gy;
@@ -259,7 +269,7 @@ __global__ void __launch_bounds__(R2* columns_per_cta(R1* R2), (R1 >= 32 ? 1 : 5
   for (int e = 0; e < R1; ++e) {
     const float cs = scalar_at(e) * outw;
     if (HESS) X[e] = make_float2(-X[e].x * cs, -X[e].y * cs);
-    else if (NOUT == 3) X[e] = make_float2(X[e].y * cs, -X[e].x * cs);
+    else if (NOUT >= 2) X[e] = make_float2(X[e].y * cs, -X[e].x * cs);
     else X[e] = make_float2(-X[e].y * cs, X[e].x * cs);
   }
   // ---- scatter side
@@ -292,7 +302,10 @@ __global__ void __launch_bounds__(R2* columns_per_cta(R1* R2), (R1 >= 32 ? 1 : 5
 #pragma unroll
       for (int e = 0; e < R1; ++e) {
         const float g = weight(comp, e);
-        w[(e / R2) + J * (e % R2)] = make_float2(X[e].x * g, X[e].y * g);  // inverse-transform input order
+        if (MODE == FORCE2 && comp == 1)  // the potential: c X, i.e. i times the -(i) c X held in X
+          w[(e / R2) + J * (e % R2)] = make_float2(-X[e].y, X[e].x);
+        else
+          w[(e / R2) + J * (e % R2)] = make_float2(X[e].x * g, X[e].y * g);  // inverse-transform input order
       }
       col_fft<R1, R2, +1>(w, t, ((nfft + comp) & 1) ? cb1 : cb0, tw);
       if (active) {
@@ -340,6 +353,8 @@ static int launch_mode(int mode, stream_t st, const Args& a) {
     case HESS_K: return launch<R1, R2, HESS_K>(st, a);
     case FORCE_TK: return launch<R1, R2, FORCE_TK>(st, a);
     case HESS_TK: return launch<R1, R2, HESS_TK>(st, a);
+    case FORCE2: return launch<R1, R2, FORCE2>(st, a);
+    case FORCE2_T: return launch<R1, R2, FORCE2_T>(st, a);
   }
   set_error("xfuse: unknown mode");
   return MCPM_EINVAL;

@@ -119,6 +119,8 @@ class SlabPM:
         # mesh (one more paint + force evaluation per step instead of 16 bytes per extended cell and step: at 1024^3 on 8
         # GPUs with 20 steps that is 59 GB per GPU) -- the trade of the reference's checkpointed adjoint (nbody.py:999)
         self.tape_forces = os.environ.get("MCPM_SLAB_TAPE_FORCES", "1") != "0"
+        # two_field: the step loop's distributed x-transforms carry two fields instead of three (xfft_kernel.h: FORCE2)
+        self.two_field = os.environ.get("MCPM_SLAB_TWO_FIELD", "1") != "0"
         self.sections = _Sections()
         if self.sections.on and self.A.device.type == "cuda":  # nested sections: inner times are included in outer ones
             self.sections.wrap(self, ["halo_reduce", "halo_gather", "forces_from_density", "density_cotangent",
@@ -196,10 +198,16 @@ class SlabPM:
         fused kernel on my ky block reading / writing every rank's buffer, barrier, local 2-D C2R."""
         st = self._st()
         self._call("mcpm_slabfft_r2c_yz", self._fft, st, real_in.data_ptr(), self._sym_in.data_ptr(), nb_in)
+        two = self.two_field  # move (F_x, potential) / (C_x, g_y C_y + g_z C_z) through the exchange instead of 3 fields:
+        # the y and z gradient factors do not depend on x, so they are applied on the local (y,z) spectra
+        if two and transpose:
+            self._call("mcpm_yz_gradients", st, self._sym_in.data_ptr(), self.xl, self.ny, self.nz, 0, 1)
         self._h_in.barrier()
-        self._call("mcpm_xfuse_force_peer", st, self._peer_in, self._peer_out, self.P, int(transpose), self.nx, self.ny,
-                   self.nz, self.kyl, self.y0, 0, 0, 0.0, 0, 1.0 / self.N)
+        self._call("mcpm_xfuse_force_peer", st, self._peer_in, self._peer_out, self.P, int(transpose) + (2 if two else 0),
+                   self.nx, self.ny, self.nz, self.kyl, self.y0, 0, 0, 0.0, 0, 1.0 / self.N)
         self._h_out.barrier()
+        if two and not transpose:
+            self._call("mcpm_yz_gradients", st, self._sym_out.data_ptr(), self.xl, self.ny, self.nz, 0, 0)
         nb_out = 1 if transpose else 3
         out = self.A.empty((nb_out, self.xl, self.ny, self.nz)) if out is None else out
         self._call("mcpm_slabfft_c2r_yz", self._fft, st, self._sym_out.data_ptr(), out.data_ptr(), nb_out)

@@ -168,3 +168,40 @@ def test_lpt_and_its_vjp(ops, shape, lpt_order, read_order, fd):
         dpo, vlo = dpo - d2 * f2, vlo - dv2 * f2
     tol = 5e-5 if shape[0] <= 256 else 3e-4  # float32 on a 512-cell axis (see test_forces_and_vjp)
     assert rel(res[True][0], dpo.numpy()) < tol and rel(res[True][1], vlo.numpy()) < tol
+
+
+@pytest.mark.parametrize("nx,ny,nz,grad_fd", [(64, 12, 16, 0), (128, 8, 10, 4), (512, 6, 4, 2)])
+def test_two_field_forms_match_the_three_field_ones(ops, nx, ny, nz, grad_fd):
+    """The two-field forms of the distributed force transform (xfft_kernel.h: FORCE2 / FORCE2_T + fourier.cu: yz_gradients)
+    against the three-field ones, through the peer entry point with ONE rank (its own buffers as the peer table): the y and
+    z gradient factors applied on the local (y,z) spectra before / after the x-transform give the same three force spectra
+    (1 -> 3) and the same density cotangent (3 -> 1), Nyquist rows and planes included.  2e-6."""
+    import ctypes as C
+    rng = np.random.default_rng(nx + grad_fd)
+    nzc = nz // 2 + 1
+    A = ops.A
+    st = A.stream()
+    shape_c = (nx, ny, nzc)
+    x1 = (rng.normal(size=(1, *shape_c)) + 1j * rng.normal(size=(1, *shape_c))).astype(np.complex64)
+    x3 = (rng.normal(size=(3, *shape_c)) + 1j * rng.normal(size=(3, *shape_c))).astype(np.complex64)
+    tab = lambda t: (C.c_void_p * 1)(A.ptr(t))
+    rel = lambda a, b: float(np.linalg.norm(to_numpy(a).astype(np.complex128) - to_numpy(b).astype(np.complex128))
+                             / np.linalg.norm(to_numpy(b).astype(np.complex128)))
+
+    def peer(inp, out, transpose):
+        ops._call("mcpm_xfuse_force_peer", st, tab(inp), tab(out), 1, transpose, nx, ny, nz, ny, 0, 0, grad_fd, 0.0, 0, 0.37)
+
+    # 1 -> 3
+    d_in = A.prepare(x1, "c64")
+    ref3, two3 = A.empty((3, *shape_c), "c64"), A.zeros((3, *shape_c), "c64")
+    peer(d_in, ref3, 0)
+    peer(d_in, two3, 2)
+    ops._call("mcpm_yz_gradients", st, A.ptr(two3), nx, ny, nz, grad_fd, 0)
+    assert rel(two3, ref3) < 2e-6
+    # 3 -> 1
+    d_in3, d_in3b = A.prepare(x3, "c64"), A.prepare(x3.copy(), "c64")
+    ref1, two1 = A.empty((1, *shape_c), "c64"), A.empty((1, *shape_c), "c64")
+    peer(d_in3, ref1, 1)
+    ops._call("mcpm_yz_gradients", st, A.ptr(d_in3b), nx, ny, nz, grad_fd, 1)
+    peer(d_in3b, two1, 3)
+    assert rel(two1, ref1) < 2e-6

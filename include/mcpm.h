@@ -543,6 +543,41 @@ int mcpm_nufft_rsd_vjp(mcpm_engine* eng, void* stream, const float* pos, const f
                        int interlace_order, int paint_deconv, const void* outbar_k, float* posbar, float* velbar,
                        float* weightsbar);
 
+/* nufft of OBSERVED positions with the general observation chain of model.py:780-799 applied inside the paint kernels:
+ * cell -> physical (bricks.py:628-636) -> line of sight and scale factor (:747-766) -> redshift-space distortion
+ * (:781-792, with the velocity bias `dvel`) -> Alcock-Paczynski (ap_auto :795-813 | ap_param :847-856) -> cell
+ * (:638-646), for a box placed and rotated with respect to the observer, curved or flat sky, a scalar a_obs or the
+ * light cone.  The transformed positions are never written.  Everything that depends on the cosmology comes in as
+ * numbers the caller computes from it: `gf` = D(a_obs) f(a_obs), or -- lightcone -- tab_gf[k] = (D f)(a(r_k)), and
+ * -- ap == 1 -- tab_ap[k] = chi_fid(a(r_k)) / r_k - 1, on the uniform radius grid r_k = r0 + k * dr, k < nt (device
+ * arrays, linearly interpolated, clamped at the ends).
+ *   cell[d]   Mpc/h per unit of pos;   origin = R^T box_center - box_size / 2;   los = R^T box_center / |box_center|
+ *   rot       R (row-major), used for `dvel` [np,3] (observer frame, Mpc/h, nullable) only
+ *   ap        0 none | 1 table | 2 parametrised: a_par, a_perp (curved sky: a_par = alpha_iso)
+ *   rsd       0: no redshift-space term (vel may be NULL)
+ * _vjp returns posbar, velbar, dvelbar, weightsbar (each nullable) and parbar (nullable), float64
+ * [MCPM_OBS_SLOTS][3 + 2 nt] of which ROW 0 holds the result on return: cotangents of gf, a_par, a_perp, tab_gf[nt],
+ * tab_ap[nt] (the other rows are scratch for the accumulation).  kcut > 0: Kaiser-Bessel window of that cut. */
+#define MCPM_OBS_SLOTS 32
+typedef struct mcpm_obs {
+  int curved, lightcone, ap, rsd;
+  float cell[3], origin[3], los[3];
+  float gf, a_par, a_perp;
+  float r0, dr;
+  int nt;
+  const float* tab_gf;
+  const float* tab_ap;
+  const float* dvel;
+  float rot[9];
+} mcpm_obs;
+int mcpm_nufft_obs(mcpm_engine* eng, void* stream, const float* pos, const float* vel, const mcpm_obs* obs,
+                   const float* weights, float wscalar, int64_t np, const float scale[3], int paint_order, float kcut,
+                   int interlace_order, int paint_deconv, void* out_k);
+int mcpm_nufft_obs_vjp(mcpm_engine* eng, void* stream, const float* pos, const float* vel, const mcpm_obs* obs,
+                       const float* weights, float wscalar, int64_t np, const float scale[3], int paint_order, float kcut,
+                       int interlace_order, int paint_deconv, const void* outbar_k, float* posbar, float* velbar,
+                       float* dvelbar, float* weightsbar, double* parbar);
+
 /* nufft / its VJP with kernel_type = 'kaiser_bessel' (nbody.py:532-577 with the window of 280-312). */
 int mcpm_nufft_kb(mcpm_engine* eng, void* stream, const float* pos, const float* weights, float wscalar, int64_t np,
                   const float scale[3], int paint_order, float kcut, int interlace_order, int paint_deconv,

@@ -8,6 +8,17 @@ import ctypes as C
 vp, f32, f64, i32, i64, sz = C.c_void_p, C.c_float, C.c_double, C.c_int, C.c_int64, C.c_size_t
 hp = C.POINTER(C.c_float)  # host float array
 
+OBS_SLOTS = 32  # MCPM_OBS_SLOTS
+
+
+class McpmObs(C.Structure):
+    """mcpm_obs of include/mcpm.h (the general observation transform applied inside the paint)."""
+    _fields_ = [("curved", i32), ("lightcone", i32), ("ap", i32), ("rsd", i32),
+                ("cell", f32 * 3), ("origin", f32 * 3), ("los", f32 * 3),
+                ("gf", f32), ("a_par", f32), ("a_perp", f32), ("r0", f32), ("dr", f32), ("nt", i32),
+                ("tab_gf", vp), ("tab_ap", vp), ("dvel", vp), ("rot", f32 * 9)]
+
+
 MESH = [i32, i32, i32]
 XF = [hp, f32]  # scale[3] (host), shift
 
@@ -124,6 +135,8 @@ SIGNATURES = {
     "mcpm_nufft": ([vp, vp, vp, vp, f32, i64, hp, i32, i32, i32, vp], i32),
     "mcpm_nufft_rsd": ([vp, vp, vp, vp, hp, f32, vp, f32, i64, hp, i32, i32, i32, vp], i32),
     "mcpm_nufft_rsd_vjp": ([vp, vp, vp, vp, hp, f32, vp, f32, i64, hp, i32, i32, i32, vp, vp, vp, vp], i32),
+    "mcpm_nufft_obs": ([vp, vp, vp, vp, vp, vp, f32, i64, hp, i32, f32, i32, i32, vp], i32),
+    "mcpm_nufft_obs_vjp": ([vp, vp, vp, vp, vp, vp, f32, i64, hp, i32, f32, i32, i32, vp, vp, vp, vp, vp, vp], i32),
     "mcpm_nufft_vjp": ([vp, vp, vp, vp, f32, i64, hp, i32, i32, i32, vp, vp, vp], i32),
     "mcpm_nufft_kb": ([vp, vp, vp, vp, f32, i64, hp, i32, f32, i32, i32, vp], i32),
     "mcpm_nufft_vjp_kb": ([vp, vp, vp, vp, f32, i64, hp, i32, f32, i32, i32, vp, vp, vp], i32),

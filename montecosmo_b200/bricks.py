@@ -612,6 +612,70 @@ def rsd_ap_auto(pos, vel, rpos, los, a, cosmo, cosmo_fid, curved_sky=True):
     return pos * alpha if curved_sky else scale_pos(pos, los, alpha, 1.0)
 
 
+def observation(cosmo, box_center, box_rot, box_size, mesh_shape, a_obs=None, curved_sky=True, rsd=True, ap_auto=None,
+                cosmo_fid=None, ap=None, n_table=8192, pad=None):
+    """The observation chain of model.py:780-799 as a descriptor for nbody.nufft_observed, which applies it INSIDE the
+    final paint (csrc/obs.h): cell2phys_pos, los_scalefactor_pos, rsd, ap_auto | ap_param, phys2cell_pos for particles
+    in `mesh_shape` cells of a box placed (`box_center`) and rotated (`box_rot`) with respect to the observer.
+
+    What depends on the cosmology is computed HERE, in float64 from cosmo.py's tables, and stays differentiable:
+      par     [3]  D(a_obs) f(a_obs) (0 on the light cone), and the parallel / perpendicular Alcock-Paczynski factors of
+                   ap_param (`ap` = dict(alpha_iso, alpha_ap); a curved sky uses alpha_iso alone, bricks.py:851-852)
+      tab_gf  [n_table]  (D f)(a(r)) on a uniform radius grid -- the light cone (a_obs None, bricks.py:761-762)
+      tab_ap  [n_table]  chi_fid(a(r)) / r - 1 -- ap_auto (bricks.py:799-801)
+    The grid spans the distances the box can reach plus `pad` (default 10 % of the largest side + 50 Mpc/h); the kernels
+    interpolate linearly and clamp beyond the ends.  With 8192 nodes the tables reproduce the reference's own
+    piecewise-linear lookups to ~1e-7 relative (tests/test_api_model.py: test_fused_observation_chain)."""
+    box = np.asarray(box_size, dtype=np.float64)
+    shape = np.asarray(mesh_shape, dtype=np.float64)
+    center = np.asarray(box_center, dtype=np.float64)
+    R = np.eye(3) if box_rot is None else (box_rot.as_matrix() if hasattr(box_rot, "as_matrix")
+                                           else np.asarray(box_rot, dtype=np.float64))
+    ct = R.T @ center
+    nrm = np.linalg.norm(center)
+    los = ct / nrm if nrm != 0 else np.zeros(3)
+    origin = ct - box / 2
+    lightcone = a_obs is None
+    mode = 0 if ap_auto is None else (1 if ap_auto else 2)
+    out = dict(curved=bool(curved_sky), lightcone=bool(lightcone and rsd), ap=mode, rsd=bool(rsd),
+               cell=tuple(box / shape), origin=tuple(origin), los=tuple(los), rot=R.tolist(), r0=0.0, dr=0.0)
+    one = torch.ones((), dtype=torch.float64)
+    gf = torch.zeros((), dtype=torch.float64)
+    if rsd and not lightcone:
+        gf = (_cosmo.a2g(cosmo, a_obs) * _cosmo.a2f(cosmo, a_obs)).reshape(()).to(torch.float64)
+    a_par = a_perp = one
+    if mode == 2:
+        if ap is None:
+            raise ValueError("ap_auto=False needs the Alcock-Paczynski parameters `ap` (alpha_iso, alpha_ap)")
+        if curved_sky:
+            a_par = _cosmo._t(ap["alpha_iso"]).reshape(())
+        else:
+            a_par, a_perp = (_cosmo._t(x).reshape(()) for x in isoap2parperp(_cosmo._t(ap["alpha_iso"]), _cosmo._t(ap["alpha_ap"])))
+    out["par"] = torch.stack([gf, a_par.to(torch.float64), a_perp.to(torch.float64)])
+    if out["lightcone"] or mode == 1:
+        corners = np.array([[origin[d] + (box[d] if (i >> d) & 1 else 0.0) for d in range(3)] for i in range(8)])
+        lo, hi = corners.min(0), corners.max(0)
+        pad = 0.1 * box.max() + 50.0 if pad is None else float(pad)
+        if curved_sky:
+            rmax = np.linalg.norm(corners, axis=1).max()
+            rmin = np.linalg.norm(np.maximum(np.maximum(lo, -hi), 0.0))  # distance from the observer to the box
+        else:
+            t = corners @ los
+            rmax = np.abs(t).max()
+            rmin = 0.0 if t.min() < 0 < t.max() else np.abs(t).min()
+        r0 = max(rmin - pad, 1e-3 * (rmax + pad))
+        r = torch.linspace(r0, rmax + pad, int(n_table), dtype=torch.float64)
+        a_r = _cosmo.chi2a(cosmo, r)
+        out["r0"], out["dr"] = float(r[0]), float(r[1] - r[0])
+        if out["lightcone"]:
+            out["tab_gf"] = _cosmo.a2g(cosmo, a_r) * _cosmo.a2f(cosmo, a_r)
+        if mode == 1:
+            if cosmo_fid is None:
+                raise ValueError("ap_auto=True needs the fiducial cosmology")
+            out["tab_ap"] = _cosmo.a2chi(cosmo_fid, a_r) / r - 1.0
+    return out
+
+
 def redges_and_scalefactors(cosmo, rmin, rmax, n_shells):
     """Radius shell edges, linearly spaced in growth factor, and their effective scale factors (bricks.py:700-710)."""
     gmin = float(_cosmo.a2g(cosmo, _cosmo.chi2a(cosmo, rmax)))

@@ -1245,6 +1245,78 @@ int mcpm_nufft_rsd_vjp(mcpm_engine* eng, void* stream, const float* pos, const f
   API_END
 }
 
+// mcpm_obs (ABI) -> ObsGen (kernels)
+static_assert(kObsSlots == MCPM_OBS_SLOTS, "obs.h and mcpm.h must agree");
+static int make_obs_gen(const mcpm_obs* o, const float* vel, ObsGen& g) {
+  if (!o) {
+    set_error("nufft_obs: null observation descriptor");
+    return MCPM_EINVAL;
+  }
+  if ((o->lightcone && o->rsd && !o->tab_gf) || (o->ap == 1 && !o->tab_ap) || ((o->lightcone || o->ap == 1) && (o->nt < 2 || !(o->dr > 0.0f)))) {
+    set_error("nufft_obs: the light cone / ap_auto need their radius tables (nt >= 2, dr > 0)");
+    return MCPM_EINVAL;
+  }
+  if (o->ap < 0 || o->ap > 2 || (o->rsd && !vel)) {
+    set_error("nufft_obs: ap must be 0 | 1 | 2, and rsd needs velocities");
+    return MCPM_EINVAL;
+  }
+  g.on = 1;
+  g.curved = o->curved != 0;
+  g.lightcone = o->lightcone != 0;
+  g.ap = o->ap;
+  g.rsd = o->rsd != 0;
+  g.cx = o->cell[0], g.cy = o->cell[1], g.cz = o->cell[2];
+  g.ox = o->origin[0], g.oy = o->origin[1], g.oz = o->origin[2];
+  g.lx = o->los[0], g.ly = o->los[1], g.lz = o->los[2];
+  g.gf = o->gf, g.a_par = o->a_par, g.a_perp = o->a_perp;
+  g.r0 = o->r0;
+  g.inv_dr = o->dr > 0.0f ? 1.0f / o->dr : 0.0f;
+  g.nt = o->nt > 0 ? o->nt : 0;
+  g.tab_gf = o->tab_gf, g.tab_ap = o->tab_ap;
+  g.vel = vel, g.dvel = o->rsd ? o->dvel : nullptr;
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) g.rt[3 * a + b] = o->rot[3 * b + a];
+  return 0;
+}
+
+int mcpm_nufft_obs(mcpm_engine* eng, void* stream, const float* pos, const float* vel, const mcpm_obs* obs,
+                   const float* weights, float wscalar, int64_t np, const float scale[3], int paint_order, float kcut,
+                   int interlace_order, int paint_deconv, void* out_k) {
+  API_BEGIN
+  NEED(eng && out_k && (np == 0 || pos || eng->e->rel), "nufft_obs: null pointer");
+  BIND(eng);
+  ObsGen g;
+  if (int e = make_obs_gen(obs, vel, g)) return e;
+  ObsShift sh;
+  sh.gen = &g;
+  return nufft(eng->e, as_stream(stream), pos, weights, wscalar, np, scale, paint_order, interlace_order, paint_deconv,
+               C(out_k), kcut > 0.0f ? kcut : 0.0f, &sh);
+  API_END
+}
+
+int mcpm_nufft_obs_vjp(mcpm_engine* eng, void* stream, const float* pos, const float* vel, const mcpm_obs* obs,
+                       const float* weights, float wscalar, int64_t np, const float scale[3], int paint_order, float kcut,
+                       int interlace_order, int paint_deconv, const void* outbar_k, float* posbar, float* velbar,
+                       float* dvelbar, float* weightsbar, double* parbar) {
+  API_BEGIN
+  NEED(eng && outbar_k && (np == 0 || pos || eng->e->rel), "nufft_obs_vjp: null pointer");
+  BIND(eng);
+  ObsGen g;
+  if (int e = make_obs_gen(obs, vel, g)) return e;
+  stream_t st = as_stream(stream);
+  const int64_t row = 3 + 2 * (int64_t)g.nt;
+  g.dvelbar = g.dvel ? dvelbar : nullptr;
+  g.parbar = parbar;
+  if (parbar && rt_memset(parbar, 0, sizeof(double) * (size_t)(kObsSlots * row), st)) return MCPM_ECUDA;
+  ObsShift sh;
+  sh.gen = &g;
+  if (int e = nufft_vjp(eng->e, st, pos, weights, wscalar, np, scale, paint_order, interlace_order, paint_deconv,
+                        C(outbar_k), posbar, weightsbar, kcut > 0.0f ? kcut : 0.0f, &sh, velbar))
+    return e;
+  return parbar ? obs_reduce_slots(st, parbar, row) : 0;  // the slots' partial sums into row 0
+  API_END
+}
+
 int mcpm_nufft_kb(mcpm_engine* eng, void* stream, const float* pos, const float* weights, float wscalar, int64_t np,
                   const float scale[3], int paint_order, float kcut, int interlace_order, int paint_deconv,
                   void* out_k) {

@@ -79,7 +79,7 @@ static int paint_fresh(Engine* E, stream_t st, const float* pos, const float* we
   Frame f;
   const Frame* fr = E->frame(f);
 #ifndef MCPM_HOSTEMU
-  if (brick_path(E, order, scale) && pos) {
+  if (brick_path(E, order, scale) && pos && !(obs && obs->gen)) {  // the general observation transform: generic kernels
     if (!prezeroed && rt_memset(mesh, 0, sizeof(float) * (size_t)E->N, st)) return MCPM_ECUDA;
     int r = brick_paint_cic(st, E->lat, pos, weights, wscalar, shift, np, E->nx, E->ny, E->nz, mesh, fr, obs);
     if (r < 0) return MCPM_ECUDA;

@@ -1,6 +1,7 @@
 // engine.h -- internal declarations shared by the engine translation units.
 #pragma once
 #include "frame.h"
+#include "obs.h"
 #include "rt.h"
 
 namespace mcpm {
@@ -17,6 +18,9 @@ struct Lattice {
 struct ObsShift {
   const float* vel = nullptr;
   float lx = 0.f, ly = 0.f, lz = 0.f, coef = 0.f;
+  // the general observation transform (obs.h) instead: a HOST pointer, copied into the generic assignment kernels'
+  // arguments (paint.cu); the brick-tiled paint does not implement it and is bypassed
+  const ObsGen* gen = nullptr;
 };
 
 // Performance knobs (never change which result is computed).  mcpm_tune sets the process-wide defaults, which every
@@ -120,6 +124,7 @@ int bias_weights_vjp(stream_t, const float* vals, int K, float gs, const float* 
                      float* gbar_arr);
 int absmax_strided(stream_t, const float* x, int64_t n, int stride, float* out);
 int yz_gradients(stream_t, cfloat* buf3, int xl, int ny, int nz, int grad_fd, int transpose);
+int obs_reduce_slots(stream_t st, double* parbar, int64_t row);  // paint.cu
 int rsd_shift(stream_t, const float* pos, const float* vel, float lx, float ly, float lz, float coef, int64_t np,
               float* pos_out);
 int rsd_shift_vjp(stream_t, const float* posbar, float lx, float ly, float lz, float coef, int64_t np, float* velbar,

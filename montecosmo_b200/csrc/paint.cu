@@ -20,6 +20,7 @@ struct PosXform {
   float sx, sy, sz, shift;
   Frame fr;  // absolute or lattice-relative positions (frame.h)
   ObsShift obs;  // optional redshift-space shift added to the position before scale / shift (engine.h)
+  ObsGen gen;    // ... or the general observation transform (obs.h)
 };
 
 // Transformed coordinate of particle p as an exact integer part b (its lattice site; 0 for absolute frames) plus a small
@@ -39,9 +40,24 @@ MCPM_HD void load_site_disp(const float* pos, int64_t p, const PosXform& xf, int
     d[2] = d[2] + sh * xf.obs.lz;
   }
 }
+// Absolute position of particle p in the units of `pos` (the geometry of the observation transform needs it).
+MCPM_HD void abs_pos(const PosXform& xf, const int* b, const float* r, const float* d, float* x) {
+  x[0] = ((float)b[0] + r[0]) / xf.sx + d[0];  // relative frames give the site in target-mesh cells
+  x[1] = ((float)b[1] + r[1]) / xf.sy + d[1];
+  x[2] = ((float)b[2] + r[2]) / xf.sz + d[2];
+}
 MCPM_HD void load_pos(const float* pos, int64_t p, const PosXform& xf, int* b, float* u) {
   float r[3], d[3];
   load_site_disp(pos, p, xf, b, r, d);
+  if (xf.gen.on) {
+    float x[3], delta[3];
+    ObsState s;
+    abs_pos(xf, b, r, d, x);
+    obs_forward(xf.gen, x, p, s, delta);
+    d[0] += delta[0];
+    d[1] += delta[1];
+    d[2] += delta[2];
+  }
   u[0] = r[0] + (d[0] * xf.sx + xf.shift);
   u[1] = r[1] + (d[1] * xf.sy + xf.shift);
   u[2] = r[2] + (d[2] * xf.sz + xf.shift);
@@ -253,6 +269,15 @@ static void paint_vjp_impl(stream_t st, const float* pos, const float* weights, 
     int sb[3];
     float sr[3], sd[3];
     load_site_disp(pos, p, xf, sb, sr, sd);
+    ObsState os;
+    if (xf.gen.on) {  // general observation transform: keep its state for the transpose below
+      float x[3], delta[3];
+      abs_pos(xf, sb, sr, sd, x);
+      obs_forward(xf.gen, x, p, os, delta);
+      sd[0] += delta[0];
+      sd[1] += delta[1];
+      sd[2] += delta[2];
+    }
     float r = 0.0f, g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
     for (int t = 0; t < nshift; ++t) {
       const float sh = xf.shift + (float)t / (float)nshift;  // exactly the shifts the forward paints used (engine.cu: nufft)
@@ -290,6 +315,24 @@ static void paint_vjp_impl(stream_t st, const float* pos, const float* weights, 
     }
     float wp = weights ? weights[p] * wscalar : wscalar;
     if (wbar) wbar[p] = (accumulate ? wbar[p] : 0.0f) + r * wscalar;
+    if (xf.gen.on) {  // cotangent of the observed position -> positions, velocities, velocity bias, parameters
+      const float gd[3] = {g0 * xf.sx * wp, g1 * xf.sy * wp, g2 * xf.sz * wp};
+      float xadd[3], vb[3];
+      obs_transpose(xf.gen, os, p, gd, xadd, vb, accumulate != 0);
+      if (posbar) {
+        float* g = posbar + 3 * p;
+        g[0] = (accumulate ? g[0] : 0.0f) + (gd[0] + xadd[0]);
+        g[1] = (accumulate ? g[1] : 0.0f) + (gd[1] + xadd[1]);
+        g[2] = (accumulate ? g[2] : 0.0f) + (gd[2] + xadd[2]);
+      }
+      if (velbar) {
+        float* o = velbar + 3 * p;
+        o[0] = (accumulate ? o[0] : 0.0f) + vb[0];
+        o[1] = (accumulate ? o[1] : 0.0f) + vb[1];
+        o[2] = (accumulate ? o[2] : 0.0f) + vb[2];
+      }
+      return;
+    }
     if (posbar) {
       float* g = posbar + 3 * p;
       g[0] = (accumulate ? g[0] : 0.0f) + g0 * xf.sx * wp;
@@ -383,7 +426,11 @@ static int check_mesh(int nx, int ny, int nz, int order) {
 }
 
 static PosXform make_xform(const float* scale, float shift, const Frame* fr = nullptr, const ObsShift* obs = nullptr) {
-  PosXform xf = {1.0f, 1.0f, 1.0f, shift, fr ? *fr : Frame(), obs ? *obs : ObsShift()};
+  PosXform xf = {1.0f, 1.0f, 1.0f, shift, fr ? *fr : Frame(), obs ? *obs : ObsShift(), ObsGen()};
+  if (obs && obs->gen) {
+    xf.gen = *obs->gen;
+    xf.obs = ObsShift();
+  }
   if (scale) {
     xf.sx = scale[0];
     xf.sy = scale[1];
@@ -531,7 +578,7 @@ int paint_vjp(stream_t st, const float* pos, const float* weights, float wscalar
   }
   MeshDims n = {nx, ny, nz};
   PosXform xf = make_xform(scale, shift, fr, obs);
-  if (!(obs && obs->vel)) velbar = nullptr;
+  if (!(obs && (obs->vel || (obs->gen && obs->gen->rsd)))) velbar = nullptr;
   if (nshift < 1) nshift = 1;
   if (kb_kcut > 0.0f) {
     KbWin kb = make_kbwin(order, kb_kcut);
@@ -618,6 +665,16 @@ int lpt_combine(stream_t st, const float* pos, const float* f1, const float* f2,
 int axpby(stream_t st, const float* x, float a, const float* y, float b, float c, int64_t n, float* out) {
   launch_1d(st, n, [=] MCPM_LAMBDA(int64_t i) { out[i] = a * x[i] + (y ? b * y[i] : 0.0f) + c; });
   return rt_check("axpby");
+}
+
+// parameter cotangents of the general observation transform: the kObsSlots partial rows summed into row 0
+int obs_reduce_slots(stream_t st, double* parbar, int64_t row) {
+  launch_1d(st, row, [=] MCPM_LAMBDA(int64_t k) {
+    double acc = parbar[k];
+    for (int s = 1; s < kObsSlots; ++s) acc += parbar[(int64_t)s * row + k];
+    parbar[k] = acc;
+  });
+  return rt_check("obs_reduce_slots");
 }
 
 // flat-sky redshift-space shift in cell units (bricks.py:781-792): pos_out = pos + (vel . los) * coef * los

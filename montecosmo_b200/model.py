@@ -248,8 +248,9 @@ class FieldLevelModel(FieldModel):
 
     def __init__(self, mesh_shape=(64, 64, 64), box_size=(640.0, 640.0, 640.0), evol_oversamp=1.0, ptcl_oversamp=1.0,
                  box_center=(0.0, 0.0, 0.0), box_rot=None, curved_sky=False, bias=None, png=None, png_type=None,
-                 ap_auto=None, cosmo_fid=None, kernel_type="rectangular", **kw):
+                 ap_auto=None, cosmo_fid=None, kernel_type="rectangular", fused_observation=True, **kw):
         super().__init__(mesh_shape, box_size, **kw)
+        self.fused_observation = bool(fused_observation)
         self.init_shape = self.mesh_shape
         self.evol_shape = nb.scale_shape(self.init_shape, evol_oversamp)
         self.ptcl_shape = nb.scale_shape(self.evol_shape, ptcl_oversamp)
@@ -293,16 +294,27 @@ class FieldLevelModel(FieldModel):
             pos, vel = pos[-1], vel[-1]
         else:
             raise ValueError(f"unknown evolution {self.evolution}")
-        los, a = B.los_scalefactor_pos(pos, *geo, self.evol_shape, c, self.a_obs, self.curved_sky)
-        pos = B.cell2phys_pos(pos, *geo, self.evol_shape)
-        if self.rsd:
-            pos = pos + B.rsd(c, vel, los, a, self.box_rot, self.box_size, self.evol_shape, dvel)
-        if self.ap_auto is not None:
-            pos = B.ap_auto(pos, los, c, self.cosmo_fid, self.curved_sky) if self.ap_auto else \
-                B.ap_param(pos, los, ap, self.curved_sky)
-        pos = B.phys2cell_pos(pos, *geo, self.init_shape)
-        gxy = nb.nufft(pos, self.init_shape, self.paint_shape if self.paint_shape != self.init_shape else None, weights,
-                       self.paint_order, self.interlace_order, self.kernel_type, self.paint_deconv)
+        paint_shape = self.paint_shape if self.paint_shape != self.init_shape else None
+        if self.fused_observation:
+            # cell -> physical, line of sight and scale factor, redshift-space distortion, Alcock-Paczynski, physical ->
+            # cell (model.py:780-799) applied inside the paint kernels: the cosmology enters through the descriptor's
+            # scalars and radius tables, no position array is transformed in between
+            obs = B.observation(c, *geo, self.evol_shape, self.a_obs, self.curved_sky, self.rsd, self.ap_auto,
+                                self.cosmo_fid, ap)
+            gxy = nb.nufft_observed(pos, vel if self.rsd else None, self.init_shape, obs, paint_shape, weights,
+                                    dvel if (self.rsd and torch.is_tensor(dvel)) else None, self.paint_order,
+                                    self.interlace_order, self.kernel_type, self.paint_deconv, pos_shape=self.evol_shape)
+        else:  # the same chain as elementwise passes over the particle arrays (cross-check)
+            los, a = B.los_scalefactor_pos(pos, *geo, self.evol_shape, c, self.a_obs, self.curved_sky)
+            pos = B.cell2phys_pos(pos, *geo, self.evol_shape)
+            if self.rsd:
+                pos = pos + B.rsd(c, vel, los, a, self.box_rot, self.box_size, self.evol_shape, dvel)
+            if self.ap_auto is not None:
+                pos = B.ap_auto(pos, los, c, self.cosmo_fid, self.curved_sky) if self.ap_auto else \
+                    B.ap_param(pos, los, ap, self.curved_sky)
+            pos = B.phys2cell_pos(pos, *geo, self.init_shape)
+            gxy = nb.nufft(pos, self.init_shape, paint_shape, weights, self.paint_order, self.interlace_order,
+                           self.kernel_type, self.paint_deconv)
         gxy = gxy * float(np.divide(self.init_shape, self.ptcl_shape).prod())  # particle units -> mesh units
         if self.paint_shape != self.init_shape and self.out_shape == "paint":
             gxy = nb.chreshape(gxy, r2chshape(self.paint_shape))

@@ -302,6 +302,44 @@ class _NufftPaint(torch.autograd.Function):
         return pb, wb, None, None, None, None, None, None, None, None, vb, None, None
 
 
+class _NufftObserved(torch.autograd.Function):
+    """nufft of the observed positions: the general observation chain inside the paint (mcpm_nufft_obs).  Differentiable
+    in the positions, velocities, velocity bias, weights, the scalars (D f at a_obs, Alcock-Paczynski factors) and the
+    nodes of the two radius tables -- through which the cosmology's gradient flows back to the caller's tables."""
+
+    @staticmethod
+    def forward(ctx, pos, vel, dvel, weights, par, tab_gf, tab_ap, static, paint_shape, wscalar, scale, paint_order,
+                interlace_order, paint_deconv, kb, lattice):
+        obs = dict(static)
+        obs["gf"], obs["a_par"], obs["a_perp"] = (float(v) for v in par.detach().cpu())
+        obs["tab_gf"] = None if tab_gf is None else _f32(tab_gf.detach())
+        obs["tab_ap"] = None if tab_ap is None else _f32(tab_ap.detach())
+        obs["dvel"] = dvel
+        ctx.save_for_backward(pos, vel, dvel, weights, obs["tab_gf"], obs["tab_ap"])
+        ctx.obs = {k: v for k, v in obs.items() if k not in ("tab_gf", "tab_ap", "dvel")}
+        ctx.cfg = (paint_shape, wscalar, scale, paint_order, interlace_order, paint_deconv, kb, lattice)
+        ctx.like = (par, tab_gf, tab_ap)
+        return ops().nufft_observed(pos, vel, obs, paint_shape, weights, wscalar, scale, paint_order, interlace_order,
+                                    paint_deconv, kb, lattice)
+
+    @staticmethod
+    def backward(ctx, kbar):
+        pos, vel, dvel, weights, tg, ta = ctx.saved_tensors
+        obs = dict(ctx.obs, tab_gf=tg, tab_ap=ta, dvel=dvel)
+        par, tab_gf, tab_ap = ctx.like
+        want_par = any(ctx.needs_input_grad[4:7])
+        pb, vb, db, wb, parbar = ops().nufft_observed_vjp(pos, vel, obs, kbar.contiguous(), *ctx.cfg[:1], weights,
+                                                          *ctx.cfg[1:], want_par=want_par)
+        back = lambda g, like: None if (g is None or like is None) else g.to(device=like.device, dtype=like.dtype)
+        nt = 0 if tg is None and ta is None else int((tg if tg is not None else ta).shape[0])
+        gpar = ggf = gap = None
+        if parbar is not None:
+            gpar = back(parbar[:3], par)
+            ggf = back(parbar[3:3 + nt], tab_gf)
+            gap = back(parbar[3 + nt:3 + 2 * nt], tab_ap)
+        return (pb, vb, db, wb, gpar, ggf, gap) + (None,) * 9
+
+
 class _PmForcesPaint(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pos, shape, order, paint_deconv, lap_fd, grad_fd, kcut):
@@ -468,6 +506,41 @@ def nufft(pos, final_shape: tuple, paint_shape=None, weights=1.0, paint_order: i
     mesh = _NufftPaint.apply(_f32(pos), w, paint_shape, ws, scale, int(paint_order), int(interlace_order),
                              bool(paint_deconv), kb, None if lattice is None else tuple(int(s) for s in lattice),
                              vel, los, coef)
+    if final_shape != paint_shape:
+        mesh = chreshape(mesh, r2chshape(final_shape))
+    return mesh
+
+
+def nufft_observed(pos, vel, final_shape: tuple, obs: dict, paint_shape=None, weights=1.0, dvel=None, paint_order: int = 2,
+                   interlace_order: int = 2, kernel_type="rectangular", paint_deconv=True, lattice=None, pos_shape=None):
+    """nufft (nbody.py:532-577) of the positions as the observer sees them, the chain model.py:780-799 builds between
+    the evolution and the paint -- cell2phys_pos, los_scalefactor_pos, rsd (with the velocity bias `dvel`), ap_auto |
+    ap_param, phys2cell_pos -- applied inside the paint kernels: no transformed position array, no elementwise pass.
+
+    `obs` comes from bricks.observation(...): the static geometry plus the differentiable tensors `par` (D f at a_obs,
+    a_par, a_perp) and `tab_gf` / `tab_ap` (light-cone growth and ap_auto rescaling on a uniform radius grid).
+    `pos` and `vel` are in the cells the geometry was built for: those of `pos_shape` (model.py: evol_shape; default
+    final_shape), which phys2cell_pos converts to final_shape cells (model.py:796, init_shape) -- here one scale factor
+    of the paint; the paint lands on `paint_shape` and is brought to `final_shape`, as in nufft."""
+    final_shape = tuple(int(s) for s in final_shape)
+    if paint_shape is None:
+        paint_shape, paint_oversamp = final_shape, 1.0
+    elif isinstance(paint_shape, float):
+        paint_oversamp = paint_shape
+        paint_shape = scale_shape(final_shape, paint_oversamp)
+    else:
+        paint_shape = tuple(int(s) for s in paint_shape)
+        paint_oversamp = float(np.exp(np.log(np.divide(final_shape, paint_shape)).mean()))
+    kb = _kb_kcut(kernel_type, paint_oversamp)
+    pos_shape = final_shape if pos_shape is None else tuple(int(s) for s in pos_shape)
+    scale = tuple(float(p) / float(f) for p, f in zip(paint_shape, pos_shape))
+    w, ws = _split_weights(weights)
+    ws = ws * float(np.divide(pos_shape, final_shape).prod())  # the Jacobian is final -> paint units (nbody.py:571)
+    static = {k: v for k, v in obs.items() if k not in ("par", "tab_gf", "tab_ap")}
+    mesh = _NufftObserved.apply(_f32(pos), None if vel is None else _f32(vel), None if dvel is None else _f32(dvel), w,
+                                obs["par"], obs.get("tab_gf"), obs.get("tab_ap"), static, paint_shape, ws, scale,
+                                int(paint_order), int(interlace_order), bool(paint_deconv), kb,
+                                None if lattice is None else tuple(int(s) for s in lattice))
     if final_shape != paint_shape:
         mesh = chreshape(mesh, r2chshape(final_shape))
     return mesh

@@ -460,6 +460,69 @@ class Ops:
                    n, sc, *oa, interlace_order, int(paint_deconv), A.ptr(outbar), A.ptr(pb), A.ptr(wb))
         return pb, wb
 
+    def _obs_struct(self, obs):
+        """mcpm_obs from a dict: curved, lightcone, ap, rsd, cell[3], origin[3], los[3], gf, a_par, a_perp, r0, dr,
+        tab_gf / tab_ap (float32 arrays of equal length, or None), dvel ([np,3] or None), rot (3 x 3 or None).  Returns
+        the struct and the prepared arrays (to keep alive across the call)."""
+        from ._capi import McpmObs
+        A = self.A
+        o = McpmObs()
+        o.curved, o.lightcone = int(bool(obs.get("curved", False))), int(bool(obs.get("lightcone", False)))
+        o.ap, o.rsd = int(obs.get("ap", 0)), int(bool(obs.get("rsd", True)))
+        for name, default in (("cell", (1.0,) * 3), ("origin", (0.0,) * 3), ("los", (0.0,) * 3)):
+            getattr(o, name)[:] = [float(v) for v in obs.get(name, default)]
+        o.gf, o.a_par, o.a_perp = (float(obs.get(k, d)) for k, d in (("gf", 0.0), ("a_par", 1.0), ("a_perp", 1.0)))
+        o.r0, o.dr = float(obs.get("r0", 0.0)), float(obs.get("dr", 0.0))
+        keep = [None if obs.get(k) is None else A.prepare(obs[k]) for k in ("tab_gf", "tab_ap", "dvel")]
+        nts = {A.shape(t)[0] for t in keep[:2] if t is not None}
+        if len(nts) > 1:
+            raise ValueError("tab_gf and tab_ap must have the same number of nodes")
+        o.nt = nts.pop() if nts else 0
+        o.tab_gf, o.tab_ap, o.dvel = (A.ptr(t) for t in keep)
+        rot = obs.get("rot")
+        o.rot[:] = [1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0] if rot is None else [float(v) for r in rot for v in r]
+        return o, keep
+
+    def nufft_observed(self, pos, vel, obs, paint_shape, weights=None, wscalar=1.0, scale=None, paint_order=2,
+                       interlace_order=2, paint_deconv=True, kb_kcut=0.0, lattice=None):
+        """nufft of the OBSERVED positions, the general observation chain of model.py:780-799 applied inside the paint
+        kernels (mcpm_nufft_obs; `obs` as _obs_struct takes it)."""
+        A = self.A
+        pos = A.prepare(pos)
+        vel = None if vel is None else A.prepare(vel)
+        weights = None if weights is None else A.prepare(weights)
+        out = A.empty(r2chshape(paint_shape), "c64")
+        sc, _ = self._xf(scale, 0.0)
+        o, keep = self._obs_struct(obs)
+        self._call("mcpm_nufft_obs", self._frame(paint_shape, lattice).handle, A.stream(), A.ptr(pos), A.ptr(vel),
+                   C.addressof(o), A.ptr(weights), wscalar, A.shape(pos)[0], sc, paint_order, float(kb_kcut),
+                   interlace_order, int(paint_deconv), A.ptr(out))
+        del keep
+        return out
+
+    def nufft_observed_vjp(self, pos, vel, obs, outbar, paint_shape, weights=None, wscalar=1.0, scale=None,
+                           paint_order=2, interlace_order=2, paint_deconv=True, kb_kcut=0.0, lattice=None,
+                           want_par=True):
+        """-> posbar, velbar (None without rsd), dvelbar (None without dvel), weightsbar, parbar: float64
+        [3 + 2 nt] cotangents of (gf, a_par, a_perp, tab_gf nodes, tab_ap nodes), or None."""
+        from ._capi import OBS_SLOTS
+        A = self.A
+        pos, outbar = A.prepare(pos), A.prepare(outbar, "c64")
+        vel = None if vel is None else A.prepare(vel)
+        weights = None if weights is None else A.prepare(weights)
+        n = A.shape(pos)[0]
+        sc, _ = self._xf(scale, 0.0)
+        o, keep = self._obs_struct(obs)
+        pb, wb = A.empty((n, 3)), (A.empty((n,)) if weights is not None else None)
+        vb = A.empty((n, 3)) if o.rsd else None
+        db = A.empty((n, 3)) if (o.rsd and keep[2] is not None) else None
+        par = A.empty((OBS_SLOTS, 3 + 2 * o.nt), "f64") if want_par else None
+        self._call("mcpm_nufft_obs_vjp", self._frame(paint_shape, lattice).handle, A.stream(), A.ptr(pos), A.ptr(vel),
+                   C.addressof(o), A.ptr(weights), wscalar, n, sc, paint_order, float(kb_kcut), interlace_order,
+                   int(paint_deconv), A.ptr(outbar), A.ptr(pb), A.ptr(vb), A.ptr(db), A.ptr(wb), A.ptr(par))
+        del keep
+        return pb, vb, db, wb, (None if par is None else par[0])
+
     # ------------------------------------------------------------------------------------------------ glue
     def chreshape_vjp(self, outbar, in_cshape):
         A = self.A

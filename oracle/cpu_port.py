@@ -23,7 +23,7 @@ SRC = os.path.join(ROOT, "montecosmo_b200", "csrc")
 OUT_DIR = os.path.join(ROOT, "oracle", "_build")
 OUT = os.path.join(OUT_DIR, "libmcpm_cpu.so")
 SOURCES = ["api.cu", "engine.cu", "paint.cu", "fourier.cu", "bias.cu", "fft.cu", "cic4.cu", "cic4_tma.cu", "halo.cu", "brick.cu", "xfft.cu", "yzfft.cu", "xfft_large.cu", "xfft_1024.cu"]
-HEADERS = ["rt.h", "engine.h", "window.h", "frame.h", "tma.h", "kspace.h", "xfft_kernel.h"]
+HEADERS = ["rt.h", "engine.h", "window.h", "frame.h", "obs.h", "tma.h", "kspace.h", "xfft_kernel.h"]
 
 _HOOK = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int)
 _keep = []

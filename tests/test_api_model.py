@@ -665,6 +665,86 @@ def test_observation_chain_golden(nb, golden):
     assert bool(torch.isfinite(vl.grad).all()) and float(vl.grad.abs().sum()) > 0 and float(ocl.grad.abs()) > 0
 
 
+OBS_CASES = {
+    # name: (curved, a_obs, ap_auto, rotated, velocity bias, lattice-relative positions, paint shape, rsd)
+    "curved_lightcone_auto": (True, None, True, True, True, False, (24, 24, 24), True),
+    "flat_lightcone_auto": (False, None, True, True, True, False, None, True),
+    "flat_scalar_param": (False, 0.7, False, True, False, False, (24, 24, 24), True),
+    "curved_scalar_param": (True, 0.7, False, False, True, True, None, True),
+    "flat_scalar_plain": (False, 0.5, None, False, False, True, None, True),
+    "curved_no_rsd_auto": (True, None, True, True, False, False, None, False),
+}
+
+
+@pytest.mark.parametrize("case", list(OBS_CASES))
+def test_fused_observation_chain(nb, case):
+    """nufft_observed -- the observation chain of model.py:780-799 applied inside the paint kernels (csrc/obs.h,
+    mcpm_nufft_obs) -- against the chain itself in float64: cell2phys_pos, los_scalefactor_pos, rsd, ap_auto | ap_param,
+    phys2cell_pos (the mirrors pinned to the reference source by test_observation_chain_golden) followed by the
+    oracle's nufft.  Half spectrum 2e-5 relative L2; cotangents of the positions, velocities, velocity bias and weights
+    1e-4; of Omega_c (through the light-cone growth table, the scalar D f and the ap_auto table) and of the
+    Alcock-Paczynski parameters 2e-4.  Rotated and unrotated boxes 1.5 Gpc/h from the observer, curved and flat sky,
+    absolute positions and lattice-relative displacements, paint mesh 1.5x the final one or equal to it."""
+    from scipy.spatial.transform import Rotation
+    from montecosmo_b200 import bricks as B
+    from montecosmo_b200.cosmo import Cosmology
+    curved, a_obs, ap_auto, rotated, with_dvel, relative, paint, rsd_on = OBS_CASES[case]
+    rng = np.random.default_rng(sum(map(ord, case)))
+    shape, box, center = (16, 16, 16), (640.0, 480.0, 560.0), (300.0, -200.0, 1500.0)
+    rot = Rotation.from_rotvec([0.2, -0.4, 0.6]) if rotated else None
+    n = int(np.prod(shape))
+    q = O.regular_pos(shape)
+    disp = torch.tensor(rng.normal(scale=0.7, size=q.shape))
+    vel0 = torch.tensor(rng.normal(scale=0.4, size=q.shape))
+    dvel0 = torch.tensor(rng.normal(scale=3.0, size=q.shape)) if with_dvel else None
+    w0 = torch.tensor(rng.uniform(0.3, 2.0, n))
+    cshape = (shape[0], shape[1], shape[2] // 2 + 1)
+    ck = torch.tensor(rng.normal(size=cshape) + 1j * rng.normal(size=cshape))
+    fid = Cosmology(Omega_c=0.21, Omega_b=0.05, h=0.7)
+    apv = dict(alpha_iso=1.03, alpha_ap=0.97)
+
+    def cosmo_and_ap():
+        oc = torch.tensor(0.2589, dtype=torch.float64, requires_grad=True)
+        ap = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in apv.items()}
+        return oc, Cosmology(Omega_c=oc), ap
+
+    # the engine, transform inside the paint
+    oc, cosmo, ap = cosmo_and_ap()
+    pos = leaf(disp if relative else q + disp, nb, torch.float32)
+    vel, w = leaf(vel0, nb, torch.float32), leaf(w0, nb, torch.float32)
+    dvel = leaf(dvel0, nb, torch.float32) if with_dvel else None
+    obs = B.observation(cosmo, center, rot, box, shape, a_obs, curved, rsd_on, ap_auto, fid, ap)
+    out = nb.nufft_observed(pos, vel if rsd_on else None, shape, obs, paint, w, dvel, 2, 2, paint_deconv=True,
+                            lattice=shape if relative else None)
+    (out * ck.to(torch.complex64).to(dev(nb)).conj()).real.sum().backward()
+    # the chain in float64
+    oc2, cosmo2, ap2 = cosmo_and_ap()
+    po, vo, wo = leaf(q + disp), leaf(vel0), leaf(w0)
+    do = leaf(dvel0) if with_dvel else 0.0
+    geo = (center, rot, box)
+    los, a = B.los_scalefactor_pos(po, *geo, shape, cosmo2, a_obs, curved)
+    phys = B.cell2phys_pos(po, *geo, shape)
+    if rsd_on:
+        phys = phys + B.rsd(cosmo2, vo, los, a, rot, box, shape, do)
+    if ap_auto is not None:
+        phys = B.ap_auto(phys, los, cosmo2, fid, curved) if ap_auto else B.ap_param(phys, los, ap2, curved)
+    ref = O.nufft(B.phys2cell_pos(phys, *geo, shape), shape, paint, wo, 2, 2, paint_deconv=True)
+    (ref * ck.conj()).real.sum().backward()
+    print(case, "spectrum", rel(out, ref.detach()), "pos", rel(pos.grad, po.grad), "w", rel(w.grad, wo.grad),
+          "Omega_c", None if oc.grad is None else (float(oc.grad), float(oc2.grad)))
+    assert rel(out, ref.detach()) < 2e-5
+    assert rel(pos.grad, po.grad) < 1e-4 and rel(w.grad, wo.grad) < 1e-4
+    if rsd_on:
+        assert rel(vel.grad, vo.grad) < 1e-4
+    if with_dvel and rsd_on:
+        assert rel(dvel.grad, do.grad) < 1e-4
+    if oc2.grad is not None and float(oc2.grad.abs()) > 0:
+        assert oc.grad is not None and abs(float(oc.grad) - float(oc2.grad)) < 1e-3 * abs(float(oc2.grad)), (oc.grad, oc2.grad)
+    if ap_auto is False:
+        for k in (("alpha_iso",) if curved else ("alpha_iso", "alpha_ap")):
+            assert abs(float(ap[k].grad) - float(ap2[k].grad)) < 2e-4 * abs(float(ap2[k].grad)), k
+
+
 @pytest.mark.parametrize("case", ["lightcone_lpt_curved", "nbody_flat"])
 def test_general_evolve_against_oracle(nb, case):
     """FieldLevelModel.evolve -- the general 'lpt' / 'nbody' branch of model.py:683-837 -- against the oracle's float64
@@ -704,6 +784,28 @@ def test_general_evolve_against_oracle(nb, case):
     (out * cot.float().to(dev(nb))).sum().backward()
     (ref * cot).sum().backward()
     assert rel(w.grad, wo.grad) < 1e-3
+
+
+def test_general_evolve_fused_observation_matches_elementwise_chain(nb):
+    """FieldLevelModel.evolve with the observation chain inside the paint (the default) against the same model with the
+    chain as elementwise passes over the particle arrays (fused_observation=False), where the evolution mesh is 1.5x the
+    initial one (positions in evol_shape cells painted onto init_shape: model.py:796) and the Alcock-Paczynski factors
+    are parameters: predicted mesh 2e-5, gradient w.r.t. the white field 2e-4."""
+    from montecosmo_b200.model import FieldLevelModel
+    rng = np.random.default_rng(5)
+    shape, box = (8, 8, 8), (400.0, 400.0, 400.0)
+    white = rng.normal(size=shape).astype(np.float32)
+    cot = torch.tensor(rng.normal(size=shape)).float().to(dev(nb))
+    res = []
+    for fused in (True, False):
+        m = FieldLevelModel(shape, box, evolution="lpt", a_obs=0.6, box_center=(100.0, 50.0, 1200.0), curved_sky=False,
+                            bias=dict(b1=0.8, b2=0.1, bnpar=4.0), evol_oversamp=1.5, ap_auto=False, fused_observation=fused)
+        w = leaf(torch.tensor(white), nb)
+        out = m.evolve(w, ap=dict(alpha_iso=1.02, alpha_ap=0.98))
+        (out * cot).sum().backward()
+        res.append((out.detach(), w.grad))
+    assert tuple(res[0][0].shape) == shape
+    assert rel(res[0][0], res[1][0]) < 2e-5 and rel(res[0][1], res[1][1]) < 2e-4
 
 
 def test_kaiser_model_golden(nb, golden):

@@ -46,10 +46,13 @@ MCPM_HD void abs_pos(const PosXform& xf, const int* b, const float* r, const flo
   x[1] = ((float)b[1] + r[1]) / xf.sy + d[1];
   x[2] = ((float)b[2] + r[2]) / xf.sz + d[2];
 }
+// GEN: the general observation transform is compiled in (only the paint and its transpose are instantiated with it, so
+// every other kernel -- and the paints of the step loop -- keep the register budget they had without it)
+template <bool GEN = false>
 MCPM_HD void load_pos(const float* pos, int64_t p, const PosXform& xf, int* b, float* u) {
   float r[3], d[3];
   load_site_disp(pos, p, xf, b, r, d);
-  if (xf.gen.on) {
+  if (GEN && xf.gen.on) {
     float x[3], delta[3];
     ObsState s;
     abs_pos(xf, b, r, d, x);
@@ -63,13 +66,13 @@ MCPM_HD void load_pos(const float* pos, int64_t p, const PosXform& xf, int* b, f
   u[2] = r[2] + (d[2] * xf.sz + xf.shift);
 }
 
-template <int ORDER, class WIN = RectWin>
+template <int ORDER, class WIN = RectWin, bool GEN = false>
 static void paint_impl(stream_t st, const float* pos, const float* weights, float wscalar, int64_t np, MeshDims n,
                        PosXform xf, float* mesh, WIN win = WIN()) {
   launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
     int sb[3], fx, fy, fz;
     float su[3];
-    load_pos(pos, p, xf, sb, su);
+    load_pos<GEN>(pos, p, xf, sb, su);
     float wx[ORDER], wy[ORDER], wz[ORDER];
     win.template weights<ORDER>(su[0], fx, wx);
     win.template weights<ORDER>(su[1], fy, wy);
@@ -261,7 +264,7 @@ static void paint3_impl(stream_t st, const float* pos, const float* A, float ca,
 // nshift > 1: the transposes of `nshift` interlaced paints in ONE gather -- mesh cotangent t = mbar + t * mesh_stride was
 // painted at shift xf.shift + t / nshift (nufft, nbody.py:524) -- so the particle arrays are read once and every output
 // is written once (two passes over the particles cost 0.77 ms of a 256^3 evaluation, with accumulating outputs).
-template <int ORDER, class WIN = RectWin>
+template <int ORDER, class WIN = RectWin, bool GEN = false>
 static void paint_vjp_impl(stream_t st, const float* pos, const float* weights, float wscalar, const float* mbar,
                            int64_t np, MeshDims n, PosXform xf, float* posbar, float* wbar, int accumulate,
                            float* velbar, int nshift, int64_t mesh_stride, WIN win = WIN()) {
@@ -270,7 +273,7 @@ static void paint_vjp_impl(stream_t st, const float* pos, const float* weights, 
     float sr[3], sd[3];
     load_site_disp(pos, p, xf, sb, sr, sd);
     ObsState os;
-    if (xf.gen.on) {  // general observation transform: keep its state for the transpose below
+    if (GEN && xf.gen.on) {  // general observation transform: keep its state for the transpose below
       float x[3], delta[3];
       abs_pos(xf, sb, sr, sd, x);
       obs_forward(xf.gen, x, p, os, delta);
@@ -315,7 +318,7 @@ static void paint_vjp_impl(stream_t st, const float* pos, const float* weights, 
     }
     float wp = weights ? weights[p] * wscalar : wscalar;
     if (wbar) wbar[p] = (accumulate ? wbar[p] : 0.0f) + r * wscalar;
-    if (xf.gen.on) {  // cotangent of the observed position -> positions, velocities, velocity bias, parameters
+    if (GEN && xf.gen.on) {  // cotangent of the observed position -> positions, velocities, velocity bias, parameters
       const float gd[3] = {g0 * xf.sx * wp, g1 * xf.sy * wp, g2 * xf.sz * wp};
       float xadd[3], vb[3];
       obs_transpose(xf.gen, os, p, gd, xadd, vb, accumulate != 0);
@@ -450,6 +453,25 @@ int paint(stream_t st, const float* pos, const float* weights, float wscalar, in
   MeshDims n = {nx, ny, nz};
   PosXform xf = make_xform(scale, shift, fr, obs);
   if (!accumulate) rt_memset(mesh, 0, sizeof(float) * (size_t)nx * ny * nz, st);
+  if (xf.gen.on) {  // the instantiations with the general observation transform
+    if (kb_kcut > 0.0f) {
+      KbWin kb = make_kbwin(order, kb_kcut);
+      switch (order) {
+        case 1: paint_impl<1, KbWin, true>(st, pos, weights, wscalar, np, n, xf, mesh, kb); break;
+        case 2: paint_impl<2, KbWin, true>(st, pos, weights, wscalar, np, n, xf, mesh, kb); break;
+        case 3: paint_impl<3, KbWin, true>(st, pos, weights, wscalar, np, n, xf, mesh, kb); break;
+        default: paint_impl<4, KbWin, true>(st, pos, weights, wscalar, np, n, xf, mesh, kb); break;
+      }
+    } else {
+      switch (order) {
+        case 1: paint_impl<1, RectWin, true>(st, pos, weights, wscalar, np, n, xf, mesh); break;
+        case 2: paint_impl<2, RectWin, true>(st, pos, weights, wscalar, np, n, xf, mesh); break;
+        case 3: paint_impl<3, RectWin, true>(st, pos, weights, wscalar, np, n, xf, mesh); break;
+        default: paint_impl<4, RectWin, true>(st, pos, weights, wscalar, np, n, xf, mesh); break;
+      }
+    }
+    return rt_check("paint");
+  }
   if (kb_kcut > 0.0f) {
     KbWin kb = make_kbwin(order, kb_kcut);
     switch (order) {
@@ -580,6 +602,25 @@ int paint_vjp(stream_t st, const float* pos, const float* weights, float wscalar
   PosXform xf = make_xform(scale, shift, fr, obs);
   if (!(obs && (obs->vel || (obs->gen && obs->gen->rsd)))) velbar = nullptr;
   if (nshift < 1) nshift = 1;
+  if (xf.gen.on) {  // the instantiations with the general observation transform
+    if (kb_kcut > 0.0f) {
+      KbWin kb = make_kbwin(order, kb_kcut);
+      switch (order) {
+        case 1: paint_vjp_impl<1, KbWin, true>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar, nshift, mesh_stride, kb); break;
+        case 2: paint_vjp_impl<2, KbWin, true>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar, nshift, mesh_stride, kb); break;
+        case 3: paint_vjp_impl<3, KbWin, true>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar, nshift, mesh_stride, kb); break;
+        default: paint_vjp_impl<4, KbWin, true>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar, nshift, mesh_stride, kb); break;
+      }
+    } else {
+      switch (order) {
+        case 1: paint_vjp_impl<1, RectWin, true>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar, nshift, mesh_stride); break;
+        case 2: paint_vjp_impl<2, RectWin, true>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar, nshift, mesh_stride); break;
+        case 3: paint_vjp_impl<3, RectWin, true>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar, nshift, mesh_stride); break;
+        default: paint_vjp_impl<4, RectWin, true>(st, pos, weights, wscalar, mbar, np, n, xf, posbar, wbar, accumulate, velbar, nshift, mesh_stride); break;
+      }
+    }
+    return rt_check("paint_vjp");
+  }
   if (kb_kcut > 0.0f) {
     KbWin kb = make_kbwin(order, kb_kcut);
     switch (order) {

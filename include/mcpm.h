@@ -569,6 +569,8 @@ typedef struct mcpm_obs {
   const float* tab_ap;
   const float* dvel;
   float rot[9];
+  const float* par; /* device [3] = gf, a_par, a_perp replacing the three host values above (a caller whose scalars are
+                       traced device values, e.g. under XLA); NULL: the host values */
 } mcpm_obs;
 int mcpm_nufft_obs(mcpm_engine* eng, void* stream, const float* pos, const float* vel, const mcpm_obs* obs,
                    const float* weights, float wscalar, int64_t np, const float scale[3], int paint_order, float kcut,

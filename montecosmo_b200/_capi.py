@@ -16,7 +16,7 @@ class McpmObs(C.Structure):
     _fields_ = [("curved", i32), ("lightcone", i32), ("ap", i32), ("rsd", i32),
                 ("cell", f32 * 3), ("origin", f32 * 3), ("los", f32 * 3),
                 ("gf", f32), ("a_par", f32), ("a_perp", f32), ("r0", f32), ("dr", f32), ("nt", i32),
-                ("tab_gf", vp), ("tab_ap", vp), ("dvel", vp), ("rot", f32 * 9)]
+                ("tab_gf", vp), ("tab_ap", vp), ("dvel", vp), ("rot", f32 * 9), ("par", vp)]
 
 
 MESH = [i32, i32, i32]

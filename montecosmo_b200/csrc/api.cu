@@ -1269,6 +1269,7 @@ static int make_obs_gen(const mcpm_obs* o, const float* vel, ObsGen& g) {
   g.ox = o->origin[0], g.oy = o->origin[1], g.oz = o->origin[2];
   g.lx = o->los[0], g.ly = o->los[1], g.lz = o->los[2];
   g.gf = o->gf, g.a_par = o->a_par, g.a_perp = o->a_perp;
+  g.par = o->par;
   g.r0 = o->r0;
   g.inv_dr = o->dr > 0.0f ? 1.0f / o->dr : 0.0f;
   g.nt = o->nt > 0 ? o->nt : 0;

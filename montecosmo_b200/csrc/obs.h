@@ -40,6 +40,7 @@ struct ObsGen {
   float ox = 0.f, oy = 0.f, oz = 0.f;  // q = pos * c + o
   float lx = 0.f, ly = 0.f, lz = 0.f;  // flat-sky line of sight in the box frame
   float gf = 0.f, a_par = 1.f, a_perp = 1.f;
+  const float* par = nullptr;  // the same three numbers in device memory (a caller whose scalars are traced values)
   float r0 = 0.f, inv_dr = 0.f;  // table nodes r0 + k / inv_dr, k = 0 .. nt - 1
   int nt = 0;
   const float* tab_gf = nullptr;
@@ -71,7 +72,7 @@ MCPM_HD float obs_interp(const float* tab, const ObsGen& o, float r, ObsTabCell&
 
 struct ObsState {
   float q[3], l[3], u[3], q1[3];
-  float r, sgn, s, gf, r1, sgn1, t1, am1;
+  float r, sgn, s, gf, r1, sgn1, t1, am1, a_par, a_perp;
   ObsTabCell cg, ca;
 };
 
@@ -82,6 +83,8 @@ MCPM_HD void obs_forward(const ObsGen& o, const float* x, int64_t p, ObsState& s
   s.q[1] = x[1] * o.cy + o.oy;
   s.q[2] = x[2] * o.cz + o.oz;
   s.sgn = 0.0f;
+  s.a_par = o.par ? o.par[1] : o.a_par;
+  s.a_perp = o.par ? o.par[2] : o.a_perp;
   if (o.curved) {
     s.r = sqrtf(s.q[0] * s.q[0] + s.q[1] * s.q[1] + s.q[2] * s.q[2]);
     const float ir = s.r > 0.0f ? 1.0f / s.r : 0.0f;  // safe_div
@@ -101,7 +104,7 @@ MCPM_HD void obs_forward(const ObsGen& o, const float* x, int64_t p, ObsState& s
   s.gf = 0.0f;
   s.u[0] = s.u[1] = s.u[2] = 0.0f;
   if (o.rsd) {
-    s.gf = o.lightcone ? obs_interp(o.tab_gf, o, s.r, s.cg) : o.gf;
+    s.gf = o.lightcone ? obs_interp(o.tab_gf, o, s.r, s.cg) : (o.par ? o.par[0] : o.gf);
     const float* v = o.vel + 3 * p;
     for (int a = 0; a < 3; ++a) s.u[a] = v[a] * c[a] * s.gf;
     if (o.dvel) {
@@ -127,9 +130,9 @@ MCPM_HD void obs_forward(const ObsGen& o, const float* x, int64_t p, ObsState& s
     for (int a = 0; a < 3; ++a) d[a] += s.am1 * s.q1[a];
   } else if (o.ap == 2) {
     if (o.curved) {
-      for (int a = 0; a < 3; ++a) d[a] += (o.a_par - 1.0f) * s.q1[a];
+      for (int a = 0; a < 3; ++a) d[a] += (s.a_par - 1.0f) * s.q1[a];
     } else {
-      for (int a = 0; a < 3; ++a) d[a] += (o.a_par - 1.0f) * s.t1 * s.l[a] + (o.a_perp - 1.0f) * (s.q1[a] - s.t1 * s.l[a]);
+      for (int a = 0; a < 3; ++a) d[a] += (s.a_par - 1.0f) * s.t1 * s.l[a] + (s.a_perp - 1.0f) * (s.q1[a] - s.t1 * s.l[a]);
     }
   }
   for (int a = 0; a < 3; ++a) delta[a] = d[a] / c[a];
@@ -161,10 +164,10 @@ MCPM_DEV void obs_transpose(const ObsGen& o, const ObsState& s, int64_t p, const
     }
   } else if (o.ap == 2) {
     if (o.curved) {
-      for (int a = 0; a < 3; ++a) q1b[a] = (o.a_par - 1.0f) * h[a];
+      for (int a = 0; a < 3; ++a) q1b[a] = (s.a_par - 1.0f) * h[a];
       if (par) atomic_add(par + 1, (double)hq1);
     } else {
-      for (int a = 0; a < 3; ++a) q1b[a] = (o.a_perp - 1.0f) * h[a] + (o.a_par - o.a_perp) * hl * s.l[a];
+      for (int a = 0; a < 3; ++a) q1b[a] = (s.a_perp - 1.0f) * h[a] + (s.a_par - s.a_perp) * hl * s.l[a];
       if (par) {
         atomic_add(par + 1, (double)(s.t1 * hl));
         atomic_add(par + 2, (double)(hq1 - s.t1 * hl));

@@ -45,7 +45,7 @@ HANDLERS = {
     "mcpm_nufft_rsd": "McpmNufftRsd", "mcpm_nufft_rsd_vjp": "McpmNufftRsdVjp", "mcpm_bias_spectra": "McpmBiasSpectra",
     "mcpm_bias_spectra_vjp": "McpmBiasSpectraVjp", "mcpm_shear_invariants": "McpmShearInvariants",
     "mcpm_shear_invariants_vjp": "McpmShearInvariantsVjp", "mcpm_bias_weights": "McpmBiasWeights",
-    "mcpm_bias_weights_vjp": "McpmBiasWeightsVjp",
+    "mcpm_bias_weights_vjp": "McpmBiasWeightsVjp", "mcpm_nufft_obs": "McpmNufftObs", "mcpm_nufft_obs_vjp": "McpmNufftObsVjp",
 }
 for _name, _sym in HANDLERS.items():
     jax.ffi.register_ffi_target(_name, jax.ffi.pycapsule(getattr(_SHIM, _sym)), platform="CUDA")
@@ -255,6 +255,76 @@ def nufft(pos, final_shape: tuple, paint_shape=None, weights=1.0, paint_order: i
         return mesh if final_shape == paint_shape else chreshape(mesh, r2chshape(final_shape))
     mesh = _nufft_paint(pos, paint_shape, _weights(weights, pos.shape[0]), scale, paint_order, interlace_order,
                         kernel_type, bool(paint_deconv), None if lattice is None else tuple(lattice))
+    return mesh if final_shape == paint_shape else chreshape(mesh, r2chshape(final_shape))
+
+
+# the same paint of the positions as the observer sees them: the chain model.py:780-799 builds between the evolution and
+# the paint (frames, line of sight, light-cone scale factor, redshift-space distortion, Alcock-Paczynski) inside the kernels
+OBS_SLOTS = 32  # MCPM_OBS_SLOTS
+
+
+def _obs_attrs(static, scale, paint_order, kcut, interlace_order, paint_deconv, lattice):
+    flags = np.asarray([static["curved"], static["lightcone"], static["ap"], static["rsd"]], np.int32)
+    geom = np.asarray([*static["cell"], *static["origin"], *static["los"], static["r0"], static["dr"]], np.float32)
+    return dict(flags=flags, geom=geom, rot=np.asarray(static["rot"], np.float32).reshape(9), wscalar=np.float32(static["wscalar"]),
+                scale=np.asarray(scale, np.float32), paint_order=i32(paint_order), kcut=np.float32(kcut),
+                interlace_order=i32(interlace_order), paint_deconv=i32(paint_deconv),
+                lattice=_NOLAT if lattice is None else np.asarray(lattice, np.int32), relative=i32(lattice is not None))
+
+
+@partial(jax.custom_vjp, nondiff_argnums=(7, 8, 9, 10, 11, 12, 13, 14))
+def _nufft_paint_obs(pos, vel, dvel, weights, par, tab_gf, tab_ap, static, paint_shape, scale, paint_order, kcut,
+                     interlace_order, paint_deconv, lattice):
+    """`static`: a hashable tuple of (key, value) pairs -- curved, lightcone, ap, rsd, cell, origin, los, rot, r0, dr,
+    wscalar (bricks.observation's geometry); par = (D f, a_par, a_perp) and the tables are traced float32 arrays."""
+    attrs = _obs_attrs(dict(static), scale, paint_order, kcut, interlace_order, paint_deconv, lattice)
+    return jax.ffi.ffi_call("mcpm_nufft_obs", _sds(r2chshape(paint_shape), c64))(
+        pos.astype(f32), vel.astype(f32), dvel.astype(f32), weights, par.astype(f32), tab_gf.astype(f32), tab_ap.astype(f32),
+        **attrs)
+
+
+def _nufft_obs_fwd(pos, vel, dvel, weights, par, tab_gf, tab_ap, *cfg):
+    return _nufft_paint_obs(pos, vel, dvel, weights, par, tab_gf, tab_ap, *cfg), (pos, vel, dvel, weights, par, tab_gf, tab_ap)
+
+
+def _nufft_obs_bwd(static, paint_shape, scale, paint_order, kcut, interlace_order, paint_deconv, lattice, res, kbar):
+    pos, vel, dvel, weights, par, tab_gf, tab_ap = res
+    nt = max(tab_gf.shape[0], tab_ap.shape[0])
+    attrs = _obs_attrs(dict(static), scale, paint_order, kcut, interlace_order, paint_deconv, lattice)
+    pb, vb, db, wb, parbar = jax.ffi.ffi_call(
+        "mcpm_nufft_obs_vjp", (_sds(pos.shape), _sds(vel.shape), _sds(dvel.shape), _sds(weights.shape),
+                               _sds((OBS_SLOTS, 3 + 2 * nt), jnp.float64)))(
+        pos.astype(f32), vel.astype(f32), dvel.astype(f32), weights, par.astype(f32), tab_gf.astype(f32), tab_ap.astype(f32),
+        jnp.conj(kbar), **attrs)
+    row = parbar[0]
+    return (pb, vb, db, wb, row[:3].astype(par.dtype), row[3:3 + tab_gf.shape[0]].astype(tab_gf.dtype),
+            row[3 + nt:3 + nt + tab_ap.shape[0]].astype(tab_ap.dtype))
+
+
+_nufft_paint_obs.defvjp(_nufft_obs_fwd, _nufft_obs_bwd)
+
+
+def nufft_observed(pos, vel, final_shape: tuple, obs: dict, paint_shape=None, weights=1.0, dvel=None, paint_order: int = 2,
+                   interlace_order: int = 2, kernel_type="rectangular", paint_deconv=True, lattice=None, pos_shape=None):
+    """The signature of montecosmo_b200.nbody.nufft_observed: `obs` holds the static geometry and the traced `par`,
+    `tab_gf`, `tab_ap` (what bricks.observation computes from the cosmology, here with jax_cosmo by the caller)."""
+    final_shape = tuple(int(s) for s in final_shape)
+    if paint_shape is None:
+        paint_shape = final_shape
+    elif isinstance(paint_shape, float):
+        paint_shape = tuple(int(2 * round(s * paint_shape / 2)) for s in final_shape)
+    paint_shape = tuple(int(s) for s in paint_shape)
+    pos_shape = final_shape if pos_shape is None else tuple(int(s) for s in pos_shape)
+    scale = tuple(p / f for p, f in zip(paint_shape, pos_shape))
+    kc = _kcut(kernel_type, float(np.exp(np.log(np.divide(final_shape, paint_shape)).mean())))
+    static = {k: (tuple(map(tuple, v)) if k == "rot" else (tuple(v) if isinstance(v, (list, tuple, np.ndarray)) else v))
+              for k, v in obs.items() if k not in ("par", "tab_gf", "tab_ap")}
+    static["wscalar"] = float(np.divide(pos_shape, final_shape).prod())  # the Jacobian is final -> paint units
+    none = _NONE()
+    mesh = _nufft_paint_obs(pos, none if vel is None else vel, none if dvel is None else dvel, _weights(weights, pos.shape[0]),
+                            jnp.asarray(obs["par"]), obs.get("tab_gf", none), obs.get("tab_ap", none),
+                            tuple(sorted(static.items())), paint_shape, scale, paint_order, kc, interlace_order,
+                            bool(paint_deconv), None if lattice is None else tuple(lattice))
     return mesh if final_shape == paint_shape else chreshape(mesh, r2chshape(final_shape))
 
 

@@ -300,6 +300,45 @@ ffi::Error NufftRsdVjp(cudaStream_t st, int32_t dev, F32 pos, F32 vel, F32 weigh
                                    pos.dimensions()[0], scale3(scale, sc), paint_order, interlace_order, paint_deconv,
                                    outbar.typed_data(), optr(posbar), velbar->typed_data(), optr(weightsbar)));
 }
+// nufft of OBSERVED positions, the general observation chain (model.py:780-799) applied inside the paint kernels.  What
+// depends on the cosmology arrives as traced arrays: par [3] = (D f at a_obs, a_par, a_perp) and the two radius tables;
+// zero-size buffers stand for "absent" (vel without rsd, dvel, the tables).
+static mcpm_obs make_obs(F32 par, F32 tab_gf, F32 tab_ap, F32 dvel, Ints flags, Floats geom, Floats rot) {
+  mcpm_obs o = {};
+  o.curved = flags[0], o.lightcone = flags[1], o.ap = flags[2], o.rsd = flags[3];
+  for (int d = 0; d < 3; ++d) o.cell[d] = geom[d], o.origin[d] = geom[3 + d], o.los[d] = geom[6 + d];
+  o.r0 = geom[9], o.dr = geom[10];
+  o.nt = (int)(tab_gf.element_count() ? tab_gf.element_count() : tab_ap.element_count());
+  o.tab_gf = opt(tab_gf), o.tab_ap = opt(tab_ap), o.dvel = opt(dvel);
+  for (int k = 0; k < 9; ++k) o.rot[k] = rot[k];
+  o.par = par.typed_data();
+  return o;
+}
+ffi::Error NufftObs(cudaStream_t st, int32_t dev, F32 pos, F32 vel, F32 dvel, F32 weights, F32 par, F32 tab_gf, F32 tab_ap,
+                    Ints flags, Floats geom, Floats rot, float wscalar, Floats scale, int32_t paint_order, float kcut,
+                    int32_t interlace_order, int32_t paint_deconv, Ints lattice, int32_t relative, RC64 out) {
+  auto m = real_shape_of_spectrum(*out);
+  EngineCall e(dev, m[0], m[1], m[2], lattice, relative);
+  if (e.err.failure()) return e.err;
+  float sc[3];
+  const mcpm_obs o = make_obs(par, tab_gf, tab_ap, dvel, flags, geom, rot);
+  return status(mcpm_nufft_obs(e.eng(), st, pos.typed_data(), opt(vel), &o, opt(weights), wscalar, pos.dimensions()[0],
+                               scale3(scale, sc), paint_order, kcut, interlace_order, paint_deconv, out->typed_data()));
+}
+// parbar: float64 [MCPM_OBS_SLOTS, 3 + 2 nt], row 0 holds the cotangents of (par, tab_gf, tab_ap) on return
+ffi::Error NufftObsVjp(cudaStream_t st, int32_t dev, F32 pos, F32 vel, F32 dvel, F32 weights, F32 par, F32 tab_gf,
+                       F32 tab_ap, C64 outbar, Ints flags, Floats geom, Floats rot, float wscalar, Floats scale,
+                       int32_t paint_order, float kcut, int32_t interlace_order, int32_t paint_deconv, Ints lattice,
+                       int32_t relative, RF32 posbar, RF32 velbar, RF32 dvelbar, RF32 weightsbar, RF64 parbar) {
+  auto m = real_shape_of_spectrum(outbar);
+  EngineCall e(dev, m[0], m[1], m[2], lattice, relative);
+  if (e.err.failure()) return e.err;
+  float sc[3];
+  const mcpm_obs o = make_obs(par, tab_gf, tab_ap, dvel, flags, geom, rot);
+  return status(mcpm_nufft_obs_vjp(e.eng(), st, pos.typed_data(), opt(vel), &o, opt(weights), wscalar, pos.dimensions()[0],
+                                   scale3(scale, sc), paint_order, kcut, interlace_order, paint_deconv, outbar.typed_data(),
+                                   optr(posbar), optr(velbar), optr(dvelbar), optr(weightsbar), parbar->typed_data()));
+}
 // Lagrangian bias expansion (bricks.py:327-452) as fused passes: Fourier multipliers, shear invariants, polynomial
 ffi::Error BiasSpectra(cudaStream_t st, C64 dk, F32 inv_transfer, Floats cells_per_len, RC64 out) {
   auto m = real_shape_of_spectrum(dk);
@@ -479,6 +518,16 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(McpmNufftRsdVjp, NufftRsdVjp,
     MCPM_STREAM_DEV.Arg<F32>().Arg<F32>().Arg<F32>().Arg<C64>().Attr<Floats>("los").Attr<float>("coef")
         .Attr<float>("wscalar").Attr<Floats>("scale").Attr<int32_t>("paint_order").Attr<int32_t>("interlace_order")
         .Attr<int32_t>("paint_deconv") LATTICE.Ret<F32>().Ret<F32>().Ret<F32>());
+#define OBS .Attr<Ints>("flags").Attr<Floats>("geom").Attr<Floats>("rot")
+XLA_FFI_DEFINE_HANDLER_SYMBOL(McpmNufftObs, NufftObs,
+    MCPM_STREAM_DEV.Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>() OBS.Attr<float>("wscalar")
+        .Attr<Floats>("scale").Attr<int32_t>("paint_order").Attr<float>("kcut").Attr<int32_t>("interlace_order")
+        .Attr<int32_t>("paint_deconv") LATTICE.Ret<C64>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(McpmNufftObsVjp, NufftObsVjp,
+    MCPM_STREAM_DEV.Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<C64>() OBS
+        .Attr<float>("wscalar").Attr<Floats>("scale").Attr<int32_t>("paint_order").Attr<float>("kcut")
+        .Attr<int32_t>("interlace_order").Attr<int32_t>("paint_deconv")
+            LATTICE.Ret<F32>().Ret<F32>().Ret<F32>().Ret<F32>().Ret<F64>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(McpmBiasSpectra, BiasSpectra,
     MCPM_STREAM.Arg<C64>().Arg<F32>().Attr<Floats>("cells_per_len").Ret<C64>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(McpmBiasSpectraVjp, BiasSpectraVjp,

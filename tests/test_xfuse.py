@@ -205,3 +205,33 @@ def test_two_field_forms_match_the_three_field_ones(ops, nx, ny, nz, grad_fd):
     ops._call("mcpm_yz_gradients", st, A.ptr(d_in3b), nx, ny, nz, grad_fd, 1)
     peer(d_in3b, two1, 3)
     assert rel(two1, ref1) < 2e-6
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("nx,ny,nz,grad_fd", [(64, 12, 16, 0), (256, 8, 6, 4)])
+def test_peer_transform_with_two_emulated_ranks(ops, mode, nx, ny, nz, grad_fd):
+    """The distributed x-transform kernel (mcpm_xfuse_force_peer) with TWO ranks' buffers on one device: each "rank" owns
+    nx/2 x-planes of every component and transforms half of the ky rows, reading and writing both buffers through the
+    peer table -- against the same operator on the whole spectrum with one rank.  All four modes (1 -> 3, 3 -> 1 and the
+    two-field forms 1 -> 2, 2 -> 1 of the slab step loop): identical arithmetic per column, 1e-6."""
+    import ctypes as C
+    P = 2
+    xl, kyl, nzc = nx // P, ny // P, nz // 2 + 1
+    n_in, n_out = {0: (1, 3), 1: (3, 1), 2: (1, 2), 3: (2, 1)}[mode]
+    rng = np.random.default_rng(10 * nx + mode)
+    A = ops.A
+    st = A.stream()
+    x = (rng.normal(size=(n_in, nx, ny, nzc)) + 1j * rng.normal(size=(n_in, nx, ny, nzc))).astype(np.complex64)
+    tab = lambda ts: (C.c_void_p * len(ts))(*[A.ptr(t) for t in ts])
+    whole_in, whole_out = A.prepare(x, "c64"), A.zeros((n_out, nx, ny, nzc), "c64")
+    ops._call("mcpm_xfuse_force_peer", st, tab([whole_in]), tab([whole_out]), 1, mode, nx, ny, nz, ny, 0, 0, grad_fd, 0.0,
+              0, 0.25)
+    parts_in = [A.prepare(np.ascontiguousarray(x[:, r * xl:(r + 1) * xl]), "c64") for r in range(P)]
+    parts_out = [A.zeros((n_out, xl, ny, nzc), "c64") for _ in range(P)]
+    for r in range(P):
+        ops._call("mcpm_xfuse_force_peer", st, tab(parts_in), tab(parts_out), P, mode, nx, ny, nz, kyl, r * kyl, 0,
+                  grad_fd, 0.0, 0, 0.25)
+    got = np.concatenate([to_numpy(t) for t in parts_out], axis=1)
+    ref = to_numpy(whole_out)
+    assert np.abs(ref).max() > 0
+    assert np.linalg.norm((got - ref).ravel()) <= 1e-6 * np.linalg.norm(ref.ravel())

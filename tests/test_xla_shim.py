@@ -61,7 +61,7 @@ def test_shim_calls_match_the_abi_prototypes():
 
 def _expand_macros(src):
     macros = dict(re.findall(r"#define\s+(\w+)\s+((?:[^\n\\]|\\\n)*)", src))
-    macros = {k: v.replace("\\\n", " ") for k, v in macros.items() if k in ("XF", "LATTICE", "FD", "STEPS")}
+    macros = {k: v.replace("\\\n", " ") for k, v in macros.items() if k in ("XF", "LATTICE", "FD", "STEPS", "OBS")}
     for _ in range(3):
         for k, v in macros.items():
             src = re.sub(rf"\b{k}\b", v, src)
@@ -84,6 +84,11 @@ def test_jax_module_and_shim_agree_on_handlers_and_attributes():
     # every ffi_call("target", ...)(..., attr=...) passes only attributes the handler binds
     steps_attrs = {"mesh", "alpha", "beta", "drift_pre", "drift_post", "order", "paint_deconv", "lap_fd", "grad_fd", "lattice",
                    "relative"}
+    obs_attrs = {"flags", "geom", "rot", "wscalar", "scale", "paint_order", "kcut", "interlace_order", "paint_deconv",
+                 "lattice", "relative"}
+    fn = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "_obs_attrs")
+    ret = next(n for n in ast.walk(fn) if isinstance(n, ast.Return))
+    assert {k.arg for k in ret.value.keywords} == obs_attrs  # what **attrs of the observed nufft expands to
     checked = 0
     for node in ast.walk(tree):
         if isinstance(node, ast.Call) and isinstance(node.func, ast.Call):
@@ -92,8 +97,8 @@ def test_jax_module_and_shim_agree_on_handlers_and_attributes():
                 target = inner.args[0].value
                 bound = defs[handlers[target]]
                 passed = {k.arg for k in node.keywords if k.arg is not None}
-                if any(k.arg is None for k in node.keywords):  # **_steps_attrs(...)
-                    passed |= steps_attrs
+                if any(k.arg is None for k in node.keywords):  # **_steps_attrs(...) / **attrs of the observed nufft
+                    passed |= obs_attrs if target.startswith("mcpm_nufft_obs") else steps_attrs
                 assert passed == bound, f"{target}: module passes {sorted(passed)}, handler binds {sorted(bound)}"
                 checked += 1
     assert checked >= 15

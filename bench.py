@@ -695,7 +695,9 @@ def run_slab(args, world, rank, dev, timed, barrier, sampler):
     # transform, 8 B x (cells/2) / P x (P-1)/P each, + the halo planes of every paint / readout
     cells = float(np.prod(shape))
     ns = wl["n_steps"]
-    nfft = 13 + 13 + 8 * ns + (2 + 2 + 2 * 3 + 2)
+    # per step 1 + 3 fields forward and 3 + 1 in reverse, or 1 + 2 and 2 + 1 with the two-field transform (dist.py)
+    per_step = 6 if (getattr(pm, "two_field", False) and getattr(pm, "p2p", False)) else 8
+    nfft = 13 + 13 + per_step * ns + (2 + 2 + 2 * 3 + 2)
     a2a = nfft * 8 * (cells / 2) / world * (world - 1) / world * (1 + 2.0 / shape[2])
     plane = shape[1] * shape[2] * 4.0
     h_steps = float(np.mean(sched)) if sched else float(halo_used)  # mean active planes of the step-loop exchanges

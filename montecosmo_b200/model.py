@@ -282,16 +282,25 @@ class FieldLevelModel(FieldModel):
         if self.png_type is not None:
             init_mesh = B.add_png(c, self.png["fNL"], init_mesh, self.box_size, self.kpow_sigma8_1())
             init_mesh = nb.chreshape(nb.chreshape(init_mesh, r2chshape(self.init_shape)), r2chshape(self.evol_shape))
+        # With the observation chain inside the paint the particles can stay float32 DISPLACEMENTS from their lattice
+        # sites all the way (nufft_observed's `lattice`): the absolute sum q + dpos costs 1e-5 cell at the faces where
+        # the CIC derivative jumps (tools/obs_accuracy.py at 64^3: gradient 1.2e-3 -> 5e-4 against float64)
+        lattice = None
         if self.evolution == "lpt":
             dpos, vel = nb.lpt(c, init_mesh, pos, a, self.lpt_order, 1)
-            pos = pos + dpos
+            if self.fused_observation:
+                pos, lattice = dpos, self.ptcl_shape
+            else:
+                pos = pos + dpos
         elif self.evolution == "nbody":
             if np.ndim(a) != 0:
                 raise AssertionError("N-body light-cone not implemented yet")  # model.py:768
+            declared = self.ptcl_shape == self.evol_shape
+            rel = True if (self.fused_observation and declared) else None
             pos, vel = nb.nbody_bf(c, init_mesh, pos, self.a_start, a, self.n_steps, self.paint_order, self.lpt_order,
-                                   paint_deconv=False, ptcl_shape=self.ptcl_shape if self.ptcl_shape == self.evol_shape
-                                   else None)
+                                   paint_deconv=False, ptcl_shape=self.ptcl_shape if declared else None, relative=rel)
             pos, vel = pos[-1], vel[-1]
+            lattice = self.ptcl_shape if rel else None
         else:
             raise ValueError(f"unknown evolution {self.evolution}")
         paint_shape = self.paint_shape if self.paint_shape != self.init_shape else None
@@ -303,7 +312,8 @@ class FieldLevelModel(FieldModel):
                                 self.cosmo_fid, ap)
             gxy = nb.nufft_observed(pos, vel if self.rsd else None, self.init_shape, obs, paint_shape, weights,
                                     dvel if (self.rsd and torch.is_tensor(dvel)) else None, self.paint_order,
-                                    self.interlace_order, self.kernel_type, self.paint_deconv, pos_shape=self.evol_shape)
+                                    self.interlace_order, self.kernel_type, self.paint_deconv, lattice=lattice,
+                                    pos_shape=self.evol_shape)
         else:  # the same chain as elementwise passes over the particle arrays (cross-check)
             los, a = B.los_scalefactor_pos(pos, *geo, self.evol_shape, c, self.a_obs, self.curved_sky)
             pos = B.cell2phys_pos(pos, *geo, self.evol_shape)

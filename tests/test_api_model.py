@@ -745,14 +745,16 @@ def test_fused_observation_chain(nb, case):
             assert abs(float(ap[k].grad) - float(ap2[k].grad)) < 2e-4 * abs(float(ap2[k].grad)), k
 
 
-@pytest.mark.parametrize("case", ["lightcone_lpt_curved", "nbody_flat"])
+@pytest.mark.parametrize("case", ["lightcone_lpt_curved", "nbody_flat", "nbody_curved_lattice"])
 def test_general_evolve_against_oracle(nb, case):
     """FieldLevelModel.evolve -- the general 'lpt' / 'nbody' branch of model.py:683-837 -- against the oracle's float64
     restatement of the same chain (every callee of which is pinned to golden vectors of the reference source):
     predicted mesh 1e-4 relative L2, gradient of a linear functional w.r.t. the white field 1e-3.
       lightcone_lpt_curved: rotated box 1500 Mpc/h from the observer, curved sky, per-particle scale factors from the
         comoving distance, full bias expansion with the velocity term, RSD, automatic Alcock-Paczynski, 1.5x paint mesh;
-      nbody_flat: 3 BullFrog steps to a scalar a_obs, flat sky along the box centre, 8^3 particles in a 16^3 mesh."""
+      nbody_flat: 3 BullFrog steps to a scalar a_obs, flat sky along the box centre, 8^3 particles in a 16^3 mesh;
+      nbody_curved_lattice: 2 steps, one particle per cell (displacements carried from the loop into the observed paint),
+        rotated box, curved sky, velocity bias, automatic Alcock-Paczynski."""
     from scipy.spatial.transform import Rotation
     from montecosmo_b200.cosmo import Cosmology
     from montecosmo_b200.model import FieldLevelModel
@@ -765,6 +767,14 @@ def test_general_evolve_against_oracle(nb, case):
                    bias=bias, paint_oversamp=1.5, ap_auto=True, cosmo_fid=Cosmology(Omega_c=0.21, Omega_b=0.05, h=0.7))
         okw = dict(evolution="lpt", a_obs=None, box_center=cfg["box_center"], box_rot=rot, curved_sky=True, bias=bias,
                    paint_shape=(24, 24, 24), ap_fid=O.Cosmology(Omega_c=0.21, Omega_b=0.05, h=0.7))
+    elif case == "nbody_curved_lattice":
+        # one particle per cell: the loop and the observed paint carry lattice-relative displacements (model.py mirror)
+        rot = Rotation.from_rotvec([-0.3, 0.1, 0.2])
+        bias = dict(b1=0.8, b2=-0.1, bnpar=3.0)
+        cfg = dict(evolution="nbody", n_steps=2, a_start=0.1, a_obs=0.7, box_center=(-400.0, 250.0, 1300.0), box_rot=rot,
+                   curved_sky=True, bias=bias, ap_auto=True, cosmo_fid=Cosmology(Omega_c=0.21, Omega_b=0.05, h=0.7))
+        okw = dict(evolution="nbody", n_steps=2, a_start=0.1, a_obs=0.7, box_center=cfg["box_center"], box_rot=rot,
+                   curved_sky=True, bias=bias, ap_fid=O.Cosmology(Omega_c=0.21, Omega_b=0.05, h=0.7))
     else:
         bias = dict(b1=0.7, b2=0.2)
         cfg = dict(evolution="nbody", n_steps=3, a_start=0.1, a_obs=0.8, box_center=(0.0, 0.0, 2000.0), curved_sky=False,

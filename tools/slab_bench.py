@@ -195,7 +195,7 @@ def main():
     if rank == 0:
         per = float(ms) / a.steps
         # NVLink bytes out of each GPU per evaluation: all-to-alls (8 B * N/P * (P-1)/P per transform) + halo planes
-        nfft = 13 + 13 + 8 * a.nbody_steps
+        nfft = 13 + 13 + (6 if (pm.two_field and pm.p2p) else 8) * a.nbody_steps  # two-field step-loop transforms (dist.py)
         a2a = nfft * 8 * (n ** 3 / 2) / world * (world - 1) / world * 1.004
         halo = a.nbody_steps * (2 + 2 * 4 + 2 * 4 + 2) * pm.H * n * n * 4
         if a.model:  # + white rfftn / its transpose, bias irfftn / its transpose, final paint: 2 R2C + 1 C2R and transposes

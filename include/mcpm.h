@@ -580,6 +580,17 @@ int mcpm_nufft_obs_vjp(mcpm_engine* eng, void* stream, const float* pos, const f
                        int interlace_order, int paint_deconv, const void* outbar_k, float* posbar, float* velbar,
                        float* dvelbar, float* weightsbar, double* parbar);
 
+/* Functions of the comoving distance evaluated at the particles -- the light cone: los_scalefactor_pos
+ * (bricks.py:747-766: r = |cell2phys_pos(pos)| on a curved sky, |l . cell2phys_pos(pos)| on a flat one) followed by the
+ * growth lookups a2g, a2g2, a2f, ... of lagrangian_bias (bricks.py:341) and lpt (nbody.py:651-665) -- as ONE pass:
+ * out[p, k] = tab_k(r_p), tabs = device [ntab][nt] on the radius grid of `geom` (r0, dr, nt), which also supplies
+ * curved, cell, origin and los (the other fields are ignored).  _vjp: posbar [np,3] (nullable) and tabbar (nullable),
+ * float64 [MCPM_OBS_SLOTS][ntab][nt] whose first [ntab][nt] block holds the cotangent of the tables on return. */
+int mcpm_radial_tables(void* stream, const float* pos, int64_t np, const mcpm_obs* geom, int ntab, const float* tabs,
+                       float* out);
+int mcpm_radial_tables_vjp(void* stream, const float* pos, int64_t np, const mcpm_obs* geom, int ntab, const float* tabs,
+                           const float* outbar, float* posbar, double* tabbar);
+
 /* nufft / its VJP with kernel_type = 'kaiser_bessel' (nbody.py:532-577 with the window of 280-312). */
 int mcpm_nufft_kb(mcpm_engine* eng, void* stream, const float* pos, const float* weights, float wscalar, int64_t np,
                   const float scale[3], int paint_order, float kcut, int interlace_order, int paint_deconv,

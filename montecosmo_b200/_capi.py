@@ -135,6 +135,8 @@ SIGNATURES = {
     "mcpm_nufft": ([vp, vp, vp, vp, f32, i64, hp, i32, i32, i32, vp], i32),
     "mcpm_nufft_rsd": ([vp, vp, vp, vp, hp, f32, vp, f32, i64, hp, i32, i32, i32, vp], i32),
     "mcpm_nufft_rsd_vjp": ([vp, vp, vp, vp, hp, f32, vp, f32, i64, hp, i32, i32, i32, vp, vp, vp, vp], i32),
+    "mcpm_radial_tables": ([vp, vp, i64, vp, i32, vp, vp], i32),
+    "mcpm_radial_tables_vjp": ([vp, vp, i64, vp, i32, vp, vp, vp, vp], i32),
     "mcpm_nufft_obs": ([vp, vp, vp, vp, vp, vp, f32, i64, hp, i32, f32, i32, i32, vp], i32),
     "mcpm_nufft_obs_vjp": ([vp, vp, vp, vp, vp, vp, f32, i64, hp, i32, f32, i32, i32, vp, vp, vp, vp, vp, vp], i32),
     "mcpm_nufft_vjp": ([vp, vp, vp, vp, f32, i64, hp, i32, i32, i32, vp, vp, vp], i32),

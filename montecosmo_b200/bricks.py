@@ -257,7 +257,8 @@ class _BiasWeights(torch.autograd.Function):
         return vb, gbar, cbar
 
 
-def lagrangian_bias(cosmo, pos, a, box_size, lin_mesh, bias, png=None, png_type=None, kpow=None, read_order: int = 2):
+def lagrangian_bias(cosmo, pos, a, box_size, lin_mesh, bias, png=None, png_type=None, kpow=None, read_order: int = 2,
+                    growth=None):
     """Lagrangian bias expansion weights (bricks.py:327-452):
     w = 1 + b1 d + b2 (d^2 - <d^2>)/2 + bs2 (s^2 - <s^2>) + b3 (d^3 - 3<d^2> d)/6 + bds2 d s^2 + bs3 s^3 + bn2 lap d,
     and the higher-derivative velocity term dvel = bnpar grad d; with png_type not None also (bricks.py:411-438)
@@ -273,9 +274,12 @@ def lagrangian_bias(cosmo, pos, a, box_size, lin_mesh, bias, png=None, png_type=
     pos = _nb._f32(pos)
     dev = lin_mesh.device
     mesh_shape = _nb.ch2rshape(tuple(lin_mesh.shape))
-    a_host = a.detach().to("cpu", torch.float64) if isinstance(a, torch.Tensor) else a  # growth tables live on the host
-    growth = torch.as_tensor(_cosmo.a2g(cosmo, a_host), dtype=torch.float64).reshape(-1)
-    growth = growth.reshape(()) if growth.numel() == 1 else growth.to(device=dev, dtype=torch.float32)
+    if growth is not None:  # extension: the growth factor of every particle, already on the device (lightcone_functions)
+        growth = _nb._f32(growth).reshape(-1)
+    else:
+        a_host = a.detach().to("cpu", torch.float64) if isinstance(a, torch.Tensor) else a  # growth tables live on the host
+        growth = torch.as_tensor(_cosmo.a2g(cosmo, a_host), dtype=torch.float64).reshape(-1)
+        growth = growth.reshape(()) if growth.numel() == 1 else growth.to(device=dev, dtype=torch.float32)
     if png_type is None:
         f = {k: 0.0 for k in _PNG_KEYS}
     coef = torch.stack([torch.as_tensor(v, dtype=torch.float64).reshape(()).cpu()
@@ -612,6 +616,55 @@ def rsd_ap_auto(pos, vel, rpos, los, a, cosmo, cosmo_fid, curved_sky=True):
     return pos * alpha if curved_sky else scale_pos(pos, los, alpha, 1.0)
 
 
+def _box_geometry(box_center, box_rot, box_size, mesh_shape):
+    """The box in its own (unrotated) frame, as csrc/obs.h takes it: Mpc/h per cell, the position of cell 0 relative to the
+    observer (R^T centre - box / 2), the flat-sky line of sight R^T centre / |centre|, and R."""
+    box = np.asarray(box_size, dtype=np.float64)
+    center = np.asarray(box_center, dtype=np.float64)
+    R = np.eye(3) if box_rot is None else (box_rot.as_matrix() if hasattr(box_rot, "as_matrix")
+                                           else np.asarray(box_rot, dtype=np.float64))
+    ct = R.T @ center
+    nrm = np.linalg.norm(center)
+    los = ct / nrm if nrm != 0 else np.zeros(3)
+    return dict(cell=tuple(box / np.asarray(mesh_shape, dtype=np.float64)), origin=tuple(ct - box / 2), los=tuple(los),
+                rot=R.tolist())
+
+
+def _radius_grid(geo, box_size, curved_sky, n_table, pad=None):
+    """Uniform float64 grid over the distances the box can reach (curved sky: from the observer; flat: along the line of
+    sight) plus `pad` (default 10 % of the largest side + 50 Mpc/h), starting above zero."""
+    box, origin, los = np.asarray(box_size, dtype=np.float64), np.asarray(geo["origin"]), np.asarray(geo["los"])
+    corners = np.array([[origin[d] + (box[d] if (i >> d) & 1 else 0.0) for d in range(3)] for i in range(8)])
+    lo, hi = corners.min(0), corners.max(0)
+    pad = 0.1 * box.max() + 50.0 if pad is None else float(pad)
+    if curved_sky:
+        rmax = np.linalg.norm(corners, axis=1).max()
+        rmin = np.linalg.norm(np.maximum(np.maximum(lo, -hi), 0.0))  # distance from the observer to the box
+    else:
+        t = corners @ los
+        rmax = np.abs(t).max()
+        rmin = 0.0 if t.min() < 0 < t.max() else np.abs(t).min()
+    r0 = max(rmin - pad, 1e-3 * (rmax + pad))
+    return torch.linspace(r0, rmax + pad, int(n_table), dtype=torch.float64)
+
+
+def lightcone_functions(cosmo, pos, box_center, box_rot, box_size, mesh_shape, curved_sky=True, fns=(), n_table=8192,
+                        pad=None):
+    """fn(cosmo, a_p) for every fn in `fns` at the light-cone scale factor a_p = chi2a(r_p) of each particle
+    (los_scalefactor_pos with a_obs None, bricks.py:747-766, followed by the growth lookups of lagrangian_bias :341 and
+    lpt nbody.py:651-665): each fn is tabulated in float64 on a uniform radius grid from the (differentiable) cosmology
+    and ONE engine pass interpolates all tables at the particles' distances (mcpm_radial_tables) -- no per-particle
+    scale factor array, nothing evaluated on the host per particle.  Returns a list of [Np] float32 tensors on the
+    engine's device, differentiable in the cosmology (node by node) and in the positions."""
+    geo = _box_geometry(box_center, box_rot, box_size, mesh_shape)
+    r = _radius_grid(geo, box_size, curved_sky, n_table, pad)
+    a_r = _cosmo.chi2a(cosmo, r)
+    tabs = torch.stack([torch.as_tensor(fn(cosmo, a_r), dtype=torch.float64) for fn in fns])
+    geom = dict(curved=bool(curved_sky), r0=float(r[0]), dr=float(r[1] - r[0]), **geo)
+    out = _nb.radial_tables(pos, tabs, geom)
+    return [out[:, k] for k in range(len(fns))]
+
+
 def observation(cosmo, box_center, box_rot, box_size, mesh_shape, a_obs=None, curved_sky=True, rsd=True, ap_auto=None,
                 cosmo_fid=None, ap=None, n_table=8192, pad=None):
     """The observation chain of model.py:780-799 as a descriptor for nbody.nufft_observed, which applies it INSIDE the
@@ -626,19 +679,10 @@ def observation(cosmo, box_center, box_rot, box_size, mesh_shape, a_obs=None, cu
     The grid spans the distances the box can reach plus `pad` (default 10 % of the largest side + 50 Mpc/h); the kernels
     interpolate linearly and clamp beyond the ends.  With 8192 nodes the tables reproduce the reference's own
     piecewise-linear lookups to ~1e-7 relative (tests/test_api_model.py: test_fused_observation_chain)."""
-    box = np.asarray(box_size, dtype=np.float64)
-    shape = np.asarray(mesh_shape, dtype=np.float64)
-    center = np.asarray(box_center, dtype=np.float64)
-    R = np.eye(3) if box_rot is None else (box_rot.as_matrix() if hasattr(box_rot, "as_matrix")
-                                           else np.asarray(box_rot, dtype=np.float64))
-    ct = R.T @ center
-    nrm = np.linalg.norm(center)
-    los = ct / nrm if nrm != 0 else np.zeros(3)
-    origin = ct - box / 2
+    geo = _box_geometry(box_center, box_rot, box_size, mesh_shape)
     lightcone = a_obs is None
     mode = 0 if ap_auto is None else (1 if ap_auto else 2)
-    out = dict(curved=bool(curved_sky), lightcone=bool(lightcone and rsd), ap=mode, rsd=bool(rsd),
-               cell=tuple(box / shape), origin=tuple(origin), los=tuple(los), rot=R.tolist(), r0=0.0, dr=0.0)
+    out = dict(curved=bool(curved_sky), lightcone=bool(lightcone and rsd), ap=mode, rsd=bool(rsd), r0=0.0, dr=0.0, **geo)
     one = torch.ones((), dtype=torch.float64)
     gf = torch.zeros((), dtype=torch.float64)
     if rsd and not lightcone:
@@ -653,18 +697,7 @@ def observation(cosmo, box_center, box_rot, box_size, mesh_shape, a_obs=None, cu
             a_par, a_perp = (_cosmo._t(x).reshape(()) for x in isoap2parperp(_cosmo._t(ap["alpha_iso"]), _cosmo._t(ap["alpha_ap"])))
     out["par"] = torch.stack([gf, a_par.to(torch.float64), a_perp.to(torch.float64)])
     if out["lightcone"] or mode == 1:
-        corners = np.array([[origin[d] + (box[d] if (i >> d) & 1 else 0.0) for d in range(3)] for i in range(8)])
-        lo, hi = corners.min(0), corners.max(0)
-        pad = 0.1 * box.max() + 50.0 if pad is None else float(pad)
-        if curved_sky:
-            rmax = np.linalg.norm(corners, axis=1).max()
-            rmin = np.linalg.norm(np.maximum(np.maximum(lo, -hi), 0.0))  # distance from the observer to the box
-        else:
-            t = corners @ los
-            rmax = np.abs(t).max()
-            rmin = 0.0 if t.min() < 0 < t.max() else np.abs(t).min()
-        r0 = max(rmin - pad, 1e-3 * (rmax + pad))
-        r = torch.linspace(r0, rmax + pad, int(n_table), dtype=torch.float64)
+        r = _radius_grid(geo, box_size, curved_sky, n_table, pad)
         a_r = _cosmo.chi2a(cosmo, r)
         out["r0"], out["dr"] = float(r[0]), float(r[1] - r[0])
         if out["lightcone"]:

@@ -1318,6 +1318,46 @@ int mcpm_nufft_obs_vjp(mcpm_engine* eng, void* stream, const float* pos, const f
   API_END
 }
 
+static int make_radial_geom(const mcpm_obs* o, ObsGen& g) {
+  if (!o || o->nt < 2 || !(o->dr > 0.0f)) {
+    set_error("radial_tables: needs the radius grid (nt >= 2, dr > 0)");
+    return MCPM_EINVAL;
+  }
+  g.on = 1;
+  g.curved = o->curved != 0;
+  g.cx = o->cell[0], g.cy = o->cell[1], g.cz = o->cell[2];
+  g.ox = o->origin[0], g.oy = o->origin[1], g.oz = o->origin[2];
+  g.lx = o->los[0], g.ly = o->los[1], g.lz = o->los[2];
+  g.r0 = o->r0;
+  g.inv_dr = 1.0f / o->dr;
+  g.nt = o->nt;
+  return 0;
+}
+
+int mcpm_radial_tables(void* stream, const float* pos, int64_t np, const mcpm_obs* geom, int ntab, const float* tabs,
+                       float* out) {
+  API_BEGIN
+  NEED(ntab >= 1 && tabs && (np == 0 || (pos && out)), "radial_tables: null pointer or no table");
+  ObsGen g;
+  if (int e = make_radial_geom(geom, g)) return e;
+  return radial_tables(as_stream(stream), pos, np, g, ntab, tabs, out);
+  API_END
+}
+
+int mcpm_radial_tables_vjp(void* stream, const float* pos, int64_t np, const mcpm_obs* geom, int ntab, const float* tabs,
+                           const float* outbar, float* posbar, double* tabbar) {
+  API_BEGIN
+  NEED(ntab >= 1 && tabs && (np == 0 || (pos && outbar)), "radial_tables_vjp: null pointer or no table");
+  ObsGen g;
+  if (int e = make_radial_geom(geom, g)) return e;
+  stream_t st = as_stream(stream);
+  const int64_t row = (int64_t)ntab * g.nt;
+  if (tabbar && rt_memset(tabbar, 0, sizeof(double) * (size_t)(kObsSlots * row), st)) return MCPM_ECUDA;
+  if (int e = radial_tables_vjp(st, pos, np, g, ntab, tabs, outbar, posbar, tabbar)) return e;
+  return tabbar ? obs_reduce_slots(st, tabbar, row) : 0;
+  API_END
+}
+
 int mcpm_nufft_kb(mcpm_engine* eng, void* stream, const float* pos, const float* weights, float wscalar, int64_t np,
                   const float scale[3], int paint_order, float kcut, int interlace_order, int paint_deconv,
                   void* out_k) {

@@ -125,6 +125,9 @@ int bias_weights_vjp(stream_t, const float* vals, int K, float gs, const float* 
 int absmax_strided(stream_t, const float* x, int64_t n, int stride, float* out);
 int yz_gradients(stream_t, cfloat* buf3, int xl, int ny, int nz, int grad_fd, int transpose);
 int obs_reduce_slots(stream_t st, double* parbar, int64_t row);  // paint.cu
+int radial_tables(stream_t st, const float* pos, int64_t np, ObsGen g, int ntab, const float* tabs, float* out);
+int radial_tables_vjp(stream_t st, const float* pos, int64_t np, ObsGen g, int ntab, const float* tabs, const float* outbar,
+                      float* posbar, double* tabbar);
 int rsd_shift(stream_t, const float* pos, const float* vel, float lx, float ly, float lz, float coef, int64_t np,
               float* pos_out);
 int rsd_shift_vjp(stream_t, const float* posbar, float lx, float ly, float lz, float coef, int64_t np, float* velbar,

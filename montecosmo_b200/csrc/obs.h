@@ -70,6 +70,27 @@ MCPM_HD float obs_interp(const float* tab, const ObsGen& o, float r, ObsTabCell&
   return a + c.w * (b - a);
 }
 
+// Distance of a particle at x (units of pos) from the observer (curved sky) or along the line of sight (flat).
+// dir (nullable): d r / d q up to the sign `sgn` (1 on a curved sky).
+MCPM_HD float obs_radius(const ObsGen& o, const float* x, float* dir, float* sgn) {
+  const float q0 = x[0] * o.cx + o.ox, q1 = x[1] * o.cy + o.oy, q2 = x[2] * o.cz + o.oz;
+  if (o.curved) {
+    const float r = sqrtf(q0 * q0 + q1 * q1 + q2 * q2);
+    if (dir) {
+      const float ir = r > 0.0f ? 1.0f / r : 0.0f;
+      dir[0] = q0 * ir, dir[1] = q1 * ir, dir[2] = q2 * ir;
+      *sgn = 1.0f;
+    }
+    return r;
+  }
+  const float t = q0 * o.lx + q1 * o.ly + q2 * o.lz;
+  if (dir) {
+    dir[0] = o.lx, dir[1] = o.ly, dir[2] = o.lz;
+    *sgn = t > 0.0f ? 1.0f : (t < 0.0f ? -1.0f : 0.0f);
+  }
+  return fabsf(t);
+}
+
 struct ObsState {
   float q[3], l[3], u[3], q1[3];
   float r, sgn, s, gf, r1, sgn1, t1, am1, a_par, a_perp;

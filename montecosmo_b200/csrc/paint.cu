@@ -708,6 +708,44 @@ int axpby(stream_t st, const float* x, float a, const float* y, float b, float c
   return rt_check("axpby");
 }
 
+// Functions of the comoving distance at the particles -- the light cone (bricks.py:747-766 followed by a2g, a2f, ...):
+// out[p, k] = tab_k(r_p), r_p = |q_p| (curved sky) or |q_p . l| (flat), q = pos * cell + origin; tabs [ntab][nt].
+int radial_tables(stream_t st, const float* pos, int64_t np, ObsGen g, int ntab, const float* tabs, float* out) {
+  launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
+    ObsTabCell c;
+    const float r = obs_radius(g, pos + 3 * p, nullptr, nullptr);
+    for (int k = 0; k < ntab; ++k) out[p * ntab + k] = obs_interp(tabs + (int64_t)k * g.nt, g, r, c);
+  });
+  return rt_check("radial_tables");
+}
+// transpose: tabbar [kObsSlots][ntab][nt] float64 (partial rows, zeroed by the caller, summed by obs_reduce_slots);
+// posbar [np,3] (nullable) = sum_k outbar[p,k] tab_k'(r) dr/dpos
+int radial_tables_vjp(stream_t st, const float* pos, int64_t np, ObsGen g, int ntab, const float* tabs, const float* outbar,
+                      float* posbar, double* tabbar) {
+  launch_1d(st, np, [=] MCPM_LAMBDA(int64_t p) {
+    ObsTabCell c;
+    float dir[3], sgn;
+    const float r = obs_radius(g, pos + 3 * p, dir, &sgn);
+    double* row = tabbar ? tabbar + (size_t)(p & (kObsSlots - 1)) * (size_t)ntab * g.nt : nullptr;
+    float rb = 0.0f;
+    for (int k = 0; k < ntab; ++k) {
+      obs_interp(tabs + (int64_t)k * g.nt, g, r, c);
+      const float ob = outbar[p * ntab + k];
+      rb += ob * c.slope;
+      if (row) {
+        atomic_add(row + (size_t)k * g.nt + c.i, (double)((1.0f - c.w) * ob));
+        atomic_add(row + (size_t)k * g.nt + c.i + 1, (double)(c.w * ob));
+      }
+    }
+    if (posbar) {
+      posbar[3 * p] = rb * sgn * dir[0] * g.cx;
+      posbar[3 * p + 1] = rb * sgn * dir[1] * g.cy;
+      posbar[3 * p + 2] = rb * sgn * dir[2] * g.cz;
+    }
+  });
+  return rt_check("radial_tables_vjp");
+}
+
 // parameter cotangents of the general observation transform: the kObsSlots partial rows summed into row 0
 int obs_reduce_slots(stream_t st, double* parbar, int64_t row) {
   launch_1d(st, row, [=] MCPM_LAMBDA(int64_t k) {

@@ -46,6 +46,7 @@ HANDLERS = {
     "mcpm_bias_spectra_vjp": "McpmBiasSpectraVjp", "mcpm_shear_invariants": "McpmShearInvariants",
     "mcpm_shear_invariants_vjp": "McpmShearInvariantsVjp", "mcpm_bias_weights": "McpmBiasWeights",
     "mcpm_bias_weights_vjp": "McpmBiasWeightsVjp", "mcpm_nufft_obs": "McpmNufftObs", "mcpm_nufft_obs_vjp": "McpmNufftObsVjp",
+    "mcpm_radial_tables": "McpmRadialTables", "mcpm_radial_tables_vjp": "McpmRadialTablesVjp",
 }
 for _name, _sym in HANDLERS.items():
     jax.ffi.register_ffi_target(_name, jax.ffi.pycapsule(getattr(_SHIM, _sym)), platform="CUDA")
@@ -326,6 +327,37 @@ def nufft_observed(pos, vel, final_shape: tuple, obs: dict, paint_shape=None, we
                             tuple(sorted(static.items())), paint_shape, scale, paint_order, kc, interlace_order,
                             bool(paint_deconv), None if lattice is None else tuple(lattice))
     return mesh if final_shape == paint_shape else chreshape(mesh, r2chshape(final_shape))
+
+
+# functions of the comoving distance at the particles (the light cone): tabs [K, nt] on the radius grid of `geom`
+@partial(jax.custom_vjp, nondiff_argnums=(2,))
+def _radial_tables(pos, tabs, geom):
+    g = dict(geom)
+    return jax.ffi.ffi_call("mcpm_radial_tables", _sds((pos.shape[0], tabs.shape[0])))(
+        pos.astype(f32), tabs.astype(f32), flags=np.asarray([g["curved"], 0, 0, 0], np.int32),
+        geom=np.asarray([*g["cell"], *g["origin"], *g["los"], g["r0"], g["dr"]], np.float32))
+
+
+def _radial_fwd(pos, tabs, geom):
+    return _radial_tables(pos, tabs, geom), (pos, tabs)
+
+
+def _radial_bwd(geom, res, outbar):
+    pos, tabs = res
+    g = dict(geom)
+    pb, tb = jax.ffi.ffi_call("mcpm_radial_tables_vjp", (_sds(pos.shape), _sds((OBS_SLOTS, *tabs.shape), jnp.float64)))(
+        pos.astype(f32), tabs.astype(f32), outbar.astype(f32), flags=np.asarray([g["curved"], 0, 0, 0], np.int32),
+        geom=np.asarray([*g["cell"], *g["origin"], *g["los"], g["r0"], g["dr"]], np.float32))
+    return pb.astype(pos.dtype), tb[0].astype(tabs.dtype)
+
+
+_radial_tables.defvjp(_radial_fwd, _radial_bwd)
+
+
+def radial_tables(pos, tabs, geom: dict):
+    """montecosmo_b200.nbody.radial_tables: [Np, K] = the K tables at every particle's distance (light-cone growth)."""
+    return _radial_tables(pos, tabs, tuple(sorted((k, tuple(v) if isinstance(v, (list, tuple, np.ndarray)) else v)
+                                                  for k, v in geom.items() if k != "rot")))
 
 
 # ------------------------------------------------------------------------------------------------ forces, lpt

@@ -276,9 +276,18 @@ class FieldLevelModel(FieldModel):
                 gxy = nb.irfftn(nb.chreshape(nb.rfftn(gxy), r2chshape(self.init_shape)))
             return gxy
         pos = B.regular_pos(self.evol_shape, self.ptcl_shape)
-        _, a = B.los_scalefactor_pos(pos, *geo, self.evol_shape, c, self.a_obs, self.curved_sky)
+        growth = None
+        if self.a_obs is None and self.fused_observation:
+            # the light cone: growth factors at every particle's own scale factor, one engine pass over the lattice
+            # (bricks.lightcone_functions) instead of a per-particle scale factor array looked up on the host
+            a = None
+            growth = B.lightcone_functions(c, pos, *geo, self.evol_shape, self.curved_sky,
+                                           (_cosmo.a2g, _cosmo.a2g2, _cosmo.a2dg2dg))
+        else:
+            _, a = B.los_scalefactor_pos(pos, *geo, self.evol_shape, c, self.a_obs, self.curved_sky)
         weights, dvel, _ = B.lagrangian_bias(c, pos, a, self.box_size, init_mesh, self.bias, self.png, self.png_type,
-                                             self.kpow_sigma8_1() if self.png_type is not None else None, read_order=1)
+                                             self.kpow_sigma8_1() if self.png_type is not None else None, read_order=1,
+                                             growth=None if growth is None else growth[0])
         if self.png_type is not None:
             init_mesh = B.add_png(c, self.png["fNL"], init_mesh, self.box_size, self.kpow_sigma8_1())
             init_mesh = nb.chreshape(nb.chreshape(init_mesh, r2chshape(self.init_shape)), r2chshape(self.evol_shape))
@@ -287,13 +296,13 @@ class FieldLevelModel(FieldModel):
         # the CIC derivative jumps (tools/obs_accuracy.py at 64^3: gradient 1.2e-3 -> 5e-4 against float64)
         lattice = None
         if self.evolution == "lpt":
-            dpos, vel = nb.lpt(c, init_mesh, pos, a, self.lpt_order, 1)
+            dpos, vel = nb.lpt(c, init_mesh, pos, a, self.lpt_order, 1, growth=growth)
             if self.fused_observation:
                 pos, lattice = dpos, self.ptcl_shape
             else:
                 pos = pos + dpos
         elif self.evolution == "nbody":
-            if np.ndim(a) != 0:
+            if self.a_obs is None or np.ndim(a) != 0:
                 raise AssertionError("N-body light-cone not implemented yet")  # model.py:768
             declared = self.ptcl_shape == self.evol_shape
             rel = True if (self.fused_observation and declared) else None

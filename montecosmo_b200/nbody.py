@@ -340,6 +340,31 @@ class _NufftObserved(torch.autograd.Function):
         return (pb, vb, db, wb, gpar, ggf, gap) + (None,) * 9
 
 
+class _RadialTables(torch.autograd.Function):
+    """Functions of the comoving distance at the particles (the light cone): one pass over the positions evaluating every
+    table; differentiable in the table nodes (the cosmology) and in the positions."""
+
+    @staticmethod
+    def forward(ctx, pos, tabs, geom):
+        tabs32 = _f32(tabs.detach())
+        ctx.save_for_backward(pos, tabs32)
+        ctx.geom, ctx.like = geom, tabs
+        return ops().radial_tables(pos, geom, tabs32)
+
+    @staticmethod
+    def backward(ctx, outbar):
+        pos, tabs32 = ctx.saved_tensors
+        pb, tb = ops().radial_tables_vjp(pos, ctx.geom, tabs32, outbar.contiguous(), want_pos=ctx.needs_input_grad[0])
+        return pb, tb.to(device=ctx.like.device, dtype=ctx.like.dtype), None
+
+
+def radial_tables(pos, tabs, geom):
+    """[Np, K]: the K tables `tabs` [K, nt] (on the uniform radius grid of `geom`: r0, dr) interpolated at the distance
+    of every particle from the observer -- curved sky -- or along the line of sight -- flat (bricks.py:747-766); `geom`
+    from bricks.observation / bricks.lightcone_functions."""
+    return _RadialTables.apply(_f32(pos), tabs, geom)
+
+
 class _PmForcesPaint(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pos, shape, order, paint_deconv, lap_fd, grad_fd, kcut):
@@ -571,10 +596,11 @@ def pm_forces2(pos, mesh, read_order: int = 2, grad_fd=np.inf, lap_fd=np.inf):
 
 
 def lpt(cosmo, init_mesh, pos, a, lpt_order: int = 2, read_order: int = 2, grad_fd=np.inf, lap_fd=np.inf,
-        _displaced=False):
+        _displaced=False, growth=None):
     """First or second order LPT displacement at scale factor `a` (nbody.py:634-667).  `a` is a scalar, or one scale
     factor per particle ([Np] or [Np, 1], the light-cone use of nbody.py:651-653): the two force fields then come from
-    the engine and the per-particle growth factors multiply them here."""
+    the engine and the per-particle growth factors multiply them here.  `growth` (extension) = the per-particle
+    (a2g, a2g2, a2dg2dg) as [Np] device arrays, e.g. from bricks.lightcone_functions: `a` is then not looked at."""
     if lpt_order not in (1, 2):
         raise ValueError("lpt_order must be 1 or 2")
     init_mesh = torch.as_tensor(init_mesh)
@@ -583,6 +609,14 @@ def lpt(cosmo, init_mesh, pos, a, lpt_order: int = 2, read_order: int = 2, grad_
     if pos is None:  # extension: the particles sit on the cells of the mesh (regular_pos(mesh_shape)); scalar `a` only
         coef = _coef_tensor(_cosmo.a2g(cosmo, a), _cosmo.a2g2(cosmo, a), _cosmo.a2dg2dg(cosmo, a))
         return _Lpt.apply(_c64(init_mesh), coef, None, int(lpt_order), int(read_order), lap_fd, grad_fd, False)
+    if growth is not None:
+        force1 = pm_forces(pos, init_mesh, read_order, grad_fd=grad_fd, lap_fd=lap_fd)
+        g1, g2, dg2 = (_f32(g).reshape(-1, 1) for g in growth)
+        dpos, vel = g1 * force1, force1
+        if lpt_order == 2:
+            force2 = pm_forces2(pos, init_mesh, read_order, grad_fd=grad_fd, lap_fd=lap_fd)
+            dpos, vel = dpos - g2 * force2, vel - dg2 * force2
+        return (dpos + _f32(pos), vel) if _displaced else (dpos, vel)
     if np.ndim(a) != 0:
         a_col = torch.as_tensor(a, dtype=torch.float64).detach().cpu().reshape(-1, 1)
         force1 = pm_forces(pos, init_mesh, read_order, grad_fd=grad_fd, lap_fd=lap_fd)

@@ -523,6 +523,34 @@ class Ops:
         del keep
         return pb, vb, db, wb, (None if par is None else par[0])
 
+    def radial_tables(self, pos, geom, tabs):
+        """out[p, k] = tab_k(r_p): functions of the comoving distance at the particles (mcpm_radial_tables; `geom` as
+        _obs_struct takes it: curved, cell, origin, los, r0, dr; tabs [ntab, nt])."""
+        A = self.A
+        pos, tabs = A.prepare(pos), A.prepare(tabs)
+        ntab, nt = A.shape(tabs)
+        o, keep = self._obs_struct(dict(geom, tab_gf=None, tab_ap=None, dvel=None))
+        o.nt = nt
+        n = A.shape(pos)[0]
+        out = A.empty((n, ntab))
+        self._call("mcpm_radial_tables", A.stream(), A.ptr(pos), n, C.addressof(o), ntab, A.ptr(tabs), A.ptr(out))
+        return out
+
+    def radial_tables_vjp(self, pos, geom, tabs, outbar, want_pos=False):
+        """-> (posbar [np,3] or None, tabbar float64 [ntab, nt])."""
+        from ._capi import OBS_SLOTS
+        A = self.A
+        pos, tabs, outbar = A.prepare(pos), A.prepare(tabs), A.prepare(outbar)
+        ntab, nt = A.shape(tabs)
+        o, keep = self._obs_struct(dict(geom, tab_gf=None, tab_ap=None, dvel=None))
+        o.nt = nt
+        n = A.shape(pos)[0]
+        pb = A.empty((n, 3)) if want_pos else None
+        tb = A.empty((OBS_SLOTS, ntab, nt), "f64")
+        self._call("mcpm_radial_tables_vjp", A.stream(), A.ptr(pos), n, C.addressof(o), ntab, A.ptr(tabs), A.ptr(outbar),
+                   A.ptr(pb), A.ptr(tb))
+        return pb, tb[0]
+
     # ------------------------------------------------------------------------------------------------ glue
     def chreshape_vjp(self, outbar, in_cshape):
         A = self.A

@@ -339,6 +339,24 @@ ffi::Error NufftObsVjp(cudaStream_t st, int32_t dev, F32 pos, F32 vel, F32 dvel,
                                    scale3(scale, sc), paint_order, kcut, interlace_order, paint_deconv, outbar.typed_data(),
                                    optr(posbar), optr(velbar), optr(dvelbar), optr(weightsbar), parbar->typed_data()));
 }
+// functions of the comoving distance at the particles (the light cone): tabs [ntab, nt] on the radius grid of geom[9..10]
+ffi::Error RadialTables(cudaStream_t st, F32 pos, F32 tabs, Ints flags, Floats geom, RF32 out) {
+  mcpm_obs o = {};
+  o.curved = flags[0];
+  for (int d = 0; d < 3; ++d) o.cell[d] = geom[d], o.origin[d] = geom[3 + d], o.los[d] = geom[6 + d];
+  o.r0 = geom[9], o.dr = geom[10], o.nt = (int)tabs.dimensions()[1];
+  return status(mcpm_radial_tables(st, pos.typed_data(), pos.dimensions()[0], &o, (int)tabs.dimensions()[0],
+                                   tabs.typed_data(), out->typed_data()));
+}
+ffi::Error RadialTablesVjp(cudaStream_t st, F32 pos, F32 tabs, F32 outbar, Ints flags, Floats geom, RF32 posbar,
+                           RF64 tabbar) {
+  mcpm_obs o = {};
+  o.curved = flags[0];
+  for (int d = 0; d < 3; ++d) o.cell[d] = geom[d], o.origin[d] = geom[3 + d], o.los[d] = geom[6 + d];
+  o.r0 = geom[9], o.dr = geom[10], o.nt = (int)tabs.dimensions()[1];
+  return status(mcpm_radial_tables_vjp(st, pos.typed_data(), pos.dimensions()[0], &o, (int)tabs.dimensions()[0],
+                                       tabs.typed_data(), outbar.typed_data(), optr(posbar), tabbar->typed_data()));
+}
 // Lagrangian bias expansion (bricks.py:327-452) as fused passes: Fourier multipliers, shear invariants, polynomial
 ffi::Error BiasSpectra(cudaStream_t st, C64 dk, F32 inv_transfer, Floats cells_per_len, RC64 out) {
   auto m = real_shape_of_spectrum(dk);
@@ -528,6 +546,10 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(McpmNufftObsVjp, NufftObsVjp,
         .Attr<float>("wscalar").Attr<Floats>("scale").Attr<int32_t>("paint_order").Attr<float>("kcut")
         .Attr<int32_t>("interlace_order").Attr<int32_t>("paint_deconv")
             LATTICE.Ret<F32>().Ret<F32>().Ret<F32>().Ret<F32>().Ret<F64>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(McpmRadialTables, RadialTables,
+    MCPM_STREAM.Arg<F32>().Arg<F32>().Attr<Ints>("flags").Attr<Floats>("geom").Ret<F32>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(McpmRadialTablesVjp, RadialTablesVjp,
+    MCPM_STREAM.Arg<F32>().Arg<F32>().Arg<F32>().Attr<Ints>("flags").Attr<Floats>("geom").Ret<F32>().Ret<F64>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(McpmBiasSpectra, BiasSpectra,
     MCPM_STREAM.Arg<C64>().Arg<F32>().Attr<Floats>("cells_per_len").Ret<C64>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(McpmBiasSpectraVjp, BiasSpectraVjp,

@@ -745,6 +745,37 @@ def test_fused_observation_chain(nb, case):
             assert abs(float(ap[k].grad) - float(ap2[k].grad)) < 2e-4 * abs(float(ap2[k].grad)), k
 
 
+@pytest.mark.parametrize("curved", [True, False])
+def test_lightcone_functions_on_the_device(nb, curved):
+    """bricks.lightcone_functions (one engine pass, mcpm_radial_tables: growth lookups of the light cone at every
+    particle's comoving distance) against the chain it replaces -- los_scalefactor_pos with a_obs None followed by a2g,
+    a2g2, a2dg2dg, a2f on the host's float64 tables: values 2e-6 of the largest; cotangents of Omega_c (through every
+    table node) 2e-4 and of the positions 2e-3 (the slope of a re-tabulated piecewise-linear function)."""
+    from scipy.spatial.transform import Rotation
+    from montecosmo_b200 import bricks as B
+    from montecosmo_b200 import cosmo as CO
+    rng = np.random.default_rng(3 + curved)
+    shape, box, center = (12, 10, 14), (600.0, 500.0, 700.0), (250.0, -300.0, 1400.0)
+    rot = Rotation.from_rotvec([0.3, 0.2, -0.5])
+    pos0 = torch.tensor(rng.uniform(-1.0, 1.0, size=(500, 3)) + rng.uniform(0, 1, size=(500, 3)) * np.asarray(shape))
+    cot = torch.tensor(rng.normal(size=(500, 4)))
+    fns = (CO.a2g, CO.a2g2, CO.a2dg2dg, CO.a2f)
+    oc = torch.tensor(0.2589, dtype=torch.float64, requires_grad=True)
+    pos = leaf(pos0, nb, torch.float32)
+    out = torch.stack(B.lightcone_functions(CO.Cosmology(Omega_c=oc), pos, center, rot, box, shape, curved, fns), dim=1)
+    (out * cot.float().to(dev(nb))).sum().backward()
+    oc2 = torch.tensor(0.2589, dtype=torch.float64, requires_grad=True)
+    po = leaf(pos0)
+    c2 = CO.Cosmology(Omega_c=oc2)
+    _, a = B.los_scalefactor_pos(po, center, rot, box, shape, c2, None, curved)
+    ref = torch.stack([fn(c2, a.reshape(-1)) for fn in fns], dim=1)
+    (ref * cot).sum().backward()
+    err = (out.detach().cpu().double() - ref.detach()).abs().max(0).values / ref.detach().abs().max(0).values
+    assert float(err.max()) < 2e-6, err
+    assert abs(float(oc.grad) - float(oc2.grad)) < 2e-4 * abs(float(oc2.grad)), (oc.grad, oc2.grad)
+    assert rel(pos.grad, po.grad) < 2e-3
+
+
 @pytest.mark.parametrize("case", ["lightcone_lpt_curved", "nbody_flat", "nbody_curved_lattice"])
 def test_general_evolve_against_oracle(nb, case):
     """FieldLevelModel.evolve -- the general 'lpt' / 'nbody' branch of model.py:683-837 -- against the oracle's float64

@@ -148,6 +148,40 @@ def test_empty_inputs_and_rejected_arguments(ops):
         ops.read(bad, mesh)
 
 
+def test_observed_nufft_edge_cases(ops):
+    """mcpm_nufft_obs / mcpm_radial_tables at their edges: an empty particle set paints a zero mesh; a descriptor that
+    does nothing (no redshift-space term, no Alcock-Paczynski) reproduces mcpm_nufft (1e-6: atomics order); a light cone or ap_auto
+    without its radius table, an unknown Alcock-Paczynski mode, a redshift-space term without velocities and a radius
+    grid with dr = 0 come back as MCPM_EINVAL; distances beyond either end of the radius grid clamp to the end values."""
+    from montecosmo_b200._capi import McpmError
+    shape = (8, 6, 10)
+    rng = np.random.default_rng(4)
+    geo = dict(curved=True, cell=(50.0, 40.0, 30.0), origin=(100.0, -80.0, 900.0), los=(0.0, 0.0, 1.0))
+    e = np.zeros((0, 3), np.float32)
+    assert not to_numpy(ops.nufft_observed(e, e, dict(geo, rsd=True, gf=0.5), shape)).any()
+    pos = f32(rng.uniform(0, 1, size=(200, 3)) * np.asarray(shape))
+    vel = f32(rng.normal(size=(200, 3)))
+    w = f32(rng.uniform(0.5, 1.5, 200))
+    plain = to_numpy(ops.nufft_paint(pos, shape, w))
+    same = to_numpy(ops.nufft_observed(pos, None, dict(geo, rsd=False, ap=0), shape, w))
+    assert rel(same, plain) < 1e-6  # the same deposits, summed by atomics in whatever order
+    for bad in (dict(geo, rsd=True, lightcone=True, r0=1.0, dr=1.0),                  # light cone without tab_gf
+                dict(geo, rsd=False, ap=1, r0=1.0, dr=1.0),                           # ap_auto without tab_ap
+                dict(geo, rsd=False, ap=3),                                           # unknown mode
+                dict(geo, rsd=False, ap=1, tab_ap=f32(np.zeros(16)), r0=1.0, dr=0.0)):  # no radius grid
+        with pytest.raises(McpmError) as ei:
+            ops.nufft_observed(pos, vel, bad, shape, w)
+        assert ei.value.code == 1 and str(ei.value)
+    with pytest.raises(McpmError):
+        ops.nufft_observed(pos, None, dict(geo, rsd=True, gf=0.5), shape, w)         # rsd without velocities
+    with pytest.raises(McpmError):
+        ops.radial_tables(pos, dict(geo, r0=1.0, dr=0.0), f32(np.zeros((2, 8))))
+    tabs = f32(np.stack([np.linspace(1.0, 2.0, 8), np.linspace(-3.0, 4.0, 8)]))
+    near_far = f32([[-2.0, 2.0, -30.0], [0.0, 0.0, 1e6]])                             # r ~ 0 and r ~ 3e7 Mpc/h
+    out = to_numpy(ops.radial_tables(near_far, dict(geo, r0=500.0, dr=100.0), tabs))
+    assert np.allclose(out, [[1.0, -3.0], [2.0, 4.0]])
+
+
 @pytest.mark.parametrize("order", [2, 3, 4])
 def test_paint_read_vjp(ops, order):
     """Gathers of the window gradient vs oracle autograd (1e-5)."""

@@ -1247,7 +1247,7 @@ int mcpm_nufft_rsd_vjp(mcpm_engine* eng, void* stream, const float* pos, const f
 
 // mcpm_obs (ABI) -> ObsGen (kernels)
 static_assert(kObsSlots == MCPM_OBS_SLOTS, "obs.h and mcpm.h must agree");
-static int make_obs_gen(const mcpm_obs* o, const float* vel, ObsGen& g) {
+static int make_obs_gen(const mcpm_obs* o, const float* vel, int64_t np, ObsGen& g) {
   if (!o) {
     set_error("nufft_obs: null observation descriptor");
     return MCPM_EINVAL;
@@ -1256,7 +1256,7 @@ static int make_obs_gen(const mcpm_obs* o, const float* vel, ObsGen& g) {
     set_error("nufft_obs: the light cone / ap_auto need their radius tables (nt >= 2, dr > 0)");
     return MCPM_EINVAL;
   }
-  if (o->ap < 0 || o->ap > 2 || (o->rsd && !vel)) {
+  if (o->ap < 0 || o->ap > 2 || (o->rsd && !vel && np > 0)) {  // an empty particle set may come with null arrays
     set_error("nufft_obs: ap must be 0 | 1 | 2, and rsd needs velocities");
     return MCPM_EINVAL;
   }
@@ -1287,7 +1287,7 @@ int mcpm_nufft_obs(mcpm_engine* eng, void* stream, const float* pos, const float
   NEED(eng && out_k && (np == 0 || pos || eng->e->rel), "nufft_obs: null pointer");
   BIND(eng);
   ObsGen g;
-  if (int e = make_obs_gen(obs, vel, g)) return e;
+  if (int e = make_obs_gen(obs, vel, np, g)) return e;
   ObsShift sh;
   sh.gen = &g;
   return nufft(eng->e, as_stream(stream), pos, weights, wscalar, np, scale, paint_order, interlace_order, paint_deconv,
@@ -1303,7 +1303,7 @@ int mcpm_nufft_obs_vjp(mcpm_engine* eng, void* stream, const float* pos, const f
   NEED(eng && outbar_k && (np == 0 || pos || eng->e->rel), "nufft_obs_vjp: null pointer");
   BIND(eng);
   ObsGen g;
-  if (int e = make_obs_gen(obs, vel, g)) return e;
+  if (int e = make_obs_gen(obs, vel, np, g)) return e;
   stream_t st = as_stream(stream);
   const int64_t row = 3 + 2 * (int64_t)g.nt;
   g.dvelbar = g.dvel ? dvelbar : nullptr;

@@ -159,6 +159,7 @@ def test_observed_nufft_edge_cases(ops):
     geo = dict(curved=True, cell=(50.0, 40.0, 30.0), origin=(100.0, -80.0, 900.0), los=(0.0, 0.0, 1.0))
     e = np.zeros((0, 3), np.float32)
     assert not to_numpy(ops.nufft_observed(e, e, dict(geo, rsd=True, gf=0.5), shape)).any()
+    assert not to_numpy(ops.nufft_observed(e, None, dict(geo, rsd=True, gf=0.5), shape)).any()  # null arrays with np = 0
     pos = f32(rng.uniform(0, 1, size=(200, 3)) * np.asarray(shape))
     vel = f32(rng.normal(size=(200, 3)))
     w = f32(rng.uniform(0.5, 1.5, 200))

@@ -745,6 +745,45 @@ def test_fused_observation_chain(nb, case):
             assert abs(float(ap[k].grad) - float(ap2[k].grad)) < 2e-4 * abs(float(ap2[k].grad)), k
 
 
+@pytest.mark.parametrize("order", [3, 4])
+def test_fused_observation_chain_other_windows(order):
+    """The observed paint with the assignment windows the benchmark does not use -- TSC / PCS, and the Kaiser-Bessel
+    family on a 1.5x paint mesh -- against the float64 chain + the oracle's nufft: the window only changes how the
+    observed position is deposited, so the same transform and transpose serve every instantiation.  CPU port only (the
+    B200 runs of this transform use the CIC instantiation; these share its source).  Spectrum 2e-5, cotangents 1e-4."""
+    import montecosmo_b200.nbody as nbody
+    from montecosmo_b200 import bricks as B
+    from montecosmo_b200.cosmo import Cosmology
+    from oracle import cpu_port
+    old = nbody._OPS
+    nbody._OPS = cpu_port.cpu_ops()
+    try:
+        rng = np.random.default_rng(order)
+        shape, paint, box, center = (12, 12, 12), (18, 18, 18), (480.0, 480.0, 480.0), (-200.0, 300.0, 1200.0)
+        q = O.regular_pos(shape)
+        disp, vel0 = torch.tensor(rng.normal(scale=0.7, size=q.shape)), torch.tensor(rng.normal(scale=0.4, size=q.shape))
+        w0 = torch.tensor(rng.uniform(0.3, 2.0, q.shape[0]))
+        cshape = (shape[0], shape[1], shape[2] // 2 + 1)
+        ck = torch.tensor(rng.normal(size=cshape) + 1j * rng.normal(size=cshape))
+        fid = Cosmology(Omega_c=0.21, Omega_b=0.05, h=0.7)
+        for kernel_type in ("rectangular", "kaiser_bessel"):
+            cosmo = Cosmology()
+            pos, vel, w = leaf(q + disp, None, torch.float32), leaf(vel0, None, torch.float32), leaf(w0, None, torch.float32)
+            obs = B.observation(cosmo, center, None, box, shape, None, True, True, True, fid)
+            out = nbody.nufft_observed(pos, vel, shape, obs, paint, w, None, order, 2, kernel_type, True)
+            (out * ck.to(torch.complex64).conj()).real.sum().backward()
+            po, vo, wo = leaf(q + disp), leaf(vel0), leaf(w0)
+            los, a = B.los_scalefactor_pos(po, center, None, box, shape, cosmo, None, True)
+            phys = B.cell2phys_pos(po, center, None, box, shape) + B.rsd(cosmo, vo, los, a, None, box, shape)
+            phys = B.ap_auto(phys, los, cosmo, fid, True)
+            ref = O.nufft(B.phys2cell_pos(phys, center, None, box, shape), shape, paint, wo, order, 2, kernel_type, True)
+            (ref * ck.conj()).real.sum().backward()
+            assert rel(out, ref.detach()) < 2e-5, kernel_type
+            assert rel(pos.grad, po.grad) < 1e-4 and rel(vel.grad, vo.grad) < 1e-4 and rel(w.grad, wo.grad) < 1e-4, kernel_type
+    finally:
+        nbody._OPS = old
+
+
 @pytest.mark.parametrize("curved", [True, False])
 def test_lightcone_functions_on_the_device(nb, curved):
     """bricks.lightcone_functions (one engine pass, mcpm_radial_tables: growth lookups of the light cone at every

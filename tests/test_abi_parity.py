@@ -148,6 +148,46 @@ def test_empty_inputs_and_rejected_arguments(ops):
         ops.read(bad, mesh)
 
 
+@pytest.mark.parametrize("grad_fd", [0, 2, 4])
+def test_yz_gradients_of_the_two_field_slab_transform(grad_fd):
+    """mcpm_yz_gradients -- the y / z halves of the force operator that a slab-decomposed caller applies on its own (y,z)
+    spectra so that two fields instead of three cross the distributed x-transform (dist.py) -- against a NumPy float64
+    restatement of gradient_hat (nbody.py:136-163) with the Hermitian projection on the self-conjugate planes, and as
+    an adjoint pair:  <T0 Phi, C> = <Phi, conj-transpose>  i.e.  sum conj(F_y) C_y + conj(F_z) C_z = sum conj(Phi) i (g_y C_y
+    + g_z C_z).  Values 2e-6.  CPU port (the B200 checks the same kernel inside tests/test_xfuse.py's two-field tests)."""
+    ops = _make_ops("hostemu")
+    rng = np.random.default_rng(grad_fd)
+    xl, ny, nz = 5, 8, 12
+    nzc = nz // 2 + 1
+    A = ops.A
+    cx = lambda *sh: (rng.normal(size=sh) + 1j * rng.normal(size=sh)).astype(np.complex64)
+    term = {0: lambda k: k, 2: np.sin, 4: lambda k: (8 * np.sin(k) - np.sin(2 * k)) / 6}[grad_fd]
+    ky = 2 * np.pi * np.fft.fftfreq(ny)
+    kz = 2 * np.pi * np.fft.rfftfreq(nz)
+    gy = np.broadcast_to(term(ky)[:, None], (ny, nzc)).copy()
+    gz = np.broadcast_to(term(kz)[None, :], (ny, nzc)).copy()
+    sc = np.zeros(nzc, bool)
+    sc[0] = sc[nz // 2] = True
+    gy[ny // 2, sc] = 0.0   # ky Nyquist on the self-conjugate kz planes
+    gz[:, nz // 2] = 0.0    # kz Nyquist
+    buf = cx(3, xl, ny, nzc)
+    phi = buf[1].astype(np.complex128)
+    d = A.prepare(buf.copy(), "c64")
+    ops._call("mcpm_yz_gradients", A.stream(), A.ptr(d), xl, ny, nz, grad_fd, 0)
+    out = to_numpy(d)
+    assert np.array_equal(out[0], buf[0])
+    assert rel(out[1], -1j * gy * phi) < 2e-6 and rel(out[2], -1j * gz * phi) < 2e-6
+    cot = cx(3, xl, ny, nzc)
+    d2 = A.prepare(cot.copy(), "c64")
+    ops._call("mcpm_yz_gradients", A.stream(), A.ptr(d2), xl, ny, nz, grad_fd, 1)
+    comb = to_numpy(d2)
+    assert np.array_equal(comb[0], cot[0])
+    assert rel(comb[1], gy * cot[1].astype(np.complex128) + gz * cot[2].astype(np.complex128)) < 2e-6
+    lhs = np.vdot(out[1].astype(np.complex128), cot[1]) + np.vdot(out[2].astype(np.complex128), cot[2])
+    rhs = np.vdot(phi, 1j * comb[1].astype(np.complex128))
+    assert abs(lhs - rhs) < 1e-5 * abs(lhs)
+
+
 def test_observed_nufft_edge_cases(ops):
     """mcpm_nufft_obs / mcpm_radial_tables at their edges: an empty particle set paints a zero mesh; a descriptor that
     does nothing (no redshift-space term, no Alcock-Paczynski) reproduces mcpm_nufft (1e-6: atomics order); a light cone or ap_auto

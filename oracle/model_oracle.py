@@ -188,6 +188,15 @@ def rsd(cosmo, vel, los, a, rot, box, shape, dvel=0.0):
     return (vel * los).sum(-1, keepdim=True) * los
 
 
+def ap_param(pos, los, alpha_iso, alpha_ap, curved_sky=True):
+    """bricks.py:847-856 with isoap2parperp (730-736) and scale_pos (712-720)."""
+    if curved_sky:
+        return pos * alpha_iso
+    a_par, a_perp = alpha_iso * alpha_ap ** (2 / 3), alpha_iso * alpha_ap ** (-1 / 3)
+    par = (pos * los).sum(-1, keepdim=True) * los
+    return par * a_par + (pos - par) * a_perp
+
+
 def ap_auto(pos, los, cosmo, cosmo_fid, curved_sky=True):
     """bricks.py:795-813."""
     rpos = pos.norm(dim=-1, keepdim=True) if curved_sky else (pos * los).sum(-1, keepdim=True).abs()

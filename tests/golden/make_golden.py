@@ -406,7 +406,38 @@ def main():
     d["fullsky2count"] = A(bricks.fullsky2count(chunks, cosmo, 0.65, flos, csize, ccenter, crotvec, (12, 14, 12), None))
     out["observation"] = d
 
+    # ---- the whole observation chain followed by nufft, in the order model.py:780-805 composes it (what the engine
+    # applies inside its paint kernels: mcpm_nufft_obs) -- its own generator, so the fixtures above keep their streams
+    rng = np.random.default_rng(21)
+    shape, paint, box, center = (12, 10, 14), (18, 16, 20), (600.0, 500.0, 700.0), (250.0, -300.0, 1400.0)
+    rot = Rotation.from_rotvec([0.3, 0.2, -0.5])
+    q = lattice(shape)
+    pos = q + rng.normal(scale=0.7, size=q.shape)
+    vel = rng.normal(scale=0.3, size=q.shape)
+    dvel = rng.normal(scale=2.0, size=q.shape)
+    wts = rng.uniform(0.3, 2.0, q.shape[0])
+    ap = dict(alpha_iso=1.03, alpha_ap=0.97)
+    d = {"shape": np.array(shape), "paint_shape": np.array(paint), "box_size": np.array(box), "box_center": np.array(center),
+         "rot_matrix": rot.as_matrix(), "pos": pos, "vel": vel, "dvel": dvel, "weights": wts,
+         "alpha_iso": np.array(ap["alpha_iso"]), "alpha_ap": np.array(ap["alpha_ap"]), "a_obs": np.array(0.7)}
+    for tag, curved, a_obs, ap_auto in (("curved_lightcone_auto", True, None, True), ("flat_lightcone_auto", False, None, True),
+                                        ("curved_scalar_param", True, 0.7, False), ("flat_scalar_param", False, 0.7, False),
+                                        ("flat_scalar_plain", False, 0.7, None)):
+        cosmo._workspace, fid._workspace = {}, {}
+        los, a = bricks.los_scalefactor_pos(jnp.asarray(pos), np.array(center), rot, box, shape, cosmo, a_obs, curved)
+        p = bricks.cell2phys_pos(jnp.asarray(pos), center, rot, box, shape)
+        p = p + bricks.rsd(cosmo, jnp.asarray(vel), los, a, rot, box, shape, jnp.asarray(dvel))
+        if ap_auto is not None:
+            p = bricks.ap_auto(p, los, cosmo, fid, curved) if ap_auto else bricks.ap_param(p, los, dict(ap), curved)
+        p = bricks.phys2cell_pos(p, center, rot, box, shape)
+        d[f"pos_{tag}"] = A(p)
+        d[f"nufft_{tag}"] = A(nbody.nufft(p, shape, paint, jnp.asarray(wts), 2, 2, "rectangular", True))
+    out["observed_nufft"] = d
+
+    only = set(sys.argv[1:])  # e.g. `make_golden.py observed_nufft`: write that fixture alone
     for name, dd in out.items():
+        if only and name not in only:
+            continue
         path = os.path.join(HERE, f"{name}.npz")
         np.savez_compressed(path, **{k: np.asarray(v) for k, v in dd.items()})
         print(f"{name:18s} {os.path.getsize(path) / 1024:8.1f} KiB  {len(dd)} arrays")

@@ -745,6 +745,31 @@ def test_fused_observation_chain(nb, case):
             assert abs(float(ap[k].grad) - float(ap2[k].grad)) < 2e-4 * abs(float(ap2[k].grad)), k
 
 
+def test_observed_nufft_golden(nb, golden):
+    """nufft_observed (the observation chain inside the paint kernels, mcpm_nufft_obs) against golden vectors of the
+    REFERENCE SOURCE: bricks.los_scalefactor_pos, cell2phys_pos, rsd with a velocity bias, ap_auto | ap_param,
+    phys2cell_pos composed as model.py:780-805 does, followed by nbody.nufft on a 1.5x paint mesh
+    (tests/golden/make_golden.py: observed_nufft).  Curved and flat sky, light cone and scalar a_obs, both
+    Alcock-Paczynski forms and none: half spectrum 2e-5 relative L2."""
+    from scipy.spatial.transform import Rotation
+    from montecosmo_b200 import bricks as B
+    from montecosmo_b200.cosmo import Cosmology
+    g, gr = golden("observed_nufft"), golden("growth")
+    shape, paint = tuple(int(s) for s in g["shape"]), tuple(int(s) for s in g["paint_shape"])
+    box, center, rot = tuple(g["box_size"]), tuple(g["box_center"]), Rotation.from_matrix(g["rot_matrix"])
+    oc, ob, h, ns, s8 = gr["other_params"]
+    cosmo, fid = Cosmology(), Cosmology(Omega_c=oc, Omega_b=ob, h=h, n_s=ns, sigma8=s8)
+    d = dev(nb)
+    pos, vel, dvel, w = (torch.tensor(g[k], dtype=torch.float32, device=d) for k in ("pos", "vel", "dvel", "weights"))
+    ap = dict(alpha_iso=float(g["alpha_iso"]), alpha_ap=float(g["alpha_ap"]))
+    for tag, curved, a_obs, ap_auto in (("curved_lightcone_auto", True, None, True), ("flat_lightcone_auto", False, None, True),
+                                        ("curved_scalar_param", True, 0.7, False), ("flat_scalar_param", False, 0.7, False),
+                                        ("flat_scalar_plain", False, 0.7, None)):
+        obs = B.observation(cosmo, center, rot, box, shape, a_obs, curved, True, ap_auto, fid, ap)
+        out = nb.nufft_observed(pos, vel, shape, obs, paint, w, dvel, 2, 2, "rectangular", True)
+        assert rel(out, g[f"nufft_{tag}"]) < 2e-5, tag
+
+
 @pytest.mark.parametrize("order", [3, 4])
 def test_fused_observation_chain_other_windows(order):
     """The observed paint with the assignment windows the benchmark does not use -- TSC / PCS, and the Kaiser-Bessel

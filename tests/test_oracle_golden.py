@@ -296,3 +296,31 @@ def test_observation_chain(golden):
         close(a, g[f"a_{tag}"], rtol=1e-10)
         close(MO.rsd(cosmo, vel, los, a, rot, box, shape, dvel=0.01), g[f"rsd_{tag}"], rtol=1e-9)
         close(MO.ap_auto(phys, los, cosmo, fid, curved), g[f"ap_auto_{tag}"], rtol=1e-10)
+
+
+OBSERVED = (("curved_lightcone_auto", True, None, True), ("flat_lightcone_auto", False, None, True),
+            ("curved_scalar_param", True, 0.7, False), ("flat_scalar_param", False, 0.7, False),
+            ("flat_scalar_plain", False, 0.7, None))
+
+
+def test_observed_nufft(golden):
+    """The whole observation chain in the order model.py:780-805 composes it -- los_scalefactor_pos, cell2phys_pos, rsd
+    with a velocity bias, ap_auto | ap_param, phys2cell_pos -- followed by nufft, float64 restatement against the
+    reference source: observed positions 1e-10, half spectra 1e-9."""
+    from scipy.spatial.transform import Rotation
+    from oracle import model_oracle as MO
+    g, gr = golden("observed_nufft"), golden("growth")
+    shape, paint = tuple(int(s) for s in g["shape"]), tuple(int(s) for s in g["paint_shape"])
+    box, center, rot = tuple(g["box_size"]), tuple(g["box_center"]), Rotation.from_matrix(g["rot_matrix"])
+    oc, ob, h, ns, s8 = gr["other_params"]
+    cosmo, fid = O.Cosmology(), O.Cosmology(Omega_c=oc, Omega_b=ob, h=h, n_s=ns, sigma8=s8)
+    pos, vel, dvel, w = (O._t(g[k]) for k in ("pos", "vel", "dvel", "weights"))
+    for tag, curved, a_obs, ap_auto in OBSERVED:
+        los, a = MO.los_scalefactor_pos(pos, center, rot, box, shape, cosmo, a_obs, curved)
+        p = MO.cell2phys_pos(pos, center, rot, box, shape) + MO.rsd(cosmo, vel, los, a, rot, box, shape, dvel)
+        if ap_auto is not None:
+            p = MO.ap_auto(p, los, cosmo, fid, curved) if ap_auto else \
+                MO.ap_param(p, los, float(g["alpha_iso"]), float(g["alpha_ap"]), curved)
+        p = MO.phys2cell_pos(p, center, rot, box, shape)
+        close(p, g[f"pos_{tag}"], rtol=1e-10)
+        close(O.nufft(p, shape, paint, w, 2, 2, "rectangular", True), g[f"nufft_{tag}"], rtol=1e-9)
